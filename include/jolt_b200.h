@@ -1,0 +1,343 @@
+/* jolt_b200.h -- C ABI of the B200-native rigid-body step (libjolt_b200.so).
+ *
+ * Drop-in boundary for the hot path of jrouwe/JoltPhysics: PhysicsSystem::Update and the BodyInterface /
+ * ContactListener / BodyActivationListener surface around it.  The reference has no whole-step plugin API
+ * (PhysicsSystem is a concrete class, Jolt/Physics/PhysicsSystem.h:29-396, the broadphase is a #define,
+ * Jolt/Physics/PhysicsSystem.cpp:46-47), so the boundary is source-level: a facade with the reference's
+ * signatures forwards to the entry points below.  Each entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain C structs, caller-allocated buffers, integer return codes (0 = OK, <0 = error, see
+ * b2j_last_error), no callbacks across the ABI, no exceptions.  Thread-compatible (external synchronisation),
+ * like the reference's PhysicsSystem::Update.  All floating point is fp32; ids are the reference's 32-bit BodyID
+ * (23-bit index | 8-bit sequence number << 23, Jolt/Physics/Body/BodyID.h:18-21).
+ *
+ * There is NO CPU fallback: every function that touches a world needs a CUDA device (sm_100a).
+ */
+#ifndef JOLT_B200_H
+#define JOLT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2J_VERSION 1
+
+/* ---- enums (values identical to the reference) ------------------------------------------------------------- */
+
+/* EMotionType, Jolt/Physics/Body/MotionType.h */
+enum { B2J_MOTION_STATIC = 0, B2J_MOTION_KINEMATIC = 1, B2J_MOTION_DYNAMIC = 2 };
+
+/* EPhysicsUpdateError bits, Jolt/Physics/EPhysicsUpdateError.h:12-16 */
+enum {
+	B2J_ERR_NONE = 0,
+	B2J_ERR_MANIFOLD_CACHE_FULL = 1,
+	B2J_ERR_BODY_PAIR_CACHE_FULL = 2,
+	B2J_ERR_CONTACT_CONSTRAINTS_FULL = 4
+};
+
+/* Shape kinds on the path (EShapeSubType subset, Jolt/Physics/Collision/Shape/Shape.h) */
+enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4 };
+
+/* Body flags */
+enum {
+	B2J_BODY_SENSOR = 1u << 0,                 /* Body::IsSensor */
+	B2J_BODY_ALLOW_SLEEPING = 1u << 1,         /* MotionProperties::mAllowSleeping */
+	B2J_BODY_USE_MANIFOLD_REDUCTION = 1u << 2, /* Body::EFlags::UseManifoldReduction */
+	B2J_BODY_GYROSCOPIC = 1u << 3,             /* Body::EFlags::ApplyGyroscopicForce */
+	B2J_BODY_KIN_VS_NONDYN = 1u << 4,          /* Body::EFlags::CollideKinematicVsNonDynamic */
+	B2J_BODY_INVALIDATE_CACHE = 1u << 5        /* Body::EFlags::InvalidateContactCache */
+};
+
+#define B2J_INACTIVE_INDEX 0xffffffffu /* Body::cInactiveIndex */
+#define B2J_INVALID_ID     0xffffffffu /* BodyID::cInvalidBodyID */
+
+/* Contact event kinds (ContactListener, Jolt/Physics/Collision/ContactListener.h:96-140) */
+enum { B2J_EVENT_CONTACT_ADDED = 0, B2J_EVENT_CONTACT_PERSISTED = 1, B2J_EVENT_CONTACT_REMOVED = 2 };
+/* Activation event kinds (BodyActivationListener, Jolt/Physics/Body/BodyActivationListener.h:13-26) */
+enum { B2J_EVENT_BODY_ACTIVATED = 0, B2J_EVENT_BODY_DEACTIVATED = 1 };
+
+/* ---- settings ------------------------------------------------------------------------------------------------ */
+
+/* The subset of PhysicsSettings (Jolt/Physics/PhysicsSettings.h:30-129) that the path reads; same defaults. */
+typedef struct b2j_settings {
+	float    speculative_contact_distance;     /* mSpeculativeContactDistance        0.02 */
+	float    penetration_slop;                 /* mPenetrationSlop                   0.02 */
+	float    baumgarte;                        /* mBaumgarte                         0.2  */
+	float    max_penetration_distance;         /* mMaxPenetrationDistance            0.2  */
+	float    manifold_tolerance;               /* mManifoldTolerance                 1e-3 */
+	float    body_pair_cache_max_delta_position_sq;       /* 1e-6 (Square(0.001)) */
+	float    body_pair_cache_cos_max_delta_rotation_div2; /* cos(2deg/2) = 0.99984769515639123915701155881391 */
+	float    contact_normal_cos_max_delta_rotation;       /* cos(5deg)   = 0.99619469809174553229501040247389 */
+	float    contact_point_preserve_lambda_max_dist_sq;   /* 1e-4 (Square(0.01)) */
+	float    min_velocity_for_restitution;     /* mMinVelocityForRestitution         1.0  */
+	float    time_before_sleep;                /* mTimeBeforeSleep                   0.5  */
+	float    point_velocity_sleep_threshold;   /* mPointVelocitySleepThreshold       0.03 */
+	uint32_t num_velocity_steps;               /* mNumVelocitySteps                  10   */
+	uint32_t num_position_steps;               /* mNumPositionSteps                  2    */
+	uint8_t  deterministic_simulation;         /* mDeterministicSimulation (always honoured; must be 1) */
+	uint8_t  constraint_warm_start;            /* mConstraintWarmStart               1 */
+	uint8_t  use_body_pair_contact_cache;      /* mUseBodyPairContactCache           1 */
+	uint8_t  use_manifold_reduction;           /* mUseManifoldReduction              1 */
+	uint8_t  use_large_island_splitter;        /* mUseLargeIslandSplitter            1 */
+	uint8_t  allow_sleeping;                   /* mAllowSleeping                     1 */
+	uint8_t  check_active_edges;               /* mCheckActiveEdges                  1 */
+	uint8_t  _pad;
+} b2j_settings;
+
+/* Fills *s with the reference's defaults (PhysicsSettings.h). */
+void b2j_settings_default(b2j_settings *s);
+
+/* ---- world --------------------------------------------------------------------------------------------------- */
+
+typedef struct b2j_world b2j_world; /* opaque */
+
+/* Replaces PhysicsSystem::Init(maxBodies, numBodyMutexes, maxBodyPairs, maxContactConstraints, bpLayerInterface,
+ * objectVsBpFilter, objectPairFilter) -- PhysicsSystem.h:59.  The three virtual filter objects are sampled into
+ * tables by the caller (as ObjectVsBroadPhaseLayerFilterTable does, .../BroadPhase/ObjectVsBroadPhaseLayerFilterTable.h:38-50). */
+typedef struct b2j_world_desc {
+	uint32_t        max_bodies;
+	uint32_t        max_body_pairs;
+	uint32_t        max_contact_constraints;
+	uint32_t        num_object_layers;       /* <= 64 */
+	uint32_t        num_broadphase_layers;   /* <= 8  */
+	const uint8_t  *object_to_broadphase;    /* [num_object_layers]                          BroadPhaseLayerInterface::GetBroadPhaseLayer */
+	const uint8_t  *object_vs_broadphase;    /* [num_object_layers][num_broadphase_layers]   ObjectVsBroadPhaseLayerFilter::ShouldCollide */
+	const uint8_t  *object_vs_object;        /* [num_object_layers][num_object_layers]       ObjectLayerPairFilter::ShouldCollide */
+	b2j_settings    settings;
+	float           gravity[3];              /* PhysicsSystem::SetGravity, default (0,-9.81,0) */
+	int32_t         device;                  /* CUDA device ordinal */
+} b2j_world_desc;
+
+b2j_world  *b2j_world_create(const b2j_world_desc *desc);           /* NULL on failure, see b2j_last_error */
+void        b2j_world_destroy(b2j_world *w);
+const char *b2j_last_error(void);
+int         b2j_world_set_gravity(b2j_world *w, const float g[3]);  /* PhysicsSystem::SetGravity  PhysicsSystem.h:194 */
+int         b2j_world_set_settings(b2j_world *w, const b2j_settings *s); /* SetPhysicsSettings  PhysicsSystem.h:111 */
+int         b2j_world_get_settings(const b2j_world *w, b2j_settings *s);
+/* mPreviousStepDeltaTime (PhysicsSystem.h:395) drives the warm start ratio; part of a snapshot. */
+int         b2j_world_set_previous_delta_time(b2j_world *w, float dt);
+
+/* ---- shapes (immutable once uploaded; Shape is RefConst and immutable in the reference, Body.h:451) ------------ */
+
+/* Cooked convex hull exactly as ConvexHullShape stores it (Jolt/Physics/Collision/Shape/ConvexHullShape.h:167-195);
+ * cooking (ConvexHullBuilder) is host-side and out of scope -- pass the reference's output. */
+typedef struct b2j_hull_desc {
+	uint32_t        num_points;           /* <= 256 */
+	const float    *points;               /* [num_points][3]  relative to the centre of mass */
+	const int32_t  *point_num_faces;      /* [num_points]     Point::mNumFaces */
+	const int32_t  *point_faces;          /* [num_points][3]  Point::mFaces */
+	uint32_t        num_faces;
+	const uint16_t *face_first_vertex;    /* [num_faces]      Face::mFirstVertex */
+	const uint16_t *face_num_vertices;    /* [num_faces]      Face::mNumVertices */
+	const float    *planes;               /* [num_faces][4]   (nx,ny,nz,c) */
+	uint32_t        num_vertex_idx;
+	const uint8_t  *vertex_idx;           /* [num_vertex_idx] */
+	float           convex_radius;
+	float           center_of_mass[3];
+	float           local_bounds_min[3], local_bounds_max[3];
+	float           inner_radius;
+} b2j_hull_desc;
+
+/* MeshShape's cooked byte buffer verbatim (NodeCodecQuadTreeHalfFloat + TriangleCodecIndexed8BitPackSOA4Flags,
+ * Jolt/Physics/Collision/Shape/MeshShape.cpp:491-553); cooking is host-side and out of scope. */
+typedef struct b2j_mesh_desc {
+	const uint8_t  *tree;                 /* MeshShape::mTree */
+	uint32_t        tree_size;
+	float           local_bounds_min[3], local_bounds_max[3];
+} b2j_mesh_desc;
+
+/* All return a shape id >= 0, or < 0 on error. */
+int32_t b2j_shape_sphere(b2j_world *w, float radius);                                        /* SphereShape */
+int32_t b2j_shape_box(b2j_world *w, const float half_extent[3], float convex_radius);        /* BoxShape */
+int32_t b2j_shape_capsule(b2j_world *w, float half_height_of_cylinder, float radius);        /* CapsuleShape */
+int32_t b2j_shape_convex_hull(b2j_world *w, const b2j_hull_desc *hull);                      /* ConvexHullShape */
+int32_t b2j_shape_mesh(b2j_world *w, const b2j_mesh_desc *mesh);                             /* MeshShape (static bodies) */
+
+/* ---- bodies (BodyInterface, Jolt/Physics/Body/BodyInterface.h:39-313) ------------------------------------------ */
+
+/* Everything one step depends on for a body: Body (Body.h:445-471) + MotionProperties
+ * (MotionProperties.h:288-330).  position is the CENTRE OF MASS position (Body::mPosition). */
+typedef struct b2j_body_desc {
+	uint32_t id;                    /* BodyID (index | sequence << 23); the index selects the slot */
+	int32_t  shape;                 /* shape id */
+	uint8_t  motion_type;           /* B2J_MOTION_* */
+	uint8_t  allowed_dofs;          /* EAllowedDOFs bit mask (0x3f = all) */
+	uint8_t  num_velocity_steps_override;
+	uint8_t  num_position_steps_override;
+	uint16_t object_layer;
+	uint16_t flags;                 /* B2J_BODY_* */
+	float    position[3];
+	float    rotation[4];           /* x y z w */
+	float    linear_velocity[3];
+	float    angular_velocity[3];
+	float    force[3];              /* accumulated force  (MotionProperties::mForce) */
+	float    torque[3];
+	float    inv_mass;
+	float    inv_inertia_diag[3];   /* mInvInertiaDiagonal */
+	float    inertia_rotation[4];   /* mInertiaRotation */
+	float    linear_damping, angular_damping;
+	float    max_linear_velocity, max_angular_velocity;
+	float    gravity_factor;
+	float    friction, restitution;
+	float    bounds_min[3], bounds_max[3];   /* cached world AABB (Body::mBounds); ignored unless has_bounds */
+	float    sleep_spheres[3][4];            /* mSleepTestSpheres (centre xyz, radius) */
+	float    sleep_timer;                    /* mSleepTestTimer */
+	uint8_t  has_bounds;                     /* 1: take bounds_* / sleep_* as given (snapshot); 0: compute */
+	uint8_t  active;                         /* add to the active list (BodyInterface::AddBody EActivation) */
+	uint8_t  _pad[2];
+} b2j_body_desc;
+
+/* BodyInterface::AddBody / AddBodiesPrepare+Finalize (BodyInterface.h:89,124-133). Bodies with active=1 are appended
+ * to the active list in array order. */
+int b2j_bodies_add(b2j_world *w, const b2j_body_desc *bodies, uint32_t n);
+/* BodyInterface::RemoveBody(s) (:99,:137) */
+int b2j_bodies_remove(b2j_world *w, const uint32_t *ids, uint32_t n);
+/* BodyInterface::ActivateBody / DeactivateBody (:142-145) */
+int b2j_bodies_activate(b2j_world *w, const uint32_t *ids, uint32_t n);
+int b2j_bodies_deactivate(b2j_world *w, const uint32_t *ids, uint32_t n);
+/* Snapshot helper: sets the active list to exactly ids[0..n) in this order (BodyManager::mActiveBodies). */
+int b2j_set_active_list(b2j_world *w, const uint32_t *ids, uint32_t n);
+
+/* SoA state block for get/set; any pointer may be NULL (skipped). All arrays have n entries. */
+typedef struct b2j_body_state {
+	float    *position;         /* [n][3] centre of mass position */
+	float    *rotation;         /* [n][4] */
+	float    *linear_velocity;  /* [n][3] */
+	float    *angular_velocity; /* [n][3] */
+	float    *bounds;           /* [n][6] min xyz, max xyz */
+	uint32_t *active_index;     /* [n]    index in the active list or B2J_INACTIVE_INDEX */
+	float    *sleep_timer;      /* [n] */
+} b2j_body_state;
+
+/* BodyInterface::GetPositionAndRotation / GetLinearAndAngularVelocity (:187-216); ids==NULL means slots 0..n-1. */
+int b2j_bodies_get_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_state *out);
+/* BodyInterface::SetPositionAndRotation / SetLinearAndAngularVelocity; NULL members are left untouched. */
+int b2j_bodies_set_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_state *in);
+/* BodyInterface::AddForce / AddTorque (:220-226): accumulate into mForce / mTorque (either may be NULL). */
+int b2j_bodies_add_force_torque(b2j_world *w, const uint32_t *ids, uint32_t n, const float *force, const float *torque);
+
+uint32_t b2j_num_bodies(const b2j_world *w);          /* PhysicsSystem::GetNumBodies        PhysicsSystem.h:219 */
+uint32_t b2j_num_active_bodies(const b2j_world *w);   /* PhysicsSystem::GetNumActiveBodies  :222 */
+/* PhysicsSystem::GetActiveBodies (:240): copies up to cap ids in active-list order, returns the count. */
+uint32_t b2j_get_active_bodies(b2j_world *w, uint32_t *ids, uint32_t cap);
+
+/* ---- contact cache snapshot (ContactConstraintManager::ManifoldCache, SaveState stream sections
+ *      Jolt/Physics/Constraints/ContactConstraintManager.cpp:467-548) -------------------------------------------- */
+
+typedef struct b2j_cached_body_pair {
+	uint32_t body1, body2;          /* body1 < body2 */
+	float    delta_position[3];     /* CachedBodyPair::mDeltaPosition (in body-1 space) */
+	float    delta_rotation[3];     /* CachedBodyPair::mDeltaRotation (xyz, w >= 0 reconstructed) */
+	uint32_t first_manifold;        /* index into the manifold array */
+	uint32_t num_manifolds;
+} b2j_cached_body_pair;
+
+typedef struct b2j_cached_manifold {
+	uint32_t sub_shape1, sub_shape2;   /* SubShapeIDPair (body ids come from the owning pair) */
+	float    normal[3];                /* CachedManifold::mContactNormal (body-2 space) */
+	float    friction_lambda[2];
+	float    angular_friction_lambda;
+	uint32_t num_points;               /* 1..4 */
+	uint32_t flags;                    /* CachedManifold::EFlags */
+	float    position1[4][3];          /* CachedContactPoint::mPosition1 (body-1 space) */
+	float    position2[4][3];
+	float    non_penetration_lambda[4];
+} b2j_cached_manifold;
+
+/* Replaces RestoreState(Contacts): installs the READ cache (what the next step warm-starts from). */
+int b2j_contact_cache_import(b2j_world *w, const b2j_cached_body_pair *pairs, uint32_t num_pairs,
+                             const b2j_cached_manifold *manifolds, uint32_t num_manifolds);
+/* Replaces SaveState(Contacts): pairs sorted by (body1, body2); returns counts through the out params. */
+int b2j_contact_cache_export(b2j_world *w, b2j_cached_body_pair *pairs, uint32_t pairs_cap, uint32_t *num_pairs,
+                             b2j_cached_manifold *manifolds, uint32_t manifolds_cap, uint32_t *num_manifolds);
+/* PhysicsSystem::WereBodiesInContact (PhysicsSystem.h:251) */
+int b2j_were_bodies_in_contact(b2j_world *w, uint32_t id1, uint32_t id2);
+
+/* ---- step ---------------------------------------------------------------------------------------------------- */
+
+/* Per-step counters the roofline is computed from; all are totals over the collision steps of the call. */
+typedef struct b2j_step_stats {
+	uint32_t num_active_bodies;       /* N_a at the end of the step */
+	uint32_t num_bodies;              /* N_all */
+	uint32_t num_body_pairs;          /* P   candidate pairs from the broadphase */
+	uint32_t num_pairs_from_cache;    /* P_hit */
+	uint32_t num_manifolds;           /* M   manifolds written to the cache */
+	uint32_t num_contact_points;      /* sum of c */
+	uint32_t num_constraints;         /* contact constraints solved */
+	uint32_t num_islands;
+	uint32_t num_large_islands;
+	uint32_t num_phases;              /* dependent solver phases per iteration (launch/barrier count) */
+	uint32_t velocity_iterations;     /* V executed (max over islands) */
+	uint32_t position_iterations;     /* Pp */
+	uint32_t num_activated, num_deactivated;
+	uint32_t kernel_launches;         /* CUDA kernels launched by this call */
+	uint32_t error_bits;
+	float    gpu_ms;                  /* device time of the step (CUDA events on the world's stream) */
+	float    kinetic_energy;          /* filled only when requested by b2j_step flags */
+} b2j_step_stats;
+
+/* Replaces PhysicsSystem::Update(deltaTime, collisionSteps, TempAllocator*, JobSystem*) -- PhysicsSystem.h:162.
+ * Returns the EPhysicsUpdateError bit field (>= 0) or < 0 on a CUDA failure. stats may be NULL. */
+int b2j_step(b2j_world *w, float delta_time, int collision_steps, b2j_step_stats *stats);
+
+/* ---- events (replayed into ContactListener / BodyActivationListener by the facade after the step) ------------- */
+
+typedef struct b2j_contact_event {
+	uint32_t kind;                 /* B2J_EVENT_CONTACT_* */
+	uint32_t body1, body2;         /* body1 < body2 (ContactListener.h:102,116) */
+	uint32_t sub_shape1, sub_shape2;
+	uint32_t num_points;           /* 0 for removed */
+	float    base_offset[3];       /* ContactManifold::mBaseOffset */
+	float    normal[3];            /* mWorldSpaceNormal */
+	float    penetration_depth;
+	float    points1[4][3];        /* mRelativeContactPointsOn1 */
+	float    points2[4][3];
+} b2j_contact_event;
+
+typedef struct b2j_activation_event {
+	uint32_t kind;                 /* B2J_EVENT_BODY_* */
+	uint32_t body;
+} b2j_activation_event;
+
+/* Copies up to cap events of the last b2j_step (sorted by kind, body1, body2, sub shapes) and returns the total
+ * number produced (may exceed cap). */
+uint32_t b2j_events_drain(b2j_world *w, b2j_contact_event *out, uint32_t cap);
+uint32_t b2j_activation_events_drain(b2j_world *w, b2j_activation_event *out, uint32_t cap);
+
+/* ---- parity hooks (debug; read the intermediate products of the LAST step) ------------------------------------ */
+
+/* Candidate body pairs of the broadphase as (min id, max id), sorted; returns the total count. */
+uint32_t b2j_debug_get_pairs(b2j_world *w, uint32_t *pairs /* [cap][2] */, uint32_t cap);
+
+typedef struct b2j_debug_manifold {
+	uint32_t body1, body2, sub_shape1, sub_shape2;
+	uint32_t num_points;
+	uint32_t from_cache;           /* 1 if copied by the body-pair cache */
+	float    normal[3];            /* world space */
+	float    penetration_depth;
+} b2j_debug_manifold;
+/* Manifolds written this step sorted by (body1, body2, sub1, sub2); returns the total count. */
+uint32_t b2j_debug_get_manifolds(b2j_world *w, b2j_debug_manifold *out, uint32_t cap);
+
+/* Only the broadphase of a step on the current state: fills the pair list for b2j_debug_get_pairs. */
+int b2j_debug_find_pairs(b2j_world *w);
+
+/* ---- batched independent worlds (config 5) --------------------------------------------------------- */
+
+typedef struct b2j_batch b2j_batch; /* opaque: n identical-layout worlds stepped together on one device */
+
+/* Clones `proto` n_worlds times on its device. The prototype stays usable on its own. */
+b2j_batch *b2j_batch_create(const b2j_world *proto, uint32_t n_worlds);
+void       b2j_batch_destroy(b2j_batch *b);
+/* Steps every world of the batch once; stats (may be NULL) receives the SUM over worlds. */
+int        b2j_batch_step(b2j_batch *b, float delta_time, int collision_steps, b2j_step_stats *stats);
+b2j_world *b2j_batch_world(b2j_batch *b, uint32_t i);
+uint32_t   b2j_batch_size(const b2j_batch *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOLT_B200_H */

@@ -1,0 +1,615 @@
+// ref_harness.cpp -- TEST INFRASTRUCTURE. A C interface around the UNMODIFIED reference (jrouwe/JoltPhysics, compiled by
+// oracle/Makefile from /root/reference into oracle/_ref/libjoltref_{det,fast}.so). It builds the benchmark scenes with the
+// reference's own API, steps them with JobSystemThreadPool, records what the parity tests compare against (candidate body
+// pairs, contact events, manifolds, post-step body state) and can re-create a live reference world inside a b2j_world through
+// the C ABI (jolt_adapter.h). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs load it.
+//
+// Scenes follow the specifications in PerformanceTest/PyramidScene.h:23-47, PerformanceTest/ConvexVsMeshScene.h:28-117,
+// PerformanceTest/MaxBodiesScene.h:44-80 and SURVEY.md 8(d) config 4 (Pile); they are re-stated here, not copied.
+
+#include "jolt_adapter.h"
+
+#include <Jolt/RegisterTypes.h>
+#include <Jolt/Core/Factory.h>
+#include <Jolt/Core/TempAllocator.h>
+#include <Jolt/Core/JobSystemThreadPool.h>
+#include <Jolt/Physics/PhysicsSettings.h>
+#include <Jolt/Physics/Collision/Shape/ConvexHullShape.h>
+#include <Jolt/Physics/Collision/Shape/MeshShape.h>
+#include <Jolt/Physics/Collision/BroadPhase/BroadPhase.h>
+#include <Jolt/Physics/Collision/ContactListener.h>
+#include <Jolt/Physics/Body/BodyActivationListener.h>
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <random>
+#include <thread>
+
+using namespace JPH;
+
+namespace {
+
+// ---- layers: the 2 object layer / 2 broadphase layer configuration used by PerformanceTest/Layers.h and UnitTests/Layers.h
+namespace Layers { constexpr ObjectLayer NON_MOVING = 0, MOVING = 1, NUM_LAYERS = 2; }
+namespace BPLayers { constexpr BroadPhaseLayer NON_MOVING(0), MOVING(1); constexpr uint NUM_LAYERS = 2; }
+
+class OLPairFilter final : public ObjectLayerPairFilter
+{
+public:
+	bool ShouldCollide(ObjectLayer in1, ObjectLayer in2) const override { return in1 == Layers::MOVING || in2 == Layers::MOVING; }
+};
+
+class BPLInterface final : public BroadPhaseLayerInterface
+{
+public:
+	uint GetNumBroadPhaseLayers() const override { return BPLayers::NUM_LAYERS; }
+	BroadPhaseLayer GetBroadPhaseLayer(ObjectLayer inLayer) const override { return inLayer == Layers::NON_MOVING? BPLayers::NON_MOVING : BPLayers::MOVING; }
+#if defined(JPH_EXTERNAL_PROFILE) || defined(JPH_PROFILE_ENABLED)
+	const char *GetBroadPhaseLayerName(BroadPhaseLayer) const override { return "layer"; }
+#endif
+};
+
+class OVBPFilter final : public ObjectVsBroadPhaseLayerFilter
+{
+public:
+	bool ShouldCollide(ObjectLayer in1, BroadPhaseLayer in2) const override { return in1 == Layers::MOVING || in2 == BPLayers::MOVING; }
+};
+
+// ---- recorded contact / activation events
+struct ContactRecord
+{
+	uint32 kind;        // b2j event kind
+	uint32 body1, body2, sub1, sub2, num_points;
+	float base_offset[3], normal[3], depth;
+	float p1[4][3], p2[4][3];
+};
+
+class RecordingContactListener final : public ContactListener
+{
+public:
+	void Record(uint32 inKind, const Body &inBody1, const Body &inBody2, const ContactManifold &inManifold)
+	{
+		ContactRecord r;
+		memset(&r, 0, sizeof(r));
+		r.kind = inKind;
+		r.body1 = inBody1.GetID().GetIndexAndSequenceNumber();
+		r.body2 = inBody2.GetID().GetIndexAndSequenceNumber();
+		r.sub1 = inManifold.mSubShapeID1.GetValue();
+		r.sub2 = inManifold.mSubShapeID2.GetValue();
+		r.num_points = (uint32)inManifold.mRelativeContactPointsOn1.size();
+		b2j_adapter::sStore(Vec3(inManifold.mBaseOffset), r.base_offset);
+		b2j_adapter::sStore(inManifold.mWorldSpaceNormal, r.normal);
+		r.depth = inManifold.mPenetrationDepth;
+		for (uint32 i = 0; i < r.num_points && i < 4; ++i)
+		{
+			b2j_adapter::sStore(inManifold.mRelativeContactPointsOn1[i], r.p1[i]);
+			b2j_adapter::sStore(inManifold.mRelativeContactPointsOn2[i], r.p2[i]);
+		}
+		std::lock_guard<std::mutex> lock(mMutex);
+		mRecords.push_back(r);
+	}
+
+	void OnContactAdded(const Body &inBody1, const Body &inBody2, const ContactManifold &inManifold, ContactSettings &) override { Record(B2J_EVENT_CONTACT_ADDED, inBody1, inBody2, inManifold); }
+	void OnContactPersisted(const Body &inBody1, const Body &inBody2, const ContactManifold &inManifold, ContactSettings &) override { Record(B2J_EVENT_CONTACT_PERSISTED, inBody1, inBody2, inManifold); }
+	void OnContactRemoved(const SubShapeIDPair &inPair) override
+	{
+		ContactRecord r;
+		memset(&r, 0, sizeof(r));
+		r.kind = B2J_EVENT_CONTACT_REMOVED;
+		r.body1 = inPair.GetBody1ID().GetIndexAndSequenceNumber();
+		r.body2 = inPair.GetBody2ID().GetIndexAndSequenceNumber();
+		r.sub1 = inPair.GetSubShapeID1().GetValue();
+		r.sub2 = inPair.GetSubShapeID2().GetValue();
+		std::lock_guard<std::mutex> lock(mMutex);
+		mRecords.push_back(r);
+	}
+
+	std::mutex mMutex;
+	std::vector<ContactRecord> mRecords;
+};
+
+class RecordingActivationListener final : public BodyActivationListener
+{
+public:
+	void OnBodyActivated(const BodyID &inID, uint64) override { std::lock_guard<std::mutex> lock(mMutex); mRecords.push_back({ B2J_EVENT_BODY_ACTIVATED, inID.GetIndexAndSequenceNumber() }); }
+	void OnBodyDeactivated(const BodyID &inID, uint64) override { std::lock_guard<std::mutex> lock(mMutex); mRecords.push_back({ B2J_EVENT_BODY_DEACTIVATED, inID.GetIndexAndSequenceNumber() }); }
+	std::mutex mMutex;
+	std::vector<b2j_activation_event> mRecords;
+};
+
+struct World
+{
+	BPLInterface bpl;
+	OVBPFilter ovbp;
+	OLPairFilter olp;
+	PhysicsSystem system;
+	TempAllocator *temp = nullptr;
+	JobSystemThreadPool *jobs = nullptr;
+	int jobs_threads = -1;
+	RecordingContactListener contacts;
+	RecordingActivationListener activations;
+	uint max_body_pairs = 0, max_contact_constraints = 0;
+	uint num_dynamic = 0;
+
+	~World() { delete jobs; delete temp; }
+};
+
+std::once_flag sInitFlag;
+b2j_adapter::Api sApi;
+String sLastError;
+
+void sInit()
+{
+	std::call_once(sInitFlag, []() {
+		RegisterDefaultAllocator();
+		Factory::sInstance = new Factory();
+		RegisterTypes();
+	});
+}
+
+World *sNewWorld(uint inMaxBodies, uint inMaxBodyPairs, uint inMaxContactConstraints, uint inTempMB)
+{
+	sInit();
+	World *w = new World;
+	w->max_body_pairs = inMaxBodyPairs;
+	w->max_contact_constraints = inMaxContactConstraints;
+	w->system.Init(inMaxBodies, 0, inMaxBodyPairs, inMaxContactConstraints, w->bpl, w->ovbp, w->olp);
+	if (inTempMB == 0)
+		w->temp = new TempAllocatorMalloc();
+	else
+		w->temp = new TempAllocatorImpl(size_t(inTempMB) * 1024 * 1024);
+	return w;
+}
+
+void sEnsureJobs(World *w, int inNumThreads)
+{
+	if (inNumThreads <= 0)
+		inNumThreads = (int)std::thread::hardware_concurrency();
+	if (w->jobs == nullptr || w->jobs_threads != inNumThreads)
+	{
+		delete w->jobs;
+		// N threads = N-1 workers + the calling thread (PerformanceTest/PerformanceTest.cpp:314)
+		w->jobs = new JobSystemThreadPool(cMaxPhysicsJobs, cMaxPhysicsBarriers, inNumThreads - 1);
+		w->jobs_threads = inNumThreads;
+	}
+}
+
+// ---- scenes -------------------------------------------------------------------------------------------------
+
+World *sScenePyramid(int inHeight)
+{
+	// PerformanceTest/PyramidScene.h:23-47 (height 15 -> 1240 boxes); limits as PerformanceTest.cpp (10240 bodies, 65536 pairs, 20480 constraints)
+	World *w = sNewWorld(10240, 65536, 20480, 32);
+	BodyInterface &bi = w->system.GetBodyInterface();
+	bi.CreateAndAddBody(BodyCreationSettings(new BoxShape(Vec3(50.0f, 1.0f, 50.0f), 0.0f), RVec3(0.0f, -1.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING), EActivation::DontActivate);
+	const float box_size = 2.0f, separation = 0.5f, half = 1.0f;
+	RefConst<Shape> box = new BoxShape(Vec3::sReplicate(half), 0.0f);
+	for (int i = 0; i < inHeight; ++i)
+		for (int j = i / 2; j < inHeight - (i + 1) / 2; ++j)
+			for (int k = i / 2; k < inHeight - (i + 1) / 2; ++k)
+			{
+				RVec3 pos(float(-inHeight) + box_size * j + ((i & 1)? half : 0.0f), 1.0f + (box_size + separation) * i, float(-inHeight) + box_size * k + ((i & 1)? half : 0.0f));
+				BodyCreationSettings s(box, pos, Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+				s.mAllowSleeping = false;
+				bi.CreateAndAddBody(s, EActivation::Activate);
+				w->num_dynamic++;
+			}
+	return w;
+}
+
+Ref<Shape> sTerrainMesh(int n, float cell_size, float max_height)
+{
+	VertexList vertices;
+	vertices.resize((n + 1) * (n + 1));
+	for (int x = 0; x <= n; ++x)
+		for (int z = 0; z <= n; ++z)
+		{
+			float height = Sin(float(x) * 50.0f / n) * Cos(float(z) * 50.0f / n);
+			vertices[z * (n + 1) + x] = Float3(cell_size * x, max_height * height, cell_size * z);
+		}
+	IndexedTriangleList indices;
+	indices.resize(n * n * 2);
+	IndexedTriangle *next = indices.data();
+	for (int x = 0; x < n; ++x)
+		for (int z = 0; z < n; ++z)
+		{
+			int start = (n + 1) * z + x;
+			next->mIdx[0] = start; next->mIdx[1] = start + n + 1; next->mIdx[2] = start + 1; next++;
+			next->mIdx[0] = start + 1; next->mIdx[1] = start + n + 1; next->mIdx[2] = start + n + 2; next++;
+		}
+	Ref<MeshShapeSettings> settings = new MeshShapeSettings(vertices, indices);
+	settings->mMaxTrianglesPerLeaf = 4;
+	return settings->Create().Get();
+}
+
+World *sSceneConvexVsMesh(int inHalfGrid)
+{
+	// PerformanceTest/ConvexVsMeshScene.h:28-117 (half grid 10 -> 21*4*21 = 1764 bodies on a 20000 triangle mesh)
+	World *w = sNewWorld(10240, 65536, 20480, 32);
+	PhysicsSettings settings = w->system.GetPhysicsSettings();
+	settings.mNumVelocitySteps = 4;
+	settings.mNumPositionSteps = 1;
+	w->system.SetPhysicsSettings(settings);
+
+	const int n = 100;
+	const float cell_size = 3.0f, max_height = 5.0f, center = n * cell_size / 2;
+	BodyCreationSettings mesh(sTerrainMesh(n, cell_size, max_height), RVec3(-center, max_height, -center), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+	mesh.mFriction = 0.5f;
+	mesh.mRestitution = 0.6f;
+	BodyInterface &bi = w->system.GetBodyInterface();
+	bi.CreateAndAddBody(mesh, EActivation::DontActivate);
+
+	Array<Ref<Shape>> shapes = {
+		new BoxShape(Vec3(0.5f, 0.75f, 1.0f)),
+		new SphereShape(0.5f),
+		new CapsuleShape(0.75f, 0.5f),
+		ConvexHullShapeSettings({ Vec3(0, 1, 0), Vec3(1, 0, 0), Vec3(-1, 0, 0), Vec3(0, 0, 1), Vec3(0, 0, -1) }).Create().Get(),
+	};
+	for (int x = -inHalfGrid; x <= inHalfGrid; ++x)
+		for (int y = 0; y < (int)shapes.size(); ++y)
+			for (int z = -inHalfGrid; z <= inHalfGrid; ++z)
+			{
+				BodyCreationSettings s;
+				s.mMotionType = EMotionType::Dynamic;
+				s.mObjectLayer = Layers::MOVING;
+				s.mPosition = RVec3(7.5f * x, 15.0f + 2.0f * y, 7.5f * z);
+				s.mFriction = 0.5f;
+				s.mRestitution = 0.6f;
+				s.SetShape(shapes[y]);
+				bi.CreateAndAddBody(s, EActivation::Activate);
+				w->num_dynamic++;
+			}
+	return w;
+}
+
+World *sSceneMaxBodies(int inNumBodies)
+{
+	// PerformanceTest/MaxBodiesScene.h:44-80 restated for N bodies: unit boxes of mass 1000 on a cubic grid, x neighbours touching.
+	uint n = (uint)inNumBodies;
+	World *w = sNewWorld(n, std::max(65536u, n), std::max(20480u, n), 0);
+	PhysicsSettings settings = w->system.GetPhysicsSettings();
+	settings.mNumVelocitySteps = 4;
+	settings.mNumPositionSteps = 1;
+	w->system.SetPhysicsSettings(settings);
+	BodyInterface &bi = w->system.GetBodyInterface();
+	uint side = (uint)ceil(cbrt(double(n)));
+	BodyCreationSettings s;
+	s.SetShape(new BoxShape(Vec3::sReplicate(0.5f)));
+	s.mMotionType = EMotionType::Dynamic;
+	s.mObjectLayer = Layers::MOVING;
+	s.mOverrideMassProperties = EOverrideMassProperties::CalculateInertia;
+	s.mMassPropertiesOverride.mMass = 1000.0f;
+	std::vector<BodyID> ids;
+	ids.reserve(n);
+	uint count = 0;
+	for (uint x = 0; x < side && count < n; ++x)
+		for (uint y = 0; y < side && count < n; ++y)
+			for (uint z = 0; z < side && count < n; ++z, ++count)
+			{
+				s.mPosition = RVec3(1.0f * x, 3.0f * y, 3.0f * z);
+				ids.push_back(bi.CreateBody(s)->GetID());
+			}
+	BodyInterface::AddState state = bi.AddBodiesPrepare(ids.data(), (int)ids.size());
+	bi.AddBodiesFinalize(ids.data(), (int)ids.size(), state, EActivation::Activate);
+	w->num_dynamic = n;
+	return w;
+}
+
+Ref<Shape> sRandomHull(std::mt19937 &ioRandom, float inExtent)
+{
+	std::uniform_real_distribution<float> d(-inExtent, inExtent);
+	Array<Vec3> points;
+	for (int i = 0; i < 12; ++i)
+	{
+		float x = d(ioRandom), y = d(ioRandom), z = d(ioRandom);
+		points.push_back(Vec3(x, y, z));
+	}
+	return ConvexHullShapeSettings(points).Create().Get();
+}
+
+Quat sRandomQuat(std::mt19937 &ioRandom)
+{
+	std::normal_distribution<float> n(0.0f, 1.0f);
+	float x = n(ioRandom), y = n(ioRandom), z = n(ioRandom), q = n(ioRandom);
+	return Quat(x, y, z, q).Normalized();
+}
+
+World *sScenePile(int inNumBodies, int inShapeMask)
+{
+	// seed 12345; container of 5 static boxes; bodies i mod 4 -> sphere / box / capsule / 12 point hull on a
+	// jittered cubic grid with spacing 1.15; friction 0.5, restitution 0.1. inShapeMask selects which of the 4 kinds are used (bit per kind).
+	uint n = (uint)inNumBodies;
+	uint side = (uint)ceil(cbrt(double(n)));
+	float spacing = 1.15f;
+	float half_width = 0.5f * side * spacing + 2.0f;
+	World *w = sNewWorld(n + 128, std::max(65536u, 16 * n), std::max(20480u, 8 * n), 0);
+	BodyInterface &bi = w->system.GetBodyInterface();
+
+	auto add_static = [&](Vec3 inHalfExtent, Vec3 inPos) {
+		BodyCreationSettings s(new BoxShape(inHalfExtent), RVec3(inPos), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		s.mFriction = 0.5f; s.mRestitution = 0.1f;
+		bi.CreateAndAddBody(s, EActivation::DontActivate);
+	};
+	float wall_h = 0.5f * side * spacing + 2.0f;
+	add_static(Vec3(half_width + 2.0f, 1.0f, half_width + 2.0f), Vec3(0, -1.0f, 0));
+	add_static(Vec3(1.0f, wall_h, half_width + 2.0f), Vec3(-half_width - 1.0f, wall_h, 0));
+	add_static(Vec3(1.0f, wall_h, half_width + 2.0f), Vec3(half_width + 1.0f, wall_h, 0));
+	add_static(Vec3(half_width + 2.0f, wall_h, 1.0f), Vec3(0, wall_h, -half_width - 1.0f));
+	add_static(Vec3(half_width + 2.0f, wall_h, 1.0f), Vec3(0, wall_h, half_width + 1.0f));
+
+	std::mt19937 random(12345);
+	std::uniform_real_distribution<float> jitter(-0.05f, 0.05f);
+	Ref<Shape> sphere = new SphereShape(0.5f);
+	Ref<Shape> box = new BoxShape(Vec3(0.5f, 0.4f, 0.3f), 0.05f);
+	Ref<Shape> capsule = new CapsuleShape(0.4f, 0.3f);
+	std::vector<int> kinds;
+	for (int k = 0; k < 4; ++k)
+		if (inShapeMask & (1 << k))
+			kinds.push_back(k);
+	if (kinds.empty())
+		kinds = { 0, 1, 2, 3 };
+
+	std::vector<BodyID> ids;
+	ids.reserve(n);
+	uint count = 0;
+	for (uint y = 0; y < side && count < n; ++y)
+		for (uint x = 0; x < side && count < n; ++x)
+			for (uint z = 0; z < side && count < n; ++z, ++count)
+			{
+				BodyCreationSettings s;
+				switch (kinds[count % kinds.size()])
+				{
+				case 0: s.SetShape(sphere); break;
+				case 1: s.SetShape(box); break;
+				case 2: s.SetShape(capsule); break;
+				default: s.SetShape(sRandomHull(random, 0.5f)); break;
+				}
+				s.mMotionType = EMotionType::Dynamic;
+				s.mObjectLayer = Layers::MOVING;
+				float jx = jitter(random), jy = jitter(random), jz = jitter(random);
+				s.mPosition = RVec3((float(x) - 0.5f * (side - 1)) * spacing + jx, 0.8f + float(y) * spacing + jy, (float(z) - 0.5f * (side - 1)) * spacing + jz);
+				s.mRotation = sRandomQuat(random);
+				s.mFriction = 0.5f;
+				s.mRestitution = 0.1f;
+				ids.push_back(bi.CreateBody(s)->GetID());
+			}
+	BodyInterface::AddState state = bi.AddBodiesPrepare(ids.data(), (int)ids.size());
+	bi.AddBodiesFinalize(ids.data(), (int)ids.size(), state, EActivation::Activate);
+	w->num_dynamic = n;
+	return w;
+}
+
+World *sSceneSmallStack(int inVariant)
+{
+	// Small scenes for fast unit-level parity: a floor and a handful of bodies (variant picks the shapes), allows sleeping.
+	World *w = sNewWorld(1024, 4096, 1024, 4);
+	BodyInterface &bi = w->system.GetBodyInterface();
+	bi.CreateAndAddBody(BodyCreationSettings(new BoxShape(Vec3(100.0f, 1.0f, 100.0f), 0.0f), RVec3(0.0f, -1.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING), EActivation::DontActivate);
+	std::mt19937 random(777 + inVariant);
+	Ref<Shape> shapes[4] = { new SphereShape(0.5f), new BoxShape(Vec3(0.5f, 0.5f, 0.5f)), new CapsuleShape(0.5f, 0.3f), sRandomHull(random, 0.6f) };
+	for (int i = 0; i < 24; ++i)
+	{
+		int kind = inVariant < 4? inVariant : i % 4;
+		BodyCreationSettings s(shapes[kind], RVec3(float(i % 3) * 0.9f - 0.9f, 0.6f + 1.1f * float(i / 3), float(i % 2) * 0.4f), inVariant < 4 && kind == 1? Quat::sIdentity() : sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+		s.mFriction = 0.5f;
+		s.mRestitution = (i % 5 == 0)? 0.5f : 0.0f;
+		bi.CreateAndAddBody(s, EActivation::Activate);
+		w->num_dynamic++;
+	}
+	return w;
+}
+
+} // namespace
+
+// ---- C interface ------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+const char *jref_last_error() { return sLastError.c_str(); }
+
+// 0 on success. Resolves the b2j C ABI from a shared library (the product libjolt_b200.so on a GPU box).
+int jref_bind_b2j(const char *inLibPath)
+{
+	sInit();
+	return sApi.Load(inLibPath, sLastError)? 0 : -1;
+}
+
+void *jref_create_scene(const char *inName, int inParam0, int inParam1)
+{
+	String name(inName);
+	World *w = nullptr;
+	if (name == "pyramid") w = sScenePyramid(inParam0 > 0? inParam0 : 15);
+	else if (name == "convex_vs_mesh") w = sSceneConvexVsMesh(inParam0 > 0? inParam0 : 10);
+	else if (name == "max_bodies") w = sSceneMaxBodies(inParam0 > 0? inParam0 : 10000);
+	else if (name == "pile") w = sScenePile(inParam0 > 0? inParam0 : 1000, inParam1 > 0? inParam1 : 15);
+	else if (name == "small_stack") w = sSceneSmallStack(inParam0);
+	else { sLastError = "unknown scene"; return nullptr; }
+	w->system.SetContactListener(&w->contacts);
+	w->system.SetBodyActivationListener(&w->activations);
+	w->system.OptimizeBroadPhase();
+	return w;
+}
+
+void jref_destroy(void *h) { delete (World *)h; }
+
+// Turn the recording listeners off (timing runs) or on.
+void jref_set_recording(void *h, int inOn)
+{
+	World *w = (World *)h;
+	w->system.SetContactListener(inOn? &w->contacts : nullptr);
+	w->system.SetBodyActivationListener(inOn? &w->activations : nullptr);
+}
+
+// PhysicsSystem::Update; clears the event records first. Returns EPhysicsUpdateError bits.
+int jref_step(void *h, float inDeltaTime, int inCollisionSteps, int inNumThreads)
+{
+	World *w = (World *)h;
+	sEnsureJobs(w, inNumThreads);
+	w->contacts.mRecords.clear();
+	w->activations.mRecords.clear();
+	return (int)w->system.Update(inDeltaTime, inCollisionSteps, w->temp, w->jobs);
+}
+
+// Times inNumSteps calls of Update(dt, 1) exactly as PerformanceTest.cpp:380-391 does (chrono around Update only). Returns seconds.
+double jref_time_steps(void *h, float inDeltaTime, int inNumSteps, int inNumThreads)
+{
+	World *w = (World *)h;
+	sEnsureJobs(w, inNumThreads);
+	double total = 0.0;
+	for (int i = 0; i < inNumSteps; ++i)
+	{
+		w->contacts.mRecords.clear();
+		w->activations.mRecords.clear();
+		auto t0 = std::chrono::high_resolution_clock::now();
+		w->system.Update(inDeltaTime, 1, w->temp, w->jobs);
+		auto t1 = std::chrono::high_resolution_clock::now();
+		total += std::chrono::duration<double>(t1 - t0).count();
+	}
+	return total;
+}
+
+int jref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+uint32_t jref_num_bodies(void *h) { return ((World *)h)->system.GetNumBodies(); }
+uint32_t jref_num_dynamic(void *h) { return ((World *)h)->num_dynamic; }
+uint32_t jref_num_active(void *h) { return ((World *)h)->system.GetNumActiveBodies(EBodyType::RigidBody); }
+uint32_t jref_max_bodies(void *h) { return ((World *)h)->system.GetMaxBodies(); }
+
+// Body state by slot (body index) for slots [0, n): arrays may be null. ids[i] = 0xffffffff for empty slots.
+void jref_get_state(void *h, uint32_t n, uint32_t *ids, float *pos, float *rot, float *lin, float *ang, float *bounds, uint32_t *active_index, float *sleep_timer)
+{
+	World *w = (World *)h;
+	const BodyVector &bodies = w->system.mBodyManager.GetBodies();
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const Body *b = i < bodies.size() && BodyManager::sIsValidBodyPointer(bodies[i])? bodies[i] : nullptr;
+		if (ids) ids[i] = b? b->GetID().GetIndexAndSequenceNumber() : 0xffffffffu;
+		if (b == nullptr) continue;
+		if (pos) b2j_adapter::sStore(Vec3(b->GetCenterOfMassPosition()), pos + 3 * i);
+		if (rot) b2j_adapter::sStore(b->GetRotation(), rot + 4 * i);
+		if (lin) b2j_adapter::sStore(b->IsStatic()? Vec3::sZero() : b->GetLinearVelocity(), lin + 3 * i);
+		if (ang) b2j_adapter::sStore(b->IsStatic()? Vec3::sZero() : b->GetAngularVelocity(), ang + 3 * i);
+		if (bounds) { b2j_adapter::sStore(b->GetWorldSpaceBounds().mMin, bounds + 6 * i); b2j_adapter::sStore(b->GetWorldSpaceBounds().mMax, bounds + 6 * i + 3); }
+		if (active_index) active_index[i] = b->IsStatic()? 0xffffffffu : b->GetMotionPropertiesUnchecked()->GetIndexInActiveBodiesInternal();
+		if (sleep_timer) sleep_timer[i] = b->IsStatic()? 0.0f : b->GetMotionPropertiesUnchecked()->mSleepTestTimer;
+	}
+}
+
+// Candidate pairs of the CURRENT state through the public virtual BroadPhase::FindCollidingPairs (BroadPhase.h:93), as (min id, max id).
+uint32_t jref_find_pairs(void *h, uint32_t *outPairs, uint32_t inCap)
+{
+	World *w = (World *)h;
+	BodyIDVector active;
+	w->system.GetActiveBodies(EBodyType::RigidBody, active);
+	struct Collector : public BodyPairCollector
+	{
+		void AddHit(const BodyPair &inPair) override { pairs.push_back(inPair); }
+		std::vector<BodyPair> pairs;
+	} collector;
+	if (!active.empty())
+	{
+		const BroadPhase &bp = static_cast<const BroadPhase &>(w->system.GetBroadPhaseQuery());
+		bp.FindCollidingPairs(active.data(), (int)active.size(), w->system.GetPhysicsSettings().mSpeculativeContactDistance, w->ovbp, w->olp, collector);
+	}
+	std::vector<std::pair<uint32_t, uint32_t>> sorted;
+	for (const BodyPair &p : collector.pairs)
+	{
+		uint32_t a = p.mBodyA.GetIndexAndSequenceNumber(), b = p.mBodyB.GetIndexAndSequenceNumber();
+		sorted.emplace_back(std::min(a, b), std::max(a, b));
+	}
+	std::sort(sorted.begin(), sorted.end());
+	for (uint32_t i = 0; i < sorted.size() && i < inCap; ++i) { outPairs[2 * i] = sorted[i].first; outPairs[2 * i + 1] = sorted[i].second; }
+	return (uint32_t)sorted.size();
+}
+
+// Body pairs / manifolds of the contact cache written by the LAST step (every candidate pair gets an entry,
+// ContactConstraintManager.cpp:1090-1128), sorted.
+uint32_t jref_get_cache(void *h, b2j_cached_body_pair *outPairs, uint32_t inPairsCap, b2j_cached_manifold *outManifolds, uint32_t inManifoldsCap, uint32_t *outNumManifolds)
+{
+	World *w = (World *)h;
+	std::vector<b2j_cached_body_pair> pairs;
+	std::vector<b2j_cached_manifold> manifolds;
+	b2j_adapter::sExportContactCache(w->system, pairs, manifolds);
+	for (uint32_t i = 0; i < pairs.size() && i < inPairsCap; ++i) outPairs[i] = pairs[i];
+	for (uint32_t i = 0; i < manifolds.size() && i < inManifoldsCap; ++i) outManifolds[i] = manifolds[i];
+	if (outNumManifolds) *outNumManifolds = (uint32_t)manifolds.size();
+	return (uint32_t)pairs.size();
+}
+
+// Contact events recorded during the last jref_step, sorted by (kind, body1, body2, sub1, sub2).
+uint32_t jref_get_contact_events(void *h, b2j_contact_event *outEvents, uint32_t inCap)
+{
+	World *w = (World *)h;
+	std::vector<ContactRecord> &r = w->contacts.mRecords;
+	std::sort(r.begin(), r.end(), [](const ContactRecord &a, const ContactRecord &b) {
+		if (a.kind != b.kind) return a.kind < b.kind;
+		if (a.body1 != b.body1) return a.body1 < b.body1;
+		if (a.body2 != b.body2) return a.body2 < b.body2;
+		if (a.sub1 != b.sub1) return a.sub1 < b.sub1;
+		return a.sub2 < b.sub2;
+	});
+	for (uint32_t i = 0; i < r.size() && i < inCap; ++i)
+	{
+		b2j_contact_event &e = outEvents[i];
+		memset(&e, 0, sizeof(e));
+		e.kind = r[i].kind; e.body1 = r[i].body1; e.body2 = r[i].body2; e.sub_shape1 = r[i].sub1; e.sub_shape2 = r[i].sub2;
+		e.num_points = r[i].num_points;
+		memcpy(e.base_offset, r[i].base_offset, sizeof(e.base_offset));
+		memcpy(e.normal, r[i].normal, sizeof(e.normal));
+		e.penetration_depth = r[i].depth;
+		memcpy(e.points1, r[i].p1, sizeof(e.points1));
+		memcpy(e.points2, r[i].p2, sizeof(e.points2));
+	}
+	return (uint32_t)r.size();
+}
+
+uint32_t jref_get_activation_events(void *h, b2j_activation_event *outEvents, uint32_t inCap)
+{
+	World *w = (World *)h;
+	std::vector<b2j_activation_event> &r = w->activations.mRecords;
+	std::sort(r.begin(), r.end(), [](const b2j_activation_event &a, const b2j_activation_event &b) { return a.kind != b.kind? a.kind < b.kind : a.body < b.body; });
+	for (uint32_t i = 0; i < r.size() && i < inCap; ++i) outEvents[i] = r[i];
+	return (uint32_t)r.size();
+}
+
+uint32_t jref_get_active_bodies(void *h, uint32_t *outIDs, uint32_t inCap)
+{
+	World *w = (World *)h;
+	BodyIDVector active;
+	w->system.GetActiveBodies(EBodyType::RigidBody, active);
+	for (uint32_t i = 0; i < active.size() && i < inCap; ++i) outIDs[i] = active[i].GetIndexAndSequenceNumber();
+	return (uint32_t)active.size();
+}
+
+// Re-creates the current state of the reference world inside a new b2j_world (needs jref_bind_b2j first). NULL on failure.
+void *jref_export_to_b2j(void *h, int inDevice)
+{
+	World *w = (World *)h;
+	if (sApi.handle == nullptr) { sLastError = "jref_bind_b2j not called"; return nullptr; }
+	return b2j_adapter::sExportWorld(sApi, w->system, Layers::NUM_LAYERS, inDevice, w->max_body_pairs, w->max_contact_constraints, sLastError);
+}
+
+void jref_get_settings(void *h, b2j_settings *outSettings) { b2j_adapter::sFillSettings(((World *)h)->system.GetPhysicsSettings(), *outSettings); }
+
+// Total kinetic energy 0.5 m v^2 + 0.5 w^T I w over dynamic bodies (long-run comparison, SURVEY 8d parity protocol).
+double jref_kinetic_energy(void *h)
+{
+	World *w = (World *)h;
+	double e = 0.0;
+	for (const Body *b : w->system.mBodyManager.GetBodies())
+		if (BodyManager::sIsValidBodyPointer(b) && b->IsDynamic())
+		{
+			const MotionProperties *mp = b->GetMotionProperties();
+			float inv_m = mp->GetInverseMass();
+			if (inv_m > 0.0f)
+				e += 0.5 * double(mp->GetLinearVelocity().LengthSq()) / double(inv_m);
+			Vec3 wl = (b->GetRotation() * mp->GetInertiaRotation()).InverseRotate(mp->GetAngularVelocity());
+			Vec3 d = mp->GetInverseInertiaDiagonal();
+			for (int i = 0; i < 3; ++i)
+				if (d[i] > 0.0f)
+					e += 0.5 * double(wl[i]) * double(wl[i]) / double(d[i]);
+		}
+	return e;
+}
+
+} // extern "C"
