@@ -1,0 +1,512 @@
+// b2j_narrowphase.h -- body pair processing: contact cache test, convex vs convex collision, manifold creation, and the
+// device resident contact cache (double buffered, warm start data).
+//
+// Restates:
+//   PhysicsSystem::ProcessBodyPair                      PhysicsSystem.cpp:1049-1349 (pair orientation, reduction collector)
+//   ContactConstraintManager::GetContactsFromCache      ContactConstraintManager.cpp:1001-1088, :843-999
+//   ContactConstraintManager::AddBodyPair               :1090-1128
+//   ContactConstraintManager::TemplatedAddContactConstraint / AddContactConstraint  :1130-1385
+//   ConvexShape::sCollideConvexVsConvex                 Shape/ConvexShape.cpp:45-164
+// One thread per body pair; pairs that need EPA are compacted into a second launch that owns a global memory scratch
+// slot per thread (b2j_gjk.h EpaScratch). Constraints are NOT built here: every manifold that needs one gets a ConstraintSrc
+// record; after island/schedule building the setup kernel (b2j_solver.h) writes constraints straight into solve order.
+#pragma once
+
+#include "b2j_world.h"
+#include "b2j_shapes.h"
+#include "b2j_gjk.h"
+#include "b2j_manifold.h"
+#include "b2j_broadphase.h"
+
+namespace b2j {
+
+struct CollideItem { uint32_t b1, b2; uint32_t pair_entry, old_pair; }; // b1 = body whose space the collision is done in
+struct CachedItem { uint32_t pair_entry, old_pair; };
+struct EpaItem { CollideItem c; GjkSimplex s; V3 axis; };
+
+// World space data of a manifold created this step (not from the cache), indexed like write_cache.manifolds
+struct ManifoldWS { float normal[3]; float p1[4][3], p2[4][3]; };
+
+// One future contact constraint
+struct ConstraintSrc
+{
+	uint64_t sort_key;       // FNV-1a of SubShapeIDPair (mSortKey)
+	uint32_t manifold;       // index in write_cache.manifolds
+	uint32_t b1, b2;         // body slots, id(b1) < id(b2)
+};
+
+struct NarrowCtx
+{
+	BodyPair *pairs;
+	CollideItem *collide_convex, *collide_mesh;
+	CachedItem *cached;
+	EpaItem *epa;
+	EpaScratch *scratch;         // [num_scratch]
+	uint32_t num_scratch;
+	ManifoldWS *man_ws;
+	ConstraintSrc *con_src;
+	uint32_t *woken_flag;        // per slot
+	uint32_t *woken_list;
+	b2j_contact_event *events;
+	uint32_t max_events;
+	uint32_t max_epa;
+};
+
+// ---- pair hash table ---------------------------------------------------------------------------------------------
+B2J_HD uint64_t pair_key(uint32_t id1, uint32_t id2) { return ((uint64_t)id2 << 32) | id1; } // BodyPair{A, B} read as a little endian uint64
+
+B2J_D void pair_table_insert(const DWorld &w, const ContactCache &c, uint32_t id1, uint32_t id2, uint32_t entry)
+{
+	uint32_t mask = w.pair_table_size - 1;
+	uint32_t h = (uint32_t)hash64(pair_key(id1, id2)) & mask;
+	for (;;)
+	{
+		if (atomic_cas(&c.pair_table[h], 0xffffffffu, entry) == 0xffffffffu)
+			return;
+		h = (h + 1) & mask;
+	}
+}
+
+B2J_D uint32_t pair_table_find(const DWorld &w, const ContactCache &c, uint32_t id1, uint32_t id2)
+{
+	uint32_t mask = w.pair_table_size - 1;
+	uint32_t h = (uint32_t)hash64(pair_key(id1, id2)) & mask;
+	for (;;)
+	{
+		uint32_t e = c.pair_table[h];
+		if (e == 0xffffffffu)
+			return 0xffffffffu;
+		if (c.pairs[e].body1 == id1 && c.pairs[e].body2 == id2)
+			return e;
+		h = (h + 1) & mask;
+	}
+}
+
+B2J_D void set_error(const DWorld &w, uint32_t bits) { atomic_or(&w.counters->error_bits, bits); }
+
+// ---- KProcessPairs: orientation, cache test, work list routing ---------------------------------------------------
+struct KProcessPairs
+{
+	DWorld w; NarrowCtx c;
+	const uint32_t *first_ptr; // device: first pair of this round
+	B2J_D void operator()(uint32_t k) const
+	{
+		BodyPair bp = c.pairs[*first_ptr + k];
+		uint32_t b1 = bp.a, b2 = bp.b;
+		BodyInfo i1 = w.info[b1], i2 = w.info[b2];
+		// body1 = higher motion type, ties -> lower id (PhysicsSystem.cpp:1072-1077)
+		if (i1.motion_type < i2.motion_type || (i1.motion_type == i2.motion_type && i2.id < i1.id))
+		{
+			uint32_t tb = b1; b1 = b2; b2 = tb;
+			BodyInfo ti = i1; i1 = i2; i2 = ti;
+		}
+		// cache orientation: lower id first
+		uint32_t cb1 = b1, cb2 = b2;
+		uint32_t id1 = i1.id, id2 = i2.id;
+		if (id2 < id1) { cb1 = b2; cb2 = b1; uint32_t t = id1; id1 = id2; id2 = t; }
+
+		uint32_t entry = atomic_add(w.write_cache.num_pairs, 1u);
+		if (entry >= w.max_body_pairs)
+		{
+			set_error(w, B2J_ERR_BODY_PAIR_CACHE_FULL);
+			return;
+		}
+
+		Q4 r1 = to_q4(w.rotation[cb1]), r2 = to_q4(w.rotation[cb2]);
+		V3 x1 = to_v3(w.position[cb1]), x2 = to_v3(w.position[cb2]);
+		Q4 inv_r1 = q4_conj(r1);
+		V3 delta_position = rotate(inv_r1, x2 - x1);
+		Q4 delta_rotation = inv_r1 * r2;
+
+		CachedPair &out = w.write_cache.pairs[entry];
+		out.body1 = id1; out.body2 = id2;
+		out.first_manifold = 0; out.num_manifolds = 0;
+
+		uint32_t old = 0xffffffffu;
+		bool handled = false;
+		if (w.settings.use_body_pair_contact_cache)
+			old = pair_table_find(w, w.read_cache, id1, id2);
+		if (old != 0xffffffffu && !((i1.flags | i2.flags) & B2J_BODY_INVALIDATE_CACHE))
+		{
+			const CachedPair &in = w.read_cache.pairs[old];
+			V3 old_dp = v3_load(in.dpos);
+			if (!(length_sq(delta_position - old_dp) > w.settings.body_pair_cache_max_delta_position_sq))
+			{
+				Q4 old_dr = q4_from_xyz(v3_load(in.drot));
+				if (!(fabs_(q4_dot(delta_rotation, old_dr)) < w.settings.body_pair_cache_cos_max_delta_rotation_div2))
+				{
+					handled = true;
+					// memcpy of the old CachedBodyPair: the deltas are NOT refreshed (ContactConstraintManager.cpp:1059)
+					for (int i = 0; i < 3; ++i) { out.dpos[i] = in.dpos[i]; out.drot[i] = in.drot[i]; }
+					atomic_add(&w.counters->num_pairs_from_cache, 1u);
+					if (in.num_manifolds != 0)
+					{
+						uint32_t ci = atomic_add(&w.counters->num_cached, 1u);
+						CachedItem item; item.pair_entry = entry; item.old_pair = old;
+						c.cached[ci] = item;
+					}
+				}
+			}
+		}
+		if (!handled)
+		{
+			v3_store(delta_position, out.dpos);
+			v3_store(q4_xyz(q4_ensure_w_positive(delta_rotation)), out.drot);
+			CollideItem item; item.b1 = b1; item.b2 = b2; item.pair_entry = entry; item.old_pair = old;
+			if (w.shapes[i2.shape].kind == B2J_SHAPE_MESH || w.shapes[i1.shape].kind == B2J_SHAPE_MESH)
+				c.collide_mesh[atomic_add(&w.counters->num_collide_mesh, 1u)] = item;
+			else
+				c.collide_convex[atomic_add(&w.counters->num_collide_convex, 1u)] = item;
+		}
+		pair_table_insert(w, w.write_cache, id1, id2, entry);
+	}
+};
+
+// ---- helpers shared by the cached and the collide path ---------------------------------------------------------
+B2J_D void wake_body(const DWorld &w, const NarrowCtx &c, uint32_t slot)
+{
+	if (atomic_exch(&c.woken_flag[slot], 1u) == 0u)
+		c.woken_list[atomic_add(&w.counters->num_woken, 1u)] = slot;
+}
+
+B2J_D void emit_event(const DWorld &w, const NarrowCtx &c, uint32_t kind, uint32_t id1, uint32_t id2, uint32_t sub1, uint32_t sub2,
+	V3 base_offset, V3 normal, float depth, const V3 *p1, const V3 *p2, int n)
+{
+	if (c.events == nullptr)
+		return;
+	uint32_t e = atomic_add(&w.counters->num_events, 1u);
+	if (e >= c.max_events)
+		return;
+	b2j_contact_event &ev = c.events[e];
+	ev.kind = kind; ev.body1 = id1; ev.body2 = id2; ev.sub_shape1 = sub1; ev.sub_shape2 = sub2; ev.num_points = (uint32_t)n;
+	v3_store(base_offset, ev.base_offset);
+	v3_store(normal, ev.normal);
+	ev.penetration_depth = depth;
+	for (int i = 0; i < 4; ++i)
+	{
+		v3_store(i < n? p1[i] : v3_zero(), ev.points1[i]);
+		v3_store(i < n? p2[i] : v3_zero(), ev.points2[i]);
+	}
+}
+
+// Registers a constraint for manifold m between cache-ordered bodies cb1 (id1) / cb2 (id2): wake up + ConstraintSrc.
+// (CreateConstraint ContactConstraintManager.cpp:767-841 minus the constraint itself.)
+B2J_D bool register_constraint(const DWorld &w, const NarrowCtx &c, uint32_t m, uint32_t cb1, uint32_t cb2, const BodyInfo &i1, const BodyInfo &i2, uint64_t key_hash, int num_points)
+{
+	bool sensor = ((i1.flags | i2.flags) & B2J_BODY_SENSOR) != 0;
+	bool dyn1 = i1.motion_type == B2J_MOTION_DYNAMIC, dyn2 = i2.motion_type == B2J_MOTION_DYNAMIC;
+	if (sensor || !(dyn1 || dyn2))
+		return false;
+	uint32_t ci = atomic_add(&w.counters->num_constraints, 1u);
+	if (ci >= w.max_constraints)
+	{
+		set_error(w, B2J_ERR_CONTACT_CONSTRAINTS_FULL);
+		return false;
+	}
+	if (dyn1 && w.active_index[cb1] == B2J_INACTIVE_INDEX) wake_body(w, c, cb1);
+	if (dyn2 && w.active_index[cb2] == B2J_INACTIVE_INDEX) wake_body(w, c, cb2);
+	ConstraintSrc s;
+	s.sort_key = key_hash; s.manifold = m; s.b1 = cb1; s.b2 = cb2;
+	c.con_src[ci] = s;
+	atomic_add(&w.counters->num_contact_points, (uint32_t)num_points);
+	return true;
+}
+
+// ---- KCopyCached: GetContactsFromCache for pairs whose relative pose did not change ----------------------------
+struct KCopyCached
+{
+	DWorld w; NarrowCtx c;
+	B2J_D void operator()(uint32_t k) const
+	{
+		CachedItem item = c.cached[k];
+		const CachedPair &in = w.read_cache.pairs[item.old_pair];
+		CachedPair &out = w.write_cache.pairs[item.pair_entry];
+		uint32_t n = in.num_manifolds;
+		uint32_t base = atomic_add(w.write_cache.num_manifolds, n);
+		if (base + n > w.max_constraints)
+		{
+			set_error(w, B2J_ERR_MANIFOLD_CACHE_FULL);
+			return;
+		}
+		uint32_t cb1 = slot_of(in.body1), cb2 = slot_of(in.body2);
+		BodyInfo i1 = w.info[cb1], i2 = w.info[cb2];
+		for (uint32_t j = 0; j < n; ++j)
+		{
+			CachedManifold &src = w.read_cache.manifolds[in.first_manifold + j];
+			CachedManifold &dst = w.write_cache.manifolds[base + j];
+			dst = src;
+			dst.flags = MANIFOLD_FROM_CACHE;
+			src.flags |= MANIFOLD_PERSISTED;
+			uint64_t hash = hash_sub_shape_id_pair(in.body1, src.sub1, in.body2, src.sub2);
+			if (c.events != nullptr)
+			{
+				// OnContactPersisted with the manifold reconstructed from the cache (ContactConstraintManager.cpp:890-913)
+				Q4 q1 = to_q4(w.rotation[cb1]), q2 = to_q4(w.rotation[cb2]);
+				V3 x1 = to_v3(w.position[cb1]), x2 = to_v3(w.position[cb2]);
+				M33 r1 = m33_rotation(q1);
+				Xf local2 = xf(m33_rotation(q2), x2 + (-x1));
+				V3 wn = normalized(mul(local2.r, v3_load(src.normal)));
+				V3 p1[4], p2[4];
+				float depth = -FLT_MAX;
+				for (int i = 0; i < src.num_points; ++i)
+				{
+					p1[i] = mul(r1, v3_load(src.p1[i]));
+					p2[i] = mul(local2, v3_load(src.p2[i]));
+					depth = fmax_(depth, dot(p1[i] - p2[i], wn));
+				}
+				emit_event(w, c, B2J_EVENT_CONTACT_PERSISTED, in.body1, in.body2, src.sub1, src.sub2, x1, wn, depth, p1, p2, src.num_points);
+			}
+			if (!register_constraint(w, c, base + j, cb1, cb2, i1, i2, hash, src.num_points))
+			{
+				// no constraint: the cached lambdas are kept as they are (memcpy semantics)
+			}
+		}
+		out.first_manifold = base;
+		out.num_manifolds = n;
+	}
+};
+
+// A manifold in the collision space of body 1 (points relative to its centre of mass)
+struct ManifoldOut
+{
+	V3 normal;           // world space, normalised
+	float depth;
+	uint32_t sub1, sub2;
+	int n;
+	V3 p1[4], p2[4];
+};
+
+// AddContactConstraint + TemplatedAddContactConstraint for all manifolds of one pair. b1/b2: collision order bodies,
+// base_offset = centre of mass of b1.
+B2J_D void add_manifolds(const DWorld &w, const NarrowCtx &c, const CollideItem &item, ManifoldOut *mans, int count)
+{
+	if (count == 0)
+		return;
+	uint32_t base = atomic_add(w.write_cache.num_manifolds, (uint32_t)count);
+	if (base + (uint32_t)count > w.max_constraints)
+	{
+		set_error(w, B2J_ERR_MANIFOLD_CACHE_FULL);
+		return;
+	}
+	uint32_t b1 = item.b1, b2 = item.b2;
+	BodyInfo i1 = w.info[b1], i2 = w.info[b2];
+	V3 base_offset = to_v3(w.position[b1]);
+	bool swap = i2.id < i1.id;
+	uint32_t cb1 = swap? b2 : b1, cb2 = swap? b1 : b2;
+	BodyInfo ci1 = swap? i2 : i1, ci2 = swap? i1 : i2;
+	Xf inv1 = xf_inverse_rotation_translation(to_q4(w.rotation[cb1]), to_v3(w.position[cb1]));
+	Xf inv2 = xf_inverse_rotation_translation(to_q4(w.rotation[cb2]), to_v3(w.position[cb2]));
+	const CachedPair *old_pair = item.old_pair != 0xffffffffu? &w.read_cache.pairs[item.old_pair] : nullptr;
+	bool makes_constraint = !((ci1.flags | ci2.flags) & B2J_BODY_SENSOR) && (ci1.motion_type == B2J_MOTION_DYNAMIC || ci2.motion_type == B2J_MOTION_DYNAMIC);
+
+	for (int mi = 0; mi < count; ++mi)
+	{
+		ManifoldOut &m = mans[mi];
+		// SwapShapes when body 2 has the lower id
+		V3 normal = swap? -m.normal : m.normal;
+		uint32_t sub1 = swap? m.sub2 : m.sub1, sub2 = swap? m.sub1 : m.sub2;
+		const V3 *rp1 = swap? m.p2 : m.p1;
+		const V3 *rp2 = swap? m.p1 : m.p2;
+
+		uint64_t key_hash = hash_sub_shape_id_pair(ci1.id, sub1, ci2.id, sub2);
+		uint32_t mslot = base + (uint32_t)mi;
+		CachedManifold &nm = w.write_cache.manifolds[mslot];
+		nm.body1 = ci1.id; nm.body2 = ci2.id; nm.sub1 = sub1; nm.sub2 = sub2;
+		nm.num_points = (uint16_t)m.n;
+		nm.flags = 0;
+		v3_store(normalized(mul(inv2.r, normal)), nm.normal);
+
+		// old manifold with the same SubShapeIDPair (mReadCache->Find(key))
+		CachedManifold *old_m = nullptr;
+		if (old_pair != nullptr)
+			for (uint32_t j = 0; j < old_pair->num_manifolds; ++j)
+			{
+				CachedManifold &cand = w.read_cache.manifolds[old_pair->first_manifold + j];
+				if (cand.sub1 == sub1 && cand.sub2 == sub2) { old_m = &cand; break; }
+			}
+		if (old_m != nullptr)
+			old_m->flags |= MANIFOLD_PERSISTED;
+		emit_event(w, c, old_m != nullptr? B2J_EVENT_CONTACT_PERSISTED : B2J_EVENT_CONTACT_ADDED, ci1.id, ci2.id, sub1, sub2, base_offset, normal, m.depth, rp1, rp2, m.n);
+
+		ManifoldWS &ws = c.man_ws[mslot];
+		v3_store(normal, ws.normal);
+		for (int i = 0; i < m.n; ++i)
+		{
+			V3 p1_ws = base_offset + rp1[i];
+			V3 p2_ws = base_offset + rp2[i];
+			v3_store(p1_ws, ws.p1[i]);
+			v3_store(p2_ws, ws.p2[i]);
+			V3 p1_ls = mul(inv1, p1_ws);
+			V3 p2_ls = mul(inv2, p2_ws);
+			v3_store(p1_ls, nm.p1[i]);
+			v3_store(p2_ls, nm.p2[i]);
+			float lambda = 0.0f;
+			if (makes_constraint && old_m != nullptr)
+				for (int j = 0; j < old_m->num_points; ++j)
+					if (is_close(v3_load(old_m->p1[j]), p1_ls, w.settings.contact_point_preserve_lambda_max_dist_sq)
+						&& is_close(v3_load(old_m->p2[j]), p2_ls, w.settings.contact_point_preserve_lambda_max_dist_sq))
+					{
+						lambda = old_m->lambda[j];
+						break;
+					}
+			nm.lambda[i] = lambda;
+		}
+		for (int i = m.n; i < 4; ++i)
+		{
+			nm.lambda[i] = 0.0f;
+			for (int k = 0; k < 3; ++k) { nm.p1[i][k] = 0.0f; nm.p2[i][k] = 0.0f; }
+		}
+		if (makes_constraint && old_m != nullptr)
+		{
+			nm.friction_lambda[0] = old_m->friction_lambda[0];
+			nm.friction_lambda[1] = old_m->friction_lambda[1];
+			nm.angular_lambda = old_m->angular_lambda;
+		}
+		else
+		{
+			nm.friction_lambda[0] = nm.friction_lambda[1] = 0.0f;
+			nm.angular_lambda = 0.0f;
+		}
+		if (makes_constraint)
+			register_constraint(w, c, mslot, cb1, cb2, ci1, ci2, key_hash, m.n);
+	}
+	CachedPair &out = w.write_cache.pairs[item.pair_entry];
+	out.first_manifold = base;
+	out.num_manifolds = (uint32_t)count;
+}
+
+// Result of a convex vs convex test in the space of body 1 (CollideShapeResult relative to body 1's centre of mass)
+struct ConvexHit
+{
+	V3 point1, point2, axis;   // world orientation, relative to body 1 COM
+	float depth;
+};
+
+// Everything of sCollideConvexVsConvex after the penetration depth is known: world space conversion + supporting faces +
+// (ProcessBodyPair) manifold creation for a single hit. transform1 = R(q1), transform2 = T2 - x1 (PhysicsSystem.cpp:1110-1112).
+B2J_D void finish_convex_pair(const DWorld &w, const NarrowCtx &c, const CollideItem &item, const Xf &transform1, const Xf &transform2, const Xf &transform_2_to_1,
+	V3 point1, V3 point2, V3 penetration_axis, float max_separation_distance)
+{
+	float penetration_depth = length(point2 - point1) - max_separation_distance;
+	// collector early out fraction is FLT_MAX: -depth >= FLT_MAX never true for finite depth
+	if (-penetration_depth >= FLT_MAX)
+		return;
+	float penetration_axis_len = length(penetration_axis);
+	if (penetration_axis_len > 0.0f)
+		point1 -= penetration_axis * (max_separation_distance / penetration_axis_len);
+	point1 = mul(transform1, point1);
+	point2 = mul(transform1, point2);
+	V3 axis_world = mul(transform1.r, penetration_axis);
+
+	BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
+	const ShapeDesc &s1 = w.shapes[i1.shape], &s2 = w.shapes[i2.shape];
+	V3 face1[MAX_FACE_VERTS], face2[MAX_FACE_VERTS];
+	int n1 = supporting_face(w, s1, -penetration_axis, transform1, face1);
+	int n2 = supporting_face(w, s2, mul_transposed(transform_2_to_1.r, penetration_axis), transform2, face2);
+
+	V3 pts1[MAX_MANIFOLD_POINTS], pts2[MAX_MANIFOLD_POINTS], scratch[3 * MAX_CLIP_VERTS];
+	int num = 0;
+	bool reduction = w.settings.use_manifold_reduction && (i1.flags & B2J_BODY_USE_MANIFOLD_REDUCTION) && (i2.flags & B2J_BODY_USE_MANIFOLD_REDUCTION);
+	V3 normal = normalized(axis_world);
+	manifold_between_two_faces(point1, point2, axis_world, w.settings.speculative_contact_distance + w.settings.manifold_tolerance, face1, n1, face2, n2, pts1, pts2, num, scratch);
+	if (reduction)
+	{
+		// ReductionCollideShapeCollector: prune at > 32 against the first normal, then the summed normal is normalised again
+		if (num > 32)
+			prune_contact_points(normal, pts1, pts2, num, scratch);
+		normal = normalized(normal);
+	}
+	if (num > 4)
+		prune_contact_points(normal, pts1, pts2, num, scratch);
+
+	ManifoldOut m;
+	m.normal = normal; m.depth = penetration_depth; m.sub1 = 0xffffffffu; m.sub2 = 0xffffffffu; m.n = num;
+	for (int i = 0; i < num; ++i) { m.p1[i] = pts1[i]; m.p2[i] = pts2[i]; }
+	add_manifolds(w, c, item, &m, 1);
+}
+
+struct ConvexPairSetup
+{
+	Xf transform1, transform2, transform_2_to_1;
+	float max_separation_distance;
+};
+
+B2J_D ConvexPairSetup convex_pair_setup(const DWorld &w, const CollideItem &item)
+{
+	ConvexPairSetup s;
+	BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
+	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
+	Q4 q1 = to_q4(w.rotation[item.b1]), q2 = to_q4(w.rotation[item.b2]);
+	s.transform1 = xf(m33_rotation(q1), v3_zero());
+	s.transform2 = xf(m33_rotation(q2), x2 + (-x1)); // GetCenterOfMassTransform().PostTranslated(-offset)
+	// inverse_transform1 = transform1.InversedRotationTranslation(); transform_2_to_1 = inverse_transform1 * transform2
+	M33 rt = transposed(s.transform1.r);
+	Xf inv1 = xf(rt, -mul(rt, s.transform1.t));
+	s.transform_2_to_1 = mul(inv1, s.transform2);
+	s.max_separation_distance = ((i1.flags | i2.flags) & B2J_BODY_SENSOR)? 0.0f : w.settings.speculative_contact_distance;
+	return s;
+}
+
+// ---- KCollideConvex: OBB pre-test + GJK; finishes shallow hits, queues deep ones for EPA -------------------------
+struct KCollideConvex
+{
+	DWorld w; NarrowCtx c;
+	B2J_D void operator()(uint32_t k) const
+	{
+		CollideItem item = c.collide_convex[k];
+		ConvexPairSetup s = convex_pair_setup(w, item);
+		const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
+
+		V3 bb1_min = s1.local_min - v3_rep(s.max_separation_distance), bb1_max = s1.local_max + v3_rep(s.max_separation_distance);
+		if (!obb_vs_aabb(s.transform_2_to_1, s2.local_min, s2.local_max, bb1_min, bb1_max))
+			return;
+
+		V3 penetration_axis = s.transform_2_to_1.t;
+		if (is_near_zero(penetration_axis))
+			penetration_axis = v3(1.0f, 0.0f, 0.0f);
+
+		ConvexSupport a_excl = make_support(w, s1, SUPPORT_EXCLUDE_CONVEX_RADIUS);
+		TransformedSupport b_excl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_EXCLUDE_CONVEX_RADIUS));
+		GjkSimplex simplex;
+		V3 point1, point2;
+		int status = pen_depth_step_gjk(simplex, a_excl, a_excl.convex_radius + s.max_separation_distance, b_excl, b_excl.s.convex_radius,
+			1.0e-4f /* cDefaultCollisionTolerance */, penetration_axis, point1, point2);
+		if (status == PEN_NOT_COLLIDING)
+			return;
+		if (status == PEN_INDETERMINATE)
+		{
+			uint32_t e = atomic_add(&w.counters->num_epa, 1u);
+			if (e < c.max_epa)
+			{
+				EpaItem &ei = c.epa[e];
+				ei.c = item; ei.s = simplex; ei.axis = penetration_axis;
+			}
+			return;
+		}
+		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, point1, point2, penetration_axis, s.max_separation_distance);
+	}
+};
+
+// ---- KCollideEpa: EPA for the deep pairs; `slot` selects the scratch block -------------------------------------------
+struct KCollideEpa
+{
+	DWorld w; NarrowCtx c;
+	B2J_D void run(uint32_t k, uint32_t slot) const
+	{
+		const EpaItem &ei = c.epa[k];
+		CollideItem item = ei.c;
+		ConvexPairSetup s = convex_pair_setup(w, item);
+		const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
+		float max_separation_distance = fmin_(s.max_separation_distance, 1.0f);
+		AddRadiusSupport a_incl;
+		a_incl.s = make_support(w, s1, SUPPORT_INCLUDE_CONVEX_RADIUS);
+		a_incl.radius = max_separation_distance;
+		TransformedSupport b_incl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_INCLUDE_CONVEX_RADIUS));
+		V3 penetration_axis = ei.axis, point1, point2;
+		if (!pen_depth_step_epa(c.scratch[slot], ei.s, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2))
+			return;
+		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, point1, point2, penetration_axis, max_separation_distance);
+	}
+};
+
+} // namespace b2j

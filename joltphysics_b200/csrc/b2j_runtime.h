@@ -1,0 +1,271 @@
+// b2j_runtime.h -- device memory, kernel launch and device-wide primitives (sort / scan).
+//
+// CUDA build: plain cudaMalloc'd arrays, grid-stride launches sized in multiples of the SM count, CUB radix sort / scan.
+// B2J_HOSTSIM build (tests/hostsim only, never shipped): the same kernels run as serial loops, see b2j_platform.h.
+#pragma once
+
+#include "b2j_platform.h"
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+#include <stdio.h>
+#include <stdlib.h>
+
+#ifndef B2J_HOSTSIM
+#include <cub/cub.cuh>
+#endif
+
+namespace b2j {
+
+inline std::string &last_error() { static thread_local std::string e; return e; }
+
+#ifndef B2J_HOSTSIM
+#define B2J_CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { last_error() = std::string(#expr) + ": " + cudaGetErrorString(_e); return false; } } while (0)
+
+template <class K> __global__ void __launch_bounds__(128) run_kernel(const K k, uint32_t n)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		k(i);
+}
+// n = min(*n_ptr, cap) - *begin_ptr (begin_ptr may be null); the functor receives indices relative to begin
+template <class K> __global__ void __launch_bounds__(128) run_kernel_dev(const K k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap)
+{
+	uint32_t n = *n_ptr;
+	if (n > cap) n = cap;
+	uint32_t begin = begin_ptr != nullptr? *begin_ptr : 0;
+	n = n > begin? n - begin : 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		k(i);
+}
+// like run_kernel_dev but the functor also gets a unique slot per thread (scratch ownership)
+template <class K> __global__ void __launch_bounds__(128) run_kernel_slot(const K k, const uint32_t *n_ptr, uint32_t cap)
+{
+	uint32_t n = *n_ptr;
+	if (n > cap) n = cap;
+	uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	for (uint32_t i = slot; i < n; i += gridDim.x * blockDim.x)
+		k.run(i, slot);
+}
+#endif
+
+struct Runtime
+{
+	int device = 0;
+	int num_sms = 148;
+	uint32_t launches = 0;          // kernels launched since the last reset
+	void *cub_temp = nullptr;
+	size_t cub_temp_size = 0;
+#ifndef B2J_HOSTSIM
+	cudaStream_t stream = nullptr;
+#endif
+
+	bool init(int dev)
+	{
+		device = dev;
+#ifndef B2J_HOSTSIM
+		int count = 0;
+		cudaError_t e = cudaGetDeviceCount(&count);
+		if (e != cudaSuccess || count == 0)
+		{
+			last_error() = std::string("no CUDA device available (libjolt_b200 has no CPU fallback): ") + cudaGetErrorString(e);
+			return false;
+		}
+		B2J_CUDA_CHECK(cudaSetDevice(dev));
+		cudaDeviceProp prop;
+		B2J_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+		num_sms = prop.multiProcessorCount;
+		B2J_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+#endif
+		return true;
+	}
+
+	void shutdown()
+	{
+#ifndef B2J_HOSTSIM
+		if (cub_temp) cudaFree(cub_temp);
+		if (stream) cudaStreamDestroy(stream);
+#else
+		free(cub_temp);
+#endif
+		cub_temp = nullptr;
+	}
+
+	template <class T> T *alloc(size_t n, bool zero = true)
+	{
+		if (n == 0) n = 1;
+		T *p = nullptr;
+#ifndef B2J_HOSTSIM
+		if (cudaMalloc((void **)&p, n * sizeof(T)) != cudaSuccess) { last_error() = "cudaMalloc failed"; return nullptr; }
+		if (zero) cudaMemsetAsync(p, 0, n * sizeof(T), stream);
+#else
+		p = (T *)malloc(n * sizeof(T));
+		if (zero) memset((void *)p, 0, n * sizeof(T));
+#endif
+		return p;
+	}
+	template <class T> void free_(T *&p)
+	{
+		if (p == nullptr) return;
+#ifndef B2J_HOSTSIM
+		cudaFree((void *)p);
+#else
+		free((void *)p);
+#endif
+		p = nullptr;
+	}
+	template <class T> void upload(T *dst, const T *src, size_t n)
+	{
+		if (n == 0) return;
+#ifndef B2J_HOSTSIM
+		cudaMemcpyAsync((void *)dst, (const void *)src, n * sizeof(T), cudaMemcpyHostToDevice, stream);
+		cudaStreamSynchronize(stream); // src is usually pageable / temporary
+#else
+		memcpy((void *)dst, (const void *)src, n * sizeof(T));
+#endif
+	}
+	template <class T> void download(T *dst, const T *src, size_t n)
+	{
+		if (n == 0) return;
+#ifndef B2J_HOSTSIM
+		cudaMemcpyAsync((void *)dst, (const void *)src, n * sizeof(T), cudaMemcpyDeviceToHost, stream);
+		cudaStreamSynchronize(stream);
+#else
+		memcpy((void *)dst, (const void *)src, n * sizeof(T));
+#endif
+	}
+	template <class T> void copy(T *dst, const T *src, size_t n)
+	{
+		if (n == 0) return;
+#ifndef B2J_HOSTSIM
+		cudaMemcpyAsync((void *)dst, (const void *)src, n * sizeof(T), cudaMemcpyDeviceToDevice, stream);
+#else
+		memcpy((void *)dst, (const void *)src, n * sizeof(T));
+#endif
+	}
+	void memset_(void *p, int v, size_t bytes)
+	{
+		if (bytes == 0) return;
+#ifndef B2J_HOSTSIM
+		cudaMemsetAsync(p, v, bytes, stream);
+#else
+		memset(p, v, bytes);
+#endif
+	}
+	void sync()
+	{
+#ifndef B2J_HOSTSIM
+		cudaStreamSynchronize(stream);
+#endif
+	}
+	bool check(const char *what)
+	{
+#ifndef B2J_HOSTSIM
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) { last_error() = std::string(what) + ": " + cudaGetErrorString(e); return false; }
+#endif
+		(void)what;
+		return true;
+	}
+
+	uint32_t grid_for(uint32_t n, uint32_t block) const
+	{
+		uint32_t g = (n + block - 1) / block;
+		uint32_t cap = (uint32_t)num_sms * 16;
+		return g < 1? 1 : (g > cap? cap : g);
+	}
+
+	// host-known count
+	template <class K> void launch(const K &k, uint32_t n)
+	{
+		if (n == 0) return;
+		++launches;
+#ifndef B2J_HOSTSIM
+		run_kernel<K><<<grid_for(n, 128), 128, 0, stream>>>(k, n);
+#else
+		for (uint32_t i = 0; i < n; ++i) k(i);
+#endif
+	}
+	// device-resident count (no host sync): processes [*begin, min(*n_ptr, cap))
+	template <class K> void launch_dev(const K &k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap)
+	{
+		if (cap == 0) return;
+		++launches;
+#ifndef B2J_HOSTSIM
+		uint32_t g = grid_for(cap, 128);
+		uint32_t gmax = (uint32_t)num_sms * 8;
+		run_kernel_dev<K><<<g > gmax? gmax : g, 128, 0, stream>>>(k, n_ptr, begin_ptr, cap);
+#else
+		uint32_t n = *n_ptr < cap? *n_ptr : cap;
+		uint32_t begin = begin_ptr? *begin_ptr : 0;
+		for (uint32_t i = 0; begin + i < n; ++i) k(i);
+#endif
+	}
+	// device-resident count with per-thread scratch slots: at most num_slots threads
+	template <class K> void launch_slot(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots)
+	{
+		if (cap == 0) return;
+		++launches;
+#ifndef B2J_HOSTSIM
+		uint32_t g = num_slots / 128;
+		if (g < 1) g = 1;
+		uint32_t gn = grid_for(cap, 128);
+		if (gn < g) g = gn;
+		run_kernel_slot<K><<<g, 128, 0, stream>>>(k, n_ptr, cap);
+#else
+		(void)num_slots;
+		uint32_t n = *n_ptr < cap? *n_ptr : cap;
+		for (uint32_t i = 0; i < n; ++i) k.run(i, 0);
+#endif
+	}
+
+	void ensure_temp(size_t bytes)
+	{
+		if (bytes <= cub_temp_size) return;
+#ifndef B2J_HOSTSIM
+		if (cub_temp) { cudaStreamSynchronize(stream); cudaFree(cub_temp); }
+		cudaMalloc(&cub_temp, bytes);
+#else
+		free(cub_temp);
+		cub_temp = malloc(bytes);
+#endif
+		cub_temp_size = bytes;
+	}
+
+	// stable sort of (key, value) pairs, n known on the host; results in keys_out / vals_out
+	template <class KeyT> void sort_pairs(const KeyT *keys_in, KeyT *keys_out, const uint32_t *vals_in, uint32_t *vals_out, uint32_t n, int end_bit = (int)sizeof(KeyT) * 8)
+	{
+		if (n == 0) return;
+		launches += 1;
+#ifndef B2J_HOSTSIM
+		size_t bytes = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, stream);
+		ensure_temp(bytes);
+		cub::DeviceRadixSort::SortPairs(cub_temp, bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, stream);
+#else
+		(void)end_bit;
+		std::vector<uint32_t> idx(n);
+		std::iota(idx.begin(), idx.end(), 0u);
+		std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return keys_in[a] < keys_in[b]; });
+		for (uint32_t i = 0; i < n; ++i) { keys_out[i] = keys_in[idx[i]]; vals_out[i] = vals_in[idx[i]]; }
+#endif
+	}
+
+	void exclusive_scan(const uint32_t *in, uint32_t *out, uint32_t n)
+	{
+		if (n == 0) return;
+		launches += 1;
+#ifndef B2J_HOSTSIM
+		size_t bytes = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, stream);
+		ensure_temp(bytes);
+		cub::DeviceScan::ExclusiveSum(cub_temp, bytes, in, out, (int)n, stream);
+#else
+		uint32_t s = 0;
+		for (uint32_t i = 0; i < n; ++i) { uint32_t v = in[i]; out[i] = s; s += v; }
+#endif
+	}
+};
+
+} // namespace b2j

@@ -1,0 +1,1108 @@
+// b2j_solver.h -- islands, solve schedule, contact constraint setup, velocity / position solve, integration, sleeping.
+//
+// Restates the arithmetic of
+//   ContactConstraintManager: CalculateNonPenetrationConstraintProperties (.cpp:39-134), CalculateFrictionConstraintProperties
+//     (:140-189), TemplatedGetContactsFromCache (:843-999), TemplatedAddContactConstraint (:1130-1332), sWarmStartConstraint
+//     (:1587-1622), sSolveVelocityConstraint (:1683-1767), sStoreAppliedImpulses (:1819-1835), sSolvePositionConstraint (:1880-1939)
+//   ContactConstraintPart.h:85-252, AngularFrictionConstraintPart.h:40-138
+//   MotionProperties.inl (ApplyForceTorqueAndDragInternal :127-149, gyroscopic :99-125, GetInverseInertiaForRotation :69-85)
+//   PhysicsSystem.cpp JobApplyGravity :746-791, JobIntegrateVelocity :1583-1711, CheckSleepAndUpdateBounds :2511-2564
+//   Body::AddRotationStep Body.inl:81-112, Body::UpdateSleepStateInternal Body.cpp:145-184
+//   IslandBuilder::LinkBodies IslandBuilder.cpp:99-156 (union by lowest index), LargeIslandSplitter::AssignSplit/SplitIsland
+//     LargeIslandSplitter.cpp:236-490 (greedy 32 bit masks in sorted order, splits < 32 items merged into the serial split)
+//
+// B200 design: the reference solves island by island, batch by batch (job graph + spinning). Here every constraint gets a
+// PHASE such that running phases 0,1,2,... with all constraints of one phase in parallel is bit-identical to the reference's
+// order: small islands (< 128 items) are serial in sort-key order -> phase = dependency depth in that order; large islands use
+// the reference's own colouring -> phase = colour, the serial split -> 32 + dependency depth. Constraints are then built
+// directly in (phase, sort order) into structure-of-arrays storage so the solver streams them fully coalesced.
+#pragma once
+
+#include "b2j_world.h"
+#include "b2j_shapes.h"
+#include "b2j_narrowphase.h"
+
+namespace b2j {
+
+// ---- constraint storage (SoA, solve order) ----------------------------------------------------------------------
+// cf[field * capacity + i]
+enum
+{
+	CF_NX = 0, CF_NY, CF_NZ, CF_FRICTION, CF_INVM1, CF_INVM2,
+	CF_FR0 = 6,      // 2 friction parts of 15 floats: R1X(3) I1(3) R2X(3) I2(3) EFF BIAS LAMBDA
+	CF_ANG = 36,     // I1(3) I2(3) EFF BIAS LAMBDA
+	CF_PT0 = 45,     // 4 points of 22 floats: part(15) DIST LP1(3) LP2(3)
+	CF_PT_STRIDE = 22,
+	CF_NUM = CF_PT0 + 4 * CF_PT_STRIDE
+};
+enum { PART_R1X = 0, PART_I1 = 3, PART_R2X = 6, PART_I2 = 9, PART_EFF = 12, PART_BIAS = 13, PART_LAMBDA = 14, PT_DIST = 15, PT_LP1 = 16, PT_LP2 = 19 };
+enum { ANG_I1 = 0, ANG_I2 = 3, ANG_EFF = 6, ANG_BIAS = 7, ANG_LAMBDA = 8 };
+
+// meta bits: num points (3) | type1 (2) << 3 | type2 (2) << 5 | velocity steps << 8 | position steps << 16
+struct Constraints
+{
+	float *cf;
+	uint32_t *b1, *b2, *manifold, *meta;
+	uint32_t capacity;
+};
+
+struct SolveCtx
+{
+	Constraints con;
+	ConstraintSrc *src;          // unsorted constraint sources
+	ManifoldWS *man_ws;
+	uint32_t *order;             // [M] sorted position -> src index (sorted by sort key)
+	uint32_t *final_pos;         // [M] sorted position -> solve position
+	uint32_t *solve_src;         // [M] solve position -> src index
+	uint32_t *phase;             // [M] by sorted position
+	uint32_t *phase_count;       // [max_phases + 1] histogram / offsets
+	uint32_t max_phases;
+	// islands (indexed by body slot)
+	uint32_t *uf_parent;
+	uint32_t *root;              // flattened root per slot
+	uint32_t *island_items;      // per root slot: number of constraints
+	uint32_t *island_large;      // per root slot: compact large island index + 1, 0 = small
+	uint32_t *island_steps;      // per root slot: max vel override | max pos override << 8 | apply default vel << 16 | apply default pos << 17
+	uint32_t *island_can_sleep;  // per root slot
+	uint32_t *large_color_count; // [num_large * 32]
+	// per body adjacency (CSR by slot)
+	uint32_t *body_deg, *body_off, *body_fill, *body_cur, *body_mask;
+	uint32_t *adj;
+	uint32_t num_slots;
+	uint32_t *sched_flag;        // [2] remaining flags
+};
+
+B2J_HD float &cf_at(const Constraints &c, int field, uint32_t i) { return c.cf[(size_t)field * c.capacity + i]; }
+B2J_HD V3 cf_v3(const Constraints &c, int field, uint32_t i) { return v3(cf_at(c, field, i), cf_at(c, field + 1, i), cf_at(c, field + 2, i)); }
+B2J_HD void cf_set_v3(const Constraints &c, int field, uint32_t i, V3 v) { cf_at(c, field, i) = v.x; cf_at(c, field + 1, i) = v.y; cf_at(c, field + 2, i) = v.z; }
+
+// ---- body helpers ------------------------------------------------------------------------------------------------
+B2J_HD V3 lock_translation(V3 v, uint32_t dofs) { return v3((dofs & 1)? v.x : 0.0f, (dofs & 2)? v.y : 0.0f, (dofs & 4)? v.z : 0.0f); }
+B2J_HD V3 lock_angular(V3 v, uint32_t dofs) { return v3((dofs & 8)? v.x : 0.0f, (dofs & 16)? v.y : 0.0f, (dofs & 32)? v.z : 0.0f); }
+
+// MotionProperties::GetInverseInertiaForRotation
+B2J_HD M33 inverse_inertia_for_rotation(const M33 &body_rotation, Q4 inertia_rotation, V3 inv_inertia_diag, uint32_t dofs)
+{
+	M33 rotation = mul(body_rotation, m33_rotation(inertia_rotation));
+	M33 rms = m33(inv_inertia_diag.x * rotation.c0, inv_inertia_diag.y * rotation.c1, inv_inertia_diag.z * rotation.c2);
+	M33 inv = mul_right_transposed(rotation, rms);
+	bool ax = (dofs & 8) != 0, ay = (dofs & 16) != 0, az = (dofs & 32) != 0;
+	if (!(ax && ay && az))
+	{
+		// column j masked by (mask & splat(mask[j]))
+		inv.c0 = v3(ax && ax? inv.c0.x : 0.0f, ay && ax? inv.c0.y : 0.0f, az && ax? inv.c0.z : 0.0f);
+		inv.c1 = v3(ax && ay? inv.c1.x : 0.0f, ay && ay? inv.c1.y : 0.0f, az && ay? inv.c1.z : 0.0f);
+		inv.c2 = v3(ax && az? inv.c2.x : 0.0f, ay && az? inv.c2.y : 0.0f, az && az? inv.c2.z : 0.0f);
+	}
+	return inv;
+}
+
+// MotionProperties::MultiplyWorldSpaceInverseInertiaByVector
+B2J_HD V3 multiply_ws_inverse_inertia(Q4 body_rotation, Q4 inertia_rotation, V3 inv_inertia_diag, uint32_t dofs, V3 v_in)
+{
+	V3 v = lock_angular(v_in, dofs);
+	M33 rotation = m33_rotation(body_rotation * inertia_rotation);
+	V3 result = mul(rotation, inv_inertia_diag * mul_transposed(rotation, v));
+	return lock_angular(result, dofs);
+}
+
+B2J_HD void clamp_velocity(V3 &v, float max_v)
+{
+	float len_sq = length_sq(v);
+	if (len_sq > square(max_v))
+		v *= max_v / sqrt_(len_sq);
+}
+
+// Body::AddRotationStep / SubRotationStep
+B2J_HD Q4 add_rotation_step(Q4 rotation, V3 w_dt, bool sub)
+{
+	float len = length(w_dt);
+	if (len > 1.0e-6f)
+		return q4_normalized(q4_rotation(w_dt / len, sub? -len : len) * rotation);
+	return rotation;
+}
+
+// ---- KApplyGravity (JobApplyGravity) -----------------------------------------------------------------------------
+struct KApplyGravity
+{
+	DWorld w; float dt;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		BodyInfo info = w.info[b];
+		if (info.motion_type != B2J_MOTION_DYNAMIC)
+			return;
+		BodyParams p = w.params[b];
+		Q4 rot = to_q4(w.rotation[b]);
+		V3 v = to_v3(w.linear_velocity[b]), av = to_v3(w.angular_velocity[b]);
+		V3 diag = to_v3(w.inv_inertia_diag[b]);
+		Q4 irot = to_q4(w.inertia_rotation[b]);
+		if (info.flags & B2J_BODY_GYROSCOPIC)
+		{
+			// MotionProperties::ApplyGyroscopicForceInternal
+			V3 denom = v3(diag.x == 0.0f? 1.0f : diag.x, diag.y == 0.0f? 1.0f : diag.y, diag.z == 0.0f? 1.0f : diag.z);
+			V3 nom = v3(diag.x == 0.0f? 0.0f : 1.0f, diag.y == 0.0f? 0.0f : 1.0f, diag.z == 0.0f? 0.0f : 1.0f);
+			V3 local_inertia = nom / denom;
+			Q4 i2w = rot * irot;
+			V3 local_av = inverse_rotate(i2w, av);
+			V3 local_momentum = local_inertia * local_av;
+			V3 new_local_momentum = local_momentum - dt * cross(local_av, local_momentum);
+			float nl = length_sq(new_local_momentum);
+			new_local_momentum = nl > 0.0f? new_local_momentum * sqrt_(length_sq(local_momentum) / nl) : v3_zero();
+			av = rotate(i2w, diag * new_local_momentum);
+		}
+		// ApplyForceTorqueAndDragInternal
+		V3 force = to_v3(w.force[b]), torque = to_v3(w.torque[b]);
+		v = lock_translation(v + dt * (p.gravity_factor * w.gravity + p.inv_mass * force), info.allowed_dofs);
+		av += dt * multiply_ws_inverse_inertia(rot, irot, diag, info.allowed_dofs, torque);
+		v *= fmax_(0.0f, 1.0f - p.linear_damping * dt);
+		av *= fmax_(0.0f, 1.0f - p.angular_damping * dt);
+		clamp_velocity(v, p.max_linear_velocity);
+		clamp_velocity(av, p.max_angular_velocity);
+		w.linear_velocity[b] = f4(v);
+		w.angular_velocity[b] = f4(av);
+	}
+};
+
+// ---- islands: union find over body slots, root = lowest slot ----------------------------------------------------------
+struct KUfInit
+{
+	SolveCtx s;
+	B2J_D void operator()(uint32_t slot) const
+	{
+		s.uf_parent[slot] = slot;
+		s.island_items[slot] = 0;
+		s.island_large[slot] = 0;
+		s.island_steps[slot] = 0;
+		s.island_can_sleep[slot] = 1;
+		s.body_deg[slot] = 0;
+		s.body_fill[slot] = 0;
+		s.body_cur[slot] = 0;
+		s.body_mask[slot] = 0;
+	}
+};
+
+B2J_D uint32_t uf_find(uint32_t *parent, uint32_t x)
+{
+	for (;;)
+	{
+		uint32_t p = volatile_load(&parent[x]);
+		if (p == x) return x;
+		x = p;
+	}
+}
+
+struct KUfUnion
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const ConstraintSrc &c = s.src[i];
+		bool dyn1 = w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC, dyn2 = w.info[c.b2].motion_type == B2J_MOTION_DYNAMIC;
+		if (dyn1) atomic_add(&s.body_deg[c.b1], 1u);
+		if (dyn2) atomic_add(&s.body_deg[c.b2], 1u);
+		if (!(dyn1 && dyn2))
+			return;
+		uint32_t a = c.b1, b = c.b2;
+		for (;;)
+		{
+			a = uf_find(s.uf_parent, a);
+			b = uf_find(s.uf_parent, b);
+			if (a == b) break;
+			if (a < b) { if (atomic_cas(&s.uf_parent[b], b, a) == b) break; }
+			else { if (atomic_cas(&s.uf_parent[a], a, b) == a) break; }
+		}
+	}
+};
+
+struct KUfFlatten
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		s.root[b] = uf_find(s.uf_parent, b);
+	}
+};
+
+// per constraint: island item count + solver step overrides (CalculateSolverSteps over the dynamic bodies of contacts)
+struct KIslandCount
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const ConstraintSrc &c = s.src[i];
+		BodyInfo i1 = w.info[c.b1], i2 = w.info[c.b2];
+		bool dyn1 = i1.motion_type == B2J_MOTION_DYNAMIC, dyn2 = i2.motion_type == B2J_MOTION_DYNAMIC;
+		uint32_t r = s.root[dyn1? c.b1 : c.b2];
+		atomic_add(&s.island_items[r], 1u);
+		uint32_t vmax = 0, pmax = 0, flags = 0;
+		if (dyn1) { uint32_t v = i1.steps_override & 15, p = i1.steps_override >> 4; vmax = v; pmax = p; if (v == 0) flags |= 1u << 16; if (p == 0) flags |= 1u << 17; }
+		if (dyn2) { uint32_t v = i2.steps_override & 15, p = i2.steps_override >> 4; if (v > vmax) vmax = v; if (p > pmax) pmax = p; if (v == 0) flags |= 1u << 16; if (p == 0) flags |= 1u << 17; }
+		// max of two packed bytes: do them separately to keep atomics simple
+		uint32_t cur = volatile_load(&s.island_steps[r]);
+		for (;;)
+		{
+			uint32_t cv = cur & 0xff, cp = (cur >> 8) & 0xff;
+			uint32_t nv = cv > vmax? cv : vmax, np = cp > pmax? cp : pmax;
+			uint32_t nw = nv | (np << 8) | (cur & 0x30000u) | flags;
+			if (nw == cur) break;
+			uint32_t prev = atomic_cas(&s.island_steps[r], cur, nw);
+			if (prev == cur) break;
+			cur = prev;
+		}
+	}
+};
+
+// compact index for large islands (>= 128 items, LargeIslandSplitter.h:34)
+struct KIslandClassify
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		if (s.root[b] != b)
+			return;
+		atomic_add(&w.counters->num_islands, 1u);
+		if (w.settings.use_large_island_splitter && s.island_items[b] >= 128)
+		{
+			uint32_t li = atomic_add(&w.counters->num_large_islands, 1u);
+			s.island_large[b] = li + 1;
+			for (int c = 0; c < 32; ++c) s.large_color_count[li * 32 + c] = 0;
+		}
+	}
+};
+
+// adjacency fill: i = sorted position
+struct KAdjFill
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const ConstraintSrc &c = s.src[s.order[i]];
+		s.phase[i] = 0xffffffffu;
+		if (w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC)
+			s.adj[s.body_off[c.b1] + atomic_add(&s.body_fill[c.b1], 1u)] = i;
+		if (w.info[c.b2].motion_type == B2J_MOTION_DYNAMIC)
+			s.adj[s.body_off[c.b2] + atomic_add(&s.body_fill[c.b2], 1u)] = i;
+	}
+};
+
+// per active body: sort its adjacency list ascending (insertion sort, lists are short)
+struct KAdjSort
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		uint32_t n = s.body_deg[b];
+		uint32_t *a = s.adj + s.body_off[b];
+		for (uint32_t i = 1; i < n; ++i)
+		{
+			uint32_t v = a[i];
+			uint32_t j = i;
+			while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; --j; }
+			a[j] = v;
+		}
+	}
+};
+
+// ---- wavefront scheduling ------------------------------------------------------------------------------------------
+enum { PHASE_UNSCHEDULED = 0xffffffffu, PHASE_PENDING_SERIAL = 0xfffffffeu };
+
+// decide step: one thread per active body; `pass` 0 = levels / colours, 1 = serial splits of large islands
+struct KSchedDecide
+{
+	DWorld w; SolveCtx s; uint32_t round; uint32_t pass;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		uint32_t cur = s.body_cur[b];
+		if (cur >= s.body_deg[b])
+			return;
+		uint32_t i = s.adj[s.body_off[b] + cur];
+		const ConstraintSrc &c = s.src[s.order[i]];
+		bool dyn1 = w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC, dyn2 = w.info[c.b2].motion_type == B2J_MOTION_DYNAMIC;
+		uint32_t owner = dyn1? c.b1 : c.b2;
+		if (owner != b)
+			return;
+		uint32_t other = (dyn1 && dyn2)? c.b2 : 0xffffffffu;
+		if (other != 0xffffffffu)
+		{
+			uint32_t oc = s.body_cur[other];
+			if (oc >= s.body_deg[other] || s.adj[s.body_off[other] + oc] != i)
+				return;
+		}
+		uint32_t r = s.root[b];
+		uint32_t large = s.island_large[r];
+		if (pass == 0)
+		{
+			if (large != 0)
+			{
+				// LargeIslandSplitter::AssignSplit
+				uint32_t m = s.body_mask[b] | (other != 0xffffffffu? s.body_mask[other] : 0u);
+				int split = ctz32(~m);
+				if (split > 31) split = 31;
+				uint32_t bit = 1u << split;
+				s.body_mask[b] |= bit;
+				if (other != 0xffffffffu) s.body_mask[other] |= bit;
+				s.phase[i] = (uint32_t)split;
+				atomic_add(&s.large_color_count[(large - 1) * 32 + split], 1u);
+			}
+			else
+				s.phase[i] = round;
+		}
+		else
+			s.phase[i] = 32 + round;
+	}
+};
+
+// advance step: move every body's cursor past scheduled constraints (pass 1: past everything that is not pending serial)
+struct KSchedAdvance
+{
+	DWorld w; SolveCtx s; uint32_t pass; uint32_t flag_index;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		uint32_t cur = s.body_cur[b], deg = s.body_deg[b];
+		const uint32_t *a = s.adj + s.body_off[b];
+		if (pass == 0)
+			while (cur < deg && s.phase[a[cur]] != PHASE_UNSCHEDULED) ++cur;
+		else
+			while (cur < deg && s.phase[a[cur]] != PHASE_PENDING_SERIAL) ++cur;
+		s.body_cur[b] = cur;
+		if (cur < deg)
+			s.sched_flag[flag_index] = 1;
+	}
+};
+
+// after pass 0: colours of large islands with < 32 items and colour 31 go to the serial split (SplitIsland :375-412)
+struct KSchedSerialize
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const ConstraintSrc &c = s.src[s.order[i]];
+		bool dyn1 = w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC;
+		uint32_t large = s.island_large[s.root[dyn1? c.b1 : c.b2]];
+		if (large == 0)
+			return;
+		uint32_t color = s.phase[i];
+		if (color == 31 || s.large_color_count[(large - 1) * 32 + color] < 32)
+			s.phase[i] = PHASE_PENDING_SERIAL;
+	}
+};
+
+struct KSchedResetCursors
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t ai) const { s.body_cur[w.active[ai]] = 0; }
+};
+
+// histogram of phases
+struct KPhaseCount
+{
+	DWorld w; SolveCtx s;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t p = s.phase[i];
+		if (p >= s.max_phases) { p = s.max_phases - 1; s.phase[i] = p; atomic_or(&w.counters->error_bits, 0x100u); }
+		atomic_add(&s.phase_count[p], 1u);
+		atomic_max(&w.counters->num_phases, p + 1);
+	}
+};
+
+// ---- constraint setup in solve order ------------------------------------------------------------------------------
+
+struct BodyKin
+{
+	V3 x, v, av;
+	Q4 q;
+	uint32_t type, dofs;
+	float inv_mass, gravity_factor;
+	V3 force;
+	M33 inv_i;
+};
+
+B2J_D BodyKin load_body_kin(const DWorld &w, uint32_t b)
+{
+	BodyKin k;
+	BodyInfo info = w.info[b];
+	k.type = info.motion_type;
+	k.dofs = info.allowed_dofs;
+	k.x = to_v3(w.position[b]);
+	k.q = to_q4(w.rotation[b]);
+	if (k.type != B2J_MOTION_STATIC)
+	{
+		k.v = to_v3(w.linear_velocity[b]);
+		k.av = to_v3(w.angular_velocity[b]);
+	}
+	else
+	{
+		k.v = v3_zero(); k.av = v3_zero();
+	}
+	BodyParams p = w.params[b];
+	k.gravity_factor = p.gravity_factor;
+	if (k.type == B2J_MOTION_DYNAMIC)
+	{
+		k.inv_mass = p.inv_mass;
+		k.force = to_v3(w.force[b]);
+		k.inv_i = inverse_inertia_for_rotation(m33_rotation(k.q), to_q4(w.inertia_rotation[b]), to_v3(w.inv_inertia_diag[b]), k.dofs);
+	}
+	else
+	{
+		k.inv_mass = 0.0f;
+		k.force = v3_zero();
+		k.inv_i = m33_zero();
+	}
+	return k;
+}
+
+// ContactConstraintPart::CalculateConstraintProperties; writes the 14 part floats (lambda untouched)
+B2J_D void part_calculate(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, float inv_m1, const M33 &inv_i1, V3 r1,
+	float inv_m2, const M33 &inv_i2, V3 r2, V3 axis, float bias)
+{
+	cf_at(c, base + PART_BIAS, i) = bias;
+	float inv_effective_mass;
+	if (type1 != B2J_MOTION_STATIC)
+	{
+		V3 r1x = cross(r1, axis);
+		cf_set_v3(c, base + PART_R1X, i, r1x);
+		if (type1 == B2J_MOTION_DYNAMIC)
+		{
+			V3 i1 = mul(inv_i1, r1x);
+			cf_set_v3(c, base + PART_I1, i, i1);
+			inv_effective_mass = inv_m1 + dot(i1, r1x);
+		}
+		else
+			inv_effective_mass = 0.0f;
+	}
+	else
+		inv_effective_mass = 0.0f;
+	if (type2 != B2J_MOTION_STATIC)
+	{
+		V3 r2x = cross(r2, axis);
+		cf_set_v3(c, base + PART_R2X, i, r2x);
+		if (type2 == B2J_MOTION_DYNAMIC)
+		{
+			V3 i2 = mul(inv_i2, r2x);
+			cf_set_v3(c, base + PART_I2, i, i2);
+			inv_effective_mass += inv_m2 + dot(i2, r2x);
+		}
+	}
+	if (inv_effective_mass == 0.0f)
+	{
+		// Deactivate(): effective mass AND total lambda are cleared
+		cf_at(c, base + PART_EFF, i) = 0.0f;
+		cf_at(c, base + PART_LAMBDA, i) = 0.0f;
+	}
+	else
+		cf_at(c, base + PART_EFF, i) = 1.0f / inv_effective_mass;
+}
+
+struct KSetupConstraints
+{
+	DWorld w; SolveCtx s; float dt;
+	B2J_D void operator()(uint32_t i) const // i = solve position
+	{
+		const Constraints &c = s.con;
+		const ConstraintSrc &src = s.src[s.solve_src[i]];
+		uint32_t m = src.manifold;
+		const CachedManifold &cm = w.write_cache.manifolds[m];
+		BodyKin k1 = load_body_kin(w, src.b1), k2 = load_body_kin(w, src.b2);
+		uint32_t type1 = k1.type, type2 = k2.type;
+		int n = cm.num_points;
+
+		// island solver steps
+		uint32_t r = s.root[type1 == B2J_MOTION_DYNAMIC? src.b1 : src.b2];
+		uint32_t steps = s.island_steps[r];
+		uint32_t vsteps = steps & 0xff, psteps = (steps >> 8) & 0xff;
+		if (steps & (1u << 16)) vsteps = vsteps > w.settings.num_velocity_steps? vsteps : w.settings.num_velocity_steps;
+		if (steps & (1u << 17)) psteps = psteps > w.settings.num_position_steps? psteps : w.settings.num_position_steps;
+		atomic_max(&w.counters->max_velocity_steps, vsteps);
+		atomic_max(&w.counters->max_position_steps, psteps);
+
+		c.b1[i] = src.b1; c.b2[i] = src.b2; c.manifold[i] = m;
+		c.meta[i] = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16);
+
+		BodyParams p1 = w.params[src.b1], p2 = w.params[src.b2];
+		float combined_friction = sqrt_(p1.friction * p2.friction);
+		float combined_restitution = fmax_(p1.restitution, p2.restitution);
+
+		V3 normal;
+		V3 p1_ws[4], p2_ws[4];
+		if (cm.flags & MANIFOLD_FROM_CACHE)
+		{
+			Xf t1 = xf_rotation_translation(k1.q, k1.x), t2 = xf_rotation_translation(k2.q, k2.x);
+			normal = normalized(mul(t2.r, v3_load(cm.normal)));
+			for (int p = 0; p < n; ++p)
+			{
+				p1_ws[p] = mul(t1, v3_load(cm.p1[p]));
+				p2_ws[p] = mul(t2, v3_load(cm.p2[p]));
+			}
+		}
+		else
+		{
+			const ManifoldWS &ws = s.man_ws[m];
+			normal = v3_load(ws.normal);
+			for (int p = 0; p < n; ++p)
+			{
+				p1_ws[p] = v3_load(ws.p1[p]);
+				p2_ws[p] = v3_load(ws.p2[p]);
+			}
+		}
+		cf_set_v3(c, CF_NX, i, normal);
+		cf_at(c, CF_FRICTION, i) = combined_friction;
+		cf_at(c, CF_INVM1, i) = k1.inv_mass;
+		cf_at(c, CF_INVM2, i) = k2.inv_mass;
+
+		V3 ws_contacts[4];
+		for (int p = 0; p < n; ++p)
+		{
+			int base = CF_PT0 + p * CF_PT_STRIDE;
+			ws_contacts[p] = 0.5f * (p1_ws[p] + p2_ws[p]);
+			cf_at(c, base + PART_LAMBDA, i) = cm.lambda[p];
+			cf_set_v3(c, base + PT_LP1, i, v3_load(cm.p1[p]));
+			cf_set_v3(c, base + PT_LP2, i, v3_load(cm.p2[p]));
+
+			// CalculateNonPenetrationConstraintProperties
+			V3 pm = 0.5f * (p1_ws[p] + p2_ws[p]);
+			V3 r1 = pm - k1.x, r2 = pm - k2.x;
+			V3 relative_velocity;
+			if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC)
+				relative_velocity = (k2.v + cross(k2.av, r2)) - (k1.v + cross(k1.av, r1));
+			else if (type1 != B2J_MOTION_STATIC)
+				relative_velocity = -(k1.v + cross(k1.av, r1));
+			else
+				relative_velocity = k2.v + cross(k2.av, r2);
+			float normal_velocity = dot(relative_velocity, normal);
+			float penetration = dot(p1_ws[p] - p2_ws[p], normal);
+			float speculative_contact_velocity_bias = fmax_(0.0f, -penetration / dt);
+			float normal_velocity_bias;
+			if (combined_restitution > 0.0f && normal_velocity < -w.settings.min_velocity_for_restitution)
+			{
+				if (normal_velocity < -speculative_contact_velocity_bias)
+				{
+					V3 relative_acceleration;
+					if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC)
+						relative_acceleration = w.gravity * (k2.gravity_factor - k1.gravity_factor);
+					else if (type1 != B2J_MOTION_STATIC)
+						relative_acceleration = -w.gravity * k1.gravity_factor;
+					else
+						relative_acceleration = w.gravity * k2.gravity_factor;
+					if (type1 == B2J_MOTION_DYNAMIC) relative_acceleration -= k1.force * k1.inv_mass;
+					if (type2 == B2J_MOTION_DYNAMIC) relative_acceleration += k2.force * k2.inv_mass;
+					float force_delta_velocity = fmin_(0.0f, dot(relative_acceleration, normal) * dt);
+					normal_velocity_bias = combined_restitution * (normal_velocity - force_delta_velocity);
+				}
+				else
+					normal_velocity_bias = speculative_contact_velocity_bias;
+			}
+			else
+				normal_velocity_bias = speculative_contact_velocity_bias;
+			part_calculate(c, base, i, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, normal, normal_velocity_bias);
+		}
+
+		// friction (CalculateFrictionConstraintProperties)
+		cf_at(c, CF_FR0 + PART_LAMBDA, i) = cm.friction_lambda[0];
+		cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i) = cm.friction_lambda[1];
+		cf_at(c, CF_ANG + ANG_LAMBDA, i) = cm.angular_lambda;
+		if (combined_friction > 0.0f)
+		{
+			V3 t1 = normalized_perpendicular(normal);
+			V3 t2 = cross(normal, t1);
+			V3 friction_point = v3_zero();
+			for (int p = 0; p < n; ++p) friction_point += ws_contacts[p];
+			friction_point = friction_point / (float)n;
+			for (int p = 0; p < n; ++p)
+			{
+				V3 delta = ws_contacts[p] - friction_point;
+				cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i) = length(delta - dot(delta, normal) * normal);
+			}
+			V3 r1 = friction_point - k1.x, r2 = friction_point - k2.x;
+			part_calculate(c, CF_FR0, i, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t1, 0.0f);
+			part_calculate(c, CF_FR0 + 15, i, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t2, 0.0f);
+			if (n > 1)
+			{
+				// AngularFrictionConstraintPart::CalculateConstraintProperties
+				cf_at(c, CF_ANG + ANG_BIAS, i) = 0.0f;
+				V3 i1a = v3_zero(), i2a = v3_zero();
+				if (type1 == B2J_MOTION_DYNAMIC) { i1a = mul(k1.inv_i, normal); cf_set_v3(c, CF_ANG + ANG_I1, i, i1a); }
+				if (type2 == B2J_MOTION_DYNAMIC) { i2a = mul(k2.inv_i, normal); cf_set_v3(c, CF_ANG + ANG_I2, i, i2a); }
+				float inv_effective_mass = 0.0f;
+				if (type1 == B2J_MOTION_DYNAMIC && type2 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i1a + i2a);
+				else if (type1 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i1a);
+				else if (type2 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i2a);
+				if (inv_effective_mass == 0.0f) { cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f; cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f; }
+				else cf_at(c, CF_ANG + ANG_EFF, i) = 1.0f / inv_effective_mass;
+			}
+			else
+			{
+				cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f;
+				cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f;
+			}
+		}
+		else
+		{
+			// Deactivate() x3
+			cf_at(c, CF_FR0 + PART_EFF, i) = 0.0f; cf_at(c, CF_FR0 + PART_LAMBDA, i) = 0.0f;
+			cf_at(c, CF_FR0 + 15 + PART_EFF, i) = 0.0f; cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i) = 0.0f;
+			cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f; cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f;
+			for (int p = 0; p < n; ++p) cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i) = 0.0f;
+		}
+	}
+};
+
+// ---- velocity solve --------------------------------------------------------------------------------------------------
+
+struct VelState { V3 v1, w1, v2, w2; };
+
+// ContactConstraintPart::ApplyVelocityStep
+B2J_D bool part_apply_velocity_step(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, VelState &s, float inv_m1, float inv_m2, V3 axis, float lambda)
+{
+	if (lambda != 0.0f)
+	{
+		if (type1 == B2J_MOTION_DYNAMIC)
+		{
+			s.v1 -= (lambda * inv_m1) * axis;
+			s.w1 -= lambda * cf_v3(c, base + PART_I1, i);
+		}
+		if (type2 == B2J_MOTION_DYNAMIC)
+		{
+			s.v2 += (lambda * inv_m2) * axis;
+			s.w2 += lambda * cf_v3(c, base + PART_I2, i);
+		}
+		return true;
+	}
+	return false;
+}
+
+// SolveVelocityConstraintGetTotalLambda
+B2J_D float part_get_total_lambda(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, const VelState &s, V3 axis)
+{
+	float jv;
+	if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC)
+		jv = dot(axis, s.v1 - s.v2);
+	else if (type1 != B2J_MOTION_STATIC)
+		jv = dot(axis, s.v1);
+	else
+		jv = dot(axis, -s.v2);
+	if (type1 != B2J_MOTION_STATIC)
+		jv += dot(cf_v3(c, base + PART_R1X, i), s.w1);
+	if (type2 != B2J_MOTION_STATIC)
+		jv -= dot(cf_v3(c, base + PART_R2X, i), s.w2);
+	float lambda = cf_at(c, base + PART_EFF, i) * (jv - cf_at(c, base + PART_BIAS, i));
+	return cf_at(c, base + PART_LAMBDA, i) + lambda;
+}
+
+// SolveVelocityConstraintApplyLambda
+B2J_D bool part_apply_lambda(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, VelState &s, float inv_m1, float inv_m2, V3 axis, float total_lambda)
+{
+	float delta_lambda = total_lambda - cf_at(c, base + PART_LAMBDA, i);
+	cf_at(c, base + PART_LAMBDA, i) = total_lambda;
+	return part_apply_velocity_step(c, base, i, type1, type2, s, inv_m1, inv_m2, axis, delta_lambda);
+}
+
+B2J_D void load_vel_state(const DWorld &w, uint32_t b1, uint32_t b2, uint32_t type1, uint32_t type2, VelState &s)
+{
+	if (type1 != B2J_MOTION_STATIC) { s.v1 = to_v3(w.linear_velocity[b1]); s.w1 = to_v3(w.angular_velocity[b1]); }
+	else { s.v1 = v3_zero(); s.w1 = v3_zero(); }
+	if (type2 != B2J_MOTION_STATIC) { s.v2 = to_v3(w.linear_velocity[b2]); s.w2 = to_v3(w.angular_velocity[b2]); }
+	else { s.v2 = v3_zero(); s.w2 = v3_zero(); }
+}
+
+B2J_D void store_vel_state(const DWorld &w, uint32_t b1, uint32_t b2, uint32_t type1, uint32_t type2, const VelState &s)
+{
+	if (type1 == B2J_MOTION_DYNAMIC)
+	{
+		w.linear_velocity[b1] = f4(lock_translation(s.v1, w.info[b1].allowed_dofs));
+		w.angular_velocity[b1] = f4(s.w1);
+	}
+	if (type2 == B2J_MOTION_DYNAMIC)
+	{
+		w.linear_velocity[b2] = f4(lock_translation(s.v2, w.info[b2].allowed_dofs));
+		w.angular_velocity[b2] = f4(s.w2);
+	}
+}
+
+// sWarmStartConstraint for solve positions [begin, begin + n)
+struct KWarmStart
+{
+	DWorld w; Constraints c; uint32_t begin; float ratio;
+	B2J_D void operator()(uint32_t k) const
+	{
+		uint32_t i = begin + k;
+		uint32_t meta = c.meta[i];
+		int n = (int)(meta & 7);
+		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+		uint32_t b1 = c.b1[i], b2 = c.b2[i];
+		VelState s;
+		load_vel_state(w, b1, b2, type1, type2, s);
+		V3 normal = cf_v3(c, CF_NX, i);
+		V3 t1 = normalized_perpendicular(normal);
+		V3 t2 = cross(normal, t1);
+		float inv_m1 = cf_at(c, CF_INVM1, i), inv_m2 = cf_at(c, CF_INVM2, i);
+		bool any = false;
+		for (int f = 0; f < 2; ++f)
+		{
+			int base = CF_FR0 + 15 * f;
+			if (cf_at(c, base + PART_EFF, i) != 0.0f)
+			{
+				float l = cf_at(c, base + PART_LAMBDA, i) * ratio;
+				cf_at(c, base + PART_LAMBDA, i) = l;
+				if (part_apply_velocity_step(c, base, i, type1, type2, s, inv_m1, inv_m2, f == 0? t1 : t2, l)) any = true;
+			}
+		}
+		if (cf_at(c, CF_ANG + ANG_EFF, i) != 0.0f)
+		{
+			float l = cf_at(c, CF_ANG + ANG_LAMBDA, i) * ratio;
+			cf_at(c, CF_ANG + ANG_LAMBDA, i) = l;
+			if (l != 0.0f)
+			{
+				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= l * cf_v3(c, CF_ANG + ANG_I1, i);
+				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += l * cf_v3(c, CF_ANG + ANG_I2, i);
+				any = true;
+			}
+		}
+		for (int p = 0; p < n; ++p)
+		{
+			int base = CF_PT0 + p * CF_PT_STRIDE;
+			float l = cf_at(c, base + PART_LAMBDA, i) * ratio;
+			cf_at(c, base + PART_LAMBDA, i) = l;
+			if (part_apply_velocity_step(c, base, i, type1, type2, s, inv_m1, inv_m2, normal, l)) any = true;
+		}
+		if (any)
+			store_vel_state(w, b1, b2, type1, type2, s);
+	}
+};
+
+// sSolveVelocityConstraint; iteration = 0 based velocity step index (constraints of islands with fewer steps skip)
+struct KSolveVelocity
+{
+	DWorld w; Constraints c; uint32_t begin; uint32_t iteration;
+	B2J_D void operator()(uint32_t k) const
+	{
+		uint32_t i = begin + k;
+		uint32_t meta = c.meta[i];
+		if (iteration >= ((meta >> 8) & 0xff))
+			return;
+		int n = (int)(meta & 7);
+		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+		uint32_t b1 = c.b1[i], b2 = c.b2[i];
+		VelState s;
+		load_vel_state(w, b1, b2, type1, type2, s);
+		V3 normal = cf_v3(c, CF_NX, i);
+		V3 t1 = normalized_perpendicular(normal);
+		V3 t2 = cross(normal, t1);
+		float inv_m1 = cf_at(c, CF_INVM1, i), inv_m2 = cf_at(c, CF_INVM2, i);
+		bool any = false;
+
+		bool f1_active = cf_at(c, CF_FR0 + PART_EFF, i) != 0.0f, f2_active = cf_at(c, CF_FR0 + 15 + PART_EFF, i) != 0.0f;
+		bool linear_friction_active = f1_active || f2_active;
+		bool angular_friction_active = cf_at(c, CF_ANG + ANG_EFF, i) != 0.0f;
+		float max_linear_lambda = 0.0f, max_angular_lambda = 0.0f;
+		if (linear_friction_active || angular_friction_active)
+		{
+			for (int p = 0; p < n; ++p)
+			{
+				int base = CF_PT0 + p * CF_PT_STRIDE;
+				float lambda = cf_at(c, base + PART_LAMBDA, i);
+				max_linear_lambda += lambda;
+				max_angular_lambda += cf_at(c, base + PT_DIST, i) * lambda;
+			}
+			float mu = cf_at(c, CF_FRICTION, i);
+			max_linear_lambda *= mu;
+			max_angular_lambda *= mu;
+		}
+		if (linear_friction_active)
+		{
+			float lambda1 = part_get_total_lambda(c, CF_FR0, i, type1, type2, s, t1);
+			float lambda2 = part_get_total_lambda(c, CF_FR0 + 15, i, type1, type2, s, t2);
+			float total_lambda_sq = square(lambda1) + square(lambda2);
+			if (total_lambda_sq > square(max_linear_lambda))
+			{
+				float scale = max_linear_lambda / sqrt_(total_lambda_sq);
+				lambda1 *= scale;
+				lambda2 *= scale;
+			}
+			if (part_apply_lambda(c, CF_FR0, i, type1, type2, s, inv_m1, inv_m2, t1, lambda1)) any = true;
+			if (part_apply_lambda(c, CF_FR0 + 15, i, type1, type2, s, inv_m1, inv_m2, t2, lambda2)) any = true;
+		}
+		if (angular_friction_active)
+		{
+			// AngularFrictionConstraintPart::SolveVelocityConstraint
+			float jv;
+			if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC) jv = dot(normal, s.w1 - s.w2);
+			else if (type1 != B2J_MOTION_STATIC) jv = dot(normal, s.w1);
+			else jv = -dot(normal, s.w2);
+			float total = cf_at(c, CF_ANG + ANG_LAMBDA, i);
+			float lambda = cf_at(c, CF_ANG + ANG_EFF, i) * (jv - cf_at(c, CF_ANG + ANG_BIAS, i));
+			float new_lambda = clamp_(total + lambda, -max_angular_lambda, max_angular_lambda);
+			lambda = new_lambda - total;
+			cf_at(c, CF_ANG + ANG_LAMBDA, i) = new_lambda;
+			if (lambda != 0.0f)
+			{
+				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= lambda * cf_v3(c, CF_ANG + ANG_I1, i);
+				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += lambda * cf_v3(c, CF_ANG + ANG_I2, i);
+				any = true;
+			}
+		}
+		for (int p = 0; p < n; ++p)
+		{
+			int base = CF_PT0 + p * CF_PT_STRIDE;
+			float total_lambda = part_get_total_lambda(c, base, i, type1, type2, s, normal);
+			total_lambda = fmax_(total_lambda, 0.0f);
+			if (part_apply_lambda(c, base, i, type1, type2, s, inv_m1, inv_m2, normal, total_lambda)) any = true;
+		}
+		if (any)
+			store_vel_state(w, b1, b2, type1, type2, s);
+	}
+};
+
+// sStoreAppliedImpulses
+struct KStoreImpulses
+{
+	DWorld w; Constraints c;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t meta = c.meta[i];
+		int n = (int)(meta & 7);
+		CachedManifold &cm = w.write_cache.manifolds[c.manifold[i]];
+		for (int p = 0; p < n; ++p)
+			cm.lambda[p] = cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PART_LAMBDA, i);
+		cm.friction_lambda[0] = cf_at(c, CF_FR0 + PART_LAMBDA, i);
+		cm.friction_lambda[1] = cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i);
+		cm.angular_lambda = cf_at(c, CF_ANG + ANG_LAMBDA, i);
+	}
+};
+
+// ---- integrate (JobIntegrateVelocity, discrete motion quality) -------------------------------------------------------
+struct KIntegrate
+{
+	DWorld w; float dt;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		BodyInfo info = w.info[b];
+		V3 v = to_v3(w.linear_velocity[b]), av = to_v3(w.angular_velocity[b]);
+		if (info.motion_type == B2J_MOTION_DYNAMIC)
+		{
+			BodyParams p = w.params[b];
+			clamp_velocity(v, p.max_linear_velocity);
+			clamp_velocity(av, p.max_angular_velocity);
+			w.linear_velocity[b] = f4(v);
+			w.angular_velocity[b] = f4(av);
+		}
+		w.rotation[b] = f4(add_rotation_step(to_q4(w.rotation[b]), av * dt, false));
+		V3 x = to_v3(w.position[b]);
+		x += lock_translation(v * dt, info.allowed_dofs);
+		w.position[b] = f4(x);
+	}
+};
+
+// ---- position solve (sSolvePositionConstraint) ------------------------------------------------------------------------
+struct KSolvePosition
+{
+	DWorld w; Constraints c; uint32_t begin; uint32_t iteration;
+	B2J_D void operator()(uint32_t k) const
+	{
+		uint32_t i = begin + k;
+		uint32_t meta = c.meta[i];
+		if (iteration >= ((meta >> 16) & 0xff))
+			return;
+		int n = (int)(meta & 7);
+		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+		uint32_t b1 = c.b1[i], b2 = c.b2[i];
+		V3 x1 = to_v3(w.position[b1]), x2 = to_v3(w.position[b2]);
+		Q4 q1 = to_q4(w.rotation[b1]), q2 = to_q4(w.rotation[b2]);
+		uint32_t dofs1 = w.info[b1].allowed_dofs, dofs2 = w.info[b2].allowed_dofs;
+		// transforms are fetched once per constraint, inertia / positions are re-read per point (bodies move between points)
+		Xf transform1 = xf_rotation_translation(q1, x1), transform2 = xf_rotation_translation(q2, x2);
+		V3 normal = cf_v3(c, CF_NX, i);
+		float inv_m1 = cf_at(c, CF_INVM1, i), inv_m2 = cf_at(c, CF_INVM2, i);
+		V3 diag1 = v3_zero(), diag2 = v3_zero();
+		Q4 irot1 = q4_identity(), irot2 = q4_identity();
+		if (type1 == B2J_MOTION_DYNAMIC) { diag1 = to_v3(w.inv_inertia_diag[b1]); irot1 = to_q4(w.inertia_rotation[b1]); }
+		if (type2 == B2J_MOTION_DYNAMIC) { diag2 = to_v3(w.inv_inertia_diag[b2]); irot2 = to_q4(w.inertia_rotation[b2]); }
+		bool any = false;
+		for (int p = 0; p < n; ++p)
+		{
+			int base = CF_PT0 + p * CF_PT_STRIDE;
+			V3 p1 = mul(transform1, cf_v3(c, base + PT_LP1, i));
+			V3 p2 = mul(transform2, cf_v3(c, base + PT_LP2, i));
+			float separation = fmax_(dot(p2 - p1, normal) + w.settings.penetration_slop, -w.settings.max_penetration_distance);
+			if (separation < 0.0f)
+			{
+				M33 inv_i1 = type1 == B2J_MOTION_DYNAMIC? inverse_inertia_for_rotation(m33_rotation(q1), irot1, diag1, dofs1) : m33_zero();
+				M33 inv_i2 = type2 == B2J_MOTION_DYNAMIC? inverse_inertia_for_rotation(m33_rotation(q2), irot2, diag2, dofs2) : m33_zero();
+				V3 pm = 0.5f * (p1 + p2);
+				V3 r1 = pm - x1, r2 = pm - x2;
+				part_calculate(c, base, i, type1, type2, inv_m1, inv_i1, r1, inv_m2, inv_i2, r2, normal, 0.0f);
+				// ContactConstraintPart::SolvePositionConstraint
+				if (separation != 0.0f)
+				{
+					float lambda = -cf_at(c, base + PART_EFF, i) * w.settings.baumgarte * separation;
+					if (type1 == B2J_MOTION_DYNAMIC)
+					{
+						x1 -= lock_translation((lambda * inv_m1) * normal, dofs1);
+						q1 = add_rotation_step(q1, lambda * cf_v3(c, base + PART_I1, i), true);
+					}
+					if (type2 == B2J_MOTION_DYNAMIC)
+					{
+						x2 += lock_translation((lambda * inv_m2) * normal, dofs2);
+						q2 = add_rotation_step(q2, lambda * cf_v3(c, base + PART_I2, i), false);
+					}
+					any = true;
+				}
+			}
+		}
+		if (any)
+		{
+			if (type1 == B2J_MOTION_DYNAMIC) { w.position[b1] = f4(x1); w.rotation[b1] = f4(q1); }
+			if (type2 == B2J_MOTION_DYNAMIC) { w.position[b2] = f4(x2); w.rotation[b2] = f4(q2); }
+		}
+	}
+};
+
+// ---- bounds + sleeping (CheckSleepAndUpdateBounds, last collision step) ------------------------------------------------
+struct KBoundsAndSleep
+{
+	DWorld w; SolveCtx s; float dt; uint32_t is_last;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		BodyInfo info = w.info[b];
+		const ShapeDesc &shape = w.shapes[info.shape];
+		V3 x = to_v3(w.position[b]);
+		Q4 q = to_q4(w.rotation[b]);
+		V3 mn, mx;
+		world_bounds(shape, x, q, mn, mx);
+		w.bounds_min[b] = f4(mn);
+		w.bounds_max[b] = f4(mx);
+		if (!is_last)
+			return;
+		// Body::UpdateSleepStateInternal
+		bool can_sleep = false;
+		if ((info.flags & B2J_BODY_ALLOW_SLEEPING) && !(info.flags & B2J_BODY_SENSOR))
+		{
+			float max_movement = w.settings.point_velocity_sleep_threshold * w.settings.time_before_sleep;
+			V3 points[3];
+			sleep_test_points(shape, x, q, points);
+			bool reset = false;
+			for (int i = 0; i < 3 && !reset; ++i)
+			{
+				F4 sp = w.sleep_spheres[b * 3 + i];
+				V3 center = to_v3(sp);
+				float radius = sp.w;
+				// Sphere::EncapsulatePoint
+				V3 d_vec = points[i] - center;
+				float d_sq = length_sq(d_vec);
+				if (d_sq > square(radius))
+				{
+					float d = sqrt_(d_sq);
+					float new_radius = 0.5f * (radius + d);
+					center += (new_radius - radius) / d * d_vec;
+					radius = new_radius;
+					w.sleep_spheres[b * 3 + i] = f4(center, radius);
+				}
+				if (radius > max_movement)
+					reset = true;
+			}
+			if (reset)
+			{
+				for (int i = 0; i < 3; ++i) w.sleep_spheres[b * 3 + i] = f4(points[i], 0.0f);
+				w.sleep_timer[b] = 0.0f;
+			}
+			else
+			{
+				float t = w.sleep_timer[b] + dt;
+				w.sleep_timer[b] = t;
+				can_sleep = t >= w.settings.time_before_sleep;
+			}
+		}
+		if (!(can_sleep && w.settings.allow_sleeping))
+			s.island_can_sleep[s.root[b]] = 0;
+		// reset force and torque
+		w.force[b] = f4(0, 0, 0, 0);
+		w.torque[b] = f4(0, 0, 0, 0);
+	}
+};
+
+// marks sleeping bodies, zeroes their velocity, computes the keep flag for the compaction of the active list
+struct KDeactivate
+{
+	DWorld w; SolveCtx s; uint32_t *keep; b2j_activation_event *events; uint32_t max_events;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		bool sleep = s.island_can_sleep[s.root[b]] != 0;
+		keep[ai] = sleep? 0u : 1u;
+		if (sleep)
+		{
+			w.linear_velocity[b] = f4(0, 0, 0, 0);
+			w.angular_velocity[b] = f4(0, 0, 0, 0);
+			w.active_index[b] = B2J_INACTIVE_INDEX;
+			atomic_add(&w.counters->num_deactivated, 1u);
+			if (events != nullptr)
+			{
+				uint32_t e = atomic_add(&w.counters->num_activation_events, 1u);
+				if (e < max_events) { events[e].kind = B2J_EVENT_BODY_DEACTIVATED; events[e].body = w.info[b].id; }
+			}
+		}
+	}
+};
+
+// stable compaction of the active list: keep_scan = exclusive prefix sum of keep
+struct KCompactActive
+{
+	DWorld w; const uint32_t *keep, *keep_scan; uint32_t *new_active;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		if (keep[ai])
+		{
+			uint32_t b = w.active[ai];
+			uint32_t ni = keep_scan[ai];
+			new_active[ni] = b;
+			w.active_index[b] = ni;
+		}
+	}
+};
+
+// appends the bodies woken by contacts (sorted by slot for determinism) to the active list (BodyManager::ActivateBodies)
+struct KActivateWoken
+{
+	DWorld w; const uint32_t *woken_sorted; uint32_t base; uint32_t *woken_flag; b2j_activation_event *events; uint32_t max_events;
+	B2J_D void operator()(uint32_t k) const
+	{
+		uint32_t b = woken_sorted[k];
+		BodyInfo info = w.info[b];
+		w.active[base + k] = b;
+		w.active_index[b] = base + k;
+		woken_flag[b] = 0;
+		// Body::ResetSleepTimer
+		V3 points[3];
+		sleep_test_points(w.shapes[info.shape], to_v3(w.position[b]), to_q4(w.rotation[b]), points);
+		for (int i = 0; i < 3; ++i) w.sleep_spheres[b * 3 + i] = f4(points[i], 0.0f);
+		w.sleep_timer[b] = 0.0f;
+		if (events != nullptr)
+		{
+			uint32_t e = atomic_add(&w.counters->num_activation_events, 1u);
+			if (e < max_events) { events[e].kind = B2J_EVENT_BODY_ACTIVATED; events[e].body = info.id; }
+		}
+	}
+};
+
+// contact removed events: manifolds of the read cache that were not persisted (ManifoldCache::ContactPointRemovedCallbacks)
+struct KRemovedEvents
+{
+	DWorld w; NarrowCtx c;
+	B2J_D void operator()(uint32_t m) const
+	{
+		const CachedManifold &cm = w.read_cache.manifolds[m];
+		if (cm.flags & MANIFOLD_PERSISTED)
+			return;
+		emit_event(w, c, B2J_EVENT_CONTACT_REMOVED, cm.body1, cm.body2, cm.sub1, cm.sub2, v3_zero(), v3_zero(), 0.0f, nullptr, nullptr, 0);
+	}
+};
+
+} // namespace b2j

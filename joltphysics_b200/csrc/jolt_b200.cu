@@ -1,0 +1,1449 @@
+// jolt_b200.cu -- world management, the step (PhysicsSystem::Update replacement) and the C ABI of include/jolt_b200.h.
+//
+// One translation unit: all kernels are header-defined functors (b2j_*.h) instantiated through Runtime::launch*.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -ffp-contract=off (see __graft_entry__.build()).
+#include "b2j_runtime.h"
+#include "b2j_world.h"
+#include "b2j_shapes.h"
+#include "b2j_broadphase.h"
+#include "b2j_narrowphase.h"
+#include "b2j_mesh.h"
+#include "b2j_solver.h"
+
+#include <chrono>
+
+using namespace b2j;
+
+// ---- small API kernels ---------------------------------------------------------------------------------------------
+namespace b2j {
+
+struct KAddBodies
+{
+	DWorld w; const b2j_body_desc *descs;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const b2j_body_desc &d = descs[i];
+		uint32_t b = slot_of(d.id);
+		BodyInfo info;
+		info.id = d.id; info.shape = d.shape; info.object_layer = d.object_layer; info.motion_type = d.motion_type;
+		info.bp_layer = w.object_to_bp[d.object_layer];
+		info.flags = d.flags; info.allowed_dofs = d.allowed_dofs;
+		uint32_t vs = d.num_velocity_steps_override > 15? 15 : d.num_velocity_steps_override;
+		uint32_t ps = d.num_position_steps_override > 15? 15 : d.num_position_steps_override;
+		info.steps_override = (uint8_t)(vs | (ps << 4));
+		w.info[b] = info;
+		BodyParams p;
+		p.inv_mass = d.motion_type == B2J_MOTION_DYNAMIC? d.inv_mass : 0.0f;
+		p.linear_damping = d.linear_damping; p.angular_damping = d.angular_damping;
+		p.max_linear_velocity = d.max_linear_velocity; p.max_angular_velocity = d.max_angular_velocity;
+		p.gravity_factor = d.gravity_factor; p.friction = d.friction; p.restitution = d.restitution;
+		w.params[b] = p;
+		V3 x = v3_load(d.position);
+		Q4 q = q4_load(d.rotation);
+		w.position[b] = f4(x);
+		w.rotation[b] = f4(q);
+		w.linear_velocity[b] = f4(v3_load(d.linear_velocity));
+		w.angular_velocity[b] = f4(v3_load(d.angular_velocity));
+		w.force[b] = f4(v3_load(d.force));
+		w.torque[b] = f4(v3_load(d.torque));
+		w.inv_inertia_diag[b] = f4(v3_load(d.inv_inertia_diag));
+		w.inertia_rotation[b] = f4(q4_load(d.inertia_rotation));
+		w.active_index[b] = B2J_INACTIVE_INDEX;
+		const ShapeDesc &s = w.shapes[d.shape];
+		if (d.has_bounds)
+		{
+			w.bounds_min[b] = f4(v3_load(d.bounds_min));
+			w.bounds_max[b] = f4(v3_load(d.bounds_max));
+			for (int k = 0; k < 3; ++k)
+				w.sleep_spheres[b * 3 + k] = f4(d.sleep_spheres[k][0], d.sleep_spheres[k][1], d.sleep_spheres[k][2], d.sleep_spheres[k][3]);
+			w.sleep_timer[b] = d.sleep_timer;
+		}
+		else
+		{
+			V3 mn, mx;
+			world_bounds(s, x, q, mn, mx);
+			w.bounds_min[b] = f4(mn);
+			w.bounds_max[b] = f4(mx);
+			V3 pts[3];
+			sleep_test_points(s, x, q, pts);
+			for (int k = 0; k < 3; ++k) w.sleep_spheres[b * 3 + k] = f4(pts[k], 0.0f);
+			w.sleep_timer[b] = 0.0f;
+		}
+	}
+};
+
+struct KSetActive
+{
+	DWorld w; const uint32_t *ids; uint32_t base;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = slot_of(ids[i]);
+		w.active[base + i] = b;
+		w.active_index[b] = base + i;
+	}
+};
+
+struct KClearActiveIndex
+{
+	DWorld w;
+	B2J_D void operator()(uint32_t ai) const { w.active_index[w.active[ai]] = B2J_INACTIVE_INDEX; }
+};
+
+struct KGetState
+{
+	DWorld w; const uint32_t *ids; float *pos, *rot, *lin, *ang, *bounds; uint32_t *active_index; float *sleep_timer;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = ids != nullptr? slot_of(ids[i]) : i;
+		if (pos) v3_store(to_v3(w.position[b]), pos + 3 * i);
+		if (rot) q4_store(to_q4(w.rotation[b]), rot + 4 * i);
+		if (lin) v3_store(to_v3(w.linear_velocity[b]), lin + 3 * i);
+		if (ang) v3_store(to_v3(w.angular_velocity[b]), ang + 3 * i);
+		if (bounds) { v3_store(to_v3(w.bounds_min[b]), bounds + 6 * i); v3_store(to_v3(w.bounds_max[b]), bounds + 6 * i + 3); }
+		if (active_index) active_index[i] = w.active_index[b];
+		if (sleep_timer) sleep_timer[i] = w.sleep_timer[b];
+	}
+};
+
+struct KSetState
+{
+	DWorld w; const uint32_t *ids; const float *pos, *rot, *lin, *ang;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = ids != nullptr? slot_of(ids[i]) : i;
+		if (pos) w.position[b] = f4(v3_load(pos + 3 * i));
+		if (rot) w.rotation[b] = f4(q4_load(rot + 4 * i));
+		if (lin) w.linear_velocity[b] = f4(v3_load(lin + 3 * i));
+		if (ang) w.angular_velocity[b] = f4(v3_load(ang + 3 * i));
+		if (pos || rot)
+		{
+			V3 mn, mx;
+			world_bounds(w.shapes[w.info[b].shape], to_v3(w.position[b]), to_q4(w.rotation[b]), mn, mx);
+			w.bounds_min[b] = f4(mn);
+			w.bounds_max[b] = f4(mx);
+		}
+	}
+};
+
+struct KAddForceTorque
+{
+	DWorld w; const uint32_t *ids; const float *force, *torque;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = slot_of(ids[i]);
+		if (force) w.force[b] = f4(to_v3(w.force[b]) + v3_load(force + 3 * i));
+		if (torque) w.torque[b] = f4(to_v3(w.torque[b]) + v3_load(torque + 3 * i));
+	}
+};
+
+struct KImportCache
+{
+	DWorld w; const b2j_cached_body_pair *pairs; const b2j_cached_manifold *manifolds;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const b2j_cached_body_pair &p = pairs[i];
+		CachedPair &o = w.read_cache.pairs[i];
+		o.body1 = p.body1; o.body2 = p.body2;
+		for (int k = 0; k < 3; ++k) { o.dpos[k] = p.delta_position[k]; o.drot[k] = p.delta_rotation[k]; }
+		o.first_manifold = p.first_manifold; o.num_manifolds = p.num_manifolds;
+		for (uint32_t j = 0; j < p.num_manifolds; ++j)
+		{
+			const b2j_cached_manifold &m = manifolds[p.first_manifold + j];
+			CachedManifold &cm = w.read_cache.manifolds[p.first_manifold + j];
+			cm.body1 = p.body1; cm.body2 = p.body2; cm.sub1 = m.sub_shape1; cm.sub2 = m.sub_shape2;
+			for (int k = 0; k < 3; ++k) cm.normal[k] = m.normal[k];
+			cm.friction_lambda[0] = m.friction_lambda[0]; cm.friction_lambda[1] = m.friction_lambda[1];
+			cm.angular_lambda = m.angular_friction_lambda;
+			cm.num_points = (uint16_t)(m.num_points > 4? 4 : m.num_points);
+			cm.flags = 0;
+			for (int q = 0; q < 4; ++q)
+			{
+				for (int k = 0; k < 3; ++k) { cm.p1[q][k] = m.position1[q][k]; cm.p2[q][k] = m.position2[q][k]; }
+				cm.lambda[q] = m.non_penetration_lambda[q];
+			}
+		}
+		pair_table_insert(w, w.read_cache, p.body1, p.body2, i);
+	}
+};
+
+struct KExportCache
+{
+	DWorld w; b2j_cached_body_pair *pairs; b2j_cached_manifold *manifolds;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const CachedPair &p = w.read_cache.pairs[i];
+		b2j_cached_body_pair &o = pairs[i];
+		o.body1 = p.body1; o.body2 = p.body2;
+		for (int k = 0; k < 3; ++k) { o.delta_position[k] = p.dpos[k]; o.delta_rotation[k] = p.drot[k]; }
+		o.first_manifold = p.first_manifold; o.num_manifolds = p.num_manifolds;
+		for (uint32_t j = 0; j < p.num_manifolds; ++j)
+		{
+			const CachedManifold &cm = w.read_cache.manifolds[p.first_manifold + j];
+			b2j_cached_manifold &m = manifolds[p.first_manifold + j];
+			m.sub_shape1 = cm.sub1; m.sub_shape2 = cm.sub2;
+			for (int k = 0; k < 3; ++k) m.normal[k] = cm.normal[k];
+			m.friction_lambda[0] = cm.friction_lambda[0]; m.friction_lambda[1] = cm.friction_lambda[1];
+			m.angular_friction_lambda = cm.angular_lambda;
+			m.num_points = cm.num_points;
+			m.flags = cm.flags;
+			for (int q = 0; q < 4; ++q)
+			{
+				for (int k = 0; k < 3; ++k) { m.position1[q][k] = cm.p1[q][k]; m.position2[q][k] = cm.p2[q][k]; }
+				m.non_penetration_lambda[q] = cm.lambda[q];
+			}
+		}
+	}
+};
+
+// round bookkeeping on the device: pairs found so far become "processed", work lists restart
+struct KNextRound
+{
+	DWorld w; uint32_t *round_begin;
+	B2J_D void operator()(uint32_t) const
+	{
+		StepCounters &c = *w.counters;
+		uint32_t n = c.num_pairs < w.max_body_pairs? c.num_pairs : w.max_body_pairs;
+		if (c.num_pairs > w.max_body_pairs) c.error_bits |= B2J_ERR_BODY_PAIR_CACHE_FULL;
+		*round_begin = n;
+		c.num_collide_convex = 0; c.num_collide_mesh = 0; c.num_cached = 0; c.num_epa = 0; c.num_woken = 0;
+	}
+};
+
+struct KPhaseScatter
+{
+	SolveCtx s; uint32_t *phase_fill;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t p = s.phase[i];
+		uint32_t pos = s.phase_count[p] + atomic_add(&phase_fill[p], 1u);
+		s.final_pos[i] = pos;
+		s.solve_src[pos] = s.order[i];
+	}
+};
+
+struct KGatherSortKeys
+{
+	SolveCtx s; uint64_t *keys; uint32_t *vals;
+	B2J_D void operator()(uint32_t i) const { keys[i] = s.src[i].sort_key; vals[i] = i; }
+};
+
+struct KCountTies
+{
+	DWorld w; const uint64_t *keys;
+	B2J_D void operator()(uint32_t i) const { if (i > 0 && keys[i] == keys[i - 1]) atomic_add(&w.counters->hash_tie, 1u); }
+};
+
+struct KFinishCompact
+{
+	DWorld w; const uint32_t *keep, *keep_scan; uint32_t n;
+	B2J_D void operator()(uint32_t) const { w.counters->new_active_count = n == 0? 0 : keep_scan[n - 1] + keep[n - 1]; }
+};
+
+struct KKineticEnergy
+{
+	DWorld w; float *out;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		if (w.info[b].motion_type != B2J_MOTION_DYNAMIC) return;
+		BodyParams p = w.params[b];
+		float e = 0.0f;
+		if (p.inv_mass > 0.0f) e += 0.5f * length_sq(to_v3(w.linear_velocity[b])) / p.inv_mass;
+		V3 wl = inverse_rotate(to_q4(w.rotation[b]) * to_q4(w.inertia_rotation[b]), to_v3(w.angular_velocity[b]));
+		V3 d = to_v3(w.inv_inertia_diag[b]);
+		if (d.x > 0.0f) e += 0.5f * wl.x * wl.x / d.x;
+		if (d.y > 0.0f) e += 0.5f * wl.y * wl.y / d.y;
+		if (d.z > 0.0f) e += 0.5f * wl.z * wl.z / d.z;
+#ifndef B2J_HOSTSIM
+		atomicAdd(out, e);
+#else
+		*out += e;
+#endif
+	}
+};
+
+} // namespace b2j
+
+// ---- the world -------------------------------------------------------------------------------------------------------
+
+struct b2j_world
+{
+	Runtime rt;
+	DWorld d;
+	b2j_world_desc desc;
+	std::vector<uint8_t> t_o2bp, t_ovbp, t_ovo;
+	uint8_t *d_o2bp = nullptr, *d_ovbp = nullptr, *d_ovo = nullptr;
+
+	// host mirrors
+	std::vector<uint32_t> h_ids;           // per slot: id or invalid
+	std::vector<uint8_t> h_layer;          // per slot: broadphase layer
+	std::vector<std::vector<uint32_t>> layer_bodies;
+	std::vector<uint8_t> layer_list_dirty, layer_needs_build, layer_has_moving;
+	uint32_t num_bodies = 0, num_active = 0, num_slots = 0;
+
+	// shapes
+	std::vector<ShapeDesc> h_shapes;
+	std::vector<F4> h_hull_points, h_hull_shrunk, h_hull_planes;
+	std::vector<uint32_t> h_hull_faces;
+	std::vector<uint8_t> h_hull_vtx, h_mesh_bytes;
+	bool shapes_dirty = false;
+	ShapeDesc *d_shapes = nullptr; F4 *d_hull_points = nullptr, *d_hull_shrunk = nullptr, *d_hull_planes = nullptr;
+	uint32_t *d_hull_faces = nullptr; uint8_t *d_hull_vtx = nullptr, *d_mesh_bytes = nullptr;
+
+	// broadphase
+	Tree trees[8];
+	uint32_t tree_capacity[8] = { 0 };
+	uint32_t *d_tree_vals_in = nullptr; uint32_t tree_vals_capacity = 0;
+
+	// active list double buffer
+	uint32_t *active_buf[2] = { nullptr, nullptr };
+	int active_cur = 0;
+	uint32_t *d_keep = nullptr, *d_keep_scan = nullptr;
+
+	// contact caches
+	ContactCache cache[2];
+	int write_idx = 0;
+	uint32_t cache_num_pairs[2] = { 0, 0 }, cache_num_manifolds[2] = { 0, 0 };
+
+	// narrow phase + solver work memory
+	NarrowCtx nc;
+	SolveCtx sc;
+	uint32_t *d_round_begin = nullptr;
+	uint64_t *d_sort_keys[2] = { nullptr, nullptr };
+	uint32_t *d_sort_vals = nullptr;
+	uint32_t *d_phase_fill = nullptr;
+	uint32_t *d_woken_sorted = nullptr;
+	uint32_t *d_woken_keys = nullptr;
+	b2j_activation_event *d_act_events = nullptr;
+	uint32_t max_events = 0, max_act_events = 0;
+	float *d_energy = nullptr;
+
+	float prev_dt = 0.0f;
+	StepCounters h_counters;
+	std::vector<uint32_t> h_phase_offsets;
+	uint32_t last_num_events = 0, last_num_act_events = 0, last_num_pairs = 0;
+#ifndef B2J_HOSTSIM
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+#endif
+};
+
+struct b2j_batch
+{
+	std::vector<b2j_world *> worlds;
+};
+
+namespace {
+
+template <class T> bool grow(Runtime &rt, T *&ptr, uint32_t &capacity, uint32_t needed, bool keep)
+{
+	if (needed <= capacity) return true;
+	uint32_t ncap = capacity == 0? needed : capacity;
+	while (ncap < needed) ncap *= 2;
+	T *np = rt.alloc<T>(ncap);
+	if (np == nullptr) return false;
+	if (keep && ptr != nullptr) rt.copy(np, ptr, capacity);
+	rt.sync();
+	rt.free_(ptr);
+	ptr = np;
+	capacity = ncap;
+	return true;
+}
+
+uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+void upload_shapes(b2j_world *W)
+{
+	if (!W->shapes_dirty) return;
+	Runtime &rt = W->rt;
+	rt.sync();
+	rt.free_(W->d_shapes); rt.free_(W->d_hull_points); rt.free_(W->d_hull_shrunk); rt.free_(W->d_hull_planes);
+	rt.free_(W->d_hull_faces); rt.free_(W->d_hull_vtx); rt.free_(W->d_mesh_bytes);
+	W->d_shapes = rt.alloc<ShapeDesc>(W->h_shapes.size()); rt.upload(W->d_shapes, W->h_shapes.data(), W->h_shapes.size());
+	W->d_hull_points = rt.alloc<F4>(W->h_hull_points.size()); rt.upload(W->d_hull_points, W->h_hull_points.data(), W->h_hull_points.size());
+	W->d_hull_shrunk = rt.alloc<F4>(W->h_hull_shrunk.size()); rt.upload(W->d_hull_shrunk, W->h_hull_shrunk.data(), W->h_hull_shrunk.size());
+	W->d_hull_planes = rt.alloc<F4>(W->h_hull_planes.size()); rt.upload(W->d_hull_planes, W->h_hull_planes.data(), W->h_hull_planes.size());
+	W->d_hull_faces = rt.alloc<uint32_t>(W->h_hull_faces.size()); rt.upload(W->d_hull_faces, W->h_hull_faces.data(), W->h_hull_faces.size());
+	W->d_hull_vtx = rt.alloc<uint8_t>(W->h_hull_vtx.size() + 16); rt.upload(W->d_hull_vtx, W->h_hull_vtx.data(), W->h_hull_vtx.size());
+	W->d_mesh_bytes = rt.alloc<uint8_t>(W->h_mesh_bytes.size() + 16); rt.upload(W->d_mesh_bytes, W->h_mesh_bytes.data(), W->h_mesh_bytes.size());
+	W->d.shapes = W->d_shapes; W->d.hull_points = W->d_hull_points; W->d.hull_shrunk = W->d_hull_shrunk; W->d.hull_planes = W->d_hull_planes;
+	W->d.hull_faces = W->d_hull_faces; W->d.hull_vtx = W->d_hull_vtx; W->d.mesh_bytes = W->d_mesh_bytes;
+	W->shapes_dirty = false;
+}
+
+// (re)build the tree of one broadphase layer from the current cached body bounds
+bool build_tree(b2j_world *W, uint32_t layer)
+{
+	Runtime &rt = W->rt;
+	Tree &t = W->trees[layer];
+	std::vector<uint32_t> &list = W->layer_bodies[layer];
+	uint32_t n = (uint32_t)list.size();
+	if (n > W->tree_capacity[layer])
+	{
+		uint32_t cap = next_pow2(n < 16? 16 : n);
+		rt.sync();
+		rt.free_(t.bodies); rt.free_(t.keys_in); rt.free_(t.keys_out); rt.free_(t.leaf_body); rt.free_(t.child_left); rt.free_(t.child_right);
+		rt.free_(t.parent); rt.free_(t.node_min); rt.free_(t.node_max); rt.free_(t.visit);
+		t.bodies = rt.alloc<uint32_t>(cap); t.keys_in = rt.alloc<uint32_t>(cap); t.keys_out = rt.alloc<uint32_t>(cap); t.leaf_body = rt.alloc<uint32_t>(cap);
+		t.child_left = rt.alloc<int32_t>(cap); t.child_right = rt.alloc<int32_t>(cap); t.parent = rt.alloc<int32_t>(2 * cap);
+		t.node_min = rt.alloc<F4>(2 * cap); t.node_max = rt.alloc<F4>(2 * cap); t.visit = rt.alloc<uint32_t>(cap);
+		if (!t.visit) return false;
+		W->tree_capacity[layer] = cap;
+		W->layer_list_dirty[layer] = 1;
+	}
+	if (W->layer_list_dirty[layer])
+	{
+		rt.upload(t.bodies, list.data(), n);
+		W->layer_list_dirty[layer] = 0;
+	}
+	t.n = n;
+	if (n == 0) return true;
+	KMorton km; km.w = W->d; km.t = t;
+	rt.launch(km, n);
+	rt.sort_pairs<uint32_t>(t.keys_in, t.keys_out, t.bodies, t.leaf_body, n, 30);
+	if (n > 1)
+	{
+		KBuildHierarchy kb; kb.t = t;
+		rt.launch(kb, n - 1);
+	}
+	KRefit kr; kr.w = W->d; kr.t = t;
+	rt.launch(kr, n);
+	return rt.check("build_tree");
+}
+
+void sync_dworld(b2j_world *W)
+{
+	W->d.active = W->active_buf[W->active_cur];
+	W->d.write_cache = W->cache[W->write_idx];
+	W->d.read_cache = W->cache[W->write_idx ^ 1];
+}
+
+void clear_cache(b2j_world *W, int idx)
+{
+	Runtime &rt = W->rt;
+	rt.memset_(W->cache[idx].pair_table, 0xff, (size_t)W->d.pair_table_size * 4);
+	rt.memset_(W->cache[idx].num_pairs, 0, 4);
+	rt.memset_(W->cache[idx].num_manifolds, 0, 4);
+	W->cache_num_pairs[idx] = 0;
+	W->cache_num_manifolds[idx] = 0;
+}
+
+bool read_counters(b2j_world *W)
+{
+	W->rt.download(&W->h_counters, W->d.counters, 1);
+	return W->rt.check("read_counters");
+}
+
+// One collision step. Returns false on a CUDA failure.
+bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last, b2j_step_stats *stats)
+{
+	Runtime &rt = W->rt;
+	DWorld &d = W->d;
+	sync_dworld(W);
+	rt.memset_(d.counters, 0, sizeof(StepCounters));
+	rt.memset_(W->d_round_begin, 0, 4);
+
+	// (a2) gravity, forces, damping
+	{ KApplyGravity k; k.w = d; k.dt = dt; rt.launch(k, W->num_active); }
+
+	// (a4) broadphase maintenance: rebuild the trees whose bodies moved / changed
+	for (uint32_t l = 0; l < d.num_bp_layers; ++l)
+		if (W->layer_needs_build[l])
+		{
+			if (!build_tree(W, l)) return false;
+			W->layer_needs_build[l] = 0;
+		}
+
+	// (a3, a5..a9) find pairs + narrow phase; repeated for the bodies woken up by contacts until no new body wakes up
+	uint32_t first_active = 0, n_query = W->num_active;
+	uint32_t woken_total = 0;
+	for (int round = 0; round < 64; ++round)
+	{
+		{ KFindPairs k; k.w = d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = first_active; rt.launch(k, n_query); }
+		{ KProcessPairs k; k.w = d; k.c = W->nc; k.first_ptr = W->d_round_begin; rt.launch_dev(k, &d.counters->num_pairs, W->d_round_begin, d.max_body_pairs); }
+		{ KCopyCached k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_cached, nullptr, d.max_body_pairs); }
+		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
+		{ KCollideEpa k; k.w = d; k.c = W->nc; rt.launch_slot(k, &d.counters->num_epa, W->nc.max_epa, W->nc.num_scratch); }
+		{ KCollideMesh k; k.w = d; k.c = W->nc; rt.launch_slot(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
+		if (!read_counters(W)) return false;
+		uint32_t woken = W->h_counters.num_woken;
+		if (W->h_counters.num_epa > W->nc.max_epa) { last_error() = "EPA queue overflow"; return false; }
+		{ KNextRound k; k.w = d; k.round_begin = W->d_round_begin; rt.launch(k, 1); }
+		if (woken == 0)
+			break;
+		// activate the woken bodies in slot order (BodyManager::ActivateBodies), then query only them
+		rt.sort_pairs<uint32_t>(W->nc.woken_list, W->d_woken_keys, W->nc.woken_list, W->d_woken_sorted, woken, 23);
+		{ KActivateWoken k; k.w = d; k.woken_sorted = W->d_woken_sorted; k.base = W->num_active; k.woken_flag = W->nc.woken_flag; k.events = W->d_act_events; k.max_events = W->max_act_events; rt.launch(k, woken); }
+		first_active = W->num_active;
+		n_query = woken;
+		W->num_active += woken;
+		woken_total += woken;
+	}
+	uint32_t M = W->h_counters.num_constraints < d.max_constraints? W->h_counters.num_constraints : d.max_constraints;
+	uint32_t num_pairs = W->h_counters.num_pairs < d.max_body_pairs? W->h_counters.num_pairs : d.max_body_pairs;
+	W->last_num_pairs = num_pairs;
+	uint32_t na = W->num_active;
+
+	// (a12) islands
+	SolveCtx &sc = W->sc;
+	sc.num_slots = W->num_slots;
+	{ KUfInit k; k.s = sc; rt.launch(k, W->num_slots); }
+	sc.src = W->nc.con_src;
+	{ KUfUnion k; k.w = d; k.s = sc; rt.launch(k, M); }
+	{ KUfFlatten k; k.w = d; k.s = sc; rt.launch(k, na); }
+	{ KIslandCount k; k.w = d; k.s = sc; rt.launch(k, M); }
+	{ KIslandClassify k; k.w = d; k.s = sc; rt.launch(k, na); }
+
+	uint32_t num_phases = 0, vsteps = 0, psteps = 0;
+	if (M > 0)
+	{
+		// (a14 SortContacts) order by sort key
+		{ KGatherSortKeys k; k.s = sc; k.keys = W->d_sort_keys[0]; k.vals = W->d_sort_vals; rt.launch(k, M); }
+		rt.sort_pairs<uint64_t>(W->d_sort_keys[0], W->d_sort_keys[1], W->d_sort_vals, sc.order, M);
+		{ KCountTies k; k.w = d; k.keys = W->d_sort_keys[1]; rt.launch(k, M); }
+
+		// body -> constraints adjacency in sorted order
+		rt.exclusive_scan(sc.body_deg, sc.body_off, W->num_slots);
+		{ KAdjFill k; k.w = d; k.s = sc; rt.launch(k, M); }
+		{ KAdjSort k; k.w = d; k.s = sc; rt.launch(k, na); }
+
+		// (a13) schedule: wavefronts in sorted order; pass 0 = levels (small islands) / colours (large islands)
+		const uint32_t rounds_per_check = 8;
+		for (uint32_t pass = 0; pass < 2; ++pass)
+		{
+			if (pass == 1)
+			{
+				if (W->h_counters.num_large_islands == 0)
+				{
+					read_counters(W);
+					if (W->h_counters.num_large_islands == 0) break;
+				}
+				{ KSchedSerialize k; k.w = d; k.s = sc; rt.launch(k, M); }
+				{ KSchedResetCursors k; k.w = d; k.s = sc; rt.launch(k, na); }
+			}
+			rt.memset_(sc.sched_flag, 0, 4096 * 4);
+			{ KSchedAdvance k; k.w = d; k.s = sc; k.pass = pass; k.flag_index = 0; rt.launch(k, na); }
+			uint32_t round = 0;
+			for (;;)
+			{
+				uint32_t flag_index = 0;
+				for (uint32_t r = 0; r < rounds_per_check; ++r, ++round)
+				{
+					flag_index = 1 + (round % 4095);
+					{ KSchedDecide k; k.w = d; k.s = sc; k.round = round; k.pass = pass; rt.launch(k, na); }
+					{ KSchedAdvance k; k.w = d; k.s = sc; k.pass = pass; k.flag_index = flag_index; rt.launch(k, na); }
+				}
+				uint32_t remaining = 0;
+				rt.download(&remaining, sc.sched_flag + flag_index, 1);
+				if (remaining == 0) break;
+				if (round >= 4000) rt.memset_(sc.sched_flag, 0, 4096 * 4);
+				if (round > 1000000) { last_error() = "schedule did not converge"; return false; }
+			}
+		}
+
+		// phases -> solve order
+		rt.memset_(sc.phase_count, 0, (sc.max_phases + 1) * 4);
+		rt.memset_(W->d_phase_fill, 0, (sc.max_phases + 1) * 4);
+		{ KPhaseCount k; k.w = d; k.s = sc; rt.launch(k, M); }
+		rt.exclusive_scan(sc.phase_count, sc.phase_count, sc.max_phases + 1);
+		{ KPhaseScatter k; k.s = sc; k.phase_fill = W->d_phase_fill; rt.launch(k, M); }
+
+		// (a11) constraint setup straight into solve order
+		{ KSetupConstraints k; k.w = d; k.s = sc; k.dt = dt; rt.launch(k, M); }
+
+		if (!read_counters(W)) return false;
+		num_phases = W->h_counters.num_phases;
+		vsteps = W->h_counters.max_velocity_steps;
+		psteps = W->h_counters.max_position_steps;
+		W->h_phase_offsets.resize(num_phases + 1);
+		rt.download(W->h_phase_offsets.data(), sc.phase_count, num_phases + 1);
+
+		// (a14) warm start + velocity iterations, one launch per phase
+		for (uint32_t p = 0; p < num_phases; ++p)
+		{
+			uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+			KWarmStart k; k.w = d; k.c = sc.con; k.begin = begin; k.ratio = warm_start_ratio; rt.launch(k, n);
+		}
+		for (uint32_t it = 0; it < vsteps; ++it)
+			for (uint32_t p = 0; p < num_phases; ++p)
+			{
+				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+				KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it; rt.launch(k, n);
+			}
+		{ KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
+	}
+
+	// (a15) integrate
+	{ KIntegrate k; k.w = d; k.dt = dt; rt.launch(k, na); }
+
+	// (a10) contact removed events for manifolds that were not persisted
+	if (W->nc.events != nullptr)
+	{
+		uint32_t old_m = W->cache_num_manifolds[W->write_idx ^ 1];
+		KRemovedEvents k; k.w = d; k.c = W->nc; rt.launch(k, old_m);
+	}
+
+	// (a16) position iterations
+	for (uint32_t it = 0; it < psteps; ++it)
+		for (uint32_t p = 0; p < num_phases; ++p)
+		{
+			uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+			KSolvePosition k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it; rt.launch(k, n);
+		}
+
+	// (a16, a17) bounds, sleeping, active list compaction
+	{ KBoundsAndSleep k; k.w = d; k.s = sc; k.dt = dt; k.is_last = is_last? 1u : 0u; rt.launch(k, na); }
+	uint32_t new_active = na;
+	if (is_last)
+	{
+		{ KDeactivate k; k.w = d; k.s = sc; k.keep = W->d_keep; k.events = W->d_act_events; k.max_events = W->max_act_events; rt.launch(k, na); }
+		rt.exclusive_scan(W->d_keep, W->d_keep_scan, na);
+		uint32_t *new_list = W->active_buf[W->active_cur ^ 1];
+		{ KCompactActive k; k.w = d; k.keep = W->d_keep; k.keep_scan = W->d_keep_scan; k.new_active = new_list; rt.launch(k, na); }
+		{ KFinishCompact k; k.w = d; k.keep = W->d_keep; k.keep_scan = W->d_keep_scan; k.n = na; rt.launch(k, 1); }
+		W->active_cur ^= 1;
+	}
+	if (stats != nullptr && stats->kinetic_energy < 0.0f)
+	{
+		rt.memset_(W->d_energy, 0, 4);
+		KKineticEnergy k; k.w = d; k.out = W->d_energy; rt.launch(k, na);
+	}
+	if (!read_counters(W)) return false;
+	if (is_last) new_active = W->h_counters.new_active_count;
+
+	// swap the caches: this step's write cache is the next step's read cache
+	uint32_t wi = W->write_idx;
+	W->cache_num_pairs[wi] = W->h_counters.num_pairs < d.max_body_pairs? W->h_counters.num_pairs : d.max_body_pairs;
+	rt.download(&W->cache_num_manifolds[wi], W->cache[wi].num_manifolds, 1);
+	if (W->cache_num_manifolds[wi] > d.max_constraints) W->cache_num_manifolds[wi] = d.max_constraints;
+	rt.download(&W->cache_num_pairs[wi], W->cache[wi].num_pairs, 1);
+	if (W->cache_num_pairs[wi] > d.max_body_pairs) W->cache_num_pairs[wi] = d.max_body_pairs;
+	W->write_idx ^= 1;
+	clear_cache(W, W->write_idx);
+	W->num_active = new_active;
+	sync_dworld(W);
+
+	// every layer that holds non-static bodies needs a rebuild next step
+	for (uint32_t l = 0; l < d.num_bp_layers; ++l)
+		if (W->layer_has_moving[l])
+			W->layer_needs_build[l] = 1;
+
+	if (stats != nullptr)
+	{
+		const StepCounters &c = W->h_counters;
+		stats->num_body_pairs += num_pairs;
+		stats->num_pairs_from_cache += c.num_pairs_from_cache;
+		stats->num_manifolds += W->cache_num_manifolds[wi];
+		stats->num_contact_points += c.num_contact_points;
+		stats->num_constraints += M;
+		stats->num_islands += c.num_islands;
+		stats->num_large_islands += c.num_large_islands;
+		stats->num_phases += num_phases;
+		stats->velocity_iterations = vsteps > stats->velocity_iterations? vsteps : stats->velocity_iterations;
+		stats->position_iterations = psteps > stats->position_iterations? psteps : stats->position_iterations;
+		stats->num_activated += woken_total;
+		stats->num_deactivated += c.num_deactivated;
+		stats->error_bits |= c.error_bits & 7u;
+		if (stats->kinetic_energy < 0.0f) { float e = 0.0f; rt.download(&e, W->d_energy, 1); stats->kinetic_energy = e; }
+	}
+	W->last_num_events = W->h_counters.num_events;
+	W->last_num_act_events = W->h_counters.num_activation_events;
+	return rt.check("collision_step");
+}
+
+// hull points shrunk by the convex radius (ConvexHullShape::GetSupportFunction, ExcludeConvexRadius, unscaled: ConvexHullShape.cpp:551-590)
+void shrink_hull_points(const b2j_hull_desc *h, std::vector<F4> &out)
+{
+	float cr = h->convex_radius;
+	for (uint32_t i = 0; i < h->num_points; ++i)
+	{
+		V3 pos = v3_load(h->points + 3 * i);
+		int nf = h->point_num_faces[i];
+		const int32_t *faces = h->point_faces + 3 * i;
+		auto plane = [&](int f, V3 &n, float &c) { n = v3_load(h->planes + 4 * f); c = h->planes[4 * f + 3]; };
+		V3 new_point;
+		if (cr == 0.0f || nf <= 0)
+			new_point = pos;
+		else if (nf == 1)
+		{
+			V3 n; float c; plane(faces[0], n, c);
+			new_point = pos - n * cr;
+		}
+		else
+		{
+			// planes offset inwards: Plane::Offset(-r) = (n, c - (-r))
+			V3 n1, n2, n3; float c1, c2, c3;
+			plane(faces[0], n1, c1); c1 = c1 - (-cr);
+			plane(faces[1], n2, c2); c2 = c2 - (-cr);
+			if (nf == 3) { plane(faces[2], n3, c3); c3 = c3 - (-cr); }
+			else { n3 = cross(n1, n2); c3 = -dot(n3, pos); }
+			// Plane::sIntersectPlanes (Plane.h:63-93)
+			float denominator = dot(n1, cross(n2, n3));
+			if (denominator == 0.0f)
+				new_point = pos - n1 * cr;
+			else
+			{
+				float ax = n1.x, ay = n1.y, az = n1.z, aw = c1, bx = n2.x, by = n2.y, bz = n2.z, bw = c2, cx = n3.x, cy = n3.y, cz = n3.z, cw = c3;
+				V3 numerator = v3(
+					aw * (bz * cy - by * cz) + ay * (bw * cz - bz * cw) + az * (by * cw - bw * cy),
+					aw * (bx * cz - bz * cx) + ax * (bz * cw - bw * cz) + az * (bw * cx - bx * cw),
+					aw * (by * cx - bx * cy) + ax * (bw * cy - by * cw) + ay * (bx * cw - bw * cx));
+				new_point = numerator / denominator;
+			}
+		}
+		out.push_back(f4(new_point));
+	}
+}
+
+} // namespace
+
+// ---- C ABI -------------------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+const char *b2j_last_error(void) { return last_error().c_str(); }
+
+void b2j_settings_default(b2j_settings *s)
+{
+	memset(s, 0, sizeof(*s));
+	s->speculative_contact_distance = 0.02f;
+	s->penetration_slop = 0.02f;
+	s->baumgarte = 0.2f;
+	s->max_penetration_distance = 0.2f;
+	s->manifold_tolerance = 1.0e-3f;
+	s->body_pair_cache_max_delta_position_sq = 0.001f * 0.001f;
+	s->body_pair_cache_cos_max_delta_rotation_div2 = 0.99984769515639123915701155881391f;
+	s->contact_normal_cos_max_delta_rotation = 0.99619469809174553229501040247389f;
+	s->contact_point_preserve_lambda_max_dist_sq = 0.01f * 0.01f;
+	s->min_velocity_for_restitution = 1.0f;
+	s->time_before_sleep = 0.5f;
+	s->point_velocity_sleep_threshold = 0.03f;
+	s->num_velocity_steps = 10;
+	s->num_position_steps = 2;
+	s->deterministic_simulation = 1;
+	s->constraint_warm_start = 1;
+	s->use_body_pair_contact_cache = 1;
+	s->use_manifold_reduction = 1;
+	s->use_large_island_splitter = 1;
+	s->allow_sleeping = 1;
+	s->check_active_edges = 1;
+}
+
+b2j_world *b2j_world_create(const b2j_world_desc *desc)
+{
+	if (desc == nullptr || desc->max_bodies == 0 || desc->num_object_layers == 0 || desc->num_object_layers > 64 || desc->num_broadphase_layers == 0 || desc->num_broadphase_layers > 8)
+	{
+		last_error() = "invalid world description";
+		return nullptr;
+	}
+	b2j_world *W = new b2j_world;
+	if (!W->rt.init(desc->device)) { delete W; return nullptr; }
+	Runtime &rt = W->rt;
+	W->desc = *desc;
+	uint32_t no = desc->num_object_layers, nb = desc->num_broadphase_layers;
+	W->t_o2bp.assign(desc->object_to_broadphase, desc->object_to_broadphase + no);
+	W->t_ovbp.assign(desc->object_vs_broadphase, desc->object_vs_broadphase + no * nb);
+	W->t_ovo.assign(desc->object_vs_object, desc->object_vs_object + no * no);
+	W->d_o2bp = rt.alloc<uint8_t>(no); rt.upload(W->d_o2bp, W->t_o2bp.data(), no);
+	W->d_ovbp = rt.alloc<uint8_t>(no * nb); rt.upload(W->d_ovbp, W->t_ovbp.data(), no * nb);
+	W->d_ovo = rt.alloc<uint8_t>(no * no); rt.upload(W->d_ovo, W->t_ovo.data(), no * no);
+
+	DWorld &d = W->d;
+	memset(&d, 0, sizeof(d));
+	uint32_t nbod = desc->max_bodies;
+	d.max_bodies = nbod;
+	d.max_body_pairs = desc->max_body_pairs < 4? 4 : desc->max_body_pairs;
+	d.max_constraints = desc->max_contact_constraints < 4? 4 : desc->max_contact_constraints;
+	d.pair_table_size = next_pow2(d.max_body_pairs * 2);
+	d.num_object_layers = no; d.num_bp_layers = nb;
+	d.settings = desc->settings;
+	d.gravity = v3_load(desc->gravity);
+	d.object_to_bp = W->d_o2bp; d.object_vs_bp = W->d_ovbp; d.object_vs_object = W->d_ovo;
+
+	d.info = rt.alloc<BodyInfo>(nbod); d.params = rt.alloc<BodyParams>(nbod);
+	d.position = rt.alloc<F4>(nbod); d.rotation = rt.alloc<F4>(nbod);
+	d.linear_velocity = rt.alloc<F4>(nbod); d.angular_velocity = rt.alloc<F4>(nbod);
+	d.force = rt.alloc<F4>(nbod); d.torque = rt.alloc<F4>(nbod);
+	d.inv_inertia_diag = rt.alloc<F4>(nbod); d.inertia_rotation = rt.alloc<F4>(nbod);
+	d.bounds_min = rt.alloc<F4>(nbod); d.bounds_max = rt.alloc<F4>(nbod);
+	d.sleep_spheres = rt.alloc<F4>((size_t)nbod * 3); d.sleep_timer = rt.alloc<float>(nbod);
+	d.active_index = rt.alloc<uint32_t>(nbod);
+	rt.memset_(d.active_index, 0xff, (size_t)nbod * 4);
+	W->active_buf[0] = rt.alloc<uint32_t>(nbod); W->active_buf[1] = rt.alloc<uint32_t>(nbod);
+	d.num_active = rt.alloc<uint32_t>(1);
+	d.counters = rt.alloc<StepCounters>(1);
+	W->d_keep = rt.alloc<uint32_t>(nbod); W->d_keep_scan = rt.alloc<uint32_t>(nbod);
+
+	for (int i = 0; i < 2; ++i)
+	{
+		W->cache[i].pairs = rt.alloc<CachedPair>(d.max_body_pairs);
+		W->cache[i].manifolds = rt.alloc<CachedManifold>(d.max_constraints);
+		W->cache[i].pair_table = rt.alloc<uint32_t>(d.pair_table_size);
+		W->cache[i].num_pairs = rt.alloc<uint32_t>(1);
+		W->cache[i].num_manifolds = rt.alloc<uint32_t>(1);
+		rt.memset_(W->cache[i].pair_table, 0xff, (size_t)d.pair_table_size * 4);
+	}
+
+	NarrowCtx &nc = W->nc;
+	memset(&nc, 0, sizeof(nc));
+	nc.pairs = rt.alloc<BodyPair>(d.max_body_pairs);
+	nc.collide_convex = rt.alloc<CollideItem>(d.max_body_pairs);
+	nc.collide_mesh = rt.alloc<CollideItem>(d.max_body_pairs);
+	nc.cached = rt.alloc<CachedItem>(d.max_body_pairs);
+	nc.max_epa = d.max_body_pairs;
+	nc.epa = rt.alloc<EpaItem>(nc.max_epa, false);
+#ifndef B2J_HOSTSIM
+	nc.num_scratch = (uint32_t)rt.num_sms * 128;
+	if (nc.num_scratch > next_pow2(d.max_body_pairs)) nc.num_scratch = next_pow2(d.max_body_pairs);
+	if (nc.num_scratch < 128) nc.num_scratch = 128;
+#else
+	nc.num_scratch = 1;
+#endif
+	nc.scratch = rt.alloc<EpaScratch>(nc.num_scratch, false);
+	nc.man_ws = rt.alloc<ManifoldWS>(d.max_constraints, false);
+	nc.con_src = rt.alloc<ConstraintSrc>(d.max_constraints, false);
+	nc.woken_flag = rt.alloc<uint32_t>(nbod);
+	nc.woken_list = rt.alloc<uint32_t>(nbod);
+	W->max_events = 2 * d.max_constraints + 16;
+	nc.events = rt.alloc<b2j_contact_event>(W->max_events, false);
+	nc.max_events = W->max_events;
+	W->max_act_events = 2 * nbod;
+	W->d_act_events = rt.alloc<b2j_activation_event>(W->max_act_events, false);
+	W->d_woken_sorted = rt.alloc<uint32_t>(nbod); W->d_woken_keys = rt.alloc<uint32_t>(nbod);
+	W->d_round_begin = rt.alloc<uint32_t>(1);
+	W->d_energy = rt.alloc<float>(1);
+
+	SolveCtx &sc = W->sc;
+	memset(&sc, 0, sizeof(sc));
+	uint32_t mc = d.max_constraints;
+	sc.con.capacity = mc;
+	sc.con.cf = rt.alloc<float>((size_t)CF_NUM * mc, false);
+	sc.con.b1 = rt.alloc<uint32_t>(mc); sc.con.b2 = rt.alloc<uint32_t>(mc); sc.con.manifold = rt.alloc<uint32_t>(mc); sc.con.meta = rt.alloc<uint32_t>(mc);
+	sc.man_ws = nc.man_ws;
+	sc.order = rt.alloc<uint32_t>(mc); sc.final_pos = rt.alloc<uint32_t>(mc); sc.solve_src = rt.alloc<uint32_t>(mc); sc.phase = rt.alloc<uint32_t>(mc);
+	sc.max_phases = 8192;
+	sc.phase_count = rt.alloc<uint32_t>(sc.max_phases + 2);
+	W->d_phase_fill = rt.alloc<uint32_t>(sc.max_phases + 2);
+	sc.uf_parent = rt.alloc<uint32_t>(nbod); sc.root = rt.alloc<uint32_t>(nbod); sc.island_items = rt.alloc<uint32_t>(nbod);
+	sc.island_large = rt.alloc<uint32_t>(nbod); sc.island_steps = rt.alloc<uint32_t>(nbod); sc.island_can_sleep = rt.alloc<uint32_t>(nbod);
+	sc.large_color_count = rt.alloc<uint32_t>((size_t)(mc / 128 + 2) * 32);
+	sc.body_deg = rt.alloc<uint32_t>(nbod + 1); sc.body_off = rt.alloc<uint32_t>(nbod + 1); sc.body_fill = rt.alloc<uint32_t>(nbod);
+	sc.body_cur = rt.alloc<uint32_t>(nbod); sc.body_mask = rt.alloc<uint32_t>(nbod);
+	sc.adj = rt.alloc<uint32_t>((size_t)2 * mc);
+	sc.sched_flag = rt.alloc<uint32_t>(4096);
+	W->d_sort_keys[0] = rt.alloc<uint64_t>(mc); W->d_sort_keys[1] = rt.alloc<uint64_t>(mc);
+	W->d_sort_vals = rt.alloc<uint32_t>(mc);
+
+	if (W->d_sort_vals == nullptr || sc.con.cf == nullptr || nc.scratch == nullptr)
+	{
+		last_error() = "out of device memory";
+		b2j_world_destroy(W);
+		return nullptr;
+	}
+
+	memset(W->trees, 0, sizeof(W->trees));
+	for (uint32_t l = 0; l < nb; ++l)
+	{
+		W->trees[l].layer_bounds = rt.alloc<F4>(2);
+		F4 init[2] = { f4(-1000.0f, -1000.0f, -1000.0f, 0.0f), f4(1000.0f, 1000.0f, 1000.0f, 0.0f) };
+		rt.upload(W->trees[l].layer_bounds, init, 2);
+	}
+	W->layer_bodies.resize(nb);
+	W->layer_list_dirty.assign(nb, 1);
+	W->layer_needs_build.assign(nb, 1);
+	W->layer_has_moving.assign(nb, 0);
+	W->h_ids.assign(nbod, B2J_INVALID_ID);
+	W->h_layer.assign(nbod, 0);
+	W->shapes_dirty = true;
+#ifndef B2J_HOSTSIM
+	cudaEventCreate(&W->ev_begin);
+	cudaEventCreate(&W->ev_end);
+#endif
+	sync_dworld(W);
+	rt.sync();
+	if (!rt.check("b2j_world_create")) { b2j_world_destroy(W); return nullptr; }
+	return W;
+}
+
+void b2j_world_destroy(b2j_world *W)
+{
+	if (W == nullptr) return;
+	Runtime &rt = W->rt;
+	rt.sync();
+	DWorld &d = W->d;
+	rt.free_(W->d_o2bp); rt.free_(W->d_ovbp); rt.free_(W->d_ovo);
+	rt.free_(d.info); rt.free_(d.params); rt.free_(d.position); rt.free_(d.rotation); rt.free_(d.linear_velocity); rt.free_(d.angular_velocity);
+	rt.free_(d.force); rt.free_(d.torque); rt.free_(d.inv_inertia_diag); rt.free_(d.inertia_rotation); rt.free_(d.bounds_min); rt.free_(d.bounds_max);
+	rt.free_(d.sleep_spheres); rt.free_(d.sleep_timer); rt.free_(d.active_index); rt.free_(W->active_buf[0]); rt.free_(W->active_buf[1]);
+	rt.free_(d.num_active); rt.free_(d.counters); rt.free_(W->d_keep); rt.free_(W->d_keep_scan);
+	for (int i = 0; i < 2; ++i)
+	{
+		rt.free_(W->cache[i].pairs); rt.free_(W->cache[i].manifolds); rt.free_(W->cache[i].pair_table); rt.free_(W->cache[i].num_pairs); rt.free_(W->cache[i].num_manifolds);
+	}
+	NarrowCtx &nc = W->nc;
+	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.scratch);
+	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(nc.events);
+	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
+	SolveCtx &sc = W->sc;
+	rt.free_(sc.con.cf); rt.free_(sc.con.b1); rt.free_(sc.con.b2); rt.free_(sc.con.manifold); rt.free_(sc.con.meta);
+	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count); rt.free_(W->d_phase_fill);
+	rt.free_(sc.uf_parent); rt.free_(sc.root); rt.free_(sc.island_items); rt.free_(sc.island_large); rt.free_(sc.island_steps); rt.free_(sc.island_can_sleep);
+	rt.free_(sc.large_color_count); rt.free_(sc.body_deg); rt.free_(sc.body_off); rt.free_(sc.body_fill); rt.free_(sc.body_cur); rt.free_(sc.body_mask);
+	rt.free_(sc.adj); rt.free_(sc.sched_flag);
+	rt.free_(W->d_sort_keys[0]); rt.free_(W->d_sort_keys[1]); rt.free_(W->d_sort_vals);
+	for (int l = 0; l < 8; ++l)
+	{
+		Tree &t = W->trees[l];
+		rt.free_(t.bodies); rt.free_(t.keys_in); rt.free_(t.keys_out); rt.free_(t.leaf_body); rt.free_(t.child_left); rt.free_(t.child_right);
+		rt.free_(t.parent); rt.free_(t.node_min); rt.free_(t.node_max); rt.free_(t.visit); rt.free_(t.layer_bounds);
+	}
+	rt.free_(W->d_shapes); rt.free_(W->d_hull_points); rt.free_(W->d_hull_shrunk); rt.free_(W->d_hull_planes);
+	rt.free_(W->d_hull_faces); rt.free_(W->d_hull_vtx); rt.free_(W->d_mesh_bytes);
+#ifndef B2J_HOSTSIM
+	if (W->ev_begin) cudaEventDestroy(W->ev_begin);
+	if (W->ev_end) cudaEventDestroy(W->ev_end);
+#endif
+	rt.shutdown();
+	delete W;
+}
+
+int b2j_world_set_gravity(b2j_world *W, const float g[3]) { W->d.gravity = v3_load(g); return 0; }
+int b2j_world_set_settings(b2j_world *W, const b2j_settings *s) { W->d.settings = *s; return 0; }
+int b2j_world_get_settings(const b2j_world *W, b2j_settings *s) { *s = W->d.settings; return 0; }
+int b2j_world_set_previous_delta_time(b2j_world *W, float dt) { W->prev_dt = dt; return 0; }
+
+static int32_t add_shape(b2j_world *W, const ShapeDesc &s)
+{
+	W->h_shapes.push_back(s);
+	W->shapes_dirty = true;
+	return (int32_t)W->h_shapes.size() - 1;
+}
+
+int32_t b2j_shape_sphere(b2j_world *W, float radius)
+{
+	ShapeDesc s; memset(&s, 0, sizeof(s));
+	s.kind = B2J_SHAPE_SPHERE; s.radius = radius; s.inner_radius = radius;
+	s.local_min = -v3_rep(radius); s.local_max = v3_rep(radius);
+	return add_shape(W, s);
+}
+
+int32_t b2j_shape_box(b2j_world *W, const float he[3], float convex_radius)
+{
+	ShapeDesc s; memset(&s, 0, sizeof(s));
+	s.kind = B2J_SHAPE_BOX; s.half_extent = v3_load(he); s.convex_radius = convex_radius;
+	s.inner_radius = reduce_min(s.half_extent);
+	s.local_min = -s.half_extent; s.local_max = s.half_extent;
+	return add_shape(W, s);
+}
+
+int32_t b2j_shape_capsule(b2j_world *W, float half_height, float radius)
+{
+	ShapeDesc s; memset(&s, 0, sizeof(s));
+	s.kind = B2J_SHAPE_CAPSULE; s.half_height = half_height; s.radius = radius; s.inner_radius = radius;
+	V3 extent = v3_rep(radius) + v3(0.0f, half_height, 0.0f);
+	s.local_min = -extent; s.local_max = extent;
+	return add_shape(W, s);
+}
+
+int32_t b2j_shape_convex_hull(b2j_world *W, const b2j_hull_desc *h)
+{
+	if (h == nullptr || h->num_points == 0 || h->num_points > 256 || h->num_faces == 0) { last_error() = "invalid hull"; return -1; }
+	ShapeDesc s; memset(&s, 0, sizeof(s));
+	s.kind = B2J_SHAPE_CONVEX_HULL; s.convex_radius = h->convex_radius; s.inner_radius = h->inner_radius;
+	s.local_min = v3_load(h->local_bounds_min); s.local_max = v3_load(h->local_bounds_max);
+	s.center_of_mass = v3_load(h->center_of_mass);
+	s.hull_point_offset = (uint32_t)W->h_hull_points.size(); s.hull_num_points = h->num_points;
+	for (uint32_t i = 0; i < h->num_points; ++i) W->h_hull_points.push_back(f4(v3_load(h->points + 3 * i)));
+	shrink_hull_points(h, W->h_hull_shrunk);
+	s.hull_face_offset = (uint32_t)W->h_hull_planes.size(); s.hull_num_faces = h->num_faces;
+	for (uint32_t i = 0; i < h->num_faces; ++i)
+	{
+		W->h_hull_planes.push_back(f4(h->planes[4 * i], h->planes[4 * i + 1], h->planes[4 * i + 2], h->planes[4 * i + 3]));
+		W->h_hull_faces.push_back((uint32_t)h->face_first_vertex[i] | ((uint32_t)h->face_num_vertices[i] << 16));
+	}
+	s.hull_vtx_offset = (uint32_t)W->h_hull_vtx.size();
+	W->h_hull_vtx.insert(W->h_hull_vtx.end(), h->vertex_idx, h->vertex_idx + h->num_vertex_idx);
+	return add_shape(W, s);
+}
+
+int32_t b2j_shape_mesh(b2j_world *W, const b2j_mesh_desc *m)
+{
+	if (m == nullptr || m->tree == nullptr || m->tree_size < 32) { last_error() = "invalid mesh"; return -1; }
+	ShapeDesc s; memset(&s, 0, sizeof(s));
+	s.kind = B2J_SHAPE_MESH;
+	s.local_min = v3_load(m->local_bounds_min); s.local_max = v3_load(m->local_bounds_max);
+	while (W->h_mesh_bytes.size() % 16 != 0) W->h_mesh_bytes.push_back(0);
+	s.mesh_offset = (uint32_t)W->h_mesh_bytes.size(); s.mesh_size = m->tree_size;
+	W->h_mesh_bytes.insert(W->h_mesh_bytes.end(), m->tree, m->tree + m->tree_size);
+	return add_shape(W, s);
+}
+
+int b2j_bodies_add(b2j_world *W, const b2j_body_desc *bodies, uint32_t n)
+{
+	if (n == 0) return 0;
+	Runtime &rt = W->rt;
+	upload_shapes(W);
+	std::vector<uint32_t> to_activate;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t slot = slot_of(bodies[i].id);
+		if (slot >= W->d.max_bodies) { last_error() = "body index out of range"; return -1; }
+		if (W->h_ids[slot] != B2J_INVALID_ID) { last_error() = "body slot already in use"; return -1; }
+		if (bodies[i].shape < 0 || bodies[i].shape >= (int32_t)W->h_shapes.size()) { last_error() = "invalid shape id"; return -1; }
+		if (bodies[i].object_layer >= W->d.num_object_layers) { last_error() = "invalid object layer"; return -1; }
+	}
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t slot = slot_of(bodies[i].id);
+		W->h_ids[slot] = bodies[i].id;
+		uint8_t layer = W->t_o2bp[bodies[i].object_layer];
+		W->h_layer[slot] = layer;
+		W->layer_bodies[layer].push_back(slot);
+		W->layer_list_dirty[layer] = 1;
+		W->layer_needs_build[layer] = 1;
+		if (bodies[i].motion_type != B2J_MOTION_STATIC) W->layer_has_moving[layer] = 1;
+		if (slot + 1 > W->num_slots) W->num_slots = slot + 1;
+		if (bodies[i].active && bodies[i].motion_type != B2J_MOTION_STATIC) to_activate.push_back(bodies[i].id);
+	}
+	W->num_bodies += n;
+	b2j_body_desc *tmp = rt.alloc<b2j_body_desc>(n, false);
+	if (tmp == nullptr) return -1;
+	rt.upload(tmp, bodies, n);
+	sync_dworld(W);
+	KAddBodies k; k.w = W->d; k.descs = tmp;
+	rt.launch(k, n);
+	rt.sync();
+	rt.free_(tmp);
+	if (!to_activate.empty())
+		return b2j_bodies_activate(W, to_activate.data(), (uint32_t)to_activate.size());
+	return rt.check("b2j_bodies_add")? 0 : -1;
+}
+
+int b2j_bodies_remove(b2j_world *W, const uint32_t *ids, uint32_t n)
+{
+	if (b2j_bodies_deactivate(W, ids, n) != 0) return -1;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t slot = slot_of(ids[i]);
+		if (slot >= W->d.max_bodies || W->h_ids[slot] != ids[i]) continue;
+		W->h_ids[slot] = B2J_INVALID_ID;
+		std::vector<uint32_t> &list = W->layer_bodies[W->h_layer[slot]];
+		list.erase(std::remove(list.begin(), list.end(), slot), list.end());
+		W->layer_list_dirty[W->h_layer[slot]] = 1;
+		W->layer_needs_build[W->h_layer[slot]] = 1;
+		W->num_bodies--;
+	}
+	return 0;
+}
+
+int b2j_set_active_list(b2j_world *W, const uint32_t *ids, uint32_t n)
+{
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	{ KClearActiveIndex k; k.w = W->d; rt.launch(k, W->num_active); }
+	W->num_active = 0;
+	if (n > 0)
+	{
+		uint32_t *tmp = rt.alloc<uint32_t>(n, false);
+		rt.upload(tmp, ids, n);
+		KSetActive k; k.w = W->d; k.ids = tmp; k.base = 0;
+		rt.launch(k, n);
+		rt.sync();
+		rt.free_(tmp);
+		W->num_active = n;
+	}
+	return rt.check("b2j_set_active_list")? 0 : -1;
+}
+
+int b2j_bodies_activate(b2j_world *W, const uint32_t *ids, uint32_t n)
+{
+	// append the bodies that are not active yet, in argument order (BodyManager::ActivateBodies)
+	Runtime &rt = W->rt;
+	if (n == 0) return 0;
+	std::vector<uint32_t> idx(n);
+	uint32_t *d_ids = rt.alloc<uint32_t>(n, false), *d_idx = rt.alloc<uint32_t>(n, false);
+	rt.upload(d_ids, ids, n);
+	sync_dworld(W);
+	{ KGetState k; memset(&k, 0, sizeof(k)); k.w = W->d; k.ids = d_ids; k.active_index = d_idx; rt.launch(k, n); }
+	rt.download(idx.data(), d_idx, n);
+	std::vector<uint32_t> add;
+	for (uint32_t i = 0; i < n; ++i)
+		if (idx[i] == B2J_INACTIVE_INDEX && std::find(add.begin(), add.end(), ids[i]) == add.end())
+			add.push_back(ids[i]);
+	if (!add.empty())
+	{
+		rt.upload(d_ids, add.data(), add.size());
+		KSetActive k; k.w = W->d; k.ids = d_ids; k.base = W->num_active;
+		rt.launch(k, (uint32_t)add.size());
+		// Body::ResetSleepTimer
+		rt.memset_(W->d.counters, 0, sizeof(StepCounters));
+		uint32_t *d_slots = rt.alloc<uint32_t>(add.size(), false);
+		std::vector<uint32_t> slots;
+		for (uint32_t id : add) slots.push_back(slot_of(id));
+		rt.upload(d_slots, slots.data(), slots.size());
+		KActivateWoken ka; ka.w = W->d; ka.woken_sorted = d_slots; ka.base = W->num_active; ka.woken_flag = W->nc.woken_flag; ka.events = nullptr; ka.max_events = 0;
+		rt.launch(ka, (uint32_t)add.size());
+		rt.sync();
+		rt.free_(d_slots);
+		W->num_active += (uint32_t)add.size();
+	}
+	rt.sync();
+	rt.free_(d_ids); rt.free_(d_idx);
+	return rt.check("b2j_bodies_activate")? 0 : -1;
+}
+
+int b2j_bodies_deactivate(b2j_world *W, const uint32_t *ids, uint32_t n)
+{
+	// rebuild the active list without the given bodies (stable; the reference swaps with the last element)
+	Runtime &rt = W->rt;
+	if (n == 0 || W->num_active == 0) return 0;
+	std::vector<uint32_t> active(W->num_active);
+	sync_dworld(W);
+	rt.download(active.data(), W->d.active, W->num_active);
+	std::vector<uint32_t> remaining;
+	std::vector<uint32_t> removed_ids;
+	for (uint32_t slot : active)
+	{
+		bool remove = false;
+		for (uint32_t i = 0; i < n; ++i) if (slot_of(ids[i]) == slot) { remove = true; break; }
+		if (!remove) remaining.push_back(W->h_ids[slot]); else removed_ids.push_back(W->h_ids[slot]);
+	}
+	if (removed_ids.empty()) return 0;
+	if (b2j_set_active_list(W, remaining.data(), (uint32_t)remaining.size()) != 0) return -1;
+	// zero the velocities of the deactivated bodies
+	std::vector<float> zeros(removed_ids.size() * 3, 0.0f);
+	b2j_body_state st; memset(&st, 0, sizeof(st));
+	st.linear_velocity = zeros.data(); st.angular_velocity = zeros.data();
+	return b2j_bodies_set_state(W, removed_ids.data(), (uint32_t)removed_ids.size(), &st);
+}
+
+int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_state *out)
+{
+	if (n == 0) return 0;
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	KGetState k; memset(&k, 0, sizeof(k)); k.w = W->d;
+	uint32_t *d_ids = nullptr;
+	if (ids != nullptr) { d_ids = rt.alloc<uint32_t>(n, false); rt.upload(d_ids, ids, n); }
+	else if (n > W->d.max_bodies) { last_error() = "n exceeds max_bodies"; return -1; }
+	k.ids = d_ids;
+	if (out->position) k.pos = rt.alloc<float>((size_t)n * 3, false);
+	if (out->rotation) k.rot = rt.alloc<float>((size_t)n * 4, false);
+	if (out->linear_velocity) k.lin = rt.alloc<float>((size_t)n * 3, false);
+	if (out->angular_velocity) k.ang = rt.alloc<float>((size_t)n * 3, false);
+	if (out->bounds) k.bounds = rt.alloc<float>((size_t)n * 6, false);
+	if (out->active_index) k.active_index = rt.alloc<uint32_t>(n, false);
+	if (out->sleep_timer) k.sleep_timer = rt.alloc<float>(n, false);
+	rt.launch(k, n);
+	if (k.pos) rt.download(out->position, k.pos, (size_t)n * 3);
+	if (k.rot) rt.download(out->rotation, k.rot, (size_t)n * 4);
+	if (k.lin) rt.download(out->linear_velocity, k.lin, (size_t)n * 3);
+	if (k.ang) rt.download(out->angular_velocity, k.ang, (size_t)n * 3);
+	if (k.bounds) rt.download(out->bounds, k.bounds, (size_t)n * 6);
+	if (k.active_index) rt.download(out->active_index, k.active_index, n);
+	if (k.sleep_timer) rt.download(out->sleep_timer, k.sleep_timer, n);
+	rt.sync();
+	rt.free_(d_ids); rt.free_(k.pos); rt.free_(k.rot); rt.free_(k.lin); rt.free_(k.ang); rt.free_(k.bounds); rt.free_(k.active_index); rt.free_(k.sleep_timer);
+	return rt.check("b2j_bodies_get_state")? 0 : -1;
+}
+
+int b2j_bodies_set_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_state *in)
+{
+	if (n == 0) return 0;
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	upload_shapes(W);
+	KSetState k; memset(&k, 0, sizeof(k)); k.w = W->d;
+	uint32_t *d_ids = nullptr;
+	if (ids != nullptr) { d_ids = rt.alloc<uint32_t>(n, false); rt.upload(d_ids, ids, n); }
+	k.ids = d_ids;
+	float *dp = nullptr, *dr = nullptr, *dl = nullptr, *da = nullptr;
+	if (in->position) { dp = rt.alloc<float>((size_t)n * 3, false); rt.upload(dp, (const float *)in->position, (size_t)n * 3); }
+	if (in->rotation) { dr = rt.alloc<float>((size_t)n * 4, false); rt.upload(dr, (const float *)in->rotation, (size_t)n * 4); }
+	if (in->linear_velocity) { dl = rt.alloc<float>((size_t)n * 3, false); rt.upload(dl, (const float *)in->linear_velocity, (size_t)n * 3); }
+	if (in->angular_velocity) { da = rt.alloc<float>((size_t)n * 3, false); rt.upload(da, (const float *)in->angular_velocity, (size_t)n * 3); }
+	k.pos = dp; k.rot = dr; k.lin = dl; k.ang = da;
+	rt.launch(k, n);
+	rt.sync();
+	rt.free_(d_ids); rt.free_(dp); rt.free_(dr); rt.free_(dl); rt.free_(da);
+	if (in->position || in->rotation)
+		for (uint32_t l = 0; l < W->d.num_bp_layers; ++l) W->layer_needs_build[l] = 1;
+	return rt.check("b2j_bodies_set_state")? 0 : -1;
+}
+
+int b2j_bodies_add_force_torque(b2j_world *W, const uint32_t *ids, uint32_t n, const float *force, const float *torque)
+{
+	if (n == 0) return 0;
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	uint32_t *d_ids = rt.alloc<uint32_t>(n, false); rt.upload(d_ids, ids, n);
+	float *df = nullptr, *dt = nullptr;
+	if (force) { df = rt.alloc<float>((size_t)n * 3, false); rt.upload(df, force, (size_t)n * 3); }
+	if (torque) { dt = rt.alloc<float>((size_t)n * 3, false); rt.upload(dt, torque, (size_t)n * 3); }
+	KAddForceTorque k; k.w = W->d; k.ids = d_ids; k.force = df; k.torque = dt;
+	rt.launch(k, n);
+	rt.sync();
+	rt.free_(d_ids); rt.free_(df); rt.free_(dt);
+	return rt.check("b2j_bodies_add_force_torque")? 0 : -1;
+}
+
+uint32_t b2j_num_bodies(const b2j_world *W) { return W->num_bodies; }
+uint32_t b2j_num_active_bodies(const b2j_world *W) { return W->num_active; }
+
+uint32_t b2j_get_active_bodies(b2j_world *W, uint32_t *ids, uint32_t cap)
+{
+	uint32_t n = W->num_active < cap? W->num_active : cap;
+	if (n > 0)
+	{
+		std::vector<uint32_t> slots(n);
+		sync_dworld(W);
+		W->rt.download(slots.data(), W->d.active, n);
+		for (uint32_t i = 0; i < n; ++i) ids[i] = W->h_ids[slots[i]];
+	}
+	return W->num_active;
+}
+
+int b2j_contact_cache_import(b2j_world *W, const b2j_cached_body_pair *pairs, uint32_t num_pairs, const b2j_cached_manifold *manifolds, uint32_t num_manifolds)
+{
+	Runtime &rt = W->rt;
+	if (num_pairs > W->d.max_body_pairs || num_manifolds > W->d.max_constraints) { last_error() = "contact cache snapshot exceeds the world limits"; return -1; }
+	int ri = W->write_idx ^ 1;
+	clear_cache(W, ri);
+	sync_dworld(W);
+	if (num_pairs > 0)
+	{
+		b2j_cached_body_pair *dp = rt.alloc<b2j_cached_body_pair>(num_pairs, false);
+		b2j_cached_manifold *dm = rt.alloc<b2j_cached_manifold>(num_manifolds, false);
+		rt.upload(dp, pairs, num_pairs);
+		rt.upload(dm, manifolds, num_manifolds);
+		KImportCache k; k.w = W->d; k.pairs = dp; k.manifolds = dm;
+		rt.launch(k, num_pairs);
+		rt.upload(W->cache[ri].num_pairs, &num_pairs, 1);
+		rt.upload(W->cache[ri].num_manifolds, &num_manifolds, 1);
+		rt.sync();
+		rt.free_(dp); rt.free_(dm);
+	}
+	W->cache_num_pairs[ri] = num_pairs;
+	W->cache_num_manifolds[ri] = num_manifolds;
+	return rt.check("b2j_contact_cache_import")? 0 : -1;
+}
+
+int b2j_contact_cache_export(b2j_world *W, b2j_cached_body_pair *pairs, uint32_t pairs_cap, uint32_t *num_pairs, b2j_cached_manifold *manifolds, uint32_t manifolds_cap, uint32_t *num_manifolds)
+{
+	Runtime &rt = W->rt;
+	int ri = W->write_idx ^ 1;
+	uint32_t np = W->cache_num_pairs[ri], nm = W->cache_num_manifolds[ri];
+	if (num_pairs) *num_pairs = np;
+	if (num_manifolds) *num_manifolds = nm;
+	if (np == 0 || pairs == nullptr || manifolds == nullptr) return 0;
+	sync_dworld(W);
+	b2j_cached_body_pair *dp = rt.alloc<b2j_cached_body_pair>(np);
+	b2j_cached_manifold *dm = rt.alloc<b2j_cached_manifold>(nm);
+	KExportCache k; k.w = W->d; k.pairs = dp; k.manifolds = dm;
+	rt.launch(k, np);
+	std::vector<b2j_cached_body_pair> hp(np);
+	std::vector<b2j_cached_manifold> hm(nm);
+	rt.download(hp.data(), dp, np);
+	rt.download(hm.data(), dm, nm);
+	rt.free_(dp); rt.free_(dm);
+	// sorted by (body1, body2); manifolds of a pair sorted by (sub1, sub2), re-packed contiguously
+	std::vector<uint32_t> order(np);
+	std::iota(order.begin(), order.end(), 0u);
+	std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hp[a].body1 != hp[b].body1? hp[a].body1 < hp[b].body1 : hp[a].body2 < hp[b].body2; });
+	uint32_t mo = 0;
+	for (uint32_t i = 0; i < np; ++i)
+	{
+		b2j_cached_body_pair p = hp[order[i]];
+		std::vector<b2j_cached_manifold> ms(hm.begin() + p.first_manifold, hm.begin() + p.first_manifold + p.num_manifolds);
+		std::sort(ms.begin(), ms.end(), [](const b2j_cached_manifold &a, const b2j_cached_manifold &b) { return a.sub_shape1 != b.sub_shape1? a.sub_shape1 < b.sub_shape1 : a.sub_shape2 < b.sub_shape2; });
+		p.first_manifold = mo;
+		for (const b2j_cached_manifold &m : ms) { if (mo < manifolds_cap) manifolds[mo] = m; ++mo; }
+		if (i < pairs_cap) pairs[i] = p;
+	}
+	return rt.check("b2j_contact_cache_export")? 0 : -1;
+}
+
+int b2j_were_bodies_in_contact(b2j_world *W, uint32_t id1, uint32_t id2)
+{
+	uint32_t np = 0, nm = 0;
+	b2j_contact_cache_export(W, nullptr, 0, &np, nullptr, 0, &nm);
+	std::vector<b2j_cached_body_pair> p(np);
+	std::vector<b2j_cached_manifold> m(nm);
+	if (b2j_contact_cache_export(W, p.data(), np, &np, m.data(), nm, &nm) != 0) return -1;
+	uint32_t a = id1 < id2? id1 : id2, b = id1 < id2? id2 : id1;
+	for (const b2j_cached_body_pair &cp : p)
+		if (cp.body1 == a && cp.body2 == b)
+			return cp.num_manifolds > 0? 1 : 0;
+	return 0;
+}
+
+int b2j_step(b2j_world *W, float delta_time, int collision_steps, b2j_step_stats *stats)
+{
+	Runtime &rt = W->rt;
+	bool want_energy = stats != nullptr && stats->kinetic_energy < 0.0f;
+	if (stats != nullptr) { memset(stats, 0, sizeof(*stats)); if (want_energy) stats->kinetic_energy = -1.0f; }
+	if (collision_steps < 1) collision_steps = 1;
+	upload_shapes(W);
+	sync_dworld(W);
+	rt.launches = 0;
+	W->last_num_events = 0;
+	W->last_num_act_events = 0;
+	if (W->num_active == 0 || delta_time <= 0.0f)
+	{
+		// PhysicsSystem.cpp:191-207: nothing to simulate; if time passes all cached contacts are reported as removed
+		if (delta_time > 0.0f)
+		{
+			rt.memset_(W->d.counters, 0, sizeof(StepCounters));
+			uint32_t old_m = W->cache_num_manifolds[W->write_idx ^ 1];
+			if (W->nc.events != nullptr) { KRemovedEvents k; k.w = W->d; k.c = W->nc; rt.launch(k, old_m); }
+			read_counters(W);
+			W->last_num_events = W->h_counters.num_events;
+			W->write_idx ^= 1;
+			clear_cache(W, W->write_idx);
+			sync_dworld(W);
+		}
+		if (stats != nullptr) { stats->num_bodies = W->num_bodies; stats->kernel_launches = rt.launches; }
+		return rt.check("b2j_step")? 0 : -1;
+	}
+#ifndef B2J_HOSTSIM
+	cudaEventRecord(W->ev_begin, rt.stream);
+#else
+	auto t0 = std::chrono::high_resolution_clock::now();
+#endif
+	float step_dt = delta_time / (float)collision_steps;
+	float ratio = W->prev_dt > 0.0f? step_dt / W->prev_dt : 0.0f;
+	W->prev_dt = step_dt;
+	if (!W->d.settings.constraint_warm_start) ratio = 0.0f;
+	uint32_t errors = 0;
+	for (int s = 0; s < collision_steps; ++s)
+	{
+		float r = s == 0? ratio : (W->d.settings.constraint_warm_start? 1.0f : 0.0f);
+		if (!collision_step(W, step_dt, r, s == collision_steps - 1, stats))
+			return -1;
+		errors |= W->h_counters.error_bits;
+	}
+	if (stats != nullptr)
+	{
+#ifndef B2J_HOSTSIM
+		cudaEventRecord(W->ev_end, rt.stream);
+		cudaEventSynchronize(W->ev_end);
+		cudaEventElapsedTime(&stats->gpu_ms, W->ev_begin, W->ev_end);
+#else
+		stats->gpu_ms = (float)std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+#endif
+		stats->num_active_bodies = W->num_active;
+		stats->num_bodies = W->num_bodies;
+		stats->kernel_launches = rt.launches;
+		stats->error_bits = errors & 7u;
+	}
+	if (errors & 0x100u) { last_error() = "solver phase limit exceeded"; return -1; }
+	return (int)(errors & 7u);
+}
+
+uint32_t b2j_events_drain(b2j_world *W, b2j_contact_event *out, uint32_t cap)
+{
+	uint32_t n = W->last_num_events < W->max_events? W->last_num_events : W->max_events;
+	if (n > 0 && out != nullptr && cap > 0)
+	{
+		std::vector<b2j_contact_event> ev(n);
+		W->rt.download(ev.data(), W->nc.events, n);
+		std::sort(ev.begin(), ev.end(), [](const b2j_contact_event &a, const b2j_contact_event &b) {
+			if (a.kind != b.kind) return a.kind < b.kind;
+			if (a.body1 != b.body1) return a.body1 < b.body1;
+			if (a.body2 != b.body2) return a.body2 < b.body2;
+			if (a.sub_shape1 != b.sub_shape1) return a.sub_shape1 < b.sub_shape1;
+			return a.sub_shape2 < b.sub_shape2;
+		});
+		for (uint32_t i = 0; i < n && i < cap; ++i) out[i] = ev[i];
+	}
+	return n;
+}
+
+uint32_t b2j_activation_events_drain(b2j_world *W, b2j_activation_event *out, uint32_t cap)
+{
+	uint32_t n = W->last_num_act_events < W->max_act_events? W->last_num_act_events : W->max_act_events;
+	if (n > 0 && out != nullptr && cap > 0)
+	{
+		std::vector<b2j_activation_event> ev(n);
+		W->rt.download(ev.data(), W->d_act_events, n);
+		std::sort(ev.begin(), ev.end(), [](const b2j_activation_event &a, const b2j_activation_event &b) { return a.kind != b.kind? a.kind < b.kind : a.body < b.body; });
+		for (uint32_t i = 0; i < n && i < cap; ++i) out[i] = ev[i];
+	}
+	return n;
+}
+
+uint32_t b2j_debug_get_pairs(b2j_world *W, uint32_t *pairs, uint32_t cap)
+{
+	uint32_t n = W->last_num_pairs;
+	if (n > 0 && pairs != nullptr)
+	{
+		std::vector<BodyPair> bp(n);
+		W->rt.download(bp.data(), W->nc.pairs, n);
+		std::vector<std::pair<uint32_t, uint32_t>> sorted(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			uint32_t a = W->h_ids[bp[i].a], b = W->h_ids[bp[i].b];
+			sorted[i] = std::make_pair(a < b? a : b, a < b? b : a);
+		}
+		std::sort(sorted.begin(), sorted.end());
+		for (uint32_t i = 0; i < n && i < cap; ++i) { pairs[2 * i] = sorted[i].first; pairs[2 * i + 1] = sorted[i].second; }
+	}
+	return n;
+}
+
+uint32_t b2j_debug_get_manifolds(b2j_world *W, b2j_debug_manifold *out, uint32_t cap)
+{
+	// manifolds of the cache written by the last step (now the read cache)
+	int ri = W->write_idx ^ 1;
+	uint32_t nm = W->cache_num_manifolds[ri];
+	if (nm > 0 && out != nullptr)
+	{
+		std::vector<CachedManifold> m(nm);
+		W->rt.download(m.data(), W->cache[ri].manifolds, nm);
+		std::vector<ManifoldWS> ws(nm);
+		W->rt.download(ws.data(), W->nc.man_ws, nm);
+		std::vector<b2j_debug_manifold> r(nm);
+		for (uint32_t i = 0; i < nm; ++i)
+		{
+			r[i].body1 = m[i].body1; r[i].body2 = m[i].body2; r[i].sub_shape1 = m[i].sub1; r[i].sub_shape2 = m[i].sub2;
+			r[i].num_points = m[i].num_points;
+			r[i].from_cache = (m[i].flags & MANIFOLD_FROM_CACHE)? 1 : 0;
+			for (int k = 0; k < 3; ++k) r[i].normal[k] = r[i].from_cache? m[i].normal[k] : ws[i].normal[k];
+			r[i].penetration_depth = 0.0f;
+		}
+		std::sort(r.begin(), r.end(), [](const b2j_debug_manifold &a, const b2j_debug_manifold &b) {
+			if (a.body1 != b.body1) return a.body1 < b.body1;
+			if (a.body2 != b.body2) return a.body2 < b.body2;
+			if (a.sub_shape1 != b.sub_shape1) return a.sub_shape1 < b.sub_shape1;
+			return a.sub_shape2 < b.sub_shape2;
+		});
+		for (uint32_t i = 0; i < nm && i < cap; ++i) out[i] = r[i];
+	}
+	return nm;
+}
+
+int b2j_debug_find_pairs(b2j_world *W)
+{
+	Runtime &rt = W->rt;
+	upload_shapes(W);
+	sync_dworld(W);
+	rt.memset_(W->d.counters, 0, sizeof(StepCounters));
+	for (uint32_t l = 0; l < W->d.num_bp_layers; ++l)
+		if (W->layer_needs_build[l])
+		{
+			if (!build_tree(W, l)) return -1;
+			W->layer_needs_build[l] = 0;
+		}
+	KFindPairs k; k.w = W->d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = 0;
+	rt.launch(k, W->num_active);
+	if (!read_counters(W)) return -1;
+	W->last_num_pairs = W->h_counters.num_pairs < W->d.max_body_pairs? W->h_counters.num_pairs : W->d.max_body_pairs;
+	return 0;
+}
+
+b2j_batch *b2j_batch_create(const b2j_world *, uint32_t) { last_error() = "b2j_batch_create: not implemented yet"; return nullptr; }
+void b2j_batch_destroy(b2j_batch *b) { delete b; }
+int b2j_batch_step(b2j_batch *, float, int, b2j_step_stats *) { last_error() = "b2j_batch_step: not implemented yet"; return -1; }
+b2j_world *b2j_batch_world(b2j_batch *b, uint32_t i) { return b != nullptr && i < b->worlds.size()? b->worlds[i] : nullptr; }
+uint32_t b2j_batch_size(const b2j_batch *b) { return b != nullptr? (uint32_t)b->worlds.size() : 0; }
+
+} // extern "C"

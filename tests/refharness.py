@@ -1,0 +1,273 @@
+"""ctypes wrapper of oracle/_ref/libjoltref_{det,fast}.so (the UNMODIFIED reference + oracle/ref_harness.cpp).
+
+Test infrastructure only. `RefWorld` builds a reference scene, steps it, and can re-create its current state inside a
+b2j world through the C ABI (jref_export_to_b2j), which is how every parity test gets "an identical snapshot of a
+Jolt-created world".
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from joltphysics_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def ref_lib_path(variant="det"):
+    return os.path.join(REF_DIR, f"libjoltref_{variant}.so")
+
+
+def have_ref(variant="det"):
+    return os.path.exists(ref_lib_path(variant))
+
+
+_libs = {}
+
+
+def ref_lib(variant="det"):
+    if variant not in _libs:
+        L = C.CDLL(ref_lib_path(variant), mode=C.RTLD_LOCAL)
+        vp, u32p, fp = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+        L.jref_last_error.restype = C.c_char_p
+        L.jref_bind_b2j.argtypes = [C.c_char_p]
+        L.jref_create_scene.restype = vp
+        L.jref_create_scene.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        L.jref_destroy.argtypes = [vp]
+        L.jref_set_recording.argtypes = [vp, C.c_int]
+        L.jref_step.argtypes = [vp, C.c_float, C.c_int, C.c_int]
+        L.jref_time_steps.restype = C.c_double
+        L.jref_time_steps.argtypes = [vp, C.c_float, C.c_int, C.c_int]
+        for f in ("jref_num_bodies", "jref_num_dynamic", "jref_num_active", "jref_max_bodies"):
+            getattr(L, f).restype = C.c_uint32
+            getattr(L, f).argtypes = [vp]
+        L.jref_get_state.argtypes = [vp, C.c_uint32, u32p, fp, fp, fp, fp, fp, u32p, fp]
+        L.jref_find_pairs.restype = C.c_uint32
+        L.jref_find_pairs.argtypes = [vp, u32p, C.c_uint32]
+        L.jref_get_cache.restype = C.c_uint32
+        L.jref_get_cache.argtypes = [vp, C.POINTER(_capi.CachedBodyPair), C.c_uint32, C.POINTER(_capi.CachedManifold), C.c_uint32, u32p]
+        L.jref_get_contact_events.restype = C.c_uint32
+        L.jref_get_contact_events.argtypes = [vp, C.POINTER(_capi.ContactEvent), C.c_uint32]
+        L.jref_get_activation_events.restype = C.c_uint32
+        L.jref_get_activation_events.argtypes = [vp, C.POINTER(_capi.ActivationEvent), C.c_uint32]
+        L.jref_get_active_bodies.restype = C.c_uint32
+        L.jref_get_active_bodies.argtypes = [vp, u32p, C.c_uint32]
+        L.jref_export_to_b2j.restype = vp
+        L.jref_export_to_b2j.argtypes = [vp, C.c_int]
+        L.jref_get_settings.argtypes = [vp, C.POINTER(_capi.Settings)]
+        L.jref_kinetic_energy.restype = C.c_double
+        L.jref_kinetic_energy.argtypes = [vp]
+        _libs[variant] = L
+    return _libs[variant]
+
+
+def _u32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class State:
+    """Body state by slot."""
+
+    def __init__(self, n):
+        self.ids = np.full(n, 0xffffffff, np.uint32)
+        self.pos = np.zeros((n, 3), np.float32)
+        self.rot = np.zeros((n, 4), np.float32)
+        self.lin = np.zeros((n, 3), np.float32)
+        self.ang = np.zeros((n, 3), np.float32)
+        self.bounds = np.zeros((n, 6), np.float32)
+        self.active_index = np.full(n, 0xffffffff, np.uint32)
+        self.sleep_timer = np.zeros(n, np.float32)
+
+
+class RefWorld:
+    def __init__(self, scene, p0=0, p1=0, variant="det"):
+        self.L = ref_lib(variant)
+        self.h = self.L.jref_create_scene(scene.encode(), p0, p1)
+        if not self.h:
+            raise RuntimeError("jref_create_scene failed: " + self.L.jref_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.jref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def step(self, dt=1.0 / 60.0, collision_steps=1, threads=1):
+        return self.L.jref_step(self.h, dt, collision_steps, threads)
+
+    def time_steps(self, n, dt=1.0 / 60.0, threads=0):
+        return self.L.jref_time_steps(self.h, dt, n, threads)
+
+    def set_recording(self, on):
+        self.L.jref_set_recording(self.h, 1 if on else 0)
+
+    @property
+    def num_bodies(self):
+        return self.L.jref_num_bodies(self.h)
+
+    @property
+    def num_dynamic(self):
+        return self.L.jref_num_dynamic(self.h)
+
+    @property
+    def num_active(self):
+        return self.L.jref_num_active(self.h)
+
+    def num_slots(self):
+        return self.num_bodies  # harness scenes never remove bodies: slots are dense
+
+    def state(self):
+        n = self.num_slots()
+        s = State(n)
+        self.L.jref_get_state(self.h, n, _u32p(s.ids), _fp(s.pos), _fp(s.rot), _fp(s.lin), _fp(s.ang), _fp(s.bounds), _u32p(s.active_index), _fp(s.sleep_timer))
+        return s
+
+    def find_pairs(self):
+        cap = 1 << 16
+        while True:
+            out = np.zeros((cap, 2), np.uint32)
+            n = self.L.jref_find_pairs(self.h, _u32p(out), cap)
+            if n <= cap:
+                return out[:n].copy()
+            cap = n
+
+    def cache(self):
+        """(pairs, manifolds) of the contact cache written by the last step, as ctypes arrays."""
+        nm = C.c_uint32(0)
+        n = self.L.jref_get_cache(self.h, None, 0, None, 0, C.byref(nm))
+        pairs = (_capi.CachedBodyPair * max(n, 1))()
+        mans = (_capi.CachedManifold * max(nm.value, 1))()
+        self.L.jref_get_cache(self.h, pairs, n, mans, nm.value, C.byref(nm))
+        return pairs, n, mans, nm.value
+
+    def contact_events(self):
+        n = self.L.jref_get_contact_events(self.h, None, 0)
+        ev = (_capi.ContactEvent * max(n, 1))()
+        self.L.jref_get_contact_events(self.h, ev, n)
+        return [ev[i] for i in range(n)]
+
+    def activation_events(self):
+        n = self.L.jref_get_activation_events(self.h, None, 0)
+        ev = (_capi.ActivationEvent * max(n, 1))()
+        self.L.jref_get_activation_events(self.h, ev, n)
+        return [(ev[i].kind, ev[i].body) for i in range(n)]
+
+    def active_bodies(self):
+        n = self.num_active
+        out = np.zeros(max(n, 1), np.uint32)
+        self.L.jref_get_active_bodies(self.h, _u32p(out), n)
+        return out[:n]
+
+    def kinetic_energy(self):
+        return self.L.jref_kinetic_energy(self.h)
+
+    def export(self, api, device=0):
+        """Re-creates the current reference state inside a new b2j world of library `api`; returns a B2JWorld."""
+        if self.L.jref_bind_b2j(api.path.encode()) != 0:
+            raise RuntimeError("jref_bind_b2j failed: " + self.L.jref_last_error().decode())
+        w = self.L.jref_export_to_b2j(self.h, device)
+        if not w:
+            raise RuntimeError("jref_export_to_b2j failed: " + self.L.jref_last_error().decode())
+        return B2JWorld(api, w, self.num_slots())
+
+
+class B2JWorld:
+    """Thin convenience wrapper around a b2j_world handle."""
+
+    def __init__(self, api, handle, num_slots):
+        self.api = api
+        self.h = handle
+        self.n = num_slots
+
+    def close(self):
+        if self.h:
+            self.api.b2j_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def step(self, dt=1.0 / 60.0, collision_steps=1):
+        stats = _capi.StepStats()
+        r = self.api.b2j_step(self.h, dt, collision_steps, C.byref(stats))
+        if r < 0:
+            raise RuntimeError("b2j_step failed: " + self.api.last_error())
+        return r, stats
+
+    def state(self):
+        s = State(self.n)
+        st = _capi.BodyState(s.pos.ctypes.data, s.rot.ctypes.data, s.lin.ctypes.data, s.ang.ctypes.data, s.bounds.ctypes.data, s.active_index.ctypes.data, s.sleep_timer.ctypes.data)
+        if self.api.b2j_bodies_get_state(self.h, None, self.n, C.byref(st)) != 0:
+            raise RuntimeError("b2j_bodies_get_state failed: " + self.api.last_error())
+        return s
+
+    def find_pairs(self):
+        if self.api.b2j_debug_find_pairs(self.h) != 0:
+            raise RuntimeError("b2j_debug_find_pairs failed: " + self.api.last_error())
+        return self.pairs()
+
+    def pairs(self):
+        n = self.api.b2j_debug_get_pairs(self.h, None, 0)
+        out = np.zeros((max(n, 1), 2), np.uint32)
+        self.api.b2j_debug_get_pairs(self.h, _u32p(out), n)
+        return out[:n].copy()
+
+    def cache(self):
+        np_, nm = C.c_uint32(0), C.c_uint32(0)
+        self.api.b2j_contact_cache_export(self.h, None, 0, C.byref(np_), None, 0, C.byref(nm))
+        pairs = (_capi.CachedBodyPair * max(np_.value, 1))()
+        mans = (_capi.CachedManifold * max(nm.value, 1))()
+        if self.api.b2j_contact_cache_export(self.h, pairs, np_.value, C.byref(np_), mans, nm.value, C.byref(nm)) != 0:
+            raise RuntimeError("b2j_contact_cache_export failed: " + self.api.last_error())
+        return pairs, np_.value, mans, nm.value
+
+    def contact_events(self):
+        n = self.api.b2j_events_drain(self.h, None, 0)
+        ev = (_capi.ContactEvent * max(n, 1))()
+        self.api.b2j_events_drain(self.h, ev, n)
+        return [ev[i] for i in range(n)]
+
+    def activation_events(self):
+        n = self.api.b2j_activation_events_drain(self.h, None, 0)
+        ev = (_capi.ActivationEvent * max(n, 1))()
+        self.api.b2j_activation_events_drain(self.h, ev, n)
+        return [(ev[i].kind, ev[i].body) for i in range(n)]
+
+    def active_bodies(self):
+        n = self.api.b2j_num_active_bodies(self.h)
+        out = np.zeros(max(n, 1), np.uint32)
+        self.api.b2j_get_active_bodies(self.h, _u32p(out), n)
+        return out[:n]
+
+
+def cache_summary(pairs, n_pairs, mans, n_mans):
+    """{(body1, body2): [(sub1, sub2, num_points), ...]} from a cache export."""
+    out = {}
+    for i in range(n_pairs):
+        p = pairs[i]
+        out[(p.body1, p.body2)] = [(mans[j].sub_shape1, mans[j].sub_shape2, mans[j].num_points) for j in range(p.first_manifold, p.first_manifold + p.num_manifolds)]
+    return out
+
+
+def compare_states(ref, got, rel=1e-4, abs_pos=1e-5):
+    """Max violation of |d| <= max(abs, rel * |ref|) over position / rotation / velocities (north star tolerance)."""
+    worst = {}
+    valid = ref.ids != 0xffffffff
+    for name in ("pos", "rot", "lin", "ang"):
+        a, b = getattr(ref, name)[valid], getattr(got, name)[valid]
+        if name == "rot":  # q and -q are the same rotation
+            sign = np.sign(np.sum(a * b, axis=1, keepdims=True))
+            sign[sign == 0] = 1
+            b = b * sign
+        err = np.linalg.norm(a - b, axis=1)
+        tol = np.maximum(abs_pos, rel * np.linalg.norm(a, axis=1))
+        worst[name] = float(np.max(err / tol)) if len(err) else 0.0
+        worst[name + "_abs"] = float(np.max(err)) if len(err) else 0.0
+    return worst
