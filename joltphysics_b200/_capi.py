@@ -153,7 +153,7 @@ class CApi:
 
     def __init__(self, path):
         self.path = os.path.abspath(path)
-        self.lib = C.CDLL(self.path, mode=C.RTLD_GLOBAL)
+        self.lib = C.CDLL(self.path, mode=C.RTLD_LOCAL)
         for name, (restype, argtypes) in PROTOTYPES.items():
             fn = getattr(self.lib, name)  # raises AttributeError if the symbol is missing
             fn.restype = restype

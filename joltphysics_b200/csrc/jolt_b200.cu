@@ -441,6 +441,12 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	sync_dworld(W);
 	rt.memset_(d.counters, 0, sizeof(StepCounters));
 	rt.memset_(W->d_round_begin, 0, 4);
+	if (W->last_num_events != 0 || W->last_num_act_events != 0)
+	{
+		// events accumulate over the collision steps of one b2j_step
+		rt.upload(&d.counters->num_events, &W->last_num_events, 1);
+		rt.upload(&d.counters->num_activation_events, &W->last_num_act_events, 1);
+	}
 
 	// (a2) gravity, forces, damping
 	{ KApplyGravity k; k.w = d; k.dt = dt; rt.launch(k, W->num_active); }
@@ -696,8 +702,9 @@ void shrink_hull_points(const b2j_hull_desc *h, std::vector<F4> &out)
 
 } // namespace
 
-// ---- C ABI -------------------------------------------------------------------------------------------------------------
+// ---- C ABI (the only symbols with default visibility; everything else is hidden: -fvisibility=hidden) -------------------
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char *b2j_last_error(void) { return last_error().c_str(); }
@@ -1447,3 +1454,4 @@ b2j_world *b2j_batch_world(b2j_batch *b, uint32_t i) { return b != nullptr && i 
 uint32_t b2j_batch_size(const b2j_batch *b) { return b != nullptr? (uint32_t)b->worlds.size() : 0; }
 
 } // extern "C"
+#pragma GCC visibility pop

@@ -39,7 +39,7 @@ struct Api
 
 	bool Load(const char *inPath, String &outError)
 	{
-		handle = dlopen(inPath, RTLD_NOW | RTLD_GLOBAL);
+		handle = dlopen(inPath, RTLD_NOW | RTLD_LOCAL);
 		if (handle == nullptr) { outError = dlerror(); return false; }
 #define B2J_FN(name) name = (decltype(name))dlsym(handle, #name); if (name == nullptr) { outError = String("missing symbol ") + #name; return false; }
 		B2J_FN(b2j_world_create) B2J_FN(b2j_world_destroy) B2J_FN(b2j_last_error) B2J_FN(b2j_settings_default)
