@@ -309,6 +309,7 @@ struct b2j_world
 	NarrowCtx nc;
 	SolveCtx sc;
 	uint32_t *d_round_begin = nullptr;
+	MeshScratch *d_mesh_scratch = nullptr;   // allocated when the first mesh shape is uploaded
 	uint64_t *d_sort_keys[2] = { nullptr, nullptr };
 	uint32_t *d_sort_vals = nullptr;
 	uint32_t *d_phase_fill = nullptr;
@@ -365,6 +366,7 @@ void upload_shapes(b2j_world *W)
 	W->d_hull_faces = rt.alloc<uint32_t>(W->h_hull_faces.size()); rt.upload(W->d_hull_faces, W->h_hull_faces.data(), W->h_hull_faces.size());
 	W->d_hull_vtx = rt.alloc<uint8_t>(W->h_hull_vtx.size() + 16); rt.upload(W->d_hull_vtx, W->h_hull_vtx.data(), W->h_hull_vtx.size());
 	W->d_mesh_bytes = rt.alloc<uint8_t>(W->h_mesh_bytes.size() + 16); rt.upload(W->d_mesh_bytes, W->h_mesh_bytes.data(), W->h_mesh_bytes.size());
+	if (!W->h_mesh_bytes.empty() && W->d_mesh_scratch == nullptr) W->d_mesh_scratch = rt.alloc<MeshScratch>(W->nc.num_scratch, false);
 	W->d.shapes = W->d_shapes; W->d.hull_points = W->d_hull_points; W->d.hull_shrunk = W->d_hull_shrunk; W->d.hull_planes = W->d_hull_planes;
 	W->d.hull_faces = W->d_hull_faces; W->d.hull_vtx = W->d_hull_vtx; W->d.mesh_bytes = W->d_mesh_bytes;
 	W->shapes_dirty = false;
@@ -469,7 +471,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KCopyCached k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_cached, nullptr, d.max_body_pairs); }
 		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
 		{ KCollideEpa k; k.w = d; k.c = W->nc; rt.launch_slot(k, &d.counters->num_epa, W->nc.max_epa, W->nc.num_scratch); }
-		{ KCollideMesh k; k.w = d; k.c = W->nc; rt.launch_slot(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
+		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_slot(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
 		if (!read_counters(W)) return false;
 		uint32_t woken = W->h_counters.num_woken;
 		if (W->h_counters.num_epa > W->nc.max_epa) { last_error() = "EPA queue overflow"; return false; }
@@ -889,6 +891,7 @@ void b2j_world_destroy(b2j_world *W)
 	NarrowCtx &nc = W->nc;
 	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.scratch);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(nc.events);
+	rt.free_(W->d_mesh_scratch);
 	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
 	rt.free_(sc.con.cf); rt.free_(sc.con.b1); rt.free_(sc.con.b2); rt.free_(sc.con.manifold); rt.free_(sc.con.meta);
