@@ -325,6 +325,12 @@ uint32_t b2j_debug_get_manifolds(b2j_world *w, b2j_debug_manifold *out, uint32_t
 /* Only the broadphase of a step on the current state: fills the pair list for b2j_debug_get_pairs. */
 int b2j_debug_find_pairs(b2j_world *w);
 
+/* ---- per kernel timing (measurement hook for bench.py; CUDA events around every launch on the world's stream) ---- */
+int      b2j_world_set_profiling(b2j_world *w, int on);   /* on != 0: start (resets the accumulators), 0: stop */
+/* Accumulated device time / launch count per kernel since profiling was switched on. names: [cap][name_stride] chars.
+ * Returns the number of kernel categories that ran. */
+uint32_t b2j_world_get_profile(b2j_world *w, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap);
+
 /* ---- batched independent worlds (config 5) --------------------------------------------------------- */
 
 typedef struct b2j_batch b2j_batch; /* opaque: n identical-layout worlds stepped together on one device */

@@ -1,0 +1,961 @@
+// jolt_b200_facade.h -- C++ host side above the C ABI: the reference's public surface for the hot path.
+//
+// Mirrors (names, argument meaning, error behaviour) of
+//   PhysicsSystem      Jolt/Physics/PhysicsSystem.h:29-396      Init / Update / SetGravity / SetPhysicsSettings / listeners / GetBodyInterface
+//   BodyInterface      Jolt/Physics/Body/BodyInterface.h:39-313  CreateBody / AddBody / CreateAndAddBody / RemoveBody / Activate / getters / setters / AddForce
+//   ContactListener    Jolt/Physics/Collision/ContactListener.h:78-141 (observer semantics: callbacks are replayed after the step)
+//   BodyActivationListener  Jolt/Physics/Body/BodyActivationListener.h:13-26
+//   BodyCreationSettings    Jolt/Physics/Body/BodyCreationSettings.h (same defaults), MassProperties / MotionProperties::SetMassProperties
+// in namespace JPH_B200 so that `namespace JPH = JPH_B200;` makes reference-style code compile against it.
+// Header only; links against libjolt_b200.so (include/jolt_b200.h). No exceptions, no RTTI needed.
+//
+// Documented deviations: listeners cannot alter the step they are reported in (OnContactValidate is not called,
+// ContactSettings edits are ignored); virtual layer filters are sampled into tables at Init; JobSystem / TempAllocator
+// arguments of Update are accepted and ignored (the GPU owns the step).
+#pragma once
+
+#include "jolt_b200.h"
+
+#include <cmath>
+#include <cfloat>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+namespace JPH_B200 {
+
+using uint = unsigned int;
+using uint8 = uint8_t;
+using uint16 = uint16_t;
+using uint32 = uint32_t;
+using uint64 = uint64_t;
+
+static constexpr float JPH_PI = 3.14159265358979323846f;
+
+struct Vec3
+{
+	float x = 0, y = 0, z = 0;
+	Vec3() = default;
+	Vec3(float inX, float inY, float inZ) : x(inX), y(inY), z(inZ) { }
+	static Vec3 sZero() { return Vec3(0, 0, 0); }
+	static Vec3 sReplicate(float v) { return Vec3(v, v, v); }
+	float GetX() const { return x; } float GetY() const { return y; } float GetZ() const { return z; }
+	float operator[](int i) const { return i == 0? x : (i == 1? y : z); }
+	Vec3 operator+(const Vec3 &o) const { return Vec3(x + o.x, y + o.y, z + o.z); }
+	Vec3 operator-(const Vec3 &o) const { return Vec3(x - o.x, y - o.y, z - o.z); }
+	Vec3 operator-() const { return Vec3(0.0f - x, 0.0f - y, 0.0f - z); }
+	Vec3 operator*(float s) const { return Vec3(x * s, y * s, z * s); }
+	Vec3 operator*(const Vec3 &o) const { return Vec3(x * o.x, y * o.y, z * o.z); }
+	Vec3 Cross(const Vec3 &b) const { return Vec3(y * b.z - z * b.y, z * b.x - x * b.z, x * b.y - y * b.x); }
+	float Dot(const Vec3 &b) const { return (x * b.x + y * b.y) + (z * b.z + 0.0f); }
+	float LengthSq() const { return Dot(*this); }
+	float Length() const { return std::sqrt(LengthSq()); }
+};
+using RVec3 = Vec3;
+inline Vec3 operator*(float s, const Vec3 &v) { return Vec3(s * v.x, s * v.y, s * v.z); }
+
+struct Quat
+{
+	float x = 0, y = 0, z = 0, w = 1;
+	Quat() = default;
+	Quat(float inX, float inY, float inZ, float inW) : x(inX), y(inY), z(inZ), w(inW) { }
+	static Quat sIdentity() { return Quat(0, 0, 0, 1); }
+	float GetX() const { return x; } float GetY() const { return y; } float GetZ() const { return z; } float GetW() const { return w; }
+	Quat Normalized() const { float l = std::sqrt((x * x + y * y) + (z * z + w * w)); return Quat(x / l, y / l, z / l, w / l); }
+	// Quat::operator*(Vec3) (Jolt/Math/Quat.inl:383-405)
+	Vec3 operator*(const Vec3 &p) const
+	{
+		Vec3 c(p.z * y - z * p.y, p.x * z - x * p.z, p.y * x - y * p.x);
+		Vec3 cc(c.z * y - z * c.y, c.x * z - x * c.z, c.y * x - y * c.x);
+		Vec3 v = Vec3(w * c.x, w * c.y, w * c.z) + cc;
+		return p + (v + v);
+	}
+};
+
+using ObjectLayer = uint16;
+struct BroadPhaseLayer
+{
+	using Type = uint8;
+	constexpr BroadPhaseLayer() = default;
+	explicit constexpr BroadPhaseLayer(Type inValue) : mValue(inValue) { }
+	explicit constexpr operator Type() const { return mValue; }
+	constexpr bool operator==(const BroadPhaseLayer &o) const { return mValue == o.mValue; }
+	Type mValue = 0xff;
+};
+
+enum class EMotionType : uint8 { Static = 0, Kinematic = 1, Dynamic = 2 };
+enum class EMotionQuality : uint8 { Discrete = 0, LinearCast = 1 };
+enum class EActivation { Activate, DontActivate };
+enum class EAllowedDOFs : uint8 { None = 0, All = 0x3f, TranslationX = 1, TranslationY = 2, TranslationZ = 4, RotationX = 8, RotationY = 16, RotationZ = 32, Plane2D = 1 | 2 | 32 };
+enum class EPhysicsUpdateError : uint32 { None = 0, ManifoldCacheFull = 1, BodyPairCacheFull = 2, ContactConstraintsFull = 4 };
+inline EPhysicsUpdateError operator|(EPhysicsUpdateError a, EPhysicsUpdateError b) { return EPhysicsUpdateError(uint32(a) | uint32(b)); }
+enum class EOverrideMassProperties : uint8 { CalculateMassAndInertia, CalculateInertia, MassAndInertiaProvided };
+enum class EShapeSubType : uint8 { Sphere = B2J_SHAPE_SPHERE, Box = B2J_SHAPE_BOX, Capsule = B2J_SHAPE_CAPSULE, ConvexHull = B2J_SHAPE_CONVEX_HULL, Mesh = B2J_SHAPE_MESH };
+
+class BroadPhaseLayerInterface { public: virtual ~BroadPhaseLayerInterface() = default; virtual uint GetNumBroadPhaseLayers() const = 0; virtual BroadPhaseLayer GetBroadPhaseLayer(ObjectLayer inLayer) const = 0; };
+class ObjectVsBroadPhaseLayerFilter { public: virtual ~ObjectVsBroadPhaseLayerFilter() = default; virtual bool ShouldCollide(ObjectLayer, BroadPhaseLayer) const { return true; } };
+class ObjectLayerPairFilter { public: virtual ~ObjectLayerPairFilter() = default; virtual bool ShouldCollide(ObjectLayer, ObjectLayer) const { return true; } };
+
+// Accepted by Update for signature compatibility; the step runs on the GPU
+class TempAllocator { public: virtual ~TempAllocator() = default; };
+class TempAllocatorImpl : public TempAllocator { public: explicit TempAllocatorImpl(size_t) { } };
+class JobSystem { public: virtual ~JobSystem() = default; };
+class JobSystemThreadPool : public JobSystem { public: JobSystemThreadPool(uint = 0, uint = 0, int = -1) { } };
+
+struct BodyID
+{
+	static constexpr uint32 cInvalidBodyID = 0xffffffff;
+	BodyID() = default;
+	explicit BodyID(uint32 inID) : mID(inID) { }
+	BodyID(uint32 inIndex, uint8 inSequence) : mID((uint32(inSequence) << 23) | inIndex) { }
+	uint32 GetIndex() const { return mID & 0x7fffff; }
+	uint8 GetSequenceNumber() const { return uint8(mID >> 23); }
+	uint32 GetIndexAndSequenceNumber() const { return mID; }
+	bool IsInvalid() const { return mID == cInvalidBodyID; }
+	bool operator==(const BodyID &o) const { return mID == o.mID; }
+	bool operator!=(const BodyID &o) const { return mID != o.mID; }
+	bool operator<(const BodyID &o) const { return mID < o.mID; }
+	uint32 mID = cInvalidBodyID;
+};
+
+struct SubShapeID { uint32 mValue = 0xffffffff; uint32 GetValue() const { return mValue; } };
+struct SubShapeIDPair
+{
+	BodyID mBody1ID; SubShapeID mSubShapeID1; BodyID mBody2ID; SubShapeID mSubShapeID2;
+	const BodyID &GetBody1ID() const { return mBody1ID; } const BodyID &GetBody2ID() const { return mBody2ID; }
+	const SubShapeID &GetSubShapeID1() const { return mSubShapeID1; } const SubShapeID &GetSubShapeID2() const { return mSubShapeID2; }
+};
+
+// MassProperties (Jolt/Physics/Body/MassProperties.h): mass + 3x3 inertia (column major)
+struct MassProperties
+{
+	float mMass = 0.0f;
+	float mInertia[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } }; // [column][row]
+
+	void SetDiagonal(float a, float b, float c) { memset(mInertia, 0, sizeof(mInertia)); mInertia[0][0] = a; mInertia[1][1] = b; mInertia[2][2] = c; }
+	// MassProperties::SetMassAndInertiaOfSolidBox (MassProperties.cpp:66-75)
+	void SetMassAndInertiaOfSolidBox(const Vec3 &inBoxSize, float inDensity)
+	{
+		mMass = inBoxSize.x * inBoxSize.y * inBoxSize.z * inDensity;
+		Vec3 size_sq = inBoxSize * inBoxSize;
+		float s = mMass / 12.0f;
+		SetDiagonal((size_sq.y + size_sq.z) * s, (size_sq.x + size_sq.z) * s, (size_sq.x + size_sq.y) * s);
+	}
+	// MassProperties::ScaleToMass
+	void ScaleToMass(float inMass)
+	{
+		if (mMass > 0.0f)
+		{
+			float mass_scale = inMass / mMass;
+			mMass = inMass;
+			for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) mInertia[c][r] *= mass_scale;
+		}
+		else
+			mMass = inMass;
+	}
+
+	// EigenValueSymmetric (Jolt/Math/EigenValueSymmetric.h) + sort + handedness (MassProperties.cpp:23-57) + Mat44::GetQuaternion
+	bool DecomposePrincipalMomentsOfInertia(Quat &outRotation, Vec3 &outDiagonal) const
+	{
+		const int n = 3;
+		float a[3][3]; // a(row, col) = a[row][col]
+		for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) a[r][c] = mInertia[c][r];
+		float vec[3][3] = { { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } }; // vec(row, col)
+		float val[3], b[3], z[3];
+		for (int ip = 0; ip < n; ++ip) { b[ip] = a[ip][ip]; val[ip] = a[ip][ip]; z[ip] = 0.0f; }
+		bool converged = false;
+		for (int sweep = 0; sweep < 50 && !converged; ++sweep)
+		{
+			float sm = 0.0f;
+			for (int ip = 0; ip < n - 1; ++ip) for (int iq = ip + 1; iq < n; ++iq) sm += std::fabs(a[ip][iq]);
+			float avg_sm = sm / float(n * n);
+			if (avg_sm < FLT_MIN) { converged = true; break; }
+			float thresh = sweep < 4? 0.2f * avg_sm : FLT_MIN;
+			for (int ip = 0; ip < n - 1; ++ip)
+				for (int iq = ip + 1; iq < n; ++iq)
+				{
+					float &a_pq = a[ip][iq];
+					float &eigval_p = val[ip];
+					float &eigval_q = val[iq];
+					float abs_a_pq = std::fabs(a_pq);
+					float g = 100.0f * abs_a_pq;
+					if (sweep > 4 && std::fabs(eigval_p) + g == std::fabs(eigval_p) && std::fabs(eigval_q) + g == std::fabs(eigval_q))
+						a_pq = 0.0f;
+					else if (abs_a_pq > thresh)
+					{
+						float h = eigval_q - eigval_p;
+						float abs_h = std::fabs(h);
+						float t;
+						if (abs_h + g == abs_h)
+							t = a_pq / h;
+						else
+						{
+							float theta = 0.5f * h / a_pq;
+							t = 1.0f / (std::fabs(theta) + std::sqrt(1.0f + theta * theta));
+							if (theta < 0.0f) t = -t;
+						}
+						float c = 1.0f / std::sqrt(1.0f + t * t);
+						float s = t * c;
+						float tau = s / (1.0f + c);
+						h = t * a_pq;
+						a_pq = 0.0f;
+						z[ip] -= h; z[iq] += h;
+						eigval_p -= h; eigval_q += h;
+						auto rotate = [&](float (&m)[3][3], int i, int j, int k, int l) { float gg = m[i][j], hh = m[k][l]; m[i][j] = gg - s * (hh + gg * tau); m[k][l] = hh + s * (gg - hh * tau); };
+						int j;
+						for (j = 0; j < ip; ++j) rotate(a, j, ip, j, iq);
+						for (j = ip + 1; j < iq; ++j) rotate(a, ip, j, j, iq);
+						for (j = iq + 1; j < n; ++j) rotate(a, ip, j, iq, j);
+						for (j = 0; j < n; ++j) rotate(vec, j, ip, j, iq);
+					}
+				}
+			for (int ip = 0; ip < n; ++ip) { b[ip] += z[ip]; val[ip] = b[ip]; z[ip] = 0.0f; }
+		}
+		if (!converged)
+			return false;
+		// insertion sort, biggest first
+		int indices[3] = { 0, 1, 2 };
+		for (int i = 1; i < 3; ++i)
+		{
+			int x = indices[i], j = i;
+			while (j > 0 && val[x] > val[indices[j - 1]]) { indices[j] = indices[j - 1]; --j; }
+			indices[j] = x;
+		}
+		Vec3 col[3];
+		float diag[3];
+		for (int i = 0; i < 3; ++i)
+		{
+			col[i] = Vec3(vec[0][indices[i]], vec[1][indices[i]], vec[2][indices[i]]);
+			diag[i] = val[indices[i]];
+		}
+		if (col[0].Cross(col[1]).Dot(col[2]) < 0.0f)
+			col[2] = -col[2];
+		outDiagonal = Vec3(diag[0], diag[1], diag[2]);
+		// Mat44::GetQuaternion (Mat44.inl:998-1050); m(row, col) = col[col][row]
+		float m00 = col[0].x, m11 = col[1].y, m22 = col[2].z;
+		float tr = m00 + m11 + m22;
+		if (tr >= 0.0f)
+		{
+			float s = std::sqrt(tr + 1.0f), is = 0.5f / s;
+			outRotation = Quat((col[1].z - col[2].y) * is, (col[2].x - col[0].z) * is, (col[0].y - col[1].x) * is, 0.5f * s);
+		}
+		else
+		{
+			int i = 0;
+			if (m11 > m00) i = 1;
+			if (m22 > (i == 0? m00 : m11)) i = 2;
+			if (i == 0)
+			{
+				float s = std::sqrt(m00 - (m11 + m22) + 1), is = 0.5f / s;
+				outRotation = Quat(0.5f * s, (col[1].x + col[0].y) * is, (col[0].z + col[2].x) * is, (col[1].z - col[2].y) * is);
+			}
+			else if (i == 1)
+			{
+				float s = std::sqrt(m11 - (m22 + m00) + 1), is = 0.5f / s;
+				outRotation = Quat((col[1].x + col[0].y) * is, 0.5f * s, (col[2].y + col[1].z) * is, (col[2].x - col[0].z) * is);
+			}
+			else
+			{
+				float s = std::sqrt(m22 - (m00 + m11) + 1), is = 0.5f / s;
+				outRotation = Quat((col[0].z + col[2].x) * is, (col[2].y + col[1].z) * is, 0.5f * s, (col[0].y - col[1].x) * is);
+			}
+		}
+		return true;
+	}
+};
+
+// ---- shapes (immutable, shared) -----------------------------------------------------------------------------------
+class Shape
+{
+public:
+	virtual ~Shape() = default;
+	virtual EShapeSubType GetSubType() const = 0;
+	virtual MassProperties GetMassProperties() const = 0;
+	virtual Vec3 GetCenterOfMass() const { return Vec3::sZero(); }
+	virtual int32_t Upload(b2j_world *inWorld) const = 0;
+};
+using ShapeRef = std::shared_ptr<const Shape>;
+
+class ConvexShape : public Shape { public: void SetDensity(float d) { mDensity = d; } float GetDensity() const { return mDensity; } protected: float mDensity = 1000.0f; };
+
+class SphereShape final : public ConvexShape
+{
+public:
+	explicit SphereShape(float inRadius) : mRadius(inRadius) { }
+	float GetRadius() const { return mRadius; }
+	EShapeSubType GetSubType() const override { return EShapeSubType::Sphere; }
+	MassProperties GetMassProperties() const override // SphereShape.cpp:143-156
+	{
+		MassProperties p;
+		float r2 = mRadius * mRadius;
+		p.mMass = (4.0f / 3.0f * JPH_PI) * mRadius * r2 * GetDensity();
+		float inertia = (2.0f / 5.0f) * p.mMass * r2;
+		p.SetDiagonal(inertia, inertia, inertia);
+		return p;
+	}
+	int32_t Upload(b2j_world *w) const override { return b2j_shape_sphere(w, mRadius); }
+private:
+	float mRadius;
+};
+
+class BoxShape final : public ConvexShape
+{
+public:
+	explicit BoxShape(const Vec3 &inHalfExtent, float inConvexRadius = 0.05f) : mHalfExtent(inHalfExtent), mConvexRadius(inConvexRadius) { }
+	Vec3 GetHalfExtent() const { return mHalfExtent; }
+	float GetConvexRadius() const { return mConvexRadius; }
+	EShapeSubType GetSubType() const override { return EShapeSubType::Box; }
+	MassProperties GetMassProperties() const override { MassProperties p; p.SetMassAndInertiaOfSolidBox(2.0f * mHalfExtent, GetDensity()); return p; } // BoxShape.cpp:149-154
+	int32_t Upload(b2j_world *w) const override { float he[3] = { mHalfExtent.x, mHalfExtent.y, mHalfExtent.z }; return b2j_shape_box(w, he, mConvexRadius); }
+private:
+	Vec3 mHalfExtent;
+	float mConvexRadius;
+};
+
+class CapsuleShape final : public ConvexShape
+{
+public:
+	CapsuleShape(float inHalfHeightOfCylinder, float inRadius) : mHalfHeightOfCylinder(inHalfHeightOfCylinder), mRadius(inRadius) { }
+	EShapeSubType GetSubType() const override { return EShapeSubType::Capsule; }
+	MassProperties GetMassProperties() const override // CapsuleShape.cpp:218-248
+	{
+		MassProperties p;
+		float density = GetDensity();
+		float radius_sq = mRadius * mRadius;
+		float height = 2.0f * mHalfHeightOfCylinder;
+		float cylinder_mass = JPH_PI * height * radius_sq * density;
+		float hemisphere_mass = (2.0f * JPH_PI / 3.0f) * radius_sq * mRadius * density;
+		float height_sq = height * height;
+		float inertia_y = radius_sq * cylinder_mass * 0.5f;
+		float inertia_xz = inertia_y * 0.5f + cylinder_mass * height_sq / 12.0f;
+		float temp = hemisphere_mass * 4.0f * radius_sq / 5.0f;
+		inertia_y += temp;
+		inertia_xz += temp + hemisphere_mass * (0.5f * height_sq + (3.0f / 4.0f) * height * mRadius);
+		p.mMass = cylinder_mass + hemisphere_mass * 2.0f;
+		p.SetDiagonal(inertia_xz, inertia_y, inertia_xz);
+		return p;
+	}
+	int32_t Upload(b2j_world *w) const override { return b2j_shape_capsule(w, mHalfHeightOfCylinder, mRadius); }
+private:
+	float mHalfHeightOfCylinder, mRadius;
+};
+
+// A convex hull cooked by the reference's ConvexHullBuilder (host-side cooking is out of scope, SURVEY 2a Jolt/Geometry)
+class ConvexHullShape final : public ConvexShape
+{
+public:
+	std::vector<float> mPoints, mPlanes;          // [n][3], [f][4]
+	std::vector<int32_t> mPointNumFaces, mPointFaces;
+	std::vector<uint16_t> mFaceFirstVertex, mFaceNumVertices;
+	std::vector<uint8_t> mVertexIdx;
+	float mConvexRadius = 0.0f, mInnerRadius = 0.0f, mVolume = 0.0f;
+	float mCenterOfMass[3] = { 0, 0, 0 }, mBoundsMin[3] = { 0, 0, 0 }, mBoundsMax[3] = { 0, 0, 0 };
+	float mInertia[3][3] = { { 0 } };           // density 1, [column][row]
+	EShapeSubType GetSubType() const override { return EShapeSubType::ConvexHull; }
+	Vec3 GetCenterOfMass() const override { return Vec3(mCenterOfMass[0], mCenterOfMass[1], mCenterOfMass[2]); }
+	MassProperties GetMassProperties() const override // ConvexHullShape.cpp:356-370
+	{
+		MassProperties p;
+		float density = GetDensity();
+		p.mMass = density * mVolume;
+		for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) p.mInertia[c][r] = density * mInertia[c][r];
+		return p;
+	}
+	int32_t Upload(b2j_world *w) const override
+	{
+		b2j_hull_desc d;
+		memset(&d, 0, sizeof(d));
+		d.num_points = (uint32_t)mPointNumFaces.size(); d.points = mPoints.data(); d.point_num_faces = mPointNumFaces.data(); d.point_faces = mPointFaces.data();
+		d.num_faces = (uint32_t)mFaceFirstVertex.size(); d.face_first_vertex = mFaceFirstVertex.data(); d.face_num_vertices = mFaceNumVertices.data(); d.planes = mPlanes.data();
+		d.num_vertex_idx = (uint32_t)mVertexIdx.size(); d.vertex_idx = mVertexIdx.data(); d.convex_radius = mConvexRadius; d.inner_radius = mInnerRadius;
+		memcpy(d.center_of_mass, mCenterOfMass, 12); memcpy(d.local_bounds_min, mBoundsMin, 12); memcpy(d.local_bounds_max, mBoundsMax, 12);
+		return b2j_shape_convex_hull(w, &d);
+	}
+};
+
+// A mesh cooked by the reference's MeshShapeSettings (tree byte buffer verbatim)
+class MeshShape final : public Shape
+{
+public:
+	std::vector<uint8_t> mTree;
+	float mBoundsMin[3] = { 0, 0, 0 }, mBoundsMax[3] = { 0, 0, 0 };
+	EShapeSubType GetSubType() const override { return EShapeSubType::Mesh; }
+	MassProperties GetMassProperties() const override { return MassProperties(); } // static only
+	int32_t Upload(b2j_world *w) const override
+	{
+		b2j_mesh_desc d;
+		memset(&d, 0, sizeof(d));
+		d.tree = mTree.data(); d.tree_size = (uint32_t)mTree.size();
+		memcpy(d.local_bounds_min, mBoundsMin, 12); memcpy(d.local_bounds_max, mBoundsMax, 12);
+		return b2j_shape_mesh(w, &d);
+	}
+};
+
+// ---- BodyCreationSettings (same defaults as the reference) ------------------------------------------------------
+class BodyCreationSettings
+{
+public:
+	BodyCreationSettings() = default;
+	BodyCreationSettings(ShapeRef inShape, const RVec3 &inPosition, const Quat &inRotation, EMotionType inMotionType, ObjectLayer inObjectLayer) :
+		mPosition(inPosition), mRotation(inRotation), mObjectLayer(inObjectLayer), mMotionType(inMotionType), mShape(std::move(inShape)) { }
+	void SetShape(ShapeRef inShape) { mShape = std::move(inShape); }
+	const ShapeRef &GetShape() const { return mShape; }
+	bool HasMassProperties() const { return mAllowDynamicOrKinematic || mMotionType != EMotionType::Static; }
+	MassProperties GetMassProperties() const // BodyCreationSettings.cpp:196-218
+	{
+		MassProperties mp;
+		switch (mOverrideMassProperties)
+		{
+		case EOverrideMassProperties::CalculateMassAndInertia:
+			mp = mShape->GetMassProperties();
+			for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) mp.mInertia[c][r] *= mInertiaMultiplier;
+			break;
+		case EOverrideMassProperties::CalculateInertia:
+			mp = mShape->GetMassProperties();
+			mp.ScaleToMass(mMassPropertiesOverride.mMass);
+			for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) mp.mInertia[c][r] *= mInertiaMultiplier;
+			break;
+		case EOverrideMassProperties::MassAndInertiaProvided:
+			mp = mMassPropertiesOverride;
+			break;
+		}
+		return mp;
+	}
+
+	RVec3 mPosition = RVec3::sZero();
+	Quat mRotation = Quat::sIdentity();
+	Vec3 mLinearVelocity = Vec3::sZero();
+	Vec3 mAngularVelocity = Vec3::sZero();
+	uint64 mUserData = 0;
+	ObjectLayer mObjectLayer = 0;
+	EMotionType mMotionType = EMotionType::Dynamic;
+	EAllowedDOFs mAllowedDOFs = EAllowedDOFs::All;
+	bool mAllowDynamicOrKinematic = false;
+	bool mIsSensor = false;
+	bool mCollideKinematicVsNonDynamic = false;
+	bool mUseManifoldReduction = true;
+	bool mApplyGyroscopicForce = false;
+	EMotionQuality mMotionQuality = EMotionQuality::Discrete;
+	bool mAllowSleeping = true;
+	float mFriction = 0.2f;
+	float mRestitution = 0.0f;
+	float mLinearDamping = 0.05f;
+	float mAngularDamping = 0.05f;
+	float mMaxLinearVelocity = 500.0f;
+	float mMaxAngularVelocity = 0.25f * JPH_PI * 60.0f;
+	float mGravityFactor = 1.0f;
+	uint mNumVelocityStepsOverride = 0;
+	uint mNumPositionStepsOverride = 0;
+	EOverrideMassProperties mOverrideMassProperties = EOverrideMassProperties::CalculateMassAndInertia;
+	float mInertiaMultiplier = 1.0f;
+	MassProperties mMassPropertiesOverride;
+private:
+	ShapeRef mShape;
+};
+
+struct PhysicsSettings
+{
+	float mBaumgarte = 0.2f;
+	float mSpeculativeContactDistance = 0.02f;
+	float mPenetrationSlop = 0.02f;
+	float mMaxPenetrationDistance = 0.2f;
+	float mManifoldTolerance = 1.0e-3f;
+	float mMinVelocityForRestitution = 1.0f;
+	float mTimeBeforeSleep = 0.5f;
+	float mPointVelocitySleepThreshold = 0.03f;
+	uint mNumVelocitySteps = 10;
+	uint mNumPositionSteps = 2;
+	bool mDeterministicSimulation = true;
+	bool mConstraintWarmStart = true;
+	bool mUseBodyPairContactCache = true;
+	bool mUseManifoldReduction = true;
+	bool mUseLargeIslandSplitter = true;
+	bool mAllowSleeping = true;
+	bool mCheckActiveEdges = true;
+};
+
+// ---- listeners ------------------------------------------------------------------------------------------------------
+struct ContactManifold
+{
+	RVec3 mBaseOffset;
+	Vec3 mWorldSpaceNormal;
+	float mPenetrationDepth = 0.0f;
+	SubShapeID mSubShapeID1, mSubShapeID2;
+	std::vector<Vec3> mRelativeContactPointsOn1, mRelativeContactPointsOn2;
+};
+struct ContactSettings { float mCombinedFriction = 0, mCombinedRestitution = 0; bool mIsSensor = false; };
+
+// Host mirror of a body (what the reference hands to listeners)
+class Body
+{
+public:
+	const BodyID &GetID() const { return mID; }
+	RVec3 GetCenterOfMassPosition() const { return mPosition; }
+	Quat GetRotation() const { return mRotation; }
+	Vec3 GetLinearVelocity() const { return mLinearVelocity; }
+	Vec3 GetAngularVelocity() const { return mAngularVelocity; }
+	RVec3 GetPosition() const { return mPosition - mRotation * mShape->GetCenterOfMass(); }
+	bool IsActive() const { return mActive; }
+	bool IsStatic() const { return mMotionType == EMotionType::Static; }
+	bool IsDynamic() const { return mMotionType == EMotionType::Dynamic; }
+	EMotionType GetMotionType() const { return mMotionType; }
+	ObjectLayer GetObjectLayer() const { return mObjectLayer; }
+	uint64 GetUserData() const { return mUserData; }
+	const Shape *GetShape() const { return mShape.get(); }
+
+	BodyID mID;
+	RVec3 mPosition;              // centre of mass position
+	Quat mRotation;
+	Vec3 mLinearVelocity, mAngularVelocity;
+	ShapeRef mShape;
+	EMotionType mMotionType = EMotionType::Static;
+	ObjectLayer mObjectLayer = 0;
+	uint64 mUserData = 0;
+	bool mActive = false, mInWorld = false, mDestroyed = false;
+	b2j_body_desc mDesc;          // creation time descriptor (uploaded by AddBody)
+};
+
+class ContactListener
+{
+public:
+	virtual ~ContactListener() = default;
+	virtual void OnContactAdded(const Body &, const Body &, const ContactManifold &, ContactSettings &) { }
+	virtual void OnContactPersisted(const Body &, const Body &, const ContactManifold &, ContactSettings &) { }
+	virtual void OnContactRemoved(const SubShapeIDPair &) { }
+};
+
+class BodyActivationListener
+{
+public:
+	virtual ~BodyActivationListener() = default;
+	virtual void OnBodyActivated(const BodyID &, uint64) = 0;
+	virtual void OnBodyDeactivated(const BodyID &, uint64) = 0;
+};
+
+class PhysicsSystem;
+
+// ---- BodyInterface ----------------------------------------------------------------------------------------------------
+class BodyInterface
+{
+public:
+	// BodyInterface::CreateBody (BodyInterface.cpp:30-39): nullptr when out of bodies
+	Body *CreateBody(const BodyCreationSettings &inSettings);
+	void AddBody(const BodyID &inBodyID, EActivation inActivationMode);
+	BodyID CreateAndAddBody(const BodyCreationSettings &inSettings, EActivation inActivationMode)
+	{
+		Body *b = CreateBody(inSettings);
+		if (b == nullptr) return BodyID();
+		AddBody(b->GetID(), inActivationMode);
+		return b->GetID();
+	}
+	// Bulk add (AddBodiesPrepare / Finalize, BodyInterface.h:124-133): one upload for all bodies
+	void AddBodies(const BodyID *inBodies, int inNumber, EActivation inActivationMode);
+	void RemoveBody(const BodyID &inBodyID);
+	void DestroyBody(const BodyID &inBodyID);
+	void ActivateBody(const BodyID &inBodyID) { uint32 id = inBodyID.mID; Flush(); b2j_bodies_activate(World(), &id, 1); }
+	void DeactivateBody(const BodyID &inBodyID) { uint32 id = inBodyID.mID; Flush(); b2j_bodies_deactivate(World(), &id, 1); }
+	bool IsActive(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->mActive; }
+	bool IsAdded(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->mInWorld; }
+
+	RVec3 GetPosition(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetPosition() : RVec3::sZero(); }
+	RVec3 GetCenterOfMassPosition(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mPosition : RVec3::sZero(); }
+	Quat GetRotation(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mRotation : Quat::sIdentity(); }
+	Vec3 GetLinearVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mLinearVelocity : Vec3::sZero(); }
+	Vec3 GetAngularVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mAngularVelocity : Vec3::sZero(); }
+	void GetPositionAndRotation(const BodyID &id, RVec3 &outPosition, Quat &outRotation) const { outPosition = GetPosition(id); outRotation = GetRotation(id); }
+	void SetPositionAndRotation(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, EActivation inActivationMode);
+	void SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity);
+	void SetLinearVelocity(const BodyID &id, const Vec3 &v) { SetLinearAndAngularVelocity(id, v, GetAngularVelocity(id)); }
+	void SetAngularVelocity(const BodyID &id, const Vec3 &v) { SetLinearAndAngularVelocity(id, GetLinearVelocity(id), v); }
+	void AddForce(const BodyID &id, const Vec3 &inForce);
+	void AddTorque(const BodyID &id, const Vec3 &inTorque);
+	// Bulk force application from host arrays (n bodies, force/torque [n][3], either may be null): the RL pattern
+	void AddForcesAndTorques(const BodyID *inBodies, int inNumber, const float *inForces, const float *inTorques);
+	uint64 GetUserData(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mUserData : 0; }
+	const Shape *GetShape(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mShape.get() : nullptr; }
+	const Body *TryGet(const BodyID &id) const;
+
+private:
+	friend class PhysicsSystem;
+	b2j_world *World() const;
+	void Flush();
+	PhysicsSystem *mSystem = nullptr;
+};
+
+// ---- PhysicsSystem ----------------------------------------------------------------------------------------------------
+class PhysicsSystem
+{
+public:
+	PhysicsSystem() { mBodyInterface.mSystem = this; }
+	~PhysicsSystem() { if (mWorld) b2j_world_destroy(mWorld); }
+	PhysicsSystem(const PhysicsSystem &) = delete;
+
+	// PhysicsSystem::Init (PhysicsSystem.h:59). inNumBodyMutexes is ignored (the GPU owns the bodies during a step).
+	// inNumObjectLayers tells how many object layers to sample the virtual filters for (the reference has no such query).
+	bool Init(uint inMaxBodies, uint inNumBodyMutexes, uint inMaxBodyPairs, uint inMaxContactConstraints, const BroadPhaseLayerInterface &inBroadPhaseLayerInterface,
+		const ObjectVsBroadPhaseLayerFilter &inObjectVsBroadPhaseLayerFilter, const ObjectLayerPairFilter &inObjectLayerPairFilter, uint inNumObjectLayers = 2, int inDevice = 0)
+	{
+		(void)inNumBodyMutexes;
+		uint nb = inBroadPhaseLayerInterface.GetNumBroadPhaseLayers();
+		std::vector<uint8_t> o2bp(inNumObjectLayers), ovbp(inNumObjectLayers * nb), ovo(inNumObjectLayers * inNumObjectLayers);
+		for (uint o = 0; o < inNumObjectLayers; ++o)
+		{
+			o2bp[o] = (uint8_t)(BroadPhaseLayer::Type)inBroadPhaseLayerInterface.GetBroadPhaseLayer((ObjectLayer)o);
+			for (uint b = 0; b < nb; ++b) ovbp[o * nb + b] = inObjectVsBroadPhaseLayerFilter.ShouldCollide((ObjectLayer)o, BroadPhaseLayer((BroadPhaseLayer::Type)b));
+			for (uint o2 = 0; o2 < inNumObjectLayers; ++o2) ovo[o * inNumObjectLayers + o2] = inObjectLayerPairFilter.ShouldCollide((ObjectLayer)o, (ObjectLayer)o2);
+		}
+		b2j_world_desc desc;
+		memset(&desc, 0, sizeof(desc));
+		desc.max_bodies = inMaxBodies; desc.max_body_pairs = inMaxBodyPairs; desc.max_contact_constraints = inMaxContactConstraints;
+		desc.num_object_layers = inNumObjectLayers; desc.num_broadphase_layers = nb;
+		desc.object_to_broadphase = o2bp.data(); desc.object_vs_broadphase = ovbp.data(); desc.object_vs_object = ovo.data();
+		FillSettings(desc.settings);
+		desc.gravity[0] = mGravity.x; desc.gravity[1] = mGravity.y; desc.gravity[2] = mGravity.z;
+		desc.device = inDevice;
+		mWorld = b2j_world_create(&desc);
+		mBodies.clear();
+		mBodies.reserve(1024);
+		mMaxBodies = inMaxBodies;
+		return mWorld != nullptr;
+	}
+
+	void SetGravity(const Vec3 &g) { mGravity = g; if (mWorld) { float v[3] = { g.x, g.y, g.z }; b2j_world_set_gravity(mWorld, v); } }
+	Vec3 GetGravity() const { return mGravity; }
+	void SetPhysicsSettings(const PhysicsSettings &s) { mSettings = s; if (mWorld) { b2j_settings bs; FillSettings(bs); b2j_world_set_settings(mWorld, &bs); } }
+	const PhysicsSettings &GetPhysicsSettings() const { return mSettings; }
+	void SetContactListener(ContactListener *l) { mContactListener = l; }
+	ContactListener *GetContactListener() const { return mContactListener; }
+	void SetBodyActivationListener(BodyActivationListener *l) { mActivationListener = l; }
+	BodyActivationListener *GetBodyActivationListener() const { return mActivationListener; }
+	BodyInterface &GetBodyInterface() { return mBodyInterface; }
+	BodyInterface &GetBodyInterfaceNoLock() { return mBodyInterface; }
+	void OptimizeBroadPhase() { } // the device broadphase is rebuilt from scratch every step
+	uint GetNumBodies() const { return mWorld? b2j_num_bodies(mWorld) : 0; }
+	uint GetNumActiveBodies() const { return mWorld? b2j_num_active_bodies(mWorld) : 0; }
+	uint GetMaxBodies() const { return mMaxBodies; }
+	bool WereBodiesInContact(const BodyID &a, const BodyID &b) const { return mWorld && b2j_were_bodies_in_contact(mWorld, a.mID, b.mID) == 1; }
+	const b2j_step_stats &GetLastStepStats() const { return mStats; }
+	b2j_world *GetWorld() const { return mWorld; }
+	const char *GetLastError() const { return b2j_last_error(); }
+
+	// PhysicsSystem::Update (PhysicsSystem.h:162): uploads pending API mutations, runs the step on the GPU, mirrors the body state
+	// back to the host and replays contact / activation events into the listeners on the calling thread.
+	EPhysicsUpdateError Update(float inDeltaTime, int inCollisionSteps, TempAllocator *, JobSystem *)
+	{
+		mBodyInterface.Flush();
+		int r = b2j_step(mWorld, inDeltaTime, inCollisionSteps, &mStats);
+		if (r < 0)
+			return EPhysicsUpdateError(0x80000000u);
+		DownloadState();
+		ReplayEvents();
+		return EPhysicsUpdateError(r);
+	}
+
+private:
+	friend class BodyInterface;
+
+	void FillSettings(b2j_settings &s) const
+	{
+		b2j_settings_default(&s);
+		s.baumgarte = mSettings.mBaumgarte; s.speculative_contact_distance = mSettings.mSpeculativeContactDistance; s.penetration_slop = mSettings.mPenetrationSlop;
+		s.max_penetration_distance = mSettings.mMaxPenetrationDistance; s.manifold_tolerance = mSettings.mManifoldTolerance;
+		s.min_velocity_for_restitution = mSettings.mMinVelocityForRestitution; s.time_before_sleep = mSettings.mTimeBeforeSleep;
+		s.point_velocity_sleep_threshold = mSettings.mPointVelocitySleepThreshold; s.num_velocity_steps = mSettings.mNumVelocitySteps; s.num_position_steps = mSettings.mNumPositionSteps;
+		s.constraint_warm_start = mSettings.mConstraintWarmStart; s.use_body_pair_contact_cache = mSettings.mUseBodyPairContactCache; s.use_manifold_reduction = mSettings.mUseManifoldReduction;
+		s.use_large_island_splitter = mSettings.mUseLargeIslandSplitter; s.allow_sleeping = mSettings.mAllowSleeping; s.check_active_edges = mSettings.mCheckActiveEdges;
+	}
+
+	int32_t ShapeID(const ShapeRef &inShape)
+	{
+		for (size_t i = 0; i < mShapes.size(); ++i) if (mShapes[i].get() == inShape.get()) return mShapeIDs[i];
+		int32_t id = inShape->Upload(mWorld);
+		mShapes.push_back(inShape); mShapeIDs.push_back(id);
+		return id;
+	}
+
+	void DownloadState()
+	{
+		uint32 n = (uint32)mBodies.size();
+		if (n == 0) return;
+		mPos.resize(3 * n); mRot.resize(4 * n); mLin.resize(3 * n); mAng.resize(3 * n); mActiveIndex.resize(n);
+		b2j_body_state st;
+		memset(&st, 0, sizeof(st));
+		st.position = mPos.data(); st.rotation = mRot.data(); st.linear_velocity = mLin.data(); st.angular_velocity = mAng.data(); st.active_index = mActiveIndex.data();
+		b2j_bodies_get_state(mWorld, nullptr, n, &st);
+		for (uint32 i = 0; i < n; ++i)
+		{
+			Body &b = *mBodies[i];
+			if (!b.mInWorld) continue;
+			b.mPosition = Vec3(mPos[3 * i], mPos[3 * i + 1], mPos[3 * i + 2]);
+			b.mRotation = Quat(mRot[4 * i], mRot[4 * i + 1], mRot[4 * i + 2], mRot[4 * i + 3]);
+			b.mLinearVelocity = Vec3(mLin[3 * i], mLin[3 * i + 1], mLin[3 * i + 2]);
+			b.mAngularVelocity = Vec3(mAng[3 * i], mAng[3 * i + 1], mAng[3 * i + 2]);
+			b.mActive = mActiveIndex[i] != B2J_INACTIVE_INDEX;
+		}
+	}
+
+	void ReplayEvents()
+	{
+		if (mActivationListener != nullptr)
+		{
+			uint32 n = b2j_activation_events_drain(mWorld, nullptr, 0);
+			mActEvents.resize(n);
+			if (n > 0) b2j_activation_events_drain(mWorld, mActEvents.data(), n);
+			for (const b2j_activation_event &e : mActEvents)
+			{
+				BodyID id(e.body);
+				const Body *b = mBodyInterface.TryGet(id);
+				if (e.kind == B2J_EVENT_BODY_ACTIVATED) mActivationListener->OnBodyActivated(id, b? b->mUserData : 0);
+				else mActivationListener->OnBodyDeactivated(id, b? b->mUserData : 0);
+			}
+		}
+		if (mContactListener != nullptr)
+		{
+			uint32 n = b2j_events_drain(mWorld, nullptr, 0);
+			mContactEvents.resize(n);
+			if (n > 0) b2j_events_drain(mWorld, mContactEvents.data(), n);
+			for (const b2j_contact_event &e : mContactEvents)
+			{
+				if (e.kind == B2J_EVENT_CONTACT_REMOVED)
+				{
+					SubShapeIDPair p;
+					p.mBody1ID = BodyID(e.body1); p.mBody2ID = BodyID(e.body2); p.mSubShapeID1.mValue = e.sub_shape1; p.mSubShapeID2.mValue = e.sub_shape2;
+					mContactListener->OnContactRemoved(p);
+					continue;
+				}
+				const Body *b1 = mBodyInterface.TryGet(BodyID(e.body1)), *b2 = mBodyInterface.TryGet(BodyID(e.body2));
+				if (b1 == nullptr || b2 == nullptr) continue;
+				ContactManifold m;
+				m.mBaseOffset = Vec3(e.base_offset[0], e.base_offset[1], e.base_offset[2]);
+				m.mWorldSpaceNormal = Vec3(e.normal[0], e.normal[1], e.normal[2]);
+				m.mPenetrationDepth = e.penetration_depth;
+				m.mSubShapeID1.mValue = e.sub_shape1; m.mSubShapeID2.mValue = e.sub_shape2;
+				for (uint32 i = 0; i < e.num_points; ++i)
+				{
+					m.mRelativeContactPointsOn1.push_back(Vec3(e.points1[i][0], e.points1[i][1], e.points1[i][2]));
+					m.mRelativeContactPointsOn2.push_back(Vec3(e.points2[i][0], e.points2[i][1], e.points2[i][2]));
+				}
+				ContactSettings s;
+				if (e.kind == B2J_EVENT_CONTACT_ADDED) mContactListener->OnContactAdded(*b1, *b2, m, s);
+				else mContactListener->OnContactPersisted(*b1, *b2, m, s);
+			}
+		}
+	}
+
+	b2j_world *mWorld = nullptr;
+	uint mMaxBodies = 0;
+	Vec3 mGravity = Vec3(0.0f, -9.81f, 0.0f);
+	PhysicsSettings mSettings;
+	ContactListener *mContactListener = nullptr;
+	BodyActivationListener *mActivationListener = nullptr;
+	BodyInterface mBodyInterface;
+	std::vector<std::unique_ptr<Body>> mBodies;   // by body index
+	std::vector<uint32> mFreeIndices;
+	std::vector<ShapeRef> mShapes;
+	std::vector<int32_t> mShapeIDs;
+	std::vector<b2j_body_desc> mPendingAdd;       // bodies added since the last flush
+	std::vector<uint32> mPendingActivate;
+	std::vector<uint32> mForceIDs;                // accumulated AddForce / AddTorque calls
+	std::vector<float> mForces, mTorques;
+	b2j_step_stats mStats = b2j_step_stats();
+	std::vector<float> mPos, mRot, mLin, mAng;
+	std::vector<uint32> mActiveIndex;
+	std::vector<b2j_contact_event> mContactEvents;
+	std::vector<b2j_activation_event> mActEvents;
+};
+
+// ---- BodyInterface implementation -----------------------------------------------------------------------------------
+inline b2j_world *BodyInterface::World() const { return mSystem->mWorld; }
+
+inline const Body *BodyInterface::TryGet(const BodyID &id) const
+{
+	uint32 idx = id.GetIndex();
+	if (id.IsInvalid() || idx >= mSystem->mBodies.size() || !mSystem->mBodies[idx] || mSystem->mBodies[idx]->mID != id || mSystem->mBodies[idx]->mDestroyed) return nullptr;
+	return mSystem->mBodies[idx].get();
+}
+
+inline Body *BodyInterface::CreateBody(const BodyCreationSettings &s)
+{
+	PhysicsSystem &sys = *mSystem;
+	uint32 index;
+	uint8 sequence = 1; // BodyManager::AddBody: sequence numbers start at 1 (BodyManager.cpp GetNextSequenceNumber)
+	if (!sys.mFreeIndices.empty()) { index = sys.mFreeIndices.back(); sys.mFreeIndices.pop_back(); sequence = uint8(sys.mBodies[index]? sys.mBodies[index]->mID.GetSequenceNumber() + 1 : 1); }
+	else
+	{
+		if (sys.mBodies.size() >= sys.mMaxBodies) return nullptr; // out of bodies
+		index = (uint32)sys.mBodies.size();
+		sys.mBodies.emplace_back();
+	}
+	std::unique_ptr<Body> body(new Body);
+	body->mID = BodyID(index, sequence);
+	body->mShape = s.GetShape();
+	body->mMotionType = s.mMotionType;
+	body->mObjectLayer = s.mObjectLayer;
+	body->mUserData = s.mUserData;
+	body->mRotation = s.mRotation;
+	// Body::SetPositionAndRotationInternal: mPosition = inPosition + inRotation * shape centre of mass
+	body->mPosition = s.mPosition + s.mRotation * body->mShape->GetCenterOfMass();
+	body->mLinearVelocity = s.mLinearVelocity;
+	body->mAngularVelocity = s.mAngularVelocity;
+
+	b2j_body_desc &d = body->mDesc;
+	memset(&d, 0, sizeof(d));
+	d.id = body->mID.mID;
+	d.shape = sys.ShapeID(body->mShape);
+	d.motion_type = (uint8_t)s.mMotionType;
+	d.allowed_dofs = (uint8_t)s.mAllowedDOFs;
+	d.num_velocity_steps_override = (uint8_t)s.mNumVelocityStepsOverride;
+	d.num_position_steps_override = (uint8_t)s.mNumPositionStepsOverride;
+	d.object_layer = s.mObjectLayer;
+	d.flags = (uint16_t)((s.mIsSensor? B2J_BODY_SENSOR : 0) | (s.mAllowSleeping? B2J_BODY_ALLOW_SLEEPING : 0) | (s.mUseManifoldReduction? B2J_BODY_USE_MANIFOLD_REDUCTION : 0)
+		| (s.mApplyGyroscopicForce? B2J_BODY_GYROSCOPIC : 0) | (s.mCollideKinematicVsNonDynamic? B2J_BODY_KIN_VS_NONDYN : 0));
+	d.position[0] = body->mPosition.x; d.position[1] = body->mPosition.y; d.position[2] = body->mPosition.z;
+	d.rotation[0] = s.mRotation.x; d.rotation[1] = s.mRotation.y; d.rotation[2] = s.mRotation.z; d.rotation[3] = s.mRotation.w;
+	d.linear_velocity[0] = s.mLinearVelocity.x; d.linear_velocity[1] = s.mLinearVelocity.y; d.linear_velocity[2] = s.mLinearVelocity.z;
+	d.angular_velocity[0] = s.mAngularVelocity.x; d.angular_velocity[1] = s.mAngularVelocity.y; d.angular_velocity[2] = s.mAngularVelocity.z;
+	d.inertia_rotation[3] = 1.0f;
+	d.linear_damping = s.mLinearDamping; d.angular_damping = s.mAngularDamping;
+	d.max_linear_velocity = s.mMaxLinearVelocity; d.max_angular_velocity = s.mMaxAngularVelocity;
+	d.gravity_factor = s.mGravityFactor; d.friction = s.mFriction; d.restitution = s.mRestitution;
+	if (s.HasMassProperties() && s.mMotionType != EMotionType::Static)
+	{
+		// MotionProperties::SetMassProperties (MotionProperties.cpp:12-61)
+		MassProperties mp = s.GetMassProperties();
+		uint dofs = (uint)s.mAllowedDOFs;
+		d.inv_mass = (dofs & 7) == 0? 0.0f : 1.0f / mp.mMass;
+		if (((dofs >> 3) & 7) != 0)
+		{
+			Quat rot; Vec3 diag;
+			if (mp.DecomposePrincipalMomentsOfInertia(rot, diag) && !(diag.LengthSq() <= 1.0e-12f))
+			{
+				d.inv_inertia_diag[0] = 1.0f / diag.x; d.inv_inertia_diag[1] = 1.0f / diag.y; d.inv_inertia_diag[2] = 1.0f / diag.z;
+				d.inertia_rotation[0] = rot.x; d.inertia_rotation[1] = rot.y; d.inertia_rotation[2] = rot.z; d.inertia_rotation[3] = rot.w;
+			}
+			else
+				d.inv_inertia_diag[0] = d.inv_inertia_diag[1] = d.inv_inertia_diag[2] = 2.5f * d.inv_mass;
+		}
+		if (s.mMotionType != EMotionType::Dynamic) d.inv_mass = 0.0f;
+	}
+	d.has_bounds = 0; // bounds and sleep test spheres are computed on the device from shape + pose
+	Body *result = body.get();
+	sys.mBodies[index] = std::move(body);
+	return result;
+}
+
+inline void BodyInterface::AddBodies(const BodyID *inBodies, int inNumber, EActivation inActivationMode)
+{
+	PhysicsSystem &sys = *mSystem;
+	for (int i = 0; i < inNumber; ++i)
+	{
+		Body *b = const_cast<Body *>(TryGet(inBodies[i]));
+		if (b == nullptr || b->mInWorld) continue;
+		b->mInWorld = true;
+		sys.mPendingAdd.push_back(b->mDesc);
+		if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static)
+		{
+			sys.mPendingActivate.push_back(b->mID.mID);
+			b->mActive = true;
+		}
+	}
+}
+
+inline void BodyInterface::AddBody(const BodyID &inBodyID, EActivation inActivationMode) { AddBodies(&inBodyID, 1, inActivationMode); }
+
+inline void BodyInterface::Flush()
+{
+	PhysicsSystem &sys = *mSystem;
+	if (!sys.mPendingAdd.empty())
+	{
+		b2j_bodies_add(sys.mWorld, sys.mPendingAdd.data(), (uint32)sys.mPendingAdd.size());
+		sys.mPendingAdd.clear();
+	}
+	if (!sys.mPendingActivate.empty())
+	{
+		b2j_bodies_activate(sys.mWorld, sys.mPendingActivate.data(), (uint32)sys.mPendingActivate.size());
+		sys.mPendingActivate.clear();
+	}
+	if (!sys.mForceIDs.empty())
+	{
+		b2j_bodies_add_force_torque(sys.mWorld, sys.mForceIDs.data(), (uint32)sys.mForceIDs.size(), sys.mForces.data(), sys.mTorques.data());
+		sys.mForceIDs.clear(); sys.mForces.clear(); sys.mTorques.clear();
+	}
+}
+
+inline void BodyInterface::RemoveBody(const BodyID &inBodyID)
+{
+	Body *b = const_cast<Body *>(TryGet(inBodyID));
+	if (b == nullptr || !b->mInWorld) return;
+	Flush();
+	uint32 id = inBodyID.mID;
+	b2j_bodies_remove(World(), &id, 1);
+	b->mInWorld = false; b->mActive = false;
+}
+
+inline void BodyInterface::DestroyBody(const BodyID &inBodyID)
+{
+	Body *b = const_cast<Body *>(TryGet(inBodyID));
+	if (b == nullptr) return;
+	if (b->mInWorld) RemoveBody(inBodyID);
+	mSystem->mFreeIndices.push_back(inBodyID.GetIndex());
+	b->mShape.reset();
+	b->mDestroyed = true; // the slot keeps the Body for its sequence number; it can no longer be looked up
+}
+
+inline void BodyInterface::SetPositionAndRotation(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, EActivation inActivationMode)
+{
+	Body *b = const_cast<Body *>(TryGet(id));
+	if (b == nullptr) return;
+	b->mRotation = inRotation;
+	b->mPosition = inPosition + inRotation * b->mShape->GetCenterOfMass();
+	if (!b->mInWorld) { b->mDesc.position[0] = b->mPosition.x; b->mDesc.position[1] = b->mPosition.y; b->mDesc.position[2] = b->mPosition.z; b->mDesc.rotation[0] = inRotation.x; b->mDesc.rotation[1] = inRotation.y; b->mDesc.rotation[2] = inRotation.z; b->mDesc.rotation[3] = inRotation.w; return; }
+	Flush();
+	uint32 bid = id.mID;
+	float pos[3] = { b->mPosition.x, b->mPosition.y, b->mPosition.z }, rot[4] = { inRotation.x, inRotation.y, inRotation.z, inRotation.w };
+	b2j_body_state st;
+	memset(&st, 0, sizeof(st));
+	st.position = pos; st.rotation = rot;
+	b2j_bodies_set_state(World(), &bid, 1, &st);
+	if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static) b2j_bodies_activate(World(), &bid, 1);
+}
+
+inline void BodyInterface::SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &lv, const Vec3 &av)
+{
+	Body *b = const_cast<Body *>(TryGet(id));
+	if (b == nullptr || b->mMotionType == EMotionType::Static) return;
+	b->mLinearVelocity = lv; b->mAngularVelocity = av;
+	if (!b->mInWorld) { memcpy(b->mDesc.linear_velocity, &lv, 12); memcpy(b->mDesc.angular_velocity, &av, 12); return; }
+	Flush();
+	uint32 bid = id.mID;
+	float l[3] = { lv.x, lv.y, lv.z }, a[3] = { av.x, av.y, av.z };
+	b2j_body_state st;
+	memset(&st, 0, sizeof(st));
+	st.linear_velocity = l; st.angular_velocity = a;
+	b2j_bodies_set_state(World(), &bid, 1, &st);
+	// BodyInterface::SetLinearAndAngularVelocity activates the body when the velocity is non zero
+	if (lv.LengthSq() > 0.0f || av.LengthSq() > 0.0f) b2j_bodies_activate(World(), &bid, 1);
+}
+
+inline void BodyInterface::AddForce(const BodyID &id, const Vec3 &f)
+{
+	PhysicsSystem &sys = *mSystem;
+	sys.mForceIDs.push_back(id.mID);
+	sys.mForces.push_back(f.x); sys.mForces.push_back(f.y); sys.mForces.push_back(f.z);
+	sys.mTorques.push_back(0); sys.mTorques.push_back(0); sys.mTorques.push_back(0);
+}
+
+inline void BodyInterface::AddTorque(const BodyID &id, const Vec3 &t)
+{
+	PhysicsSystem &sys = *mSystem;
+	sys.mForceIDs.push_back(id.mID);
+	sys.mForces.push_back(0); sys.mForces.push_back(0); sys.mForces.push_back(0);
+	sys.mTorques.push_back(t.x); sys.mTorques.push_back(t.y); sys.mTorques.push_back(t.z);
+}
+
+inline void BodyInterface::AddForcesAndTorques(const BodyID *inBodies, int inNumber, const float *inForces, const float *inTorques)
+{
+	Flush();
+	static_assert(sizeof(BodyID) == sizeof(uint32_t), "BodyID must be a plain 32 bit id");
+	b2j_bodies_add_force_torque(World(), reinterpret_cast<const uint32_t *>(inBodies), (uint32)inNumber, inForces, inTorques);
+}
+
+} // namespace JPH_B200

@@ -12,6 +12,8 @@
 #include <vector>
 #include <stdio.h>
 #include <stdlib.h>
+#include <typeinfo>
+#include <cxxabi.h>
 
 #ifndef B2J_HOSTSIM
 #include <cub/cub.cuh>
@@ -50,9 +52,66 @@ template <class K> __global__ void __launch_bounds__(128) run_kernel_slot(const 
 }
 #endif
 
+// kernel categories for the optional per kernel timing (one id per kernel functor type, process wide)
+inline std::vector<std::string> &profile_names() { static std::vector<std::string> n; return n; }
+template <class K> inline int profile_category()
+{
+	static int id = [] {
+		int status = 0;
+		char *dm = abi::__cxa_demangle(typeid(K).name(), nullptr, nullptr, &status);
+		std::string name = dm != nullptr? dm : typeid(K).name();
+		free(dm);
+		size_t p = name.rfind("::");
+		if (p != std::string::npos) name = name.substr(p + 2);
+		profile_names().push_back(name);
+		return (int)profile_names().size() - 1;
+	}();
+	return id;
+}
+
 struct Runtime
 {
 	int device = 0;
+	bool profiling = false;
+	std::vector<double> prof_ms;
+	std::vector<uint32_t> prof_launches;
+#ifndef B2J_HOSTSIM
+	struct ProfEvent { cudaEvent_t a, b; int cat; };
+	std::vector<ProfEvent> prof_pending, prof_free;
+	void prof_begin(int cat)
+	{
+		ProfEvent e;
+		if (!prof_free.empty()) { e = prof_free.back(); prof_free.pop_back(); }
+		else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
+		e.cat = cat;
+		cudaEventRecord(e.a, stream);
+		prof_pending.push_back(e);
+	}
+	void prof_end() { cudaEventRecord(prof_pending.back().b, stream); }
+#else
+	void prof_begin(int) { }
+	void prof_end() { }
+#endif
+	// accumulate the timings of all launches since the last call (the stream must be idle)
+	void prof_collect()
+	{
+#ifndef B2J_HOSTSIM
+		for (ProfEvent &e : prof_pending)
+		{
+			float ms = 0.0f;
+			if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess)
+			{
+				if ((size_t)e.cat >= prof_ms.size()) { prof_ms.resize(e.cat + 1, 0.0); prof_launches.resize(e.cat + 1, 0); }
+				prof_ms[e.cat] += ms;
+				prof_launches[e.cat] += 1;
+			}
+			prof_free.push_back(e);
+		}
+		prof_pending.clear();
+#endif
+	}
+	void prof_reset() { prof_collect(); prof_ms.assign(prof_ms.size(), 0.0); prof_launches.assign(prof_launches.size(), 0); }
+
 	int num_sms = 148;
 	uint32_t launches = 0;          // kernels launched since the last reset
 	void *cub_temp = nullptr;
@@ -182,7 +241,9 @@ struct Runtime
 		if (n == 0) return;
 		++launches;
 #ifndef B2J_HOSTSIM
+		if (profiling) prof_begin(profile_category<K>());
 		run_kernel<K><<<grid_for(n, 128), 128, 0, stream>>>(k, n);
+		if (profiling) prof_end();
 #else
 		for (uint32_t i = 0; i < n; ++i) k(i);
 #endif
@@ -195,7 +256,9 @@ struct Runtime
 #ifndef B2J_HOSTSIM
 		uint32_t g = grid_for(cap, 128);
 		uint32_t gmax = (uint32_t)num_sms * 8;
+		if (profiling) prof_begin(profile_category<K>());
 		run_kernel_dev<K><<<g > gmax? gmax : g, 128, 0, stream>>>(k, n_ptr, begin_ptr, cap);
+		if (profiling) prof_end();
 #else
 		uint32_t n = *n_ptr < cap? *n_ptr : cap;
 		uint32_t begin = begin_ptr? *begin_ptr : 0;
@@ -212,7 +275,9 @@ struct Runtime
 		if (g < 1) g = 1;
 		uint32_t gn = grid_for(cap, 128);
 		if (gn < g) g = gn;
+		if (profiling) prof_begin(profile_category<K>());
 		run_kernel_slot<K><<<g, 128, 0, stream>>>(k, n_ptr, cap);
+		if (profiling) prof_end();
 #else
 		(void)num_slots;
 		uint32_t n = *n_ptr < cap? *n_ptr : cap;

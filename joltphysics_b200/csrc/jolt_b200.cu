@@ -921,6 +921,33 @@ int b2j_world_set_settings(b2j_world *W, const b2j_settings *s) { W->d.settings 
 int b2j_world_get_settings(const b2j_world *W, b2j_settings *s) { *s = W->d.settings; return 0; }
 int b2j_world_set_previous_delta_time(b2j_world *W, float dt) { W->prev_dt = dt; return 0; }
 
+int b2j_world_set_profiling(b2j_world *W, int on)
+{
+	W->rt.sync();
+	W->rt.prof_reset();
+	W->rt.profiling = on != 0;
+	return 0;
+}
+
+uint32_t b2j_world_get_profile(b2j_world *W, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap)
+{
+	W->rt.sync();
+	W->rt.prof_collect();
+	uint32_t n = 0;
+	for (size_t i = 0; i < W->rt.prof_ms.size(); ++i)
+	{
+		if (W->rt.prof_launches[i] == 0) continue;
+		if (n < cap)
+		{
+			if (names != nullptr && name_stride > 0) { strncpy(names + (size_t)n * name_stride, profile_names()[i].c_str(), name_stride - 1); names[(size_t)n * name_stride + name_stride - 1] = 0; }
+			if (ms != nullptr) ms[n] = (float)W->rt.prof_ms[i];
+			if (launches != nullptr) launches[n] = W->rt.prof_launches[i];
+		}
+		++n;
+	}
+	return n;
+}
+
 static int32_t add_shape(b2j_world *W, const ShapeDesc &s)
 {
 	W->h_shapes.push_back(s);
@@ -1331,6 +1358,7 @@ int b2j_step(b2j_world *W, float delta_time, int collision_steps, b2j_step_stats
 			return -1;
 		errors |= W->h_counters.error_bits;
 	}
+	if (rt.profiling) { rt.sync(); rt.prof_collect(); }
 	if (stats != nullptr)
 	{
 #ifndef B2J_HOSTSIM

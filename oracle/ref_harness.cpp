@@ -338,6 +338,14 @@ World *sScenePile(int inNumBodies, int inShapeMask)
 	add_static(Vec3(half_width + 2.0f, wall_h, 1.0f), Vec3(0, wall_h, -half_width - 1.0f));
 	add_static(Vec3(half_width + 2.0f, wall_h, 1.0f), Vec3(0, wall_h, half_width + 1.0f));
 
+	// palette of 256 random 12 point hulls (own generator so that the body loop below only draws jitter + rotation)
+	std::mt19937 hull_random(4242);
+	Array<Ref<Shape>> hulls;
+	if (inShapeMask <= 0 || (inShapeMask & 8))
+		for (int i = 0; i < 256; ++i)
+			hulls.push_back(sRandomHull(hull_random, 0.5f));
+	uint hull_idx = 0;
+
 	std::mt19937 random(12345);
 	std::uniform_real_distribution<float> jitter(-0.05f, 0.05f);
 	Ref<Shape> sphere = new SphereShape(0.5f);
@@ -363,7 +371,7 @@ World *sScenePile(int inNumBodies, int inShapeMask)
 				case 0: s.SetShape(sphere); break;
 				case 1: s.SetShape(box); break;
 				case 2: s.SetShape(capsule); break;
-				default: s.SetShape(sRandomHull(random, 0.5f)); break;
+				default: s.SetShape(hulls[hull_idx++ % hulls.size()]); break;
 				}
 				s.mMotionType = EMotionType::Dynamic;
 				s.mObjectLayer = Layers::MOVING;
@@ -587,6 +595,60 @@ void *jref_export_to_b2j(void *h, int inDevice)
 	World *w = (World *)h;
 	if (sApi.handle == nullptr) { sLastError = "jref_bind_b2j not called"; return nullptr; }
 	return b2j_adapter::sExportWorld(sApi, w->system, Layers::NUM_LAYERS, inDevice, w->max_body_pairs, w->max_contact_constraints, sLastError);
+}
+
+// Writes the cooked convex hulls and meshes of the world (unique shapes, in body order) to a 'B2JS' file: the cooked assets the
+// product's facade loads (cooking is host-side and out of scope). Returns the number of shapes written or -1.
+int jref_dump_cooked_shapes(void *h, const char *inPath)
+{
+	World *w = (World *)h;
+	FILE *f = fopen(inPath, "wb");
+	if (f == nullptr) return -1;
+	std::vector<const Shape *> shapes;
+	BodyIDVector ids;
+	w->system.GetBodies(ids);
+	const BodyLockInterfaceNoLock &li = w->system.GetBodyLockInterfaceNoLock();
+	for (BodyID id : ids)
+	{
+		const Shape *s = li.TryGetBody(id)->GetShape();
+		if ((s->GetSubType() == EShapeSubType::ConvexHull || s->GetSubType() == EShapeSubType::Mesh) && std::find(shapes.begin(), shapes.end(), s) == shapes.end())
+			shapes.push_back(s);
+	}
+	auto put32 = [f](uint32_t v) { fwrite(&v, 4, 1, f); };
+	auto putf = [f](float v) { fwrite(&v, 4, 1, f); };
+	auto putv = [&](Vec3Arg v) { putf(v.GetX()); putf(v.GetY()); putf(v.GetZ()); };
+	put32(0x534a3242u);
+	put32((uint32_t)shapes.size());
+	for (const Shape *s : shapes)
+	{
+		if (s->GetSubType() == EShapeSubType::ConvexHull)
+		{
+			const ConvexHullShape *hull = static_cast<const ConvexHullShape *>(s);
+			put32(B2J_SHAPE_CONVEX_HULL);
+			put32((uint32_t)hull->mPoints.size()); put32((uint32_t)hull->mFaces.size()); put32((uint32_t)hull->mVertexIdx.size());
+			putf(hull->mConvexRadius); putv(hull->mCenterOfMass); putv(hull->mLocalBounds.mMin); putv(hull->mLocalBounds.mMax);
+			putf(hull->mInnerRadius); putf(hull->mVolume);
+			for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) putf(hull->mInertia(r, c));
+			for (const ConvexHullShape::Point &p : hull->mPoints) putv(p.mPosition);
+			for (const ConvexHullShape::Point &p : hull->mPoints) put32((uint32_t)p.mNumFaces);
+			for (const ConvexHullShape::Point &p : hull->mPoints) for (int i = 0; i < 3; ++i) put32((uint32_t)p.mFaces[i]);
+			for (const ConvexHullShape::Face &fc : hull->mFaces) fwrite(&fc.mFirstVertex, 2, 1, f);
+			for (const ConvexHullShape::Face &fc : hull->mFaces) fwrite(&fc.mNumVertices, 2, 1, f);
+			for (const Plane &p : hull->mPlanes) { putv(p.GetNormal()); putf(p.GetConstant()); }
+			fwrite(hull->mVertexIdx.data(), 1, hull->mVertexIdx.size(), f);
+		}
+		else
+		{
+			const MeshShape *mesh = static_cast<const MeshShape *>(s);
+			put32(B2J_SHAPE_MESH);
+			put32((uint32_t)mesh->mTree.size());
+			AABox b = mesh->GetLocalBounds();
+			putv(b.mMin); putv(b.mMax);
+			fwrite(mesh->mTree.data(), 1, mesh->mTree.size(), f);
+		}
+	}
+	fclose(f);
+	return (int)shapes.size();
 }
 
 void jref_get_settings(void *h, b2j_settings *outSettings) { b2j_adapter::sFillSettings(((World *)h)->system.GetPhysicsSettings(), *outSettings); }

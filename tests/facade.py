@@ -1,0 +1,61 @@
+"""ctypes wrapper of the facade C interface (joltphysics_b200/host/facade_capi.cpp): scenes built through the C++ facade."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from joltphysics_b200 import _capi
+import refharness as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ASSETS = os.path.join(ROOT, "bench_assets")
+
+
+class FacadeLib:
+    def __init__(self, path, api):
+        self.api = api
+        self.lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        L = self.lib
+        L.b2jf_last_error.restype = C.c_char_p
+        L.b2jf_scene_create.restype = C.c_void_p
+        L.b2jf_scene_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+        L.b2jf_scene_destroy.argtypes = [C.c_void_p]
+        L.b2jf_scene_world.restype = C.c_void_p
+        L.b2jf_scene_world.argtypes = [C.c_void_p]
+        L.b2jf_scene_num_dynamic.restype = C.c_uint32
+        L.b2jf_scene_num_dynamic.argtypes = [C.c_void_p]
+        L.b2jf_scene_num_bodies.restype = C.c_uint32
+        L.b2jf_scene_num_bodies.argtypes = [C.c_void_p]
+        L.b2jf_scene_flush.argtypes = [C.c_void_p]
+        L.b2jf_scene_update.argtypes = [C.c_void_p, C.c_float, C.c_int, C.POINTER(_capi.StepStats)]
+        L.b2jf_scene_step_e2e.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+
+
+class FacadeScene:
+    def __init__(self, flib, name, p0=0, p1=0):
+        self.flib = flib
+        self.h = flib.lib.b2jf_scene_create(name.encode(), p0, p1, ASSETS.encode())
+        if not self.h:
+            raise RuntimeError("b2jf_scene_create failed: " + flib.lib.b2jf_last_error().decode())
+        flib.lib.b2jf_scene_flush(self.h)
+        self.num_dynamic = flib.lib.b2jf_scene_num_dynamic(self.h)
+        self.num_bodies = flib.lib.b2jf_scene_num_bodies(self.h)
+        # a non-owning view of the underlying b2j world for state queries
+        self.world = R.B2JWorld(flib.api, flib.lib.b2jf_scene_world(self.h), self.num_bodies)
+
+    def close(self):
+        if self.h:
+            self.world.h = None  # owned by the scene
+            self.flib.lib.b2jf_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def update(self, dt=1.0 / 60.0, collision_steps=1):
+        stats = _capi.StepStats()
+        r = self.flib.lib.b2jf_scene_update(self.h, dt, collision_steps, C.byref(stats))
+        return r, stats
+
+    def step_e2e(self, dt, forces, out_positions):
+        return self.flib.lib.b2jf_scene_step_e2e(self.h, dt, forces.ctypes.data if forces is not None else None, out_positions.ctypes.data if out_positions is not None else None)

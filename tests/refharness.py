@@ -240,6 +240,19 @@ class B2JWorld:
         self.api.b2j_activation_events_drain(self.h, ev, n)
         return [(ev[i].kind, ev[i].body) for i in range(n)]
 
+    def profile(self):
+        """{kernel name: {"ms": device time, "launches": count}} accumulated since b2j_world_set_profiling(1)."""
+        cap, stride = 128, 64
+        names = C.create_string_buffer(cap * stride)
+        ms = (C.c_float * cap)()
+        launches = (C.c_uint32 * cap)()
+        n = self.api.b2j_world_get_profile(self.h, names, stride, ms, launches, cap)
+        out = {}
+        for i in range(min(n, cap)):
+            name = names.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()
+            out[name] = {"ms": float(ms[i]), "launches": int(launches[i])}
+        return out
+
     def active_bodies(self):
         n = self.api.b2j_num_active_bodies(self.h)
         out = np.zeros(max(n, 1), np.uint32)
