@@ -228,14 +228,13 @@ B2J_D void mesh_collide_sphere_triangle(const DWorld &w, const MeshCollideCtx &c
 struct KCollideMesh
 {
 	DWorld w; NarrowCtx c; MeshScratch *mesh_scratch;
-	B2J_D void run(uint32_t k, uint32_t slot) const
+	B2J_D void run(uint32_t k, uint32_t slot, EpaScratch &epa) const
 	{
 		CollideItem item = c.collide_mesh[k];
 		BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
 		const ShapeDesc &s1 = w.shapes[i1.shape], &s2 = w.shapes[i2.shape];
 		if (s2.kind != B2J_SHAPE_MESH || s1.kind == B2J_SHAPE_MESH)
 			return; // mesh as body 1 (sReversedCollideShape) is not on the path: meshes are static, body 1 has the higher motion type
-		EpaScratch &epa = c.scratch[slot];
 		MeshScratch &ms = mesh_scratch[slot];
 
 		MeshCollideCtx cc;

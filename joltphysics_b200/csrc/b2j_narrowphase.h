@@ -41,8 +41,7 @@ struct NarrowCtx
 	CollideItem *collide_convex, *collide_mesh;
 	CachedItem *cached;
 	EpaItem *epa;
-	EpaScratch *scratch;         // [num_scratch]
-	uint32_t num_scratch;
+	uint32_t num_scratch;        // number of warps the scratch hungry kernels (EPA, mesh) may use
 	ManifoldWS *man_ws;
 	ConstraintSrc *con_src;
 	uint32_t *woken_flag;        // per slot
@@ -491,8 +490,9 @@ struct KCollideConvex
 struct KCollideEpa
 {
 	DWorld w; NarrowCtx c;
-	B2J_D void run(uint32_t k, uint32_t slot) const
+	B2J_D void run(uint32_t k, uint32_t slot, EpaScratch &scratch) const
 	{
+		(void)slot;
 		const EpaItem &ei = c.epa[k];
 		CollideItem item = ei.c;
 		ConvexPairSetup s = convex_pair_setup(w, item);
@@ -503,7 +503,7 @@ struct KCollideEpa
 		a_incl.radius = max_separation_distance;
 		TransformedSupport b_incl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_INCLUDE_CONVEX_RADIUS));
 		V3 penetration_axis = ei.axis, point1, point2;
-		if (!pen_depth_step_epa(c.scratch[slot], ei.s, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2))
+		if (!pen_depth_step_epa(scratch, ei.s, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2))
 			return;
 		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, point1, point2, penetration_axis, max_separation_distance);
 	}

@@ -41,14 +41,22 @@ template <class K> __global__ void __launch_bounds__(128) run_kernel_dev(const K
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 		k(i);
 }
-// like run_kernel_dev but the functor also gets a unique slot per thread (scratch ownership)
-template <class K> __global__ void __launch_bounds__(128) run_kernel_slot(const K k, const uint32_t *n_ptr, uint32_t cap)
+// One WARP per work item for serial, scratch hungry item bodies (EPA): lane 0 runs the item with an S scratch block in shared
+// memory (low latency instead of a global memory slot); slot = global warp id (ownership of any global side scratch).
+template <class K, class S> __global__ void __launch_bounds__(128) run_kernel_warp_smem(const K k, const uint32_t *n_ptr, uint32_t cap)
 {
+	extern __shared__ __align__(16) unsigned char b2j_smem[];
 	uint32_t n = *n_ptr;
 	if (n > cap) n = cap;
-	uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-	for (uint32_t i = slot; i < n; i += gridDim.x * blockDim.x)
-		k.run(i, slot);
+	uint32_t warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
+	uint32_t slot = blockIdx.x * warps_per_block + warp_in_block;
+	S *scratch = reinterpret_cast<S *>(b2j_smem) + warp_in_block;
+	for (uint32_t i = slot; i < n; i += gridDim.x * warps_per_block)
+	{
+		if (lane == 0)
+			k.run(i, slot, *scratch);
+		__syncwarp();
+	}
 }
 #endif
 
@@ -144,10 +152,15 @@ struct Runtime
 	{
 #ifndef B2J_HOSTSIM
 		if (cub_temp) cudaFree(cub_temp);
+		if (stage_dev) cudaFree(stage_dev);
+		if (stage_host) cudaFreeHost(stage_host);
+		for (ProfEvent &e : prof_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+		prof_free.clear();
 		if (stream) cudaStreamDestroy(stream);
 #else
-		free(cub_temp);
+		free(cub_temp); free(stage_dev); free(stage_host);
 #endif
+		stage_dev = stage_host = nullptr; stage_cap = 0;
 		cub_temp = nullptr;
 	}
 
@@ -265,23 +278,82 @@ struct Runtime
 		for (uint32_t i = 0; begin + i < n; ++i) k(i);
 #endif
 	}
-	// device-resident count with per-thread scratch slots: at most num_slots threads
-	template <class K> void launch_slot(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots)
+	// device-resident count, one warp per item with an S scratch block in shared memory; uses at most num_slots warps
+	template <class K, class S> void launch_warp_smem(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots)
 	{
 		if (cap == 0) return;
 		++launches;
 #ifndef B2J_HOSTSIM
-		uint32_t g = num_slots / 128;
+		static bool configured = false;
+		if (!configured)
+		{
+			cudaFuncSetAttribute(run_kernel_warp_smem<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(S)));
+			configured = true;
+		}
+		uint32_t g = num_slots / 4;
 		if (g < 1) g = 1;
-		uint32_t gn = grid_for(cap, 128);
+		uint32_t gn = (cap + 3) / 4;
 		if (gn < g) g = gn;
 		if (profiling) prof_begin(profile_category<K>());
-		run_kernel_slot<K><<<g, 128, 0, stream>>>(k, n_ptr, cap);
+		run_kernel_warp_smem<K, S><<<g, 128, 4 * sizeof(S), stream>>>(k, n_ptr, cap);
 		if (profiling) prof_end();
 #else
 		(void)num_slots;
+		static S scratch;
 		uint32_t n = *n_ptr < cap? *n_ptr : cap;
-		for (uint32_t i = 0; i < n; ++i) k.run(i, 0);
+		for (uint32_t i = 0; i < n; ++i) k.run(i, 0, scratch);
+#endif
+	}
+
+	// ---- persistent staging: one device buffer + one pinned host mirror, bump allocated per API call (no cudaMalloc per call)
+	unsigned char *stage_dev = nullptr, *stage_host = nullptr;
+	size_t stage_cap = 0, stage_used = 0;
+	void stage_begin(size_t bytes)
+	{
+		bytes += 256 * 16;
+		if (bytes > stage_cap)
+		{
+			sync();
+			size_t ncap = bytes + bytes / 2;
+#ifndef B2J_HOSTSIM
+			if (stage_dev) cudaFree(stage_dev);
+			if (stage_host) cudaFreeHost(stage_host);
+			cudaMalloc((void **)&stage_dev, ncap);
+			cudaMallocHost((void **)&stage_host, ncap);
+#else
+			free(stage_dev); free(stage_host);
+			stage_dev = (unsigned char *)malloc(ncap);
+			stage_host = (unsigned char *)malloc(ncap);
+#endif
+			stage_cap = ncap;
+		}
+		stage_used = 0;
+	}
+	// returns the device pointer; *host receives the pinned mirror of the same region
+	template <class T> T *stage_alloc(size_t n, T **host)
+	{
+		size_t off = (stage_used + 255) & ~(size_t)255;
+		stage_used = off + n * sizeof(T);
+		*host = reinterpret_cast<T *>(stage_host + off);
+		return reinterpret_cast<T *>(stage_dev + off);
+	}
+	void stage_to_device(size_t begin, size_t end)
+	{
+		if (end <= begin) return;
+#ifndef B2J_HOSTSIM
+		cudaMemcpyAsync(stage_dev + begin, stage_host + begin, end - begin, cudaMemcpyHostToDevice, stream);
+#else
+		memcpy(stage_dev + begin, stage_host + begin, end - begin);
+#endif
+	}
+	void stage_to_host(size_t begin, size_t end)
+	{
+		if (end <= begin) return;
+#ifndef B2J_HOSTSIM
+		cudaMemcpyAsync(stage_host + begin, stage_dev + begin, end - begin, cudaMemcpyDeviceToHost, stream);
+		cudaStreamSynchronize(stream);
+#else
+		memcpy(stage_host + begin, stage_dev + begin, end - begin);
 #endif
 	}
 

@@ -470,8 +470,8 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KProcessPairs k; k.w = d; k.c = W->nc; k.first_ptr = W->d_round_begin; rt.launch_dev(k, &d.counters->num_pairs, W->d_round_begin, d.max_body_pairs); }
 		{ KCopyCached k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_cached, nullptr, d.max_body_pairs); }
 		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
-		{ KCollideEpa k; k.w = d; k.c = W->nc; rt.launch_slot(k, &d.counters->num_epa, W->nc.max_epa, W->nc.num_scratch); }
-		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_slot(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
+		{ KCollideEpa k; k.w = d; k.c = W->nc; rt.launch_warp_smem<KCollideEpa, EpaScratch>(k, &d.counters->num_epa, W->nc.max_epa, W->nc.num_scratch); }
+		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_warp_smem<KCollideMesh, EpaScratch>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
 		if (!read_counters(W)) return false;
 		uint32_t woken = W->h_counters.num_woken;
 		if (W->h_counters.num_epa > W->nc.max_epa) { last_error() = "EPA queue overflow"; return false; }
@@ -798,16 +798,13 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	nc.collide_convex = rt.alloc<CollideItem>(d.max_body_pairs);
 	nc.collide_mesh = rt.alloc<CollideItem>(d.max_body_pairs);
 	nc.cached = rt.alloc<CachedItem>(d.max_body_pairs);
-	nc.max_epa = d.max_body_pairs;
+	nc.max_epa = d.max_body_pairs / 4 + 1024;
 	nc.epa = rt.alloc<EpaItem>(nc.max_epa, false);
 #ifndef B2J_HOSTSIM
-	nc.num_scratch = (uint32_t)rt.num_sms * 128;
-	if (nc.num_scratch > next_pow2(d.max_body_pairs)) nc.num_scratch = next_pow2(d.max_body_pairs);
-	if (nc.num_scratch < 128) nc.num_scratch = 128;
+	nc.num_scratch = (uint32_t)rt.num_sms * 8; // 2 blocks of 4 warps per SM, each warp owns an EpaScratch in shared memory
 #else
 	nc.num_scratch = 1;
 #endif
-	nc.scratch = rt.alloc<EpaScratch>(nc.num_scratch, false);
 	nc.man_ws = rt.alloc<ManifoldWS>(d.max_constraints, false);
 	nc.con_src = rt.alloc<ConstraintSrc>(d.max_constraints, false);
 	nc.woken_flag = rt.alloc<uint32_t>(nbod);
@@ -842,7 +839,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	W->d_sort_keys[0] = rt.alloc<uint64_t>(mc); W->d_sort_keys[1] = rt.alloc<uint64_t>(mc);
 	W->d_sort_vals = rt.alloc<uint32_t>(mc);
 
-	if (W->d_sort_vals == nullptr || sc.con.cf == nullptr || nc.scratch == nullptr)
+	if (W->d_sort_vals == nullptr || sc.con.cf == nullptr )
 	{
 		last_error() = "out of device memory";
 		b2j_world_destroy(W);
@@ -889,7 +886,7 @@ void b2j_world_destroy(b2j_world *W)
 		rt.free_(W->cache[i].pairs); rt.free_(W->cache[i].manifolds); rt.free_(W->cache[i].pair_table); rt.free_(W->cache[i].num_pairs); rt.free_(W->cache[i].num_manifolds);
 	}
 	NarrowCtx &nc = W->nc;
-	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.scratch);
+	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(nc.events);
 	rt.free_(W->d_mesh_scratch);
 	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
@@ -1158,28 +1155,34 @@ int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 	if (n == 0) return 0;
 	Runtime &rt = W->rt;
 	sync_dworld(W);
+	if (ids == nullptr && n > W->d.max_bodies) { last_error() = "n exceeds max_bodies"; return -1; }
 	KGetState k; memset(&k, 0, sizeof(k)); k.w = W->d;
-	uint32_t *d_ids = nullptr;
-	if (ids != nullptr) { d_ids = rt.alloc<uint32_t>(n, false); rt.upload(d_ids, ids, n); }
-	else if (n > W->d.max_bodies) { last_error() = "n exceeds max_bodies"; return -1; }
-	k.ids = d_ids;
-	if (out->position) k.pos = rt.alloc<float>((size_t)n * 3, false);
-	if (out->rotation) k.rot = rt.alloc<float>((size_t)n * 4, false);
-	if (out->linear_velocity) k.lin = rt.alloc<float>((size_t)n * 3, false);
-	if (out->angular_velocity) k.ang = rt.alloc<float>((size_t)n * 3, false);
-	if (out->bounds) k.bounds = rt.alloc<float>((size_t)n * 6, false);
-	if (out->active_index) k.active_index = rt.alloc<uint32_t>(n, false);
-	if (out->sleep_timer) k.sleep_timer = rt.alloc<float>(n, false);
+	// one persistent staging buffer (device + pinned mirror): ids up, one kernel, one copy down
+	rt.stage_begin((size_t)n * (4 + 12 + 16 + 12 + 12 + 24 + 4 + 4));
+	uint32_t *h_ids = nullptr; float *h_pos = nullptr, *h_rot = nullptr, *h_lin = nullptr, *h_ang = nullptr, *h_bounds = nullptr, *h_timer = nullptr; uint32_t *h_active = nullptr;
+	if (ids != nullptr)
+	{
+		k.ids = rt.stage_alloc<uint32_t>(n, &h_ids);
+		memcpy(h_ids, ids, (size_t)n * 4);
+		rt.stage_to_device(0, rt.stage_used);
+	}
+	size_t out_begin = rt.stage_used;
+	if (out->position) k.pos = rt.stage_alloc<float>((size_t)n * 3, &h_pos);
+	if (out->rotation) k.rot = rt.stage_alloc<float>((size_t)n * 4, &h_rot);
+	if (out->linear_velocity) k.lin = rt.stage_alloc<float>((size_t)n * 3, &h_lin);
+	if (out->angular_velocity) k.ang = rt.stage_alloc<float>((size_t)n * 3, &h_ang);
+	if (out->bounds) k.bounds = rt.stage_alloc<float>((size_t)n * 6, &h_bounds);
+	if (out->active_index) k.active_index = rt.stage_alloc<uint32_t>(n, &h_active);
+	if (out->sleep_timer) k.sleep_timer = rt.stage_alloc<float>(n, &h_timer);
 	rt.launch(k, n);
-	if (k.pos) rt.download(out->position, k.pos, (size_t)n * 3);
-	if (k.rot) rt.download(out->rotation, k.rot, (size_t)n * 4);
-	if (k.lin) rt.download(out->linear_velocity, k.lin, (size_t)n * 3);
-	if (k.ang) rt.download(out->angular_velocity, k.ang, (size_t)n * 3);
-	if (k.bounds) rt.download(out->bounds, k.bounds, (size_t)n * 6);
-	if (k.active_index) rt.download(out->active_index, k.active_index, n);
-	if (k.sleep_timer) rt.download(out->sleep_timer, k.sleep_timer, n);
-	rt.sync();
-	rt.free_(d_ids); rt.free_(k.pos); rt.free_(k.rot); rt.free_(k.lin); rt.free_(k.ang); rt.free_(k.bounds); rt.free_(k.active_index); rt.free_(k.sleep_timer);
+	rt.stage_to_host(out_begin, rt.stage_used);
+	if (h_pos) memcpy(out->position, h_pos, (size_t)n * 12);
+	if (h_rot) memcpy(out->rotation, h_rot, (size_t)n * 16);
+	if (h_lin) memcpy(out->linear_velocity, h_lin, (size_t)n * 12);
+	if (h_ang) memcpy(out->angular_velocity, h_ang, (size_t)n * 12);
+	if (h_bounds) memcpy(out->bounds, h_bounds, (size_t)n * 24);
+	if (h_active) memcpy(out->active_index, h_active, (size_t)n * 4);
+	if (h_timer) memcpy(out->sleep_timer, h_timer, (size_t)n * 4);
 	return rt.check("b2j_bodies_get_state")? 0 : -1;
 }
 
@@ -1190,18 +1193,16 @@ int b2j_bodies_set_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 	sync_dworld(W);
 	upload_shapes(W);
 	KSetState k; memset(&k, 0, sizeof(k)); k.w = W->d;
-	uint32_t *d_ids = nullptr;
-	if (ids != nullptr) { d_ids = rt.alloc<uint32_t>(n, false); rt.upload(d_ids, ids, n); }
-	k.ids = d_ids;
-	float *dp = nullptr, *dr = nullptr, *dl = nullptr, *da = nullptr;
-	if (in->position) { dp = rt.alloc<float>((size_t)n * 3, false); rt.upload(dp, (const float *)in->position, (size_t)n * 3); }
-	if (in->rotation) { dr = rt.alloc<float>((size_t)n * 4, false); rt.upload(dr, (const float *)in->rotation, (size_t)n * 4); }
-	if (in->linear_velocity) { dl = rt.alloc<float>((size_t)n * 3, false); rt.upload(dl, (const float *)in->linear_velocity, (size_t)n * 3); }
-	if (in->angular_velocity) { da = rt.alloc<float>((size_t)n * 3, false); rt.upload(da, (const float *)in->angular_velocity, (size_t)n * 3); }
-	k.pos = dp; k.rot = dr; k.lin = dl; k.ang = da;
+	rt.stage_begin((size_t)n * (4 + 12 + 16 + 12 + 12));
+	uint32_t *h_ids = nullptr; float *h = nullptr;
+	if (ids != nullptr) { k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4); }
+	if (in->position) { k.pos = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, in->position, (size_t)n * 12); }
+	if (in->rotation) { k.rot = rt.stage_alloc<float>((size_t)n * 4, &h); memcpy(h, in->rotation, (size_t)n * 16); }
+	if (in->linear_velocity) { k.lin = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, in->linear_velocity, (size_t)n * 12); }
+	if (in->angular_velocity) { k.ang = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, in->angular_velocity, (size_t)n * 12); }
+	rt.stage_to_device(0, rt.stage_used);
 	rt.launch(k, n);
-	rt.sync();
-	rt.free_(d_ids); rt.free_(dp); rt.free_(dr); rt.free_(dl); rt.free_(da);
+	rt.sync(); // the staging buffer is reused by the next call
 	if (in->position || in->rotation)
 		for (uint32_t l = 0; l < W->d.num_bp_layers; ++l) W->layer_needs_build[l] = 1;
 	return rt.check("b2j_bodies_set_state")? 0 : -1;
@@ -1212,14 +1213,16 @@ int b2j_bodies_add_force_torque(b2j_world *W, const uint32_t *ids, uint32_t n, c
 	if (n == 0) return 0;
 	Runtime &rt = W->rt;
 	sync_dworld(W);
-	uint32_t *d_ids = rt.alloc<uint32_t>(n, false); rt.upload(d_ids, ids, n);
-	float *df = nullptr, *dt = nullptr;
-	if (force) { df = rt.alloc<float>((size_t)n * 3, false); rt.upload(df, force, (size_t)n * 3); }
-	if (torque) { dt = rt.alloc<float>((size_t)n * 3, false); rt.upload(dt, torque, (size_t)n * 3); }
-	KAddForceTorque k; k.w = W->d; k.ids = d_ids; k.force = df; k.torque = dt;
+	KAddForceTorque k; k.w = W->d;
+	rt.stage_begin((size_t)n * (4 + 12 + 12));
+	uint32_t *h_ids = nullptr; float *h = nullptr;
+	k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4);
+	k.force = nullptr; k.torque = nullptr;
+	if (force) { k.force = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, force, (size_t)n * 12); }
+	if (torque) { k.torque = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, torque, (size_t)n * 12); }
+	rt.stage_to_device(0, rt.stage_used);
 	rt.launch(k, n);
 	rt.sync();
-	rt.free_(d_ids); rt.free_(df); rt.free_(dt);
 	return rt.check("b2j_bodies_add_force_torque")? 0 : -1;
 }
 
