@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- PerformanceTest-style throughput of the B200 rigid-body step (steps/s and body-steps/s).
 
-  python bench.py --gpus N --steps K --warmup W [--workload pile|pyramid|convex_vs_mesh|max_bodies] [--bodies B]
+  python bench.py --gpus N --steps K --warmup W [--workload batch|pile|pyramid|convex_vs_mesh|max_bodies]
   python bench.py --impl reference ...     # the reference's own CPU implementation (oracle/_ref) on the same config
 
-A "step" is one PhysicsSystem::Update(1/60, 1) of the workload world, timed as PerformanceTest.cpp:380-391 does (Update only).
-`value` = body-steps/s with the world resident in HBM (CUDA events on the library's stream); `e2e` = the same metric through
-the reference-facing facade with HOST buffers every step (forces in, positions out). One world per GPU: under torchrun every
-rank steps its own replica (a single world does not shard) and the values are summed (weak scaling).
+Default workload = BASELINE.json configs[4], the one the "1/2/4/8 B200" metric is quoted on: 4096 independent Pyramid worlds
+(PerformanceTest -s=Pyramid, 1240 boxes each) batched RL-env style, sharded world_id -> rank over the N GPUs with no inter-GPU
+traffic on the data path (only the final statistics are reduced over NCCL). A "step" advances EVERY world of the job by one
+PhysicsSystem::Update(1/60, 1), timed as PerformanceTest.cpp:380-391 does (Update only); body-steps/s = steps/s x dynamic bodies.
+`value` = device resident (CUDA events on the library's stream), `e2e` = through the C ABI with HOST buffers every step
+(per body forces in, positions out). Single world workloads (--workload pile ...) run one replica per GPU.
 """
 import argparse
 import ctypes as C
@@ -23,46 +25,45 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DT = 1.0 / 60.0
-# SURVEY 8(d) byte constants
-S_V = 24
+S_V = 24  # bytes of (v, w) of one body
+PYRAMID_BODIES = 1240
+BATCH_PAIRS_PER_WORLD, BATCH_CONSTRAINTS_PER_WORLD = 16384, 12288  # SURVEY 8(d) config 5 limits
 
 
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=120)
-    p.add_argument("--warmup", type=int, default=120)
+    p.add_argument("--steps", type=int, default=60)
+    p.add_argument("--warmup", type=int, default=60)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--workload", default=os.environ.get("B2J_BENCH_WORKLOAD", "pile"))
-    p.add_argument("--bodies", type=int, default=int(os.environ.get("B2J_BENCH_BODIES", "1000000")))
-    p.add_argument("--ref-bodies", type=int, default=100000, help="bodies of the bounded sample the reference arm / cpu_baseline steps")
+    p.add_argument("--workload", default=os.environ.get("B2J_BENCH_WORKLOAD", "batch"))
+    p.add_argument("--worlds", type=int, default=int(os.environ.get("B2J_BENCH_WORLDS", "4096")), help="total worlds of the batch workload (sharded over the GPUs)")
+    p.add_argument("--bodies", type=int, default=int(os.environ.get("B2J_BENCH_BODIES", "1000000")), help="bodies of the pile / max_bodies workloads")
+    p.add_argument("--ref-bodies", type=int, default=100000, help="bodies of the bounded sample the CPU legs step for pile / max_bodies")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline leg")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-pile", action="store_true", help="skip the secondary single-world Pile-1M measurement at N=1")
     return p.parse_args()
 
 
-def scene_params(args, bodies=None):
-    b = bodies if bodies is not None else args.bodies
-    if args.workload == "pile":
-        return "pile", b, 15
-    if args.workload == "max_bodies":
-        return "max_bodies", b, 0
-    if args.workload == "pyramid":
+def scene_params(workload, bodies):
+    if workload == "pile":
+        return "pile", bodies, 15
+    if workload == "max_bodies":
+        return "max_bodies", bodies, 0
+    if workload in ("pyramid", "batch"):
         return "pyramid", 15, 0
-    if args.workload == "convex_vs_mesh":
+    if workload == "convex_vs_mesh":
         return "convex_vs_mesh", 10, 0
-    raise SystemExit("unknown workload " + args.workload)
+    raise SystemExit("unknown workload " + workload)
 
 
-def config_of(args, num_dynamic, extra=None):
-    cfg = {"workload": {"pile": "Pile (SURVEY 8d config 4: mixed sphere/box/capsule/12-point hull in a static box container)",
-                        "pyramid": "PerformanceTest -s=Pyramid", "convex_vs_mesh": "PerformanceTest -s=ConvexVsMesh",
-                        "max_bodies": "PerformanceTest -s=MaxBodies (N bodies)"}[args.workload],
-           "bodies": num_dynamic, "dt": DT, "collision_steps": 1,
-           "timing": "every step moves the whole world state through HBM (working set >> L2 for >= 1e5 bodies); no L2 flush between steps"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+WORKLOAD_NAMES = {
+    "batch": "4096 independent Pyramid worlds batched (BASELINE.json configs[4])",
+    "pile": "Pile (BASELINE.json configs[3] / SURVEY 8d config 4: mixed sphere/box/capsule/12-point hull in a static box container, one world)",
+    "pyramid": "PerformanceTest -s=Pyramid (configs[0])", "convex_vs_mesh": "PerformanceTest -s=ConvexVsMesh (configs[1])",
+    "max_bodies": "PerformanceTest -s=MaxBodies (configs[2], N bodies)",
+}
 
 
 class ClockSampler(threading.Thread):
@@ -70,11 +71,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.stop_flag = False
-        self.proc = None
+        self.index, self.samples, self.reasons, self.stop_flag, self.proc = index, [], set(), False, None
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -106,73 +103,220 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(self.reasons)}
 
 
-def run_reference(args):
-    """The reference's own CPU implementation (oracle/_ref, FMA build, all host threads) on a bounded sample of the config."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle/_ref = the unmodified reference compiled with plain g++, FMA build)
+# ---------------------------------------------------------------------------------------------------------------------
+
+def cpu_run(args, warmup, steps, budget_s):
+    """Times the reference on the host cores on a bounded sample of the workload. Returns (value, steps, warm, description, threads)."""
     import refharness as R
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    L = R.ref_lib("fast")
+    threads = L.jref_hardware_threads()
+    if args.workload == "batch":
+        # many small independent worlds: every host thread owns one world and steps it with a single threaded job system
+        # (no cross thread synchronisation -- the best case for the CPU); throughput scales with the number of worlds in flight
+        L.jref_time_worlds_parallel.restype = C.c_double
+        L.jref_time_worlds_parallel.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+        probe = L.jref_time_worlds_parallel(b"pyramid", 15, 0, threads, 1, 2, DT) / 2.0  # seconds per step with all threads busy
+        warm = max(3, min(warmup, int(0.35 * budget_s / max(probe, 1e-4))))
+        n = max(1, min(steps, int(0.55 * budget_s / max(probe, 1e-4))))
+        wall = L.jref_time_worlds_parallel(b"pyramid", 15, 0, threads, warm, n, DT)
+        value = threads * n * PYRAMID_BODIES / wall
+        return value, n, warm, f"{threads} concurrent Pyramid worlds (one per host thread, single threaded job system each) of the {args.worlds}, steps {warm}..{warm + n}", threads
+    bodies = min(args.bodies, args.ref_bodies) if args.workload in ("pile", "max_bodies") else args.bodies
+    scene, p0, p1 = scene_params(args.workload, bodies)
+    ref = R.RefWorld(scene, p0, p1, variant="fast")
+    ref.set_recording(False)
+    nd = ref.num_dynamic
+    t_first = ref.time_steps(1, DT, threads)
+    warm = max(3, min(warmup, int(0.35 * budget_s / max(t_first, 1e-4))))
+    n = max(1, min(steps, int(0.55 * budget_s / max(t_first, 1e-4))))
+    ref.time_steps(warm - 1, DT, threads)
+    t = ref.time_steps(n, DT, threads)
+    return n * nd / t, n, warm, f"{scene} with {nd} dynamic bodies, steps {warm}..{warm + n}, JobSystemThreadPool with {threads} threads", threads
+
+
+def run_reference(args):
+    import refharness as R
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     if not R.have_ref("fast"):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libjoltref_fast.so missing"}))
         return
-    bodies = min(args.bodies, args.ref_bodies)
-    scene, p0, p1 = scene_params(args, bodies)
-    ref = R.RefWorld(scene, p0, p1, variant="fast")
-    ref.set_recording(False)
-    threads = ref.L.jref_hardware_threads()
-    nd = ref.num_dynamic
-    # bound the run: time the first warm-up step, then scale steps so that the whole run stays within ~4 minutes
-    t_first = ref.time_steps(1, DT, threads)
-    budget = 200.0
-    warm = max(3, min(args.warmup, int(0.4 * budget / max(t_first, 1e-4))))
-    steps = max(1, min(args.steps, int(0.6 * budget / max(t_first, 1e-4))))
-    ref.time_steps(warm - 1, DT, threads)
-    t = ref.time_steps(steps, DT, threads)
-    value = steps * nd / t
+    value, steps, warm, sample, threads = cpu_run(args, args.warmup, args.steps, 200.0)
+    bodies = args.worlds * PYRAMID_BODIES if args.workload == "batch" else None
     line = {
         "impl": "reference", "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": 1000.0 * t / steps, "steps_per_sec": steps / t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_of(args, nd, {"sample": f"{nd} of {args.bodies} bodies" if nd != args.bodies else "full"}),
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference",
-                         "sample": f"{scene} with {nd} dynamic bodies, steps {warm}..{warm + steps} of the run, JobSystemThreadPool with {threads} threads, FMA build"},
+        "ms_per_step": None, "higher_is_better": True, "scaling": "strong" if args.workload == "batch" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "bodies": bodies, "dt": DT, "collision_steps": 1, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample + "; FMA build of the unmodified reference (oracle/_ref)"},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def cpu_baseline(args):
-    """oracle/_ref timed on the host cores on a bounded sample (about args.cpu_seconds of CPU work)."""
-    import refharness as R
-    if not R.have_ref("fast"):
+# ---------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+class Workload:
+    """One rank's share of the workload behind a uniform step / e2e / profile interface."""
+
+    def __init__(self, args, api, flib, rank, world_size):
+        import numpy as np
+        import refharness as R
+        from joltphysics_b200 import _capi
+        import facade as F
+        self.api, self.np, self._capi = api, np, _capi
+        self.kind = args.workload
+        scene, p0, p1 = scene_params(args.workload, args.bodies)
+        self.scene = F.FacadeScene(flib, scene, p0, p1)
+        self.batch = None
+        if self.kind == "batch":
+            # world_id -> rank: contiguous blocks
+            base, rem = divmod(args.worlds, world_size)
+            self.n_worlds = base + (1 if rank < rem else 0)
+            self.batch = api.b2j_batch_create(self.scene.world.h, self.n_worlds, BATCH_PAIRS_PER_WORLD, BATCH_CONSTRAINTS_PER_WORLD)
+            if not self.batch:
+                raise SystemExit("b2j_batch_create failed: " + api.last_error())
+            self.num_dynamic = self.n_worlds * self.scene.num_dynamic
+            self.num_slots = self.n_worlds * self.scene.num_bodies
+        else:
+            self.n_worlds = 1
+            self.num_dynamic = self.scene.num_dynamic
+            self.num_slots = self.scene.num_bodies
+        self.stats = _capi.StepStats()
+
+    def step(self):
+        if self.batch:
+            r = self.api.b2j_batch_step(self.batch, DT, 1, C.byref(self.stats))
+        else:
+            r = self.api.b2j_step(self.scene.world.h, DT, 1, C.byref(self.stats))
+        if r < 0:
+            raise SystemExit("step failed: " + self.api.last_error())
+        return self.stats
+
+    def set_profiling(self, on):
+        if self.batch:
+            self.api.b2j_batch_set_profiling(self.batch, on)
+        else:
+            self.api.b2j_world_set_profiling(self.scene.world.h, on)
+
+    def profile(self):
+        cap, stride = 128, 64
+        names = C.create_string_buffer(cap * stride)
+        ms, launches = (C.c_float * cap)(), (C.c_uint32 * cap)()
+        if self.batch:
+            n = self.api.b2j_batch_get_profile(self.batch, names, stride, ms, launches, cap)
+        else:
+            n = self.api.b2j_world_get_profile(self.scene.world.h, names, stride, ms, launches, cap)
+        return {names.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode(): {"ms": float(ms[i]), "launches": int(launches[i])} for i in range(min(n, cap))}
+
+    def e2e_buffers(self, torch):
+        n = self.num_slots if self.batch else self.num_dynamic
+        self.forces = torch.zeros((n, 3), dtype=torch.float32).pin_memory().numpy()
+        self.positions = torch.zeros((self.num_slots if self.batch else self.num_dynamic, 3), dtype=torch.float32).pin_memory().numpy()
+        fp = C.POINTER(C.c_float)
+        self._f = self.forces.ctypes.data_as(fp)
+        self._st = self._capi.BodyState(self.positions.ctypes.data, None, None, None, None, None, None)
+        if self.batch:
+            return n * 12, self.num_slots * 12
+        return self.num_dynamic * (12 + 4), self.scene.num_bodies * (12 + 16 + 12 + 12 + 4)
+
+    def step_e2e(self):
+        """One step through the reference-facing boundary with host buffers: forces in (H2D), step, positions out (D2H)."""
+        if self.batch:
+            self.api.b2j_batch_add_force_torque(self.batch, self.num_slots, self._f, None)
+            self.api.b2j_batch_step(self.batch, DT, 1, C.byref(self.stats))
+            self.api.b2j_batch_get_state(self.batch, 0xffffffff, self.num_slots, C.byref(self._st))
+        else:
+            self.scene.step_e2e(DT, self.forces, self.positions)  # facade: BodyInterface::AddForce..., PhysicsSystem::Update, GetPosition
+
+
+COUNTERS = ("num_body_pairs", "num_pairs_from_cache", "num_manifolds", "num_contact_points", "num_constraints", "num_phases", "velocity_iterations", "position_iterations", "num_active_bodies")
+
+
+def measure(args, wl, torch, dist, world_size, local_rank, steps, warmup, with_e2e=True):
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        wl.step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    gpu_ms, launches, agg = 0.0, 0, {}
+    for _ in range(steps):
+        st = wl.step()
+        gpu_ms += st.gpu_ms
+        launches += st.kernel_launches
+        for k in COUNTERS:
+            agg[k] = agg.get(k, 0) + getattr(st, k)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.finish()
+
+    # per kernel device time over extra steps continuing the same run (event records perturb back-to-back launches,
+    # so this is kept out of the timed region)
+    prof_steps = max(1, min(steps, 10))
+    wl.set_profiling(1)
+    prof_gpu_ms, pagg = 0.0, {}
+    for _ in range(prof_steps):
+        st = wl.step()
+        prof_gpu_ms += st.gpu_ms
+        for k in ("num_contact_points", "num_constraints", "velocity_iterations"):
+            pagg[k] = pagg.get(k, 0) + getattr(st, k)
+    prof = wl.profile()
+    wl.set_profiling(0)
+
+    e2e = None
+    if with_e2e:
+        h2d, d2h = wl.e2e_buffers(torch)
+        e2e_steps = max(1, min(steps, 20))
+        wl.step_e2e()  # first call sizes the staging buffers
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            wl.step_e2e()
+        barrier()
+        e2e = {"wall": time.perf_counter() - t1, "steps": e2e_steps, "h2d": h2d, "d2h": d2h}
+    return {"gpu_ms": gpu_ms, "wall": wall, "launches": launches, "agg": agg, "clocks": clocks, "prof": prof, "prof_steps": prof_steps,
+            "prof_gpu_ms": prof_gpu_ms, "pagg": pagg, "e2e": e2e}
+
+
+def roofline_of(m):
+    """Roofline of the dominant kernel class (velocity solve), SURVEY 8(d) row (5): per constraint and iteration
+    C(c) + 4*S_v + 4*(3+c) algorithmic bytes with C(c) = 220 + 64 c."""
+    prof, ps, pagg = m["prof"], m["prof_steps"], m["pagg"]
+    solve = prof.get("KSolveVelocity")
+    if not solve or solve["ms"] <= 0:
         return None
-    bodies = min(args.bodies, args.ref_bodies)
-    scene, p0, p1 = scene_params(args, bodies)
-    ref = R.RefWorld(scene, p0, p1, variant="fast")
-    ref.set_recording(False)
-    threads = ref.L.jref_hardware_threads()
-    nd = ref.num_dynamic
-    t0 = time.time()
-    steps, total = 0, 0.0
-    warm = 0
-    # skip the first steps (no contacts yet) up to a third of the budget, then time the rest
-    while time.time() - t0 < args.cpu_seconds / 3 and warm < args.warmup:
-        ref.time_steps(1, DT, threads)
-        warm += 1
-    while time.time() - t0 < args.cpu_seconds and steps < args.steps:
-        total += ref.time_steps(1, DT, threads)
-        steps += 1
-    if steps == 0:
-        return None
-    return {"value": steps * nd / total, "unit": "body-steps/s", "cores": threads, "kind": "reference",
-            "sample": f"{scene} with {nd} dynamic bodies (of {args.bodies}), steps {warm}..{warm + steps}, JobSystemThreadPool {threads} threads, FMA build, {total:.1f} s"}
+    M = pagg["num_constraints"] / ps
+    cbar = pagg["num_contact_points"] / max(pagg["num_constraints"], 1)
+    V = pagg["velocity_iterations"] / ps
+    total_bytes = V * M * ((220 + 64 * cbar) + 4 * S_V + 4 * (3 + cbar)) * ps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = total_bytes / (solve["ms"] / 1000.0) / 1e9
+    return {"bound": "hbm", "kernel": "KSolveVelocity", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
+            "bytes_per_launch": total_bytes / max(solve["launches"], 1), "avg_launch_us": 1000.0 * solve["ms"] / max(solve["launches"], 1),
+            "share_of_step": solve["ms"] / max(m["prof_gpu_ms"], 1e-9), "measured_over": f"{ps} profiled steps after the timed region",
+            "constraints_per_step": M, "points_per_constraint": cbar}
 
 
 def run_b200(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
     import joltphysics_b200
-    from joltphysics_b200 import _capi
     import facade as F
 
     rank = int(os.environ.get("RANK", "0"))
@@ -183,127 +327,65 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+    os.environ["B2J_DEVICE"] = str(local_rank)
     api = joltphysics_b200.load()
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), api)
-    os.environ["B2J_DEVICE"] = str(local_rank)
-    scene, p0, p1 = scene_params(args)
-    fs = F.FacadeScene(flib, scene, p0, p1)
-    world = fs.world
-    nd = fs.num_dynamic
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    wl = Workload(args, api, flib, rank, world_size)
+    m = measure(args, wl, torch, dist, world_size, local_rank, args.steps, args.warmup)
 
-    # ---- warm-up (untimed); the per-step times are kept to compare with the CPU sample on the same early steps
-    warm_ms = []
-    for _ in range(args.warmup):
-        _, st = world.step(DT)
-        warm_ms.append(st.gpu_ms)
-
-    # ---- device resident timing
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    gpu_ms, launches = 0.0, 0
-    agg = {}
-    for _ in range(args.steps):
-        _, st = world.step(DT)
-        gpu_ms += st.gpu_ms
-        launches += st.kernel_launches
-        for k in ("num_body_pairs", "num_pairs_from_cache", "num_manifolds", "num_contact_points", "num_constraints", "num_phases", "velocity_iterations", "position_iterations", "num_active_bodies"):
-            agg[k] = agg.get(k, 0) + getattr(st, k)
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.finish()
-
-    # ---- per kernel device time (CUDA events around every launch on the library's stream) over extra steps that continue the
-    # same run; kept out of the timed region above because the event records perturb back-to-back launches
-    prof_steps = max(1, min(args.steps, 20))
-    api.b2j_world_set_profiling(world.h, 1)
-    prof_gpu_ms = 0.0
-    pagg = {}
-    for _ in range(prof_steps):
-        _, st = world.step(DT)
-        prof_gpu_ms += st.gpu_ms
-        for k in ("num_contact_points", "num_constraints", "velocity_iterations"):
-            pagg[k] = pagg.get(k, 0) + getattr(st, k)
-    prof = world.profile()
-    api.b2j_world_set_profiling(world.h, 0)
-
-    # ---- end to end through the facade with host buffers (pinned): forces in, positions out, every step
-    forces = torch.zeros((nd, 3), dtype=torch.float32).pin_memory().numpy()
-    positions = torch.zeros((nd, 3), dtype=torch.float32).pin_memory().numpy()
-    e2e_steps = max(1, min(args.steps, 30))
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(e2e_steps):
-        fs.step_e2e(DT, forces, positions)
-    barrier()
-    e2e_wall = time.perf_counter() - t1
-    nb = fs.num_bodies
-    h2d = nd * (12 + 4)
-    d2h = nb * (12 + 16 + 12 + 12 + 4)
-
-    # ---- max over ranks, sum of work
-    t_dev = gpu_ms / 1000.0
-    vals = torch.tensor([t_dev, wall, e2e_wall, float(nd), float(launches)], dtype=torch.float64, device="cuda")
+    # max over ranks of the times, sum of the work (the only collective: a reduction of the statistics)
+    t_dev, wall, e2e_wall = m["gpu_ms"] / 1000.0, m["wall"], m["e2e"]["wall"]
+    vals = torch.tensor([t_dev, wall, e2e_wall, float(wl.num_dynamic), float(m["launches"]), float(wl.n_worlds)], dtype=torch.float64, device="cuda")
     if world_size > 1:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         t_dev, wall, e2e_wall = mx[0].item(), mx[1].item(), mx[2].item()
-        total_bodies, launches = sm[3].item(), int(sm[4].item())
+        total_bodies, launches, total_worlds = sm[3].item(), int(sm[4].item()), int(sm[5].item())
     else:
-        total_bodies = float(nd)
+        total_bodies, launches, total_worlds = float(wl.num_dynamic), m["launches"], wl.n_worlds
     if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
         return
 
     K = args.steps
-    value = K * total_bodies / t_dev
-    # roofline of the dominant kernel (velocity solve), SURVEY 8(d) row (5): per constraint and iteration
-    # C(c) + 4*S_v + 4*(3+c) algorithmic bytes, C(c) = 220 + 64 c
-    M = pagg["num_constraints"] / prof_steps
-    cbar = pagg["num_contact_points"] / max(pagg["num_constraints"], 1)
-    V = pagg["velocity_iterations"] / prof_steps
-    bytes_per_constraint_iter = (220 + 64 * cbar) + 4 * S_V + 4 * (3 + cbar)
-    solve = prof.get("KSolveVelocity", {"ms": 0.0, "launches": 0})
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = None
-    if solve["ms"] > 0:
-        total_bytes = V * M * bytes_per_constraint_iter * prof_steps
-        achieved = total_bytes / (solve["ms"] / 1000.0) / 1e9
-        roofline = {"bound": "hbm", "kernel": "KSolveVelocity", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
-                    "bytes_per_launch": total_bytes / max(solve["launches"], 1), "avg_launch_us": 1000.0 * solve["ms"] / max(solve["launches"], 1),
-                    "share_of_step": solve["ms"] / max(prof_gpu_ms, 1e-9), "measured_over": f"{prof_steps} profiled steps after the timed region"}
+    batch = args.workload == "batch"
     line = {
-        "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * t_dev / K, "steps_per_sec": K / t_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": config_of(args, nd, {"parallelism": f"replicas x{world_size}" if world_size > 1 else "single world"}),
-        "clocks": clocks,
-        "e2e": {"value": e2e_steps * total_bodies / e2e_wall, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "metric": "body_steps_per_sec", "value": K * total_bodies / t_dev, "unit": "body-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * t_dev / K, "steps_per_sec": K / t_dev, "world_steps_per_sec": K * total_worlds / t_dev, "higher_is_better": True,
+        "scaling": "strong" if batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "worlds": total_worlds, "bodies": int(total_bodies), "dt": DT, "collision_steps": 1,
+                   "parallelism": (f"worlds sharded over {world_size} GPUs (world_id -> rank blocks), no data-path collective" if batch else f"one world per GPU x{world_size} (replicas only)"),
+                   "timing": "every step streams the whole job state through HBM (working set >> 126 MB L2); no L2 flush between steps"},
+        "clocks": m["clocks"],
+        "e2e": {"value": m["e2e"]["steps"] * total_bodies / e2e_wall, "unit": "body-steps/s", "h2d_bytes_per_step": m["e2e"]["h2d"], "d2h_bytes_per_step": m["e2e"]["d2h"], "steps": m["e2e"]["steps"],
+                "path": "b2j_batch_add_force_torque + b2j_batch_step + b2j_batch_get_state (C ABI, pinned host buffers)" if batch else "facade: BodyInterface::AddForce..., PhysicsSystem::Update, BodyInterface::GetPosition"},
         "gpu_launches": launches,
         "wall_ms_per_step": 1000.0 * wall / K,
-        "roofline": roofline,
-        "step_counters_mean": {k: v / K for k, v in agg.items()},
-        "kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]},
-        "profiled_ms_per_step": prof_gpu_ms / prof_steps,
+        "roofline": roofline_of(m),
+        "step_counters_mean": {k: v / K for k, v in m["agg"].items()},
+        "kernel_ms_per_step": {k: v["ms"] / m["prof_steps"] for k, v in sorted(m["prof"].items(), key=lambda kv: -kv[1]["ms"])[:14]},
+        "profiled_ms_per_step": m["prof_gpu_ms"] / m["prof_steps"],
     }
-    if world_size == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline(args)
-        if cb is not None:
-            # GPU on the same early steps as the CPU sample (per step times recorded during warm-up)
-            line["cpu_baseline"] = cb
+    if world_size == 1:
+        if not args.no_cpu_baseline:
+            try:
+                value, steps, warm, sample, threads = cpu_run(args, args.warmup, args.steps, args.cpu_seconds)
+                line["cpu_baseline"] = {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample + "; FMA build of the unmodified reference (oracle/_ref)"}
+            except Exception as e:  # the CPU leg must never take the GPU line down
+                line["cpu_baseline"] = {"error": str(e)}
+        if batch and not args.no_pile:
+            # secondary headline: configs[3], one 1M body world on one B200 (reported next to the batch line, not instead of it)
+            del wl
+            pargs = argparse.Namespace(**vars(args))
+            pargs.workload = "pile"
+            pw = Workload(pargs, api, flib, 0, 1)
+            pm = measure(pargs, pw, torch, dist, 1, local_rank, 30, 120, with_e2e=False)
+            line["pile"] = {"config": WORKLOAD_NAMES["pile"], "bodies": pw.num_dynamic, "steps": 30, "warmup": 120,
+                            "value": 30 * pw.num_dynamic / (pm["gpu_ms"] / 1000.0), "unit": "body-steps/s", "ms_per_step": pm["gpu_ms"] / 30,
+                            "roofline": roofline_of(pm), "step_counters_mean": {k: v / 30 for k, v in pm["agg"].items()},
+                            "kernel_ms_per_step": {k: v["ms"] / pm["prof_steps"] for k, v in sorted(pm["prof"].items(), key=lambda kv: -kv[1]["ms"])[:10]}}
     print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()

@@ -333,15 +333,25 @@ uint32_t b2j_world_get_profile(b2j_world *w, char *names, uint32_t name_stride, 
 
 /* ---- batched independent worlds (config 5) --------------------------------------------------------- */
 
-typedef struct b2j_batch b2j_batch; /* opaque: n identical-layout worlds stepped together on one device */
+typedef struct b2j_batch b2j_batch; /* opaque: n independent worlds with identical layout stepped together on one device */
 
-/* Clones `proto` n_worlds times on its device. The prototype stays usable on its own. */
-b2j_batch *b2j_batch_create(const b2j_world *proto, uint32_t n_worlds);
+/* Clones the bodies / shapes / active list of `proto` n_worlds times on its device (the contact cache is NOT cloned: use a
+ * freshly populated prototype). All worlds live in one device world (slot = world * stride + body index) and never interact:
+ * the broadphase tree is cut per world, body pair keys carry the world. Per world limits (0 = the prototype's) size the shared
+ * caches. The prototype stays usable on its own. Contact / activation events are not recorded for batches.
+ * Every world evolves bit-identically to the prototype stepped alone (TestMultiplePhysicsSystems pattern, PhysicsTests.cpp:1548). */
+b2j_batch *b2j_batch_create(b2j_world *proto, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world);
 void       b2j_batch_destroy(b2j_batch *b);
-/* Steps every world of the batch once; stats (may be NULL) receives the SUM over worlds. */
+/* Steps every world of the batch once; stats (may be NULL) receives the totals over all worlds. */
 int        b2j_batch_step(b2j_batch *b, float delta_time, int collision_steps, b2j_step_stats *stats);
-b2j_world *b2j_batch_world(b2j_batch *b, uint32_t i);
 uint32_t   b2j_batch_size(const b2j_batch *b);
+/* State of the bodies in slots [0, n) of one world (see b2j_bodies_get_state with ids == NULL). world_index = 0xffffffff:
+ * the first n slots of the whole batch (world major, stride = body slots of the prototype), i.e. all worlds in one call. */
+int        b2j_batch_get_state(b2j_batch *b, uint32_t world_index, uint32_t n, const b2j_body_state *out);
+/* BodyInterface::AddForce / AddTorque for the first n slots of the whole batch (world major); arrays [n][3], either may be NULL. */
+int        b2j_batch_add_force_torque(b2j_batch *b, uint32_t n, const float *force, const float *torque);
+int        b2j_batch_set_profiling(b2j_batch *b, int on);
+uint32_t   b2j_batch_get_profile(b2j_batch *b, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,8 @@ struct Tree
 {
 	uint32_t n;                  // number of bodies (leaves)
 	uint32_t *bodies;            // [n] body slots in the layer (unsorted, maintained by the host)
-	uint32_t *keys_in, *keys_out;   // [n] morton codes
+	uint64_t *keys_in, *keys_out;   // [n] world index << 32 | 30 bit morton code
+	int32_t *world_root;         // batched worlds: [num_worlds] node that spans exactly the bodies of one world (-1: none), else null
 	uint32_t *leaf_body;         // [n] body slot per sorted leaf (sort output)
 	int32_t *child_left, *child_right; // [n-1] node ids
 	int32_t *parent;             // [2n-1]
@@ -58,17 +59,18 @@ struct KMorton
 		if (!(fx == fx)) fx = 0.0f;
 		if (!(fy == fy)) fy = 0.0f;
 		if (!(fz == fz)) fz = 0.0f;
-		t.keys_in[i] = (expand_bits_10((uint32_t)fx) << 2) | (expand_bits_10((uint32_t)fy) << 1) | expand_bits_10((uint32_t)fz);
+		uint32_t morton = (expand_bits_10((uint32_t)fx) << 2) | (expand_bits_10((uint32_t)fy) << 1) | expand_bits_10((uint32_t)fz);
+		t.keys_in[i] = ((uint64_t)world_of(w, body) << 32) | morton;
 	}
 };
 
-// delta(i, j): common prefix length of the 64 bit keys (morton << 32 | index), -1 out of range
-B2J_D int lbvh_delta(const uint32_t *keys, int n, int i, int j)
+// delta(i, j): common prefix length of the keys, ties broken by the index (keys are made unique), -1 out of range
+B2J_D int lbvh_delta(const uint64_t *keys, int n, int i, int j)
 {
 	if (j < 0 || j >= n) return -1;
-	uint64_t a = ((uint64_t)keys[i] << 32) | (uint32_t)i;
-	uint64_t b = ((uint64_t)keys[j] << 32) | (uint32_t)j;
-	return clz64(a ^ b);
+	uint64_t a = keys[i], b = keys[j];
+	if (a != b) return clz64(a ^ b);
+	return 64 + clz32((uint32_t)i ^ (uint32_t)j);
 }
 
 struct KBuildHierarchy
@@ -77,7 +79,7 @@ struct KBuildHierarchy
 	B2J_D void operator()(uint32_t idx) const
 	{
 		int n = (int)t.n, i = (int)idx;
-		const uint32_t *keys = t.keys_out;
+		const uint64_t *keys = t.keys_out;
 		int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0? 1 : -1;
 		int delta_min = lbvh_delta(keys, n, i, i - d);
 		int lmax = 2;
@@ -105,6 +107,13 @@ struct KBuildHierarchy
 		t.parent[right] = i;
 		if (i == 0) t.parent[0] = -1;
 		t.visit[i] = 0;
+		if (t.world_root != nullptr)
+		{
+			// the node whose key range is exactly one world becomes the traversal root of that world
+			uint32_t wlo = (uint32_t)(keys[lo] >> 32), whi = (uint32_t)(keys[hi] >> 32);
+			if (wlo == whi && (lo == 0 || (uint32_t)(keys[lo - 1] >> 32) != wlo) && (hi == n - 1 || (uint32_t)(keys[hi + 1] >> 32) != wlo))
+				t.world_root[wlo] = i;
+		}
 	}
 };
 
@@ -119,6 +128,13 @@ struct KRefit
 		F4 mn = w.bounds_min[body], mx = w.bounds_max[body];
 		t.node_min[node] = mn;
 		t.node_max[node] = mx;
+		if (t.world_root != nullptr)
+		{
+			// a world with a single body in this layer: the leaf is its root
+			uint32_t wi = (uint32_t)(t.keys_out[i] >> 32);
+			if ((i == 0 || (uint32_t)(t.keys_out[i - 1] >> 32) != wi) && ((int)i == n - 1 || (uint32_t)(t.keys_out[i + 1] >> 32) != wi))
+				t.world_root[wi] = node;
+		}
 		if (n == 1)
 		{
 			t.layer_bounds[0] = mn; t.layer_bounds[1] = mx;
@@ -185,9 +201,16 @@ struct KFindPairs
 			if (t.n == 0 || !w.object_vs_bp[i1.object_layer * w.num_bp_layers + l])
 				continue;
 			int n = (int)t.n;
-			int stack[64];
+			int stack[128];
 			int top = 0;
-			stack[0] = n == 1? 0 + (n - 1) : 0;
+			stack[0] = 0; // the root (for n == 1 node 0 is the only leaf)
+			if (t.world_root != nullptr)
+			{
+				int wr = t.world_root[world_of(w, b1)];
+				if (wr < 0)
+					continue; // this world has no body in the layer
+				stack[0] = wr;
+			}
 			while (top >= 0)
 			{
 				int node = stack[top--];
@@ -215,8 +238,8 @@ struct KFindPairs
 					int l2 = t.child_left[node], r2 = t.child_right[node];
 					bool ol = aabb_overlaps(min1, max1, to_v3(t.node_min[l2]), to_v3(t.node_max[l2]));
 					bool orr = aabb_overlaps(min1, max1, to_v3(t.node_min[r2]), to_v3(t.node_max[r2]));
-					if (ol && top < 62) stack[++top] = l2;
-					if (orr && top < 62) stack[++top] = r2;
+					if (ol && top < 126) stack[++top] = l2;
+					if (orr && top < 126) stack[++top] = r2;
 				}
 			}
 		}

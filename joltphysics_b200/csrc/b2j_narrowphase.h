@@ -52,12 +52,13 @@ struct NarrowCtx
 };
 
 // ---- pair hash table ---------------------------------------------------------------------------------------------
-B2J_HD uint64_t pair_key(uint32_t id1, uint32_t id2) { return ((uint64_t)id2 << 32) | id1; } // BodyPair{A, B} read as a little endian uint64
+// The table is keyed by the two body SLOTS (lower id first): unique across batched worlds, same as the ids in a single world
+B2J_HD uint64_t pair_key(uint32_t slot1, uint32_t slot2) { return ((uint64_t)slot2 << 32) | slot1; }
 
-B2J_D void pair_table_insert(const DWorld &w, const ContactCache &c, uint32_t id1, uint32_t id2, uint32_t entry)
+B2J_D void pair_table_insert(const DWorld &w, const ContactCache &c, uint32_t slot1, uint32_t slot2, uint32_t entry)
 {
 	uint32_t mask = w.pair_table_size - 1;
-	uint32_t h = (uint32_t)hash64(pair_key(id1, id2)) & mask;
+	uint32_t h = (uint32_t)hash64(pair_key(slot1, slot2)) & mask;
 	for (;;)
 	{
 		if (atomic_cas(&c.pair_table[h], 0xffffffffu, entry) == 0xffffffffu)
@@ -66,16 +67,16 @@ B2J_D void pair_table_insert(const DWorld &w, const ContactCache &c, uint32_t id
 	}
 }
 
-B2J_D uint32_t pair_table_find(const DWorld &w, const ContactCache &c, uint32_t id1, uint32_t id2)
+B2J_D uint32_t pair_table_find(const DWorld &w, const ContactCache &c, uint32_t slot1, uint32_t slot2)
 {
 	uint32_t mask = w.pair_table_size - 1;
-	uint32_t h = (uint32_t)hash64(pair_key(id1, id2)) & mask;
+	uint32_t h = (uint32_t)hash64(pair_key(slot1, slot2)) & mask;
 	for (;;)
 	{
 		uint32_t e = c.pair_table[h];
 		if (e == 0xffffffffu)
 			return 0xffffffffu;
-		if (c.pairs[e].body1 == id1 && c.pairs[e].body2 == id2)
+		if (c.pairs[e].slot1 == slot1 && c.pairs[e].slot2 == slot2)
 			return e;
 		h = (h + 1) & mask;
 	}
@@ -119,12 +120,13 @@ struct KProcessPairs
 
 		CachedPair &out = w.write_cache.pairs[entry];
 		out.body1 = id1; out.body2 = id2;
+		out.slot1 = cb1; out.slot2 = cb2;
 		out.first_manifold = 0; out.num_manifolds = 0;
 
 		uint32_t old = 0xffffffffu;
 		bool handled = false;
 		if (w.settings.use_body_pair_contact_cache)
-			old = pair_table_find(w, w.read_cache, id1, id2);
+			old = pair_table_find(w, w.read_cache, cb1, cb2);
 		if (old != 0xffffffffu && !((i1.flags | i2.flags) & B2J_BODY_INVALIDATE_CACHE))
 		{
 			const CachedPair &in = w.read_cache.pairs[old];
@@ -157,7 +159,7 @@ struct KProcessPairs
 			else
 				c.collide_convex[atomic_add(&w.counters->num_collide_convex, 1u)] = item;
 		}
-		pair_table_insert(w, w.write_cache, id1, id2, entry);
+		pair_table_insert(w, w.write_cache, cb1, cb2, entry);
 	}
 };
 
@@ -227,7 +229,7 @@ struct KCopyCached
 			set_error(w, B2J_ERR_MANIFOLD_CACHE_FULL);
 			return;
 		}
-		uint32_t cb1 = slot_of(in.body1), cb2 = slot_of(in.body2);
+		uint32_t cb1 = in.slot1, cb2 = in.slot2;
 		BodyInfo i1 = w.info[cb1], i2 = w.info[cb2];
 		for (uint32_t j = 0; j < n; ++j)
 		{

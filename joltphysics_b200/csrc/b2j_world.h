@@ -58,6 +58,7 @@ struct ShapeDesc
 struct CachedPair
 {
 	uint32_t body1, body2;       // full ids, body1 < body2
+	uint32_t slot1, slot2;       // body slots (differ from the id index in batched worlds)
 	float dpos[3], drot[3];
 	uint32_t first_manifold, num_manifolds;
 };
@@ -116,6 +117,7 @@ struct DWorld
 	// capacities
 	uint32_t max_bodies, max_body_pairs, max_constraints, pair_table_size;
 	uint32_t num_object_layers, num_bp_layers;
+	uint32_t world_stride;       // batched independent worlds: slots per world (world = slot / world_stride), 0 = a single world
 	b2j_settings settings;
 	V3 gravity;
 
@@ -152,5 +154,6 @@ struct DWorld
 };
 
 B2J_HD uint32_t slot_of(uint32_t id) { return id & 0x7fffffu; }
+B2J_HD uint32_t world_of(const DWorld &w, uint32_t slot) { return w.world_stride != 0? slot / w.world_stride : 0u; }
 
 } // namespace b2j

@@ -91,10 +91,10 @@ struct KClearActiveIndex
 
 struct KGetState
 {
-	DWorld w; const uint32_t *ids; float *pos, *rot, *lin, *ang, *bounds; uint32_t *active_index; float *sleep_timer;
+	DWorld w; const uint32_t *ids; float *pos, *rot, *lin, *ang, *bounds; uint32_t *active_index; float *sleep_timer; uint32_t first;
 	B2J_D void operator()(uint32_t i) const
 	{
-		uint32_t b = ids != nullptr? slot_of(ids[i]) : i;
+		uint32_t b = ids != nullptr? slot_of(ids[i]) : first + i;
 		if (pos) v3_store(to_v3(w.position[b]), pos + 3 * i);
 		if (rot) q4_store(to_q4(w.rotation[b]), rot + 4 * i);
 		if (lin) v3_store(to_v3(w.linear_velocity[b]), lin + 3 * i);
@@ -130,7 +130,7 @@ struct KAddForceTorque
 	DWorld w; const uint32_t *ids; const float *force, *torque;
 	B2J_D void operator()(uint32_t i) const
 	{
-		uint32_t b = slot_of(ids[i]);
+		uint32_t b = ids != nullptr? slot_of(ids[i]) : i;
 		if (force) w.force[b] = f4(to_v3(w.force[b]) + v3_load(force + 3 * i));
 		if (torque) w.torque[b] = f4(to_v3(w.torque[b]) + v3_load(torque + 3 * i));
 	}
@@ -144,6 +144,7 @@ struct KImportCache
 		const b2j_cached_body_pair &p = pairs[i];
 		CachedPair &o = w.read_cache.pairs[i];
 		o.body1 = p.body1; o.body2 = p.body2;
+		o.slot1 = slot_of(p.body1); o.slot2 = slot_of(p.body2);
 		for (int k = 0; k < 3; ++k) { o.dpos[k] = p.delta_position[k]; o.drot[k] = p.delta_rotation[k]; }
 		o.first_manifold = p.first_manifold; o.num_manifolds = p.num_manifolds;
 		for (uint32_t j = 0; j < p.num_manifolds; ++j)
@@ -162,7 +163,7 @@ struct KImportCache
 				cm.lambda[q] = m.non_penetration_lambda[q];
 			}
 		}
-		pair_table_insert(w, w.read_cache, p.body1, p.body2, i);
+		pair_table_insert(w, w.read_cache, slot_of(p.body1), slot_of(p.body2), i);
 	}
 };
 
@@ -192,6 +193,26 @@ struct KExportCache
 				m.non_penetration_lambda[q] = cm.lambda[q];
 			}
 		}
+	}
+};
+
+// batched worlds: dst[world * dst_stride + j] = src[j] for j < n_src
+template <class T> struct KReplicate
+{
+	T *dst; const T *src; uint32_t n_src, dst_stride;
+	B2J_D void operator()(uint32_t i) const { uint32_t wi = i / n_src, j = i % n_src; dst[(size_t)wi * dst_stride + j] = src[j]; }
+};
+
+// batched worlds: the active list of the prototype repeated per world (world major keeps the order inside every world)
+struct KReplicateActive
+{
+	DWorld w; const uint32_t *src_active; uint32_t na, stride;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t wi = i / na, k = i % na;
+		uint32_t slot = src_active[k] + wi * stride;
+		w.active[i] = slot;
+		w.active_index[slot] = i;
 	}
 };
 
@@ -280,6 +301,8 @@ struct b2j_world
 	std::vector<std::vector<uint32_t>> layer_bodies;
 	std::vector<uint8_t> layer_list_dirty, layer_needs_build, layer_has_moving;
 	uint32_t num_bodies = 0, num_active = 0, num_slots = 0;
+	uint32_t num_worlds = 1;               // > 1: batched independent worlds (b2j_batch)
+	uint32_t get_state_first = 0;          // slot offset of b2j_bodies_get_state with ids == NULL (batch world selection)
 
 	// shapes
 	std::vector<ShapeDesc> h_shapes;
@@ -330,7 +353,8 @@ struct b2j_world
 
 struct b2j_batch
 {
-	std::vector<b2j_world *> worlds;
+	b2j_world *big = nullptr;    // all worlds live in ONE device world: slot = world * stride + body index
+	uint32_t n_worlds = 0, stride = 0, bodies_per_world = 0;
 };
 
 namespace {
@@ -385,7 +409,7 @@ bool build_tree(b2j_world *W, uint32_t layer)
 		rt.sync();
 		rt.free_(t.bodies); rt.free_(t.keys_in); rt.free_(t.keys_out); rt.free_(t.leaf_body); rt.free_(t.child_left); rt.free_(t.child_right);
 		rt.free_(t.parent); rt.free_(t.node_min); rt.free_(t.node_max); rt.free_(t.visit);
-		t.bodies = rt.alloc<uint32_t>(cap); t.keys_in = rt.alloc<uint32_t>(cap); t.keys_out = rt.alloc<uint32_t>(cap); t.leaf_body = rt.alloc<uint32_t>(cap);
+		t.bodies = rt.alloc<uint32_t>(cap); t.keys_in = rt.alloc<uint64_t>(cap); t.keys_out = rt.alloc<uint64_t>(cap); t.leaf_body = rt.alloc<uint32_t>(cap);
 		t.child_left = rt.alloc<int32_t>(cap); t.child_right = rt.alloc<int32_t>(cap); t.parent = rt.alloc<int32_t>(2 * cap);
 		t.node_min = rt.alloc<F4>(2 * cap); t.node_max = rt.alloc<F4>(2 * cap); t.visit = rt.alloc<uint32_t>(cap);
 		if (!t.visit) return false;
@@ -401,7 +425,8 @@ bool build_tree(b2j_world *W, uint32_t layer)
 	if (n == 0) return true;
 	KMorton km; km.w = W->d; km.t = t;
 	rt.launch(km, n);
-	rt.sort_pairs<uint32_t>(t.keys_in, t.keys_out, t.bodies, t.leaf_body, n, 30);
+	if (t.world_root != nullptr) rt.memset_(t.world_root, 0xff, (size_t)W->num_worlds * 4);
+	rt.sort_pairs<uint64_t>(t.keys_in, t.keys_out, t.bodies, t.leaf_body, n, W->num_worlds > 1? 64 : 30);
 	if (n > 1)
 	{
 		KBuildHierarchy kb; kb.t = t;
@@ -737,6 +762,8 @@ void b2j_settings_default(b2j_settings *s)
 	s->check_active_edges = 1;
 }
 
+static bool g_create_without_events = false;
+
 b2j_world *b2j_world_create(const b2j_world_desc *desc)
 {
 	if (desc == nullptr || desc->max_bodies == 0 || desc->num_object_layers == 0 || desc->num_object_layers > 64 || desc->num_broadphase_layers == 0 || desc->num_broadphase_layers > 8)
@@ -809,11 +836,19 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	nc.con_src = rt.alloc<ConstraintSrc>(d.max_constraints, false);
 	nc.woken_flag = rt.alloc<uint32_t>(nbod);
 	nc.woken_list = rt.alloc<uint32_t>(nbod);
-	W->max_events = 2 * d.max_constraints + 16;
-	nc.events = rt.alloc<b2j_contact_event>(W->max_events, false);
-	nc.max_events = W->max_events;
-	W->max_act_events = 2 * nbod;
-	W->d_act_events = rt.alloc<b2j_activation_event>(W->max_act_events, false);
+	if (g_create_without_events)
+	{
+		// batched worlds: events are not recorded (no per world listener replay)
+		W->max_events = 0; nc.events = nullptr; nc.max_events = 0; W->max_act_events = 0; W->d_act_events = nullptr;
+	}
+	else
+	{
+		W->max_events = 2 * d.max_constraints + 16;
+		nc.events = rt.alloc<b2j_contact_event>(W->max_events, false);
+		nc.max_events = W->max_events;
+		W->max_act_events = 2 * nbod;
+		W->d_act_events = rt.alloc<b2j_activation_event>(W->max_act_events, false);
+	}
 	W->d_woken_sorted = rt.alloc<uint32_t>(nbod); W->d_woken_keys = rt.alloc<uint32_t>(nbod);
 	W->d_round_begin = rt.alloc<uint32_t>(1);
 	W->d_energy = rt.alloc<float>(1);
@@ -901,7 +936,7 @@ void b2j_world_destroy(b2j_world *W)
 	{
 		Tree &t = W->trees[l];
 		rt.free_(t.bodies); rt.free_(t.keys_in); rt.free_(t.keys_out); rt.free_(t.leaf_body); rt.free_(t.child_left); rt.free_(t.child_right);
-		rt.free_(t.parent); rt.free_(t.node_min); rt.free_(t.node_max); rt.free_(t.visit); rt.free_(t.layer_bounds);
+		rt.free_(t.parent); rt.free_(t.node_min); rt.free_(t.node_max); rt.free_(t.visit); rt.free_(t.layer_bounds); rt.free_(t.world_root);
 	}
 	rt.free_(W->d_shapes); rt.free_(W->d_hull_points); rt.free_(W->d_hull_shrunk); rt.free_(W->d_hull_planes);
 	rt.free_(W->d_hull_faces); rt.free_(W->d_hull_vtx); rt.free_(W->d_mesh_bytes);
@@ -1156,7 +1191,7 @@ int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 	Runtime &rt = W->rt;
 	sync_dworld(W);
 	if (ids == nullptr && n > W->d.max_bodies) { last_error() = "n exceeds max_bodies"; return -1; }
-	KGetState k; memset(&k, 0, sizeof(k)); k.w = W->d;
+	KGetState k; memset(&k, 0, sizeof(k)); k.w = W->d; k.first = W->get_state_first;
 	// one persistent staging buffer (device + pinned mirror): ids up, one kernel, one copy down
 	rt.stage_begin((size_t)n * (4 + 12 + 16 + 12 + 12 + 24 + 4 + 4));
 	uint32_t *h_ids = nullptr; float *h_pos = nullptr, *h_rot = nullptr, *h_lin = nullptr, *h_ang = nullptr, *h_bounds = nullptr, *h_timer = nullptr; uint32_t *h_active = nullptr;
@@ -1216,7 +1251,8 @@ int b2j_bodies_add_force_torque(b2j_world *W, const uint32_t *ids, uint32_t n, c
 	KAddForceTorque k; k.w = W->d;
 	rt.stage_begin((size_t)n * (4 + 12 + 12));
 	uint32_t *h_ids = nullptr; float *h = nullptr;
-	k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4);
+	k.ids = nullptr;
+	if (ids != nullptr) { k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4); } // NULL: slots 0..n-1
 	k.force = nullptr; k.torque = nullptr;
 	if (force) { k.force = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, force, (size_t)n * 12); }
 	if (torque) { k.torque = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, torque, (size_t)n * 12); }
@@ -1481,11 +1517,121 @@ int b2j_debug_find_pairs(b2j_world *W)
 	return 0;
 }
 
-b2j_batch *b2j_batch_create(const b2j_world *, uint32_t) { last_error() = "b2j_batch_create: not implemented yet"; return nullptr; }
-void b2j_batch_destroy(b2j_batch *b) { delete b; }
-int b2j_batch_step(b2j_batch *, float, int, b2j_step_stats *) { last_error() = "b2j_batch_step: not implemented yet"; return -1; }
-b2j_world *b2j_batch_world(b2j_batch *b, uint32_t i) { return b != nullptr && i < b->worlds.size()? b->worlds[i] : nullptr; }
-uint32_t b2j_batch_size(const b2j_batch *b) { return b != nullptr? (uint32_t)b->worlds.size() : 0; }
+} // extern "C" (paused for a template helper)
+
+template <class T> static void replicate(Runtime &rt, T *dst, const T *src, uint32_t n_src, uint32_t stride, uint32_t n_worlds)
+{
+	KReplicate<T> k; k.dst = dst; k.src = src; k.n_src = n_src; k.dst_stride = stride;
+	uint64_t total = (uint64_t)n_src * n_worlds;
+	// launches are limited to 2^32 items: split by worlds
+	uint32_t worlds_per_launch = n_src == 0? n_worlds : (uint32_t)std::max<uint64_t>(1, 0x7fffffffull / n_src);
+	for (uint32_t w0 = 0; w0 < n_worlds; w0 += worlds_per_launch)
+	{
+		uint32_t nw = std::min(worlds_per_launch, n_worlds - w0);
+		KReplicate<T> kk = k; kk.dst = dst + (size_t)w0 * stride;
+		rt.launch(kk, n_src * nw);
+	}
+	(void)total;
+}
+
+extern "C" {
+
+b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
+{
+	if (P == nullptr || n_worlds == 0 || P->num_worlds != 1) { last_error() = "b2j_batch_create: invalid prototype"; return nullptr; }
+	upload_shapes(P);
+	sync_dworld(P);
+	uint32_t stride = P->num_slots;
+	if (stride == 0 || (uint64_t)stride * n_worlds > 0xfffffff0ull) { last_error() = "b2j_batch_create: too many bodies"; return nullptr; }
+	b2j_world_desc desc = P->desc;
+	desc.object_to_broadphase = P->t_o2bp.data(); desc.object_vs_broadphase = P->t_ovbp.data(); desc.object_vs_object = P->t_ovo.data();
+	desc.settings = P->d.settings;
+	v3_store(P->d.gravity, desc.gravity);
+	desc.max_bodies = stride * n_worlds;
+	uint64_t pairs = (uint64_t)(max_body_pairs_per_world != 0? max_body_pairs_per_world : P->d.max_body_pairs) * n_worlds;
+	uint64_t cons = (uint64_t)(max_contact_constraints_per_world != 0? max_contact_constraints_per_world : P->d.max_constraints) * n_worlds;
+	if (pairs > 0x7ffffff0ull || cons > 0x7ffffff0ull) { last_error() = "b2j_batch_create: limits exceed 2^31"; return nullptr; }
+	desc.max_body_pairs = (uint32_t)pairs;
+	desc.max_contact_constraints = (uint32_t)cons;
+	g_create_without_events = true;
+	b2j_world *B = b2j_world_create(&desc);
+	g_create_without_events = false;
+	if (B == nullptr) return nullptr;
+	Runtime &rt = B->rt;
+	B->num_worlds = n_worlds;
+	B->d.world_stride = stride;
+	B->prev_dt = P->prev_dt;
+	// shapes are shared by all worlds
+	B->h_shapes = P->h_shapes; B->h_hull_points = P->h_hull_points; B->h_hull_shrunk = P->h_hull_shrunk; B->h_hull_planes = P->h_hull_planes;
+	B->h_hull_faces = P->h_hull_faces; B->h_hull_vtx = P->h_hull_vtx; B->h_mesh_bytes = P->h_mesh_bytes;
+	B->shapes_dirty = true;
+	upload_shapes(B);
+	// body state: world w occupies the slots [w * stride, (w + 1) * stride)
+	P->rt.sync();
+	const DWorld &s = P->d; DWorld &d = B->d;
+	replicate(rt, d.info, s.info, stride, stride, n_worlds); replicate(rt, d.params, s.params, stride, stride, n_worlds);
+	replicate(rt, d.position, s.position, stride, stride, n_worlds); replicate(rt, d.rotation, s.rotation, stride, stride, n_worlds);
+	replicate(rt, d.linear_velocity, s.linear_velocity, stride, stride, n_worlds); replicate(rt, d.angular_velocity, s.angular_velocity, stride, stride, n_worlds);
+	replicate(rt, d.force, s.force, stride, stride, n_worlds); replicate(rt, d.torque, s.torque, stride, stride, n_worlds);
+	replicate(rt, d.inv_inertia_diag, s.inv_inertia_diag, stride, stride, n_worlds); replicate(rt, d.inertia_rotation, s.inertia_rotation, stride, stride, n_worlds);
+	replicate(rt, d.bounds_min, s.bounds_min, stride, stride, n_worlds); replicate(rt, d.bounds_max, s.bounds_max, stride, stride, n_worlds);
+	replicate(rt, d.sleep_spheres, s.sleep_spheres, stride * 3, stride * 3, n_worlds); replicate(rt, d.sleep_timer, s.sleep_timer, stride, stride, n_worlds);
+	// host mirrors
+	B->num_slots = stride * n_worlds;
+	B->num_bodies = P->num_bodies * n_worlds;
+	for (uint32_t w = 0; w < n_worlds; ++w)
+		for (uint32_t i = 0; i < stride; ++i)
+		{
+			B->h_ids[(size_t)w * stride + i] = P->h_ids[i];
+			B->h_layer[(size_t)w * stride + i] = P->h_layer[i];
+		}
+	for (uint32_t l = 0; l < d.num_bp_layers; ++l)
+	{
+		B->layer_bodies[l].reserve(P->layer_bodies[l].size() * n_worlds);
+		for (uint32_t w = 0; w < n_worlds; ++w)
+			for (uint32_t slot : P->layer_bodies[l])
+				B->layer_bodies[l].push_back(slot + w * stride);
+		B->layer_list_dirty[l] = 1; B->layer_needs_build[l] = 1; B->layer_has_moving[l] = P->layer_has_moving[l];
+		B->trees[l].world_root = rt.alloc<int32_t>(n_worlds);
+	}
+	// active list
+	sync_dworld(B);
+	if (P->num_active > 0)
+	{
+		KReplicateActive k; k.w = B->d; k.src_active = P->d.active; k.na = P->num_active; k.stride = stride;
+		rt.launch(k, P->num_active * n_worlds);
+	}
+	B->num_active = P->num_active * n_worlds;
+	rt.sync();
+	if (!rt.check("b2j_batch_create")) { b2j_world_destroy(B); return nullptr; }
+	b2j_batch *b = new b2j_batch;
+	b->big = B; b->n_worlds = n_worlds; b->stride = stride; b->bodies_per_world = P->num_bodies;
+	return b;
+}
+
+void b2j_batch_destroy(b2j_batch *b) { if (b != nullptr) { b2j_world_destroy(b->big); delete b; } }
+int b2j_batch_step(b2j_batch *b, float dt, int collision_steps, b2j_step_stats *stats) { return b2j_step(b->big, dt, collision_steps, stats); }
+uint32_t b2j_batch_size(const b2j_batch *b) { return b != nullptr? b->n_worlds : 0; }
+
+int b2j_batch_get_state(b2j_batch *b, uint32_t world_index, uint32_t n, const b2j_body_state *out)
+{
+	if (b != nullptr && world_index == 0xffffffffu && n <= b->stride * b->n_worlds)
+		return b2j_bodies_get_state(b->big, nullptr, n, out); // all worlds: slots [0, n)
+	if (b == nullptr || world_index >= b->n_worlds || n > b->stride) { last_error() = "b2j_batch_get_state: invalid arguments"; return -1; }
+	b->big->get_state_first = world_index * b->stride;
+	int r = b2j_bodies_get_state(b->big, nullptr, n, out);
+	b->big->get_state_first = 0;
+	return r;
+}
+
+int b2j_batch_add_force_torque(b2j_batch *b, uint32_t n, const float *force, const float *torque)
+{
+	if (b == nullptr || n > b->stride * b->n_worlds) { last_error() = "b2j_batch_add_force_torque: invalid arguments"; return -1; }
+	return b2j_bodies_add_force_torque(b->big, nullptr, n, force, torque);
+}
+
+int b2j_batch_set_profiling(b2j_batch *b, int on) { return b2j_world_set_profiling(b->big, on); }
+uint32_t b2j_batch_get_profile(b2j_batch *b, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap) { return b2j_world_get_profile(b->big, names, name_stride, ms, launches, cap); }
 
 } // extern "C"
 #pragma GCC visibility pop

@@ -21,6 +21,7 @@
 #include <Jolt/Physics/Body/BodyActivationListener.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <random>
@@ -478,6 +479,45 @@ double jref_time_steps(void *h, float inDeltaTime, int inNumSteps, int inNumThre
 }
 
 int jref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// CPU side of the batched-worlds config: inNumThreads host threads each own one independent world of the
+// scene and step it inNumSteps times with a single threaded job system (no cross thread synchronisation: the best case for the
+// CPU when there are many small worlds, TestMultiplePhysicsSystems pattern). inWarmup untimed steps first.
+// Returns the wall time in seconds of the timed part; total work = inNumThreads * inNumSteps world steps.
+double jref_time_worlds_parallel(const char *inName, int inParam0, int inParam1, int inNumThreads, int inWarmup, int inNumSteps, float inDeltaTime)
+{
+	sInit();
+	if (inNumThreads <= 0) inNumThreads = (int)std::thread::hardware_concurrency();
+	std::vector<World *> worlds(inNumThreads, nullptr);
+	std::vector<std::thread> threads;
+	std::atomic<int> ready { 0 };
+	std::atomic<bool> go { false };
+	std::vector<double> seconds(inNumThreads, 0.0);
+	String name(inName);
+	for (int t = 0; t < inNumThreads; ++t)
+		threads.emplace_back([&, t]() {
+			World *w = nullptr;
+			if (name == "pyramid") w = sScenePyramid(inParam0 > 0? inParam0 : 15);
+			else if (name == "convex_vs_mesh") w = sSceneConvexVsMesh(inParam0 > 0? inParam0 : 10);
+			else w = sScenePile(inParam0 > 0? inParam0 : 1000, inParam1 > 0? inParam1 : 15);
+			w->system.OptimizeBroadPhase();
+			sEnsureJobs(w, 1);
+			for (int i = 0; i < inWarmup; ++i) w->system.Update(inDeltaTime, 1, w->temp, w->jobs);
+			ready++;
+			while (!go.load()) std::this_thread::yield();
+			auto t0 = std::chrono::high_resolution_clock::now();
+			for (int i = 0; i < inNumSteps; ++i) w->system.Update(inDeltaTime, 1, w->temp, w->jobs);
+			seconds[t] = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+			worlds[t] = w;
+		});
+	while (ready.load() < inNumThreads) std::this_thread::yield();
+	auto t0 = std::chrono::high_resolution_clock::now();
+	go = true;
+	for (std::thread &t : threads) t.join();
+	double wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+	for (World *w : worlds) delete w;
+	return wall;
+}
 uint32_t jref_num_bodies(void *h) { return ((World *)h)->system.GetNumBodies(); }
 uint32_t jref_num_dynamic(void *h) { return ((World *)h)->num_dynamic; }
 uint32_t jref_num_active(void *h) { return ((World *)h)->system.GetNumActiveBodies(EBodyType::RigidBody); }

@@ -1,0 +1,61 @@
+"""Batched independent worlds (config 5): n clones of one prototype world live in ONE device world and must evolve exactly like
+the prototype stepped alone (the reference's TestMultiplePhysicsSystems pattern, PhysicsTests.cpp:1548)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import refharness as R
+import facade as F
+from joltphysics_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _batch_state(api, batch, world, n):
+    s = R.State(n)
+    st = _capi.BodyState(s.pos.ctypes.data, s.rot.ctypes.data, s.lin.ctypes.data, s.ang.ctypes.data, s.bounds.ctypes.data, s.active_index.ctypes.data, s.sleep_timer.ctypes.data)
+    assert api.b2j_batch_get_state(batch, world, n, C.byref(st)) == 0, api.last_error()
+    return s
+
+
+def _check_batch(api, flib, scene, p0, p1, n_worlds, steps):
+    proto = F.FacadeScene(flib, scene, p0, p1)
+    n = proto.num_bodies
+    batch = api.b2j_batch_create(proto.world.h, n_worlds, 0, 0)
+    assert batch, api.last_error()
+    assert api.b2j_batch_size(batch) == n_worlds
+    stats = _capi.StepStats()
+    single = None
+    for _ in range(steps):
+        assert api.b2j_batch_step(batch, 1.0 / 60.0, 1, C.byref(stats)) == 0, api.last_error()
+        _, single = proto.world.step()
+    assert stats.num_constraints == n_worlds * single.num_constraints
+    assert stats.num_body_pairs == n_worlds * single.num_body_pairs
+    want = proto.world.state()
+    for w in sorted({0, n_worlds // 2, n_worlds - 1}):
+        got = _batch_state(api, batch, w, n)
+        for name in ("pos", "rot", "lin", "ang", "bounds"):
+            assert np.array_equal(getattr(want, name), getattr(got, name)), f"world {w}: {name} differs from the prototype stepped alone"
+        # active indices are per batch (world major): same active flags
+        assert np.array_equal(want.active_index != 0xffffffff, got.active_index != 0xffffffff)
+    api.b2j_batch_destroy(batch)
+    proto.close()
+
+
+@pytest.fixture(scope="session")
+def hostsim_facade(hostsim_api):
+    return F.FacadeLib(os.path.join(ROOT, "tests", "hostsim", "_build", "libb2j_facade_hostsim.so"), hostsim_api)
+
+
+@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 4, 0, 5, 40), ("pile", 300, 15, 3, 60), ("convex_vs_mesh", 1, 0, 4, 80)])
+def test_batch_matches_single_world_hostsim(hostsim_api, hostsim_facade, scene, p0, p1, n_worlds, steps):
+    _check_batch(hostsim_api, hostsim_facade, scene, p0, p1, n_worlds, steps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 15, 0, 16, 60), ("pile", 1000, 15, 8, 90), ("convex_vs_mesh", 3, 0, 6, 120)])
+def test_batch_matches_single_world_gpu(gpu_api, scene, p0, p1, n_worlds, steps):
+    flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
+    _check_batch(gpu_api, flib, scene, p0, p1, n_worlds, steps)
