@@ -22,7 +22,7 @@ namespace b2j {
 
 struct CollideItem { uint32_t b1, b2; uint32_t pair_entry, old_pair; }; // b1 = body whose space the collision is done in
 struct CachedItem { uint32_t pair_entry, old_pair; };
-struct EpaItem { CollideItem c; GjkSimplex s; V3 axis; };
+struct EpaItem { CollideItem c; }; // the EPA kernel re-runs the (deterministic) GJK step instead of carrying the simplex through HBM
 
 // World space data of a manifold created this step (not from the cache), indexed like write_cache.manifolds
 struct ManifoldWS { float normal[3]; float p1[4][3], p2[4][3]; };
@@ -479,8 +479,7 @@ struct KCollideConvex
 			uint32_t e = atomic_add(&w.counters->num_epa, 1u);
 			if (e < c.max_epa)
 			{
-				EpaItem &ei = c.epa[e];
-				ei.c = item; ei.s = simplex; ei.axis = penetration_axis;
+				c.epa[e].c = item;
 			}
 			return;
 		}
@@ -504,8 +503,18 @@ struct KCollideEpa
 		a_incl.s = make_support(w, s1, SUPPORT_INCLUDE_CONVEX_RADIUS);
 		a_incl.radius = max_separation_distance;
 		TransformedSupport b_incl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_INCLUDE_CONVEX_RADIUS));
-		V3 penetration_axis = ei.axis, point1, point2;
-		if (!pen_depth_step_epa(scratch, ei.s, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2))
+		// same GJK step as KCollideConvex (bit identical): yields the simplex and the initial axis EPA starts from
+		V3 penetration_axis = s.transform_2_to_1.t, point1, point2;
+		if (is_near_zero(penetration_axis))
+			penetration_axis = v3(1.0f, 0.0f, 0.0f);
+		GjkSimplex simplex;
+		{
+			ConvexSupport a_excl = make_support(w, s1, SUPPORT_EXCLUDE_CONVEX_RADIUS);
+			TransformedSupport b_excl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_EXCLUDE_CONVEX_RADIUS));
+			if (pen_depth_step_gjk(simplex, a_excl, a_excl.convex_radius + s.max_separation_distance, b_excl, b_excl.s.convex_radius, 1.0e-4f, penetration_axis, point1, point2) != PEN_INDETERMINATE)
+				return;
+		}
+		if (!pen_depth_step_epa(scratch, simplex, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2))
 			return;
 		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, point1, point2, penetration_axis, max_separation_distance);
 	}

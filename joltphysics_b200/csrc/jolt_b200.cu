@@ -825,7 +825,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	nc.collide_convex = rt.alloc<CollideItem>(d.max_body_pairs);
 	nc.collide_mesh = rt.alloc<CollideItem>(d.max_body_pairs);
 	nc.cached = rt.alloc<CachedItem>(d.max_body_pairs);
-	nc.max_epa = d.max_body_pairs / 4 + 1024;
+	nc.max_epa = d.max_body_pairs;
 	nc.epa = rt.alloc<EpaItem>(nc.max_epa, false);
 #ifndef B2J_HOSTSIM
 	nc.num_scratch = (uint32_t)rt.num_sms * 8; // 2 blocks of 4 warps per SM, each warp owns an EpaScratch in shared memory
