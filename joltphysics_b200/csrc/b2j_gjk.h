@@ -392,17 +392,44 @@ struct EpaTriangle
 	uint16_t next_free;
 };
 
-// Scratch of one EPA run (~24 KB); lives in a global memory slot owned by the running thread.
+struct EpaStackEntry { uint16_t tri; int8_t edge; int8_t iter; };
+
+// Working set of one EPA run: a VIEW onto storage of some physical capacity. The reference's limits (256 triangles, 128 points,
+// 128 edges) are semantic (hitting them makes EPA fail like the reference does); a smaller PHYSICAL capacity only raises
+// `overflow`, in which case the caller discards the run and repeats it on full size storage (two tier scheme: the common shallow
+// cases run out of ~4 KB of shared memory per warp, 5x more of them per SM than with the 21 KB worst case block).
 struct EpaScratch
 {
-	EpaTriangle tri[EPA_MAX_TRIANGLES];
-	V3 y[EPA_MAX_POINTS], p[EPA_MAX_POINTS], q[EPA_MAX_POINTS];
-	uint16_t queue[EPA_MAX_TRIANGLES];
-	EpaEdge edges[EPA_MAX_EDGE_LENGTH];
-	uint16_t new_triangles[EPA_MAX_EDGE_LENGTH];
-	struct { uint16_t tri; int8_t edge; int8_t iter; } stack[EPA_MAX_EDGE_LENGTH];
+	EpaTriangle *tri;
+	V3 *y, *p, *q;
+	uint16_t *queue;
+	EpaEdge *edges;
+	uint16_t *new_triangles;
+	EpaStackEntry *stack;
+	int cap_tri, cap_pts, cap_edge;
+	int overflow;
 	int num_points, queue_size, next_free, high_watermark, num_new_triangles;
 };
+
+template <int TRI, int PTS, int EDGE> struct EpaStorage
+{
+	EpaTriangle tri[TRI];
+	V3 y[PTS], p[PTS], q[PTS];
+	uint16_t queue[TRI];
+	EpaEdge edges[EDGE];
+	uint16_t new_triangles[EDGE];
+	EpaStackEntry stack[EDGE];
+	B2J_HD EpaScratch view()
+	{
+		EpaScratch e;
+		e.tri = tri; e.y = y; e.p = p; e.q = q; e.queue = queue; e.edges = edges; e.new_triangles = new_triangles; e.stack = stack;
+		e.cap_tri = TRI; e.cap_pts = PTS; e.cap_edge = EDGE; e.overflow = 0;
+		e.num_points = 0; e.queue_size = 0; e.next_free = 0; e.high_watermark = 0; e.num_new_triangles = 0;
+		return e;
+	}
+};
+using EpaStorageFull = EpaStorage<EPA_MAX_TRIANGLES, EPA_MAX_POINTS, EPA_MAX_EDGE_LENGTH>;   // 21 KB: can never overflow
+using EpaStorageSmall = EpaStorage<48, 24, 24>;                                                  // ~4 KB
 
 B2J_HD bool epa_tri_is_facing(const EpaTriangle &t, V3 pos) { return dot(t.normal, pos - t.centroid) > 0.0f; }
 B2J_HD bool epa_tri_is_facing_origin(const EpaTriangle &t) { return dot(t.normal, t.centroid) < 0.0f; }
@@ -479,6 +506,7 @@ B2J_HD int epa_create_triangle(EpaScratch &e, int idx0, int idx1, int idx2)
 	{
 		if (e.high_watermark >= EPA_MAX_TRIANGLES)
 			return -1;
+		if (e.high_watermark >= e.cap_tri) { e.overflow = 1; return -1; }
 		t = e.high_watermark++;
 	}
 	epa_tri_init(e.tri[t], idx0, idx1, idx2, e.y);
@@ -585,8 +613,7 @@ B2J_HD int epa_find_edge(EpaScratch &e, int facing_triangle, V3 vertex)
 				{
 					e.tri[n].removed = 1;
 					cur_stack_pos++;
-					if (cur_stack_pos >= EPA_MAX_EDGE_LENGTH)
-						return -1; // reference asserts; treat as failure
+					if (cur_stack_pos >= e.cap_edge) { e.overflow = e.cap_edge < EPA_MAX_EDGE_LENGTH; --cur_stack_pos; return -1; } // (the reference asserts at 128)
 					e.stack[cur_stack_pos].tri = (uint16_t)n;
 					e.stack[cur_stack_pos].edge = (int8_t)ed.neighbour_edge;
 					e.stack[cur_stack_pos].iter = 0;
@@ -596,8 +623,7 @@ B2J_HD int epa_find_edge(EpaScratch &e, int facing_triangle, V3 vertex)
 					if ((int)ed.start_idx != next_expected_start_idx && next_expected_start_idx != -1)
 						return -1;
 					next_expected_start_idx = e.tri[n].edge[ed.neighbour_edge].start_idx;
-					if (num_edges >= EPA_MAX_EDGE_LENGTH)
-						return -1;
+					if (num_edges >= e.cap_edge) { e.overflow = e.cap_edge < EPA_MAX_EDGE_LENGTH; return -1; }
 					e.edges[num_edges++] = ed;
 				}
 			}
@@ -638,6 +664,13 @@ B2J_HD V3 epa_add_support(EpaScratch &e, const A &a, const B &b, V3 direction, i
 	V3 p = a.support(direction);
 	V3 q = b.support(-direction);
 	V3 w = p - q;
+	if (e.num_points >= e.cap_pts)
+	{
+		// physical capacity reached (semantic limits are checked by the callers before this can happen on full storage)
+		e.overflow = 1;
+		out_index = e.cap_pts - 1;
+		return w;
+	}
 	out_index = e.num_points++;
 	e.y[out_index] = w; e.p[out_index] = p; e.q[out_index] = q;
 	return w;
@@ -647,6 +680,7 @@ B2J_HD V3 epa_add_support(EpaScratch &e, const A &a, const B &b, V3 direction, i
 template <class AI, class BI>
 B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_incl, const BI &b_incl, float tolerance, V3 &out_v, V3 &out_point_a, V3 &out_point_b)
 {
+	e.overflow = 0;
 	e.num_points = s.num_points;
 	for (int i = 0; i < s.num_points; ++i) { e.y[i] = s.y[i]; e.p[i] = s.p[i]; e.q[i] = s.q[i]; }
 	e.queue_size = 0;
@@ -682,7 +716,7 @@ B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_i
 	default:
 		break;
 	}
-	if (e.num_points < 3)
+	if (e.num_points < 3 || e.overflow)
 		return false;
 
 	// hull.Initialize(0, 1, 2)
@@ -737,6 +771,8 @@ B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_i
 		epa_queue_pop(e);
 		int new_index;
 		V3 w = epa_add_support(e, a_incl, b_incl, e.tri[t].normal, new_index);
+		if (e.overflow)
+			return false;
 		if (!epa_tri_is_facing(e.tri[t], w) || !epa_add_point(e, t, new_index, FLT_MAX))
 			return false;
 		epa_free_triangle(e, t);
@@ -764,6 +800,8 @@ B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_i
 		int new_index;
 		V3 tn = e.tri[t].normal;
 		V3 w = epa_add_support(e, a_incl, b_incl, tn, new_index);
+		if (e.overflow)
+			return false;
 		float dt = dot(tn, w);
 		if (dt < 0.0f)
 			return false;
@@ -774,7 +812,11 @@ B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_i
 		if (!epa_tri_is_facing(e.tri[t], w))
 			break;
 		if (!epa_add_point(e, t, new_index, closest_dist_sq))
+		{
+			if (e.overflow)
+				return false;
 			break;
+		}
 		bool has_defect = false;
 		for (int i = 0; i < e.num_new_triangles; ++i)
 			if (epa_tri_is_facing_origin(e.tri[e.new_triangles[i]])) { has_defect = true; break; }
@@ -789,7 +831,7 @@ B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_i
 	}
 	while (e.queue_size > 0 && e.num_points < EPA_MAX_POINTS);
 
-	if (last < 0)
+	if (last < 0 || e.overflow)
 		return false;
 
 	const EpaTriangle &lt = e.tri[last];

@@ -22,6 +22,7 @@ namespace b2j {
 
 struct CollideItem { uint32_t b1, b2; uint32_t pair_entry, old_pair; }; // b1 = body whose space the collision is done in
 struct CachedItem { uint32_t pair_entry, old_pair; };
+struct EpaResult { CollideItem c; float point1[3], point2[3], axis[3]; }; // penetration found by EPA, finished by KFinishEpa
 struct EpaItem { CollideItem c; }; // the EPA kernel re-runs the (deterministic) GJK step instead of carrying the simplex through HBM
 
 // World space data of a manifold created this step (not from the cache), indexed like write_cache.manifolds
@@ -41,6 +42,10 @@ struct NarrowCtx
 	CollideItem *collide_convex, *collide_mesh;
 	CachedItem *cached;
 	EpaItem *epa;
+	EpaItem *epa_overflow;       // deep pairs that did not fit the small EPA tier (re-run on full size storage)
+	uint32_t *num_epa_overflow;  // device counter
+	EpaResult *epa_results;      // EPA output; supporting faces / clipping / manifold run thread-per-item in KFinishEpa
+	uint32_t *num_epa_results;   // device counter
 	uint32_t num_scratch;        // number of warps the scratch hungry kernels (EPA, mesh) may use
 	ManifoldWS *man_ws;
 	ConstraintSrc *con_src;
@@ -488,13 +493,15 @@ struct KCollideConvex
 };
 
 // ---- KCollideEpa: EPA for the deep pairs; `slot` selects the scratch block -------------------------------------------
-struct KCollideEpa
+// Storage = EpaStorageSmall: first tier, reads c.epa, overflowing items go to c.epa_overflow; EpaStorageFull: second tier over c.epa_overflow
+template <class Storage, bool kFirstTier> struct KCollideEpa
 {
 	DWorld w; NarrowCtx c;
-	B2J_D void run(uint32_t k, uint32_t slot, EpaScratch &scratch) const
+	B2J_D void run(uint32_t k, uint32_t slot, Storage &storage) const
 	{
 		(void)slot;
-		const EpaItem &ei = c.epa[k];
+		EpaScratch scratch = storage.view();
+		const EpaItem &ei = kFirstTier? c.epa[k] : c.epa_overflow[k];
 		CollideItem item = ei.c;
 		ConvexPairSetup s = convex_pair_setup(w, item);
 		const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
@@ -515,8 +522,29 @@ struct KCollideEpa
 				return;
 		}
 		if (!pen_depth_step_epa(scratch, simplex, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2))
+		{
+			if (kFirstTier && scratch.overflow)
+				c.epa_overflow[atomic_add(c.num_epa_overflow, 1u)].c = item;
 			return;
-		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, point1, point2, penetration_axis, max_separation_distance);
+		}
+		// The rest of the pair (supporting faces, clipping, manifold) needs ~5 KB of thread local arrays: with one active lane per warp
+		// that local memory is 1/32 utilised, so it runs in KFinishEpa with every lane busy instead.
+		EpaResult &r = c.epa_results[atomic_add(c.num_epa_results, 1u)];
+		r.c = item;
+		v3_store(point1, r.point1); v3_store(point2, r.point2); v3_store(penetration_axis, r.axis);
+	}
+};
+
+struct KFinishEpa
+{
+	DWorld w; NarrowCtx c;
+	B2J_D void operator()(uint32_t k) const
+	{
+		const EpaResult &r = c.epa_results[k];
+		CollideItem item = r.c;
+		ConvexPairSetup s = convex_pair_setup(w, item);
+		float max_separation_distance = fmin_(s.max_separation_distance, 1.0f);
+		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, v3_load(r.point1), v3_load(r.point2), v3_load(r.axis), max_separation_distance);
 	}
 };
 

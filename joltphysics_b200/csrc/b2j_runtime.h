@@ -43,7 +43,7 @@ template <class K> __global__ void __launch_bounds__(128) run_kernel_dev(const K
 }
 // One WARP per work item for serial, scratch hungry item bodies (EPA): lane 0 runs the item with an S scratch block in shared
 // memory (low latency instead of a global memory slot); slot = global warp id (ownership of any global side scratch).
-template <class K, class S> __global__ void __launch_bounds__(128) run_kernel_warp_smem(const K k, const uint32_t *n_ptr, uint32_t cap)
+template <class K, class S, int MINB> __global__ void __launch_bounds__(256, MINB) run_kernel_warp_smem(const K k, const uint32_t *n_ptr, uint32_t cap)
 {
 	extern __shared__ __align__(16) unsigned char b2j_smem[];
 	uint32_t n = *n_ptr;
@@ -279,7 +279,7 @@ struct Runtime
 #endif
 	}
 	// device-resident count, one warp per item with an S scratch block in shared memory; uses at most num_slots warps
-	template <class K, class S> void launch_warp_smem(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots)
+	template <class K, class S, int MINB = 1> void launch_warp_smem(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots, uint32_t warps_per_block = 4)
 	{
 		if (cap == 0) return;
 		++launches;
@@ -287,15 +287,15 @@ struct Runtime
 		static bool configured = false;
 		if (!configured)
 		{
-			cudaFuncSetAttribute(run_kernel_warp_smem<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(S)));
+			cudaFuncSetAttribute(run_kernel_warp_smem<K, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(S) < 227 * 1024? 8 * sizeof(S) : 4 * sizeof(S)));
 			configured = true;
 		}
-		uint32_t g = num_slots / 4;
+		uint32_t g = num_slots / warps_per_block;
 		if (g < 1) g = 1;
-		uint32_t gn = (cap + 3) / 4;
+		uint32_t gn = (cap + warps_per_block - 1) / warps_per_block;
 		if (gn < g) g = gn;
 		if (profiling) prof_begin(profile_category<K>());
-		run_kernel_warp_smem<K, S><<<g, 128, 4 * sizeof(S), stream>>>(k, n_ptr, cap);
+		run_kernel_warp_smem<K, S, MINB><<<g, 32 * warps_per_block, warps_per_block * sizeof(S), stream>>>(k, n_ptr, cap);
 		if (profiling) prof_end();
 #else
 		(void)num_slots;

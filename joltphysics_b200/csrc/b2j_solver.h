@@ -38,7 +38,8 @@ enum
 enum { PART_R1X = 0, PART_I1 = 3, PART_R2X = 6, PART_I2 = 9, PART_EFF = 12, PART_BIAS = 13, PART_LAMBDA = 14, PT_DIST = 15, PT_LP1 = 16, PT_LP2 = 19 };
 enum { ANG_I1 = 0, ANG_I2 = 3, ANG_EFF = 6, ANG_BIAS = 7, ANG_LAMBDA = 8 };
 
-// meta bits: num points (3) | type1 (2) << 3 | type2 (2) << 5 | velocity steps << 8 | position steps << 16
+// meta bits: num points (3) | type1 (2) << 3 | type2 (2) << 5 | velocity steps << 8 | position steps << 16 | friction parts active << 24
+enum : uint32_t { META_LINEAR_FRICTION = 1u << 24, META_ANGULAR_FRICTION = 1u << 25 };
 struct Constraints
 {
 	float *cf;
@@ -75,6 +76,17 @@ struct SolveCtx
 B2J_HD float &cf_at(const Constraints &c, int field, uint32_t i) { return c.cf[(size_t)field * c.capacity + i]; }
 B2J_HD V3 cf_v3(const Constraints &c, int field, uint32_t i) { return v3(cf_at(c, field, i), cf_at(c, field + 1, i), cf_at(c, field + 2, i)); }
 B2J_HD void cf_set_v3(const Constraints &c, int field, uint32_t i, V3 v) { cf_at(c, field, i) = v.x; cf_at(c, field + 1, i) = v.y; cf_at(c, field + 2, i) = v.z; }
+// Read of a field the running kernel never writes (everything but the lambdas in the solve kernels): goes through the non coherent
+// path, which also tells the compiler that the lambda stores cannot alias it, so all loads of a constraint issue up front.
+B2J_HD float cf_ro(const Constraints &c, int field, uint32_t i)
+{
+#if defined(__CUDA_ARCH__)
+	return __ldg(&c.cf[(size_t)field * c.capacity + i]);
+#else
+	return c.cf[(size_t)field * c.capacity + i];
+#endif
+}
+B2J_HD V3 cf_ro_v3(const Constraints &c, int field, uint32_t i) { return v3(cf_ro(c, field, i), cf_ro(c, field + 1, i), cf_ro(c, field + 2, i)); }
 
 // ---- body helpers ------------------------------------------------------------------------------------------------
 B2J_HD V3 lock_translation(V3 v, uint32_t dofs) { return v3((dofs & 1)? v.x : 0.0f, (dofs & 2)? v.y : 0.0f, (dofs & 4)? v.z : 0.0f); }
@@ -399,16 +411,36 @@ struct KSchedResetCursors
 	B2J_D void operator()(uint32_t ai) const { s.body_cur[w.active[ai]] = 0; }
 };
 
-// histogram of phases
-struct KPhaseCount
+// Phases -> solve order. The constraints are radix sorted by phase (stable: sort key order inside a phase, deterministic layout,
+// no histogram atomics); KPhaseClamp bounds the key and finds the phase count, KPhasePlace scatters and writes the phase offsets.
+struct KPhaseClamp
 {
 	DWorld w; SolveCtx s;
 	B2J_D void operator()(uint32_t i) const
 	{
 		uint32_t p = s.phase[i];
 		if (p >= s.max_phases) { p = s.max_phases - 1; s.phase[i] = p; atomic_or(&w.counters->error_bits, 0x100u); }
-		atomic_add(&s.phase_count[p], 1u);
-		atomic_max(&w.counters->num_phases, p + 1);
+		if (p + 1 > *(volatile const uint32_t *)&w.counters->num_phases) // almost always false: keeps the atomic off the hot path
+			atomic_max(&w.counters->num_phases, p + 1);
+	}
+};
+
+struct KPhasePlace
+{
+	SolveCtx s; const uint32_t *sorted_phase, *sorted_idx; uint32_t n;
+	B2J_D void operator()(uint32_t pos) const
+	{
+		uint32_t i = sorted_idx[pos];
+		s.final_pos[i] = pos;
+		s.solve_src[pos] = s.order[i];
+		// phase_count[q] = first position of phase q (empty phases included), phase_count[last + 1 ...] = n
+		uint32_t p = sorted_phase[pos];
+		uint32_t first = pos == 0? 0 : sorted_phase[pos - 1] + 1;
+		for (uint32_t q = first; q <= p; ++q)
+			s.phase_count[q] = pos;
+		if (pos == n - 1)
+			for (uint32_t q = p + 1; q <= s.max_phases; ++q)
+				s.phase_count[q] = n;
 	}
 };
 
@@ -458,21 +490,23 @@ B2J_D BodyKin load_body_kin(const DWorld &w, uint32_t b)
 	return k;
 }
 
-// ContactConstraintPart::CalculateConstraintProperties; writes the 14 part floats (lambda untouched)
-B2J_D void part_calculate(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, float inv_m1, const M33 &inv_i1, V3 r1,
+// One ContactConstraintPart (Jolt/Physics/Constraints/ConstraintPart/AxisConstraintPart.h members) held in registers
+struct PartRegs { V3 r1x, i1, r2x, i2; float eff, bias, lambda; };
+
+// ContactConstraintPart::CalculateConstraintProperties; r.lambda holds the current total lambda on entry (Deactivate() clears it)
+B2J_D void part_calculate(PartRegs &r, uint32_t type1, uint32_t type2, float inv_m1, const M33 &inv_i1, V3 r1,
 	float inv_m2, const M33 &inv_i2, V3 r2, V3 axis, float bias)
 {
-	cf_at(c, base + PART_BIAS, i) = bias;
+	r.bias = bias;
+	r.r1x = v3_zero(); r.i1 = v3_zero(); r.r2x = v3_zero(); r.i2 = v3_zero();
 	float inv_effective_mass;
 	if (type1 != B2J_MOTION_STATIC)
 	{
-		V3 r1x = cross(r1, axis);
-		cf_set_v3(c, base + PART_R1X, i, r1x);
+		r.r1x = cross(r1, axis);
 		if (type1 == B2J_MOTION_DYNAMIC)
 		{
-			V3 i1 = mul(inv_i1, r1x);
-			cf_set_v3(c, base + PART_I1, i, i1);
-			inv_effective_mass = inv_m1 + dot(i1, r1x);
+			r.i1 = mul(inv_i1, r.r1x);
+			inv_effective_mass = inv_m1 + dot(r.i1, r.r1x);
 		}
 		else
 			inv_effective_mass = 0.0f;
@@ -481,23 +515,46 @@ B2J_D void part_calculate(const Constraints &c, int base, uint32_t i, uint32_t t
 		inv_effective_mass = 0.0f;
 	if (type2 != B2J_MOTION_STATIC)
 	{
-		V3 r2x = cross(r2, axis);
-		cf_set_v3(c, base + PART_R2X, i, r2x);
+		r.r2x = cross(r2, axis);
 		if (type2 == B2J_MOTION_DYNAMIC)
 		{
-			V3 i2 = mul(inv_i2, r2x);
-			cf_set_v3(c, base + PART_I2, i, i2);
-			inv_effective_mass += inv_m2 + dot(i2, r2x);
+			r.i2 = mul(inv_i2, r.r2x);
+			inv_effective_mass += inv_m2 + dot(r.i2, r.r2x);
 		}
 	}
 	if (inv_effective_mass == 0.0f)
 	{
 		// Deactivate(): effective mass AND total lambda are cleared
-		cf_at(c, base + PART_EFF, i) = 0.0f;
-		cf_at(c, base + PART_LAMBDA, i) = 0.0f;
+		r.eff = 0.0f;
+		r.lambda = 0.0f;
 	}
 	else
-		cf_at(c, base + PART_EFF, i) = 1.0f / inv_effective_mass;
+		r.eff = 1.0f / inv_effective_mass;
+}
+
+// the fields the solve kernels read for these motion types (the rest is never read)
+B2J_D void part_store(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, const PartRegs &r)
+{
+	if (type1 != B2J_MOTION_STATIC) cf_set_v3(c, base + PART_R1X, i, r.r1x);
+	if (type1 == B2J_MOTION_DYNAMIC) cf_set_v3(c, base + PART_I1, i, r.i1);
+	if (type2 != B2J_MOTION_STATIC) cf_set_v3(c, base + PART_R2X, i, r.r2x);
+	if (type2 == B2J_MOTION_DYNAMIC) cf_set_v3(c, base + PART_I2, i, r.i2);
+	cf_at(c, base + PART_EFF, i) = r.eff;
+	cf_at(c, base + PART_BIAS, i) = r.bias;
+	cf_at(c, base + PART_LAMBDA, i) = r.lambda;
+}
+
+B2J_D PartRegs part_load(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2)
+{
+	PartRegs r;
+	r.r1x = type1 != B2J_MOTION_STATIC? cf_ro_v3(c, base + PART_R1X, i) : v3_zero();
+	r.i1 = type1 == B2J_MOTION_DYNAMIC? cf_ro_v3(c, base + PART_I1, i) : v3_zero();
+	r.r2x = type2 != B2J_MOTION_STATIC? cf_ro_v3(c, base + PART_R2X, i) : v3_zero();
+	r.i2 = type2 == B2J_MOTION_DYNAMIC? cf_ro_v3(c, base + PART_I2, i) : v3_zero();
+	r.eff = cf_ro(c, base + PART_EFF, i);
+	r.bias = cf_ro(c, base + PART_BIAS, i);
+	r.lambda = cf_at(c, base + PART_LAMBDA, i);
+	return r;
 }
 
 struct KSetupConstraints
@@ -523,7 +580,7 @@ struct KSetupConstraints
 		atomic_max(&w.counters->max_position_steps, psteps);
 
 		c.b1[i] = src.b1; c.b2[i] = src.b2; c.manifold[i] = m;
-		c.meta[i] = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16);
+		uint32_t meta = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16);
 
 		BodyParams p1 = w.params[src.b1], p2 = w.params[src.b2];
 		float combined_friction = sqrt_(p1.friction * p2.friction);
@@ -561,7 +618,6 @@ struct KSetupConstraints
 		{
 			int base = CF_PT0 + p * CF_PT_STRIDE;
 			ws_contacts[p] = 0.5f * (p1_ws[p] + p2_ws[p]);
-			cf_at(c, base + PART_LAMBDA, i) = cm.lambda[p];
 			cf_set_v3(c, base + PT_LP1, i, v3_load(cm.p1[p]));
 			cf_set_v3(c, base + PT_LP2, i, v3_load(cm.p2[p]));
 
@@ -600,13 +656,13 @@ struct KSetupConstraints
 			}
 			else
 				normal_velocity_bias = speculative_contact_velocity_bias;
-			part_calculate(c, base, i, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, normal, normal_velocity_bias);
+			PartRegs part;
+			part.lambda = cm.lambda[p];
+			part_calculate(part, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, normal, normal_velocity_bias);
+			part_store(c, base, i, type1, type2, part);
 		}
 
 		// friction (CalculateFrictionConstraintProperties)
-		cf_at(c, CF_FR0 + PART_LAMBDA, i) = cm.friction_lambda[0];
-		cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i) = cm.friction_lambda[1];
-		cf_at(c, CF_ANG + ANG_LAMBDA, i) = cm.angular_lambda;
 		if (combined_friction > 0.0f)
 		{
 			V3 t1 = normalized_perpendicular(normal);
@@ -620,8 +676,15 @@ struct KSetupConstraints
 				cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i) = length(delta - dot(delta, normal) * normal);
 			}
 			V3 r1 = friction_point - k1.x, r2 = friction_point - k2.x;
-			part_calculate(c, CF_FR0, i, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t1, 0.0f);
-			part_calculate(c, CF_FR0 + 15, i, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t2, 0.0f);
+			PartRegs f1, f2;
+			f1.lambda = cm.friction_lambda[0];
+			f2.lambda = cm.friction_lambda[1];
+			part_calculate(f1, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t1, 0.0f);
+			part_calculate(f2, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t2, 0.0f);
+			part_store(c, CF_FR0, i, type1, type2, f1);
+			part_store(c, CF_FR0 + 15, i, type1, type2, f2);
+			if (f1.eff != 0.0f || f2.eff != 0.0f) meta |= META_LINEAR_FRICTION;
+			float angular_lambda = cm.angular_lambda, angular_eff = 0.0f;
 			if (n > 1)
 			{
 				// AngularFrictionConstraintPart::CalculateConstraintProperties
@@ -633,14 +696,14 @@ struct KSetupConstraints
 				if (type1 == B2J_MOTION_DYNAMIC && type2 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i1a + i2a);
 				else if (type1 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i1a);
 				else if (type2 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i2a);
-				if (inv_effective_mass == 0.0f) { cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f; cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f; }
-				else cf_at(c, CF_ANG + ANG_EFF, i) = 1.0f / inv_effective_mass;
+				if (inv_effective_mass == 0.0f) angular_lambda = 0.0f;
+				else angular_eff = 1.0f / inv_effective_mass;
 			}
 			else
-			{
-				cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f;
-				cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f;
-			}
+				angular_lambda = 0.0f;
+			cf_at(c, CF_ANG + ANG_EFF, i) = angular_eff;
+			cf_at(c, CF_ANG + ANG_LAMBDA, i) = angular_lambda;
+			if (angular_eff != 0.0f) meta |= META_ANGULAR_FRICTION;
 		}
 		else
 		{
@@ -650,6 +713,7 @@ struct KSetupConstraints
 			cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f; cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f;
 			for (int p = 0; p < n; ++p) cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i) = 0.0f;
 		}
+		c.meta[i] = meta;
 	}
 };
 
@@ -658,19 +722,19 @@ struct KSetupConstraints
 struct VelState { V3 v1, w1, v2, w2; };
 
 // ContactConstraintPart::ApplyVelocityStep
-B2J_D bool part_apply_velocity_step(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, VelState &s, float inv_m1, float inv_m2, V3 axis, float lambda)
+B2J_D bool part_apply_velocity_step(const PartRegs &r, uint32_t type1, uint32_t type2, VelState &s, float inv_m1, float inv_m2, V3 axis, float lambda)
 {
 	if (lambda != 0.0f)
 	{
 		if (type1 == B2J_MOTION_DYNAMIC)
 		{
 			s.v1 -= (lambda * inv_m1) * axis;
-			s.w1 -= lambda * cf_v3(c, base + PART_I1, i);
+			s.w1 -= lambda * r.i1;
 		}
 		if (type2 == B2J_MOTION_DYNAMIC)
 		{
 			s.v2 += (lambda * inv_m2) * axis;
-			s.w2 += lambda * cf_v3(c, base + PART_I2, i);
+			s.w2 += lambda * r.i2;
 		}
 		return true;
 	}
@@ -678,7 +742,7 @@ B2J_D bool part_apply_velocity_step(const Constraints &c, int base, uint32_t i, 
 }
 
 // SolveVelocityConstraintGetTotalLambda
-B2J_D float part_get_total_lambda(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, const VelState &s, V3 axis)
+B2J_D float part_get_total_lambda(const PartRegs &r, uint32_t type1, uint32_t type2, const VelState &s, V3 axis)
 {
 	float jv;
 	if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC)
@@ -688,19 +752,19 @@ B2J_D float part_get_total_lambda(const Constraints &c, int base, uint32_t i, ui
 	else
 		jv = dot(axis, -s.v2);
 	if (type1 != B2J_MOTION_STATIC)
-		jv += dot(cf_v3(c, base + PART_R1X, i), s.w1);
+		jv += dot(r.r1x, s.w1);
 	if (type2 != B2J_MOTION_STATIC)
-		jv -= dot(cf_v3(c, base + PART_R2X, i), s.w2);
-	float lambda = cf_at(c, base + PART_EFF, i) * (jv - cf_at(c, base + PART_BIAS, i));
-	return cf_at(c, base + PART_LAMBDA, i) + lambda;
+		jv -= dot(r.r2x, s.w2);
+	float lambda = r.eff * (jv - r.bias);
+	return r.lambda + lambda;
 }
 
 // SolveVelocityConstraintApplyLambda
-B2J_D bool part_apply_lambda(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, VelState &s, float inv_m1, float inv_m2, V3 axis, float total_lambda)
+B2J_D bool part_apply_lambda(PartRegs &r, uint32_t type1, uint32_t type2, VelState &s, float inv_m1, float inv_m2, V3 axis, float total_lambda)
 {
-	float delta_lambda = total_lambda - cf_at(c, base + PART_LAMBDA, i);
-	cf_at(c, base + PART_LAMBDA, i) = total_lambda;
-	return part_apply_velocity_step(c, base, i, type1, type2, s, inv_m1, inv_m2, axis, delta_lambda);
+	float delta_lambda = total_lambda - r.lambda;
+	r.lambda = total_lambda;
+	return part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, axis, delta_lambda);
 }
 
 B2J_D void load_vel_state(const DWorld &w, uint32_t b1, uint32_t b2, uint32_t type1, uint32_t type2, VelState &s)
@@ -738,45 +802,49 @@ struct KWarmStart
 		uint32_t b1 = c.b1[i], b2 = c.b2[i];
 		VelState s;
 		load_vel_state(w, b1, b2, type1, type2, s);
-		V3 normal = cf_v3(c, CF_NX, i);
+		V3 normal = cf_ro_v3(c, CF_NX, i);
 		V3 t1 = normalized_perpendicular(normal);
 		V3 t2 = cross(normal, t1);
-		float inv_m1 = cf_at(c, CF_INVM1, i), inv_m2 = cf_at(c, CF_INVM2, i);
+		float inv_m1 = cf_ro(c, CF_INVM1, i), inv_m2 = cf_ro(c, CF_INVM2, i);
 		bool any = false;
 		for (int f = 0; f < 2; ++f)
 		{
 			int base = CF_FR0 + 15 * f;
-			if (cf_at(c, base + PART_EFF, i) != 0.0f)
+			if (cf_ro(c, base + PART_EFF, i) != 0.0f)
 			{
-				float l = cf_at(c, base + PART_LAMBDA, i) * ratio;
+				PartRegs r = part_load(c, base, i, type1, type2);
+				float l = r.lambda * ratio;
 				cf_at(c, base + PART_LAMBDA, i) = l;
-				if (part_apply_velocity_step(c, base, i, type1, type2, s, inv_m1, inv_m2, f == 0? t1 : t2, l)) any = true;
+				if (part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, f == 0? t1 : t2, l)) any = true;
 			}
 		}
-		if (cf_at(c, CF_ANG + ANG_EFF, i) != 0.0f)
+		if (meta & META_ANGULAR_FRICTION)
 		{
 			float l = cf_at(c, CF_ANG + ANG_LAMBDA, i) * ratio;
 			cf_at(c, CF_ANG + ANG_LAMBDA, i) = l;
 			if (l != 0.0f)
 			{
-				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= l * cf_v3(c, CF_ANG + ANG_I1, i);
-				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += l * cf_v3(c, CF_ANG + ANG_I2, i);
+				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= l * cf_ro_v3(c, CF_ANG + ANG_I1, i);
+				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += l * cf_ro_v3(c, CF_ANG + ANG_I2, i);
 				any = true;
 			}
 		}
 		for (int p = 0; p < n; ++p)
 		{
 			int base = CF_PT0 + p * CF_PT_STRIDE;
-			float l = cf_at(c, base + PART_LAMBDA, i) * ratio;
+			PartRegs r = part_load(c, base, i, type1, type2);
+			float l = r.lambda * ratio;
 			cf_at(c, base + PART_LAMBDA, i) = l;
-			if (part_apply_velocity_step(c, base, i, type1, type2, s, inv_m1, inv_m2, normal, l)) any = true;
+			if (part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, normal, l)) any = true;
 		}
 		if (any)
 			store_vel_state(w, b1, b2, type1, type2, s);
 	}
 };
 
-// sSolveVelocityConstraint; iteration = 0 based velocity step index (constraints of islands with fewer steps skip)
+// sSolveVelocityConstraint; iteration = 0 based velocity step index (constraints of islands with fewer steps skip).
+// Everything the constraint needs is loaded into registers up front (one DRAM round trip per constraint instead of one per part),
+// the lambdas are written back at the end.
 struct KSolveVelocity
 {
 	DWorld w; Constraints c; uint32_t begin; uint32_t iteration;
@@ -789,35 +857,67 @@ struct KSolveVelocity
 		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
 		uint32_t b1 = c.b1[i], b2 = c.b2[i];
+		bool linear_friction_active = (meta & META_LINEAR_FRICTION) != 0;
+		bool angular_friction_active = (meta & META_ANGULAR_FRICTION) != 0;
+
+		// ---- loads
 		VelState s;
 		load_vel_state(w, b1, b2, type1, type2, s);
-		V3 normal = cf_v3(c, CF_NX, i);
+		V3 normal = cf_ro_v3(c, CF_NX, i);
+		float inv_m1 = cf_ro(c, CF_INVM1, i), inv_m2 = cf_ro(c, CF_INVM2, i);
+		float mu = cf_ro(c, CF_FRICTION, i);
+		PartRegs pt[4];
+		float dist[4];
+#if defined(__CUDA_ARCH__)
+		#pragma unroll
+#endif
+		for (int p = 0; p < 4; ++p)
+			if (p < n)
+			{
+				pt[p] = part_load(c, CF_PT0 + p * CF_PT_STRIDE, i, type1, type2);
+				dist[p] = cf_ro(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i);
+			}
+		PartRegs f1, f2;
+		if (linear_friction_active)
+		{
+			f1 = part_load(c, CF_FR0, i, type1, type2);
+			f2 = part_load(c, CF_FR0 + 15, i, type1, type2);
+		}
+		float ang_eff = 0.0f, ang_bias = 0.0f, ang_lambda = 0.0f;
+		V3 ang_i1 = v3_zero(), ang_i2 = v3_zero();
+		if (angular_friction_active)
+		{
+			ang_eff = cf_ro(c, CF_ANG + ANG_EFF, i);
+			ang_bias = cf_ro(c, CF_ANG + ANG_BIAS, i);
+			ang_lambda = cf_at(c, CF_ANG + ANG_LAMBDA, i);
+			if (type1 == B2J_MOTION_DYNAMIC) ang_i1 = cf_ro_v3(c, CF_ANG + ANG_I1, i);
+			if (type2 == B2J_MOTION_DYNAMIC) ang_i2 = cf_ro_v3(c, CF_ANG + ANG_I2, i);
+		}
+
+		// ---- solve
 		V3 t1 = normalized_perpendicular(normal);
 		V3 t2 = cross(normal, t1);
-		float inv_m1 = cf_at(c, CF_INVM1, i), inv_m2 = cf_at(c, CF_INVM2, i);
 		bool any = false;
-
-		bool f1_active = cf_at(c, CF_FR0 + PART_EFF, i) != 0.0f, f2_active = cf_at(c, CF_FR0 + 15 + PART_EFF, i) != 0.0f;
-		bool linear_friction_active = f1_active || f2_active;
-		bool angular_friction_active = cf_at(c, CF_ANG + ANG_EFF, i) != 0.0f;
 		float max_linear_lambda = 0.0f, max_angular_lambda = 0.0f;
 		if (linear_friction_active || angular_friction_active)
 		{
-			for (int p = 0; p < n; ++p)
-			{
-				int base = CF_PT0 + p * CF_PT_STRIDE;
-				float lambda = cf_at(c, base + PART_LAMBDA, i);
-				max_linear_lambda += lambda;
-				max_angular_lambda += cf_at(c, base + PT_DIST, i) * lambda;
-			}
-			float mu = cf_at(c, CF_FRICTION, i);
+#if defined(__CUDA_ARCH__)
+			#pragma unroll
+#endif
+			for (int p = 0; p < 4; ++p)
+				if (p < n)
+				{
+					float lambda = pt[p].lambda;
+					max_linear_lambda += lambda;
+					max_angular_lambda += dist[p] * lambda;
+				}
 			max_linear_lambda *= mu;
 			max_angular_lambda *= mu;
 		}
 		if (linear_friction_active)
 		{
-			float lambda1 = part_get_total_lambda(c, CF_FR0, i, type1, type2, s, t1);
-			float lambda2 = part_get_total_lambda(c, CF_FR0 + 15, i, type1, type2, s, t2);
+			float lambda1 = part_get_total_lambda(f1, type1, type2, s, t1);
+			float lambda2 = part_get_total_lambda(f2, type1, type2, s, t2);
 			float total_lambda_sq = square(lambda1) + square(lambda2);
 			if (total_lambda_sq > square(max_linear_lambda))
 			{
@@ -825,8 +925,10 @@ struct KSolveVelocity
 				lambda1 *= scale;
 				lambda2 *= scale;
 			}
-			if (part_apply_lambda(c, CF_FR0, i, type1, type2, s, inv_m1, inv_m2, t1, lambda1)) any = true;
-			if (part_apply_lambda(c, CF_FR0 + 15, i, type1, type2, s, inv_m1, inv_m2, t2, lambda2)) any = true;
+			if (part_apply_lambda(f1, type1, type2, s, inv_m1, inv_m2, t1, lambda1)) any = true;
+			if (part_apply_lambda(f2, type1, type2, s, inv_m1, inv_m2, t2, lambda2)) any = true;
+			cf_at(c, CF_FR0 + PART_LAMBDA, i) = f1.lambda;
+			cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i) = f2.lambda;
 		}
 		if (angular_friction_active)
 		{
@@ -835,25 +937,29 @@ struct KSolveVelocity
 			if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC) jv = dot(normal, s.w1 - s.w2);
 			else if (type1 != B2J_MOTION_STATIC) jv = dot(normal, s.w1);
 			else jv = -dot(normal, s.w2);
-			float total = cf_at(c, CF_ANG + ANG_LAMBDA, i);
-			float lambda = cf_at(c, CF_ANG + ANG_EFF, i) * (jv - cf_at(c, CF_ANG + ANG_BIAS, i));
+			float total = ang_lambda;
+			float lambda = ang_eff * (jv - ang_bias);
 			float new_lambda = clamp_(total + lambda, -max_angular_lambda, max_angular_lambda);
 			lambda = new_lambda - total;
 			cf_at(c, CF_ANG + ANG_LAMBDA, i) = new_lambda;
 			if (lambda != 0.0f)
 			{
-				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= lambda * cf_v3(c, CF_ANG + ANG_I1, i);
-				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += lambda * cf_v3(c, CF_ANG + ANG_I2, i);
+				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= lambda * ang_i1;
+				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += lambda * ang_i2;
 				any = true;
 			}
 		}
-		for (int p = 0; p < n; ++p)
-		{
-			int base = CF_PT0 + p * CF_PT_STRIDE;
-			float total_lambda = part_get_total_lambda(c, base, i, type1, type2, s, normal);
-			total_lambda = fmax_(total_lambda, 0.0f);
-			if (part_apply_lambda(c, base, i, type1, type2, s, inv_m1, inv_m2, normal, total_lambda)) any = true;
-		}
+#if defined(__CUDA_ARCH__)
+		#pragma unroll
+#endif
+		for (int p = 0; p < 4; ++p)
+			if (p < n)
+			{
+				float total_lambda = part_get_total_lambda(pt[p], type1, type2, s, normal);
+				total_lambda = fmax_(total_lambda, 0.0f);
+				if (part_apply_lambda(pt[p], type1, type2, s, inv_m1, inv_m2, normal, total_lambda)) any = true;
+				cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PART_LAMBDA, i) = pt[p].lambda;
+			}
 		if (any)
 			store_vel_state(w, b1, b2, type1, type2, s);
 	}
@@ -918,8 +1024,8 @@ struct KSolvePosition
 		uint32_t dofs1 = w.info[b1].allowed_dofs, dofs2 = w.info[b2].allowed_dofs;
 		// transforms are fetched once per constraint, inertia / positions are re-read per point (bodies move between points)
 		Xf transform1 = xf_rotation_translation(q1, x1), transform2 = xf_rotation_translation(q2, x2);
-		V3 normal = cf_v3(c, CF_NX, i);
-		float inv_m1 = cf_at(c, CF_INVM1, i), inv_m2 = cf_at(c, CF_INVM2, i);
+		V3 normal = cf_ro_v3(c, CF_NX, i);
+		float inv_m1 = cf_ro(c, CF_INVM1, i), inv_m2 = cf_ro(c, CF_INVM2, i);
 		V3 diag1 = v3_zero(), diag2 = v3_zero();
 		Q4 irot1 = q4_identity(), irot2 = q4_identity();
 		if (type1 == B2J_MOTION_DYNAMIC) { diag1 = to_v3(w.inv_inertia_diag[b1]); irot1 = to_q4(w.inertia_rotation[b1]); }
@@ -928,8 +1034,8 @@ struct KSolvePosition
 		for (int p = 0; p < n; ++p)
 		{
 			int base = CF_PT0 + p * CF_PT_STRIDE;
-			V3 p1 = mul(transform1, cf_v3(c, base + PT_LP1, i));
-			V3 p2 = mul(transform2, cf_v3(c, base + PT_LP2, i));
+			V3 p1 = mul(transform1, cf_ro_v3(c, base + PT_LP1, i));
+			V3 p2 = mul(transform2, cf_ro_v3(c, base + PT_LP2, i));
 			float separation = fmax_(dot(p2 - p1, normal) + w.settings.penetration_slop, -w.settings.max_penetration_distance);
 			if (separation < 0.0f)
 			{
@@ -937,20 +1043,24 @@ struct KSolvePosition
 				M33 inv_i2 = type2 == B2J_MOTION_DYNAMIC? inverse_inertia_for_rotation(m33_rotation(q2), irot2, diag2, dofs2) : m33_zero();
 				V3 pm = 0.5f * (p1 + p2);
 				V3 r1 = pm - x1, r2 = pm - x2;
-				part_calculate(c, base, i, type1, type2, inv_m1, inv_i1, r1, inv_m2, inv_i2, r2, normal, 0.0f);
+				// the part is recomputed in registers only: nothing reads the stored part after the velocity solve (the impulses
+				// were already saved by KStoreImpulses)
+				PartRegs part;
+				part.lambda = 0.0f;
+				part_calculate(part, type1, type2, inv_m1, inv_i1, r1, inv_m2, inv_i2, r2, normal, 0.0f);
 				// ContactConstraintPart::SolvePositionConstraint
 				if (separation != 0.0f)
 				{
-					float lambda = -cf_at(c, base + PART_EFF, i) * w.settings.baumgarte * separation;
+					float lambda = -part.eff * w.settings.baumgarte * separation;
 					if (type1 == B2J_MOTION_DYNAMIC)
 					{
 						x1 -= lock_translation((lambda * inv_m1) * normal, dofs1);
-						q1 = add_rotation_step(q1, lambda * cf_v3(c, base + PART_I1, i), true);
+						q1 = add_rotation_step(q1, lambda * part.i1, true);
 					}
 					if (type2 == B2J_MOTION_DYNAMIC)
 					{
 						x2 += lock_translation((lambda * inv_m2) * normal, dofs2);
-						q2 = add_rotation_step(q2, lambda * cf_v3(c, base + PART_I2, i), false);
+						q2 = add_rotation_step(q2, lambda * part.i2, false);
 					}
 					any = true;
 				}

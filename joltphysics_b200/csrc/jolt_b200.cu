@@ -230,18 +230,6 @@ struct KNextRound
 	}
 };
 
-struct KPhaseScatter
-{
-	SolveCtx s; uint32_t *phase_fill;
-	B2J_D void operator()(uint32_t i) const
-	{
-		uint32_t p = s.phase[i];
-		uint32_t pos = s.phase_count[p] + atomic_add(&phase_fill[p], 1u);
-		s.final_pos[i] = pos;
-		s.solve_src[pos] = s.order[i];
-	}
-};
-
 struct KGatherSortKeys
 {
 	SolveCtx s; uint64_t *keys; uint32_t *vals;
@@ -335,7 +323,6 @@ struct b2j_world
 	MeshScratch *d_mesh_scratch = nullptr;   // allocated when the first mesh shape is uploaded
 	uint64_t *d_sort_keys[2] = { nullptr, nullptr };
 	uint32_t *d_sort_vals = nullptr;
-	uint32_t *d_phase_fill = nullptr;
 	uint32_t *d_woken_sorted = nullptr;
 	uint32_t *d_woken_keys = nullptr;
 	b2j_activation_event *d_act_events = nullptr;
@@ -495,8 +482,13 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KProcessPairs k; k.w = d; k.c = W->nc; k.first_ptr = W->d_round_begin; rt.launch_dev(k, &d.counters->num_pairs, W->d_round_begin, d.max_body_pairs); }
 		{ KCopyCached k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_cached, nullptr, d.max_body_pairs); }
 		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
-		{ KCollideEpa k; k.w = d; k.c = W->nc; rt.launch_warp_smem<KCollideEpa, EpaScratch>(k, &d.counters->num_epa, W->nc.max_epa, W->nc.num_scratch); }
-		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_warp_smem<KCollideMesh, EpaScratch>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
+		// deep pairs: small EPA tier first (8 warps x 4 KB of shared memory per block), the few that overflow it re-run on full size storage
+		rt.memset_(W->nc.num_epa_overflow, 0, 4);
+		rt.memset_(W->nc.num_epa_results, 0, 4);
+		{ KCollideEpa<EpaStorageSmall, true> k; k.w = d; k.c = W->nc; rt.launch_warp_smem<KCollideEpa<EpaStorageSmall, true>, EpaStorageSmall, 4>(k, &d.counters->num_epa, W->nc.max_epa, (uint32_t)rt.num_sms * 32, 8); }
+		{ KCollideEpa<EpaStorageFull, false> k; k.w = d; k.c = W->nc; rt.launch_warp_smem<KCollideEpa<EpaStorageFull, false>, EpaStorageFull>(k, W->nc.num_epa_overflow, W->nc.max_epa, W->nc.num_scratch, 4); }
+		{ KFinishEpa k; k.w = d; k.c = W->nc; rt.launch_dev(k, W->nc.num_epa_results, nullptr, W->nc.max_epa); }
+		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_warp_smem<KCollideMesh, EpaStorageFull>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
 		if (!read_counters(W)) return false;
 		uint32_t woken = W->h_counters.num_woken;
 		if (W->h_counters.num_epa > W->nc.max_epa) { last_error() = "EPA queue overflow"; return false; }
@@ -574,11 +566,13 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		}
 
 		// phases -> solve order
-		rt.memset_(sc.phase_count, 0, (sc.max_phases + 1) * 4);
-		rt.memset_(W->d_phase_fill, 0, (sc.max_phases + 1) * 4);
-		{ KPhaseCount k; k.w = d; k.s = sc; rt.launch(k, M); }
-		rt.exclusive_scan(sc.phase_count, sc.phase_count, sc.max_phases + 1);
-		{ KPhaseScatter k; k.s = sc; k.phase_fill = W->d_phase_fill; rt.launch(k, M); }
+		{
+			// the 64 bit key buffers of the constraint sort are free again: reuse them for the (phase, index) sort; d_sort_vals still holds 0..M-1
+			uint32_t *sorted_phase = reinterpret_cast<uint32_t *>(W->d_sort_keys[0]), *sorted_idx = reinterpret_cast<uint32_t *>(W->d_sort_keys[1]);
+			{ KPhaseClamp k; k.w = d; k.s = sc; rt.launch(k, M); }
+			rt.sort_pairs<uint32_t>(sc.phase, sorted_phase, W->d_sort_vals, sorted_idx, M, 13);
+			{ KPhasePlace k; k.s = sc; k.sorted_phase = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
+		}
 
 		// (a11) constraint setup straight into solve order
 		{ KSetupConstraints k; k.w = d; k.s = sc; k.dt = dt; rt.launch(k, M); }
@@ -827,6 +821,10 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	nc.cached = rt.alloc<CachedItem>(d.max_body_pairs);
 	nc.max_epa = d.max_body_pairs;
 	nc.epa = rt.alloc<EpaItem>(nc.max_epa, false);
+	nc.epa_overflow = rt.alloc<EpaItem>(nc.max_epa, false);
+	nc.num_epa_overflow = rt.alloc<uint32_t>(1);
+	nc.epa_results = rt.alloc<EpaResult>(nc.max_epa, false);
+	nc.num_epa_results = rt.alloc<uint32_t>(1);
 #ifndef B2J_HOSTSIM
 	nc.num_scratch = (uint32_t)rt.num_sms * 8; // 2 blocks of 4 warps per SM, each warp owns an EpaScratch in shared memory
 #else
@@ -863,7 +861,6 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	sc.order = rt.alloc<uint32_t>(mc); sc.final_pos = rt.alloc<uint32_t>(mc); sc.solve_src = rt.alloc<uint32_t>(mc); sc.phase = rt.alloc<uint32_t>(mc);
 	sc.max_phases = 8192;
 	sc.phase_count = rt.alloc<uint32_t>(sc.max_phases + 2);
-	W->d_phase_fill = rt.alloc<uint32_t>(sc.max_phases + 2);
 	sc.uf_parent = rt.alloc<uint32_t>(nbod); sc.root = rt.alloc<uint32_t>(nbod); sc.island_items = rt.alloc<uint32_t>(nbod);
 	sc.island_large = rt.alloc<uint32_t>(nbod); sc.island_steps = rt.alloc<uint32_t>(nbod); sc.island_can_sleep = rt.alloc<uint32_t>(nbod);
 	sc.large_color_count = rt.alloc<uint32_t>((size_t)(mc / 128 + 2) * 32);
@@ -921,13 +918,13 @@ void b2j_world_destroy(b2j_world *W)
 		rt.free_(W->cache[i].pairs); rt.free_(W->cache[i].manifolds); rt.free_(W->cache[i].pair_table); rt.free_(W->cache[i].num_pairs); rt.free_(W->cache[i].num_manifolds);
 	}
 	NarrowCtx &nc = W->nc;
-	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa);
+	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(nc.events);
 	rt.free_(W->d_mesh_scratch);
 	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
 	rt.free_(sc.con.cf); rt.free_(sc.con.b1); rt.free_(sc.con.b2); rt.free_(sc.con.manifold); rt.free_(sc.con.meta);
-	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count); rt.free_(W->d_phase_fill);
+	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count);
 	rt.free_(sc.uf_parent); rt.free_(sc.root); rt.free_(sc.island_items); rt.free_(sc.island_large); rt.free_(sc.island_steps); rt.free_(sc.island_can_sleep);
 	rt.free_(sc.large_color_count); rt.free_(sc.body_deg); rt.free_(sc.body_off); rt.free_(sc.body_fill); rt.free_(sc.body_cur); rt.free_(sc.body_mask);
 	rt.free_(sc.adj); rt.free_(sc.sched_flag);
