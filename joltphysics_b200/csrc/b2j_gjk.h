@@ -293,63 +293,78 @@ B2J_HD void gjk_calculate_point_a_and_b(const GjkSimplex &s, V3 &out_a, V3 &out_
 }
 
 // GJKClosestPoint::GetClosestPoints. A and B provide V3 support(V3 dir) const.
+// One iteration of the GetClosestPoints loop; returns false when the loop ends (separated = the early out above max_dist_sq)
 template <class A, class B>
-B2J_HD float gjk_get_closest_points(GjkSimplex &s, const A &a, const B &b, float tolerance, float max_dist_sq, V3 &io_v, V3 &out_point_a, V3 &out_point_b)
+B2J_HD bool gjk_closest_points_iteration(GjkSimplex &s, const A &a, const B &b, float tolerance_sq, float max_dist_sq, V3 &io_v, float &v_len_sq, float &prev_v_len_sq, bool &separated)
+{
+	V3 p = a.support(io_v);
+	V3 q = b.support(-io_v);
+	V3 w = p - q;
+	float dt = dot(io_v, w);
+	if (dt < 0.0f && dt * dt > v_len_sq * max_dist_sq)
+	{
+		separated = true;
+		return false;
+	}
+
+	s.y[s.num_points] = w; s.p[s.num_points] = p; s.q[s.num_points] = q;
+	++s.num_points;
+
+	uint32_t set;
+	if (!gjk_get_closest(s, prev_v_len_sq, io_v, v_len_sq, set))
+	{
+		--s.num_points;
+		return false;
+	}
+	if (set == 0xf)
+	{
+		io_v = v3_zero();
+		v_len_sq = 0.0f;
+		return false;
+	}
+	// UpdatePointSetYPQ
+	{
+		int n = 0;
+		for (int i = 0; i < s.num_points; ++i)
+			if (set & (1u << i)) { s.y[n] = s.y[i]; s.p[n] = s.p[i]; s.q[n] = s.q[i]; ++n; }
+		s.num_points = n;
+	}
+	if (v_len_sq <= tolerance_sq)
+	{
+		io_v = v3_zero();
+		v_len_sq = 0.0f;
+		return false;
+	}
+	float max_y = length_sq(s.y[0]);
+	for (int i = 1; i < s.num_points; ++i) max_y = fmax_(max_y, length_sq(s.y[i]));
+	if (v_len_sq <= FLT_EPSILON * max_y)
+	{
+		io_v = v3_zero();
+		v_len_sq = 0.0f;
+		return false;
+	}
+	io_v = -io_v;
+	if (prev_v_len_sq - v_len_sq <= FLT_EPSILON * prev_v_len_sq)
+		return false;
+	prev_v_len_sq = v_len_sq;
+	return true;
+}
+
+// GJKClosestPoint::GetClosestPoints. kLockstep (thread-per-pair kernels whose 32 lanes ALL call this, `alive` = lane has work): the
+// loop trip count is made warp uniform with a vote so the lanes reconverge every iteration instead of drifting apart for good.
+template <bool kLockstep = false, class A, class B>
+B2J_HD float gjk_get_closest_points(GjkSimplex &s, const A &a, const B &b, float tolerance, float max_dist_sq, V3 &io_v, V3 &out_point_a, V3 &out_point_b, bool alive = true)
 {
 	float tolerance_sq = square(tolerance);
 	s.num_points = 0;
 	float v_len_sq = length_sq(io_v);
 	float prev_v_len_sq = FLT_MAX;
-	for (;;)
-	{
-		V3 p = a.support(io_v);
-		V3 q = b.support(-io_v);
-		V3 w = p - q;
-		float dt = dot(io_v, w);
-		if (dt < 0.0f && dt * dt > v_len_sq * max_dist_sq)
-			return FLT_MAX;
-
-		s.y[s.num_points] = w; s.p[s.num_points] = p; s.q[s.num_points] = q;
-		++s.num_points;
-
-		uint32_t set;
-		if (!gjk_get_closest(s, prev_v_len_sq, io_v, v_len_sq, set))
-		{
-			--s.num_points;
-			break;
-		}
-		if (set == 0xf)
-		{
-			io_v = v3_zero();
-			v_len_sq = 0.0f;
-			break;
-		}
-		// UpdatePointSetYPQ
-		{
-			int n = 0;
-			for (int i = 0; i < s.num_points; ++i)
-				if (set & (1u << i)) { s.y[n] = s.y[i]; s.p[n] = s.p[i]; s.q[n] = s.q[i]; ++n; }
-			s.num_points = n;
-		}
-		if (v_len_sq <= tolerance_sq)
-		{
-			io_v = v3_zero();
-			v_len_sq = 0.0f;
-			break;
-		}
-		float max_y = length_sq(s.y[0]);
-		for (int i = 1; i < s.num_points; ++i) max_y = fmax_(max_y, length_sq(s.y[i]));
-		if (v_len_sq <= FLT_EPSILON * max_y)
-		{
-			io_v = v3_zero();
-			v_len_sq = 0.0f;
-			break;
-		}
-		io_v = -io_v;
-		if (prev_v_len_sq - v_len_sq <= FLT_EPSILON * prev_v_len_sq)
-			break;
-		prev_v_len_sq = v_len_sq;
-	}
+	bool separated = false, run = alive;
+	while (warp_any<kLockstep>(run))
+		if (run)
+			run = gjk_closest_points_iteration(s, a, b, tolerance_sq, max_dist_sq, io_v, v_len_sq, prev_v_len_sq, separated);
+	if (separated || !alive)
+		return FLT_MAX;
 	gjk_calculate_point_a_and_b(s, out_point_a, out_point_b);
 	return v_len_sq;
 }
@@ -357,12 +372,12 @@ B2J_HD float gjk_get_closest_points(GjkSimplex &s, const A &a, const B &b, float
 enum { PEN_NOT_COLLIDING = 0, PEN_COLLIDING = 1, PEN_INDETERMINATE = 2 };
 
 // EPAPenetrationDepth::GetPenetrationDepthStepGJK
-template <class AE, class BE>
-B2J_HD int pen_depth_step_gjk(GjkSimplex &s, const AE &a_excl, float convex_radius_a, const BE &b_excl, float convex_radius_b, float tolerance, V3 &io_v, V3 &out_point_a, V3 &out_point_b)
+template <bool kLockstep = false, class AE, class BE>
+B2J_HD int pen_depth_step_gjk(GjkSimplex &s, const AE &a_excl, float convex_radius_a, const BE &b_excl, float convex_radius_b, float tolerance, V3 &io_v, V3 &out_point_a, V3 &out_point_b, bool alive = true)
 {
 	float combined_radius = convex_radius_a + convex_radius_b;
 	float combined_radius_sq = combined_radius * combined_radius;
-	float closest_points_dist_sq = gjk_get_closest_points(s, a_excl, b_excl, tolerance, combined_radius_sq, io_v, out_point_a, out_point_b);
+	float closest_points_dist_sq = gjk_get_closest_points<kLockstep>(s, a_excl, b_excl, tolerance, combined_radius_sq, io_v, out_point_a, out_point_b, alive);
 	if (closest_points_dist_sq > combined_radius_sq)
 		return PEN_NOT_COLLIDING;
 	if (closest_points_dist_sq > 0.0f)
@@ -429,7 +444,7 @@ template <int TRI, int PTS, int EDGE> struct EpaStorage
 	}
 };
 using EpaStorageFull = EpaStorage<EPA_MAX_TRIANGLES, EPA_MAX_POINTS, EPA_MAX_EDGE_LENGTH>;   // 21 KB: can never overflow
-using EpaStorageSmall = EpaStorage<48, 24, 24>;                                                  // ~4 KB
+using EpaStorageSmall = EpaStorage<24, 14, 12>;                                                  // 2 KB: one per THREAD, 3 warps per SM
 
 B2J_HD bool epa_tri_is_facing(const EpaTriangle &t, V3 pos) { return dot(t.normal, pos - t.centroid) > 0.0f; }
 B2J_HD bool epa_tri_is_facing_origin(const EpaTriangle &t) { return dot(t.normal, t.centroid) < 0.0f; }
@@ -676,9 +691,9 @@ B2J_HD V3 epa_add_support(EpaScratch &e, const A &a, const B &b, V3 direction, i
 	return w;
 }
 
-// EPAPenetrationDepth::GetPenetrationDepthStepEPA. The GJK simplex comes in through `s`.
+// First half of EPAPenetrationDepth::GetPenetrationDepthStepEPA: complete the GJK simplex `s` to a hull (no long loops)
 template <class AI, class BI>
-B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_incl, const BI &b_incl, float tolerance, V3 &out_v, V3 &out_point_a, V3 &out_point_b)
+B2J_HD bool epa_begin(EpaScratch &e, const GjkSimplex &s, const AI &a_incl, const BI &b_incl)
 {
 	e.overflow = 0;
 	e.num_points = s.num_points;
@@ -753,69 +768,65 @@ B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_i
 			if (!epa_add_point(e, best, i, FLT_MAX))
 				return false;
 	}
+	return true;
+}
 
-	// Loop until the origin is inside the hull
-	for (;;)
+// One iteration of the "loop until the origin is inside the hull"; returns false when the loop ends, failed = EPA gives up
+template <class AI, class BI>
+B2J_HD bool epa_include_origin_iteration(EpaScratch &e, const AI &a_incl, const BI &b_incl, bool &failed)
+{
+	int t = e.queue[0];
+	if (e.tri[t].removed)
 	{
-		int t = e.queue[0];
-		if (e.tri[t].removed)
-		{
-			epa_queue_pop(e);
-			if (e.queue_size == 0)
-				return false;
-			epa_free_triangle(e, t);
-			continue;
-		}
-		if (e.tri[t].closest_len_sq >= 0.0f)
-			break;
 		epa_queue_pop(e);
-		int new_index;
-		V3 w = epa_add_support(e, a_incl, b_incl, e.tri[t].normal, new_index);
-		if (e.overflow)
-			return false;
-		if (!epa_tri_is_facing(e.tri[t], w) || !epa_add_point(e, t, new_index, FLT_MAX))
-			return false;
+		if (e.queue_size == 0) { failed = true; return false; }
 		epa_free_triangle(e, t);
-		if (e.queue_size == 0 || e.num_points >= EPA_MAX_POINTS_TO_INCLUDE_ORIGIN)
-			return false;
+		return true;
 	}
+	if (e.tri[t].closest_len_sq >= 0.0f)
+		return false;
+	epa_queue_pop(e);
+	int new_index;
+	V3 w = epa_add_support(e, a_incl, b_incl, e.tri[t].normal, new_index);
+	if (e.overflow || !epa_tri_is_facing(e.tri[t], w) || !epa_add_point(e, t, new_index, FLT_MAX)) { failed = true; return false; }
+	epa_free_triangle(e, t);
+	if (e.queue_size == 0 || e.num_points >= EPA_MAX_POINTS_TO_INCLUDE_ORIGIN) { failed = true; return false; }
+	return true;
+}
 
-	float closest_dist_sq = FLT_MAX;
-	int last = -1;
-	bool flip_v_sign = false;
-	do
+struct EpaMainState { float closest_dist_sq; int last; bool flip_v_sign; };
+
+// One iteration of the main EPA loop; returns false when the loop ends, failed = EPA gives up
+template <class AI, class BI>
+B2J_HD bool epa_main_iteration(EpaScratch &e, EpaMainState &m, const AI &a_incl, const BI &b_incl, float tolerance, bool &failed)
+{
+	int t = epa_queue_pop(e);
+	if (e.tri[t].removed)
+		epa_free_triangle(e, t);
+	else
 	{
-		int t = epa_queue_pop(e);
-		if (e.tri[t].removed)
-		{
-			epa_free_triangle(e, t);
-			continue;
-		}
-		if (e.tri[t].closest_len_sq >= closest_dist_sq)
-			break;
-		if (last >= 0)
-			epa_free_triangle(e, last);
-		last = t;
+		if (e.tri[t].closest_len_sq >= m.closest_dist_sq)
+			return false;
+		if (m.last >= 0)
+			epa_free_triangle(e, m.last);
+		m.last = t;
 
 		int new_index;
 		V3 tn = e.tri[t].normal;
 		V3 w = epa_add_support(e, a_incl, b_incl, tn, new_index);
-		if (e.overflow)
-			return false;
+		if (e.overflow) { failed = true; return false; }
 		float dt = dot(tn, w);
-		if (dt < 0.0f)
-			return false;
+		if (dt < 0.0f) { failed = true; return false; }
 		float dist_sq = square(dt) / length_sq(tn);
 		if (dist_sq - e.tri[t].closest_len_sq < e.tri[t].closest_len_sq * tolerance)
-			break;
-		closest_dist_sq = fmin_(closest_dist_sq, dist_sq);
+			return false;
+		m.closest_dist_sq = fmin_(m.closest_dist_sq, dist_sq);
 		if (!epa_tri_is_facing(e.tri[t], w))
-			break;
-		if (!epa_add_point(e, t, new_index, closest_dist_sq))
+			return false;
+		if (!epa_add_point(e, t, new_index, m.closest_dist_sq))
 		{
-			if (e.overflow)
-				return false;
-			break;
+			if (e.overflow) failed = true;
+			return false;
 		}
 		bool has_defect = false;
 		for (int i = 0; i < e.num_new_triangles; ++i)
@@ -825,20 +836,42 @@ B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_i
 			V3 w2 = a_incl.support(-tn) - b_incl.support(tn);
 			float dot2 = -dot(tn, w2);
 			if (dot2 < dt)
-				flip_v_sign = true;
-			break;
+				m.flip_v_sign = true;
+			return false;
 		}
 	}
-	while (e.queue_size > 0 && e.num_points < EPA_MAX_POINTS);
+	return e.queue_size > 0 && e.num_points < EPA_MAX_POINTS;
+}
 
-	if (last < 0 || e.overflow)
+// EPAPenetrationDepth::GetPenetrationDepthStepEPA. The GJK simplex comes in through `s`. kLockstep / alive: see gjk_get_closest_points
+// (the two long loops run with warp uniform trip counts so that the lanes of a thread-per-pair warp reconverge every iteration).
+template <bool kLockstep = false, class AI, class BI>
+B2J_HD bool pen_depth_step_epa(EpaScratch &e, const GjkSimplex &s, const AI &a_incl, const BI &b_incl, float tolerance, V3 &out_v, V3 &out_point_a, V3 &out_point_b, bool alive = true)
+{
+	if (alive)
+		alive = epa_begin(e, s, a_incl, b_incl);
+
+	// Loop until the origin is inside the hull
+	bool failed = false, run = alive;
+	while (warp_any<kLockstep>(run))
+		if (run)
+			run = epa_include_origin_iteration(e, a_incl, b_incl, failed);
+
+	EpaMainState m;
+	m.closest_dist_sq = FLT_MAX; m.last = -1; m.flip_v_sign = false;
+	run = alive && !failed;
+	while (warp_any<kLockstep>(run))
+		if (run)
+			run = epa_main_iteration(e, m, a_incl, b_incl, tolerance, failed);
+
+	if (!alive || failed || m.last < 0 || e.overflow)
 		return false;
 
-	const EpaTriangle &lt = e.tri[last];
+	const EpaTriangle &lt = e.tri[m.last];
 	out_v = (dot(lt.centroid, lt.normal) / length_sq(lt.normal)) * lt.normal;
 	if (is_near_zero(out_v))
 		return false;
-	if (flip_v_sign)
+	if (m.flip_v_sign)
 		out_v = -out_v;
 
 	V3 p0 = e.p[lt.edge[0].start_idx], p1 = e.p[lt.edge[1].start_idx], p2 = e.p[lt.edge[2].start_idx];

@@ -228,8 +228,9 @@ B2J_D void mesh_collide_sphere_triangle(const DWorld &w, const MeshCollideCtx &c
 struct KCollideMesh
 {
 	DWorld w; NarrowCtx c; MeshScratch *mesh_scratch;
-	B2J_D void run(uint32_t k, uint32_t slot, EpaStorageFull &epa_storage) const
+	B2J_D void run(uint32_t k, bool valid, uint32_t slot, EpaStorageFull &epa_storage) const
 	{
+		(void)valid;
 		EpaScratch epa = epa_storage.view();
 		CollideItem item = c.collide_mesh[k];
 		BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];

@@ -497,33 +497,43 @@ struct KCollideConvex
 template <class Storage, bool kFirstTier> struct KCollideEpa
 {
 	DWorld w; NarrowCtx c;
-	B2J_D void run(uint32_t k, uint32_t slot, Storage &storage) const
+	// Thread per pair: all 32 lanes of the warp call run() together (valid = lane has a pair), the GJK / EPA loops run in lockstep
+	B2J_D void run(uint32_t k, bool valid, uint32_t slot, Storage &storage) const
 	{
 		(void)slot;
+		constexpr bool kLockstep = true;
 		EpaScratch scratch = storage.view();
-		const EpaItem &ei = kFirstTier? c.epa[k] : c.epa_overflow[k];
-		CollideItem item = ei.c;
-		ConvexPairSetup s = convex_pair_setup(w, item);
-		const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
-		float max_separation_distance = fmin_(s.max_separation_distance, 1.0f);
-		AddRadiusSupport a_incl;
-		a_incl.s = make_support(w, s1, SUPPORT_INCLUDE_CONVEX_RADIUS);
-		a_incl.radius = max_separation_distance;
-		TransformedSupport b_incl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_INCLUDE_CONVEX_RADIUS));
+		bool alive = valid;
+		CollideItem item = {};
+		ConvexPairSetup s = {};
+		AddRadiusSupport a_incl = {};
+		TransformedSupport b_incl = {};
+		ConvexSupport a_excl = {};
+		TransformedSupport b_excl = {};
+		float max_separation_distance = 0.0f;
+		if (alive)
+		{
+			const EpaItem &ei = kFirstTier? c.epa[k] : c.epa_overflow[k];
+			item = ei.c;
+			s = convex_pair_setup(w, item);
+			const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
+			max_separation_distance = fmin_(s.max_separation_distance, 1.0f);
+			a_incl.s = make_support(w, s1, SUPPORT_INCLUDE_CONVEX_RADIUS);
+			a_incl.radius = max_separation_distance;
+			b_incl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_INCLUDE_CONVEX_RADIUS));
+			a_excl = make_support(w, s1, SUPPORT_EXCLUDE_CONVEX_RADIUS);
+			b_excl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_EXCLUDE_CONVEX_RADIUS));
+		}
 		// same GJK step as KCollideConvex (bit identical): yields the simplex and the initial axis EPA starts from
-		V3 penetration_axis = s.transform_2_to_1.t, point1, point2;
+		V3 penetration_axis = s.transform_2_to_1.t, point1 = v3_zero(), point2 = v3_zero();
 		if (is_near_zero(penetration_axis))
 			penetration_axis = v3(1.0f, 0.0f, 0.0f);
 		GjkSimplex simplex;
+		if (pen_depth_step_gjk<kLockstep>(simplex, a_excl, a_excl.convex_radius + s.max_separation_distance, b_excl, b_excl.s.convex_radius, 1.0e-4f, penetration_axis, point1, point2, alive) != PEN_INDETERMINATE)
+			alive = false;
+		if (!pen_depth_step_epa<kLockstep>(scratch, simplex, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2, alive))
 		{
-			ConvexSupport a_excl = make_support(w, s1, SUPPORT_EXCLUDE_CONVEX_RADIUS);
-			TransformedSupport b_excl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_EXCLUDE_CONVEX_RADIUS));
-			if (pen_depth_step_gjk(simplex, a_excl, a_excl.convex_radius + s.max_separation_distance, b_excl, b_excl.s.convex_radius, 1.0e-4f, penetration_axis, point1, point2) != PEN_INDETERMINATE)
-				return;
-		}
-		if (!pen_depth_step_epa(scratch, simplex, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2))
-		{
-			if (kFirstTier && scratch.overflow)
+			if (kFirstTier && alive && scratch.overflow)
 				c.epa_overflow[atomic_add(c.num_epa_overflow, 1u)].c = item;
 			return;
 		}

@@ -38,6 +38,7 @@ B2J_D uint32_t atomic_cas(uint32_t *p, uint32_t cmp, uint32_t v) { uint32_t o = 
 B2J_D uint32_t atomic_exch(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 B2J_D unsigned long long atomic_cas64(unsigned long long *p, unsigned long long cmp, unsigned long long v) { unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 B2J_D uint32_t volatile_load(const uint32_t *p) { return *p; }
+template <bool kLockstep> B2J_D bool warp_any(bool p) { return p; }
 B2J_D void mem_fence() { }
 B2J_D int ctz32(uint32_t v) { return v == 0? 32 : __builtin_ctz(v); }
 B2J_D int clz32(uint32_t v) { return v == 0? 32 : __builtin_clz(v); }
@@ -52,6 +53,14 @@ B2J_D uint32_t atomic_cas(uint32_t *p, uint32_t cmp, uint32_t v) { return atomic
 B2J_D uint32_t atomic_exch(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
 B2J_D unsigned long long atomic_cas64(unsigned long long *p, unsigned long long cmp, unsigned long long v) { return atomicCAS(p, cmp, v); }
 B2J_D uint32_t volatile_load(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+// vote over the whole warp when kLockstep (every lane of the warp must call it), identity otherwise
+template <bool kLockstep> B2J_HD bool warp_any(bool p)
+{
+#if defined(__CUDA_ARCH__)
+	if (kLockstep) return __any_sync(0xffffffffu, p) != 0;
+#endif
+	return p;
+}
 B2J_D void mem_fence() { __threadfence(); }
 B2J_D int ctz32(uint32_t v) { return v == 0? 32 : __ffs((int)v) - 1; }
 B2J_D int clz32(uint32_t v) { return __clz((int)v); }

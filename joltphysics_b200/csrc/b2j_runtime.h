@@ -31,6 +31,12 @@ template <class K> __global__ void __launch_bounds__(128) run_kernel(const K k, 
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 		k(i);
 }
+// same with an explicit block size / minimum resident blocks (register budget) for kernels tuned by measurement
+template <class K, int THREADS, int MINB> __global__ void __launch_bounds__(THREADS, MINB) run_kernel_cfg(const K k, uint32_t n)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		k(i);
+}
 // n = min(*n_ptr, cap) - *begin_ptr (begin_ptr may be null); the functor receives indices relative to begin
 template <class K> __global__ void __launch_bounds__(128) run_kernel_dev(const K k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap)
 {
@@ -43,7 +49,7 @@ template <class K> __global__ void __launch_bounds__(128) run_kernel_dev(const K
 }
 // One WARP per work item for serial, scratch hungry item bodies (EPA): lane 0 runs the item with an S scratch block in shared
 // memory (low latency instead of a global memory slot); slot = global warp id (ownership of any global side scratch).
-template <class K, class S, int MINB> __global__ void __launch_bounds__(256, MINB) run_kernel_warp_smem(const K k, const uint32_t *n_ptr, uint32_t cap)
+template <class K, class S> __global__ void __launch_bounds__(256) run_kernel_warp_smem(const K k, const uint32_t *n_ptr, uint32_t cap)
 {
 	extern __shared__ __align__(16) unsigned char b2j_smem[];
 	uint32_t n = *n_ptr;
@@ -54,7 +60,25 @@ template <class K, class S, int MINB> __global__ void __launch_bounds__(256, MIN
 	for (uint32_t i = slot; i < n; i += gridDim.x * warps_per_block)
 	{
 		if (lane == 0)
-			k.run(i, slot, *scratch);
+			k.run(i, true, slot, *scratch);
+		__syncwarp();
+	}
+}
+// One THREAD per work item with a private S scratch block in LOCAL memory (EPA: 2 KB or 21 KB per lane): local memory is word
+// interleaved across the lanes of a warp, so lockstep lanes touching the same field coalesce, and it is L1/L2 cached. Every lane
+// calls run() every round (valid = the lane has an item): the item bodies keep the warp in lockstep with votes (warp_any<true>),
+// otherwise lanes drift apart for good (measured: 1.8 active lanes per instruction, 4x slower). Measured against a warp-per-item
+// form with the scratch in shared memory (instruction fetch bound: 77% stall_no_inst) and a shared memory thread-per-item form.
+template <class K, class S> __global__ void __launch_bounds__(128) run_kernel_lane_local(const K k, const uint32_t *n_ptr, uint32_t cap)
+{
+	S scratch;
+	uint32_t n = *n_ptr;
+	if (n > cap) n = cap;
+	uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+	{
+		uint32_t i = base + threadIdx.x;
+		k.run(i, i < n, slot, scratch);
 		__syncwarp();
 	}
 }
@@ -261,6 +285,18 @@ struct Runtime
 		for (uint32_t i = 0; i < n; ++i) k(i);
 #endif
 	}
+	template <class K, int THREADS, int MINB> void launch_cfg(const K &k, uint32_t n)
+	{
+		if (n == 0) return;
+		++launches;
+#ifndef B2J_HOSTSIM
+		if (profiling) prof_begin(profile_category<K>());
+		run_kernel_cfg<K, THREADS, MINB><<<grid_for(n, THREADS), THREADS, 0, stream>>>(k, n);
+		if (profiling) prof_end();
+#else
+		for (uint32_t i = 0; i < n; ++i) k(i);
+#endif
+	}
 	// device-resident count (no host sync): processes [*begin, min(*n_ptr, cap))
 	template <class K> void launch_dev(const K &k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap)
 	{
@@ -279,7 +315,7 @@ struct Runtime
 #endif
 	}
 	// device-resident count, one warp per item with an S scratch block in shared memory; uses at most num_slots warps
-	template <class K, class S, int MINB = 1> void launch_warp_smem(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots, uint32_t warps_per_block = 4)
+	template <class K, class S> void launch_warp_smem(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots, uint32_t warps_per_block = 4)
 	{
 		if (cap == 0) return;
 		++launches;
@@ -287,7 +323,7 @@ struct Runtime
 		static bool configured = false;
 		if (!configured)
 		{
-			cudaFuncSetAttribute(run_kernel_warp_smem<K, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(S) < 227 * 1024? 8 * sizeof(S) : 4 * sizeof(S)));
+			cudaFuncSetAttribute(run_kernel_warp_smem<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(S) < 227 * 1024? 8 * sizeof(S) : 4 * sizeof(S)));
 			configured = true;
 		}
 		uint32_t g = num_slots / warps_per_block;
@@ -295,13 +331,32 @@ struct Runtime
 		uint32_t gn = (cap + warps_per_block - 1) / warps_per_block;
 		if (gn < g) g = gn;
 		if (profiling) prof_begin(profile_category<K>());
-		run_kernel_warp_smem<K, S, MINB><<<g, 32 * warps_per_block, warps_per_block * sizeof(S), stream>>>(k, n_ptr, cap);
+		run_kernel_warp_smem<K, S><<<g, 32 * warps_per_block, warps_per_block * sizeof(S), stream>>>(k, n_ptr, cap);
 		if (profiling) prof_end();
 #else
 		(void)num_slots;
 		static S scratch;
 		uint32_t n = *n_ptr < cap? *n_ptr : cap;
-		for (uint32_t i = 0; i < n; ++i) k.run(i, 0, scratch);
+		for (uint32_t i = 0; i < n; ++i) k.run(i, true, 0, scratch);
+#endif
+	}
+
+	template <class K, class S> void launch_lane_local(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t blocks_per_sm)
+	{
+		if (cap == 0) return;
+		++launches;
+#ifndef B2J_HOSTSIM
+		uint32_t g = (uint32_t)num_sms * blocks_per_sm;
+		uint32_t gn = (cap + 127) / 128;
+		if (gn < g) g = gn;
+		if (profiling) prof_begin(profile_category<K>());
+		run_kernel_lane_local<K, S><<<g, 128, 0, stream>>>(k, n_ptr, cap);
+		if (profiling) prof_end();
+#else
+		(void)blocks_per_sm;
+		static S scratch;
+		uint32_t n = *n_ptr < cap? *n_ptr : cap;
+		for (uint32_t i = 0; i < n; ++i) k.run(i, true, 0, scratch);
 #endif
 	}
 

@@ -40,10 +40,11 @@ enum { ANG_I1 = 0, ANG_I2 = 3, ANG_EFF = 6, ANG_BIAS = 7, ANG_LAMBDA = 8 };
 
 // meta bits: num points (3) | type1 (2) << 3 | type2 (2) << 5 | velocity steps << 8 | position steps << 16 | friction parts active << 24
 enum : uint32_t { META_LINEAR_FRICTION = 1u << 24, META_ANGULAR_FRICTION = 1u << 25 };
+struct alignas(16) ConstraintHeader { uint32_t b1, b2, manifold, meta; };
 struct Constraints
 {
 	float *cf;
-	uint32_t *b1, *b2, *manifold, *meta;
+	ConstraintHeader *hdr;       // one 16 byte load gives the solve kernels everything their other loads depend on
 	uint32_t capacity;
 };
 
@@ -579,7 +580,6 @@ struct KSetupConstraints
 		atomic_max(&w.counters->max_velocity_steps, vsteps);
 		atomic_max(&w.counters->max_position_steps, psteps);
 
-		c.b1[i] = src.b1; c.b2[i] = src.b2; c.manifold[i] = m;
 		uint32_t meta = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16);
 
 		BodyParams p1 = w.params[src.b1], p2 = w.params[src.b2];
@@ -713,7 +713,8 @@ struct KSetupConstraints
 			cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f; cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f;
 			for (int p = 0; p < n; ++p) cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i) = 0.0f;
 		}
-		c.meta[i] = meta;
+		ConstraintHeader hdr; hdr.b1 = src.b1; hdr.b2 = src.b2; hdr.manifold = m; hdr.meta = meta;
+		c.hdr[i] = hdr;
 	}
 };
 
@@ -796,10 +797,11 @@ struct KWarmStart
 	B2J_D void operator()(uint32_t k) const
 	{
 		uint32_t i = begin + k;
-		uint32_t meta = c.meta[i];
+		ConstraintHeader hdr = c.hdr[i];
+		uint32_t meta = hdr.meta;
 		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-		uint32_t b1 = c.b1[i], b2 = c.b2[i];
+		uint32_t b1 = hdr.b1, b2 = hdr.b2;
 		VelState s;
 		load_vel_state(w, b1, b2, type1, type2, s);
 		V3 normal = cf_ro_v3(c, CF_NX, i);
@@ -851,12 +853,13 @@ struct KSolveVelocity
 	B2J_D void operator()(uint32_t k) const
 	{
 		uint32_t i = begin + k;
-		uint32_t meta = c.meta[i];
+		ConstraintHeader hdr = c.hdr[i];
+		uint32_t meta = hdr.meta;
 		if (iteration >= ((meta >> 8) & 0xff))
 			return;
 		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-		uint32_t b1 = c.b1[i], b2 = c.b2[i];
+		uint32_t b1 = hdr.b1, b2 = hdr.b2;
 		bool linear_friction_active = (meta & META_LINEAR_FRICTION) != 0;
 		bool angular_friction_active = (meta & META_ANGULAR_FRICTION) != 0;
 
@@ -971,9 +974,10 @@ struct KStoreImpulses
 	DWorld w; Constraints c;
 	B2J_D void operator()(uint32_t i) const
 	{
-		uint32_t meta = c.meta[i];
+		ConstraintHeader hdr = c.hdr[i];
+		uint32_t meta = hdr.meta;
 		int n = (int)(meta & 7);
-		CachedManifold &cm = w.write_cache.manifolds[c.manifold[i]];
+		CachedManifold &cm = w.write_cache.manifolds[hdr.manifold];
 		for (int p = 0; p < n; ++p)
 			cm.lambda[p] = cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PART_LAMBDA, i);
 		cm.friction_lambda[0] = cf_at(c, CF_FR0 + PART_LAMBDA, i);
@@ -1013,12 +1017,13 @@ struct KSolvePosition
 	B2J_D void operator()(uint32_t k) const
 	{
 		uint32_t i = begin + k;
-		uint32_t meta = c.meta[i];
+		ConstraintHeader hdr = c.hdr[i];
+		uint32_t meta = hdr.meta;
 		if (iteration >= ((meta >> 16) & 0xff))
 			return;
 		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-		uint32_t b1 = c.b1[i], b2 = c.b2[i];
+		uint32_t b1 = hdr.b1, b2 = hdr.b2;
 		V3 x1 = to_v3(w.position[b1]), x2 = to_v3(w.position[b2]);
 		Q4 q1 = to_q4(w.rotation[b1]), q2 = to_q4(w.rotation[b2]);
 		uint32_t dofs1 = w.info[b1].allowed_dofs, dofs2 = w.info[b2].allowed_dofs;

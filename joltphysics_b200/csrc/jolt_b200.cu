@@ -482,11 +482,12 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KProcessPairs k; k.w = d; k.c = W->nc; k.first_ptr = W->d_round_begin; rt.launch_dev(k, &d.counters->num_pairs, W->d_round_begin, d.max_body_pairs); }
 		{ KCopyCached k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_cached, nullptr, d.max_body_pairs); }
 		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
-		// deep pairs: small EPA tier first (8 warps x 4 KB of shared memory per block), the few that overflow it re-run on full size storage
+		// deep pairs: thread per pair, lanes in lockstep, EPA scratch in (lane interleaved, L1/L2 cached) local memory. Small tier first
+		// (2 KB per lane covers ~88% of the pairs, 16 warps per SM); the pairs that overflow it re-run on full size storage (21 KB per lane).
 		rt.memset_(W->nc.num_epa_overflow, 0, 4);
 		rt.memset_(W->nc.num_epa_results, 0, 4);
-		{ KCollideEpa<EpaStorageSmall, true> k; k.w = d; k.c = W->nc; rt.launch_warp_smem<KCollideEpa<EpaStorageSmall, true>, EpaStorageSmall, 4>(k, &d.counters->num_epa, W->nc.max_epa, (uint32_t)rt.num_sms * 32, 8); }
-		{ KCollideEpa<EpaStorageFull, false> k; k.w = d; k.c = W->nc; rt.launch_warp_smem<KCollideEpa<EpaStorageFull, false>, EpaStorageFull>(k, W->nc.num_epa_overflow, W->nc.max_epa, W->nc.num_scratch, 4); }
+		{ KCollideEpa<EpaStorageSmall, true> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageSmall, true>, EpaStorageSmall>(k, &d.counters->num_epa, W->nc.max_epa, 4); }
+		{ KCollideEpa<EpaStorageFull, false> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageFull, false>, EpaStorageFull>(k, W->nc.num_epa_overflow, W->nc.max_epa, 2); }
 		{ KFinishEpa k; k.w = d; k.c = W->nc; rt.launch_dev(k, W->nc.num_epa_results, nullptr, W->nc.max_epa); }
 		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_warp_smem<KCollideMesh, EpaStorageFull>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
 		if (!read_counters(W)) return false;
@@ -594,7 +595,8 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			for (uint32_t p = 0; p < num_phases; ++p)
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
-				KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it; rt.launch(k, n);
+				KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
+				rt.launch(k, n);
 			}
 		{ KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
 	}
@@ -856,7 +858,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	uint32_t mc = d.max_constraints;
 	sc.con.capacity = mc;
 	sc.con.cf = rt.alloc<float>((size_t)CF_NUM * mc, false);
-	sc.con.b1 = rt.alloc<uint32_t>(mc); sc.con.b2 = rt.alloc<uint32_t>(mc); sc.con.manifold = rt.alloc<uint32_t>(mc); sc.con.meta = rt.alloc<uint32_t>(mc);
+	sc.con.hdr = rt.alloc<ConstraintHeader>(mc);
 	sc.man_ws = nc.man_ws;
 	sc.order = rt.alloc<uint32_t>(mc); sc.final_pos = rt.alloc<uint32_t>(mc); sc.solve_src = rt.alloc<uint32_t>(mc); sc.phase = rt.alloc<uint32_t>(mc);
 	sc.max_phases = 8192;
@@ -923,7 +925,7 @@ void b2j_world_destroy(b2j_world *W)
 	rt.free_(W->d_mesh_scratch);
 	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
-	rt.free_(sc.con.cf); rt.free_(sc.con.b1); rt.free_(sc.con.b2); rt.free_(sc.con.manifold); rt.free_(sc.con.meta);
+	rt.free_(sc.con.cf); rt.free_(sc.con.hdr);
 	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count);
 	rt.free_(sc.uf_parent); rt.free_(sc.root); rt.free_(sc.island_items); rt.free_(sc.island_large); rt.free_(sc.island_steps); rt.free_(sc.island_can_sleep);
 	rt.free_(sc.large_color_count); rt.free_(sc.body_deg); rt.free_(sc.body_off); rt.free_(sc.body_fill); rt.free_(sc.body_cur); rt.free_(sc.body_mask);
