@@ -24,26 +24,32 @@
 
 namespace b2j {
 
-// ---- constraint storage (SoA, solve order) ----------------------------------------------------------------------
-// cf[field * capacity + i]
+// ---- constraint storage (solve order) ---------------------------------------------------------------------------
+// float4 PLANES, plane major: cp[plane * capacity + i]. A warp reads 512 contiguous bytes of a plane with one LDG.128 (the first
+// version used 133 scalar field arrays: 4x the load instructions / requests in flight for the same bytes, latency bound at 28% of HBM).
 enum
 {
-	CF_NX = 0, CF_NY, CF_NZ, CF_FRICTION, CF_INVM1, CF_INVM2,
-	CF_FR0 = 6,      // 2 friction parts of 15 floats: R1X(3) I1(3) R2X(3) I2(3) EFF BIAS LAMBDA
-	CF_ANG = 36,     // I1(3) I2(3) EFF BIAS LAMBDA
-	CF_PT0 = 45,     // 4 points of 22 floats: part(15) DIST LP1(3) LP2(3)
-	CF_PT_STRIDE = 22,
-	CF_NUM = CF_PT0 + 4 * CF_PT_STRIDE
+	CP_NORMAL = 0,          // world space normal xyz, combined friction
+	CP_MASS,                // inv_m1, inv_m2, dist0, dist1      (dist p = distance of contact point p to the friction point)
+	CP_DIST,                // dist2, dist3, angular friction effective mass, angular friction bias
+	CP_LAMBDA_PT,           // total lambda of the 4 contact points    (read + written by the solve kernels)
+	CP_LAMBDA_FR,           // total lambda friction 1, friction 2, angular friction, unused
+	CP_ANG_I1,              // angular friction: inverse inertia * normal of body 1 / 2 (xyz)
+	CP_ANG_I2,
+	CP_FR0,                 // 2 friction parts of 4 planes (CP_PART_*)
+	CP_PT0 = CP_FR0 + 8,    // 4 contact point parts of 4 planes
+	CP_LP0 = CP_PT0 + 16,   // per contact point: local point on body 1 xyz, local point on body 2 xyz (position solve)
+	CP_NUM = CP_LP0 + 8
 };
-enum { PART_R1X = 0, PART_I1 = 3, PART_R2X = 6, PART_I2 = 9, PART_EFF = 12, PART_BIAS = 13, PART_LAMBDA = 14, PT_DIST = 15, PT_LP1 = 16, PT_LP2 = 19 };
-enum { ANG_I1 = 0, ANG_I2 = 3, ANG_EFF = 6, ANG_BIAS = 7, ANG_LAMBDA = 8 };
+// planes of one ContactConstraintPart: r1 x axis + effective mass, invI1 (r1 x axis) + bias, r2 x axis, invI2 (r2 x axis)
+enum { CP_PART_R1X_EFF = 0, CP_PART_I1_BIAS, CP_PART_R2X, CP_PART_I2 };
 
 // meta bits: num points (3) | type1 (2) << 3 | type2 (2) << 5 | velocity steps << 8 | position steps << 16 | friction parts active << 24
 enum : uint32_t { META_LINEAR_FRICTION = 1u << 24, META_ANGULAR_FRICTION = 1u << 25 };
 struct alignas(16) ConstraintHeader { uint32_t b1, b2, manifold, meta; };
 struct Constraints
 {
-	float *cf;
+	F4 *cp;
 	ConstraintHeader *hdr;       // one 16 byte load gives the solve kernels everything their other loads depend on
 	uint32_t capacity;
 };
@@ -74,20 +80,18 @@ struct SolveCtx
 	uint32_t *sched_flag;        // [2] remaining flags
 };
 
-B2J_HD float &cf_at(const Constraints &c, int field, uint32_t i) { return c.cf[(size_t)field * c.capacity + i]; }
-B2J_HD V3 cf_v3(const Constraints &c, int field, uint32_t i) { return v3(cf_at(c, field, i), cf_at(c, field + 1, i), cf_at(c, field + 2, i)); }
-B2J_HD void cf_set_v3(const Constraints &c, int field, uint32_t i, V3 v) { cf_at(c, field, i) = v.x; cf_at(c, field + 1, i) = v.y; cf_at(c, field + 2, i) = v.z; }
-// Read of a field the running kernel never writes (everything but the lambdas in the solve kernels): goes through the non coherent
+B2J_HD F4 &cp_at(const Constraints &c, int plane, uint32_t i) { return c.cp[(size_t)plane * c.capacity + i]; }
+// Read of a plane the running kernel never writes (everything but the lambdas in the solve kernels): goes through the non coherent
 // path, which also tells the compiler that the lambda stores cannot alias it, so all loads of a constraint issue up front.
-B2J_HD float cf_ro(const Constraints &c, int field, uint32_t i)
+B2J_HD F4 cp_ro(const Constraints &c, int plane, uint32_t i)
 {
 #if defined(__CUDA_ARCH__)
-	return __ldg(&c.cf[(size_t)field * c.capacity + i]);
+	float4 v = __ldg(reinterpret_cast<const float4 *>(&c.cp[(size_t)plane * c.capacity + i]));
+	return f4(v.x, v.y, v.z, v.w);
 #else
-	return c.cf[(size_t)field * c.capacity + i];
+	return c.cp[(size_t)plane * c.capacity + i];
 #endif
 }
-B2J_HD V3 cf_ro_v3(const Constraints &c, int field, uint32_t i) { return v3(cf_ro(c, field, i), cf_ro(c, field + 1, i), cf_ro(c, field + 2, i)); }
 
 // ---- body helpers ------------------------------------------------------------------------------------------------
 B2J_HD V3 lock_translation(V3 v, uint32_t dofs) { return v3((dofs & 1)? v.x : 0.0f, (dofs & 2)? v.y : 0.0f, (dofs & 4)? v.z : 0.0f); }
@@ -533,28 +537,26 @@ B2J_D void part_calculate(PartRegs &r, uint32_t type1, uint32_t type2, float inv
 		r.eff = 1.0f / inv_effective_mass;
 }
 
-// the fields the solve kernels read for these motion types (the rest is never read)
+// the planes the solve kernels read for these motion types (the rest is never read); the lambda goes to the lambda planes
 B2J_D void part_store(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2, const PartRegs &r)
 {
-	if (type1 != B2J_MOTION_STATIC) cf_set_v3(c, base + PART_R1X, i, r.r1x);
-	if (type1 == B2J_MOTION_DYNAMIC) cf_set_v3(c, base + PART_I1, i, r.i1);
-	if (type2 != B2J_MOTION_STATIC) cf_set_v3(c, base + PART_R2X, i, r.r2x);
-	if (type2 == B2J_MOTION_DYNAMIC) cf_set_v3(c, base + PART_I2, i, r.i2);
-	cf_at(c, base + PART_EFF, i) = r.eff;
-	cf_at(c, base + PART_BIAS, i) = r.bias;
-	cf_at(c, base + PART_LAMBDA, i) = r.lambda;
+	cp_at(c, base + CP_PART_R1X_EFF, i) = f4(r.r1x, r.eff);
+	cp_at(c, base + CP_PART_I1_BIAS, i) = f4(r.i1, r.bias);
+	if (type2 != B2J_MOTION_STATIC) cp_at(c, base + CP_PART_R2X, i) = f4(r.r2x);
+	if (type2 == B2J_MOTION_DYNAMIC) cp_at(c, base + CP_PART_I2, i) = f4(r.i2);
 }
 
+// everything but the lambda
 B2J_D PartRegs part_load(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2)
 {
 	PartRegs r;
-	r.r1x = type1 != B2J_MOTION_STATIC? cf_ro_v3(c, base + PART_R1X, i) : v3_zero();
-	r.i1 = type1 == B2J_MOTION_DYNAMIC? cf_ro_v3(c, base + PART_I1, i) : v3_zero();
-	r.r2x = type2 != B2J_MOTION_STATIC? cf_ro_v3(c, base + PART_R2X, i) : v3_zero();
-	r.i2 = type2 == B2J_MOTION_DYNAMIC? cf_ro_v3(c, base + PART_I2, i) : v3_zero();
-	r.eff = cf_ro(c, base + PART_EFF, i);
-	r.bias = cf_ro(c, base + PART_BIAS, i);
-	r.lambda = cf_at(c, base + PART_LAMBDA, i);
+	F4 a = cp_ro(c, base + CP_PART_R1X_EFF, i), b = cp_ro(c, base + CP_PART_I1_BIAS, i);
+	r.r1x = to_v3(a); r.eff = a.w;
+	r.i1 = to_v3(b); r.bias = b.w;
+	r.r2x = type2 != B2J_MOTION_STATIC? to_v3(cp_ro(c, base + CP_PART_R2X, i)) : v3_zero();
+	r.i2 = type2 == B2J_MOTION_DYNAMIC? to_v3(cp_ro(c, base + CP_PART_I2, i)) : v3_zero();
+	r.lambda = 0.0f;
+	(void)type1;
 	return r;
 }
 
@@ -608,18 +610,16 @@ struct KSetupConstraints
 				p2_ws[p] = v3_load(ws.p2[p]);
 			}
 		}
-		cf_set_v3(c, CF_NX, i, normal);
-		cf_at(c, CF_FRICTION, i) = combined_friction;
-		cf_at(c, CF_INVM1, i) = k1.inv_mass;
-		cf_at(c, CF_INVM2, i) = k2.inv_mass;
+		cp_at(c, CP_NORMAL, i) = f4(normal, combined_friction);
 
 		V3 ws_contacts[4];
+		float lambda_pt[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, dist[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
 		for (int p = 0; p < n; ++p)
 		{
-			int base = CF_PT0 + p * CF_PT_STRIDE;
+			int base = CP_PT0 + p * 4;
 			ws_contacts[p] = 0.5f * (p1_ws[p] + p2_ws[p]);
-			cf_set_v3(c, base + PT_LP1, i, v3_load(cm.p1[p]));
-			cf_set_v3(c, base + PT_LP2, i, v3_load(cm.p2[p]));
+			cp_at(c, CP_LP0 + p * 2, i) = f4(v3_load(cm.p1[p]));
+			cp_at(c, CP_LP0 + p * 2 + 1, i) = f4(v3_load(cm.p2[p]));
 
 			// CalculateNonPenetrationConstraintProperties
 			V3 pm = 0.5f * (p1_ws[p] + p2_ws[p]);
@@ -660,9 +660,12 @@ struct KSetupConstraints
 			part.lambda = cm.lambda[p];
 			part_calculate(part, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, normal, normal_velocity_bias);
 			part_store(c, base, i, type1, type2, part);
+			lambda_pt[p] = part.lambda;
 		}
+		cp_at(c, CP_LAMBDA_PT, i) = f4(lambda_pt[0], lambda_pt[1], lambda_pt[2], lambda_pt[3]);
 
 		// friction (CalculateFrictionConstraintProperties)
+		float lambda_f1 = 0.0f, lambda_f2 = 0.0f, angular_lambda = 0.0f, angular_eff = 0.0f;
 		if (combined_friction > 0.0f)
 		{
 			V3 t1 = normalized_perpendicular(normal);
@@ -673,7 +676,7 @@ struct KSetupConstraints
 			for (int p = 0; p < n; ++p)
 			{
 				V3 delta = ws_contacts[p] - friction_point;
-				cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i) = length(delta - dot(delta, normal) * normal);
+				dist[p] = length(delta - dot(delta, normal) * normal);
 			}
 			V3 r1 = friction_point - k1.x, r2 = friction_point - k2.x;
 			PartRegs f1, f2;
@@ -681,17 +684,17 @@ struct KSetupConstraints
 			f2.lambda = cm.friction_lambda[1];
 			part_calculate(f1, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t1, 0.0f);
 			part_calculate(f2, type1, type2, k1.inv_mass, k1.inv_i, r1, k2.inv_mass, k2.inv_i, r2, t2, 0.0f);
-			part_store(c, CF_FR0, i, type1, type2, f1);
-			part_store(c, CF_FR0 + 15, i, type1, type2, f2);
+			part_store(c, CP_FR0, i, type1, type2, f1);
+			part_store(c, CP_FR0 + 4, i, type1, type2, f2);
+			lambda_f1 = f1.lambda; lambda_f2 = f2.lambda;
 			if (f1.eff != 0.0f || f2.eff != 0.0f) meta |= META_LINEAR_FRICTION;
-			float angular_lambda = cm.angular_lambda, angular_eff = 0.0f;
 			if (n > 1)
 			{
-				// AngularFrictionConstraintPart::CalculateConstraintProperties
-				cf_at(c, CF_ANG + ANG_BIAS, i) = 0.0f;
+				// AngularFrictionConstraintPart::CalculateConstraintProperties (bias = 0)
+				angular_lambda = cm.angular_lambda;
 				V3 i1a = v3_zero(), i2a = v3_zero();
-				if (type1 == B2J_MOTION_DYNAMIC) { i1a = mul(k1.inv_i, normal); cf_set_v3(c, CF_ANG + ANG_I1, i, i1a); }
-				if (type2 == B2J_MOTION_DYNAMIC) { i2a = mul(k2.inv_i, normal); cf_set_v3(c, CF_ANG + ANG_I2, i, i2a); }
+				if (type1 == B2J_MOTION_DYNAMIC) { i1a = mul(k1.inv_i, normal); cp_at(c, CP_ANG_I1, i) = f4(i1a); }
+				if (type2 == B2J_MOTION_DYNAMIC) { i2a = mul(k2.inv_i, normal); cp_at(c, CP_ANG_I2, i) = f4(i2a); }
 				float inv_effective_mass = 0.0f;
 				if (type1 == B2J_MOTION_DYNAMIC && type2 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i1a + i2a);
 				else if (type1 == B2J_MOTION_DYNAMIC) inv_effective_mass = dot(normal, i1a);
@@ -699,20 +702,12 @@ struct KSetupConstraints
 				if (inv_effective_mass == 0.0f) angular_lambda = 0.0f;
 				else angular_eff = 1.0f / inv_effective_mass;
 			}
-			else
-				angular_lambda = 0.0f;
-			cf_at(c, CF_ANG + ANG_EFF, i) = angular_eff;
-			cf_at(c, CF_ANG + ANG_LAMBDA, i) = angular_lambda;
 			if (angular_eff != 0.0f) meta |= META_ANGULAR_FRICTION;
 		}
-		else
-		{
-			// Deactivate() x3
-			cf_at(c, CF_FR0 + PART_EFF, i) = 0.0f; cf_at(c, CF_FR0 + PART_LAMBDA, i) = 0.0f;
-			cf_at(c, CF_FR0 + 15 + PART_EFF, i) = 0.0f; cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i) = 0.0f;
-			cf_at(c, CF_ANG + ANG_EFF, i) = 0.0f; cf_at(c, CF_ANG + ANG_LAMBDA, i) = 0.0f;
-			for (int p = 0; p < n; ++p) cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i) = 0.0f;
-		}
+		// (no friction: Deactivate() x3 = the zero lambdas / effective masses below; the friction part planes are never read)
+		cp_at(c, CP_MASS, i) = f4(k1.inv_mass, k2.inv_mass, dist[0], dist[1]);
+		cp_at(c, CP_DIST, i) = f4(dist[2], dist[3], angular_eff, 0.0f);
+		cp_at(c, CP_LAMBDA_FR, i) = f4(lambda_f1, lambda_f2, angular_lambda, 0.0f);
 		ConstraintHeader hdr; hdr.b1 = src.b1; hdr.b2 = src.b2; hdr.manifold = m; hdr.meta = meta;
 		c.hdr[i] = hdr;
 	}
@@ -804,41 +799,51 @@ struct KWarmStart
 		uint32_t b1 = hdr.b1, b2 = hdr.b2;
 		VelState s;
 		load_vel_state(w, b1, b2, type1, type2, s);
-		V3 normal = cf_ro_v3(c, CF_NX, i);
+		V3 normal = to_v3(cp_ro(c, CP_NORMAL, i));
 		V3 t1 = normalized_perpendicular(normal);
 		V3 t2 = cross(normal, t1);
-		float inv_m1 = cf_ro(c, CF_INVM1, i), inv_m2 = cf_ro(c, CF_INVM2, i);
+		F4 mass = cp_ro(c, CP_MASS, i);
+		float inv_m1 = mass.x, inv_m2 = mass.y;
+		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);
 		bool any = false;
-		for (int f = 0; f < 2; ++f)
+		if (meta & META_LINEAR_FRICTION)
 		{
-			int base = CF_FR0 + 15 * f;
-			if (cf_ro(c, base + PART_EFF, i) != 0.0f)
+			PartRegs f1 = part_load(c, CP_FR0, i, type1, type2), f2 = part_load(c, CP_FR0 + 4, i, type1, type2);
+			if (f1.eff != 0.0f)
 			{
-				PartRegs r = part_load(c, base, i, type1, type2);
-				float l = r.lambda * ratio;
-				cf_at(c, base + PART_LAMBDA, i) = l;
-				if (part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, f == 0? t1 : t2, l)) any = true;
+				lfr.x *= ratio;
+				if (part_apply_velocity_step(f1, type1, type2, s, inv_m1, inv_m2, t1, lfr.x)) any = true;
+			}
+			if (f2.eff != 0.0f)
+			{
+				lfr.y *= ratio;
+				if (part_apply_velocity_step(f2, type1, type2, s, inv_m1, inv_m2, t2, lfr.y)) any = true;
 			}
 		}
 		if (meta & META_ANGULAR_FRICTION)
 		{
-			float l = cf_at(c, CF_ANG + ANG_LAMBDA, i) * ratio;
-			cf_at(c, CF_ANG + ANG_LAMBDA, i) = l;
+			lfr.z *= ratio;
+			float l = lfr.z;
 			if (l != 0.0f)
 			{
-				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= l * cf_ro_v3(c, CF_ANG + ANG_I1, i);
-				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += l * cf_ro_v3(c, CF_ANG + ANG_I2, i);
+				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= l * to_v3(cp_ro(c, CP_ANG_I1, i));
+				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += l * to_v3(cp_ro(c, CP_ANG_I2, i));
 				any = true;
 			}
 		}
-		for (int p = 0; p < n; ++p)
-		{
-			int base = CF_PT0 + p * CF_PT_STRIDE;
-			PartRegs r = part_load(c, base, i, type1, type2);
-			float l = r.lambda * ratio;
-			cf_at(c, base + PART_LAMBDA, i) = l;
-			if (part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, normal, l)) any = true;
-		}
+		float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
+#if defined(__CUDA_ARCH__)
+		#pragma unroll
+#endif
+		for (int p = 0; p < 4; ++p)
+			if (p < n)
+			{
+				PartRegs r = part_load(c, CP_PT0 + p * 4, i, type1, type2);
+				lp[p] *= ratio;
+				if (part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, normal, lp[p])) any = true;
+			}
+		cp_at(c, CP_LAMBDA_PT, i) = f4(lp[0], lp[1], lp[2], lp[3]);
+		cp_at(c, CP_LAMBDA_FR, i) = lfr;
 		if (any)
 			store_vel_state(w, b1, b2, type1, type2, s);
 	}
@@ -866,35 +871,35 @@ struct KSolveVelocity
 		// ---- loads
 		VelState s;
 		load_vel_state(w, b1, b2, type1, type2, s);
-		V3 normal = cf_ro_v3(c, CF_NX, i);
-		float inv_m1 = cf_ro(c, CF_INVM1, i), inv_m2 = cf_ro(c, CF_INVM2, i);
-		float mu = cf_ro(c, CF_FRICTION, i);
+		F4 nf = cp_ro(c, CP_NORMAL, i), mass = cp_ro(c, CP_MASS, i), dd = cp_ro(c, CP_DIST, i);
+		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);
+		V3 normal = to_v3(nf);
+		float mu = nf.w, inv_m1 = mass.x, inv_m2 = mass.y;
+		float dist[4] = { mass.z, mass.w, dd.x, dd.y };
+		float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
 		PartRegs pt[4];
-		float dist[4];
 #if defined(__CUDA_ARCH__)
 		#pragma unroll
 #endif
 		for (int p = 0; p < 4; ++p)
 			if (p < n)
 			{
-				pt[p] = part_load(c, CF_PT0 + p * CF_PT_STRIDE, i, type1, type2);
-				dist[p] = cf_ro(c, CF_PT0 + p * CF_PT_STRIDE + PT_DIST, i);
+				pt[p] = part_load(c, CP_PT0 + p * 4, i, type1, type2);
+				pt[p].lambda = lp[p];
 			}
 		PartRegs f1, f2;
 		if (linear_friction_active)
 		{
-			f1 = part_load(c, CF_FR0, i, type1, type2);
-			f2 = part_load(c, CF_FR0 + 15, i, type1, type2);
+			f1 = part_load(c, CP_FR0, i, type1, type2);
+			f2 = part_load(c, CP_FR0 + 4, i, type1, type2);
+			f1.lambda = lfr.x; f2.lambda = lfr.y;
 		}
-		float ang_eff = 0.0f, ang_bias = 0.0f, ang_lambda = 0.0f;
+		float ang_eff = dd.z, ang_bias = dd.w, ang_lambda = lfr.z;
 		V3 ang_i1 = v3_zero(), ang_i2 = v3_zero();
 		if (angular_friction_active)
 		{
-			ang_eff = cf_ro(c, CF_ANG + ANG_EFF, i);
-			ang_bias = cf_ro(c, CF_ANG + ANG_BIAS, i);
-			ang_lambda = cf_at(c, CF_ANG + ANG_LAMBDA, i);
-			if (type1 == B2J_MOTION_DYNAMIC) ang_i1 = cf_ro_v3(c, CF_ANG + ANG_I1, i);
-			if (type2 == B2J_MOTION_DYNAMIC) ang_i2 = cf_ro_v3(c, CF_ANG + ANG_I2, i);
+			if (type1 == B2J_MOTION_DYNAMIC) ang_i1 = to_v3(cp_ro(c, CP_ANG_I1, i));
+			if (type2 == B2J_MOTION_DYNAMIC) ang_i2 = to_v3(cp_ro(c, CP_ANG_I2, i));
 		}
 
 		// ---- solve
@@ -930,8 +935,7 @@ struct KSolveVelocity
 			}
 			if (part_apply_lambda(f1, type1, type2, s, inv_m1, inv_m2, t1, lambda1)) any = true;
 			if (part_apply_lambda(f2, type1, type2, s, inv_m1, inv_m2, t2, lambda2)) any = true;
-			cf_at(c, CF_FR0 + PART_LAMBDA, i) = f1.lambda;
-			cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i) = f2.lambda;
+			lfr.x = f1.lambda; lfr.y = f2.lambda;
 		}
 		if (angular_friction_active)
 		{
@@ -944,7 +948,7 @@ struct KSolveVelocity
 			float lambda = ang_eff * (jv - ang_bias);
 			float new_lambda = clamp_(total + lambda, -max_angular_lambda, max_angular_lambda);
 			lambda = new_lambda - total;
-			cf_at(c, CF_ANG + ANG_LAMBDA, i) = new_lambda;
+			lfr.z = new_lambda;
 			if (lambda != 0.0f)
 			{
 				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= lambda * ang_i1;
@@ -961,8 +965,11 @@ struct KSolveVelocity
 				float total_lambda = part_get_total_lambda(pt[p], type1, type2, s, normal);
 				total_lambda = fmax_(total_lambda, 0.0f);
 				if (part_apply_lambda(pt[p], type1, type2, s, inv_m1, inv_m2, normal, total_lambda)) any = true;
-				cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PART_LAMBDA, i) = pt[p].lambda;
+				lp[p] = pt[p].lambda;
 			}
+		cp_at(c, CP_LAMBDA_PT, i) = f4(lp[0], lp[1], lp[2], lp[3]);
+		if (linear_friction_active || angular_friction_active)
+			cp_at(c, CP_LAMBDA_FR, i) = lfr;
 		if (any)
 			store_vel_state(w, b1, b2, type1, type2, s);
 	}
@@ -975,14 +982,15 @@ struct KStoreImpulses
 	B2J_D void operator()(uint32_t i) const
 	{
 		ConstraintHeader hdr = c.hdr[i];
-		uint32_t meta = hdr.meta;
-		int n = (int)(meta & 7);
+		int n = (int)(hdr.meta & 7);
 		CachedManifold &cm = w.write_cache.manifolds[hdr.manifold];
+		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);
+		float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
 		for (int p = 0; p < n; ++p)
-			cm.lambda[p] = cf_at(c, CF_PT0 + p * CF_PT_STRIDE + PART_LAMBDA, i);
-		cm.friction_lambda[0] = cf_at(c, CF_FR0 + PART_LAMBDA, i);
-		cm.friction_lambda[1] = cf_at(c, CF_FR0 + 15 + PART_LAMBDA, i);
-		cm.angular_lambda = cf_at(c, CF_ANG + ANG_LAMBDA, i);
+			cm.lambda[p] = lp[p];
+		cm.friction_lambda[0] = lfr.x;
+		cm.friction_lambda[1] = lfr.y;
+		cm.angular_lambda = lfr.z;
 	}
 };
 
@@ -1029,8 +1037,9 @@ struct KSolvePosition
 		uint32_t dofs1 = w.info[b1].allowed_dofs, dofs2 = w.info[b2].allowed_dofs;
 		// transforms are fetched once per constraint, inertia / positions are re-read per point (bodies move between points)
 		Xf transform1 = xf_rotation_translation(q1, x1), transform2 = xf_rotation_translation(q2, x2);
-		V3 normal = cf_ro_v3(c, CF_NX, i);
-		float inv_m1 = cf_ro(c, CF_INVM1, i), inv_m2 = cf_ro(c, CF_INVM2, i);
+		V3 normal = to_v3(cp_ro(c, CP_NORMAL, i));
+		F4 mass = cp_ro(c, CP_MASS, i);
+		float inv_m1 = mass.x, inv_m2 = mass.y;
 		V3 diag1 = v3_zero(), diag2 = v3_zero();
 		Q4 irot1 = q4_identity(), irot2 = q4_identity();
 		if (type1 == B2J_MOTION_DYNAMIC) { diag1 = to_v3(w.inv_inertia_diag[b1]); irot1 = to_q4(w.inertia_rotation[b1]); }
@@ -1038,9 +1047,8 @@ struct KSolvePosition
 		bool any = false;
 		for (int p = 0; p < n; ++p)
 		{
-			int base = CF_PT0 + p * CF_PT_STRIDE;
-			V3 p1 = mul(transform1, cf_ro_v3(c, base + PT_LP1, i));
-			V3 p2 = mul(transform2, cf_ro_v3(c, base + PT_LP2, i));
+			V3 p1 = mul(transform1, to_v3(cp_ro(c, CP_LP0 + p * 2, i)));
+			V3 p2 = mul(transform2, to_v3(cp_ro(c, CP_LP0 + p * 2 + 1, i)));
 			float separation = fmax_(dot(p2 - p1, normal) + w.settings.penetration_slop, -w.settings.max_penetration_distance);
 			if (separation < 0.0f)
 			{

@@ -11,7 +11,7 @@
 
 namespace b2j {
 
-struct F4 { float x, y, z, w; };
+struct alignas(16) F4 { float x, y, z, w; };   // 16 byte aligned: one LDG.128 / STG.128
 B2J_HD F4 f4(float x, float y, float z, float w) { F4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 B2J_HD F4 f4(V3 v, float w = 0.0f) { return f4(v.x, v.y, v.z, w); }
 B2J_HD V3 to_v3(F4 f) { return v3(f.x, f.y, f.z); }
@@ -19,7 +19,7 @@ B2J_HD Q4 to_q4(F4 f) { return q4(f.x, f.y, f.z, f.w); }
 B2J_HD F4 f4(Q4 q) { return f4(q.x, q.y, q.z, q.w); }
 
 // Static per-body info (16 B)
-struct BodyInfo
+struct alignas(16) BodyInfo
 {
 	uint32_t id;                 // full BodyID (index | sequence << 23), B2J_INVALID_ID for an empty slot
 	int32_t  shape;              // index into shapes
@@ -32,7 +32,7 @@ struct BodyInfo
 };
 
 // Per-body scalar parameters (32 B)
-struct BodyParams
+struct alignas(16) BodyParams
 {
 	float inv_mass, linear_damping, angular_damping, max_linear_velocity;
 	float max_angular_velocity, gravity_factor, friction, restitution;
@@ -55,7 +55,7 @@ struct ShapeDesc
 };
 
 // Body pair cache entry (CachedBodyPair, ContactConstraintManager.h:335-355)
-struct CachedPair
+struct alignas(8) CachedPair
 {
 	uint32_t body1, body2;       // full ids, body1 < body2
 	uint32_t slot1, slot2;       // body slots (differ from the id index in batched worlds)
@@ -64,7 +64,7 @@ struct CachedPair
 };
 
 // Cached manifold (CachedManifold + CachedContactPoint, ContactConstraintManager.h:265-327), fixed 4 point slots
-struct CachedManifold
+struct alignas(16) CachedManifold
 {
 	uint32_t body1, body2, sub1, sub2;
 	float normal[3];             // in body 2 space

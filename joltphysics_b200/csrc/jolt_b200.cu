@@ -857,7 +857,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	memset(&sc, 0, sizeof(sc));
 	uint32_t mc = d.max_constraints;
 	sc.con.capacity = mc;
-	sc.con.cf = rt.alloc<float>((size_t)CF_NUM * mc, false);
+	sc.con.cp = rt.alloc<F4>((size_t)CP_NUM * mc, false);
 	sc.con.hdr = rt.alloc<ConstraintHeader>(mc);
 	sc.man_ws = nc.man_ws;
 	sc.order = rt.alloc<uint32_t>(mc); sc.final_pos = rt.alloc<uint32_t>(mc); sc.solve_src = rt.alloc<uint32_t>(mc); sc.phase = rt.alloc<uint32_t>(mc);
@@ -873,7 +873,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	W->d_sort_keys[0] = rt.alloc<uint64_t>(mc); W->d_sort_keys[1] = rt.alloc<uint64_t>(mc);
 	W->d_sort_vals = rt.alloc<uint32_t>(mc);
 
-	if (W->d_sort_vals == nullptr || sc.con.cf == nullptr )
+	if (W->d_sort_vals == nullptr || sc.con.cp == nullptr )
 	{
 		last_error() = "out of device memory";
 		b2j_world_destroy(W);
@@ -925,7 +925,7 @@ void b2j_world_destroy(b2j_world *W)
 	rt.free_(W->d_mesh_scratch);
 	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
-	rt.free_(sc.con.cf); rt.free_(sc.con.hdr);
+	rt.free_(sc.con.cp); rt.free_(sc.con.hdr);
 	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count);
 	rt.free_(sc.uf_parent); rt.free_(sc.root); rt.free_(sc.island_items); rt.free_(sc.island_large); rt.free_(sc.island_steps); rt.free_(sc.island_can_sleep);
 	rt.free_(sc.large_color_count); rt.free_(sc.body_deg); rt.free_(sc.body_off); rt.free_(sc.body_fill); rt.free_(sc.body_cur); rt.free_(sc.body_mask);
