@@ -22,7 +22,7 @@ namespace b2j {
 
 struct CollideItem { uint32_t b1, b2; uint32_t pair_entry, old_pair; }; // b1 = body whose space the collision is done in
 struct CachedItem { uint32_t pair_entry, old_pair; };
-struct EpaResult { CollideItem c; float point1[3], point2[3], axis[3]; }; // penetration found by EPA, finished by KFinishEpa
+struct EpaResult { CollideItem c; float point1[3], point2[3], axis[3]; float max_separation_distance; }; // penetration found by GJK / EPA, finished by KFinishPairs
 struct EpaItem { CollideItem c; }; // the EPA kernel re-runs the (deterministic) GJK step instead of carrying the simplex through HBM
 
 // World space data of a manifold created this step (not from the cache), indexed like write_cache.manifolds
@@ -44,7 +44,7 @@ struct NarrowCtx
 	EpaItem *epa;
 	EpaItem *epa_overflow;       // deep pairs that did not fit the small EPA tier (re-run on full size storage)
 	uint32_t *num_epa_overflow;  // device counter
-	EpaResult *epa_results;      // EPA output; supporting faces / clipping / manifold run thread-per-item in KFinishEpa
+	EpaResult *epa_results;      // GJK / EPA output; supporting faces / clipping / manifold run in KFinishPairs
 	uint32_t *num_epa_results;   // device counter
 	uint32_t num_scratch;        // number of warps the scratch hungry kernels (EPA, mesh) may use
 	ManifoldWS *man_ws;
@@ -453,42 +453,53 @@ B2J_D ConvexPairSetup convex_pair_setup(const DWorld &w, const CollideItem &item
 	return s;
 }
 
-// ---- KCollideConvex: OBB pre-test + GJK; finishes shallow hits, queues deep ones for EPA -------------------------
+// ---- KCollideConvex: OBB pre-test + GJK; queues shallow hits for KFinishPairs and deep ones for EPA ------------------
+// Thread per pair with the GJK loop in lockstep (all 32 lanes call run(), valid = lane has a pair).
 struct KCollideConvex
 {
 	DWorld w; NarrowCtx c;
-	B2J_D void operator()(uint32_t k) const
+	B2J_D void run(uint32_t k, bool valid) const
 	{
-		CollideItem item = c.collide_convex[k];
-		ConvexPairSetup s = convex_pair_setup(w, item);
-		const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
-
-		V3 bb1_min = s1.local_min - v3_rep(s.max_separation_distance), bb1_max = s1.local_max + v3_rep(s.max_separation_distance);
-		if (!obb_vs_aabb(s.transform_2_to_1, s2.local_min, s2.local_max, bb1_min, bb1_max))
-			return;
-
+		bool alive = valid;
+		CollideItem item = {};
+		ConvexPairSetup s = {};
+		ConvexSupport a_excl = {};
+		TransformedSupport b_excl = {};
+		if (alive)
+		{
+			item = c.collide_convex[k];
+			s = convex_pair_setup(w, item);
+			const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
+			V3 bb1_min = s1.local_min - v3_rep(s.max_separation_distance), bb1_max = s1.local_max + v3_rep(s.max_separation_distance);
+			if (!obb_vs_aabb(s.transform_2_to_1, s2.local_min, s2.local_max, bb1_min, bb1_max))
+				alive = false;
+			else
+			{
+				a_excl = make_support(w, s1, SUPPORT_EXCLUDE_CONVEX_RADIUS);
+				b_excl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_EXCLUDE_CONVEX_RADIUS));
+			}
+		}
 		V3 penetration_axis = s.transform_2_to_1.t;
 		if (is_near_zero(penetration_axis))
 			penetration_axis = v3(1.0f, 0.0f, 0.0f);
-
-		ConvexSupport a_excl = make_support(w, s1, SUPPORT_EXCLUDE_CONVEX_RADIUS);
-		TransformedSupport b_excl = make_transformed(s.transform_2_to_1, make_support(w, s2, SUPPORT_EXCLUDE_CONVEX_RADIUS));
 		GjkSimplex simplex;
-		V3 point1, point2;
-		int status = pen_depth_step_gjk(simplex, a_excl, a_excl.convex_radius + s.max_separation_distance, b_excl, b_excl.s.convex_radius,
-			1.0e-4f /* cDefaultCollisionTolerance */, penetration_axis, point1, point2);
-		if (status == PEN_NOT_COLLIDING)
+		V3 point1 = v3_zero(), point2 = v3_zero();
+		int status = pen_depth_step_gjk<true>(simplex, a_excl, a_excl.convex_radius + s.max_separation_distance, b_excl, b_excl.s.convex_radius,
+			1.0e-4f /* cDefaultCollisionTolerance */, penetration_axis, point1, point2, alive);
+		if (!alive || status == PEN_NOT_COLLIDING)
 			return;
 		if (status == PEN_INDETERMINATE)
 		{
 			uint32_t e = atomic_add(&w.counters->num_epa, 1u);
 			if (e < c.max_epa)
-			{
 				c.epa[e].c = item;
-			}
 			return;
 		}
-		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, point1, point2, penetration_axis, s.max_separation_distance);
+		// supporting faces / clipping / manifold: KFinishPairs (keeps this kernel small and its lanes converged)
+		EpaResult &r = c.epa_results[atomic_add(c.num_epa_results, 1u)];
+		r.c = item;
+		v3_store(point1, r.point1); v3_store(point2, r.point2); v3_store(penetration_axis, r.axis);
+		r.max_separation_distance = s.max_separation_distance;
 	}
 };
 
@@ -537,15 +548,15 @@ template <class Storage, bool kFirstTier> struct KCollideEpa
 				c.epa_overflow[atomic_add(c.num_epa_overflow, 1u)].c = item;
 			return;
 		}
-		// The rest of the pair (supporting faces, clipping, manifold) needs ~5 KB of thread local arrays: with one active lane per warp
-		// that local memory is 1/32 utilised, so it runs in KFinishEpa with every lane busy instead.
+		// the rest of the pair (supporting faces, clipping, manifold; ~5 KB of thread local arrays) runs in KFinishPairs
 		EpaResult &r = c.epa_results[atomic_add(c.num_epa_results, 1u)];
 		r.c = item;
 		v3_store(point1, r.point1); v3_store(point2, r.point2); v3_store(penetration_axis, r.axis);
+		r.max_separation_distance = max_separation_distance;
 	}
 };
 
-struct KFinishEpa
+struct KFinishPairs
 {
 	DWorld w; NarrowCtx c;
 	B2J_D void operator()(uint32_t k) const
@@ -553,8 +564,7 @@ struct KFinishEpa
 		const EpaResult &r = c.epa_results[k];
 		CollideItem item = r.c;
 		ConvexPairSetup s = convex_pair_setup(w, item);
-		float max_separation_distance = fmin_(s.max_separation_distance, 1.0f);
-		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, v3_load(r.point1), v3_load(r.point2), v3_load(r.axis), max_separation_distance);
+		finish_convex_pair(w, c, item, s.transform1, s.transform2, s.transform_2_to_1, v3_load(r.point1), v3_load(r.point2), v3_load(r.axis), r.max_separation_distance);
 	}
 };
 

@@ -47,6 +47,20 @@ template <class K> __global__ void __launch_bounds__(128) run_kernel_dev(const K
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 		k(i);
 }
+// Lockstep form: EVERY lane calls k.run(i, valid) every round so that the item body can keep the warp converged with votes
+template <class K> __global__ void __launch_bounds__(128) run_kernel_dev_lockstep(const K k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap)
+{
+	uint32_t n = *n_ptr;
+	if (n > cap) n = cap;
+	uint32_t begin = begin_ptr != nullptr? *begin_ptr : 0;
+	n = n > begin? n - begin : 0;
+	for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x)
+	{
+		uint32_t i = base + threadIdx.x;
+		k.run(i, i < n);
+		__syncwarp();
+	}
+}
 // One WARP per work item for serial, scratch hungry item bodies (EPA): lane 0 runs the item with an S scratch block in shared
 // memory (low latency instead of a global memory slot); slot = global warp id (ownership of any global side scratch).
 template <class K, class S> __global__ void __launch_bounds__(256) run_kernel_warp_smem(const K k, const uint32_t *n_ptr, uint32_t cap)
@@ -315,6 +329,22 @@ struct Runtime
 #endif
 	}
 	// device-resident count, one warp per item with an S scratch block in shared memory; uses at most num_slots warps
+	template <class K> void launch_dev_lockstep(const K &k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap)
+	{
+		if (cap == 0) return;
+		++launches;
+#ifndef B2J_HOSTSIM
+		uint32_t g = grid_for(cap, 128);
+		uint32_t gmax = (uint32_t)num_sms * 8;
+		if (profiling) prof_begin(profile_category<K>());
+		run_kernel_dev_lockstep<K><<<g > gmax? gmax : g, 128, 0, stream>>>(k, n_ptr, begin_ptr, cap);
+		if (profiling) prof_end();
+#else
+		uint32_t n = *n_ptr < cap? *n_ptr : cap;
+		uint32_t begin = begin_ptr? *begin_ptr : 0;
+		for (uint32_t i = begin; i < n; ++i) k.run(i - begin, true);
+#endif
+	}
 	template <class K, class S> void launch_warp_smem(const K &k, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots, uint32_t warps_per_block = 4)
 	{
 		if (cap == 0) return;

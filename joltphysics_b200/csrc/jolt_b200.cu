@@ -481,14 +481,15 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KFindPairs k; k.w = d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = first_active; rt.launch(k, n_query); }
 		{ KProcessPairs k; k.w = d; k.c = W->nc; k.first_ptr = W->d_round_begin; rt.launch_dev(k, &d.counters->num_pairs, W->d_round_begin, d.max_body_pairs); }
 		{ KCopyCached k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_cached, nullptr, d.max_body_pairs); }
-		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
-		// deep pairs: thread per pair, lanes in lockstep, EPA scratch in (lane interleaved, L1/L2 cached) local memory. Small tier first
-		// (2 KB per lane covers ~88% of the pairs, 16 warps per SM); the pairs that overflow it re-run on full size storage (21 KB per lane).
+		// convex pairs: GJK (thread per pair, lockstep) queues shallow hits as results and deep ones for EPA
 		rt.memset_(W->nc.num_epa_overflow, 0, 4);
 		rt.memset_(W->nc.num_epa_results, 0, 4);
+		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev_lockstep(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
+		// deep pairs: thread per pair, lanes in lockstep, EPA scratch in (lane interleaved, L1/L2 cached) local memory. Small tier first
+		// (2 KB per lane covers ~88% of the pairs, 16 warps per SM); the pairs that overflow it re-run on full size storage (21 KB per lane).
 		{ KCollideEpa<EpaStorageSmall, true> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageSmall, true>, EpaStorageSmall>(k, &d.counters->num_epa, W->nc.max_epa, 4); }
 		{ KCollideEpa<EpaStorageFull, false> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageFull, false>, EpaStorageFull>(k, W->nc.num_epa_overflow, W->nc.max_epa, 2); }
-		{ KFinishEpa k; k.w = d; k.c = W->nc; rt.launch_dev(k, W->nc.num_epa_results, nullptr, W->nc.max_epa); }
+		{ KFinishPairs k; k.w = d; k.c = W->nc; rt.launch_dev(k, W->nc.num_epa_results, nullptr, W->nc.max_epa); }
 		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_warp_smem<KCollideMesh, EpaStorageFull>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
 		if (!read_counters(W)) return false;
 		uint32_t woken = W->h_counters.num_woken;
