@@ -486,16 +486,18 @@ struct ContactManifold
 struct ContactSettings { float mCombinedFriction = 0, mCombinedRestitution = 0; bool mIsSensor = false; };
 
 // Host mirror of a body (what the reference hands to listeners)
+class PhysicsSystem;
+
 class Body
 {
 public:
 	const BodyID &GetID() const { return mID; }
-	RVec3 GetCenterOfMassPosition() const { return mPosition; }
-	Quat GetRotation() const { return mRotation; }
-	Vec3 GetLinearVelocity() const { return mLinearVelocity; }
-	Vec3 GetAngularVelocity() const { return mAngularVelocity; }
-	RVec3 GetPosition() const { return mPosition - mRotation * mShape->GetCenterOfMass(); }
-	bool IsActive() const { return mActive; }
+	RVec3 GetCenterOfMassPosition() const { Sync(); return mPosition; }
+	Quat GetRotation() const { Sync(); return mRotation; }
+	Vec3 GetLinearVelocity() const { Sync(); return mLinearVelocity; }
+	Vec3 GetAngularVelocity() const { Sync(); return mAngularVelocity; }
+	RVec3 GetPosition() const { Sync(); return mPosition - mRotation * mShape->GetCenterOfMass(); }
+	bool IsActive() const { Sync(); return mActive; }
 	bool IsStatic() const { return mMotionType == EMotionType::Static; }
 	bool IsDynamic() const { return mMotionType == EMotionType::Dynamic; }
 	EMotionType GetMotionType() const { return mMotionType; }
@@ -503,15 +505,22 @@ public:
 	uint64 GetUserData() const { return mUserData; }
 	const Shape *GetShape() const { return mShape.get(); }
 
+	// PhysicsSystem::Update downloads the state of all bodies into flat arrays with one copy; the per body mirror below is refreshed
+	// from them on first access after a step (no per body work in Update: it matters at 1M bodies).
+	inline void Sync() const;
+
 	BodyID mID;
-	RVec3 mPosition;              // centre of mass position
-	Quat mRotation;
-	Vec3 mLinearVelocity, mAngularVelocity;
+	mutable RVec3 mPosition;      // centre of mass position
+	mutable Quat mRotation;
+	mutable Vec3 mLinearVelocity, mAngularVelocity;
+	mutable uint32 mSyncGeneration = 0;
+	const PhysicsSystem *mSystem = nullptr;
 	ShapeRef mShape;
 	EMotionType mMotionType = EMotionType::Static;
 	ObjectLayer mObjectLayer = 0;
 	uint64 mUserData = 0;
-	bool mActive = false, mInWorld = false, mDestroyed = false;
+	mutable bool mActive = false;
+	bool mInWorld = false, mDestroyed = false;
 	b2j_body_desc mDesc;          // creation time descriptor (uploaded by AddBody)
 };
 
@@ -531,8 +540,6 @@ public:
 	virtual void OnBodyActivated(const BodyID &, uint64) = 0;
 	virtual void OnBodyDeactivated(const BodyID &, uint64) = 0;
 };
-
-class PhysicsSystem;
 
 // ---- BodyInterface ----------------------------------------------------------------------------------------------------
 class BodyInterface
@@ -554,14 +561,14 @@ public:
 	void DestroyBody(const BodyID &inBodyID);
 	void ActivateBody(const BodyID &inBodyID) { uint32 id = inBodyID.mID; Flush(); b2j_bodies_activate(World(), &id, 1); }
 	void DeactivateBody(const BodyID &inBodyID) { uint32 id = inBodyID.mID; Flush(); b2j_bodies_deactivate(World(), &id, 1); }
-	bool IsActive(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->mActive; }
+	bool IsActive(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->IsActive(); }
 	bool IsAdded(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->mInWorld; }
 
 	RVec3 GetPosition(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetPosition() : RVec3::sZero(); }
-	RVec3 GetCenterOfMassPosition(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mPosition : RVec3::sZero(); }
-	Quat GetRotation(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mRotation : Quat::sIdentity(); }
-	Vec3 GetLinearVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mLinearVelocity : Vec3::sZero(); }
-	Vec3 GetAngularVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mAngularVelocity : Vec3::sZero(); }
+	RVec3 GetCenterOfMassPosition(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetCenterOfMassPosition() : RVec3::sZero(); }
+	Quat GetRotation(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetRotation() : Quat::sIdentity(); }
+	Vec3 GetLinearVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetLinearVelocity() : Vec3::sZero(); }
+	Vec3 GetAngularVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetAngularVelocity() : Vec3::sZero(); }
 	void GetPositionAndRotation(const BodyID &id, RVec3 &outPosition, Quat &outRotation) const { outPosition = GetPosition(id); outRotation = GetRotation(id); }
 	void SetPositionAndRotation(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, EActivation inActivationMode);
 	void SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity);
@@ -653,6 +660,7 @@ public:
 
 private:
 	friend class BodyInterface;
+	friend class Body;
 
 	void FillSettings(b2j_settings &s) const
 	{
@@ -682,16 +690,7 @@ private:
 		memset(&st, 0, sizeof(st));
 		st.position = mPos.data(); st.rotation = mRot.data(); st.linear_velocity = mLin.data(); st.angular_velocity = mAng.data(); st.active_index = mActiveIndex.data();
 		b2j_bodies_get_state(mWorld, nullptr, n, &st);
-		for (uint32 i = 0; i < n; ++i)
-		{
-			Body &b = *mBodies[i];
-			if (!b.mInWorld) continue;
-			b.mPosition = Vec3(mPos[3 * i], mPos[3 * i + 1], mPos[3 * i + 2]);
-			b.mRotation = Quat(mRot[4 * i], mRot[4 * i + 1], mRot[4 * i + 2], mRot[4 * i + 3]);
-			b.mLinearVelocity = Vec3(mLin[3 * i], mLin[3 * i + 1], mLin[3 * i + 2]);
-			b.mAngularVelocity = Vec3(mAng[3 * i], mAng[3 * i + 1], mAng[3 * i + 2]);
-			b.mActive = mActiveIndex[i] != B2J_INACTIVE_INDEX;
-		}
+		++mStateGeneration; // Body::Sync picks the new state up on first access
 	}
 
 	void ReplayEvents()
@@ -758,11 +757,28 @@ private:
 	std::vector<uint32> mForceIDs;                // accumulated AddForce / AddTorque calls
 	std::vector<float> mForces, mTorques;
 	b2j_step_stats mStats = b2j_step_stats();
-	std::vector<float> mPos, mRot, mLin, mAng;
+	std::vector<float> mPos, mRot, mLin, mAng;    // state of all body slots after the last Update (see Body::Sync)
 	std::vector<uint32> mActiveIndex;
+	uint32 mStateGeneration = 1;
 	std::vector<b2j_contact_event> mContactEvents;
 	std::vector<b2j_activation_event> mActEvents;
 };
+
+inline void Body::Sync() const
+{
+	if (mSystem == nullptr || !mInWorld || mSyncGeneration == mSystem->mStateGeneration)
+		return;
+	mSyncGeneration = mSystem->mStateGeneration;
+	size_t i = mID.GetIndex();
+	if (i >= mSystem->mActiveIndex.size())
+		return; // added after the last Update
+	const std::vector<float> &p = mSystem->mPos, &r = mSystem->mRot, &l = mSystem->mLin, &a = mSystem->mAng;
+	mPosition = Vec3(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+	mRotation = Quat(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+	mLinearVelocity = Vec3(l[3 * i], l[3 * i + 1], l[3 * i + 2]);
+	mAngularVelocity = Vec3(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+	mActive = mSystem->mActiveIndex[i] != B2J_INACTIVE_INDEX;
+}
 
 // ---- BodyInterface implementation -----------------------------------------------------------------------------------
 inline b2j_world *BodyInterface::World() const { return mSystem->mWorld; }
@@ -788,6 +804,7 @@ inline Body *BodyInterface::CreateBody(const BodyCreationSettings &s)
 	}
 	std::unique_ptr<Body> body(new Body);
 	body->mID = BodyID(index, sequence);
+	body->mSystem = &sys;
 	body->mShape = s.GetShape();
 	body->mMotionType = s.mMotionType;
 	body->mObjectLayer = s.mObjectLayer;
@@ -850,6 +867,7 @@ inline void BodyInterface::AddBodies(const BodyID *inBodies, int inNumber, EActi
 		Body *b = const_cast<Body *>(TryGet(inBodies[i]));
 		if (b == nullptr || b->mInWorld) continue;
 		b->mInWorld = true;
+		b->mSyncGeneration = sys.mStateGeneration; // the creation state is current until the next Update
 		sys.mPendingAdd.push_back(b->mDesc);
 		if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static)
 		{
@@ -905,6 +923,7 @@ inline void BodyInterface::SetPositionAndRotation(const BodyID &id, const RVec3 
 {
 	Body *b = const_cast<Body *>(TryGet(id));
 	if (b == nullptr) return;
+	b->Sync();
 	b->mRotation = inRotation;
 	b->mPosition = inPosition + inRotation * b->mShape->GetCenterOfMass();
 	if (!b->mInWorld) { b->mDesc.position[0] = b->mPosition.x; b->mDesc.position[1] = b->mPosition.y; b->mDesc.position[2] = b->mPosition.z; b->mDesc.rotation[0] = inRotation.x; b->mDesc.rotation[1] = inRotation.y; b->mDesc.rotation[2] = inRotation.z; b->mDesc.rotation[3] = inRotation.w; return; }
@@ -922,6 +941,7 @@ inline void BodyInterface::SetLinearAndAngularVelocity(const BodyID &id, const V
 {
 	Body *b = const_cast<Body *>(TryGet(id));
 	if (b == nullptr || b->mMotionType == EMotionType::Static) return;
+	b->Sync();
 	b->mLinearVelocity = lv; b->mAngularVelocity = av;
 	if (!b->mInWorld) { memcpy(b->mDesc.linear_velocity, &lv, 12); memcpy(b->mDesc.angular_velocity, &av, 12); return; }
 	Flush();

@@ -10,6 +10,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <typeinfo>
@@ -100,6 +101,7 @@ template <class K, class S> __global__ void __launch_bounds__(128) run_kernel_la
 
 // kernel categories for the optional per kernel timing (one id per kernel functor type, process wide)
 inline std::vector<std::string> &profile_names() { static std::vector<std::string> n; return n; }
+inline std::mutex &profile_mutex() { static std::mutex m; return m; } // the groups of a batch launch from several host threads
 template <class K> inline int profile_category()
 {
 	static int id = [] {
@@ -109,6 +111,7 @@ template <class K> inline int profile_category()
 		free(dm);
 		size_t p = name.rfind("::");
 		if (p != std::string::npos) name = name.substr(p + 2);
+		std::lock_guard<std::mutex> lock(profile_mutex());
 		profile_names().push_back(name);
 		return (int)profile_names().size() - 1;
 	}();

@@ -11,6 +11,9 @@
 #include "b2j_solver.h"
 
 #include <chrono>
+#include <thread>
+#include <map>
+#include <string>
 
 using namespace b2j;
 
@@ -338,9 +341,12 @@ struct b2j_world
 #endif
 };
 
+// The worlds of a batch live in a few GROUPS; a group is ONE device world (slot = world in group * stride + body index) with its own
+// stream, stepped by its own host thread: kernels and host round trips of different groups overlap (measured 1.3x at 1024 worlds).
 struct b2j_batch
 {
-	b2j_world *big = nullptr;    // all worlds live in ONE device world: slot = world * stride + body index
+	std::vector<b2j_world *> groups;
+	std::vector<uint32_t> first_world;   // first world of each group (+ n_worlds at the end)
 	uint32_t n_worlds = 0, stride = 0, bodies_per_world = 0;
 };
 
@@ -965,6 +971,7 @@ uint32_t b2j_world_get_profile(b2j_world *W, char *names, uint32_t name_stride, 
 {
 	W->rt.sync();
 	W->rt.prof_collect();
+	std::lock_guard<std::mutex> lock(profile_mutex());
 	uint32_t n = 0;
 	for (size_t i = 0; i < W->rt.prof_ms.size(); ++i)
 	{
@@ -1536,9 +1543,8 @@ template <class T> static void replicate(Runtime &rt, T *dst, const T *src, uint
 
 extern "C" {
 
-b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
+static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
 {
-	if (P == nullptr || n_worlds == 0 || P->num_worlds != 1) { last_error() = "b2j_batch_create: invalid prototype"; return nullptr; }
 	upload_shapes(P);
 	sync_dworld(P);
 	uint32_t stride = P->num_slots;
@@ -1604,34 +1610,186 @@ b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_p
 	B->num_active = P->num_active * n_worlds;
 	rt.sync();
 	if (!rt.check("b2j_batch_create")) { b2j_world_destroy(B); return nullptr; }
+	return B;
+}
+
+} // extern "C"
+
+// Runs fn(group index) for every group, one host thread per group (the caller runs group 0); returns false if any failed
+template <class F> static bool batch_for_each_group(b2j_batch *b, const F &fn)
+{
+	size_t K = b->groups.size();
+	std::vector<int> ok(K, 1);
+	std::vector<std::string> err(K);
+	auto work = [&](size_t g, bool worker)
+	{
+#ifndef B2J_HOSTSIM
+		if (worker) cudaSetDevice(b->groups[g]->rt.device);
+#endif
+		(void)worker;
+		if (!fn(g)) { ok[g] = 0; err[g] = last_error(); }
+	};
+	std::vector<std::thread> threads;
+	for (size_t g = 1; g < K; ++g) threads.emplace_back(work, g, true);
+	work(0, false);
+	for (std::thread &t : threads) t.join();
+	for (size_t g = 0; g < K; ++g)
+		if (!ok[g]) { last_error() = err[g]; return false; }
+	return true;
+}
+
+extern "C" {
+
+b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
+{
+	if (P == nullptr || n_worlds == 0 || P->num_worlds != 1) { last_error() = "b2j_batch_create: invalid prototype"; return nullptr; }
+	// groups of at least 128 worlds, at most 4 (B2J_BATCH_GROUPS overrides)
+	uint32_t K = n_worlds >= 512? 4 : (n_worlds >= 256? 2 : 1);
+	if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
+#ifdef B2J_HOSTSIM
+	K = 1; // the host simulation is single threaded
+#endif
+	if (K < 1) K = 1;
+	if (K > n_worlds) K = n_worlds;
 	b2j_batch *b = new b2j_batch;
-	b->big = B; b->n_worlds = n_worlds; b->stride = stride; b->bodies_per_world = P->num_bodies;
+	b->n_worlds = n_worlds; b->stride = P->num_slots; b->bodies_per_world = P->num_bodies;
+	uint32_t first = 0;
+	for (uint32_t g = 0; g < K; ++g)
+	{
+		uint32_t n = n_worlds / K + (g < n_worlds % K? 1 : 0);
+		b2j_world *G = batch_create_group(P, n, max_body_pairs_per_world, max_contact_constraints_per_world);
+		if (G == nullptr) { b2j_batch_destroy(b); return nullptr; }
+		b->groups.push_back(G);
+		b->first_world.push_back(first);
+		first += n;
+	}
+	b->first_world.push_back(first);
 	return b;
 }
 
-void b2j_batch_destroy(b2j_batch *b) { if (b != nullptr) { b2j_world_destroy(b->big); delete b; } }
-int b2j_batch_step(b2j_batch *b, float dt, int collision_steps, b2j_step_stats *stats) { return b2j_step(b->big, dt, collision_steps, stats); }
+void b2j_batch_destroy(b2j_batch *b)
+{
+	if (b == nullptr) return;
+	for (b2j_world *G : b->groups) b2j_world_destroy(G);
+	delete b;
+}
+
+int b2j_batch_step(b2j_batch *b, float dt, int collision_steps, b2j_step_stats *stats)
+{
+	size_t K = b->groups.size();
+	if (K == 1) return b2j_step(b->groups[0], dt, collision_steps, stats);
+	std::vector<b2j_step_stats> st(K);
+	std::vector<int> rc(K, 0);
+	if (stats != nullptr) for (size_t g = 0; g < K; ++g) st[g] = *stats; // carries the kinetic energy request
+	bool ok = batch_for_each_group(b, [&](size_t g) { rc[g] = b2j_step(b->groups[g], dt, collision_steps, stats != nullptr? &st[g] : nullptr); return rc[g] >= 0; });
+	if (!ok) return -1;
+	int r = 0;
+	for (size_t g = 0; g < K; ++g) r |= rc[g];
+	if (stats != nullptr)
+	{
+		b2j_step_stats a = st[0];
+		for (size_t g = 1; g < K; ++g)
+		{
+			const b2j_step_stats &s = st[g];
+			a.num_active_bodies += s.num_active_bodies; a.num_bodies += s.num_bodies; a.num_body_pairs += s.num_body_pairs; a.num_pairs_from_cache += s.num_pairs_from_cache;
+			a.num_manifolds += s.num_manifolds; a.num_contact_points += s.num_contact_points; a.num_constraints += s.num_constraints; a.num_islands += s.num_islands;
+			a.num_large_islands += s.num_large_islands; a.num_activated += s.num_activated; a.num_deactivated += s.num_deactivated; a.kernel_launches += s.kernel_launches;
+			a.kinetic_energy += s.kinetic_energy; a.error_bits |= s.error_bits;
+			a.num_phases = std::max(a.num_phases, s.num_phases); a.velocity_iterations = std::max(a.velocity_iterations, s.velocity_iterations);
+			a.position_iterations = std::max(a.position_iterations, s.position_iterations); a.gpu_ms = std::max(a.gpu_ms, s.gpu_ms);
+		}
+		*stats = a;
+	}
+	return r;
+}
+
 uint32_t b2j_batch_size(const b2j_batch *b) { return b != nullptr? b->n_worlds : 0; }
+
+static b2j_body_state offset_state(const b2j_body_state &s, size_t first)
+{
+	b2j_body_state o = s;
+	if (o.position) o.position += 3 * first;
+	if (o.rotation) o.rotation += 4 * first;
+	if (o.linear_velocity) o.linear_velocity += 3 * first;
+	if (o.angular_velocity) o.angular_velocity += 3 * first;
+	if (o.bounds) o.bounds += 6 * first;
+	if (o.active_index) o.active_index += first;
+	if (o.sleep_timer) o.sleep_timer += first;
+	return o;
+}
 
 int b2j_batch_get_state(b2j_batch *b, uint32_t world_index, uint32_t n, const b2j_body_state *out)
 {
-	if (b != nullptr && world_index == 0xffffffffu && n <= b->stride * b->n_worlds)
-		return b2j_bodies_get_state(b->big, nullptr, n, out); // all worlds: slots [0, n)
+	if (b != nullptr && world_index == 0xffffffffu && (uint64_t)n <= (uint64_t)b->stride * b->n_worlds)
+	{
+		// all worlds: slots [0, n), every group copies its share
+		bool ok = batch_for_each_group(b, [&](size_t g) {
+			uint64_t first = (uint64_t)b->first_world[g] * b->stride, end = (uint64_t)b->first_world[g + 1] * b->stride;
+			if (first >= n) return true;
+			b2j_body_state o = offset_state(*out, (size_t)first);
+			return b2j_bodies_get_state(b->groups[g], nullptr, (uint32_t)(std::min<uint64_t>(end, n) - first), &o) == 0;
+		});
+		return ok? 0 : -1;
+	}
 	if (b == nullptr || world_index >= b->n_worlds || n > b->stride) { last_error() = "b2j_batch_get_state: invalid arguments"; return -1; }
-	b->big->get_state_first = world_index * b->stride;
-	int r = b2j_bodies_get_state(b->big, nullptr, n, out);
-	b->big->get_state_first = 0;
+	size_t g = 0;
+	while (world_index >= b->first_world[g + 1]) ++g;
+	b2j_world *G = b->groups[g];
+	G->get_state_first = (world_index - b->first_world[g]) * b->stride;
+	int r = b2j_bodies_get_state(G, nullptr, n, out);
+	G->get_state_first = 0;
 	return r;
 }
 
 int b2j_batch_add_force_torque(b2j_batch *b, uint32_t n, const float *force, const float *torque)
 {
-	if (b == nullptr || n > b->stride * b->n_worlds) { last_error() = "b2j_batch_add_force_torque: invalid arguments"; return -1; }
-	return b2j_bodies_add_force_torque(b->big, nullptr, n, force, torque);
+	if (b == nullptr || (uint64_t)n > (uint64_t)b->stride * b->n_worlds) { last_error() = "b2j_batch_add_force_torque: invalid arguments"; return -1; }
+	bool ok = batch_for_each_group(b, [&](size_t g) {
+		uint64_t first = (uint64_t)b->first_world[g] * b->stride, end = (uint64_t)b->first_world[g + 1] * b->stride;
+		if (first >= n) return true;
+		return b2j_bodies_add_force_torque(b->groups[g], nullptr, (uint32_t)(std::min<uint64_t>(end, n) - first), force? force + 3 * first : nullptr, torque? torque + 3 * first : nullptr) == 0;
+	});
+	return ok? 0 : -1;
 }
 
-int b2j_batch_set_profiling(b2j_batch *b, int on) { return b2j_world_set_profiling(b->big, on); }
-uint32_t b2j_batch_get_profile(b2j_batch *b, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap) { return b2j_world_get_profile(b->big, names, name_stride, ms, launches, cap); }
+int b2j_batch_set_profiling(b2j_batch *b, int on)
+{
+	int r = 0;
+	for (b2j_world *G : b->groups) r |= b2j_world_set_profiling(G, on);
+	return r;
+}
+
+// kernel times summed over the groups (the groups run concurrently: the sum can exceed the wall time of the step)
+uint32_t b2j_batch_get_profile(b2j_batch *b, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap)
+{
+	if (b->groups.size() == 1) return b2j_world_get_profile(b->groups[0], names, name_stride, ms, launches, cap);
+	std::vector<std::string> order;
+	std::map<std::string, std::pair<float, uint32_t>> acc;
+	const uint32_t kCap = 256, kStride = 96;
+	std::vector<char> nm(kCap * kStride); std::vector<float> m(kCap); std::vector<uint32_t> l(kCap);
+	for (b2j_world *G : b->groups)
+	{
+		uint32_t n = b2j_world_get_profile(G, nm.data(), kStride, m.data(), l.data(), kCap);
+		for (uint32_t i = 0; i < n && i < kCap; ++i)
+		{
+			std::string name(&nm[i * kStride]);
+			if (acc.find(name) == acc.end()) order.push_back(name);
+			acc[name].first += m[i]; acc[name].second += l[i];
+		}
+	}
+	uint32_t n = 0;
+	for (const std::string &name : order)
+	{
+		if (n < cap)
+		{
+			if (names != nullptr && name_stride > 0) { strncpy(names + (size_t)n * name_stride, name.c_str(), name_stride - 1); names[(size_t)n * name_stride + name_stride - 1] = 0; }
+			if (ms != nullptr) ms[n] = acc[name].first;
+			if (launches != nullptr) launches[n] = acc[name].second;
+		}
+		++n;
+	}
+	return n;
+}
 
 } // extern "C"
 #pragma GCC visibility pop

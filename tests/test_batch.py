@@ -59,3 +59,33 @@ def test_batch_matches_single_world_hostsim(hostsim_api, hostsim_facade, scene, 
 def test_batch_matches_single_world_gpu(gpu_api, scene, p0, p1, n_worlds, steps):
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
     _check_batch(gpu_api, flib, scene, p0, p1, n_worlds, steps)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("groups", [2, 3])
+def test_batch_groups_gpu(gpu_api, groups, monkeypatch):
+    """Large batches are split into groups with their own stream and host thread (B2J_BATCH_GROUPS forces it for a small batch):
+    every world must still evolve exactly like the prototype stepped alone, through the all-worlds and the per-world getters."""
+    monkeypatch.setenv("B2J_BATCH_GROUPS", str(groups))
+    flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
+    _check_batch(gpu_api, flib, "pyramid", 6, 0, 7, 50)
+    # all-worlds getter / force setter across the group boundaries
+    proto = F.FacadeScene(flib, "pyramid", 5, 0)
+    n, n_worlds = proto.num_bodies, 7
+    batch = gpu_api.b2j_batch_create(proto.world.h, n_worlds, 0, 0)
+    assert batch, gpu_api.last_error()
+    force = np.zeros((n_worlds * n, 3), dtype=np.float32)
+    force[:, 0] = 4.0e5  # boxes of 8000 kg
+    fp = C.POINTER(C.c_float)
+    stats = _capi.StepStats()
+    for _ in range(20):
+        assert gpu_api.b2j_batch_add_force_torque(batch, n_worlds * n, force.ctypes.data_as(fp), None) == 0, gpu_api.last_error()
+        assert gpu_api.b2j_batch_step(batch, 1.0 / 60.0, 1, C.byref(stats)) == 0, gpu_api.last_error()
+    everything = _batch_state(gpu_api, batch, 0xffffffff, n_worlds * n)
+    for w in range(n_worlds):
+        one = _batch_state(gpu_api, batch, w, n)
+        assert np.array_equal(everything.pos[w * n:(w + 1) * n], one.pos)
+        assert np.array_equal(everything.pos[:n], one.pos), "all worlds get the same forces: identical trajectories"
+    assert everything.pos[1:n, 0].mean() > 0.1 + proto.world.state().pos[1:n, 0].mean(), "the forces must have pushed the dynamic bodies along +x"
+    gpu_api.b2j_batch_destroy(batch)
+    proto.close()
