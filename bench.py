@@ -159,6 +159,23 @@ def run_reference(args):
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------------------
 
+def shard_worlds(total_worlds, rank, world_size):
+    """world_id -> rank: contiguous blocks, the first (total % world_size) ranks hold one world more. Returns (first, count)."""
+    base, rem = divmod(total_worlds, world_size)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def reduce_job(dist, world_size, times, work, device):
+    """The job's only collective: MAX over ranks of the times, SUM of the work counters (tensors live on `device`)."""
+    import torch
+    t = torch.tensor(list(times), dtype=torch.float64, device=device)
+    w = torch.tensor(list(work), dtype=torch.float64, device=device)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    return t.tolist(), w.tolist()
+
+
 class Workload:
     """One rank's share of the workload behind a uniform step / e2e / profile interface."""
 
@@ -174,8 +191,7 @@ class Workload:
         self.batch = None
         if self.kind == "batch":
             # world_id -> rank: contiguous blocks
-            base, rem = divmod(args.worlds, world_size)
-            self.n_worlds = base + (1 if rank < rem else 0)
+            self.first_world, self.n_worlds = shard_worlds(args.worlds, rank, world_size)
             self.batch = api.b2j_batch_create(self.scene.world.h, self.n_worlds, BATCH_PAIRS_PER_WORLD, BATCH_CONSTRAINTS_PER_WORLD)
             if not self.batch:
                 raise SystemExit("b2j_batch_create failed: " + api.last_error())
@@ -335,15 +351,9 @@ def run_b200(args):
     m = measure(args, wl, torch, dist, world_size, local_rank, args.steps, args.warmup)
 
     # max over ranks of the times, sum of the work (the only collective: a reduction of the statistics)
-    t_dev, wall, e2e_wall = m["gpu_ms"] / 1000.0, m["wall"], m["e2e"]["wall"]
-    vals = torch.tensor([t_dev, wall, e2e_wall, float(wl.num_dynamic), float(m["launches"]), float(wl.n_worlds)], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        t_dev, wall, e2e_wall = mx[0].item(), mx[1].item(), mx[2].item()
-        total_bodies, launches, total_worlds = sm[3].item(), int(sm[4].item()), int(sm[5].item())
-    else:
-        total_bodies, launches, total_worlds = float(wl.num_dynamic), m["launches"], wl.n_worlds
+    (t_dev, wall, e2e_wall), (total_bodies, launches, total_worlds, h2d, d2h) = reduce_job(
+        dist, world_size, (m["gpu_ms"] / 1000.0, m["wall"], m["e2e"]["wall"]), (wl.num_dynamic, m["launches"], wl.n_worlds, m["e2e"]["h2d"], m["e2e"]["d2h"]), "cuda")
+    launches, total_worlds, h2d, d2h = int(launches), int(total_worlds), int(h2d), int(d2h)
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
@@ -359,7 +369,7 @@ def run_b200(args):
                    "parallelism": (f"worlds sharded over {world_size} GPUs (world_id -> rank blocks), no data-path collective" if batch else f"one world per GPU x{world_size} (replicas only)"),
                    "timing": "every step streams the whole job state through HBM (working set >> 126 MB L2); no L2 flush between steps"},
         "clocks": m["clocks"],
-        "e2e": {"value": m["e2e"]["steps"] * total_bodies / e2e_wall, "unit": "body-steps/s", "h2d_bytes_per_step": m["e2e"]["h2d"], "d2h_bytes_per_step": m["e2e"]["d2h"], "steps": m["e2e"]["steps"],
+        "e2e": {"value": m["e2e"]["steps"] * total_bodies / e2e_wall, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": m["e2e"]["steps"],
                 "path": "b2j_batch_add_force_torque + b2j_batch_step + b2j_batch_get_state (C ABI, pinned host buffers)" if batch else "facade: BodyInterface::AddForce..., PhysicsSystem::Update, BodyInterface::GetPosition"},
         "gpu_launches": launches,
         "wall_ms_per_step": 1000.0 * wall / K,

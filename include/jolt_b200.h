@@ -219,6 +219,16 @@ int b2j_bodies_set_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2
 /* BodyInterface::AddForce / AddTorque (:220-226): accumulate into mForce / mTorque (either may be NULL). */
 int b2j_bodies_add_force_torque(b2j_world *w, const uint32_t *ids, uint32_t n, const float *force, const float *torque);
 
+/* BodyInterface::SetFriction / SetRestitution / SetGravityFactor / SetMaxLinearVelocity / SetMaxAngularVelocity and
+ * MotionProperties::SetLinearDamping / SetAngularDamping (BodyInterface.h:241-281): per body scalars, [n] each, NULL members are
+ * left untouched. */
+typedef struct b2j_body_params {
+	const float *friction, *restitution, *gravity_factor;
+	const float *linear_damping, *angular_damping;
+	const float *max_linear_velocity, *max_angular_velocity;
+} b2j_body_params;
+int b2j_bodies_set_params(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_params *in);
+
 uint32_t b2j_num_bodies(const b2j_world *w);          /* PhysicsSystem::GetNumBodies        PhysicsSystem.h:219 */
 uint32_t b2j_num_active_bodies(const b2j_world *w);   /* PhysicsSystem::GetNumActiveBodies  :222 */
 /* PhysicsSystem::GetActiveBodies (:240): copies up to cap ids in active-list order, returns the count. */

@@ -62,6 +62,12 @@ struct Quat
 	static Quat sIdentity() { return Quat(0, 0, 0, 1); }
 	float GetX() const { return x; } float GetY() const { return y; } float GetZ() const { return z; } float GetW() const { return w; }
 	Quat Normalized() const { float l = std::sqrt((x * x + y * y) + (z * z + w * w)); return Quat(x / l, y / l, z / l, w / l); }
+	// Quat::operator*(Quat) (Jolt/Math/Quat.inl, scalar path), same operation order as the device code (b2j_math.h)
+	Quat operator*(const Quat &r) const
+	{
+		float a = x, b = y, c = z, d = w;
+		return Quat((a * r.w + b * r.z) + (d * r.x - c * r.y), (b * r.w + c * r.x) + (d * r.y - a * r.z), (c * r.w + a * r.y) + (d * r.z - b * r.x), -(a * r.x + b * r.y) + (d * r.w - c * r.z));
+	}
 	// Quat::operator*(Vec3) (Jolt/Math/Quat.inl:383-405)
 	Vec3 operator*(const Vec3 &p) const
 	{
@@ -487,6 +493,8 @@ struct ContactSettings { float mCombinedFriction = 0, mCombinedRestitution = 0; 
 
 // Host mirror of a body (what the reference hands to listeners)
 class PhysicsSystem;
+enum class EBodyType : uint8 { RigidBody, SoftBody };   // Jolt/Physics/Body/BodyType.h (soft bodies are out of scope)
+using BodyIDVector = std::vector<BodyID>;
 
 class Body
 {
@@ -555,12 +563,18 @@ public:
 		AddBody(b->GetID(), inActivationMode);
 		return b->GetID();
 	}
-	// Bulk add (AddBodiesPrepare / Finalize, BodyInterface.h:124-133): one upload for all bodies
+	// Bulk add (AddBodiesPrepare / Finalize / Abort, BodyInterface.h:124-133): one upload for all bodies. The reference prepares a
+	// broadphase sub tree in Prepare; here the state handle only remembers the batch and Finalize queues it.
+	using AddState = void *;
+	AddState AddBodiesPrepare(BodyID *ioBodies, int inNumber) { (void)ioBodies; return inNumber > 0? (AddState)this : nullptr; }
+	void AddBodiesFinalize(BodyID *ioBodies, int inNumber, AddState inAddState, EActivation inActivationMode) { if (inAddState != nullptr) AddBodies(ioBodies, inNumber, inActivationMode); }
+	void AddBodiesAbort(BodyID *ioBodies, int inNumber, AddState inAddState) { (void)ioBodies; (void)inNumber; (void)inAddState; }
 	void AddBodies(const BodyID *inBodies, int inNumber, EActivation inActivationMode);
 	void RemoveBody(const BodyID &inBodyID);
+	void RemoveBodies(BodyID *ioBodies, int inNumber) { for (int i = 0; i < inNumber; ++i) RemoveBody(ioBodies[i]); }
 	void DestroyBody(const BodyID &inBodyID);
-	void ActivateBody(const BodyID &inBodyID) { uint32 id = inBodyID.mID; Flush(); b2j_bodies_activate(World(), &id, 1); }
-	void DeactivateBody(const BodyID &inBodyID) { uint32 id = inBodyID.mID; Flush(); b2j_bodies_deactivate(World(), &id, 1); }
+	void ActivateBody(const BodyID &inBodyID) { SetActive(inBodyID, true); }
+	void DeactivateBody(const BodyID &inBodyID) { SetActive(inBodyID, false); }
 	bool IsActive(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->IsActive(); }
 	bool IsAdded(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->mInWorld; }
 
@@ -574,8 +588,25 @@ public:
 	void SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity);
 	void SetLinearVelocity(const BodyID &id, const Vec3 &v) { SetLinearAndAngularVelocity(id, v, GetAngularVelocity(id)); }
 	void SetAngularVelocity(const BodyID &id, const Vec3 &v) { SetLinearAndAngularVelocity(id, GetLinearVelocity(id), v); }
-	void AddForce(const BodyID &id, const Vec3 &inForce);
-	void AddTorque(const BodyID &id, const Vec3 &inTorque);
+	void AddForce(const BodyID &id, const Vec3 &inForce, EActivation inActivationMode = EActivation::Activate);
+	void AddTorque(const BodyID &id, const Vec3 &inTorque, EActivation inActivationMode = EActivation::Activate);
+	// BodyInterface::AddImpulse / AddAngularImpulse (BodyInterface.h:227-230, Body.inl AddImpulse): dynamic bodies only, activates the body
+	void AddImpulse(const BodyID &id, const Vec3 &inImpulse);
+	void AddImpulse(const BodyID &id, const Vec3 &inImpulse, const RVec3 &inPoint);
+	void AddAngularImpulse(const BodyID &id, const Vec3 &inAngularImpulse);
+	// per body material / motion parameters (BodyInterface.h:241-281)
+	void SetFriction(const BodyID &id, float v) { SetParam(id, &b2j_body_desc::friction, &b2j_body_params::friction, v); }
+	float GetFriction(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mDesc.friction : 0.0f; }
+	void SetRestitution(const BodyID &id, float v) { SetParam(id, &b2j_body_desc::restitution, &b2j_body_params::restitution, v); }
+	float GetRestitution(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mDesc.restitution : 0.0f; }
+	void SetGravityFactor(const BodyID &id, float v) { SetParam(id, &b2j_body_desc::gravity_factor, &b2j_body_params::gravity_factor, v); }
+	float GetGravityFactor(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mDesc.gravity_factor : 1.0f; }
+	void SetMaxLinearVelocity(const BodyID &id, float v) { SetParam(id, &b2j_body_desc::max_linear_velocity, &b2j_body_params::max_linear_velocity, v); }
+	float GetMaxLinearVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mDesc.max_linear_velocity : 0.0f; }
+	void SetMaxAngularVelocity(const BodyID &id, float v) { SetParam(id, &b2j_body_desc::max_angular_velocity, &b2j_body_params::max_angular_velocity, v); }
+	float GetMaxAngularVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mDesc.max_angular_velocity : 0.0f; }
+	EMotionType GetMotionType(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mMotionType : EMotionType::Static; }
+	ObjectLayer GetObjectLayer(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mObjectLayer : 0; }
 	// Bulk force application from host arrays (n bodies, force/torque [n][3], either may be null): the RL pattern
 	void AddForcesAndTorques(const BodyID *inBodies, int inNumber, const float *inForces, const float *inTorques);
 	uint64 GetUserData(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mUserData : 0; }
@@ -586,6 +617,8 @@ private:
 	friend class PhysicsSystem;
 	b2j_world *World() const;
 	void Flush();
+	void SetActive(const BodyID &id, bool inActive);
+	void SetParam(const BodyID &id, float b2j_body_desc::*inDescMember, const float *b2j_body_params::*inParamMember, float inValue);
 	PhysicsSystem *mSystem = nullptr;
 };
 
@@ -640,6 +673,21 @@ public:
 	uint GetNumBodies() const { return mWorld? b2j_num_bodies(mWorld) : 0; }
 	uint GetNumActiveBodies() const { return mWorld? b2j_num_active_bodies(mWorld) : 0; }
 	uint GetMaxBodies() const { return mMaxBodies; }
+	// PhysicsSystem::GetBodies / GetActiveBodies (PhysicsSystem.h:226-240); active bodies come back in the device's active list order
+	void GetBodies(BodyIDVector &outBodyIDs) const
+	{
+		outBodyIDs.clear();
+		for (const std::unique_ptr<Body> &b : mBodies) if (b && !b->mDestroyed && b->mInWorld) outBodyIDs.push_back(b->mID);
+	}
+	void GetActiveBodies(EBodyType inType, BodyIDVector &outBodyIDs) const
+	{
+		outBodyIDs.clear();
+		if (inType != EBodyType::RigidBody || mWorld == nullptr) return;
+		const_cast<PhysicsSystem *>(this)->mBodyInterface.Flush();
+		std::vector<uint32> ids(b2j_num_active_bodies(mWorld));
+		uint32 n = ids.empty()? 0 : b2j_get_active_bodies(mWorld, ids.data(), (uint32)ids.size());
+		for (uint32 i = 0; i < n; ++i) { BodyID id; id.mID = ids[i]; outBodyIDs.push_back(id); }
+	}
 	bool WereBodiesInContact(const BodyID &a, const BodyID &b) const { return mWorld && b2j_were_bodies_in_contact(mWorld, a.mID, b.mID) == 1; }
 	const b2j_step_stats &GetLastStepStats() const { return mStats; }
 	b2j_world *GetWorld() const { return mWorld; }
@@ -955,20 +1003,91 @@ inline void BodyInterface::SetLinearAndAngularVelocity(const BodyID &id, const V
 	if (lv.LengthSq() > 0.0f || av.LengthSq() > 0.0f) b2j_bodies_activate(World(), &bid, 1);
 }
 
-inline void BodyInterface::AddForce(const BodyID &id, const Vec3 &f)
+inline void BodyInterface::AddForce(const BodyID &id, const Vec3 &f, EActivation inActivationMode)
 {
 	PhysicsSystem &sys = *mSystem;
+	// BodyInterface::AddForce (BodyInterface.cpp): dynamic bodies only; applied when the body is active or gets activated
+	const Body *b = TryGet(id);
+	if (b == nullptr || b->mMotionType != EMotionType::Dynamic || !(inActivationMode == EActivation::Activate || b->IsActive())) return;
+	if (inActivationMode == EActivation::Activate && b->mInWorld) sys.mPendingActivate.push_back(id.mID);
 	sys.mForceIDs.push_back(id.mID);
 	sys.mForces.push_back(f.x); sys.mForces.push_back(f.y); sys.mForces.push_back(f.z);
 	sys.mTorques.push_back(0); sys.mTorques.push_back(0); sys.mTorques.push_back(0);
 }
 
-inline void BodyInterface::AddTorque(const BodyID &id, const Vec3 &t)
+inline void BodyInterface::AddTorque(const BodyID &id, const Vec3 &t, EActivation inActivationMode)
 {
 	PhysicsSystem &sys = *mSystem;
+	const Body *b = TryGet(id);
+	if (b == nullptr || b->mMotionType != EMotionType::Dynamic || !(inActivationMode == EActivation::Activate || b->IsActive())) return;
+	if (inActivationMode == EActivation::Activate && b->mInWorld) sys.mPendingActivate.push_back(id.mID);
 	sys.mForceIDs.push_back(id.mID);
 	sys.mForces.push_back(0); sys.mForces.push_back(0); sys.mForces.push_back(0);
 	sys.mTorques.push_back(t.x); sys.mTorques.push_back(t.y); sys.mTorques.push_back(t.z);
+}
+
+inline void BodyInterface::SetActive(const BodyID &id, bool inActive)
+{
+	const Body *b = TryGet(id);
+	if (b == nullptr || !b->mInWorld || b->mMotionType == EMotionType::Static) return;
+	uint32 bid = id.mID;
+	Flush();
+	if (inActive) b2j_bodies_activate(World(), &bid, 1); else b2j_bodies_deactivate(World(), &bid, 1);
+	b->Sync();
+	b->mActive = inActive;
+	if (!inActive) { b->mLinearVelocity = Vec3::sZero(); b->mAngularVelocity = Vec3::sZero(); } // BodyManager::DeactivateBodies resets the velocities
+}
+
+inline void BodyInterface::SetParam(const BodyID &id, float b2j_body_desc::*inDescMember, const float *b2j_body_params::*inParamMember, float inValue)
+{
+	Body *b = const_cast<Body *>(TryGet(id));
+	if (b == nullptr) return;
+	b->mDesc.*inDescMember = inValue;
+	if (!b->mInWorld) return; // uploaded with the body
+	Flush();
+	b2j_body_params p;
+	memset(&p, 0, sizeof(p));
+	p.*inParamMember = &inValue;
+	uint32 bid = id.mID;
+	b2j_bodies_set_params(World(), &bid, 1, &p);
+}
+
+inline void BodyInterface::AddImpulse(const BodyID &id, const Vec3 &inImpulse)
+{
+	const Body *b = TryGet(id);
+	if (b == nullptr || b->mMotionType != EMotionType::Dynamic) return;
+	// Body::AddImpulse: v += invM * impulse
+	SetLinearVelocity(id, b->GetLinearVelocity() + b->mDesc.inv_mass * inImpulse);
+	if (b->mInWorld) ActivateBody(id);
+}
+
+inline void BodyInterface::AddAngularImpulse(const BodyID &id, const Vec3 &inAngularImpulse)
+{
+	const Body *b = TryGet(id);
+	if (b == nullptr || b->mMotionType != EMotionType::Dynamic) return;
+	// MotionProperties::MultiplyWorldSpaceInverseInertiaByVector (MotionProperties.inl:77-92): R D R^T v with R = body rotation * inertia rotation
+	const b2j_body_desc &d = b->mDesc;
+	Quat q = b->GetRotation() * Quat(d.inertia_rotation[0], d.inertia_rotation[1], d.inertia_rotation[2], d.inertia_rotation[3]);
+	// Mat44::sRotation(q) columns (Mat44.inl), then rotation.Multiply3x3(invI * rotation.Multiply3x3Transposed(v))
+	float tx = q.x + q.x, ty = q.y + q.y, tz = q.z + q.z;
+	float xx = tx * q.x, yy = ty * q.y, zz = tz * q.z, xy = tx * q.y, xz = tx * q.z, xw = tx * q.w, yz = ty * q.z, yw = ty * q.w, zw = tz * q.w;
+	Vec3 c0((1.0f - yy) - zz, xy + zw, xz - yw), c1(xy - zw, (1.0f - zz) - xx, yz + xw), c2(xz + yw, yz - xw, (1.0f - xx) - yy);
+	const Vec3 &v = inAngularImpulse;
+	Vec3 local(c0.x * v.x + c0.y * v.y + c0.z * v.z, c1.x * v.x + c1.y * v.y + c1.z * v.z, c2.x * v.x + c2.y * v.y + c2.z * v.z);
+	local = Vec3(d.inv_inertia_diag[0] * local.x, d.inv_inertia_diag[1] * local.y, d.inv_inertia_diag[2] * local.z);
+	Vec3 delta(c0.x * local.x + c1.x * local.y + c2.x * local.z, c0.y * local.x + c1.y * local.y + c2.y * local.z, c0.z * local.x + c1.z * local.y + c2.z * local.z);
+	SetAngularVelocity(id, b->GetAngularVelocity() + delta);
+	if (b->mInWorld) ActivateBody(id);
+}
+
+inline void BodyInterface::AddImpulse(const BodyID &id, const Vec3 &inImpulse, const RVec3 &inPoint)
+{
+	const Body *b = TryGet(id);
+	if (b == nullptr || b->mMotionType != EMotionType::Dynamic) return;
+	// Body::AddImpulse(impulse, point): linear part + angular part (point - centre of mass) x impulse
+	Vec3 r = inPoint - b->GetCenterOfMassPosition();
+	AddImpulse(id, inImpulse);
+	AddAngularImpulse(id, r.Cross(inImpulse));
 }
 
 inline void BodyInterface::AddForcesAndTorques(const BodyID *inBodies, int inNumber, const float *inForces, const float *inTorques)

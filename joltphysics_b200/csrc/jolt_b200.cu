@@ -128,6 +128,22 @@ struct KSetState
 	}
 };
 
+struct KSetParams
+{
+	DWorld w; const uint32_t *ids; const float *friction, *restitution, *gravity_factor, *linear_damping, *angular_damping, *max_linear_velocity, *max_angular_velocity;
+	B2J_D void operator()(uint32_t i) const
+	{
+		BodyParams &p = w.params[slot_of(ids[i])];
+		if (friction) p.friction = friction[i];
+		if (restitution) p.restitution = restitution[i];
+		if (gravity_factor) p.gravity_factor = gravity_factor[i];
+		if (linear_damping) p.linear_damping = linear_damping[i];
+		if (angular_damping) p.angular_damping = angular_damping[i];
+		if (max_linear_velocity) p.max_linear_velocity = max_linear_velocity[i];
+		if (max_angular_velocity) p.max_angular_velocity = max_angular_velocity[i];
+	}
+};
+
 struct KAddForceTorque
 {
 	DWorld w; const uint32_t *ids; const float *force, *torque;
@@ -1250,6 +1266,26 @@ int b2j_bodies_set_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 	return rt.check("b2j_bodies_set_state")? 0 : -1;
 }
 
+int b2j_bodies_set_params(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_params *in)
+{
+	if (n == 0) return 0;
+	if (ids == nullptr || in == nullptr) { last_error() = "b2j_bodies_set_params: ids and in are required"; return -1; }
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	KSetParams k; memset(&k, 0, sizeof(k)); k.w = W->d;
+	rt.stage_begin((size_t)n * 4 * 8);
+	uint32_t *h_ids = nullptr; float *h = nullptr;
+	k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4);
+	const float *src[7] = { in->friction, in->restitution, in->gravity_factor, in->linear_damping, in->angular_damping, in->max_linear_velocity, in->max_angular_velocity };
+	const float **dst[7] = { &k.friction, &k.restitution, &k.gravity_factor, &k.linear_damping, &k.angular_damping, &k.max_linear_velocity, &k.max_angular_velocity };
+	for (int f = 0; f < 7; ++f)
+		if (src[f] != nullptr) { *dst[f] = rt.stage_alloc<float>(n, &h); memcpy(h, src[f], (size_t)n * 4); }
+	rt.stage_to_device(0, rt.stage_used);
+	rt.launch(k, n);
+	rt.sync(); // the staging buffer is reused by the next call
+	return rt.check("b2j_bodies_set_params")? 0 : -1;
+}
+
 int b2j_bodies_add_force_torque(b2j_world *W, const uint32_t *ids, uint32_t n, const float *force, const float *torque)
 {
 	if (n == 0) return 0;
@@ -1681,7 +1717,14 @@ int b2j_batch_step(b2j_batch *b, float dt, int collision_steps, b2j_step_stats *
 	std::vector<b2j_step_stats> st(K);
 	std::vector<int> rc(K, 0);
 	if (stats != nullptr) for (size_t g = 0; g < K; ++g) st[g] = *stats; // carries the kinetic energy request
-	bool ok = batch_for_each_group(b, [&](size_t g) { rc[g] = b2j_step(b->groups[g], dt, collision_steps, stats != nullptr? &st[g] : nullptr); return rc[g] >= 0; });
+	bool ok = true;
+	if (b->groups[0]->rt.profiling)
+	{
+		// per kernel timing: one group at a time, so that a kernel's events do not include kernels of the other streams
+		for (size_t g = 0; g < K && ok; ++g) { rc[g] = b2j_step(b->groups[g], dt, collision_steps, stats != nullptr? &st[g] : nullptr); ok = rc[g] >= 0; }
+	}
+	else
+		ok = batch_for_each_group(b, [&](size_t g) { rc[g] = b2j_step(b->groups[g], dt, collision_steps, stats != nullptr? &st[g] : nullptr); return rc[g] >= 0; });
 	if (!ok) return -1;
 	int r = 0;
 	for (size_t g = 0; g < K; ++g) r |= rc[g];

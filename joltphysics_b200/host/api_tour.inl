@@ -1,0 +1,81 @@
+// api_tour.inl -- the same USER code compiled twice: against the reference (oracle/ref_harness.cpp, namespace JPH) and against the
+// facade (facade_capi.cpp, namespace JPH_B200). It walks the BodyInterface / PhysicsSystem surface of SURVEY 8(b) that the
+// benchmark scenes do not touch (bulk add, remove / destroy / re-add, impulses, per body parameters, activation, queries) so that
+// tests/test_facade.py can check that the facade behaves like the reference call for call.
+// The including file provides: B2J_SHAPE_REF (shape reference type), B2J_NEW_SHAPE(Type, args...), Layers::MOVING / NON_MOVING.
+
+static void sApiTourCreate(PhysicsSystem &inSystem, std::vector<BodyID> &outBodies)
+{
+	BodyInterface &bi = inSystem.GetBodyInterface();
+	bi.CreateAndAddBody(BodyCreationSettings(B2J_NEW_SHAPE(BoxShape, Vec3(50.0f, 1.0f, 50.0f), 0.0f), RVec3(0.0f, -1.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING), EActivation::DontActivate);
+	B2J_SHAPE_REF shapes[3] = { B2J_NEW_SHAPE(SphereShape, 0.5f), B2J_NEW_SHAPE(BoxShape, Vec3(0.5f, 0.4f, 0.3f)), B2J_NEW_SHAPE(CapsuleShape, 0.4f, 0.3f) };
+	for (int i = 0; i < 12; ++i)
+	{
+		RVec3 position(-3.0f + 1.5f * float(i % 4), 0.6f + 1.2f * float(i / 4), 0.3f * float(i % 3));
+		BodyCreationSettings settings(shapes[i % 3], position, Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		settings.mFriction = 0.4f;
+		settings.mRestitution = 0.1f;
+		outBodies.push_back(bi.CreateAndAddBody(settings, EActivation::Activate));
+	}
+}
+
+static void sApiTourMutate(PhysicsSystem &inSystem, std::vector<BodyID> &ioBodies, int inPhase)
+{
+	BodyInterface &bi = inSystem.GetBodyInterface();
+	if (inPhase == 1)
+	{
+		// parameters, impulses, velocities, forces
+		bi.SetFriction(ioBodies[0], 0.05f);
+		bi.SetRestitution(ioBodies[1], 0.8f);
+		bi.SetGravityFactor(ioBodies[2], 0.25f);
+		bi.AddImpulse(ioBodies[3], Vec3(800.0f, 0.0f, 0.0f));
+		bi.SetMaxLinearVelocity(ioBodies[3], 2.0f);
+		bi.AddAngularImpulse(ioBodies[4], Vec3(0.0f, 300.0f, 50.0f));
+		bi.AddImpulse(ioBodies[5], Vec3(0.0f, 900.0f, 200.0f), bi.GetCenterOfMassPosition(ioBodies[5]) + Vec3(0.2f, 0.0f, 0.1f));
+		bi.SetLinearVelocity(ioBodies[6], Vec3(0.0f, 5.0f, 0.0f));
+		bi.SetAngularVelocity(ioBodies[7], Vec3(1.0f, 2.0f, 3.0f));
+		bi.SetMaxAngularVelocity(ioBodies[7], 1.5f);
+		bi.AddForce(ioBodies[8], Vec3(0.0f, 30000.0f, 0.0f));
+		bi.AddTorque(ioBodies[9], Vec3(500.0f, 0.0f, 0.0f));
+	}
+	else if (inPhase == 2)
+	{
+		// remove two bodies, destroy one of them, bulk add three new ones, re-add the other, move / deactivate
+		BodyID removed[2] = { ioBodies[0], ioBodies[5] };
+		bi.RemoveBodies(removed, 2);
+		bi.DestroyBody(ioBodies[0]);
+		BodyID added[3];
+		for (int i = 0; i < 3; ++i)
+		{
+			BodyCreationSettings settings(B2J_NEW_SHAPE(BoxShape, Vec3(0.3f, 0.3f, 0.3f)), RVec3(-8.0f + 8.0f * float(i), 3.0f, 6.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			added[i] = bi.CreateBody(settings)->GetID();
+		}
+		BodyInterface::AddState state = bi.AddBodiesPrepare(added, 3);
+		bi.AddBodiesFinalize(added, 3, state, EActivation::Activate);
+		for (int i = 0; i < 3; ++i) ioBodies.push_back(added[i]);
+		ioBodies[0] = added[0]; // the destroyed id must not be used again
+		bi.SetPositionAndRotation(ioBodies[5], RVec3(4.0f, 5.0f, -2.0f), Quat::sIdentity(), EActivation::DontActivate);
+		bi.AddBody(ioBodies[5], EActivation::Activate);
+		bi.SetPositionAndRotation(ioBodies[9], RVec3(3.0f, 4.0f, 0.0f), Quat::sIdentity(), EActivation::Activate);
+		bi.DeactivateBody(ioBodies[2]);
+	}
+}
+
+// Queries after the tour: number of bodies, active bodies (as a sorted id list written to outIDs), returns the active count
+static int sApiTourQuery(PhysicsSystem &inSystem, const std::vector<BodyID> &inBodies, uint32_t *outIDs, int inCapacity, uint32_t *outNumBodies, uint32_t *outFlags)
+{
+	BodyIDVector active;
+	inSystem.GetActiveBodies(EBodyType::RigidBody, active);
+	BodyIDVector all;
+	inSystem.GetBodies(all);
+	*outNumBodies = (uint32_t)all.size();
+	BodyInterface &bi = inSystem.GetBodyInterface();
+	uint32_t flags = 0;
+	for (size_t i = 0; i < inBodies.size() && i < 32; ++i)
+		if (bi.IsAdded(inBodies[i]) && bi.IsActive(inBodies[i])) flags |= 1u << i;
+	*outFlags = flags;
+	int n = 0;
+	for (const BodyID &id : active) if (n < inCapacity) outIDs[n++] = id.GetIndexAndSequenceNumber();
+	std::sort(outIDs, outIDs + n);
+	return (int)active.size();
+}

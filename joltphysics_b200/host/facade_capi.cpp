@@ -5,6 +5,7 @@
 // of the reference would write it; only `namespace JPH = JPH_B200` differs.
 #include "jolt_b200_facade.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -237,6 +238,17 @@ bool scene_max_bodies(Scene &s, int num_bodies)
 	return true;
 }
 
+#define B2J_SHAPE_REF ShapeRef
+#define B2J_NEW_SHAPE(Type, ...) std::make_shared<Type>(__VA_ARGS__)
+#include "api_tour.inl"
+
+bool scene_api_tour(Scene &s)
+{
+	if (!s.system.Init(1024, 0, 4096, 1024, s.bpl, s.ovbp, s.olp, Layers::NUM_LAYERS, scene_device())) return false;
+	sApiTourCreate(s.system, s.dynamic_bodies);
+	return true;
+}
+
 thread_local std::string g_error;
 
 } // namespace
@@ -255,6 +267,7 @@ B2JF_API void *b2jf_scene_create(const char *name, int p0, int p1, const char *a
 	else if (n == "convex_vs_mesh") ok = scene_convex_vs_mesh(*s, p0 > 0? p0 : 10, assets_dir);
 	else if (n == "pile") ok = scene_pile(*s, p0 > 0? p0 : 1000, p1 > 0? p1 : 15, assets_dir);
 	else if (n == "max_bodies") ok = scene_max_bodies(*s, p0 > 0? p0 : 10000);
+	else if (n == "api_tour") ok = scene_api_tour(*s);
 	else s->error = "unknown scene";
 	if (!ok)
 	{
@@ -270,6 +283,10 @@ B2JF_API void *b2jf_scene_world(void *h) { return ((Scene *)h)->system.GetWorld(
 B2JF_API uint32_t b2jf_scene_num_dynamic(void *h) { return (uint32_t)((Scene *)h)->dynamic_bodies.size(); }
 B2JF_API uint32_t b2jf_scene_num_bodies(void *h) { return ((Scene *)h)->system.GetNumBodies(); }
 B2JF_API void b2jf_scene_flush(void *h) { ((Scene *)h)->system.GetBodyInterface().AddForcesAndTorques(nullptr, 0, nullptr, nullptr); }
+
+// api_tour scene: the mutation phases and the queries of api_tour.inl
+B2JF_API void b2jf_scene_mutate(void *h, int phase) { Scene *s = (Scene *)h; sApiTourMutate(s->system, s->dynamic_bodies, phase); }
+B2JF_API int b2jf_scene_query(void *h, uint32_t *out_ids, int cap, uint32_t *out_num_bodies, uint32_t *out_flags) { Scene *s = (Scene *)h; return sApiTourQuery(s->system, s->dynamic_bodies, out_ids, cap, out_num_bodies, out_flags); }
 
 // PhysicsSystem::Update through the facade (mirrors the state to the host, replays events). Returns the error bits.
 B2JF_API int b2jf_scene_update(void *h, float dt, int collision_steps, b2j_step_stats *out_stats)

@@ -132,6 +132,7 @@ struct World
 	RecordingActivationListener activations;
 	uint max_body_pairs = 0, max_contact_constraints = 0;
 	uint num_dynamic = 0;
+	std::vector<BodyID> tour_bodies; // api_tour scene
 
 	~World() { delete jobs; delete temp; }
 };
@@ -409,6 +410,19 @@ World *sSceneSmallStack(int inVariant)
 	return w;
 }
 
+// the facade's API tour (same user code on both sides)
+#define B2J_SHAPE_REF RefConst<Shape>
+#define B2J_NEW_SHAPE(Type, ...) new Type(__VA_ARGS__)
+#include "../joltphysics_b200/host/api_tour.inl"
+
+World *sSceneApiTour()
+{
+	World *w = sNewWorld(1024, 4096, 1024, 4);
+	sApiTourCreate(w->system, w->tour_bodies);
+	w->num_dynamic = (uint)w->tour_bodies.size();
+	return w;
+}
+
 } // namespace
 
 // ---- C interface ------------------------------------------------------------------------------------------------
@@ -433,6 +447,7 @@ void *jref_create_scene(const char *inName, int inParam0, int inParam1)
 	else if (name == "max_bodies") w = sSceneMaxBodies(inParam0 > 0? inParam0 : 10000);
 	else if (name == "pile") w = sScenePile(inParam0 > 0? inParam0 : 1000, inParam1 > 0? inParam1 : 15);
 	else if (name == "small_stack") w = sSceneSmallStack(inParam0);
+	else if (name == "api_tour") w = sSceneApiTour();
 	else { sLastError = "unknown scene"; return nullptr; }
 	w->system.SetContactListener(&w->contacts);
 	w->system.SetBodyActivationListener(&w->activations);
@@ -441,6 +456,10 @@ void *jref_create_scene(const char *inName, int inParam0, int inParam1)
 }
 
 void jref_destroy(void *h) { delete (World *)h; }
+
+// api_tour scene: the mutation phases and the queries of api_tour.inl
+void jref_mutate(void *h, int inPhase) { World *w = (World *)h; sApiTourMutate(w->system, w->tour_bodies, inPhase); }
+int jref_query(void *h, uint32_t *outIDs, int inCapacity, uint32_t *outNumBodies, uint32_t *outFlags) { World *w = (World *)h; return sApiTourQuery(w->system, w->tour_bodies, outIDs, inCapacity, outNumBodies, outFlags); }
 
 // Turn the recording listeners off (timing runs) or on.
 void jref_set_recording(void *h, int inOn)

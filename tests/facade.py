@@ -29,6 +29,8 @@ class FacadeLib:
         L.b2jf_scene_flush.argtypes = [C.c_void_p]
         L.b2jf_scene_update.argtypes = [C.c_void_p, C.c_float, C.c_int, C.POINTER(_capi.StepStats)]
         L.b2jf_scene_step_e2e.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+        L.b2jf_scene_mutate.argtypes = [C.c_void_p, C.c_int]
+        L.b2jf_scene_query.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 
 
 class FacadeScene:
@@ -56,6 +58,17 @@ class FacadeScene:
         stats = _capi.StepStats()
         r = self.flib.lib.b2jf_scene_update(self.h, dt, collision_steps, C.byref(stats))
         return r, stats
+
+    def mutate(self, phase):
+        self.flib.lib.b2jf_scene_mutate(self.h, phase)
+
+    def query(self):
+        """api_tour.inl sApiTourQuery: (sorted active ids, number of bodies, active flags of the tour bodies)."""
+        import numpy as np
+        ids = np.zeros(4096, np.uint32)
+        nb, flags = C.c_uint32(), C.c_uint32()
+        n = self.flib.lib.b2jf_scene_query(self.h, ids.ctypes.data, len(ids), C.addressof(nb), C.addressof(flags))
+        return ids[:n].copy(), nb.value, flags.value
 
     def step_e2e(self, dt, forces, out_positions):
         return self.flib.lib.b2jf_scene_step_e2e(self.h, dt, forces.ctypes.data if forces is not None else None, out_positions.ctypes.data if out_positions is not None else None)

@@ -36,6 +36,8 @@ def ref_lib(variant="det"):
         L.jref_create_scene.argtypes = [C.c_char_p, C.c_int, C.c_int]
         L.jref_destroy.argtypes = [vp]
         L.jref_set_recording.argtypes = [vp, C.c_int]
+        L.jref_mutate.argtypes = [vp, C.c_int]
+        L.jref_query.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.jref_step.argtypes = [vp, C.c_float, C.c_int, C.c_int]
         L.jref_time_steps.restype = C.c_double
         L.jref_time_steps.argtypes = [vp, C.c_float, C.c_int, C.c_int]
@@ -105,6 +107,16 @@ class RefWorld:
     def time_steps(self, n, dt=1.0 / 60.0, threads=0):
         return self.L.jref_time_steps(self.h, dt, n, threads)
 
+    def mutate(self, phase):
+        self.L.jref_mutate(self.h, phase)
+
+    def query(self):
+        """api_tour.inl sApiTourQuery: (sorted active ids, number of bodies, active flags of the tour bodies)."""
+        ids = np.zeros(4096, np.uint32)
+        nb, flags = C.c_uint32(), C.c_uint32()
+        n = self.L.jref_query(self.h, ids.ctypes.data, len(ids), C.addressof(nb), C.addressof(flags))
+        return ids[:n].copy(), nb.value, flags.value
+
     def set_recording(self, on):
         self.L.jref_set_recording(self.h, 1 if on else 0)
 
@@ -123,8 +135,8 @@ class RefWorld:
     def num_slots(self):
         return self.num_bodies  # harness scenes never remove bodies: slots are dense
 
-    def state(self):
-        n = self.num_slots()
+    def state(self, n=None):
+        n = self.num_slots() if n is None else n
         s = State(n)
         self.L.jref_get_state(self.h, n, _u32p(s.ids), _fp(s.pos), _fp(s.rot), _fp(s.lin), _fp(s.ang), _fp(s.bounds), _u32p(s.active_index), _fp(s.sleep_timer))
         return s

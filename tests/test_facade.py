@@ -48,3 +48,44 @@ def test_facade_scene_matches_reference_hostsim(hostsim_facade, scene, p0, p1):
 def test_facade_scene_matches_reference_gpu(gpu_api, scene, p0, p1):
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
     _check(flib, scene, p0, p1, steps=25)
+
+
+def _check_api_tour(flib):
+    """The BodyInterface / PhysicsSystem surface of SURVEY 8(b) beyond scene building (joltphysics_b200/host/api_tour.inl): the same
+    user code runs against the reference and against the facade; states and query results must agree after every phase."""
+    ref = R.RefWorld("api_tour")
+    fs = F.FacadeScene(flib, "api_tour")
+
+    def compare(tag):
+        fs.world.n = 16  # body slots 0..15 are used by the tour (13 at creation, 3 added later, one slot reused)
+        rs, gs = ref.state(16), fs.world.state()
+        worst = R.compare_states(rs, gs)
+        for k in ("pos", "rot", "lin", "ang"):
+            assert worst[k] <= 1.0, (tag, k, worst)
+        (ra, rn, rf), (ga, gn, gf) = ref.query(), fs.query()
+        assert rn == gn, (tag, "GetBodies", rn, gn)
+        assert np.array_equal(ra, ga), (tag, "GetActiveBodies", ra, ga)
+        assert rf == gf, (tag, "IsAdded && IsActive", bin(rf), bin(gf))
+
+    compare("created")
+    for phase, steps in ((0, 10), (1, 25), (2, 40)):
+        if phase:
+            ref.mutate(phase)
+            fs.mutate(phase)
+            compare(f"after mutation {phase}")
+        for _ in range(steps):
+            ref.step()
+            err, _ = fs.update()
+            assert err == 0
+        compare(f"after the steps of phase {phase}")
+    fs.close()
+    ref.close()
+
+
+def test_facade_api_tour_hostsim(hostsim_facade):
+    _check_api_tour(hostsim_facade)
+
+
+@pytest.mark.gpu
+def test_facade_api_tour_gpu(gpu_api):
+    _check_api_tour(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api))
