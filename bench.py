@@ -264,6 +264,9 @@ def measure(args, wl, torch, dist, world_size, local_rank, steps, warmup, with_e
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
+    cuprofile = os.environ.get("B2J_BENCH_CUPROFILE") == "1"  # `ncu --profile-from-start off`: capture the timed steps only
+    if cuprofile:
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
     gpu_ms, launches, agg = 0.0, 0, {}
     for _ in range(steps):
@@ -274,6 +277,8 @@ def measure(args, wl, torch, dist, world_size, local_rank, steps, warmup, with_e
             agg[k] = agg.get(k, 0) + getattr(st, k)
     barrier()
     wall = time.perf_counter() - t0
+    if cuprofile:
+        torch.cuda.profiler.stop()
     clocks = sampler.finish()
 
     # per kernel device time over extra steps continuing the same run (event records perturb back-to-back launches,

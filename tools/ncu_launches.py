@@ -17,6 +17,8 @@ for r in rows[hi + 1:]:
     n = name(r[kn])
     if n == 'KApplyGravity' or not steps: steps.append([])
     steps[-1].append((n, us(r)))
+if len(sys.argv) > 2 and sys.argv[2] == "--total":
+    steps = [[x for st in steps for x in st]]  # concurrent batch groups interleave their launches: one table for the whole capture
 for si, st in enumerate(steps):
     tot = sum(t for _, t in st)
     agg = collections.defaultdict(lambda: [0, 0.0])
