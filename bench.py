@@ -203,6 +203,15 @@ class Workload:
             self.num_slots = self.scene.num_bodies
         self.stats = _capi.StepStats()
 
+    def close(self):
+        """Frees the device memory of the workload (the batch holds > 100 GB at 4096 worlds)."""
+        if self.batch:
+            self.api.b2j_batch_destroy(self.batch)
+            self.batch = None
+        if self.scene is not None:
+            self.scene.close()
+            self.scene = None
+
     def step(self):
         if self.batch:
             r = self.api.b2j_batch_step(self.batch, DT, 1, C.byref(self.stats))
@@ -392,7 +401,9 @@ def run_b200(args):
                 line["cpu_baseline"] = {"error": str(e)}
         if batch and not args.no_pile:
             # secondary headline: configs[3], one 1M body world on one B200 (reported next to the batch line, not instead of it)
+            wl.close()
             del wl
+            torch.cuda.synchronize()
             pargs = argparse.Namespace(**vars(args))
             pargs.workload = "pile"
             pw = Workload(pargs, api, flib, 0, 1)

@@ -1739,7 +1739,8 @@ int b2j_batch_step(b2j_batch *b, float dt, int collision_steps, b2j_step_stats *
 			a.num_large_islands += s.num_large_islands; a.num_activated += s.num_activated; a.num_deactivated += s.num_deactivated; a.kernel_launches += s.kernel_launches;
 			a.kinetic_energy += s.kinetic_energy; a.error_bits |= s.error_bits;
 			a.num_phases = std::max(a.num_phases, s.num_phases); a.velocity_iterations = std::max(a.velocity_iterations, s.velocity_iterations);
-			a.position_iterations = std::max(a.position_iterations, s.position_iterations); a.gpu_ms = std::max(a.gpu_ms, s.gpu_ms);
+			a.position_iterations = std::max(a.position_iterations, s.position_iterations);
+			a.gpu_ms = b->groups[0]->rt.profiling? a.gpu_ms + s.gpu_ms : std::max(a.gpu_ms, s.gpu_ms); // profiling steps the groups one after the other
 		}
 		*stats = a;
 	}

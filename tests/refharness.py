@@ -281,6 +281,21 @@ def cache_summary(pairs, n_pairs, mans, n_mans):
     return out
 
 
+def sorted_rows(a):
+    """Rows of an integer table in lexicographic order (set comparison of pair lists)."""
+    a = np.asarray(a, dtype=np.int64)
+    if a.size == 0:
+        return a.reshape(0, a.shape[1] if a.ndim == 2 else 0)
+    a = a.reshape(len(a), -1)
+    return a[np.lexsort(a.T[::-1])]
+
+
+def cache_rows(summary):
+    """cache_summary as a sorted table of (body1, body2, sub1, sub2, num_points) rows."""
+    rows = [(b1, b2, s1, s2, n) for (b1, b2), mans in summary.items() for (s1, s2, n) in mans]
+    return sorted_rows(np.array(rows, dtype=np.int64).reshape(-1, 5))
+
+
 def compare_states(ref, got, rel=1e-4, abs_pos=1e-5):
     """Max violation of |d| <= max(abs, rel * |ref|) over position / rotation / velocities (north star tolerance)."""
     worst = {}
