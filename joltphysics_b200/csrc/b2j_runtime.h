@@ -321,7 +321,7 @@ struct Runtime
 		++launches;
 #ifndef B2J_HOSTSIM
 		uint32_t g = grid_for(cap, 128);
-		uint32_t gmax = (uint32_t)num_sms * 16; // 64 warps per SM for the low register kernels (latency bound gathers)
+		uint32_t gmax = (uint32_t)num_sms * 8; // (16 blocks per SM measured 1% slower on the 4096 world batch)
 		if (profiling) prof_begin(profile_category<K>());
 		run_kernel_dev<K><<<g > gmax? gmax : g, 128, 0, stream>>>(k, n_ptr, begin_ptr, cap);
 		if (profiling) prof_end();
@@ -338,7 +338,7 @@ struct Runtime
 		++launches;
 #ifndef B2J_HOSTSIM
 		uint32_t g = grid_for(cap, 128);
-		uint32_t gmax = (uint32_t)num_sms * 16; // 64 warps per SM for the low register kernels (latency bound gathers)
+		uint32_t gmax = (uint32_t)num_sms * 8; // (16 blocks per SM measured 1% slower on the 4096 world batch)
 		if (profiling) prof_begin(profile_category<K>());
 		run_kernel_dev_lockstep<K><<<g > gmax? gmax : g, 128, 0, stream>>>(k, n_ptr, begin_ptr, cap);
 		if (profiling) prof_end();

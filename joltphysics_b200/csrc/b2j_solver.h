@@ -331,9 +331,9 @@ enum { PHASE_UNSCHEDULED = 0xffffffffu, PHASE_PENDING_SERIAL = 0xfffffffeu };
 struct KSchedDecide
 {
 	DWorld w; SolveCtx s; uint32_t round; uint32_t pass;
-	B2J_D void operator()(uint32_t ai) const
+	B2J_D void operator()(uint32_t ai) const { decide(w.active[ai]); }
+	B2J_D void decide(uint32_t b) const
 	{
-		uint32_t b = w.active[ai];
 		uint32_t cur = s.body_cur[b];
 		if (cur >= s.body_deg[b])
 			return;
@@ -380,7 +380,12 @@ struct KSchedAdvance
 	DWorld w; SolveCtx s; uint32_t pass; uint32_t flag_index;
 	B2J_D void operator()(uint32_t ai) const
 	{
-		uint32_t b = w.active[ai];
+		if (advance(w.active[ai]))
+			s.sched_flag[flag_index] = 1;
+	}
+	// returns true while the body still has unscheduled constraints
+	B2J_D bool advance(uint32_t b) const
+	{
 		uint32_t cur = s.body_cur[b], deg = s.body_deg[b];
 		const uint32_t *a = s.adj + s.body_off[b];
 		if (pass == 0)
@@ -388,8 +393,7 @@ struct KSchedAdvance
 		else
 			while (cur < deg && s.phase[a[cur]] != PHASE_PENDING_SERIAL) ++cur;
 		s.body_cur[b] = cur;
-		if (cur < deg)
-			s.sched_flag[flag_index] = 1;
+		return cur < deg;
 	}
 };
 
@@ -397,18 +401,83 @@ struct KSchedAdvance
 struct KSchedSerialize
 {
 	DWorld w; SolveCtx s;
-	B2J_D void operator()(uint32_t i) const
+	B2J_D void operator()(uint32_t i) const { serialize(i); }
+	// returns true if the constraint went to the serial split
+	B2J_D bool serialize(uint32_t i) const
 	{
 		const ConstraintSrc &c = s.src[s.order[i]];
 		bool dyn1 = w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC;
 		uint32_t large = s.island_large[s.root[dyn1? c.b1 : c.b2]];
 		if (large == 0)
-			return;
+			return false;
 		uint32_t color = s.phase[i];
 		if (color == 31 || s.large_color_count[(large - 1) * 32 + color] < 32)
+		{
 			s.phase[i] = PHASE_PENDING_SERIAL;
+			return true;
+		}
+		return false;
 	}
 };
+
+#if !defined(B2J_HOSTSIM) && defined(__CUDACC__)
+// The whole wavefront schedule of ONE world (a batch group: block = world; a small single world: one block) in one launch: the
+// rounds are separated by __syncthreads instead of kernel launches + host checks (54 rounds x 2 launches + 7 host round trips per
+// step for a Pyramid). Same decide / advance / serialize bodies as the multi launch path, which remains for big single worlds.
+struct KSchedBlock { }; // (profiling category)
+__global__ void __launch_bounds__(1024) sched_block_kernel(const DWorld w, const SolveCtx s, uint32_t slots_per_block)
+{
+	uint32_t first = blockIdx.x * slots_per_block, end = first + slots_per_block;
+	if (end > s.num_slots) end = s.num_slots;
+	__shared__ uint32_t any_serial;
+	if (threadIdx.x == 0) any_serial = 0;
+	for (uint32_t pass = 0; pass < 2; ++pass)
+	{
+		KSchedDecide decide; decide.w = w; decide.s = s; decide.pass = pass; decide.round = 0;
+		KSchedAdvance advance; advance.w = w; advance.s = s; advance.pass = pass; advance.flag_index = 0;
+		if (pass == 1)
+		{
+			// colours with < 32 items and colour 31 -> serial split; every constraint is visited by its owner body
+			KSchedSerialize serialize; serialize.w = w; serialize.s = s;
+			for (uint32_t b = first + threadIdx.x; b < end; b += blockDim.x)
+			{
+				uint32_t deg = s.body_deg[b];
+				const uint32_t *a = s.adj + s.body_off[b];
+				for (uint32_t j = 0; j < deg; ++j)
+				{
+					uint32_t i = a[j];
+					const ConstraintSrc &c = s.src[s.order[i]];
+					uint32_t owner = w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC? c.b1 : c.b2;
+					if (owner == b && serialize.serialize(i))
+						any_serial = 1;
+				}
+			}
+			__syncthreads();
+			if (any_serial == 0)
+				return; // (uniform: shared flag read after the barrier)
+			for (uint32_t b = first + threadIdx.x; b < end; b += blockDim.x)
+				s.body_cur[b] = 0;
+			__syncthreads();
+		}
+		int remaining = 0;
+		for (uint32_t b = first + threadIdx.x; b < end; b += blockDim.x)
+			if (advance.advance(b)) remaining = 1;
+		remaining = __syncthreads_or(remaining);
+		for (uint32_t round = 0; remaining != 0; ++round)
+		{
+			decide.round = round;
+			for (uint32_t b = first + threadIdx.x; b < end; b += blockDim.x)
+				decide.decide(b);
+			__syncthreads();
+			remaining = 0;
+			for (uint32_t b = first + threadIdx.x; b < end; b += blockDim.x)
+				if (advance.advance(b)) remaining = 1;
+			remaining = __syncthreads_or(remaining);
+			if (round > 1000000u) break; // cannot happen: every round schedules at least one constraint of an unfinished island
+		}
+	}
+}
+#endif
 
 struct KSchedResetCursors
 {
