@@ -412,6 +412,13 @@ def run_b200(args):
                             "value": 30 * pw.num_dynamic / (pm["gpu_ms"] / 1000.0), "unit": "body-steps/s", "ms_per_step": pm["gpu_ms"] / 30,
                             "roofline": roofline_of(pm), "step_counters_mean": {k: v / 30 for k, v in pm["agg"].items()},
                             "kernel_ms_per_step": {k: v["ms"] / pm["prof_steps"] for k, v in sorted(pm["prof"].items(), key=lambda kv: -kv[1]["ms"])[:10]}}
+            if not args.no_cpu_baseline:
+                try:
+                    pw.close()
+                    value, steps, warm, sample, threads = cpu_run(pargs, 120, 30, min(args.cpu_seconds, 15.0))
+                    line["pile"]["cpu_baseline"] = {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample + "; FMA build of the unmodified reference (oracle/_ref)"}
+                except Exception as e:
+                    line["pile"]["cpu_baseline"] = {"error": str(e)}
     print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()

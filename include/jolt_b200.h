@@ -354,6 +354,10 @@ b2j_batch *b2j_batch_create(b2j_world *proto, uint32_t n_worlds, uint32_t max_bo
 void       b2j_batch_destroy(b2j_batch *b);
 /* Steps every world of the batch once; stats (may be NULL) receives the totals over all worlds. */
 int        b2j_batch_step(b2j_batch *b, float delta_time, int collision_steps, b2j_step_stats *stats);
+/* Resets the given worlds to the state the batch was created with (bodies + an empty contact cache), on the device: the RL
+ * environment reset. A reset world evolves exactly like a newly created one; the other worlds are untouched. (the
+ * reference does this with SaveState / RestoreState through host memory, PhysicsSystem.h:165-168.) */
+int        b2j_batch_reset_worlds(b2j_batch *b, const uint32_t *world_indices, uint32_t n);
 uint32_t   b2j_batch_size(const b2j_batch *b);
 /* State of the bodies in slots [0, n) of one world (see b2j_bodies_get_state with ids == NULL). world_index = 0xffffffff:
  * the first n slots of the whole batch (world major, stride = body slots of the prototype), i.e. all worlds in one call. */

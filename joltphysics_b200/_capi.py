@@ -145,6 +145,7 @@ PROTOTYPES = {
     "b2j_world_get_profile": (C.c_uint32, [_VP, C.c_char_p, C.c_uint32, C.POINTER(C.c_float), _U32P, C.c_uint32]),
     "b2j_batch_create": (_VP, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "b2j_batch_destroy": (None, [_VP]),
+    "b2j_batch_reset_worlds": (C.c_int, [_VP, _U32P, C.c_uint32]),
     "b2j_batch_step": (C.c_int, [_VP, C.c_float, C.c_int, C.POINTER(StepStats)]),
     "b2j_batch_size": (C.c_uint32, [_VP]),
     "b2j_batch_get_state": (C.c_int, [_VP, C.c_uint32, C.c_uint32, C.POINTER(BodyState)]),

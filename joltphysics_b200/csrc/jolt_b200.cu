@@ -235,6 +235,67 @@ struct KReplicateActive
 	}
 };
 
+// ---- batch: reset worlds to the state they were created with (RL environment reset without a host round trip of the state) ----
+struct BatchInitState
+{
+	F4 *position, *rotation, *linear_velocity, *angular_velocity, *force, *torque, *bounds_min, *bounds_max, *sleep_spheres;
+	float *sleep_timer;
+	uint32_t *was_active;        // per slot of ONE world
+};
+
+// bodies of the reset worlds that were active at creation but sleep now go to the woken list (activated before the copy)
+struct KResetFindInactive
+{
+	DWorld w; NarrowCtx c; BatchInitState init; const uint32_t *worlds;
+	B2J_D void operator()(uint32_t t) const
+	{
+		uint32_t j = t % w.world_stride, b = worlds[t / w.world_stride] * w.world_stride + j;
+		if (init.was_active[j] != 0 && w.info[b].id != 0xffffffffu && w.active_index[b] == B2J_INACTIVE_INDEX)
+			wake_body(w, c, b);
+	}
+};
+
+struct KResetWorlds
+{
+	DWorld w; BatchInitState init; const uint32_t *worlds;
+	B2J_D void operator()(uint32_t t) const
+	{
+		uint32_t j = t % w.world_stride, b = worlds[t / w.world_stride] * w.world_stride + j;
+		w.position[b] = init.position[j]; w.rotation[b] = init.rotation[j];
+		w.linear_velocity[b] = init.linear_velocity[j]; w.angular_velocity[b] = init.angular_velocity[j];
+		w.force[b] = init.force[j]; w.torque[b] = init.torque[j];
+		w.bounds_min[b] = init.bounds_min[j]; w.bounds_max[b] = init.bounds_max[j];
+		for (int i = 0; i < 3; ++i) w.sleep_spheres[b * 3 + i] = init.sleep_spheres[j * 3 + i];
+		w.sleep_timer[b] = init.sleep_timer[j];
+	}
+};
+
+// bodies of the reset worlds that were NOT active at creation leave the active list (keep = 0), as KDeactivate does
+struct KResetMarkKeep
+{
+	DWorld w; BatchInitState init; const uint32_t *reset_flag; uint32_t *keep;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		bool drop = reset_flag[b / w.world_stride] != 0 && init.was_active[b % w.world_stride] == 0;
+		keep[ai] = drop? 0u : 1u;
+		if (drop)
+			w.active_index[b] = B2J_INACTIVE_INDEX;
+	}
+};
+
+// the contact cache entries of the reset worlds must not be found by the next step (a new world has an empty cache)
+struct KResetPurgeCache
+{
+	DWorld w; const uint32_t *reset_flag;
+	B2J_D void operator()(uint32_t i) const
+	{
+		CachedPair &p = w.read_cache.pairs[i];
+		if (p.slot1 != 0xffffffffu && reset_flag[p.slot1 / w.world_stride] != 0)
+			p.slot1 = 0xffffffffu;
+	}
+};
+
 // round bookkeeping on the device: pairs found so far become "processed", work lists restart
 struct KNextRound
 {
@@ -361,6 +422,8 @@ struct b2j_world
 // stream, stepped by its own host thread: kernels and host round trips of different groups overlap (measured 1.3x at 1024 worlds).
 struct b2j_batch
 {
+	BatchInitState init = BatchInitState();   // state of one world at creation (device, owned by group 0's runtime)
+	bool has_init_inactive = false;           // some non-static body was NOT active at creation (a reset then also compacts the active list)
 	std::vector<b2j_world *> groups;
 	std::vector<uint32_t> first_world;   // first world of each group (+ n_worlds at the end)
 	uint32_t n_worlds = 0, stride = 0, bodies_per_world = 0;
@@ -520,7 +583,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		if (woken == 0)
 			break;
 		// activate the woken bodies in slot order (BodyManager::ActivateBodies), then query only them
-		rt.sort_pairs<uint32_t>(W->nc.woken_list, W->d_woken_keys, W->nc.woken_list, W->d_woken_sorted, woken, 23);
+		rt.sort_pairs<uint32_t>(W->nc.woken_list, W->d_woken_keys, W->nc.woken_list, W->d_woken_sorted, woken, 32);
 		{ KActivateWoken k; k.w = d; k.woken_sorted = W->d_woken_sorted; k.base = W->num_active; k.woken_flag = W->nc.woken_flag; k.events = W->d_act_events; k.max_events = W->max_act_events; rt.launch(k, woken); }
 		first_active = W->num_active;
 		n_query = woken;
@@ -1715,14 +1778,105 @@ b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_p
 		first += n;
 	}
 	b->first_world.push_back(first);
+	// the creation state of one world, for b2j_batch_reset_worlds
+	{
+		Runtime &rt = b->groups[0]->rt;
+		const DWorld &s = P->d;
+		uint32_t stride = b->stride;
+		BatchInitState &in = b->init;
+		auto keep = [&](F4 *&dst, const F4 *src, uint32_t n) { dst = rt.alloc<F4>(n, false); rt.copy(dst, src, n); };
+		keep(in.position, s.position, stride); keep(in.rotation, s.rotation, stride);
+		keep(in.linear_velocity, s.linear_velocity, stride); keep(in.angular_velocity, s.angular_velocity, stride);
+		keep(in.force, s.force, stride); keep(in.torque, s.torque, stride);
+		keep(in.bounds_min, s.bounds_min, stride); keep(in.bounds_max, s.bounds_max, stride);
+		keep(in.sleep_spheres, s.sleep_spheres, stride * 3);
+		in.sleep_timer = rt.alloc<float>(stride, false); rt.copy(in.sleep_timer, s.sleep_timer, stride);
+		std::vector<uint32_t> active_index(stride), was_active(stride);
+		std::vector<BodyInfo> info(stride);
+		P->rt.download(active_index.data(), s.active_index, stride);
+		P->rt.download(info.data(), s.info, stride);
+		for (uint32_t j = 0; j < stride; ++j)
+		{
+			was_active[j] = active_index[j] != B2J_INACTIVE_INDEX? 1u : 0u;
+			if (!was_active[j] && info[j].id != 0xffffffffu && info[j].motion_type != B2J_MOTION_STATIC) b->has_init_inactive = true;
+		}
+		in.was_active = rt.alloc<uint32_t>(stride, false);
+		rt.upload(in.was_active, was_active.data(), stride);
+		rt.sync();
+	}
 	return b;
 }
 
 void b2j_batch_destroy(b2j_batch *b)
 {
 	if (b == nullptr) return;
+	if (!b->groups.empty())
+	{
+		Runtime &rt = b->groups[0]->rt;
+		BatchInitState &in = b->init;
+		rt.free_(in.position); rt.free_(in.rotation); rt.free_(in.linear_velocity); rt.free_(in.angular_velocity); rt.free_(in.force); rt.free_(in.torque);
+		rt.free_(in.bounds_min); rt.free_(in.bounds_max); rt.free_(in.sleep_spheres); rt.free_(in.sleep_timer); rt.free_(in.was_active);
+	}
 	for (b2j_world *G : b->groups) b2j_world_destroy(G);
 	delete b;
+}
+
+// Resets the given worlds to the state the batch was created with: bodies (pose, velocities, forces, bounds, sleep state, active
+// flag) and an empty contact cache, exactly as if those worlds had just been created; the other worlds are untouched. No body
+// state crosses the PCIe bus (the RL pattern: environments terminate at different steps).
+int b2j_batch_reset_worlds(b2j_batch *b, const uint32_t *world_indices, uint32_t n)
+{
+	if (b == nullptr || (n > 0 && world_indices == nullptr)) { last_error() = "b2j_batch_reset_worlds: invalid arguments"; return -1; }
+	for (uint32_t i = 0; i < n; ++i)
+		if (world_indices[i] >= b->n_worlds) { last_error() = "b2j_batch_reset_worlds: world index out of range"; return -1; }
+	if (n == 0) return 0;
+	bool ok = batch_for_each_group(b, [&](size_t g) {
+		b2j_world *G = b->groups[g];
+		Runtime &rt = G->rt;
+		uint32_t first = b->first_world[g], end = b->first_world[g + 1], nw = end - first, stride = b->stride;
+		std::vector<uint32_t> local, flags(nw, 0);
+		for (uint32_t i = 0; i < n; ++i)
+			if (world_indices[i] >= first && world_indices[i] < end && !flags[world_indices[i] - first]) { flags[world_indices[i] - first] = 1; local.push_back(world_indices[i] - first); }
+		if (local.empty()) return true;
+		sync_dworld(G);
+		uint32_t *d_local = rt.alloc<uint32_t>(local.size(), false), *d_flags = rt.alloc<uint32_t>(nw, false);
+		rt.upload(d_local, local.data(), local.size());
+		rt.upload(d_flags, flags.data(), nw);
+		uint32_t items = (uint32_t)local.size() * stride;
+		// 1. bodies that were active at creation but sleep now: back onto the active list (sorted by slot, like the step does)
+		rt.memset_(G->d.counters, 0, sizeof(StepCounters));
+		{ KResetFindInactive k; k.w = G->d; k.c = G->nc; k.init = b->init; k.worlds = d_local; rt.launch(k, items); }
+		if (!read_counters(G)) return false;
+		uint32_t woken = G->h_counters.num_woken;
+		if (woken > 0)
+		{
+			rt.sort_pairs<uint32_t>(G->nc.woken_list, G->d_woken_keys, G->nc.woken_list, G->d_woken_sorted, woken, 32);
+			KActivateWoken k; k.w = G->d; k.woken_sorted = G->d_woken_sorted; k.base = G->num_active; k.woken_flag = G->nc.woken_flag; k.events = nullptr; k.max_events = 0;
+			rt.launch(k, woken);
+			G->num_active += woken;
+		}
+		// bodies that were NOT active at creation (rare) leave the active list: the stable compaction of the end of a step
+		if (b->has_init_inactive && G->num_active > 0)
+		{
+			uint32_t na = G->num_active;
+			{ KResetMarkKeep k; k.w = G->d; k.init = b->init; k.reset_flag = d_flags; k.keep = G->d_keep; rt.launch(k, na); }
+			rt.exclusive_scan(G->d_keep, G->d_keep_scan, na);
+			uint32_t *new_list = G->active_buf[G->active_cur ^ 1];
+			{ KCompactActive k; k.w = G->d; k.keep = G->d_keep; k.keep_scan = G->d_keep_scan; k.new_active = new_list; rt.launch(k, na); }
+			{ KFinishCompact k; k.w = G->d; k.keep = G->d_keep; k.keep_scan = G->d_keep_scan; k.n = na; rt.launch(k, 1); }
+			G->active_cur ^= 1;
+			if (!read_counters(G)) return false;
+			G->num_active = G->h_counters.new_active_count;
+		}
+		// 2. state of the bodies, 3. forget the contacts of those worlds
+		{ KResetWorlds k; k.w = G->d; k.init = b->init; k.worlds = d_local; rt.launch(k, items); }
+		{ KResetPurgeCache k; k.w = G->d; k.reset_flag = d_flags; rt.launch(k, G->cache_num_pairs[G->write_idx ^ 1]); }
+		rt.sync();
+		rt.free_(d_local); rt.free_(d_flags);
+		for (uint32_t l = 0; l < G->d.num_bp_layers; ++l) G->layer_needs_build[l] = 1;
+		return rt.check("b2j_batch_reset_worlds");
+	});
+	return ok? 0 : -1;
 }
 
 int b2j_batch_step(b2j_batch *b, float dt, int collision_steps, b2j_step_stats *stats)

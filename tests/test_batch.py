@@ -89,3 +89,50 @@ def test_batch_groups_gpu(gpu_api, groups, monkeypatch):
     assert everything.pos[1:n, 0].mean() > 0.1 + proto.world.state().pos[1:n, 0].mean(), "the forces must have pushed the dynamic bodies along +x"
     gpu_api.b2j_batch_destroy(batch)
     proto.close()
+
+
+def _check_reset(api, flib, scene, p0, p1, n_worlds, steps_before, steps_after, reset):
+    """b2j_batch_reset_worlds: reset worlds evolve exactly like a newly created world, the others are not disturbed."""
+    old = F.FacadeScene(flib, scene, p0, p1)     # stepped along with the untouched worlds
+    n = old.num_bodies
+    batch = api.b2j_batch_create(old.world.h, n_worlds, 0, 0)
+    assert batch, api.last_error()
+    stats = _capi.StepStats()
+    for _ in range(steps_before):
+        assert api.b2j_batch_step(batch, 1.0 / 60.0, 1, C.byref(stats)) == 0, api.last_error()
+        old.world.step()
+    ids = np.array(reset, dtype=np.uint32)
+    assert api.b2j_batch_reset_worlds(batch, ids.ctypes.data_as(C.POINTER(C.c_uint32)), len(ids)) == 0, api.last_error()
+    new = F.FacadeScene(flib, scene, p0, p1)     # what a reset world must look like
+    for w in reset:
+        got, want = _batch_state(api, batch, w, n), new.world.state()
+        for name in ("pos", "rot", "lin", "ang", "bounds", "sleep_timer"):
+            assert np.array_equal(getattr(want, name), getattr(got, name)), f"world {w} right after the reset: {name}"
+        assert np.array_equal(want.active_index != 0xffffffff, got.active_index != 0xffffffff)
+    for _ in range(steps_after):
+        assert api.b2j_batch_step(batch, 1.0 / 60.0, 1, C.byref(stats)) == 0, api.last_error()
+        old.world.step()
+        new.world.step()
+    for w in range(n_worlds):
+        want = (new if w in reset else old).world.state()
+        got = _batch_state(api, batch, w, n)
+        for name in ("pos", "rot", "lin", "ang", "bounds"):
+            assert np.array_equal(getattr(want, name), getattr(got, name)), f"world {w} ({'reset' if w in reset else 'untouched'}): {name} differs"
+        assert np.array_equal(want.active_index != 0xffffffff, got.active_index != 0xffffffff), f"world {w}: active flags"
+    api.b2j_batch_destroy(batch)
+    old.close()
+    new.close()
+
+
+# pile: bodies fall asleep before the reset (they must be re-activated); small_stack would do as well but has no facade scene
+@pytest.mark.parametrize("scene,p0,p1,before,after", [("pyramid", 4, 0, 25, 30), ("pile", 200, 15, 260, 40)])
+def test_batch_reset_worlds_hostsim(hostsim_api, hostsim_facade, scene, p0, p1, before, after):
+    _check_reset(hostsim_api, hostsim_facade, scene, p0, p1, 5, before, after, [1, 3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,p0,p1,before,after,groups", [("pyramid", 8, 0, 40, 40, 1), ("pile", 500, 15, 300, 60, 1), ("pyramid", 6, 0, 30, 30, 3)])
+def test_batch_reset_worlds_gpu(gpu_api, monkeypatch, scene, p0, p1, before, after, groups):
+    monkeypatch.setenv("B2J_BATCH_GROUPS", str(groups))
+    flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
+    _check_reset(gpu_api, flib, scene, p0, p1, 7, before, after, [0, 2, 6])
