@@ -67,17 +67,36 @@ WORKLOAD_NAMES = {
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md), sampled through NVML in-process every 200 ms.
+    (A `nvidia-smi -lms 200` child process, the recipe's form, was measured to slow the launch-heavy 1M body pile step from 30 ms
+    to 96 ms on this box; the same NVML queries from a thread do not. nvidia-smi remains the fallback when pynvml is missing.)"""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.proc = index, [], set(), False, None
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx))
+                bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS:
+                    if bits & bit:
+                        self.reasons.add(name)
+                time.sleep(0.2)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "1000"], stdout=subprocess.PIPE, text=True)
+            names = [n for n, _ in self.REASONS]
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
@@ -97,6 +116,8 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if self.proc is not None:
             self.proc.terminate()
+        else:
+            self.join(timeout=1.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         sm = sorted(s[0] for s in self.samples)

@@ -421,6 +421,60 @@ struct KSchedSerialize
 };
 
 #if !defined(B2J_HOSTSIM) && defined(__CUDACC__)
+// Big single worlds: the same schedule as ONE cooperative launch, rounds separated by grid wide barriers (no host round trip every
+// few rounds, ~200 launches less per step: the step time of the 1M body pile no longer depends on host scheduling jitter).
+// sched_flag[r % 3] = "some body still has unscheduled constraints after round r".
+struct KSchedGrid { }; // (profiling category)
+__global__ void __launch_bounds__(256) sched_grid_kernel(const DWorld w, const SolveCtx s, uint32_t na, uint32_t num_constraints)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	volatile uint32_t *flag = s.sched_flag;
+	for (uint32_t pass = 0; pass < 2; ++pass)
+	{
+		KSchedDecide decide; decide.w = w; decide.s = s; decide.pass = pass; decide.round = 0;
+		KSchedAdvance advance; advance.w = w; advance.s = s; advance.pass = pass; advance.flag_index = 0;
+		if (pass == 1)
+		{
+			KSchedSerialize serialize; serialize.w = w; serialize.s = s;
+			if (tid == 0) { flag[0] = 0; flag[1] = 0; flag[2] = 0; }
+			grid.sync();
+			bool any = false;
+			for (uint32_t i = tid; i < num_constraints; i += nt)
+				if (serialize.serialize(i)) any = true;
+			if (any) flag[0] = 1;
+			grid.sync();
+			if (flag[0] == 0)
+				return; // (uniform)
+			for (uint32_t ai = tid; ai < na; ai += nt)
+				s.body_cur[w.active[ai]] = 0;
+			grid.sync();
+		}
+		if (tid == 0) { flag[0] = 0; flag[1] = 0; flag[2] = 0; }
+		grid.sync();
+		bool remaining = false;
+		for (uint32_t ai = tid; ai < na; ai += nt)
+			if (advance.advance(w.active[ai])) remaining = true;
+		if (remaining) flag[2] = 1;      // plays the role of "round -1"
+		grid.sync();
+		bool more = flag[2] != 0;
+		for (uint32_t round = 0; more; ++round)
+		{
+			if (tid == 0) flag[(round + 1) % 3] = 0;
+			decide.round = round;
+			for (uint32_t ai = tid; ai < na; ai += nt)
+				decide.decide(w.active[ai]);
+			grid.sync();
+			remaining = false;
+			for (uint32_t ai = tid; ai < na; ai += nt)
+				if (advance.advance(w.active[ai])) remaining = true;
+			if (remaining) flag[round % 3] = 1;
+			grid.sync();
+			more = flag[round % 3] != 0;
+		}
+	}
+}
+
 // The whole wavefront schedule of ONE world (a batch group: block = world; a small single world: one block) in one launch: the
 // rounds are separated by __syncthreads instead of kernel launches + host checks (54 rounds x 2 launches + 7 host round trips per
 // step for a Pyramid). Same decide / advance / serialize bodies as the multi launch path, which remains for big single worlds.

@@ -18,6 +18,14 @@ B2J_HD V3 to_v3(F4 f) { return v3(f.x, f.y, f.z); }
 B2J_HD Q4 to_q4(F4 f) { return q4(f.x, f.y, f.z, f.w); }
 B2J_HD F4 f4(Q4 q) { return f4(q.x, q.y, q.z, q.w); }
 
+// Two per body quantities that are (almost) always read together live in ONE array as 32 byte pairs (element 2b and 2b + 1): a random
+// access to a body then costs one DRAM sector instead of two half used ones. The views keep the kernels' `w.position[b]` spelling.
+template <int K> struct F4PairView
+{
+	F4 *base;
+	B2J_HD F4 &operator[](size_t i) const { return base[2 * i + K]; }
+};
+
 // Static per-body info (16 B)
 struct alignas(16) BodyInfo
 {
@@ -127,13 +135,12 @@ struct DWorld
 	// bodies (SoA by slot)
 	BodyInfo *info;
 	BodyParams *params;
-	F4 *position;                // centre of mass position
-	F4 *rotation;
-	F4 *linear_velocity, *angular_velocity;
-	F4 *force, *torque;
-	F4 *inv_inertia_diag;        // xyz
-	F4 *inertia_rotation;
-	F4 *bounds_min, *bounds_max;
+	F4PairView<0> position;      // centre of mass position         } pose pairs
+	F4PairView<1> rotation;      //                                  }
+	F4PairView<0> linear_velocity; F4PairView<1> angular_velocity;   // velocity pairs
+	F4PairView<0> force; F4PairView<1> torque;
+	F4PairView<0> inv_inertia_diag; F4PairView<1> inertia_rotation;  // xyz | quaternion
+	F4PairView<0> bounds_min; F4PairView<1> bounds_max;
 	F4 *sleep_spheres;           // [slot * 3 + i]
 	float *sleep_timer;
 	uint32_t *active_index;      // index in the active list or B2J_INACTIVE_INDEX

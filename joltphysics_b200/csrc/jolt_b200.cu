@@ -2,6 +2,9 @@
 //
 // One translation unit: all kernels are header-defined functors (b2j_*.h) instantiated through Runtime::launch*.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -ffp-contract=off (see __graft_entry__.build()).
+#ifndef B2J_HOSTSIM
+#include <cooperative_groups.h>
+#endif
 #include "b2j_runtime.h"
 #include "b2j_world.h"
 #include "b2j_shapes.h"
@@ -238,7 +241,7 @@ struct KReplicateActive
 // ---- batch: reset worlds to the state they were created with (RL environment reset without a host round trip of the state) ----
 struct BatchInitState
 {
-	F4 *position, *rotation, *linear_velocity, *angular_velocity, *force, *torque, *bounds_min, *bounds_max, *sleep_spheres;
+	F4 *pose, *velocity, *force_torque, *bounds, *sleep_spheres;   // pair arrays like DWorld's (2 elements per body)
 	float *sleep_timer;
 	uint32_t *was_active;        // per slot of ONE world
 };
@@ -261,10 +264,10 @@ struct KResetWorlds
 	B2J_D void operator()(uint32_t t) const
 	{
 		uint32_t j = t % w.world_stride, b = worlds[t / w.world_stride] * w.world_stride + j;
-		w.position[b] = init.position[j]; w.rotation[b] = init.rotation[j];
-		w.linear_velocity[b] = init.linear_velocity[j]; w.angular_velocity[b] = init.angular_velocity[j];
-		w.force[b] = init.force[j]; w.torque[b] = init.torque[j];
-		w.bounds_min[b] = init.bounds_min[j]; w.bounds_max[b] = init.bounds_max[j];
+		w.position[b] = init.pose[2 * j]; w.rotation[b] = init.pose[2 * j + 1];
+		w.linear_velocity[b] = init.velocity[2 * j]; w.angular_velocity[b] = init.velocity[2 * j + 1];
+		w.force[b] = init.force_torque[2 * j]; w.torque[b] = init.force_torque[2 * j + 1];
+		w.bounds_min[b] = init.bounds[2 * j]; w.bounds_max[b] = init.bounds[2 * j + 1];
 		for (int i = 0; i < 3; ++i) w.sleep_spheres[b * 3 + i] = init.sleep_spheres[j * 3 + i];
 		w.sleep_timer[b] = init.sleep_timer[j];
 	}
@@ -634,7 +637,29 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 #else
 		const bool block_sched = false;
 #endif
-		for (uint32_t pass = 0; pass < 2 && !block_sched; ++pass)
+#ifndef B2J_HOSTSIM
+		// big single world: all rounds in one cooperative launch (grid wide barriers)
+		bool grid_sched = false;
+		if (!block_sched)
+		{
+			static int blocks_per_sm = 0;
+			if (blocks_per_sm == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sched_grid_kernel, 256, 0);
+			if (blocks_per_sm > 0)
+			{
+				uint32_t arg_na = na, arg_m = M;
+				void *args[] = { (void *)&d, (void *)&sc, (void *)&arg_na, (void *)&arg_m };
+				++rt.launches;
+				if (rt.profiling) rt.prof_begin(profile_category<KSchedGrid>());
+				cudaError_t e = cudaLaunchCooperativeKernel((const void *)sched_grid_kernel, dim3((unsigned)(rt.num_sms * blocks_per_sm)), dim3(256), args, 0, rt.stream);
+				if (rt.profiling) rt.prof_end();
+				grid_sched = e == cudaSuccess;
+				if (!grid_sched) cudaGetLastError(); // fall back to the per round launches
+			}
+		}
+#else
+		const bool grid_sched = false;
+#endif
+		for (uint32_t pass = 0; pass < 2 && !block_sched && !grid_sched; ++pass)
 		{
 			if (pass == 1)
 			{
@@ -892,11 +917,12 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	d.object_to_bp = W->d_o2bp; d.object_vs_bp = W->d_ovbp; d.object_vs_object = W->d_ovo;
 
 	d.info = rt.alloc<BodyInfo>(nbod); d.params = rt.alloc<BodyParams>(nbod);
-	d.position = rt.alloc<F4>(nbod); d.rotation = rt.alloc<F4>(nbod);
-	d.linear_velocity = rt.alloc<F4>(nbod); d.angular_velocity = rt.alloc<F4>(nbod);
-	d.force = rt.alloc<F4>(nbod); d.torque = rt.alloc<F4>(nbod);
-	d.inv_inertia_diag = rt.alloc<F4>(nbod); d.inertia_rotation = rt.alloc<F4>(nbod);
-	d.bounds_min = rt.alloc<F4>(nbod); d.bounds_max = rt.alloc<F4>(nbod);
+	// 32 byte pairs (see F4PairView): pose, velocity, force / torque, inertia, bounds
+	d.position.base = d.rotation.base = rt.alloc<F4>(2 * (size_t)nbod);
+	d.linear_velocity.base = d.angular_velocity.base = rt.alloc<F4>(2 * (size_t)nbod);
+	d.force.base = d.torque.base = rt.alloc<F4>(2 * (size_t)nbod);
+	d.inv_inertia_diag.base = d.inertia_rotation.base = rt.alloc<F4>(2 * (size_t)nbod);
+	d.bounds_min.base = d.bounds_max.base = rt.alloc<F4>(2 * (size_t)nbod);
 	d.sleep_spheres = rt.alloc<F4>((size_t)nbod * 3); d.sleep_timer = rt.alloc<float>(nbod);
 	d.active_index = rt.alloc<uint32_t>(nbod);
 	rt.memset_(d.active_index, 0xff, (size_t)nbod * 4);
@@ -1011,8 +1037,8 @@ void b2j_world_destroy(b2j_world *W)
 	rt.sync();
 	DWorld &d = W->d;
 	rt.free_(W->d_o2bp); rt.free_(W->d_ovbp); rt.free_(W->d_ovo);
-	rt.free_(d.info); rt.free_(d.params); rt.free_(d.position); rt.free_(d.rotation); rt.free_(d.linear_velocity); rt.free_(d.angular_velocity);
-	rt.free_(d.force); rt.free_(d.torque); rt.free_(d.inv_inertia_diag); rt.free_(d.inertia_rotation); rt.free_(d.bounds_min); rt.free_(d.bounds_max);
+	rt.free_(d.info); rt.free_(d.params); rt.free_(d.position.base); rt.free_(d.linear_velocity.base);
+	rt.free_(d.force.base); rt.free_(d.inv_inertia_diag.base); rt.free_(d.bounds_min.base);
 	rt.free_(d.sleep_spheres); rt.free_(d.sleep_timer); rt.free_(d.active_index); rt.free_(W->active_buf[0]); rt.free_(W->active_buf[1]);
 	rt.free_(d.num_active); rt.free_(d.counters); rt.free_(W->d_keep); rt.free_(W->d_keep_scan);
 	for (int i = 0; i < 2; ++i)
@@ -1689,11 +1715,11 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	P->rt.sync();
 	const DWorld &s = P->d; DWorld &d = B->d;
 	replicate(rt, d.info, s.info, stride, stride, n_worlds); replicate(rt, d.params, s.params, stride, stride, n_worlds);
-	replicate(rt, d.position, s.position, stride, stride, n_worlds); replicate(rt, d.rotation, s.rotation, stride, stride, n_worlds);
-	replicate(rt, d.linear_velocity, s.linear_velocity, stride, stride, n_worlds); replicate(rt, d.angular_velocity, s.angular_velocity, stride, stride, n_worlds);
-	replicate(rt, d.force, s.force, stride, stride, n_worlds); replicate(rt, d.torque, s.torque, stride, stride, n_worlds);
-	replicate(rt, d.inv_inertia_diag, s.inv_inertia_diag, stride, stride, n_worlds); replicate(rt, d.inertia_rotation, s.inertia_rotation, stride, stride, n_worlds);
-	replicate(rt, d.bounds_min, s.bounds_min, stride, stride, n_worlds); replicate(rt, d.bounds_max, s.bounds_max, stride, stride, n_worlds);
+	replicate(rt, d.position.base, s.position.base, 2 * stride, 2 * stride, n_worlds);               // (pair arrays: 2 elements per body)
+	replicate(rt, d.linear_velocity.base, s.linear_velocity.base, 2 * stride, 2 * stride, n_worlds);
+	replicate(rt, d.force.base, s.force.base, 2 * stride, 2 * stride, n_worlds);
+	replicate(rt, d.inv_inertia_diag.base, s.inv_inertia_diag.base, 2 * stride, 2 * stride, n_worlds);
+	replicate(rt, d.bounds_min.base, s.bounds_min.base, 2 * stride, 2 * stride, n_worlds);
 	replicate(rt, d.sleep_spheres, s.sleep_spheres, stride * 3, stride * 3, n_worlds); replicate(rt, d.sleep_timer, s.sleep_timer, stride, stride, n_worlds);
 	// host mirrors
 	B->num_slots = stride * n_worlds;
@@ -1785,10 +1811,8 @@ b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_p
 		uint32_t stride = b->stride;
 		BatchInitState &in = b->init;
 		auto keep = [&](F4 *&dst, const F4 *src, uint32_t n) { dst = rt.alloc<F4>(n, false); rt.copy(dst, src, n); };
-		keep(in.position, s.position, stride); keep(in.rotation, s.rotation, stride);
-		keep(in.linear_velocity, s.linear_velocity, stride); keep(in.angular_velocity, s.angular_velocity, stride);
-		keep(in.force, s.force, stride); keep(in.torque, s.torque, stride);
-		keep(in.bounds_min, s.bounds_min, stride); keep(in.bounds_max, s.bounds_max, stride);
+		keep(in.pose, s.position.base, 2 * stride); keep(in.velocity, s.linear_velocity.base, 2 * stride);
+		keep(in.force_torque, s.force.base, 2 * stride); keep(in.bounds, s.bounds_min.base, 2 * stride);
 		keep(in.sleep_spheres, s.sleep_spheres, stride * 3);
 		in.sleep_timer = rt.alloc<float>(stride, false); rt.copy(in.sleep_timer, s.sleep_timer, stride);
 		std::vector<uint32_t> active_index(stride), was_active(stride);
@@ -1814,8 +1838,7 @@ void b2j_batch_destroy(b2j_batch *b)
 	{
 		Runtime &rt = b->groups[0]->rt;
 		BatchInitState &in = b->init;
-		rt.free_(in.position); rt.free_(in.rotation); rt.free_(in.linear_velocity); rt.free_(in.angular_velocity); rt.free_(in.force); rt.free_(in.torque);
-		rt.free_(in.bounds_min); rt.free_(in.bounds_max); rt.free_(in.sleep_spheres); rt.free_(in.sleep_timer); rt.free_(in.was_active);
+		rt.free_(in.pose); rt.free_(in.velocity); rt.free_(in.force_torque); rt.free_(in.bounds); rt.free_(in.sleep_spheres); rt.free_(in.sleep_timer); rt.free_(in.was_active);
 	}
 	for (b2j_world *G : b->groups) b2j_world_destroy(G);
 	delete b;

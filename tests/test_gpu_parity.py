@@ -10,6 +10,9 @@ CASES = [
     ("pyramid", 15, 0, 0), ("pyramid", 15, 0, 1), ("pyramid", 15, 0, 30), ("pyramid", 15, 0, 120), ("pyramid", 15, 0, 300),
     ("small_stack", 0, 0, 30), ("small_stack", 1, 0, 30), ("small_stack", 2, 0, 30), ("small_stack", 3, 0, 30),
     ("small_stack", 4, 0, 5), ("small_stack", 4, 0, 45), ("small_stack", 4, 0, 200),
+    ("convex_vs_mesh", 10, 0, 60), ("pile", 2000, 15, 100),
+    # worlds with more than 4096 bodies: the wavefront schedule runs as one cooperative launch (sched_grid_kernel)
+    ("pile", 6000, 15, 80), ("max_bodies", 6000, 0, 10),
 ]
 
 
