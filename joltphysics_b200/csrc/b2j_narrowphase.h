@@ -42,6 +42,8 @@ struct NarrowCtx
 	CollideItem *collide_convex, *collide_mesh;
 	CachedItem *cached;
 	EpaItem *epa;
+	const uint32_t *collide_order; // batch groups: collide_convex is processed in (pair inside the world, world) order so that the
+	                             // lanes of a warp run the same pair of different worlds (near identical control flow); null = as queued
 	EpaItem *epa_overflow;       // deep pairs that did not fit the small EPA tier (re-run on full size storage)
 	uint32_t *num_epa_overflow;  // device counter
 	EpaResult *epa_results;      // GJK / EPA output; supporting faces / clipping / manifold run in KFinishPairs
@@ -453,6 +455,19 @@ B2J_D ConvexPairSetup convex_pair_setup(const DWorld &w, const CollideItem &item
 	return s;
 }
 
+// batch groups: sort key of a queued convex pair = (body 1 inside its world, body 2 inside its world); the stable sort keeps the
+// worlds of one pair next to each other
+struct KCollideKeys
+{
+	DWorld w; NarrowCtx c; uint32_t *keys, *vals; uint32_t bits;
+	B2J_D void operator()(uint32_t k) const
+	{
+		CollideItem item = c.collide_convex[k];
+		keys[k] = ((item.b1 % w.world_stride) << bits) | (item.b2 % w.world_stride);
+		vals[k] = k;
+	}
+};
+
 // ---- KCollideConvex: OBB pre-test + GJK; queues shallow hits for KFinishPairs and deep ones for EPA ------------------
 // Thread per pair with the GJK loop in lockstep (all 32 lanes call run(), valid = lane has a pair).
 struct KCollideConvex
@@ -467,7 +482,7 @@ struct KCollideConvex
 		TransformedSupport b_excl = {};
 		if (alive)
 		{
-			item = c.collide_convex[k];
+			item = c.collide_convex[c.collide_order != nullptr? c.collide_order[k] : k];
 			s = convex_pair_setup(w, item);
 			const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
 			V3 bb1_min = s1.local_min - v3_rep(s.max_separation_distance), bb1_max = s1.local_max + v3_rep(s.max_separation_distance);

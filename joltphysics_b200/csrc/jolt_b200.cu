@@ -407,6 +407,7 @@ struct b2j_world
 	uint64_t *d_sort_keys[2] = { nullptr, nullptr };
 	uint32_t *d_sort_vals = nullptr;
 	uint32_t *d_woken_sorted = nullptr;
+	uint32_t *d_collide_keys[2] = { nullptr, nullptr }, *d_collide_vals[2] = { nullptr, nullptr }; // batch groups: ordering of the convex pair queue
 	uint32_t *d_woken_keys = nullptr;
 	b2j_activation_event *d_act_events = nullptr;
 	uint32_t max_events = 0, max_act_events = 0;
@@ -572,6 +573,22 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		// convex pairs: GJK (thread per pair, lockstep) queues shallow hits as results and deep ones for EPA
 		rt.memset_(W->nc.num_epa_overflow, 0, 4);
 		rt.memset_(W->nc.num_epa_results, 0, 4);
+		W->nc.collide_order = nullptr;
+		if (d.world_stride != 0 && d.world_stride < 65536 && W->d_collide_keys[0] != nullptr)
+		{
+			// batch group: same pair of different worlds in neighbouring lanes (GJK / EPA / manifold code paths then coincide: 15 -> ~30
+			// active lanes per instruction). Needs the queue length on the host: one small readback per round.
+			if (!read_counters(W)) return false;
+			uint32_t nq = W->h_counters.num_collide_convex < d.max_body_pairs? W->h_counters.num_collide_convex : d.max_body_pairs;
+			if (nq >= 1024)
+			{
+				uint32_t bits = 1;
+				while ((1u << bits) < d.world_stride) ++bits;
+				{ KCollideKeys k; k.w = d; k.c = W->nc; k.keys = W->d_collide_keys[0]; k.vals = W->d_collide_vals[0]; k.bits = bits; rt.launch(k, nq); }
+				rt.sort_pairs<uint32_t>(W->d_collide_keys[0], W->d_collide_keys[1], W->d_collide_vals[0], W->d_collide_vals[1], nq, (int)(2 * bits));
+				W->nc.collide_order = W->d_collide_vals[1];
+			}
+		}
 		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev_lockstep(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
 		// deep pairs: thread per pair, lanes in lockstep, EPA scratch in (lane interleaved, L1/L2 cached) local memory. Small tier first
 		// (2 KB per lane covers ~88% of the pairs, 16 warps per SM); the pairs that overflow it re-run on full size storage (21 KB per lane).
@@ -1049,6 +1066,7 @@ void b2j_world_destroy(b2j_world *W)
 	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(nc.events);
 	rt.free_(W->d_mesh_scratch);
+	for (int i = 0; i < 2; ++i) { rt.free_(W->d_collide_keys[i]); rt.free_(W->d_collide_vals[i]); }
 	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
 	rt.free_(sc.con.cp); rt.free_(sc.con.hdr);
@@ -1704,6 +1722,7 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	if (B == nullptr) return nullptr;
 	Runtime &rt = B->rt;
 	B->num_worlds = n_worlds;
+	for (int i = 0; i < 2; ++i) { B->d_collide_keys[i] = rt.alloc<uint32_t>(B->d.max_body_pairs, false); B->d_collide_vals[i] = rt.alloc<uint32_t>(B->d.max_body_pairs, false); }
 	B->d.world_stride = stride;
 	B->prev_dt = P->prev_dt;
 	// shapes are shared by all worlds
