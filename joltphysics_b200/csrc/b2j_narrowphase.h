@@ -112,7 +112,8 @@ struct KProcessPairs
 		uint32_t id1 = i1.id, id2 = i2.id;
 		if (id2 < id1) { cb1 = b2; cb2 = b1; uint32_t t = id1; id1 = id2; id2 = t; }
 
-		uint32_t entry = atomic_add(w.write_cache.num_pairs, 1u);
+		// one cache entry per candidate pair, in pair order (no allocation atomic; KNextRound publishes the count)
+		uint32_t entry = *first_ptr + k;
 		if (entry >= w.max_body_pairs)
 		{
 			set_error(w, B2J_ERR_BODY_PAIR_CACHE_FULL);

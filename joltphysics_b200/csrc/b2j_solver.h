@@ -702,8 +702,9 @@ struct KSetupConstraints
 		uint32_t vsteps = steps & 0xff, psteps = (steps >> 8) & 0xff;
 		if (steps & (1u << 16)) vsteps = vsteps > w.settings.num_velocity_steps? vsteps : w.settings.num_velocity_steps;
 		if (steps & (1u << 17)) psteps = psteps > w.settings.num_position_steps? psteps : w.settings.num_position_steps;
-		atomic_max(&w.counters->max_velocity_steps, vsteps);
-		atomic_max(&w.counters->max_position_steps, psteps);
+		// (almost always already at the maximum: keep the single address atomics off the hot path)
+		if (vsteps > volatile_load(&w.counters->max_velocity_steps)) atomic_max(&w.counters->max_velocity_steps, vsteps);
+		if (psteps > volatile_load(&w.counters->max_position_steps)) atomic_max(&w.counters->max_position_steps, psteps);
 
 		uint32_t meta = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16);
 

@@ -309,6 +309,7 @@ struct KNextRound
 		uint32_t n = c.num_pairs < w.max_body_pairs? c.num_pairs : w.max_body_pairs;
 		if (c.num_pairs > w.max_body_pairs) c.error_bits |= B2J_ERR_BODY_PAIR_CACHE_FULL;
 		*round_begin = n;
+		*w.write_cache.num_pairs = n; // cache entries = processed pairs (KProcessPairs)
 		c.num_collide_convex = 0; c.num_collide_mesh = 0; c.num_cached = 0; c.num_epa = 0; c.num_woken = 0;
 	}
 };
@@ -648,7 +649,11 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			uint32_t blocks = d.world_stride != 0? W->num_worlds : 1, slots_per_block = d.world_stride != 0? d.world_stride : W->num_slots;
 			++rt.launches;
 			if (rt.profiling) rt.prof_begin(profile_category<KSchedBlock>());
-			sched_block_kernel<<<blocks, d.world_stride != 0? 256 : 1024, 0, rt.stream>>>(d, sc, slots_per_block);
+			// as many threads per world as fit with every world of the group resident (a round costs one dependent chain of ~8 L2
+			// round trips per body a thread owns: fewer bodies per thread = shorter rounds)
+			uint32_t threads = 1024;
+			while (threads > 128 && (uint64_t)blocks * threads > (uint64_t)rt.num_sms * 2048) threads /= 2;
+			sched_block_kernel<<<blocks, threads, 0, rt.stream>>>(d, sc, slots_per_block);
 			if (rt.profiling) rt.prof_end();
 		}
 #else
