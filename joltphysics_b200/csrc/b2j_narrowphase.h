@@ -131,6 +131,8 @@ struct KProcessPairs
 		out.slot1 = cb1; out.slot2 = cb2;
 		out.first_manifold = 0; out.num_manifolds = 0;
 
+		// the cached-pair work list is indexed like the cache entries (no allocation atomic): invalid unless the pair is served from the cache
+		CachedItem cached_item; cached_item.pair_entry = 0xffffffffu; cached_item.old_pair = 0xffffffffu;
 		uint32_t old = 0xffffffffu;
 		bool handled = false;
 		if (w.settings.use_body_pair_contact_cache)
@@ -150,13 +152,12 @@ struct KProcessPairs
 					atomic_add(&w.counters->num_pairs_from_cache, 1u);
 					if (in.num_manifolds != 0)
 					{
-						uint32_t ci = atomic_add(&w.counters->num_cached, 1u);
-						CachedItem item; item.pair_entry = entry; item.old_pair = old;
-						c.cached[ci] = item;
+						cached_item.pair_entry = entry; cached_item.old_pair = old;
 					}
 				}
 			}
 		}
+		c.cached[entry] = cached_item;
 		if (!handled)
 		{
 			v3_store(delta_position, out.dpos);
@@ -225,9 +226,12 @@ B2J_D bool register_constraint(const DWorld &w, const NarrowCtx &c, uint32_t m, 
 struct KCopyCached
 {
 	DWorld w; NarrowCtx c;
+	const uint32_t *first_ptr; // device: first pair of this round
 	B2J_D void operator()(uint32_t k) const
 	{
-		CachedItem item = c.cached[k];
+		CachedItem item = c.cached[*first_ptr + k];
+		if (item.pair_entry == 0xffffffffu)
+			return;
 		const CachedPair &in = w.read_cache.pairs[item.old_pair];
 		CachedPair &out = w.write_cache.pairs[item.pair_entry];
 		uint32_t n = in.num_manifolds;

@@ -315,13 +315,13 @@ struct Runtime
 #endif
 	}
 	// device-resident count (no host sync): processes [*begin, min(*n_ptr, cap))
-	template <class K> void launch_dev(const K &k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap)
+	template <class K> void launch_dev(const K &k, const uint32_t *n_ptr, const uint32_t *begin_ptr, uint32_t cap, uint32_t blocks_per_sm = 8)
 	{
 		if (cap == 0) return;
 		++launches;
 #ifndef B2J_HOSTSIM
 		uint32_t g = grid_for(cap, 128);
-		uint32_t gmax = (uint32_t)num_sms * 8; // (16 blocks per SM measured 1% slower on the 4096 world batch)
+		uint32_t gmax = (uint32_t)num_sms * blocks_per_sm; // (16 blocks per SM for every kernel measured 1% slower on the 4096 world batch)
 		if (profiling) prof_begin(profile_category<K>());
 		run_kernel_dev<K><<<g > gmax? gmax : g, 128, 0, stream>>>(k, n_ptr, begin_ptr, cap);
 		if (profiling) prof_end();
