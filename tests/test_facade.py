@@ -45,7 +45,7 @@ def test_facade_scene_matches_reference_hostsim(hostsim_facade, scene, p0, p1):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene,p0,p1", SCENES + [("pyramid", 15, 0), ("convex_vs_mesh", 10, 0)])
-def test_facade_scene_matches_reference_gpu(gpu_api, scene, p0, p1):
+def test_facade_scene_matches_reference_gpu(gpu_api, ref_available, scene, p0, p1):
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
     _check(flib, scene, p0, p1, steps=25)
 
@@ -87,5 +87,5 @@ def test_facade_api_tour_hostsim(hostsim_facade):
 
 
 @pytest.mark.gpu
-def test_facade_api_tour_gpu(gpu_api):
+def test_facade_api_tour_gpu(gpu_api, ref_available):
     _check_api_tour(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api))

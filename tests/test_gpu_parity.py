@@ -17,16 +17,16 @@ CASES = [
 
 
 @pytest.mark.parametrize("scene,p0,p1,warm", CASES)
-def test_single_step_parity(gpu_api, scene, p0, p1, warm):
+def test_single_step_parity(gpu_api, ref_available, scene, p0, p1, warm):
     out = parity.single_step_parity(gpu_api, scene, p0, p1, warm)
     assert out["stats"]["kernel_launches"] > 0
 
 
-def test_two_collision_steps(gpu_api):
+def test_two_collision_steps(gpu_api, ref_available):
     parity.single_step_parity(gpu_api, "pyramid", 4, 0, 20, collision_steps=2)
 
 
-def test_pyramid_long_run_energy_and_heights(gpu_api):
+def test_pyramid_long_run_energy_and_heights(gpu_api, ref_available):
     # long runs: stacking chaos prevents trajectory identity -> compare resting heights and kinetic energy
     import numpy as np
     import refharness as R
