@@ -100,9 +100,10 @@ Quat random_quat(std::mt19937 &rnd)
 	return Quat(x, y, z, w).Normalized();
 }
 
-bool scene_pyramid(Scene &s, int height)
+bool scene_pyramid(Scene &s, int height, int tight_limit = 0)
 {
-	if (!s.system.Init(10240, 0, 65536, 20480, s.bpl, s.ovbp, s.olp, Layers::NUM_LAYERS, scene_device())) return false;
+	// tight_limit > 0: max body pairs = max contact constraints = that value (error path tests)
+	if (!s.system.Init(10240, 0, tight_limit > 0? (uint)tight_limit : 65536, tight_limit > 0? (uint)tight_limit : 20480, s.bpl, s.ovbp, s.olp, Layers::NUM_LAYERS, scene_device())) return false;
 	BodyInterface &bi = s.system.GetBodyInterface();
 	bi.CreateAndAddBody(BodyCreationSettings(std::make_shared<BoxShape>(Vec3(50.0f, 1.0f, 50.0f), 0.0f), RVec3(0.0f, -1.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING), EActivation::DontActivate);
 	const float box_size = 2.0f, separation = 0.5f, half = 1.0f;
@@ -264,6 +265,7 @@ B2JF_API void *b2jf_scene_create(const char *name, int p0, int p1, const char *a
 	std::string n(name);
 	bool ok = false;
 	if (n == "pyramid") ok = scene_pyramid(*s, p0 > 0? p0 : 15);
+	else if (n == "pyramid_tight") ok = scene_pyramid(*s, p0 > 0? p0 : 6, p1 > 0? p1 : 64);
 	else if (n == "convex_vs_mesh") ok = scene_convex_vs_mesh(*s, p0 > 0? p0 : 10, assets_dir);
 	else if (n == "pile") ok = scene_pile(*s, p0 > 0? p0 : 1000, p1 > 0? p1 : 15, assets_dir);
 	else if (n == "max_bodies") ok = scene_max_bodies(*s, p0 > 0? p0 : 10000);

@@ -179,10 +179,11 @@ void sEnsureJobs(World *w, int inNumThreads)
 
 // ---- scenes -------------------------------------------------------------------------------------------------
 
-World *sScenePyramid(int inHeight)
+World *sScenePyramid(int inHeight, int inTightLimit = 0)
 {
 	// PerformanceTest/PyramidScene.h:23-47 (height 15 -> 1240 boxes); limits as PerformanceTest.cpp (10240 bodies, 65536 pairs, 20480 constraints)
-	World *w = sNewWorld(10240, 65536, 20480, 32);
+	// inTightLimit > 0: max body pairs = max contact constraints = that value (error path tests: the step must report the overflow)
+	World *w = inTightLimit > 0? sNewWorld(10240, (uint)inTightLimit, (uint)inTightLimit, 32) : sNewWorld(10240, 65536, 20480, 32);
 	BodyInterface &bi = w->system.GetBodyInterface();
 	bi.CreateAndAddBody(BodyCreationSettings(new BoxShape(Vec3(50.0f, 1.0f, 50.0f), 0.0f), RVec3(0.0f, -1.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING), EActivation::DontActivate);
 	const float box_size = 2.0f, separation = 0.5f, half = 1.0f;
@@ -443,6 +444,7 @@ void *jref_create_scene(const char *inName, int inParam0, int inParam1)
 	String name(inName);
 	World *w = nullptr;
 	if (name == "pyramid") w = sScenePyramid(inParam0 > 0? inParam0 : 15);
+	else if (name == "pyramid_tight") w = sScenePyramid(inParam0 > 0? inParam0 : 6, inParam1 > 0? inParam1 : 64);
 	else if (name == "convex_vs_mesh") w = sSceneConvexVsMesh(inParam0 > 0? inParam0 : 10);
 	else if (name == "max_bodies") w = sSceneMaxBodies(inParam0 > 0? inParam0 : 10000);
 	else if (name == "pile") w = sScenePile(inParam0 > 0? inParam0 : 1000, inParam1 > 0? inParam1 : 15);

@@ -89,3 +89,34 @@ def test_facade_api_tour_hostsim(hostsim_facade):
 @pytest.mark.gpu
 def test_facade_api_tour_gpu(gpu_api, ref_available):
     _check_api_tour(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api))
+
+
+def _check_overflow(flib, limit):
+    """Error behaviour: with too small body pair / contact constraint limits Update must keep running and report the
+    overflow through the reference's EPhysicsUpdateError bits (which contacts survive an overflow is unspecified)."""
+    ref = R.RefWorld("pyramid_tight", 6, limit)
+    fs = F.FacadeScene(flib, "pyramid_tight", 6, limit)
+    seen_ref = seen_got = 0
+    for _ in range(25):
+        seen_ref |= ref.step()
+        err, _ = fs.update()
+        assert err >= 0, "the step itself must not fail"
+        seen_got |= err
+    assert seen_ref != 0, "the limits are meant to overflow"
+    # The reference allocates body pairs and manifolds from ONE byte arena (ContactConstraintManager.cpp:299-306), so one
+    # exhausted arena raises several bits there; the device has separate arrays and reports the limit that actually overflowed:
+    # a non-empty subset of the reference's bits.
+    assert seen_got != 0 and (seen_got & ~seen_ref) == 0, (bin(seen_got), bin(seen_ref))
+    fs.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("limit", [64, 200])
+def test_facade_overflow_errors_hostsim(hostsim_facade, limit):
+    _check_overflow(hostsim_facade, limit)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("limit", [64, 200])
+def test_facade_overflow_errors_gpu(gpu_api, ref_available, limit):
+    _check_overflow(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api), limit)
