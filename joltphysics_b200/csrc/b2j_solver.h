@@ -1211,6 +1211,56 @@ struct KSolvePosition
 	}
 };
 
+#if !defined(B2J_HOSTSIM) && defined(__CUDACC__)
+// Small single worlds (a few thousand constraints): one launch per phase per iteration is ~340 dependent launches of a few
+// microseconds each for a Pyramid. Here ONE small cooperative grid (8 blocks) runs warm start + all velocity iterations (or all
+// position iterations), the phases separated by grid barriers; phase offsets and iteration counts are read on the device. Same per
+// constraint functors as the per phase launches. (One block alone is too slow: 8 warps cannot hide the L2 latency; for batches of
+// worlds per phase launches over all worlds win)
+struct KSolveSmallVelocity { }; // (profiling categories)
+struct KSolveSmallPosition { };
+template <bool kPosition> __global__ void __launch_bounds__(256) solve_small_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	const uint32_t np = w.counters->num_phases;
+	const uint32_t steps = kPosition? w.counters->max_position_steps : w.counters->max_velocity_steps;
+	const uint32_t *off = s.phase_count;
+	if (!kPosition)
+	{
+		KWarmStart ws; ws.w = w; ws.c = s.con; ws.begin = 0; ws.ratio = warm_start_ratio;
+		for (uint32_t p = 0; p < np; ++p)
+		{
+			for (uint32_t k = off[p] + tid; k < off[p + 1]; k += nt) ws(k);
+			grid.sync();
+		}
+		KSolveVelocity sv; sv.w = w; sv.c = s.con; sv.begin = 0;
+		for (uint32_t it = 0; it < steps; ++it)
+		{
+			sv.iteration = it;
+			for (uint32_t p = 0; p < np; ++p)
+			{
+				for (uint32_t k = off[p] + tid; k < off[p + 1]; k += nt) sv(k);
+				grid.sync();
+			}
+		}
+	}
+	else
+	{
+		KSolvePosition sp; sp.w = w; sp.c = s.con; sp.begin = 0;
+		for (uint32_t it = 0; it < steps; ++it)
+		{
+			sp.iteration = it;
+			for (uint32_t p = 0; p < np; ++p)
+			{
+				for (uint32_t k = off[p] + tid; k < off[p + 1]; k += nt) sp(k);
+				grid.sync();
+			}
+		}
+	}
+}
+#endif
+
 // ---- bounds + sleeping (CheckSleepAndUpdateBounds, last collision step) ------------------------------------------------
 struct KBoundsAndSleep
 {

@@ -627,6 +627,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	{ KIslandClassify k; k.w = d; k.s = sc; rt.launch(k, na); }
 
 	uint32_t num_phases = 0, vsteps = 0, psteps = 0;
+	bool block_solve = false;
 	if (M > 0)
 	{
 		// (a14 SortContacts) order by sort key
@@ -729,16 +730,33 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		num_phases = W->h_counters.num_phases;
 		vsteps = W->h_counters.max_velocity_steps;
 		psteps = W->h_counters.max_position_steps;
-		W->h_phase_offsets.resize(num_phases + 1);
-		rt.download(W->h_phase_offsets.data(), sc.phase_count, num_phases + 1);
+#ifndef B2J_HOSTSIM
+		// small single world: the whole velocity solve in one small cooperative launch (solve_small_kernel)
+		block_solve = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
+		if (block_solve)
+		{
+			float ratio_arg = warm_start_ratio;
+			void *args[] = { (void *)&d, (void *)&sc, (void *)&ratio_arg };
+			++rt.launches;
+			if (rt.profiling) rt.prof_begin(profile_category<KSolveSmallVelocity>());
+			cudaError_t e = cudaLaunchCooperativeKernel((const void *)solve_small_kernel<false>, dim3(8), dim3(256), args, 0, rt.stream);
+			if (rt.profiling) rt.prof_end();
+			if (e != cudaSuccess) { cudaGetLastError(); block_solve = false; }
+		}
+		if (!block_solve)
+#endif
+		{
+			W->h_phase_offsets.resize(num_phases + 1);
+			rt.download(W->h_phase_offsets.data(), sc.phase_count, num_phases + 1);
+		}
 
 		// (a14) warm start + velocity iterations, one launch per phase
-		for (uint32_t p = 0; p < num_phases; ++p)
+		for (uint32_t p = 0; p < num_phases && !block_solve; ++p)
 		{
 			uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
 			KWarmStart k; k.w = d; k.c = sc.con; k.begin = begin; k.ratio = warm_start_ratio; rt.launch(k, n);
 		}
-		for (uint32_t it = 0; it < vsteps; ++it)
+		for (uint32_t it = 0; it < vsteps && !block_solve; ++it)
 			for (uint32_t p = 0; p < num_phases; ++p)
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
@@ -759,7 +777,19 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	}
 
 	// (a16) position iterations
-	for (uint32_t it = 0; it < psteps; ++it)
+#ifndef B2J_HOSTSIM
+	if (block_solve && psteps > 0)
+	{
+		float ratio_arg = 0.0f;
+		void *args[] = { (void *)&d, (void *)&sc, (void *)&ratio_arg };
+		++rt.launches;
+		if (rt.profiling) rt.prof_begin(profile_category<KSolveSmallPosition>());
+		cudaError_t e = cudaLaunchCooperativeKernel((const void *)solve_small_kernel<true>, dim3(8), dim3(256), args, 0, rt.stream);
+		if (rt.profiling) rt.prof_end();
+		if (e != cudaSuccess) { cudaGetLastError(); last_error() = "cooperative position solve launch failed"; return false; }
+	}
+#endif
+	for (uint32_t it = 0; it < psteps && !block_solve; ++it)
 		for (uint32_t p = 0; p < num_phases; ++p)
 		{
 			uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
