@@ -116,7 +116,7 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if self.proc is not None:
             self.proc.terminate()
-        else:
+        elif self.is_alive():
             self.join(timeout=1.0)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -292,7 +292,8 @@ def measure(args, wl, torch, dist, world_size, local_rank, steps, warmup, with_e
     for _ in range(warmup):
         wl.step()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if os.environ.get("B2J_BENCH_NO_SAMPLER") != "1":  # (diagnostics: does the sampler perturb the run?)
+        sampler.start()
     barrier()
     cuprofile = os.environ.get("B2J_BENCH_CUPROFILE") == "1"  # `ncu --profile-from-start off`: capture the timed steps only
     if cuprofile:

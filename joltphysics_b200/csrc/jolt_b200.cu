@@ -1836,10 +1836,10 @@ extern "C" {
 b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
 {
 	if (P == nullptr || n_worlds == 0 || P->num_worlds != 1) { last_error() = "b2j_batch_create: invalid prototype"; return nullptr; }
-	// groups of about 256 worlds, at most 16 (measured at 4096 worlds: 149 ms per step with 4 groups, 130 with 8, 125 with 16);
-	// B2J_BATCH_GROUPS overrides
+	// groups of about 256 worlds, at most 8 (measured at 4096 worlds: 149 ms per step with 4 groups, 130 with 8, 125 with 16 -- but the
+	// 16 group launches are small enough to lose 20% of their own HBM efficiency, so 8 it is); B2J_BATCH_GROUPS overrides
 	uint32_t K = n_worlds / 256;
-	if (K > 16) K = 16;
+	if (K > 8) K = 8;
 	if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
 #ifdef B2J_HOSTSIM
 	K = 1; // the host simulation is single threaded
