@@ -199,14 +199,19 @@ struct KUfInit
 	}
 };
 
+// find with intermediate pointer jumping (path halving): parents only ever move to smaller slots of the same set, so redirecting
+// a node to its grandparent is always valid, racing writers included
 B2J_D uint32_t uf_find(uint32_t *parent, uint32_t x)
 {
-	for (;;)
+	uint32_t p = volatile_load(&parent[x]);
+	while (p != x)
 	{
-		uint32_t p = volatile_load(&parent[x]);
-		if (p == x) return x;
+		uint32_t gp = volatile_load(&parent[p]);
+		if (gp != p) parent[x] = gp;
 		x = p;
+		p = gp;
 	}
+	return x;
 }
 
 struct KUfUnion
@@ -252,7 +257,7 @@ struct KIslandCount
 		BodyInfo i1 = w.info[c.b1], i2 = w.info[c.b2];
 		bool dyn1 = i1.motion_type == B2J_MOTION_DYNAMIC, dyn2 = i2.motion_type == B2J_MOTION_DYNAMIC;
 		uint32_t r = s.root[dyn1? c.b1 : c.b2];
-		atomic_add(&s.island_items[r], 1u);
+		atomic_add_matched(s.island_items, r, 1u); // (one giant island = one address for a million constraints: aggregate per warp)
 		uint32_t vmax = 0, pmax = 0, flags = 0;
 		if (dyn1) { uint32_t v = i1.steps_override & 15, p = i1.steps_override >> 4; vmax = v; pmax = p; if (v == 0) flags |= 1u << 16; if (p == 0) flags |= 1u << 17; }
 		if (dyn2) { uint32_t v = i2.steps_override & 15, p = i2.steps_override >> 4; if (v > vmax) vmax = v; if (p > pmax) pmax = p; if (v == 0) flags |= 1u << 16; if (p == 0) flags |= 1u << 17; }
