@@ -468,7 +468,11 @@ struct KCollideKeys
 	B2J_D void operator()(uint32_t k) const
 	{
 		CollideItem item = c.collide_convex[k];
-		keys[k] = ((item.b1 % w.world_stride) << bits) | (item.b2 % w.world_stride);
+		if (w.world_stride != 0)
+			keys[k] = ((item.b1 % w.world_stride) << bits) | (item.b2 % w.world_stride);
+		else
+			// one big world: group the pairs by the two shape types, so that a warp runs one combination of support functions
+			keys[k] = (w.shapes[w.info[item.b1].shape].kind << 3) | w.shapes[w.info[item.b2].shape].kind;
 		vals[k] = k;
 	}
 };

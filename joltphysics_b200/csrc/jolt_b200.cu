@@ -575,18 +575,20 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		rt.memset_(W->nc.num_epa_overflow, 0, 4);
 		rt.memset_(W->nc.num_epa_results, 0, 4);
 		W->nc.collide_order = nullptr;
-		if (d.world_stride != 0 && d.world_stride < 65536 && W->d_collide_keys[0] != nullptr)
+		if (d.world_stride == 0 && W->d_collide_keys[0] == nullptr && W->last_num_pairs >= 262144)
+			for (int i = 0; i < 2; ++i) { W->d_collide_keys[i] = rt.alloc<uint32_t>(d.max_body_pairs, false); W->d_collide_vals[i] = rt.alloc<uint32_t>(d.max_body_pairs, false); }
+		if (d.world_stride < 65536 && W->d_collide_keys[0] != nullptr)
 		{
 			// batch group: same pair of different worlds in neighbouring lanes (GJK / EPA / manifold code paths then coincide: 15 -> ~30
 			// active lanes per instruction). Needs the queue length on the host: one small readback per round.
 			if (!read_counters(W)) return false;
 			uint32_t nq = W->h_counters.num_collide_convex < d.max_body_pairs? W->h_counters.num_collide_convex : d.max_body_pairs;
-			if (nq >= 1024)
+			if (nq >= (d.world_stride != 0? 1024u : 65536u))
 			{
 				uint32_t bits = 1;
 				while ((1u << bits) < d.world_stride) ++bits;
 				{ KCollideKeys k; k.w = d; k.c = W->nc; k.keys = W->d_collide_keys[0]; k.vals = W->d_collide_vals[0]; k.bits = bits; rt.launch(k, nq); }
-				rt.sort_pairs<uint32_t>(W->d_collide_keys[0], W->d_collide_keys[1], W->d_collide_vals[0], W->d_collide_vals[1], nq, (int)(2 * bits));
+				rt.sort_pairs<uint32_t>(W->d_collide_keys[0], W->d_collide_keys[1], W->d_collide_vals[0], W->d_collide_vals[1], nq, d.world_stride != 0? (int)(2 * bits) : 6);
 				W->nc.collide_order = W->d_collide_vals[1];
 			}
 		}
