@@ -458,6 +458,24 @@ struct Runtime
 		cub_temp_size = bytes;
 	}
 
+	// Sizes the CUB temporary storage once for the largest sorts / scans the world can issue: growing it on demand means a cudaFree +
+	// cudaMalloc (device wide synchronisation, measured up to 0.5 s with > 100 GB allocated) whenever a count creeps up during a run.
+	void reserve_temp(uint32_t max_sort64, uint32_t max_sort32, uint32_t max_scan)
+	{
+#ifndef B2J_HOSTSIM
+		size_t need = 0, bytes = 0;
+		cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_sort64, 0, 64, stream);
+		need = bytes > need? bytes : need;
+		cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_sort32, 0, 32, stream);
+		need = bytes > need? bytes : need;
+		cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)max_scan, stream);
+		need = bytes > need? bytes : need;
+		ensure_temp(need);
+#else
+		(void)max_sort64; (void)max_sort32; (void)max_scan;
+#endif
+	}
+
 	// stable sort of (key, value) pairs, n known on the host; results in keys_out / vals_out
 	template <class KeyT> void sort_pairs(const KeyT *keys_in, KeyT *keys_out, const uint32_t *vals_in, uint32_t *vals_out, uint32_t n, int end_bit = (int)sizeof(KeyT) * 8)
 	{

@@ -1042,6 +1042,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	sc.man_ws = nc.man_ws;
 	sc.order = rt.alloc<uint32_t>(mc); sc.final_pos = rt.alloc<uint32_t>(mc); sc.solve_src = rt.alloc<uint32_t>(mc); sc.phase = rt.alloc<uint32_t>(mc);
 	sc.max_phases = 8192;
+	rt.reserve_temp(std::max(d.max_bodies, d.max_constraints), std::max(std::max(d.max_body_pairs, d.max_constraints), d.max_bodies), d.max_bodies);
 	sc.phase_count = rt.alloc<uint32_t>(sc.max_phases + 2);
 	sc.uf_parent = rt.alloc<uint32_t>(nbod); sc.root = rt.alloc<uint32_t>(nbod); sc.island_items = rt.alloc<uint32_t>(nbod);
 	sc.island_large = rt.alloc<uint32_t>(nbod); sc.island_steps = rt.alloc<uint32_t>(nbod); sc.island_can_sleep = rt.alloc<uint32_t>(nbod);
