@@ -347,9 +347,14 @@ def roofline_of(m):
     """Roofline of the dominant kernel class (velocity solve), SURVEY 8(d) row (5): per constraint and iteration
     C(c) + 4*S_v + 4*(3+c) algorithmic bytes with C(c) = 220 + 64 c."""
     prof, ps, pagg = m["prof"], m["prof_steps"], m["pagg"]
-    solve = prof.get("KSolveVelocity")
+    kernel = "KSolveVelocity"
+    solve = prof.get(kernel)
     if not solve or solve["ms"] <= 0:
-        return None
+        # small single worlds run warm start + all velocity iterations in one cooperative launch (the warm start pass is included)
+        kernel = "KSolveSmallVelocity"
+        solve = prof.get(kernel)
+        if not solve or solve["ms"] <= 0:
+            return None
     M = pagg["num_constraints"] / ps
     cbar = pagg["num_contact_points"] / max(pagg["num_constraints"], 1)
     V = pagg["velocity_iterations"] / ps
@@ -364,7 +369,7 @@ def roofline_of(m):
     # DRAM traffic of the kernel from the ncu --set full capture in profiles/r1_hot_rest.txt: 93.93 MB read + 3.88 MB written for a
     # launch over 159 488 four point constraints (95.69 MB algorithmic) -> 1.022 x the algorithmic bytes; scaled to this run's launches
     traffic = NCU_TRAFFIC_RATIO * total_bytes / max(solve["launches"], 1)
-    return {"bound": "hbm", "kernel": "KSolveVelocity", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_source": "profiles/r1_hot_rest.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch = 1.022 x algorithmic), scaled to this run's constraints per launch",
             "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
             "bytes_per_launch": total_bytes / max(solve["launches"], 1), "avg_launch_us": 1000.0 * solve["ms"] / max(solve["launches"], 1),

@@ -167,6 +167,8 @@ struct Runtime
 	size_t cub_temp_size = 0;
 #ifndef B2J_HOSTSIM
 	cudaStream_t stream = nullptr;
+	void *pinned_small = nullptr;
+	static constexpr size_t kPinnedSmall = 64 * 1024;
 #endif
 
 	bool init(int dev)
@@ -185,6 +187,7 @@ struct Runtime
 		B2J_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
 		num_sms = prop.multiProcessorCount;
 		B2J_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		B2J_CUDA_CHECK(cudaMallocHost(&pinned_small, kPinnedSmall)); // landing zone of the small per step readbacks (counters, offsets)
 #endif
 		return true;
 	}
@@ -193,6 +196,7 @@ struct Runtime
 	{
 #ifndef B2J_HOSTSIM
 		if (cub_temp) cudaFree(cub_temp);
+		if (pinned_small) cudaFreeHost(pinned_small);
 		if (stage_dev) cudaFree(stage_dev);
 		if (stage_host) cudaFreeHost(stage_host);
 		for (ProfEvent &e : prof_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -242,6 +246,14 @@ struct Runtime
 	{
 		if (n == 0) return;
 #ifndef B2J_HOSTSIM
+		if (pinned_small != nullptr && n * sizeof(T) <= kPinnedSmall)
+		{
+			// a copy into pageable memory goes through a driver staging buffer with extra synchronisation: land in pinned memory
+			cudaMemcpyAsync(pinned_small, (const void *)src, n * sizeof(T), cudaMemcpyDeviceToHost, stream);
+			cudaStreamSynchronize(stream);
+			memcpy((void *)dst, pinned_small, n * sizeof(T));
+			return;
+		}
 		cudaMemcpyAsync((void *)dst, (const void *)src, n * sizeof(T), cudaMemcpyDeviceToHost, stream);
 		cudaStreamSynchronize(stream);
 #else
