@@ -187,10 +187,24 @@ struct KFindPairs
 	Tree trees[8];
 	BodyPair *pairs;
 	uint32_t first; // first active index to query (bodies woken mid-step are queried in a later round)
+	// First round: the queries run in the (Morton sorted) LEAF order of one layer's tree instead of active list order, so that the
+	// lanes of a warp query neighbouring boxes and walk nearly the same path (inactive leaves idle). Null = active list order.
+	const uint32_t *query_leaves;
 	B2J_D void operator()(uint32_t k) const
 	{
-		uint32_t ai = first + k;
-		uint32_t b1 = w.active[ai];
+		uint32_t ai, b1;
+		if (query_leaves != nullptr)
+		{
+			b1 = query_leaves[k];
+			ai = w.active_index[b1];
+			if (ai == B2J_INACTIVE_INDEX)
+				return;
+		}
+		else
+		{
+			ai = first + k;
+			b1 = w.active[ai];
+		}
 		BodyInfo i1 = w.info[b1];
 		float sd = w.settings.speculative_contact_distance;
 		V3 min1 = to_v3(w.bounds_min[b1]) - v3_rep(sd);

@@ -568,7 +568,21 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	uint32_t woken_total = 0;
 	for (int round = 0; round < 64; ++round)
 	{
-		{ KFindPairs k; k.w = d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = first_active; rt.launch(k, n_query); }
+		{
+			KFindPairs k; k.w = d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = first_active; k.query_leaves = nullptr;
+			if (round == 0)
+			{
+				// all active bodies: one launch per layer that holds moving bodies, in the leaf order of that layer's tree
+				for (uint32_t l = 0; l < d.num_bp_layers; ++l)
+					if (W->layer_has_moving[l] && W->trees[l].n > 0)
+					{
+						k.query_leaves = W->trees[l].leaf_body;
+						rt.launch(k, W->trees[l].n);
+					}
+			}
+			else
+				rt.launch(k, n_query); // bodies woken by the previous round, active list order
+		}
 		{ KProcessPairs k; k.w = d; k.c = W->nc; k.first_ptr = W->d_round_begin; rt.launch_dev(k, &d.counters->num_pairs, W->d_round_begin, d.max_body_pairs, 16); } // 40 registers, a chain of ~6 dependent gathers: full occupancy
 		{ KCopyCached k; k.w = d; k.c = W->nc; k.first_ptr = W->d_round_begin; rt.launch_dev(k, &d.counters->num_pairs, W->d_round_begin, d.max_body_pairs); }
 		// convex pairs: GJK (thread per pair, lockstep) queues shallow hits as results and deep ones for EPA
@@ -1712,7 +1726,7 @@ int b2j_debug_find_pairs(b2j_world *W)
 			if (!build_tree(W, l)) return -1;
 			W->layer_needs_build[l] = 0;
 		}
-	KFindPairs k; k.w = W->d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = 0;
+	KFindPairs k; k.w = W->d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = 0; k.query_leaves = nullptr;
 	rt.launch(k, W->num_active);
 	if (!read_counters(W)) return -1;
 	W->last_num_pairs = W->h_counters.num_pairs < W->d.max_body_pairs? W->h_counters.num_pairs : W->d.max_body_pairs;
