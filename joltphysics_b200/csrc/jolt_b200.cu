@@ -589,7 +589,10 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		rt.memset_(W->nc.num_epa_overflow, 0, 4);
 		rt.memset_(W->nc.num_epa_results, 0, 4);
 		W->nc.collide_order = nullptr;
-		if (d.world_stride == 0 && W->d_collide_keys[0] == nullptr && W->last_num_pairs >= 262144)
+		// (B2J_COLLIDE_ORDER_MIN: queue length from which a single world orders its queue; tests lower it to cover the path on small scenes)
+		const char *order_env = getenv("B2J_COLLIDE_ORDER_MIN");
+		const uint32_t order_min = order_env != nullptr? (uint32_t)atoi(order_env) : 65536u;
+		if (d.world_stride == 0 && W->d_collide_keys[0] == nullptr && W->last_num_pairs >= 4 * order_min)
 			for (int i = 0; i < 2; ++i) { W->d_collide_keys[i] = rt.alloc<uint32_t>(d.max_body_pairs, false); W->d_collide_vals[i] = rt.alloc<uint32_t>(d.max_body_pairs, false); }
 		if (d.world_stride < 65536 && W->d_collide_keys[0] != nullptr)
 		{
@@ -597,7 +600,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			// active lanes per instruction). Needs the queue length on the host: one small readback per round.
 			if (!read_counters(W)) return false;
 			uint32_t nq = W->h_counters.num_collide_convex < d.max_body_pairs? W->h_counters.num_collide_convex : d.max_body_pairs;
-			if (nq >= (d.world_stride != 0? 1024u : 65536u))
+			if (nq >= (d.world_stride != 0? 1024u : order_min))
 			{
 				uint32_t bits = 1;
 				while ((1u << bits) < d.world_stride) ++bits;

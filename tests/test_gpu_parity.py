@@ -39,3 +39,14 @@ def test_pyramid_long_run_energy_and_heights(gpu_api, ref_available):
     assert abs(ref.kinetic_energy()) < 1.0
     ke = 0.5 * np.sum(gs.lin[1:] ** 2) * 8000.0  # box mass 2x2x2 * 1000
     assert ke < 1.0
+
+
+@pytest.mark.parametrize("scene,p0,p1,warm", [("pile", 2000, 15, 60), ("pile", 2000, 15, 140), ("convex_vs_mesh", 6, 0, 50)])
+def test_single_world_ordered_pair_queue(gpu_api, ref_available, monkeypatch, scene, p0, p1, warm):
+    """Big single worlds process the convex pair queue grouped by shape type pair (1M body pile); the threshold is lowered here so
+    that the small parity scenes take that path too."""
+    monkeypatch.setenv("B2J_COLLIDE_ORDER_MIN", "8")
+    # (the ordering buffers exist from the second step of a world on, so the check steps both sides for a while)
+    history = parity.multi_step_drift(gpu_api, scene, p0, p1, warm, steps=40)
+    for k in ("pos", "rot", "lin", "ang"):
+        assert max(h[k] for h in history) <= 1.0, (k, [h[k] for h in history])
