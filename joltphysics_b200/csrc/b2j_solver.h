@@ -1101,16 +1101,28 @@ struct KSolveVelocity
 			cp_at(c, CP_LAMBDA_FR, i) = lfr;
 		if (any)
 			store_vel_state(w, b1, b2, type1, type2, s);
+		// sStoreAppliedImpulses, fused into the last velocity iteration of the constraint's island (saves a pass over all constraints)
+		if (iteration + 1 == ((meta >> 8) & 0xff))
+		{
+			CachedManifold &cm = w.write_cache.manifolds[hdr.manifold];
+			for (int p = 0; p < n; ++p)
+				cm.lambda[p] = lp[p];
+			cm.friction_lambda[0] = lfr.x;
+			cm.friction_lambda[1] = lfr.y;
+			cm.angular_lambda = lfr.z;
+		}
 	}
 };
 
-// sStoreAppliedImpulses
+// sStoreAppliedImpulses for constraints of islands that run NO velocity iteration (the others store in their last iteration)
 struct KStoreImpulses
 {
 	DWorld w; Constraints c;
 	B2J_D void operator()(uint32_t i) const
 	{
 		ConstraintHeader hdr = c.hdr[i];
+		if (((hdr.meta >> 8) & 0xff) != 0)
+			return;
 		int n = (int)(hdr.meta & 7);
 		CachedManifold &cm = w.write_cache.manifolds[hdr.manifold];
 		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);

@@ -782,7 +782,9 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 				KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
 				rt.launch(k, n);
 			}
-		{ KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
+		// the applied impulses are stored by the last velocity iteration of every constraint; islands without iterations only exist when
+		// the default number of velocity steps is 0
+		if (d.settings.num_velocity_steps == 0) { KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
 	}
 
 	// (a15) integrate
