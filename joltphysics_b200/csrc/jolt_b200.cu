@@ -780,6 +780,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
 				KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
+				k.prefetch = 1;
 				rt.launch(k, n);
 			}
 		// the applied impulses are stored by the last velocity iteration of every constraint; islands without iterations only exist when
