@@ -78,3 +78,19 @@ def test_port_hashes_known_answers(port_lib):
         return v
     for x in (0, 1, 0x123456789abcdef):
         assert port_lib.port_hash64(x) == wang(x)
+
+
+def test_reference_known_answer_tests_pass_on_the_oracle_build(ref_available):
+    """Pins the oracle: the reference's OWN unit tests for the hot path -- GJK, EPA, closest point, CollideShape,
+    ConvexVsTriangles, ActiveEdges, ContactListener, BroadPhase, Physics, determinism, math -- compiled against the same objects
+    the parity oracle is linked from (oracle/Makefile `selftest`) must all pass."""
+    import os
+    import subprocess
+    if not os.path.isdir("/root/reference/UnitTests"):
+        pytest.skip("/root/reference absent")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(["make", "-s", "-j8", "-C", os.path.join(root, "oracle"), "selftest"], capture_output=True, text=True, timeout=1800)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "Status: SUCCESS!" in out.stdout
+    line = [l for l in out.stdout.splitlines() if "test cases:" in l][0]
+    assert " 0 failed" in line and int(line.split("|")[1].split()[0]) >= 300, line
