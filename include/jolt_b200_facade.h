@@ -579,10 +579,12 @@ public:
 	bool IsAdded(const BodyID &inBodyID) const { const Body *b = TryGet(inBodyID); return b != nullptr && b->mInWorld; }
 
 	RVec3 GetPosition(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetPosition() : RVec3::sZero(); }
-	RVec3 GetCenterOfMassPosition(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetCenterOfMassPosition() : RVec3::sZero(); }
-	Quat GetRotation(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetRotation() : Quat::sIdentity(); }
-	Vec3 GetLinearVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetLinearVelocity() : Vec3::sZero(); }
-	Vec3 GetAngularVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->GetAngularVelocity() : Vec3::sZero(); }
+	// The state getters first look in the flat arrays PhysicsSystem::Update downloaded (no Body object is touched: it matters when a
+	// caller reads a million bodies per step); bodies changed through the interface since then take the Body mirror path.
+	inline RVec3 GetCenterOfMassPosition(const BodyID &id) const;
+	inline Quat GetRotation(const BodyID &id) const;
+	inline Vec3 GetLinearVelocity(const BodyID &id) const;
+	inline Vec3 GetAngularVelocity(const BodyID &id) const;
 	void GetPositionAndRotation(const BodyID &id, RVec3 &outPosition, Quat &outRotation) const { outPosition = GetPosition(id); outRotation = GetRotation(id); }
 	void SetPositionAndRotation(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, EActivation inActivationMode);
 	void SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity);
@@ -739,6 +741,7 @@ private:
 		st.position = mPos.data(); st.rotation = mRot.data(); st.linear_velocity = mLin.data(); st.angular_velocity = mAng.data(); st.active_index = mActiveIndex.data();
 		b2j_bodies_get_state(mWorld, nullptr, n, &st);
 		++mStateGeneration; // Body::Sync picks the new state up on first access
+		for (uint8 &f : mSlotFlags) f &= 1; // the arrays are current for every body in the world
 	}
 
 	void ReplayEvents()
@@ -808,6 +811,16 @@ private:
 	std::vector<float> mPos, mRot, mLin, mAng;    // state of all body slots after the last Update (see Body::Sync)
 	std::vector<uint32> mActiveIndex;
 	uint32 mStateGeneration = 1;
+	// per body index: full id (or invalid) and flags for the getters' fast path: bit 0 = in the world, bit 1 = the Body mirror is
+	// newer than the downloaded arrays (added / changed through the interface since the last Update)
+	std::vector<uint32> mSlotID;
+	std::vector<uint8> mSlotFlags;
+	bool FastSlot(const BodyID &id, size_t &outIndex) const
+	{
+		outIndex = id.GetIndex();
+		return outIndex < mSlotID.size() && mSlotID[outIndex] == id.mID && mSlotFlags[outIndex] == 1 && outIndex < mActiveIndex.size();
+	}
+	void MarkMirrorNewer(const BodyID &id) { size_t i = id.GetIndex(); if (i < mSlotFlags.size()) mSlotFlags[i] |= 2; }
 	std::vector<b2j_contact_event> mContactEvents;
 	std::vector<b2j_activation_event> mActEvents;
 };
@@ -826,6 +839,38 @@ inline void Body::Sync() const
 	mLinearVelocity = Vec3(l[3 * i], l[3 * i + 1], l[3 * i + 2]);
 	mAngularVelocity = Vec3(a[3 * i], a[3 * i + 1], a[3 * i + 2]);
 	mActive = mSystem->mActiveIndex[i] != B2J_INACTIVE_INDEX;
+}
+
+inline RVec3 BodyInterface::GetCenterOfMassPosition(const BodyID &id) const
+{
+	size_t i;
+	if (mSystem->FastSlot(id, i)) return Vec3(mSystem->mPos[3 * i], mSystem->mPos[3 * i + 1], mSystem->mPos[3 * i + 2]);
+	const Body *b = TryGet(id);
+	return b? b->GetCenterOfMassPosition() : RVec3::sZero();
+}
+
+inline Quat BodyInterface::GetRotation(const BodyID &id) const
+{
+	size_t i;
+	if (mSystem->FastSlot(id, i)) return Quat(mSystem->mRot[4 * i], mSystem->mRot[4 * i + 1], mSystem->mRot[4 * i + 2], mSystem->mRot[4 * i + 3]);
+	const Body *b = TryGet(id);
+	return b? b->GetRotation() : Quat::sIdentity();
+}
+
+inline Vec3 BodyInterface::GetLinearVelocity(const BodyID &id) const
+{
+	size_t i;
+	if (mSystem->FastSlot(id, i)) return Vec3(mSystem->mLin[3 * i], mSystem->mLin[3 * i + 1], mSystem->mLin[3 * i + 2]);
+	const Body *b = TryGet(id);
+	return b? b->GetLinearVelocity() : Vec3::sZero();
+}
+
+inline Vec3 BodyInterface::GetAngularVelocity(const BodyID &id) const
+{
+	size_t i;
+	if (mSystem->FastSlot(id, i)) return Vec3(mSystem->mAng[3 * i], mSystem->mAng[3 * i + 1], mSystem->mAng[3 * i + 2]);
+	const Body *b = TryGet(id);
+	return b? b->GetAngularVelocity() : Vec3::sZero();
 }
 
 // ---- BodyInterface implementation -----------------------------------------------------------------------------------
@@ -904,6 +949,9 @@ inline Body *BodyInterface::CreateBody(const BodyCreationSettings &s)
 	d.has_bounds = 0; // bounds and sleep test spheres are computed on the device from shape + pose
 	Body *result = body.get();
 	sys.mBodies[index] = std::move(body);
+	if (sys.mSlotID.size() <= index) { sys.mSlotID.resize(index + 1, BodyID::cInvalidBodyID); sys.mSlotFlags.resize(index + 1, 0); }
+	sys.mSlotID[index] = result->mID.mID;
+	sys.mSlotFlags[index] = 0;
 	return result;
 }
 
@@ -916,6 +964,7 @@ inline void BodyInterface::AddBodies(const BodyID *inBodies, int inNumber, EActi
 		if (b == nullptr || b->mInWorld) continue;
 		b->mInWorld = true;
 		b->mSyncGeneration = sys.mStateGeneration; // the creation state is current until the next Update
+		sys.mSlotFlags[b->mID.GetIndex()] = 1 | 2;
 		sys.mPendingAdd.push_back(b->mDesc);
 		if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static)
 		{
@@ -954,7 +1003,9 @@ inline void BodyInterface::RemoveBody(const BodyID &inBodyID)
 	Flush();
 	uint32 id = inBodyID.mID;
 	b2j_bodies_remove(World(), &id, 1);
+	b->Sync(); // the Body keeps the state it left the world with
 	b->mInWorld = false; b->mActive = false;
+	mSystem->mSlotFlags[inBodyID.GetIndex()] = 0;
 }
 
 inline void BodyInterface::DestroyBody(const BodyID &inBodyID)
@@ -963,6 +1014,7 @@ inline void BodyInterface::DestroyBody(const BodyID &inBodyID)
 	if (b == nullptr) return;
 	if (b->mInWorld) RemoveBody(inBodyID);
 	mSystem->mFreeIndices.push_back(inBodyID.GetIndex());
+	mSystem->mSlotID[inBodyID.GetIndex()] = BodyID::cInvalidBodyID;
 	b->mShape.reset();
 	b->mDestroyed = true; // the slot keeps the Body for its sequence number; it can no longer be looked up
 }
@@ -972,6 +1024,7 @@ inline void BodyInterface::SetPositionAndRotation(const BodyID &id, const RVec3 
 	Body *b = const_cast<Body *>(TryGet(id));
 	if (b == nullptr) return;
 	b->Sync();
+	mSystem->MarkMirrorNewer(id);
 	b->mRotation = inRotation;
 	b->mPosition = inPosition + inRotation * b->mShape->GetCenterOfMass();
 	if (!b->mInWorld) { b->mDesc.position[0] = b->mPosition.x; b->mDesc.position[1] = b->mPosition.y; b->mDesc.position[2] = b->mPosition.z; b->mDesc.rotation[0] = inRotation.x; b->mDesc.rotation[1] = inRotation.y; b->mDesc.rotation[2] = inRotation.z; b->mDesc.rotation[3] = inRotation.w; return; }
@@ -990,6 +1043,7 @@ inline void BodyInterface::SetLinearAndAngularVelocity(const BodyID &id, const V
 	Body *b = const_cast<Body *>(TryGet(id));
 	if (b == nullptr || b->mMotionType == EMotionType::Static) return;
 	b->Sync();
+	mSystem->MarkMirrorNewer(id);
 	b->mLinearVelocity = lv; b->mAngularVelocity = av;
 	if (!b->mInWorld) { memcpy(b->mDesc.linear_velocity, &lv, 12); memcpy(b->mDesc.angular_velocity, &av, 12); return; }
 	Flush();
@@ -1034,6 +1088,7 @@ inline void BodyInterface::SetActive(const BodyID &id, bool inActive)
 	Flush();
 	if (inActive) b2j_bodies_activate(World(), &bid, 1); else b2j_bodies_deactivate(World(), &bid, 1);
 	b->Sync();
+	mSystem->MarkMirrorNewer(id);
 	b->mActive = inActive;
 	if (!inActive) { b->mLinearVelocity = Vec3::sZero(); b->mAngularVelocity = Vec3::sZero(); } // BodyManager::DeactivateBodies resets the velocities
 }

@@ -78,6 +78,18 @@ def _check_api_tour(flib):
             err, _ = fs.update()
             assert err == 0
         compare(f"after the steps of phase {phase}")
+    # the BodyInterface getters (flat array fast path / Body mirror) agree with the device state for every tour body
+    ref.step()
+    n_dyn = fs.flib.lib.b2jf_scene_num_dynamic(fs.h)
+    out = np.zeros((n_dyn, 3), np.float32)
+    assert fs.step_e2e(1.0 / 60.0, None, out) == 0
+    ids, rs = ref.state(16).ids, ref.state(16)
+    fs.world.n = 16
+    gs = fs.world.state()
+    got = {tuple(np.round(p, 6)) for p in out}
+    want = {tuple(np.round(gs.pos[i], 6)) for i in range(1, 16) if ids[i] != 0xffffffff}
+    assert got == want, "GetCenterOfMassPosition through the facade differs from the device state"
+    assert R.compare_states(rs, gs)["pos"] <= 1.0
     fs.close()
     ref.close()
 
