@@ -55,6 +55,11 @@ class BodyState(C.Structure):
     ]
 
 
+class BodyParams(C.Structure):
+    """b2j_body_params: optional [n] float arrays (NULL = leave untouched)."""
+    _fields_ = [(n, C.c_void_p) for n in ("friction", "restitution", "gravity_factor", "linear_damping", "angular_damping", "max_linear_velocity", "max_angular_velocity")]
+
+
 class CachedBodyPair(C.Structure):
     _fields_ = [("body1", C.c_uint32), ("body2", C.c_uint32), ("delta_position", c_f3), ("delta_rotation", c_f3),
                 ("first_manifold", C.c_uint32), ("num_manifolds", C.c_uint32)]
