@@ -9,10 +9,16 @@ REL_TOL = 1e-4   # north star: 1e-4 relative
 ABS_TOL = 1e-5   # or 1e-5 m absolute
 
 
-def single_step_parity(api, scene, p0=0, p1=0, warm=0, dt=1.0 / 60.0, collision_steps=1, check_events=True):
+FEATURES = ["kinematic", "sensor", "dof_plane2d", "gyroscopic", "step_overrides", "no_manifold_reduction", "two_moving_layers", "kinematic_vs_nondynamic", "zoo"]
+"""Variants of the `feature` scene of oracle/ref_harness.cpp (sSceneFeature): motion types, body flags (B2J_BODY_SENSOR,
+B2J_BODY_GYROSCOPIC, B2J_BODY_KIN_VS_NONDYN, B2J_BODY_USE_MANIFOLD_REDUCTION off, B2J_BODY_ALLOW_SLEEPING), allowed DOFs, per body
+solver step overrides, two moving broadphase layers; `zoo` = all of them in one world."""
+
+
+def single_step_parity(api, scene, p0=0, p1=0, warm=0, dt=1.0 / 60.0, collision_steps=1, check_events=True, warm_threads=1):
     ref = R.RefWorld(scene, p0, p1)
     for _ in range(warm):
-        ref.step(dt)
+        ref.step(dt, 1, warm_threads)  # (the deterministic build gives the same state for any thread count)
     world = ref.export(api)
     out = {}
     # (i) broadphase candidate pairs of the snapshot
@@ -20,7 +26,7 @@ def single_step_parity(api, scene, p0=0, p1=0, warm=0, dt=1.0 / 60.0, collision_
     assert np.array_equal(rp, gp), f"broadphase pair sets differ: ref {len(rp)} got {len(gp)}"
     out["pairs"] = len(rp)
     err, stats = world.step(dt, collision_steps)
-    ref_err = ref.step(dt, collision_steps)
+    ref_err = ref.step(dt, collision_steps, warm_threads)
     assert err == ref_err, (err, ref_err)
     # (ii) body pairs processed (every candidate pair gets a cache entry) and manifolds / contact point counts
     rc, gc = R.cache_summary(*ref.cache()), R.cache_summary(*world.cache())

@@ -61,6 +61,46 @@ def test_batch_matches_single_world_gpu(gpu_api, scene, p0, p1, n_worlds, steps)
     _check_batch(gpu_api, flib, scene, p0, p1, n_worlds, steps)
 
 
+def _check_batch_vs_oracle(api, scene, p0, p1, n_worlds, steps, check_every):
+    """n clones of a reference-created world against the REFERENCE itself stepped alone (not against this library's single world)."""
+    ref = R.RefWorld(scene, p0, p1)
+    proto = ref.export(api)          # step 0: empty contact cache, as b2j_batch_create requires
+    n = ref.num_slots()
+    batch = api.b2j_batch_create(proto.h, n_worlds, 0, 0)
+    assert batch, api.last_error()
+    stats = _capi.StepStats()
+    worst_all = {}
+    for step in range(1, steps + 1):
+        assert api.b2j_batch_step(batch, 1.0 / 60.0, 1, C.byref(stats)) == 0, api.last_error()
+        ref.step(1.0 / 60.0, 1, 0)
+        if step % check_every == 0 or step == steps:
+            want = ref.state()
+            for w in sorted({0, 1, n_worlds // 2, n_worlds - 1}):
+                got = _batch_state(api, batch, w, n)
+                got.ids = want.ids
+                worst = R.compare_states(want, got)
+                for k in ("pos", "rot", "lin", "ang"):
+                    assert worst[k] <= 1.0, f"step {step} world {w}: {k} out of tolerance vs the reference: {worst}"
+                    worst_all[k] = max(worst_all.get(k, 0.0), worst[k])
+                assert np.array_equal(want.active_index != 0xffffffff, got.active_index != 0xffffffff), f"step {step} world {w}: active flags"
+    api.b2j_batch_destroy(batch)
+    proto.close()
+    ref.close()
+    return worst_all
+
+
+def test_batch_vs_oracle_hostsim(hostsim_api):
+    _check_batch_vs_oracle(hostsim_api, "pyramid", 4, 0, 3, 40, 10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 15, 0, 64, 60), ("feature", 8, 0, 64, 120)], ids=["pyramid-64worlds", "feature_zoo-64worlds"])
+def test_batch_vs_oracle_gpu(gpu_api, ref_available, scene, p0, p1, n_worlds, steps):
+    """64 world batch against the reference stepped alone (the batch had only been compared with this library's own
+    single world)."""
+    _check_batch_vs_oracle(gpu_api, scene, p0, p1, n_worlds, steps, 20)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("groups", [2, 3])
 def test_batch_groups_gpu(gpu_api, groups, monkeypatch):

@@ -22,8 +22,35 @@ def test_single_step_parity(gpu_api, ref_available, scene, p0, p1, warm):
     assert out["stats"]["kernel_launches"] > 0
 
 
+FEATURE_CASES = [(name, warm) for name in parity.FEATURES for warm in ((0, 10, 30, 60, 120, 250) if name == "zoo" else (1, 30, 60, 120))]
+
+
+@pytest.mark.parametrize("feature,warm", FEATURE_CASES, ids=[f"{n}-step{w}" for n, w in FEATURE_CASES])
+def test_feature_single_step_parity(gpu_api, ref_available, feature, warm):
+    """Motion types (kinematic movers / platforms), B2J_BODY_SENSOR (static, kinematic and dynamic sensors, the kinematic vs sensor
+    pair rule), allowed DOFs (Plane2D, translation only, rotation only), B2J_BODY_GYROSCOPIC, per body velocity / position step
+    overrides, B2J_BODY_USE_MANIFOLD_REDUCTION off, two moving broadphase layers, B2J_BODY_KIN_VS_NONDYN -- and all in one world."""
+    out = parity.single_step_parity(gpu_api, "feature", parity.FEATURES.index(feature), 0, warm)
+    assert out["stats"]["kernel_launches"] > 0
+
+
+def test_feature_zoo_multi_step(gpu_api, ref_available):
+    history = parity.multi_step_drift(gpu_api, "feature", parity.FEATURES.index("zoo"), 0, 0, steps=150)
+    for k in ("pos", "rot", "lin", "ang"):
+        assert max(h[k] for h in history) <= 1.0, (k, [h[k] for h in history])
+
+
 def test_two_collision_steps(gpu_api, ref_available):
     parity.single_step_parity(gpu_api, "pyramid", 4, 0, 20, collision_steps=2)
+    parity.single_step_parity(gpu_api, "feature", parity.FEATURES.index("zoo"), 0, 30, collision_steps=3)
+
+
+@pytest.mark.parametrize("bodies,warm", [(100000, 40), (100000, 90)], ids=["pile100k-step40", "pile100k-step90"])
+def test_pile_100k_single_step_parity(gpu_api, ref_available, bodies, warm):
+    """One snapshot step of a 100 000 body pile (the size the bench's CPU leg steps): the cooperative grid scheduler, the ordered
+    convex pair queue and every counter / queue at a size where they actually fill up."""
+    out = parity.single_step_parity(gpu_api, "pile", bodies, 15, warm, warm_threads=0, check_events=False)
+    assert out["pairs"] > 100000 and out["stats"]["num_constraints"] > 10000, out["stats"]
 
 
 def test_pyramid_long_run_energy_and_heights(gpu_api, ref_available):

@@ -18,6 +18,15 @@ def test_single_step_parity(hostsim_api, scene, p0, p1, warm):
     parity.single_step_parity(hostsim_api, scene, p0, p1, warm)
 
 
+FEATURE_CASES = [(name, warm) for name in parity.FEATURES for warm in ((0, 30, 120) if name != "zoo" else (10, 60, 250))]
+
+
+@pytest.mark.parametrize("feature,warm", FEATURE_CASES, ids=[f"{n}-step{w}" for n, w in FEATURE_CASES])
+def test_feature_single_step_parity(hostsim_api, feature, warm):
+    """Motion types, body flags, DOF locks, step overrides, broadphase layers (see parity.FEATURES)."""
+    parity.single_step_parity(hostsim_api, "feature", parity.FEATURES.index(feature), 0, warm)
+
+
 def test_two_collision_steps(hostsim_api):
     parity.single_step_parity(hostsim_api, "pyramid", 4, 0, 20, collision_steps=2)
 
