@@ -317,6 +317,11 @@ typedef struct b2j_activation_event {
 uint32_t b2j_events_drain(b2j_world *w, b2j_contact_event *out, uint32_t cap);
 uint32_t b2j_activation_events_drain(b2j_world *w, b2j_activation_event *out, uint32_t cap);
 
+/* PhysicsSystem::SetContactListener / SetBodyActivationListener (PhysicsSystem.h:62-68) as seen by the device: with a kind of
+ * recording off the step writes no such events (no buffer traffic, the drains return 0). Default: both on for a world made by
+ * b2j_world_create (buffers are allocated on first use), always off for batched worlds. */
+int b2j_world_set_event_recording(b2j_world *w, int contact_events, int activation_events);
+
 /* ---- parity hooks (debug; read the intermediate products of the LAST step) ------------------------------------ */
 
 /* Candidate body pairs of the broadphase as (min id, max id), sorted; returns the total count. */

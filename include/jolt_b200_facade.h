@@ -571,7 +571,7 @@ public:
 	void AddBodiesAbort(BodyID *ioBodies, int inNumber, AddState inAddState) { (void)ioBodies; (void)inNumber; (void)inAddState; }
 	void AddBodies(const BodyID *inBodies, int inNumber, EActivation inActivationMode);
 	void RemoveBody(const BodyID &inBodyID);
-	void RemoveBodies(BodyID *ioBodies, int inNumber) { for (int i = 0; i < inNumber; ++i) RemoveBody(ioBodies[i]); }
+	void RemoveBodies(BodyID *ioBodies, int inNumber);
 	void DestroyBody(const BodyID &inBodyID);
 	void ActivateBody(const BodyID &inBodyID) { SetActive(inBodyID, true); }
 	void DeactivateBody(const BodyID &inBodyID) { SetActive(inBodyID, false); }
@@ -655,6 +655,7 @@ public:
 		desc.gravity[0] = mGravity.x; desc.gravity[1] = mGravity.y; desc.gravity[2] = mGravity.z;
 		desc.device = inDevice;
 		mWorld = b2j_world_create(&desc);
+		SyncEventRecording();
 		mBodies.clear();
 		mBodies.reserve(1024);
 		mMaxBodies = inMaxBodies;
@@ -665,9 +666,9 @@ public:
 	Vec3 GetGravity() const { return mGravity; }
 	void SetPhysicsSettings(const PhysicsSettings &s) { mSettings = s; if (mWorld) { b2j_settings bs; FillSettings(bs); b2j_world_set_settings(mWorld, &bs); } }
 	const PhysicsSettings &GetPhysicsSettings() const { return mSettings; }
-	void SetContactListener(ContactListener *l) { mContactListener = l; }
+	void SetContactListener(ContactListener *l) { mContactListener = l; SyncEventRecording(); }
 	ContactListener *GetContactListener() const { return mContactListener; }
-	void SetBodyActivationListener(BodyActivationListener *l) { mActivationListener = l; }
+	void SetBodyActivationListener(BodyActivationListener *l) { mActivationListener = l; SyncEventRecording(); }
 	BodyActivationListener *GetBodyActivationListener() const { return mActivationListener; }
 	BodyInterface &GetBodyInterface() { return mBodyInterface; }
 	BodyInterface &GetBodyInterfaceNoLock() { return mBodyInterface; }
@@ -679,7 +680,7 @@ public:
 	void GetBodies(BodyIDVector &outBodyIDs) const
 	{
 		outBodyIDs.clear();
-		for (const std::unique_ptr<Body> &b : mBodies) if (b && !b->mDestroyed && b->mInWorld) outBodyIDs.push_back(b->mID);
+		for (const std::unique_ptr<Body> &b : mBodies) if (b && !b->mDestroyed) outBodyIDs.push_back(b->mID); // BodyManager::GetBodyIDs: every created body, added or not
 	}
 	void GetActiveBodies(EBodyType inType, BodyIDVector &outBodyIDs) const
 	{
@@ -712,6 +713,9 @@ private:
 	friend class BodyInterface;
 	friend class Body;
 
+	// the device records contact / activation events only while a listener is attached (no event traffic otherwise)
+	void SyncEventRecording() { if (mWorld) b2j_world_set_event_recording(mWorld, mContactListener != nullptr, mActivationListener != nullptr); }
+
 	void FillSettings(b2j_settings &s) const
 	{
 		b2j_settings_default(&s);
@@ -742,6 +746,29 @@ private:
 		b2j_bodies_get_state(mWorld, nullptr, n, &st);
 		++mStateGeneration; // Body::Sync picks the new state up on first access
 		for (uint8 &f : mSlotFlags) f &= 1; // the arrays are current for every body in the world
+	}
+
+	// current device state of a few bodies straight into their Body mirrors (bodies whose state changed through the interface since
+	// the last Update, e.g. woken / pushed and then removed before the next step)
+	void RefreshBodies(const std::vector<uint32> &inIDs)
+	{
+		uint32 n = (uint32)inIDs.size();
+		std::vector<float> pos(3 * n), rot(4 * n), lin(3 * n), ang(3 * n);
+		std::vector<uint32> active(n);
+		b2j_body_state st;
+		memset(&st, 0, sizeof(st));
+		st.position = pos.data(); st.rotation = rot.data(); st.linear_velocity = lin.data(); st.angular_velocity = ang.data(); st.active_index = active.data();
+		if (b2j_bodies_get_state(mWorld, inIDs.data(), n, &st) != 0) return;
+		for (uint32 i = 0; i < n; ++i)
+		{
+			Body *b = mBodies[inIDs[i] & 0x7fffffu].get();
+			b->mPosition = Vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+			b->mRotation = Quat(rot[4 * i], rot[4 * i + 1], rot[4 * i + 2], rot[4 * i + 3]);
+			b->mLinearVelocity = Vec3(lin[3 * i], lin[3 * i + 1], lin[3 * i + 2]);
+			b->mAngularVelocity = Vec3(ang[3 * i], ang[3 * i + 1], ang[3 * i + 2]);
+			b->mActive = active[i] != B2J_INACTIVE_INDEX;
+			b->mSyncGeneration = mStateGeneration;
+		}
 	}
 
 	void ReplayEvents()
@@ -965,7 +992,14 @@ inline void BodyInterface::AddBodies(const BodyID *inBodies, int inNumber, EActi
 		b->mInWorld = true;
 		b->mSyncGeneration = sys.mStateGeneration; // the creation state is current until the next Update
 		sys.mSlotFlags[b->mID.GetIndex()] = 1 | 2;
-		sys.mPendingAdd.push_back(b->mDesc);
+		// the body enters the world with the state it HAS (creation state, or the state it left the world with / was given since:
+		// BodyManager keeps the Body object between RemoveBody and AddBody), not with its creation time descriptor
+		b2j_body_desc &d = b->mDesc;
+		d.position[0] = b->mPosition.x; d.position[1] = b->mPosition.y; d.position[2] = b->mPosition.z;
+		d.rotation[0] = b->mRotation.x; d.rotation[1] = b->mRotation.y; d.rotation[2] = b->mRotation.z; d.rotation[3] = b->mRotation.w;
+		d.linear_velocity[0] = b->mLinearVelocity.x; d.linear_velocity[1] = b->mLinearVelocity.y; d.linear_velocity[2] = b->mLinearVelocity.z;
+		d.angular_velocity[0] = b->mAngularVelocity.x; d.angular_velocity[1] = b->mAngularVelocity.y; d.angular_velocity[2] = b->mAngularVelocity.z;
+		sys.mPendingAdd.push_back(d);
 		if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static)
 		{
 			sys.mPendingActivate.push_back(b->mID.mID);
@@ -996,16 +1030,35 @@ inline void BodyInterface::Flush()
 	}
 }
 
-inline void BodyInterface::RemoveBody(const BodyID &inBodyID)
+inline void BodyInterface::RemoveBody(const BodyID &inBodyID) { BodyID id = inBodyID; RemoveBodies(&id, 1); }
+
+// BodyInterface::RemoveBodies (BodyInterface.cpp:259-281): one b2j_bodies_remove call for the whole batch
+inline void BodyInterface::RemoveBodies(BodyID *ioBodies, int inNumber)
 {
-	Body *b = const_cast<Body *>(TryGet(inBodyID));
-	if (b == nullptr || !b->mInWorld) return;
+	PhysicsSystem &sys = *mSystem;
+	std::vector<uint32> ids;
+	std::vector<Body *> bodies;
+	for (int i = 0; i < inNumber; ++i)
+	{
+		Body *b = const_cast<Body *>(TryGet(ioBodies[i]));
+		if (b == nullptr || !b->mInWorld) continue;
+		bodies.push_back(b);
+		ids.push_back(b->mID.mID);
+	}
+	if (ids.empty()) return;
 	Flush();
-	uint32 id = inBodyID.mID;
-	b2j_bodies_remove(World(), &id, 1);
-	b->Sync(); // the Body keeps the state it left the world with
-	b->mInWorld = false; b->mActive = false;
-	mSystem->mSlotFlags[inBodyID.GetIndex()] = 0;
+	// bodies changed through the interface since the last Update have a mirror that is newer than the downloaded arrays
+	std::vector<uint32> stale;
+	for (Body *b : bodies) if (b->mSyncGeneration != sys.mStateGeneration || (sys.mSlotFlags[b->mID.GetIndex()] & 2)) stale.push_back(b->mID.mID);
+	if (!stale.empty()) sys.RefreshBodies(stale);
+	b2j_bodies_remove(World(), ids.data(), (uint32)ids.size());
+	for (Body *b : bodies)
+	{
+		b->Sync(); // the Body keeps the pose it left the world with
+		if (b->mActive) { b->mLinearVelocity = Vec3::sZero(); b->mAngularVelocity = Vec3::sZero(); } // BodyManager::DeactivateBodies (BodyManager.cpp:529-568)
+		b->mInWorld = false; b->mActive = false;
+		sys.mSlotFlags[b->mID.GetIndex()] = 0;
+	}
 }
 
 inline void BodyInterface::DestroyBody(const BodyID &inBodyID)

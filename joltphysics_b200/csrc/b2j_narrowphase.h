@@ -137,6 +137,10 @@ struct KProcessPairs
 		bool handled = false;
 		if (w.settings.use_body_pair_contact_cache)
 			old = pair_table_find(w, w.read_cache, cb1, cb2);
+		// The table is keyed by body SLOTS; the reference keys the cache by the full BodyID (index + sequence number, BodyPair hash):
+		// an entry left behind by a destroyed body whose slot was reused is a miss, for the pair test and for the manifold lookup
+		if (old != 0xffffffffu && (w.read_cache.pairs[old].body1 != id1 || w.read_cache.pairs[old].body2 != id2))
+			old = 0xffffffffu;
 		if (old != 0xffffffffu && !((i1.flags | i2.flags) & B2J_BODY_INVALIDATE_CACHE))
 		{
 			const CachedPair &in = w.read_cache.pairs[old];

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <map>
 #include <stdio.h>
 #include <stdlib.h>
 #include <typeinfo>
@@ -162,6 +163,8 @@ struct Runtime
 	void prof_reset() { prof_collect(); prof_ms.assign(prof_ms.size(), 0.0); prof_launches.assign(prof_launches.size(), 0); }
 
 	int num_sms = 148;
+	std::map<const void *, bool> func_configured;   // kernels whose function attributes were set on this runtime's device
+	std::map<const void *, int> func_blocks_per_sm; // occupancy of the cooperative kernels on this runtime's device
 	uint32_t launches = 0;          // kernels launched since the last reset
 	void *cub_temp = nullptr;
 	size_t cub_temp_size = 0;
@@ -365,7 +368,9 @@ struct Runtime
 		if (cap == 0) return;
 		++launches;
 #ifndef B2J_HOSTSIM
-		static bool configured = false;
+		// (per Runtime = per device and per launching thread: a function attribute is a per device setting, and the groups of a batch launch
+		// from their own host threads)
+		bool &configured = func_configured[(const void *)run_kernel_warp_smem<K, S>];
 		if (!configured)
 		{
 			cudaFuncSetAttribute(run_kernel_warp_smem<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(S) < 227 * 1024? 8 * sizeof(S) : 4 * sizeof(S)));

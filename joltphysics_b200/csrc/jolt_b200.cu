@@ -20,6 +20,14 @@
 
 using namespace b2j;
 
+// Every C ABI entry that touches a world first selects the world's device (calls may come from any thread, and a process may hold
+// worlds on several devices: the reference's PhysicsSystem has no such affinity, so the boundary must not have one either)
+#ifndef B2J_HOSTSIM
+#define B2J_DEVICE_GUARD(W) do { cudaSetDevice((W)->rt.device); } while (0)
+#else
+#define B2J_DEVICE_GUARD(W) do { } while (0)
+#endif
+
 // ---- small API kernels ---------------------------------------------------------------------------------------------
 namespace b2j {
 
@@ -93,6 +101,61 @@ struct KClearActiveIndex
 {
 	DWorld w;
 	B2J_D void operator()(uint32_t ai) const { w.active_index[w.active[ai]] = B2J_INACTIVE_INDEX; }
+};
+
+// b2j_bodies_deactivate / b2j_bodies_remove on the device: keep[ai] = 0 for the listed bodies that are active (ids are validated
+// against the slot's current id: a stale id never touches the body that lives in the slot now)
+struct KFillU32
+{
+	uint32_t *dst; uint32_t value;
+	B2J_D void operator()(uint32_t i) const { dst[i] = value; }
+};
+
+struct KMarkDeactivate
+{
+	DWorld w; const uint32_t *ids; uint32_t *keep;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = slot_of(ids[i]);
+		if (b >= w.max_bodies || w.info[b].id != ids[i]) return;
+		uint32_t ai = w.active_index[b];
+		if (ai != B2J_INACTIVE_INDEX) keep[ai] = 0;
+	}
+};
+
+// BodyManager::DeactivateBodies (BodyManager.cpp:529-568): leaves the active list, velocities reset
+struct KApiDeactivate
+{
+	DWorld w; const uint32_t *keep;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		if (keep[ai] != 0) return;
+		uint32_t b = w.active[ai];
+		w.linear_velocity[b] = f4(0, 0, 0, 0);
+		w.angular_velocity[b] = f4(0, 0, 0, 0);
+		w.active_index[b] = B2J_INACTIVE_INDEX;
+	}
+};
+
+struct KClearBodies
+{
+	DWorld w; const uint32_t *ids;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = slot_of(ids[i]);
+		if (b < w.max_bodies && w.info[b].id == ids[i]) w.info[b].id = B2J_INVALID_ID;
+	}
+};
+
+// PhysicsSystem::WereBodiesInContact through the device pair table of the read cache
+struct KWereInContact
+{
+	DWorld w; uint32_t id1, id2; uint32_t *out;
+	B2J_D void operator()(uint32_t) const
+	{
+		uint32_t e = pair_table_find(w, w.read_cache, slot_of(id1), slot_of(id2));
+		*out = (e != 0xffffffffu && w.read_cache.pairs[e].body1 == id1 && w.read_cache.pairs[e].body2 == id2 && w.read_cache.pairs[e].num_manifolds > 0)? 1u : 0u;
+	}
 };
 
 struct KGetState
@@ -370,6 +433,8 @@ struct b2j_world
 	// host mirrors
 	std::vector<uint32_t> h_ids;           // per slot: id or invalid
 	std::vector<uint8_t> h_layer;          // per slot: broadphase layer
+	std::vector<uint8_t> h_static;         // per slot: 1 = static body (never on the active list)
+	std::vector<uint8_t> h_mark;           // per slot scratch marks of the bulk API calls (all zero between calls)
 	std::vector<std::vector<uint32_t>> layer_bodies;
 	std::vector<uint8_t> layer_list_dirty, layer_needs_build, layer_has_moving;
 	uint32_t num_bodies = 0, num_active = 0, num_slots = 0;
@@ -412,6 +477,8 @@ struct b2j_world
 	uint32_t *d_woken_keys = nullptr;
 	b2j_activation_event *d_act_events = nullptr;
 	uint32_t max_events = 0, max_act_events = 0;
+	b2j_contact_event *events_buf = nullptr;            // owned buffers; nc.events / d_act_events point at them while recording is on
+	b2j_activation_event *act_events_buf = nullptr;
 	float *d_energy = nullptr;
 
 	float prev_dt = 0.0f;
@@ -566,8 +633,10 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	// (a3, a5..a9) find pairs + narrow phase; repeated for the bodies woken up by contacts until no new body wakes up
 	uint32_t first_active = 0, n_query = W->num_active;
 	uint32_t woken_total = 0;
-	for (int round = 0; round < 64; ++round)
+	const int max_rounds = 64;
+	for (int round = 0; ; ++round)
 	{
+		if (round == max_rounds) { last_error() = "bodies were still waking each other up after 64 broadphase rounds in one step"; return false; }
 		{
 			KFindPairs k; k.w = d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l]; k.pairs = W->nc.pairs; k.first = first_active; k.query_leaves = nullptr;
 			if (round == 0)
@@ -684,7 +753,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		bool grid_sched = false;
 		if (!block_sched)
 		{
-			static int blocks_per_sm = 0;
+			int &blocks_per_sm = rt.func_blocks_per_sm[(const void *)sched_grid_kernel];
 			if (blocks_per_sm == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, sched_grid_kernel, 256, 0);
 			if (blocks_per_sm > 0)
 			{
@@ -1044,10 +1113,10 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	else
 	{
 		W->max_events = 2 * d.max_constraints + 16;
-		nc.events = rt.alloc<b2j_contact_event>(W->max_events, false);
+		nc.events = W->events_buf = rt.alloc<b2j_contact_event>(W->max_events, false);
 		nc.max_events = W->max_events;
 		W->max_act_events = 2 * nbod;
-		W->d_act_events = rt.alloc<b2j_activation_event>(W->max_act_events, false);
+		W->d_act_events = W->act_events_buf = rt.alloc<b2j_activation_event>(W->max_act_events, false);
 	}
 	W->d_woken_sorted = rt.alloc<uint32_t>(nbod); W->d_woken_keys = rt.alloc<uint32_t>(nbod);
 	W->d_round_begin = rt.alloc<uint32_t>(1);
@@ -1094,6 +1163,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	W->layer_has_moving.assign(nb, 0);
 	W->h_ids.assign(nbod, B2J_INVALID_ID);
 	W->h_layer.assign(nbod, 0);
+	W->h_static.assign(nbod, 0);
 	W->shapes_dirty = true;
 #ifndef B2J_HOSTSIM
 	cudaEventCreate(&W->ev_begin);
@@ -1108,6 +1178,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 void b2j_world_destroy(b2j_world *W)
 {
 	if (W == nullptr) return;
+	B2J_DEVICE_GUARD(W);
 	Runtime &rt = W->rt;
 	rt.sync();
 	DWorld &d = W->d;
@@ -1122,10 +1193,10 @@ void b2j_world_destroy(b2j_world *W)
 	}
 	NarrowCtx &nc = W->nc;
 	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
-	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(nc.events);
+	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(W->events_buf);
 	rt.free_(W->d_mesh_scratch);
 	for (int i = 0; i < 2; ++i) { rt.free_(W->d_collide_keys[i]); rt.free_(W->d_collide_vals[i]); }
-	rt.free_(W->d_act_events); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
+	rt.free_(W->act_events_buf); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
 	rt.free_(sc.con.cp); rt.free_(sc.con.hdr);
 	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count);
@@ -1154,8 +1225,38 @@ int b2j_world_set_settings(b2j_world *W, const b2j_settings *s) { W->d.settings 
 int b2j_world_get_settings(const b2j_world *W, b2j_settings *s) { *s = W->d.settings; return 0; }
 int b2j_world_set_previous_delta_time(b2j_world *W, float dt) { W->prev_dt = dt; return 0; }
 
+int b2j_world_set_event_recording(b2j_world *W, int contact_events, int activation_events)
+{
+	B2J_DEVICE_GUARD(W);
+	Runtime &rt = W->rt;
+	if (W->num_worlds > 1 && (contact_events || activation_events)) { last_error() = "events are not recorded for batched worlds"; return -1; }
+	rt.sync();
+	if (contact_events && W->events_buf == nullptr)
+	{
+		W->max_events = 2 * W->d.max_constraints + 16;
+		W->events_buf = rt.alloc<b2j_contact_event>(W->max_events, false);
+		if (W->events_buf == nullptr) return -1;
+	}
+	if (activation_events && W->act_events_buf == nullptr)
+	{
+		W->max_act_events = 2 * W->d.max_bodies;
+		W->act_events_buf = rt.alloc<b2j_activation_event>(W->max_act_events, false);
+		if (W->act_events_buf == nullptr) return -1;
+	}
+	// (the buffers are sized for the world limits, 2 x 148 bytes per contact constraint: released while nobody listens)
+	if (!contact_events) rt.free_(W->events_buf);
+	if (!activation_events) rt.free_(W->act_events_buf);
+	W->nc.events = W->events_buf;
+	W->nc.max_events = contact_events? W->max_events : 0;
+	W->d_act_events = W->act_events_buf;
+	if (!contact_events) W->last_num_events = 0;
+	if (!activation_events) W->last_num_act_events = 0;
+	return 0;
+}
+
 int b2j_world_set_profiling(b2j_world *W, int on)
 {
+	B2J_DEVICE_GUARD(W);
 	W->rt.sync();
 	W->rt.prof_reset();
 	W->rt.profiling = on != 0;
@@ -1164,6 +1265,7 @@ int b2j_world_set_profiling(b2j_world *W, int on)
 
 uint32_t b2j_world_get_profile(b2j_world *W, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap)
 {
+	B2J_DEVICE_GUARD(W);
 	W->rt.sync();
 	W->rt.prof_collect();
 	std::lock_guard<std::mutex> lock(profile_mutex());
@@ -1250,6 +1352,7 @@ int32_t b2j_shape_mesh(b2j_world *W, const b2j_mesh_desc *m)
 
 int b2j_bodies_add(b2j_world *W, const b2j_body_desc *bodies, uint32_t n)
 {
+	B2J_DEVICE_GUARD(W);
 	if (n == 0) return 0;
 	Runtime &rt = W->rt;
 	upload_shapes(W);
@@ -1259,6 +1362,7 @@ int b2j_bodies_add(b2j_world *W, const b2j_body_desc *bodies, uint32_t n)
 		uint32_t slot = slot_of(bodies[i].id);
 		if (slot >= W->d.max_bodies) { last_error() = "body index out of range"; return -1; }
 		if (W->h_ids[slot] != B2J_INVALID_ID) { last_error() = "body slot already in use"; return -1; }
+		if (bodies[i].motion_type > B2J_MOTION_DYNAMIC) { last_error() = "invalid motion type"; return -1; }
 		if (bodies[i].shape < 0 || bodies[i].shape >= (int32_t)W->h_shapes.size()) { last_error() = "invalid shape id"; return -1; }
 		if (bodies[i].object_layer >= W->d.num_object_layers) { last_error() = "invalid object layer"; return -1; }
 	}
@@ -1268,6 +1372,7 @@ int b2j_bodies_add(b2j_world *W, const b2j_body_desc *bodies, uint32_t n)
 		W->h_ids[slot] = bodies[i].id;
 		uint8_t layer = W->t_o2bp[bodies[i].object_layer];
 		W->h_layer[slot] = layer;
+		W->h_static[slot] = bodies[i].motion_type == B2J_MOTION_STATIC? 1 : 0;
 		W->layer_bodies[layer].push_back(slot);
 		W->layer_list_dirty[layer] = 1;
 		W->layer_needs_build[layer] = 1;
@@ -1276,50 +1381,92 @@ int b2j_bodies_add(b2j_world *W, const b2j_body_desc *bodies, uint32_t n)
 		if (bodies[i].active && bodies[i].motion_type != B2J_MOTION_STATIC) to_activate.push_back(bodies[i].id);
 	}
 	W->num_bodies += n;
-	b2j_body_desc *tmp = rt.alloc<b2j_body_desc>(n, false);
-	if (tmp == nullptr) return -1;
-	rt.upload(tmp, bodies, n);
+	rt.stage_begin((size_t)n * sizeof(b2j_body_desc));
+	b2j_body_desc *h_desc = nullptr;
+	b2j_body_desc *tmp = rt.stage_alloc<b2j_body_desc>(n, &h_desc);
+	memcpy(h_desc, bodies, (size_t)n * sizeof(b2j_body_desc));
+	rt.stage_to_device(0, rt.stage_used);
 	sync_dworld(W);
 	KAddBodies k; k.w = W->d; k.descs = tmp;
 	rt.launch(k, n);
 	rt.sync();
-	rt.free_(tmp);
 	if (!to_activate.empty())
 		return b2j_bodies_activate(W, to_activate.data(), (uint32_t)to_activate.size());
 	return rt.check("b2j_bodies_add")? 0 : -1;
 }
 
-int b2j_bodies_remove(b2j_world *W, const uint32_t *ids, uint32_t n)
+// ids must name live bodies of this world: a stale id (destroyed body, reused slot) or an index out of range is an error
+static bool validate_ids(b2j_world *W, const uint32_t *ids, uint32_t n, const char *what)
 {
-	if (b2j_bodies_deactivate(W, ids, n) != 0) return -1;
 	for (uint32_t i = 0; i < n; ++i)
 	{
 		uint32_t slot = slot_of(ids[i]);
-		if (slot >= W->d.max_bodies || W->h_ids[slot] != ids[i]) continue;
+		if (slot >= W->d.max_bodies || W->h_ids[slot] != ids[i])
+		{
+			char buf[160];
+			snprintf(buf, sizeof(buf), "%s: id 0x%08x (element %u) is not a body of this world", what, ids[i], i);
+			last_error() = buf;
+			return false;
+		}
+	}
+	return true;
+}
+
+int b2j_bodies_remove(b2j_world *W, const uint32_t *ids, uint32_t n)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (ids == nullptr || !validate_ids(W, ids, n, "b2j_bodies_remove")) return -1;
+	if (b2j_bodies_deactivate(W, ids, n) != 0) return -1;
+	Runtime &rt = W->rt;
+	// the slots are marked empty on the device too (id validation of the by-id kernels, device queries)
+	rt.stage_begin((size_t)n * 4);
+	uint32_t *h = nullptr;
+	uint32_t *d_ids = rt.stage_alloc<uint32_t>(n, &h);
+	memcpy(h, ids, (size_t)n * 4);
+	rt.stage_to_device(0, rt.stage_used);
+	sync_dworld(W);
+	{ KClearBodies k; k.w = W->d; k.ids = d_ids; rt.launch(k, n); }
+	rt.sync();
+	uint32_t layers_touched = 0;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t slot = slot_of(ids[i]);
+		if (W->h_ids[slot] != ids[i]) continue; // listed twice
 		W->h_ids[slot] = B2J_INVALID_ID;
-		std::vector<uint32_t> &list = W->layer_bodies[W->h_layer[slot]];
-		list.erase(std::remove(list.begin(), list.end(), slot), list.end());
-		W->layer_list_dirty[W->h_layer[slot]] = 1;
-		W->layer_needs_build[W->h_layer[slot]] = 1;
+		layers_touched |= 1u << W->h_layer[slot];
 		W->num_bodies--;
 	}
-	return 0;
+	// one pass per touched layer list (a per body erase is O(n * m))
+	for (uint32_t l = 0; l < W->d.num_bp_layers; ++l)
+		if (layers_touched & (1u << l))
+		{
+			std::vector<uint32_t> &list = W->layer_bodies[l];
+			list.erase(std::remove_if(list.begin(), list.end(), [&](uint32_t slot) { return W->h_ids[slot] == B2J_INVALID_ID; }), list.end());
+			W->layer_list_dirty[l] = 1;
+			W->layer_needs_build[l] = 1;
+		}
+	return rt.check("b2j_bodies_remove")? 0 : -1;
 }
 
 int b2j_set_active_list(b2j_world *W, const uint32_t *ids, uint32_t n)
 {
+	B2J_DEVICE_GUARD(W);
 	Runtime &rt = W->rt;
 	sync_dworld(W);
 	{ KClearActiveIndex k; k.w = W->d; rt.launch(k, W->num_active); }
 	W->num_active = 0;
 	if (n > 0)
 	{
-		uint32_t *tmp = rt.alloc<uint32_t>(n, false);
-		rt.upload(tmp, ids, n);
+		if (ids == nullptr || !validate_ids(W, ids, n, "b2j_set_active_list")) return -1;
+		rt.stage_begin((size_t)n * 4);
+		uint32_t *h = nullptr;
+		uint32_t *tmp = rt.stage_alloc<uint32_t>(n, &h);
+		memcpy(h, ids, (size_t)n * 4);
+		rt.stage_to_device(0, rt.stage_used);
 		KSetActive k; k.w = W->d; k.ids = tmp; k.base = 0;
 		rt.launch(k, n);
 		rt.sync();
-		rt.free_(tmp);
 		W->num_active = n;
 	}
 	return rt.check("b2j_set_active_list")? 0 : -1;
@@ -1330,69 +1477,87 @@ int b2j_bodies_activate(b2j_world *W, const uint32_t *ids, uint32_t n)
 	// append the bodies that are not active yet, in argument order (BodyManager::ActivateBodies)
 	Runtime &rt = W->rt;
 	if (n == 0) return 0;
-	std::vector<uint32_t> idx(n);
-	uint32_t *d_ids = rt.alloc<uint32_t>(n, false), *d_idx = rt.alloc<uint32_t>(n, false);
-	rt.upload(d_ids, ids, n);
+	B2J_DEVICE_GUARD(W);
+	if (ids == nullptr || !validate_ids(W, ids, n, "b2j_bodies_activate")) return -1;
 	sync_dworld(W);
+	// which of them sleep? (only the device knows: bodies fall asleep during steps) one staging round trip
+	rt.stage_begin((size_t)n * 8);
+	uint32_t *h_ids = nullptr, *h_idx = nullptr;
+	uint32_t *d_ids = rt.stage_alloc<uint32_t>(n, &h_ids);
+	memcpy(h_ids, ids, (size_t)n * 4);
+	rt.stage_to_device(0, rt.stage_used);
+	size_t out_begin = rt.stage_used;
+	uint32_t *d_idx = rt.stage_alloc<uint32_t>(n, &h_idx);
 	{ KGetState k; memset(&k, 0, sizeof(k)); k.w = W->d; k.ids = d_ids; k.active_index = d_idx; rt.launch(k, n); }
-	rt.download(idx.data(), d_idx, n);
+	rt.stage_to_host(out_begin, rt.stage_used);
+	// first occurrence of every sleeping, non static body (a per slot mark instead of a search per id)
+	if (W->h_mark.size() < W->d.max_bodies) W->h_mark.assign(W->d.max_bodies, 0);
 	std::vector<uint32_t> add;
 	for (uint32_t i = 0; i < n; ++i)
-		if (idx[i] == B2J_INACTIVE_INDEX && std::find(add.begin(), add.end(), ids[i]) == add.end())
-			add.push_back(ids[i]);
+	{
+		uint32_t slot = slot_of(ids[i]);
+		if (h_idx[i] == B2J_INACTIVE_INDEX && !W->h_mark[slot] && W->h_static[slot] == 0) { W->h_mark[slot] = 1; add.push_back(ids[i]); }
+	}
+	for (uint32_t id : add) W->h_mark[slot_of(id)] = 0;
 	if (!add.empty())
 	{
-		rt.upload(d_ids, add.data(), add.size());
-		KSetActive k; k.w = W->d; k.ids = d_ids; k.base = W->num_active;
-		rt.launch(k, (uint32_t)add.size());
+		uint32_t na = (uint32_t)add.size();
+		rt.stage_begin((size_t)na * 8);
+		uint32_t *h_a = nullptr, *h_s = nullptr;
+		uint32_t *d_a = rt.stage_alloc<uint32_t>(na, &h_a), *d_s = rt.stage_alloc<uint32_t>(na, &h_s);
+		for (uint32_t i = 0; i < na; ++i) { h_a[i] = add[i]; h_s[i] = slot_of(add[i]); }
+		rt.stage_to_device(0, rt.stage_used);
+		KSetActive k; k.w = W->d; k.ids = d_a; k.base = W->num_active;
+		rt.launch(k, na);
 		// Body::ResetSleepTimer
-		rt.memset_(W->d.counters, 0, sizeof(StepCounters));
-		uint32_t *d_slots = rt.alloc<uint32_t>(add.size(), false);
-		std::vector<uint32_t> slots;
-		for (uint32_t id : add) slots.push_back(slot_of(id));
-		rt.upload(d_slots, slots.data(), slots.size());
-		KActivateWoken ka; ka.w = W->d; ka.woken_sorted = d_slots; ka.base = W->num_active; ka.woken_flag = W->nc.woken_flag; ka.events = nullptr; ka.max_events = 0;
-		rt.launch(ka, (uint32_t)add.size());
-		rt.sync();
-		rt.free_(d_slots);
-		W->num_active += (uint32_t)add.size();
+		KActivateWoken ka; ka.w = W->d; ka.woken_sorted = d_s; ka.base = W->num_active; ka.woken_flag = W->nc.woken_flag; ka.events = nullptr; ka.max_events = 0;
+		rt.launch(ka, na);
+		rt.sync(); // the staging buffer is reused by the next call
+		W->num_active += na;
 	}
-	rt.sync();
-	rt.free_(d_ids); rt.free_(d_idx);
 	return rt.check("b2j_bodies_activate")? 0 : -1;
 }
 
 int b2j_bodies_deactivate(b2j_world *W, const uint32_t *ids, uint32_t n)
 {
-	// rebuild the active list without the given bodies (stable; the reference swaps with the last element)
+	// On the device: mark, reset velocities, stable compaction of the active list (the reference swaps the last body into the hole,
+	// BodyManager.cpp:470-487; the order of the active list only decides which body of a pair queries the broadphase)
 	Runtime &rt = W->rt;
 	if (n == 0 || W->num_active == 0) return 0;
-	std::vector<uint32_t> active(W->num_active);
+	B2J_DEVICE_GUARD(W);
+	if (ids == nullptr) { last_error() = "b2j_bodies_deactivate: ids is null"; return -1; }
+	for (uint32_t i = 0; i < n; ++i)
+		if (slot_of(ids[i]) >= W->d.max_bodies) { last_error() = "b2j_bodies_deactivate: body index out of range"; return -1; }
 	sync_dworld(W);
-	rt.download(active.data(), W->d.active, W->num_active);
-	std::vector<uint32_t> remaining;
-	std::vector<uint32_t> removed_ids;
-	for (uint32_t slot : active)
-	{
-		bool remove = false;
-		for (uint32_t i = 0; i < n; ++i) if (slot_of(ids[i]) == slot) { remove = true; break; }
-		if (!remove) remaining.push_back(W->h_ids[slot]); else removed_ids.push_back(W->h_ids[slot]);
-	}
-	if (removed_ids.empty()) return 0;
-	if (b2j_set_active_list(W, remaining.data(), (uint32_t)remaining.size()) != 0) return -1;
-	// zero the velocities of the deactivated bodies
-	std::vector<float> zeros(removed_ids.size() * 3, 0.0f);
-	b2j_body_state st; memset(&st, 0, sizeof(st));
-	st.linear_velocity = zeros.data(); st.angular_velocity = zeros.data();
-	return b2j_bodies_set_state(W, removed_ids.data(), (uint32_t)removed_ids.size(), &st);
+	uint32_t na = W->num_active;
+	rt.stage_begin((size_t)n * 4);
+	uint32_t *h = nullptr;
+	uint32_t *d_ids = rt.stage_alloc<uint32_t>(n, &h);
+	memcpy(h, ids, (size_t)n * 4);
+	rt.stage_to_device(0, rt.stage_used);
+	{ KFillU32 k; k.dst = W->d_keep; k.value = 1; rt.launch(k, na); }
+	{ KMarkDeactivate k; k.w = W->d; k.ids = d_ids; k.keep = W->d_keep; rt.launch(k, n); }
+	{ KApiDeactivate k; k.w = W->d; k.keep = W->d_keep; rt.launch(k, na); }
+	rt.exclusive_scan(W->d_keep, W->d_keep_scan, na);
+	uint32_t *new_list = W->active_buf[W->active_cur ^ 1];
+	{ KCompactActive k; k.w = W->d; k.keep = W->d_keep; k.keep_scan = W->d_keep_scan; k.new_active = new_list; rt.launch(k, na); }
+	rt.memset_(W->d.counters, 0, sizeof(StepCounters));
+	{ KFinishCompact k; k.w = W->d; k.keep = W->d_keep; k.keep_scan = W->d_keep_scan; k.n = na; rt.launch(k, 1); }
+	W->active_cur ^= 1;
+	sync_dworld(W);
+	if (!read_counters(W)) return -1;
+	W->num_active = W->h_counters.new_active_count;
+	return rt.check("b2j_bodies_deactivate")? 0 : -1;
 }
 
 int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_state *out)
 {
+	B2J_DEVICE_GUARD(W);
 	if (n == 0) return 0;
 	Runtime &rt = W->rt;
 	sync_dworld(W);
-	if (ids == nullptr && n > W->d.max_bodies) { last_error() = "n exceeds max_bodies"; return -1; }
+	if (ids == nullptr && (uint64_t)W->get_state_first + n > W->d.max_bodies) { last_error() = "n exceeds max_bodies"; return -1; }
+	if (ids != nullptr && !validate_ids(W, ids, n, "b2j_bodies_get_state")) return -1;
 	KGetState k; memset(&k, 0, sizeof(k)); k.w = W->d; k.first = W->get_state_first;
 	// one persistent staging buffer (device + pinned mirror): ids up, one kernel, one copy down
 	rt.stage_begin((size_t)n * (4 + 12 + 16 + 12 + 12 + 24 + 4 + 4));
@@ -1425,8 +1590,11 @@ int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 
 int b2j_bodies_set_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_state *in)
 {
+	B2J_DEVICE_GUARD(W);
 	if (n == 0) return 0;
 	Runtime &rt = W->rt;
+	if (in == nullptr) { last_error() = "b2j_bodies_set_state: in is null"; return -1; }
+	if (ids != nullptr? !validate_ids(W, ids, n, "b2j_bodies_set_state") : n > W->d.max_bodies) { if (ids == nullptr) last_error() = "n exceeds max_bodies"; return -1; }
 	sync_dworld(W);
 	upload_shapes(W);
 	KSetState k; memset(&k, 0, sizeof(k)); k.w = W->d;
@@ -1447,8 +1615,10 @@ int b2j_bodies_set_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 
 int b2j_bodies_set_params(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_params *in)
 {
+	B2J_DEVICE_GUARD(W);
 	if (n == 0) return 0;
 	if (ids == nullptr || in == nullptr) { last_error() = "b2j_bodies_set_params: ids and in are required"; return -1; }
+	if (!validate_ids(W, ids, n, "b2j_bodies_set_params")) return -1;
 	Runtime &rt = W->rt;
 	sync_dworld(W);
 	KSetParams k; memset(&k, 0, sizeof(k)); k.w = W->d;
@@ -1467,8 +1637,10 @@ int b2j_bodies_set_params(b2j_world *W, const uint32_t *ids, uint32_t n, const b
 
 int b2j_bodies_add_force_torque(b2j_world *W, const uint32_t *ids, uint32_t n, const float *force, const float *torque)
 {
+	B2J_DEVICE_GUARD(W);
 	if (n == 0) return 0;
 	Runtime &rt = W->rt;
+	if (ids != nullptr? !validate_ids(W, ids, n, "b2j_bodies_add_force_torque") : n > W->d.max_bodies) { if (ids == nullptr) last_error() = "n exceeds max_bodies"; return -1; }
 	sync_dworld(W);
 	KAddForceTorque k; k.w = W->d;
 	rt.stage_begin((size_t)n * (4 + 12 + 12));
@@ -1489,6 +1661,7 @@ uint32_t b2j_num_active_bodies(const b2j_world *W) { return W->num_active; }
 
 uint32_t b2j_get_active_bodies(b2j_world *W, uint32_t *ids, uint32_t cap)
 {
+	B2J_DEVICE_GUARD(W);
 	uint32_t n = W->num_active < cap? W->num_active : cap;
 	if (n > 0)
 	{
@@ -1502,8 +1675,15 @@ uint32_t b2j_get_active_bodies(b2j_world *W, uint32_t *ids, uint32_t cap)
 
 int b2j_contact_cache_import(b2j_world *W, const b2j_cached_body_pair *pairs, uint32_t num_pairs, const b2j_cached_manifold *manifolds, uint32_t num_manifolds)
 {
+	B2J_DEVICE_GUARD(W);
 	Runtime &rt = W->rt;
 	if (num_pairs > W->d.max_body_pairs || num_manifolds > W->d.max_constraints) { last_error() = "contact cache snapshot exceeds the world limits"; return -1; }
+	for (uint32_t i = 0; i < num_pairs; ++i)
+		if ((uint64_t)pairs[i].first_manifold + pairs[i].num_manifolds > num_manifolds || slot_of(pairs[i].body1) >= W->d.max_bodies || slot_of(pairs[i].body2) >= W->d.max_bodies)
+		{
+			last_error() = "contact cache snapshot is inconsistent (manifold range or body index out of bounds)";
+			return -1;
+		}
 	int ri = W->write_idx ^ 1;
 	clear_cache(W, ri);
 	sync_dworld(W);
@@ -1527,6 +1707,7 @@ int b2j_contact_cache_import(b2j_world *W, const b2j_cached_body_pair *pairs, ui
 
 int b2j_contact_cache_export(b2j_world *W, b2j_cached_body_pair *pairs, uint32_t pairs_cap, uint32_t *num_pairs, b2j_cached_manifold *manifolds, uint32_t manifolds_cap, uint32_t *num_manifolds)
 {
+	B2J_DEVICE_GUARD(W);
 	Runtime &rt = W->rt;
 	int ri = W->write_idx ^ 1;
 	uint32_t np = W->cache_num_pairs[ri], nm = W->cache_num_manifolds[ri];
@@ -1562,20 +1743,22 @@ int b2j_contact_cache_export(b2j_world *W, b2j_cached_body_pair *pairs, uint32_t
 
 int b2j_were_bodies_in_contact(b2j_world *W, uint32_t id1, uint32_t id2)
 {
-	uint32_t np = 0, nm = 0;
-	b2j_contact_cache_export(W, nullptr, 0, &np, nullptr, 0, &nm);
-	std::vector<b2j_cached_body_pair> p(np);
-	std::vector<b2j_cached_manifold> m(nm);
-	if (b2j_contact_cache_export(W, p.data(), np, &np, m.data(), nm, &nm) != 0) return -1;
-	uint32_t a = id1 < id2? id1 : id2, b = id1 < id2? id2 : id1;
-	for (const b2j_cached_body_pair &cp : p)
-		if (cp.body1 == a && cp.body2 == b)
-			return cp.num_manifolds > 0? 1 : 0;
-	return 0;
+	// one probe of the device pair table of the read cache (the reference probes its lock free map, ContactConstraintManager.cpp:1531-1543)
+	B2J_DEVICE_GUARD(W);
+	if (slot_of(id1) >= W->d.max_bodies || slot_of(id2) >= W->d.max_bodies) return 0;
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	uint32_t a = id1 < id2? id1 : id2, b = id1 < id2? id2 : id1, result = 0;
+	uint32_t *out = reinterpret_cast<uint32_t *>(W->d_energy); // 4 byte scratch word
+	{ KWereInContact k; k.w = W->d; k.id1 = a; k.id2 = b; k.out = out; rt.launch(k, 1); }
+	rt.download(&result, out, 1);
+	if (!rt.check("b2j_were_bodies_in_contact")) return -1;
+	return (int)result;
 }
 
 int b2j_step(b2j_world *W, float delta_time, int collision_steps, b2j_step_stats *stats)
 {
+	B2J_DEVICE_GUARD(W);
 	Runtime &rt = W->rt;
 	bool want_energy = stats != nullptr && stats->kinetic_energy < 0.0f;
 	if (stats != nullptr) { memset(stats, 0, sizeof(*stats)); if (want_energy) stats->kinetic_energy = -1.0f; }
@@ -1640,25 +1823,33 @@ int b2j_step(b2j_world *W, float delta_time, int collision_steps, b2j_step_stats
 
 uint32_t b2j_events_drain(b2j_world *W, b2j_contact_event *out, uint32_t cap)
 {
+	B2J_DEVICE_GUARD(W);
+	if (W->nc.events == nullptr) return 0;
 	uint32_t n = W->last_num_events < W->max_events? W->last_num_events : W->max_events;
 	if (n > 0 && out != nullptr && cap > 0)
 	{
 		std::vector<b2j_contact_event> ev(n);
 		W->rt.download(ev.data(), W->nc.events, n);
-		std::sort(ev.begin(), ev.end(), [](const b2j_contact_event &a, const b2j_contact_event &b) {
+		// canonical order (kind, body1, body2, sub shapes): the 148 byte records stay put, a 4 byte index array is sorted
+		std::vector<uint32_t> order(n);
+		std::iota(order.begin(), order.end(), 0u);
+		std::sort(order.begin(), order.end(), [&ev](uint32_t ia, uint32_t ib) {
+			const b2j_contact_event &a = ev[ia], &b = ev[ib];
 			if (a.kind != b.kind) return a.kind < b.kind;
 			if (a.body1 != b.body1) return a.body1 < b.body1;
 			if (a.body2 != b.body2) return a.body2 < b.body2;
 			if (a.sub_shape1 != b.sub_shape1) return a.sub_shape1 < b.sub_shape1;
 			return a.sub_shape2 < b.sub_shape2;
 		});
-		for (uint32_t i = 0; i < n && i < cap; ++i) out[i] = ev[i];
+		for (uint32_t i = 0; i < n && i < cap; ++i) out[i] = ev[order[i]];
 	}
 	return n;
 }
 
 uint32_t b2j_activation_events_drain(b2j_world *W, b2j_activation_event *out, uint32_t cap)
 {
+	B2J_DEVICE_GUARD(W);
+	if (W->d_act_events == nullptr) return 0;
 	uint32_t n = W->last_num_act_events < W->max_act_events? W->last_num_act_events : W->max_act_events;
 	if (n > 0 && out != nullptr && cap > 0)
 	{
@@ -1672,6 +1863,7 @@ uint32_t b2j_activation_events_drain(b2j_world *W, b2j_activation_event *out, ui
 
 uint32_t b2j_debug_get_pairs(b2j_world *W, uint32_t *pairs, uint32_t cap)
 {
+	B2J_DEVICE_GUARD(W);
 	uint32_t n = W->last_num_pairs;
 	if (n > 0 && pairs != nullptr)
 	{
@@ -1691,6 +1883,7 @@ uint32_t b2j_debug_get_pairs(b2j_world *W, uint32_t *pairs, uint32_t cap)
 
 uint32_t b2j_debug_get_manifolds(b2j_world *W, b2j_debug_manifold *out, uint32_t cap)
 {
+	B2J_DEVICE_GUARD(W);
 	// manifolds of the cache written by the last step (now the read cache)
 	int ri = W->write_idx ^ 1;
 	uint32_t nm = W->cache_num_manifolds[ri];
@@ -1722,6 +1915,7 @@ uint32_t b2j_debug_get_manifolds(b2j_world *W, b2j_debug_manifold *out, uint32_t
 
 int b2j_debug_find_pairs(b2j_world *W)
 {
+	B2J_DEVICE_GUARD(W);
 	Runtime &rt = W->rt;
 	upload_shapes(W);
 	sync_dworld(W);
@@ -1806,6 +2000,7 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 		{
 			B->h_ids[(size_t)w * stride + i] = P->h_ids[i];
 			B->h_layer[(size_t)w * stride + i] = P->h_layer[i];
+			B->h_static[(size_t)w * stride + i] = P->h_static[i];
 		}
 	for (uint32_t l = 0; l < d.num_bp_layers; ++l)
 	{

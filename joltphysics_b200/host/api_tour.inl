@@ -59,6 +59,25 @@ static void sApiTourMutate(PhysicsSystem &inSystem, std::vector<BodyID> &ioBodie
 		bi.SetPositionAndRotation(ioBodies[9], RVec3(3.0f, 4.0f, 0.0f), Quat::sIdentity(), EActivation::Activate);
 		bi.DeactivateBody(ioBodies[2]);
 	}
+	else if (inPhase == 3)
+	{
+		// remove bodies while they move and put them back WITHOUT touching the pose: they return where they left the world, at rest
+		// (BodyManager::DeactivateBodies reset the velocities of the active ones); a body created with a velocity keeps it
+		bi.SetLinearVelocity(ioBodies[3], Vec3(1.0f, 2.0f, 0.0f));
+		bi.SetAngularVelocity(ioBodies[6], Vec3(0.0f, 4.0f, 0.0f));
+		BodyID moving[3] = { ioBodies[3], ioBodies[6], ioBodies[8] };
+		bi.RemoveBodies(moving, 3);
+		bi.AddBody(moving[0], EActivation::Activate);
+		bi.AddBody(moving[1], EActivation::DontActivate);
+		BodyCreationSettings settings(B2J_NEW_SHAPE(BoxShape, Vec3(0.4f, 0.2f, 0.3f)), RVec3(0.0f, 6.0f, 3.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		settings.mLinearVelocity = Vec3(0.5f, 3.0f, 1.0f);
+		settings.mAngularVelocity = Vec3(1.0f, 0.0f, 0.5f);
+		Body *flying = bi.CreateBody(settings);
+		bi.AddBody(flying->GetID(), EActivation::Activate);
+		ioBodies.push_back(flying->GetID());
+		bi.RemoveBody(flying->GetID());          // leaves at once, comes back with the velocity reset
+		bi.AddBody(flying->GetID(), EActivation::Activate);
+	}
 }
 
 // Queries after the tour: number of bodies, active bodies (as a sorted id list written to outIDs), returns the active count

@@ -649,6 +649,26 @@ void jref_destroy(void *h) { delete (World *)h; }
 void jref_mutate(void *h, int inPhase) { World *w = (World *)h; sApiTourMutate(w->system, w->tour_bodies, inPhase); }
 int jref_query(void *h, uint32_t *outIDs, int inCapacity, uint32_t *outNumBodies, uint32_t *outFlags) { World *w = (World *)h; return sApiTourQuery(w->system, w->tour_bodies, outIDs, inCapacity, outNumBodies, outFlags); }
 
+// Destroys the body in slot inIndex and creates a SPHERE in its place: same slot (the freed index is reused first), same centre of mass
+// position, next sequence number. The contact cache still holds the pairs of the destroyed body (a cache keyed by body
+// slots alone would serve the new body from them). Returns the new id or 0xffffffff.
+uint32_t jref_replace_body(void *h, uint32_t inIndex, float inRadius)
+{
+	World *w = (World *)h;
+	const BodyVector &bodies = w->system.mBodyManager.GetBodies();
+	if (inIndex >= bodies.size() || !BodyManager::sIsValidBodyPointer(bodies[inIndex])) return 0xffffffffu;
+	const Body *old_body = bodies[inIndex];
+	BodyCreationSettings s(new SphereShape(inRadius), old_body->GetCenterOfMassPosition(), old_body->GetRotation(), old_body->GetMotionType(), old_body->GetObjectLayer());
+	s.mFriction = old_body->GetFriction();
+	bool active = old_body->IsActive();
+	BodyID old_id = old_body->GetID();
+	BodyInterface &bi = w->system.GetBodyInterface();
+	bi.RemoveBody(old_id);
+	bi.DestroyBody(old_id);
+	BodyID id = bi.CreateAndAddBody(s, active? EActivation::Activate : EActivation::DontActivate);
+	return id.GetIndex() == inIndex? id.GetIndexAndSequenceNumber() : 0xffffffffu;
+}
+
 // Turn the recording listeners off (timing runs) or on.
 void jref_set_recording(void *h, int inOn)
 {

@@ -15,10 +15,12 @@ B2J_BODY_GYROSCOPIC, B2J_BODY_KIN_VS_NONDYN, B2J_BODY_USE_MANIFOLD_REDUCTION off
 solver step overrides, two moving broadphase layers; `zoo` = all of them in one world."""
 
 
-def single_step_parity(api, scene, p0=0, p1=0, warm=0, dt=1.0 / 60.0, collision_steps=1, check_events=True, warm_threads=1):
+def single_step_parity(api, scene, p0=0, p1=0, warm=0, dt=1.0 / 60.0, collision_steps=1, check_events=True, warm_threads=1, before_export=None):
     ref = R.RefWorld(scene, p0, p1)
     for _ in range(warm):
         ref.step(dt, 1, warm_threads)  # (the deterministic build gives the same state for any thread count)
+    if before_export is not None:
+        before_export(ref)
     world = ref.export(api)
     out = {}
     # (i) broadphase candidate pairs of the snapshot

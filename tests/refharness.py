@@ -37,6 +37,8 @@ def ref_lib(variant="det"):
         L.jref_destroy.argtypes = [vp]
         L.jref_set_recording.argtypes = [vp, C.c_int]
         L.jref_mutate.argtypes = [vp, C.c_int]
+        L.jref_replace_body.restype = C.c_uint32
+        L.jref_replace_body.argtypes = [vp, C.c_uint32, C.c_float]
         L.jref_query.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.jref_step.argtypes = [vp, C.c_float, C.c_int, C.c_int]
         L.jref_time_steps.restype = C.c_double
@@ -116,6 +118,12 @@ class RefWorld:
         nb, flags = C.c_uint32(), C.c_uint32()
         n = self.L.jref_query(self.h, ids.ctypes.data, len(ids), C.addressof(nb), C.addressof(flags))
         return ids[:n].copy(), nb.value, flags.value
+
+    def replace_body(self, index, radius=0.5):
+        """Destroy the body in slot `index`, create a sphere there (same slot, next sequence number); returns the new id."""
+        new_id = self.L.jref_replace_body(self.h, index, radius)
+        assert new_id != 0xffffffff, "jref_replace_body: the freed slot was not reused"
+        return new_id
 
     def set_recording(self, on):
         self.L.jref_set_recording(self.h, 1 if on else 0)

@@ -57,8 +57,8 @@ def _check_api_tour(flib):
     fs = F.FacadeScene(flib, "api_tour")
 
     def compare(tag):
-        fs.world.n = 16  # body slots 0..15 are used by the tour (13 at creation, 3 added later, one slot reused)
-        rs, gs = ref.state(16), fs.world.state()
+        fs.world.n = 18  # body slots 0..16 are used by the tour (13 at creation, 4 added later, one slot reused)
+        rs, gs = ref.state(18), fs.world.state()
         worst = R.compare_states(rs, gs)
         for k in ("pos", "rot", "lin", "ang"):
             assert worst[k] <= 1.0, (tag, k, worst)
@@ -68,7 +68,7 @@ def _check_api_tour(flib):
         assert rf == gf, (tag, "IsAdded && IsActive", bin(rf), bin(gf))
 
     compare("created")
-    for phase, steps in ((0, 10), (1, 25), (2, 40)):
+    for phase, steps in ((0, 10), (1, 25), (2, 40), (3, 30)):
         if phase:
             ref.mutate(phase)
             fs.mutate(phase)
@@ -83,11 +83,11 @@ def _check_api_tour(flib):
     n_dyn = fs.flib.lib.b2jf_scene_num_dynamic(fs.h)
     out = np.zeros((n_dyn, 3), np.float32)
     assert fs.step_e2e(1.0 / 60.0, None, out) == 0
-    ids, rs = ref.state(16).ids, ref.state(16)
-    fs.world.n = 16
+    ids, rs = ref.state(18).ids, ref.state(18)
+    fs.world.n = 18
     gs = fs.world.state()
     got = {tuple(np.round(p, 6)) for p in out}
-    want = {tuple(np.round(gs.pos[i], 6)) for i in range(1, 16) if ids[i] != 0xffffffff}
+    want = {tuple(np.round(gs.pos[i], 6)) for i in range(1, 18) if ids[i] != 0xffffffff}
     assert got == want, "GetCenterOfMassPosition through the facade differs from the device state"
     assert R.compare_states(rs, gs)["pos"] <= 1.0
     fs.close()

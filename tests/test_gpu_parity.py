@@ -34,6 +34,13 @@ def test_feature_single_step_parity(gpu_api, ref_available, feature, warm):
     assert out["stats"]["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("slot", [1, 5, 24])
+def test_body_recreated_in_the_same_slot_is_not_served_from_the_cache(gpu_api, ref_available, slot):
+    """a sphere created in the slot of a destroyed resting box (next sequence number, same pose) collides afresh."""
+    out = parity.single_step_parity(gpu_api, "small_stack", 1, 0, 60, before_export=lambda ref: ref.replace_body(slot))
+    assert out["manifolds"] > 0
+
+
 def test_feature_zoo_multi_step(gpu_api, ref_available):
     history = parity.multi_step_drift(gpu_api, "feature", parity.FEATURES.index("zoo"), 0, 0, steps=150)
     for k in ("pos", "rot", "lin", "ang"):
