@@ -8,8 +8,17 @@ Default workload = BASELINE.json configs[4], the one the "1/2/4/8 B200" metric i
 (PerformanceTest -s=Pyramid, 1240 boxes each) batched RL-env style, sharded world_id -> rank over the N GPUs with no inter-GPU
 traffic on the data path (only the final statistics are reduced over NCCL). A "step" advances EVERY world of the job by one
 PhysicsSystem::Update(1/60, 1), timed as PerformanceTest.cpp:380-391 does (Update only); body-steps/s = steps/s x dynamic bodies.
-`value` = device resident (CUDA events on the library's stream), `e2e` = through the C ABI with HOST buffers every step
-(per body forces in, positions out). Single world workloads (--workload pile ...) run one replica per GPU.
+
+Every leg measures the SAME simulation window, steps [W, W + K) counted from the creation state of the scene:
+  value      device resident: CUDA events on the library's stream around b2j_step / b2j_batch_step
+  e2e        through the C ABI / facade with HOST buffers every step (per body forces in, positions out); the worlds are reset
+             to their creation state (b2j_batch_reset_worlds / a new scene) and warmed up again first
+  roofline   per kernel CUDA-event timing (b2j_world_set_profiling) of the dominant kernel over the same window after another reset
+  reference  (--impl reference, and the cpu_baseline leg) the unmodified reference on the host cores, same window
+
+At N = 1 the line also carries `pile` (configs[3], one 1M body world) and `extra` (configs[0..2]: Pyramid, ConvexVsMesh, MaxBodies),
+each with the reference timed beside it on the SAME body count and step window. Single world workloads (--workload pile ...) run one
+replica per GPU ("replicas only").
 """
 import argparse
 import ctypes as C
@@ -26,8 +35,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DT = 1.0 / 60.0
 S_V = 24  # bytes of (v, w) of one body
-PYRAMID_BODIES = 1240
+PYRAMID_BODIES = 1240           # PerformanceTest/PyramidScene.h:23-47, height 15
+CONVEX_VS_MESH_BODIES = 1764    # PerformanceTest/ConvexVsMeshScene.h:28-117
+MAX_BODIES_FULL = 8388608       # PerformanceTest/MaxBodiesScene.h:44-80 (BASELINE configs[2])
 BATCH_PAIRS_PER_WORLD, BATCH_CONSTRAINTS_PER_WORLD = 16384, 12288  # SURVEY 8(d) config 5 limits
+T_START = time.time()
 
 
 def parse_args():
@@ -38,12 +50,16 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default=os.environ.get("B2J_BENCH_WORKLOAD", "batch"))
     p.add_argument("--worlds", type=int, default=int(os.environ.get("B2J_BENCH_WORLDS", "4096")), help="total worlds of the batch workload (sharded over the GPUs)")
-    p.add_argument("--bodies", type=int, default=int(os.environ.get("B2J_BENCH_BODIES", "1000000")), help="bodies of the pile / max_bodies workloads")
-    p.add_argument("--ref-bodies", type=int, default=100000, help="bodies of the bounded sample the CPU legs step for pile / max_bodies")
-    p.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline leg")
+    p.add_argument("--bodies", type=int, default=int(os.environ.get("B2J_BENCH_BODIES", "0")), help="bodies of the pile / max_bodies workloads (default: 1 000 000 / 8 388 608)")
+    p.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline leg of the main workload")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--no-pile", action="store_true", help="skip the secondary single-world Pile-1M measurement at N=1")
-    return p.parse_args()
+    p.add_argument("--no-pile", action="store_true", help="skip the single-world Pile-1M measurement at N=1")
+    p.add_argument("--no-extras", action="store_true", help="skip the configs[0..2] measurements at N=1")
+    p.add_argument("--budget-seconds", type=float, default=float(os.environ.get("B2J_BENCH_BUDGET", "480")), help="wall clock after which the remaining secondary measurements are skipped")
+    a = p.parse_args()
+    if a.bodies <= 0:
+        a.bodies = MAX_BODIES_FULL if a.workload == "max_bodies" else 1000000
+    return a
 
 
 def scene_params(workload, bodies):
@@ -64,6 +80,24 @@ WORKLOAD_NAMES = {
     "pyramid": "PerformanceTest -s=Pyramid (configs[0])", "convex_vs_mesh": "PerformanceTest -s=ConvexVsMesh (configs[1])",
     "max_bodies": "PerformanceTest -s=MaxBodies (configs[2], N bodies)",
 }
+
+
+def job_bodies(args):
+    """Dynamic bodies of ONE replica of the workload (the whole job for the batch)."""
+    return {"batch": args.worlds * PYRAMID_BODIES, "pyramid": PYRAMID_BODIES, "convex_vs_mesh": CONVEX_VS_MESH_BODIES}.get(args.workload, args.bodies)
+
+
+def job_config(args):
+    """The `config` object: identical on the b200 arm and on the reference arm (it names the job, not how an arm runs it)."""
+    batch = args.workload == "batch"
+    return {"workload": WORKLOAD_NAMES[args.workload], "worlds": args.worlds if batch else 1, "bodies": int(job_bodies(args)), "dt": DT, "collision_steps": 1,
+            "parallelism": (f"worlds sharded over {args.gpus} GPUs (world_id -> rank blocks), no data-path collective" if batch else f"one world per GPU x{args.gpus} (replicas only)"),
+            "window": f"simulation steps [{args.warmup}, {args.warmup + args.steps}) from the creation state",
+            "timing": "every step streams the whole job state through HBM (working set >> 126 MB L2); no L2 flush between steps"}
+
+
+def over_budget(args):
+    return time.time() - T_START > args.budget_seconds
 
 
 class ClockSampler(threading.Thread):
@@ -125,36 +159,60 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU legs (oracle/_ref = the unmodified reference compiled with plain g++, FMA build)
+# CPU legs (oracle/_ref = the unmodified reference compiled with plain g++, FMA + LTO build)
 # ---------------------------------------------------------------------------------------------------------------------
 
-def cpu_run(args, warmup, steps, budget_s):
-    """Times the reference on the host cores on a bounded sample of the workload. Returns (value, steps, warm, description, threads)."""
+CPU_BUILD = "FMA + LTO build of the unmodified reference (oracle/_ref)"
+
+
+def cpu_run(workload, bodies, worlds, warmup, steps, budget_s=None):
+    """Times the reference on the host cores over simulation steps [warmup, warmup + steps) of the workload, same body count as the
+    GPU arm. With a budget (cpu_baseline leg inside the GPU arm) the window is shortened -- never the body count -- and the sample
+    string says which steps were timed. Returns (value, steps, warm, description, threads)."""
     import refharness as R
     L = R.ref_lib("fast")
     threads = L.jref_hardware_threads()
-    if args.workload == "batch":
+    if workload == "batch":
         # many small independent worlds: every host thread owns one world and steps it with a single threaded job system
         # (no cross thread synchronisation -- the best case for the CPU); throughput scales with the number of worlds in flight
         L.jref_time_worlds_parallel.restype = C.c_double
         L.jref_time_worlds_parallel.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
-        probe = L.jref_time_worlds_parallel(b"pyramid", 15, 0, threads, 1, 2, DT) / 2.0  # seconds per step with all threads busy
-        warm = max(3, min(warmup, int(0.35 * budget_s / max(probe, 1e-4))))
-        n = max(1, min(steps, int(0.55 * budget_s / max(probe, 1e-4))))
+        warm, n = warmup, steps
+        if budget_s is not None:
+            probe = L.jref_time_worlds_parallel(b"pyramid", 15, 0, threads, 1, 2, DT) / 2.0  # seconds per step with all threads busy
+            total = max(2, int(budget_s / max(probe, 1e-4)))
+            if warm + n > total:
+                warm = min(warm, max(1, total // 3))
+                n = max(1, min(n, total - warm))
         wall = L.jref_time_worlds_parallel(b"pyramid", 15, 0, threads, warm, n, DT)
         value = threads * n * PYRAMID_BODIES / wall
-        return value, n, warm, f"{threads} concurrent Pyramid worlds (one per host thread, single threaded job system each) of the {args.worlds}, steps {warm}..{warm + n}", threads
-    bodies = min(args.bodies, args.ref_bodies) if args.workload in ("pile", "max_bodies") else args.bodies
-    scene, p0, p1 = scene_params(args.workload, bodies)
+        return value, n, warm, f"{threads} concurrent Pyramid worlds (one per host thread, single threaded job system each) of the {worlds}, steps [{warm}, {warm + n})", threads
+    scene, p0, p1 = scene_params(workload, bodies)
     ref = R.RefWorld(scene, p0, p1, variant="fast")
     ref.set_recording(False)
     nd = ref.num_dynamic
-    t_first = ref.time_steps(1, DT, threads)
-    warm = max(3, min(warmup, int(0.35 * budget_s / max(t_first, 1e-4))))
-    n = max(1, min(steps, int(0.55 * budget_s / max(t_first, 1e-4))))
-    ref.time_steps(warm - 1, DT, threads)
+    warm, n = warmup, steps
+    done = 0
+    if budget_s is not None:
+        t_first = ref.time_steps(1, DT, threads)
+        done = 1
+        total = max(2, int(budget_s / max(t_first, 1e-4)))
+        if warm + n > total:
+            warm = min(warm, max(1, total // 3))
+            n = max(1, min(n, total - warm))
+    if warm > done:
+        ref.time_steps(warm - done, DT, threads)
     t = ref.time_steps(n, DT, threads)
-    return n * nd / t, n, warm, f"{scene} with {nd} dynamic bodies, steps {warm}..{warm + n}, JobSystemThreadPool with {threads} threads", threads
+    ref.close()
+    return n * nd / t, n, warm, f"{scene} with {nd} dynamic bodies, steps [{warm}, {warm + n}), JobSystemThreadPool with {threads} threads", threads
+
+
+def cpu_baseline_object(workload, bodies, worlds, warmup, steps, budget_s):
+    try:
+        value, n, warm, sample, threads = cpu_run(workload, bodies, worlds, warmup, steps, budget_s)
+        return {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "steps": n, "warmup": warm, "sample": sample + "; " + CPU_BUILD}
+    except Exception as e:  # the CPU leg must never take the GPU line down
+        return {"error": str(e)}
 
 
 def run_reference(args):
@@ -164,14 +222,15 @@ def run_reference(args):
     if not R.have_ref("fast"):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libjoltref_fast.so missing"}))
         return
-    value, steps, warm, sample, threads = cpu_run(args, args.warmup, args.steps, 200.0)
-    bodies = args.worlds * PYRAMID_BODIES if args.workload == "batch" else None
+    t0 = time.time()
+    value, steps, warm, sample, threads = cpu_run(args.workload, args.bodies, args.worlds, args.warmup, args.steps)
     line = {
         "impl": "reference", "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": None, "higher_is_better": True, "scaling": "strong" if args.workload == "batch" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "bodies": bodies, "dt": DT, "collision_steps": 1, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample + "; FMA build of the unmodified reference (oracle/_ref)"},
+        "config": job_config(args),
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample + "; " + CPU_BUILD},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
     }
     print(json.dumps(line))
 
@@ -198,31 +257,32 @@ def reduce_job(dist, world_size, times, work, device):
 
 
 class Workload:
-    """One rank's share of the workload behind a uniform step / e2e / profile interface."""
+    """One rank's share of a workload behind a uniform step / e2e / profile / reset interface."""
 
-    def __init__(self, args, api, flib, rank, world_size):
+    def __init__(self, workload, bodies, worlds, api, flib, rank, world_size):
         import numpy as np
-        import refharness as R
         from joltphysics_b200 import _capi
+        self.api, self.flib, self.np, self._capi = api, flib, np, _capi
+        self.kind, self.bodies = workload, bodies
+        self.scene, self.batch = None, None
+        self.first_world, self.n_worlds = shard_worlds(worlds, rank, world_size) if workload == "batch" else (0, 1)
+        self._create()
+        self.stats = _capi.StepStats()
+        self._e2e_ready = False
+
+    def _create(self):
         import facade as F
-        self.api, self.np, self._capi = api, np, _capi
-        self.kind = args.workload
-        scene, p0, p1 = scene_params(args.workload, args.bodies)
-        self.scene = F.FacadeScene(flib, scene, p0, p1)
-        self.batch = None
+        scene, p0, p1 = scene_params(self.kind, self.bodies)
+        self.scene = F.FacadeScene(self.flib, scene, p0, p1)
         if self.kind == "batch":
-            # world_id -> rank: contiguous blocks
-            self.first_world, self.n_worlds = shard_worlds(args.worlds, rank, world_size)
-            self.batch = api.b2j_batch_create(self.scene.world.h, self.n_worlds, BATCH_PAIRS_PER_WORLD, BATCH_CONSTRAINTS_PER_WORLD)
+            self.batch = self.api.b2j_batch_create(self.scene.world.h, self.n_worlds, BATCH_PAIRS_PER_WORLD, BATCH_CONSTRAINTS_PER_WORLD)
             if not self.batch:
-                raise SystemExit("b2j_batch_create failed: " + api.last_error())
+                raise SystemExit("b2j_batch_create failed: " + self.api.last_error())
             self.num_dynamic = self.n_worlds * self.scene.num_dynamic
             self.num_slots = self.n_worlds * self.scene.num_bodies
         else:
-            self.n_worlds = 1
             self.num_dynamic = self.scene.num_dynamic
             self.num_slots = self.scene.num_bodies
-        self.stats = _capi.StepStats()
 
     def close(self):
         """Frees the device memory of the workload (the batch holds > 100 GB at 4096 worlds)."""
@@ -232,6 +292,17 @@ class Workload:
         if self.scene is not None:
             self.scene.close()
             self.scene = None
+
+    def reset(self):
+        """Back to the creation state: the batch resets its worlds on the device (b2j_batch_reset_worlds), a single world is rebuilt."""
+        if self.batch:
+            ids = self.np.arange(self.n_worlds, dtype=self.np.uint32)
+            if self.api.b2j_batch_reset_worlds(self.batch, ids.ctypes.data_as(C.POINTER(C.c_uint32)), self.n_worlds) != 0:
+                raise SystemExit("b2j_batch_reset_worlds failed: " + self.api.last_error())
+        else:
+            self.close()
+            self._create()
+            self._e2e_ready = False
 
     def step(self):
         if self.batch:
@@ -260,11 +331,13 @@ class Workload:
 
     def e2e_buffers(self, torch):
         n = self.num_slots if self.batch else self.num_dynamic
-        self.forces = torch.zeros((n, 3), dtype=torch.float32).pin_memory().numpy()
-        self.positions = torch.zeros((self.num_slots if self.batch else self.num_dynamic, 3), dtype=torch.float32).pin_memory().numpy()
+        if not hasattr(self, "forces") or len(self.forces) != n:
+            self.forces = torch.zeros((n, 3), dtype=torch.float32).pin_memory().numpy()
+            self.positions = torch.zeros((n, 3), dtype=torch.float32).pin_memory().numpy()
         fp = C.POINTER(C.c_float)
         self._f = self.forces.ctypes.data_as(fp)
         self._st = self._capi.BodyState(self.positions.ctypes.data, None, None, None, None, None, None)
+        self._e2e_ready = True
         if self.batch:
             return n * 12, self.num_slots * 12
         return self.num_dynamic * (12 + 4), self.scene.num_bodies * (12 + 16 + 12 + 12 + 4)
@@ -282,7 +355,8 @@ class Workload:
 COUNTERS = ("num_body_pairs", "num_pairs_from_cache", "num_manifolds", "num_contact_points", "num_constraints", "num_phases", "velocity_iterations", "position_iterations", "num_active_bodies")
 
 
-def measure(args, wl, torch, dist, world_size, local_rank, steps, warmup, with_e2e=True):
+def measure(wl, torch, dist, world_size, local_rank, steps, warmup, with_e2e=True, with_profile=True, sample_clocks=True):
+    """value leg, then (after a reset + the same warm-up each) the e2e leg and the per kernel profile leg: all over steps [W, W + K)."""
     def barrier():
         torch.cuda.synchronize()
         if world_size > 1:
@@ -292,17 +366,18 @@ def measure(args, wl, torch, dist, world_size, local_rank, steps, warmup, with_e
     for _ in range(warmup):
         wl.step()
     sampler = ClockSampler(local_rank)
-    if os.environ.get("B2J_BENCH_NO_SAMPLER") != "1":  # (diagnostics: does the sampler perturb the run?)
+    if sample_clocks and os.environ.get("B2J_BENCH_NO_SAMPLER") != "1":  # (diagnostics: does the sampler perturb the run?)
         sampler.start()
     barrier()
     cuprofile = os.environ.get("B2J_BENCH_CUPROFILE") == "1"  # `ncu --profile-from-start off`: capture the timed steps only
     if cuprofile:
         torch.cuda.profiler.start()
     t0 = time.perf_counter()
-    gpu_ms, launches, agg = 0.0, 0, {}
+    gpu_ms, launches, agg, series = 0.0, 0, {}, []
     for _ in range(steps):
         st = wl.step()
         gpu_ms += st.gpu_ms
+        series.append(round(st.gpu_ms, 3))
         launches += st.kernel_launches
         for k in COUNTERS:
             agg[k] = agg.get(k, 0) + getattr(st, k)
@@ -311,54 +386,73 @@ def measure(args, wl, torch, dist, world_size, local_rank, steps, warmup, with_e
     if cuprofile:
         torch.cuda.profiler.stop()
     clocks = sampler.finish()
+    out = {"gpu_ms": gpu_ms, "wall": wall, "launches": launches, "agg": agg, "clocks": clocks, "series": series, "e2e": None, "prof": None}
 
-    # per kernel device time over extra steps continuing the same run (event records perturb back-to-back launches,
-    # so this is kept out of the timed region)
-    prof_steps = max(1, min(steps, 10))
-    wl.set_profiling(1)
-    prof_gpu_ms, pagg = 0.0, {}
-    for _ in range(prof_steps):
-        st = wl.step()
-        prof_gpu_ms += st.gpu_ms
-        for k in ("num_contact_points", "num_constraints", "velocity_iterations"):
-            pagg[k] = pagg.get(k, 0) + getattr(st, k)
-    prof = wl.profile()
-    wl.set_profiling(0)
-
-    e2e = None
     if with_e2e:
+        # same window through the host-buffer boundary: reset, warm up again (device resident, untimed), then K timed e2e steps
+        wl.reset()
         h2d, d2h = wl.e2e_buffers(torch)
-        e2e_steps = max(1, min(steps, 20))
-        wl.step_e2e()  # first call sizes the staging buffers
+        for _ in range(warmup):
+            wl.step()
         barrier()
         t1 = time.perf_counter()
-        for _ in range(e2e_steps):
+        for _ in range(steps):
             wl.step_e2e()
         barrier()
-        e2e = {"wall": time.perf_counter() - t1, "steps": e2e_steps, "h2d": h2d, "d2h": d2h}
-    return {"gpu_ms": gpu_ms, "wall": wall, "launches": launches, "agg": agg, "clocks": clocks, "prof": prof, "prof_steps": prof_steps,
-            "prof_gpu_ms": prof_gpu_ms, "pagg": pagg, "e2e": e2e}
+        out["e2e"] = {"wall": time.perf_counter() - t1, "steps": steps, "h2d": h2d, "d2h": d2h}
+
+    if with_profile:
+        # per kernel device time over the same window (event records perturb back-to-back launches, so this is its own leg)
+        wl.reset()
+        for _ in range(warmup):
+            wl.step()
+        prof_steps = max(1, min(steps, 10))
+        wl.set_profiling(1)
+        prof_gpu_ms, pagg = 0.0, {}
+        for _ in range(prof_steps):
+            st = wl.step()
+            prof_gpu_ms += st.gpu_ms
+            for k in ("num_contact_points", "num_constraints", "velocity_iterations"):
+                pagg[k] = pagg.get(k, 0) + getattr(st, k)
+        out.update({"prof": wl.profile(), "prof_steps": prof_steps, "prof_gpu_ms": prof_gpu_ms, "pagg": pagg})
+        wl.set_profiling(0)
+    return out
 
 
-NCU_TRAFFIC_RATIO = (93.932e6 + 3.881e6) / (159488 * 600.0)
+def ncu_traffic_ratio():
+    """DRAM bytes / algorithmic bytes of the velocity solve kernel from the committed ncu --set full capture (profiles/*.json written
+    by tools/ncu_traffic.py from the .ncu-rep of the round). None when there is no capture."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if name.endswith("_solve_traffic.json"):
+            try:
+                best = (json.load(open(os.path.join(pdir, name))), name)
+            except Exception:
+                pass
+    return best
+
+
+SOLVE_KERNELS = ("KSolveVelocityAll", "KSolveVelocity", "KSolveSmallVelocity")
 
 
 def roofline_of(m):
     """Roofline of the dominant kernel class (velocity solve), SURVEY 8(d) row (5): per constraint and iteration
-    C(c) + 4*S_v + 4*(3+c) algorithmic bytes with C(c) = 220 + 64 c."""
+    C(c) + 4*S_v + 4*(3+c) algorithmic bytes with C(c) = 220 + 64 c; kernels that also run the warm start pass (iteration 0 of the
+    survey's V + 1) count it."""
     prof, ps, pagg = m["prof"], m["prof_steps"], m["pagg"]
-    kernel = "KSolveVelocity"
-    solve = prof.get(kernel)
-    if not solve or solve["ms"] <= 0:
-        # small single worlds run warm start + all velocity iterations in one cooperative launch (the warm start pass is included)
-        kernel = "KSolveSmallVelocity"
-        solve = prof.get(kernel)
-        if not solve or solve["ms"] <= 0:
-            return None
+    kernel, solve = None, None
+    for k in SOLVE_KERNELS:
+        if prof.get(k) and prof[k]["ms"] > 0:
+            kernel, solve = k, prof[k]
+            break
+    if solve is None:
+        return None
     M = pagg["num_constraints"] / ps
     cbar = pagg["num_contact_points"] / max(pagg["num_constraints"], 1)
     V = pagg["velocity_iterations"] / ps
-    total_bytes = V * M * ((220 + 64 * cbar) + 4 * S_V + 4 * (3 + cbar)) * ps
+    passes = V if kernel == "KSolveVelocity" else V + 1   # the one launch kernels include the warm start pass
+    total_bytes = passes * M * ((220 + 64 * cbar) + 4 * S_V + 4 * (3 + cbar)) * ps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -366,15 +460,41 @@ def roofline_of(m):
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = total_bytes / (solve["ms"] / 1000.0) / 1e9
-    # DRAM traffic of the kernel from the ncu --set full capture in profiles/r1_hot_rest.txt: 93.93 MB read + 3.88 MB written for a
-    # launch over 159 488 four point constraints (95.69 MB algorithmic) -> 1.022 x the algorithmic bytes; scaled to this run's launches
-    traffic = NCU_TRAFFIC_RATIO * total_bytes / max(solve["launches"], 1)
+    traffic, traffic_source = None, None
+    t = ncu_traffic_ratio()
+    if t is not None and t[0].get("kernel") == kernel and t[0].get("dram_bytes_per_algorithmic_byte"):
+        traffic = t[0]["dram_bytes_per_algorithmic_byte"] * total_bytes / max(solve["launches"], 1)
+        traffic_source = f"profiles/{t[1]}: (dram__bytes_read.sum + dram__bytes_write.sum) / algorithmic bytes of the captured launch = {t[0]['dram_bytes_per_algorithmic_byte']:.3f}, scaled to this run's bytes per launch"
     return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_source": "profiles/r1_hot_rest.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch = 1.022 x algorithmic), scaled to this run's constraints per launch",
+            "traffic_source": traffic_source,
             "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s",
             "bytes_per_launch": total_bytes / max(solve["launches"], 1), "avg_launch_us": 1000.0 * solve["ms"] / max(solve["launches"], 1),
-            "share_of_step": solve["ms"] / max(m["prof_gpu_ms"], 1e-9), "measured_over": f"{ps} profiled steps after the timed region",
+            "launches": solve["launches"], "passes_per_step": passes,
+            "share_of_step": solve["ms"] / max(m["prof_gpu_ms"], 1e-9), "measured_over": f"{ps} profiled steps of the timed window (after a reset and the same warm-up)",
             "constraints_per_step": M, "points_per_constraint": cbar}
+
+
+def secondary(api, flib, torch, dist, local_rank, workload, bodies, warmup, steps, cpu_budget, with_cpu=True, with_e2e=True):
+    """One single-world measurement next to the main line: GPU value (+ e2e + roofline) and the reference on the SAME body count and
+    step window."""
+    wl = Workload(workload, bodies, 1, api, flib, 0, 1)
+    m = measure(wl, torch, dist, 1, local_rank, steps, warmup, with_e2e=with_e2e, with_profile=True, sample_clocks=False)
+    nd = wl.num_dynamic
+    out = {"config": WORKLOAD_NAMES[workload], "bodies": nd, "steps": steps, "warmup": warmup, "window": f"simulation steps [{warmup}, {warmup + steps})",
+           "value": steps * nd / (m["gpu_ms"] / 1000.0), "unit": "body-steps/s", "ms_per_step": m["gpu_ms"] / steps, "steps_per_sec": steps / (m["gpu_ms"] / 1000.0),
+           "gpu_launches": m["launches"], "roofline": roofline_of(m), "step_counters_mean": {k: v / steps for k, v in m["agg"].items()},
+           "kernel_ms_per_step": {k: round(v["ms"] / m["prof_steps"], 4) for k, v in sorted(m["prof"].items(), key=lambda kv: -kv[1]["ms"])[:10]}}
+    if m["e2e"] is not None:
+        out["e2e"] = {"value": m["e2e"]["steps"] * nd / m["e2e"]["wall"], "unit": "body-steps/s", "h2d_bytes_per_step": m["e2e"]["h2d"], "d2h_bytes_per_step": m["e2e"]["d2h"],
+                      "path": "facade: BodyInterface::AddForcesAndTorques, PhysicsSystem::Update, BodyInterface::GetCenterOfMassPosition"}
+    wl.close()
+    del wl
+    torch.cuda.synchronize()
+    if with_cpu:
+        out["cpu_baseline"] = cpu_baseline_object(workload, bodies, 1, warmup, steps, cpu_budget)
+        if "value" in out["cpu_baseline"] and out["cpu_baseline"]["steps"] == steps and out["cpu_baseline"]["warmup"] == warmup:
+            out["speedup_same_window"] = out["value"] / out["cpu_baseline"]["value"]
+    return out
 
 
 def run_b200(args):
@@ -395,8 +515,8 @@ def run_b200(args):
     api = joltphysics_b200.load()
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), api)
 
-    wl = Workload(args, api, flib, rank, world_size)
-    m = measure(args, wl, torch, dist, world_size, local_rank, args.steps, args.warmup)
+    wl = Workload(args.workload, args.bodies, args.worlds, api, flib, rank, world_size)
+    m = measure(wl, torch, dist, world_size, local_rank, args.steps, args.warmup)
 
     # max over ranks of the times, sum of the work (the only collective: a reduction of the statistics)
     (t_dev, wall, e2e_wall), (total_bodies, launches, total_worlds, h2d, d2h) = reduce_job(
@@ -409,50 +529,55 @@ def run_b200(args):
 
     K = args.steps
     batch = args.workload == "batch"
+    config = job_config(args)
     line = {
         "metric": "body_steps_per_sec", "value": K * total_bodies / t_dev, "unit": "body-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t_dev / K, "steps_per_sec": K / t_dev, "world_steps_per_sec": K * total_worlds / t_dev, "higher_is_better": True,
         "scaling": "strong" if batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "worlds": total_worlds, "bodies": int(total_bodies), "dt": DT, "collision_steps": 1,
-                   "parallelism": (f"worlds sharded over {world_size} GPUs (world_id -> rank blocks), no data-path collective" if batch else f"one world per GPU x{world_size} (replicas only)"),
-                   "timing": "every step streams the whole job state through HBM (working set >> 126 MB L2); no L2 flush between steps"},
+        "config": config,
         "clocks": m["clocks"],
         "e2e": {"value": m["e2e"]["steps"] * total_bodies / e2e_wall, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": m["e2e"]["steps"],
-                "path": "b2j_batch_add_force_torque + b2j_batch_step + b2j_batch_get_state (C ABI, pinned host buffers)" if batch else "facade: BodyInterface::AddForce..., PhysicsSystem::Update, BodyInterface::GetPosition"},
+                "window": config["window"] + " (worlds reset to the creation state and warmed up again)",
+                "path": "b2j_batch_add_force_torque + b2j_batch_step + b2j_batch_get_state (C ABI, pinned host buffers)" if batch else "facade: BodyInterface::AddForcesAndTorques, PhysicsSystem::Update, BodyInterface::GetCenterOfMassPosition"},
         "gpu_launches": launches,
         "wall_ms_per_step": 1000.0 * wall / K,
         "roofline": roofline_of(m),
         "step_counters_mean": {k: v / K for k, v in m["agg"].items()},
-        "kernel_ms_per_step": {k: v["ms"] / m["prof_steps"] for k, v in sorted(m["prof"].items(), key=lambda kv: -kv[1]["ms"])[:14]},
+        "kernel_ms_per_step": {k: round(v["ms"] / m["prof_steps"], 4) for k, v in sorted(m["prof"].items(), key=lambda kv: -kv[1]["ms"])[:14]},
         "profiled_ms_per_step": m["prof_gpu_ms"] / m["prof_steps"],
+        "ms_per_step_series": m["series"],
     }
     if world_size == 1:
+        wl.close()
+        del wl
+        torch.cuda.synchronize()
         if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_object(args.workload, args.bodies, args.worlds, args.warmup, args.steps, args.cpu_seconds)
+        if batch and not args.no_pile and not over_budget(args):
+            # configs[3], one 1M body world on one B200. Two windows: the one the reference can reach on this host inside the bench
+            # budget (same body count, same steps on both arms: the like-for-like ratio) and the formed pile (steps [120, 150), GPU only)
             try:
-                value, steps, warm, sample, threads = cpu_run(args, args.warmup, args.steps, args.cpu_seconds)
-                line["cpu_baseline"] = {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample + "; FMA build of the unmodified reference (oracle/_ref)"}
-            except Exception as e:  # the CPU leg must never take the GPU line down
-                line["cpu_baseline"] = {"error": str(e)}
-        if batch and not args.no_pile:
-            # secondary headline: configs[3], one 1M body world on one B200 (reported next to the batch line, not instead of it)
-            wl.close()
-            del wl
-            torch.cuda.synchronize()
-            pargs = argparse.Namespace(**vars(args))
-            pargs.workload = "pile"
-            pw = Workload(pargs, api, flib, 0, 1)
-            pm = measure(pargs, pw, torch, dist, 1, local_rank, 30, 120, with_e2e=False)
-            line["pile"] = {"config": WORKLOAD_NAMES["pile"], "bodies": pw.num_dynamic, "steps": 30, "warmup": 120,
-                            "value": 30 * pw.num_dynamic / (pm["gpu_ms"] / 1000.0), "unit": "body-steps/s", "ms_per_step": pm["gpu_ms"] / 30,
-                            "roofline": roofline_of(pm), "step_counters_mean": {k: v / 30 for k, v in pm["agg"].items()},
-                            "kernel_ms_per_step": {k: v["ms"] / pm["prof_steps"] for k, v in sorted(pm["prof"].items(), key=lambda kv: -kv[1]["ms"])[:10]}}
-            if not args.no_cpu_baseline:
+                line["pile"] = secondary(api, flib, torch, dist, local_rank, "pile", 1000000, 5, 10, 90.0, with_cpu=not args.no_cpu_baseline, with_e2e=True)
+                if not over_budget(args):
+                    formed = secondary(api, flib, torch, dist, local_rank, "pile", 1000000, 120, 30, 0.0, with_cpu=False, with_e2e=False)
+                    line["pile"]["formed"] = {k: formed[k] for k in ("window", "steps", "warmup", "value", "unit", "ms_per_step", "roofline", "step_counters_mean", "kernel_ms_per_step")}
+            except Exception as e:
+                line["pile"] = {"error": str(e)}
+        if batch and not args.no_extras:
+            # configs[0..2] as single worlds, the reference beside them on the same body count and window
+            line["extra"] = {}
+            for name, bodies, w, k, cpu in (("pyramid", PYRAMID_BODIES, 100, 400, True), ("convex_vs_mesh", CONVEX_VS_MESH_BODIES, 100, 400, True),
+                                            ("max_bodies", MAX_BODIES_FULL, 3, 6, False), ("max_bodies_1m", 1048576, 3, 6, True)):
+                if over_budget(args):
+                    line["extra"][name] = {"skipped": "bench wall clock budget reached"}
+                    continue
                 try:
-                    pw.close()
-                    value, steps, warm, sample, threads = cpu_run(pargs, 120, 30, min(args.cpu_seconds, 15.0))
-                    line["pile"]["cpu_baseline"] = {"value": value, "unit": "body-steps/s", "cores": threads, "kind": "reference", "sample": sample + "; FMA build of the unmodified reference (oracle/_ref)"}
+                    line["extra"][name] = secondary(api, flib, torch, dist, local_rank, name.split("_1m")[0], bodies, w, k, 60.0, with_cpu=cpu and not args.no_cpu_baseline, with_e2e=name != "max_bodies")
                 except Exception as e:
-                    line["pile"]["cpu_baseline"] = {"error": str(e)}
+                    line["extra"][name] = {"error": str(e)}
+            line["extra"]["note"] = ("max_bodies runs the reference scene at its full 8 388 608 bodies on the GPU only (the reference needs ~30 s per step at that size on "
+                                     "this host); max_bodies_1m is the same scene at 1 048 576 bodies on BOTH arms")
+    line["bench_wall_s"] = time.time() - T_START
     print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()
