@@ -342,12 +342,19 @@ class Workload:
             return n * 12, self.num_slots * 12
         return self.num_dynamic * (12 + 4), self.scene.num_bodies * (12 + 16 + 12 + 12 + 4)
 
-    def step_e2e(self):
-        """One step through the reference-facing boundary with host buffers: forces in (H2D), step, positions out (D2H)."""
+    def step_e2e(self, split=None):
+        """One step through the reference-facing boundary with host buffers: forces in (H2D), step, positions out (D2H).
+        split (a 3 element list) accumulates the wall time of the three calls."""
         if self.batch:
+            t0 = time.perf_counter()
             self.api.b2j_batch_add_force_torque(self.batch, self.num_slots, self._f, None)
+            t1 = time.perf_counter()
             self.api.b2j_batch_step(self.batch, DT, 1, C.byref(self.stats))
+            t2 = time.perf_counter()
             self.api.b2j_batch_get_state(self.batch, 0xffffffff, self.num_slots, C.byref(self._st))
+            if split is not None:
+                t3 = time.perf_counter()
+                split[0] += t1 - t0; split[1] += t2 - t1; split[2] += t3 - t2
         else:
             self.scene.step_e2e(DT, self.forces, self.positions)  # facade: BodyInterface::AddForce..., PhysicsSystem::Update, GetPosition
 
@@ -396,10 +403,11 @@ def measure(wl, torch, dist, world_size, local_rank, steps, warmup, with_e2e=Tru
             wl.step()
         barrier()
         t1 = time.perf_counter()
+        split = [0.0, 0.0, 0.0]
         for _ in range(steps):
-            wl.step_e2e()
+            wl.step_e2e(split)
         barrier()
-        out["e2e"] = {"wall": time.perf_counter() - t1, "steps": steps, "h2d": h2d, "d2h": d2h}
+        out["e2e"] = {"wall": time.perf_counter() - t1, "steps": steps, "h2d": h2d, "d2h": d2h, "split_ms": [round(1000.0 * x / steps, 3) for x in split]}
 
     if with_profile:
         # per kernel device time over the same window (event records perturb back-to-back launches, so this is its own leg)
@@ -538,6 +546,7 @@ def run_b200(args):
         "clocks": m["clocks"],
         "e2e": {"value": m["e2e"]["steps"] * total_bodies / e2e_wall, "unit": "body-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": m["e2e"]["steps"],
                 "window": config["window"] + " (worlds reset to the creation state and warmed up again)",
+                "ms_per_step": 1000.0 * e2e_wall / m["e2e"]["steps"], "forces_in__step__positions_out_ms": m["e2e"]["split_ms"],
                 "path": "b2j_batch_add_force_torque + b2j_batch_step + b2j_batch_get_state (C ABI, pinned host buffers)" if batch else "facade: BodyInterface::AddForcesAndTorques, PhysicsSystem::Update, BodyInterface::GetCenterOfMassPosition"},
         "gpu_launches": launches,
         "wall_ms_per_step": 1000.0 * wall / K,

@@ -44,6 +44,7 @@ struct NarrowCtx
 	EpaItem *epa;
 	const uint32_t *collide_order; // batch groups: collide_convex is processed in (pair inside the world, world) order so that the
 	                             // lanes of a warp run the same pair of different worlds (near identical control flow); null = as queued
+	uint32_t collide_order_n;    // entries of collide_order (queue positions past it are processed in queue order)
 	EpaItem *epa_overflow;       // deep pairs that did not fit the small EPA tier (re-run on full size storage)
 	uint32_t *num_epa_overflow;  // device counter
 	EpaResult *epa_results;      // GJK / EPA output; supporting faces / clipping / manifold run in KFinishPairs
@@ -468,16 +469,17 @@ B2J_D ConvexPairSetup convex_pair_setup(const DWorld &w, const CollideItem &item
 // worlds of one pair next to each other
 struct KCollideKeys
 {
-	DWorld w; NarrowCtx c; uint32_t *keys, *vals; uint32_t bits;
+	DWorld w; NarrowCtx c; uint32_t *keys, *vals; uint32_t bits, invalid_key;
 	B2J_D void operator()(uint32_t k) const
 	{
+		vals[k] = k;
+		if (k >= w.counters->num_collide_convex) { keys[k] = invalid_key; return; } // past the end of the queue: sorts behind every real entry
 		CollideItem item = c.collide_convex[k];
 		if (w.world_stride != 0)
 			keys[k] = ((item.b1 % w.world_stride) << bits) | (item.b2 % w.world_stride);
 		else
 			// one big world: group the pairs by the two shape types, so that a warp runs one combination of support functions
 			keys[k] = (w.shapes[w.info[item.b1].shape].kind << 3) | w.shapes[w.info[item.b2].shape].kind;
-		vals[k] = k;
 	}
 };
 
@@ -495,7 +497,7 @@ struct KCollideConvex
 		TransformedSupport b_excl = {};
 		if (alive)
 		{
-			item = c.collide_convex[c.collide_order != nullptr? c.collide_order[k] : k];
+			item = c.collide_convex[k < c.collide_order_n? c.collide_order[k] : k];
 			s = convex_pair_setup(w, item);
 			const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
 			V3 bb1_min = s1.local_min - v3_rep(s.max_separation_distance), bb1_max = s1.local_max + v3_rep(s.max_separation_distance);

@@ -451,6 +451,36 @@ struct Runtime
 		memcpy(stage_dev + begin, stage_host + begin, end - begin);
 #endif
 	}
+	// page locked host memory of the caller (cudaHostAlloc / cudaHostRegister / torch pin_memory)? Then copies go straight between it
+	// and the device instead of through the pinned mirror (one host memcpy less per direction)
+	bool is_pinned(const void *p) const
+	{
+#ifndef B2J_HOSTSIM
+		if (p == nullptr) return false;
+		cudaPointerAttributes a;
+		if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+		return a.type == cudaMemoryTypeHost;
+#else
+		(void)p;
+		return false;
+#endif
+	}
+	void copy_to_device_async(void *dev, const void *host, size_t bytes)
+	{
+#ifndef B2J_HOSTSIM
+		cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, stream);
+#else
+		memcpy(dev, host, bytes);
+#endif
+	}
+	void copy_to_host_async(void *host, const void *dev, size_t bytes)
+	{
+#ifndef B2J_HOSTSIM
+		cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream);
+#else
+		memcpy(host, dev, bytes);
+#endif
+	}
 	void stage_to_host(size_t begin, size_t end)
 	{
 		if (end <= begin) return;

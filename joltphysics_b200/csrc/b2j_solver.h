@@ -45,7 +45,9 @@ enum
 enum { CP_PART_R1X_EFF = 0, CP_PART_I1_BIAS, CP_PART_R2X, CP_PART_I2 };
 
 // meta bits: num points (3) | type1 (2) << 3 | type2 (2) << 5 | velocity steps << 8 | position steps << 16 | friction parts active << 24
-enum : uint32_t { META_LINEAR_FRICTION = 1u << 24, META_ANGULAR_FRICTION = 1u << 25 };
+//            | translation DOFs of body 1 (3) << 26 | translation DOFs of body 2 (3) << 29   (what store_vel_state masks with: no
+//            gather of the BodyInfo per body and iteration)
+enum : uint32_t { META_LINEAR_FRICTION = 1u << 24, META_ANGULAR_FRICTION = 1u << 25, META_DOFS1_SHIFT = 26, META_DOFS2_SHIFT = 29 };
 struct alignas(16) ConstraintHeader { uint32_t b1, b2, manifold, meta; };
 struct Constraints
 {
@@ -674,15 +676,40 @@ B2J_D void part_store(const Constraints &c, int base, uint32_t i, uint32_t type1
 	if (type2 == B2J_MOTION_DYNAMIC) cp_at(c, base + CP_PART_I2, i) = f4(r.i2);
 }
 
+// Where the solve kernels read the read-only planes of a constraint from: straight from HBM (per phase launches, small worlds) or
+// from the shared memory stage a TMA bulk copy filled (solve_velocity_tma_kernel). Same arithmetic on both.
+struct GlobalPlanes
+{
+	Constraints c; uint32_t i;
+	B2J_D F4 ro(int plane) const { return cp_ro(c, plane, i); }
+};
+
+// shared memory stage of one warp tile: [slot][lane] float4 (a warp reads one slot with one conflict free LDS.128), slots = the planes
+// the velocity solve reads minus the two lambda planes (read + written through registers)
+enum { SV_SLOT_NORMAL = 0, SV_SLOT_MASS, SV_SLOT_DIST, SV_SLOT_ANG_I1, SV_SLOT_ANG_I2, SV_SLOT_FR0, SV_SLOT_PT0 = SV_SLOT_FR0 + 8, SV_NUM_SLOTS = SV_SLOT_PT0 + 16 };
+B2J_HD int sv_slot_of_plane(int plane)
+{
+	return plane >= CP_FR0? SV_SLOT_FR0 + (plane - CP_FR0) : (plane == CP_ANG_I1? SV_SLOT_ANG_I1 : (plane == CP_ANG_I2? SV_SLOT_ANG_I2 : plane)); // NORMAL, MASS, DIST = 0, 1, 2
+}
+B2J_HD int sv_plane_of_slot(int slot)
+{
+	return slot >= SV_SLOT_FR0? CP_FR0 + (slot - SV_SLOT_FR0) : (slot == SV_SLOT_ANG_I1? CP_ANG_I1 : (slot == SV_SLOT_ANG_I2? CP_ANG_I2 : slot));
+}
+struct SmemPlanes
+{
+	const F4 *stage; uint32_t lane;
+	B2J_D F4 ro(int plane) const { return stage[sv_slot_of_plane(plane) * 32 + lane]; }
+};
+
 // everything but the lambda
-B2J_D PartRegs part_load(const Constraints &c, int base, uint32_t i, uint32_t type1, uint32_t type2)
+template <class Src> B2J_D PartRegs part_load(const Src &src, int base, uint32_t type1, uint32_t type2)
 {
 	PartRegs r;
-	F4 a = cp_ro(c, base + CP_PART_R1X_EFF, i), b = cp_ro(c, base + CP_PART_I1_BIAS, i);
+	F4 a = src.ro(base + CP_PART_R1X_EFF), b = src.ro(base + CP_PART_I1_BIAS);
 	r.r1x = to_v3(a); r.eff = a.w;
 	r.i1 = to_v3(b); r.bias = b.w;
-	r.r2x = type2 != B2J_MOTION_STATIC? to_v3(cp_ro(c, base + CP_PART_R2X, i)) : v3_zero();
-	r.i2 = type2 == B2J_MOTION_DYNAMIC? to_v3(cp_ro(c, base + CP_PART_I2, i)) : v3_zero();
+	r.r2x = type2 != B2J_MOTION_STATIC? to_v3(src.ro(base + CP_PART_R2X)) : v3_zero();
+	r.i2 = type2 == B2J_MOTION_DYNAMIC? to_v3(src.ro(base + CP_PART_I2)) : v3_zero();
 	r.lambda = 0.0f;
 	(void)type1;
 	return r;
@@ -711,7 +738,7 @@ struct KSetupConstraints
 		if (vsteps > volatile_load(&w.counters->max_velocity_steps)) atomic_max(&w.counters->max_velocity_steps, vsteps);
 		if (psteps > volatile_load(&w.counters->max_position_steps)) atomic_max(&w.counters->max_position_steps, psteps);
 
-		uint32_t meta = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16);
+		uint32_t meta = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16) | ((k1.dofs & 7u) << META_DOFS1_SHIFT) | ((k2.dofs & 7u) << META_DOFS2_SHIFT);
 
 		BodyParams p1 = w.params[src.b1], p2 = w.params[src.b2];
 		float combined_friction = sqrt_(p1.friction * p2.friction);
@@ -900,18 +927,192 @@ B2J_D void load_vel_state(const DWorld &w, uint32_t b1, uint32_t b2, uint32_t ty
 	else { s.v2 = v3_zero(); s.w2 = v3_zero(); }
 }
 
-B2J_D void store_vel_state(const DWorld &w, uint32_t b1, uint32_t b2, uint32_t type1, uint32_t type2, const VelState &s)
+// (Body::SetLinearVelocityClamped... MotionProperties::LockTranslation: the translation DOF masks travel in the constraint's meta word)
+B2J_D void store_vel_state(const DWorld &w, uint32_t b1, uint32_t b2, uint32_t meta, const VelState &s)
 {
+	uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
 	if (type1 == B2J_MOTION_DYNAMIC)
 	{
-		w.linear_velocity[b1] = f4(lock_translation(s.v1, w.info[b1].allowed_dofs));
+		w.linear_velocity[b1] = f4(lock_translation(s.v1, (meta >> META_DOFS1_SHIFT) & 7u));
 		w.angular_velocity[b1] = f4(s.w1);
 	}
 	if (type2 == B2J_MOTION_DYNAMIC)
 	{
-		w.linear_velocity[b2] = f4(lock_translation(s.v2, w.info[b2].allowed_dofs));
+		w.linear_velocity[b2] = f4(lock_translation(s.v2, (meta >> META_DOFS2_SHIFT) & 7u));
 		w.angular_velocity[b2] = f4(s.w2);
 	}
+}
+
+// sWarmStartConstraint (ContactConstraintManager.cpp:1587-1622) on registers: the lambdas (lpt = 4 points, lfr = friction 1, friction 2,
+// angular) are scaled by the warm start ratio and applied; returns true if a velocity changed
+template <class Src> B2J_D bool warm_start_core(const Src &src, uint32_t meta, float ratio, VelState &s, F4 &lpt, F4 &lfr)
+{
+	int n = (int)(meta & 7);
+	uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+	V3 normal = to_v3(src.ro(CP_NORMAL));
+	V3 t1 = normalized_perpendicular(normal);
+	V3 t2 = cross(normal, t1);
+	F4 mass = src.ro(CP_MASS);
+	float inv_m1 = mass.x, inv_m2 = mass.y;
+	bool any = false;
+	if (meta & META_LINEAR_FRICTION)
+	{
+		PartRegs f1 = part_load(src, CP_FR0, type1, type2), f2 = part_load(src, CP_FR0 + 4, type1, type2);
+		if (f1.eff != 0.0f)
+		{
+			lfr.x *= ratio;
+			if (part_apply_velocity_step(f1, type1, type2, s, inv_m1, inv_m2, t1, lfr.x)) any = true;
+		}
+		if (f2.eff != 0.0f)
+		{
+			lfr.y *= ratio;
+			if (part_apply_velocity_step(f2, type1, type2, s, inv_m1, inv_m2, t2, lfr.y)) any = true;
+		}
+	}
+	if (meta & META_ANGULAR_FRICTION)
+	{
+		lfr.z *= ratio;
+		float l = lfr.z;
+		if (l != 0.0f)
+		{
+			if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= l * to_v3(src.ro(CP_ANG_I1));
+			if (type2 == B2J_MOTION_DYNAMIC) s.w2 += l * to_v3(src.ro(CP_ANG_I2));
+			any = true;
+		}
+	}
+	float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
+#if defined(__CUDA_ARCH__)
+	#pragma unroll
+#endif
+	for (int p = 0; p < 4; ++p)
+		if (p < n)
+		{
+			PartRegs r = part_load(src, CP_PT0 + p * 4, type1, type2);
+			lp[p] *= ratio;
+			if (part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, normal, lp[p])) any = true;
+		}
+	lpt = f4(lp[0], lp[1], lp[2], lp[3]);
+	return any;
+}
+
+// sSolveVelocityConstraint (ContactConstraintManager.cpp:1683-1767) on registers. Everything the constraint needs is fetched up front
+// (one memory round trip per constraint instead of one per part); returns true if a velocity changed.
+template <class Src> B2J_D bool solve_velocity_core(const Src &src, uint32_t meta, VelState &s, F4 &lpt, F4 &lfr)
+{
+	int n = (int)(meta & 7);
+	uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+	bool linear_friction_active = (meta & META_LINEAR_FRICTION) != 0;
+	bool angular_friction_active = (meta & META_ANGULAR_FRICTION) != 0;
+	// ---- loads
+	F4 nf = src.ro(CP_NORMAL), mass = src.ro(CP_MASS), dd = src.ro(CP_DIST);
+	V3 normal = to_v3(nf);
+	float mu = nf.w, inv_m1 = mass.x, inv_m2 = mass.y;
+	float dist[4] = { mass.z, mass.w, dd.x, dd.y };
+	float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
+	PartRegs pt[4];
+#if defined(__CUDA_ARCH__)
+	#pragma unroll
+#endif
+	for (int p = 0; p < 4; ++p)
+		if (p < n)
+		{
+			pt[p] = part_load(src, CP_PT0 + p * 4, type1, type2);
+			pt[p].lambda = lp[p];
+		}
+	PartRegs f1, f2;
+	if (linear_friction_active)
+	{
+		f1 = part_load(src, CP_FR0, type1, type2);
+		f2 = part_load(src, CP_FR0 + 4, type1, type2);
+		f1.lambda = lfr.x; f2.lambda = lfr.y;
+	}
+	float ang_eff = dd.z, ang_bias = dd.w, ang_lambda = lfr.z;
+	V3 ang_i1 = v3_zero(), ang_i2 = v3_zero();
+	if (angular_friction_active)
+	{
+		if (type1 == B2J_MOTION_DYNAMIC) ang_i1 = to_v3(src.ro(CP_ANG_I1));
+		if (type2 == B2J_MOTION_DYNAMIC) ang_i2 = to_v3(src.ro(CP_ANG_I2));
+	}
+
+	// ---- solve
+	V3 t1 = normalized_perpendicular(normal);
+	V3 t2 = cross(normal, t1);
+	bool any = false;
+	float max_linear_lambda = 0.0f, max_angular_lambda = 0.0f;
+	if (linear_friction_active || angular_friction_active)
+	{
+#if defined(__CUDA_ARCH__)
+		#pragma unroll
+#endif
+		for (int p = 0; p < 4; ++p)
+			if (p < n)
+			{
+				float lambda = pt[p].lambda;
+				max_linear_lambda += lambda;
+				max_angular_lambda += dist[p] * lambda;
+			}
+		max_linear_lambda *= mu;
+		max_angular_lambda *= mu;
+	}
+	if (linear_friction_active)
+	{
+		float lambda1 = part_get_total_lambda(f1, type1, type2, s, t1);
+		float lambda2 = part_get_total_lambda(f2, type1, type2, s, t2);
+		float total_lambda_sq = square(lambda1) + square(lambda2);
+		if (total_lambda_sq > square(max_linear_lambda))
+		{
+			float scale = max_linear_lambda / sqrt_(total_lambda_sq);
+			lambda1 *= scale;
+			lambda2 *= scale;
+		}
+		if (part_apply_lambda(f1, type1, type2, s, inv_m1, inv_m2, t1, lambda1)) any = true;
+		if (part_apply_lambda(f2, type1, type2, s, inv_m1, inv_m2, t2, lambda2)) any = true;
+		lfr.x = f1.lambda; lfr.y = f2.lambda;
+	}
+	if (angular_friction_active)
+	{
+		// AngularFrictionConstraintPart::SolveVelocityConstraint
+		float jv;
+		if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC) jv = dot(normal, s.w1 - s.w2);
+		else if (type1 != B2J_MOTION_STATIC) jv = dot(normal, s.w1);
+		else jv = -dot(normal, s.w2);
+		float total = ang_lambda;
+		float lambda = ang_eff * (jv - ang_bias);
+		float new_lambda = clamp_(total + lambda, -max_angular_lambda, max_angular_lambda);
+		lambda = new_lambda - total;
+		lfr.z = new_lambda;
+		if (lambda != 0.0f)
+		{
+			if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= lambda * ang_i1;
+			if (type2 == B2J_MOTION_DYNAMIC) s.w2 += lambda * ang_i2;
+			any = true;
+		}
+	}
+#if defined(__CUDA_ARCH__)
+	#pragma unroll
+#endif
+	for (int p = 0; p < 4; ++p)
+		if (p < n)
+		{
+			float total_lambda = part_get_total_lambda(pt[p], type1, type2, s, normal);
+			total_lambda = fmax_(total_lambda, 0.0f);
+			if (part_apply_lambda(pt[p], type1, type2, s, inv_m1, inv_m2, normal, total_lambda)) any = true;
+			lp[p] = pt[p].lambda;
+		}
+	lpt = f4(lp[0], lp[1], lp[2], lp[3]);
+	return any;
+}
+
+// sStoreAppliedImpulses (ContactConstraintManager.cpp:1819-1835) for one constraint
+B2J_D void store_applied_impulses(const DWorld &w, uint32_t manifold, int n, F4 lpt, F4 lfr)
+{
+	CachedManifold &cm = w.write_cache.manifolds[manifold];
+	float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
+	for (int p = 0; p < n; ++p)
+		cm.lambda[p] = lp[p];
+	cm.friction_lambda[0] = lfr.x;
+	cm.friction_lambda[1] = lfr.y;
+	cm.angular_lambda = lfr.z;
 }
 
 // sWarmStartConstraint for solve positions [begin, begin + n)
@@ -923,64 +1124,20 @@ struct KWarmStart
 		uint32_t i = begin + k;
 		ConstraintHeader hdr = c.hdr[i];
 		uint32_t meta = hdr.meta;
-		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-		uint32_t b1 = hdr.b1, b2 = hdr.b2;
 		VelState s;
-		load_vel_state(w, b1, b2, type1, type2, s);
-		V3 normal = to_v3(cp_ro(c, CP_NORMAL, i));
-		V3 t1 = normalized_perpendicular(normal);
-		V3 t2 = cross(normal, t1);
-		F4 mass = cp_ro(c, CP_MASS, i);
-		float inv_m1 = mass.x, inv_m2 = mass.y;
+		load_vel_state(w, hdr.b1, hdr.b2, type1, type2, s);
 		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);
-		bool any = false;
-		if (meta & META_LINEAR_FRICTION)
-		{
-			PartRegs f1 = part_load(c, CP_FR0, i, type1, type2), f2 = part_load(c, CP_FR0 + 4, i, type1, type2);
-			if (f1.eff != 0.0f)
-			{
-				lfr.x *= ratio;
-				if (part_apply_velocity_step(f1, type1, type2, s, inv_m1, inv_m2, t1, lfr.x)) any = true;
-			}
-			if (f2.eff != 0.0f)
-			{
-				lfr.y *= ratio;
-				if (part_apply_velocity_step(f2, type1, type2, s, inv_m1, inv_m2, t2, lfr.y)) any = true;
-			}
-		}
-		if (meta & META_ANGULAR_FRICTION)
-		{
-			lfr.z *= ratio;
-			float l = lfr.z;
-			if (l != 0.0f)
-			{
-				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= l * to_v3(cp_ro(c, CP_ANG_I1, i));
-				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += l * to_v3(cp_ro(c, CP_ANG_I2, i));
-				any = true;
-			}
-		}
-		float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
-#if defined(__CUDA_ARCH__)
-		#pragma unroll
-#endif
-		for (int p = 0; p < 4; ++p)
-			if (p < n)
-			{
-				PartRegs r = part_load(c, CP_PT0 + p * 4, i, type1, type2);
-				lp[p] *= ratio;
-				if (part_apply_velocity_step(r, type1, type2, s, inv_m1, inv_m2, normal, lp[p])) any = true;
-			}
-		cp_at(c, CP_LAMBDA_PT, i) = f4(lp[0], lp[1], lp[2], lp[3]);
+		GlobalPlanes src; src.c = c; src.i = i;
+		bool any = warm_start_core(src, meta, ratio, s, lpt, lfr);
+		cp_at(c, CP_LAMBDA_PT, i) = lpt;
 		cp_at(c, CP_LAMBDA_FR, i) = lfr;
 		if (any)
-			store_vel_state(w, b1, b2, type1, type2, s);
+			store_vel_state(w, hdr.b1, hdr.b2, meta, s);
 	}
 };
 
 // sSolveVelocityConstraint; iteration = 0 based velocity step index (constraints of islands with fewer steps skip).
-// Everything the constraint needs is loaded into registers up front (one DRAM round trip per constraint instead of one per part),
-// the lambdas are written back at the end.
 struct KSolveVelocity
 {
 	DWorld w; Constraints c; uint32_t begin; uint32_t iteration; uint32_t prefetch;
@@ -993,132 +1150,27 @@ struct KSolveVelocity
 			return;
 		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-		uint32_t b1 = hdr.b1, b2 = hdr.b2;
-		bool linear_friction_active = (meta & META_LINEAR_FRICTION) != 0;
-		bool angular_friction_active = (meta & META_ANGULAR_FRICTION) != 0;
 		if (prefetch)
 		{
 			// L2 prefetch of every plane of the constraint right after the header: -5 % on the per phase launches (measured); register
 			// capped builds (more warps per SM) stay slower even with it (6.0 / 7.2 / 8.2 ms vs 5.0 ms at 128 / 96 / 80 registers)
 			for (int pl = CP_NORMAL; pl < CP_FR0; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
-			if (linear_friction_active) for (int pl = CP_FR0; pl < CP_PT0; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
+			if (meta & META_LINEAR_FRICTION) for (int pl = CP_FR0; pl < CP_PT0; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
 			for (int pl = CP_PT0; pl < CP_PT0 + 4 * n; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
 		}
-
-		// ---- loads
 		VelState s;
-		load_vel_state(w, b1, b2, type1, type2, s);
-		F4 nf = cp_ro(c, CP_NORMAL, i), mass = cp_ro(c, CP_MASS, i), dd = cp_ro(c, CP_DIST, i);
+		load_vel_state(w, hdr.b1, hdr.b2, type1, type2, s);
 		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);
-		V3 normal = to_v3(nf);
-		float mu = nf.w, inv_m1 = mass.x, inv_m2 = mass.y;
-		float dist[4] = { mass.z, mass.w, dd.x, dd.y };
-		float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
-		PartRegs pt[4];
-#if defined(__CUDA_ARCH__)
-		#pragma unroll
-#endif
-		for (int p = 0; p < 4; ++p)
-			if (p < n)
-			{
-				pt[p] = part_load(c, CP_PT0 + p * 4, i, type1, type2);
-				pt[p].lambda = lp[p];
-			}
-		PartRegs f1, f2;
-		if (linear_friction_active)
-		{
-			f1 = part_load(c, CP_FR0, i, type1, type2);
-			f2 = part_load(c, CP_FR0 + 4, i, type1, type2);
-			f1.lambda = lfr.x; f2.lambda = lfr.y;
-		}
-		float ang_eff = dd.z, ang_bias = dd.w, ang_lambda = lfr.z;
-		V3 ang_i1 = v3_zero(), ang_i2 = v3_zero();
-		if (angular_friction_active)
-		{
-			if (type1 == B2J_MOTION_DYNAMIC) ang_i1 = to_v3(cp_ro(c, CP_ANG_I1, i));
-			if (type2 == B2J_MOTION_DYNAMIC) ang_i2 = to_v3(cp_ro(c, CP_ANG_I2, i));
-		}
-
-		// ---- solve
-		V3 t1 = normalized_perpendicular(normal);
-		V3 t2 = cross(normal, t1);
-		bool any = false;
-		float max_linear_lambda = 0.0f, max_angular_lambda = 0.0f;
-		if (linear_friction_active || angular_friction_active)
-		{
-#if defined(__CUDA_ARCH__)
-			#pragma unroll
-#endif
-			for (int p = 0; p < 4; ++p)
-				if (p < n)
-				{
-					float lambda = pt[p].lambda;
-					max_linear_lambda += lambda;
-					max_angular_lambda += dist[p] * lambda;
-				}
-			max_linear_lambda *= mu;
-			max_angular_lambda *= mu;
-		}
-		if (linear_friction_active)
-		{
-			float lambda1 = part_get_total_lambda(f1, type1, type2, s, t1);
-			float lambda2 = part_get_total_lambda(f2, type1, type2, s, t2);
-			float total_lambda_sq = square(lambda1) + square(lambda2);
-			if (total_lambda_sq > square(max_linear_lambda))
-			{
-				float scale = max_linear_lambda / sqrt_(total_lambda_sq);
-				lambda1 *= scale;
-				lambda2 *= scale;
-			}
-			if (part_apply_lambda(f1, type1, type2, s, inv_m1, inv_m2, t1, lambda1)) any = true;
-			if (part_apply_lambda(f2, type1, type2, s, inv_m1, inv_m2, t2, lambda2)) any = true;
-			lfr.x = f1.lambda; lfr.y = f2.lambda;
-		}
-		if (angular_friction_active)
-		{
-			// AngularFrictionConstraintPart::SolveVelocityConstraint
-			float jv;
-			if (type1 != B2J_MOTION_STATIC && type2 != B2J_MOTION_STATIC) jv = dot(normal, s.w1 - s.w2);
-			else if (type1 != B2J_MOTION_STATIC) jv = dot(normal, s.w1);
-			else jv = -dot(normal, s.w2);
-			float total = ang_lambda;
-			float lambda = ang_eff * (jv - ang_bias);
-			float new_lambda = clamp_(total + lambda, -max_angular_lambda, max_angular_lambda);
-			lambda = new_lambda - total;
-			lfr.z = new_lambda;
-			if (lambda != 0.0f)
-			{
-				if (type1 == B2J_MOTION_DYNAMIC) s.w1 -= lambda * ang_i1;
-				if (type2 == B2J_MOTION_DYNAMIC) s.w2 += lambda * ang_i2;
-				any = true;
-			}
-		}
-#if defined(__CUDA_ARCH__)
-		#pragma unroll
-#endif
-		for (int p = 0; p < 4; ++p)
-			if (p < n)
-			{
-				float total_lambda = part_get_total_lambda(pt[p], type1, type2, s, normal);
-				total_lambda = fmax_(total_lambda, 0.0f);
-				if (part_apply_lambda(pt[p], type1, type2, s, inv_m1, inv_m2, normal, total_lambda)) any = true;
-				lp[p] = pt[p].lambda;
-			}
-		cp_at(c, CP_LAMBDA_PT, i) = f4(lp[0], lp[1], lp[2], lp[3]);
-		if (linear_friction_active || angular_friction_active)
+		GlobalPlanes src; src.c = c; src.i = i;
+		bool any = solve_velocity_core(src, meta, s, lpt, lfr);
+		cp_at(c, CP_LAMBDA_PT, i) = lpt;
+		if (meta & (META_LINEAR_FRICTION | META_ANGULAR_FRICTION))
 			cp_at(c, CP_LAMBDA_FR, i) = lfr;
 		if (any)
-			store_vel_state(w, b1, b2, type1, type2, s);
+			store_vel_state(w, hdr.b1, hdr.b2, meta, s);
 		// sStoreAppliedImpulses, fused into the last velocity iteration of the constraint's island (saves a pass over all constraints)
 		if (iteration + 1 == ((meta >> 8) & 0xff))
-		{
-			CachedManifold &cm = w.write_cache.manifolds[hdr.manifold];
-			for (int p = 0; p < n; ++p)
-				cm.lambda[p] = lp[p];
-			cm.friction_lambda[0] = lfr.x;
-			cm.friction_lambda[1] = lfr.y;
-			cm.angular_lambda = lfr.z;
-		}
+			store_applied_impulses(w, hdr.manifold, n, lpt, lfr);
 	}
 };
 
@@ -1281,6 +1333,245 @@ template <bool kPosition> __global__ void __launch_bounds__(256) solve_small_ker
 				for (uint32_t k = off[p] + tid; k < off[p + 1]; k += nt) sp(k);
 				grid.sync();
 			}
+		}
+	}
+}
+#endif
+
+#if !defined(B2J_HOSTSIM) && defined(__CUDACC__)
+// ---- the whole velocity solve in ONE persistent launch, constraint planes streamed through shared memory by TMA -------------------
+//
+// One cooperative launch runs the warm start and every velocity iteration of every phase (grid wide barriers between phases; phase
+// offsets, phase and iteration counts are read on the device: no per phase launch, no host round trip). Inside a phase every WARP
+// owns the tiles gw, gw + NW, ... of 32 consecutive constraints and runs its own two stage pipeline:
+//   * the read-only planes of tile k + 1 are copied global -> shared memory by 1-D TMA bulk copies (cp.async.bulk, UBLKCP in SASS,
+//     one 512 byte copy per plane the tile needs, issued by up to 29 lanes in parallel) that complete on the stage's mbarrier,
+//   * the headers are register prefetched two tiles ahead, the body velocities and the two lambda planes (read + written, kept on the
+//     generic proxy) one tile ahead,
+//   * tile k is solved out of shared memory (conflict free LDS.128) with the arithmetic of the per phase kernels (solve_velocity_core).
+// 7 warps x 2 stages x 29 planes x 512 B = 203 KB of shared memory per SM keep ~100 KB of loads in flight per SM, independent of the
+// register budget of the solve code (the per phase kernel: 168 registers -> 12 warps, every warp stalls for two DRAM round trips per
+// constraint: 0.27 of the HBM peak over a batch step, 0.57 on launches of several million constraints).
+enum { SV_WARPS = 7, SV_THREADS = SV_WARPS * 32, SV_STAGES = 2, SV_STAGE_F4 = SV_NUM_SLOTS * 32 };
+constexpr size_t SV_SMEM_BYTES = (size_t)SV_WARPS * SV_STAGES * SV_STAGE_F4 * sizeof(F4) + (size_t)SV_WARPS * SV_STAGES * sizeof(uint64_t);
+
+B2J_D uint32_t sv_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+B2J_D void sv_mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sv_smem_addr(bar)), "r"(count) : "memory"); }
+B2J_D void sv_mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sv_smem_addr(bar)), "r"(bytes) : "memory"); }
+B2J_D void sv_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" :: "r"(sv_smem_addr(bar)), "r"(parity) : "memory");
+}
+B2J_D void sv_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(sv_smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(sv_smem_addr(bar)) : "memory");
+}
+
+// slots of the shared memory stage a constraint reads (bit = slot); kWarm: the warm start pass does not read the r2 x axis planes
+template <bool kWarm> B2J_D uint32_t sv_slot_mask(uint32_t meta)
+{
+	uint32_t n = meta & 7, type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+	uint32_t part = (1u << CP_PART_R1X_EFF) | (1u << CP_PART_I1_BIAS);
+	if (!kWarm && type2 != B2J_MOTION_STATIC) part |= 1u << CP_PART_R2X;
+	if (type2 == B2J_MOTION_DYNAMIC) part |= 1u << CP_PART_I2;
+	uint32_t mask = (1u << SV_SLOT_NORMAL) | (1u << SV_SLOT_MASS);
+	if (!kWarm) mask |= 1u << SV_SLOT_DIST;
+	if (meta & META_LINEAR_FRICTION) mask |= (part | (part << 4)) << SV_SLOT_FR0;
+	if (meta & META_ANGULAR_FRICTION)
+	{
+		if (type1 == B2J_MOTION_DYNAMIC) mask |= 1u << SV_SLOT_ANG_I1;
+		if (type2 == B2J_MOTION_DYNAMIC) mask |= 1u << SV_SLOT_ANG_I2;
+	}
+	for (uint32_t p = 0; p < n; ++p) mask |= part << (SV_SLOT_PT0 + 4 * p);
+	return mask;
+}
+
+// what a lane prefetches into registers one tile ahead: the velocities of its two bodies and its two lambda planes
+struct SvPre { F4 v1, w1, v2, w2, lpt, lfr; };
+
+struct KSolveVelocityAll { }; // (profiling category)
+__global__ void __launch_bounds__(SV_THREADS, 1) solve_velocity_tma_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
+{
+	extern __shared__ __align__(128) unsigned char sv_smem[];
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	F4 *stages = reinterpret_cast<F4 *>(sv_smem) + (size_t)warp * SV_STAGES * SV_STAGE_F4;
+	uint64_t *bars = reinterpret_cast<uint64_t *>(sv_smem + (size_t)SV_WARPS * SV_STAGES * SV_STAGE_F4 * sizeof(F4)) + warp * SV_STAGES;
+	if (lane == 0)
+	{
+		for (int st = 0; st < SV_STAGES; ++st) sv_mbar_init(&bars[st], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	uint32_t parity_bits = 0; // bit = stage: phase parity of the stage's mbarrier
+
+	const Constraints c = s.con;
+	const uint32_t gw = blockIdx.x * SV_WARPS + warp, nw = gridDim.x * SV_WARPS;
+	const uint32_t np = w.counters->num_phases;
+	const uint32_t steps = w.counters->max_velocity_steps;
+	const uint32_t *off = s.phase_count;
+
+	for (uint32_t pass = 0; pass <= steps; ++pass) // pass 0 = warm start, pass it + 1 = velocity iteration it
+	{
+		const bool warm = pass == 0;
+		const uint32_t iteration = pass - 1;
+		for (uint32_t p = 0; p < np; ++p)
+		{
+			const uint32_t begin = off[p], end = off[p + 1];
+			if (begin == end)
+				continue; // (uniform over the grid)
+			const uint32_t ntiles = (end - begin + 31) >> 5;
+
+			// header of the lane's constraint in tile t (meta = 0 and valid = false past the end of the phase)
+			auto load_hdr = [&](uint32_t t, bool &valid) -> ConstraintHeader {
+				uint32_t i = begin + (t << 5) + lane;
+				valid = t < ntiles && i < end;
+				ConstraintHeader h; h.b1 = 0; h.b2 = 0; h.manifold = 0; h.meta = 0;
+				if (valid) { uint4 v = __ldg(reinterpret_cast<const uint4 *>(&c.hdr[i])); h.b1 = v.x; h.b2 = v.y; h.manifold = v.z; h.meta = v.w; }
+				// constraints of islands with fewer velocity steps are done: they neither load nor solve in this pass
+				if (!warm && iteration >= ((h.meta >> 8) & 0xff)) valid = false;
+				return h;
+			};
+			// TMA bulk copies of the planes tile t needs into `stage` + register prefetch of the lane's velocities and lambdas
+			auto issue = [&](uint32_t t, const ConstraintHeader &h, bool valid, int stage, SvPre &pre, uint32_t &tile_mask) {
+				uint32_t first = begin + (t << 5);
+				uint32_t count = end - first < 32u? end - first : 32u;
+				uint32_t lane_mask = valid? (warm? sv_slot_mask<true>(h.meta) : sv_slot_mask<false>(h.meta)) : 0u;
+				tile_mask = __reduce_or_sync(0xffffffffu, lane_mask);
+				if (tile_mask != 0)
+				{
+					if (lane == 0) sv_mbar_expect_tx(&bars[stage], (uint32_t)__popc(tile_mask) * count * (uint32_t)sizeof(F4));
+					__syncwarp();
+					if (lane < SV_NUM_SLOTS && ((tile_mask >> lane) & 1u))
+						sv_bulk_g2s(stages + (size_t)stage * SV_STAGE_F4 + lane * 32, &c.cp[(size_t)sv_plane_of_slot((int)lane) * c.capacity + first], count * (uint32_t)sizeof(F4), &bars[stage]);
+				}
+				if (valid)
+				{
+					uint32_t type1 = (h.meta >> 3) & 3, type2 = (h.meta >> 5) & 3;
+					uint32_t i = first + lane;
+					if (type1 != B2J_MOTION_STATIC) { pre.v1 = w.linear_velocity[h.b1]; pre.w1 = w.angular_velocity[h.b1]; }
+					if (type2 != B2J_MOTION_STATIC) { pre.v2 = w.linear_velocity[h.b2]; pre.w2 = w.angular_velocity[h.b2]; }
+					pre.lpt = cp_at(c, CP_LAMBDA_PT, i);
+					pre.lfr = cp_at(c, CP_LAMBDA_FR, i);
+				}
+			};
+
+			uint32_t t = gw;
+			bool valid0 = false, valid1 = false, valid2 = false;
+			ConstraintHeader h0 = load_hdr(t, valid0), h1 = load_hdr(t + nw, valid1), h2;
+			SvPre pre0, pre1;
+			uint32_t mask0 = 0, mask1 = 0;
+			int stage = 0;
+			if (t < ntiles) issue(t, h0, valid0, stage, pre0, mask0);
+			while (t < ntiles)
+			{
+				uint32_t tn = t + nw;
+				if (tn < ntiles) issue(tn, h1, valid1, stage ^ 1, pre1, mask1);
+				h2 = load_hdr(tn + nw, valid2);
+				if (mask0 != 0)
+				{
+					sv_mbar_wait(&bars[stage], (parity_bits >> stage) & 1u);
+					parity_bits ^= 1u << stage;
+				}
+				if (valid0)
+				{
+					uint32_t meta = h0.meta;
+					uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+					uint32_t i = begin + (t << 5) + lane;
+					VelState vs;
+					if (type1 != B2J_MOTION_STATIC) { vs.v1 = to_v3(pre0.v1); vs.w1 = to_v3(pre0.w1); } else { vs.v1 = v3_zero(); vs.w1 = v3_zero(); }
+					if (type2 != B2J_MOTION_STATIC) { vs.v2 = to_v3(pre0.v2); vs.w2 = to_v3(pre0.w2); } else { vs.v2 = v3_zero(); vs.w2 = v3_zero(); }
+					F4 lpt = pre0.lpt, lfr = pre0.lfr;
+					SmemPlanes src; src.stage = stages + (size_t)stage * SV_STAGE_F4; src.lane = lane;
+					bool any;
+					if (warm)
+					{
+						any = warm_start_core(src, meta, warm_start_ratio, vs, lpt, lfr);
+						cp_at(c, CP_LAMBDA_PT, i) = lpt;
+						cp_at(c, CP_LAMBDA_FR, i) = lfr;
+					}
+					else
+					{
+						any = solve_velocity_core(src, meta, vs, lpt, lfr);
+						cp_at(c, CP_LAMBDA_PT, i) = lpt;
+						if (meta & (META_LINEAR_FRICTION | META_ANGULAR_FRICTION))
+							cp_at(c, CP_LAMBDA_FR, i) = lfr;
+					}
+					if (any)
+						store_vel_state(w, h0.b1, h0.b2, meta, vs);
+					if (!warm && iteration + 1 == ((meta >> 8) & 0xff))
+						store_applied_impulses(w, h0.manifold, (int)(meta & 7), lpt, lfr);
+				}
+				__syncwarp(); // every lane is done reading the stage: the tile after next may overwrite it
+				h0 = h1; valid0 = valid1; pre0 = pre1; mask0 = mask1;
+				h1 = h2; valid1 = valid2;
+				stage ^= 1;
+				t = tn;
+			}
+			grid.sync();
+		}
+	}
+}
+
+// The position iterations of every phase in one cooperative launch (same per constraint functor as the per phase launches)
+struct KSolvePositionAll { };
+__global__ void __launch_bounds__(128) solve_position_all_kernel(const DWorld w, const SolveCtx s)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	const uint32_t np = w.counters->num_phases;
+	const uint32_t steps = w.counters->max_position_steps;
+	const uint32_t *off = s.phase_count;
+	KSolvePosition sp; sp.w = w; sp.c = s.con; sp.begin = 0;
+	for (uint32_t it = 0; it < steps; ++it)
+	{
+		sp.iteration = it;
+		for (uint32_t p = 0; p < np; ++p)
+		{
+			if (off[p] == off[p + 1])
+				continue;
+			for (uint32_t k = off[p] + tid; k < off[p + 1]; k += nt) sp(k);
+			grid.sync();
+		}
+	}
+}
+
+// Same for the velocity solve without the shared memory pipeline (kept for A/B measurements: B2J_SOLVE_MODE=1)
+struct KSolveVelocityAllPlain { };
+__global__ void __launch_bounds__(128) solve_velocity_all_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+	const uint32_t np = w.counters->num_phases;
+	const uint32_t steps = w.counters->max_velocity_steps;
+	const uint32_t *off = s.phase_count;
+	KWarmStart ws; ws.w = w; ws.c = s.con; ws.begin = 0; ws.ratio = warm_start_ratio;
+	for (uint32_t p = 0; p < np; ++p)
+	{
+		if (off[p] == off[p + 1])
+			continue;
+		for (uint32_t k = off[p] + tid; k < off[p + 1]; k += nt) ws(k);
+		grid.sync();
+	}
+	KSolveVelocity sv; sv.w = w; sv.c = s.con; sv.begin = 0; sv.prefetch = 1;
+	for (uint32_t it = 0; it < steps; ++it)
+	{
+		sv.iteration = it;
+		for (uint32_t p = 0; p < np; ++p)
+		{
+			if (off[p] == off[p + 1])
+				continue;
+			for (uint32_t k = off[p] + tid; k < off[p + 1]; k += nt) sv(k);
+			grid.sync();
 		}
 	}
 }

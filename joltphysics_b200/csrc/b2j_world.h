@@ -116,7 +116,8 @@ struct StepCounters
 	uint32_t new_active_count;
 	uint32_t max_velocity_steps, max_position_steps;
 	uint32_t hash_tie;               // number of equal adjacent sort keys seen (documented deviation if != 0)
-	uint32_t pad[9];
+	uint32_t cache_pairs, cache_manifolds; // sizes of the write cache, published at the end of the step
+	uint32_t pad[7];
 };
 
 // Everything a kernel needs, passed by value (pointers into HBM + scalars)

@@ -377,6 +377,13 @@ struct KNextRound
 	}
 };
 
+// the sizes of the write cache join the step counters (one readback at the end of the step)
+struct KPublishCacheCounts
+{
+	DWorld w;
+	B2J_D void operator()(uint32_t) const { w.counters->cache_pairs = *w.write_cache.num_pairs; w.counters->cache_manifolds = *w.write_cache.num_manifolds; }
+};
+
 struct KGatherSortKeys
 {
 	SolveCtx s; uint64_t *keys; uint32_t *vals;
@@ -439,6 +446,7 @@ struct b2j_world
 	std::vector<uint8_t> layer_list_dirty, layer_needs_build, layer_has_moving;
 	uint32_t num_bodies = 0, num_active = 0, num_slots = 0;
 	uint32_t num_worlds = 1;               // > 1: batched independent worlds (b2j_batch)
+	uint32_t solve_grid_div = 1;           // the one launch solvers use 1 / solve_grid_div of the SMs (groups of a batch that solve concurrently)
 	uint32_t get_state_first = 0;          // slot offset of b2j_bodies_get_state with ids == NULL (batch world selection)
 
 	// shapes
@@ -485,6 +493,7 @@ struct b2j_world
 	StepCounters h_counters;
 	std::vector<uint32_t> h_phase_offsets;
 	uint32_t last_num_events = 0, last_num_act_events = 0, last_num_pairs = 0;
+	uint32_t last_collide_convex = 0;      // longest convex pair queue of the previous step (sizes this step's queue ordering)
 #ifndef B2J_HOSTSIM
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 #endif
@@ -632,7 +641,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 
 	// (a3, a5..a9) find pairs + narrow phase; repeated for the bodies woken up by contacts until no new body wakes up
 	uint32_t first_active = 0, n_query = W->num_active;
-	uint32_t woken_total = 0;
+	uint32_t woken_total = 0, longest_queue = 0;
 	const int max_rounds = 64;
 	for (int round = 0; ; ++round)
 	{
@@ -658,6 +667,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		rt.memset_(W->nc.num_epa_overflow, 0, 4);
 		rt.memset_(W->nc.num_epa_results, 0, 4);
 		W->nc.collide_order = nullptr;
+		W->nc.collide_order_n = 0;
 		// (B2J_COLLIDE_ORDER_MIN: queue length from which a single world orders its queue; tests lower it to cover the path on small scenes)
 		const char *order_env = getenv("B2J_COLLIDE_ORDER_MIN");
 		const uint32_t order_min = order_env != nullptr? (uint32_t)atoi(order_env) : 65536u;
@@ -666,16 +676,21 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		if (d.world_stride < 65536 && W->d_collide_keys[0] != nullptr)
 		{
 			// batch group: same pair of different worlds in neighbouring lanes (GJK / EPA / manifold code paths then coincide: 15 -> ~30
-			// active lanes per instruction). Needs the queue length on the host: one small readback per round.
-			if (!read_counters(W)) return false;
-			uint32_t nq = W->h_counters.num_collide_convex < d.max_body_pairs? W->h_counters.num_collide_convex : d.max_body_pairs;
-			if (nq >= (d.world_stride != 0? 1024u : order_min))
+			// active lanes per instruction); one big world: pairs grouped by shape type pair. The queue length only exists on the device
+			// and a radix sort is sized on the host: the sort covers a CAPACITY derived from the longest queue of the previous step
+			// (entries past the real end carry the largest key and stay behind it; should the queue outgrow the capacity, the excess
+			// is processed in queue order) -- no host round trip.
+			uint32_t cap = 2 * W->last_collide_convex + 1024;
+			if (cap > d.max_body_pairs) cap = d.max_body_pairs;
+			if (W->last_collide_convex >= (d.world_stride != 0? 512u : order_min / 2))
 			{
 				uint32_t bits = 1;
 				while ((1u << bits) < d.world_stride) ++bits;
-				{ KCollideKeys k; k.w = d; k.c = W->nc; k.keys = W->d_collide_keys[0]; k.vals = W->d_collide_vals[0]; k.bits = bits; rt.launch(k, nq); }
-				rt.sort_pairs<uint32_t>(W->d_collide_keys[0], W->d_collide_keys[1], W->d_collide_vals[0], W->d_collide_vals[1], nq, d.world_stride != 0? (int)(2 * bits) : 6);
+				uint32_t key_bits = d.world_stride != 0? 2 * bits : 6;
+				{ KCollideKeys k; k.w = d; k.c = W->nc; k.keys = W->d_collide_keys[0]; k.vals = W->d_collide_vals[0]; k.bits = bits; k.invalid_key = 1u << key_bits; rt.launch(k, cap); }
+				rt.sort_pairs<uint32_t>(W->d_collide_keys[0], W->d_collide_keys[1], W->d_collide_vals[0], W->d_collide_vals[1], cap, (int)key_bits + 1);
 				W->nc.collide_order = W->d_collide_vals[1];
+				W->nc.collide_order_n = cap;
 			}
 		}
 		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev_lockstep(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
@@ -687,6 +702,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_warp_smem<KCollideMesh, EpaStorageFull>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
 		if (!read_counters(W)) return false;
 		uint32_t woken = W->h_counters.num_woken;
+		if (W->h_counters.num_collide_convex > longest_queue) longest_queue = W->h_counters.num_collide_convex;
 		if (W->h_counters.num_epa > W->nc.max_epa) { last_error() = "EPA queue overflow"; return false; }
 		{ KNextRound k; k.w = d; k.round_begin = W->d_round_begin; rt.launch(k, 1); }
 		if (woken == 0)
@@ -702,6 +718,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	uint32_t M = W->h_counters.num_constraints < d.max_constraints? W->h_counters.num_constraints : d.max_constraints;
 	uint32_t num_pairs = W->h_counters.num_pairs < d.max_body_pairs? W->h_counters.num_pairs : d.max_body_pairs;
 	W->last_num_pairs = num_pairs;
+	W->last_collide_convex = longest_queue < d.max_body_pairs? longest_queue : d.max_body_pairs;
 	uint32_t na = W->num_active;
 
 	// (a12) islands
@@ -715,7 +732,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	{ KIslandClassify k; k.w = d; k.s = sc; rt.launch(k, na); }
 
 	uint32_t num_phases = 0, vsteps = 0, psteps = 0;
-	bool block_solve = false;
+	bool block_solve = false, solved_by_phase_launches = false;
 	if (M > 0)
 	{
 		// (a14 SortContacts) order by sort key
@@ -814,11 +831,11 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		// (a11) constraint setup straight into solve order
 		{ KSetupConstraints k; k.w = d; k.s = sc; k.dt = dt; rt.launch(k, M); }
 
-		if (!read_counters(W)) return false;
-		num_phases = W->h_counters.num_phases;
-		vsteps = W->h_counters.max_velocity_steps;
-		psteps = W->h_counters.max_position_steps;
 #ifndef B2J_HOSTSIM
+		// B2J_SOLVE_MODE: 2 (default) = one persistent launch per solve, constraint planes streamed through shared memory by TMA
+		// (solve_velocity_tma_kernel); 1 = one persistent launch, loads straight from HBM; 0 = one launch per phase per iteration
+		const char *solve_mode_env = getenv("B2J_SOLVE_MODE");
+		int solve_mode = solve_mode_env != nullptr? atoi(solve_mode_env) : 2;
 		// small single world: the whole velocity solve in one small cooperative launch (solve_small_kernel)
 		block_solve = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
 		if (block_solve)
@@ -831,27 +848,69 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			if (rt.profiling) rt.prof_end();
 			if (e != cudaSuccess) { cudaGetLastError(); block_solve = false; }
 		}
-		if (!block_solve)
-#endif
+		if (!block_solve && solve_mode != 0)
 		{
+			float ratio_arg = warm_start_ratio;
+			void *args[] = { (void *)&d, (void *)&sc, (void *)&ratio_arg };
+			cudaError_t e = cudaErrorUnknown;
+			if (solve_mode == 2)
+			{
+				int &blocks_per_sm = rt.func_blocks_per_sm[(const void *)solve_velocity_tma_kernel];
+				if (blocks_per_sm == 0)
+				{
+					cudaFuncSetAttribute(solve_velocity_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_BYTES);
+					if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, solve_velocity_tma_kernel, SV_THREADS, SV_SMEM_BYTES) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = -1; }
+				}
+				if (blocks_per_sm > 0)
+				{
+					++rt.launches;
+					if (rt.profiling) rt.prof_begin(profile_category<KSolveVelocityAll>());
+					e = cudaLaunchCooperativeKernel((const void *)solve_velocity_tma_kernel, dim3((unsigned)(rt.num_sms * blocks_per_sm / W->solve_grid_div)), dim3(SV_THREADS), args, SV_SMEM_BYTES, rt.stream);
+					if (rt.profiling) rt.prof_end();
+				}
+			}
+			else
+			{
+				int &blocks_per_sm = rt.func_blocks_per_sm[(const void *)solve_velocity_all_kernel];
+				if (blocks_per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, solve_velocity_all_kernel, 128, 0) != cudaSuccess || blocks_per_sm < 1)) { cudaGetLastError(); blocks_per_sm = -1; }
+				if (blocks_per_sm > 0)
+				{
+					++rt.launches;
+					if (rt.profiling) rt.prof_begin(profile_category<KSolveVelocityAllPlain>());
+					e = cudaLaunchCooperativeKernel((const void *)solve_velocity_all_kernel, dim3((unsigned)(rt.num_sms * blocks_per_sm / W->solve_grid_div)), dim3(128), args, 0, rt.stream);
+					if (rt.profiling) rt.prof_end();
+				}
+			}
+			if (e != cudaSuccess) { cudaGetLastError(); solve_mode = 0; } // fall back to the per phase launches
+		}
+		const bool phase_launches = !block_solve && solve_mode == 0;
+#else
+		const bool phase_launches = true;
+#endif
+		if (phase_launches)
+		{
+			// per phase launches are sized on the host: phase count, iteration counts and phase offsets come back first
+			if (!read_counters(W)) return false;
+			num_phases = W->h_counters.num_phases;
+			vsteps = W->h_counters.max_velocity_steps;
 			W->h_phase_offsets.resize(num_phases + 1);
 			rt.download(W->h_phase_offsets.data(), sc.phase_count, num_phases + 1);
-		}
-
-		// (a14) warm start + velocity iterations, one launch per phase
-		for (uint32_t p = 0; p < num_phases && !block_solve; ++p)
-		{
-			uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
-			KWarmStart k; k.w = d; k.c = sc.con; k.begin = begin; k.ratio = warm_start_ratio; rt.launch(k, n);
-		}
-		for (uint32_t it = 0; it < vsteps && !block_solve; ++it)
+			// (a14) warm start + velocity iterations, one launch per phase
 			for (uint32_t p = 0; p < num_phases; ++p)
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
-				KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
-				k.prefetch = 1;
-				rt.launch(k, n);
+				KWarmStart k; k.w = d; k.c = sc.con; k.begin = begin; k.ratio = warm_start_ratio; rt.launch(k, n);
 			}
+			for (uint32_t it = 0; it < vsteps; ++it)
+				for (uint32_t p = 0; p < num_phases; ++p)
+				{
+					uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+					KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
+					k.prefetch = 1;
+					rt.launch(k, n);
+				}
+		}
+		solved_by_phase_launches = phase_launches;
 		// the applied impulses are stored by the last velocity iteration of every constraint; islands without iterations only exist when
 		// the default number of velocity steps is 0
 		if (d.settings.num_velocity_steps == 0) { KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
@@ -869,7 +928,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 
 	// (a16) position iterations
 #ifndef B2J_HOSTSIM
-	if (block_solve && psteps > 0)
+	if (block_solve && M > 0)
 	{
 		float ratio_arg = 0.0f;
 		void *args[] = { (void *)&d, (void *)&sc, (void *)&ratio_arg };
@@ -879,13 +938,39 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		if (rt.profiling) rt.prof_end();
 		if (e != cudaSuccess) { cudaGetLastError(); last_error() = "cooperative position solve launch failed"; return false; }
 	}
-#endif
-	for (uint32_t it = 0; it < psteps && !block_solve; ++it)
-		for (uint32_t p = 0; p < num_phases; ++p)
+	else if (M > 0 && !solved_by_phase_launches)
+	{
+		void *args[] = { (void *)&d, (void *)&sc };
+		int &blocks_per_sm = rt.func_blocks_per_sm[(const void *)solve_position_all_kernel];
+		if (blocks_per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, solve_position_all_kernel, 128, 0) != cudaSuccess || blocks_per_sm < 1)) { cudaGetLastError(); blocks_per_sm = -1; }
+		cudaError_t e = cudaErrorUnknown;
+		if (blocks_per_sm > 0)
 		{
-			uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
-			KSolvePosition k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it; rt.launch(k, n);
+			++rt.launches;
+			if (rt.profiling) rt.prof_begin(profile_category<KSolvePositionAll>());
+			e = cudaLaunchCooperativeKernel((const void *)solve_position_all_kernel, dim3((unsigned)(rt.num_sms * blocks_per_sm / W->solve_grid_div)), dim3(128), args, 0, rt.stream);
+			if (rt.profiling) rt.prof_end();
 		}
+		if (e != cudaSuccess) { cudaGetLastError(); solved_by_phase_launches = true; } // fall back to the per phase launches below
+	}
+#endif
+	if (M > 0 && solved_by_phase_launches)
+	{
+		if (num_phases == 0)
+		{
+			if (!read_counters(W)) return false;
+			num_phases = W->h_counters.num_phases;
+			W->h_phase_offsets.resize(num_phases + 1);
+			rt.download(W->h_phase_offsets.data(), sc.phase_count, num_phases + 1);
+		}
+		psteps = W->h_counters.max_position_steps;
+		for (uint32_t it = 0; it < psteps; ++it)
+			for (uint32_t p = 0; p < num_phases; ++p)
+			{
+				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+				KSolvePosition k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it; rt.launch(k, n);
+			}
+	}
 
 	// (a16, a17) bounds, sleeping, active list compaction
 	{ KBoundsAndSleep k; k.w = d; k.s = sc; k.dt = dt; k.is_last = is_last? 1u : 0u; rt.launch(k, na); }
@@ -904,16 +989,22 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		rt.memset_(W->d_energy, 0, 4);
 		KKineticEnergy k; k.w = d; k.out = W->d_energy; rt.launch(k, na);
 	}
+	{ KPublishCacheCounts k; k.w = d; rt.launch(k, 1); }
 	if (!read_counters(W)) return false;
 	if (is_last) new_active = W->h_counters.new_active_count;
+	if (M > 0)
+	{
+		// (the one launch solvers read these on the device; the host only reports them)
+		num_phases = W->h_counters.num_phases;
+		vsteps = W->h_counters.max_velocity_steps;
+		psteps = W->h_counters.max_position_steps;
+	}
 
 	// swap the caches: this step's write cache is the next step's read cache
 	uint32_t wi = W->write_idx;
-	W->cache_num_pairs[wi] = W->h_counters.num_pairs < d.max_body_pairs? W->h_counters.num_pairs : d.max_body_pairs;
-	rt.download(&W->cache_num_manifolds[wi], W->cache[wi].num_manifolds, 1);
-	if (W->cache_num_manifolds[wi] > d.max_constraints) W->cache_num_manifolds[wi] = d.max_constraints;
-	rt.download(&W->cache_num_pairs[wi], W->cache[wi].num_pairs, 1);
-	if (W->cache_num_pairs[wi] > d.max_body_pairs) W->cache_num_pairs[wi] = d.max_body_pairs;
+	// (the sizes of the cache written by this step came back with the counters: one readback at the end of the step, not three)
+	W->cache_num_manifolds[wi] = W->h_counters.cache_manifolds < d.max_constraints? W->h_counters.cache_manifolds : d.max_constraints;
+	W->cache_num_pairs[wi] = W->h_counters.cache_pairs < d.max_body_pairs? W->h_counters.cache_pairs : d.max_body_pairs;
 	W->write_idx ^= 1;
 	clear_cache(W, W->write_idx);
 	W->num_active = new_active;
@@ -1577,14 +1668,23 @@ int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 	if (out->active_index) k.active_index = rt.stage_alloc<uint32_t>(n, &h_active);
 	if (out->sleep_timer) k.sleep_timer = rt.stage_alloc<float>(n, &h_timer);
 	rt.launch(k, n);
-	rt.stage_to_host(out_begin, rt.stage_used);
-	if (h_pos) memcpy(out->position, h_pos, (size_t)n * 12);
-	if (h_rot) memcpy(out->rotation, h_rot, (size_t)n * 16);
-	if (h_lin) memcpy(out->linear_velocity, h_lin, (size_t)n * 12);
-	if (h_ang) memcpy(out->angular_velocity, h_ang, (size_t)n * 12);
-	if (h_bounds) memcpy(out->bounds, h_bounds, (size_t)n * 24);
-	if (h_active) memcpy(out->active_index, h_active, (size_t)n * 4);
-	if (h_timer) memcpy(out->sleep_timer, h_timer, (size_t)n * 4);
+	// page locked destination buffers receive the device arrays directly; pageable ones go through the pinned mirror
+	struct Out { void *dst; const void *dev; const void *mirror; size_t bytes; };
+	const Out outs[7] = { { out->position, k.pos, h_pos, (size_t)n * 12 }, { out->rotation, k.rot, h_rot, (size_t)n * 16 }, { out->linear_velocity, k.lin, h_lin, (size_t)n * 12 },
+		{ out->angular_velocity, k.ang, h_ang, (size_t)n * 12 }, { out->bounds, k.bounds, h_bounds, (size_t)n * 24 }, { out->active_index, k.active_index, h_active, (size_t)n * 4 },
+		{ out->sleep_timer, k.sleep_timer, h_timer, (size_t)n * 4 } };
+	bool all_pinned = n >= 4096; // (small reads: the attribute queries cost more than the copy through the mirror)
+	for (const Out &o : outs) if (o.dst != nullptr && all_pinned && !rt.is_pinned(o.dst)) all_pinned = false;
+	if (all_pinned)
+	{
+		for (const Out &o : outs) if (o.dst != nullptr) rt.copy_to_host_async(o.dst, o.dev, o.bytes);
+		rt.sync();
+	}
+	else
+	{
+		rt.stage_to_host(out_begin, rt.stage_used);
+		for (const Out &o : outs) if (o.dst != nullptr) memcpy(o.dst, o.mirror, o.bytes);
+	}
 	return rt.check("b2j_bodies_get_state")? 0 : -1;
 }
 
@@ -1648,9 +1748,19 @@ int b2j_bodies_add_force_torque(b2j_world *W, const uint32_t *ids, uint32_t n, c
 	k.ids = nullptr;
 	if (ids != nullptr) { k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4); } // NULL: slots 0..n-1
 	k.force = nullptr; k.torque = nullptr;
-	if (force) { k.force = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, force, (size_t)n * 12); }
-	if (torque) { k.torque = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, torque, (size_t)n * 12); }
-	rt.stage_to_device(0, rt.stage_used);
+	// page locked source arrays are copied to the device directly; pageable ones through the pinned mirror
+	bool direct = n >= 4096 && (force == nullptr || rt.is_pinned(force)) && (torque == nullptr || rt.is_pinned(torque));
+	size_t mirror_end = rt.stage_used;
+	float *d_force = nullptr, *d_torque = nullptr;
+	if (force) { d_force = rt.stage_alloc<float>((size_t)n * 3, &h); if (!direct) { memcpy(h, force, (size_t)n * 12); mirror_end = rt.stage_used; } }
+	if (torque) { d_torque = rt.stage_alloc<float>((size_t)n * 3, &h); if (!direct) { memcpy(h, torque, (size_t)n * 12); mirror_end = rt.stage_used; } }
+	k.force = d_force; k.torque = d_torque;
+	rt.stage_to_device(0, mirror_end);
+	if (direct)
+	{
+		if (force) rt.copy_to_device_async(d_force, force, (size_t)n * 12);
+		if (torque) rt.copy_to_device_async(d_torque, torque, (size_t)n * 12);
+	}
 	rt.launch(k, n);
 	rt.sync();
 	return rt.check("b2j_bodies_add_force_torque")? 0 : -1;
@@ -2072,6 +2182,8 @@ b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_p
 		uint32_t n = n_worlds / K + (g < n_worlds % K? 1 : 0);
 		b2j_world *G = batch_create_group(P, n, max_body_pairs_per_world, max_contact_constraints_per_world);
 		if (G == nullptr) { b2j_batch_destroy(b); return nullptr; }
+		// (experiments: the one launch solvers of the groups share the SMs instead of taking turns on all of them)
+		if (const char *e = getenv("B2J_SOLVE_GRID_DIV")) { int v = atoi(e); G->solve_grid_div = v < 1? 1u : (uint32_t)v; }
 		b->groups.push_back(G);
 		b->first_world.push_back(first);
 		first += n;
