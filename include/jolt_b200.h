@@ -266,6 +266,20 @@ int b2j_contact_cache_export(b2j_world *w, b2j_cached_body_pair *pairs, uint32_t
 /* PhysicsSystem::WereBodiesInContact (PhysicsSystem.h:251) */
 int b2j_were_bodies_in_contact(b2j_world *w, uint32_t id1, uint32_t id2);
 
+/* ---- state snapshots on the device (PhysicsSystem::SaveState / RestoreState, PhysicsSystem.cpp:2899-2964; what a snapshot holds:
+ *      EStateRecorderState::Global | Bodies | Contacts, i.e. mPreviousStepDeltaTime + gravity, every body's state and the contact
+ *      cache ContactConstraintManager::SaveState writes, .cpp:467-548 -- plus the order of the active list, which the reference
+ *      leaves to the caller). The snapshot stays in HBM: rollback / environment reset without a host round trip of the state. -------- */
+
+typedef struct b2j_snapshot b2j_snapshot; /* opaque; owned by the caller, tied to the world (or batch) it was taken from */
+
+b2j_snapshot *b2j_world_save_state(b2j_world *w);                        /* NULL on failure */
+/* Restores bodies (also the set of bodies: bodies added / removed since the save are undone), active list, contact cache and the
+ * previous step's delta time. Shapes uploaded since the save stay. */
+int           b2j_world_restore_state(b2j_world *w, const b2j_snapshot *s);
+void          b2j_snapshot_destroy(b2j_snapshot *s);
+uint64_t      b2j_snapshot_size(const b2j_snapshot *s);                  /* bytes of device memory the snapshot holds */
+
 /* ---- step ---------------------------------------------------------------------------------------------------- */
 
 /* Per-step counters the roofline is computed from; all are totals over the collision steps of the call. */
@@ -369,6 +383,9 @@ uint32_t   b2j_batch_size(const b2j_batch *b);
 int        b2j_batch_get_state(b2j_batch *b, uint32_t world_index, uint32_t n, const b2j_body_state *out);
 /* BodyInterface::AddForce / AddTorque for the first n slots of the whole batch (world major); arrays [n][3], either may be NULL. */
 int        b2j_batch_add_force_torque(b2j_batch *b, uint32_t n, const float *force, const float *torque);
+/* SaveState / RestoreState of every world of the batch (device resident, see b2j_world_save_state). */
+b2j_snapshot *b2j_batch_save_state(b2j_batch *b);
+int        b2j_batch_restore_state(b2j_batch *b, const b2j_snapshot *s);
 int        b2j_batch_set_profiling(b2j_batch *b, int on);
 uint32_t   b2j_batch_get_profile(b2j_batch *b, char *names, uint32_t name_stride, float *ms, uint32_t *launches, uint32_t cap);
 

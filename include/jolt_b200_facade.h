@@ -493,6 +493,22 @@ struct ContactSettings { float mCombinedFriction = 0, mCombinedRestitution = 0; 
 
 // Host mirror of a body (what the reference hands to listeners)
 class PhysicsSystem;
+// StateRecorder (Jolt/Physics/StateRecorder.h) as the facade sees it: the recorded state is a snapshot that STAYS ON THE DEVICE
+// (b2j_world_save_state); the recorder owns it. SaveState replaces what the recorder held.
+enum class EStateRecorderState : uint8 { None = 0, Global = 1, Bodies = 2, Contacts = 4, Constraints = 8, All = 15 };
+class StateRecorder
+{
+public:
+	StateRecorder() = default;
+	StateRecorder(const StateRecorder &) = delete;
+	~StateRecorder() { Clear(); }
+	void Clear() { if (mSnapshot != nullptr) b2j_snapshot_destroy(mSnapshot); mSnapshot = nullptr; }
+	void Rewind() { }
+	bool IsFailed() const { return false; }
+	uint64 GetDataSize() const { return mSnapshot != nullptr? b2j_snapshot_size(mSnapshot) : 0; }
+	b2j_snapshot *mSnapshot = nullptr;
+};
+using StateRecorderImpl = StateRecorder;
 enum class EBodyType : uint8 { RigidBody, SoftBody };   // Jolt/Physics/Body/BodyType.h (soft bodies are out of scope)
 using BodyIDVector = std::vector<BodyID>;
 
@@ -695,6 +711,23 @@ public:
 	const b2j_step_stats &GetLastStepStats() const { return mStats; }
 	b2j_world *GetWorld() const { return mWorld; }
 	const char *GetLastError() const { return b2j_last_error(); }
+
+	// PhysicsSystem::SaveState / RestoreState (PhysicsSystem.h:165-168): always the whole state (Global | Bodies | Contacts); filters
+	// are not supported. As in the reference the same Body objects must exist at restore time.
+	void SaveState(StateRecorder &inStream, EStateRecorderState = EStateRecorderState::All) const
+	{
+		const_cast<PhysicsSystem *>(this)->mBodyInterface.Flush();
+		inStream.Clear();
+		inStream.mSnapshot = b2j_world_save_state(mWorld);
+	}
+	bool RestoreState(StateRecorder &inStream)
+	{
+		if (inStream.mSnapshot == nullptr) return false;
+		mBodyInterface.Flush();
+		if (b2j_world_restore_state(mWorld, inStream.mSnapshot) != 0) return false;
+		DownloadState(); // the Body mirrors follow the restored device state
+		return true;
+	}
 
 	// PhysicsSystem::Update (PhysicsSystem.h:162): uploads pending API mutations, runs the step on the GPU, mirrors the body state
 	// back to the host and replays contact / activation events into the listeners on the calling thread.

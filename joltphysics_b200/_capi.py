@@ -148,6 +148,12 @@ PROTOTYPES = {
     "b2j_debug_find_pairs": (C.c_int, [_VP]),
     "b2j_world_set_profiling": (C.c_int, [_VP, C.c_int]),
     "b2j_world_set_event_recording": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "b2j_world_save_state": (_VP, [_VP]),
+    "b2j_world_restore_state": (C.c_int, [_VP, _VP]),
+    "b2j_snapshot_destroy": (None, [_VP]),
+    "b2j_snapshot_size": (C.c_uint64, [_VP]),
+    "b2j_batch_save_state": (_VP, [_VP]),
+    "b2j_batch_restore_state": (C.c_int, [_VP, _VP]),
     "b2j_world_get_profile": (C.c_uint32, [_VP, C.c_char_p, C.c_uint32, C.POINTER(C.c_float), _U32P, C.c_uint32]),
     "b2j_batch_create": (_VP, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "b2j_batch_destroy": (None, [_VP]),

@@ -1352,8 +1352,11 @@ template <bool kPosition> __global__ void __launch_bounds__(256) solve_small_ker
 // 7 warps x 2 stages x 29 planes x 512 B = 203 KB of shared memory per SM keep ~100 KB of loads in flight per SM, independent of the
 // register budget of the solve code (the per phase kernel: 168 registers -> 12 warps, every warp stalls for two DRAM round trips per
 // constraint: 0.27 of the HBM peak over a batch step, 0.57 on launches of several million constraints).
-enum { SV_WARPS = 7, SV_THREADS = SV_WARPS * 32, SV_STAGES = 2, SV_STAGE_F4 = SV_NUM_SLOTS * 32 };
-constexpr size_t SV_SMEM_BYTES = (size_t)SV_WARPS * SV_STAGES * SV_STAGE_F4 * sizeof(F4) + (size_t)SV_WARPS * SV_STAGES * sizeof(uint64_t);
+// Two shapes are instantiated (B2J_SOLVE_TMA_SHAPE picks one): 7 warps x 2 stages (loads of tile k + 1 overlap the arithmetic of tile k
+// inside the warp) and 14 warps x 1 stage (twice the warps to cover the ~5 us dependent instruction chain of a tile, the copy of the
+// next tile is issued when the warp is done with the stage; registers capped at 146).
+enum { SV_STAGE_F4 = SV_NUM_SLOTS * 32 };
+constexpr size_t sv_smem_bytes(int warps, int stages) { return (size_t)warps * stages * SV_STAGE_F4 * sizeof(F4) + (size_t)warps * stages * sizeof(uint64_t); }
 
 B2J_D uint32_t sv_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 B2J_D void sv_mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sv_smem_addr(bar)), "r"(count) : "memory"); }
@@ -1399,7 +1402,7 @@ template <bool kWarm> B2J_D uint32_t sv_slot_mask(uint32_t meta)
 struct SvPre { F4 v1, w1, v2, w2, lpt, lfr; };
 
 struct KSolveVelocityAll { }; // (profiling category)
-__global__ void __launch_bounds__(SV_THREADS, 1) solve_velocity_tma_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
+template <int SV_WARPS, int SV_STAGES> __global__ void __launch_bounds__(SV_WARPS * 32, 1) solve_velocity_tma_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
 {
 	extern __shared__ __align__(128) unsigned char sv_smem[];
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
@@ -1475,7 +1478,7 @@ __global__ void __launch_bounds__(SV_THREADS, 1) solve_velocity_tma_kernel(const
 			while (t < ntiles)
 			{
 				uint32_t tn = t + nw;
-				if (tn < ntiles) issue(tn, h1, valid1, stage ^ 1, pre1, mask1);
+				if (SV_STAGES == 2 && tn < ntiles) issue(tn, h1, valid1, stage ^ 1, pre1, mask1);
 				h2 = load_hdr(tn + nw, valid2);
 				if (mask0 != 0)
 				{
@@ -1511,10 +1514,11 @@ __global__ void __launch_bounds__(SV_THREADS, 1) solve_velocity_tma_kernel(const
 					if (!warm && iteration + 1 == ((meta >> 8) & 0xff))
 						store_applied_impulses(w, h0.manifold, (int)(meta & 7), lpt, lfr);
 				}
-				__syncwarp(); // every lane is done reading the stage: the tile after next may overwrite it
+				__syncwarp(); // every lane is done reading the stage: the tile after next (two stages) / the next tile (one stage) may overwrite it
+				if (SV_STAGES == 1 && tn < ntiles) issue(tn, h1, valid1, stage, pre1, mask1);
 				h0 = h1; valid0 = valid1; pre0 = pre1; mask0 = mask1;
 				h1 = h2; valid1 = valid2;
-				stage ^= 1;
+				if (SV_STAGES == 2) stage ^= 1;
 				t = tn;
 			}
 			grid.sync();

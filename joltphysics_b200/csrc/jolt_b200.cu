@@ -377,6 +377,18 @@ struct KNextRound
 	}
 };
 
+// RestoreState: the pair table of the restored read cache is rebuilt from its pairs (a snapshot does not store the table)
+struct KRebuildPairTable
+{
+	DWorld w;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const CachedPair &p = w.read_cache.pairs[i];
+		if (p.slot1 != 0xffffffffu) // (entries of reset worlds were made unfindable: b2j_batch_reset_worlds)
+			pair_table_insert(w, w.read_cache, p.slot1, p.slot2, i);
+	}
+};
+
 // the sizes of the write cache join the step counters (one readback at the end of the step)
 struct KPublishCacheCounts
 {
@@ -508,6 +520,29 @@ struct b2j_batch
 	std::vector<b2j_world *> groups;
 	std::vector<uint32_t> first_world;   // first world of each group (+ n_worlds at the end)
 	uint32_t n_worlds = 0, stride = 0, bodies_per_world = 0;
+};
+
+// Device resident snapshot of one world (PhysicsSystem::SaveState with Global | Bodies | Contacts + the active list order); a batch
+// snapshot holds one per group.
+struct WorldSnapshot
+{
+	b2j_world *owner = nullptr;
+	uint32_t num_slots = 0, num_active = 0, num_bodies = 0, num_pairs = 0, num_manifolds = 0;
+	float prev_dt = 0.0f;
+	V3 gravity;
+	BodyInfo *info = nullptr; BodyParams *params = nullptr;
+	F4 *pose = nullptr, *velocity = nullptr, *force_torque = nullptr, *inertia = nullptr, *bounds = nullptr, *sleep_spheres = nullptr;
+	float *sleep_timer = nullptr; uint32_t *active_index = nullptr, *active = nullptr;
+	CachedPair *pairs = nullptr; CachedManifold *manifolds = nullptr;
+	// host mirrors of the world (the set of bodies is part of the state)
+	std::vector<uint32_t> h_ids; std::vector<uint8_t> h_layer, h_static, layer_has_moving;
+	std::vector<std::vector<uint32_t>> layer_bodies;
+	uint64_t bytes = 0;
+};
+struct b2j_snapshot
+{
+	b2j_batch *batch = nullptr;           // non null: a batch snapshot (one WorldSnapshot per group)
+	std::vector<WorldSnapshot> worlds;
 };
 
 namespace {
@@ -855,17 +890,26 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			cudaError_t e = cudaErrorUnknown;
 			if (solve_mode == 2)
 			{
-				int &blocks_per_sm = rt.func_blocks_per_sm[(const void *)solve_velocity_tma_kernel];
+				// shape of the TMA pipeline (warps x stages): 0 = 7 x 2, 1 = 14 x 1, 2 = 12 x 1, 3 = 10 x 1
+				const char *shape_env = getenv("B2J_SOLVE_TMA_SHAPE");
+				const int shape = shape_env != nullptr? atoi(shape_env) : 1;
+				const void *fns[4] = { (const void *)solve_velocity_tma_kernel<7, 2>, (const void *)solve_velocity_tma_kernel<14, 1>, (const void *)solve_velocity_tma_kernel<12, 1>, (const void *)solve_velocity_tma_kernel<10, 1> };
+				const int warps[4] = { 7, 14, 12, 10 }, stages[4] = { 2, 1, 1, 1 };
+				const int sh = shape < 0 || shape > 3? 1 : shape;
+				const void *fn = fns[sh];
+				const int threads = warps[sh] * 32;
+				const size_t smem = sv_smem_bytes(warps[sh], stages[sh]);
+				int &blocks_per_sm = rt.func_blocks_per_sm[fn];
 				if (blocks_per_sm == 0)
 				{
-					cudaFuncSetAttribute(solve_velocity_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM_BYTES);
-					if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, solve_velocity_tma_kernel, SV_THREADS, SV_SMEM_BYTES) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = -1; }
+					cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+					if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, threads, smem) != cudaSuccess || blocks_per_sm < 1) { cudaGetLastError(); blocks_per_sm = -1; }
 				}
 				if (blocks_per_sm > 0)
 				{
 					++rt.launches;
 					if (rt.profiling) rt.prof_begin(profile_category<KSolveVelocityAll>());
-					e = cudaLaunchCooperativeKernel((const void *)solve_velocity_tma_kernel, dim3((unsigned)(rt.num_sms * blocks_per_sm / W->solve_grid_div)), dim3(SV_THREADS), args, SV_SMEM_BYTES, rt.stream);
+					e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)(rt.num_sms * blocks_per_sm / W->solve_grid_div)), dim3(threads), args, smem, rt.stream);
 					if (rt.profiling) rt.prof_end();
 				}
 			}
@@ -1866,6 +1910,121 @@ int b2j_were_bodies_in_contact(b2j_world *W, uint32_t id1, uint32_t id2)
 	return (int)result;
 }
 
+static void snapshot_free(WorldSnapshot &ws)
+{
+	if (ws.owner == nullptr) return;
+	B2J_DEVICE_GUARD(ws.owner);
+	Runtime &rt = ws.owner->rt;
+	rt.sync();
+	rt.free_(ws.info); rt.free_(ws.params); rt.free_(ws.pose); rt.free_(ws.velocity); rt.free_(ws.force_torque); rt.free_(ws.inertia); rt.free_(ws.bounds);
+	rt.free_(ws.sleep_spheres); rt.free_(ws.sleep_timer); rt.free_(ws.active_index); rt.free_(ws.active); rt.free_(ws.pairs); rt.free_(ws.manifolds);
+	ws.owner = nullptr;
+}
+
+static bool snapshot_take(b2j_world *W, WorldSnapshot &ws)
+{
+	B2J_DEVICE_GUARD(W);
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	const DWorld &d = W->d;
+	ws.owner = W;
+	uint32_t n = W->num_slots, na = W->num_active;
+	int ri = W->write_idx ^ 1;
+	uint32_t np = W->cache_num_pairs[ri], nm = W->cache_num_manifolds[ri];
+	ws.num_slots = n; ws.num_active = na; ws.num_bodies = W->num_bodies; ws.num_pairs = np; ws.num_manifolds = nm;
+	ws.prev_dt = W->prev_dt; ws.gravity = d.gravity;
+	bool ok = true;
+	auto keep = [&](auto *&dst, const auto *src, size_t count) {
+		typedef typename std::remove_reference<decltype(*dst)>::type T;
+		dst = rt.alloc<T>(count, false);
+		if (dst == nullptr) { ok = false; return; }
+		rt.copy(dst, (const T *)src, count);
+		ws.bytes += count * sizeof(T);
+	};
+	keep(ws.info, d.info, n); keep(ws.params, d.params, n);
+	keep(ws.pose, d.position.base, 2 * (size_t)n); keep(ws.velocity, d.linear_velocity.base, 2 * (size_t)n); keep(ws.force_torque, d.force.base, 2 * (size_t)n);
+	keep(ws.inertia, d.inv_inertia_diag.base, 2 * (size_t)n); keep(ws.bounds, d.bounds_min.base, 2 * (size_t)n);
+	keep(ws.sleep_spheres, d.sleep_spheres, 3 * (size_t)n); keep(ws.sleep_timer, d.sleep_timer, n); keep(ws.active_index, d.active_index, n);
+	keep(ws.active, d.active, na);
+	keep(ws.pairs, d.read_cache.pairs, np); keep(ws.manifolds, d.read_cache.manifolds, nm);
+	ws.h_ids.assign(W->h_ids.begin(), W->h_ids.begin() + n); ws.h_layer.assign(W->h_layer.begin(), W->h_layer.begin() + n); ws.h_static.assign(W->h_static.begin(), W->h_static.begin() + n);
+	ws.layer_bodies = W->layer_bodies; ws.layer_has_moving = W->layer_has_moving;
+	rt.sync();
+	if (!ok || !rt.check("b2j_world_save_state")) { snapshot_free(ws); last_error() = "b2j_world_save_state: out of device memory"; return false; }
+	return true;
+}
+
+static bool snapshot_restore(b2j_world *W, const WorldSnapshot &ws)
+{
+	if (ws.owner != W) { last_error() = "b2j_world_restore_state: the snapshot was taken from another world"; return false; }
+	B2J_DEVICE_GUARD(W);
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	DWorld &d = W->d;
+	uint32_t n = ws.num_slots;
+	// bodies added since the save live in slots the snapshot may not cover: empty them
+	if (W->num_slots > n)
+	{
+		uint32_t extra = W->num_slots - n;
+		{ KFillU32 k; k.dst = d.active_index + n; k.value = B2J_INACTIVE_INDEX; rt.launch(k, extra); }
+		std::vector<BodyInfo> empty(extra);
+		memset(empty.data(), 0, sizeof(BodyInfo) * extra);
+		for (BodyInfo &i : empty) i.id = B2J_INVALID_ID;
+		rt.upload(d.info + n, empty.data(), extra);
+		for (uint32_t slot = n; slot < W->num_slots; ++slot) W->h_ids[slot] = B2J_INVALID_ID;
+	}
+	rt.copy(d.info, ws.info, n); rt.copy(d.params, ws.params, n);
+	rt.copy(d.position.base, ws.pose, 2 * (size_t)n); rt.copy(d.linear_velocity.base, ws.velocity, 2 * (size_t)n); rt.copy(d.force.base, ws.force_torque, 2 * (size_t)n);
+	rt.copy(d.inv_inertia_diag.base, ws.inertia, 2 * (size_t)n); rt.copy(d.bounds_min.base, ws.bounds, 2 * (size_t)n);
+	rt.copy(d.sleep_spheres, ws.sleep_spheres, 3 * (size_t)n); rt.copy(d.sleep_timer, ws.sleep_timer, n); rt.copy(d.active_index, ws.active_index, n);
+	rt.copy(d.active, ws.active, ws.num_active);
+	// contact cache: the snapshot becomes the read cache, the write cache is empty between steps
+	int ri = W->write_idx ^ 1;
+	clear_cache(W, ri);
+	rt.copy(W->cache[ri].pairs, ws.pairs, ws.num_pairs); rt.copy(W->cache[ri].manifolds, ws.manifolds, ws.num_manifolds);
+	rt.upload(W->cache[ri].num_pairs, &ws.num_pairs, 1); rt.upload(W->cache[ri].num_manifolds, &ws.num_manifolds, 1);
+	W->cache_num_pairs[ri] = ws.num_pairs; W->cache_num_manifolds[ri] = ws.num_manifolds;
+	{ KRebuildPairTable k; k.w = d; rt.launch(k, ws.num_pairs); }
+	rt.memset_(W->nc.woken_flag, 0, (size_t)d.max_bodies * 4);
+	// host side of the world
+	W->num_slots = n; W->num_active = ws.num_active; W->num_bodies = ws.num_bodies; W->prev_dt = ws.prev_dt; d.gravity = ws.gravity;
+	std::copy(ws.h_ids.begin(), ws.h_ids.end(), W->h_ids.begin()); std::copy(ws.h_layer.begin(), ws.h_layer.end(), W->h_layer.begin()); std::copy(ws.h_static.begin(), ws.h_static.end(), W->h_static.begin());
+	W->layer_bodies = ws.layer_bodies; W->layer_has_moving = ws.layer_has_moving;
+	for (uint32_t l = 0; l < d.num_bp_layers; ++l) { W->layer_list_dirty[l] = 1; W->layer_needs_build[l] = 1; }
+	W->last_num_events = 0; W->last_num_act_events = 0;
+	rt.sync();
+	return rt.check("b2j_world_restore_state");
+}
+
+b2j_snapshot *b2j_world_save_state(b2j_world *W)
+{
+	if (W == nullptr) { last_error() = "b2j_world_save_state: null world"; return nullptr; }
+	b2j_snapshot *s = new b2j_snapshot;
+	s->worlds.resize(1);
+	if (!snapshot_take(W, s->worlds[0])) { delete s; return nullptr; }
+	return s;
+}
+
+int b2j_world_restore_state(b2j_world *W, const b2j_snapshot *s)
+{
+	if (W == nullptr || s == nullptr || s->batch != nullptr || s->worlds.size() != 1) { last_error() = "b2j_world_restore_state: not a snapshot of a single world"; return -1; }
+	return snapshot_restore(W, s->worlds[0])? 0 : -1;
+}
+
+void b2j_snapshot_destroy(b2j_snapshot *s)
+{
+	if (s == nullptr) return;
+	for (WorldSnapshot &ws : s->worlds) snapshot_free(ws);
+	delete s;
+}
+
+uint64_t b2j_snapshot_size(const b2j_snapshot *s)
+{
+	uint64_t total = 0;
+	if (s != nullptr) for (const WorldSnapshot &ws : s->worlds) total += ws.bytes;
+	return total;
+}
+
 int b2j_step(b2j_world *W, float delta_time, int collision_steps, b2j_step_stats *stats)
 {
 	B2J_DEVICE_GUARD(W);
@@ -2285,6 +2444,23 @@ int b2j_batch_reset_worlds(b2j_batch *b, const uint32_t *world_indices, uint32_t
 		return rt.check("b2j_batch_reset_worlds");
 	});
 	return ok? 0 : -1;
+}
+
+b2j_snapshot *b2j_batch_save_state(b2j_batch *b)
+{
+	if (b == nullptr) { last_error() = "b2j_batch_save_state: null batch"; return nullptr; }
+	b2j_snapshot *s = new b2j_snapshot;
+	s->batch = b;
+	s->worlds.resize(b->groups.size());
+	bool ok = batch_for_each_group(b, [&](size_t g) { return snapshot_take(b->groups[g], s->worlds[g]); });
+	if (!ok) { std::string e = last_error(); b2j_snapshot_destroy(s); last_error() = e; return nullptr; }
+	return s;
+}
+
+int b2j_batch_restore_state(b2j_batch *b, const b2j_snapshot *s)
+{
+	if (b == nullptr || s == nullptr || s->batch != b || s->worlds.size() != b->groups.size()) { last_error() = "b2j_batch_restore_state: not a snapshot of this batch"; return -1; }
+	return batch_for_each_group(b, [&](size_t g) { return snapshot_restore(b->groups[g], s->worlds[g]); })? 0 : -1;
 }
 
 int b2j_batch_step(b2j_batch *b, float dt, int collision_steps, b2j_step_stats *stats)

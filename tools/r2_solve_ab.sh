@@ -3,10 +3,10 @@
 # usage: tools/r2_solve_ab.sh "<mode>:<groups>[:<griddiv>] ..."   results -> gpurun_out/ab_<mode>_<groups>_<div>.json
 mkdir -p gpurun_out
 for cfg in $1; do
-  IFS=: read mode groups div <<< "$cfg"
+  IFS=: read mode groups div shape <<< "$cfg"
   div=${div:-1}
-  out=gpurun_out/ab_${mode}_${groups}_${div}.json
-  B2J_SOLVE_MODE=$mode B2J_BATCH_GROUPS=$groups B2J_SOLVE_GRID_DIV=$div timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-pile --no-extras --no-cpu-baseline > $out 2> ${out%.json}.err
+  out=gpurun_out/ab_${mode}_${groups}_${div}_${shape:-1}.json
+  B2J_SOLVE_MODE=$mode B2J_BATCH_GROUPS=$groups B2J_SOLVE_GRID_DIV=$div B2J_SOLVE_TMA_SHAPE=${shape:-1} timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-pile --no-extras --no-cpu-baseline > $out 2> ${out%.json}.err
   echo "== mode $mode groups $groups div $div rc $?"
   python - "$out" <<'PY'
 import json, sys
