@@ -441,7 +441,7 @@ def ncu_traffic_ratio():
     return best
 
 
-SOLVE_KERNELS = ("KSolveVelocityAll", "KSolveVelocity", "KSolveSmallVelocity")
+SOLVE_KERNELS = ("KSolveVelocityWorlds", "KSolveVelocityAll", "KSolveVelocityAllPlain", "KSolveVelocity", "KSolveSmallVelocity")
 
 
 def roofline_of(m):

@@ -266,6 +266,22 @@ int b2j_contact_cache_export(b2j_world *w, b2j_cached_body_pair *pairs, uint32_t
 /* PhysicsSystem::WereBodiesInContact (PhysicsSystem.h:251) */
 int b2j_were_bodies_in_contact(b2j_world *w, uint32_t id1, uint32_t id2);
 
+/* ---- queries on the device broadphase / shapes, batched: thousands per call, one thread per query ------------------ */
+
+/* RayCast (Jolt/Physics/Collision/RayCast.h): origin + fraction * direction, fraction in [0, 1] */
+typedef struct b2j_ray { float origin[3]; float direction[3]; } b2j_ray;
+/* RayCastResult (Jolt/Physics/Collision/CastResult.h): body = B2J_INVALID_ID and fraction = 1 + FLT_EPSILON when nothing was hit */
+typedef struct b2j_ray_hit { uint32_t body; uint32_t sub_shape; float fraction; } b2j_ray_hit;
+
+/* NarrowPhaseQuery::CastRay, closest hit (NarrowPhaseQuery.h:31), for n rays at once. object_layer: the layer the rays collide as
+ * (the world's ObjectVsBroadPhaseLayerFilter / ObjectLayerPairFilter tables play DefaultBroadPhaseLayerFilter / DefaultObjectLayerFilter,
+ * Jolt/Physics/Collision/BroadPhase/BroadPhaseLayer.h:112, ObjectLayer.h:77); 0xffffffff = collide with every layer. */
+int b2j_query_cast_rays(b2j_world *w, const b2j_ray *rays, uint32_t n, uint32_t object_layer, b2j_ray_hit *hits);
+/* BroadPhaseQuery::CollideAABox (BroadPhaseQuery.h:38) for n boxes ([n][6] min xyz, max xyz): counts[i] = bodies whose world space
+ * bounds overlap box i, ids[i * max_hits ...] = the first max_hits of them. Exact body bounds (the reference reports the possibly
+ * widened bounds of its tree: a superset). */
+int b2j_query_collide_aabox(b2j_world *w, const float *boxes, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids);
+
 /* ---- state snapshots on the device (PhysicsSystem::SaveState / RestoreState, PhysicsSystem.cpp:2899-2964; what a snapshot holds:
  *      EStateRecorderState::Global | Bodies | Contacts, i.e. mPreviousStepDeltaTime + gravity, every body's state and the contact
  *      cache ContactConstraintManager::SaveState writes, .cpp:467-548 -- plus the order of the active list, which the reference
@@ -383,6 +399,8 @@ uint32_t   b2j_batch_size(const b2j_batch *b);
 int        b2j_batch_get_state(b2j_batch *b, uint32_t world_index, uint32_t n, const b2j_body_state *out);
 /* BodyInterface::AddForce / AddTorque for the first n slots of the whole batch (world major); arrays [n][3], either may be NULL. */
 int        b2j_batch_add_force_torque(b2j_batch *b, uint32_t n, const float *force, const float *torque);
+/* b2j_query_cast_rays for batched worlds: ray i is cast in world ray_world[i] (the RL observation pattern). */
+int        b2j_batch_query_cast_rays(b2j_batch *b, const uint32_t *ray_world, const b2j_ray *rays, uint32_t n, uint32_t object_layer, b2j_ray_hit *hits);
 /* SaveState / RestoreState of every world of the batch (device resident, see b2j_world_save_state). */
 b2j_snapshot *b2j_batch_save_state(b2j_batch *b);
 int        b2j_batch_restore_state(b2j_batch *b, const b2j_snapshot *s);

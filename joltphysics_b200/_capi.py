@@ -108,6 +108,14 @@ class MeshDesc(C.Structure):
     _fields_ = [("tree", C.POINTER(C.c_uint8)), ("tree_size", C.c_uint32), ("local_bounds_min", c_f3), ("local_bounds_max", c_f3)]
 
 
+class Ray(C.Structure):
+    _fields_ = [("origin", c_f3), ("direction", c_f3)]
+
+
+class RayHit(C.Structure):
+    _fields_ = [("body", C.c_uint32), ("sub_shape", C.c_uint32), ("fraction", C.c_float)]
+
+
 # every symbol include/jolt_b200.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
 _U32P = C.POINTER(C.c_uint32)
@@ -148,6 +156,9 @@ PROTOTYPES = {
     "b2j_debug_find_pairs": (C.c_int, [_VP]),
     "b2j_world_set_profiling": (C.c_int, [_VP, C.c_int]),
     "b2j_world_set_event_recording": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "b2j_query_cast_rays": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP]),
+    "b2j_query_collide_aabox": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP]),
+    "b2j_batch_query_cast_rays": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, _VP]),
     "b2j_world_save_state": (_VP, [_VP]),
     "b2j_world_restore_state": (C.c_int, [_VP, _VP]),
     "b2j_snapshot_destroy": (None, [_VP]),

@@ -12,6 +12,7 @@
 #include "b2j_narrowphase.h"
 #include "b2j_mesh.h"
 #include "b2j_solver.h"
+#include "b2j_query.h"
 
 #include <chrono>
 #include <thread>
@@ -767,7 +768,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	{ KIslandClassify k; k.w = d; k.s = sc; rt.launch(k, na); }
 
 	uint32_t num_phases = 0, vsteps = 0, psteps = 0;
-	bool block_solve = false, solved_by_phase_launches = false;
+	bool block_solve = false, solved_by_phase_launches = false, solved_world_major = false;
 	if (M > 0)
 	{
 		// (a14 SortContacts) order by sort key
@@ -854,13 +855,39 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			}
 		}
 
+		// B2J_SOLVE_MODE: how the velocity / position solve is launched.
+		//   3 = batched worlds only (their default): world major layout, one warp walks one world through all phases and iterations,
+		//       planes streamed through shared memory by TMA (solve_velocity_worlds_kernel)
+		//   2 = one persistent cooperative launch, phases separated by grid barriers, TMA staged planes (solve_velocity_tma_kernel)
+		//   1 = one persistent cooperative launch, loads straight from HBM        0 = one launch per phase per iteration
+#ifndef B2J_HOSTSIM
+		const char *solve_mode_env = getenv("B2J_SOLVE_MODE");
+		int solve_mode = solve_mode_env != nullptr? atoi(solve_mode_env) : (d.world_stride != 0? 3 : 2);
+		if (solve_mode == 3 && (d.world_stride == 0 || W->num_worlds > (1u << 18))) solve_mode = 2;
+		const bool world_major = solve_mode == 3;
+#else
+		const bool world_major = false;
+#endif
 		// phases -> solve order
 		{
 			// the 64 bit key buffers of the constraint sort are free again: reuse them for the (phase, index) sort; d_sort_vals still holds 0..M-1
 			uint32_t *sorted_phase = reinterpret_cast<uint32_t *>(W->d_sort_keys[0]), *sorted_idx = reinterpret_cast<uint32_t *>(W->d_sort_keys[1]);
 			{ KPhaseClamp k; k.w = d; k.s = sc; rt.launch(k, M); }
-			rt.sort_pairs<uint32_t>(sc.phase, sorted_phase, W->d_sort_vals, sorted_idx, M, 13);
-			{ KPhasePlace k; k.s = sc; k.sorted_phase = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
+			if (world_major)
+			{
+				// solve position = (world, phase, sort key): one more key field, the second half of the first key buffer holds the unsorted keys
+				uint32_t *keys_in = sorted_phase + d.max_constraints;
+				uint32_t world_bits = 1;
+				while ((1u << world_bits) < W->num_worlds) ++world_bits;
+				{ KPlaceKeysWorlds k; k.w = d; k.s = sc; k.keys = keys_in; rt.launch(k, M); }
+				rt.sort_pairs<uint32_t>(keys_in, sorted_phase, W->d_sort_vals, sorted_idx, M, (int)(13 + world_bits));
+				{ KPhasePlaceWorlds k; k.s = sc; k.sorted_key = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
+			}
+			else
+			{
+				rt.sort_pairs<uint32_t>(sc.phase, sorted_phase, W->d_sort_vals, sorted_idx, M, 13);
+				{ KPhasePlace k; k.s = sc; k.sorted_phase = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
+			}
 		}
 
 		// (a11) constraint setup straight into solve order
@@ -869,8 +896,6 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 #ifndef B2J_HOSTSIM
 		// B2J_SOLVE_MODE: 2 (default) = one persistent launch per solve, constraint planes streamed through shared memory by TMA
 		// (solve_velocity_tma_kernel); 1 = one persistent launch, loads straight from HBM; 0 = one launch per phase per iteration
-		const char *solve_mode_env = getenv("B2J_SOLVE_MODE");
-		int solve_mode = solve_mode_env != nullptr? atoi(solve_mode_env) : 2;
 		// small single world: the whole velocity solve in one small cooperative launch (solve_small_kernel)
 		block_solve = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
 		if (block_solve)
@@ -888,7 +913,20 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			float ratio_arg = warm_start_ratio;
 			void *args[] = { (void *)&d, (void *)&sc, (void *)&ratio_arg };
 			cudaError_t e = cudaErrorUnknown;
-			if (solve_mode == 2)
+			if (solve_mode == 3)
+			{
+				const int warps = 12;
+				const void *fn = (const void *)solve_velocity_worlds_kernel<12>;
+				const size_t smem = sv_smem_bytes(warps, 1);
+				bool &configured = rt.func_configured[fn];
+				if (!configured) { cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+				++rt.launches;
+				if (rt.profiling) rt.prof_begin(profile_category<KSolveVelocityWorlds>());
+				solve_velocity_worlds_kernel<12><<<(W->num_worlds + warps - 1) / warps, warps * 32, smem, rt.stream>>>(d, sc, ratio_arg);
+				if (rt.profiling) rt.prof_end();
+				e = cudaGetLastError();
+			}
+			else if (solve_mode == 2)
 			{
 				// shape of the TMA pipeline (warps x stages): 0 = 7 x 2, 1 = 14 x 1, 2 = 12 x 1, 3 = 10 x 1
 				const char *shape_env = getenv("B2J_SOLVE_TMA_SHAPE");
@@ -925,7 +963,12 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 					if (rt.profiling) rt.prof_end();
 				}
 			}
-			if (e != cudaSuccess) { cudaGetLastError(); solve_mode = 0; } // fall back to the per phase launches
+			if (e != cudaSuccess)
+			{
+				cudaGetLastError();
+				if (world_major) { last_error() = std::string("world major velocity solve launch failed: ") + cudaGetErrorString(e); return false; } // (the layout has no per phase form)
+				solve_mode = 0; // fall back to the per phase launches
+			}
 		}
 		const bool phase_launches = !block_solve && solve_mode == 0;
 #else
@@ -955,6 +998,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 				}
 		}
 		solved_by_phase_launches = phase_launches;
+		solved_world_major = world_major;
 		// the applied impulses are stored by the last velocity iteration of every constraint; islands without iterations only exist when
 		// the default number of velocity steps is 0
 		if (d.settings.num_velocity_steps == 0) { KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
@@ -981,6 +1025,13 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		cudaError_t e = cudaLaunchCooperativeKernel((const void *)solve_small_kernel<true>, dim3(8), dim3(256), args, 0, rt.stream);
 		if (rt.profiling) rt.prof_end();
 		if (e != cudaSuccess) { cudaGetLastError(); last_error() = "cooperative position solve launch failed"; return false; }
+	}
+	else if (M > 0 && solved_world_major)
+	{
+		++rt.launches;
+		if (rt.profiling) rt.prof_begin(profile_category<KSolvePositionWorlds>());
+		solve_position_worlds_kernel<<<(W->num_worlds + 3) / 4, 128, 0, rt.stream>>>(d, sc);
+		if (rt.profiling) rt.prof_end();
 	}
 	else if (M > 0 && !solved_by_phase_launches)
 	{
@@ -1266,6 +1317,8 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	sc.man_ws = nc.man_ws;
 	sc.order = rt.alloc<uint32_t>(mc); sc.final_pos = rt.alloc<uint32_t>(mc); sc.solve_src = rt.alloc<uint32_t>(mc); sc.phase = rt.alloc<uint32_t>(mc);
 	sc.max_phases = 8192;
+	sc.solve_phase = rt.alloc<uint32_t>(mc, false);
+	sc.num_worlds = 1;
 	rt.reserve_temp(std::max(d.max_bodies, d.max_constraints), std::max(std::max(d.max_body_pairs, d.max_constraints), d.max_bodies), d.max_bodies);
 	sc.phase_count = rt.alloc<uint32_t>(sc.max_phases + 2);
 	sc.uf_parent = rt.alloc<uint32_t>(nbod); sc.root = rt.alloc<uint32_t>(nbod); sc.island_items = rt.alloc<uint32_t>(nbod);
@@ -1334,7 +1387,7 @@ void b2j_world_destroy(b2j_world *W)
 	rt.free_(W->act_events_buf); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
 	rt.free_(sc.con.cp); rt.free_(sc.con.hdr);
-	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count);
+	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count); rt.free_(sc.solve_phase); rt.free_(sc.world_begin);
 	rt.free_(sc.uf_parent); rt.free_(sc.root); rt.free_(sc.island_items); rt.free_(sc.island_large); rt.free_(sc.island_steps); rt.free_(sc.island_can_sleep);
 	rt.free_(sc.large_color_count); rt.free_(sc.body_deg); rt.free_(sc.body_off); rt.free_(sc.body_fill); rt.free_(sc.body_cur); rt.free_(sc.body_mask);
 	rt.free_(sc.adj); rt.free_(sc.sched_flag);
@@ -1910,6 +1963,80 @@ int b2j_were_bodies_in_contact(b2j_world *W, uint32_t id1, uint32_t id2)
 	return (int)result;
 }
 
+// trees of the current body bounds (the step rebuilds them lazily: bodies may have moved / been added since)
+static bool ensure_trees(b2j_world *W)
+{
+	upload_shapes(W);
+	sync_dworld(W);
+	for (uint32_t l = 0; l < W->d.num_bp_layers; ++l)
+		if (W->layer_needs_build[l])
+		{
+			if (!build_tree(W, l)) return false;
+			W->layer_needs_build[l] = 0;
+		}
+	return true;
+}
+
+static int cast_rays(b2j_world *W, const uint32_t *ray_world, uint32_t first_world, const b2j_ray *rays, uint32_t n, uint32_t object_layer, b2j_ray_hit *hits)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (rays == nullptr || hits == nullptr) { last_error() = "b2j_query_cast_rays: rays and hits are required"; return -1; }
+	if (object_layer != 0xffffffffu && object_layer >= W->d.num_object_layers) { last_error() = "b2j_query_cast_rays: invalid object layer"; return -1; }
+	Runtime &rt = W->rt;
+	if (!ensure_trees(W)) return -1;
+	rt.stage_begin((size_t)n * (sizeof(b2j_ray) + sizeof(b2j_ray_hit) + 4));
+	b2j_ray *h_rays = nullptr; b2j_ray_hit *h_hits = nullptr; uint32_t *h_world = nullptr;
+	KCastRays k; k.w = W->d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l];
+	k.rays = rt.stage_alloc<b2j_ray>(n, &h_rays);
+	memcpy(h_rays, rays, (size_t)n * sizeof(b2j_ray));
+	k.ray_world = nullptr; k.first_world = first_world; k.num_worlds = W->num_worlds;
+	if (ray_world != nullptr) { k.ray_world = rt.stage_alloc<uint32_t>(n, &h_world); memcpy(h_world, ray_world, (size_t)n * 4); }
+	rt.stage_to_device(0, rt.stage_used);
+	size_t out_begin = rt.stage_used;
+	k.hits = rt.stage_alloc<b2j_ray_hit>(n, &h_hits);
+	k.object_layer = object_layer;
+	if (ray_world != nullptr) rt.memset_(k.hits, 0xff, (size_t)n * sizeof(b2j_ray_hit)); // rays of other groups' worlds stay "not mine" (body = 0xffffffff, fraction = NaN)
+	rt.launch(k, n);
+	rt.stage_to_host(out_begin, rt.stage_used);
+	if (ray_world == nullptr)
+		memcpy(hits, h_hits, (size_t)n * sizeof(b2j_ray_hit));
+	else
+		for (uint32_t i = 0; i < n; ++i)
+			if (ray_world[i] >= first_world && ray_world[i] < first_world + W->num_worlds) hits[i] = h_hits[i];
+	return rt.check("b2j_query_cast_rays")? 0 : -1;
+}
+
+int b2j_query_cast_rays(b2j_world *W, const b2j_ray *rays, uint32_t n, uint32_t object_layer, b2j_ray_hit *hits)
+{
+	return cast_rays(W, nullptr, 0, rays, n, object_layer, hits);
+}
+
+int b2j_query_collide_aabox(b2j_world *W, const float *boxes, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (boxes == nullptr || counts == nullptr || (max_hits > 0 && ids == nullptr)) { last_error() = "b2j_query_collide_aabox: boxes, counts and ids are required"; return -1; }
+	if (object_layer != 0xffffffffu && object_layer >= W->d.num_object_layers) { last_error() = "b2j_query_collide_aabox: invalid object layer"; return -1; }
+	Runtime &rt = W->rt;
+	if (!ensure_trees(W)) return -1;
+	rt.stage_begin((size_t)n * (24 + 4 + (size_t)max_hits * 4));
+	float *h_boxes = nullptr; uint32_t *h_counts = nullptr, *h_ids = nullptr;
+	KCollideAABox k; k.w = W->d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l];
+	k.boxes = rt.stage_alloc<float>((size_t)n * 6, &h_boxes);
+	memcpy(h_boxes, boxes, (size_t)n * 24);
+	rt.stage_to_device(0, rt.stage_used);
+	size_t out_begin = rt.stage_used;
+	k.counts = rt.stage_alloc<uint32_t>(n, &h_counts);
+	k.ids = rt.stage_alloc<uint32_t>((size_t)n * max_hits, &h_ids);
+	k.max_hits = max_hits; k.box_world = nullptr; k.first_world = 0; k.num_worlds = 1; k.object_layer = object_layer;
+	rt.launch(k, n);
+	rt.stage_to_host(out_begin, rt.stage_used);
+	memcpy(counts, h_counts, (size_t)n * 4);
+	if (max_hits > 0) memcpy(ids, h_ids, (size_t)n * max_hits * 4);
+	return rt.check("b2j_query_collide_aabox")? 0 : -1;
+}
+
 static void snapshot_free(WorldSnapshot &ws)
 {
 	if (ws.owner == nullptr) return;
@@ -2243,6 +2370,8 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	if (B == nullptr) return nullptr;
 	Runtime &rt = B->rt;
 	B->num_worlds = n_worlds;
+	B->sc.num_worlds = n_worlds;
+	B->sc.world_begin = rt.alloc<uint32_t>((size_t)n_worlds + 1);
 	for (int i = 0; i < 2; ++i) { B->d_collide_keys[i] = rt.alloc<uint32_t>(B->d.max_body_pairs, false); B->d_collide_vals[i] = rt.alloc<uint32_t>(B->d.max_body_pairs, false); }
 	B->d.world_stride = stride;
 	B->prev_dt = P->prev_dt;
@@ -2444,6 +2573,15 @@ int b2j_batch_reset_worlds(b2j_batch *b, const uint32_t *world_indices, uint32_t
 		return rt.check("b2j_batch_reset_worlds");
 	});
 	return ok? 0 : -1;
+}
+
+int b2j_batch_query_cast_rays(b2j_batch *b, const uint32_t *ray_world, const b2j_ray *rays, uint32_t n, uint32_t object_layer, b2j_ray_hit *hits)
+{
+	if (b == nullptr || (n > 0 && ray_world == nullptr)) { last_error() = "b2j_batch_query_cast_rays: batch and ray_world are required"; return -1; }
+	for (uint32_t i = 0; i < n; ++i)
+		if (ray_world[i] >= b->n_worlds) { last_error() = "b2j_batch_query_cast_rays: world index out of range"; return -1; }
+	// every group casts the rays of its own worlds (each ray is answered by exactly one group)
+	return batch_for_each_group(b, [&](size_t g) { return cast_rays(b->groups[g], ray_world, b->first_world[g], rays, n, object_layer, hits) == 0; })? 0 : -1;
 }
 
 b2j_snapshot *b2j_batch_save_state(b2j_batch *b)

@@ -19,6 +19,10 @@
 #include <Jolt/Physics/Collision/BroadPhase/BroadPhase.h>
 #include <Jolt/Physics/Collision/ContactListener.h>
 #include <Jolt/Physics/Body/BodyActivationListener.h>
+#include <Jolt/Physics/Collision/RayCast.h>
+#include <Jolt/Physics/Collision/CastResult.h>
+#include <Jolt/Physics/Collision/NarrowPhaseQuery.h>
+#include <Jolt/Physics/Collision/CollisionCollectorImpl.h>
 
 #include <algorithm>
 #include <atomic>
@@ -667,6 +671,52 @@ uint32_t jref_replace_body(void *h, uint32_t inIndex, float inRadius)
 	bi.DestroyBody(old_id);
 	BodyID id = bi.CreateAndAddBody(s, active? EActivation::Activate : EActivation::DontActivate);
 	return id.GetIndex() == inIndex? id.GetIndexAndSequenceNumber() : 0xffffffffu;
+}
+
+// NarrowPhaseQuery::CastRay (closest hit) for n rays; inObjectLayer = the layer the rays collide as (0xffffffff: no layer filtering)
+void jref_cast_rays(void *h, const b2j_ray *inRays, uint32_t inNum, uint32_t inObjectLayer, b2j_ray_hit *outHits)
+{
+	World *w = (World *)h;
+	const NarrowPhaseQuery &query = w->system.GetNarrowPhaseQueryNoLock();
+	for (uint32_t i = 0; i < inNum; ++i)
+	{
+		RRayCast ray(RVec3(inRays[i].origin[0], inRays[i].origin[1], inRays[i].origin[2]), Vec3(inRays[i].direction[0], inRays[i].direction[1], inRays[i].direction[2]));
+		RayCastResult hit;
+		bool had_hit;
+		if (inObjectLayer == 0xffffffffu)
+			had_hit = query.CastRay(ray, hit);
+		else
+			had_hit = query.CastRay(ray, hit, DefaultBroadPhaseLayerFilter(w->ovbp, (ObjectLayer)inObjectLayer), DefaultObjectLayerFilter(w->olp, (ObjectLayer)inObjectLayer));
+		outHits[i].body = had_hit? hit.mBodyID.GetIndexAndSequenceNumber() : 0xffffffffu;
+		outHits[i].sub_shape = had_hit? hit.mSubShapeID2.GetValue() : 0xffffffffu;
+		outHits[i].fraction = had_hit? hit.mFraction : 1.0f + FLT_EPSILON;
+	}
+}
+
+// BroadPhaseQuery::CollideAABox for n boxes, narrowed to the bodies whose TRUE world space bounds overlap (the tree keeps widened
+// bounds of moving bodies, so the raw result is a superset). outIDs: [n][inMaxHits] sorted ascending.
+void jref_collide_aabox(void *h, const float *inBoxes, uint32_t inNum, uint32_t inObjectLayer, uint32_t inMaxHits, uint32_t *outCounts, uint32_t *outIDs)
+{
+	World *w = (World *)h;
+	const BodyLockInterfaceNoLock &li = w->system.GetBodyLockInterfaceNoLock();
+	for (uint32_t i = 0; i < inNum; ++i)
+	{
+		AABox box(Vec3(inBoxes[6 * i], inBoxes[6 * i + 1], inBoxes[6 * i + 2]), Vec3(inBoxes[6 * i + 3], inBoxes[6 * i + 4], inBoxes[6 * i + 5]));
+		AllHitCollisionCollector<CollideShapeBodyCollector> collector;
+		if (inObjectLayer == 0xffffffffu)
+			w->system.GetBroadPhaseQuery().CollideAABox(box, collector);
+		else
+			w->system.GetBroadPhaseQuery().CollideAABox(box, collector, DefaultBroadPhaseLayerFilter(w->ovbp, (ObjectLayer)inObjectLayer), DefaultObjectLayerFilter(w->olp, (ObjectLayer)inObjectLayer));
+		std::vector<uint32_t> ids;
+		for (const BodyID &id : collector.mHits)
+		{
+			const Body *b = li.TryGetBody(id);
+			if (b != nullptr && b->GetWorldSpaceBounds().Overlaps(box)) ids.push_back(id.GetIndexAndSequenceNumber());
+		}
+		std::sort(ids.begin(), ids.end());
+		outCounts[i] = (uint32_t)ids.size();
+		for (uint32_t j = 0; j < ids.size() && j < inMaxHits; ++j) outIDs[(size_t)i * inMaxHits + j] = ids[j];
+	}
 }
 
 // Turn the recording listeners off (timing runs) or on.

@@ -37,6 +37,8 @@ def ref_lib(variant="det"):
         L.jref_destroy.argtypes = [vp]
         L.jref_set_recording.argtypes = [vp, C.c_int]
         L.jref_mutate.argtypes = [vp, C.c_int]
+        L.jref_cast_rays.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.jref_collide_aabox.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.jref_replace_body.restype = C.c_uint32
         L.jref_replace_body.argtypes = [vp, C.c_uint32, C.c_float]
         L.jref_query.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -72,6 +74,9 @@ def _u32p(a):
 
 def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+HIT_DTYPE = np.dtype([("body", np.uint32), ("sub_shape", np.uint32), ("fraction", np.float32)])
 
 
 class State:
@@ -118,6 +123,20 @@ class RefWorld:
         nb, flags = C.c_uint32(), C.c_uint32()
         n = self.L.jref_query(self.h, ids.ctypes.data, len(ids), C.addressof(nb), C.addressof(flags))
         return ids[:n].copy(), nb.value, flags.value
+
+    def cast_rays(self, rays, object_layer=0xffffffff):
+        """rays: float32 [n][6] (origin, direction) -> structured array of hits (body, sub_shape, fraction)."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        self.L.jref_cast_rays(self.h, rays.ctypes.data, len(rays), object_layer, hits.ctypes.data)
+        return hits
+
+    def collide_aabox(self, boxes, object_layer=0xffffffff, max_hits=64):
+        boxes = np.ascontiguousarray(boxes, np.float32)
+        counts = np.zeros(len(boxes), np.uint32)
+        ids = np.full((len(boxes), max_hits), 0xffffffff, np.uint32)
+        self.L.jref_collide_aabox(self.h, boxes.ctypes.data, len(boxes), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data)
+        return counts, ids
 
     def replace_body(self, index, radius=0.5):
         """Destroy the body in slot `index`, create a sphere there (same slot, next sequence number); returns the new id."""
@@ -259,6 +278,21 @@ class B2JWorld:
         ev = (_capi.ActivationEvent * max(n, 1))()
         self.api.b2j_activation_events_drain(self.h, ev, n)
         return [(ev[i].kind, ev[i].body) for i in range(n)]
+
+    def cast_rays(self, rays, object_layer=0xffffffff):
+        rays = np.ascontiguousarray(rays, np.float32)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        if self.api.b2j_query_cast_rays(self.h, rays.ctypes.data, len(rays), object_layer, hits.ctypes.data) != 0:
+            raise RuntimeError("b2j_query_cast_rays failed: " + self.api.last_error())
+        return hits
+
+    def collide_aabox(self, boxes, object_layer=0xffffffff, max_hits=64):
+        boxes = np.ascontiguousarray(boxes, np.float32)
+        counts = np.zeros(len(boxes), np.uint32)
+        ids = np.full((len(boxes), max_hits), 0xffffffff, np.uint32)
+        if self.api.b2j_query_collide_aabox(self.h, boxes.ctypes.data, len(boxes), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data) != 0:
+            raise RuntimeError("b2j_query_collide_aabox failed: " + self.api.last_error())
+        return counts, ids
 
     def profile(self):
         """{kernel name: {"ms": device time, "launches": count}} accumulated since b2j_world_set_profiling(1)."""
