@@ -214,6 +214,11 @@ typedef struct b2j_body_state {
 
 /* BodyInterface::GetPositionAndRotation / GetLinearAndAngularVelocity (:187-216); ids==NULL means slots 0..n-1. */
 int b2j_bodies_get_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_state *out);
+/* State of the bodies the LAST b2j_step simulated (every body that was active at some point of it: the active list before the
+ * sleepers left it, bodies woken by contacts included), i.e. exactly the bodies whose state changed: the incremental download of
+ * SURVEY 8f-1 (a world of mostly sleeping bodies mirrors only what moved). Copies up to cap ids + state rows (same order) and
+ * returns the number of simulated bodies (may exceed cap). */
+uint32_t b2j_bodies_get_stepped_state(b2j_world *w, uint32_t cap, uint32_t *ids, const b2j_body_state *out);
 /* BodyInterface::SetPositionAndRotation / SetLinearAndAngularVelocity; NULL members are left untouched. */
 int b2j_bodies_set_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_state *in);
 /* BodyInterface::AddForce / AddTorque (:220-226): accumulate into mForce / mTorque (either may be NULL). */

@@ -480,6 +480,46 @@ struct PhysicsSettings
 	bool mCheckActiveEdges = true;
 };
 
+class PhysicsSystem;
+// ---- queries (NarrowPhaseQuery / BroadPhaseQuery, Jolt/Physics/Collision/NarrowPhaseQuery.h:31, BroadPhase/BroadPhaseQuery.h:38) ----
+struct AABox { Vec3 mMin, mMax; AABox() = default; AABox(const Vec3 &inMin, const Vec3 &inMax) : mMin(inMin), mMax(inMax) { } };
+struct RRayCast { RVec3 mOrigin; Vec3 mDirection; RRayCast() = default; RRayCast(const RVec3 &o, const Vec3 &d) : mOrigin(o), mDirection(d) { } };
+using RayCast = RRayCast;
+struct RayCastResult { BodyID mBodyID; float mFraction = 1.0f + FLT_EPSILON; SubShapeID mSubShapeID2; };
+
+// Closest hit ray casts on the device broadphase + shapes. The reference casts one ray per call; the device wants thousands, so next
+// to the reference's signature there is a batched form (the RL observation pattern: all rays of a step in one call).
+class NarrowPhaseQuery
+{
+public:
+	// NarrowPhaseQuery::CastRay(inRay, ioHit): true if the ray hits closer than ioHit.mFraction
+	bool CastRay(const RRayCast &inRay, RayCastResult &ioHit) const
+	{
+		RayCastResult hit;
+		CastRays(&inRay, 1, &hit);
+		if (hit.mBodyID.IsInvalid() || !(hit.mFraction < ioHit.mFraction)) return false;
+		ioHit = hit;
+		return true;
+	}
+	// n rays at once; inObjectLayer: the layer the rays collide as (DefaultBroadPhaseLayerFilter / DefaultObjectLayerFilter of the
+	// tables given to Init), cNoLayer = collide with everything (the reference's default filters)
+	static constexpr uint32 cNoLayer = 0xffffffffu;
+	inline void CastRays(const RRayCast *inRays, int inNumber, RayCastResult *outHits, uint32 inObjectLayer = cNoLayer) const;
+private:
+	friend class PhysicsSystem;
+	PhysicsSystem *mSystem = nullptr;
+};
+
+class BroadPhaseQuery
+{
+public:
+	// BroadPhaseQuery::CollideAABox with an all hits collector: ids of the bodies whose world space bounds overlap the box
+	inline void CollideAABox(const AABox &inBox, std::vector<BodyID> &outBodies, uint32 inObjectLayer = NarrowPhaseQuery::cNoLayer) const;
+private:
+	friend class PhysicsSystem;
+	PhysicsSystem *mSystem = nullptr;
+};
+
 // ---- listeners ------------------------------------------------------------------------------------------------------
 struct ContactManifold
 {
@@ -633,6 +673,8 @@ public:
 
 private:
 	friend class PhysicsSystem;
+	friend class NarrowPhaseQuery;
+	friend class BroadPhaseQuery;
 	b2j_world *World() const;
 	void Flush();
 	void SetActive(const BodyID &id, bool inActive);
@@ -644,7 +686,11 @@ private:
 class PhysicsSystem
 {
 public:
-	PhysicsSystem() { mBodyInterface.mSystem = this; }
+	PhysicsSystem() { mBodyInterface.mSystem = this; mNarrowPhaseQuery.mSystem = this; mBroadPhaseQuery.mSystem = this; }
+	// PhysicsSystem::GetNarrowPhaseQuery / GetBroadPhaseQuery (PhysicsSystem.h:121-130)
+	const NarrowPhaseQuery &GetNarrowPhaseQuery() const { return mNarrowPhaseQuery; }
+	const NarrowPhaseQuery &GetNarrowPhaseQueryNoLock() const { return mNarrowPhaseQuery; }
+	const BroadPhaseQuery &GetBroadPhaseQuery() const { return mBroadPhaseQuery; }
 	~PhysicsSystem() { if (mWorld) b2j_world_destroy(mWorld); }
 	PhysicsSystem(const PhysicsSystem &) = delete;
 
@@ -745,6 +791,8 @@ public:
 private:
 	friend class BodyInterface;
 	friend class Body;
+	friend class NarrowPhaseQuery;
+	friend class BroadPhaseQuery;
 
 	// the device records contact / activation events only while a listener is attached (no event traffic otherwise)
 	void SyncEventRecording() { if (mWorld) b2j_world_set_event_recording(mWorld, mContactListener != nullptr, mActivationListener != nullptr); }
@@ -859,6 +907,8 @@ private:
 	ContactListener *mContactListener = nullptr;
 	BodyActivationListener *mActivationListener = nullptr;
 	BodyInterface mBodyInterface;
+	NarrowPhaseQuery mNarrowPhaseQuery;
+	BroadPhaseQuery mBroadPhaseQuery;
 	std::vector<std::unique_ptr<Body>> mBodies;   // by body index
 	std::vector<uint32> mFreeIndices;
 	std::vector<ShapeRef> mShapes;
@@ -884,6 +934,38 @@ private:
 	std::vector<b2j_contact_event> mContactEvents;
 	std::vector<b2j_activation_event> mActEvents;
 };
+
+inline void NarrowPhaseQuery::CastRays(const RRayCast *inRays, int inNumber, RayCastResult *outHits, uint32 inObjectLayer) const
+{
+	if (inNumber <= 0) return;
+	mSystem->mBodyInterface.Flush();
+	static_assert(sizeof(RRayCast) == sizeof(b2j_ray), "RRayCast must be origin + direction as 6 floats");
+	std::vector<b2j_ray_hit> hits((size_t)inNumber);
+	if (b2j_query_cast_rays(mSystem->mWorld, reinterpret_cast<const b2j_ray *>(inRays), (uint32)inNumber, inObjectLayer, hits.data()) != 0) return;
+	for (int i = 0; i < inNumber; ++i)
+	{
+		outHits[i].mBodyID = BodyID(hits[i].body);
+		outHits[i].mFraction = hits[i].fraction;
+		outHits[i].mSubShapeID2.mValue = hits[i].sub_shape;
+	}
+}
+
+inline void BroadPhaseQuery::CollideAABox(const AABox &inBox, std::vector<BodyID> &outBodies, uint32 inObjectLayer) const
+{
+	mSystem->mBodyInterface.Flush();
+	outBodies.clear();
+	float box[6] = { inBox.mMin.x, inBox.mMin.y, inBox.mMin.z, inBox.mMax.x, inBox.mMax.y, inBox.mMax.z };
+	uint32 count = 0, cap = 64;
+	std::vector<uint32> ids;
+	for (;;)
+	{
+		ids.resize(cap);
+		if (b2j_query_collide_aabox(mSystem->mWorld, box, 1, inObjectLayer, cap, &count, ids.data()) != 0) return;
+		if (count <= cap) break;
+		cap = count;
+	}
+	for (uint32 i = 0; i < count; ++i) outBodies.push_back(BodyID(ids[i]));
+}
 
 inline void Body::Sync() const
 {

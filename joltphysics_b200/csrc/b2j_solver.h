@@ -80,10 +80,6 @@ struct SolveCtx
 	uint32_t *adj;
 	uint32_t num_slots;
 	uint32_t *sched_flag;        // [2] remaining flags
-	// batched worlds, world major solve layout (solve position = (world, phase, sort key)): see solve_velocity_worlds_kernel
-	uint32_t *solve_phase;       // [M] by solve position: phase of the constraint
-	uint32_t *world_begin;       // [num_worlds + 1] first solve position of every world
-	uint32_t num_worlds;
 };
 
 B2J_HD F4 &cp_at(const Constraints &c, int plane, uint32_t i) { return c.cp[(size_t)plane * c.capacity + i]; }
@@ -552,51 +548,23 @@ struct KSchedResetCursors
 
 // Phases -> solve order. The constraints are radix sorted by phase (stable: sort key order inside a phase, deterministic layout,
 // no histogram atomics); KPhaseClamp bounds the key and finds the phase count, KPhasePlace scatters and writes the phase offsets.
+// (the placement key = phase | solve class: inside a phase the constraints are free to take any order -- they touch disjoint dynamic
+// bodies -- so they are laid out class by class (motion type pair, number of contact points), sort key order inside a class)
+enum { PLACE_CLASS_BITS = 4 };
 struct KPhaseClamp
 {
-	DWorld w; SolveCtx s;
+	DWorld w; SolveCtx s; uint32_t *keys;
 	B2J_D void operator()(uint32_t i) const
 	{
 		uint32_t p = s.phase[i];
 		if (p >= s.max_phases) { p = s.max_phases - 1; s.phase[i] = p; atomic_or(&w.counters->error_bits, 0x100u); }
 		if (p + 1 > *(volatile const uint32_t *)&w.counters->num_phases) // almost always false: keeps the atomic off the hot path
 			atomic_max(&w.counters->num_phases, p + 1);
+		keys[i] = (p << PLACE_CLASS_BITS) | (s.src[s.order[i]].cls & ((1u << PLACE_CLASS_BITS) - 1u));
 	}
 };
 
 struct KPhasePlace
-{
-	SolveCtx s; const uint32_t *sorted_phase, *sorted_idx; uint32_t n;
-	B2J_D void operator()(uint32_t pos) const
-	{
-		uint32_t i = sorted_idx[pos];
-		s.final_pos[i] = pos;
-		s.solve_src[pos] = s.order[i];
-		// phase_count[q] = first position of phase q (empty phases included), phase_count[last + 1 ...] = n
-		uint32_t p = sorted_phase[pos];
-		uint32_t first = pos == 0? 0 : sorted_phase[pos - 1] + 1;
-		for (uint32_t q = first; q <= p; ++q)
-			s.phase_count[q] = pos;
-		if (pos == n - 1)
-			for (uint32_t q = p + 1; q <= s.max_phases; ++q)
-				s.phase_count[q] = n;
-	}
-};
-
-// Batched worlds: the worlds never interact, so nothing forces them through the phases in lockstep. World major layout: solve
-// position = (world, phase, sort key); a warp then walks ONE world through all its phases and iterations on its own
-// (solve_velocity_worlds_kernel) -- no grid wide barrier per phase, no per phase launch.
-struct KPlaceKeysWorlds
-{
-	DWorld w; SolveCtx s; uint32_t *keys;
-	B2J_D void operator()(uint32_t i) const // i = position sorted by sort key
-	{
-		const ConstraintSrc &c = s.src[s.order[i]];
-		keys[i] = ((c.b1 / w.world_stride) << 13) | s.phase[i];
-	}
-};
-
-struct KPhasePlaceWorlds
 {
 	SolveCtx s; const uint32_t *sorted_key, *sorted_idx; uint32_t n;
 	B2J_D void operator()(uint32_t pos) const
@@ -604,16 +572,14 @@ struct KPhasePlaceWorlds
 		uint32_t i = sorted_idx[pos];
 		s.final_pos[i] = pos;
 		s.solve_src[pos] = s.order[i];
-		uint32_t key = sorted_key[pos];
-		s.solve_phase[pos] = key & 0x1fffu;
-		// world_begin[q] = first position of world q (worlds without constraints included), world_begin[last + 1 ...] = n
-		uint32_t wd = key >> 13;
-		uint32_t first = pos == 0? 0 : (sorted_key[pos - 1] >> 13) + 1;
-		for (uint32_t q = first; q <= wd; ++q)
-			s.world_begin[q] = pos;
+		// phase_count[q] = first position of phase q (empty phases included), phase_count[last + 1 ...] = n
+		uint32_t p = sorted_key[pos] >> PLACE_CLASS_BITS;
+		uint32_t first = pos == 0? 0 : (sorted_key[pos - 1] >> PLACE_CLASS_BITS) + 1;
+		for (uint32_t q = first; q <= p; ++q)
+			s.phase_count[q] = pos;
 		if (pos == n - 1)
-			for (uint32_t q = wd + 1; q <= s.num_worlds; ++q)
-				s.world_begin[q] = n;
+			for (uint32_t q = p + 1; q <= s.max_phases; ++q)
+				s.phase_count[q] = n;
 	}
 };
 
@@ -1560,179 +1526,6 @@ template <int SV_WARPS, int SV_STAGES> __global__ void __launch_bounds__(SV_WARP
 				t = tn;
 			}
 			grid.sync();
-		}
-	}
-}
-
-// ---- batched worlds: one WARP walks one world through warm start and all velocity iterations -------------------------------------
-// World major layout (KPhasePlaceWorlds). The warp processes its world's constraints in solve order, a tile = up to 32 consecutive
-// constraints of ONE phase (found by comparing the phase ids of the next 32 positions); tiles of a phase are independent, phases are
-// ordered by program order + __syncwarp (the velocities of a world are only ever touched by its warp). Planes arrive by TMA bulk copies
-// in the warp's shared memory stage exactly as in solve_velocity_tma_kernel; while a warp waits for its copies the other warps of the
-// SM (other worlds) compute. No grid barrier, no cooperative launch: worlds are independent work items, and the launch overlaps with
-// whatever the other groups of the batch run on their streams.
-struct KSolveVelocityWorlds { }; // (profiling category)
-template <int SV_WARPS> __global__ void __launch_bounds__(SV_WARPS * 32, 1) solve_velocity_worlds_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
-{
-	extern __shared__ __align__(128) unsigned char sv_smem[];
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	F4 *stage = reinterpret_cast<F4 *>(sv_smem) + (size_t)warp * SV_STAGE_F4;
-	uint64_t *bar = reinterpret_cast<uint64_t *>(sv_smem + (size_t)SV_WARPS * SV_STAGE_F4 * sizeof(F4)) + warp;
-	const uint32_t world = blockIdx.x * SV_WARPS + warp;
-	if (world >= s.num_worlds)
-		return;
-	const uint32_t wb = s.world_begin[world], we = s.world_begin[world + 1];
-	if (wb == we)
-		return;
-	if (lane == 0)
-	{
-		sv_mbar_init(bar, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncwarp();
-	uint32_t parity = 0;
-	const Constraints c = s.con;
-	const uint32_t steps = w.counters->max_velocity_steps;
-
-	// raw look ahead of the 32 positions from `cur`: phase id and header of the lane's position
-	struct Raw { uint32_t start, phase; ConstraintHeader h; bool in_range; };
-	auto scan = [&](uint32_t cur) -> Raw {
-		Raw r; r.start = cur;
-		uint32_t i = cur + lane;
-		r.in_range = i < we;
-		r.phase = 0xffffffffu; r.h.b1 = 0; r.h.b2 = 0; r.h.manifold = 0; r.h.meta = 0;
-		if (r.in_range)
-		{
-			r.phase = s.solve_phase[i];
-			uint4 v = __ldg(reinterpret_cast<const uint4 *>(&c.hdr[i])); r.h.b1 = v.x; r.h.b2 = v.y; r.h.manifold = v.z; r.h.meta = v.w;
-		}
-		return r;
-	};
-
-	for (uint32_t pass = 0; pass <= steps; ++pass) // pass 0 = warm start, pass it + 1 = velocity iteration it
-	{
-		const bool warm = pass == 0;
-		const uint32_t iteration = pass - 1;
-		// tile = the leading positions of the look ahead that share the phase of the first one
-		auto tile_of = [&](const Raw &r, uint32_t &count, bool &valid) {
-			uint32_t ph0 = __shfl_sync(0xffffffffu, r.phase, 0);
-			uint32_t same = __ballot_sync(0xffffffffu, r.in_range && r.phase == ph0);
-			count = same == 0xffffffffu? 32u : (uint32_t)(__ffs((int)~same) - 1);
-			valid = lane < count;
-			// constraints of islands with fewer velocity steps are done: they neither load nor solve in this pass
-			if (!warm && iteration >= ((r.h.meta >> 8) & 0xff)) valid = false;
-		};
-		// TMA bulk copies of the planes the tile needs + register prefetch of the lane's velocities and lambdas
-		auto issue = [&](const Raw &r, uint32_t count, bool valid, SvPre &pre, uint32_t &tile_mask) {
-			uint32_t lane_mask = valid? (warm? sv_slot_mask<true>(r.h.meta) : sv_slot_mask<false>(r.h.meta)) : 0u;
-			tile_mask = __reduce_or_sync(0xffffffffu, lane_mask);
-			if (tile_mask != 0)
-			{
-				if (lane == 0) sv_mbar_expect_tx(bar, (uint32_t)__popc(tile_mask) * count * (uint32_t)sizeof(F4));
-				__syncwarp();
-				if (lane < SV_NUM_SLOTS && ((tile_mask >> lane) & 1u))
-					sv_bulk_g2s(stage + lane * 32, &c.cp[(size_t)sv_plane_of_slot((int)lane) * c.capacity + r.start], count * (uint32_t)sizeof(F4), bar);
-			}
-			if (valid)
-			{
-				uint32_t type1 = (r.h.meta >> 3) & 3, type2 = (r.h.meta >> 5) & 3;
-				uint32_t i = r.start + lane;
-				if (type1 != B2J_MOTION_STATIC) { pre.v1 = w.linear_velocity[r.h.b1]; pre.w1 = w.angular_velocity[r.h.b1]; }
-				if (type2 != B2J_MOTION_STATIC) { pre.v2 = w.linear_velocity[r.h.b2]; pre.w2 = w.angular_velocity[r.h.b2]; }
-				pre.lpt = cp_at(c, CP_LAMBDA_PT, i);
-				pre.lfr = cp_at(c, CP_LAMBDA_FR, i);
-			}
-		};
-
-		Raw cur = scan(wb), next;
-		uint32_t count0 = 0, mask0 = 0;
-		bool valid0 = false;
-		SvPre pre0;
-		tile_of(cur, count0, valid0);
-		uint32_t cursor = wb + count0; // start of the tile after `cur`
-		bool have_next = cursor < we;
-		if (have_next) next = scan(cursor);
-		issue(cur, count0, valid0, pre0, mask0);
-		for (;;)
-		{
-			if (mask0 != 0)
-			{
-				sv_mbar_wait(bar, parity);
-				parity ^= 1;
-			}
-			if (valid0)
-			{
-				uint32_t meta = cur.h.meta;
-				uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-				uint32_t i = cur.start + lane;
-				VelState vs;
-				if (type1 != B2J_MOTION_STATIC) { vs.v1 = to_v3(pre0.v1); vs.w1 = to_v3(pre0.w1); } else { vs.v1 = v3_zero(); vs.w1 = v3_zero(); }
-				if (type2 != B2J_MOTION_STATIC) { vs.v2 = to_v3(pre0.v2); vs.w2 = to_v3(pre0.w2); } else { vs.v2 = v3_zero(); vs.w2 = v3_zero(); }
-				F4 lpt = pre0.lpt, lfr = pre0.lfr;
-				SmemPlanes src; src.stage = stage; src.lane = lane;
-				bool any;
-				if (warm)
-				{
-					any = warm_start_core(src, meta, warm_start_ratio, vs, lpt, lfr);
-					cp_at(c, CP_LAMBDA_PT, i) = lpt;
-					cp_at(c, CP_LAMBDA_FR, i) = lfr;
-				}
-				else
-				{
-					any = solve_velocity_core(src, meta, vs, lpt, lfr);
-					cp_at(c, CP_LAMBDA_PT, i) = lpt;
-					if (meta & (META_LINEAR_FRICTION | META_ANGULAR_FRICTION))
-						cp_at(c, CP_LAMBDA_FR, i) = lfr;
-				}
-				if (any)
-					store_vel_state(w, cur.h.b1, cur.h.b2, meta, vs);
-				if (!warm && iteration + 1 == ((meta >> 8) & 0xff))
-					store_applied_impulses(w, cur.h.manifold, (int)(meta & 7), lpt, lfr);
-			}
-			// every lane is done with the stage and its velocity stores are ordered before the loads of the next tile (which may belong
-			// to the next phase and read the bodies this tile wrote)
-			__syncwarp();
-			if (!have_next)
-				break;
-			cur = next;
-			tile_of(cur, count0, valid0);
-			cursor += count0;
-			have_next = cursor < we;
-			if (have_next) next = scan(cursor);
-			issue(cur, count0, valid0, pre0, mask0);
-		}
-	}
-}
-
-// Position iterations of batched worlds: one warp per world, same walk (no shared memory stage: KSolvePosition reads few planes)
-struct KSolvePositionWorlds { };
-__global__ void __launch_bounds__(128) solve_position_worlds_kernel(const DWorld w, const SolveCtx s)
-{
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t world = blockIdx.x * (blockDim.x >> 5) + warp;
-	if (world >= s.num_worlds)
-		return;
-	const uint32_t wb = s.world_begin[world], we = s.world_begin[world + 1];
-	if (wb == we)
-		return;
-	const uint32_t steps = w.counters->max_position_steps;
-	KSolvePosition sp; sp.w = w; sp.c = s.con; sp.begin = 0;
-	for (uint32_t it = 0; it < steps; ++it)
-	{
-		sp.iteration = it;
-		uint32_t cursor = wb;
-		while (cursor < we)
-		{
-			uint32_t i = cursor + lane;
-			bool in_range = i < we;
-			uint32_t ph = in_range? s.solve_phase[i] : 0xffffffffu;
-			uint32_t ph0 = __shfl_sync(0xffffffffu, ph, 0);
-			uint32_t same = __ballot_sync(0xffffffffu, in_range && ph == ph0);
-			uint32_t count = same == 0xffffffffu? 32u : (uint32_t)(__ffs((int)~same) - 1);
-			if (lane < count)
-				sp(i);
-			__syncwarp(); // the pose stores of this tile are ordered before the loads of the next one (possibly the next phase)
-			cursor += count;
 		}
 	}
 }

@@ -175,6 +175,24 @@ struct KGetState
 	}
 };
 
+// b2j_bodies_get_stepped_state: like KGetState over a list of body slots, the ids come back too
+struct KGetStepped
+{
+	DWorld w; const uint32_t *slots; uint32_t *ids; float *pos, *rot, *lin, *ang, *bounds; uint32_t *active_index; float *sleep_timer;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = slots[i];
+		ids[i] = w.info[b].id;
+		if (pos) v3_store(to_v3(w.position[b]), pos + 3 * i);
+		if (rot) q4_store(to_q4(w.rotation[b]), rot + 4 * i);
+		if (lin) v3_store(to_v3(w.linear_velocity[b]), lin + 3 * i);
+		if (ang) v3_store(to_v3(w.angular_velocity[b]), ang + 3 * i);
+		if (bounds) { v3_store(to_v3(w.bounds_min[b]), bounds + 6 * i); v3_store(to_v3(w.bounds_max[b]), bounds + 6 * i + 3); }
+		if (active_index) active_index[i] = w.active_index[b];
+		if (sleep_timer) sleep_timer[i] = w.sleep_timer[b];
+	}
+};
+
 struct KSetState
 {
 	DWorld w; const uint32_t *ids; const float *pos, *rot, *lin, *ang;
@@ -506,6 +524,7 @@ struct b2j_world
 	StepCounters h_counters;
 	std::vector<uint32_t> h_phase_offsets;
 	uint32_t last_num_events = 0, last_num_act_events = 0, last_num_pairs = 0;
+	const uint32_t *stepped_list = nullptr; uint32_t stepped_count = 0; // body slots the last step simulated (b2j_bodies_get_stepped_state)
 	uint32_t last_collide_convex = 0;      // longest convex pair queue of the previous step (sizes this step's queue ordering)
 #ifndef B2J_HOSTSIM
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -649,6 +668,25 @@ bool read_counters(b2j_world *W)
 	return W->rt.check("read_counters");
 }
 
+// B2J_TRACE_STEP=1: wall clock per stage of a step with the stream drained after every stage (diagnostics for small worlds, where the
+// step is a chain of ~60 dependent launches: which stage pays how much launch / round trip latency). Prints to stderr.
+struct StepTrace
+{
+	bool on; Runtime &rt; std::chrono::high_resolution_clock::time_point t0; std::string line;
+	explicit StepTrace(Runtime &r) : on(getenv("B2J_TRACE_STEP") != nullptr), rt(r) { if (on) { rt.sync(); t0 = std::chrono::high_resolution_clock::now(); } }
+	void mark(const char *stage)
+	{
+		if (!on) return;
+		rt.sync();
+		auto t1 = std::chrono::high_resolution_clock::now();
+		char buf[64];
+		snprintf(buf, sizeof(buf), " %s %.0f", stage, std::chrono::duration<double, std::micro>(t1 - t0).count());
+		line += buf;
+		t0 = t1;
+	}
+	~StepTrace() { if (on) fprintf(stderr, "[b2j step us]%s launches %u\n", line.c_str(), rt.launches); }
+};
+
 // One collision step. Returns false on a CUDA failure.
 bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last, b2j_step_stats *stats)
 {
@@ -664,6 +702,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		rt.upload(&d.counters->num_activation_events, &W->last_num_act_events, 1);
 	}
 
+	StepTrace trace(rt);
 	// (a2) gravity, forces, damping
 	{ KApplyGravity k; k.w = d; k.dt = dt; rt.launch(k, W->num_active); }
 
@@ -675,6 +714,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			W->layer_needs_build[l] = 0;
 		}
 
+	trace.mark("gravity+trees");
 	// (a3, a5..a9) find pairs + narrow phase; repeated for the bodies woken up by contacts until no new body wakes up
 	uint32_t first_active = 0, n_query = W->num_active;
 	uint32_t woken_total = 0, longest_queue = 0;
@@ -757,6 +797,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	W->last_collide_convex = longest_queue < d.max_body_pairs? longest_queue : d.max_body_pairs;
 	uint32_t na = W->num_active;
 
+	trace.mark("pairs+narrowphase");
 	// (a12) islands
 	SolveCtx &sc = W->sc;
 	sc.num_slots = W->num_slots;
@@ -768,7 +809,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	{ KIslandClassify k; k.w = d; k.s = sc; rt.launch(k, na); }
 
 	uint32_t num_phases = 0, vsteps = 0, psteps = 0;
-	bool block_solve = false, solved_by_phase_launches = false, solved_world_major = false;
+	bool block_solve = false, solved_by_phase_launches = false;
 	if (M > 0)
 	{
 		// (a14 SortContacts) order by sort key
@@ -781,6 +822,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KAdjFill k; k.w = d; k.s = sc; rt.launch(k, M); }
 		{ KAdjSort k; k.w = d; k.s = sc; rt.launch(k, na); }
 
+		trace.mark("islands+sort+adjacency");
 		// (a13) schedule: wavefronts in sorted order; pass 0 = levels (small islands) / colours (large islands)
 		const uint32_t rounds_per_check = 8;
 #ifndef B2J_HOSTSIM
@@ -856,38 +898,22 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		}
 
 		// B2J_SOLVE_MODE: how the velocity / position solve is launched.
-		//   3 = batched worlds only (their default): world major layout, one warp walks one world through all phases and iterations,
-		//       planes streamed through shared memory by TMA (solve_velocity_worlds_kernel)
-		//   2 = one persistent cooperative launch, phases separated by grid barriers, TMA staged planes (solve_velocity_tma_kernel)
-		//   1 = one persistent cooperative launch, loads straight from HBM        0 = one launch per phase per iteration
+		//   0 = one launch per phase per iteration (default: the groups of a batch overlap on their streams)
+		//   1 = one persistent cooperative launch, phases separated by grid barriers, loads straight from HBM
+		//   2 = the same with the constraint planes streamed through shared memory by TMA (solve_velocity_tma_kernel)
 #ifndef B2J_HOSTSIM
 		const char *solve_mode_env = getenv("B2J_SOLVE_MODE");
-		int solve_mode = solve_mode_env != nullptr? atoi(solve_mode_env) : (d.world_stride != 0? 3 : 2);
-		if (solve_mode == 3 && (d.world_stride == 0 || W->num_worlds > (1u << 18))) solve_mode = 2;
-		const bool world_major = solve_mode == 3;
-#else
-		const bool world_major = false;
+		int solve_mode = solve_mode_env != nullptr? atoi(solve_mode_env) : 0;
 #endif
 		// phases -> solve order
 		{
 			// the 64 bit key buffers of the constraint sort are free again: reuse them for the (phase, index) sort; d_sort_vals still holds 0..M-1
 			uint32_t *sorted_phase = reinterpret_cast<uint32_t *>(W->d_sort_keys[0]), *sorted_idx = reinterpret_cast<uint32_t *>(W->d_sort_keys[1]);
-			{ KPhaseClamp k; k.w = d; k.s = sc; rt.launch(k, M); }
-			if (world_major)
-			{
-				// solve position = (world, phase, sort key): one more key field, the second half of the first key buffer holds the unsorted keys
-				uint32_t *keys_in = sorted_phase + d.max_constraints;
-				uint32_t world_bits = 1;
-				while ((1u << world_bits) < W->num_worlds) ++world_bits;
-				{ KPlaceKeysWorlds k; k.w = d; k.s = sc; k.keys = keys_in; rt.launch(k, M); }
-				rt.sort_pairs<uint32_t>(keys_in, sorted_phase, W->d_sort_vals, sorted_idx, M, (int)(13 + world_bits));
-				{ KPhasePlaceWorlds k; k.s = sc; k.sorted_key = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
-			}
-			else
-			{
-				rt.sort_pairs<uint32_t>(sc.phase, sorted_phase, W->d_sort_vals, sorted_idx, M, 13);
-				{ KPhasePlace k; k.s = sc; k.sorted_phase = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
-			}
+			// (placement key = phase | solve class; the unsorted keys live in the second half of the first key buffer)
+			uint32_t *keys_in = sorted_phase + d.max_constraints;
+			{ KPhaseClamp k; k.w = d; k.s = sc; k.keys = keys_in; rt.launch(k, M); }
+			rt.sort_pairs<uint32_t>(keys_in, sorted_phase, W->d_sort_vals, sorted_idx, M, 13 + PLACE_CLASS_BITS);
+			{ KPhasePlace k; k.s = sc; k.sorted_key = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
 		}
 
 		// (a11) constraint setup straight into solve order
@@ -913,20 +939,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			float ratio_arg = warm_start_ratio;
 			void *args[] = { (void *)&d, (void *)&sc, (void *)&ratio_arg };
 			cudaError_t e = cudaErrorUnknown;
-			if (solve_mode == 3)
-			{
-				const int warps = 12;
-				const void *fn = (const void *)solve_velocity_worlds_kernel<12>;
-				const size_t smem = sv_smem_bytes(warps, 1);
-				bool &configured = rt.func_configured[fn];
-				if (!configured) { cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-				++rt.launches;
-				if (rt.profiling) rt.prof_begin(profile_category<KSolveVelocityWorlds>());
-				solve_velocity_worlds_kernel<12><<<(W->num_worlds + warps - 1) / warps, warps * 32, smem, rt.stream>>>(d, sc, ratio_arg);
-				if (rt.profiling) rt.prof_end();
-				e = cudaGetLastError();
-			}
-			else if (solve_mode == 2)
+			if (solve_mode == 2)
 			{
 				// shape of the TMA pipeline (warps x stages): 0 = 7 x 2, 1 = 14 x 1, 2 = 12 x 1, 3 = 10 x 1
 				const char *shape_env = getenv("B2J_SOLVE_TMA_SHAPE");
@@ -963,12 +976,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 					if (rt.profiling) rt.prof_end();
 				}
 			}
-			if (e != cudaSuccess)
-			{
-				cudaGetLastError();
-				if (world_major) { last_error() = std::string("world major velocity solve launch failed: ") + cudaGetErrorString(e); return false; } // (the layout has no per phase form)
-				solve_mode = 0; // fall back to the per phase launches
-			}
+			if (e != cudaSuccess) { cudaGetLastError(); solve_mode = 0; } // fall back to the per phase launches
 		}
 		const bool phase_launches = !block_solve && solve_mode == 0;
 #else
@@ -998,12 +1006,12 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 				}
 		}
 		solved_by_phase_launches = phase_launches;
-		solved_world_major = world_major;
 		// the applied impulses are stored by the last velocity iteration of every constraint; islands without iterations only exist when
 		// the default number of velocity steps is 0
 		if (d.settings.num_velocity_steps == 0) { KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
 	}
 
+	trace.mark("velocity");
 	// (a15) integrate
 	{ KIntegrate k; k.w = d; k.dt = dt; rt.launch(k, na); }
 
@@ -1025,13 +1033,6 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		cudaError_t e = cudaLaunchCooperativeKernel((const void *)solve_small_kernel<true>, dim3(8), dim3(256), args, 0, rt.stream);
 		if (rt.profiling) rt.prof_end();
 		if (e != cudaSuccess) { cudaGetLastError(); last_error() = "cooperative position solve launch failed"; return false; }
-	}
-	else if (M > 0 && solved_world_major)
-	{
-		++rt.launches;
-		if (rt.profiling) rt.prof_begin(profile_category<KSolvePositionWorlds>());
-		solve_position_worlds_kernel<<<(W->num_worlds + 3) / 4, 128, 0, rt.stream>>>(d, sc);
-		if (rt.profiling) rt.prof_end();
 	}
 	else if (M > 0 && !solved_by_phase_launches)
 	{
@@ -1067,6 +1068,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			}
 	}
 
+	trace.mark("integrate+position");
 	// (a16, a17) bounds, sleeping, active list compaction
 	{ KBoundsAndSleep k; k.w = d; k.s = sc; k.dt = dt; k.is_last = is_last? 1u : 0u; rt.launch(k, na); }
 	uint32_t new_active = na;
@@ -1079,6 +1081,9 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KFinishCompact k; k.w = d; k.keep = W->d_keep; k.keep_scan = W->d_keep_scan; k.n = na; rt.launch(k, 1); }
 		W->active_cur ^= 1;
 	}
+	// the bodies this step simulated: the active list as it was before the sleepers left it (the buffer that is no longer current)
+	W->stepped_list = is_last? W->active_buf[W->active_cur ^ 1] : W->active_buf[W->active_cur];
+	W->stepped_count = na;
 	if (stats != nullptr && stats->kinetic_energy < 0.0f)
 	{
 		rt.memset_(W->d_energy, 0, 4);
@@ -1095,6 +1100,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		psteps = W->h_counters.max_position_steps;
 	}
 
+	trace.mark("sleep+compact+readback");
 	// swap the caches: this step's write cache is the next step's read cache
 	uint32_t wi = W->write_idx;
 	// (the sizes of the cache written by this step came back with the counters: one readback at the end of the step, not three)
@@ -1317,8 +1323,6 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	sc.man_ws = nc.man_ws;
 	sc.order = rt.alloc<uint32_t>(mc); sc.final_pos = rt.alloc<uint32_t>(mc); sc.solve_src = rt.alloc<uint32_t>(mc); sc.phase = rt.alloc<uint32_t>(mc);
 	sc.max_phases = 8192;
-	sc.solve_phase = rt.alloc<uint32_t>(mc, false);
-	sc.num_worlds = 1;
 	rt.reserve_temp(std::max(d.max_bodies, d.max_constraints), std::max(std::max(d.max_body_pairs, d.max_constraints), d.max_bodies), d.max_bodies);
 	sc.phase_count = rt.alloc<uint32_t>(sc.max_phases + 2);
 	sc.uf_parent = rt.alloc<uint32_t>(nbod); sc.root = rt.alloc<uint32_t>(nbod); sc.island_items = rt.alloc<uint32_t>(nbod);
@@ -1387,7 +1391,7 @@ void b2j_world_destroy(b2j_world *W)
 	rt.free_(W->act_events_buf); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
 	rt.free_(sc.con.cp); rt.free_(sc.con.hdr);
-	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count); rt.free_(sc.solve_phase); rt.free_(sc.world_begin);
+	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count);
 	rt.free_(sc.uf_parent); rt.free_(sc.root); rt.free_(sc.island_items); rt.free_(sc.island_large); rt.free_(sc.island_steps); rt.free_(sc.island_can_sleep);
 	rt.free_(sc.large_color_count); rt.free_(sc.body_deg); rt.free_(sc.body_off); rt.free_(sc.body_fill); rt.free_(sc.body_cur); rt.free_(sc.body_mask);
 	rt.free_(sc.adj); rt.free_(sc.sched_flag);
@@ -1785,6 +1789,39 @@ int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 	return rt.check("b2j_bodies_get_state")? 0 : -1;
 }
 
+uint32_t b2j_bodies_get_stepped_state(b2j_world *W, uint32_t cap, uint32_t *ids, const b2j_body_state *out)
+{
+	B2J_DEVICE_GUARD(W);
+	uint32_t total = W->stepped_list != nullptr? W->stepped_count : 0;
+	uint32_t n = total < cap? total : cap;
+	if (n == 0 || ids == nullptr || out == nullptr) return total;
+	Runtime &rt = W->rt;
+	sync_dworld(W);
+	KGetStepped k; memset(&k, 0, sizeof(k)); k.w = W->d; k.slots = W->stepped_list;
+	rt.stage_begin((size_t)n * (4 + 12 + 16 + 12 + 12 + 24 + 4 + 4));
+	uint32_t *h_ids = nullptr, *h_active = nullptr; float *h_pos = nullptr, *h_rot = nullptr, *h_lin = nullptr, *h_ang = nullptr, *h_bounds = nullptr, *h_timer = nullptr;
+	k.ids = rt.stage_alloc<uint32_t>(n, &h_ids);
+	if (out->position) k.pos = rt.stage_alloc<float>((size_t)n * 3, &h_pos);
+	if (out->rotation) k.rot = rt.stage_alloc<float>((size_t)n * 4, &h_rot);
+	if (out->linear_velocity) k.lin = rt.stage_alloc<float>((size_t)n * 3, &h_lin);
+	if (out->angular_velocity) k.ang = rt.stage_alloc<float>((size_t)n * 3, &h_ang);
+	if (out->bounds) k.bounds = rt.stage_alloc<float>((size_t)n * 6, &h_bounds);
+	if (out->active_index) k.active_index = rt.stage_alloc<uint32_t>(n, &h_active);
+	if (out->sleep_timer) k.sleep_timer = rt.stage_alloc<float>(n, &h_timer);
+	rt.launch(k, n);
+	rt.stage_to_host(0, rt.stage_used);
+	memcpy(ids, h_ids, (size_t)n * 4);
+	if (h_pos) memcpy(out->position, h_pos, (size_t)n * 12);
+	if (h_rot) memcpy(out->rotation, h_rot, (size_t)n * 16);
+	if (h_lin) memcpy(out->linear_velocity, h_lin, (size_t)n * 12);
+	if (h_ang) memcpy(out->angular_velocity, h_ang, (size_t)n * 12);
+	if (h_bounds) memcpy(out->bounds, h_bounds, (size_t)n * 24);
+	if (h_active) memcpy(out->active_index, h_active, (size_t)n * 4);
+	if (h_timer) memcpy(out->sleep_timer, h_timer, (size_t)n * 4);
+	if (!rt.check("b2j_bodies_get_stepped_state")) return 0;
+	return total;
+}
+
 int b2j_bodies_set_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_state *in)
 {
 	B2J_DEVICE_GUARD(W);
@@ -2114,6 +2151,7 @@ static bool snapshot_restore(b2j_world *W, const WorldSnapshot &ws)
 	{ KRebuildPairTable k; k.w = d; rt.launch(k, ws.num_pairs); }
 	rt.memset_(W->nc.woken_flag, 0, (size_t)d.max_bodies * 4);
 	// host side of the world
+	W->stepped_list = nullptr; W->stepped_count = 0;
 	W->num_slots = n; W->num_active = ws.num_active; W->num_bodies = ws.num_bodies; W->prev_dt = ws.prev_dt; d.gravity = ws.gravity;
 	std::copy(ws.h_ids.begin(), ws.h_ids.end(), W->h_ids.begin()); std::copy(ws.h_layer.begin(), ws.h_layer.end(), W->h_layer.begin()); std::copy(ws.h_static.begin(), ws.h_static.end(), W->h_static.begin());
 	W->layer_bodies = ws.layer_bodies; W->layer_has_moving = ws.layer_has_moving;
@@ -2370,8 +2408,6 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	if (B == nullptr) return nullptr;
 	Runtime &rt = B->rt;
 	B->num_worlds = n_worlds;
-	B->sc.num_worlds = n_worlds;
-	B->sc.world_begin = rt.alloc<uint32_t>((size_t)n_worlds + 1);
 	for (int i = 0; i < 2; ++i) { B->d_collide_keys[i] = rt.alloc<uint32_t>(B->d.max_body_pairs, false); B->d_collide_vals[i] = rt.alloc<uint32_t>(B->d.max_body_pairs, false); }
 	B->d.world_stride = stride;
 	B->prev_dt = P->prev_dt;

@@ -290,6 +290,30 @@ B2JF_API void b2jf_scene_flush(void *h) { ((Scene *)h)->system.GetBodyInterface(
 B2JF_API void b2jf_scene_mutate(void *h, int phase) { Scene *s = (Scene *)h; sApiTourMutate(s->system, s->dynamic_bodies, phase); }
 B2JF_API int b2jf_scene_query(void *h, uint32_t *out_ids, int cap, uint32_t *out_num_bodies, uint32_t *out_flags) { Scene *s = (Scene *)h; return sApiTourQuery(s->system, s->dynamic_bodies, out_ids, cap, out_num_bodies, out_flags); }
 
+// NarrowPhaseQuery::CastRays / BroadPhaseQuery::CollideAABox through the facade (rays: [n][6] floats; hits: body, sub shape, fraction)
+B2JF_API void b2jf_scene_cast_rays(void *h, const float *rays, int n, uint32_t *out_body, uint32_t *out_sub, float *out_fraction)
+{
+	Scene *s = (Scene *)h;
+	std::vector<RayCastResult> hits((size_t)n);
+	s->system.GetNarrowPhaseQuery().CastRays(reinterpret_cast<const RRayCast *>(rays), n, hits.data());
+	for (int i = 0; i < n; ++i) { out_body[i] = hits[i].mBodyID.GetIndexAndSequenceNumber(); out_sub[i] = hits[i].mSubShapeID2.GetValue(); out_fraction[i] = hits[i].mFraction; }
+	// the single ray form agrees with the batch
+	if (n > 0)
+	{
+		RayCastResult one;
+		bool hit = s->system.GetNarrowPhaseQuery().CastRay(reinterpret_cast<const RRayCast *>(rays)[0], one);
+		if (hit != !hits[0].mBodyID.IsInvalid() || (hit && one.mFraction != hits[0].mFraction)) out_body[0] = 0xdeadbeefu;
+	}
+}
+B2JF_API int b2jf_scene_collide_aabox(void *h, const float *box, uint32_t *out_ids, int cap)
+{
+	Scene *s = (Scene *)h;
+	std::vector<BodyID> ids;
+	s->system.GetBroadPhaseQuery().CollideAABox(AABox(Vec3(box[0], box[1], box[2]), Vec3(box[3], box[4], box[5])), ids);
+	for (size_t i = 0; i < ids.size() && (int)i < cap; ++i) out_ids[i] = ids[i].GetIndexAndSequenceNumber();
+	return (int)ids.size();
+}
+
 // PhysicsSystem::Update through the facade (mirrors the state to the host, replays events). Returns the error bits.
 B2JF_API int b2jf_scene_update(void *h, float dt, int collision_steps, b2j_step_stats *out_stats)
 {

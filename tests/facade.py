@@ -30,6 +30,9 @@ class FacadeLib:
         L.b2jf_scene_update.argtypes = [C.c_void_p, C.c_float, C.c_int, C.POINTER(_capi.StepStats)]
         L.b2jf_scene_step_e2e.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.b2jf_scene_mutate.argtypes = [C.c_void_p, C.c_int]
+        L.b2jf_scene_cast_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2jf_scene_collide_aabox.restype = C.c_int
+        L.b2jf_scene_collide_aabox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.b2jf_scene_query.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 
 
@@ -69,6 +72,22 @@ class FacadeScene:
         nb, flags = C.c_uint32(), C.c_uint32()
         n = self.flib.lib.b2jf_scene_query(self.h, ids.ctypes.data, len(ids), C.addressof(nb), C.addressof(flags))
         return ids[:n].copy(), nb.value, flags.value
+
+    def cast_rays(self, rays):
+        """NarrowPhaseQuery::CastRays through the facade -> structured hits like B2JWorld.cast_rays."""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = len(rays)
+        body, sub, frac = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        self.flib.lib.b2jf_scene_cast_rays(self.h, rays.ctypes.data, n, body.ctypes.data, sub.ctypes.data, frac.ctypes.data)
+        hits = np.zeros(n, R.HIT_DTYPE)
+        hits["body"], hits["sub_shape"], hits["fraction"] = body, sub, frac
+        return hits
+
+    def collide_aabox(self, box, cap=256):
+        box = np.ascontiguousarray(box, np.float32)
+        ids = np.zeros(cap, np.uint32)
+        n = self.flib.lib.b2jf_scene_collide_aabox(self.h, box.ctypes.data, ids.ctypes.data, cap)
+        return np.sort(ids[:min(n, cap)])
 
     def step_e2e(self, dt, forces, out_positions):
         return self.flib.lib.b2jf_scene_step_e2e(self.h, dt, forces.ctypes.data if forces is not None else None, out_positions.ctypes.data if out_positions is not None else None)
