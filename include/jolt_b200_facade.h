@@ -755,6 +755,8 @@ public:
 	}
 	bool WereBodiesInContact(const BodyID &a, const BodyID &b) const { return mWorld && b2j_were_bodies_in_contact(mWorld, a.mID, b.mID) == 1; }
 	const b2j_step_stats &GetLastStepStats() const { return mStats; }
+	// (diagnostics / tests: how many body rows the last refresh of the host mirror fetched -- see EnsureState)
+	uint32 GetLastDownloadCount() const { EnsureState(); return mLastDownloadCount; }
 	b2j_world *GetWorld() const { return mWorld; }
 	const char *GetLastError() const { return b2j_last_error(); }
 
@@ -771,7 +773,7 @@ public:
 		if (inStream.mSnapshot == nullptr) return false;
 		mBodyInterface.Flush();
 		if (b2j_world_restore_state(mWorld, inStream.mSnapshot) != 0) return false;
-		DownloadState(); // the Body mirrors follow the restored device state
+		DownloadState(); // the Body mirrors follow the restored device state (full download)
 		return true;
 	}
 
@@ -783,7 +785,11 @@ public:
 		int r = b2j_step(mWorld, inDeltaTime, inCollisionSteps, &mStats);
 		if (r < 0)
 			return EPhysicsUpdateError(0x80000000u);
-		DownloadState();
+		// the host mirror of the body state is refreshed on first use after the step (EnsureState), and only for the bodies the step
+		// simulated unless something else changed the device state since the last download
+		++mStateGeneration; // Body::Sync picks the new state up on first access
+		for (uint8 &f : mSlotFlags) f &= 1;
+		mStatePending = true;
 		ReplayEvents();
 		return EPhysicsUpdateError(r);
 	}
@@ -816,9 +822,11 @@ private:
 		return id;
 	}
 
+	// Full download of every body slot (first use, after RestoreState, after API calls that changed device state behind the arrays)
 	void DownloadState()
 	{
 		uint32 n = (uint32)mBodies.size();
+		mStatePending = false; mNeedFullDownload = false;
 		if (n == 0) return;
 		mPos.resize(3 * n); mRot.resize(4 * n); mLin.resize(3 * n); mAng.resize(3 * n); mActiveIndex.resize(n);
 		b2j_body_state st;
@@ -827,7 +835,37 @@ private:
 		b2j_bodies_get_state(mWorld, nullptr, n, &st);
 		++mStateGeneration; // Body::Sync picks the new state up on first access
 		for (uint8 &f : mSlotFlags) f &= 1; // the arrays are current for every body in the world
+		mLastDownloadCount = n;
 	}
+
+	// The state getters call this first. After a step only the bodies the step simulated changed on the device: when nothing else
+	// touched the device state since the arrays were filled, just those rows are fetched (b2j_bodies_get_stepped_state) and scattered
+	// into the arrays -- a world of mostly sleeping bodies mirrors only what moved (incremental download).
+	void EnsureState() const { if (mStatePending) const_cast<PhysicsSystem *>(this)->RefreshState(); }
+	void RefreshState()
+	{
+		uint32 n = (uint32)mBodies.size();
+		if (mNeedFullDownload || mActiveIndex.size() != n) { --mStateGeneration; DownloadState(); return; } // (the generation was advanced by Update)
+		mStatePending = false;
+		uint32 count = b2j_bodies_get_stepped_state(mWorld, 0, nullptr, nullptr);
+		mLastDownloadCount = count;
+		if (count == 0) return;
+		if (count > n / 2) { --mStateGeneration; DownloadState(); return; } // most bodies moved: one bulk copy is cheaper than a scatter
+		mSteppedIDs.resize(count); mSteppedPos.resize(3 * (size_t)count); mSteppedRot.resize(4 * (size_t)count); mSteppedLin.resize(3 * (size_t)count); mSteppedAng.resize(3 * (size_t)count); mSteppedActive.resize(count);
+		b2j_body_state st;
+		memset(&st, 0, sizeof(st));
+		st.position = mSteppedPos.data(); st.rotation = mSteppedRot.data(); st.linear_velocity = mSteppedLin.data(); st.angular_velocity = mSteppedAng.data(); st.active_index = mSteppedActive.data();
+		b2j_bodies_get_stepped_state(mWorld, count, mSteppedIDs.data(), &st);
+		for (uint32 k = 0; k < count; ++k)
+		{
+			size_t i = mSteppedIDs[k] & 0x7fffffu;
+			if (i >= n) continue;
+			memcpy(&mPos[3 * i], &mSteppedPos[3 * (size_t)k], 12); memcpy(&mRot[4 * i], &mSteppedRot[4 * (size_t)k], 16);
+			memcpy(&mLin[3 * i], &mSteppedLin[3 * (size_t)k], 12); memcpy(&mAng[3 * i], &mSteppedAng[3 * (size_t)k], 12);
+			mActiveIndex[i] = mSteppedActive[k];
+		}
+	}
+
 
 	// current device state of a few bodies straight into their Body mirrors (bodies whose state changed through the interface since
 	// the last Update, e.g. woken / pushed and then removed before the next step)
@@ -920,6 +958,11 @@ private:
 	b2j_step_stats mStats = b2j_step_stats();
 	std::vector<float> mPos, mRot, mLin, mAng;    // state of all body slots after the last Update (see Body::Sync)
 	std::vector<uint32> mActiveIndex;
+	std::vector<uint32> mSteppedIDs, mSteppedActive;   // scratch of the incremental download
+	std::vector<float> mSteppedPos, mSteppedRot, mSteppedLin, mSteppedAng;
+	bool mStatePending = false;                   // a step ran since the arrays were refreshed
+	bool mNeedFullDownload = true;                // device state changed behind the arrays (API mutation, restore): next refresh is a full download
+	uint32 mLastDownloadCount = 0;
 	uint32 mStateGeneration = 1;
 	// per body index: full id (or invalid) and flags for the getters' fast path: bit 0 = in the world, bit 1 = the Body mirror is
 	// newer than the downloaded arrays (added / changed through the interface since the last Update)
@@ -927,10 +970,11 @@ private:
 	std::vector<uint8> mSlotFlags;
 	bool FastSlot(const BodyID &id, size_t &outIndex) const
 	{
+		EnsureState();
 		outIndex = id.GetIndex();
 		return outIndex < mSlotID.size() && mSlotID[outIndex] == id.mID && mSlotFlags[outIndex] == 1 && outIndex < mActiveIndex.size();
 	}
-	void MarkMirrorNewer(const BodyID &id) { size_t i = id.GetIndex(); if (i < mSlotFlags.size()) mSlotFlags[i] |= 2; }
+	void MarkMirrorNewer(const BodyID &id) { size_t i = id.GetIndex(); if (i < mSlotFlags.size()) mSlotFlags[i] |= 2; mNeedFullDownload = true; }
 	std::vector<b2j_contact_event> mContactEvents;
 	std::vector<b2j_activation_event> mActEvents;
 };
@@ -971,6 +1015,7 @@ inline void Body::Sync() const
 {
 	if (mSystem == nullptr || !mInWorld || mSyncGeneration == mSystem->mStateGeneration)
 		return;
+	mSystem->EnsureState();
 	mSyncGeneration = mSystem->mStateGeneration;
 	size_t i = mID.GetIndex();
 	if (i >= mSystem->mActiveIndex.size())
@@ -1115,6 +1160,7 @@ inline void BodyInterface::AddBodies(const BodyID *inBodies, int inNumber, EActi
 		d.linear_velocity[0] = b->mLinearVelocity.x; d.linear_velocity[1] = b->mLinearVelocity.y; d.linear_velocity[2] = b->mLinearVelocity.z;
 		d.angular_velocity[0] = b->mAngularVelocity.x; d.angular_velocity[1] = b->mAngularVelocity.y; d.angular_velocity[2] = b->mAngularVelocity.z;
 		sys.mPendingAdd.push_back(d);
+		sys.mNeedFullDownload = true; // (a body added asleep is not among the bodies the next step simulates)
 		if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static)
 		{
 			sys.mPendingActivate.push_back(b->mID.mID);
@@ -1167,6 +1213,7 @@ inline void BodyInterface::RemoveBodies(BodyID *ioBodies, int inNumber)
 	for (Body *b : bodies) if (b->mSyncGeneration != sys.mStateGeneration || (sys.mSlotFlags[b->mID.GetIndex()] & 2)) stale.push_back(b->mID.mID);
 	if (!stale.empty()) sys.RefreshBodies(stale);
 	b2j_bodies_remove(World(), ids.data(), (uint32)ids.size());
+	sys.mNeedFullDownload = true;
 	for (Body *b : bodies)
 	{
 		b->Sync(); // the Body keeps the pose it left the world with
@@ -1255,6 +1302,7 @@ inline void BodyInterface::SetActive(const BodyID &id, bool inActive)
 	uint32 bid = id.mID;
 	Flush();
 	if (inActive) b2j_bodies_activate(World(), &bid, 1); else b2j_bodies_deactivate(World(), &bid, 1);
+	mSystem->mNeedFullDownload = true;
 	b->Sync();
 	mSystem->MarkMirrorNewer(id);
 	b->mActive = inActive;

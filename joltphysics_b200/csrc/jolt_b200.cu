@@ -1732,6 +1732,7 @@ int b2j_bodies_deactivate(b2j_world *W, const uint32_t *ids, uint32_t n)
 	{ KApiDeactivate k; k.w = W->d; k.keep = W->d_keep; rt.launch(k, na); }
 	rt.exclusive_scan(W->d_keep, W->d_keep_scan, na);
 	uint32_t *new_list = W->active_buf[W->active_cur ^ 1];
+	W->stepped_list = nullptr; W->stepped_count = 0; // (that buffer held the list of the last step)
 	{ KCompactActive k; k.w = W->d; k.keep = W->d_keep; k.keep_scan = W->d_keep_scan; k.new_active = new_list; rt.launch(k, na); }
 	rt.memset_(W->d.counters, 0, sizeof(StepCounters));
 	{ KFinishCompact k; k.w = W->d; k.keep = W->d_keep; k.keep_scan = W->d_keep_scan; k.n = na; rt.launch(k, 1); }
@@ -2202,6 +2203,7 @@ int b2j_step(b2j_world *W, float delta_time, int collision_steps, b2j_step_stats
 	rt.launches = 0;
 	W->last_num_events = 0;
 	W->last_num_act_events = 0;
+	W->stepped_list = nullptr; W->stepped_count = 0;
 	if (W->num_active == 0 || delta_time <= 0.0f)
 	{
 		// PhysicsSystem.cpp:191-207: nothing to simulate; if time passes all cached contacts are reported as removed

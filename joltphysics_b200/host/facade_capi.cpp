@@ -314,6 +314,9 @@ B2JF_API int b2jf_scene_collide_aabox(void *h, const float *box, uint32_t *out_i
 	return (int)ids.size();
 }
 
+// rows of body state the last refresh of the host mirror fetched (the incremental download: only what the step simulated)
+B2JF_API uint32_t b2jf_scene_last_download_count(void *h) { return ((Scene *)h)->system.GetLastDownloadCount(); }
+
 // PhysicsSystem::Update through the facade (mirrors the state to the host, replays events). Returns the error bits.
 B2JF_API int b2jf_scene_update(void *h, float dt, int collision_steps, b2j_step_stats *out_stats)
 {

@@ -30,6 +30,8 @@ class FacadeLib:
         L.b2jf_scene_update.argtypes = [C.c_void_p, C.c_float, C.c_int, C.POINTER(_capi.StepStats)]
         L.b2jf_scene_step_e2e.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.b2jf_scene_mutate.argtypes = [C.c_void_p, C.c_int]
+        L.b2jf_scene_last_download_count.restype = C.c_uint32
+        L.b2jf_scene_last_download_count.argtypes = [C.c_void_p]
         L.b2jf_scene_cast_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2jf_scene_collide_aabox.restype = C.c_int
         L.b2jf_scene_collide_aabox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]

@@ -94,6 +94,35 @@ def _check_api_tour(flib):
     ref.close()
 
 
+def _check_incremental_download(flib):
+    """once bodies sleep, Update mirrors only the bodies the step simulated; the getters still agree with the device for
+    EVERY body (sleeping ones keep the rows of an earlier download)."""
+    fs = F.FacadeScene(flib, "convex_vs_mesh", 2, 0)       # 100 bodies on the terrain mesh (slot 0): they settle and sleep one by one
+    n_dyn = fs.flib.lib.b2jf_scene_num_dynamic(fs.h)
+    out = np.zeros((n_dyn, 3), np.float32)
+    counts = []
+    for step in range(900):
+        assert fs.step_e2e(1.0 / 60.0, None, out) == 0     # Update + GetCenterOfMassPosition of every dynamic body
+        counts.append(fs.flib.lib.b2jf_scene_last_download_count(fs.h))
+        if step % 50 == 49 or step > 890:
+            gs = fs.world.state()
+            assert np.array_equal(out, gs.pos[1:1 + n_dyn]), f"step {step}: getters differ from the device state"
+    active = fs.flib.api.b2j_num_active_bodies(fs.world.h)
+    assert counts[0] == fs.num_bodies, "the first refresh is a full download"
+    assert active < n_dyn // 2, "most bodies should have gone to sleep"
+    assert counts[-1] <= max(2 * active + 8, 8), f"only the simulated bodies are mirrored once the scene sleeps: {counts[-1]} rows for {active} active bodies"
+    fs.close()
+
+
+def test_facade_incremental_download_hostsim(hostsim_facade):
+    _check_incremental_download(hostsim_facade)
+
+
+@pytest.mark.gpu
+def test_facade_incremental_download_gpu(gpu_api):
+    _check_incremental_download(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api))
+
+
 def test_facade_api_tour_hostsim(hostsim_facade):
     _check_api_tour(hostsim_facade)
 
