@@ -34,16 +34,7 @@ struct ConstraintSrc
 	uint64_t sort_key;       // FNV-1a of SubShapeIDPair (mSortKey)
 	uint32_t manifold;       // index in write_cache.manifolds
 	uint32_t b1, b2;         // body slots, id(b1) < id(b2)
-	uint32_t cls;            // solve class: (num points - 1) | motion type pair << 2 (CLS_*): constraints of a phase are laid out class by
-	                         // class, so the lanes of a warp run the same specialised solve path
 };
-enum { CLS_DYN_DYN = 0, CLS_DYN_STATIC = 1, CLS_STATIC_DYN = 2, CLS_OTHER = 3 };
-B2J_HD uint32_t solve_class(uint32_t type1, uint32_t type2, int num_points)
-{
-	uint32_t t = type1 == B2J_MOTION_DYNAMIC && type2 == B2J_MOTION_DYNAMIC? CLS_DYN_DYN
-		: (type1 == B2J_MOTION_DYNAMIC && type2 == B2J_MOTION_STATIC? CLS_DYN_STATIC : (type1 == B2J_MOTION_STATIC && type2 == B2J_MOTION_DYNAMIC? CLS_STATIC_DYN : CLS_OTHER));
-	return (uint32_t)((num_points - 1) & 3) | (t << 2);
-}
 
 struct NarrowCtx
 {
@@ -231,7 +222,6 @@ B2J_D bool register_constraint(const DWorld &w, const NarrowCtx &c, uint32_t m, 
 	if (dyn2 && w.active_index[cb2] == B2J_INACTIVE_INDEX) wake_body(w, c, cb2);
 	ConstraintSrc s;
 	s.sort_key = key_hash; s.manifold = m; s.b1 = cb1; s.b2 = cb2;
-	s.cls = solve_class(i1.motion_type, i2.motion_type, num_points);
 	c.con_src[ci] = s;
 	atomic_add(&w.counters->num_contact_points, (uint32_t)num_points);
 	return true;

@@ -80,6 +80,7 @@ struct SolveCtx
 	uint32_t *adj;
 	uint32_t num_slots;
 	uint32_t *sched_flag;        // [2] remaining flags
+	uint32_t *grid_barrier;      // arrival counter of solve_velocity_tma_kernel's grid barrier (zeroed before the launch)
 };
 
 B2J_HD F4 &cp_at(const Constraints &c, int plane, uint32_t i) { return c.cp[(size_t)plane * c.capacity + i]; }
@@ -548,33 +549,29 @@ struct KSchedResetCursors
 
 // Phases -> solve order. The constraints are radix sorted by phase (stable: sort key order inside a phase, deterministic layout,
 // no histogram atomics); KPhaseClamp bounds the key and finds the phase count, KPhasePlace scatters and writes the phase offsets.
-// (the placement key = phase | solve class: inside a phase the constraints are free to take any order -- they touch disjoint dynamic
-// bodies -- so they are laid out class by class (motion type pair, number of contact points), sort key order inside a class)
-enum { PLACE_CLASS_BITS = 4 };
 struct KPhaseClamp
 {
-	DWorld w; SolveCtx s; uint32_t *keys;
+	DWorld w; SolveCtx s;
 	B2J_D void operator()(uint32_t i) const
 	{
 		uint32_t p = s.phase[i];
 		if (p >= s.max_phases) { p = s.max_phases - 1; s.phase[i] = p; atomic_or(&w.counters->error_bits, 0x100u); }
 		if (p + 1 > *(volatile const uint32_t *)&w.counters->num_phases) // almost always false: keeps the atomic off the hot path
 			atomic_max(&w.counters->num_phases, p + 1);
-		keys[i] = (p << PLACE_CLASS_BITS) | (s.src[s.order[i]].cls & ((1u << PLACE_CLASS_BITS) - 1u));
 	}
 };
 
 struct KPhasePlace
 {
-	SolveCtx s; const uint32_t *sorted_key, *sorted_idx; uint32_t n;
+	SolveCtx s; const uint32_t *sorted_phase, *sorted_idx; uint32_t n;
 	B2J_D void operator()(uint32_t pos) const
 	{
 		uint32_t i = sorted_idx[pos];
 		s.final_pos[i] = pos;
 		s.solve_src[pos] = s.order[i];
 		// phase_count[q] = first position of phase q (empty phases included), phase_count[last + 1 ...] = n
-		uint32_t p = sorted_key[pos] >> PLACE_CLASS_BITS;
-		uint32_t first = pos == 0? 0 : (sorted_key[pos - 1] >> PLACE_CLASS_BITS) + 1;
+		uint32_t p = sorted_phase[pos];
+		uint32_t first = pos == 0? 0 : sorted_phase[pos - 1] + 1;
 		for (uint32_t q = first; q <= p; ++q)
 			s.phase_count[q] = pos;
 		if (pos == n - 1)
@@ -1345,22 +1342,23 @@ template <bool kPosition> __global__ void __launch_bounds__(256) solve_small_ker
 #if !defined(B2J_HOSTSIM) && defined(__CUDACC__)
 // ---- the whole velocity solve in ONE persistent launch, constraint planes streamed through shared memory by TMA -------------------
 //
-// One cooperative launch runs the warm start and every velocity iteration of every phase (grid wide barriers between phases; phase
+// One cooperative launch runs the warm start and every velocity iteration of every phase (a grid wide barrier between phases; phase
 // offsets, phase and iteration counts are read on the device: no per phase launch, no host round trip). Inside a phase every WARP
-// owns the tiles gw, gw + NW, ... of 32 consecutive constraints and runs its own two stage pipeline:
-//   * the read-only planes of tile k + 1 are copied global -> shared memory by 1-D TMA bulk copies (cp.async.bulk, UBLKCP in SASS,
-//     one 512 byte copy per plane the tile needs, issued by up to 29 lanes in parallel) that complete on the stage's mbarrier,
-//   * the headers are register prefetched two tiles ahead, the body velocities and the two lambda planes (read + written, kept on the
-//     generic proxy) one tile ahead,
-//   * tile k is solved out of shared memory (conflict free LDS.128) with the arithmetic of the per phase kernels (solve_velocity_core).
-// 7 warps x 2 stages x 29 planes x 512 B = 203 KB of shared memory per SM keep ~100 KB of loads in flight per SM, independent of the
-// register budget of the solve code (the per phase kernel: 168 registers -> 12 warps, every warp stalls for two DRAM round trips per
-// constraint: 0.27 of the HBM peak over a batch step, 0.57 on launches of several million constraints).
-// Two shapes are instantiated (B2J_SOLVE_TMA_SHAPE picks one): 7 warps x 2 stages (loads of tile k + 1 overlap the arithmetic of tile k
-// inside the warp) and 14 warps x 1 stage (twice the warps to cover the ~5 us dependent instruction chain of a tile, the copy of the
-// next tile is issued when the warp is done with the stage; registers capped at 146).
+// owns the tiles gw, gw + NW, ... of 32 consecutive constraints:
+//   * the read-only planes of a tile are copied global -> shared memory by 1-D TMA bulk copies (cp.async.bulk, UBLKCP in SASS: one
+//     512 byte copy per plane the tile needs) that complete on the warp's mbarrier; the copy of the next tile is issued as soon as the
+//     warp is done with the stage, and while it is in flight the other warps of the SM compute (12 warps x 14.5 KB = 174 KB of shared
+//     memory per SM in flight, independent of the register budget of the solve code),
+//   * headers are register prefetched a tile ahead, the body velocities (L2 loads: other SMs wrote them in the previous phase) and
+//     the two lambda planes (read + written, generic proxy) are loaded with the copy,
+//   * the tile is solved out of shared memory (conflict free LDS.128) with the arithmetic of the per phase kernels.
+// The grid barrier is split: a block ARRIVES (one atomic), then prepares its first tile of the next phase (header loads, plane copies:
+// read-only data, safe before the barrier completes), then WAITS; only the velocities / lambdas are fetched after it.
+// Measured (4096 Pyramid worlds in one group, steps 5..25): 28.7 ms per step = 0.55 of the HBM peak against 0.26 for the per phase
+// launches -- the kernel is bound by the dependent instruction chain of a tile (~900 FP32 instructions without FMA), not by memory;
+// twice the warps at 128 registers spill and lose.
 enum { SV_STAGE_F4 = SV_NUM_SLOTS * 32 };
-constexpr size_t sv_smem_bytes(int warps, int stages) { return (size_t)warps * stages * SV_STAGE_F4 * sizeof(F4) + (size_t)warps * stages * sizeof(uint64_t); }
+constexpr size_t sv_smem_bytes(int warps) { return (size_t)warps * SV_STAGE_F4 * sizeof(F4) + (size_t)warps * sizeof(uint64_t); }
 
 B2J_D uint32_t sv_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 B2J_D void sv_mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sv_smem_addr(bar)), "r"(count) : "memory"); }
@@ -1382,6 +1380,8 @@ B2J_D void sv_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uin
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 		:: "r"(sv_smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(sv_smem_addr(bar)) : "memory");
 }
+// L2 load of a body quantity another SM may have written before the last grid barrier (the barrier does not invalidate L1)
+B2J_D F4 sv_load_l2(const F4 *p) { float4 v = __ldcg(reinterpret_cast<const float4 *>(p)); return f4(v.x, v.y, v.z, v.w); }
 
 // slots of the shared memory stage a constraint reads (bit = slot); kWarm: the warm start pass does not read the r2 x axis planes
 template <bool kWarm> B2J_D uint32_t sv_slot_mask(uint32_t meta)
@@ -1402,130 +1402,150 @@ template <bool kWarm> B2J_D uint32_t sv_slot_mask(uint32_t meta)
 	return mask;
 }
 
-// what a lane prefetches into registers one tile ahead: the velocities of its two bodies and its two lambda planes
+// what a lane fetches into registers with the copy of its tile: the velocities of its two bodies and its two lambda planes
 struct SvPre { F4 v1, w1, v2, w2, lpt, lfr; };
 
 struct KSolveVelocityAll { }; // (profiling category)
-template <int SV_WARPS, int SV_STAGES> __global__ void __launch_bounds__(SV_WARPS * 32, 1) solve_velocity_tma_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
+template <int SV_WARPS> __global__ void __launch_bounds__(SV_WARPS * 32, 1) solve_velocity_tma_kernel(const DWorld w, const SolveCtx s, float warm_start_ratio)
 {
 	extern __shared__ __align__(128) unsigned char sv_smem[];
-	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	F4 *stages = reinterpret_cast<F4 *>(sv_smem) + (size_t)warp * SV_STAGES * SV_STAGE_F4;
-	uint64_t *bars = reinterpret_cast<uint64_t *>(sv_smem + (size_t)SV_WARPS * SV_STAGES * SV_STAGE_F4 * sizeof(F4)) + warp * SV_STAGES;
+	F4 *stage = reinterpret_cast<F4 *>(sv_smem) + (size_t)warp * SV_STAGE_F4;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(sv_smem + (size_t)SV_WARPS * SV_STAGE_F4 * sizeof(F4)) + warp;
 	if (lane == 0)
 	{
-		for (int st = 0; st < SV_STAGES; ++st) sv_mbar_init(&bars[st], 1);
+		sv_mbar_init(bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncwarp();
-	uint32_t parity_bits = 0; // bit = stage: phase parity of the stage's mbarrier
+	uint32_t parity = 0;
 
 	const Constraints c = s.con;
 	const uint32_t gw = blockIdx.x * SV_WARPS + warp, nw = gridDim.x * SV_WARPS;
 	const uint32_t np = w.counters->num_phases;
 	const uint32_t steps = w.counters->max_velocity_steps;
 	const uint32_t *off = s.phase_count;
+	volatile uint32_t *grid_bar = s.grid_barrier;   // zeroed before the launch, counts block arrivals
+	uint32_t barrier_target = 0;
 
-	for (uint32_t pass = 0; pass <= steps; ++pass) // pass 0 = warm start, pass it + 1 = velocity iteration it
-	{
-		const bool warm = pass == 0;
-		const uint32_t iteration = pass - 1;
-		for (uint32_t p = 0; p < np; ++p)
+	// the (pass, phase) steps of the solve in order, empty phases skipped: pass 0 = warm start, pass it + 1 = velocity iteration it
+	uint32_t pass = 0, p = 0;
+	auto skip_empty = [&]() { while (pass <= steps) { while (p < np && off[p] == off[p + 1]) ++p; if (p < np) return; p = 0; ++pass; } };
+	skip_empty();
+
+	uint32_t begin = 0, end = 0, ntiles = 0;
+	bool warm = true; uint32_t iteration = 0;
+	auto enter_phase = [&]() { begin = off[p]; end = off[p + 1]; ntiles = (end - begin + 31) >> 5; warm = pass == 0; iteration = pass - 1; };
+	// header of the lane's constraint in tile t of the current phase (valid = false past the end of the phase / nothing to do this pass)
+	auto load_hdr = [&](uint32_t t, bool &valid) -> ConstraintHeader {
+		uint32_t i = begin + (t << 5) + lane;
+		valid = t < ntiles && i < end;
+		ConstraintHeader h; h.b1 = 0; h.b2 = 0; h.manifold = 0; h.meta = 0;
+		if (valid) { uint4 v = __ldg(reinterpret_cast<const uint4 *>(&c.hdr[i])); h.b1 = v.x; h.b2 = v.y; h.manifold = v.z; h.meta = v.w; }
+		// constraints of islands with fewer velocity steps are done: they neither load nor solve in this pass
+		if (!warm && iteration >= ((h.meta >> 8) & 0xff)) valid = false;
+		return h;
+	};
+	// TMA bulk copies of the planes tile t needs
+	auto issue_planes = [&](uint32_t t, const ConstraintHeader &h, bool valid, uint32_t &tile_mask) {
+		uint32_t first = begin + (t << 5);
+		uint32_t count = end - first < 32u? end - first : 32u;
+		uint32_t lane_mask = valid? (warm? sv_slot_mask<true>(h.meta) : sv_slot_mask<false>(h.meta)) : 0u;
+		tile_mask = __reduce_or_sync(0xffffffffu, lane_mask);
+		if (tile_mask != 0)
 		{
-			const uint32_t begin = off[p], end = off[p + 1];
-			if (begin == end)
-				continue; // (uniform over the grid)
-			const uint32_t ntiles = (end - begin + 31) >> 5;
+			if (lane == 0) sv_mbar_expect_tx(bar, (uint32_t)__popc(tile_mask) * count * (uint32_t)sizeof(F4));
+			__syncwarp();
+			if (lane < SV_NUM_SLOTS && ((tile_mask >> lane) & 1u))
+				sv_bulk_g2s(stage + lane * 32, &c.cp[(size_t)sv_plane_of_slot((int)lane) * c.capacity + first], count * (uint32_t)sizeof(F4), bar);
+		}
+	};
+	// the lane's velocities and lambdas (only valid once the previous phase is complete on the whole grid)
+	auto load_pre = [&](uint32_t t, const ConstraintHeader &h, bool valid, SvPre &pre) {
+		if (valid)
+		{
+			uint32_t type1 = (h.meta >> 3) & 3, type2 = (h.meta >> 5) & 3;
+			uint32_t i = begin + (t << 5) + lane;
+			if (type1 != B2J_MOTION_STATIC) { pre.v1 = sv_load_l2(&w.linear_velocity[h.b1]); pre.w1 = sv_load_l2(&w.angular_velocity[h.b1]); }
+			if (type2 != B2J_MOTION_STATIC) { pre.v2 = sv_load_l2(&w.linear_velocity[h.b2]); pre.w2 = sv_load_l2(&w.angular_velocity[h.b2]); }
+			pre.lpt = cp_at(c, CP_LAMBDA_PT, i);
+			pre.lfr = cp_at(c, CP_LAMBDA_FR, i);
+		}
+	};
 
-			// header of the lane's constraint in tile t (meta = 0 and valid = false past the end of the phase)
-			auto load_hdr = [&](uint32_t t, bool &valid) -> ConstraintHeader {
-				uint32_t i = begin + (t << 5) + lane;
-				valid = t < ntiles && i < end;
-				ConstraintHeader h; h.b1 = 0; h.b2 = 0; h.manifold = 0; h.meta = 0;
-				if (valid) { uint4 v = __ldg(reinterpret_cast<const uint4 *>(&c.hdr[i])); h.b1 = v.x; h.b2 = v.y; h.manifold = v.z; h.meta = v.w; }
-				// constraints of islands with fewer velocity steps are done: they neither load nor solve in this pass
-				if (!warm && iteration >= ((h.meta >> 8) & 0xff)) valid = false;
-				return h;
-			};
-			// TMA bulk copies of the planes tile t needs into `stage` + register prefetch of the lane's velocities and lambdas
-			auto issue = [&](uint32_t t, const ConstraintHeader &h, bool valid, int stage, SvPre &pre, uint32_t &tile_mask) {
-				uint32_t first = begin + (t << 5);
-				uint32_t count = end - first < 32u? end - first : 32u;
-				uint32_t lane_mask = valid? (warm? sv_slot_mask<true>(h.meta) : sv_slot_mask<false>(h.meta)) : 0u;
-				tile_mask = __reduce_or_sync(0xffffffffu, lane_mask);
-				if (tile_mask != 0)
-				{
-					if (lane == 0) sv_mbar_expect_tx(&bars[stage], (uint32_t)__popc(tile_mask) * count * (uint32_t)sizeof(F4));
-					__syncwarp();
-					if (lane < SV_NUM_SLOTS && ((tile_mask >> lane) & 1u))
-						sv_bulk_g2s(stages + (size_t)stage * SV_STAGE_F4 + lane * 32, &c.cp[(size_t)sv_plane_of_slot((int)lane) * c.capacity + first], count * (uint32_t)sizeof(F4), &bars[stage]);
-				}
-				if (valid)
-				{
-					uint32_t type1 = (h.meta >> 3) & 3, type2 = (h.meta >> 5) & 3;
-					uint32_t i = first + lane;
-					if (type1 != B2J_MOTION_STATIC) { pre.v1 = w.linear_velocity[h.b1]; pre.w1 = w.angular_velocity[h.b1]; }
-					if (type2 != B2J_MOTION_STATIC) { pre.v2 = w.linear_velocity[h.b2]; pre.w2 = w.angular_velocity[h.b2]; }
-					pre.lpt = cp_at(c, CP_LAMBDA_PT, i);
-					pre.lfr = cp_at(c, CP_LAMBDA_FR, i);
-				}
-			};
-
-			uint32_t t = gw;
-			bool valid0 = false, valid1 = false, valid2 = false;
-			ConstraintHeader h0 = load_hdr(t, valid0), h1 = load_hdr(t + nw, valid1), h2;
-			SvPre pre0, pre1;
-			uint32_t mask0 = 0, mask1 = 0;
-			int stage = 0;
-			if (t < ntiles) issue(t, h0, valid0, stage, pre0, mask0);
-			while (t < ntiles)
+	ConstraintHeader h0, h1;
+	bool valid0 = false, valid1 = false;
+	uint32_t mask0 = 0, mask1 = 0;
+	SvPre pre0, pre1;
+	if (pass <= steps)
+	{
+		enter_phase();
+		h0 = load_hdr(gw, valid0);
+		if (gw < ntiles) issue_planes(gw, h0, valid0, mask0);
+	}
+	while (pass <= steps)
+	{
+		// ---- the tiles of this warp in the current phase (h0 / mask0 were prepared before the barrier)
+		uint32_t t = gw;
+		if (t < ntiles) load_pre(t, h0, valid0, pre0);
+		while (t < ntiles)
+		{
+			uint32_t tn = t + nw;
+			h1 = load_hdr(tn, valid1);
+			if (mask0 != 0)
 			{
-				uint32_t tn = t + nw;
-				if (SV_STAGES == 2 && tn < ntiles) issue(tn, h1, valid1, stage ^ 1, pre1, mask1);
-				h2 = load_hdr(tn + nw, valid2);
-				if (mask0 != 0)
-				{
-					sv_mbar_wait(&bars[stage], (parity_bits >> stage) & 1u);
-					parity_bits ^= 1u << stage;
-				}
-				if (valid0)
-				{
-					uint32_t meta = h0.meta;
-					uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-					uint32_t i = begin + (t << 5) + lane;
-					VelState vs;
-					if (type1 != B2J_MOTION_STATIC) { vs.v1 = to_v3(pre0.v1); vs.w1 = to_v3(pre0.w1); } else { vs.v1 = v3_zero(); vs.w1 = v3_zero(); }
-					if (type2 != B2J_MOTION_STATIC) { vs.v2 = to_v3(pre0.v2); vs.w2 = to_v3(pre0.w2); } else { vs.v2 = v3_zero(); vs.w2 = v3_zero(); }
-					F4 lpt = pre0.lpt, lfr = pre0.lfr;
-					SmemPlanes src; src.stage = stages + (size_t)stage * SV_STAGE_F4; src.lane = lane;
-					bool any;
-					if (warm)
-					{
-						any = warm_start_core(src, meta, warm_start_ratio, vs, lpt, lfr);
-						cp_at(c, CP_LAMBDA_PT, i) = lpt;
-						cp_at(c, CP_LAMBDA_FR, i) = lfr;
-					}
-					else
-					{
-						any = solve_velocity_core(src, meta, vs, lpt, lfr);
-						cp_at(c, CP_LAMBDA_PT, i) = lpt;
-						if (meta & (META_LINEAR_FRICTION | META_ANGULAR_FRICTION))
-							cp_at(c, CP_LAMBDA_FR, i) = lfr;
-					}
-					if (any)
-						store_vel_state(w, h0.b1, h0.b2, meta, vs);
-					if (!warm && iteration + 1 == ((meta >> 8) & 0xff))
-						store_applied_impulses(w, h0.manifold, (int)(meta & 7), lpt, lfr);
-				}
-				__syncwarp(); // every lane is done reading the stage: the tile after next (two stages) / the next tile (one stage) may overwrite it
-				if (SV_STAGES == 1 && tn < ntiles) issue(tn, h1, valid1, stage, pre1, mask1);
-				h0 = h1; valid0 = valid1; pre0 = pre1; mask0 = mask1;
-				h1 = h2; valid1 = valid2;
-				if (SV_STAGES == 2) stage ^= 1;
-				t = tn;
+				sv_mbar_wait(bar, parity);
+				parity ^= 1;
 			}
-			grid.sync();
+			if (valid0)
+			{
+				uint32_t meta = h0.meta;
+				uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+				uint32_t i = begin + (t << 5) + lane;
+				VelState vs;
+				if (type1 != B2J_MOTION_STATIC) { vs.v1 = to_v3(pre0.v1); vs.w1 = to_v3(pre0.w1); } else { vs.v1 = v3_zero(); vs.w1 = v3_zero(); }
+				if (type2 != B2J_MOTION_STATIC) { vs.v2 = to_v3(pre0.v2); vs.w2 = to_v3(pre0.w2); } else { vs.v2 = v3_zero(); vs.w2 = v3_zero(); }
+				F4 lpt = pre0.lpt, lfr = pre0.lfr;
+				SmemPlanes src; src.stage = stage; src.lane = lane;
+				bool any;
+				if (warm)
+				{
+					any = warm_start_core(src, meta, warm_start_ratio, vs, lpt, lfr);
+					cp_at(c, CP_LAMBDA_PT, i) = lpt;
+					cp_at(c, CP_LAMBDA_FR, i) = lfr;
+				}
+				else
+				{
+					any = solve_velocity_core(src, meta, vs, lpt, lfr);
+					cp_at(c, CP_LAMBDA_PT, i) = lpt;
+					if (meta & (META_LINEAR_FRICTION | META_ANGULAR_FRICTION))
+						cp_at(c, CP_LAMBDA_FR, i) = lfr;
+				}
+				if (any)
+					store_vel_state(w, h0.b1, h0.b2, meta, vs);
+				if (!warm && iteration + 1 == ((meta >> 8) & 0xff))
+					store_applied_impulses(w, h0.manifold, (int)(meta & 7), lpt, lfr);
+			}
+			__syncwarp(); // every lane is done reading the stage: the copy of the next tile may overwrite it
+			mask1 = 0;
+			if (tn < ntiles) { issue_planes(tn, h1, valid1, mask1); load_pre(tn, h1, valid1, pre1); }
+			h0 = h1; valid0 = valid1; pre0 = pre1; mask0 = mask1;
+			t = tn;
+		}
+		// ---- split grid barrier: arrive, prepare the first tile of the next phase while the other blocks finish, wait
+		++p;
+		skip_empty();
+		__syncthreads();
+		barrier_target += gridDim.x;
+		if (threadIdx.x == 0) { __threadfence(); atomicAdd((uint32_t *)grid_bar, 1u); }
+		mask0 = 0; valid0 = false;
+		if (pass <= steps)
+		{
+			enter_phase();
+			h0 = load_hdr(gw, valid0);
+			if (gw < ntiles) issue_planes(gw, h0, valid0, mask0);
+			if (threadIdx.x == 0) { while (*grid_bar < barrier_target) { } __threadfence(); }
+			__syncthreads();
 		}
 	}
 }

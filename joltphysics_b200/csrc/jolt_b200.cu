@@ -14,6 +14,9 @@
 #include "b2j_solver.h"
 #include "b2j_query.h"
 
+#ifndef B2J_HOSTSIM
+#include <nvtx3/nvToolsExt.h>   // header only: ranges are no-ops unless a tool (nsys / ncu --nvtx) is attached
+#endif
 #include <chrono>
 #include <thread>
 #include <map>
@@ -668,23 +671,50 @@ bool read_counters(b2j_world *W)
 	return W->rt.check("read_counters");
 }
 
-// B2J_TRACE_STEP=1: wall clock per stage of a step with the stream drained after every stage (diagnostics for small worlds, where the
-// step is a chain of ~60 dependent launches: which stage pays how much launch / round trip latency). Prints to stderr.
+// Stages of a step as NVTX ranges (the reference marks the same stages with JPH_PROFILE scopes, PhysicsSystem.cpp), and with
+// B2J_TRACE_STEP=1 their wall clock with the stream drained after every stage (diagnostics for small worlds, where the step is a chain
+// of ~60 dependent launches: which stage pays how much launch / round trip latency). The trace prints to stderr.
 struct StepTrace
 {
 	bool on; Runtime &rt; std::chrono::high_resolution_clock::time_point t0; std::string line;
-	explicit StepTrace(Runtime &r) : on(getenv("B2J_TRACE_STEP") != nullptr), rt(r) { if (on) { rt.sync(); t0 = std::chrono::high_resolution_clock::now(); } }
-	void mark(const char *stage)
+	static void push(const char *name)
 	{
+#ifndef B2J_HOSTSIM
+		nvtxRangePushA(name);
+#else
+		(void)name;
+#endif
+	}
+	static void pop()
+	{
+#ifndef B2J_HOSTSIM
+		nvtxRangePop();
+#endif
+	}
+	StepTrace(Runtime &r, const char *first_stage) : on(getenv("B2J_TRACE_STEP") != nullptr), rt(r)
+	{
+		push("b2j collision step");
+		push(first_stage);
+		if (on) { rt.sync(); t0 = std::chrono::high_resolution_clock::now(); }
+	}
+	// the stage `finished` is over, `next` begins
+	void mark(const char *finished, const char *next)
+	{
+		pop();
+		push(next);
 		if (!on) return;
 		rt.sync();
 		auto t1 = std::chrono::high_resolution_clock::now();
 		char buf[64];
-		snprintf(buf, sizeof(buf), " %s %.0f", stage, std::chrono::duration<double, std::micro>(t1 - t0).count());
+		snprintf(buf, sizeof(buf), " %s %.0f", finished, std::chrono::duration<double, std::micro>(t1 - t0).count());
 		line += buf;
 		t0 = t1;
 	}
-	~StepTrace() { if (on) fprintf(stderr, "[b2j step us]%s launches %u\n", line.c_str(), rt.launches); }
+	~StepTrace()
+	{
+		pop(); pop();
+		if (on) fprintf(stderr, "[b2j step us]%s launches %u\n", line.c_str(), rt.launches);
+	}
 };
 
 // One collision step. Returns false on a CUDA failure.
@@ -702,7 +732,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		rt.upload(&d.counters->num_activation_events, &W->last_num_act_events, 1);
 	}
 
-	StepTrace trace(rt);
+	StepTrace trace(rt, "gravity + broadphase trees");
 	// (a2) gravity, forces, damping
 	{ KApplyGravity k; k.w = d; k.dt = dt; rt.launch(k, W->num_active); }
 
@@ -714,7 +744,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			W->layer_needs_build[l] = 0;
 		}
 
-	trace.mark("gravity+trees");
+	trace.mark("gravity+trees", "find pairs + narrowphase");
 	// (a3, a5..a9) find pairs + narrow phase; repeated for the bodies woken up by contacts until no new body wakes up
 	uint32_t first_active = 0, n_query = W->num_active;
 	uint32_t woken_total = 0, longest_queue = 0;
@@ -797,7 +827,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	W->last_collide_convex = longest_queue < d.max_body_pairs? longest_queue : d.max_body_pairs;
 	uint32_t na = W->num_active;
 
-	trace.mark("pairs+narrowphase");
+	trace.mark("pairs+narrowphase", "islands + sort + adjacency");
 	// (a12) islands
 	SolveCtx &sc = W->sc;
 	sc.num_slots = W->num_slots;
@@ -822,7 +852,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KAdjFill k; k.w = d; k.s = sc; rt.launch(k, M); }
 		{ KAdjSort k; k.w = d; k.s = sc; rt.launch(k, na); }
 
-		trace.mark("islands+sort+adjacency");
+		trace.mark("islands+sort+adjacency", "solve schedule");
 		// (a13) schedule: wavefronts in sorted order; pass 0 = levels (small islands) / colours (large islands)
 		const uint32_t rounds_per_check = 8;
 #ifndef B2J_HOSTSIM
@@ -897,6 +927,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			}
 		}
 
+		trace.mark("schedule", "placement + constraint setup");
 		// B2J_SOLVE_MODE: how the velocity / position solve is launched.
 		//   0 = one launch per phase per iteration (default: the groups of a batch overlap on their streams)
 		//   1 = one persistent cooperative launch, phases separated by grid barriers, loads straight from HBM
@@ -909,19 +940,16 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{
 			// the 64 bit key buffers of the constraint sort are free again: reuse them for the (phase, index) sort; d_sort_vals still holds 0..M-1
 			uint32_t *sorted_phase = reinterpret_cast<uint32_t *>(W->d_sort_keys[0]), *sorted_idx = reinterpret_cast<uint32_t *>(W->d_sort_keys[1]);
-			// (placement key = phase | solve class; the unsorted keys live in the second half of the first key buffer)
-			uint32_t *keys_in = sorted_phase + d.max_constraints;
-			{ KPhaseClamp k; k.w = d; k.s = sc; k.keys = keys_in; rt.launch(k, M); }
-			rt.sort_pairs<uint32_t>(keys_in, sorted_phase, W->d_sort_vals, sorted_idx, M, 13 + PLACE_CLASS_BITS);
-			{ KPhasePlace k; k.s = sc; k.sorted_key = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
+			{ KPhaseClamp k; k.w = d; k.s = sc; rt.launch(k, M); }
+			rt.sort_pairs<uint32_t>(sc.phase, sorted_phase, W->d_sort_vals, sorted_idx, M, 13);
+			{ KPhasePlace k; k.s = sc; k.sorted_phase = sorted_phase; k.sorted_idx = sorted_idx; k.n = M; rt.launch(k, M); }
 		}
 
 		// (a11) constraint setup straight into solve order
 		{ KSetupConstraints k; k.w = d; k.s = sc; k.dt = dt; rt.launch(k, M); }
 
+		trace.mark("place+setup", "velocity solve");
 #ifndef B2J_HOSTSIM
-		// B2J_SOLVE_MODE: 2 (default) = one persistent launch per solve, constraint planes streamed through shared memory by TMA
-		// (solve_velocity_tma_kernel); 1 = one persistent launch, loads straight from HBM; 0 = one launch per phase per iteration
 		// small single world: the whole velocity solve in one small cooperative launch (solve_small_kernel)
 		block_solve = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
 		if (block_solve)
@@ -941,15 +969,12 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			cudaError_t e = cudaErrorUnknown;
 			if (solve_mode == 2)
 			{
-				// shape of the TMA pipeline (warps x stages): 0 = 7 x 2, 1 = 14 x 1, 2 = 12 x 1, 3 = 10 x 1
-				const char *shape_env = getenv("B2J_SOLVE_TMA_SHAPE");
-				const int shape = shape_env != nullptr? atoi(shape_env) : 1;
-				const void *fns[4] = { (const void *)solve_velocity_tma_kernel<7, 2>, (const void *)solve_velocity_tma_kernel<14, 1>, (const void *)solve_velocity_tma_kernel<12, 1>, (const void *)solve_velocity_tma_kernel<10, 1> };
-				const int warps[4] = { 7, 14, 12, 10 }, stages[4] = { 2, 1, 1, 1 };
-				const int sh = shape < 0 || shape > 3? 1 : shape;
-				const void *fn = fns[sh];
-				const int threads = warps[sh] * 32;
-				const size_t smem = sv_smem_bytes(warps[sh], stages[sh]);
+				// warps per block of the TMA pipeline (B2J_SOLVE_TMA_WARPS: 12 (default), 10 or 8)
+				const char *warps_env = getenv("B2J_SOLVE_TMA_WARPS");
+				const int wsel = warps_env != nullptr? atoi(warps_env) : 12;
+				const void *fn = wsel == 8? (const void *)solve_velocity_tma_kernel<8> : (wsel == 10? (const void *)solve_velocity_tma_kernel<10> : (const void *)solve_velocity_tma_kernel<12>);
+				const int threads = (wsel == 8? 8 : (wsel == 10? 10 : 12)) * 32;
+				const size_t smem = sv_smem_bytes(threads / 32);
 				int &blocks_per_sm = rt.func_blocks_per_sm[fn];
 				if (blocks_per_sm == 0)
 				{
@@ -959,6 +984,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 				if (blocks_per_sm > 0)
 				{
 					++rt.launches;
+					rt.memset_(sc.grid_barrier, 0, 4);
 					if (rt.profiling) rt.prof_begin(profile_category<KSolveVelocityAll>());
 					e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)(rt.num_sms * blocks_per_sm / W->solve_grid_div)), dim3(threads), args, smem, rt.stream);
 					if (rt.profiling) rt.prof_end();
@@ -1011,7 +1037,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		if (d.settings.num_velocity_steps == 0) { KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
 	}
 
-	trace.mark("velocity");
+	trace.mark("velocity", "integrate + position solve");
 	// (a15) integrate
 	{ KIntegrate k; k.w = d; k.dt = dt; rt.launch(k, na); }
 
@@ -1068,7 +1094,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			}
 	}
 
-	trace.mark("integrate+position");
+	trace.mark("integrate+position", "bounds + sleep + compaction");
 	// (a16, a17) bounds, sleeping, active list compaction
 	{ KBoundsAndSleep k; k.w = d; k.s = sc; k.dt = dt; k.is_last = is_last? 1u : 0u; rt.launch(k, na); }
 	uint32_t new_active = na;
@@ -1100,7 +1126,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		psteps = W->h_counters.max_position_steps;
 	}
 
-	trace.mark("sleep+compact+readback");
+	trace.mark("sleep+compact+readback", "cache swap");
 	// swap the caches: this step's write cache is the next step's read cache
 	uint32_t wi = W->write_idx;
 	// (the sizes of the cache written by this step came back with the counters: one readback at the end of the step, not three)
@@ -1332,6 +1358,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	sc.body_cur = rt.alloc<uint32_t>(nbod); sc.body_mask = rt.alloc<uint32_t>(nbod);
 	sc.adj = rt.alloc<uint32_t>((size_t)2 * mc);
 	sc.sched_flag = rt.alloc<uint32_t>(4096);
+	sc.grid_barrier = rt.alloc<uint32_t>(1);
 	W->d_sort_keys[0] = rt.alloc<uint64_t>(mc); W->d_sort_keys[1] = rt.alloc<uint64_t>(mc);
 	W->d_sort_vals = rt.alloc<uint32_t>(mc);
 
@@ -1394,7 +1421,7 @@ void b2j_world_destroy(b2j_world *W)
 	rt.free_(sc.order); rt.free_(sc.final_pos); rt.free_(sc.solve_src); rt.free_(sc.phase); rt.free_(sc.phase_count);
 	rt.free_(sc.uf_parent); rt.free_(sc.root); rt.free_(sc.island_items); rt.free_(sc.island_large); rt.free_(sc.island_steps); rt.free_(sc.island_can_sleep);
 	rt.free_(sc.large_color_count); rt.free_(sc.body_deg); rt.free_(sc.body_off); rt.free_(sc.body_fill); rt.free_(sc.body_cur); rt.free_(sc.body_mask);
-	rt.free_(sc.adj); rt.free_(sc.sched_flag);
+	rt.free_(sc.adj); rt.free_(sc.sched_flag); rt.free_(sc.grid_barrier);
 	rt.free_(W->d_sort_keys[0]); rt.free_(W->d_sort_keys[1]); rt.free_(W->d_sort_vals);
 	for (int l = 0; l < 8; ++l)
 	{
