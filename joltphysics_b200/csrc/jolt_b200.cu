@@ -839,7 +839,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	{ KIslandClassify k; k.w = d; k.s = sc; rt.launch(k, na); }
 
 	uint32_t num_phases = 0, vsteps = 0, psteps = 0;
-	bool block_solve = false, solved_by_phase_launches = false;
+	bool block_solve = false, solved_by_phase_launches = false, diag_skipped = false;
 	if (M > 0)
 	{
 		// (a14 SortContacts) order by sort key
@@ -1004,7 +1004,10 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			}
 			if (e != cudaSuccess) { cudaGetLastError(); solve_mode = 0; } // fall back to the per phase launches
 		}
-		const bool phase_launches = !block_solve && solve_mode == 0;
+		bool phase_launches = !block_solve && solve_mode == 0;
+		// (diagnostics only, results are WRONG: B2J_DIAG_SKIP_SOLVE=1 skips the velocity / position solve to time the rest of the step)
+		const bool diag_skip_solve = getenv("B2J_DIAG_SKIP_SOLVE") != nullptr;
+		if (diag_skip_solve) phase_launches = false;
 #else
 		const bool phase_launches = true;
 #endif
@@ -1032,6 +1035,9 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 				}
 		}
 		solved_by_phase_launches = phase_launches;
+#ifndef B2J_HOSTSIM
+		if (diag_skip_solve) diag_skipped = true;
+#endif
 		// the applied impulses are stored by the last velocity iteration of every constraint; islands without iterations only exist when
 		// the default number of velocity steps is 0
 		if (d.settings.num_velocity_steps == 0) { KStoreImpulses k; k.w = d; k.c = sc.con; rt.launch(k, M); }
@@ -1060,7 +1066,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		if (rt.profiling) rt.prof_end();
 		if (e != cudaSuccess) { cudaGetLastError(); last_error() = "cooperative position solve launch failed"; return false; }
 	}
-	else if (M > 0 && !solved_by_phase_launches)
+	else if (M > 0 && !solved_by_phase_launches && !diag_skipped)
 	{
 		void *args[] = { (void *)&d, (void *)&sc };
 		int &blocks_per_sm = rt.func_blocks_per_sm[(const void *)solve_position_all_kernel];

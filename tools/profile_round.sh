@@ -1,22 +1,28 @@
 #!/bin/bash
-# Round profile capture (run under gpurun, ONE GPU): launch list of the bench command's timed steps + one full capture of every hot
-# kernel, summarised to text ON THE BOX (gpurun only copies 64 MiB back). Outputs: gpurun_out/<tag>_*.txt|csv (+ the .ncu-rep files
-# while they fit). usage: tools/profile_round.sh <tag> [worlds]
-TAG=${1:-r1}; WORLDS=${2:-256}
+# Round profile capture (run under gpurun, ONE GPU): launch list of one timed step of the bench command + one full capture of every hot
+# kernel, summarised to text ON THE BOX (gpurun only copies 64 MiB back). Outputs: gpurun_out/<tag>_*.txt|csv|json (+ the .ncu-rep
+# files while they fit). usage: tools/profile_round.sh <tag> [worlds]
+# Steps: "impact" = step 15 of the driver's bench window (steps 5..25: the boxes are landing), "rest" = step 110 (pyramids at rest).
+TAG=${1:-r2}; WORLDS=${2:-256}
 export B2J_BENCH_CUPROFILE=1 B2J_BATCH_GROUPS=1
 mkdir -p gpurun_out
-HOT='KFindPairs|KProcessPairs|KCopyCached|KCollideConvex|KCollideEpa|KFinishPairs|KSetupConstraints|KSolveVelocity'
-for PHASE in impact:60 rest:110; do
+HOT='KFindPairs|KProcessPairs|KCopyCached|KCollideConvex|KCollideEpa|KFinishPairs|KSetupConstraints|KSolveVelocity|KSolvePosition|solve_velocity_tma|sched_block'
+for PHASE in impact:15 rest:110; do
   NAME=${PHASE%%:*}; WARM=${PHASE##*:}
-  BENCH="python bench.py --worlds $WORLDS --steps 1 --warmup $WARM --no-cpu-baseline --no-pile"
+  BENCH="python bench.py --worlds $WORLDS --steps 1 --warmup $WARM --no-cpu-baseline --no-pile --no-extras"
   # every launch of the timed step with its device time
   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches_${NAME}.csv $BENCH > gpurun_out/${TAG}_launches_${NAME}.log 2>&1
   python tools/ncu_launches.py gpurun_out/${TAG}_launches_${NAME}.csv > gpurun_out/${TAG}_launches_${NAME}.txt 2>&1
-  # full metric set: the first launch of each hot kernel of the step (+ the first velocity phases)
-  ncu --set full --clock-control none --profile-from-start off --kernel-name-base demangled -k regex:"$HOT" -c 12 -f -o gpurun_out/${TAG}_hot_${NAME} $BENCH > gpurun_out/${TAG}_hot_${NAME}.log 2>&1
+  # full metric set: the first launches of each hot kernel of the step
+  ncu --set full --clock-control none --profile-from-start off --import-source on --kernel-name-base demangled -k regex:"$HOT" -c 14 -f -o gpurun_out/${TAG}_hot_${NAME} $BENCH > gpurun_out/${TAG}_hot_${NAME}.log 2>&1
   python tools/ncu_summary.py gpurun_out/${TAG}_hot_${NAME}.ncu-rep > gpurun_out/${TAG}_hot_${NAME}.txt 2>&1
 done
+# DRAM traffic of the velocity solve kernel against its algorithmic bytes (bench.py's roofline.traffic)
+python tools/ncu_traffic.py gpurun_out/${TAG}_hot_rest.ncu-rep gpurun_out/${TAG}_hot_rest.log > gpurun_out/${TAG}_solve_traffic.json 2> gpurun_out/${TAG}_solve_traffic.err
+# the one launch TMA solve (B2J_SOLVE_MODE=2) on the same resting step
+B2J_SOLVE_MODE=2 ncu --set full --clock-control none --profile-from-start off --import-source on --kernel-name-base demangled -k regex:"solve_velocity_tma|solve_position_all" -c 2 -f -o gpurun_out/${TAG}_hot_tma \
+  python bench.py --worlds $WORLDS --steps 1 --warmup 110 --no-cpu-baseline --no-pile --no-extras > gpurun_out/${TAG}_hot_tma.log 2>&1
+python tools/ncu_summary.py gpurun_out/${TAG}_hot_tma.ncu-rep > gpurun_out/${TAG}_hot_tma.txt 2>&1
 du -sh gpurun_out; ls -la gpurun_out | grep ${TAG}_
 # stay below the copy-back limit: drop the binary reports first if needed
-if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/${TAG}_hot_impact.ncu-rep; fi
-if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/${TAG}_hot_rest.ncu-rep; fi
+for f in hot_impact hot_rest hot_tma; do if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/${TAG}_$f.ncu-rep; fi; done
