@@ -372,6 +372,11 @@ typedef struct b2j_debug_manifold {
 /* Manifolds written this step sorted by (body1, body2, sub1, sub2); returns the total count. */
 uint32_t b2j_debug_get_manifolds(b2j_world *w, b2j_debug_manifold *out, uint32_t cap);
 
+/* Checks the solve schedule of the LAST step: constraints of one phase run in parallel, so no dynamic body may be touched by two
+ * constraints of the same phase (the reference asserts the same of its splits, LargeIslandSplitter.cpp). Returns the number of
+ * (body, phase) conflicts -- 0 for a valid schedule -- or < 0 on a CUDA failure. */
+int b2j_debug_check_schedule(b2j_world *w);
+
 /* Only the broadphase of a step on the current state: fills the pair list for b2j_debug_get_pairs. */
 int b2j_debug_find_pairs(b2j_world *w);
 
@@ -391,6 +396,12 @@ typedef struct b2j_batch b2j_batch; /* opaque: n independent worlds with identic
  * caches. The prototype stays usable on its own. Contact / activation events are not recorded for batches.
  * Every world evolves bit-identically to the prototype stepped alone (TestMultiplePhysicsSystems pattern, PhysicsTests.cpp:1548). */
 b2j_batch *b2j_batch_create(b2j_world *proto, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world);
+/* Library level multi device batch: the worlds are split in contiguous blocks over the given CUDA devices of THIS
+ * process (device_ids[0] must be the prototype's device; the others need peer access to it), each block in groups as above. Stepping
+ * moves no data between the devices: every group is stepped by its own host thread on its own device and stream, b2j_batch_step
+ * sums the statistics on the host. (One process per GPU with the statistics reduced over NCCL is the other deployment: bench.py.) */
+b2j_batch *b2j_batch_create_on_devices(b2j_world *proto, uint32_t n_worlds, const int32_t *device_ids, uint32_t n_devices,
+                                       uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world);
 void       b2j_batch_destroy(b2j_batch *b);
 /* Steps every world of the batch once; stats (may be NULL) receives the totals over all worlds. */
 int        b2j_batch_step(b2j_batch *b, float delta_time, int collision_steps, b2j_step_stats *stats);

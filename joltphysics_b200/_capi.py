@@ -155,6 +155,7 @@ PROTOTYPES = {
     "b2j_debug_get_pairs": (C.c_uint32, [_VP, _U32P, C.c_uint32]),
     "b2j_debug_get_manifolds": (C.c_uint32, [_VP, C.POINTER(DebugManifold), C.c_uint32]),
     "b2j_debug_find_pairs": (C.c_int, [_VP]),
+    "b2j_debug_check_schedule": (C.c_int, [_VP]),
     "b2j_world_set_profiling": (C.c_int, [_VP, C.c_int]),
     "b2j_world_set_event_recording": (C.c_int, [_VP, C.c_int, C.c_int]),
     "b2j_query_cast_rays": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP]),
@@ -168,6 +169,7 @@ PROTOTYPES = {
     "b2j_batch_restore_state": (C.c_int, [_VP, _VP]),
     "b2j_world_get_profile": (C.c_uint32, [_VP, C.c_char_p, C.c_uint32, C.POINTER(C.c_float), _U32P, C.c_uint32]),
     "b2j_batch_create": (_VP, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "b2j_batch_create_on_devices": (_VP, [_VP, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, C.c_uint32, C.c_uint32]),
     "b2j_batch_destroy": (None, [_VP]),
     "b2j_batch_reset_worlds": (C.c_int, [_VP, _U32P, C.c_uint32]),
     "b2j_batch_step": (C.c_int, [_VP, C.c_float, C.c_int, C.POINTER(StepStats)]),

@@ -541,6 +541,25 @@ __global__ void __launch_bounds__(1024) sched_block_kernel(const DWorld w, const
 }
 #endif
 
+// Debug check of the solve schedule (the reference asserts split disjointness in LargeIslandSplitter): all constraints of one
+// phase run in parallel, so no dynamic body may appear in two constraints of the same phase. One thread per active body over its
+// adjacency list (sorted positions) of the last step; counts the (body, phase) conflicts.
+struct KCheckSchedule
+{
+	DWorld w; SolveCtx s; uint32_t *conflicts;
+	B2J_D void operator()(uint32_t ai) const
+	{
+		uint32_t b = w.active[ai];
+		if (w.info[b].motion_type != B2J_MOTION_DYNAMIC) return;
+		uint32_t deg = s.body_deg[b];
+		const uint32_t *a = s.adj + s.body_off[b];
+		for (uint32_t i = 1; i < deg; ++i)
+			for (uint32_t j = 0; j < i; ++j)
+				if (s.phase[a[i]] == s.phase[a[j]])
+					atomic_add(conflicts, 1u);
+	}
+};
+
 struct KSchedResetCursors
 {
 	DWorld w; SolveCtx s;

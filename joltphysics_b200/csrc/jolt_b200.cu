@@ -2382,6 +2382,24 @@ uint32_t b2j_debug_get_manifolds(b2j_world *W, b2j_debug_manifold *out, uint32_t
 	return nm;
 }
 
+int b2j_debug_check_schedule(b2j_world *W)
+{
+	B2J_DEVICE_GUARD(W);
+	Runtime &rt = W->rt;
+	if (W->stepped_list == nullptr || W->stepped_count == 0) return 0;
+	sync_dworld(W);
+	uint32_t *out = reinterpret_cast<uint32_t *>(W->d_energy);
+	rt.memset_(out, 0, 4);
+	// (the active list of the last step = the list before the sleepers left it)
+	DWorld d = W->d;
+	d.active = const_cast<uint32_t *>(W->stepped_list);
+	{ KCheckSchedule k; k.w = d; k.s = W->sc; k.conflicts = out; rt.launch(k, W->stepped_count); }
+	uint32_t n = 0;
+	rt.download(&n, out, 1);
+	if (!rt.check("b2j_debug_check_schedule")) return -1;
+	return (int)n;
+}
+
 int b2j_debug_find_pairs(b2j_world *W)
 {
 	B2J_DEVICE_GUARD(W);
@@ -2421,8 +2439,9 @@ template <class T> static void replicate(Runtime &rt, T *dst, const T *src, uint
 
 extern "C" {
 
-static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
+static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world, int device)
 {
+	B2J_DEVICE_GUARD(P);
 	upload_shapes(P);
 	sync_dworld(P);
 	uint32_t stride = P->num_slots;
@@ -2437,6 +2456,21 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	if (pairs > 0x7ffffff0ull || cons > 0x7ffffff0ull) { last_error() = "b2j_batch_create: limits exceed 2^31"; return nullptr; }
 	desc.max_body_pairs = (uint32_t)pairs;
 	desc.max_contact_constraints = (uint32_t)cons;
+	desc.device = device;
+#ifndef B2J_HOSTSIM
+	if (device != P->rt.device)
+	{
+		// the group lives on another device of this process: its creation kernels read the prototype over NVLink (peer access), and the
+		// reset kernels read the creation state kept on the first group's device
+		int can = 0;
+		cudaDeviceCanAccessPeer(&can, device, P->rt.device);
+		if (!can) { last_error() = "b2j_batch_create_on_devices: no peer access between the devices"; return nullptr; }
+		cudaSetDevice(device);
+		cudaError_t pe = cudaDeviceEnablePeerAccess(P->rt.device, 0);
+		if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { last_error() = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe); return nullptr; }
+		cudaGetLastError();
+	}
+#endif
 	g_create_without_events = true;
 	b2j_world *B = b2j_world_create(&desc);
 	g_create_without_events = false;
@@ -2520,36 +2554,10 @@ template <class F> static bool batch_for_each_group(b2j_batch *b, const F &fn)
 
 extern "C" {
 
-b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
+// the creation state of one world (device resident, on the first group's device), for b2j_batch_reset_worlds
+static bool batch_keep_init_state(b2j_batch *b, b2j_world *P)
 {
-	if (P == nullptr || n_worlds == 0 || P->num_worlds != 1) { last_error() = "b2j_batch_create: invalid prototype"; return nullptr; }
-	// groups of about 256 worlds, at most 8 (measured at 4096 worlds: 149 ms per step with 4 groups, 130 with 8, 125 with 16 -- but the
-	// 16 group launches are small enough to lose 20% of their own HBM efficiency, so 8 it is); B2J_BATCH_GROUPS overrides
-	uint32_t K = n_worlds / 256;
-	if (K > 8) K = 8;
-	if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
-#ifdef B2J_HOSTSIM
-	K = 1; // the host simulation is single threaded
-#endif
-	if (K < 1) K = 1;
-	if (K > n_worlds) K = n_worlds;
-	b2j_batch *b = new b2j_batch;
-	b->n_worlds = n_worlds; b->stride = P->num_slots; b->bodies_per_world = P->num_bodies;
-	uint32_t first = 0;
-	for (uint32_t g = 0; g < K; ++g)
-	{
-		uint32_t n = n_worlds / K + (g < n_worlds % K? 1 : 0);
-		b2j_world *G = batch_create_group(P, n, max_body_pairs_per_world, max_contact_constraints_per_world);
-		if (G == nullptr) { b2j_batch_destroy(b); return nullptr; }
-		// (experiments: the one launch solvers of the groups share the SMs instead of taking turns on all of them)
-		if (const char *e = getenv("B2J_SOLVE_GRID_DIV")) { int v = atoi(e); G->solve_grid_div = v < 1? 1u : (uint32_t)v; }
-		b->groups.push_back(G);
-		b->first_world.push_back(first);
-		first += n;
-	}
-	b->first_world.push_back(first);
-	// the creation state of one world, for b2j_batch_reset_worlds
-	{
+	B2J_DEVICE_GUARD(b->groups[0]);
 		Runtime &rt = b->groups[0]->rt;
 		const DWorld &s = P->d;
 		uint32_t stride = b->stride;
@@ -2571,7 +2579,86 @@ b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_p
 		in.was_active = rt.alloc<uint32_t>(stride, false);
 		rt.upload(in.was_active, was_active.data(), stride);
 		rt.sync();
+	return rt.check("b2j_batch_create");
+}
+
+b2j_batch *b2j_batch_create(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
+{
+	if (P == nullptr) { last_error() = "b2j_batch_create: invalid prototype"; return nullptr; }
+	int32_t device = P->rt.device;
+	return b2j_batch_create_on_devices(P, n_worlds, &device, 1, max_body_pairs_per_world, max_contact_constraints_per_world);
+}
+
+b2j_batch *b2j_batch_create_on_devices(b2j_world *P, uint32_t n_worlds, const int32_t *device_ids, uint32_t n_devices, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world)
+{
+	if (P == nullptr || n_worlds == 0 || P->num_worlds != 1 || device_ids == nullptr || n_devices == 0 || n_devices > n_worlds) { last_error() = "b2j_batch_create: invalid prototype or device list"; return nullptr; }
+	if (device_ids[0] != P->rt.device) { last_error() = "b2j_batch_create_on_devices: the first device must be the prototype's"; return nullptr; }
+	if (n_devices > 1)
+	{
+		// contiguous blocks of worlds per device, each block split into groups like a single device batch; the groups of all devices form
+		// ONE batch (world index -> group -> device), stepped by one host thread per group with no inter device traffic
+		b2j_batch *b = new b2j_batch;
+		b->n_worlds = n_worlds; b->stride = P->num_slots; b->bodies_per_world = P->num_bodies;
+		uint32_t first = 0;
+		for (uint32_t dv = 0; dv < n_devices; ++dv)
+		{
+			uint32_t nd = n_worlds / n_devices + (dv < n_worlds % n_devices? 1 : 0);
+			uint32_t K = nd / 256;
+			if (K > 8) K = 8;
+			if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
+			if (K < 1) K = 1;
+			if (K > nd) K = nd;
+			for (uint32_t g = 0; g < K; ++g)
+			{
+				uint32_t n = nd / K + (g < nd % K? 1 : 0);
+				b2j_world *G = batch_create_group(P, n, max_body_pairs_per_world, max_contact_constraints_per_world, device_ids[dv]);
+				if (G == nullptr) { b2j_batch_destroy(b); return nullptr; }
+				b->groups.push_back(G);
+				b->first_world.push_back(first);
+				first += n;
+			}
+		}
+		b->first_world.push_back(first);
+		if (!batch_keep_init_state(b, P)) { b2j_batch_destroy(b); return nullptr; }
+#ifndef B2J_HOSTSIM
+		// the reset kernels of the other devices read the creation state from the first group's device
+		for (b2j_world *G : b->groups)
+			if (G->rt.device != b->groups[0]->rt.device)
+			{
+				cudaSetDevice(G->rt.device);
+				cudaDeviceEnablePeerAccess(b->groups[0]->rt.device, 0);
+				cudaGetLastError();
+			}
+		cudaSetDevice(P->rt.device);
+#endif
+		return b;
 	}
+	// groups of about 256 worlds, at most 8 (measured at 4096 worlds: 149 ms per step with 4 groups, 130 with 8, 125 with 16 -- but the
+	// 16 group launches are small enough to lose 20% of their own HBM efficiency, so 8 it is); B2J_BATCH_GROUPS overrides
+	uint32_t K = n_worlds / 256;
+	if (K > 8) K = 8;
+	if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
+#ifdef B2J_HOSTSIM
+	K = 1; // the host simulation is single threaded
+#endif
+	if (K < 1) K = 1;
+	if (K > n_worlds) K = n_worlds;
+	b2j_batch *b = new b2j_batch;
+	b->n_worlds = n_worlds; b->stride = P->num_slots; b->bodies_per_world = P->num_bodies;
+	uint32_t first = 0;
+	for (uint32_t g = 0; g < K; ++g)
+	{
+		uint32_t n = n_worlds / K + (g < n_worlds % K? 1 : 0);
+		b2j_world *G = batch_create_group(P, n, max_body_pairs_per_world, max_contact_constraints_per_world, P->rt.device);
+		if (G == nullptr) { b2j_batch_destroy(b); return nullptr; }
+		// (experiments: the one launch solvers of the groups share the SMs instead of taking turns on all of them)
+		if (const char *e = getenv("B2J_SOLVE_GRID_DIV")) { int v = atoi(e); G->solve_grid_div = v < 1? 1u : (uint32_t)v; }
+		b->groups.push_back(G);
+		b->first_world.push_back(first);
+		first += n;
+	}
+	b->first_world.push_back(first);
+	if (!batch_keep_init_state(b, P)) { b2j_batch_destroy(b); return nullptr; }
 	return b;
 }
 

@@ -50,6 +50,8 @@ def single_step_parity(api, scene, p0=0, p1=0, warm=0, dt=1.0 / 60.0, collision_
         key = lambda e: (e.kind, e.body1, e.body2, e.sub_shape1, e.sub_shape2, e.num_points)
         assert sorted(map(key, re_)) == sorted(map(key, ge)), f"contact events differ: ref {len(re_)} got {len(ge)}"
         assert sorted(ref.activation_events()) == sorted(world.activation_events()), "activation events differ"
+    # the solve schedule of the step: every phase touches disjoint dynamic bodies
+    assert api.b2j_debug_check_schedule(world.h) == 0, "a dynamic body is touched by two constraints of the same phase"
     out["worst"] = worst
     out["stats"] = stats.as_dict()
     world.close()

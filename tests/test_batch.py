@@ -176,3 +176,45 @@ def test_batch_reset_worlds_gpu(gpu_api, monkeypatch, scene, p0, p1, before, aft
     monkeypatch.setenv("B2J_BATCH_GROUPS", str(groups))
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
     _check_reset(gpu_api, flib, scene, p0, p1, 7, before, after, [0, 2, 6])
+
+
+@pytest.mark.gpu
+def test_batch_on_two_devices_gpu(gpu_api):
+    """Library level multi device batch (b2j_batch_create_on_devices): worlds split over two GPUs of one process, every world still
+    evolves exactly like the prototype stepped alone; reset and snapshots work across the devices."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices (gpurun --gpus 2)")
+    flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
+    proto = F.FacadeScene(flib, "pyramid", 6, 0)
+    n, n_worlds = proto.num_bodies, 7
+    devices = (C.c_int32 * 2)(0, 1)
+    batch = gpu_api.b2j_batch_create_on_devices(proto.world.h, n_worlds, devices, 2, 0, 0)
+    assert batch, gpu_api.last_error()
+    stats = _capi.StepStats()
+    for _ in range(40):
+        assert gpu_api.b2j_batch_step(batch, 1.0 / 60.0, 1, C.byref(stats)) == 0, gpu_api.last_error()
+        _, single = proto.world.step()
+    assert stats.num_constraints == n_worlds * single.num_constraints
+    want = proto.world.state()
+    for w in range(n_worlds):
+        got = _batch_state(gpu_api, batch, w, n)
+        for name in ("pos", "rot", "lin", "ang", "bounds"):
+            assert np.array_equal(getattr(want, name), getattr(got, name)), f"world {w}: {name} differs from the prototype stepped alone"
+    snap = gpu_api.b2j_batch_save_state(batch)
+    assert snap, gpu_api.last_error()
+    for _ in range(10):
+        assert gpu_api.b2j_batch_step(batch, 1.0 / 60.0, 1, C.byref(stats)) == 0
+    assert gpu_api.b2j_batch_restore_state(batch, snap) == 0, gpu_api.last_error()
+    for w in (0, n_worlds - 1):
+        got = _batch_state(gpu_api, batch, w, n)
+        assert np.array_equal(want.pos, got.pos), f"world {w} after the restore"
+    ids = np.array([1, n_worlds - 1], dtype=np.uint32)
+    assert gpu_api.b2j_batch_reset_worlds(batch, ids.ctypes.data_as(C.POINTER(C.c_uint32)), 2) == 0, gpu_api.last_error()
+    fresh = F.FacadeScene(flib, "pyramid", 6, 0)
+    for w in (1, n_worlds - 1):
+        assert np.array_equal(fresh.world.state().pos, _batch_state(gpu_api, batch, w, n).pos), f"world {w} after the reset"
+    gpu_api.b2j_snapshot_destroy(snap)
+    gpu_api.b2j_batch_destroy(batch)
+    fresh.close()
+    proto.close()
