@@ -234,6 +234,26 @@ typedef struct b2j_body_params {
 } b2j_body_params;
 int b2j_bodies_set_params(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_params *in);
 
+/* BodyInterface::SetMotionType (BodyInterface.h:241, Body::SetMotionType Body.cpp), SetObjectLayer (:181), SetShape (:169) and
+ * InvalidateContactCache (:300) for bodies that are in the world. [n] arrays, NULL members are left untouched.
+ *  motion_type: a body that becomes static leaves the active list and stops, static / kinematic bodies lose their accumulated force and
+ *    torque; inv_mass (required with motion_type) = the inverse mass the body has as a DYNAMIC body (the device keeps 0 for the others).
+ *  object_layer: the body moves to the broadphase tree of the new layer.
+ *  shape: the centre of mass position follows the new shape's centre of mass, the bounds are recomputed, the body's cached contacts
+ *    are not reused by the next step (BodyManager::InvalidateContactCacheForBody); mass properties change only if the three mass
+ *    arrays are given (SetShape's inUpdateMassProperties).
+ *  invalidate_contact_cache != 0: BodyInterface::InvalidateContactCache for all n bodies. */
+typedef struct b2j_body_info_update {
+	const uint8_t  *motion_type;
+	const float    *inv_mass;
+	const uint16_t *object_layer;
+	const int32_t  *shape;
+	const float    *inv_inertia_diag;   /* [n][3] with shape */
+	const float    *inertia_rotation;   /* [n][4] with shape */
+	uint32_t        invalidate_contact_cache;
+} b2j_body_info_update;
+int b2j_bodies_set_info(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_info_update *in);
+
 uint32_t b2j_num_bodies(const b2j_world *w);          /* PhysicsSystem::GetNumBodies        PhysicsSystem.h:219 */
 uint32_t b2j_num_active_bodies(const b2j_world *w);   /* PhysicsSystem::GetNumActiveBodies  :222 */
 /* PhysicsSystem::GetActiveBodies (:240): copies up to cap ids in active-list order, returns the count. */

@@ -93,6 +93,8 @@ enum class EMotionType : uint8 { Static = 0, Kinematic = 1, Dynamic = 2 };
 enum class EMotionQuality : uint8 { Discrete = 0, LinearCast = 1 };
 enum class EActivation { Activate, DontActivate };
 enum class EAllowedDOFs : uint8 { None = 0, All = 0x3f, TranslationX = 1, TranslationY = 2, TranslationZ = 4, RotationX = 8, RotationY = 16, RotationZ = 32, Plane2D = 1 | 2 | 32 };
+inline constexpr EAllowedDOFs operator|(EAllowedDOFs a, EAllowedDOFs b) { return EAllowedDOFs(uint8(a) | uint8(b)); }
+inline constexpr EAllowedDOFs operator&(EAllowedDOFs a, EAllowedDOFs b) { return EAllowedDOFs(uint8(a) & uint8(b)); }
 enum class EPhysicsUpdateError : uint32 { None = 0, ManifoldCacheFull = 1, BodyPairCacheFull = 2, ContactConstraintsFull = 4 };
 inline EPhysicsUpdateError operator|(EPhysicsUpdateError a, EPhysicsUpdateError b) { return EPhysicsUpdateError(uint32(a) | uint32(b)); }
 enum class EOverrideMassProperties : uint8 { CalculateMassAndInertia, CalculateInertia, MassAndInertiaProvided };
@@ -586,6 +588,8 @@ public:
 	mutable bool mActive = false;
 	bool mInWorld = false, mDestroyed = false;
 	b2j_body_desc mDesc;          // creation time descriptor (uploaded by AddBody)
+	float mDynamicInvMass = 0.0f; // MotionProperties::mInvMass (the device holds 0 while the body is not dynamic)
+	bool mHasMotionProperties = false;
 };
 
 class ContactListener
@@ -665,6 +669,11 @@ public:
 	float GetMaxAngularVelocity(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mDesc.max_angular_velocity : 0.0f; }
 	EMotionType GetMotionType(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mMotionType : EMotionType::Static; }
 	ObjectLayer GetObjectLayer(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mObjectLayer : 0; }
+	// BodyInterface::SetMotionType / SetObjectLayer / SetShape / InvalidateContactCache (BodyInterface.h:241,181,169,300)
+	void SetMotionType(const BodyID &id, EMotionType inMotionType, EActivation inActivationMode);
+	void SetObjectLayer(const BodyID &id, ObjectLayer inLayer);
+	void SetShape(const BodyID &id, const ShapeRef &inShape, bool inUpdateMassProperties, EActivation inActivationMode);
+	void InvalidateContactCache(const BodyID &id);
 	// Bulk force application from host arrays (n bodies, force/torque [n][3], either may be null): the RL pattern
 	void AddForcesAndTorques(const BodyID *inBodies, int inNumber, const float *inForces, const float *inTorques);
 	uint64 GetUserData(const BodyID &id) const { const Body *b = TryGet(id); return b? b->mUserData : 0; }
@@ -1114,7 +1123,8 @@ inline Body *BodyInterface::CreateBody(const BodyCreationSettings &s)
 	d.linear_damping = s.mLinearDamping; d.angular_damping = s.mAngularDamping;
 	d.max_linear_velocity = s.mMaxLinearVelocity; d.max_angular_velocity = s.mMaxAngularVelocity;
 	d.gravity_factor = s.mGravityFactor; d.friction = s.mFriction; d.restitution = s.mRestitution;
-	if (s.HasMassProperties() && s.mMotionType != EMotionType::Static)
+	body->mHasMotionProperties = s.HasMassProperties();
+	if (s.HasMassProperties())
 	{
 		// MotionProperties::SetMassProperties (MotionProperties.cpp:12-61)
 		MassProperties mp = s.GetMassProperties();
@@ -1131,6 +1141,7 @@ inline Body *BodyInterface::CreateBody(const BodyCreationSettings &s)
 			else
 				d.inv_inertia_diag[0] = d.inv_inertia_diag[1] = d.inv_inertia_diag[2] = 2.5f * d.inv_mass;
 		}
+		body->mDynamicInvMass = d.inv_mass;
 		if (s.mMotionType != EMotionType::Dynamic) d.inv_mass = 0.0f;
 	}
 	d.has_bounds = 0; // bounds and sleep test spheres are computed on the device from shape + pose
@@ -1307,6 +1318,100 @@ inline void BodyInterface::SetActive(const BodyID &id, bool inActive)
 	mSystem->MarkMirrorNewer(id);
 	b->mActive = inActive;
 	if (!inActive) { b->mLinearVelocity = Vec3::sZero(); b->mAngularVelocity = Vec3::sZero(); } // BodyManager::DeactivateBodies resets the velocities
+}
+
+inline void BodyInterface::SetMotionType(const BodyID &id, EMotionType inMotionType, EActivation inActivationMode)
+{
+	Body *b = const_cast<Body *>(TryGet(id));
+	if (b == nullptr || b->mMotionType == inMotionType) { if (b != nullptr && b->mInWorld && inMotionType != EMotionType::Static && inActivationMode == EActivation::Activate) ActivateBody(id); return; }
+	if (inMotionType != EMotionType::Static && !b->mHasMotionProperties) return; // Body::SetMotionType asserts: created without mAllowDynamicOrKinematic
+	b->Sync();
+	b->mMotionType = inMotionType;
+	b->mDesc.motion_type = (uint8_t)inMotionType;
+	b->mDesc.inv_mass = inMotionType == EMotionType::Dynamic? b->mDynamicInvMass : 0.0f;
+	if (inMotionType == EMotionType::Static) { b->mLinearVelocity = Vec3::sZero(); b->mAngularVelocity = Vec3::sZero(); b->mActive = false; }
+	if (inMotionType != EMotionType::Dynamic) { memset(b->mDesc.force, 0, sizeof(b->mDesc.force)); memset(b->mDesc.torque, 0, sizeof(b->mDesc.torque)); }
+	if (!b->mInWorld) return;
+	Flush();
+	uint32 bid = id.mID; uint8_t mt = (uint8_t)inMotionType;
+	b2j_body_info_update u;
+	memset(&u, 0, sizeof(u));
+	u.motion_type = &mt; u.inv_mass = &b->mDynamicInvMass;
+	b2j_bodies_set_info(World(), &bid, 1, &u);
+	mSystem->MarkMirrorNewer(id);
+	if (inMotionType != EMotionType::Static && inActivationMode == EActivation::Activate) ActivateBody(id);
+}
+
+inline void BodyInterface::SetObjectLayer(const BodyID &id, ObjectLayer inLayer)
+{
+	Body *b = const_cast<Body *>(TryGet(id));
+	if (b == nullptr || b->mObjectLayer == inLayer) return;
+	b->mObjectLayer = inLayer;
+	b->mDesc.object_layer = inLayer;
+	if (!b->mInWorld) return;
+	Flush();
+	uint32 bid = id.mID; uint16_t layer = inLayer;
+	b2j_body_info_update u;
+	memset(&u, 0, sizeof(u));
+	u.object_layer = &layer;
+	b2j_bodies_set_info(World(), &bid, 1, &u);
+}
+
+inline void BodyInterface::SetShape(const BodyID &id, const ShapeRef &inShape, bool inUpdateMassProperties, EActivation inActivationMode)
+{
+	Body *b = const_cast<Body *>(TryGet(id));
+	if (b == nullptr || b->mShape.get() == inShape.get()) return;
+	b->Sync();
+	// Body::SetShapeInternal: the centre of mass position follows the new shape
+	Vec3 old_com = b->mShape->GetCenterOfMass();
+	b->mShape = inShape;
+	b->mPosition = b->mPosition + b->mRotation * (inShape->GetCenterOfMass() - old_com);
+	b2j_body_desc &d = b->mDesc;
+	d.shape = mSystem->ShapeID(inShape);
+	d.position[0] = b->mPosition.x; d.position[1] = b->mPosition.y; d.position[2] = b->mPosition.z;
+	if (inUpdateMassProperties && b->mHasMotionProperties)
+	{
+		// Body::UpdateCenterOfMassInternal -> MotionProperties::SetMassProperties(allowed DOFs, shape mass properties)
+		MassProperties mp = inShape->GetMassProperties();
+		uint dofs = d.allowed_dofs;
+		b->mDynamicInvMass = (dofs & 7) == 0? 0.0f : 1.0f / mp.mMass;
+		d.inv_inertia_diag[0] = d.inv_inertia_diag[1] = d.inv_inertia_diag[2] = 0.0f;
+		d.inertia_rotation[0] = d.inertia_rotation[1] = d.inertia_rotation[2] = 0.0f; d.inertia_rotation[3] = 1.0f;
+		if (((dofs >> 3) & 7) != 0)
+		{
+			Quat rot; Vec3 diag;
+			if (mp.DecomposePrincipalMomentsOfInertia(rot, diag) && !(diag.LengthSq() <= 1.0e-12f))
+			{
+				d.inv_inertia_diag[0] = 1.0f / diag.x; d.inv_inertia_diag[1] = 1.0f / diag.y; d.inv_inertia_diag[2] = 1.0f / diag.z;
+				d.inertia_rotation[0] = rot.x; d.inertia_rotation[1] = rot.y; d.inertia_rotation[2] = rot.z; d.inertia_rotation[3] = rot.w;
+			}
+			else
+				d.inv_inertia_diag[0] = d.inv_inertia_diag[1] = d.inv_inertia_diag[2] = 2.5f * b->mDynamicInvMass;
+		}
+		d.inv_mass = b->mMotionType == EMotionType::Dynamic? b->mDynamicInvMass : 0.0f;
+	}
+	if (!b->mInWorld) return;
+	Flush();
+	uint32 bid = id.mID; int32_t shape = d.shape;
+	b2j_body_info_update u;
+	memset(&u, 0, sizeof(u));
+	u.shape = &shape;
+	if (inUpdateMassProperties && b->mHasMotionProperties) { u.inv_mass = &b->mDynamicInvMass; u.inv_inertia_diag = d.inv_inertia_diag; u.inertia_rotation = d.inertia_rotation; }
+	b2j_bodies_set_info(World(), &bid, 1, &u);
+	mSystem->MarkMirrorNewer(id);
+	if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static) ActivateBody(id);
+}
+
+inline void BodyInterface::InvalidateContactCache(const BodyID &id)
+{
+	const Body *b = TryGet(id);
+	if (b == nullptr || !b->mInWorld) return;
+	Flush();
+	uint32 bid = id.mID;
+	b2j_body_info_update u;
+	memset(&u, 0, sizeof(u));
+	u.invalidate_contact_cache = 1;
+	b2j_bodies_set_info(World(), &bid, 1, &u);
 }
 
 inline void BodyInterface::SetParam(const BodyID &id, float b2j_body_desc::*inDescMember, const float *b2j_body_params::*inParamMember, float inValue)

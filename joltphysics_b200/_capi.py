@@ -142,6 +142,7 @@ PROTOTYPES = {
     "b2j_bodies_set_state": (C.c_int, [_VP, _U32P, C.c_uint32, C.POINTER(BodyState)]),
     "b2j_bodies_get_stepped_state": (C.c_uint32, [_VP, C.c_uint32, _U32P, C.POINTER(BodyState)]),
     "b2j_bodies_set_params": (C.c_int, [_VP, _U32P, C.c_uint32, C.c_void_p]),
+    "b2j_bodies_set_info": (C.c_int, [_VP, _U32P, C.c_uint32, C.c_void_p]),
     "b2j_bodies_add_force_torque": (C.c_int, [_VP, _U32P, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "b2j_num_bodies": (C.c_uint32, [_VP]),
     "b2j_num_active_bodies": (C.c_uint32, [_VP]),

@@ -232,6 +232,59 @@ struct KSetParams
 	}
 };
 
+// b2j_bodies_set_info: Body::SetMotionType / SetObjectLayerInternal / SetShapeInternal on the device
+struct KSetInfo
+{
+	DWorld w; const uint32_t *ids; const uint8_t *motion_type; const float *inv_mass; const uint16_t *object_layer; const int32_t *shape;
+	const float *inv_inertia_diag, *inertia_rotation; uint32_t invalidate;
+	B2J_D void operator()(uint32_t i) const
+	{
+		uint32_t b = slot_of(ids[i]);
+		BodyInfo info = w.info[b];
+		if (motion_type != nullptr && motion_type[i] != info.motion_type)
+		{
+			info.motion_type = motion_type[i];
+			w.params[b].inv_mass = info.motion_type == B2J_MOTION_DYNAMIC? inv_mass[i] : 0.0f;
+			if (info.motion_type == B2J_MOTION_STATIC) { w.linear_velocity[b] = f4(0, 0, 0, 0); w.angular_velocity[b] = f4(0, 0, 0, 0); }
+			if (info.motion_type != B2J_MOTION_DYNAMIC) { w.force[b] = f4(0, 0, 0, 0); w.torque[b] = f4(0, 0, 0, 0); }
+		}
+		if (object_layer != nullptr)
+		{
+			info.object_layer = object_layer[i];
+			info.bp_layer = w.object_to_bp[object_layer[i]];
+		}
+		if (shape != nullptr && shape[i] != info.shape)
+		{
+			// Body::SetShapeInternal -> UpdateCenterOfMassInternal: mPosition += mRotation * (new centre of mass - old centre of mass)
+			V3 old_com = w.shapes[info.shape].center_of_mass, new_com = w.shapes[shape[i]].center_of_mass;
+			info.shape = shape[i];
+			Q4 q = to_q4(w.rotation[b]);
+			V3 x = to_v3(w.position[b]) + rotate(q, new_com - old_com);
+			w.position[b] = f4(x);
+			if (inv_inertia_diag != nullptr)
+			{
+				if (info.motion_type == B2J_MOTION_DYNAMIC && inv_mass != nullptr) w.params[b].inv_mass = inv_mass[i];
+				w.inv_inertia_diag[b] = f4(v3_load(inv_inertia_diag + 3 * i));
+				w.inertia_rotation[b] = f4(q4_load(inertia_rotation + 4 * i));
+			}
+			V3 mn, mx;
+			world_bounds(w.shapes[info.shape], x, q, mn, mx);
+			w.bounds_min[b] = f4(mn);
+			w.bounds_max[b] = f4(mx);
+			info.flags |= B2J_BODY_INVALIDATE_CACHE;
+		}
+		if (invalidate) info.flags |= B2J_BODY_INVALIDATE_CACHE;
+		w.info[b] = info;
+	}
+};
+
+// BodyManager::ValidateContactCacheForAllBodies at the end of a step (PhysicsSystem.cpp JobContactRemovedCallbacks)
+struct KValidateContactCache
+{
+	DWorld w; const uint32_t *slots;
+	B2J_D void operator()(uint32_t i) const { w.info[slots[i]].flags &= (uint16_t)~B2J_BODY_INVALIDATE_CACHE; }
+};
+
 struct KAddForceTorque
 {
 	DWorld w; const uint32_t *ids; const float *force, *torque;
@@ -527,6 +580,8 @@ struct b2j_world
 	StepCounters h_counters;
 	std::vector<uint32_t> h_phase_offsets;
 	uint32_t last_num_events = 0, last_num_act_events = 0, last_num_pairs = 0;
+	std::vector<uint32_t> h_cache_invalid;  // slots whose InvalidateContactCache flag is set (cleared after the next step, BodyManager::mBodiesCacheInvalid)
+	uint32_t *d_cache_invalid = nullptr; uint32_t cache_invalid_capacity = 0;
 	const uint32_t *stepped_list = nullptr; uint32_t stepped_count = 0; // body slots the last step simulated (b2j_bodies_get_stepped_state)
 	uint32_t last_collide_convex = 0;      // longest convex pair queue of the previous step (sizes this step's queue ordering)
 #ifndef B2J_HOSTSIM
@@ -1419,7 +1474,7 @@ void b2j_world_destroy(b2j_world *W)
 	NarrowCtx &nc = W->nc;
 	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(W->events_buf);
-	rt.free_(W->d_mesh_scratch);
+	rt.free_(W->d_mesh_scratch); rt.free_(W->d_cache_invalid);
 	for (int i = 0; i < 2; ++i) { rt.free_(W->d_collide_keys[i]); rt.free_(W->d_collide_vals[i]); }
 	rt.free_(W->act_events_buf); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
@@ -1604,6 +1659,7 @@ int b2j_bodies_add(b2j_world *W, const b2j_body_desc *bodies, uint32_t n)
 		if (bodies[i].motion_type != B2J_MOTION_STATIC) W->layer_has_moving[layer] = 1;
 		if (slot + 1 > W->num_slots) W->num_slots = slot + 1;
 		if (bodies[i].active && bodies[i].motion_type != B2J_MOTION_STATIC) to_activate.push_back(bodies[i].id);
+		if (bodies[i].flags & B2J_BODY_INVALIDATE_CACHE) W->h_cache_invalid.push_back(slot); // (a snapshot taken between InvalidateContactCache and the next update)
 	}
 	W->num_bodies += n;
 	rt.stage_begin((size_t)n * sizeof(b2j_body_desc));
@@ -1932,6 +1988,73 @@ int b2j_bodies_add_force_torque(b2j_world *W, const uint32_t *ids, uint32_t n, c
 	rt.launch(k, n);
 	rt.sync();
 	return rt.check("b2j_bodies_add_force_torque")? 0 : -1;
+}
+
+int b2j_bodies_set_info(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j_body_info_update *in)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (ids == nullptr || in == nullptr) { last_error() = "b2j_bodies_set_info: ids and in are required"; return -1; }
+	if (!validate_ids(W, ids, n, "b2j_bodies_set_info")) return -1;
+	if (in->motion_type != nullptr && in->inv_mass == nullptr) { last_error() = "b2j_bodies_set_info: motion_type needs inv_mass"; return -1; }
+	if ((in->inv_inertia_diag != nullptr) != (in->inertia_rotation != nullptr)) { last_error() = "b2j_bodies_set_info: inv_inertia_diag and inertia_rotation go together"; return -1; }
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		if (in->motion_type != nullptr && in->motion_type[i] > B2J_MOTION_DYNAMIC) { last_error() = "b2j_bodies_set_info: invalid motion type"; return -1; }
+		if (in->object_layer != nullptr && in->object_layer[i] >= W->d.num_object_layers) { last_error() = "b2j_bodies_set_info: invalid object layer"; return -1; }
+		if (in->shape != nullptr && (in->shape[i] < 0 || in->shape[i] >= (int32_t)W->h_shapes.size())) { last_error() = "b2j_bodies_set_info: invalid shape id"; return -1; }
+	}
+	Runtime &rt = W->rt;
+	upload_shapes(W);
+	// bodies that become static leave the active list first (BodyInterface::SetMotionType)
+	if (in->motion_type != nullptr)
+	{
+		std::vector<uint32_t> to_static;
+		for (uint32_t i = 0; i < n; ++i)
+			if (in->motion_type[i] == B2J_MOTION_STATIC && !W->h_static[slot_of(ids[i])]) to_static.push_back(ids[i]);
+		if (!to_static.empty() && b2j_bodies_deactivate(W, to_static.data(), (uint32_t)to_static.size()) != 0) return -1;
+	}
+	sync_dworld(W);
+	KSetInfo k; memset(&k, 0, sizeof(k)); k.w = W->d; k.invalidate = in->invalidate_contact_cache;
+	rt.stage_begin((size_t)n * (4 + 1 + 4 + 2 + 4 + 12 + 16) + 1024);
+	uint32_t *h_ids = nullptr;
+	k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4);
+	if (in->motion_type) { uint8_t *h; k.motion_type = rt.stage_alloc<uint8_t>(n, &h); memcpy(h, in->motion_type, n); }
+	if (in->inv_mass) { float *h; k.inv_mass = rt.stage_alloc<float>(n, &h); memcpy(h, in->inv_mass, (size_t)n * 4); }
+	if (in->object_layer) { uint16_t *h; k.object_layer = rt.stage_alloc<uint16_t>(n, &h); memcpy(h, in->object_layer, (size_t)n * 2); }
+	if (in->shape) { int32_t *h; k.shape = rt.stage_alloc<int32_t>(n, &h); memcpy(h, in->shape, (size_t)n * 4); }
+	if (in->inv_inertia_diag) { float *h; k.inv_inertia_diag = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, in->inv_inertia_diag, (size_t)n * 12); }
+	if (in->inertia_rotation) { float *h; k.inertia_rotation = rt.stage_alloc<float>((size_t)n * 4, &h); memcpy(h, in->inertia_rotation, (size_t)n * 16); }
+	rt.stage_to_device(0, rt.stage_used);
+	rt.launch(k, n);
+	rt.sync();
+	// host mirrors: static flags, broadphase layer lists, the list of bodies whose contact cache flag is set
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t slot = slot_of(ids[i]);
+		if (in->motion_type != nullptr)
+		{
+			W->h_static[slot] = in->motion_type[i] == B2J_MOTION_STATIC? 1 : 0;
+			if (in->motion_type[i] != B2J_MOTION_STATIC) W->layer_has_moving[W->h_layer[slot]] = 1;
+		}
+		if (in->object_layer != nullptr)
+		{
+			uint8_t layer = W->t_o2bp[in->object_layer[i]];
+			if (layer != W->h_layer[slot])
+			{
+				std::vector<uint32_t> &from = W->layer_bodies[W->h_layer[slot]];
+				from.erase(std::find(from.begin(), from.end(), slot));
+				W->layer_list_dirty[W->h_layer[slot]] = 1; W->layer_needs_build[W->h_layer[slot]] = 1;
+				W->layer_bodies[layer].push_back(slot);
+				W->layer_list_dirty[layer] = 1; W->layer_needs_build[layer] = 1;
+				if (!W->h_static[slot]) W->layer_has_moving[layer] = 1;
+				W->h_layer[slot] = layer;
+			}
+		}
+		if (in->shape != nullptr || in->invalidate_contact_cache) W->h_cache_invalid.push_back(slot);
+		if (in->shape != nullptr) W->layer_needs_build[W->h_layer[slot]] = 1;
+	}
+	return rt.check("b2j_bodies_set_info")? 0 : -1;
 }
 
 uint32_t b2j_num_bodies(const b2j_world *W) { return W->num_bodies; }
@@ -2270,6 +2393,16 @@ int b2j_step(b2j_world *W, float delta_time, int collision_steps, b2j_step_stats
 		if (!collision_step(W, step_dt, r, s == collision_steps - 1, stats))
 			return -1;
 		errors |= W->h_counters.error_bits;
+	}
+	if (!W->h_cache_invalid.empty())
+	{
+		// BodyManager::ValidateContactCacheForAllBodies: the flags only live for one update
+		uint32_t n = (uint32_t)W->h_cache_invalid.size();
+		if (!grow(rt, W->d_cache_invalid, W->cache_invalid_capacity, n, false)) return -1;
+		rt.upload(W->d_cache_invalid, W->h_cache_invalid.data(), n);
+		sync_dworld(W);
+		{ KValidateContactCache k; k.w = W->d; k.slots = W->d_cache_invalid; rt.launch(k, n); }
+		W->h_cache_invalid.clear();
 	}
 	if (rt.profiling) { rt.sync(); rt.prof_collect(); }
 	if (stats != nullptr)

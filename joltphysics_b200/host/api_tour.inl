@@ -78,6 +78,19 @@ static void sApiTourMutate(PhysicsSystem &inSystem, std::vector<BodyID> &ioBodie
 		bi.RemoveBody(flying->GetID());          // leaves at once, comes back with the velocity reset
 		bi.AddBody(flying->GetID(), EActivation::Activate);
 	}
+	else if (inPhase == 4)
+	{
+		// SetMotionType / SetObjectLayer / SetShape / InvalidateContactCache on bodies that are in the world
+		bi.SetMotionType(ioBodies[1], EMotionType::Kinematic, EActivation::Activate);      // a resting dynamic body becomes a kinematic mover
+		bi.SetLinearVelocity(ioBodies[1], Vec3(0.8f, 0.0f, 0.0f));
+		bi.SetMotionType(ioBodies[2], EMotionType::Static, EActivation::DontActivate);     // ... a static obstacle
+		bi.SetMotionType(ioBodies[4], EMotionType::Kinematic, EActivation::Activate);
+		bi.SetMotionType(ioBodies[4], EMotionType::Dynamic, EActivation::Activate);        // and back: mass properties survive
+		bi.SetObjectLayer(ioBodies[7], Layers::NON_MOVING);                                // no longer collides with the floor: falls through
+		bi.SetShape(ioBodies[9], B2J_NEW_SHAPE(SphereShape, 0.45f), true, EActivation::Activate);
+		bi.SetShape(ioBodies[10], B2J_NEW_SHAPE(BoxShape, Vec3(0.6f, 0.2f, 0.4f)), false, EActivation::Activate);
+		bi.InvalidateContactCache(ioBodies[11]);
+	}
 }
 
 // Queries after the tour: number of bodies, active bodies (as a sorted id list written to outIDs), returns the active count

@@ -22,17 +22,27 @@ namespace {
 // CUDA device of the scenes (one process per GPU: bench.py sets B2J_DEVICE = LOCAL_RANK)
 int scene_device() { const char *e = getenv("B2J_DEVICE"); return e != nullptr? atoi(e) : 0; }
 
-namespace Layers { constexpr ObjectLayer NON_MOVING = 0, MOVING = 1, NUM_LAYERS = 2; }
-namespace BPLayers { constexpr BroadPhaseLayer NON_MOVING(0), MOVING(1); constexpr uint NUM_LAYERS = 2; }
+// the layer configuration of the reference harness (oracle/ref_harness.cpp): NON_MOVING, MOVING and DEBRIS (a second moving layer in
+// its own broadphase tree that collides with the other two but not with itself)
+namespace Layers { constexpr ObjectLayer NON_MOVING = 0, MOVING = 1, DEBRIS = 2, NUM_LAYERS = 3; }
+namespace BPLayers { constexpr BroadPhaseLayer NON_MOVING(0), MOVING(1), DEBRIS(2); constexpr uint NUM_LAYERS = 3; }
 
-class OLPairFilter final : public ObjectLayerPairFilter { public: bool ShouldCollide(ObjectLayer a, ObjectLayer b) const override { return a == Layers::MOVING || b == Layers::MOVING; } };
+class OLPairFilter final : public ObjectLayerPairFilter
+{
+public:
+	bool ShouldCollide(ObjectLayer a, ObjectLayer b) const override { if (a == Layers::MOVING || b == Layers::MOVING) return true; return a != b; }
+};
 class BPLInterface final : public BroadPhaseLayerInterface
 {
 public:
 	uint GetNumBroadPhaseLayers() const override { return BPLayers::NUM_LAYERS; }
-	BroadPhaseLayer GetBroadPhaseLayer(ObjectLayer l) const override { return l == Layers::NON_MOVING? BPLayers::NON_MOVING : BPLayers::MOVING; }
+	BroadPhaseLayer GetBroadPhaseLayer(ObjectLayer l) const override { return l == Layers::NON_MOVING? BPLayers::NON_MOVING : (l == Layers::MOVING? BPLayers::MOVING : BPLayers::DEBRIS); }
 };
-class OVBPFilter final : public ObjectVsBroadPhaseLayerFilter { public: bool ShouldCollide(ObjectLayer a, BroadPhaseLayer b) const override { return a == Layers::MOVING || b == BPLayers::MOVING; } };
+class OVBPFilter final : public ObjectVsBroadPhaseLayerFilter
+{
+public:
+	bool ShouldCollide(ObjectLayer a, BroadPhaseLayer b) const override { if (a == Layers::MOVING || b == BPLayers::MOVING) return true; return (a == Layers::NON_MOVING) != (b == BPLayers::NON_MOVING); }
+};
 
 struct Scene
 {
@@ -243,6 +253,25 @@ bool scene_max_bodies(Scene &s, int num_bodies)
 #define B2J_NEW_SHAPE(Type, ...) std::make_shared<Type>(__VA_ARGS__)
 #include "api_tour.inl"
 
+static Quat sRandomQuat(std::mt19937 &r) { return random_quat(r); }
+#include "feature_scenes.inl"
+
+// the feature scenes of feature_scenes.inl (same user code as the reference harness compiles); the hull is the first cooked hull of
+// bench_assets/pile_hulls.b2js
+bool scene_feature(Scene &s, int variant, const char *assets_dir)
+{
+	std::vector<ShapeRef> hulls;
+	if (!load_cooked_shapes((std::string(assets_dir) + "/pile_hulls.b2js").c_str(), hulls, s.error) || hulls.empty()) return false;
+	if (!s.system.Init(1024, 0, 8192, 4096, s.bpl, s.ovbp, s.olp, Layers::NUM_LAYERS, scene_device())) return false;
+	uint32_t num_dynamic = 0;
+	sFeatureCreate(s.system, variant, hulls[0], num_dynamic);
+	// (dynamic_bodies = every non static body in creation order, for the e2e getters)
+	BodyIDVector all;
+	s.system.GetBodies(all);
+	for (const BodyID &id : all) if (s.system.GetBodyInterface().GetMotionType(id) != EMotionType::Static) s.dynamic_bodies.push_back(id);
+	return s.dynamic_bodies.size() == num_dynamic;
+}
+
 bool scene_api_tour(Scene &s)
 {
 	if (!s.system.Init(1024, 0, 4096, 1024, s.bpl, s.ovbp, s.olp, Layers::NUM_LAYERS, scene_device())) return false;
@@ -270,6 +299,7 @@ B2JF_API void *b2jf_scene_create(const char *name, int p0, int p1, const char *a
 	else if (n == "pile") ok = scene_pile(*s, p0 > 0? p0 : 1000, p1 > 0? p1 : 15, assets_dir);
 	else if (n == "max_bodies") ok = scene_max_bodies(*s, p0 > 0? p0 : 10000);
 	else if (n == "api_tour") ok = scene_api_tour(*s);
+	else if (n == "feature") ok = scene_feature(*s, p0, assets_dir);
 	else s->error = "unknown scene";
 	if (!ok)
 	{

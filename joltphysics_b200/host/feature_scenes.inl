@@ -1,0 +1,175 @@
+// feature_scenes.inl -- the same USER code compiled twice (like api_tour.inl): against the reference (oracle/ref_harness.cpp) and
+// against the facade (facade_capi.cpp). Small worlds that exercise every motion type / body flag / per body override the step has a
+// branch for; patterns follow UnitTests/Physics/SensorTests.cpp (sensor vs dynamic / kinematic / static), PhysicsTests.cpp
+// (kinematic movers, allowed DOFs, gyroscopic force, solver step overrides, broadphase layers), ContactListenerTests.cpp (manifold
+// reduction off).
+// The including file provides: B2J_SHAPE_REF, B2J_NEW_SHAPE(Type, args...), Layers::{NON_MOVING, MOVING, DEBRIS}, sRandomQuat(std::mt19937 &).
+// Variants: 0 kinematic, 1 sensor, 2 dof_plane2d, 3 gyroscopic, 4 step_overrides, 5 no_manifold_reduction, 6 two_moving_layers,
+// 7 kinematic_vs_nondynamic, 8 zoo (all of them in one world). inHull: a cooked convex hull (cooking is host side and out of scope).
+
+static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHAPE_REF &inHull, uint32_t &outNumDynamic)
+{
+	BodyInterface &bi = inSystem.GetBodyInterface();
+	std::mt19937 random(4321 + inVariant);
+	bool zoo = inVariant == 8;
+	auto add = [&](BodyCreationSettings &s, EActivation a = EActivation::Activate) { BodyID id = bi.CreateAndAddBody(s, a); if (s.mMotionType != EMotionType::Static) outNumDynamic++; return id; };
+	{
+		BodyCreationSettings floor(B2J_NEW_SHAPE(BoxShape, Vec3(100.0f, 1.0f, 100.0f), 0.0f), RVec3(0.0f, -1.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		floor.mFriction = 0.6f;
+		add(floor, EActivation::DontActivate);
+	}
+	B2J_SHAPE_REF box = B2J_NEW_SHAPE(BoxShape, Vec3::sReplicate(0.5f)), sphere = B2J_NEW_SHAPE(SphereShape, 0.5f), capsule = B2J_NEW_SHAPE(CapsuleShape, 0.5f, 0.3f), slab = B2J_NEW_SHAPE(BoxShape, Vec3(2.0f, 0.25f, 2.0f));
+	B2J_SHAPE_REF hull = inHull;
+	float x0 = 0.0f; // every feature gets its own strip of the floor along x when they share a world (zoo)
+
+	if (inVariant == 0 || zoo)
+	{
+		// kinematic mover pushing a stack + a rotating kinematic platform carrying dynamic bodies + a kinematic that is put to sleep
+		for (int i = 0; i < 9; ++i)
+		{
+			BodyCreationSettings s(i % 2? box : hull, RVec3(x0 + 2.0f + 1.05f * float(i % 3), 0.55f + 1.1f * float(i / 3), 0.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			add(s);
+		}
+		BodyCreationSettings pusher(B2J_NEW_SHAPE(BoxShape, Vec3(0.5f, 1.5f, 2.0f)), RVec3(x0 - 0.5f, 1.6f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
+		pusher.mLinearVelocity = Vec3(2.5f, 0.0f, 0.0f);
+		pusher.mAngularVelocity = Vec3(0.0f, 0.4f, 0.0f);
+		add(pusher);
+		BodyCreationSettings platform(slab, RVec3(x0 + 2.0f, 3.0f, 6.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
+		platform.mAngularVelocity = Vec3(0.0f, 1.0f, 0.3f);
+		platform.mLinearVelocity = Vec3(0.0f, 0.5f, 0.0f);
+		platform.mFriction = 0.9f;
+		add(platform);
+		for (int i = 0; i < 4; ++i)
+		{
+			BodyCreationSettings s(i % 2? sphere : capsule, RVec3(x0 + 1.0f + float(i), 3.9f, 6.0f + 0.5f * float(i % 2)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			add(s);
+		}
+		BodyCreationSettings idle(box, RVec3(x0 + 8.0f, 0.5f, -4.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING); // zero velocity: goes to sleep
+		add(idle);
+		x0 += 20.0f;
+	}
+	if (inVariant == 1 || zoo)
+	{
+		// sensors: static sensor volume, kinematic sensor sweeping through dynamic / static / sleeping bodies, dynamic sensor (falls through
+		// everything but still reports), kinematic non sensor vs static sensor (the kinematic vs sensor pair rule, Body.inl:41-44)
+		BodyCreationSettings trigger(B2J_NEW_SHAPE(BoxShape, Vec3(3.0f, 1.0f, 3.0f)), RVec3(x0, 2.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::MOVING);
+		trigger.mIsSensor = true;
+		add(trigger, EActivation::DontActivate);
+		for (int i = 0; i < 6; ++i)
+		{
+			BodyCreationSettings s(i % 3 == 0? sphere : (i % 3 == 1? box : hull), RVec3(x0 - 2.0f + 0.9f * float(i), 3.6f + 0.3f * float(i % 2), -1.0f + 0.7f * float(i % 3)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			add(s);
+		}
+		BodyCreationSettings sweeper(B2J_NEW_SHAPE(BoxShape, Vec3(0.5f, 2.0f, 3.0f)), RVec3(x0 - 6.0f, 1.5f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
+		sweeper.mIsSensor = true;
+		sweeper.mLinearVelocity = Vec3(3.0f, 0.0f, 0.0f);
+		add(sweeper);
+		BodyCreationSettings kin(box, RVec3(x0 + 6.0f, 2.0f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING); // non sensor kinematic entering the static sensor
+		kin.mLinearVelocity = Vec3(-2.0f, 0.0f, 0.0f);
+		add(kin);
+		BodyCreationSettings ghost(sphere, RVec3(x0, 5.5f, 2.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING); // dynamic sensor
+		ghost.mIsSensor = true;
+		add(ghost);
+		BodyCreationSettings sleeper(box, RVec3(x0 - 3.5f, 0.5f, 1.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING); // asleep: a sensor must not wake it
+		add(sleeper, EActivation::DontActivate);
+		x0 += 20.0f;
+	}
+	if (inVariant == 2 || zoo)
+	{
+		// EAllowedDOFs: a 2D stack (Plane2D), translation only and rotation only bodies hit by free bodies
+		for (int i = 0; i < 8; ++i)
+		{
+			BodyCreationSettings s(i % 2? box : capsule, RVec3(x0 + 0.6f * float(i % 2), 0.6f + 1.15f * float(i), 0.0f), Quat(0.0f, 0.0f, 0.1f * float(i), 1.0f).Normalized(), EMotionType::Dynamic, Layers::MOVING);
+			s.mAllowedDOFs = EAllowedDOFs::Plane2D;
+			add(s);
+		}
+		BodyCreationSettings slider(box, RVec3(x0 + 4.0f, 0.5f, 0.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		slider.mAllowedDOFs = EAllowedDOFs::TranslationX | EAllowedDOFs::TranslationZ;
+		slider.mLinearVelocity = Vec3(-1.0f, 0.0f, 0.5f);
+		add(slider);
+		BodyCreationSettings spinner(B2J_NEW_SHAPE(BoxShape, Vec3(1.5f, 0.2f, 0.3f)), RVec3(x0 + 4.0f, 2.5f, 3.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		spinner.mAllowedDOFs = EAllowedDOFs::RotationY | EAllowedDOFs::RotationX;
+		spinner.mAngularVelocity = Vec3(0.0f, 3.0f, 0.0f);
+		spinner.mGravityFactor = 0.0f;
+		add(spinner);
+		for (int i = 0; i < 3; ++i)
+		{
+			BodyCreationSettings s(sphere, RVec3(x0 + 3.0f + float(i), 4.0f + float(i), 3.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			add(s);
+		}
+		x0 += 20.0f;
+	}
+	if (inVariant == 3 || zoo)
+	{
+		// gyroscopic force (MotionProperties::ApplyGyroscopicForceInternal): tumbling T-handle like boxes, some of them landing on the floor
+		for (int i = 0; i < 6; ++i)
+		{
+			BodyCreationSettings s(B2J_NEW_SHAPE(BoxShape, Vec3(0.2f + 0.1f * float(i % 3), 0.5f, 1.0f)), RVec3(x0 + 2.0f * float(i), 1.2f + 0.8f * float(i % 3), 0.0f), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			s.mApplyGyroscopicForce = true;
+			s.mAngularVelocity = Vec3(0.1f, 8.0f + float(i), 0.2f);
+			s.mAngularDamping = 0.0f;
+			s.mMaxAngularVelocity = 60.0f;
+			s.mGravityFactor = i < 3? 0.0f : 1.0f;
+			add(s);
+		}
+		x0 += 20.0f;
+	}
+	if (inVariant == 4 || zoo)
+	{
+		// per body solver step overrides (CalculateSolverSteps.h): islands with 0 / higher / lower iteration counts than the default
+		for (int stack = 0; stack < 4; ++stack)
+			for (int i = 0; i < 4; ++i)
+			{
+				BodyCreationSettings s(i % 2? box : sphere, RVec3(x0 + 3.0f * float(stack), 0.55f + 1.05f * float(i), 0.1f * float(i)), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+				if (i == 1)
+				{
+					s.mNumVelocityStepsOverride = stack == 0? 0 : (stack == 1? 14 : (stack == 2? 3 : 1));
+					s.mNumPositionStepsOverride = stack == 0? 0 : (stack == 1? 5 : (stack == 2? 1 : 4));
+				}
+				if (stack == 2 && i != 1) { s.mNumVelocityStepsOverride = 2; s.mNumPositionStepsOverride = 1; } // every body overrides: the default does not apply
+				if (stack == 3 && i == 2) s.mNumVelocityStepsOverride = 12;
+				add(s);
+			}
+		x0 += 20.0f;
+	}
+	if (inVariant == 5 || zoo)
+	{
+		// manifold reduction switched off per body: hull / box / capsule resting on each other and on a reduced body
+		for (int i = 0; i < 8; ++i)
+		{
+			BodyCreationSettings s(i % 4 == 0? hull : (i % 4 == 1? box : (i % 4 == 2? capsule : slab)), RVec3(x0 + 0.3f * float(i % 3), 0.7f + 1.2f * float(i), 0.2f * float(i % 2)), i % 4 == 3? Quat::sIdentity() : sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			s.mUseManifoldReduction = (i % 3) == 0;
+			add(s);
+		}
+		x0 += 20.0f;
+	}
+	if (inVariant == 6 || zoo)
+	{
+		// two moving broadphase layers: DEBRIS lives in its own tree, collides with MOVING and NON_MOVING but not with itself
+		for (int i = 0; i < 12; ++i)
+		{
+			BodyCreationSettings s(i % 2? box : sphere, RVec3(x0 + 0.8f * float(i % 4), 0.6f + 1.1f * float(i / 4), 0.7f * float(i % 2)), Quat::sIdentity(), EMotionType::Dynamic, (i % 3) == 0? Layers::MOVING : Layers::DEBRIS);
+			add(s);
+		}
+		BodyCreationSettings kin(slab, RVec3(x0 + 1.0f, 5.0f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::DEBRIS);
+		kin.mLinearVelocity = Vec3(0.0f, -1.0f, 0.0f);
+		add(kin);
+		x0 += 20.0f;
+	}
+	if (inVariant == 7 || zoo)
+	{
+		// CollideKinematicVsNonDynamic: a kinematic body with the flag reports contacts against static and kinematic bodies
+		BodyCreationSettings probe(box, RVec3(x0, 0.45f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
+		probe.mCollideKinematicVsNonDynamic = true;
+		probe.mLinearVelocity = Vec3(1.5f, 0.0f, 0.0f);
+		add(probe);
+		BodyCreationSettings other(box, RVec3(x0 + 1.5f, 0.5f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING); // no flag
+		other.mLinearVelocity = Vec3(0.2f, 0.0f, 0.0f);
+		add(other);
+		BodyCreationSettings pillar(B2J_NEW_SHAPE(BoxShape, Vec3(0.5f, 2.0f, 0.5f)), RVec3(x0 + 4.0f, 2.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::MOVING);
+		add(pillar, EActivation::DontActivate);
+		BodyCreationSettings dyn(sphere, RVec3(x0 + 2.6f, 0.5f, 0.3f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		add(dyn);
+		x0 += 20.0f;
+	}
+}

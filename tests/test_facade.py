@@ -50,6 +50,44 @@ def test_facade_scene_matches_reference_gpu(gpu_api, ref_available, scene, p0, p
     _check(flib, scene, p0, p1, steps=25)
 
 
+def _check_feature(flib, variant, steps):
+    """feature_scenes.inl is ONE piece of user code compiled against the reference and against the facade: every motion type, body flag
+    and per body override travels BodyCreationSettings -> facade -> C ABI -> device and must give the world the reference builds
+    (creation state incl. DOF restricted mass properties) and the evolution the reference computes."""
+    ref = R.RefWorld("feature", variant)
+    fs = F.FacadeScene(flib, "feature", variant, 0)
+    assert fs.num_bodies == ref.num_bodies and fs.num_dynamic == ref.num_dynamic
+    rs, gs = ref.state(), fs.world.state()
+    assert np.array_equal(rs.pos, gs.pos) and np.array_equal(rs.rot, gs.rot) and np.array_equal(rs.lin, gs.lin) and np.array_equal(rs.ang, gs.ang)
+    assert np.array_equal(rs.bounds, gs.bounds)
+    assert np.array_equal(np.sort(ref.active_bodies()), np.sort(fs.world.active_bodies()))
+    for step in range(steps):
+        ref.step()
+        err, _ = fs.update()
+        assert err == 0
+        if step % 20 == 19:
+            worst = R.compare_states(ref.state(), fs.world.state())
+            for k in ("pos", "rot", "lin", "ang"):
+                assert worst[k] <= 1.0, (step, k, worst)
+            assert np.array_equal(ref.state().active_index != 0xffffffff, fs.world.state().active_index != 0xffffffff), f"step {step}: active flags"
+    fs.close()
+    ref.close()
+
+
+FEATURE_IDS = ["kinematic", "sensor", "dof_plane2d", "gyroscopic", "step_overrides", "no_manifold_reduction", "two_moving_layers", "kinematic_vs_nondynamic", "zoo"]
+
+
+@pytest.mark.parametrize("variant", range(9), ids=FEATURE_IDS)
+def test_facade_feature_scene_matches_reference_hostsim(hostsim_facade, variant):
+    _check_feature(hostsim_facade, variant, 120)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", range(9), ids=FEATURE_IDS)
+def test_facade_feature_scene_matches_reference_gpu(gpu_api, ref_available, variant):
+    _check_feature(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api), variant, 200)
+
+
 def _check_api_tour(flib):
     """The BodyInterface / PhysicsSystem surface of SURVEY 8(b) beyond scene building (joltphysics_b200/host/api_tour.inl): the same
     user code runs against the reference and against the facade; states and query results must agree after every phase."""
@@ -68,7 +106,7 @@ def _check_api_tour(flib):
         assert rf == gf, (tag, "IsAdded && IsActive", bin(rf), bin(gf))
 
     compare("created")
-    for phase, steps in ((0, 10), (1, 25), (2, 40), (3, 30)):
+    for phase, steps in ((0, 10), (1, 25), (2, 40), (3, 30), (4, 60)):
         if phase:
             ref.mutate(phase)
             fs.mutate(phase)
