@@ -219,6 +219,12 @@ int b2j_bodies_get_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2
  * SURVEY 8f-1 (a world of mostly sleeping bodies mirrors only what moved). Copies up to cap ids + state rows (same order) and
  * returns the number of simulated bodies (may exceed cap). */
 uint32_t b2j_bodies_get_stepped_state(b2j_world *w, uint32_t cap, uint32_t *ids, const b2j_body_state *out);
+/* Page locks a caller owned host buffer (cudaHostRegister) so that b2j_bodies_get_state / b2j_batch_get_state / b2j_*_add_force_torque
+ * copy between it and the device directly instead of through the library's pinned staging buffer. Buffers from cudaHostAlloc /
+ * torch.Tensor.pin_memory need no registration. Unregister before freeing the buffer. Returns 0, or -1 (the buffer then simply
+ * stays pageable: still correct, one host memcpy slower). */
+int b2j_host_buffer_register(void *ptr, size_t bytes);
+int b2j_host_buffer_unregister(void *ptr);
 /* BodyInterface::SetPositionAndRotation / SetLinearAndAngularVelocity; NULL members are left untouched. */
 int b2j_bodies_set_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_state *in);
 /* BodyInterface::AddForce / AddTorque (:220-226): accumulate into mForce / mTorque (either may be NULL). */

@@ -700,7 +700,11 @@ public:
 	const NarrowPhaseQuery &GetNarrowPhaseQuery() const { return mNarrowPhaseQuery; }
 	const NarrowPhaseQuery &GetNarrowPhaseQueryNoLock() const { return mNarrowPhaseQuery; }
 	const BroadPhaseQuery &GetBroadPhaseQuery() const { return mBroadPhaseQuery; }
-	~PhysicsSystem() { if (mWorld) b2j_world_destroy(mWorld); }
+	~PhysicsSystem()
+	{
+		if (mStateRegistered) { b2j_host_buffer_unregister(mPos.data()); b2j_host_buffer_unregister(mRot.data()); b2j_host_buffer_unregister(mLin.data()); b2j_host_buffer_unregister(mAng.data()); b2j_host_buffer_unregister(mActiveIndex.data()); }
+		if (mWorld) b2j_world_destroy(mWorld);
+	}
 	PhysicsSystem(const PhysicsSystem &) = delete;
 
 	// PhysicsSystem::Init (PhysicsSystem.h:59). inNumBodyMutexes is ignored (the GPU owns the bodies during a step).
@@ -798,7 +802,7 @@ public:
 		// simulated unless something else changed the device state since the last download
 		++mStateGeneration; // Body::Sync picks the new state up on first access
 		for (uint8 &f : mSlotFlags) f &= 1;
-		mStatePending = true;
+		MarkStateStale();
 		ReplayEvents();
 		return EPhysicsUpdateError(r);
 	}
@@ -831,50 +835,115 @@ private:
 		return id;
 	}
 
-	// Full download of every body slot (first use, after RestoreState, after API calls that changed device state behind the arrays)
-	void DownloadState()
-	{
-		uint32 n = (uint32)mBodies.size();
-		mStatePending = false; mNeedFullDownload = false;
-		if (n == 0) return;
-		mPos.resize(3 * n); mRot.resize(4 * n); mLin.resize(3 * n); mAng.resize(3 * n); mActiveIndex.resize(n);
-		b2j_body_state st;
-		memset(&st, 0, sizeof(st));
-		st.position = mPos.data(); st.rotation = mRot.data(); st.linear_velocity = mLin.data(); st.angular_velocity = mAng.data(); st.active_index = mActiveIndex.data();
-		b2j_bodies_get_state(mWorld, nullptr, n, &st);
-		++mStateGeneration; // Body::Sync picks the new state up on first access
-		for (uint8 &f : mSlotFlags) f &= 1; // the arrays are current for every body in the world
-		mLastDownloadCount = n;
-	}
+	// ---- host mirror of the body state ------------------------------------------------------------------------------------
+	// Flat arrays by body index, refreshed LAZILY on first use after a step and only as far as needed:
+	//  * nothing but the step touched the device state since the arrays were filled -> only the rows of the bodies the step simulated
+	//    are fetched and scattered (b2j_bodies_get_stepped_state; SURVEY 8f-1 incremental download),
+	//  * otherwise (first use, API mutations, RestoreState, most bodies moving) a bulk copy of only the ARRAYS the caller reads: a
+	//    loop that reads a million positions per step moves 12 bytes per body, not the 56 of the whole state.
+	// The arrays are page locked (b2j_host_buffer_register) so the bulk copies are direct DMA.
+	enum : uint32 { cStatePos = 1, cStateRot = 2, cStateLin = 4, cStateAng = 8, cStateActive = 16, cStateAll = 31 };
 
-	// The state getters call this first. After a step only the bodies the step simulated changed on the device: when nothing else
-	// touched the device state since the arrays were filled, just those rows are fetched (b2j_bodies_get_stepped_state) and scattered
-	// into the arrays -- a world of mostly sleeping bodies mirrors only what moved (incremental download).
-	void EnsureState() const { if (mStatePending) const_cast<PhysicsSystem *>(this)->RefreshState(); }
-	void RefreshState()
+	void ResizeStateArrays(uint32 n)
 	{
-		uint32 n = (uint32)mBodies.size();
-		if (mNeedFullDownload || mActiveIndex.size() != n) { --mStateGeneration; DownloadState(); return; } // (the generation was advanced by Update)
-		mStatePending = false;
-		uint32 count = b2j_bodies_get_stepped_state(mWorld, 0, nullptr, nullptr);
-		mLastDownloadCount = count;
-		if (count == 0) return;
-		if (count > n / 2) { --mStateGeneration; DownloadState(); return; } // most bodies moved: one bulk copy is cheaper than a scatter
-		mSteppedIDs.resize(count); mSteppedPos.resize(3 * (size_t)count); mSteppedRot.resize(4 * (size_t)count); mSteppedLin.resize(3 * (size_t)count); mSteppedAng.resize(3 * (size_t)count); mSteppedActive.resize(count);
-		b2j_body_state st;
-		memset(&st, 0, sizeof(st));
-		st.position = mSteppedPos.data(); st.rotation = mSteppedRot.data(); st.linear_velocity = mSteppedLin.data(); st.angular_velocity = mSteppedAng.data(); st.active_index = mSteppedActive.data();
-		b2j_bodies_get_stepped_state(mWorld, count, mSteppedIDs.data(), &st);
-		for (uint32 k = 0; k < count; ++k)
+		if (mActiveIndex.size() == n) return;
+		void *old[5] = { mPos.data(), mRot.data(), mLin.data(), mAng.data(), mActiveIndex.data() };
+		if (mStateRegistered) for (void *p : old) if (p != nullptr) b2j_host_buffer_unregister(p);
+		mPos.resize(3 * (size_t)n); mRot.resize(4 * (size_t)n); mLin.resize(3 * (size_t)n); mAng.resize(3 * (size_t)n); mActiveIndex.resize(n);
+		mStateRegistered = n >= 4096; // (small worlds: the staging path is as fast and registration is not free)
+		if (mStateRegistered)
 		{
-			size_t i = mSteppedIDs[k] & 0x7fffffu;
-			if (i >= n) continue;
-			memcpy(&mPos[3 * i], &mSteppedPos[3 * (size_t)k], 12); memcpy(&mRot[4 * i], &mSteppedRot[4 * (size_t)k], 16);
-			memcpy(&mLin[3 * i], &mSteppedLin[3 * (size_t)k], 12); memcpy(&mAng[3 * i], &mSteppedAng[3 * (size_t)k], 12);
-			mActiveIndex[i] = mSteppedActive[k];
+			b2j_host_buffer_register(mPos.data(), mPos.size() * 4); b2j_host_buffer_register(mRot.data(), mRot.size() * 4);
+			b2j_host_buffer_register(mLin.data(), mLin.size() * 4); b2j_host_buffer_register(mAng.data(), mAng.size() * 4);
+			b2j_host_buffer_register(mActiveIndex.data(), mActiveIndex.size() * 4);
 		}
 	}
 
+	// bulk copy of the given arrays for every body slot
+	void DownloadArrays(uint32 inMask)
+	{
+		uint32 n = (uint32)mBodies.size();
+		if (n == 0 || inMask == 0) return;
+		ResizeStateArrays(n);
+		b2j_body_state st;
+		memset(&st, 0, sizeof(st));
+		if (inMask & cStatePos) st.position = mPos.data();
+		if (inMask & cStateRot) st.rotation = mRot.data();
+		if (inMask & cStateLin) st.linear_velocity = mLin.data();
+		if (inMask & cStateAng) st.angular_velocity = mAng.data();
+		if (inMask & cStateActive) st.active_index = mActiveIndex.data();
+		b2j_bodies_get_state(mWorld, nullptr, n, &st);
+		mLastDownloadCount = n;
+	}
+
+	// Eager full refresh (RestoreState): every array, new generation for the Body mirrors
+	void DownloadState()
+	{
+		DownloadArrays(cStateAll);
+		mStaleMask = 0; mBehindMask = 0;
+		++mStateGeneration; // Body::Sync picks the new state up on first access
+		for (uint8 &f : mSlotFlags) f &= 1; // the arrays are current for every body in the world
+	}
+
+	// The state getters call this first with the arrays they read.
+	// mStaleMask: arrays that do not reflect the last step yet. mBehindMask: arrays that missed more than the last step (never filled,
+	// not read for a while, or the device state was changed through the API): only a bulk copy makes them current. An array that is
+	// exactly one step behind can be brought up to date from the rows of the bodies that step simulated.
+	void EnsureState(uint32 inMask = cStateAll) const { if (mStaleMask & inMask) const_cast<PhysicsSystem *>(this)->RefreshState(inMask); }
+	void RefreshState(uint32 inMask)
+	{
+		uint32 n = (uint32)mBodies.size();
+		if (mActiveIndex.size() != n) mBehindMask = cStateAll;
+		uint32 need = inMask & mStaleMask;
+		uint32 bulk = need & mBehindMask;
+		uint32 one_behind = mStaleMask & ~mBehindMask;   // every array the incremental rows can update, asked for or not
+		if (need & ~mBehindMask)
+		{
+			uint32 count = b2j_bodies_get_stepped_state(mWorld, 0, nullptr, nullptr);
+			if (count <= n / 2)
+			{
+				mLastDownloadCount = count;
+				if (count > 0)
+				{
+					mSteppedIDs.resize(count); mSteppedPos.resize(3 * (size_t)count); mSteppedRot.resize(4 * (size_t)count); mSteppedLin.resize(3 * (size_t)count); mSteppedAng.resize(3 * (size_t)count); mSteppedActive.resize(count);
+					b2j_body_state st;
+					memset(&st, 0, sizeof(st));
+					if (one_behind & cStatePos) st.position = mSteppedPos.data();
+					if (one_behind & cStateRot) st.rotation = mSteppedRot.data();
+					if (one_behind & cStateLin) st.linear_velocity = mSteppedLin.data();
+					if (one_behind & cStateAng) st.angular_velocity = mSteppedAng.data();
+					if (one_behind & cStateActive) st.active_index = mSteppedActive.data();
+					b2j_bodies_get_stepped_state(mWorld, count, mSteppedIDs.data(), &st);
+					for (uint32 k = 0; k < count; ++k)
+					{
+						size_t i = mSteppedIDs[k] & 0x7fffffu;
+						if (i >= n) continue;
+						if (one_behind & cStatePos) memcpy(&mPos[3 * i], &mSteppedPos[3 * (size_t)k], 12);
+						if (one_behind & cStateRot) memcpy(&mRot[4 * i], &mSteppedRot[4 * (size_t)k], 16);
+						if (one_behind & cStateLin) memcpy(&mLin[3 * i], &mSteppedLin[3 * (size_t)k], 12);
+						if (one_behind & cStateAng) memcpy(&mAng[3 * i], &mSteppedAng[3 * (size_t)k], 12);
+						if (one_behind & cStateActive) mActiveIndex[i] = mSteppedActive[k];
+					}
+				}
+				mStaleMask &= ~one_behind;
+			}
+			else
+				bulk = need; // most bodies moved: bulk copies (of the arrays that get read) are cheaper than a scatter
+		}
+		if (bulk != 0)
+		{
+			DownloadArrays(bulk);
+			mStaleMask &= ~bulk;
+			mBehindMask &= ~bulk;
+		}
+	}
+	// after a step: everything is stale until read; what was still stale has now missed more than one step
+	void MarkStateStale()
+	{
+		ResizeStateArrays((uint32)mBodies.size());
+		mBehindMask |= mStaleMask;
+		mStaleMask = cStateAll;
+	}
 
 	// current device state of a few bodies straight into their Body mirrors (bodies whose state changed through the interface since
 	// the last Update, e.g. woken / pushed and then removed before the next step)
@@ -969,21 +1038,22 @@ private:
 	std::vector<uint32> mActiveIndex;
 	std::vector<uint32> mSteppedIDs, mSteppedActive;   // scratch of the incremental download
 	std::vector<float> mSteppedPos, mSteppedRot, mSteppedLin, mSteppedAng;
-	bool mStatePending = false;                   // a step ran since the arrays were refreshed
-	bool mNeedFullDownload = true;                // device state changed behind the arrays (API mutation, restore): next refresh is a full download
+	uint32 mStaleMask = 0;                        // arrays (cState*) a step ran over since they were refreshed
+	uint32 mBehindMask = 31;                      // arrays only a bulk copy can make current (see RefreshState)
+	bool mStateRegistered = false;                // the arrays are page locked
 	uint32 mLastDownloadCount = 0;
 	uint32 mStateGeneration = 1;
 	// per body index: full id (or invalid) and flags for the getters' fast path: bit 0 = in the world, bit 1 = the Body mirror is
 	// newer than the downloaded arrays (added / changed through the interface since the last Update)
 	std::vector<uint32> mSlotID;
 	std::vector<uint8> mSlotFlags;
-	bool FastSlot(const BodyID &id, size_t &outIndex) const
+	bool FastSlot(const BodyID &id, size_t &outIndex, uint32 inArrays) const
 	{
-		EnsureState();
+		EnsureState(inArrays);
 		outIndex = id.GetIndex();
 		return outIndex < mSlotID.size() && mSlotID[outIndex] == id.mID && mSlotFlags[outIndex] == 1 && outIndex < mActiveIndex.size();
 	}
-	void MarkMirrorNewer(const BodyID &id) { size_t i = id.GetIndex(); if (i < mSlotFlags.size()) mSlotFlags[i] |= 2; mNeedFullDownload = true; }
+	void MarkMirrorNewer(const BodyID &id) { size_t i = id.GetIndex(); if (i < mSlotFlags.size()) mSlotFlags[i] |= 2; mBehindMask = cStateAll; }
 	std::vector<b2j_contact_event> mContactEvents;
 	std::vector<b2j_activation_event> mActEvents;
 };
@@ -1040,7 +1110,7 @@ inline void Body::Sync() const
 inline RVec3 BodyInterface::GetCenterOfMassPosition(const BodyID &id) const
 {
 	size_t i;
-	if (mSystem->FastSlot(id, i)) return Vec3(mSystem->mPos[3 * i], mSystem->mPos[3 * i + 1], mSystem->mPos[3 * i + 2]);
+	if (mSystem->FastSlot(id, i, PhysicsSystem::cStatePos)) return Vec3(mSystem->mPos[3 * i], mSystem->mPos[3 * i + 1], mSystem->mPos[3 * i + 2]);
 	const Body *b = TryGet(id);
 	return b? b->GetCenterOfMassPosition() : RVec3::sZero();
 }
@@ -1048,7 +1118,7 @@ inline RVec3 BodyInterface::GetCenterOfMassPosition(const BodyID &id) const
 inline Quat BodyInterface::GetRotation(const BodyID &id) const
 {
 	size_t i;
-	if (mSystem->FastSlot(id, i)) return Quat(mSystem->mRot[4 * i], mSystem->mRot[4 * i + 1], mSystem->mRot[4 * i + 2], mSystem->mRot[4 * i + 3]);
+	if (mSystem->FastSlot(id, i, PhysicsSystem::cStateRot)) return Quat(mSystem->mRot[4 * i], mSystem->mRot[4 * i + 1], mSystem->mRot[4 * i + 2], mSystem->mRot[4 * i + 3]);
 	const Body *b = TryGet(id);
 	return b? b->GetRotation() : Quat::sIdentity();
 }
@@ -1056,7 +1126,7 @@ inline Quat BodyInterface::GetRotation(const BodyID &id) const
 inline Vec3 BodyInterface::GetLinearVelocity(const BodyID &id) const
 {
 	size_t i;
-	if (mSystem->FastSlot(id, i)) return Vec3(mSystem->mLin[3 * i], mSystem->mLin[3 * i + 1], mSystem->mLin[3 * i + 2]);
+	if (mSystem->FastSlot(id, i, PhysicsSystem::cStateLin)) return Vec3(mSystem->mLin[3 * i], mSystem->mLin[3 * i + 1], mSystem->mLin[3 * i + 2]);
 	const Body *b = TryGet(id);
 	return b? b->GetLinearVelocity() : Vec3::sZero();
 }
@@ -1064,7 +1134,7 @@ inline Vec3 BodyInterface::GetLinearVelocity(const BodyID &id) const
 inline Vec3 BodyInterface::GetAngularVelocity(const BodyID &id) const
 {
 	size_t i;
-	if (mSystem->FastSlot(id, i)) return Vec3(mSystem->mAng[3 * i], mSystem->mAng[3 * i + 1], mSystem->mAng[3 * i + 2]);
+	if (mSystem->FastSlot(id, i, PhysicsSystem::cStateAng)) return Vec3(mSystem->mAng[3 * i], mSystem->mAng[3 * i + 1], mSystem->mAng[3 * i + 2]);
 	const Body *b = TryGet(id);
 	return b? b->GetAngularVelocity() : Vec3::sZero();
 }
@@ -1171,7 +1241,7 @@ inline void BodyInterface::AddBodies(const BodyID *inBodies, int inNumber, EActi
 		d.linear_velocity[0] = b->mLinearVelocity.x; d.linear_velocity[1] = b->mLinearVelocity.y; d.linear_velocity[2] = b->mLinearVelocity.z;
 		d.angular_velocity[0] = b->mAngularVelocity.x; d.angular_velocity[1] = b->mAngularVelocity.y; d.angular_velocity[2] = b->mAngularVelocity.z;
 		sys.mPendingAdd.push_back(d);
-		sys.mNeedFullDownload = true; // (a body added asleep is not among the bodies the next step simulates)
+		sys.mBehindMask = PhysicsSystem::cStateAll; // (a body added asleep is not among the bodies the next step simulates)
 		if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static)
 		{
 			sys.mPendingActivate.push_back(b->mID.mID);
@@ -1224,7 +1294,7 @@ inline void BodyInterface::RemoveBodies(BodyID *ioBodies, int inNumber)
 	for (Body *b : bodies) if (b->mSyncGeneration != sys.mStateGeneration || (sys.mSlotFlags[b->mID.GetIndex()] & 2)) stale.push_back(b->mID.mID);
 	if (!stale.empty()) sys.RefreshBodies(stale);
 	b2j_bodies_remove(World(), ids.data(), (uint32)ids.size());
-	sys.mNeedFullDownload = true;
+	sys.mBehindMask = PhysicsSystem::cStateAll;
 	for (Body *b : bodies)
 	{
 		b->Sync(); // the Body keeps the pose it left the world with
@@ -1313,7 +1383,7 @@ inline void BodyInterface::SetActive(const BodyID &id, bool inActive)
 	uint32 bid = id.mID;
 	Flush();
 	if (inActive) b2j_bodies_activate(World(), &bid, 1); else b2j_bodies_deactivate(World(), &bid, 1);
-	mSystem->mNeedFullDownload = true;
+	mSystem->mBehindMask = PhysicsSystem::cStateAll;
 	b->Sync();
 	mSystem->MarkMirrorNewer(id);
 	b->mActive = inActive;

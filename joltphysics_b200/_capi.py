@@ -140,6 +140,8 @@ PROTOTYPES = {
     "b2j_set_active_list": (C.c_int, [_VP, _U32P, C.c_uint32]),
     "b2j_bodies_get_state": (C.c_int, [_VP, _U32P, C.c_uint32, C.POINTER(BodyState)]),
     "b2j_bodies_set_state": (C.c_int, [_VP, _U32P, C.c_uint32, C.POINTER(BodyState)]),
+    "b2j_host_buffer_register": (C.c_int, [_VP, C.c_size_t]),
+    "b2j_host_buffer_unregister": (C.c_int, [_VP]),
     "b2j_bodies_get_stepped_state": (C.c_uint32, [_VP, C.c_uint32, _U32P, C.POINTER(BodyState)]),
     "b2j_bodies_set_params": (C.c_int, [_VP, _U32P, C.c_uint32, C.c_void_p]),
     "b2j_bodies_set_info": (C.c_int, [_VP, _U32P, C.c_uint32, C.c_void_p]),

@@ -1879,6 +1879,31 @@ int b2j_bodies_get_state(b2j_world *W, const uint32_t *ids, uint32_t n, const b2
 	return rt.check("b2j_bodies_get_state")? 0 : -1;
 }
 
+int b2j_host_buffer_register(void *ptr, size_t bytes)
+{
+#ifndef B2J_HOSTSIM
+	if (ptr == nullptr || bytes == 0) return -1;
+	cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) { cudaGetLastError(); last_error() = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return -1; }
+	return 0;
+#else
+	(void)ptr; (void)bytes;
+	return 0;
+#endif
+}
+
+int b2j_host_buffer_unregister(void *ptr)
+{
+#ifndef B2J_HOSTSIM
+	if (ptr == nullptr) return -1;
+	cudaError_t e = cudaHostUnregister(ptr);
+	if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+#else
+	(void)ptr;
+#endif
+	return 0;
+}
+
 uint32_t b2j_bodies_get_stepped_state(b2j_world *W, uint32_t cap, uint32_t *ids, const b2j_body_state *out)
 {
 	B2J_DEVICE_GUARD(W);
