@@ -80,6 +80,23 @@ template <class K, class S> __global__ void __launch_bounds__(256) run_kernel_wa
 		__syncwarp();
 	}
 }
+// One WARP per work item, all 32 lanes inside the item body (run_warp): S = the warp's big scratch block, H = its small hand-over area,
+// both in shared memory.
+template <class K, class S, class H> __global__ void __launch_bounds__(256) run_kernel_warp_coop(const K k, const uint32_t *n_ptr, uint32_t cap)
+{
+	extern __shared__ __align__(16) unsigned char b2j_smem[];
+	uint32_t n = *n_ptr;
+	if (n > cap) n = cap;
+	uint32_t warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+	uint32_t slot = blockIdx.x * warps_per_block + warp_in_block;
+	S *scratch = reinterpret_cast<S *>(b2j_smem) + warp_in_block;
+	H *hand = reinterpret_cast<H *>(b2j_smem + (size_t)warps_per_block * sizeof(S)) + warp_in_block;
+	for (uint32_t i = slot; i < n; i += gridDim.x * warps_per_block)
+	{
+		k.run_warp(i, slot, *scratch, *hand);
+		__syncwarp();
+	}
+}
 // One THREAD per work item with a private S scratch block in LOCAL memory (EPA: 2 KB or 21 KB per lane): local memory is word
 // interleaved across the lanes of a warp, so lockstep lanes touching the same field coalesce, and it is L1/L2 cached. Every lane
 // calls run() every round (valid = the lane has an item): the item bodies keep the warp in lockstep with votes (warp_any<true>),
@@ -388,6 +405,36 @@ struct Runtime
 		static S scratch;
 		uint32_t n = *n_ptr < cap? *n_ptr : cap;
 		for (uint32_t i = 0; i < n; ++i) k.run(i, true, 0, scratch);
+#endif
+	}
+
+	// KW = the warp cooperative form of the item body (the device runs it), KS = its serial statement (what the host simulation runs)
+	template <class KW, class KS, class S, class H> void launch_warp_coop(const KW &kw, const KS &ks, const uint32_t *n_ptr, uint32_t cap, uint32_t num_slots, uint32_t warps_per_block = 4)
+	{
+		if (cap == 0) return;
+		++launches;
+#ifndef B2J_HOSTSIM
+		(void)ks;
+		static_assert(sizeof(S) % 16 == 0, "scratch blocks are packed back to back");
+		size_t smem = (size_t)warps_per_block * (sizeof(S) + sizeof(H));
+		bool &configured = func_configured[(const void *)run_kernel_warp_coop<KW, S, H>];
+		if (!configured)
+		{
+			cudaFuncSetAttribute(run_kernel_warp_coop<KW, S, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			configured = true;
+		}
+		uint32_t g = num_slots / warps_per_block;
+		if (g < 1) g = 1;
+		uint32_t gn = (cap + warps_per_block - 1) / warps_per_block;
+		if (gn < g) g = gn;
+		if (profiling) prof_begin(profile_category<KS>());
+		run_kernel_warp_coop<KW, S, H><<<g, 32 * warps_per_block, smem, stream>>>(kw, n_ptr, cap);
+		if (profiling) prof_end();
+#else
+		(void)num_slots; (void)kw; (void)warps_per_block;
+		static S scratch;
+		uint32_t n = *n_ptr < cap? *n_ptr : cap;
+		for (uint32_t i = 0; i < n; ++i) ks.run(i, true, 0, scratch);
 #endif
 	}
 

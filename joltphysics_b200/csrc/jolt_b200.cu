@@ -860,7 +860,23 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		{ KCollideEpa<EpaStorageSmall, true> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageSmall, true>, EpaStorageSmall>(k, &d.counters->num_epa, W->nc.max_epa, 4); }
 		{ KCollideEpa<EpaStorageFull, false> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageFull, false>, EpaStorageFull>(k, W->nc.num_epa_overflow, W->nc.max_epa, 2); }
 		{ KFinishPairs k; k.w = d; k.c = W->nc; rt.launch_dev(k, W->nc.num_epa_results, nullptr, W->nc.max_epa); }
-		if (W->d_mesh_scratch != nullptr) { KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch; rt.launch_warp_smem<KCollideMesh, EpaStorageFull>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch); }
+		if (W->d_mesh_scratch != nullptr)
+		{
+			// all 32 lanes work on the triangles of one (convex, mesh) pair; the serial form is what tests/hostsim runs (and B2J_MESH_SERIAL=1)
+			KCollideMesh k; k.w = d; k.c = W->nc; k.mesh_scratch = W->d_mesh_scratch;
+#ifndef B2J_HOSTSIM
+			static const bool serial = getenv("B2J_MESH_SERIAL") != nullptr && atoi(getenv("B2J_MESH_SERIAL")) != 0;
+			if (serial)
+				rt.launch_warp_smem<KCollideMesh, EpaStorageFull>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch);
+			else
+			{
+				KCollideMeshWarp kw; kw.w = d; kw.c = W->nc; kw.mesh_scratch = W->d_mesh_scratch;
+				rt.launch_warp_coop<KCollideMeshWarp, KCollideMesh, EpaStorageFull, MeshWarpShared>(kw, k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch);
+			}
+#else
+			rt.launch_warp_smem<KCollideMesh, EpaStorageFull>(k, &d.counters->num_collide_mesh, d.max_body_pairs, W->nc.num_scratch);
+#endif
+		}
 		if (!read_counters(W)) return false;
 		uint32_t woken = W->h_counters.num_woken;
 		if (W->h_counters.num_collide_convex > longest_queue) longest_queue = W->h_counters.num_collide_convex;
@@ -2696,7 +2712,7 @@ template <class F> static bool batch_for_each_group(b2j_batch *b, const F &fn)
 	auto work = [&](size_t g, bool worker)
 	{
 #ifndef B2J_HOSTSIM
-		if (worker) cudaSetDevice(b->groups[g]->rt.device);
+		cudaSetDevice(b->groups[g]->rt.device); // (the calling thread too: an earlier call may have left another device of the batch current)
 #endif
 		(void)worker;
 		if (!fn(g)) { ok[g] = 0; err[g] = last_error(); }
