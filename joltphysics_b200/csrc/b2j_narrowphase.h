@@ -533,16 +533,24 @@ struct KCollideConvex
 	}
 };
 
-// ---- KCollideEpa: EPA for the deep pairs; `slot` selects the scratch block -------------------------------------------
-// Storage = EpaStorageSmall: first tier, reads c.epa, overflowing items go to c.epa_overflow; EpaStorageFull: second tier over c.epa_overflow
-template <class Storage, bool kFirstTier> struct KCollideEpa
+// ---- KCollideEpa: EPA for the deep pairs, in two capacity tiers ------------------------------------------------------------
+// EPA's cost is decided by the pair: most finish within a dozen support points on a hull of < 24 triangles; box faces resting on box
+// faces under convex radius rounding build hulls of > 64 triangles and often need > 48 points, and a few per thousand run to the
+// reference's limit of 128 points (~124 iterations). A run that exceeds the PHYSICAL capacity of its tier is discarded and repeated
+// from its GJK simplex by the next tier (results only ever come from a run that fitted):
+//   tier 0: EpaStorageSmall (2 KB per lane),  thread per pair, lanes in lockstep, reads c.epa -> overflow to c.epa_overflow
+//   tier 1: EpaStorageFull  (21 KB per lane), the same over c.epa_overflow; can never overflow
+// Measured and NOT kept: a point capped middle tier followed by one pair per warp with the hull in SHARED memory (lane 0
+// working, kLockstep = false). A 124 iteration pair takes 0.85 ms there instead of ~6 ms, but only 8 pairs per SM run at a time
+// (3.5 M pairs/s against 33 M pairs/s for the lockstep form): -0.6 ms on the 1 M body pile, +0.14 ms on the single Pyramid, +5 ms
+// per step on a batch at impact unless the route is chosen per step on the device.
+template <class Storage, int kTier, bool kLockstep> struct KCollideEpa
 {
 	DWorld w; NarrowCtx c;
-	// Thread per pair: all 32 lanes of the warp call run() together (valid = lane has a pair), the GJK / EPA loops run in lockstep
+	// kLockstep: all 32 lanes of the warp call run() together (valid = lane has a pair), the GJK / EPA loops run in lockstep
 	B2J_D void run(uint32_t k, bool valid, uint32_t slot, Storage &storage) const
 	{
 		(void)slot;
-		constexpr bool kLockstep = true;
 		EpaScratch scratch = storage.view();
 		bool alive = valid;
 		CollideItem item = {};
@@ -554,7 +562,7 @@ template <class Storage, bool kFirstTier> struct KCollideEpa
 		float max_separation_distance = 0.0f;
 		if (alive)
 		{
-			const EpaItem &ei = kFirstTier? c.epa[k] : c.epa_overflow[k];
+			const EpaItem &ei = kTier == 1? c.epa_overflow[k] : c.epa[k];
 			item = ei.c;
 			s = convex_pair_setup(w, item);
 			const ShapeDesc &s1 = w.shapes[w.info[item.b1].shape], &s2 = w.shapes[w.info[item.b2].shape];
@@ -574,7 +582,7 @@ template <class Storage, bool kFirstTier> struct KCollideEpa
 			alive = false;
 		if (!pen_depth_step_epa<kLockstep>(scratch, simplex, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2, alive))
 		{
-			if (kFirstTier && alive && scratch.overflow)
+			if (kTier == 0 && alive && scratch.overflow)
 				c.epa_overflow[atomic_add(c.num_epa_overflow, 1u)].c = item;
 			return;
 		}
@@ -585,6 +593,8 @@ template <class Storage, bool kFirstTier> struct KCollideEpa
 		r.max_separation_distance = max_separation_distance;
 	}
 };
+using KCollideEpaSmall = KCollideEpa<EpaStorageSmall, 0, true>;
+using KCollideEpaFull = KCollideEpa<EpaStorageFull, 1, true>;
 
 struct KFinishPairs
 {

@@ -39,6 +39,7 @@ B2J_D uint32_t atomic_exch(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v; r
 B2J_D unsigned long long atomic_cas64(unsigned long long *p, unsigned long long cmp, unsigned long long v) { unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 B2J_D uint32_t volatile_load(const uint32_t *p) { return *p; }
 B2J_D void prefetch_l2(const void *) { }
+B2J_D void grid_dependency_sync() { }
 B2J_D void atomic_add_matched(uint32_t *arr, uint32_t index, uint32_t v) { arr[index] += v; }
 template <bool kLockstep> B2J_D bool warp_any(bool p) { return p; }
 B2J_D void mem_fence() { }
@@ -56,6 +57,14 @@ B2J_D uint32_t atomic_exch(uint32_t *p, uint32_t v) { return atomicExch(p, v); }
 B2J_D unsigned long long atomic_cas64(unsigned long long *p, unsigned long long cmp, unsigned long long v) { return atomicCAS(p, cmp, v); }
 B2J_D uint32_t volatile_load(const uint32_t *p) { return *(const volatile uint32_t *)p; }
 B2J_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// Programmatic dependent launch (Runtime::launch_pdl): everything before this call may run while the previous kernel of the stream is
+// still running, so it may only touch data that kernel does not write. wait = the previous kernel has completed and its writes are
+// visible; launch_dependents = the next kernel of the stream may start its own prologue now.
+B2J_D void grid_dependency_sync()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 // arr[index] += v where many lanes of a warp are likely to hit the same index: lanes with equal index are combined into one atomic
 B2J_D void atomic_add_matched(uint32_t *arr, uint32_t index, uint32_t v)
 {

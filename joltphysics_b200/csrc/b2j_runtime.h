@@ -127,8 +127,7 @@ template <class K> inline int profile_category()
 		char *dm = abi::__cxa_demangle(typeid(K).name(), nullptr, nullptr, &status);
 		std::string name = dm != nullptr? dm : typeid(K).name();
 		free(dm);
-		size_t p = name.rfind("::");
-		if (p != std::string::npos) name = name.substr(p + 2);
+		for (size_t p = name.find("b2j::"); p != std::string::npos; p = name.find("b2j::")) name.erase(p, 5);
 		std::lock_guard<std::mutex> lock(profile_mutex());
 		profile_names().push_back(name);
 		return (int)profile_names().size() - 1;
@@ -332,6 +331,25 @@ struct Runtime
 		if (profiling) prof_end();
 #else
 		for (uint32_t i = 0; i < n; ++i) k(i);
+#endif
+	}
+	// Programmatic dependent launch: the kernel may start while the previous kernel of the stream is still running; K calls
+	// grid_dependency_sync() before it touches anything that kernel writes (chains of small dependent launches: the solver phases)
+	template <class K> void launch_pdl(const K &k, uint32_t n)
+	{
+		if (n == 0) return;
+#ifndef B2J_HOSTSIM
+		if (profiling) { K serial = k; serial.pdl = 0; launch(serial, n); return; } // (per kernel event timing wants the kernels apart)
+		++launches;
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(grid_for(n, 128)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr; cfg.numAttrs = 1;
+		cudaLaunchKernelEx(&cfg, run_kernel<K>, k, n);
+#else
+		launch(k, n);
 #endif
 	}
 	template <class K, int THREADS, int MINB> void launch_cfg(const K &k, uint32_t n)

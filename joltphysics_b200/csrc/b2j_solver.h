@@ -1136,15 +1136,34 @@ B2J_D void store_applied_impulses(const DWorld &w, uint32_t manifold, int n, F4 
 }
 
 // sWarmStartConstraint for solve positions [begin, begin + n)
+// What a velocity solve thread may do BEFORE the previous phase's kernel has finished (programmatic dependent launch): the header is
+// written by the setup kernel; prefetches only pull lines into L2 (the coherence point), they read no values.
+B2J_D void solve_prologue_prefetch(const DWorld &w, const Constraints &c, const ConstraintHeader &hdr, uint32_t i, bool warm_start)
+{
+	uint32_t meta = hdr.meta;
+	int n = (int)(meta & 7);
+	for (int pl = CP_NORMAL; pl < CP_FR0; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
+	if (meta & META_LINEAR_FRICTION) for (int pl = CP_FR0; pl < CP_PT0; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
+	for (int pl = CP_PT0; pl < CP_PT0 + 4 * n; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
+	(void)warm_start;
+	if (((meta >> 3) & 3) != B2J_MOTION_STATIC) { prefetch_l2(&w.linear_velocity[hdr.b1]); prefetch_l2(&w.angular_velocity[hdr.b1]); }
+	if (((meta >> 5) & 3) != B2J_MOTION_STATIC) { prefetch_l2(&w.linear_velocity[hdr.b2]); prefetch_l2(&w.angular_velocity[hdr.b2]); }
+}
+
 struct KWarmStart
 {
-	DWorld w; Constraints c; uint32_t begin; float ratio;
+	DWorld w; Constraints c; uint32_t begin; float ratio; uint32_t pdl = 0;
 	B2J_D void operator()(uint32_t k) const
 	{
 		uint32_t i = begin + k;
 		ConstraintHeader hdr = c.hdr[i];
 		uint32_t meta = hdr.meta;
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+		if (pdl)
+		{
+			solve_prologue_prefetch(w, c, hdr, i, true);
+			grid_dependency_sync();
+		}
 		VelState s;
 		load_vel_state(w, hdr.b1, hdr.b2, type1, type2, s);
 		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);
@@ -1160,17 +1179,24 @@ struct KWarmStart
 // sSolveVelocityConstraint; iteration = 0 based velocity step index (constraints of islands with fewer steps skip).
 struct KSolveVelocity
 {
-	DWorld w; Constraints c; uint32_t begin; uint32_t iteration; uint32_t prefetch;
+	DWorld w; Constraints c; uint32_t begin; uint32_t iteration; uint32_t prefetch; uint32_t pdl = 0;
 	B2J_D void operator()(uint32_t k) const
 	{
 		uint32_t i = begin + k;
 		ConstraintHeader hdr = c.hdr[i];
 		uint32_t meta = hdr.meta;
-		if (iteration >= ((meta >> 8) & 0xff))
+		const bool skip = iteration >= ((meta >> 8) & 0xff);
+		if (pdl)
+		{
+			// (every thread synchronises before it leaves, also the ones whose island is done: the kernel after this one relies on it)
+			if (!skip) solve_prologue_prefetch(w, c, hdr, i, false);
+			grid_dependency_sync();
+		}
+		if (skip)
 			return;
 		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
-		if (prefetch)
+		if (prefetch && !pdl)
 		{
 			// L2 prefetch of every plane of the constraint right after the header: -5 % on the per phase launches (measured); register
 			// capped builds (more warps per SM) stay slower even with it (6.0 / 7.2 / 8.2 ms vs 5.0 ms at 128 / 96 / 80 registers)
@@ -1242,13 +1268,27 @@ struct KIntegrate
 // ---- position solve (sSolvePositionConstraint) ------------------------------------------------------------------------
 struct KSolvePosition
 {
-	DWorld w; Constraints c; uint32_t begin; uint32_t iteration;
+	DWorld w; Constraints c; uint32_t begin; uint32_t iteration; uint32_t pdl = 0;
 	B2J_D void operator()(uint32_t k) const
 	{
 		uint32_t i = begin + k;
 		ConstraintHeader hdr = c.hdr[i];
 		uint32_t meta = hdr.meta;
-		if (iteration >= ((meta >> 16) & 0xff))
+		const bool skip = iteration >= ((meta >> 16) & 0xff);
+		if (pdl)
+		{
+			if (!skip)
+			{
+				int np = (int)(meta & 7);
+				prefetch_l2(&c.cp[(size_t)CP_NORMAL * c.capacity + i]);
+				prefetch_l2(&c.cp[(size_t)CP_MASS * c.capacity + i]);
+				for (int pl = CP_LP0; pl < CP_LP0 + 2 * np; ++pl) prefetch_l2(&c.cp[(size_t)pl * c.capacity + i]);
+				prefetch_l2(&w.position[hdr.b1]); prefetch_l2(&w.rotation[hdr.b1]);
+				prefetch_l2(&w.position[hdr.b2]); prefetch_l2(&w.rotation[hdr.b2]);
+			}
+			grid_dependency_sync();
+		}
+		if (skip)
 			return;
 		int n = (int)(meta & 7);
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;

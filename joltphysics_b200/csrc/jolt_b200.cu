@@ -726,6 +726,17 @@ bool read_counters(b2j_world *W)
 	return W->rt.check("read_counters");
 }
 
+// B2J_SOLVE_PDL=0 turns programmatic dependent launch of the per phase solver kernels off (A/B measurements)
+static bool solve_pdl_enabled()
+{
+#ifndef B2J_HOSTSIM
+	static const bool on = getenv("B2J_SOLVE_PDL") == nullptr || atoi(getenv("B2J_SOLVE_PDL")) != 0;
+	return on;
+#else
+	return false;
+#endif
+}
+
 // Stages of a step as NVTX ranges (the reference marks the same stages with JPH_PROFILE scopes, PhysicsSystem.cpp), and with
 // B2J_TRACE_STEP=1 their wall clock with the stream drained after every stage (diagnostics for small worlds, where the step is a chain
 // of ~60 dependent launches: which stage pays how much launch / round trip latency). The trace prints to stderr.
@@ -856,9 +867,9 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		}
 		{ KCollideConvex k; k.w = d; k.c = W->nc; rt.launch_dev_lockstep(k, &d.counters->num_collide_convex, nullptr, d.max_body_pairs); }
 		// deep pairs: thread per pair, lanes in lockstep, EPA scratch in (lane interleaved, L1/L2 cached) local memory. Small tier first
-		// (2 KB per lane covers ~88% of the pairs, 16 warps per SM); the pairs that overflow it re-run on full size storage (21 KB per lane).
-		{ KCollideEpa<EpaStorageSmall, true> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageSmall, true>, EpaStorageSmall>(k, &d.counters->num_epa, W->nc.max_epa, 4); }
-		{ KCollideEpa<EpaStorageFull, false> k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpa<EpaStorageFull, false>, EpaStorageFull>(k, W->nc.num_epa_overflow, W->nc.max_epa, 2); }
+		// (2 KB per lane, 16 warps per SM); the pairs that overflow it re-run on full size storage (21 KB per lane).
+		{ KCollideEpaSmall k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpaSmall, EpaStorageSmall>(k, &d.counters->num_epa, W->nc.max_epa, 4); }
+		{ KCollideEpaFull k; k.w = d; k.c = W->nc; rt.launch_lane_local<KCollideEpaFull, EpaStorageFull>(k, W->nc.num_epa_overflow, W->nc.max_epa, 2); }
 		{ KFinishPairs k; k.w = d; k.c = W->nc; rt.launch_dev(k, W->nc.num_epa_results, nullptr, W->nc.max_epa); }
 		if (W->d_mesh_scratch != nullptr)
 		{
@@ -878,6 +889,18 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 #endif
 		}
 		if (!read_counters(W)) return false;
+#ifndef B2J_HOSTSIM
+		{
+			// B2J_TRACE_EPA=1: how many pairs each EPA tier received this round (diagnostics, stderr)
+			static const bool trace_epa = getenv("B2J_TRACE_EPA") != nullptr;
+			if (trace_epa)
+			{
+				uint32_t n1 = 0, nr = 0;
+				rt.download(&n1, W->nc.num_epa_overflow, 1); rt.download(&nr, W->nc.num_epa_results, 1);
+				fprintf(stderr, "[b2j epa] collide %u gjk->epa %u full tier %u results %u\n", W->h_counters.num_collide_convex, W->h_counters.num_epa, n1, nr);
+			}
+		}
+#endif
 		uint32_t woken = W->h_counters.num_woken;
 		if (W->h_counters.num_collide_convex > longest_queue) longest_queue = W->h_counters.num_collide_convex;
 		if (W->h_counters.num_epa > W->nc.max_epa) { last_error() = "EPA queue overflow"; return false; }
@@ -1094,7 +1117,8 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			for (uint32_t p = 0; p < num_phases; ++p)
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
-				KWarmStart k; k.w = d; k.c = sc.con; k.begin = begin; k.ratio = warm_start_ratio; rt.launch(k, n);
+				KWarmStart k; k.w = d; k.c = sc.con; k.begin = begin; k.ratio = warm_start_ratio;
+				if (solve_pdl_enabled()) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
 			}
 			for (uint32_t it = 0; it < vsteps; ++it)
 				for (uint32_t p = 0; p < num_phases; ++p)
@@ -1102,7 +1126,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 					uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
 					KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
 					k.prefetch = 1;
-					rt.launch(k, n);
+					if (solve_pdl_enabled()) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
 				}
 		}
 		solved_by_phase_launches = phase_launches;
@@ -1167,7 +1191,8 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			for (uint32_t p = 0; p < num_phases; ++p)
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
-				KSolvePosition k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it; rt.launch(k, n);
+				KSolvePosition k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
+				if (solve_pdl_enabled()) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
 			}
 	}
 
@@ -2613,6 +2638,18 @@ template <class T> static void replicate(Runtime &rt, T *dst, const T *src, uint
 
 extern "C" {
 
+// How many groups (device worlds with their own stream and host thread) the worlds of one device are spread over: groups of at least
+// 128 worlds, at most 8. Measured with Pyramid worlds: at 4096 worlds 149 ms per step with 4 groups, 130 with 8, 125 with 16 (but the
+// 16 group launches are small enough to lose 20% of their own HBM efficiency); at 512 worlds (the share of one GPU of eight) 11.9 ms
+// with 1 group, 10.7 with 2, 9.9 with 4, 10.6 with 8. B2J_BATCH_GROUPS overrides.
+static uint32_t batch_default_groups(uint32_t n_worlds)
+{
+	uint32_t K = n_worlds / 128;
+	if (K > 8) K = 8;
+	if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
+	return K;
+}
+
 static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t max_body_pairs_per_world, uint32_t max_contact_constraints_per_world, int device)
 {
 	B2J_DEVICE_GUARD(P);
@@ -2777,9 +2814,7 @@ b2j_batch *b2j_batch_create_on_devices(b2j_world *P, uint32_t n_worlds, const in
 		for (uint32_t dv = 0; dv < n_devices; ++dv)
 		{
 			uint32_t nd = n_worlds / n_devices + (dv < n_worlds % n_devices? 1 : 0);
-			uint32_t K = nd / 256;
-			if (K > 8) K = 8;
-			if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
+			uint32_t K = batch_default_groups(nd);
 			if (K < 1) K = 1;
 			if (K > nd) K = nd;
 			for (uint32_t g = 0; g < K; ++g)
@@ -2807,11 +2842,7 @@ b2j_batch *b2j_batch_create_on_devices(b2j_world *P, uint32_t n_worlds, const in
 #endif
 		return b;
 	}
-	// groups of about 256 worlds, at most 8 (measured at 4096 worlds: 149 ms per step with 4 groups, 130 with 8, 125 with 16 -- but the
-	// 16 group launches are small enough to lose 20% of their own HBM efficiency, so 8 it is); B2J_BATCH_GROUPS overrides
-	uint32_t K = n_worlds / 256;
-	if (K > 8) K = 8;
-	if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
+	uint32_t K = batch_default_groups(n_worlds);
 #ifdef B2J_HOSTSIM
 	K = 1; // the host simulation is single threaded
 #endif
