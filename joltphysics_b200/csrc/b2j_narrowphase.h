@@ -47,6 +47,7 @@ struct NarrowCtx
 	uint32_t collide_order_n;    // entries of collide_order (queue positions past it are processed in queue order)
 	EpaItem *epa_overflow;       // deep pairs that did not fit the small EPA tier (re-run on full size storage)
 	uint32_t *num_epa_overflow;  // device counter
+	uint32_t *epa_hist;          // B2J_TRACE_EPA only (else null): histogram of the support points the full tier's runs ended with
 	EpaResult *epa_results;      // GJK / EPA output; supporting faces / clipping / manifold run in KFinishPairs
 	uint32_t *num_epa_results;   // device counter
 	uint32_t num_scratch;        // number of warps the scratch hungry kernels (EPA, mesh) may use
@@ -580,7 +581,10 @@ template <class Storage, int kTier, bool kLockstep> struct KCollideEpa
 		GjkSimplex simplex;
 		if (pen_depth_step_gjk<kLockstep>(simplex, a_excl, a_excl.convex_radius + s.max_separation_distance, b_excl, b_excl.s.convex_radius, 1.0e-4f, penetration_axis, point1, point2, alive) != PEN_INDETERMINATE)
 			alive = false;
-		if (!pen_depth_step_epa<kLockstep>(scratch, simplex, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2, alive))
+		bool epa_ok = pen_depth_step_epa<kLockstep>(scratch, simplex, a_incl, b_incl, 1.0e-4f /* cDefaultPenetrationTolerance */, penetration_axis, point1, point2, alive);
+		if (kTier == 1 && c.epa_hist != nullptr && alive)
+			atomic_add(&c.epa_hist[scratch.num_points < 129? scratch.num_points : 129], 1u);
+		if (!epa_ok)
 		{
 			if (kTier == 0 && alive && scratch.overflow)
 				c.epa_overflow[atomic_add(c.num_epa_overflow, 1u)].c = item;

@@ -895,9 +895,14 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			static const bool trace_epa = getenv("B2J_TRACE_EPA") != nullptr;
 			if (trace_epa)
 			{
-				uint32_t n1 = 0, nr = 0;
+				uint32_t n1 = 0, nr = 0, hist[130];
 				rt.download(&n1, W->nc.num_epa_overflow, 1); rt.download(&nr, W->nc.num_epa_results, 1);
-				fprintf(stderr, "[b2j epa] collide %u gjk->epa %u full tier %u results %u\n", W->h_counters.num_collide_convex, W->h_counters.num_epa, n1, nr);
+				rt.download(hist, W->nc.epa_hist, 130);
+				rt.memset_(W->nc.epa_hist, 0, 130 * 4);
+				uint32_t over[5] = { 0, 0, 0, 0, 0 };
+				const uint32_t limits[5] = { 32, 48, 64, 96, 127 };
+				for (uint32_t p = 0; p < 130; ++p) for (int j = 0; j < 5; ++j) if (p > limits[j]) over[j] += hist[p];
+				fprintf(stderr, "[b2j epa] collide %u gjk->epa %u full tier %u (points > 32: %u, > 48: %u, > 64: %u, > 96: %u, 128: %u) results %u\n", W->h_counters.num_collide_convex, W->h_counters.num_epa, n1, over[0], over[1], over[2], over[3], over[4], nr);
 			}
 		}
 #endif
@@ -1414,6 +1419,7 @@ b2j_world *b2j_world_create(const b2j_world_desc *desc)
 	nc.epa = rt.alloc<EpaItem>(nc.max_epa, false);
 	nc.epa_overflow = rt.alloc<EpaItem>(nc.max_epa, false);
 	nc.num_epa_overflow = rt.alloc<uint32_t>(1);
+	nc.epa_hist = getenv("B2J_TRACE_EPA") != nullptr? rt.alloc<uint32_t>(130) : nullptr;
 	nc.epa_results = rt.alloc<EpaResult>(nc.max_epa, false);
 	nc.num_epa_results = rt.alloc<uint32_t>(1);
 #ifndef B2J_HOSTSIM
@@ -1513,7 +1519,7 @@ void b2j_world_destroy(b2j_world *W)
 		rt.free_(W->cache[i].pairs); rt.free_(W->cache[i].manifolds); rt.free_(W->cache[i].pair_table); rt.free_(W->cache[i].num_pairs); rt.free_(W->cache[i].num_manifolds);
 	}
 	NarrowCtx &nc = W->nc;
-	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
+	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); if (nc.epa_hist != nullptr) rt.free_(nc.epa_hist); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(W->events_buf);
 	rt.free_(W->d_mesh_scratch); rt.free_(W->d_cache_invalid);
 	for (int i = 0; i < 2; ++i) { rt.free_(W->d_collide_keys[i]); rt.free_(W->d_collide_vals[i]); }
