@@ -583,7 +583,7 @@ struct b2j_world
 	std::vector<uint32_t> h_cache_invalid;  // slots whose InvalidateContactCache flag is set (cleared after the next step, BodyManager::mBodiesCacheInvalid)
 	uint32_t *d_cache_invalid = nullptr; uint32_t cache_invalid_capacity = 0;
 	const uint32_t *stepped_list = nullptr; uint32_t stepped_count = 0; // body slots the last step simulated (b2j_bodies_get_stepped_state)
-	uint32_t last_collide_convex = 0;      // longest convex pair queue of the previous step (sizes this step's queue ordering)
+	uint32_t last_collide_convex = 0;      // longest convex pair queue of the previous steps, halved per step (sizes this step's queue ordering)
 #ifndef B2J_HOSTSIM
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 #endif
@@ -923,6 +923,9 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	uint32_t M = W->h_counters.num_constraints < d.max_constraints? W->h_counters.num_constraints : d.max_constraints;
 	uint32_t num_pairs = W->h_counters.num_pairs < d.max_body_pairs? W->h_counters.num_pairs : d.max_body_pairs;
 	W->last_num_pairs = num_pairs;
+	// (decaying maximum: the queue of a scene at impact alternates between long and short from step to step, and a queue that outgrows the
+	// capacity derived from this number is only partly ordered)
+	if (longest_queue < W->last_collide_convex / 2) longest_queue = W->last_collide_convex / 2;
 	W->last_collide_convex = longest_queue < d.max_body_pairs? longest_queue : d.max_body_pairs;
 	uint32_t na = W->num_active;
 
