@@ -155,6 +155,15 @@ int32_t b2j_shape_box(b2j_world *w, const float half_extent[3], float convex_rad
 int32_t b2j_shape_capsule(b2j_world *w, float half_height_of_cylinder, float radius);        /* CapsuleShape */
 int32_t b2j_shape_convex_hull(b2j_world *w, const b2j_hull_desc *hull);                      /* ConvexHullShape */
 int32_t b2j_shape_mesh(b2j_world *w, const b2j_mesh_desc *mesh);                             /* MeshShape (static bodies) */
+/* Decorated convex shapes. `inner` = a sphere / box / capsule / convex hull or one of these two around one.
+ * ScaledShape (Jolt/Physics/Collision/Shape/ScaledShape.cpp:190-204: the scale is handed down to the leaf's support function,
+ * supporting face and bounds): positive scales; uniform for spheres and capsules (SphereShape::IsValidScale) and for an inner
+ * RotatedTranslatedShape with a rotation (no RotateScale). */
+int32_t b2j_shape_scaled(b2j_world *w, int32_t inner, const float scale[3]);
+/* RotatedTranslatedShape (RotatedTranslatedShape.cpp:33-60,183-192): the inner shape rotated by `rotation` (x,y,z,w) about its centre of
+ * mass; the translation only moves the centre of mass, which is where the body's position is anyway: center_of_mass = position +
+ * rotation * inner centre of mass, as the reference computes it (returned by state getters that report the body origin). */
+int32_t b2j_shape_rotated_translated(b2j_world *w, int32_t inner, const float rotation[4], const float center_of_mass[3]);
 
 /* ---- bodies (BodyInterface, Jolt/Physics/Body/BodyInterface.h:39-313) ------------------------------------------ */
 

@@ -98,7 +98,7 @@ inline constexpr EAllowedDOFs operator&(EAllowedDOFs a, EAllowedDOFs b) { return
 enum class EPhysicsUpdateError : uint32 { None = 0, ManifoldCacheFull = 1, BodyPairCacheFull = 2, ContactConstraintsFull = 4 };
 inline EPhysicsUpdateError operator|(EPhysicsUpdateError a, EPhysicsUpdateError b) { return EPhysicsUpdateError(uint32(a) | uint32(b)); }
 enum class EOverrideMassProperties : uint8 { CalculateMassAndInertia, CalculateInertia, MassAndInertiaProvided };
-enum class EShapeSubType : uint8 { Sphere = B2J_SHAPE_SPHERE, Box = B2J_SHAPE_BOX, Capsule = B2J_SHAPE_CAPSULE, ConvexHull = B2J_SHAPE_CONVEX_HULL, Mesh = B2J_SHAPE_MESH };
+enum class EShapeSubType : uint8 { Sphere = B2J_SHAPE_SPHERE, Box = B2J_SHAPE_BOX, Capsule = B2J_SHAPE_CAPSULE, ConvexHull = B2J_SHAPE_CONVEX_HULL, Mesh = B2J_SHAPE_MESH, RotatedTranslated = 64, Scaled = 65 };
 
 class BroadPhaseLayerInterface { public: virtual ~BroadPhaseLayerInterface() = default; virtual uint GetNumBroadPhaseLayers() const = 0; virtual BroadPhaseLayer GetBroadPhaseLayer(ObjectLayer inLayer) const = 0; };
 class ObjectVsBroadPhaseLayerFilter { public: virtual ~ObjectVsBroadPhaseLayerFilter() = default; virtual bool ShouldCollide(ObjectLayer, BroadPhaseLayer) const { return true; } };
@@ -148,6 +148,39 @@ struct MassProperties
 		Vec3 size_sq = inBoxSize * inBoxSize;
 		float s = mMass / 12.0f;
 		SetDiagonal((size_sq.y + size_sq.z) * s, (size_sq.x + size_sq.z) * s, (size_sq.x + size_sq.y) * s);
+	}
+	// MassProperties::Scale (MassProperties.cpp:103-155): what ScaledShape::GetMassProperties applies to the inner shape's properties
+	void Scale(const Vec3 &inScale)
+	{
+		Vec3 diagonal(mInertia[0][0], mInertia[1][1], mInertia[2][2]);
+		Vec3 xyz_sq = Vec3::sReplicate(Vec3::sReplicate(0.5f).Dot(diagonal)) - diagonal;
+		Vec3 xyz_scaled_sq = inScale * inScale * xyz_sq;
+		float i_xx = xyz_scaled_sq.y + xyz_scaled_sq.z, i_yy = xyz_scaled_sq.x + xyz_scaled_sq.z, i_zz = xyz_scaled_sq.x + xyz_scaled_sq.y;
+		float i_xy = inScale.x * inScale.y * mInertia[1][0], i_xz = inScale.x * inScale.z * mInertia[2][0], i_yz = inScale.y * inScale.z * mInertia[2][1]; // mInertia(r, c) = [c][r]
+		mInertia[0][0] = i_xx; mInertia[1][0] = i_xy; mInertia[0][1] = i_xy; mInertia[1][1] = i_yy;
+		mInertia[2][0] = i_xz; mInertia[0][2] = i_xz; mInertia[2][1] = i_yz; mInertia[1][2] = i_yz; mInertia[2][2] = i_zz;
+		float mass_scale = std::fabs(inScale.x * inScale.y * inScale.z);
+		mMass *= mass_scale;
+		for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) mInertia[c][r] *= mass_scale;
+	}
+	// MassProperties::Rotate with Mat44::sRotation(inRotation) (MassProperties.cpp:157-160): R.Multiply3x3(I).Multiply3x3RightTransposed(R)
+	void Rotate(const Quat &inRotation)
+	{
+		// Mat44::sRotation(Quat) (Mat44.inl), columns
+		float x = inRotation.x, y = inRotation.y, z = inRotation.z, w = inRotation.w;
+		float tx = x + x, ty = y + y, tz = z + z;
+		float xx = tx * x, yy = ty * y, zz = tz * z, xy = tx * y, xz = tx * z, xw = tx * w, yz = ty * z, yw = ty * w, zw = tz * w;
+		Vec3 rc[3] = { Vec3((1.0f - yy) - zz, xy + zw, xz - yw), Vec3(xy - zw, (1.0f - zz) - xx, yz + xw), Vec3(xz + yw, yz - xw, (1.0f - xx) - yy) };
+		Vec3 ic[3], tc[3];
+		for (int c = 0; c < 3; ++c) ic[c] = Vec3(mInertia[c][0], mInertia[c][1], mInertia[c][2]);
+		// Multiply3x3: column i = (R.c0 * I[i].x + R.c1 * I[i].y) + R.c2 * I[i].z
+		for (int i = 0; i < 3; ++i) tc[i] = (rc[0] * ic[i].x + rc[1] * ic[i].y) + rc[2] * ic[i].z;
+		// Multiply3x3RightTransposed: column j = (T.c0 * R.c0[j] + T.c1 * R.c1[j]) + T.c2 * R.c2[j]
+		for (int j = 0; j < 3; ++j)
+		{
+			Vec3 col = (tc[0] * rc[0][j] + tc[1] * rc[1][j]) + tc[2] * rc[2][j];
+			mInertia[j][0] = col.x; mInertia[j][1] = col.y; mInertia[j][2] = col.z;
+		}
 	}
 	// MassProperties::ScaleToMass
 	void ScaleToMass(float inMass)
@@ -397,6 +430,61 @@ public:
 		memcpy(d.local_bounds_min, mBoundsMin, 12); memcpy(d.local_bounds_max, mBoundsMax, 12);
 		return b2j_shape_mesh(w, &d);
 	}
+};
+
+// ---- decorated shapes around convex shapes (DecoratedShape.h, ScaledShape.h, RotatedTranslatedShape.h) ------------
+class DecoratedShape : public Shape
+{
+public:
+	explicit DecoratedShape(ShapeRef inInnerShape) : mInnerShape(std::move(inInnerShape)) { }
+	const Shape *GetInnerShape() const { return mInnerShape.get(); }
+protected:
+	ShapeRef mInnerShape;
+};
+
+// ScaledShape(shape, scale): positive scales; spheres / capsules / rotated inner shapes take uniform scales (b2j_shape_scaled)
+class ScaledShape final : public DecoratedShape
+{
+public:
+	ScaledShape(ShapeRef inShape, const Vec3 &inScale) : DecoratedShape(std::move(inShape)), mScale(inScale) { }
+	Vec3 GetScale() const { return mScale; }
+	EShapeSubType GetSubType() const override { return EShapeSubType::Scaled; }
+	Vec3 GetCenterOfMass() const override { return mScale * mInnerShape->GetCenterOfMass(); }                                   // ScaledShape.h:56
+	MassProperties GetMassProperties() const override { MassProperties p = mInnerShape->GetMassProperties(); p.Scale(mScale); return p; } // ScaledShape.cpp:49-54
+	int32_t Upload(b2j_world *w) const override
+	{
+		int32_t inner = mInnerShape->Upload(w);
+		if (inner < 0) return inner;
+		float scale[3] = { mScale.x, mScale.y, mScale.z };
+		return b2j_shape_scaled(w, inner, scale);
+	}
+private:
+	Vec3 mScale;
+};
+
+// RotatedTranslatedShape(position, rotation, shape): the inner shape rotated and moved relative to the body (RotatedTranslatedShape.cpp:50-67)
+class RotatedTranslatedShape final : public DecoratedShape
+{
+public:
+	RotatedTranslatedShape(const Vec3 &inPosition, const Quat &inRotation, ShapeRef inShape) : DecoratedShape(std::move(inShape)), mRotation(inRotation)
+	{
+		mCenterOfMass = inPosition + inRotation * mInnerShape->GetCenterOfMass();
+	}
+	Quat GetRotation() const { return mRotation; }
+	Vec3 GetPosition() const { return mCenterOfMass - mRotation * mInnerShape->GetCenterOfMass(); }
+	EShapeSubType GetSubType() const override { return EShapeSubType::RotatedTranslated; }
+	Vec3 GetCenterOfMass() const override { return mCenterOfMass; }
+	MassProperties GetMassProperties() const override { MassProperties p = mInnerShape->GetMassProperties(); p.Rotate(mRotation); return p; }
+	int32_t Upload(b2j_world *w) const override
+	{
+		int32_t inner = mInnerShape->Upload(w);
+		if (inner < 0) return inner;
+		float rotation[4] = { mRotation.x, mRotation.y, mRotation.z, mRotation.w }, com[3] = { mCenterOfMass.x, mCenterOfMass.y, mCenterOfMass.z };
+		return b2j_shape_rotated_translated(w, inner, rotation, com);
+	}
+private:
+	Quat mRotation;
+	Vec3 mCenterOfMass;
 };
 
 // ---- BodyCreationSettings (same defaults as the reference) ------------------------------------------------------

@@ -319,7 +319,7 @@ B2J_D MeshCollideCtx mesh_collide_ctx(const DWorld &w, const CollideItem &item, 
 {
 	MeshCollideCtx cc;
 	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
-	cc.transform1 = xf(m33_rotation(to_q4(w.rotation[item.b1])), v3_zero());
+	cc.transform1 = shape_transform(s1, xf(m33_rotation(to_q4(w.rotation[item.b1])), v3_zero()));
 	cc.transform2 = xf(m33_rotation(to_q4(w.rotation[item.b2])), x2 + (-x1));
 	cc.max_separation_distance = ((i1.flags | i2.flags) & B2J_BODY_SENSOR)? 0.0f : w.settings.speculative_contact_distance;
 	cc.check_active_edges = w.settings.check_active_edges != 0;

@@ -456,8 +456,8 @@ B2J_D ConvexPairSetup convex_pair_setup(const DWorld &w, const CollideItem &item
 	BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
 	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
 	Q4 q1 = to_q4(w.rotation[item.b1]), q2 = to_q4(w.rotation[item.b2]);
-	s.transform1 = xf(m33_rotation(q1), v3_zero());
-	s.transform2 = xf(m33_rotation(q2), x2 + (-x1)); // GetCenterOfMassTransform().PostTranslated(-offset)
+	s.transform1 = shape_transform(w.shapes[i1.shape], xf(m33_rotation(q1), v3_zero()));
+	s.transform2 = shape_transform(w.shapes[i2.shape], xf(m33_rotation(q2), x2 + (-x1))); // GetCenterOfMassTransform().PostTranslated(-offset)
 	// inverse_transform1 = transform1.InversedRotationTranslation(); transform_2_to_1 = inverse_transform1 * transform2
 	M33 rt = transposed(s.transform1.r);
 	Xf inv1 = xf(rt, -mul(rt, s.transform1.t));

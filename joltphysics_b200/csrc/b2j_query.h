@@ -274,8 +274,25 @@ B2J_D bool ray_mesh(const DWorld &w, const ShapeDesc &s, V3 o, V3 d, float &io_f
 }
 
 // Shape::CastRay in the centre of mass space of the shape: improves io_fraction / out_sub when the ray hits closer
-B2J_D bool ray_shape(const DWorld &w, const ShapeDesc &s, V3 o, V3 d, float &io_fraction, uint32_t &out_sub)
+B2J_D bool ray_shape(const DWorld &w, const ShapeDesc &decorated, V3 o, V3 d, float &io_fraction, uint32_t &out_sub)
 {
+	if (decorated.flags & SHAPE_LOCAL_ROTATION)
+	{
+		// RotatedTranslatedShape::CastRay: inRay.Transformed(Mat44::sRotation(mRotation.Conjugated())) (RotatedTranslatedShape.cpp:127-137)
+		M33 inv = transposed(decorated.local_rot);
+		V3 lo = mul(inv, o);
+		d = mul(inv, o + d) - lo;
+		o = lo;
+	}
+	const bool scaled = decorated.scale.x != 1.0f || decorated.scale.y != 1.0f || decorated.scale.z != 1.0f;
+	if (scaled)
+	{
+		// ScaledShape::CastRay: the ray is scaled by 1 / scale and cast against the UNSCALED inner shape (ScaledShape.cpp:114-119)
+		V3 inv_scale = v3(1.0f / decorated.scale.x, 1.0f / decorated.scale.y, 1.0f / decorated.scale.z);
+		o = inv_scale * o;
+		d = inv_scale * d;
+	}
+	const ShapeDesc &s = scaled? w.shapes[decorated.base_leaf] : decorated;
 	float fraction = FLT_MAX;
 	switch (s.kind)
 	{

@@ -88,6 +88,13 @@ B2J_HD ConvexSupport make_support(const DWorld &w, const ShapeDesc &s, int mode)
 	return c;
 }
 
+// Centre of mass transform of the convex leaf of a (possibly decorated) shape: RotatedTranslatedShape hands
+// inCenterOfMassTransform * Mat44::sRotation(mRotation) down to its inner shape (RotatedTranslatedShape.cpp:73-77,183-192)
+B2J_HD Xf shape_transform(const ShapeDesc &s, const Xf &body)
+{
+	return (s.flags & SHAPE_LOCAL_ROTATION)? mul(body, xf(s.local_rot, v3_zero())) : body;
+}
+
 // TransformedConvexObject (ConvexSupport.h)
 struct TransformedSupport
 {
@@ -190,6 +197,15 @@ B2J_HD int supporting_face(const DWorld &w, const ShapeDesc &s, V3 dir, const Xf
 			const int max_vertices_to_return = 16; // SupportingFace capacity 32 / 2
 			int delta = (num + max_vertices_to_return) / max_vertices_to_return;
 			int n = 0;
+			if (s.flags & SHAPE_SCALED_HULL)
+			{
+				// (the planes in the pool are already inv_scale * normal) transform = inCenterOfMassTransform.PreScaled(inScale), applied to the
+				// unscaled points (ConvexHullShape.cpp:702-719; positive scales only: no winding flip)
+				Xf scaled = xf(m33(s.scale.x * xform.r.c0, s.scale.y * xform.r.c1, s.scale.z * xform.r.c2), xform.t);
+				for (int v = first; v < first + num; v += delta)
+					out[n++] = mul(scaled, to_v3(w.hull_points[s.hull_orig_offset + w.hull_vtx[s.hull_vtx_offset + v]]));
+				return n;
+			}
 			for (int v = first; v < first + num; v += delta)
 				out[n++] = mul(xform, to_v3(w.hull_points[s.hull_point_offset + w.hull_vtx[s.hull_vtx_offset + v]]));
 			return n;
@@ -211,7 +227,7 @@ B2J_HD void world_bounds(const ShapeDesc &s, V3 pos, Q4 rot, V3 &out_min, V3 &ou
 		break;
 	case B2J_SHAPE_CAPSULE: // CapsuleShape.cpp:266-277
 		{
-			Xf x = xf_rotation_translation(rot, pos);
+			Xf x = shape_transform(s, xf_rotation_translation(rot, pos));
 			V3 extent = v3_rep(s.radius);
 			V3 height = v3(0.0f, s.half_height, 0.0f);
 			V3 p1 = mul(x, -height), p2 = mul(x, height);
@@ -221,7 +237,7 @@ B2J_HD void world_bounds(const ShapeDesc &s, V3 pos, Q4 rot, V3 &out_min, V3 &ou
 		break;
 	default: // AABox::Transformed (AABox.h:193-213)
 		{
-			M33 r = m33_rotation(rot);
+			M33 r = shape_transform(s, xf_rotation_translation(rot, pos)).r;
 			V3 new_min = pos, new_max = pos;
 			for (int c = 0; c < 3; ++c)
 			{
@@ -242,7 +258,7 @@ B2J_HD void world_bounds(const ShapeDesc &s, V3 pos, Q4 rot, V3 &out_min, V3 &ou
 B2J_HD void sleep_test_points(const ShapeDesc &s, V3 pos, Q4 rot, V3 *out)
 {
 	out[0] = pos;
-	V3 extent = 0.5f * (s.local_max - s.local_min);
+	V3 extent = 0.5f * (s.outer_max - s.outer_min); // (the bounds of the body's own shape, decorators included, in the body's frame)
 	int lowest = lowest_component_index(extent);
 	M33 r = m33_rotation(rot);
 	switch (lowest)

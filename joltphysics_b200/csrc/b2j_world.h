@@ -60,7 +60,17 @@ struct ShapeDesc
 	uint32_t hull_face_offset, hull_num_faces;     // hull_planes / hull_faces
 	uint32_t hull_vtx_offset;                      // hull_vtx
 	uint32_t mesh_offset, mesh_size;               // mesh_bytes
+	// decorated convex shapes (ScaledShape / RotatedTranslatedShape around a convex leaf): the scale is baked into the
+	// leaf parameters above by the host (box / sphere / capsule: exactly what the reference's scaled support functions compute; hull:
+	// scaled points, shrunk points and planes), the rotation composes with the body's centre of mass transform where the shape is used
+	uint32_t flags;                                // SHAPE_*
+	uint32_t hull_orig_offset;                     // hull_points: the UNSCALED points (supporting face vertices = PreScaled(transform) * point)
+	uint32_t base_leaf;                            // the undecorated leaf shape (ray casts scale the RAY and test the unscaled leaf, ScaledShape.cpp:114-119)
+	V3 scale;                                      // accumulated scale (hull supporting face)
+	M33 local_rot;                                 // Mat44::sRotation(RotatedTranslatedShape::mRotation)
+	V3 outer_min, outer_max;                       // GetLocalBounds() of the outermost shape (Body::GetSleepTestPoints)
 };
+enum { SHAPE_LOCAL_ROTATION = 1, SHAPE_SCALED_HULL = 2 };
 
 // Body pair cache entry (CachedBodyPair, ContactConstraintManager.h:335-355)
 struct alignas(8) CachedPair

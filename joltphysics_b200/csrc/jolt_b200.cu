@@ -538,6 +538,10 @@ struct b2j_world
 
 	// shapes
 	std::vector<ShapeDesc> h_shapes;
+	// host side bookkeeping per shape for the decorators: the leaf a decorated shape was derived from, what has been accumulated on the way
+	// down to it (ScaledShape: inScale * mScale, RotatedTranslatedShape: transform * rotation) and the hull connectivity the scaled shrink needs
+	struct ShapeMeta { int32_t leaf = -1; V3 scale = { 1.0f, 1.0f, 1.0f }; bool scaled = false; Q4 rotation = { 0.0f, 0.0f, 0.0f, 1.0f }; bool rotated = false; std::vector<int32_t> point_num_faces, point_faces; };
+	std::vector<ShapeMeta> h_shape_meta;
 	std::vector<F4> h_hull_points, h_hull_shrunk, h_hull_planes;
 	std::vector<uint32_t> h_hull_faces;
 	std::vector<uint8_t> h_hull_vtx, h_mesh_bytes;
@@ -1614,9 +1618,21 @@ uint32_t b2j_world_get_profile(b2j_world *W, char *names, uint32_t name_stride, 
 	return n;
 }
 
-static int32_t add_shape(b2j_world *W, const ShapeDesc &s)
+static int32_t add_shape(b2j_world *W, const ShapeDesc &desc, const b2j_world::ShapeMeta *meta = nullptr)
 {
+	ShapeDesc s = desc;
+	if (meta == nullptr)
+	{
+		// a leaf: no decoration
+		s.flags = 0; s.scale = v3_rep(1.0f); s.local_rot = m33_rotation(q4_identity());
+		s.outer_min = s.local_min; s.outer_max = s.local_max;
+		s.hull_orig_offset = s.hull_point_offset;
+		s.base_leaf = (uint32_t)W->h_shapes.size();
+	}
 	W->h_shapes.push_back(s);
+	W->h_shape_meta.resize(W->h_shapes.size());
+	if (meta != nullptr) W->h_shape_meta.back() = *meta;
+	else W->h_shape_meta.back().leaf = (int32_t)W->h_shapes.size() - 1;
 	W->shapes_dirty = true;
 	return (int32_t)W->h_shapes.size() - 1;
 }
@@ -1665,7 +1681,152 @@ int32_t b2j_shape_convex_hull(b2j_world *W, const b2j_hull_desc *h)
 	}
 	s.hull_vtx_offset = (uint32_t)W->h_hull_vtx.size();
 	W->h_hull_vtx.insert(W->h_hull_vtx.end(), h->vertex_idx, h->vertex_idx + h->num_vertex_idx);
-	return add_shape(W, s);
+	int32_t id = add_shape(W, s);
+	W->h_shape_meta[id].point_num_faces.assign(h->point_num_faces, h->point_num_faces + h->num_points);
+	W->h_shape_meta[id].point_faces.assign(h->point_faces, h->point_faces + 3 * (size_t)h->num_points);
+	return id;
+}
+
+// The device description of `leaf` under an accumulated scale and rotation (what the reference's dispatch hands to the leaf's collide /
+// support / bounds functions after peeling the decorators, ScaledShape.cpp:190-204, RotatedTranslatedShape.cpp:183-192)
+static int32_t add_decorated_shape(b2j_world *W, int32_t leaf, V3 scale, bool scaled, Q4 rotation, bool rotated, V3 center_of_mass)
+{
+	const ShapeDesc base = W->h_shapes[leaf];
+	ShapeDesc s = base;
+	s.flags = 0; s.scale = v3_rep(1.0f); s.local_rot = m33_rotation(q4_identity());
+	s.hull_orig_offset = base.hull_point_offset;
+	s.base_leaf = (uint32_t)leaf;
+	s.center_of_mass = center_of_mass;
+	if (scaled)
+	{
+		V3 abs_scale = v3_abs(scale);
+		s.scale = scale;
+		// GetLocalBounds().Scaled(inScale) (ConvexShape.cpp:52-56, AABox::Scaled): what the OBB pre-test and the default world bounds use
+		s.local_min = v3_min(base.local_min * scale, base.local_max * scale); s.local_max = v3_max(base.local_min * scale, base.local_max * scale);
+		switch (base.kind)
+		{
+		case B2J_SHAPE_SPHERE: // SphereShape::GetSupportFunction / GetWorldSpaceBounds: scaled_radius = abs(scale.x) * mRadius
+			s.radius = abs_scale.x * base.radius; s.inner_radius = s.radius;
+			break;
+		case B2J_SHAPE_BOX: // BoxShape::GetSupportFunction: scaled half extent = |scale| * h, convex radius = ScaleHelpers::ScaleConvexRadius
+			s.half_extent = abs_scale * base.half_extent;
+			s.convex_radius = fmin_(base.convex_radius * reduce_min(abs_scale), 0.05f /* cDefaultConvexRadius */);
+			s.inner_radius = reduce_min(s.half_extent);
+			break;
+		case B2J_SHAPE_CAPSULE: // CapsuleShape::GetSupportFunction: abs_scale = |scale.x| for both
+			s.half_height = abs_scale.x * base.half_height; s.radius = abs_scale.x * base.radius; s.inner_radius = s.radius;
+			break;
+		default: // ConvexHullShape::GetSupportFunction with a scale (ConvexHullShape.cpp:486-657)
+			{
+				const b2j_world::ShapeMeta &bm = W->h_shape_meta[leaf];
+				s.flags |= SHAPE_SCALED_HULL;
+				s.convex_radius = fmin_(base.convex_radius * reduce_min(abs_scale), 0.05f);
+				s.hull_point_offset = (uint32_t)W->h_hull_points.size();
+				V3 inv_scale = v3(1.0f / scale.x, 1.0f / scale.y, 1.0f / scale.z);
+				// planes: inv_scale * normal (GetSupportingFace divides by its length itself), constant unchanged (nobody reads it on this path)
+				s.hull_face_offset = (uint32_t)W->h_hull_planes.size();
+				for (uint32_t f = 0; f < base.hull_num_faces; ++f)
+				{
+					F4 pl = W->h_hull_planes[base.hull_face_offset + f];
+					V3 n = inv_scale * to_v3(pl);
+					W->h_hull_planes.push_back(f4(n.x, n.y, n.z, pl.w));
+					W->h_hull_faces.push_back(W->h_hull_faces[base.hull_face_offset + f]);
+				}
+				float cr = s.convex_radius;
+				for (uint32_t i = 0; i < base.hull_num_points; ++i)
+				{
+					V3 pos = scale * to_v3(W->h_hull_points[base.hull_point_offset + i]);
+					W->h_hull_points.push_back(f4(pos));
+					V3 new_point = pos;
+					int nf = bm.point_num_faces[i];
+					const int32_t *faces = bm.point_faces.data() + 3 * (size_t)i;
+					auto normal = [&](int f) { return normalized(inv_scale * to_v3(W->h_hull_planes[base.hull_face_offset + f])); };
+					if (base.convex_radius != 0.0f && nf > 0)
+					{
+						V3 n1 = normal(faces[0]);
+						if (nf == 1)
+							new_point = pos - n1 * cr;
+						else
+						{
+							V3 n2 = normal(faces[1]);
+							// Plane::sFromPointAndNormal(pos, n).Offset(-cr): constant = -n.pos, then c - (-cr)
+							float c1 = -dot(n1, pos) - (-cr), c2 = -dot(n2, pos) - (-cr), c3;
+							V3 n3;
+							if (nf == 3) { n3 = normal(faces[2]); c3 = -dot(n3, pos) - (-cr); }
+							else { n3 = cross(n1, n2); c3 = -dot(n3, pos); }
+							float denominator = dot(n1, cross(n2, n3));
+							if (denominator == 0.0f)
+								new_point = pos - n1 * cr;
+							else
+							{
+								float ax = n1.x, ay = n1.y, az = n1.z, aw = c1, bx = n2.x, by = n2.y, bz = n2.z, bw = c2, cx = n3.x, cy = n3.y, cz = n3.z, cw = c3;
+								V3 numerator = v3(
+									aw * (bz * cy - by * cz) + ay * (bw * cz - bz * cw) + az * (by * cw - bw * cy),
+									aw * (bx * cz - bz * cx) + ax * (bz * cw - bw * cz) + az * (bw * cx - bx * cw),
+									aw * (by * cx - bx * cy) + ax * (bw * cy - by * cw) + ay * (bx * cw - bw * cx));
+								new_point = numerator / denominator;
+							}
+						}
+					}
+					W->h_hull_shrunk.push_back(f4(new_point));
+				}
+			}
+			break;
+		}
+	}
+	s.outer_min = s.local_min; s.outer_max = s.local_max;
+	if (rotated)
+	{
+		s.flags |= SHAPE_LOCAL_ROTATION;
+		s.local_rot = m33_rotation(rotation);
+		// RotatedTranslatedShape::GetLocalBounds: inner bounds .Transformed(Mat44::sRotation(mRotation)) (AABox.h:193-213)
+		V3 new_min = v3_zero(), new_max = v3_zero();
+		for (int c = 0; c < 3; ++c)
+		{
+			V3 col = m33_col(s.local_rot, c);
+			V3 a = col * v3_get(s.local_min, c), b = col * v3_get(s.local_max, c);
+			new_min += v3_min(a, b); new_max += v3_max(a, b);
+		}
+		s.outer_min = new_min; s.outer_max = new_max;
+	}
+	b2j_world::ShapeMeta meta;
+	meta.leaf = leaf; meta.scale = scale; meta.scaled = scaled; meta.rotation = rotation; meta.rotated = rotated;
+	return add_shape(W, s, &meta);
+}
+
+static bool is_uniform_scale(V3 s) { V3 d = v3(s.y, s.z, s.x) - s; return length_sq(d) <= 1.0e-8f; } // ScaleHelpers::IsUniformScale
+
+int32_t b2j_shape_scaled(b2j_world *W, int32_t inner, const float scale_in[3])
+{
+	if (inner < 0 || inner >= (int32_t)W->h_shapes.size() || scale_in == nullptr) { last_error() = "invalid shape id"; return -1; }
+	V3 scale = v3_load(scale_in);
+	if (!(scale.x > 1.0e-6f && scale.y > 1.0e-6f && scale.z > 1.0e-6f)) { last_error() = "ScaledShape: only positive scales are supported"; return -1; }
+	const b2j_world::ShapeMeta im = W->h_shape_meta[inner];
+	const ShapeDesc &leaf = W->h_shapes[im.leaf];
+	if (leaf.kind == B2J_SHAPE_MESH) { last_error() = "ScaledShape: a mesh cannot be decorated"; return -1; }
+	if (im.scaled) { last_error() = "ScaledShape: nested scales are not supported"; return -1; }
+	if ((leaf.kind == B2J_SHAPE_SPHERE || leaf.kind == B2J_SHAPE_CAPSULE || im.rotated) && !is_uniform_scale(scale))
+	{ last_error() = "ScaledShape: this inner shape only takes a uniform scale"; return -1; }
+	// ScaledShape::sCollideScaledVsShape: the inner shape sees inScale * mScale; ScaledShape::GetCenterOfMass = mScale * inner centre of mass
+	const ShapeDesc inner_desc = W->h_shapes[inner];
+	int32_t id = add_decorated_shape(W, im.leaf, scale, true, im.rotation, im.rotated, scale * inner_desc.center_of_mass);
+	if (id >= 0 && im.rotated)
+	{
+		// ScaledShape::GetLocalBounds of a rotated inner shape: the inner shape's (rotated) bounds, scaled
+		ShapeDesc &s = W->h_shapes[id];
+		s.outer_min = v3_min(inner_desc.outer_min * scale, inner_desc.outer_max * scale); s.outer_max = v3_max(inner_desc.outer_min * scale, inner_desc.outer_max * scale);
+	}
+	return id;
+}
+
+int32_t b2j_shape_rotated_translated(b2j_world *W, int32_t inner, const float rotation[4], const float center_of_mass[3])
+{
+	if (inner < 0 || inner >= (int32_t)W->h_shapes.size() || rotation == nullptr || center_of_mass == nullptr) { last_error() = "invalid shape id"; return -1; }
+	const b2j_world::ShapeMeta im = W->h_shape_meta[inner];
+	if (W->h_shapes[im.leaf].kind == B2J_SHAPE_MESH) { last_error() = "RotatedTranslatedShape: a mesh cannot be decorated"; return -1; }
+	if (im.rotated) { last_error() = "RotatedTranslatedShape: nested rotations are not supported"; return -1; }
+	Q4 q; q.x = rotation[0]; q.y = rotation[1]; q.z = rotation[2]; q.w = rotation[3];
+	return add_decorated_shape(W, im.leaf, im.scale, im.scaled, q, true, v3_load(center_of_mass));
 }
 
 int32_t b2j_shape_mesh(b2j_world *W, const b2j_mesh_desc *m)
@@ -2701,7 +2862,7 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	B->d.world_stride = stride;
 	B->prev_dt = P->prev_dt;
 	// shapes are shared by all worlds
-	B->h_shapes = P->h_shapes; B->h_hull_points = P->h_hull_points; B->h_hull_shrunk = P->h_hull_shrunk; B->h_hull_planes = P->h_hull_planes;
+	B->h_shapes = P->h_shapes; B->h_shape_meta = P->h_shape_meta; B->h_hull_points = P->h_hull_points; B->h_hull_shrunk = P->h_hull_shrunk; B->h_hull_planes = P->h_hull_planes;
 	B->h_hull_faces = P->h_hull_faces; B->h_hull_vtx = P->h_hull_vtx; B->h_mesh_bytes = P->h_mesh_bytes;
 	B->shapes_dirty = true;
 	upload_shapes(B);

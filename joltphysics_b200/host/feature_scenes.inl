@@ -5,7 +5,8 @@
 // reduction off).
 // The including file provides: B2J_SHAPE_REF, B2J_NEW_SHAPE(Type, args...), Layers::{NON_MOVING, MOVING, DEBRIS}, sRandomQuat(std::mt19937 &).
 // Variants: 0 kinematic, 1 sensor, 2 dof_plane2d, 3 gyroscopic, 4 step_overrides, 5 no_manifold_reduction, 6 two_moving_layers,
-// 7 kinematic_vs_nondynamic, 8 zoo (all of them in one world). inHull: a cooked convex hull (cooking is host side and out of scope).
+// 7 kinematic_vs_nondynamic, 8 zoo (0..7 in one world), 9 decorated (ScaledShape / RotatedTranslatedShape around convex shapes).
+// inHull: a cooked convex hull (cooking is host side and out of scope).
 
 static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHAPE_REF &inHull, uint32_t &outNumDynamic)
 {
@@ -171,5 +172,39 @@ static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHA
 		BodyCreationSettings dyn(sphere, RVec3(x0 + 2.6f, 0.5f, 0.3f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
 		add(dyn);
 		x0 += 20.0f;
+	}
+	if (inVariant == 9)
+	{
+		// decorated convex shapes: every leaf type scaled (non uniform where the leaf allows it), rotated + translated, and both nested
+		// either way round; dynamic bodies dropped in a heap, a static rotated slab as a ramp, a kinematic scaled pusher
+		Quat tilt = Quat(0.0f, 0.38268343f, 0.0f, 0.92387953f), roll = Quat(0.25881905f, 0.0f, 0.0f, 0.96592583f), yaw = Quat(0.0f, 0.0f, 0.70710678f, 0.70710678f);
+		B2J_SHAPE_REF shapes[10] = {
+			B2J_NEW_SHAPE(ScaledShape, box, Vec3(1.5f, 0.5f, 0.8f)),
+			B2J_NEW_SHAPE(ScaledShape, hull, Vec3(0.7f, 1.3f, 1.1f)),
+			B2J_NEW_SHAPE(ScaledShape, sphere, Vec3::sReplicate(1.4f)),
+			B2J_NEW_SHAPE(ScaledShape, capsule, Vec3::sReplicate(0.8f)),
+			B2J_NEW_SHAPE(RotatedTranslatedShape, Vec3(0.3f, 0.2f, -0.1f), tilt, box),
+			B2J_NEW_SHAPE(RotatedTranslatedShape, Vec3(-0.2f, 0.4f, 0.0f), roll, hull),
+			B2J_NEW_SHAPE(RotatedTranslatedShape, Vec3(0.0f, 0.5f, 0.0f), yaw, capsule),
+			B2J_NEW_SHAPE(RotatedTranslatedShape, Vec3(0.1f, -0.3f, 0.2f), roll, B2J_SHAPE_REF(B2J_NEW_SHAPE(ScaledShape, box, Vec3(0.6f, 1.2f, 0.9f)))),
+			B2J_NEW_SHAPE(ScaledShape, B2J_SHAPE_REF(B2J_NEW_SHAPE(RotatedTranslatedShape, Vec3(0.2f, 0.0f, 0.3f), tilt, hull)), Vec3::sReplicate(1.25f)),
+			box };
+		for (int i = 0; i < 30; ++i)
+		{
+			BodyCreationSettings s(shapes[i % 10], RVec3(-2.0f + 1.3f * float(i % 4), 1.2f + 1.1f * float(i / 4), -1.5f + 1.4f * float((i / 2) % 3)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			s.mFriction = 0.4f + 0.05f * float(i % 5);
+			s.mRestitution = i % 6 == 0? 0.5f : 0.0f;
+			add(s);
+		}
+		BodyCreationSettings ramp(B2J_NEW_SHAPE(RotatedTranslatedShape, Vec3(0.0f, 0.5f, 0.0f), roll, slab), RVec3(5.0f, 0.3f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		add(ramp, EActivation::DontActivate);
+		for (int i = 0; i < 4; ++i)
+		{
+			BodyCreationSettings s(shapes[(3 * i + 1) % 10], RVec3(4.0f + 0.7f * float(i), 2.5f + 0.9f * float(i), -0.6f + 0.4f * float(i)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			add(s);
+		}
+		BodyCreationSettings pusher(B2J_NEW_SHAPE(ScaledShape, box, Vec3(1.0f, 3.0f, 4.0f)), RVec3(-6.0f, 1.6f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
+		pusher.mLinearVelocity = Vec3(1.5f, 0.0f, 0.0f);
+		add(pusher);
 	}
 }

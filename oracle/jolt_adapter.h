@@ -14,6 +14,8 @@
 #include <Jolt/Physics/Collision/Shape/CapsuleShape.h>
 #include <Jolt/Physics/Collision/Shape/ConvexHullShape.h>
 #include <Jolt/Physics/Collision/Shape/MeshShape.h>
+#include <Jolt/Physics/Collision/Shape/ScaledShape.h>
+#include <Jolt/Physics/Collision/Shape/RotatedTranslatedShape.h>
 
 #include <jolt_b200.h>
 
@@ -33,7 +35,7 @@ struct Api
 #define B2J_FN(name) decltype(&::name) name = nullptr;
 	B2J_FN(b2j_world_create) B2J_FN(b2j_world_destroy) B2J_FN(b2j_last_error) B2J_FN(b2j_settings_default)
 	B2J_FN(b2j_world_set_previous_delta_time)
-	B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh)
+	B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
 	B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
 #undef B2J_FN
 
@@ -44,7 +46,7 @@ struct Api
 #define B2J_FN(name) name = (decltype(name))dlsym(handle, #name); if (name == nullptr) { outError = String("missing symbol ") + #name; return false; }
 		B2J_FN(b2j_world_create) B2J_FN(b2j_world_destroy) B2J_FN(b2j_last_error) B2J_FN(b2j_settings_default)
 		B2J_FN(b2j_world_set_previous_delta_time)
-		B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh)
+		B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
 		B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
 #undef B2J_FN
 		return true;
@@ -156,6 +158,32 @@ inline int32_t sUploadShape(const Api &inApi, b2j_world *inWorld, const Shape *i
 			sStore(bounds.mMin, desc.local_bounds_min);
 			sStore(bounds.mMax, desc.local_bounds_max);
 			return inApi.b2j_shape_mesh(inWorld, &desc);
+		}
+
+	case EShapeSubType::Scaled:
+		{
+			// ScaledShape around a convex shape: the inner shape first, then the decoration
+			const ScaledShape *scaled = static_cast<const ScaledShape *>(inShape);
+			int32_t inner = sUploadShape(inApi, inWorld, scaled->GetInnerShape(), outError);
+			if (inner < 0) return -1;
+			float scale[3];
+			sStore(scaled->GetScale(), scale);
+			int32_t id = inApi.b2j_shape_scaled(inWorld, inner, scale);
+			if (id < 0) outError = inApi.b2j_last_error();
+			return id;
+		}
+
+	case EShapeSubType::RotatedTranslated:
+		{
+			const RotatedTranslatedShape *rt = static_cast<const RotatedTranslatedShape *>(inShape);
+			int32_t inner = sUploadShape(inApi, inWorld, rt->GetInnerShape(), outError);
+			if (inner < 0) return -1;
+			float rotation[4], center_of_mass[3];
+			sStore(rt->GetRotation(), rotation);
+			sStore(rt->GetCenterOfMass(), center_of_mass);
+			int32_t id = inApi.b2j_shape_rotated_translated(inWorld, inner, rotation, center_of_mass);
+			if (id < 0) outError = inApi.b2j_last_error();
+			return id;
 		}
 
 	default:

@@ -240,7 +240,7 @@ Ref<Shape> sTerrainMesh(int n, float cell_size, float max_height)
 	return settings->Create().Get();
 }
 
-World *sSceneConvexVsMesh(int inHalfGrid)
+World *sSceneConvexVsMesh(int inHalfGrid, int inDecorated = 0)
 {
 	// PerformanceTest/ConvexVsMeshScene.h:28-117 (half grid 10 -> 21*4*21 = 1764 bodies on a 20000 triangle mesh)
 	World *w = sNewWorld(10240, 65536, 20480, 32);
@@ -263,6 +263,15 @@ World *sSceneConvexVsMesh(int inHalfGrid)
 		new CapsuleShape(0.75f, 0.5f),
 		ConvexHullShapeSettings({ Vec3(0, 1, 0), Vec3(1, 0, 0), Vec3(-1, 0, 0), Vec3(0, 0, 1), Vec3(0, 0, -1) }).Create().Get(),
 	};
+	if (inDecorated != 0)
+	{
+		// the same bodies behind ScaledShape / RotatedTranslatedShape decorators (decorated convex shapes against the mesh)
+		Quat tilt = Quat(0.0f, 0.38268343f, 0.0f, 0.92387953f), roll = Quat(0.25881905f, 0.0f, 0.0f, 0.96592583f);
+		shapes[0] = new ScaledShape(shapes[0], Vec3(1.3f, 0.6f, 0.9f));
+		shapes[1] = new RotatedTranslatedShape(Vec3(0.2f, 0.1f, 0.0f), roll, new ScaledShape(shapes[1], Vec3::sReplicate(1.3f)));
+		shapes[2] = new RotatedTranslatedShape(Vec3(0.0f, 0.3f, 0.1f), tilt * roll, shapes[2]);
+		shapes[3] = new ScaledShape(new RotatedTranslatedShape(Vec3(0.1f, 0.0f, -0.2f), tilt, shapes[3]), Vec3::sReplicate(0.8f));
+	}
 	for (int x = -inHalfGrid; x <= inHalfGrid; ++x)
 		for (int y = 0; y < (int)shapes.size(); ++y)
 			for (int z = -inHalfGrid; z <= inHalfGrid; ++z)
@@ -475,7 +484,7 @@ void *jref_create_scene(const char *inName, int inParam0, int inParam1)
 	World *w = nullptr;
 	if (name == "pyramid") w = sScenePyramid(inParam0 > 0? inParam0 : 15);
 	else if (name == "pyramid_tight") w = sScenePyramid(inParam0 > 0? inParam0 : 6, inParam1 > 0? inParam1 : 64);
-	else if (name == "convex_vs_mesh") w = sSceneConvexVsMesh(inParam0 > 0? inParam0 : 10);
+	else if (name == "convex_vs_mesh") w = sSceneConvexVsMesh(inParam0 > 0? inParam0 : 10, inParam1);
 	else if (name == "max_bodies") w = sSceneMaxBodies(inParam0 > 0? inParam0 : 10000);
 	else if (name == "pile") w = sScenePile(inParam0 > 0? inParam0 : 1000, inParam1 > 0? inParam1 : 15);
 	else if (name == "small_stack") w = sSceneSmallStack(inParam0);

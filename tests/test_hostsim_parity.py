@@ -10,6 +10,8 @@ CASES = [
     ("pyramid", 9, 0, 60),          # 330 boxes: one large island, exercises the split colouring
     ("small_stack", 0, 0, 30), ("small_stack", 1, 0, 30), ("small_stack", 2, 0, 30), ("small_stack", 3, 0, 30),
     ("small_stack", 4, 0, 5), ("small_stack", 4, 0, 45), ("small_stack", 4, 0, 200),
+    # ScaledShape / RotatedTranslatedShape decorated convex bodies landing on the mesh (p1 = 1)
+    ("convex_vs_mesh", 1, 1, 90), ("convex_vs_mesh", 1, 1, 150),
 ]
 
 
