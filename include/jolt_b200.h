@@ -155,7 +155,7 @@ int32_t b2j_shape_box(b2j_world *w, const float half_extent[3], float convex_rad
 int32_t b2j_shape_capsule(b2j_world *w, float half_height_of_cylinder, float radius);        /* CapsuleShape */
 int32_t b2j_shape_convex_hull(b2j_world *w, const b2j_hull_desc *hull);                      /* ConvexHullShape */
 int32_t b2j_shape_mesh(b2j_world *w, const b2j_mesh_desc *mesh);                             /* MeshShape (static bodies) */
-/* Decorated convex shapes. `inner` = a sphere / box / capsule / convex hull or one of these two around one.
+/* Decorated shapes. `inner` = a sphere / box / capsule / convex hull / mesh or one of these two around one.
  * ScaledShape (Jolt/Physics/Collision/Shape/ScaledShape.cpp:190-204: the scale is handed down to the leaf's support function,
  * supporting face and bounds): positive scales; uniform for spheres and capsules (SphereShape::IsValidScale) and for an inner
  * RotatedTranslatedShape with a rotation (no RotateScale). */

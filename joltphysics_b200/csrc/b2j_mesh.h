@@ -71,6 +71,7 @@ struct MeshCollideCtx
 	float max_separation_distance;
 	bool check_active_edges;
 	V3 active_edge_movement_direction;
+	V3 scale2;                       // ScaledShape around the mesh: node bounds and vertices are scaled on the fly (MeshShape.cpp:1150-1152, CollideConvexVsTriangles.cpp:43-45)
 	// convex
 	Xf transform_2_to_1;
 	V3 bounds1_min, bounds1_max;                 // mBoundsOf1 (expanded)
@@ -200,7 +201,7 @@ B2J_D V3 active_edges_fix_normal(V3 v0, V3 v1, V3 v2, V3 triangle_normal, uint32
 B2J_D void mesh_collide_convex_triangle(const DWorld &w, const ShapeDesc &s1, const MeshCollideCtx &c, EpaScratch &epa, MeshScratch &ms, int &num_manifolds,
 	V3 in_v0, V3 in_v1, V3 in_v2, uint32_t active_edges, uint32_t sub2)
 {
-	V3 v0 = mul(c.transform_2_to_1, in_v0), v1 = mul(c.transform_2_to_1, in_v1), v2 = mul(c.transform_2_to_1, in_v2);
+	V3 v0 = mul(c.transform_2_to_1, c.scale2 * in_v0), v1 = mul(c.transform_2_to_1, c.scale2 * in_v1), v2 = mul(c.transform_2_to_1, c.scale2 * in_v2);
 	V3 triangle_normal = 1.0f * cross(v1 - v0, v2 - v0);
 	bool back_facing = dot(triangle_normal, v0) > 0.0f;
 	if (back_facing)
@@ -245,7 +246,7 @@ B2J_D void mesh_collide_convex_triangle(const DWorld &w, const ShapeDesc &s1, co
 // CollideSphereVsTriangles::Collide
 B2J_D void mesh_collide_sphere_triangle(const DWorld &w, const MeshCollideCtx &c, MeshScratch &ms, int &num_manifolds, V3 in_v0, V3 in_v1, V3 in_v2, uint32_t active_edges, uint32_t sub2)
 {
-	V3 v0 = in_v0 - c.sphere_center_in2, v1 = in_v1 - c.sphere_center_in2, v2 = in_v2 - c.sphere_center_in2;
+	V3 v0 = c.scale2 * in_v0 - c.sphere_center_in2, v1 = c.scale2 * in_v1 - c.sphere_center_in2, v2 = c.scale2 * in_v2 - c.sphere_center_in2;
 	V3 triangle_normal = 1.0f * cross(v1 - v0, v2 - v0);
 	bool back_facing = dot(triangle_normal, v0) > 0.0f;
 	if (back_facing)
@@ -283,6 +284,9 @@ B2J_D bool mesh_child_overlaps(const MeshCollideCtx &cc, const uint8_t *node, in
 {
 	float mnx = half_to_float(load_u16(node + 0 + 2 * ch)), mny = half_to_float(load_u16(node + 8 + 2 * ch)), mnz = half_to_float(load_u16(node + 16 + 2 * ch));
 	float mxx = half_to_float(load_u16(node + 24 + 2 * ch)), mxy = half_to_float(load_u16(node + 32 + 2 * ch)), mxz = half_to_float(load_u16(node + 40 + 2 * ch));
+	// AABox4Scale (positive scales: minimum and maximum keep their roles; times one is exact)
+	mnx = cc.scale2.x * mnx; mny = cc.scale2.y * mny; mnz = cc.scale2.z * mnz;
+	mxx = cc.scale2.x * mxx; mxy = cc.scale2.y * mxy; mxz = cc.scale2.z * mxz;
 	if (cc.sphere)
 	{
 		V3 p = cc.sphere_center_in2;
@@ -320,7 +324,9 @@ B2J_D MeshCollideCtx mesh_collide_ctx(const DWorld &w, const CollideItem &item, 
 	MeshCollideCtx cc;
 	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
 	cc.transform1 = shape_transform(s1, xf(m33_rotation(to_q4(w.rotation[item.b1])), v3_zero()));
-	cc.transform2 = xf(m33_rotation(to_q4(w.rotation[item.b2])), x2 + (-x1));
+	const ShapeDesc &s2 = w.shapes[i2.shape];
+	cc.transform2 = shape_transform(s2, xf(m33_rotation(to_q4(w.rotation[item.b2])), x2 + (-x1)));
+	cc.scale2 = s2.scale;
 	cc.max_separation_distance = ((i1.flags | i2.flags) & B2J_BODY_SENSOR)? 0.0f : w.settings.speculative_contact_distance;
 	cc.check_active_edges = w.settings.check_active_edges != 0;
 	V3 lv1 = i1.motion_type != B2J_MOTION_STATIC? to_v3(w.linear_velocity[item.b1]) : v3_zero();
@@ -397,26 +403,7 @@ struct KCollideMesh
 				uint32_t props[4];
 				int n = 0;
 				for (int ch = 0; ch < 4; ++ch)
-				{
-					float mnx = half_to_float(load_u16(node + 0 + 2 * ch)), mny = half_to_float(load_u16(node + 8 + 2 * ch)), mnz = half_to_float(load_u16(node + 16 + 2 * ch));
-					float mxx = half_to_float(load_u16(node + 24 + 2 * ch)), mxy = half_to_float(load_u16(node + 32 + 2 * ch)), mxz = half_to_float(load_u16(node + 40 + 2 * ch));
-					bool hit;
-					if (cc.sphere)
-					{
-						// AABox4VsSphere
-						V3 p = cc.sphere_center_in2;
-						float cx = fmin_(fmax_(p.x, mnx), mxx), cy = fmin_(fmax_(p.y, mny), mxy), cz = fmin_(fmax_(p.z, mnz), mxz);
-						float d = square(cx - p.x) + square(cy - p.y) + square(cz - p.z);
-						hit = d <= cc.radius_plus_max_sep_sq;
-					}
-					else
-					{
-						// AABox4VsBox
-						const V3 &bmn = cc.bounds1_in2_min, &bmx = cc.bounds1_in2_max;
-						hit = !((bmn.x > mxx || mnx > bmx.x) || (bmn.y > mxy || mny > bmx.y) || (bmn.z > mxz || mnz > bmx.z));
-					}
-					if (hit) props[n++] = load_u32(node + 48 + 4 * ch);
-				}
+					if (mesh_child_overlaps(cc, node, ch)) props[n++] = load_u32(node + 48 + 4 * ch);
 				for (int j = 0; j < n && top + j < 128; ++j) stack[top + j] = props[j];
 				top += n;
 			}
@@ -562,8 +549,8 @@ struct KCollideMeshWarp
 			{
 				V3 v[3];
 				mesh_decode_triangle(tree, sh.cand_block[lane], sh.cand_tri[lane], block_id_bits, tri_offset, tri_scale, v, active_edges, sub2);
-				if (cc.sphere) { v0 = v[0] - cc.sphere_center_in2; v1 = v[1] - cc.sphere_center_in2; v2 = v[2] - cc.sphere_center_in2; }
-				else { v0 = mul(cc.transform_2_to_1, v[0]); v1 = mul(cc.transform_2_to_1, v[1]); v2 = mul(cc.transform_2_to_1, v[2]); }
+				if (cc.sphere) { v0 = cc.scale2 * v[0] - cc.sphere_center_in2; v1 = cc.scale2 * v[1] - cc.sphere_center_in2; v2 = cc.scale2 * v[2] - cc.sphere_center_in2; }
+				else { v0 = mul(cc.transform_2_to_1, cc.scale2 * v[0]); v1 = mul(cc.transform_2_to_1, cc.scale2 * v[1]); v2 = mul(cc.transform_2_to_1, cc.scale2 * v[2]); }
 				triangle_normal = 1.0f * cross(v1 - v0, v2 - v0);
 				back_facing = dot(triangle_normal, v0) > 0.0f;
 				if (back_facing)

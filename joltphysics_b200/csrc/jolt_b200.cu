@@ -1716,6 +1716,8 @@ static int32_t add_decorated_shape(b2j_world *W, int32_t leaf, V3 scale, bool sc
 		case B2J_SHAPE_CAPSULE: // CapsuleShape::GetSupportFunction: abs_scale = |scale.x| for both
 			s.half_height = abs_scale.x * base.half_height; s.radius = abs_scale.x * base.radius; s.inner_radius = s.radius;
 			break;
+		case B2J_SHAPE_MESH: // the mesh kernels scale node bounds and vertices on the fly (s.scale)
+			break;
 		default: // ConvexHullShape::GetSupportFunction with a scale (ConvexHullShape.cpp:486-657)
 			{
 				const b2j_world::ShapeMeta &bm = W->h_shape_meta[leaf];
@@ -1803,7 +1805,6 @@ int32_t b2j_shape_scaled(b2j_world *W, int32_t inner, const float scale_in[3])
 	if (!(scale.x > 1.0e-6f && scale.y > 1.0e-6f && scale.z > 1.0e-6f)) { last_error() = "ScaledShape: only positive scales are supported"; return -1; }
 	const b2j_world::ShapeMeta im = W->h_shape_meta[inner];
 	const ShapeDesc &leaf = W->h_shapes[im.leaf];
-	if (leaf.kind == B2J_SHAPE_MESH) { last_error() = "ScaledShape: a mesh cannot be decorated"; return -1; }
 	if (im.scaled) { last_error() = "ScaledShape: nested scales are not supported"; return -1; }
 	if ((leaf.kind == B2J_SHAPE_SPHERE || leaf.kind == B2J_SHAPE_CAPSULE || im.rotated) && !is_uniform_scale(scale))
 	{ last_error() = "ScaledShape: this inner shape only takes a uniform scale"; return -1; }
@@ -1823,7 +1824,6 @@ int32_t b2j_shape_rotated_translated(b2j_world *W, int32_t inner, const float ro
 {
 	if (inner < 0 || inner >= (int32_t)W->h_shapes.size() || rotation == nullptr || center_of_mass == nullptr) { last_error() = "invalid shape id"; return -1; }
 	const b2j_world::ShapeMeta im = W->h_shape_meta[inner];
-	if (W->h_shapes[im.leaf].kind == B2J_SHAPE_MESH) { last_error() = "RotatedTranslatedShape: a mesh cannot be decorated"; return -1; }
 	if (im.rotated) { last_error() = "RotatedTranslatedShape: nested rotations are not supported"; return -1; }
 	Q4 q; q.x = rotation[0]; q.y = rotation[1]; q.z = rotation[2]; q.w = rotation[3];
 	return add_decorated_shape(W, im.leaf, im.scale, im.scaled, q, true, v3_load(center_of_mass));

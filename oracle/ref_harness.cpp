@@ -251,7 +251,10 @@ World *sSceneConvexVsMesh(int inHalfGrid, int inDecorated = 0)
 
 	const int n = 100;
 	const float cell_size = 3.0f, max_height = 5.0f, center = n * cell_size / 2;
-	BodyCreationSettings mesh(sTerrainMesh(n, cell_size, max_height), RVec3(-center, max_height, -center), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+	RefConst<Shape> terrain = sTerrainMesh(n, cell_size, max_height);
+	if ((inDecorated & 2) != 0) // the mesh itself scaled (non uniform) and rotated a little
+		terrain = new RotatedTranslatedShape(Vec3(1.0f, 0.5f, -2.0f), Quat(0.04361939f, 0.0f, 0.0f, 0.99904822f), new ScaledShape(terrain, Vec3(1.2f, 0.7f, 0.9f)));
+	BodyCreationSettings mesh(terrain, RVec3(-center, max_height, -center), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
 	mesh.mFriction = 0.5f;
 	mesh.mRestitution = 0.6f;
 	BodyInterface &bi = w->system.GetBodyInterface();
@@ -263,7 +266,7 @@ World *sSceneConvexVsMesh(int inHalfGrid, int inDecorated = 0)
 		new CapsuleShape(0.75f, 0.5f),
 		ConvexHullShapeSettings({ Vec3(0, 1, 0), Vec3(1, 0, 0), Vec3(-1, 0, 0), Vec3(0, 0, 1), Vec3(0, 0, -1) }).Create().Get(),
 	};
-	if (inDecorated != 0)
+	if ((inDecorated & 1) != 0)
 	{
 		// the same bodies behind ScaledShape / RotatedTranslatedShape decorators (decorated convex shapes against the mesh)
 		Quat tilt = Quat(0.0f, 0.38268343f, 0.0f, 0.92387953f), roll = Quat(0.25881905f, 0.0f, 0.0f, 0.96592583f);

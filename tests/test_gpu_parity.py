@@ -13,6 +13,8 @@ CASES = [
     ("convex_vs_mesh", 10, 0, 60), ("pile", 2000, 15, 100),
     # ScaledShape / RotatedTranslatedShape decorated convex bodies landing on the mesh (p1 = 1)
     ("convex_vs_mesh", 4, 1, 90), ("convex_vs_mesh", 4, 1, 120), ("convex_vs_mesh", 4, 1, 200),
+    # ... and with the mesh itself scaled + rotated (p1 bit 1)
+    ("convex_vs_mesh", 4, 2, 200), ("convex_vs_mesh", 4, 3, 150), ("convex_vs_mesh", 4, 3, 300),
     # worlds with more than 4096 bodies: the wavefront schedule runs as one cooperative launch (sched_grid_kernel)
     ("pile", 6000, 15, 80), ("max_bodies", 6000, 0, 10),
 ]

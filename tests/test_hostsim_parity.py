@@ -12,6 +12,8 @@ CASES = [
     ("small_stack", 4, 0, 5), ("small_stack", 4, 0, 45), ("small_stack", 4, 0, 200),
     # ScaledShape / RotatedTranslatedShape decorated convex bodies landing on the mesh (p1 = 1)
     ("convex_vs_mesh", 1, 1, 90), ("convex_vs_mesh", 1, 1, 150),
+    # ... and with the mesh itself scaled + rotated (p1 bit 1)
+    ("convex_vs_mesh", 1, 2, 300), ("convex_vs_mesh", 1, 3, 200),
 ]
 
 
