@@ -39,7 +39,7 @@ enum {
 };
 
 /* Shape kinds on the path (EShapeSubType subset, Jolt/Physics/Collision/Shape/Shape.h) */
-enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4 };
+enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4, B2J_SHAPE_CYLINDER = 5 };
 
 /* Body flags */
 enum {
@@ -153,6 +153,7 @@ typedef struct b2j_mesh_desc {
 int32_t b2j_shape_sphere(b2j_world *w, float radius);                                        /* SphereShape */
 int32_t b2j_shape_box(b2j_world *w, const float half_extent[3], float convex_radius);        /* BoxShape */
 int32_t b2j_shape_capsule(b2j_world *w, float half_height_of_cylinder, float radius);        /* CapsuleShape */
+int32_t b2j_shape_cylinder(b2j_world *w, float half_height, float radius, float convex_radius); /* CylinderShape (axis = y; CylinderShape.cpp) */
 int32_t b2j_shape_convex_hull(b2j_world *w, const b2j_hull_desc *hull);                      /* ConvexHullShape */
 int32_t b2j_shape_mesh(b2j_world *w, const b2j_mesh_desc *mesh);                             /* MeshShape (static bodies) */
 /* Decorated shapes. `inner` = a sphere / box / capsule / convex hull / mesh or one of these two around one.

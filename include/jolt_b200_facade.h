@@ -98,7 +98,7 @@ inline constexpr EAllowedDOFs operator&(EAllowedDOFs a, EAllowedDOFs b) { return
 enum class EPhysicsUpdateError : uint32 { None = 0, ManifoldCacheFull = 1, BodyPairCacheFull = 2, ContactConstraintsFull = 4 };
 inline EPhysicsUpdateError operator|(EPhysicsUpdateError a, EPhysicsUpdateError b) { return EPhysicsUpdateError(uint32(a) | uint32(b)); }
 enum class EOverrideMassProperties : uint8 { CalculateMassAndInertia, CalculateInertia, MassAndInertiaProvided };
-enum class EShapeSubType : uint8 { Sphere = B2J_SHAPE_SPHERE, Box = B2J_SHAPE_BOX, Capsule = B2J_SHAPE_CAPSULE, ConvexHull = B2J_SHAPE_CONVEX_HULL, Mesh = B2J_SHAPE_MESH, RotatedTranslated = 64, Scaled = 65 };
+enum class EShapeSubType : uint8 { Sphere = B2J_SHAPE_SPHERE, Box = B2J_SHAPE_BOX, Capsule = B2J_SHAPE_CAPSULE, ConvexHull = B2J_SHAPE_CONVEX_HULL, Mesh = B2J_SHAPE_MESH, Cylinder = B2J_SHAPE_CYLINDER, RotatedTranslated = 64, Scaled = 65 };
 
 class BroadPhaseLayerInterface { public: virtual ~BroadPhaseLayerInterface() = default; virtual uint GetNumBroadPhaseLayers() const = 0; virtual BroadPhaseLayer GetBroadPhaseLayer(ObjectLayer inLayer) const = 0; };
 class ObjectVsBroadPhaseLayerFilter { public: virtual ~ObjectVsBroadPhaseLayerFilter() = default; virtual bool ShouldCollide(ObjectLayer, BroadPhaseLayer) const { return true; } };
@@ -379,6 +379,28 @@ public:
 	int32_t Upload(b2j_world *w) const override { return b2j_shape_capsule(w, mHalfHeightOfCylinder, mRadius); }
 private:
 	float mHalfHeightOfCylinder, mRadius;
+};
+
+class CylinderShape final : public ConvexShape
+{
+public:
+	CylinderShape(float inHalfHeight, float inRadius, float inConvexRadius = 0.05f) : mHalfHeight(inHalfHeight), mRadius(inRadius), mConvexRadius(std::min(inConvexRadius, std::min(inHalfHeight, inRadius))) { }
+	float GetHalfHeight() const { return mHalfHeight; } float GetRadius() const { return mRadius; } float GetConvexRadius() const { return mConvexRadius; }
+	EShapeSubType GetSubType() const override { return EShapeSubType::Cylinder; }
+	MassProperties GetMassProperties() const override // CylinderShape.cpp:246-263
+	{
+		MassProperties p;
+		float radius_sq = mRadius * mRadius;
+		float height = 2.0f * mHalfHeight;
+		p.mMass = JPH_PI * radius_sq * height * GetDensity();
+		float inertia_y = radius_sq * p.mMass * 0.5f;
+		float inertia_x = inertia_y * 0.5f + p.mMass * height * height / 12.0f;
+		p.SetDiagonal(inertia_x, inertia_y, inertia_x);
+		return p;
+	}
+	int32_t Upload(b2j_world *w) const override { return b2j_shape_cylinder(w, mHalfHeight, mRadius, mConvexRadius); }
+private:
+	float mHalfHeight, mRadius, mConvexRadius;
 };
 
 // A convex hull cooked by the reference's ConvexHullBuilder (host-side cooking is out of scope, SURVEY 2a Jolt/Geometry)

@@ -105,6 +105,27 @@ B2J_HD float ray_cylinder(V3 o, V3 d, float radius)
 	return 0.0f;
 }
 
+// RayCylinder (finite, RayCylinder.h:56-107): the infinite cylinder, then the cap the ray travels towards
+B2J_HD float ray_cylinder_finite(V3 o, V3 d, float half_height, float radius)
+{
+	float fraction = ray_cylinder(o, d, radius);
+	if (fraction == FLT_MAX)
+		return FLT_MAX;
+	if (fabs_(o.y + fraction * d.y) <= half_height)
+		return fraction;
+	if (d.y != 0.0f)
+	{
+		float plane_fraction = d.y < 0.0f? (half_height - o.y) / d.y : -(half_height + o.y) / d.y;
+		if (plane_fraction >= 0.0f)
+		{
+			V3 point = o + plane_fraction * d;
+			if (square(point.x) + square(point.z) <= square(radius))
+				return plane_fraction;
+		}
+	}
+	return FLT_MAX;
+}
+
 // RayCapsule
 B2J_HD float ray_capsule(V3 o, V3 d, float half_height, float radius)
 {
@@ -299,6 +320,7 @@ B2J_D bool ray_shape(const DWorld &w, const ShapeDesc &decorated, V3 o, V3 d, fl
 	case B2J_SHAPE_SPHERE: fraction = ray_sphere(o, d, v3_zero(), s.radius); break;
 	case B2J_SHAPE_BOX: fraction = fmax_(ray_aabox(o, ray_inv_direction(d), -s.half_extent, s.half_extent), 0.0f); break;
 	case B2J_SHAPE_CAPSULE: fraction = ray_capsule(o, d, s.half_height, s.radius); break;
+	case B2J_SHAPE_CYLINDER: fraction = ray_cylinder_finite(o, d, s.half_height, s.radius); break;
 	case B2J_SHAPE_CONVEX_HULL: { float f; if (ray_hull(w, s, o, d, f)) fraction = f; break; }
 	case B2J_SHAPE_MESH: return ray_mesh(w, s, o, d, io_fraction, out_sub);
 	default: break;

@@ -17,7 +17,7 @@ struct ConvexSupport
 	uint32_t kind;
 	float radius;            // sphere / capsule radius added by the support function itself (include mode) else 0
 	float convex_radius;     // Support::GetConvexRadius()
-	V3 ext;                  // box: (reduced) half extent, capsule: (0, half height, 0)
+	V3 ext;                  // box: (reduced) half extent, capsule: (0, half height, 0), cylinder: (radius, half height, 0) of this mode
 	const F4 *points;        // hull points for this mode
 	uint32_t num_points;
 
@@ -40,6 +40,14 @@ struct ConvexSupport
 				float len = length(dir);
 				V3 r = len > 0.0f? dir * (radius / len) : v3_zero();
 				return dir.y > 0.0f? r + ext : r - ext;
+			}
+		case B2J_SHAPE_CYLINDER: // CylinderShape::Cylinder::GetSupport (CylinderShape.cpp:143-152)
+			{
+				float o = sqrt_(square(dir.x) + square(dir.z));
+				float y = (dir.y < 0.0f? -1.0f : 1.0f) * ext.y; // Sign(y) * mHalfHeight
+				if (o > 0.0f)
+					return v3((ext.x * dir.x) / o, y, (ext.x * dir.z) / o);
+				return v3(0.0f, y, 0.0f);
 			}
 		default: // hull: first vertex with strictly greatest dot (ConvexHullShape.cpp:412-421)
 			{
@@ -78,6 +86,10 @@ B2J_HD ConvexSupport make_support(const DWorld &w, const ShapeDesc &s, int mode)
 	case B2J_SHAPE_CAPSULE:
 		c.ext = v3(0.0f, s.half_height, 0.0f);
 		if (mode == SUPPORT_INCLUDE_CONVEX_RADIUS) c.radius = s.radius; else c.convex_radius = s.radius;
+		break;
+	case B2J_SHAPE_CYLINDER: // CylinderShape::GetSupportFunction (CylinderShape.cpp:171-196)
+		if (mode == SUPPORT_INCLUDE_CONVEX_RADIUS) c.ext = v3(s.radius, s.half_height, 0.0f);
+		else { c.ext = v3(s.radius - s.convex_radius, s.half_height - s.convex_radius, 0.0f); c.convex_radius = s.convex_radius; }
 		break;
 	default:
 		c.num_points = s.hull_num_points;
@@ -179,6 +191,36 @@ B2J_HD int supporting_face(const DWorld &w, const ShapeDesc &s, V3 dir, const Xf
 				return 2;
 			}
 			return 0;
+		}
+	case B2J_SHAPE_CYLINDER: // CylinderShape::GetSupportingFace (CylinderShape.cpp:198-244)
+		{
+			float x = dir.x, y = dir.y, z = dir.z;
+			float xz_sq = square(x) + square(z);
+			float y_sq = square(y);
+			if (xz_sq > y_sq)
+			{
+				// an edge of the side
+				float f = (0.0f - s.radius) / sqrt_(xz_sq);
+				float vx = x * f, vz = z * f;
+				out[0] = mul(xform, v3(vx, s.half_height, vz));
+				out[1] = mul(xform, v3(vx, 0.0f - s.half_height, vz));
+				return 2;
+			}
+			// top or bottom: the 8 vertex approximation of the cap, rotated so that one vertex points along the direction
+			Xf transform = xform;
+			if (xz_sq > 0.00765427f * y_sq)
+			{
+				float inv = sqrt_(xz_sq);
+				V3 base_x = v3(x / inv, 0.0f / inv, z / inv);
+				V3 base_z = v3(base_x.z * -1.0f, base_x.y * 0.0f, base_x.x * 1.0f);
+				transform = mul(transform, xf(m33(base_x, v3(0.0f, 1.0f, 0.0f), base_z), v3_zero()));
+			}
+			V3 multiplier = y < 0.0f? v3(s.radius, s.half_height, s.radius) : v3(0.0f - s.radius, 0.0f - s.half_height, s.radius);
+			transform = xf(m33(multiplier.x * transform.r.c0, multiplier.y * transform.r.c1, multiplier.z * transform.r.c2), transform.t); // PreScaled
+			const float h = 0.707106769f;
+			const V3 top_face[8] = { v3(0.0f, 1.0f, 1.0f), v3(h, 1.0f, h), v3(1.0f, 1.0f, 0.0f), v3(h, 1.0f, -h), v3(-0.0f, 1.0f, -1.0f), v3(-h, 1.0f, -h), v3(-1.0f, 1.0f, 0.0f), v3(-h, 1.0f, h) };
+			for (int i = 0; i < 8; ++i) out[i] = mul(transform, top_face[i]);
+			return 8;
 		}
 	default:
 		{

@@ -1663,6 +1663,18 @@ int32_t b2j_shape_capsule(b2j_world *W, float half_height, float radius)
 	return add_shape(W, s);
 }
 
+int32_t b2j_shape_cylinder(b2j_world *W, float half_height, float radius, float convex_radius)
+{
+	if (!(half_height >= 0.0f && radius >= 0.0f && convex_radius >= 0.0f)) { last_error() = "invalid cylinder"; return -1; }
+	ShapeDesc s; memset(&s, 0, sizeof(s));
+	s.kind = B2J_SHAPE_CYLINDER; s.half_height = half_height; s.radius = radius;
+	s.convex_radius = fmin_(convex_radius, fmin_(half_height, radius)); // CylinderShape::CylinderShape
+	s.inner_radius = fmin_(half_height, radius);
+	V3 extent = v3(radius, half_height, radius);
+	s.local_min = -extent; s.local_max = extent;
+	return add_shape(W, s);
+}
+
 int32_t b2j_shape_convex_hull(b2j_world *W, const b2j_hull_desc *h)
 {
 	if (h == nullptr || h->num_points == 0 || h->num_points > 256 || h->num_faces == 0) { last_error() = "invalid hull"; return -1; }
@@ -1715,6 +1727,11 @@ static int32_t add_decorated_shape(b2j_world *W, int32_t leaf, V3 scale, bool sc
 			break;
 		case B2J_SHAPE_CAPSULE: // CapsuleShape::GetSupportFunction: abs_scale = |scale.x| for both
 			s.half_height = abs_scale.x * base.half_height; s.radius = abs_scale.x * base.radius; s.inner_radius = s.radius;
+			break;
+		case B2J_SHAPE_CYLINDER: // CylinderShape::GetSupportFunction: scale_xz = |scale.x|, scale_y = |scale.y| (IsValidScale: x == z)
+			s.half_height = abs_scale.y * base.half_height; s.radius = abs_scale.x * base.radius;
+			s.convex_radius = fmin_(base.convex_radius * reduce_min(abs_scale), 0.05f);
+			s.inner_radius = fmin_(s.half_height, s.radius);
 			break;
 		case B2J_SHAPE_MESH: // the mesh kernels scale node bounds and vertices on the fly (s.scale)
 			break;
@@ -1808,6 +1825,7 @@ int32_t b2j_shape_scaled(b2j_world *W, int32_t inner, const float scale_in[3])
 	if (im.scaled) { last_error() = "ScaledShape: nested scales are not supported"; return -1; }
 	if ((leaf.kind == B2J_SHAPE_SPHERE || leaf.kind == B2J_SHAPE_CAPSULE || im.rotated) && !is_uniform_scale(scale))
 	{ last_error() = "ScaledShape: this inner shape only takes a uniform scale"; return -1; }
+	if (leaf.kind == B2J_SHAPE_CYLINDER && !(square(scale.z - scale.x) <= 1.0e-8f)) { last_error() = "ScaledShape: a cylinder takes the same scale in x and z"; return -1; }
 	// ScaledShape::sCollideScaledVsShape: the inner shape sees inScale * mScale; ScaledShape::GetCenterOfMass = mScale * inner centre of mass
 	const ShapeDesc inner_desc = W->h_shapes[inner];
 	int32_t id = add_decorated_shape(W, im.leaf, scale, true, im.rotation, im.rotated, scale * inner_desc.center_of_mass);

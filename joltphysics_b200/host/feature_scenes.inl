@@ -5,7 +5,8 @@
 // reduction off).
 // The including file provides: B2J_SHAPE_REF, B2J_NEW_SHAPE(Type, args...), Layers::{NON_MOVING, MOVING, DEBRIS}, sRandomQuat(std::mt19937 &).
 // Variants: 0 kinematic, 1 sensor, 2 dof_plane2d, 3 gyroscopic, 4 step_overrides, 5 no_manifold_reduction, 6 two_moving_layers,
-// 7 kinematic_vs_nondynamic, 8 zoo (0..7 in one world), 9 decorated (ScaledShape / RotatedTranslatedShape around convex shapes).
+// 7 kinematic_vs_nondynamic, 8 zoo (0..7 in one world), 9 decorated (ScaledShape / RotatedTranslatedShape around convex shapes),
+// 10 cylinder (CylinderShape plain, scaled and rotated against every other convex shape).
 // inHull: a cooked convex hull (cooking is host side and out of scope).
 
 static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHAPE_REF &inHull, uint32_t &outNumDynamic)
@@ -206,5 +207,41 @@ static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHA
 		BodyCreationSettings pusher(B2J_NEW_SHAPE(ScaledShape, box, Vec3(1.0f, 3.0f, 4.0f)), RVec3(-6.0f, 1.6f, 0.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
 		pusher.mLinearVelocity = Vec3(1.5f, 0.0f, 0.0f);
 		add(pusher);
+	}
+	if (inVariant == 10)
+	{
+		// CylinderShape: standing and lying stacks (cap on cap, side on cap, side on side), cylinders rolling down a tilted slab, thin discs,
+		// zero convex radius, scaled (non uniform: xz / y) and rotated cylinders, mixed with the other convex shapes
+		B2J_SHAPE_REF cyl = B2J_NEW_SHAPE(CylinderShape, 0.5f, 0.4f), disc = B2J_NEW_SHAPE(CylinderShape, 0.08f, 0.7f), sharp = B2J_NEW_SHAPE(CylinderShape, 0.4f, 0.3f, 0.0f);
+		Quat lying = Quat(0.0f, 0.0f, 0.70710678f, 0.70710678f), tilt = Quat(0.0f, 0.0f, 0.08715574f, 0.9961947f);
+		B2J_SHAPE_REF shapes[8] = {
+			cyl, disc, sharp,
+			B2J_NEW_SHAPE(ScaledShape, cyl, Vec3(1.5f, 0.6f, 1.5f)),
+			B2J_NEW_SHAPE(RotatedTranslatedShape, Vec3(0.0f, 0.2f, 0.1f), lying, cyl),
+			box, hull, capsule };
+		for (int i = 0; i < 5; ++i) // standing stack
+		{
+			BodyCreationSettings s(i % 2? cyl : sharp, RVec3(0.0f, 0.52f + 1.02f * float(i), 0.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			add(s);
+		}
+		for (int i = 0; i < 4; ++i) // lying, side on side
+		{
+			BodyCreationSettings s(cyl, RVec3(3.0f + 0.85f * float(i % 2), 0.42f + 0.8f * float(i / 2), 0.0f), lying, EMotionType::Dynamic, Layers::MOVING);
+			add(s);
+		}
+		BodyCreationSettings ramp(slab, RVec3(-5.0f, 1.0f, 0.0f), tilt, EMotionType::Static, Layers::NON_MOVING);
+		add(ramp, EActivation::DontActivate);
+		for (int i = 0; i < 3; ++i) // rolling down the ramp
+		{
+			BodyCreationSettings s(i == 1? disc : cyl, RVec3(-6.0f + 1.0f * float(i), 2.0f, -1.0f + 1.0f * float(i)), Quat(0.70710678f, 0.0f, 0.0f, 0.70710678f), EMotionType::Dynamic, Layers::MOVING);
+			s.mFriction = 0.8f;
+			add(s);
+		}
+		for (int i = 0; i < 24; ++i) // a heap of everything
+		{
+			BodyCreationSettings s(shapes[i % 8], RVec3(8.0f + 1.2f * float(i % 3), 1.0f + 1.0f * float(i / 3), -1.2f + 1.2f * float((i / 2) % 3)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			s.mRestitution = i % 5 == 0? 0.4f : 0.0f;
+			add(s);
+		}
 	}
 }

@@ -12,6 +12,7 @@
 #include <Jolt/Physics/Collision/Shape/SphereShape.h>
 #include <Jolt/Physics/Collision/Shape/BoxShape.h>
 #include <Jolt/Physics/Collision/Shape/CapsuleShape.h>
+#include <Jolt/Physics/Collision/Shape/CylinderShape.h>
 #include <Jolt/Physics/Collision/Shape/ConvexHullShape.h>
 #include <Jolt/Physics/Collision/Shape/MeshShape.h>
 #include <Jolt/Physics/Collision/Shape/ScaledShape.h>
@@ -35,7 +36,7 @@ struct Api
 #define B2J_FN(name) decltype(&::name) name = nullptr;
 	B2J_FN(b2j_world_create) B2J_FN(b2j_world_destroy) B2J_FN(b2j_last_error) B2J_FN(b2j_settings_default)
 	B2J_FN(b2j_world_set_previous_delta_time)
-	B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
+	B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
 	B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
 #undef B2J_FN
 
@@ -46,7 +47,7 @@ struct Api
 #define B2J_FN(name) name = (decltype(name))dlsym(handle, #name); if (name == nullptr) { outError = String("missing symbol ") + #name; return false; }
 		B2J_FN(b2j_world_create) B2J_FN(b2j_world_destroy) B2J_FN(b2j_last_error) B2J_FN(b2j_settings_default)
 		B2J_FN(b2j_world_set_previous_delta_time)
-		B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
+		B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
 		B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
 #undef B2J_FN
 		return true;
@@ -103,6 +104,12 @@ inline int32_t sUploadShape(const Api &inApi, b2j_world *inWorld, const Shape *i
 		{
 			const CapsuleShape *capsule = static_cast<const CapsuleShape *>(inShape);
 			return inApi.b2j_shape_capsule(inWorld, capsule->GetHalfHeightOfCylinder(), capsule->GetRadius());
+		}
+
+	case EShapeSubType::Cylinder:
+		{
+			const CylinderShape *cylinder = static_cast<const CylinderShape *>(inShape);
+			return inApi.b2j_shape_cylinder(inWorld, cylinder->GetHalfHeight(), cylinder->GetRadius(), cylinder->GetConvexRadius());
 		}
 
 	case EShapeSubType::ConvexHull:
