@@ -39,7 +39,7 @@ enum {
 };
 
 /* Shape kinds on the path (EShapeSubType subset, Jolt/Physics/Collision/Shape/Shape.h) */
-enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4, B2J_SHAPE_CYLINDER = 5 };
+enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4, B2J_SHAPE_CYLINDER = 5, B2J_SHAPE_COMPOUND = 6 };
 
 /* Body flags */
 enum {
@@ -156,6 +156,26 @@ int32_t b2j_shape_capsule(b2j_world *w, float half_height_of_cylinder, float rad
 int32_t b2j_shape_cylinder(b2j_world *w, float half_height, float radius, float convex_radius); /* CylinderShape (axis = y; CylinderShape.cpp) */
 int32_t b2j_shape_convex_hull(b2j_world *w, const b2j_hull_desc *hull);                      /* ConvexHullShape */
 int32_t b2j_shape_mesh(b2j_world *w, const b2j_mesh_desc *mesh);                             /* MeshShape (static bodies) */
+/* StaticCompoundShape (Jolt/Physics/Collision/Shape/StaticCompoundShape.h, CompoundShape.h:170-260) of convex sub shapes (plain or
+ * decorated). The quad tree over the sub shapes is passed as the reference built it (StaticCompoundShape::mNodes, 64 bytes per node:
+ * building it is host side cooking like the convex hull and mesh builders); it decides the order in which sub shapes are tested and
+ * with it the order of the contact manifolds. */
+typedef struct b2j_compound_sub {
+	int32_t shape;                        /* a convex shape id (sphere / box / capsule / cylinder / hull, optionally scaled / rotated) */
+	float   position_com[3];              /* SubShape::GetPositionCOM: relative to the compound's centre of mass */
+	float   rotation[4];                  /* SubShape::GetRotation (x,y,z,w) */
+} b2j_compound_sub;
+typedef struct b2j_compound_desc {
+	uint32_t                num_subs;
+	const b2j_compound_sub *subs;
+	uint32_t                num_nodes;
+	const uint8_t          *nodes;        /* [num_nodes][64] */
+	float                   center_of_mass[3];
+	float                   local_bounds_min[3], local_bounds_max[3];
+	float                   inner_radius;
+} b2j_compound_desc;
+int32_t b2j_shape_static_compound(b2j_world *w, const b2j_compound_desc *compound);
+
 /* Decorated shapes. `inner` = a sphere / box / capsule / convex hull / mesh or one of these two around one.
  * ScaledShape (Jolt/Physics/Collision/Shape/ScaledShape.cpp:190-204: the scale is handed down to the leaf's support function,
  * supporting face and bounds): positive scales; uniform for spheres and capsules (SphereShape::IsValidScale) and for an inner

@@ -134,6 +134,7 @@ PROTOTYPES = {
     "b2j_shape_convex_hull": (C.c_int32, [_VP, C.POINTER(HullDesc)]),
     "b2j_shape_mesh": (C.c_int32, [_VP, C.POINTER(MeshDesc)]),
     "b2j_shape_cylinder": (C.c_int32, [_VP, C.c_float, C.c_float, C.c_float]),
+    "b2j_shape_static_compound": (C.c_int32, [_VP, _VP]),
     "b2j_shape_scaled": (C.c_int32, [_VP, C.c_int32, C.POINTER(C.c_float)]),
     "b2j_shape_rotated_translated": (C.c_int32, [_VP, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "b2j_bodies_add": (C.c_int, [_VP, C.POINTER(BodyDesc), C.c_uint32]),

@@ -71,6 +71,7 @@ struct MeshCollideCtx
 	float max_separation_distance;
 	bool check_active_edges;
 	V3 active_edge_movement_direction;
+	uint32_t sub1;                   // sub shape id of shape 1 in its body (empty = 0xffffffff; a sub shape of a compound, b2j_compound.h)
 	V3 scale2;                       // ScaledShape around the mesh: node bounds and vertices are scaled on the fly (MeshShape.cpp:1150-1152, CollideConvexVsTriangles.cpp:43-45)
 	// convex
 	Xf transform_2_to_1;
@@ -88,7 +89,7 @@ struct MeshHit
 {
 	V3 world_space_normal;       // normalised penetration axis
 	float depth;
-	uint32_t sub2;
+	uint32_t sub1, sub2;
 	int n;                       // contact point pairs of the hit, in the order ManifoldBetweenTwoFaces emits them
 };
 
@@ -127,7 +128,7 @@ B2J_D void mesh_merge_hit(const DWorld &w, MeshScratch &ms, int &num_manifolds, 
 			mi = num_manifolds++;
 		MeshManifold &m = ms.manifolds[mi];
 		m.normal_sum = hit.world_space_normal; m.first_normal = hit.world_space_normal; m.depth = hit.depth;
-		m.sub1 = 0xffffffffu; m.sub2 = hit.sub2; m.n = 0;
+		m.sub1 = hit.sub1; m.sub2 = hit.sub2; m.n = 0;
 	}
 	MeshManifold &m = ms.manifolds[mi];
 	for (int i = 0; i < hit.n && m.n < MAX_MANIFOLD_POINTS; ++i) { m.p1[m.n] = pts1[i]; m.p2[m.n] = pts2[i]; ++m.n; }
@@ -136,7 +137,7 @@ B2J_D void mesh_merge_hit(const DWorld &w, MeshScratch &ms, int &num_manifolds, 
 }
 
 // ReductionCollideShapeCollector::AddHit
-B2J_D void mesh_add_hit(const DWorld &w, MeshScratch &ms, int &num_manifolds, V3 point1, V3 point2, V3 axis_world, float depth, uint32_t sub2,
+B2J_D void mesh_add_hit(const DWorld &w, MeshScratch &ms, int &num_manifolds, V3 point1, V3 point2, V3 axis_world, float depth, uint32_t sub1, uint32_t sub2,
 	const V3 *face1, int n1, const V3 *face2, int n2)
 {
 	V3 world_space_normal = normalized(axis_world);
@@ -163,7 +164,7 @@ B2J_D void mesh_add_hit(const DWorld &w, MeshScratch &ms, int &num_manifolds, V3
 			mi = num_manifolds++;
 		MeshManifold &m = ms.manifolds[mi];
 		m.normal_sum = world_space_normal; m.first_normal = world_space_normal; m.depth = depth;
-		m.sub1 = 0xffffffffu; m.sub2 = sub2; m.n = 0;
+		m.sub1 = sub1; m.sub2 = sub2; m.n = 0;
 	}
 	MeshManifold &m = ms.manifolds[mi];
 	manifold_between_two_faces(point1, point2, axis_world, w.settings.speculative_contact_distance + w.settings.manifold_tolerance, face1, n1, face2, n2, m.p1, m.p2, m.n, ms.clip);
@@ -240,7 +241,7 @@ B2J_D void mesh_collide_convex_triangle(const DWorld &w, const ShapeDesc &s1, co
 	V3 face1[MAX_FACE_VERTS], face2[3];
 	int n1 = supporting_face(w, s1, -penetration_axis, c.transform1, face1);
 	face2[0] = mul(c.transform1, v0); face2[1] = mul(c.transform1, v1); face2[2] = mul(c.transform1, v2);
-	mesh_add_hit(w, ms, num_manifolds, point1, point2, axis_world, penetration_depth, sub2, face1, n1, face2, 3);
+	mesh_add_hit(w, ms, num_manifolds, point1, point2, axis_world, penetration_depth, c.sub1, sub2, face1, n1, face2, 3);
 }
 
 // CollideSphereVsTriangles::Collide
@@ -276,7 +277,7 @@ B2J_D void mesh_collide_sphere_triangle(const DWorld &w, const MeshCollideCtx &c
 	face2[0] = mul(c.transform2, c.sphere_center_in2 + v0);
 	face2[1] = mul(c.transform2, c.sphere_center_in2 + v1);
 	face2[2] = mul(c.transform2, c.sphere_center_in2 + v2);
-	mesh_add_hit(w, ms, num_manifolds, point1, point2, axis_world, penetration_depth, sub2, nullptr, 0, face2, 3);
+	mesh_add_hit(w, ms, num_manifolds, point1, point2, axis_world, penetration_depth, c.sub1, sub2, nullptr, 0, face2, 3);
 }
 
 // NodeCodecQuadTreeHalfFloat: does child ch of a 64 byte node overlap the query volume of the pair (AABox4VsSphere / AABox4VsBox)
@@ -318,20 +319,20 @@ B2J_D void mesh_decode_triangle(const uint8_t *tree, uint32_t block_id, uint32_t
 	sub2 = (block_sub & ~(7u << block_id_bits)) | (t << block_id_bits);
 }
 
-// Everything of MeshShape::sCollideConvexVsMesh / sCollideSphereVsMesh that is computed once per (convex, mesh) pair
-B2J_D MeshCollideCtx mesh_collide_ctx(const DWorld &w, const CollideItem &item, const BodyInfo &i1, const BodyInfo &i2, const ShapeDesc &s1)
+// Everything of MeshShape::sCollideConvexVsMesh / sCollideSphereVsMesh that is computed once per (convex, mesh) pair;
+// transform1 / transform2: the centre of mass transforms the dispatch hands to sCollideConvexVsMesh for the two shapes BEFORE their own
+// decorators are peeled (a body's transform, or a compound's sub shape transform), relative to the centre of mass of body 1
+B2J_D MeshCollideCtx mesh_collide_ctx_from(const DWorld &w, const ShapeDesc &s1, const Xf &transform1, const ShapeDesc &s2, const Xf &transform2,
+	float max_separation_distance, V3 active_edge_movement_direction, uint32_t sub1)
 {
 	MeshCollideCtx cc;
-	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
-	cc.transform1 = shape_transform(s1, xf(m33_rotation(to_q4(w.rotation[item.b1])), v3_zero()));
-	const ShapeDesc &s2 = w.shapes[i2.shape];
-	cc.transform2 = shape_transform(s2, xf(m33_rotation(to_q4(w.rotation[item.b2])), x2 + (-x1)));
+	cc.transform1 = shape_transform(s1, transform1);
+	cc.transform2 = shape_transform(s2, transform2);
 	cc.scale2 = s2.scale;
-	cc.max_separation_distance = ((i1.flags | i2.flags) & B2J_BODY_SENSOR)? 0.0f : w.settings.speculative_contact_distance;
+	cc.sub1 = sub1;
+	cc.max_separation_distance = max_separation_distance;
 	cc.check_active_edges = w.settings.check_active_edges != 0;
-	V3 lv1 = i1.motion_type != B2J_MOTION_STATIC? to_v3(w.linear_velocity[item.b1]) : v3_zero();
-	V3 lv2 = i2.motion_type != B2J_MOTION_STATIC? to_v3(w.linear_velocity[item.b2]) : v3_zero();
-	cc.active_edge_movement_direction = lv1 - lv2;
+	cc.active_edge_movement_direction = active_edge_movement_direction;
 	cc.sphere = s1.kind == B2J_SHAPE_SPHERE;
 	if (cc.sphere)
 	{
@@ -366,6 +367,85 @@ B2J_D MeshCollideCtx mesh_collide_ctx(const DWorld &w, const CollideItem &item, 
 	return cc;
 }
 
+// PhysicsSystem::ProcessBodyPair: mActiveEdgeMovementDirection = velocity of body 1 relative to body 2 (PhysicsSystem.cpp:1106-1108)
+B2J_D V3 pair_movement_direction(const DWorld &w, const CollideItem &item, const BodyInfo &i1, const BodyInfo &i2)
+{
+	V3 lv1 = i1.motion_type != B2J_MOTION_STATIC? to_v3(w.linear_velocity[item.b1]) : v3_zero();
+	V3 lv2 = i2.motion_type != B2J_MOTION_STATIC? to_v3(w.linear_velocity[item.b2]) : v3_zero();
+	return lv1 - lv2;
+}
+
+B2J_D MeshCollideCtx mesh_collide_ctx(const DWorld &w, const CollideItem &item, const BodyInfo &i1, const BodyInfo &i2, const ShapeDesc &s1)
+{
+	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
+	float max_separation_distance = ((i1.flags | i2.flags) & B2J_BODY_SENSOR)? 0.0f : w.settings.speculative_contact_distance;
+	return mesh_collide_ctx_from(w, s1, xf(m33_rotation(to_q4(w.rotation[item.b1])), v3_zero()), w.shapes[i2.shape], xf(m33_rotation(to_q4(w.rotation[item.b2])), x2 + (-x1)),
+		max_separation_distance, pair_movement_direction(w, item, i1, i2), 0xffffffffu);
+}
+
+// MeshShape::WalkTreePerTriangle for one (convex, mesh) pair, serial: every hit joins ms / num_manifolds (mesh_add_hit)
+B2J_D void mesh_walk_serial(const DWorld &w, const ShapeDesc &s1, const ShapeDesc &s2, const MeshCollideCtx &cc, EpaScratch &epa, MeshScratch &ms, int &num_manifolds)
+{
+	const uint8_t *tree = w.mesh_bytes + s2.mesh_offset;
+	// NodeCodec header (32 B): root bounds min/max, root properties, block id bits; then TriangleHeader: offset, scale
+	uint32_t root_properties = load_u32(tree + 24);
+	uint32_t block_id_bits = tree[28];
+	V3 tri_offset = v3(load_f32(tree + 32), load_f32(tree + 36), load_f32(tree + 40));
+	V3 tri_scale = v3(load_f32(tree + 44), load_f32(tree + 48), load_f32(tree + 52));
+	uint32_t stack[128];
+	int top = 0;
+	stack[0] = root_properties;
+	do
+	{
+		uint32_t node_properties = stack[top];
+		uint32_t tri_count = node_properties >> 28;
+		if (tri_count == 0)
+		{
+			const uint8_t *node = tree + ((size_t)node_properties << 2);
+			uint32_t props[4];
+			int n = 0;
+			for (int ch = 0; ch < 4; ++ch)
+				if (mesh_child_overlaps(cc, node, ch)) props[n++] = load_u32(node + 48 + 4 * ch);
+			for (int j = 0; j < n && top + j < 128; ++j) stack[top + j] = props[j];
+			top += n;
+		}
+		else if (tri_count != 15)
+		{
+			uint32_t block_id = node_properties & 0x0fffffffu;
+			for (uint32_t t = 0; t < tri_count; ++t)
+			{
+				V3 v[3];
+				uint32_t active_edges, sub2;
+				mesh_decode_triangle(tree, block_id, t, block_id_bits, tri_offset, tri_scale, v, active_edges, sub2);
+				if (cc.sphere)
+					mesh_collide_sphere_triangle(w, cc, ms, num_manifolds, v[0], v[1], v[2], active_edges, sub2);
+				else
+					mesh_collide_convex_triangle(w, s1, cc, epa, ms, num_manifolds, v[0], v[1], v[2], active_edges, sub2);
+			}
+		}
+		--top;
+	}
+	while (top >= 0);
+}
+
+// ProcessBodyPair after the collector is full: normalise the summed normals, prune to 4, add the contacts
+B2J_D void mesh_finish_pair(const DWorld &w, const NarrowCtx &c, const CollideItem &item, MeshScratch &ms, int num_manifolds)
+{
+	for (int i = 0; i < num_manifolds; ++i)
+	{
+		MeshManifold &m = ms.manifolds[i];
+		V3 normal = normalized(m.normal_sum);
+		if (m.n > 4)
+			prune_contact_points(normal, m.p1, m.p2, m.n, ms.clip);
+		ManifoldOut &o = ms.out[i];
+		o.normal = normal; o.depth = m.depth; o.sub1 = m.sub1; o.sub2 = m.sub2; o.n = m.n;
+		for (int p = 0; p < m.n; ++p) { o.p1[p] = m.p1[p]; o.p2[p] = m.p2[p]; }
+	}
+	add_manifolds(w, c, item, ms.out, num_manifolds);
+}
+
+B2J_D void compound_collide_pair(const DWorld &w, const NarrowCtx &c, const CollideItem &item, EpaScratch &epa, MeshScratch &ms); // b2j_compound.h
+
 struct KCollideMesh
 {
 	DWorld w; NarrowCtx c; MeshScratch *mesh_scratch;
@@ -376,85 +456,19 @@ struct KCollideMesh
 		CollideItem item = c.collide_mesh[k];
 		BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
 		const ShapeDesc &s1 = w.shapes[i1.shape], &s2 = w.shapes[i2.shape];
+		MeshScratch &ms = mesh_scratch[slot];
+		if (s1.kind == B2J_SHAPE_COMPOUND || s2.kind == B2J_SHAPE_COMPOUND)
+		{
+			compound_collide_pair(w, c, item, epa, ms);
+			return;
+		}
 		if (s2.kind != B2J_SHAPE_MESH || s1.kind == B2J_SHAPE_MESH)
 			return; // mesh as body 1 (sReversedCollideShape) is not on the path: meshes are static, body 1 has the higher motion type
-		MeshScratch &ms = mesh_scratch[slot];
 
 		MeshCollideCtx cc = mesh_collide_ctx(w, item, i1, i2, s1);
-
-		const uint8_t *tree = w.mesh_bytes + s2.mesh_offset;
-		// NodeCodec header (32 B): root bounds min/max, root properties, block id bits; then TriangleHeader: offset, scale
-		uint32_t root_properties = load_u32(tree + 24);
-		uint32_t block_id_bits = tree[28];
-		V3 tri_offset = v3(load_f32(tree + 32), load_f32(tree + 36), load_f32(tree + 40));
-		V3 tri_scale = v3(load_f32(tree + 44), load_f32(tree + 48), load_f32(tree + 52));
-
 		int num_manifolds = 0;
-		uint32_t stack[128];
-		int top = 0;
-		stack[0] = root_properties;
-		do
-		{
-			uint32_t node_properties = stack[top];
-			uint32_t tri_count = node_properties >> 28;
-			if (tri_count == 0)
-			{
-				const uint8_t *node = tree + ((size_t)node_properties << 2);
-				uint32_t props[4];
-				int n = 0;
-				for (int ch = 0; ch < 4; ++ch)
-					if (mesh_child_overlaps(cc, node, ch)) props[n++] = load_u32(node + 48 + 4 * ch);
-				for (int j = 0; j < n && top + j < 128; ++j) stack[top + j] = props[j];
-				top += n;
-			}
-			else if (tri_count != 15)
-			{
-				uint32_t block_id = node_properties & 0x0fffffffu;
-				const uint8_t *block_start = tree + ((size_t)block_id << 2);
-				uint32_t header_flags = load_u32(block_start);
-				const uint8_t *vertices = block_start + ((size_t)(header_flags & 0x1fffffffu) << 2);
-				const uint8_t *blocks = block_start + 4;
-				// sub shape id of the block: PushID(block_id, 0, block_id_bits) on an empty id
-				uint32_t block_sub = block_id_bits >= 32? block_id : ((0xffffffffu & ~((1u << block_id_bits) - 1u)) | block_id);
-				for (uint32_t t = 0; t < tri_count; ++t)
-				{
-					const uint8_t *blk = blocks + 16 * (t >> 2);
-					uint32_t lane = t & 3;
-					V3 v[3];
-					for (int vi = 0; vi < 3; ++vi)
-					{
-						uint32_t idx = blk[4 * vi + lane];
-						uint32_t c1 = load_u32(vertices + 8 * idx), c2 = load_u32(vertices + 8 * idx + 4);
-						uint32_t xc = c1 & 0x1fffffu;
-						uint32_t yc = (c1 >> 21) | ((c2 >> 21) << 11);
-						uint32_t zc = c2 & 0x1fffffu;
-						v[vi] = v3((float)(int32_t)xc * tri_scale.x + tri_offset.x, (float)(int32_t)yc * tri_scale.y + tri_offset.y, (float)(int32_t)zc * tri_scale.z + tri_offset.z);
-					}
-					uint32_t flags = blk[12 + lane];
-					uint32_t active_edges = (flags >> 5) & 7;
-					uint32_t sub2 = (block_sub & ~(7u << block_id_bits)) | (t << block_id_bits);
-					if (cc.sphere)
-						mesh_collide_sphere_triangle(w, cc, ms, num_manifolds, v[0], v[1], v[2], active_edges, sub2);
-					else
-						mesh_collide_convex_triangle(w, s1, cc, epa, ms, num_manifolds, v[0], v[1], v[2], active_edges, sub2);
-				}
-			}
-			--top;
-		}
-		while (top >= 0);
-
-		// ProcessBodyPair: normalise the summed normals, prune to 4, add the contacts
-		for (int i = 0; i < num_manifolds; ++i)
-		{
-			MeshManifold &m = ms.manifolds[i];
-			V3 normal = normalized(m.normal_sum);
-			if (m.n > 4)
-				prune_contact_points(normal, m.p1, m.p2, m.n, ms.clip);
-			ManifoldOut &o = ms.out[i];
-			o.normal = normal; o.depth = m.depth; o.sub1 = m.sub1; o.sub2 = m.sub2; o.n = m.n;
-			for (int p = 0; p < m.n; ++p) { o.p1[p] = m.p1[p]; o.p2[p] = m.p2[p]; }
-		}
-		add_manifolds(w, c, item, ms.out, num_manifolds);
+		mesh_walk_serial(w, s1, s2, cc, epa, ms, num_manifolds);
+		mesh_finish_pair(w, c, item, ms, num_manifolds);
 	}
 };
 
@@ -483,9 +497,16 @@ struct KCollideMeshWarp
 		CollideItem item = c.collide_mesh[k];
 		BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
 		const ShapeDesc &s1 = w.shapes[i1.shape], &s2 = w.shapes[i2.shape];
+		MeshScratch &ms = mesh_scratch[slot];
+		if (s1.kind == B2J_SHAPE_COMPOUND || s2.kind == B2J_SHAPE_COMPOUND)
+		{
+			// a pair with a StaticCompoundShape: lane 0 runs the sub shape loops (b2j_compound.h)
+			if (lane == 0) { EpaScratch epa = epa_storage.view(); compound_collide_pair(w, c, item, epa, ms); }
+			__syncwarp();
+			return;
+		}
 		if (s2.kind != B2J_SHAPE_MESH || s1.kind == B2J_SHAPE_MESH)
 			return; // (uniform over the warp)
-		MeshScratch &ms = mesh_scratch[slot];
 		const MeshCollideCtx cc = mesh_collide_ctx(w, item, i1, i2, s1);
 
 		const uint8_t *tree = w.mesh_bytes + s2.mesh_offset;
@@ -556,7 +577,7 @@ struct KCollideMeshWarp
 				if (back_facing)
 					alive = false; // EBackFaceMode::IgnoreBackFaces
 			}
-			MeshHit hit; hit.n = 0; hit.depth = 0.0f; hit.sub2 = sub2; hit.world_space_normal = v3_zero();
+			MeshHit hit; hit.n = 0; hit.depth = 0.0f; hit.sub1 = 0xffffffffu; hit.sub2 = sub2; hit.world_space_normal = v3_zero();
 			V3 pts1[MAX_MANIFOLD_POINTS], pts2[MAX_MANIFOLD_POINTS];
 			bool have_hit = false;
 			if (cc.sphere)

@@ -169,7 +169,9 @@ struct KProcessPairs
 			v3_store(delta_position, out.dpos);
 			v3_store(q4_xyz(q4_ensure_w_positive(delta_rotation)), out.drot);
 			CollideItem item; item.b1 = b1; item.b2 = b2; item.pair_entry = entry; item.old_pair = old;
-			if (w.shapes[i2.shape].kind == B2J_SHAPE_MESH || w.shapes[i1.shape].kind == B2J_SHAPE_MESH)
+			uint32_t kind1 = w.shapes[i1.shape].kind, kind2 = w.shapes[i2.shape].kind;
+			// pairs that collect several hits per pair (mesh triangles, compound sub shapes) share the collector kernel (b2j_mesh.h)
+			if (kind1 == B2J_SHAPE_MESH || kind2 == B2J_SHAPE_MESH || kind1 == B2J_SHAPE_COMPOUND || kind2 == B2J_SHAPE_COMPOUND)
 				c.collide_mesh[atomic_add(&w.counters->num_collide_mesh, 1u)] = item;
 			else
 				c.collide_convex[atomic_add(&w.counters->num_collide_convex, 1u)] = item;

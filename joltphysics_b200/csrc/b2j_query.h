@@ -295,8 +295,33 @@ B2J_D bool ray_mesh(const DWorld &w, const ShapeDesc &s, V3 o, V3 d, float &io_f
 }
 
 // Shape::CastRay in the centre of mass space of the shape: improves io_fraction / out_sub when the ray hits closer
+B2J_D bool ray_shape(const DWorld &w, const ShapeDesc &decorated, V3 o, V3 d, float &io_fraction, uint32_t &out_sub);
+
+// StaticCompoundShape::CastRay, closest hit: every sub shape in its own space (CastRayVisitor::VisitShape, CompoundShapeVisitors.h:
+// Mat44::sInverseRotationTranslation(sub rotation, sub position)); the tree only prunes, the closest hit does not depend on the order
+B2J_D bool ray_compound(const DWorld &w, const ShapeDesc &s, V3 o, V3 d, float &io_fraction, uint32_t &out_sub)
+{
+	bool hit = false;
+	for (uint32_t i = 0; i < s.compound_num_subs; ++i)
+	{
+		const CompoundSub &sub = w.compound_subs[s.compound_sub_offset + i];
+		Xf inv = xf_inverse_rotation_translation(to_q4(sub.rotation), to_v3(sub.position_com));
+		V3 lo = mul(inv, o);
+		V3 ld = mul(inv, o + d) - lo;
+		uint32_t leaf_sub;
+		if (ray_shape(w, w.shapes[sub.shape], lo, ld, io_fraction, leaf_sub))
+		{
+			hit = true;
+			out_sub = s.compound_sub_bits == 0? 0xffffffffu : ((0xffffffffu & ~((1u << s.compound_sub_bits) - 1u)) | i);
+		}
+	}
+	return hit;
+}
+
 B2J_D bool ray_shape(const DWorld &w, const ShapeDesc &decorated, V3 o, V3 d, float &io_fraction, uint32_t &out_sub)
 {
+	if (decorated.kind == B2J_SHAPE_COMPOUND)
+		return ray_compound(w, decorated, o, d, io_fraction, out_sub);
 	if (decorated.flags & SHAPE_LOCAL_ROTATION)
 	{
 		// RotatedTranslatedShape::CastRay: inRay.Transformed(Mat44::sRotation(mRotation.Conjugated())) (RotatedTranslatedShape.cpp:127-137)

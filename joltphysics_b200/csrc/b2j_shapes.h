@@ -255,21 +255,24 @@ B2J_HD int supporting_face(const DWorld &w, const ShapeDesc &s, V3 dir, const Xf
 	}
 }
 
-// Body::CalculateWorldSpaceBoundsInternal -> Shape::GetWorldSpaceBounds(com transform, one)
-B2J_HD void world_bounds(const ShapeDesc &s, V3 pos, Q4 rot, V3 &out_min, V3 &out_max)
+// SubShape::GetLocalTransformNoScale(one): Mat44::sRotationTranslation(rotation, position relative to the compound's centre of mass)
+B2J_HD Xf compound_sub_transform(const CompoundSub &sub) { return xf(m33_rotation(to_q4(sub.rotation)), to_v3(sub.position_com)); }
+
+// Shape::GetWorldSpaceBounds(inCenterOfMassTransform, one) of a convex shape or mesh; x_in = the transform before the shape's own decorators
+B2J_HD void world_bounds_leaf(const ShapeDesc &s, const Xf &x_in, V3 &out_min, V3 &out_max)
 {
+	Xf x = shape_transform(s, x_in);
 	switch (s.kind)
 	{
 	case B2J_SHAPE_SPHERE: // SphereShape.cpp:67-74
 		{
 			V3 he = v3_rep(s.radius);
-			out_min = -he + pos;
-			out_max = he + pos;
+			out_min = -he + x.t;
+			out_max = he + x.t;
 		}
 		break;
 	case B2J_SHAPE_CAPSULE: // CapsuleShape.cpp:266-277
 		{
-			Xf x = shape_transform(s, xf_rotation_translation(rot, pos));
 			V3 extent = v3_rep(s.radius);
 			V3 height = v3(0.0f, s.half_height, 0.0f);
 			V3 p1 = mul(x, -height), p2 = mul(x, height);
@@ -279,11 +282,10 @@ B2J_HD void world_bounds(const ShapeDesc &s, V3 pos, Q4 rot, V3 &out_min, V3 &ou
 		break;
 	default: // AABox::Transformed (AABox.h:193-213)
 		{
-			M33 r = shape_transform(s, xf_rotation_translation(rot, pos)).r;
-			V3 new_min = pos, new_max = pos;
+			V3 new_min = x.t, new_max = x.t;
 			for (int c = 0; c < 3; ++c)
 			{
-				V3 col = m33_col(r, c);
+				V3 col = m33_col(x.r, c);
 				V3 a = col * v3_get(s.local_min, c);
 				V3 b = col * v3_get(s.local_max, c);
 				new_min += v3_min(a, b);
@@ -294,6 +296,27 @@ B2J_HD void world_bounds(const ShapeDesc &s, V3 pos, Q4 rot, V3 &out_min, V3 &ou
 		}
 		break;
 	}
+}
+
+// Body::CalculateWorldSpaceBoundsInternal -> Shape::GetWorldSpaceBounds(com transform, one)
+B2J_HD void world_bounds(const DWorld &w, const ShapeDesc &s, V3 pos, Q4 rot, V3 &out_min, V3 &out_max)
+{
+	Xf x = xf_rotation_translation(rot, pos);
+	if (s.kind == B2J_SHAPE_COMPOUND && s.compound_num_subs <= 10)
+	{
+		// CompoundShape::GetWorldSpaceBounds (CompoundShape.cpp:93-115): up to 10 sub shapes are bounded one by one
+		V3 mn = v3_rep(FLT_MAX), mx = v3_rep(-FLT_MAX);
+		for (uint32_t i = 0; i < s.compound_num_subs; ++i)
+		{
+			const CompoundSub &sub = w.compound_subs[s.compound_sub_offset + i];
+			V3 a, b;
+			world_bounds_leaf(w.shapes[sub.shape], mul(x, compound_sub_transform(sub)), a, b);
+			mn = v3_min(mn, a); mx = v3_max(mx, b);
+		}
+		out_min = mn; out_max = mx;
+		return;
+	}
+	world_bounds_leaf(s, x, out_min, out_max);
 }
 
 // Body::GetSleepTestPoints (Body.inl:156-188)

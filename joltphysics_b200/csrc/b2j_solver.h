@@ -1676,7 +1676,7 @@ struct KBoundsAndSleep
 		V3 x = to_v3(w.position[b]);
 		Q4 q = to_q4(w.rotation[b]);
 		V3 mn, mx;
-		world_bounds(shape, x, q, mn, mx);
+		world_bounds(w, shape, x, q, mn, mx);
 		w.bounds_min[b] = f4(mn);
 		w.bounds_max[b] = f4(mx);
 		if (!is_last)

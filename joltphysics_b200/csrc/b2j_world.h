@@ -59,7 +59,8 @@ struct ShapeDesc
 	uint32_t hull_point_offset, hull_num_points;   // hull_points / hull_shrunk (same indexing)
 	uint32_t hull_face_offset, hull_num_faces;     // hull_planes / hull_faces
 	uint32_t hull_vtx_offset;                      // hull_vtx
-	uint32_t mesh_offset, mesh_size;               // mesh_bytes
+	uint32_t mesh_offset, mesh_size;               // mesh_bytes (mesh: the cooked tree; compound: the 64 byte quad tree nodes)
+	uint32_t compound_sub_offset, compound_num_subs, compound_sub_bits; // compound_subs; CompoundShape::GetSubShapeIDBits
 	// decorated convex shapes (ScaledShape / RotatedTranslatedShape around a convex leaf): the scale is baked into the
 	// leaf parameters above by the host (box / sphere / capsule: exactly what the reference's scaled support functions compute; hull:
 	// scaled points, shrunk points and planes), the rotation composes with the body's centre of mass transform where the shape is used
@@ -71,6 +72,9 @@ struct ShapeDesc
 	V3 outer_min, outer_max;                       // GetLocalBounds() of the outermost shape (Body::GetSleepTestPoints)
 };
 enum { SHAPE_LOCAL_ROTATION = 1, SHAPE_SCALED_HULL = 2 };
+
+// CompoundShape::SubShape (CompoundShape.h:170-260): a convex shape placed in the compound, position relative to the compound's centre of mass
+struct CompoundSub { uint32_t shape; uint32_t pad[3]; F4 position_com; F4 rotation; };
 
 // Body pair cache entry (CachedBodyPair, ContactConstraintManager.h:335-355)
 struct alignas(8) CachedPair
@@ -164,6 +168,7 @@ struct DWorld
 	const uint32_t *hull_faces;  // first vertex | num vertices << 16
 	const uint8_t *hull_vtx;
 	const uint8_t *mesh_bytes;
+	const CompoundSub *compound_subs;
 
 	// contact caches
 	ContactCache read_cache, write_cache;

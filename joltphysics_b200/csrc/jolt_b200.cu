@@ -11,6 +11,7 @@
 #include "b2j_broadphase.h"
 #include "b2j_narrowphase.h"
 #include "b2j_mesh.h"
+#include "b2j_compound.h"
 #include "b2j_solver.h"
 #include "b2j_query.h"
 
@@ -79,7 +80,7 @@ struct KAddBodies
 		else
 		{
 			V3 mn, mx;
-			world_bounds(s, x, q, mn, mx);
+			world_bounds(w, s, x, q, mn, mx);
 			w.bounds_min[b] = f4(mn);
 			w.bounds_max[b] = f4(mx);
 			V3 pts[3];
@@ -209,7 +210,7 @@ struct KSetState
 		if (pos || rot)
 		{
 			V3 mn, mx;
-			world_bounds(w.shapes[w.info[b].shape], to_v3(w.position[b]), to_q4(w.rotation[b]), mn, mx);
+			world_bounds(w, w.shapes[w.info[b].shape], to_v3(w.position[b]), to_q4(w.rotation[b]), mn, mx);
 			w.bounds_min[b] = f4(mn);
 			w.bounds_max[b] = f4(mx);
 		}
@@ -268,7 +269,7 @@ struct KSetInfo
 				w.inertia_rotation[b] = f4(q4_load(inertia_rotation + 4 * i));
 			}
 			V3 mn, mx;
-			world_bounds(w.shapes[info.shape], x, q, mn, mx);
+			world_bounds(w, w.shapes[info.shape], x, q, mn, mx);
 			w.bounds_min[b] = f4(mn);
 			w.bounds_max[b] = f4(mx);
 			info.flags |= B2J_BODY_INVALIDATE_CACHE;
@@ -545,6 +546,8 @@ struct b2j_world
 	std::vector<F4> h_hull_points, h_hull_shrunk, h_hull_planes;
 	std::vector<uint32_t> h_hull_faces;
 	std::vector<uint8_t> h_hull_vtx, h_mesh_bytes;
+	std::vector<CompoundSub> h_compound_subs;
+	CompoundSub *d_compound_subs = nullptr;
 	bool shapes_dirty = false;
 	ShapeDesc *d_shapes = nullptr; F4 *d_hull_points = nullptr, *d_hull_shrunk = nullptr, *d_hull_planes = nullptr;
 	uint32_t *d_hull_faces = nullptr; uint8_t *d_hull_vtx = nullptr, *d_mesh_bytes = nullptr;
@@ -652,7 +655,8 @@ void upload_shapes(b2j_world *W)
 	Runtime &rt = W->rt;
 	rt.sync();
 	rt.free_(W->d_shapes); rt.free_(W->d_hull_points); rt.free_(W->d_hull_shrunk); rt.free_(W->d_hull_planes);
-	rt.free_(W->d_hull_faces); rt.free_(W->d_hull_vtx); rt.free_(W->d_mesh_bytes);
+	rt.free_(W->d_hull_faces); rt.free_(W->d_hull_vtx); rt.free_(W->d_mesh_bytes); rt.free_(W->d_compound_subs);
+	W->d_compound_subs = rt.alloc<CompoundSub>(W->h_compound_subs.size()); rt.upload(W->d_compound_subs, W->h_compound_subs.data(), W->h_compound_subs.size());
 	W->d_shapes = rt.alloc<ShapeDesc>(W->h_shapes.size()); rt.upload(W->d_shapes, W->h_shapes.data(), W->h_shapes.size());
 	W->d_hull_points = rt.alloc<F4>(W->h_hull_points.size()); rt.upload(W->d_hull_points, W->h_hull_points.data(), W->h_hull_points.size());
 	W->d_hull_shrunk = rt.alloc<F4>(W->h_hull_shrunk.size()); rt.upload(W->d_hull_shrunk, W->h_hull_shrunk.data(), W->h_hull_shrunk.size());
@@ -662,7 +666,7 @@ void upload_shapes(b2j_world *W)
 	W->d_mesh_bytes = rt.alloc<uint8_t>(W->h_mesh_bytes.size() + 16); rt.upload(W->d_mesh_bytes, W->h_mesh_bytes.data(), W->h_mesh_bytes.size());
 	if (!W->h_mesh_bytes.empty() && W->d_mesh_scratch == nullptr) W->d_mesh_scratch = rt.alloc<MeshScratch>(W->nc.num_scratch, false);
 	W->d.shapes = W->d_shapes; W->d.hull_points = W->d_hull_points; W->d.hull_shrunk = W->d_hull_shrunk; W->d.hull_planes = W->d_hull_planes;
-	W->d.hull_faces = W->d_hull_faces; W->d.hull_vtx = W->d_hull_vtx; W->d.mesh_bytes = W->d_mesh_bytes;
+	W->d.hull_faces = W->d_hull_faces; W->d.hull_vtx = W->d_hull_vtx; W->d.mesh_bytes = W->d_mesh_bytes; W->d.compound_subs = W->d_compound_subs;
 	W->shapes_dirty = false;
 }
 
@@ -1545,7 +1549,7 @@ void b2j_world_destroy(b2j_world *W)
 		rt.free_(t.parent); rt.free_(t.node_min); rt.free_(t.node_max); rt.free_(t.visit); rt.free_(t.layer_bounds); rt.free_(t.world_root);
 	}
 	rt.free_(W->d_shapes); rt.free_(W->d_hull_points); rt.free_(W->d_hull_shrunk); rt.free_(W->d_hull_planes);
-	rt.free_(W->d_hull_faces); rt.free_(W->d_hull_vtx); rt.free_(W->d_mesh_bytes);
+	rt.free_(W->d_hull_faces); rt.free_(W->d_hull_vtx); rt.free_(W->d_mesh_bytes); rt.free_(W->d_compound_subs);
 #ifndef B2J_HOSTSIM
 	if (W->ev_begin) cudaEventDestroy(W->ev_begin);
 	if (W->ev_end) cudaEventDestroy(W->ev_end);
@@ -1699,6 +1703,39 @@ int32_t b2j_shape_convex_hull(b2j_world *W, const b2j_hull_desc *h)
 	return id;
 }
 
+int32_t b2j_shape_static_compound(b2j_world *W, const b2j_compound_desc *cd)
+{
+	if (cd == nullptr || cd->num_subs == 0 || cd->subs == nullptr || cd->num_nodes == 0 || cd->nodes == nullptr) { last_error() = "invalid compound"; return -1; }
+	for (uint32_t i = 0; i < cd->num_subs; ++i)
+	{
+		int32_t sh = cd->subs[i].shape;
+		if (sh < 0 || sh >= (int32_t)W->h_shapes.size()) { last_error() = "compound: invalid sub shape id"; return -1; }
+		uint32_t kind = W->h_shapes[sh].kind;
+		if (kind == B2J_SHAPE_MESH || kind == B2J_SHAPE_COMPOUND) { last_error() = "compound: sub shapes must be convex"; return -1; }
+	}
+	ShapeDesc s; memset(&s, 0, sizeof(s));
+	s.kind = B2J_SHAPE_COMPOUND; s.inner_radius = cd->inner_radius;
+	s.local_min = v3_load(cd->local_bounds_min); s.local_max = v3_load(cd->local_bounds_max);
+	s.center_of_mass = v3_load(cd->center_of_mass);
+	while (W->h_mesh_bytes.size() % 16 != 0) W->h_mesh_bytes.push_back(0);
+	s.mesh_offset = (uint32_t)W->h_mesh_bytes.size(); s.mesh_size = cd->num_nodes * 64;
+	W->h_mesh_bytes.insert(W->h_mesh_bytes.end(), cd->nodes, cd->nodes + (size_t)cd->num_nodes * 64);
+	s.compound_sub_offset = (uint32_t)W->h_compound_subs.size(); s.compound_num_subs = cd->num_subs;
+	// CompoundShape::GetSubShapeIDBits: 32 - CountLeadingZeros(n - 1)
+	uint32_t bits = 0;
+	while (bits < 32 && (cd->num_subs - 1) >> bits != 0) ++bits;
+	s.compound_sub_bits = bits;
+	for (uint32_t i = 0; i < cd->num_subs; ++i)
+	{
+		CompoundSub sub; memset(&sub, 0, sizeof(sub));
+		sub.shape = (uint32_t)cd->subs[i].shape;
+		sub.position_com = f4(v3_load(cd->subs[i].position_com));
+		sub.rotation = f4(cd->subs[i].rotation[0], cd->subs[i].rotation[1], cd->subs[i].rotation[2], cd->subs[i].rotation[3]);
+		W->h_compound_subs.push_back(sub);
+	}
+	return add_shape(W, s);
+}
+
 // The device description of `leaf` under an accumulated scale and rotation (what the reference's dispatch hands to the leaf's collide /
 // support / bounds functions after peeling the decorators, ScaledShape.cpp:190-204, RotatedTranslatedShape.cpp:183-192)
 static int32_t add_decorated_shape(b2j_world *W, int32_t leaf, V3 scale, bool scaled, Q4 rotation, bool rotated, V3 center_of_mass)
@@ -1823,6 +1860,7 @@ int32_t b2j_shape_scaled(b2j_world *W, int32_t inner, const float scale_in[3])
 	const b2j_world::ShapeMeta im = W->h_shape_meta[inner];
 	const ShapeDesc &leaf = W->h_shapes[im.leaf];
 	if (im.scaled) { last_error() = "ScaledShape: nested scales are not supported"; return -1; }
+	if (leaf.kind == B2J_SHAPE_COMPOUND) { last_error() = "ScaledShape: a compound cannot be decorated"; return -1; }
 	if ((leaf.kind == B2J_SHAPE_SPHERE || leaf.kind == B2J_SHAPE_CAPSULE || im.rotated) && !is_uniform_scale(scale))
 	{ last_error() = "ScaledShape: this inner shape only takes a uniform scale"; return -1; }
 	if (leaf.kind == B2J_SHAPE_CYLINDER && !(square(scale.z - scale.x) <= 1.0e-8f)) { last_error() = "ScaledShape: a cylinder takes the same scale in x and z"; return -1; }
@@ -1843,6 +1881,7 @@ int32_t b2j_shape_rotated_translated(b2j_world *W, int32_t inner, const float ro
 	if (inner < 0 || inner >= (int32_t)W->h_shapes.size() || rotation == nullptr || center_of_mass == nullptr) { last_error() = "invalid shape id"; return -1; }
 	const b2j_world::ShapeMeta im = W->h_shape_meta[inner];
 	if (im.rotated) { last_error() = "RotatedTranslatedShape: nested rotations are not supported"; return -1; }
+	if (W->h_shapes[im.leaf].kind == B2J_SHAPE_COMPOUND) { last_error() = "RotatedTranslatedShape: a compound cannot be decorated"; return -1; }
 	Q4 q; q.x = rotation[0]; q.y = rotation[1]; q.z = rotation[2]; q.w = rotation[3];
 	return add_decorated_shape(W, im.leaf, im.scale, im.scaled, q, true, v3_load(center_of_mass));
 }
@@ -2881,7 +2920,7 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	B->prev_dt = P->prev_dt;
 	// shapes are shared by all worlds
 	B->h_shapes = P->h_shapes; B->h_shape_meta = P->h_shape_meta; B->h_hull_points = P->h_hull_points; B->h_hull_shrunk = P->h_hull_shrunk; B->h_hull_planes = P->h_hull_planes;
-	B->h_hull_faces = P->h_hull_faces; B->h_hull_vtx = P->h_hull_vtx; B->h_mesh_bytes = P->h_mesh_bytes;
+	B->h_hull_faces = P->h_hull_faces; B->h_hull_vtx = P->h_hull_vtx; B->h_mesh_bytes = P->h_mesh_bytes; B->h_compound_subs = P->h_compound_subs;
 	B->shapes_dirty = true;
 	upload_shapes(B);
 	// body state: world w occupies the slots [w * stride, (w + 1) * stride)

@@ -15,6 +15,7 @@
 #include <Jolt/Physics/Collision/Shape/CylinderShape.h>
 #include <Jolt/Physics/Collision/Shape/ConvexHullShape.h>
 #include <Jolt/Physics/Collision/Shape/MeshShape.h>
+#include <Jolt/Physics/Collision/Shape/StaticCompoundShape.h>
 #include <Jolt/Physics/Collision/Shape/ScaledShape.h>
 #include <Jolt/Physics/Collision/Shape/RotatedTranslatedShape.h>
 
@@ -36,7 +37,7 @@ struct Api
 #define B2J_FN(name) decltype(&::name) name = nullptr;
 	B2J_FN(b2j_world_create) B2J_FN(b2j_world_destroy) B2J_FN(b2j_last_error) B2J_FN(b2j_settings_default)
 	B2J_FN(b2j_world_set_previous_delta_time)
-	B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
+	B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated) B2J_FN(b2j_shape_static_compound)
 	B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
 #undef B2J_FN
 
@@ -47,7 +48,7 @@ struct Api
 #define B2J_FN(name) name = (decltype(name))dlsym(handle, #name); if (name == nullptr) { outError = String("missing symbol ") + #name; return false; }
 		B2J_FN(b2j_world_create) B2J_FN(b2j_world_destroy) B2J_FN(b2j_last_error) B2J_FN(b2j_settings_default)
 		B2J_FN(b2j_world_set_previous_delta_time)
-		B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated)
+		B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated) B2J_FN(b2j_shape_static_compound)
 		B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
 #undef B2J_FN
 		return true;
@@ -165,6 +166,34 @@ inline int32_t sUploadShape(const Api &inApi, b2j_world *inWorld, const Shape *i
 			sStore(bounds.mMin, desc.local_bounds_min);
 			sStore(bounds.mMax, desc.local_bounds_max);
 			return inApi.b2j_shape_mesh(inWorld, &desc);
+		}
+
+	case EShapeSubType::StaticCompound:
+		{
+			// sub shapes first, then the compound with the tree exactly as the reference built it (mNodes: private, the harness is a friend
+			// by way of its access define)
+			const StaticCompoundShape *compound = static_cast<const StaticCompoundShape *>(inShape);
+			Array<b2j_compound_sub> subs;
+			for (const CompoundShape::SubShape &sub : compound->GetSubShapes())
+			{
+				b2j_compound_sub out;
+				out.shape = sUploadShape(inApi, inWorld, sub.mShape, outError);
+				if (out.shape < 0) return -1;
+				sStore(sub.GetPositionCOM(), out.position_com);
+				sStore(sub.GetRotation(), out.rotation);
+				subs.push_back(out);
+			}
+			b2j_compound_desc desc;
+			memset(&desc, 0, sizeof(desc));
+			desc.num_subs = (uint32_t)subs.size(); desc.subs = subs.data();
+			desc.num_nodes = (uint32_t)compound->mNodes.size(); desc.nodes = reinterpret_cast<const uint8_t *>(compound->mNodes.data());
+			sStore(compound->GetCenterOfMass(), desc.center_of_mass);
+			AABox bounds = compound->GetLocalBounds();
+			sStore(bounds.mMin, desc.local_bounds_min); sStore(bounds.mMax, desc.local_bounds_max);
+			desc.inner_radius = compound->GetInnerRadius();
+			int32_t id = inApi.b2j_shape_static_compound(inWorld, &desc);
+			if (id < 0) outError = inApi.b2j_last_error();
+			return id;
 		}
 
 	case EShapeSubType::Scaled:

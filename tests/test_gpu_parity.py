@@ -15,6 +15,9 @@ CASES = [
     ("convex_vs_mesh", 4, 1, 90), ("convex_vs_mesh", 4, 1, 120), ("convex_vs_mesh", 4, 1, 200),
     # ... and with the mesh itself scaled + rotated (p1 bit 1)
     ("convex_vs_mesh", 4, 2, 200), ("convex_vs_mesh", 4, 3, 150), ("convex_vs_mesh", 4, 3, 300),
+    # StaticCompoundShape bodies against a floor / each other / a static compound staircase (p0 = 0) and on a terrain mesh (p0 = 1)
+    ("compound", 0, 0, 0), ("compound", 0, 0, 60), ("compound", 0, 0, 90), ("compound", 0, 0, 120), ("compound", 0, 0, 300),
+    ("compound", 1, 0, 80), ("compound", 1, 0, 120), ("compound", 1, 0, 200), ("compound", 1, 0, 450),
     # worlds with more than 4096 bodies: the wavefront schedule runs as one cooperative launch (sched_grid_kernel)
     ("pile", 6000, 15, 80), ("max_bodies", 6000, 0, 10),
 ]

@@ -14,6 +14,10 @@ CASES = [
     ("convex_vs_mesh", 1, 1, 90), ("convex_vs_mesh", 1, 1, 150),
     # ... and with the mesh itself scaled + rotated (p1 bit 1)
     ("convex_vs_mesh", 1, 2, 300), ("convex_vs_mesh", 1, 3, 200),
+    # StaticCompoundShape bodies (dumbbells, L shapes, tables, a 9 part cross with decorated parts) against a floor / each other / a
+    # static compound staircase (p0 = 0) and on a terrain mesh (p0 = 1)
+    ("compound", 0, 0, 0), ("compound", 0, 0, 60), ("compound", 0, 0, 100), ("compound", 0, 0, 300),
+    ("compound", 1, 0, 80), ("compound", 1, 0, 120), ("compound", 1, 0, 300),
 ]
 
 

@@ -72,7 +72,8 @@ def _check_boxes(ref, world, state, n, seed, layer=0xffffffff):
 SCENES = [("small_stack", 4, 0, 40, 6.0), ("pyramid", 6, 0, 30, 20.0), ("convex_vs_mesh", 2, 0, 60, 30.0), ("pile", 500, 15, 80, 12.0),
           ("feature", parity.FEATURES.index("zoo"), 0, 50, 60.0), ("feature", parity.FEATURES.index("decorated"), 0, 70, 10.0),
           ("convex_vs_mesh", 1, 3, 150, 30.0),  # decorated bodies on a scaled + rotated mesh
-          ("feature", parity.FEATURES.index("cylinder"), 0, 70, 12.0)]
+          ("feature", parity.FEATURES.index("cylinder"), 0, 70, 12.0),
+          ("compound", 0, 0, 120, 12.0), ("compound", 1, 0, 150, 20.0)]
 
 
 def _run(api, scene, p0, p1, warm, span, n_rays, n_boxes):
