@@ -17,6 +17,7 @@
 #include "jolt_b200.h"
 
 #include <cmath>
+#include <algorithm>
 #include <cfloat>
 #include <cstring>
 #include <memory>
@@ -98,7 +99,7 @@ inline constexpr EAllowedDOFs operator&(EAllowedDOFs a, EAllowedDOFs b) { return
 enum class EPhysicsUpdateError : uint32 { None = 0, ManifoldCacheFull = 1, BodyPairCacheFull = 2, ContactConstraintsFull = 4 };
 inline EPhysicsUpdateError operator|(EPhysicsUpdateError a, EPhysicsUpdateError b) { return EPhysicsUpdateError(uint32(a) | uint32(b)); }
 enum class EOverrideMassProperties : uint8 { CalculateMassAndInertia, CalculateInertia, MassAndInertiaProvided };
-enum class EShapeSubType : uint8 { Sphere = B2J_SHAPE_SPHERE, Box = B2J_SHAPE_BOX, Capsule = B2J_SHAPE_CAPSULE, ConvexHull = B2J_SHAPE_CONVEX_HULL, Mesh = B2J_SHAPE_MESH, Cylinder = B2J_SHAPE_CYLINDER, RotatedTranslated = 64, Scaled = 65 };
+enum class EShapeSubType : uint8 { Sphere = B2J_SHAPE_SPHERE, Box = B2J_SHAPE_BOX, Capsule = B2J_SHAPE_CAPSULE, ConvexHull = B2J_SHAPE_CONVEX_HULL, Mesh = B2J_SHAPE_MESH, Cylinder = B2J_SHAPE_CYLINDER, StaticCompound = B2J_SHAPE_COMPOUND, RotatedTranslated = 64, Scaled = 65 };
 
 class BroadPhaseLayerInterface { public: virtual ~BroadPhaseLayerInterface() = default; virtual uint GetNumBroadPhaseLayers() const = 0; virtual BroadPhaseLayer GetBroadPhaseLayer(ObjectLayer inLayer) const = 0; };
 class ObjectVsBroadPhaseLayerFilter { public: virtual ~ObjectVsBroadPhaseLayerFilter() = default; virtual bool ShouldCollide(ObjectLayer, BroadPhaseLayer) const { return true; } };
@@ -132,6 +133,58 @@ struct SubShapeIDPair
 	BodyID mBody1ID; SubShapeID mSubShapeID1; BodyID mBody2ID; SubShapeID mSubShapeID2;
 	const BodyID &GetBody1ID() const { return mBody1ID; } const BodyID &GetBody2ID() const { return mBody2ID; }
 	const SubShapeID &GetSubShapeID1() const { return mSubShapeID1; } const SubShapeID &GetSubShapeID2() const { return mSubShapeID2; }
+};
+
+// A rotation + translation with Mat44's arithmetic (column major 3x3 + translation; Mat44.inl operator*, sRotationTranslation)
+struct Mat44RT
+{
+	Vec3 c0 = Vec3(1, 0, 0), c1 = Vec3(0, 1, 0), c2 = Vec3(0, 0, 1), t = Vec3(0, 0, 0);
+	static Mat44RT sRotationTranslation(const Quat &q, const Vec3 &inT)
+	{
+		Mat44RT m;
+		float x = q.x, y = q.y, z = q.z, w = q.w;
+		float tx = x + x, ty = y + y, tz = z + z;
+		float xx = tx * x, yy = ty * y, zz = tz * z, xy = tx * y, xz = tx * z, xw = tx * w, yz = ty * z, yw = ty * w, zw = tz * w;
+		m.c0 = Vec3((1.0f - yy) - zz, xy + zw, xz - yw); m.c1 = Vec3(xy - zw, (1.0f - zz) - xx, yz + xw); m.c2 = Vec3(xz + yw, yz - xw, (1.0f - xx) - yy);
+		m.t = inT;
+		return m;
+	}
+	static Mat44RT sRotation(const Quat &q) { return sRotationTranslation(q, Vec3::sZero()); }
+	Vec3 operator*(const Vec3 &v) const { return ((c0 * v.x + c1 * v.y) + c2 * v.z) + t; } // Mat44 * Vec3 (Mat44.inl:386-391)
+	Mat44RT operator*(const Mat44RT &b) const
+	{
+		Mat44RT r;
+		r.c0 = ((c0 * b.c0.x + c1 * b.c0.y) + c2 * b.c0.z) + t * 0.0f;
+		r.c1 = ((c0 * b.c1.x + c1 * b.c1.y) + c2 * b.c1.z) + t * 0.0f;
+		r.c2 = ((c0 * b.c2.x + c1 * b.c2.y) + c2 * b.c2.z) + t * 0.0f;
+		r.t = ((c0 * b.t.x + c1 * b.t.y) + c2 * b.t.z) + t * 1.0f;
+		return r;
+	}
+};
+
+// AABox (Jolt/Geometry/AABox.h): the operations shape bounds need
+struct AABox
+{
+	Vec3 mMin = Vec3(FLT_MAX, FLT_MAX, FLT_MAX), mMax = Vec3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+	AABox() = default;
+	AABox(const Vec3 &inMin, const Vec3 &inMax) : mMin(inMin), mMax(inMax) { }
+	static Vec3 sMin(const Vec3 &a, const Vec3 &b) { return Vec3(std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)); }
+	static Vec3 sMax(const Vec3 &a, const Vec3 &b) { return Vec3(std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)); }
+	void Encapsulate(const AABox &o) { mMin = sMin(mMin, o.mMin); mMax = sMax(mMax, o.mMax); }
+	Vec3 GetCenter() const { return 0.5f * (mMin + mMax); }
+	AABox Scaled(const Vec3 &inScale) const { Vec3 a = mMin * inScale, b = mMax * inScale; return AABox(sMin(a, b), sMax(a, b)); }
+	AABox Transformed(const Mat44RT &m) const // AABox.h:193-213
+	{
+		Vec3 new_min = m.t, new_max = m.t;
+		const Vec3 *cols[3] = { &m.c0, &m.c1, &m.c2 };
+		for (int c = 0; c < 3; ++c)
+		{
+			Vec3 a = *cols[c] * mMin[c], b = *cols[c] * mMax[c];
+			new_min = new_min + sMin(a, b);
+			new_max = new_max + sMax(a, b);
+		}
+		return AABox(new_min, new_max);
+	}
 };
 
 // MassProperties (Jolt/Physics/Body/MassProperties.h): mass + 3x3 inertia (column major)
@@ -181,6 +234,18 @@ struct MassProperties
 			Vec3 col = (tc[0] * rc[0][j] + tc[1] * rc[1][j]) + tc[2] * rc[2][j];
 			mInertia[j][0] = col.x; mInertia[j][1] = col.y; mInertia[j][2] = col.z;
 		}
+	}
+	// MassProperties::Translate (MassProperties.cpp:162-171): parallel axis theorem, I += m * (|t|^2 E - t t^T)
+	void Translate(const Vec3 &inTranslation)
+	{
+		float d = inTranslation.Dot(inTranslation);
+		for (int c = 0; c < 3; ++c)
+			for (int r = 0; r < 3; ++r)
+			{
+				float scale_term = c == r? d : 0.0f;               // Mat44::sScale(t.t)
+				float outer = inTranslation[r] * inTranslation[c];   // Mat44::sOuterProduct(t, t)(r, c) = t[r] * t[c]
+				mInertia[c][r] += mMass * (scale_term - outer);
+			}
 	}
 	// MassProperties::ScaleToMass
 	void ScaleToMass(float inMass)
@@ -314,6 +379,10 @@ public:
 	virtual MassProperties GetMassProperties() const = 0;
 	virtual Vec3 GetCenterOfMass() const { return Vec3::sZero(); }
 	virtual int32_t Upload(b2j_world *inWorld) const = 0;
+	// (what a compound needs from its sub shapes: Shape::GetLocalBounds / GetWorldSpaceBounds / GetInnerRadius)
+	virtual AABox GetLocalBounds() const = 0;
+	virtual float GetInnerRadius() const = 0;
+	virtual AABox GetWorldSpaceBounds(const Mat44RT &inCenterOfMassTransform, const Vec3 &inScale) const { return GetLocalBounds().Scaled(inScale).Transformed(inCenterOfMassTransform); } // Shape.h:221
 };
 using ShapeRef = std::shared_ptr<const Shape>;
 
@@ -335,6 +404,13 @@ public:
 		return p;
 	}
 	int32_t Upload(b2j_world *w) const override { return b2j_shape_sphere(w, mRadius); }
+	AABox GetLocalBounds() const override { return AABox(Vec3::sReplicate(-mRadius), Vec3::sReplicate(mRadius)); }
+	float GetInnerRadius() const override { return mRadius; }
+	AABox GetWorldSpaceBounds(const Mat44RT &m, const Vec3 &inScale) const override // SphereShape.cpp:67-74
+	{
+		Vec3 half_extent = Vec3::sReplicate(std::fabs(inScale.x) * mRadius);
+		return AABox(-half_extent + m.t, half_extent + m.t);
+	}
 private:
 	float mRadius;
 };
@@ -348,6 +424,8 @@ public:
 	EShapeSubType GetSubType() const override { return EShapeSubType::Box; }
 	MassProperties GetMassProperties() const override { MassProperties p; p.SetMassAndInertiaOfSolidBox(2.0f * mHalfExtent, GetDensity()); return p; } // BoxShape.cpp:149-154
 	int32_t Upload(b2j_world *w) const override { float he[3] = { mHalfExtent.x, mHalfExtent.y, mHalfExtent.z }; return b2j_shape_box(w, he, mConvexRadius); }
+	AABox GetLocalBounds() const override { return AABox(-mHalfExtent, mHalfExtent); }
+	float GetInnerRadius() const override { return std::min(mHalfExtent.x, std::min(mHalfExtent.y, mHalfExtent.z)); }
 private:
 	Vec3 mHalfExtent;
 	float mConvexRadius;
@@ -377,6 +455,15 @@ public:
 		return p;
 	}
 	int32_t Upload(b2j_world *w) const override { return b2j_shape_capsule(w, mHalfHeightOfCylinder, mRadius); }
+	AABox GetLocalBounds() const override { Vec3 extent = Vec3::sReplicate(mRadius) + Vec3(0, mHalfHeightOfCylinder, 0); return AABox(-extent, extent); } // CapsuleShape.cpp:259-264
+	float GetInnerRadius() const override { return mRadius; }
+	AABox GetWorldSpaceBounds(const Mat44RT &m, const Vec3 &inScale) const override // CapsuleShape.cpp:266-277
+	{
+		float scale = std::fabs(inScale.x);
+		Vec3 extent = Vec3::sReplicate(scale * mRadius), height = Vec3(0, scale * mHalfHeightOfCylinder, 0);
+		Vec3 p1 = m * -height, p2 = m * height;
+		return AABox(AABox::sMin(p1, p2) - extent, AABox::sMax(p1, p2) + extent);
+	}
 private:
 	float mHalfHeightOfCylinder, mRadius;
 };
@@ -399,6 +486,8 @@ public:
 		return p;
 	}
 	int32_t Upload(b2j_world *w) const override { return b2j_shape_cylinder(w, mHalfHeight, mRadius, mConvexRadius); }
+	AABox GetLocalBounds() const override { Vec3 extent(mRadius, mHalfHeight, mRadius); return AABox(-extent, extent); }
+	float GetInnerRadius() const override { return std::min(mHalfHeight, mRadius); }
 private:
 	float mHalfHeight, mRadius, mConvexRadius;
 };
@@ -416,6 +505,8 @@ public:
 	float mInertia[3][3] = { { 0 } };           // density 1, [column][row]
 	EShapeSubType GetSubType() const override { return EShapeSubType::ConvexHull; }
 	Vec3 GetCenterOfMass() const override { return Vec3(mCenterOfMass[0], mCenterOfMass[1], mCenterOfMass[2]); }
+	AABox GetLocalBounds() const override { return AABox(Vec3(mBoundsMin[0], mBoundsMin[1], mBoundsMin[2]), Vec3(mBoundsMax[0], mBoundsMax[1], mBoundsMax[2])); }
+	float GetInnerRadius() const override { return mInnerRadius; }
 	MassProperties GetMassProperties() const override // ConvexHullShape.cpp:356-370
 	{
 		MassProperties p;
@@ -444,6 +535,8 @@ public:
 	float mBoundsMin[3] = { 0, 0, 0 }, mBoundsMax[3] = { 0, 0, 0 };
 	EShapeSubType GetSubType() const override { return EShapeSubType::Mesh; }
 	MassProperties GetMassProperties() const override { return MassProperties(); } // static only
+	AABox GetLocalBounds() const override { return AABox(Vec3(mBoundsMin[0], mBoundsMin[1], mBoundsMin[2]), Vec3(mBoundsMax[0], mBoundsMax[1], mBoundsMax[2])); }
+	float GetInnerRadius() const override { return 0.0f; }
 	int32_t Upload(b2j_world *w) const override
 	{
 		b2j_mesh_desc d;
@@ -473,6 +566,9 @@ public:
 	EShapeSubType GetSubType() const override { return EShapeSubType::Scaled; }
 	Vec3 GetCenterOfMass() const override { return mScale * mInnerShape->GetCenterOfMass(); }                                   // ScaledShape.h:56
 	MassProperties GetMassProperties() const override { MassProperties p = mInnerShape->GetMassProperties(); p.Scale(mScale); return p; } // ScaledShape.cpp:49-54
+	AABox GetLocalBounds() const override { return mInnerShape->GetLocalBounds().Scaled(mScale); }
+	float GetInnerRadius() const override { return std::min(mScale.x, std::min(mScale.y, mScale.z)) * mInnerShape->GetInnerRadius(); }
+	AABox GetWorldSpaceBounds(const Mat44RT &m, const Vec3 &inScale) const override { return mInnerShape->GetWorldSpaceBounds(m, inScale * mScale); }
 	int32_t Upload(b2j_world *w) const override
 	{
 		int32_t inner = mInnerShape->Upload(w);
@@ -497,6 +593,9 @@ public:
 	EShapeSubType GetSubType() const override { return EShapeSubType::RotatedTranslated; }
 	Vec3 GetCenterOfMass() const override { return mCenterOfMass; }
 	MassProperties GetMassProperties() const override { MassProperties p = mInnerShape->GetMassProperties(); p.Rotate(mRotation); return p; }
+	AABox GetLocalBounds() const override { return mInnerShape->GetLocalBounds().Transformed(Mat44RT::sRotation(mRotation)); }
+	float GetInnerRadius() const override { return mInnerShape->GetInnerRadius(); }
+	AABox GetWorldSpaceBounds(const Mat44RT &m, const Vec3 &inScale) const override { return mInnerShape->GetWorldSpaceBounds(m * Mat44RT::sRotation(mRotation), inScale); } // (uniform scales only: TransformScale is the identity)
 	int32_t Upload(b2j_world *w) const override
 	{
 		int32_t inner = mInnerShape->Upload(w);
@@ -507,6 +606,244 @@ public:
 private:
 	Quat mRotation;
 	Vec3 mCenterOfMass;
+};
+
+// ---- StaticCompoundShape (StaticCompoundShape.h / CompoundShape.h) of convex sub shapes ------------------------------------------
+// Built the way the reference builds it, because the build decides what the simulation computes: the centre of mass (mass weighted),
+// the sub shape positions relative to it, the compressed rotations, and the quad tree over the sub shape bounds whose layout fixes
+// the order in which sub shapes are collided (StaticCompoundShape.cpp:110-357).
+class StaticCompoundShape final : public Shape
+{
+public:
+	struct SubShape { ShapeRef mShape; Vec3 mPositionCOM; Quat mRotation; bool mIsRotationIdentity = true; };
+
+	EShapeSubType GetSubType() const override { return EShapeSubType::StaticCompound; }
+	Vec3 GetCenterOfMass() const override { return mCenterOfMass; }
+	AABox GetLocalBounds() const override { return mLocalBounds; }
+	float GetInnerRadius() const override { return mInnerRadius; }
+	uint GetNumSubShapes() const { return (uint)mSubShapes.size(); }
+	const SubShape &GetSubShape(uint inIdx) const { return mSubShapes[inIdx]; }
+	MassProperties GetMassProperties() const override // CompoundShape.cpp:68-91
+	{
+		MassProperties p;
+		for (const SubShape &shape : mSubShapes)
+		{
+			MassProperties child = shape.mShape->GetMassProperties();
+			child.Rotate(shape.mRotation);
+			child.Translate(shape.mPositionCOM);
+			p.mMass += child.mMass;
+			for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) p.mInertia[c][r] += child.mInertia[c][r];
+		}
+		return p;
+	}
+	AABox GetWorldSpaceBounds(const Mat44RT &m, const Vec3 &inScale) const override // CompoundShape.cpp:93-115
+	{
+		if (mSubShapes.size() > 10)
+			return Shape::GetWorldSpaceBounds(m, inScale);
+		AABox bounds;
+		for (const SubShape &shape : mSubShapes)
+			bounds.Encapsulate(shape.mShape->GetWorldSpaceBounds(m * Mat44RT::sRotationTranslation(shape.mRotation, inScale * shape.mPositionCOM), inScale));
+		return bounds;
+	}
+	int32_t Upload(b2j_world *w) const override
+	{
+		std::vector<b2j_compound_sub> subs(mSubShapes.size());
+		for (size_t i = 0; i < mSubShapes.size(); ++i)
+		{
+			const SubShape &in = mSubShapes[i];
+			subs[i].shape = in.mShape->Upload(w);
+			if (subs[i].shape < 0) return subs[i].shape;
+			subs[i].position_com[0] = in.mPositionCOM.x; subs[i].position_com[1] = in.mPositionCOM.y; subs[i].position_com[2] = in.mPositionCOM.z;
+			subs[i].rotation[0] = in.mRotation.x; subs[i].rotation[1] = in.mRotation.y; subs[i].rotation[2] = in.mRotation.z; subs[i].rotation[3] = in.mRotation.w;
+		}
+		b2j_compound_desc d;
+		memset(&d, 0, sizeof(d));
+		d.num_subs = (uint32_t)subs.size(); d.subs = subs.data();
+		d.num_nodes = (uint32_t)mNodes.size(); d.nodes = reinterpret_cast<const uint8_t *>(mNodes.data());
+		d.center_of_mass[0] = mCenterOfMass.x; d.center_of_mass[1] = mCenterOfMass.y; d.center_of_mass[2] = mCenterOfMass.z;
+		d.local_bounds_min[0] = mLocalBounds.mMin.x; d.local_bounds_min[1] = mLocalBounds.mMin.y; d.local_bounds_min[2] = mLocalBounds.mMin.z;
+		d.local_bounds_max[0] = mLocalBounds.mMax.x; d.local_bounds_max[1] = mLocalBounds.mMax.y; d.local_bounds_max[2] = mLocalBounds.mMax.z;
+		d.inner_radius = mInnerRadius;
+		return b2j_shape_static_compound(w, &d);
+	}
+
+	// 4 child bounding boxes as half floats + 4 child properties (StaticCompoundShape::Node, 64 bytes)
+	struct Node { uint16_t mBoundsMinX[4], mBoundsMinY[4], mBoundsMinZ[4], mBoundsMaxX[4], mBoundsMaxY[4], mBoundsMaxZ[4]; uint32_t mNodeProperties[4]; };
+	static_assert(sizeof(Node) == 64, "Node should be 64 bytes");
+	enum : uint32_t { IS_SUBSHAPE = 0x80000000u, INVALID_NODE = 0x7fffffffu };
+
+private:
+	friend class StaticCompoundShapeSettings;
+	// float -> half rounding towards -inf (inUp = false) or +inf (HalfFloatConversion::FromFloat<ROUND_TO_NEG_INF / ROUND_TO_POS_INF>)
+	static uint16_t sToHalf(float inV, bool inUp)
+	{
+		uint32_t value; memcpy(&value, &inV, 4);
+		uint32_t exponent = (value >> 23) & 0xffu, mantissa = value & 0x7fffffu;
+		uint16_t sign = uint16_t(value >> 16) & 0x8000u;
+		bool away = (sign == 0) == inUp; // rounding in this direction grows the magnitude
+		if (exponent == 0xffu) return sign | (mantissa == 0? 0x7c00u : 0x7e00u);
+		int e = int(exponent) - 127 + 15;
+		if (e >= 31) return sign | (away? 0x7c00u : 0x7bffu);
+		if (e < -10) return sign | ((away && (value & 0x7fffffffu) != 0)? 1u : 0u);
+		uint16_t hf_exponent; int shift;
+		if (e <= 0) { hf_exponent = 0; mantissa |= 1u << 23; shift = 23 - 10 + 1 - e; }
+		else { hf_exponent = uint16_t(e << 10); shift = 13; }
+		uint16_t hf = sign | hf_exponent | uint16_t(mantissa >> shift);
+		if (away && (mantissa & ((1u << shift) - 1u)) != 0) ++hf;
+		return hf;
+	}
+	static void sSetChildBounds(Node &n, uint i, const AABox &b)
+	{
+		n.mBoundsMinX[i] = sToHalf(b.mMin.x, false); n.mBoundsMinY[i] = sToHalf(b.mMin.y, false); n.mBoundsMinZ[i] = sToHalf(b.mMin.z, false);
+		n.mBoundsMaxX[i] = sToHalf(b.mMax.x, true); n.mBoundsMaxY[i] = sToHalf(b.mMax.y, true); n.mBoundsMaxZ[i] = sToHalf(b.mMax.z, true);
+	}
+	static void sSetChildInvalid(Node &n, uint i)
+	{
+		n.mNodeProperties[i] = INVALID_NODE;
+		n.mBoundsMinX[i] = n.mBoundsMinY[i] = n.mBoundsMinZ[i] = n.mBoundsMaxX[i] = n.mBoundsMaxY[i] = n.mBoundsMaxZ[i] = 0x7bffu; // HALF_FLT_MAX
+	}
+	// StaticCompoundShape::sPartition: split a range of sub shapes at the middle of the widest axis of their bounds' centres
+	static void sPartition(uint *ioIdx, AABox *ioBounds, int inNumber, int &outMidPoint)
+	{
+		if (inNumber <= 4) { outMidPoint = inNumber / 2; return; }
+		Vec3 center_min = Vec3::sReplicate(FLT_MAX), center_max = Vec3::sReplicate(-FLT_MAX);
+		for (int i = 0; i < inNumber; ++i) { Vec3 c = ioBounds[i].GetCenter(); center_min = AABox::sMin(center_min, c); center_max = AABox::sMax(center_max, c); }
+		Vec3 extent = center_max - center_min;
+		int dimension = extent.x > extent.y? (extent.z > extent.x? 2 : 0) : (extent.z > extent.y? 2 : 1); // Vec3::GetHighestComponentIndex
+		float split = (0.5f * (center_min + center_max))[dimension];
+		int start = 0, end = inNumber;
+		while (start < end)
+		{
+			while (start < end && ioBounds[start].GetCenter()[dimension] < split) ++start;
+			while (start < end && ioBounds[end - 1].GetCenter()[dimension] >= split) --end;
+			if (start < end) { std::swap(ioIdx[start], ioIdx[end - 1]); std::swap(ioBounds[start], ioBounds[end - 1]); ++start; --end; }
+		}
+		outMidPoint = (start > 0 && start < inNumber)? start : inNumber / 2;
+	}
+	static void sPartition4(uint *ioIdx, AABox *ioBounds, int inBegin, int inEnd, int *outSplit)
+	{
+		uint *idx = ioIdx + inBegin; AABox *bounds = ioBounds + inBegin; int number = inEnd - inBegin;
+		sPartition(idx, bounds, number, outSplit[2]);
+		sPartition(idx, bounds, outSplit[2], outSplit[1]);
+		sPartition(idx + outSplit[2], bounds + outSplit[2], number - outSplit[2], outSplit[3]);
+		outSplit[0] = inBegin; outSplit[1] += inBegin; outSplit[2] += inBegin; outSplit[3] += outSplit[2]; outSplit[4] = inEnd;
+	}
+
+	Vec3 mCenterOfMass = Vec3::sZero();
+	AABox mLocalBounds = AABox(Vec3::sZero(), Vec3::sZero());
+	float mInnerRadius = FLT_MAX;
+	std::vector<SubShape> mSubShapes;
+	std::vector<Node> mNodes;
+};
+
+// StaticCompoundShapeSettings: AddShape(position, rotation, shape) ... Create() (CompoundShape.h:30-70, StaticCompoundShape.cpp:24-66)
+class StaticCompoundShapeSettings
+{
+public:
+	void AddShape(const Vec3 &inPosition, const Quat &inRotation, ShapeRef inShape) { mParts.push_back({ inPosition, inRotation, std::move(inShape) }); }
+	// One sub shape: the shape itself or a RotatedTranslatedShape, like the reference; none: null
+	ShapeRef Create() const
+	{
+		if (mParts.empty()) return nullptr;
+		if (mParts.size() == 1)
+		{
+			const Part &s = mParts[0];
+			if (s.mPosition.x == 0.0f && s.mPosition.y == 0.0f && s.mPosition.z == 0.0f && s.mRotation.x == 0.0f && s.mRotation.y == 0.0f && s.mRotation.z == 0.0f && s.mRotation.w == 1.0f)
+				return s.mShape;
+			return std::make_shared<RotatedTranslatedShape>(s.mPosition, s.mRotation, s.mShape);
+		}
+		auto out = std::make_shared<StaticCompoundShape>();
+		StaticCompoundShape &c = *out;
+		uint n = (uint)mParts.size();
+		c.mSubShapes.resize(n);
+		float mass = 0.0f;
+		for (uint i = 0; i < n; ++i)
+		{
+			// SubShape::FromSettings -> SetTransform(position, rotation, zero): position of the sub shape's centre of mass, rotation compressed
+			// to x, y, z with w >= 0 (Quat::StoreFloat3 / sLoadFloat3Unsafe)
+			StaticCompoundShape::SubShape &sub = c.mSubShapes[i];
+			sub.mShape = mParts[i].mShape;
+			const Quat &q = mParts[i].mRotation;
+			sub.mPositionCOM = (mParts[i].mPosition - Vec3::sZero()) + q * sub.mShape->GetCenterOfMass();
+			auto is_close = [](const Quat &a, float sign) { float dx = a.x, dy = a.y, dz = a.z, dw = a.w - sign; return (dx * dx + dy * dy) + (dz * dz + dw * dw) <= 1.0e-12f; }; // Quat::IsClose
+			sub.mIsRotationIdentity = is_close(q, 1.0f) || is_close(q, -1.0f);
+			if (sub.mIsRotationIdentity)
+				sub.mRotation = Quat::sIdentity();
+			else
+			{
+				float sign = q.w < 0.0f? -1.0f : 1.0f; // EnsureWPositive flips the sign bits
+				Vec3 v(sign < 0.0f? -q.x : q.x, sign < 0.0f? -q.y : q.y, sign < 0.0f? -q.z : q.z);
+				sub.mRotation = Quat(v.x, v.y, v.z, std::sqrt(std::max(1.0f - v.LengthSq(), 0.0f)));
+			}
+			MassProperties child = sub.mShape->GetMassProperties();
+			mass += child.mMass;
+			c.mCenterOfMass = c.mCenterOfMass + sub.mPositionCOM * child.mMass;
+		}
+		if (mass > 0.0f)
+			c.mCenterOfMass = Vec3(c.mCenterOfMass.x / mass, c.mCenterOfMass.y / mass, c.mCenterOfMass.z / mass);
+		c.mInnerRadius = FLT_MAX;
+		for (const StaticCompoundShape::SubShape &sub : c.mSubShapes) c.mInnerRadius = std::min(c.mInnerRadius, sub.mShape->GetInnerRadius());
+
+		std::vector<AABox> bounds(n);
+		std::vector<uint> idx(n);
+		for (uint i = 0; i < n; ++i)
+		{
+			StaticCompoundShape::SubShape &sub = c.mSubShapes[i];
+			sub.mPositionCOM = sub.mPositionCOM - c.mCenterOfMass;
+			bounds[i] = sub.mShape->GetWorldSpaceBounds(Mat44RT::sRotationTranslation(sub.mRotation, sub.mPositionCOM), Vec3::sReplicate(1.0f));
+			idx[i] = i;
+			c.mLocalBounds.Encapsulate(bounds[i]);
+		}
+
+		// the quad tree, built depth first with an explicit stack like the reference
+		struct StackEntry { uint32_t mNodeIdx; int mChildIdx; int mSplit[5]; AABox mBounds; };
+		std::vector<StackEntry> stack(n);
+		c.mNodes.assign(n + (n + 2) / 3, StaticCompoundShape::Node());
+		uint32_t next_node_idx = 0;
+		int top = 0;
+		stack[0].mNodeIdx = next_node_idx++; stack[0].mChildIdx = -1; stack[0].mBounds = AABox();
+		StaticCompoundShape::sPartition4(idx.data(), bounds.data(), 0, (int)n, stack[0].mSplit);
+		for (;;)
+		{
+			StackEntry &cur = stack[top];
+			cur.mChildIdx++;
+			if (cur.mChildIdx >= 4)
+			{
+				if (top <= 0) break;
+				StackEntry &prev = stack[top - 1];
+				prev.mBounds.Encapsulate(cur.mBounds);
+				StaticCompoundShape::Node &parent = c.mNodes[prev.mNodeIdx];
+				parent.mNodeProperties[prev.mChildIdx] = cur.mNodeIdx;
+				StaticCompoundShape::sSetChildBounds(parent, (uint)prev.mChildIdx, cur.mBounds);
+				--top;
+			}
+			else
+			{
+				int low = cur.mSplit[cur.mChildIdx], high = cur.mSplit[cur.mChildIdx + 1];
+				int num = high - low;
+				StaticCompoundShape::Node &node = c.mNodes[cur.mNodeIdx];
+				if (num == 0)
+					StaticCompoundShape::sSetChildInvalid(node, (uint)cur.mChildIdx);
+				else if (num == 1)
+				{
+					node.mNodeProperties[cur.mChildIdx] = idx[low] | StaticCompoundShape::IS_SUBSHAPE;
+					StaticCompoundShape::sSetChildBounds(node, (uint)cur.mChildIdx, bounds[low]);
+					cur.mBounds.Encapsulate(bounds[low]);
+				}
+				else
+				{
+					StackEntry &next = stack[++top];
+					next.mNodeIdx = next_node_idx++; next.mChildIdx = -1; next.mBounds = AABox();
+					StaticCompoundShape::sPartition4(idx.data(), bounds.data(), low, high, next.mSplit);
+				}
+			}
+		}
+		c.mNodes.resize(next_node_idx);
+		return out;
+	}
+private:
+	struct Part { Vec3 mPosition; Quat mRotation; ShapeRef mShape; };
+	std::vector<Part> mParts;
 };
 
 // ---- BodyCreationSettings (same defaults as the reference) ------------------------------------------------------
@@ -594,7 +931,6 @@ struct PhysicsSettings
 
 class PhysicsSystem;
 // ---- queries (NarrowPhaseQuery / BroadPhaseQuery, Jolt/Physics/Collision/NarrowPhaseQuery.h:31, BroadPhase/BroadPhaseQuery.h:38) ----
-struct AABox { Vec3 mMin, mMax; AABox() = default; AABox(const Vec3 &inMin, const Vec3 &inMax) : mMin(inMin), mMax(inMax) { } };
 struct RRayCast { RVec3 mOrigin; Vec3 mDirection; RRayCast() = default; RRayCast(const RVec3 &o, const Vec3 &d) : mOrigin(o), mDirection(d) { } };
 using RayCast = RRayCast;
 struct RayCastResult { BodyID mBodyID; float mFraction = 1.0f + FLT_EPSILON; SubShapeID mSubShapeID2; };

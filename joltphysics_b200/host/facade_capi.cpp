@@ -272,6 +272,23 @@ bool scene_feature(Scene &s, int variant, const char *assets_dir)
 	return s.dynamic_bodies.size() == num_dynamic;
 }
 
+#define B2J_CREATE_COMPOUND(settings) (settings).Create()
+#include "compound_scene.inl"
+
+// the compound scene of compound_scene.inl on a box floor (variant 0; the terrain variant needs a mesh the reference cooks)
+bool scene_compound(Scene &s, const char *assets_dir)
+{
+	std::vector<ShapeRef> hulls;
+	if (!load_cooked_shapes((std::string(assets_dir) + "/pile_hulls.b2js").c_str(), hulls, s.error) || hulls.empty()) return false;
+	if (!s.system.Init(1024, 0, 16384, 8192, s.bpl, s.ovbp, s.olp, Layers::NUM_LAYERS, scene_device())) return false;
+	uint32_t num_dynamic = 0;
+	sCompoundCreate(s.system, 0, hulls[0], num_dynamic);
+	BodyIDVector all;
+	s.system.GetBodies(all);
+	for (const BodyID &id : all) if (s.system.GetBodyInterface().GetMotionType(id) != EMotionType::Static) s.dynamic_bodies.push_back(id);
+	return s.dynamic_bodies.size() == num_dynamic;
+}
+
 bool scene_api_tour(Scene &s)
 {
 	if (!s.system.Init(1024, 0, 4096, 1024, s.bpl, s.ovbp, s.olp, Layers::NUM_LAYERS, scene_device())) return false;
@@ -300,6 +317,7 @@ B2JF_API void *b2jf_scene_create(const char *name, int p0, int p1, const char *a
 	else if (n == "max_bodies") ok = scene_max_bodies(*s, p0 > 0? p0 : 10000);
 	else if (n == "api_tour") ok = scene_api_tour(*s);
 	else if (n == "feature") ok = scene_feature(*s, p0, assets_dir);
+	else if (n == "compound") ok = scene_compound(*s, assets_dir);
 	else s->error = "unknown scene";
 	if (!ok)
 	{

@@ -294,71 +294,6 @@ World *sSceneConvexVsMesh(int inHalfGrid, int inDecorated = 0)
 	return w;
 }
 
-Ref<Shape> sRandomHull(std::mt19937 &ioRandom, float inExtent);
-Quat sRandomQuat(std::mt19937 &ioRandom);
-
-World *sSceneCompound(int inVariant)
-{
-	// StaticCompoundShape bodies: dumbbells (spheres + capsule), L shapes (boxes), tables (box + 4 cylinder legs: two tree
-	// levels), a 9 part cross with decorated sub shapes, dropped in a heap with plain convex bodies onto a floor (variant 0) or a terrain
-	// mesh (variant 1), next to a static compound staircase.
-	World *w = sNewWorld(1024, 16384, 8192, 0);
-	BodyInterface &bi = w->system.GetBodyInterface();
-	std::mt19937 random(777 + inVariant);
-	Quat z90 = Quat(0.0f, 0.0f, 0.70710678f, 0.70710678f), y45 = Quat(0.0f, 0.38268343f, 0.0f, 0.92387953f);
-	RefConst<Shape> sphere = new SphereShape(0.4f), capsule = new CapsuleShape(0.6f, 0.15f), box = new BoxShape(Vec3(0.4f, 0.4f, 0.4f)), leg = new CylinderShape(0.35f, 0.08f, 0.02f);
-	RefConst<Shape> hull = sRandomHull(random, 0.5f);
-	auto compound = [](std::initializer_list<std::tuple<Vec3, Quat, RefConst<Shape>>> inParts) {
-		StaticCompoundShapeSettings settings;
-		for (const auto &part : inParts) settings.AddShape(std::get<0>(part), std::get<1>(part), std::get<2>(part));
-		return RefConst<Shape>(settings.Create().Get());
-	};
-	RefConst<Shape> dumbbell = compound({ { Vec3(-0.6f, 0.0f, 0.0f), Quat::sIdentity(), sphere }, { Vec3(0.6f, 0.0f, 0.0f), Quat::sIdentity(), sphere }, { Vec3::sZero(), z90, capsule } });
-	RefConst<Shape> ell = compound({ { Vec3::sZero(), Quat::sIdentity(), new BoxShape(Vec3(0.6f, 0.2f, 0.2f)) }, { Vec3(0.4f, 0.7f, 0.0f), Quat::sIdentity(), new BoxShape(Vec3(0.2f, 0.5f, 0.2f)) } });
-	RefConst<Shape> table = compound({ { Vec3(0.0f, 0.7f, 0.0f), Quat::sIdentity(), new BoxShape(Vec3(0.8f, 0.1f, 0.6f)) },
-		{ Vec3(-0.7f, 0.3f, -0.5f), Quat::sIdentity(), leg }, { Vec3(0.7f, 0.3f, -0.5f), Quat::sIdentity(), leg }, { Vec3(-0.7f, 0.3f, 0.5f), Quat::sIdentity(), leg }, { Vec3(0.7f, 0.3f, 0.5f), Quat::sIdentity(), leg } });
-	RefConst<Shape> cross = compound({ { Vec3::sZero(), y45, hull }, { Vec3(0.9f, 0.0f, 0.0f), Quat::sIdentity(), new ScaledShape(box, Vec3(0.5f, 0.3f, 0.3f)) }, { Vec3(-0.9f, 0.0f, 0.0f), y45, box },
-		{ Vec3(0.0f, 0.9f, 0.0f), Quat::sIdentity(), sphere }, { Vec3(0.0f, -0.9f, 0.0f), z90, leg }, { Vec3(0.0f, 0.0f, 0.9f), Quat::sIdentity(), new RotatedTranslatedShape(Vec3(0.0f, 0.1f, 0.0f), z90, capsule) },
-		{ Vec3(0.0f, 0.0f, -0.9f), Quat::sIdentity(), hull }, { Vec3(0.6f, 0.6f, 0.0f), Quat::sIdentity(), new SphereShape(0.2f) }, { Vec3(-0.6f, -0.6f, 0.0f), y45, new BoxShape(Vec3(0.2f, 0.2f, 0.2f)) } });
-	if (inVariant == 1)
-	{
-		const int n = 20;
-		const float cell_size = 3.0f, max_height = 2.0f, center = n * cell_size / 2;
-		BodyCreationSettings mesh(sTerrainMesh(n, cell_size, max_height), RVec3(-center, max_height, -center), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
-		mesh.mFriction = 0.5f;
-		bi.CreateAndAddBody(mesh, EActivation::DontActivate);
-	}
-	else
-	{
-		BodyCreationSettings floor(new BoxShape(Vec3(60.0f, 1.0f, 60.0f), 0.0f), RVec3(0.0f, -1.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
-		bi.CreateAndAddBody(floor, EActivation::DontActivate);
-	}
-	{
-		// a static staircase made of one compound
-		StaticCompoundShapeSettings stairs;
-		for (int i = 0; i < 8; ++i)
-			stairs.AddShape(Vec3(0.8f * float(i), 0.2f + 0.4f * float(i), 0.0f), Quat::sIdentity(), new BoxShape(Vec3(0.4f, 0.2f, 2.0f)));
-		BodyCreationSettings s(stairs.Create().Get(), RVec3(6.0f, inVariant == 1? 4.0f : 0.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
-		bi.CreateAndAddBody(s, EActivation::DontActivate);
-	}
-	RefConst<Shape> shapes[6] = { dumbbell, ell, table, cross, box, sphere };
-	float y0 = inVariant == 1? 7.0f : 1.5f;
-	for (int i = 0; i < 36; ++i)
-	{
-		BodyCreationSettings s(shapes[i % 6], RVec3(-3.0f + 2.2f * float(i % 4), y0 + 1.9f * float(i / 4), -2.0f + 2.1f * float((i / 2) % 3)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
-		s.mFriction = 0.5f;
-		bi.CreateAndAddBody(s, EActivation::Activate);
-		w->num_dynamic++;
-	}
-	for (int i = 0; i < 6; ++i) // bodies tumbling down the staircase
-	{
-		BodyCreationSettings s(shapes[(i + 1) % 6], RVec3(6.5f + 0.9f * float(i), (inVariant == 1? 4.0f : 0.0f) + 2.5f + 0.6f * float(i), -1.0f + 0.4f * float(i)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
-		bi.CreateAndAddBody(s, EActivation::Activate);
-		w->num_dynamic++;
-	}
-	return w;
-}
-
 World *sSceneMaxBodies(int inNumBodies)
 {
 	// PerformanceTest/MaxBodiesScene.h:44-80 restated for N bodies: unit boxes of mass 1000 on a cubic grid, x neighbours touching.
@@ -521,6 +456,30 @@ World *sSceneFeature(int inVariant)
 	w->num_dynamic = num_dynamic;
 	return w;
 }
+
+#define B2J_CREATE_COMPOUND(settings) RefConst<Shape>((settings).Create().Get())
+#include "../joltphysics_b200/host/compound_scene.inl"
+
+World *sSceneCompound(int inVariant)
+{
+	// joltphysics_b200/host/compound_scene.inl (user code shared with the facade build); variant 1 puts the bodies on a terrain mesh
+	World *w = sNewWorld(1024, 16384, 8192, 0);
+	BodyInterface &bi = w->system.GetBodyInterface();
+	if (inVariant == 1)
+	{
+		const int n = 20;
+		const float cell_size = 3.0f, max_height = 2.0f, center = n * cell_size / 2;
+		BodyCreationSettings mesh(sTerrainMesh(n, cell_size, max_height), RVec3(-center, max_height, -center), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		mesh.mFriction = 0.5f;
+		bi.CreateAndAddBody(mesh, EActivation::DontActivate);
+	}
+	std::mt19937 hull_random(4242);
+	uint32_t num_dynamic = 0;
+	sCompoundCreate(w->system, inVariant, sRandomHull(hull_random, 0.5f), num_dynamic);
+	w->num_dynamic += (int)num_dynamic;
+	return w;
+}
+
 
 // the facade's API tour (same user code on both sides)
 #include "../joltphysics_b200/host/api_tour.inl"

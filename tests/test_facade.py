@@ -50,12 +50,12 @@ def test_facade_scene_matches_reference_gpu(gpu_api, ref_available, scene, p0, p
     _check(flib, scene, p0, p1, steps=25)
 
 
-def _check_feature(flib, variant, steps):
+def _check_feature(flib, variant, steps, scene="feature"):
     """feature_scenes.inl is ONE piece of user code compiled against the reference and against the facade: every motion type, body flag
     and per body override travels BodyCreationSettings -> facade -> C ABI -> device and must give the world the reference builds
     (creation state incl. DOF restricted mass properties) and the evolution the reference computes."""
-    ref = R.RefWorld("feature", variant)
-    fs = F.FacadeScene(flib, "feature", variant, 0)
+    ref = R.RefWorld(scene, variant)
+    fs = F.FacadeScene(flib, scene, variant, 0)
     assert fs.num_bodies == ref.num_bodies and fs.num_dynamic == ref.num_dynamic
     rs, gs = ref.state(), fs.world.state()
     assert np.array_equal(rs.pos, gs.pos) and np.array_equal(rs.rot, gs.rot) and np.array_equal(rs.lin, gs.lin) and np.array_equal(rs.ang, gs.ang)
@@ -70,6 +70,8 @@ def _check_feature(flib, variant, steps):
             for k in ("pos", "rot", "lin", "ang"):
                 assert worst[k] <= 1.0, (step, k, worst)
             assert np.array_equal(ref.state().active_index != 0xffffffff, fs.world.state().active_index != 0xffffffff), f"step {step}: active flags"
+            # the contact caches hold the same manifolds: body pairs, sub shape ids of both sides, point counts
+            assert np.array_equal(R.cache_rows(R.cache_summary(*ref.cache())), R.cache_rows(R.cache_summary(*fs.world.cache()))), f"step {step}: contact cache"
     fs.close()
     ref.close()
 
@@ -86,6 +88,17 @@ def test_facade_feature_scene_matches_reference_hostsim(hostsim_facade, variant)
 @pytest.mark.parametrize("variant", range(11), ids=FEATURE_IDS)
 def test_facade_feature_scene_matches_reference_gpu(gpu_api, ref_available, variant):
     _check_feature(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api), variant, 200)
+
+
+def test_facade_compound_scene_matches_reference_hostsim(hostsim_facade):
+    """StaticCompoundShapeSettings::Create in the facade builds what the reference builds: centre of mass, sub shape transforms, mass
+    properties and the quad tree (same node order -> same manifolds), joltphysics_b200/host/compound_scene.inl on both sides."""
+    _check_feature(hostsim_facade, 0, 160, scene="compound")
+
+
+@pytest.mark.gpu
+def test_facade_compound_scene_matches_reference_gpu(gpu_api, ref_available):
+    _check_feature(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api), 0, 300, scene="compound")
 
 
 def _check_api_tour(flib):
