@@ -228,6 +228,10 @@ int b2j_bodies_remove(b2j_world *w, const uint32_t *ids, uint32_t n);
 /* BodyInterface::ActivateBody / DeactivateBody (:142-145) */
 int b2j_bodies_activate(b2j_world *w, const uint32_t *ids, uint32_t n);
 int b2j_bodies_deactivate(b2j_world *w, const uint32_t *ids, uint32_t n);
+/* BodyInterface::ActivateBodyInternal (BodyInterface.cpp:20-28), what every BodyInterface call with EActivation::Activate does: sleeping
+ * bodies are activated, bodies that are active already get Body::ResetSleepTimer. And BodyInterface::ResetSleepTimer (:148) alone. */
+int b2j_bodies_activate_or_reset_sleep_timer(b2j_world *w, const uint32_t *ids, uint32_t n);
+int b2j_bodies_reset_sleep_timer(b2j_world *w, const uint32_t *ids, uint32_t n);
 /* Snapshot helper: sets the active list to exactly ids[0..n) in this order (BodyManager::mActiveBodies). */
 int b2j_set_active_list(b2j_world *w, const uint32_t *ids, uint32_t n);
 
@@ -257,7 +261,8 @@ int b2j_host_buffer_register(void *ptr, size_t bytes);
 int b2j_host_buffer_unregister(void *ptr);
 /* BodyInterface::SetPositionAndRotation / SetLinearAndAngularVelocity; NULL members are left untouched. */
 int b2j_bodies_set_state(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_state *in);
-/* BodyInterface::AddForce / AddTorque (:220-226): accumulate into mForce / mTorque (either may be NULL). */
+/* BodyInterface::AddForce / AddTorque (:220-226): accumulate into mForce / mTorque (either may be NULL). One entry per body and
+ * call: the entries are added in parallel (sum several forces of one body before the call, as the facade does). */
 int b2j_bodies_add_force_torque(b2j_world *w, const uint32_t *ids, uint32_t n, const float *force, const float *torque);
 
 /* BodyInterface::SetFriction / SetRestitution / SetGravityFactor / SetMaxLinearVelocity / SetMaxAngularVelocity and

@@ -151,6 +151,9 @@ struct Mat44RT
 	}
 	static Mat44RT sRotation(const Quat &q) { return sRotationTranslation(q, Vec3::sZero()); }
 	Vec3 operator*(const Vec3 &v) const { return ((c0 * v.x + c1 * v.y) + c2 * v.z) + t; } // Mat44 * Vec3 (Mat44.inl:386-391)
+	Vec3 GetTranslation() const { return t; }
+	Vec3 GetColumn3(int i) const { return i == 0? c0 : (i == 1? c1 : c2); }
+	Vec3 GetAxisX() const { return c0; } Vec3 GetAxisY() const { return c1; } Vec3 GetAxisZ() const { return c2; }
 	Mat44RT operator*(const Mat44RT &b) const
 	{
 		Mat44RT r;
@@ -161,6 +164,9 @@ struct Mat44RT
 		return r;
 	}
 };
+
+using Mat44 = Mat44RT;
+using RMat44 = Mat44RT;
 
 // AABox (Jolt/Geometry/AABox.h): the operations shape bounds need
 struct AABox
@@ -1096,6 +1102,27 @@ public:
 	void SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity);
 	void SetLinearVelocity(const BodyID &id, const Vec3 &v) { SetLinearAndAngularVelocity(id, v, GetAngularVelocity(id)); }
 	void SetAngularVelocity(const BodyID &id, const Vec3 &v) { SetLinearAndAngularVelocity(id, GetLinearVelocity(id), v); }
+	// the rest of the pose / velocity surface (BodyInterface.h:187-216), host side arithmetic of Body / MotionProperties on the mirror
+	void SetPosition(const BodyID &id, const RVec3 &inPosition, EActivation inActivationMode) { SetPositionAndRotation(id, inPosition, GetRotation(id), inActivationMode); }
+	void SetRotation(const BodyID &id, const Quat &inRotation, EActivation inActivationMode) { SetPositionAndRotation(id, GetPosition(id), inRotation, inActivationMode); }
+	void SetPositionAndRotationWhenChanged(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, EActivation inActivationMode);
+	void SetPositionRotationAndVelocity(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity);
+	void GetLinearAndAngularVelocity(const BodyID &id, Vec3 &outLinearVelocity, Vec3 &outAngularVelocity) const { outLinearVelocity = GetLinearVelocity(id); outAngularVelocity = GetAngularVelocity(id); }
+	void AddLinearVelocity(const BodyID &id, const Vec3 &inLinearVelocity) { SetLinearAndAngularVelocity(id, GetLinearVelocity(id) + inLinearVelocity, GetAngularVelocity(id)); }
+	void AddLinearAndAngularVelocity(const BodyID &id, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity) { SetLinearAndAngularVelocity(id, GetLinearVelocity(id) + inLinearVelocity, GetAngularVelocity(id) + inAngularVelocity); }
+	Vec3 GetPointVelocity(const BodyID &id, const RVec3 &inPoint) const; // Body::GetPointVelocity: v + w x (point - centre of mass)
+	void MoveKinematic(const BodyID &id, const RVec3 &inTargetPosition, const Quat &inTargetRotation, float inDeltaTime);
+	Mat44RT GetWorldTransform(const BodyID &id) const { return Mat44RT::sRotationTranslation(GetRotation(id), GetPosition(id)); }
+	Mat44RT GetCenterOfMassTransform(const BodyID &id) const { return Mat44RT::sRotationTranslation(GetRotation(id), GetCenterOfMassPosition(id)); }
+	Mat44RT GetInverseInertia(const BodyID &id) const; // Body::GetInverseInertia (world space, locked DOFs masked; translation part unused)
+	void AddForce(const BodyID &id, const Vec3 &inForce, const RVec3 &inPoint, EActivation inActivationMode = EActivation::Activate);
+	void AddForceAndTorque(const BodyID &id, const Vec3 &inForce, const Vec3 &inTorque, EActivation inActivationMode = EActivation::Activate) { AddForce(id, inForce, inActivationMode); AddTorque(id, inTorque, inActivationMode); }
+	void ActivateBodies(const BodyID *inBodyIDs, int inNumber) { for (int i = 0; i < inNumber; ++i) ActivateNoReset(inBodyIDs[i]); } // BodyManager::ActivateBodies: sleeping bodies only
+	void ResetSleepTimer(const BodyID &id) { const Body *b = TryGet(id); if (b == nullptr || !b->mInWorld || b->mMotionType == EMotionType::Static) return; Flush(); uint32 bid = id.mID; b2j_bodies_reset_sleep_timer(World(), &bid, 1); }
+	void DeactivateBodies(const BodyID *inBodyIDs, int inNumber) { for (int i = 0; i < inNumber; ++i) DeactivateBody(inBodyIDs[i]); }
+	void DestroyBodies(const BodyID *inBodyIDs, int inNumber) { for (int i = 0; i < inNumber; ++i) DestroyBody(inBodyIDs[i]); }
+	EMotionQuality GetMotionQuality(const BodyID &) const { return EMotionQuality::Discrete; } // (LinearCast is not on the path: SURVEY 8b)
+	void SetUserData(const BodyID &id, uint64 inUserData) const { Body *b = const_cast<Body *>(TryGet(id)); if (b != nullptr) b->mUserData = inUserData; }
 	void AddForce(const BodyID &id, const Vec3 &inForce, EActivation inActivationMode = EActivation::Activate);
 	void AddTorque(const BodyID &id, const Vec3 &inTorque, EActivation inActivationMode = EActivation::Activate);
 	// BodyInterface::AddImpulse / AddAngularImpulse (BodyInterface.h:227-230, Body.inl AddImpulse): dynamic bodies only, activates the body
@@ -1133,6 +1160,7 @@ private:
 	b2j_world *World() const;
 	void Flush();
 	void SetActive(const BodyID &id, bool inActive);
+	void ActivateNoReset(const BodyID &id) { const Body *b = TryGet(id); if (b != nullptr && !b->IsActive()) SetActive(id, true); } // (!IsActive -> BodyManager::ActivateBodies)
 	void SetParam(const BodyID &id, float b2j_body_desc::*inDescMember, const float *b2j_body_params::*inParamMember, float inValue);
 	PhysicsSystem *mSystem = nullptr;
 };
@@ -1708,11 +1736,23 @@ inline void BodyInterface::Flush()
 	}
 	if (!sys.mPendingActivate.empty())
 	{
-		b2j_bodies_activate(sys.mWorld, sys.mPendingActivate.data(), (uint32)sys.mPendingActivate.size());
+		b2j_bodies_activate_or_reset_sleep_timer(sys.mWorld, sys.mPendingActivate.data(), (uint32)sys.mPendingActivate.size()); // BodyInterface::ActivateBodyInternal
 		sys.mPendingActivate.clear();
 	}
 	if (!sys.mForceIDs.empty())
 	{
+		// several calls for one body (AddForce at a point = a force and a torque entry): summed here in call order, like the reference adds
+		// them to Body::mForce / mTorque one call after the other; the device call wants every id once
+		size_t n = sys.mForceIDs.size(), m = 0;
+		std::vector<uint32> &ids = sys.mForceIDs;
+		for (size_t i = 0; i < n; ++i)
+		{
+			size_t j = 0;
+			while (j < m && ids[j] != ids[i]) ++j; // (a handful of entries per flush)
+			if (j == m) { ids[m] = ids[i]; for (int k = 0; k < 3; ++k) { sys.mForces[3 * m + k] = sys.mForces[3 * i + k]; sys.mTorques[3 * m + k] = sys.mTorques[3 * i + k]; } ++m; }
+			else for (int k = 0; k < 3; ++k) { sys.mForces[3 * j + k] += sys.mForces[3 * i + k]; sys.mTorques[3 * j + k] += sys.mTorques[3 * i + k]; }
+		}
+		ids.resize(m);
 		b2j_bodies_add_force_torque(sys.mWorld, sys.mForceIDs.data(), (uint32)sys.mForceIDs.size(), sys.mForces.data(), sys.mTorques.data());
 		sys.mForceIDs.clear(); sys.mForces.clear(); sys.mTorques.clear();
 	}
@@ -1777,15 +1817,25 @@ inline void BodyInterface::SetPositionAndRotation(const BodyID &id, const RVec3 
 	memset(&st, 0, sizeof(st));
 	st.position = pos; st.rotation = rot;
 	b2j_bodies_set_state(World(), &bid, 1, &st);
-	if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static) b2j_bodies_activate(World(), &bid, 1);
+	if (inActivationMode == EActivation::Activate && b->mMotionType != EMotionType::Static) { b2j_bodies_activate_or_reset_sleep_timer(World(), &bid, 1); b->mActive = true; }
 }
 
-inline void BodyInterface::SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &lv, const Vec3 &av)
+// MotionProperties::LockTranslation / LockAngular (inMask3 = the three DOF bits of the vector), ClampLinear / AngularVelocity
+inline Vec3 sLockDOFs(const Vec3 &v, uint inMask3) { return Vec3((inMask3 & 1)? v.x : 0.0f, (inMask3 & 2)? v.y : 0.0f, (inMask3 & 4)? v.z : 0.0f); }
+inline Vec3 sClampVelocity(const Vec3 &v, float inMax)
+{
+	float len_sq = v.LengthSq();
+	return len_sq > inMax * inMax? v * (inMax / std::sqrt(len_sq)) : v;
+}
+
+inline void BodyInterface::SetLinearAndAngularVelocity(const BodyID &id, const Vec3 &inLV, const Vec3 &inAV)
 {
 	Body *b = const_cast<Body *>(TryGet(id));
 	if (b == nullptr || b->mMotionType == EMotionType::Static) return;
 	b->Sync();
 	mSystem->MarkMirrorNewer(id);
+	// Body::SetLinearVelocityClamped / SetAngularVelocityClamped: locked DOFs zeroed, clamped to the maximum velocities
+	Vec3 lv = sClampVelocity(sLockDOFs(inLV, b->mDesc.allowed_dofs), b->mDesc.max_linear_velocity), av = sClampVelocity(sLockDOFs(inAV, b->mDesc.allowed_dofs >> 3), b->mDesc.max_angular_velocity);
 	b->mLinearVelocity = lv; b->mAngularVelocity = av;
 	if (!b->mInWorld) { memcpy(b->mDesc.linear_velocity, &lv, 12); memcpy(b->mDesc.angular_velocity, &av, 12); return; }
 	Flush();
@@ -1796,7 +1846,7 @@ inline void BodyInterface::SetLinearAndAngularVelocity(const BodyID &id, const V
 	st.linear_velocity = l; st.angular_velocity = a;
 	b2j_bodies_set_state(World(), &bid, 1, &st);
 	// BodyInterface::SetLinearAndAngularVelocity activates the body when the velocity is non zero
-	if (lv.LengthSq() > 0.0f || av.LengthSq() > 0.0f) b2j_bodies_activate(World(), &bid, 1);
+	if (!b->mActive && (inLV.LengthSq() > 1.0e-12f || inAV.LengthSq() > 1.0e-12f)) { b2j_bodies_activate(World(), &bid, 1); b->mActive = true; } // (!IsNearZero)
 }
 
 inline void BodyInterface::AddForce(const BodyID &id, const Vec3 &f, EActivation inActivationMode)
@@ -1805,7 +1855,7 @@ inline void BodyInterface::AddForce(const BodyID &id, const Vec3 &f, EActivation
 	// BodyInterface::AddForce (BodyInterface.cpp): dynamic bodies only; applied when the body is active or gets activated
 	const Body *b = TryGet(id);
 	if (b == nullptr || b->mMotionType != EMotionType::Dynamic || !(inActivationMode == EActivation::Activate || b->IsActive())) return;
-	if (inActivationMode == EActivation::Activate && b->mInWorld) sys.mPendingActivate.push_back(id.mID);
+	if (inActivationMode == EActivation::Activate && b->mInWorld) { sys.mPendingActivate.push_back(id.mID); b->mActive = true; } // (the device follows at the next flush)
 	sys.mForceIDs.push_back(id.mID);
 	sys.mForces.push_back(f.x); sys.mForces.push_back(f.y); sys.mForces.push_back(f.z);
 	sys.mTorques.push_back(0); sys.mTorques.push_back(0); sys.mTorques.push_back(0);
@@ -1816,7 +1866,7 @@ inline void BodyInterface::AddTorque(const BodyID &id, const Vec3 &t, EActivatio
 	PhysicsSystem &sys = *mSystem;
 	const Body *b = TryGet(id);
 	if (b == nullptr || b->mMotionType != EMotionType::Dynamic || !(inActivationMode == EActivation::Activate || b->IsActive())) return;
-	if (inActivationMode == EActivation::Activate && b->mInWorld) sys.mPendingActivate.push_back(id.mID);
+	if (inActivationMode == EActivation::Activate && b->mInWorld) { sys.mPendingActivate.push_back(id.mID); b->mActive = true; } // (the device follows at the next flush)
 	sys.mForceIDs.push_back(id.mID);
 	sys.mForces.push_back(0); sys.mForces.push_back(0); sys.mForces.push_back(0);
 	sys.mTorques.push_back(t.x); sys.mTorques.push_back(t.y); sys.mTorques.push_back(t.z);
@@ -1828,7 +1878,8 @@ inline void BodyInterface::SetActive(const BodyID &id, bool inActive)
 	if (b == nullptr || !b->mInWorld || b->mMotionType == EMotionType::Static) return;
 	uint32 bid = id.mID;
 	Flush();
-	if (inActive) b2j_bodies_activate(World(), &bid, 1); else b2j_bodies_deactivate(World(), &bid, 1);
+	// (ActivateBody = BodyInterface::ActivateBodyInternal: a body that is active already gets its sleep timer reset)
+	if (inActive) b2j_bodies_activate_or_reset_sleep_timer(World(), &bid, 1); else b2j_bodies_deactivate(World(), &bid, 1);
 	mSystem->mBehindMask = PhysicsSystem::cStateAll;
 	b->Sync();
 	mSystem->MarkMirrorNewer(id);
@@ -1950,7 +2001,7 @@ inline void BodyInterface::AddImpulse(const BodyID &id, const Vec3 &inImpulse)
 	if (b == nullptr || b->mMotionType != EMotionType::Dynamic) return;
 	// Body::AddImpulse: v += invM * impulse
 	SetLinearVelocity(id, b->GetLinearVelocity() + b->mDesc.inv_mass * inImpulse);
-	if (b->mInWorld) ActivateBody(id);
+	if (b->mInWorld) ActivateNoReset(id); // (BodyInterface::AddImpulse: if (!body.IsActive()) ActivateBodies)
 }
 
 inline void BodyInterface::AddAngularImpulse(const BodyID &id, const Vec3 &inAngularImpulse)
@@ -1969,7 +2020,7 @@ inline void BodyInterface::AddAngularImpulse(const BodyID &id, const Vec3 &inAng
 	local = Vec3(d.inv_inertia_diag[0] * local.x, d.inv_inertia_diag[1] * local.y, d.inv_inertia_diag[2] * local.z);
 	Vec3 delta(c0.x * local.x + c1.x * local.y + c2.x * local.z, c0.y * local.x + c1.y * local.y + c2.y * local.z, c0.z * local.x + c1.z * local.y + c2.z * local.z);
 	SetAngularVelocity(id, b->GetAngularVelocity() + delta);
-	if (b->mInWorld) ActivateBody(id);
+	if (b->mInWorld) ActivateNoReset(id); // (BodyInterface::AddImpulse: if (!body.IsActive()) ActivateBodies)
 }
 
 inline void BodyInterface::AddImpulse(const BodyID &id, const Vec3 &inImpulse, const RVec3 &inPoint)
@@ -1980,6 +2031,121 @@ inline void BodyInterface::AddImpulse(const BodyID &id, const Vec3 &inImpulse, c
 	Vec3 r = inPoint - b->GetCenterOfMassPosition();
 	AddImpulse(id, inImpulse);
 	AddAngularImpulse(id, r.Cross(inImpulse));
+}
+
+inline void BodyInterface::SetPositionAndRotationWhenChanged(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, EActivation inActivationMode)
+{
+	// BodyInterface.cpp: only when the body is not already (close to) there: !IsClose(position) || !IsClose(rotation), default tolerances 1e-12
+	const Body *b = TryGet(id);
+	if (b == nullptr) return;
+	Vec3 dp = b->GetPosition() - inPosition;
+	Quat r = b->GetRotation();
+	float dr = ((r.x - inRotation.x) * (r.x - inRotation.x) + (r.y - inRotation.y) * (r.y - inRotation.y)) + ((r.z - inRotation.z) * (r.z - inRotation.z) + (r.w - inRotation.w) * (r.w - inRotation.w));
+	if (dp.LengthSq() > 1.0e-12f || dr > 1.0e-12f)
+		SetPositionAndRotation(id, inPosition, inRotation, inActivationMode);
+}
+
+inline void BodyInterface::SetPositionRotationAndVelocity(const BodyID &id, const RVec3 &inPosition, const Quat &inRotation, const Vec3 &inLinearVelocity, const Vec3 &inAngularVelocity)
+{
+	const Body *b = TryGet(id);
+	if (b == nullptr) return;
+	SetPositionAndRotation(id, inPosition, inRotation, EActivation::DontActivate);
+	if (b->mMotionType == EMotionType::Static) return;
+	bool was_active = b->IsActive();
+	SetLinearAndAngularVelocity(id, inLinearVelocity, inAngularVelocity); // (activates when a velocity is not near zero, like the reference)
+	(void)was_active;
+}
+
+inline Vec3 BodyInterface::GetPointVelocity(const BodyID &id, const RVec3 &inPoint) const
+{
+	const Body *b = TryGet(id);
+	if (b == nullptr || b->mMotionType == EMotionType::Static) return Vec3::sZero();
+	// MotionProperties::GetPointVelocityCOM: mLinearVelocity + mAngularVelocity.Cross(inPointRelativeToCOM)
+	return b->GetLinearVelocity() + b->GetAngularVelocity().Cross(inPoint - b->GetCenterOfMassPosition());
+}
+
+// Jolt's ACos (Vec4::ASin / ACos, Vec4.inl:1266-1305: the cephes asinf polynomial), scalar
+inline float sJoltACos(float inX)
+{
+	float sign = inX < 0.0f? -1.0f : 1.0f;
+	float a = std::min(inX < 0.0f? -inX : inX, 1.0f);
+	bool greater = a > 0.5f;
+	float z = greater? 0.5f * (1.0f - a) : a * a;
+	float x = greater? std::sqrt(z) : a;
+	z = ((((4.2163199048e-2f * z + 2.4181311049e-2f) * z + 4.5470025998e-2f) * z + 7.4953002686e-2f) * z + 1.6666752422e-1f) * z * x + x;
+	if (greater) z = 0.5f * JPH_PI - (z + z);
+	float asin = sign < 0.0f? -z : z;
+	return 0.5f * JPH_PI - asin;
+}
+
+inline void BodyInterface::MoveKinematic(const BodyID &id, const RVec3 &inTargetPosition, const Quat &inTargetRotation, float inDeltaTime)
+{
+	Body *b = const_cast<Body *>(TryGet(id));
+	if (b == nullptr || b->mMotionType == EMotionType::Static) return;
+	// Body::MoveKinematic (Body.cpp:81-95) + MotionProperties::MoveKinematic (MotionProperties.inl:9-21): the velocities that take the body
+	// to the target in inDeltaTime, not clamped
+	Vec3 new_com = inTargetPosition + inTargetRotation * b->mShape->GetCenterOfMass();
+	Vec3 delta_pos = new_com - b->GetCenterOfMassPosition();
+	Quat r = b->GetRotation();
+	Quat delta_rotation = inTargetRotation * Quat(-r.x, -r.y, -r.z, r.w);
+	Vec3 lv = sLockDOFs(Vec3(delta_pos.x / inDeltaTime, delta_pos.y / inDeltaTime, delta_pos.z / inDeltaTime), b->mDesc.allowed_dofs);
+	// Quat::GetAngularVelocity (Quat.inl:186-204)
+	bool flip = delta_rotation.w < 0.0f;
+	Vec3 xyz(flip? -delta_rotation.x : delta_rotation.x, flip? -delta_rotation.y : delta_rotation.y, flip? -delta_rotation.z : delta_rotation.z);
+	float w = flip? -delta_rotation.w : delta_rotation.w;
+	float xyz_len_sq = xyz.LengthSq();
+	Vec3 av;
+	if (xyz_len_sq < 4.0e-4f)
+		av = (2.0f / inDeltaTime) * xyz;
+	else
+	{
+		float angle = 2.0f * sJoltACos(w);
+		float d = std::sqrt(xyz_len_sq) * inDeltaTime;
+		av = Vec3(xyz.x / d, xyz.y / d, xyz.z / d) * angle;
+	}
+	av = sLockDOFs(av, b->mDesc.allowed_dofs >> 3);
+	b->Sync();
+	mSystem->MarkMirrorNewer(id);
+	b->mLinearVelocity = lv; b->mAngularVelocity = av;
+	if (!b->mInWorld) { memcpy(b->mDesc.linear_velocity, &lv, 12); memcpy(b->mDesc.angular_velocity, &av, 12); return; }
+	Flush();
+	uint32 bid = id.mID;
+	float l[3] = { lv.x, lv.y, lv.z }, a[3] = { av.x, av.y, av.z };
+	b2j_body_state st;
+	memset(&st, 0, sizeof(st));
+	st.linear_velocity = l; st.angular_velocity = a;
+	b2j_bodies_set_state(World(), &bid, 1, &st);
+	auto near_zero = [](const Vec3 &v) { return v.LengthSq() <= 1.0e-12f; };
+	if (!b->mActive && (!near_zero(lv) || !near_zero(av))) { b2j_bodies_activate(World(), &bid, 1); b->mActive = true; }
+}
+
+inline Mat44RT BodyInterface::GetInverseInertia(const BodyID &id) const
+{
+	Mat44RT out;
+	out.c0 = out.c1 = out.c2 = Vec3::sZero();
+	const Body *b = TryGet(id);
+	if (b == nullptr || b->mMotionType != EMotionType::Dynamic) return out;
+	// MotionProperties::GetInverseInertiaForRotation (MotionProperties.inl:66-81)
+	const b2j_body_desc &d = b->mDesc;
+	Mat44RT rot = Mat44RT::sRotation(b->GetRotation()), irot = Mat44RT::sRotation(Quat(d.inertia_rotation[0], d.inertia_rotation[1], d.inertia_rotation[2], d.inertia_rotation[3]));
+	Vec3 r0 = (rot.c0 * irot.c0.x + rot.c1 * irot.c0.y) + rot.c2 * irot.c0.z, r1 = (rot.c0 * irot.c1.x + rot.c1 * irot.c1.y) + rot.c2 * irot.c1.z, r2 = (rot.c0 * irot.c2.x + rot.c1 * irot.c2.y) + rot.c2 * irot.c2.z; // Multiply3x3
+	Vec3 s0 = d.inv_inertia_diag[0] * r0, s1 = d.inv_inertia_diag[1] * r1, s2 = d.inv_inertia_diag[2] * r2;
+	// rotation.Multiply3x3RightTransposed(scaled): column j = (r0 * s0[j] + r1 * s1[j]) + r2 * s2[j]
+	Vec3 cols[3];
+	for (int j = 0; j < 3; ++j) cols[j] = (r0 * s0[j] + r1 * s1[j]) + r2 * s2[j];
+	uint mask = uint(d.allowed_dofs) >> 3;
+	for (int j = 0; j < 3; ++j) cols[j] = (mask & (1u << j))? sLockDOFs(cols[j], mask) : Vec3::sZero();
+	out.c0 = cols[0]; out.c1 = cols[1]; out.c2 = cols[2];
+	return out;
+}
+
+inline void BodyInterface::AddForce(const BodyID &id, const Vec3 &inForce, const RVec3 &inPoint, EActivation inActivationMode)
+{
+	// Body::AddForce(force, position): AddForce(force); AddTorque((position - centre of mass) x force)
+	const Body *b = TryGet(id);
+	if (b == nullptr) return;
+	AddForce(id, inForce, inActivationMode);
+	AddTorque(id, (inPoint - b->GetCenterOfMassPosition()).Cross(inForce), inActivationMode);
 }
 
 inline void BodyInterface::AddForcesAndTorques(const BodyID *inBodies, int inNumber, const float *inForces, const float *inTorques)

@@ -140,6 +140,8 @@ PROTOTYPES = {
     "b2j_bodies_add": (C.c_int, [_VP, C.POINTER(BodyDesc), C.c_uint32]),
     "b2j_bodies_remove": (C.c_int, [_VP, _U32P, C.c_uint32]),
     "b2j_bodies_activate": (C.c_int, [_VP, _U32P, C.c_uint32]),
+    "b2j_bodies_activate_or_reset_sleep_timer": (C.c_int, [_VP, _U32P, C.c_uint32]),
+    "b2j_bodies_reset_sleep_timer": (C.c_int, [_VP, _U32P, C.c_uint32]),
     "b2j_bodies_deactivate": (C.c_int, [_VP, _U32P, C.c_uint32]),
     "b2j_set_active_list": (C.c_int, [_VP, _U32P, C.c_uint32]),
     "b2j_bodies_get_state": (C.c_int, [_VP, _U32P, C.c_uint32, C.POINTER(BodyState)]),

@@ -2021,7 +2021,21 @@ int b2j_set_active_list(b2j_world *W, const uint32_t *ids, uint32_t n)
 	return rt.check("b2j_set_active_list")? 0 : -1;
 }
 
-int b2j_bodies_activate(b2j_world *W, const uint32_t *ids, uint32_t n)
+// Body::ResetSleepTimer for bodies that are active already (BodyInterface::ActivateBodyInternal / ResetSleepTimer)
+struct KResetSleepTimer
+{
+	DWorld w; const uint32_t *slots;
+	B2J_D void operator()(uint32_t k) const
+	{
+		uint32_t b = slots[k];
+		V3 points[3];
+		sleep_test_points(w.shapes[w.info[b].shape], to_v3(w.position[b]), to_q4(w.rotation[b]), points);
+		for (int i = 0; i < 3; ++i) w.sleep_spheres[b * 3 + i] = f4(points[i], 0.0f);
+		w.sleep_timer[b] = 0.0f;
+	}
+};
+
+static int bodies_activate(b2j_world *W, const uint32_t *ids, uint32_t n, bool activate, bool reset_active)
 {
 	// append the bodies that are not active yet, in argument order (BodyManager::ActivateBodies)
 	Runtime &rt = W->rt;
@@ -2041,13 +2055,28 @@ int b2j_bodies_activate(b2j_world *W, const uint32_t *ids, uint32_t n)
 	rt.stage_to_host(out_begin, rt.stage_used);
 	// first occurrence of every sleeping, non static body (a per slot mark instead of a search per id)
 	if (W->h_mark.size() < W->d.max_bodies) W->h_mark.assign(W->d.max_bodies, 0);
-	std::vector<uint32_t> add;
+	std::vector<uint32_t> add, reset;
 	for (uint32_t i = 0; i < n; ++i)
 	{
 		uint32_t slot = slot_of(ids[i]);
-		if (h_idx[i] == B2J_INACTIVE_INDEX && !W->h_mark[slot] && W->h_static[slot] == 0) { W->h_mark[slot] = 1; add.push_back(ids[i]); }
+		if (W->h_mark[slot] || W->h_static[slot] != 0) continue;
+		if (h_idx[i] == B2J_INACTIVE_INDEX) { if (activate) { W->h_mark[slot] = 1; add.push_back(ids[i]); } }
+		else if (reset_active) { W->h_mark[slot] = 1; reset.push_back(slot); }
 	}
 	for (uint32_t id : add) W->h_mark[slot_of(id)] = 0;
+	for (uint32_t slot : reset) W->h_mark[slot] = 0;
+	if (!reset.empty())
+	{
+		uint32_t nr = (uint32_t)reset.size();
+		rt.stage_begin((size_t)nr * 4);
+		uint32_t *h_r = nullptr;
+		uint32_t *d_r = rt.stage_alloc<uint32_t>(nr, &h_r);
+		memcpy(h_r, reset.data(), (size_t)nr * 4);
+		rt.stage_to_device(0, rt.stage_used);
+		KResetSleepTimer k; k.w = W->d; k.slots = d_r;
+		rt.launch(k, nr);
+		rt.sync(); // the staging buffer is reused below
+	}
 	if (!add.empty())
 	{
 		uint32_t na = (uint32_t)add.size();
@@ -2066,6 +2095,10 @@ int b2j_bodies_activate(b2j_world *W, const uint32_t *ids, uint32_t n)
 	}
 	return rt.check("b2j_bodies_activate")? 0 : -1;
 }
+
+int b2j_bodies_activate(b2j_world *W, const uint32_t *ids, uint32_t n) { return bodies_activate(W, ids, n, true, false); }
+int b2j_bodies_activate_or_reset_sleep_timer(b2j_world *W, const uint32_t *ids, uint32_t n) { return bodies_activate(W, ids, n, true, true); }
+int b2j_bodies_reset_sleep_timer(b2j_world *W, const uint32_t *ids, uint32_t n) { return bodies_activate(W, ids, n, false, true); }
 
 int b2j_bodies_deactivate(b2j_world *W, const uint32_t *ids, uint32_t n)
 {

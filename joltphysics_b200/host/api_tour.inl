@@ -91,6 +91,35 @@ static void sApiTourMutate(PhysicsSystem &inSystem, std::vector<BodyID> &ioBodie
 		bi.SetShape(ioBodies[10], B2J_NEW_SHAPE(BoxShape, Vec3(0.6f, 0.2f, 0.4f)), false, EActivation::Activate);
 		bi.InvalidateContactCache(ioBodies[11]);
 	}
+	else if (inPhase == 5)
+	{
+		// the rest of the pose / velocity surface (BodyInterface.h:187-230)
+		bi.MoveKinematic(ioBodies[1], RVec3(2.0f, 1.5f, 1.0f), Quat(0.0f, 0.38268343f, 0.0f, 0.92387953f), 0.5f); // the kinematic body of phase 4
+		bi.SetPositionRotationAndVelocity(ioBodies[4], RVec3(-2.0f, 3.0f, 1.0f), Quat(0.25881905f, 0.0f, 0.0f, 0.96592583f), Vec3(1.0f, 0.0f, 0.0f), Vec3(0.0f, 2.0f, 0.0f));
+		bi.AddLinearVelocity(ioBodies[6], Vec3(0.0f, 3.0f, 0.0f));
+		bi.AddLinearAndAngularVelocity(ioBodies[7], Vec3(0.5f, 2.0f, 0.0f), Vec3(0.0f, 0.0f, 1.5f));
+		bi.AddForce(ioBodies[9], Vec3(0.0f, 20000.0f, 0.0f), bi.GetCenterOfMassPosition(ioBodies[9]) + Vec3(0.1f, 0.0f, 0.2f));
+		bi.AddForceAndTorque(ioBodies[10], Vec3(5000.0f, 15000.0f, 0.0f), Vec3(0.0f, 300.0f, 0.0f));
+		bi.SetPosition(ioBodies[11], RVec3(5.0f, 2.0f, 2.0f), EActivation::Activate);
+		bi.SetRotation(ioBodies[3], Quat(0.0f, 0.0f, 0.38268343f, 0.92387953f), EActivation::Activate);
+		bi.SetLinearVelocity(ioBodies[3], Vec3(0.0f, 900.0f, 0.0f)); // above the maximum of 2 set in phase 1: clamped
+		bi.SetPositionAndRotationWhenChanged(ioBodies[5], bi.GetPosition(ioBodies[5]), bi.GetRotation(ioBodies[5]), EActivation::Activate); // unchanged: no activation
+		// getters feed mutations, so a wrong value shows in the state
+		Vec3 point_velocity = bi.GetPointVelocity(ioBodies[7], bi.GetCenterOfMassPosition(ioBodies[7]) + Vec3(0.3f, 0.1f, 0.0f));
+		Vec3 lv, av;
+		bi.GetLinearAndAngularVelocity(ioBodies[6], lv, av);
+		bi.AddLinearVelocity(ioBodies[12], 0.1f * point_velocity + 0.1f * lv);
+		auto inverse_inertia = bi.GetInverseInertia(ioBodies[4]);
+		bi.AddAngularImpulse(ioBodies[4], 20.0f * inverse_inertia.GetColumn3(1));
+		auto world_transform = bi.GetWorldTransform(ioBodies[13]);
+		bi.SetPosition(ioBodies[13], world_transform.GetTranslation() + Vec3(0.0f, 0.5f, 0.0f), EActivation::Activate);
+		auto com_transform = bi.GetCenterOfMassTransform(ioBodies[14]);
+		bi.SetPosition(ioBodies[14], com_transform * Vec3(0.0f, 0.3f, 0.0f), EActivation::Activate);
+		bi.SetUserData(ioBodies[2], 1234);
+		BodyID two[2] = { ioBodies[6], ioBodies[11] };
+		bi.DeactivateBodies(two, 2);
+		bi.ActivateBodies(two + 1, 1);
+	}
 }
 
 // Queries after the tour: number of bodies, active bodies (as a sorted id list written to outIDs), returns the active count

@@ -49,13 +49,13 @@ def hostsim_facade(hostsim_api):
     return F.FacadeLib(os.path.join(ROOT, "tests", "hostsim", "_build", "libb2j_facade_hostsim.so"), hostsim_api)
 
 
-@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 4, 0, 5, 40), ("pile", 300, 15, 3, 60), ("convex_vs_mesh", 1, 0, 4, 80)])
+@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 4, 0, 5, 40), ("pile", 300, 15, 3, 60), ("convex_vs_mesh", 1, 0, 4, 80), ("compound", 0, 0, 3, 100)])
 def test_batch_matches_single_world_hostsim(hostsim_api, hostsim_facade, scene, p0, p1, n_worlds, steps):
     _check_batch(hostsim_api, hostsim_facade, scene, p0, p1, n_worlds, steps)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 15, 0, 16, 60), ("pile", 1000, 15, 8, 90), ("convex_vs_mesh", 3, 0, 6, 120)])
+@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 15, 0, 16, 60), ("pile", 1000, 15, 8, 90), ("convex_vs_mesh", 3, 0, 6, 120), ("compound", 0, 0, 12, 150)])
 def test_batch_matches_single_world_gpu(gpu_api, scene, p0, p1, n_worlds, steps):
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
     _check_batch(gpu_api, flib, scene, p0, p1, n_worlds, steps)

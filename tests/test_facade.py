@@ -107,27 +107,36 @@ def _check_api_tour(flib):
     ref = R.RefWorld("api_tour")
     fs = F.FacadeScene(flib, "api_tour")
 
-    def compare(tag):
+    def compare(tag, exact=False):
         fs.world.n = 18  # body slots 0..16 are used by the tour (13 at creation, 4 added later, one slot reused)
         rs, gs = ref.state(18), fs.world.state()
         worst = R.compare_states(rs, gs)
         for k in ("pos", "rot", "lin", "ang"):
             assert worst[k] <= 1.0, (tag, k, worst)
+        if exact:
+            # every step of the tour is bit identical, sleep timing included (EActivation::Activate on a body that is awake resets its
+            # sleep timer, BodyInterface::ActivateBodyInternal): checked on the bodies that are in the world
+            in_world = np.array([bool(x) for x in fs.world.state().active_index != 0xffffffff]) | (rs.active_index != 0xffffffff)
+            for name in ("pos", "rot", "lin", "ang"):
+                a, b = getattr(rs, name)[in_world], getattr(gs, name)[in_world]
+                assert np.array_equal(a, b), (tag, name, np.abs(a - b).max())
+            assert np.array_equal(rs.active_index != 0xffffffff, gs.active_index != 0xffffffff), (tag, "active flags")
         (ra, rn, rf), (ga, gn, gf) = ref.query(), fs.query()
         assert rn == gn, (tag, "GetBodies", rn, gn)
         assert np.array_equal(ra, ga), (tag, "GetActiveBodies", ra, ga)
         assert rf == gf, (tag, "IsAdded && IsActive", bin(rf), bin(gf))
 
     compare("created")
-    for phase, steps in ((0, 10), (1, 25), (2, 40), (3, 30), (4, 60)):
+    for phase, steps in ((0, 10), (1, 25), (2, 40), (3, 30), (4, 60), (5, 50)):
         if phase:
             ref.mutate(phase)
             fs.mutate(phase)
             compare(f"after mutation {phase}")
-        for _ in range(steps):
+        for step in range(steps):
             ref.step()
             err, _ = fs.update()
             assert err == 0
+            compare(f"phase {phase} step {step}", exact=True)
         compare(f"after the steps of phase {phase}")
     # the BodyInterface getters (flat array fast path / Body mirror) agree with the device state for every tour body
     ref.step()

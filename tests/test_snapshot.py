@@ -69,7 +69,8 @@ def _check_save_restore(api, scene, p0, p1, k, more):
     ref.close()
 
 
-CASES = [("small_stack", 4, 0, 30, 30), ("pyramid", 5, 0, 20, 30), ("feature", parity.FEATURES.index("zoo"), 0, 60, 30)]
+CASES = [("small_stack", 4, 0, 30, 30), ("pyramid", 5, 0, 20, 30), ("feature", parity.FEATURES.index("zoo"), 0, 60, 30),
+         ("compound", 1, 0, 100, 40)]  # compounds, decorated parts and cylinders on a mesh
 
 
 @pytest.mark.parametrize("scene,p0,p1,k,more", CASES)
