@@ -292,6 +292,8 @@ typedef struct b2j_body_info_update {
 	const float    *inv_inertia_diag;   /* [n][3] with shape */
 	const float    *inertia_rotation;   /* [n][4] with shape */
 	uint32_t        invalidate_contact_cache;
+	const uint16_t *flags_set;          /* [n] B2J_BODY_* bits to set: Body::SetIsSensor / SetUseManifoldReduction / SetAllowSleeping / */
+	const uint16_t *flags_clear;        /* [n] ... and to clear         SetApplyGyroscopicForce / SetCollideKinematicVsNonDynamic       */
 } b2j_body_info_update;
 int b2j_bodies_set_info(b2j_world *w, const uint32_t *ids, uint32_t n, const b2j_body_info_update *in);
 

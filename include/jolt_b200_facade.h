@@ -1122,6 +1122,25 @@ public:
 	void DeactivateBodies(const BodyID *inBodyIDs, int inNumber) { for (int i = 0; i < inNumber; ++i) DeactivateBody(inBodyIDs[i]); }
 	void DestroyBodies(const BodyID *inBodyIDs, int inNumber) { for (int i = 0; i < inNumber; ++i) DestroyBody(inBodyIDs[i]); }
 	EMotionQuality GetMotionQuality(const BodyID &) const { return EMotionQuality::Discrete; } // (LinearCast is not on the path: SURVEY 8b)
+	// Body flags on bodies that exist (BodyInterface.h:286-293, Body::SetIsSensor / SetUseManifoldReduction / SetAllowSleeping ...)
+	void SetIsSensor(const BodyID &id, bool inIsSensor) { SetFlag(id, B2J_BODY_SENSOR, inIsSensor); }
+	bool IsSensor(const BodyID &id) const { const Body *b = TryGet(id); return b != nullptr && (b->mDesc.flags & B2J_BODY_SENSOR) != 0; }
+	void SetUseManifoldReduction(const BodyID &id, bool inUseReduction) { SetFlag(id, B2J_BODY_USE_MANIFOLD_REDUCTION, inUseReduction); }
+	bool GetUseManifoldReduction(const BodyID &id) const { const Body *b = TryGet(id); return b != nullptr && (b->mDesc.flags & B2J_BODY_USE_MANIFOLD_REDUCTION) != 0; }
+	void SetFlag(const BodyID &id, uint16_t inFlag, bool inValue)
+	{
+		Body *b = const_cast<Body *>(TryGet(id));
+		if (b == nullptr) return;
+		if (inValue) b->mDesc.flags |= inFlag; else b->mDesc.flags &= (uint16_t)~inFlag;
+		if (!b->mInWorld) return;
+		Flush();
+		uint32 bid = id.mID;
+		b2j_body_info_update u;
+		memset(&u, 0, sizeof(u));
+		uint16_t bits = inFlag;
+		if (inValue) u.flags_set = &bits; else u.flags_clear = &bits;
+		b2j_bodies_set_info(World(), &bid, 1, &u);
+	}
 	void SetUserData(const BodyID &id, uint64 inUserData) const { Body *b = const_cast<Body *>(TryGet(id)); if (b != nullptr) b->mUserData = inUserData; }
 	void AddForce(const BodyID &id, const Vec3 &inForce, EActivation inActivationMode = EActivation::Activate);
 	void AddTorque(const BodyID &id, const Vec3 &inTorque, EActivation inActivationMode = EActivation::Activate);

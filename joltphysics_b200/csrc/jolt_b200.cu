@@ -237,11 +237,14 @@ struct KSetParams
 struct KSetInfo
 {
 	DWorld w; const uint32_t *ids; const uint8_t *motion_type; const float *inv_mass; const uint16_t *object_layer; const int32_t *shape;
-	const float *inv_inertia_diag, *inertia_rotation; uint32_t invalidate;
+	const float *inv_inertia_diag, *inertia_rotation; uint32_t invalidate; const uint16_t *flags_set, *flags_clear;
 	B2J_D void operator()(uint32_t i) const
 	{
 		uint32_t b = slot_of(ids[i]);
 		BodyInfo info = w.info[b];
+		const uint16_t settable = B2J_BODY_SENSOR | B2J_BODY_ALLOW_SLEEPING | B2J_BODY_USE_MANIFOLD_REDUCTION | B2J_BODY_GYROSCOPIC | B2J_BODY_KIN_VS_NONDYN;
+		if (flags_clear != nullptr) info.flags &= (uint16_t)~(flags_clear[i] & settable);
+		if (flags_set != nullptr) info.flags |= (uint16_t)(flags_set[i] & settable);
 		if (motion_type != nullptr && motion_type[i] != info.motion_type)
 		{
 			info.motion_type = motion_type[i];
@@ -2342,7 +2345,7 @@ int b2j_bodies_set_info(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j
 	}
 	sync_dworld(W);
 	KSetInfo k; memset(&k, 0, sizeof(k)); k.w = W->d; k.invalidate = in->invalidate_contact_cache;
-	rt.stage_begin((size_t)n * (4 + 1 + 4 + 2 + 4 + 12 + 16) + 1024);
+	rt.stage_begin((size_t)n * (4 + 1 + 4 + 2 + 4 + 12 + 16 + 2 + 2) + 1024);
 	uint32_t *h_ids = nullptr;
 	k.ids = rt.stage_alloc<uint32_t>(n, &h_ids); memcpy(h_ids, ids, (size_t)n * 4);
 	if (in->motion_type) { uint8_t *h; k.motion_type = rt.stage_alloc<uint8_t>(n, &h); memcpy(h, in->motion_type, n); }
@@ -2351,6 +2354,8 @@ int b2j_bodies_set_info(b2j_world *W, const uint32_t *ids, uint32_t n, const b2j
 	if (in->shape) { int32_t *h; k.shape = rt.stage_alloc<int32_t>(n, &h); memcpy(h, in->shape, (size_t)n * 4); }
 	if (in->inv_inertia_diag) { float *h; k.inv_inertia_diag = rt.stage_alloc<float>((size_t)n * 3, &h); memcpy(h, in->inv_inertia_diag, (size_t)n * 12); }
 	if (in->inertia_rotation) { float *h; k.inertia_rotation = rt.stage_alloc<float>((size_t)n * 4, &h); memcpy(h, in->inertia_rotation, (size_t)n * 16); }
+	if (in->flags_set) { uint16_t *h; k.flags_set = rt.stage_alloc<uint16_t>(n, &h); memcpy(h, in->flags_set, (size_t)n * 2); }
+	if (in->flags_clear) { uint16_t *h; k.flags_clear = rt.stage_alloc<uint16_t>(n, &h); memcpy(h, in->flags_clear, (size_t)n * 2); }
 	rt.stage_to_device(0, rt.stage_used);
 	rt.launch(k, n);
 	rt.sync();

@@ -116,6 +116,8 @@ static void sApiTourMutate(PhysicsSystem &inSystem, std::vector<BodyID> &ioBodie
 		auto com_transform = bi.GetCenterOfMassTransform(ioBodies[14]);
 		bi.SetPosition(ioBodies[14], com_transform * Vec3(0.0f, 0.3f, 0.0f), EActivation::Activate);
 		bi.SetUserData(ioBodies[2], 1234);
+		bi.SetIsSensor(ioBodies[12], true);               // a resting dynamic body becomes a sensor: it falls through the floor
+		bi.SetUseManifoldReduction(ioBodies[13], false);
 		BodyID two[2] = { ioBodies[6], ioBodies[11] };
 		bi.DeactivateBodies(two, 2);
 		bi.ActivateBodies(two + 1, 1);
