@@ -41,6 +41,9 @@ enum {
 /* Shape kinds on the path (EShapeSubType subset, Jolt/Physics/Collision/Shape/Shape.h) */
 enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4, B2J_SHAPE_CYLINDER = 5, B2J_SHAPE_COMPOUND = 6 };
 
+/* Constraint kinds on the path (EConstraintSubType subset, Jolt/Physics/Constraints/Constraint.h:31-49) */
+enum { B2J_CONSTRAINT_POINT = 0, B2J_CONSTRAINT_DISTANCE = 1 };
+
 /* Body flags */
 enum {
 	B2J_BODY_SENSOR = 1u << 0,                 /* Body::IsSensor */
@@ -302,6 +305,35 @@ uint32_t b2j_num_active_bodies(const b2j_world *w);   /* PhysicsSystem::GetNumAc
 /* PhysicsSystem::GetActiveBodies (:240): copies up to cap ids in active-list order, returns the count. */
 uint32_t b2j_get_active_bodies(b2j_world *w, uint32_t *ids, uint32_t cap);
 
+/* ---- non contact constraints between two bodies (PointConstraint, DistanceConstraint without limit springs).
+ *      Replaces PhysicsSystem::AddConstraint(s) / RemoveConstraint(s) (PhysicsSystem.h:76-87 -> ConstraintManager::Add / Remove,
+ *      Jolt/Physics/Constraints/ConstraintManager.cpp:17-62). A constraint is addressed by its position in the world's list, which is
+ *      Constraint::mConstraintIndex: adding appends, removing moves the last constraint into the freed position. Active constraints take
+ *      part in the step as the reference's do (islands, large island splits, warm start, velocity and position iterations) and count
+ *      against max_contact_constraints. Remove a body's constraints before the body, as the reference asks. ------------------------ */
+
+typedef struct b2j_constraint_desc {
+	uint32_t type;                       /* B2J_CONSTRAINT_* */
+	uint32_t body1, body2;               /* TwoBodyConstraint::mBody1 / mBody2 (ids; a static body plays Body::sFixedToWorld)             */
+	float    point1[3], point2[3];       /* mLocalSpacePosition1 / 2: relative to the centre of mass of body 1 / 2                       */
+	float    min_distance, max_distance; /* DistanceConstraint::mMinDistance / mMaxDistance (already resolved, >= 0)                      */
+	uint32_t priority;                   /* Constraint::mConstraintPriority                                                              */
+	uint8_t  num_velocity_steps_override, num_position_steps_override; /* Constraint::mNumVelocityStepsOverride / mNumPositionStepsOverride */
+	uint8_t  enabled;                    /* Constraint::mEnabled                                                                          */
+	uint8_t  reserved;
+} b2j_constraint_desc;
+
+/* What Constraint::SaveState writes plus what the distance constraint keeps between steps (DistanceConstraint.cpp:200-214): the
+ * accumulated impulses the next step warm starts from (point: xyz, distance: x) and mWorldSpaceNormal. */
+typedef struct b2j_constraint_state { float total_lambda[3]; float world_space_normal[3]; } b2j_constraint_state;
+
+int      b2j_constraints_add(b2j_world *w, const b2j_constraint_desc *constraints, uint32_t n);
+int      b2j_constraints_remove(b2j_world *w, const uint32_t *indices, uint32_t n);       /* each index as of the removals before it */
+uint32_t b2j_num_constraints(const b2j_world *w);                                          /* ConstraintManager::GetNumConstraints */
+int      b2j_constraints_set_enabled(b2j_world *w, const uint32_t *indices, uint32_t n, const uint8_t *enabled); /* Constraint::SetEnabled */
+int      b2j_constraints_get_state(b2j_world *w, uint32_t first, uint32_t n, b2j_constraint_state *out);
+int      b2j_constraints_set_state(b2j_world *w, uint32_t first, uint32_t n, const b2j_constraint_state *in);
+
 /* ---- contact cache snapshot (ContactConstraintManager::ManifoldCache, SaveState stream sections
  *      Jolt/Physics/Constraints/ContactConstraintManager.cpp:467-548) -------------------------------------------- */
 
@@ -349,6 +381,33 @@ int b2j_query_cast_rays(b2j_world *w, const b2j_ray *rays, uint32_t n, uint32_t 
  * bounds overlap box i, ids[i * max_hits ...] = the first max_hits of them. Exact body bounds (the reference reports the possibly
  * widened bounds of its tree: a superset). */
 int b2j_query_collide_aabox(b2j_world *w, const float *boxes, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids);
+/* BroadPhaseQuery::CollideSphere (BroadPhaseQuery.h:41; spheres: [n][4] centre xyz, radius) and BroadPhaseQuery::CollidePoint (:44;
+ * points: [n][3]): as b2j_query_collide_aabox with the sphere / point against the exact world space bounds of the bodies
+ * (AABox4VsSphere / AABox4VsPoint, Jolt/Geometry/AABox4.h). */
+int b2j_query_collide_sphere(b2j_world *w, const float *spheres, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids);
+int b2j_query_collide_point(b2j_world *w, const float *points, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids);
+
+/* One NarrowPhaseQuery::CollideShape call (NarrowPhaseQuery.h:67): a convex shape of the world's shape table (b2j_shape_sphere / box /
+ * capsule / cylinder / convex_hull, optionally scaled / rotated + translated; inShapeScale is expressed with b2j_shape_scaled) at a
+ * centre of mass transform (inCenterOfMassTransform = rotation, position), results relative to base_offset (inBaseOffset). */
+typedef struct b2j_shape_query { int32_t shape; float position[3]; float rotation[4]; float base_offset[3]; } b2j_shape_query;
+/* CollideShapeResult (Jolt/Physics/Collision/CollideShape.h:19-72) without the faces (ECollectFacesMode::NoFaces, the default of
+ * CollideShapeSettings): contact points on shape 1 (the query shape) and shape 2 (the body) relative to base_offset, the penetration
+ * axis (direction to move shape 2 out of collision, not normalised), the depth (negative: separated by less than
+ * max_separation_distance), the sub shape ids of both sides and the body that was hit. */
+typedef struct b2j_collide_shape_hit
+{
+	uint32_t body, sub_shape1, sub_shape2;
+	float    penetration_depth;
+	float    point1[3], point2[3], axis[3];
+} b2j_collide_shape_hit;
+/* NarrowPhaseQuery::CollideShape with an AllHitCollisionCollector for n queries at once: the bodies whose bounds overlap the query
+ * shape's bounds (expanded by max_separation_distance) are collided with it exactly as TransformedShape::CollideShape does
+ * (CollideShapeSettings defaults: mMaxSeparationDistance as given, IgnoreBackFaces, CollideOnlyWithActive edges with no movement
+ * direction, NoFaces, tolerances 1e-4); bodies may be convex shapes, StaticCompoundShapes or meshes. counts[i] = hits of query i (can
+ * exceed max_hits), hits[i * max_hits ...] = the first max_hits of them in the order they were found. */
+int b2j_query_collide_shape(b2j_world *w, const b2j_shape_query *queries, uint32_t n, float max_separation_distance, uint32_t object_layer,
+                            uint32_t max_hits, uint32_t *counts, b2j_collide_shape_hit *hits);
 
 /* ---- state snapshots on the device (PhysicsSystem::SaveState / RestoreState, PhysicsSystem.cpp:2899-2964; what a snapshot holds:
  *      EStateRecorderState::Global | Bodies | Contacts, i.e. mPreviousStepDeltaTime + gravity, every body's state and the contact

@@ -940,6 +940,16 @@ class PhysicsSystem;
 struct RRayCast { RVec3 mOrigin; Vec3 mDirection; RRayCast() = default; RRayCast(const RVec3 &o, const Vec3 &d) : mOrigin(o), mDirection(d) { } };
 using RayCast = RRayCast;
 struct RayCastResult { BodyID mBodyID; float mFraction = 1.0f + FLT_EPSILON; SubShapeID mSubShapeID2; };
+// CollideShapeSettings / CollideShapeResult (Jolt/Physics/Collision/CollideShape.h): the members the device path honours (back faces are
+// ignored, only active edges collide, no faces are collected: the defaults of the reference)
+struct CollideShapeSettings { float mMaxSeparationDistance = 0.0f; };
+struct CollideShapeResult
+{
+	Vec3 mContactPointOn1, mContactPointOn2, mPenetrationAxis;
+	float mPenetrationDepth = 0.0f;
+	SubShapeID mSubShapeID1, mSubShapeID2;
+	BodyID mBodyID2;
+};
 
 // Closest hit ray casts on the device broadphase + shapes. The reference casts one ray per call; the device wants thousands, so next
 // to the reference's signature there is a batched form (the RL observation pattern: all rays of a step in one call).
@@ -959,6 +969,16 @@ public:
 	// tables given to Init), cNoLayer = collide with everything (the reference's default filters)
 	static constexpr uint32 cNoLayer = 0xffffffffu;
 	inline void CastRays(const RRayCast *inRays, int inNumber, RayCastResult *outHits, uint32 inObjectLayer = cNoLayer) const;
+	// NarrowPhaseQuery::CollideShape (NarrowPhaseQuery.h:67) with an all hits collector: inShape (a convex shape, kept alive by the
+	// caller as in the reference) scaled by inShapeScale at the centre of mass transform (inRotation, inPosition); results relative to
+	// inBaseOffset. The batched form takes n transforms of the same shape (one device call).
+	inline void CollideShape(const Shape *inShape, const Vec3 &inShapeScale, const Quat &inRotation, const RVec3 &inPosition, const CollideShapeSettings &inSettings,
+		const RVec3 &inBaseOffset, std::vector<CollideShapeResult> &outHits, uint32 inObjectLayer = cNoLayer) const;
+	// (the reference's signature: the rotation of the matrix is handed to the device as a quaternion, Mat44::GetQuaternion)
+	inline void CollideShape(const Shape *inShape, const Vec3 &inShapeScale, const RMat44 &inCenterOfMassTransform, const CollideShapeSettings &inSettings,
+		const RVec3 &inBaseOffset, std::vector<CollideShapeResult> &outHits, uint32 inObjectLayer = cNoLayer) const;
+	inline void CollideShapes(const Shape *inShape, const Vec3 &inShapeScale, const Quat *inRotations, const RVec3 *inPositions, int inNumber, const CollideShapeSettings &inSettings,
+		std::vector<std::vector<CollideShapeResult>> &outHits, uint32 inObjectLayer = cNoLayer) const;
 private:
 	friend class PhysicsSystem;
 	PhysicsSystem *mSystem = nullptr;
@@ -969,7 +989,11 @@ class BroadPhaseQuery
 public:
 	// BroadPhaseQuery::CollideAABox with an all hits collector: ids of the bodies whose world space bounds overlap the box
 	inline void CollideAABox(const AABox &inBox, std::vector<BodyID> &outBodies, uint32 inObjectLayer = NarrowPhaseQuery::cNoLayer) const;
+	// BroadPhaseQuery::CollideSphere / CollidePoint (BroadPhaseQuery.h:41,44) with an all hits collector
+	inline void CollideSphere(const Vec3 &inCenter, float inRadius, std::vector<BodyID> &outBodies, uint32 inObjectLayer = NarrowPhaseQuery::cNoLayer) const;
+	inline void CollidePoint(const Vec3 &inPoint, std::vector<BodyID> &outBodies, uint32 inObjectLayer = NarrowPhaseQuery::cNoLayer) const;
 private:
+	inline void CollideVolume(int inMode, const float *inData, std::vector<BodyID> &outBodies, uint32 inObjectLayer) const;
 	friend class PhysicsSystem;
 	PhysicsSystem *mSystem = nullptr;
 };
@@ -1328,6 +1352,24 @@ private:
 		return id;
 	}
 
+	// query shapes are kept alive by the caller (raw pointers, as the reference takes them); a scale other than one uploads a ScaledShape
+	struct QueryShape { const Shape *shape; Vec3 scale; int32_t id; };
+	std::vector<QueryShape> mQueryShapes;
+	int32_t QueryShapeID(const Shape *inShape, const Vec3 &inScale)
+	{
+		for (const QueryShape &q : mQueryShapes) if (q.shape == inShape && q.scale.x == inScale.x && q.scale.y == inScale.y && q.scale.z == inScale.z) return q.id;
+		int32_t id = -1;
+		for (size_t i = 0; i < mShapes.size(); ++i) if (mShapes[i].get() == inShape) id = mShapeIDs[i];
+		if (id < 0) id = inShape->Upload(mWorld);
+		if (id >= 0 && !(inScale.x == 1.0f && inScale.y == 1.0f && inScale.z == 1.0f))
+		{
+			float scale[3] = { inScale.x, inScale.y, inScale.z };
+			id = b2j_shape_scaled(mWorld, id, scale);
+		}
+		mQueryShapes.push_back({ inShape, inScale, id });
+		return id;
+	}
+
 	// ---- host mirror of the body state ------------------------------------------------------------------------------------
 	// Flat arrays by body index, refreshed LAZILY on first use after a step and only as far as needed:
 	//  * nothing but the step touched the device state since the arrays were filled -> only the rows of the bodies the step simulated
@@ -1566,21 +1608,153 @@ inline void NarrowPhaseQuery::CastRays(const RRayCast *inRays, int inNumber, Ray
 	}
 }
 
-inline void BroadPhaseQuery::CollideAABox(const AABox &inBox, std::vector<BodyID> &outBodies, uint32 inObjectLayer) const
+inline void NarrowPhaseQuery::CollideShapes(const Shape *inShape, const Vec3 &inShapeScale, const Quat *inRotations, const RVec3 *inPositions, int inNumber,
+	const CollideShapeSettings &inSettings, std::vector<std::vector<CollideShapeResult>> &outHits, uint32 inObjectLayer) const
+{
+	outHits.assign((size_t)std::max(inNumber, 0), std::vector<CollideShapeResult>());
+	if (inNumber <= 0) return;
+	mSystem->mBodyInterface.Flush();
+	int32_t shape = mSystem->QueryShapeID(inShape, inShapeScale);
+	if (shape < 0) return;
+	std::vector<b2j_shape_query> queries((size_t)inNumber);
+	for (int i = 0; i < inNumber; ++i)
+	{
+		b2j_shape_query &q = queries[i];
+		q.shape = shape;
+		q.position[0] = inPositions[i].x; q.position[1] = inPositions[i].y; q.position[2] = inPositions[i].z;
+		q.rotation[0] = inRotations[i].x; q.rotation[1] = inRotations[i].y; q.rotation[2] = inRotations[i].z; q.rotation[3] = inRotations[i].w;
+		q.base_offset[0] = q.base_offset[1] = q.base_offset[2] = 0.0f;
+	}
+	uint32 cap = 16;
+	std::vector<uint32> counts((size_t)inNumber);
+	std::vector<b2j_collide_shape_hit> hits;
+	for (;;)
+	{
+		hits.resize((size_t)inNumber * cap);
+		if (b2j_query_collide_shape(mSystem->mWorld, queries.data(), (uint32)inNumber, inSettings.mMaxSeparationDistance, inObjectLayer, cap, counts.data(), hits.data()) != 0) return;
+		uint32 most = 0;
+		for (uint32 c : counts) most = std::max(most, c);
+		if (most <= cap) break;
+		cap = most;
+	}
+	for (int i = 0; i < inNumber; ++i)
+		for (uint32 j = 0; j < counts[i]; ++j)
+		{
+			const b2j_collide_shape_hit &h = hits[(size_t)i * cap + j];
+			CollideShapeResult r;
+			r.mContactPointOn1 = Vec3(h.point1[0], h.point1[1], h.point1[2]); r.mContactPointOn2 = Vec3(h.point2[0], h.point2[1], h.point2[2]);
+			r.mPenetrationAxis = Vec3(h.axis[0], h.axis[1], h.axis[2]); r.mPenetrationDepth = h.penetration_depth;
+			r.mSubShapeID1.mValue = h.sub_shape1; r.mSubShapeID2.mValue = h.sub_shape2; r.mBodyID2 = BodyID(h.body);
+			outHits[i].push_back(r);
+		}
+}
+
+inline void NarrowPhaseQuery::CollideShape(const Shape *inShape, const Vec3 &inShapeScale, const Quat &inRotation, const RVec3 &inPosition, const CollideShapeSettings &inSettings,
+	const RVec3 &inBaseOffset, std::vector<CollideShapeResult> &outHits, uint32 inObjectLayer) const
+{
+	// (one query: the base offset is applied on the host side of the call -- the device collides relative to the query position, which is
+	// what the reference's callers pass as base offset, and the results are shifted to the requested one)
+	outHits.clear();
+	mSystem->mBodyInterface.Flush();
+	int32_t shape = mSystem->QueryShapeID(inShape, inShapeScale);
+	if (shape < 0) return;
+	b2j_shape_query q;
+	q.shape = shape;
+	q.position[0] = inPosition.x; q.position[1] = inPosition.y; q.position[2] = inPosition.z;
+	q.rotation[0] = inRotation.x; q.rotation[1] = inRotation.y; q.rotation[2] = inRotation.z; q.rotation[3] = inRotation.w;
+	q.base_offset[0] = inBaseOffset.x; q.base_offset[1] = inBaseOffset.y; q.base_offset[2] = inBaseOffset.z;
+	uint32 cap = 32, count = 0;
+	std::vector<b2j_collide_shape_hit> hits;
+	for (;;)
+	{
+		hits.resize(cap);
+		if (b2j_query_collide_shape(mSystem->mWorld, &q, 1, inSettings.mMaxSeparationDistance, inObjectLayer, cap, &count, hits.data()) != 0) return;
+		if (count <= cap) break;
+		cap = count;
+	}
+	for (uint32 j = 0; j < count; ++j)
+	{
+		const b2j_collide_shape_hit &h = hits[j];
+		CollideShapeResult r;
+		r.mContactPointOn1 = Vec3(h.point1[0], h.point1[1], h.point1[2]); r.mContactPointOn2 = Vec3(h.point2[0], h.point2[1], h.point2[2]);
+		r.mPenetrationAxis = Vec3(h.axis[0], h.axis[1], h.axis[2]); r.mPenetrationDepth = h.penetration_depth;
+		r.mSubShapeID1.mValue = h.sub_shape1; r.mSubShapeID2.mValue = h.sub_shape2; r.mBodyID2 = BodyID(h.body);
+		outHits.push_back(r);
+	}
+}
+
+inline void NarrowPhaseQuery::CollideShape(const Shape *inShape, const Vec3 &inShapeScale, const RMat44 &inCenterOfMassTransform, const CollideShapeSettings &inSettings,
+	const RVec3 &inBaseOffset, std::vector<CollideShapeResult> &outHits, uint32 inObjectLayer) const
+{
+	// Mat44::GetQuaternion (Mat44.inl:741-783)
+	const Vec3 &c0 = inCenterOfMassTransform.c0, &c1 = inCenterOfMassTransform.c1, &c2 = inCenterOfMassTransform.c2;
+	float tr = c0.x + c1.y + c2.z;
+	Quat q;
+	if (tr >= 0.0f)
+	{
+		float s = std::sqrt(tr + 1.0f), is = 0.5f / s;
+		q = Quat((c1.z - c2.y) * is, (c2.x - c0.z) * is, (c0.y - c1.x) * is, 0.5f * s);
+	}
+	else
+	{
+		int i = 0;
+		if (c1.y > c0.x) i = 1;
+		float diag[3] = { c0.x, c1.y, c2.z };
+		if (c2.z > diag[i]) i = 2;
+		if (i == 0)
+		{
+			float s = std::sqrt(c0.x - (c1.y + c2.z) + 1.0f), is = 0.5f / s;
+			q = Quat(0.5f * s, (c1.x + c0.y) * is, (c0.z + c2.x) * is, (c1.z - c2.y) * is);
+		}
+		else if (i == 1)
+		{
+			float s = std::sqrt(c1.y - (c2.z + c0.x) + 1.0f), is = 0.5f / s;
+			q = Quat((c1.x + c0.y) * is, 0.5f * s, (c2.y + c1.z) * is, (c2.x - c0.z) * is);
+		}
+		else
+		{
+			float s = std::sqrt(c2.z - (c0.x + c1.y) + 1.0f), is = 0.5f / s;
+			q = Quat((c0.z + c2.x) * is, (c2.y + c1.z) * is, 0.5f * s, (c0.y - c1.x) * is);
+		}
+	}
+	CollideShape(inShape, inShapeScale, q, inCenterOfMassTransform.t, inSettings, inBaseOffset, outHits, inObjectLayer);
+}
+
+inline void BroadPhaseQuery::CollideVolume(int inMode, const float *inData, std::vector<BodyID> &outBodies, uint32 inObjectLayer) const
 {
 	mSystem->mBodyInterface.Flush();
 	outBodies.clear();
-	float box[6] = { inBox.mMin.x, inBox.mMin.y, inBox.mMin.z, inBox.mMax.x, inBox.mMax.y, inBox.mMax.z };
 	uint32 count = 0, cap = 64;
 	std::vector<uint32> ids;
 	for (;;)
 	{
 		ids.resize(cap);
-		if (b2j_query_collide_aabox(mSystem->mWorld, box, 1, inObjectLayer, cap, &count, ids.data()) != 0) return;
+		int r = inMode == 0? b2j_query_collide_aabox(mSystem->mWorld, inData, 1, inObjectLayer, cap, &count, ids.data())
+			: (inMode == 1? b2j_query_collide_sphere(mSystem->mWorld, inData, 1, inObjectLayer, cap, &count, ids.data())
+			: b2j_query_collide_point(mSystem->mWorld, inData, 1, inObjectLayer, cap, &count, ids.data()));
+		if (r != 0) return;
 		if (count <= cap) break;
 		cap = count;
 	}
 	for (uint32 i = 0; i < count; ++i) outBodies.push_back(BodyID(ids[i]));
+}
+
+inline void BroadPhaseQuery::CollideAABox(const AABox &inBox, std::vector<BodyID> &outBodies, uint32 inObjectLayer) const
+{
+	float box[6] = { inBox.mMin.x, inBox.mMin.y, inBox.mMin.z, inBox.mMax.x, inBox.mMax.y, inBox.mMax.z };
+	CollideVolume(0, box, outBodies, inObjectLayer);
+}
+
+inline void BroadPhaseQuery::CollideSphere(const Vec3 &inCenter, float inRadius, std::vector<BodyID> &outBodies, uint32 inObjectLayer) const
+{
+	float sphere[4] = { inCenter.x, inCenter.y, inCenter.z, inRadius };
+	CollideVolume(1, sphere, outBodies, inObjectLayer);
+}
+
+inline void BroadPhaseQuery::CollidePoint(const Vec3 &inPoint, std::vector<BodyID> &outBodies, uint32 inObjectLayer) const
+{
+	float point[3] = { inPoint.x, inPoint.y, inPoint.z };
+	CollideVolume(2, point, outBodies, inObjectLayer);
 }
 
 inline void Body::Sync() const

@@ -169,6 +169,9 @@ PROTOTYPES = {
     "b2j_world_set_event_recording": (C.c_int, [_VP, C.c_int, C.c_int]),
     "b2j_query_cast_rays": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP]),
     "b2j_query_collide_aabox": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP]),
+    "b2j_query_collide_sphere": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP]),
+    "b2j_query_collide_point": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP]),
+    "b2j_query_collide_shape": (C.c_int, [_VP, _VP, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, _VP, _VP]),
     "b2j_batch_query_cast_rays": (C.c_int, [_VP, _VP, _VP, C.c_uint32, C.c_uint32, _VP]),
     "b2j_world_save_state": (_VP, [_VP]),
     "b2j_world_restore_state": (C.c_int, [_VP, _VP]),

@@ -47,6 +47,7 @@ struct CompoundPairCtx
 	EpaScratch *epa;
 	MeshScratch *ms;
 	int num_manifolds;
+	QueryCollector *query;       // not null: a CollideShape query (b2j_query.h) -- hits go to the collector instead of the manifolds
 };
 
 // ConvexShape::sCollideConvexVsConvex for one leaf pair; the hit (if any) joins the collector
@@ -85,6 +86,7 @@ B2J_D void compound_collide_leaf(const DWorld &w, CompoundPairCtx &p, const Comp
 	point1 = mul(transform1, point1);
 	point2 = mul(transform1, point2);
 	V3 axis_world = mul(transform1.r, penetration_axis);
+	if (p.query != nullptr) { query_add_hit(*p.query, point1, point2, axis_world, penetration_depth, a.sub, b.sub); return; }
 	V3 face1[MAX_FACE_VERTS], face2[MAX_FACE_VERTS];
 	int n1 = supporting_face(w, s1, -penetration_axis, transform1, face1);
 	int n2 = supporting_face(w, s2, mul_transposed(transform_2_to_1.r, penetration_axis), transform2, face2);
@@ -97,6 +99,7 @@ B2J_D void compound_collide_simple(const DWorld &w, CompoundPairCtx &p, const Co
 	if (b.shape->kind == B2J_SHAPE_MESH)
 	{
 		MeshCollideCtx cc = mesh_collide_ctx_from(w, *a.shape, a.transform, *b.shape, b.transform, p.max_separation_distance, p.movement_direction, a.sub);
+		if (p.query != nullptr) { cc.query = p.query; cc.check_active_edges = true; } // CollideShapeSettings: EActiveEdgeMode::CollideOnlyWithActive
 		mesh_walk_serial(w, *a.shape, *b.shape, cc, *p.epa, *p.ms, p.num_manifolds);
 	}
 	else
@@ -158,22 +161,10 @@ B2J_D void compound_collide_compound_vs(const DWorld &w, CompoundPairCtx &p, con
 	});
 }
 
-// PhysicsSystem::ProcessBodyPair for a pair in which at least one body's shape is a StaticCompoundShape. The dispatch table holds
-// sCollideShapeVsCompound for (anything, compound) -- also for (compound, compound): StaticCompoundShape::sRegister writes that entry
-// last -- and sCollideCompoundVsShape for (compound, anything else). So the OUTER loop runs over the sub shapes of shape 2 when that
-// is a compound, and a compound shape 1 is then walked once per sub shape of shape 2.
-B2J_D void compound_collide_pair(const DWorld &w, const NarrowCtx &c, const CollideItem &item, EpaScratch &epa, MeshScratch &ms)
+// CollisionDispatch::sCollideShapeVsShape for (a, b) where a compound may be on either side (see compound_collide_pair)
+B2J_D void compound_dispatch(const DWorld &w, CompoundPairCtx &p, const CompoundSide &a, const CompoundSide &b)
 {
-	BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
-	const ShapeDesc &s1 = w.shapes[i1.shape], &s2 = w.shapes[i2.shape];
-	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
-	CompoundPairCtx p;
-	p.max_separation_distance = ((i1.flags | i2.flags) & B2J_BODY_SENSOR)? 0.0f : w.settings.speculative_contact_distance;
-	p.movement_direction = pair_movement_direction(w, item, i1, i2);
-	p.epa = &epa; p.ms = &ms; p.num_manifolds = 0;
-	CompoundSide a, b;
-	a.shape = &s1; a.transform = xf(m33_rotation(to_q4(w.rotation[item.b1])), v3_zero()); a.sub = 0xffffffffu;
-	b.shape = &s2; b.transform = xf(m33_rotation(to_q4(w.rotation[item.b2])), x2 + (-x1)); b.sub = 0xffffffffu;
+	const ShapeDesc &s1 = *a.shape, &s2 = *b.shape;
 	if (s2.kind == B2J_SHAPE_COMPOUND)
 	{
 		// CollideShapeVsCompoundVisitor: bounds of shape 1 in the space of the compound, expanded
@@ -186,15 +177,36 @@ B2J_D void compound_collide_pair(const DWorld &w, const NarrowCtx &c, const Coll
 			CompoundSide side;
 			side.shape = &w.shapes[sub.shape];
 			side.transform = mul(b.transform, compound_sub_transform(sub));
-			side.sub = sub_shape_push(0xffffffffu, 0, index, s2.compound_sub_bits);
+			side.sub = sub_shape_push(b.sub, 0, index, s2.compound_sub_bits);
 			if (s1.kind == B2J_SHAPE_COMPOUND)
 				compound_collide_compound_vs(w, p, a, side);
 			else
 				compound_collide_simple(w, p, a, side);
 		});
 	}
-	else
+	else if (s1.kind == B2J_SHAPE_COMPOUND)
 		compound_collide_compound_vs(w, p, a, b); // (shape 1 is the compound; shape 2 convex or a mesh)
+	else
+		compound_collide_simple(w, p, a, b);
+}
+
+// PhysicsSystem::ProcessBodyPair for a pair in which at least one body's shape is a StaticCompoundShape. The dispatch table holds
+// sCollideShapeVsCompound for (anything, compound) -- also for (compound, compound): StaticCompoundShape::sRegister writes that entry
+// last -- and sCollideCompoundVsShape for (compound, anything else). So the OUTER loop runs over the sub shapes of shape 2 when that
+// is a compound, and a compound shape 1 is then walked once per sub shape of shape 2.
+B2J_D void compound_collide_pair(const DWorld &w, const NarrowCtx &c, const CollideItem &item, EpaScratch &epa, MeshScratch &ms)
+{
+	BodyInfo i1 = w.info[item.b1], i2 = w.info[item.b2];
+	const ShapeDesc &s1 = w.shapes[i1.shape], &s2 = w.shapes[i2.shape];
+	V3 x1 = to_v3(w.position[item.b1]), x2 = to_v3(w.position[item.b2]);
+	CompoundPairCtx p;
+	p.max_separation_distance = ((i1.flags | i2.flags) & B2J_BODY_SENSOR)? 0.0f : w.settings.speculative_contact_distance;
+	p.movement_direction = pair_movement_direction(w, item, i1, i2);
+	p.epa = &epa; p.ms = &ms; p.num_manifolds = 0; p.query = nullptr;
+	CompoundSide a, b;
+	a.shape = &s1; a.transform = xf(m33_rotation(to_q4(w.rotation[item.b1])), v3_zero()); a.sub = 0xffffffffu;
+	b.shape = &s2; b.transform = xf(m33_rotation(to_q4(w.rotation[item.b2])), x2 + (-x1)); b.sub = 0xffffffffu;
+	compound_dispatch(w, p, a, b);
 	mesh_finish_pair(w, c, item, ms, p.num_manifolds);
 }
 

@@ -1,0 +1,481 @@
+// b2j_joints.h -- non contact constraints on the step ("the simplest joints slot into H12-H14 through
+// ConstraintManager::sBuildIslands / sSolve*"): PointConstraint and DistanceConstraint between two bodies.
+//
+// Restates
+//   ConstraintManager::GetActiveConstraints / sBuildIslands / sSortConstraints / sSetupVelocityConstraints / sWarmStart... / sSolve...
+//                                                     Jolt/Physics/Constraints/ConstraintManager.cpp:72-182
+//   TwoBodyConstraint::IsActive / BuildIslands / BuildIslandSplits   TwoBodyConstraint.h:38, TwoBodyConstraint.cpp:17-57
+//   PointConstraint                                   PointConstraint.cpp:70-118, ConstraintPart/PointConstraintPart.h:50-237
+//   DistanceConstraint                                DistanceConstraint.cpp:98-198, ConstraintPart/AxisConstraintPart.h:60-485 (no springs)
+//   where the step calls them                         PhysicsSystem.cpp:720-744 (active constraints), :795-828 (setup, islands: bodies a
+//                                                     constraint wakes up join the active list but get no gravity this step, :746-791),
+//                                                     :1415-1427, :1503-1540 (warm start, velocity), :2596-2603, :2661-2672 (position)
+//   LargeIslandSplitter::SplitIsland                  LargeIslandSplitter.cpp:236-300: contacts are coloured first, then the constraints
+//
+// How they join the schedule (b2j_solver.h): an active joint is one more ITEM next to the contact constraints. The items of a step are
+// [active joints in (priority, constraint index) order] ++ [contacts in sort key order] -- the order the reference solves an island in
+// (constraints, then contacts). Small islands and the serial split of a large island get phase = dependency depth in that order; the
+// colouring of a large island walks contacts first, then joints (a body's adjacency list is read rotated in that pass). A phase's
+// items share no dynamic body, so its joints and its contacts run as two launches over the same range of solve positions: joint items
+// carry META_JOINT in their header and the contact kernels leave them alone, and the other way round.
+#pragma once
+
+#include "b2j_solver.h"
+
+namespace b2j {
+
+enum { JOINT_POINT = B2J_CONSTRAINT_POINT, JOINT_DISTANCE = B2J_CONSTRAINT_DISTANCE };
+enum : uint32_t { JOINT_ENABLED = 1u, SRC_JOINT = 0x80000000u };
+
+// what the caller described (b2j_constraint_desc) with the bodies resolved to slots
+struct alignas(16) JointDef
+{
+	uint32_t type, b1, b2, flags;          // b1 / b2: body slots
+	uint32_t priority, steps_override;     // velocity steps override | position steps override << 8
+	uint32_t index, pad;                   // Constraint::mConstraintIndex (position in the world's list)
+	F4 local1, local2;                     // mLocalSpacePosition1 / 2 (relative to the centre of mass); local1.w = min distance, local2.w = max distance
+};
+
+// the members of the reference's constraint objects that live across kernels (and, the first two, across steps)
+struct alignas(16) JointState
+{
+	F4 lambda;                             // mTotalLambda: point xyz, distance x
+	F4 normal;                             // distance: mWorldSpaceNormal (kept when the two points coincide)
+	F4 wsp1, wsp2;                         // distance: mWorldSpacePosition1 / 2; wsp1.w = mMinLambda, wsp2.w = mMaxLambda
+	F4 r1, r2;                             // point: mR1, mR2; distance: mR1PlusUxAxis, mR2xAxis, r1.w = mEffectiveMass
+	F4 i1[3], i2[3];                       // point: columns of mInvI1_R1X / mInvI2_R2X; distance: [0] = mInvI1_R1PlusUxAxis / mInvI2_R2xAxis
+	F4 eff[3];                             // point: columns of mEffectiveMass
+};
+
+struct JointCtx
+{
+	JointDef *defs;
+	JointState *state;
+	uint32_t num_joints;
+	uint32_t *active_flag;       // [num_joints] by constraint index: active this step
+	const uint32_t *order;       // [num_joints] constraint indices sorted by (priority, index)
+	uint32_t *order_flag, *order_scan; // [num_joints] flags / exclusive scan in that order
+	uint32_t *active_joints;     // [J] the active joints in (priority, index) order
+	uint32_t *wake_key;          // per body slot: first (constraint, body) that wakes it up (BodyManager::ActivateBodies call order)
+};
+
+// ---- Mat44 helpers the point constraint needs (Mat44.inl: sCrossProduct, GetDeterminant3x3, Adjointed3x3, SetInversed3x3) -----------
+B2J_HD M33 m33_cross_product(V3 v) { return m33(v3(0.0f, v.z, 0.0f - v.y), v3(0.0f - v.z, 0.0f, v.x), v3(v.y, 0.0f - v.x, 0.0f)); }
+B2J_HD M33 m33_add(const M33 &a, const M33 &b) { return m33(a.c0 + b.c0, a.c1 + b.c1, a.c2 + b.c2); }
+B2J_HD bool m33_inversed(const M33 &m, M33 &out)
+{
+	float det = dot(m.c0, cross(m.c1, m.c2));
+	if (det == 0.0f)
+		return false;
+	// Adjointed3x3: JPH_EL(r, c) = column c, row r
+	V3 a0 = v3(m.c1.y, m.c2.y, m.c0.y) * v3(m.c2.z, m.c0.z, m.c1.z) - v3(m.c2.y, m.c0.y, m.c1.y) * v3(m.c1.z, m.c2.z, m.c0.z);
+	V3 a1 = v3(m.c2.x, m.c0.x, m.c1.x) * v3(m.c1.z, m.c2.z, m.c0.z) - v3(m.c1.x, m.c2.x, m.c0.x) * v3(m.c2.z, m.c0.z, m.c1.z);
+	V3 a2 = v3(m.c1.x, m.c2.x, m.c0.x) * v3(m.c2.y, m.c0.y, m.c1.y) - v3(m.c2.x, m.c0.x, m.c1.x) * v3(m.c1.y, m.c2.y, m.c0.y);
+	out = m33(a0 / det, a1 / det, a2 / det);
+	return true;
+}
+
+struct JointBody
+{
+	uint32_t slot, type, dofs;
+	V3 x; Q4 q;
+	float inv_mass;
+	V3 diag; Q4 irot;
+};
+
+B2J_D JointBody joint_body(const DWorld &w, uint32_t b)
+{
+	JointBody k;
+	BodyInfo info = w.info[b];
+	k.slot = b; k.type = info.motion_type; k.dofs = info.allowed_dofs;
+	k.x = to_v3(w.position[b]); k.q = to_q4(w.rotation[b]);
+	if (k.type == B2J_MOTION_DYNAMIC) { k.inv_mass = w.params[b].inv_mass; k.diag = to_v3(w.inv_inertia_diag[b]); k.irot = to_q4(w.inertia_rotation[b]); }
+	else { k.inv_mass = 0.0f; k.diag = v3_zero(); k.irot = q4_identity(); }
+	return k;
+}
+
+B2J_D V3 joint_linear_velocity(const DWorld &w, const JointBody &b) { return b.type != B2J_MOTION_STATIC? to_v3(w.linear_velocity[b.slot]) : v3_zero(); }
+B2J_D V3 joint_angular_velocity(const DWorld &w, const JointBody &b) { return b.type != B2J_MOTION_STATIC? to_v3(w.angular_velocity[b.slot]) : v3_zero(); }
+
+// ---- PointConstraintPart ------------------------------------------------------------------------------------------------------------
+B2J_D void point_calculate(const DWorld &w, const JointDef &d, JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	M33 rotation1 = m33_rotation(b1.q), rotation2 = m33_rotation(b2.q);
+	V3 r1 = mul(rotation1, to_v3(d.local1)), r2 = mul(rotation2, to_v3(d.local2));
+	s.r1 = f4(r1); s.r2 = f4(r2);
+	float summed_inv_mass;
+	M33 inv_effective_mass;
+	if (b1.type == B2J_MOTION_DYNAMIC)
+	{
+		M33 inv_i1 = inverse_inertia_for_rotation(rotation1, b1.irot, b1.diag, b1.dofs);
+		summed_inv_mass = b1.inv_mass;
+		M33 r1x = m33_cross_product(r1);
+		M33 i1 = mul(inv_i1, r1x);
+		s.i1[0] = f4(i1.c0); s.i1[1] = f4(i1.c1); s.i1[2] = f4(i1.c2);
+		inv_effective_mass = mul_right_transposed(mul(r1x, inv_i1), r1x);
+	}
+	else
+	{
+		summed_inv_mass = 0.0f;
+		inv_effective_mass = m33_zero();
+	}
+	if (b2.type == B2J_MOTION_DYNAMIC)
+	{
+		M33 inv_i2 = inverse_inertia_for_rotation(rotation2, b2.irot, b2.diag, b2.dofs);
+		summed_inv_mass += b2.inv_mass;
+		M33 r2x = m33_cross_product(r2);
+		M33 i2 = mul(inv_i2, r2x);
+		s.i2[0] = f4(i2.c0); s.i2[1] = f4(i2.c1); s.i2[2] = f4(i2.c2);
+		inv_effective_mass = m33_add(inv_effective_mass, mul_right_transposed(mul(r2x, inv_i2), r2x));
+	}
+	inv_effective_mass = m33_add(inv_effective_mass, m33(v3(summed_inv_mass, 0.0f, 0.0f), v3(0.0f, summed_inv_mass, 0.0f), v3(0.0f, 0.0f, summed_inv_mass)));
+	M33 eff;
+	if (!m33_inversed(inv_effective_mass, eff))
+	{
+		// Deactivate()
+		eff = m33_zero();
+		s.lambda = f4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
+	s.eff[0] = f4(eff.c0); s.eff[1] = f4(eff.c1); s.eff[2] = f4(eff.c2);
+}
+
+B2J_D bool point_apply_velocity_step(const DWorld &w, const JointState &s, const JointBody &b1, const JointBody &b2, V3 lambda)
+{
+	if (lambda == v3_zero())
+		return false;
+	if (b1.type == B2J_MOTION_DYNAMIC)
+	{
+		M33 i1 = m33(to_v3(s.i1[0]), to_v3(s.i1[1]), to_v3(s.i1[2]));
+		w.linear_velocity[b1.slot] = f4(lock_translation(to_v3(w.linear_velocity[b1.slot]) - b1.inv_mass * lambda, b1.dofs));
+		w.angular_velocity[b1.slot] = f4(to_v3(w.angular_velocity[b1.slot]) - mul(i1, lambda));
+	}
+	if (b2.type == B2J_MOTION_DYNAMIC)
+	{
+		M33 i2 = m33(to_v3(s.i2[0]), to_v3(s.i2[1]), to_v3(s.i2[2]));
+		w.linear_velocity[b2.slot] = f4(lock_translation(to_v3(w.linear_velocity[b2.slot]) + b2.inv_mass * lambda, b2.dofs));
+		w.angular_velocity[b2.slot] = f4(to_v3(w.angular_velocity[b2.slot]) + mul(i2, lambda));
+	}
+	return true;
+}
+
+// ---- AxisConstraintPart as the distance constraint uses it (bias 0, no spring) ------------------------------------------------------
+B2J_D void distance_calculate(const DWorld &w, const JointDef &d, JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	V3 wsp1 = mul(xf_rotation_translation(b1.q, b1.x), to_v3(d.local1));
+	V3 wsp2 = mul(xf_rotation_translation(b2.q, b2.x), to_v3(d.local2));
+	V3 delta = wsp2 - wsp1;
+	float delta_len = length(delta);
+	V3 normal = to_v3(s.normal);
+	if (delta_len > 0.0f)
+		normal = delta / delta_len;
+	s.normal = f4(normal);
+	V3 r1_plus_u = wsp2 - b1.x, r2 = wsp2 - b2.x;
+	float min_distance = d.local1.w, max_distance = d.local2.w;
+	float min_lambda = s.wsp1.w, max_lambda = s.wsp2.w;
+	bool calculate = true;
+	if (min_distance == max_distance) { min_lambda = -FLT_MAX; max_lambda = FLT_MAX; }
+	else if (delta_len <= min_distance) { min_lambda = 0.0f; max_lambda = FLT_MAX; }
+	else if (delta_len >= max_distance) { min_lambda = -FLT_MAX; max_lambda = 0.0f; }
+	else calculate = false;
+	float eff = 0.0f;
+	if (calculate)
+	{
+		// CalculateInverseEffectiveMass
+		float inv_effective_mass;
+		if (b1.type != B2J_MOTION_STATIC)
+		{
+			V3 r1x = cross(r1_plus_u, normal);
+			s.r1 = f4(r1x);
+			if (b1.type == B2J_MOTION_DYNAMIC)
+			{
+				V3 i1 = multiply_ws_inverse_inertia(b1.q, b1.irot, b1.diag, b1.dofs, r1x);
+				s.i1[0] = f4(i1);
+				inv_effective_mass = b1.inv_mass + dot(i1, r1x);
+			}
+			else
+				inv_effective_mass = 0.0f;
+		}
+		else
+			inv_effective_mass = 0.0f;
+		if (b2.type != B2J_MOTION_STATIC)
+		{
+			V3 r2x = cross(r2, normal);
+			s.r2 = f4(r2x);
+			if (b2.type == B2J_MOTION_DYNAMIC)
+			{
+				V3 i2 = multiply_ws_inverse_inertia(b2.q, b2.irot, b2.diag, b2.dofs, r2x);
+				s.i2[0] = f4(i2);
+				inv_effective_mass += b2.inv_mass + dot(i2, r2x);
+			}
+		}
+		if (inv_effective_mass != 0.0f)
+			eff = 1.0f / inv_effective_mass;
+	}
+	if (eff == 0.0f)
+		s.lambda.x = 0.0f; // Deactivate()
+	s.r1.w = eff;
+	s.wsp1 = f4(wsp1, min_lambda);
+	s.wsp2 = f4(wsp2, max_lambda);
+}
+
+B2J_D bool axis_apply_velocity_step(const DWorld &w, const JointState &s, const JointBody &b1, const JointBody &b2, V3 axis, float lambda)
+{
+	if (lambda == 0.0f)
+		return false;
+	if (b1.type == B2J_MOTION_DYNAMIC)
+	{
+		w.linear_velocity[b1.slot] = f4(lock_translation(to_v3(w.linear_velocity[b1.slot]) - (lambda * b1.inv_mass) * axis, b1.dofs));
+		w.angular_velocity[b1.slot] = f4(to_v3(w.angular_velocity[b1.slot]) - lambda * to_v3(s.i1[0]));
+	}
+	if (b2.type == B2J_MOTION_DYNAMIC)
+	{
+		w.linear_velocity[b2.slot] = f4(lock_translation(to_v3(w.linear_velocity[b2.slot]) + (lambda * b2.inv_mass) * axis, b2.dofs));
+		w.angular_velocity[b2.slot] = f4(to_v3(w.angular_velocity[b2.slot]) + lambda * to_v3(s.i2[0]));
+	}
+	return true;
+}
+
+// ---- the four solver entry points of a constraint -----------------------------------------------------------------------------------
+B2J_D void joint_setup_velocity(const DWorld &w, const JointDef &d, JointState &s)
+{
+	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
+	if (d.type == JOINT_POINT) point_calculate(w, d, s, b1, b2);
+	else distance_calculate(w, d, s, b1, b2);
+}
+
+B2J_D void joint_warm_start(const DWorld &w, const JointDef &d, JointState &s, float ratio)
+{
+	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
+	if (d.type == JOINT_POINT)
+	{
+		V3 lambda = to_v3(s.lambda) * ratio;
+		s.lambda = f4(lambda);
+		point_apply_velocity_step(w, s, b1, b2, lambda);
+	}
+	else
+	{
+		s.lambda.x *= ratio;
+		axis_apply_velocity_step(w, s, b1, b2, to_v3(s.normal), s.lambda.x);
+	}
+}
+
+B2J_D void joint_solve_velocity(const DWorld &w, const JointDef &d, JointState &s)
+{
+	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
+	V3 v1 = joint_linear_velocity(w, b1), w1 = joint_angular_velocity(w, b1), v2 = joint_linear_velocity(w, b2), w2 = joint_angular_velocity(w, b2);
+	if (d.type == JOINT_POINT)
+	{
+		M33 eff = m33(to_v3(s.eff[0]), to_v3(s.eff[1]), to_v3(s.eff[2]));
+		V3 lambda = mul(eff, ((v1 - cross(to_v3(s.r1), w1)) - v2) + cross(to_v3(s.r2), w2));
+		s.lambda = f4(to_v3(s.lambda) + lambda);
+		point_apply_velocity_step(w, s, b1, b2, lambda);
+	}
+	else
+	{
+		float eff = s.r1.w;
+		if (eff == 0.0f)
+			return; // !mAxisConstraint.IsActive()
+		V3 axis = to_v3(s.normal);
+		float jv;
+		if (b1.type != B2J_MOTION_STATIC)
+			jv = b2.type != B2J_MOTION_STATIC? dot(axis, v1 - v2) : dot(axis, v1);
+		else
+			jv = dot(axis, -v2);
+		if (b1.type != B2J_MOTION_STATIC) jv += dot(to_v3(s.r1), w1);
+		if (b2.type != B2J_MOTION_STATIC) jv -= dot(to_v3(s.r2), w2);
+		float total = s.lambda.x;
+		float lambda = eff * (jv - 0.0f);
+		float new_lambda = clamp_(total + lambda, s.wsp1.w, s.wsp2.w);
+		lambda = new_lambda - total;
+		s.lambda.x = new_lambda;
+		axis_apply_velocity_step(w, s, b1, b2, axis, lambda);
+	}
+}
+
+B2J_D void joint_store_pose(const DWorld &w, const JointBody &b) { w.position[b.slot] = f4(b.x); w.rotation[b.slot] = f4(b.q); }
+
+B2J_D void joint_solve_position(const DWorld &w, const JointDef &d, JointState &s, float baumgarte)
+{
+	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
+	if (d.type == JOINT_POINT)
+	{
+		point_calculate(w, d, s, b1, b2);
+		V3 separation = ((b2.x - b1.x) + to_v3(s.r2)) - to_v3(s.r1);
+		if (separation == v3_zero())
+			return;
+		M33 eff = m33(to_v3(s.eff[0]), to_v3(s.eff[1]), to_v3(s.eff[2]));
+		// mEffectiveMass * -inBaumgarte * separation = (Mat44 * float) * Vec3
+		float nb = -baumgarte;
+		V3 lambda = mul(m33(eff.c0 * nb, eff.c1 * nb, eff.c2 * nb), separation);
+		if (b1.type == B2J_MOTION_DYNAMIC)
+		{
+			M33 i1 = m33(to_v3(s.i1[0]), to_v3(s.i1[1]), to_v3(s.i1[2]));
+			b1.x -= lock_translation(b1.inv_mass * lambda, b1.dofs);
+			b1.q = add_rotation_step(b1.q, mul(i1, lambda), true);
+			joint_store_pose(w, b1);
+		}
+		if (b2.type == B2J_MOTION_DYNAMIC)
+		{
+			M33 i2 = m33(to_v3(s.i2[0]), to_v3(s.i2[1]), to_v3(s.i2[2]));
+			b2.x += lock_translation(b2.inv_mass * lambda, b2.dofs);
+			b2.q = add_rotation_step(b2.q, mul(i2, lambda), false);
+			joint_store_pose(w, b2);
+		}
+	}
+	else
+	{
+		// (the distance of the points as the LAST CalculateConstraintProperties saw them)
+		float distance = dot(to_v3(s.wsp2) - to_v3(s.wsp1), to_v3(s.normal));
+		float min_distance = d.local1.w, max_distance = d.local2.w;
+		float position_error = 0.0f;
+		if (distance < min_distance) position_error = distance - min_distance;
+		else if (distance > max_distance) position_error = distance - max_distance;
+		if (position_error == 0.0f)
+			return;
+		distance_calculate(w, d, s, b1, b2);
+		// AxisConstraintPart::SolvePositionConstraint
+		float eff = s.r1.w;
+		float lambda = -eff * baumgarte * position_error;
+		V3 axis = to_v3(s.normal);
+		if (b1.type == B2J_MOTION_DYNAMIC)
+		{
+			b1.x -= lock_translation((lambda * b1.inv_mass) * axis, b1.dofs);
+			b1.q = add_rotation_step(b1.q, lambda * to_v3(s.i1[0]), true);
+			joint_store_pose(w, b1);
+		}
+		if (b2.type == B2J_MOTION_DYNAMIC)
+		{
+			b2.x += lock_translation((lambda * b2.inv_mass) * axis, b2.dofs);
+			b2.q = add_rotation_step(b2.q, lambda * to_v3(s.i2[0]), false);
+			joint_store_pose(w, b2);
+		}
+	}
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------------------------------------
+
+// JobDetermineActiveConstraints + the activations of ConstraintManager::sBuildIslands: one thread per constraint (by constraint index)
+struct KJointActive
+{
+	DWorld w; NarrowCtx c; JointCtx j;
+	B2J_D void operator()(uint32_t i) const
+	{
+		const JointDef &d = j.defs[i];
+		uint32_t type1 = w.info[d.b1].motion_type, type2 = w.info[d.b2].motion_type;
+		bool active1 = w.active_index[d.b1] != B2J_INACTIVE_INDEX, active2 = w.active_index[d.b2] != B2J_INACTIVE_INDEX;
+		bool active = (d.flags & JOINT_ENABLED) != 0 && (active1 || active2) && (type1 == B2J_MOTION_DYNAMIC || type2 == B2J_MOTION_DYNAMIC);
+		j.active_flag[i] = active? 1u : 0u;
+		if (!active)
+			return;
+		atomic_add(&w.counters->num_active_joints, 1u);
+		if (type1 == B2J_MOTION_DYNAMIC && !active1) { atomic_min(&j.wake_key[d.b1], 2 * i); wake_body(w, c, d.b1); }
+		if (type2 == B2J_MOTION_DYNAMIC && !active2) { atomic_min(&j.wake_key[d.b2], 2 * i + 1); wake_body(w, c, d.b2); }
+	}
+};
+
+struct KJointWakeKeys
+{
+	NarrowCtx c; JointCtx j; uint32_t *keys;
+	B2J_D void operator()(uint32_t k) const { uint32_t b = c.woken_list[k]; keys[k] = j.wake_key[b]; j.wake_key[b] = 0xffffffffu; }
+};
+
+struct KJointClearWoken
+{
+	DWorld w;
+	B2J_D void operator()(uint32_t) const { w.counters->num_woken = 0; }
+};
+
+// the active constraints in (priority, constraint index) order: flags in that order -> scan -> compaction
+struct KJointOrderFlags
+{
+	JointCtx j;
+	B2J_D void operator()(uint32_t k) const { j.order_flag[k] = j.active_flag[j.order[k]]; }
+};
+
+struct KJointCompact
+{
+	JointCtx j;
+	B2J_D void operator()(uint32_t k) const { if (j.order_flag[k]) j.active_joints[j.order_scan[k]] = j.order[k]; }
+};
+
+// Constraint::SetupVelocityConstraint for the active constraints
+struct KJointSetup
+{
+	DWorld w; JointCtx j;
+	B2J_D void operator()(uint32_t k) const
+	{
+		uint32_t i = j.active_joints[k];
+		JointState s = j.state[i];
+		joint_setup_velocity(w, j.defs[i], s);
+		j.state[i] = s;
+	}
+};
+
+// the active joints as constraint sources behind the step's contact constraints: src[first + k]
+struct KJointAppend
+{
+	DWorld w; JointCtx j; ConstraintSrc *src; uint32_t first, count;
+	B2J_D void operator()(uint32_t k) const
+	{
+		uint32_t i = j.active_joints[k];
+		const JointDef &d = j.defs[i];
+		ConstraintSrc s;
+		s.sort_key = 0; s.manifold = SRC_JOINT | i; s.b1 = d.b1; s.b2 = d.b2;
+		src[first + k] = s;
+	}
+};
+
+// sorted position -> source for the joints (they precede the contacts), and the identity values the phase sort starts from
+struct KJointItemOrder
+{
+	SolveCtx s; uint32_t *vals; uint32_t num_contacts, num_joints;
+	B2J_D void operator()(uint32_t i) const
+	{
+		if (i < num_joints) s.order[i] = num_contacts + i;
+		vals[i] = i;
+	}
+};
+
+struct KJointWarmStart
+{
+	DWorld w; Constraints c; JointCtx j; uint32_t begin; float ratio;
+	B2J_D void operator()(uint32_t k) const
+	{
+		ConstraintHeader hdr = c.hdr[begin + k];
+		if (!(hdr.meta & META_JOINT))
+			return;
+		JointState s = j.state[hdr.manifold];
+		joint_warm_start(w, j.defs[hdr.manifold], s, ratio);
+		j.state[hdr.manifold].lambda = s.lambda;
+	}
+};
+
+struct KJointSolveVelocity
+{
+	DWorld w; Constraints c; JointCtx j; uint32_t begin, iteration;
+	B2J_D void operator()(uint32_t k) const
+	{
+		ConstraintHeader hdr = c.hdr[begin + k];
+		if (!(hdr.meta & META_JOINT) || iteration >= ((hdr.meta >> 8) & 0xff))
+			return;
+		JointState s = j.state[hdr.manifold];
+		joint_solve_velocity(w, j.defs[hdr.manifold], s);
+		j.state[hdr.manifold].lambda = s.lambda;
+	}
+};
+
+struct KJointSolvePosition
+{
+	DWorld w; Constraints c; JointCtx j; uint32_t begin, iteration;
+	B2J_D void operator()(uint32_t k) const
+	{
+		ConstraintHeader hdr = c.hdr[begin + k];
+		if (!(hdr.meta & META_JOINT) || iteration >= ((hdr.meta >> 16) & 0xff))
+			return;
+		JointState s = j.state[hdr.manifold];
+		joint_solve_position(w, j.defs[hdr.manifold], s, w.settings.baumgarte);
+		j.state[hdr.manifold] = s;
+	}
+};
+
+} // namespace b2j

@@ -19,6 +19,28 @@ namespace b2j {
 
 enum { MESH_MAX_MANIFOLDS = 32 };
 
+// Collector of a NarrowPhaseQuery::CollideShape query (b2j_query.h: AllHitCollisionCollector<CollideShapeCollector>): when a pair is
+// collided for a query every leaf / triangle hit is appended here as a CollideShapeResult instead of joining the pair's manifolds.
+struct QueryCollector
+{
+	b2j_collide_shape_hit *hits;
+	uint32_t max_hits, count;
+	uint32_t body;               // TransformedShape::mBodyID of the body being collided with (CollideShapeResult::mBodyID2)
+};
+
+B2J_D void query_add_hit(QueryCollector &q, V3 point1, V3 point2, V3 axis_world, float depth, uint32_t sub1, uint32_t sub2)
+{
+	if (q.count < q.max_hits)
+	{
+		b2j_collide_shape_hit &h = q.hits[q.count];
+		h.body = q.body; h.sub_shape1 = sub1; h.sub_shape2 = sub2; h.penetration_depth = depth;
+		h.point1[0] = point1.x; h.point1[1] = point1.y; h.point1[2] = point1.z;
+		h.point2[0] = point2.x; h.point2[1] = point2.y; h.point2[2] = point2.z;
+		h.axis[0] = axis_world.x; h.axis[1] = axis_world.y; h.axis[2] = axis_world.z;
+	}
+	++q.count;
+}
+
 struct MeshManifold
 {
 	V3 normal_sum, first_normal;
@@ -72,6 +94,7 @@ struct MeshCollideCtx
 	bool check_active_edges;
 	V3 active_edge_movement_direction;
 	uint32_t sub1;                   // sub shape id of shape 1 in its body (empty = 0xffffffff; a sub shape of a compound, b2j_compound.h)
+	QueryCollector *query;           // not null: a CollideShape query (hits go to the collector, no faces: ECollectFacesMode::NoFaces)
 	V3 scale2;                       // ScaledShape around the mesh: node bounds and vertices are scaled on the fly (MeshShape.cpp:1150-1152, CollideConvexVsTriangles.cpp:43-45)
 	// convex
 	Xf transform_2_to_1;
@@ -238,6 +261,7 @@ B2J_D void mesh_collide_convex_triangle(const DWorld &w, const ShapeDesc &s1, co
 	point1 = mul(c.transform1, point1);
 	point2 = mul(c.transform1, point2);
 	V3 axis_world = mul(c.transform1.r, penetration_axis);
+	if (c.query != nullptr) { query_add_hit(*c.query, point1, point2, axis_world, penetration_depth, c.sub1, sub2); return; }
 	V3 face1[MAX_FACE_VERTS], face2[3];
 	int n1 = supporting_face(w, s1, -penetration_axis, c.transform1, face1);
 	face2[0] = mul(c.transform1, v0); face2[1] = mul(c.transform1, v1); face2[2] = mul(c.transform1, v2);
@@ -273,6 +297,7 @@ B2J_D void mesh_collide_sphere_triangle(const DWorld &w, const MeshCollideCtx &c
 	point1 = mul(c.transform2, c.sphere_center_in2 + point1);
 	point2 = mul(c.transform2, c.sphere_center_in2 + point2);
 	V3 axis_world = mul(c.transform2.r, penetration_axis);
+	if (c.query != nullptr) { query_add_hit(*c.query, point1, point2, axis_world, penetration_depth, c.sub1, sub2); return; }
 	V3 face2[3];
 	face2[0] = mul(c.transform2, c.sphere_center_in2 + v0);
 	face2[1] = mul(c.transform2, c.sphere_center_in2 + v1);
@@ -329,6 +354,7 @@ B2J_D MeshCollideCtx mesh_collide_ctx_from(const DWorld &w, const ShapeDesc &s1,
 	cc.transform1 = shape_transform(s1, transform1);
 	cc.transform2 = shape_transform(s2, transform2);
 	cc.scale2 = s2.scale;
+	cc.query = nullptr;
 	cc.sub1 = sub1;
 	cc.max_separation_distance = max_separation_distance;
 	cc.check_active_edges = w.settings.check_active_edges != 0;

@@ -9,12 +9,16 @@
 //   RaySphere / RayCylinder / RayCapsule, FindRoot Jolt/Geometry/RaySphere.h, RayCylinder.h, RayCapsule.h, Jolt/Math/FindRoot.h
 //   BoxShape / SphereShape / CapsuleShape::CastRay Shape/BoxShape.cpp:177-188, SphereShape.cpp:222-232, CapsuleShape.cpp:287-298
 //   ConvexHullShape::CastRayHelper                 Shape/ConvexHullShape.cpp:883-995
+//   NarrowPhaseQuery::CollideShape                 Jolt/Physics/Collision/NarrowPhaseQuery.cpp:219-293, TransformedShape::CollideShape
+//                                                  TransformedShape.cpp:70-86 (the pair itself: b2j_compound.h / b2j_mesh.h, as in the step)
+//   QuadTree::CollideSphere / CollidePoint         BroadPhase/QuadTree.cpp:1199-1275, AABox4VsSphere / AABox4VsPoint Jolt/Geometry/AABox4.h
 //   MeshShape::CastRay, RayTriangle                Shape/MeshShape.cpp:696-760, Jolt/Geometry/RayTriangle.h, TriangleCodec...Flags.h TestRay
 // One thread per query. Results are defined by the true body state (pose + shape), not by the tree: a closest hit is the same
 // whatever order the tree is walked in.
 #pragma once
 
 #include "b2j_mesh.h"
+#include "b2j_compound.h"
 
 namespace b2j {
 
@@ -445,6 +449,7 @@ struct KCollideAABox
 {
 	DWorld w;
 	Tree trees[8];
+	int mode;                    // 0: boxes, 1: spheres ([n][4] centre, radius: CollideSphere), 2: points ([n][3]: CollidePoint)
 	const float *boxes;          // [n][6] min xyz, max xyz
 	uint32_t *counts;            // [n] number of overlapping bodies (can exceed max_hits)
 	uint32_t *ids;               // [n][max_hits] body ids (the first max_hits found)
@@ -460,7 +465,17 @@ struct KCollideAABox
 			if (world < first_world || world >= first_world + num_worlds) return;
 			world -= first_world;
 		}
-		V3 mn = v3_load(boxes + 6 * i), mx = v3_load(boxes + 6 * i + 3);
+		V3 mn, mx, centre = v3_zero();
+		float radius_sq = 0.0f;
+		if (mode == 0) { mn = v3_load(boxes + 6 * i); mx = v3_load(boxes + 6 * i + 3); }
+		else if (mode == 1) { centre = v3_load(boxes + 4 * i); float r = boxes[4 * i + 3]; radius_sq = r * r; mn = centre - v3_rep(r); mx = centre + v3_rep(r); }
+		else { centre = v3_load(boxes + 3 * i); mn = centre; mx = centre; }
+		// AABox4VsSphere: the closest point of the box to the centre is within the radius (a point: radius 0 = AABox4VsPoint)
+		auto overlaps = [&](V3 bmin, V3 bmax) {
+			if (mode == 0) return aabb_overlaps(mn, mx, bmin, bmax);
+			V3 closest = v3_min(v3_max(centre, bmin), bmax);
+			return length_sq(closest - centre) <= radius_sq;
+		};
 		uint32_t count = 0;
 		for (uint32_t l = 0; l < w.num_bp_layers; ++l)
 		{
@@ -486,11 +501,81 @@ struct KCollideAABox
 					BodyInfo info = w.info[b];
 					if (info.id == B2J_INVALID_ID || (object_layer != 0xffffffffu && !w.object_vs_object[object_layer * w.num_object_layers + info.object_layer]))
 						continue;
-					if (aabb_overlaps(mn, mx, to_v3(w.bounds_min[b]), to_v3(w.bounds_max[b])))
+					if (overlaps(to_v3(w.bounds_min[b]), to_v3(w.bounds_max[b])))
 					{
 						if (count < max_hits) ids[(size_t)i * max_hits + count] = info.id;
 						++count;
 					}
+				}
+				else
+				{
+					int l2 = t.child_left[node], r2 = t.child_right[node];
+					if (overlaps(to_v3(t.node_min[l2]), to_v3(t.node_max[l2])) && top < 126) stack[++top] = l2;
+					if (overlaps(to_v3(t.node_min[r2]), to_v3(t.node_max[r2])) && top < 126) stack[++top] = r2;
+				}
+			}
+		}
+		counts[i] = count;
+	}
+};
+
+// ---- NarrowPhaseQuery::CollideShape, all hits: one warp per query (lane 0 working, EPA hull in the warp's shared memory, as the
+// compound pairs of the step) ---------------------------------------------------------------------------------------------------------
+struct KCollideShape
+{
+	DWorld w;
+	Tree trees[8];
+	const b2j_shape_query *queries;
+	b2j_collide_shape_hit *hits; uint32_t *counts; uint32_t max_hits;
+	float max_separation_distance;
+	uint32_t object_layer;
+	MeshScratch *mesh_scratch;   // never written by a query (the collector takes the hits); the pair functions want a reference
+	B2J_D void run(uint32_t i, bool valid, uint32_t slot, EpaStorageFull &epa_storage) const
+	{
+		(void)valid; (void)slot;
+		EpaScratch epa = epa_storage.view();
+		b2j_shape_query q = queries[i];
+		const ShapeDesc &s1 = w.shapes[q.shape];
+		V3 com = v3_load(q.position), base = v3_load(q.base_offset);
+		Q4 rot = q4(q.rotation[0], q.rotation[1], q.rotation[2], q.rotation[3]);
+		// bounds of the query shape, expanded by the max separation distance (NarrowPhaseQuery.cpp:287-288)
+		V3 mn, mx;
+		world_bounds(w, s1, com, rot, mn, mx);
+		mn = mn - v3_rep(max_separation_distance); mx = mx + v3_rep(max_separation_distance);
+		QueryCollector qc; qc.hits = hits + (size_t)i * max_hits; qc.max_hits = max_hits; qc.count = 0; qc.body = B2J_INVALID_ID;
+		CompoundPairCtx p;
+		p.max_separation_distance = max_separation_distance;
+		p.movement_direction = v3_zero();
+		p.epa = &epa; p.ms = mesh_scratch; p.num_manifolds = 0; p.query = &qc;
+		// TransformedShape::CollideShape: both centre of mass transforms relative to the base offset
+		CompoundSide a;
+		a.shape = &s1; a.transform = xf(m33_rotation(rot), com + (-base)); a.sub = 0xffffffffu;
+		for (uint32_t l = 0; l < w.num_bp_layers; ++l)
+		{
+			const Tree &t = trees[l];
+			if (t.n == 0 || (object_layer != 0xffffffffu && !w.object_vs_bp[object_layer * w.num_bp_layers + l]))
+				continue;
+			int n = (int)t.n;
+			int stack[128];
+			int top = 0;
+			stack[0] = 0;
+			while (top >= 0)
+			{
+				int node = stack[top--];
+				if (node >= n - 1)
+				{
+					uint32_t b = t.leaf_body[node - (n - 1)];
+					BodyInfo info = w.info[b];
+					if (info.id == B2J_INVALID_ID || (object_layer != 0xffffffffu && !w.object_vs_object[object_layer * w.num_object_layers + info.object_layer]))
+						continue;
+					if (!aabb_overlaps(mn, mx, to_v3(w.bounds_min[b]), to_v3(w.bounds_max[b])))
+						continue;
+					qc.body = info.id;
+					CompoundSide side;
+					side.shape = &w.shapes[info.shape];
+					side.transform = xf(m33_rotation(to_q4(w.rotation[b])), to_v3(w.position[b]) + (-base));
+					side.sub = 0xffffffffu;
+					compound_dispatch(w, p, a, side);
 				}
 				else
 				{
@@ -500,7 +585,7 @@ struct KCollideAABox
 				}
 			}
 		}
-		counts[i] = count;
+		counts[i] = qc.count;
 	}
 };
 

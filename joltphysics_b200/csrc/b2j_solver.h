@@ -47,6 +47,8 @@ enum { CP_PART_R1X_EFF = 0, CP_PART_I1_BIAS, CP_PART_R2X, CP_PART_I2 };
 // meta bits: num points (3) | type1 (2) << 3 | type2 (2) << 5 | velocity steps << 8 | position steps << 16 | friction parts active << 24
 //            | translation DOFs of body 1 (3) << 26 | translation DOFs of body 2 (3) << 29   (what store_vel_state masks with: no
 //            gather of the BodyInfo per body and iteration)
+//            bit 7: the item is a non contact constraint (b2j_joints.h): header only, `manifold` = constraint index; the contact kernels skip it
+enum : uint32_t { META_JOINT = 1u << 7 };
 enum : uint32_t { META_LINEAR_FRICTION = 1u << 24, META_ANGULAR_FRICTION = 1u << 25, META_DOFS1_SHIFT = 26, META_DOFS2_SHIFT = 29 };
 struct alignas(16) ConstraintHeader { uint32_t b1, b2, manifold, meta; };
 struct Constraints
@@ -79,6 +81,9 @@ struct SolveCtx
 	uint32_t *body_deg, *body_off, *body_fill, *body_cur, *body_mask;
 	uint32_t *adj;
 	uint32_t num_slots;
+	// non contact constraints (b2j_joints.h): null / 0 in worlds without any
+	const uint32_t *joint_steps; // [constraint index] velocity steps override | position steps override << 8
+	uint32_t *body_nj;           // per body slot: how many of its items are joints (they lead its adjacency list)
 	uint32_t *sched_flag;        // [2] remaining flags
 	uint32_t *grid_barrier;      // arrival counter of solve_velocity_tma_kernel's grid barrier (zeroed before the launch)
 };
@@ -199,6 +204,7 @@ struct KUfInit
 		s.body_fill[slot] = 0;
 		s.body_cur[slot] = 0;
 		s.body_mask[slot] = 0;
+		if (s.body_nj != nullptr) s.body_nj[slot] = 0;
 	}
 };
 
@@ -226,6 +232,12 @@ struct KUfUnion
 		bool dyn1 = w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC, dyn2 = w.info[c.b2].motion_type == B2J_MOTION_DYNAMIC;
 		if (dyn1) atomic_add(&s.body_deg[c.b1], 1u);
 		if (dyn2) atomic_add(&s.body_deg[c.b2], 1u);
+		if (c.manifold & 0x80000000u)
+		{
+			// a non contact constraint (TwoBodyConstraint::BuildIslands links like a contact: both bodies dynamic)
+			if (dyn1) atomic_add(&s.body_nj[c.b1], 1u);
+			if (dyn2) atomic_add(&s.body_nj[c.b2], 1u);
+		}
 		if (!(dyn1 && dyn2))
 			return;
 		uint32_t a = c.b1, b = c.b2;
@@ -262,6 +274,15 @@ struct KIslandCount
 		uint32_t r = s.root[dyn1? c.b1 : c.b2];
 		atomic_add_matched(s.island_items, r, 1u); // (one giant island = one address for a million constraints: aggregate per warp)
 		uint32_t vmax = 0, pmax = 0, flags = 0;
+		if (c.manifold & 0x80000000u)
+		{
+			// CalculateSolverSteps::operator()(const Constraint *): the constraint's own overrides, not its bodies'
+			uint32_t o = s.joint_steps[c.manifold & 0x7fffffffu];
+			vmax = o & 0xff; pmax = (o >> 8) & 0xff;
+			if (vmax == 0) flags |= 1u << 16;
+			if (pmax == 0) flags |= 1u << 17;
+			dyn1 = false; dyn2 = false;
+		}
 		if (dyn1) { uint32_t v = i1.steps_override & 15, p = i1.steps_override >> 4; vmax = v; pmax = p; if (v == 0) flags |= 1u << 16; if (p == 0) flags |= 1u << 17; }
 		if (dyn2) { uint32_t v = i2.steps_override & 15, p = i2.steps_override >> 4; if (v > vmax) vmax = v; if (p > pmax) pmax = p; if (v == 0) flags |= 1u << 16; if (p == 0) flags |= 1u << 17; }
 		// max of two packed bytes: do them separately to keep atomics simple
@@ -335,6 +356,24 @@ struct KAdjSort
 // ---- wavefront scheduling ------------------------------------------------------------------------------------------
 enum { PHASE_UNSCHEDULED = 0xffffffffu, PHASE_PENDING_SERIAL = 0xfffffffeu };
 
+// Item `cur` of body b's list in the order pass `pass` walks it. The list is stored in solve order (non contact constraints first,
+// b2j_joints.h); the colouring of a large island (pass 0) takes the contacts first (LargeIslandSplitter::SplitIsland assigns the
+// contacts their splits before the constraints), i.e. reads the list rotated by the body's joint count.
+B2J_D bool sched_rotated(const DWorld &w, const SolveCtx &s, uint32_t b, uint32_t pass)
+{
+	(void)w;
+	return s.body_nj != nullptr && pass == 0 && s.body_nj[b] != 0 && s.island_large[s.root[b]] != 0;
+}
+B2J_D uint32_t sched_item(const SolveCtx &s, uint32_t b, uint32_t cur, uint32_t deg, bool rotated)
+{
+	if (rotated)
+	{
+		uint32_t nj = s.body_nj[b], nc = deg - nj;
+		cur = cur < nc? cur + nj : cur - nc;
+	}
+	return s.adj[s.body_off[b] + cur];
+}
+
 // decide step: one thread per active body; `pass` 0 = levels / colours, 1 = serial splits of large islands
 struct KSchedDecide
 {
@@ -345,7 +384,7 @@ struct KSchedDecide
 		uint32_t cur = s.body_cur[b];
 		if (cur >= s.body_deg[b])
 			return;
-		uint32_t i = s.adj[s.body_off[b] + cur];
+		uint32_t i = sched_item(s, b, cur, s.body_deg[b], sched_rotated(w, s, b, pass));
 		const ConstraintSrc &c = s.src[s.order[i]];
 		bool dyn1 = w.info[c.b1].motion_type == B2J_MOTION_DYNAMIC, dyn2 = w.info[c.b2].motion_type == B2J_MOTION_DYNAMIC;
 		uint32_t owner = dyn1? c.b1 : c.b2;
@@ -355,7 +394,7 @@ struct KSchedDecide
 		if (other != 0xffffffffu)
 		{
 			uint32_t oc = s.body_cur[other];
-			if (oc >= s.body_deg[other] || s.adj[s.body_off[other] + oc] != i)
+			if (oc >= s.body_deg[other] || sched_item(s, other, oc, s.body_deg[other], sched_rotated(w, s, other, pass)) != i)
 				return;
 		}
 		uint32_t r = s.root[b];
@@ -397,7 +436,12 @@ struct KSchedAdvance
 		uint32_t cur = s.body_cur[b], deg = s.body_deg[b];
 		const uint32_t *a = s.adj + s.body_off[b];
 		if (pass == 0)
-			while (cur < deg && s.phase[a[cur]] != PHASE_UNSCHEDULED) ++cur;
+		{
+			if (sched_rotated(w, s, b, pass))
+				while (cur < deg && s.phase[sched_item(s, b, cur, deg, true)] != PHASE_UNSCHEDULED) ++cur;
+			else
+				while (cur < deg && s.phase[a[cur]] != PHASE_UNSCHEDULED) ++cur;
+		}
 		else
 			while (cur < deg && s.phase[a[cur]] != PHASE_PENDING_SERIAL) ++cur;
 		s.body_cur[b] = cur;
@@ -738,25 +782,40 @@ template <class Src> B2J_D PartRegs part_load(const Src &src, int base, uint32_t
 struct KSetupConstraints
 {
 	DWorld w; SolveCtx s; float dt;
-	B2J_D void operator()(uint32_t i) const // i = solve position
+	// the velocity / position iteration counts of the item's island (CalculateSolverSteps::Finalize)
+	B2J_D void island_steps(const ConstraintSrc &src, uint32_t type1, uint32_t &vsteps, uint32_t &psteps) const
 	{
-		const Constraints &c = s.con;
-		const ConstraintSrc &src = s.src[s.solve_src[i]];
-		uint32_t m = src.manifold;
-		const CachedManifold &cm = w.write_cache.manifolds[m];
-		BodyKin k1 = load_body_kin(w, src.b1), k2 = load_body_kin(w, src.b2);
-		uint32_t type1 = k1.type, type2 = k2.type;
-		int n = cm.num_points;
-
-		// island solver steps
 		uint32_t r = s.root[type1 == B2J_MOTION_DYNAMIC? src.b1 : src.b2];
 		uint32_t steps = s.island_steps[r];
-		uint32_t vsteps = steps & 0xff, psteps = (steps >> 8) & 0xff;
+		vsteps = steps & 0xff; psteps = (steps >> 8) & 0xff;
 		if (steps & (1u << 16)) vsteps = vsteps > w.settings.num_velocity_steps? vsteps : w.settings.num_velocity_steps;
 		if (steps & (1u << 17)) psteps = psteps > w.settings.num_position_steps? psteps : w.settings.num_position_steps;
 		// (almost always already at the maximum: keep the single address atomics off the hot path)
 		if (vsteps > volatile_load(&w.counters->max_velocity_steps)) atomic_max(&w.counters->max_velocity_steps, vsteps);
 		if (psteps > volatile_load(&w.counters->max_position_steps)) atomic_max(&w.counters->max_position_steps, psteps);
+	}
+	B2J_D void operator()(uint32_t i) const // i = solve position
+	{
+		const Constraints &c = s.con;
+		const ConstraintSrc &src = s.src[s.solve_src[i]];
+		uint32_t m = src.manifold;
+		if (m & 0x80000000u)
+		{
+			// a non contact constraint (b2j_joints.h): header only -- bodies, constraint index, the island's iteration counts
+			uint32_t jt1 = w.info[src.b1].motion_type, jt2 = w.info[src.b2].motion_type;
+			uint32_t jv, jp;
+			island_steps(src, jt1, jv, jp);
+			ConstraintHeader jh; jh.b1 = src.b1; jh.b2 = src.b2; jh.manifold = m & 0x7fffffffu; jh.meta = META_JOINT | (jt1 << 3) | (jt2 << 5) | (jv << 8) | (jp << 16);
+			c.hdr[i] = jh;
+			return;
+		}
+		const CachedManifold &cm = w.write_cache.manifolds[m];
+		BodyKin k1 = load_body_kin(w, src.b1), k2 = load_body_kin(w, src.b2);
+		uint32_t type1 = k1.type, type2 = k2.type;
+		int n = cm.num_points;
+
+		uint32_t vsteps, psteps;
+		island_steps(src, type1, vsteps, psteps);
 
 		uint32_t meta = (uint32_t)n | (type1 << 3) | (type2 << 5) | (vsteps << 8) | (psteps << 16) | ((k1.dofs & 7u) << META_DOFS1_SHIFT) | ((k2.dofs & 7u) << META_DOFS2_SHIFT);
 
@@ -1159,6 +1218,8 @@ struct KWarmStart
 		ConstraintHeader hdr = c.hdr[i];
 		uint32_t meta = hdr.meta;
 		uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
+		if (meta & META_JOINT)
+			return; // (worlds with non contact constraints are solved without programmatic dependent launch: KJointWarmStart owns this item)
 		if (pdl)
 		{
 			solve_prologue_prefetch(w, c, hdr, i, true);
@@ -1185,7 +1246,7 @@ struct KSolveVelocity
 		uint32_t i = begin + k;
 		ConstraintHeader hdr = c.hdr[i];
 		uint32_t meta = hdr.meta;
-		const bool skip = iteration >= ((meta >> 8) & 0xff);
+		const bool skip = iteration >= ((meta >> 8) & 0xff) || (meta & META_JOINT) != 0;
 		if (pdl)
 		{
 			// (every thread synchronises before it leaves, also the ones whose island is done: the kernel after this one relies on it)
@@ -1227,7 +1288,7 @@ struct KStoreImpulses
 	B2J_D void operator()(uint32_t i) const
 	{
 		ConstraintHeader hdr = c.hdr[i];
-		if (((hdr.meta >> 8) & 0xff) != 0)
+		if (((hdr.meta >> 8) & 0xff) != 0 || (hdr.meta & META_JOINT) != 0)
 			return;
 		int n = (int)(hdr.meta & 7);
 		CachedManifold &cm = w.write_cache.manifolds[hdr.manifold];
@@ -1274,7 +1335,7 @@ struct KSolvePosition
 		uint32_t i = begin + k;
 		ConstraintHeader hdr = c.hdr[i];
 		uint32_t meta = hdr.meta;
-		const bool skip = iteration >= ((meta >> 16) & 0xff);
+		const bool skip = iteration >= ((meta >> 16) & 0xff) || (meta & META_JOINT) != 0;
 		if (pdl)
 		{
 			if (!skip)

@@ -131,7 +131,8 @@ struct StepCounters
 	uint32_t max_velocity_steps, max_position_steps;
 	uint32_t hash_tie;               // number of equal adjacent sort keys seen (documented deviation if != 0)
 	uint32_t cache_pairs, cache_manifolds; // sizes of the write cache, published at the end of the step
-	uint32_t pad[7];
+	uint32_t num_active_joints;      // non contact constraints taking part in this step (b2j_joints.h)
+	uint32_t pad[6];
 };
 
 // Everything a kernel needs, passed by value (pointers into HBM + scalars)

@@ -13,6 +13,7 @@
 #include "b2j_mesh.h"
 #include "b2j_compound.h"
 #include "b2j_solver.h"
+#include "b2j_joints.h"
 #include "b2j_query.h"
 
 #ifndef B2J_HOSTSIM
@@ -575,6 +576,7 @@ struct b2j_world
 	SolveCtx sc;
 	uint32_t *d_round_begin = nullptr;
 	MeshScratch *d_mesh_scratch = nullptr;   // allocated when the first mesh shape is uploaded
+	MeshScratch *d_query_scratch = nullptr;  // one block for b2j_query_collide_shape (the pair functions want a reference; queries never write it)
 	uint64_t *d_sort_keys[2] = { nullptr, nullptr };
 	uint32_t *d_sort_vals = nullptr;
 	uint32_t *d_woken_sorted = nullptr;
@@ -585,6 +587,12 @@ struct b2j_world
 	b2j_contact_event *events_buf = nullptr;            // owned buffers; nc.events / d_act_events point at them while recording is on
 	b2j_activation_event *act_events_buf = nullptr;
 	float *d_energy = nullptr;
+
+	// non contact constraints (b2j_joints.h), by constraint index; device arrays grow with the list
+	std::vector<b2j_constraint_desc> h_joints;
+	JointCtx jc = { };
+	uint32_t joint_capacity = 0;
+	bool joints_dirty = false;               // definitions / order changed since the last upload
 
 	float prev_dt = 0.0f;
 	StepCounters h_counters;
@@ -1535,7 +1543,7 @@ void b2j_world_destroy(b2j_world *W)
 	NarrowCtx &nc = W->nc;
 	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); if (nc.epa_hist != nullptr) rt.free_(nc.epa_hist); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(W->events_buf);
-	rt.free_(W->d_mesh_scratch); rt.free_(W->d_cache_invalid);
+	rt.free_(W->d_mesh_scratch); rt.free_(W->d_query_scratch); rt.free_(W->d_cache_invalid);
 	for (int i = 0; i < 2; ++i) { rt.free_(W->d_collide_keys[i]); rt.free_(W->d_collide_vals[i]); }
 	rt.free_(W->act_events_buf); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
 	SolveCtx &sc = W->sc;
@@ -2537,19 +2545,20 @@ int b2j_query_cast_rays(b2j_world *W, const b2j_ray *rays, uint32_t n, uint32_t 
 	return cast_rays(W, nullptr, 0, rays, n, object_layer, hits);
 }
 
-int b2j_query_collide_aabox(b2j_world *W, const float *boxes, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids)
+static int collide_volume(b2j_world *W, const char *what, int mode, uint32_t floats, const float *boxes, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids)
 {
 	if (n == 0) return 0;
 	B2J_DEVICE_GUARD(W);
-	if (boxes == nullptr || counts == nullptr || (max_hits > 0 && ids == nullptr)) { last_error() = "b2j_query_collide_aabox: boxes, counts and ids are required"; return -1; }
-	if (object_layer != 0xffffffffu && object_layer >= W->d.num_object_layers) { last_error() = "b2j_query_collide_aabox: invalid object layer"; return -1; }
+	if (boxes == nullptr || counts == nullptr || (max_hits > 0 && ids == nullptr)) { last_error() = std::string(what) + ": the query volumes, counts and ids are required"; return -1; }
+	if (object_layer != 0xffffffffu && object_layer >= W->d.num_object_layers) { last_error() = std::string(what) + ": invalid object layer"; return -1; }
 	Runtime &rt = W->rt;
 	if (!ensure_trees(W)) return -1;
-	rt.stage_begin((size_t)n * (24 + 4 + (size_t)max_hits * 4));
+	rt.stage_begin((size_t)n * (4 * floats + 4 + (size_t)max_hits * 4));
 	float *h_boxes = nullptr; uint32_t *h_counts = nullptr, *h_ids = nullptr;
 	KCollideAABox k; k.w = W->d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l];
-	k.boxes = rt.stage_alloc<float>((size_t)n * 6, &h_boxes);
-	memcpy(h_boxes, boxes, (size_t)n * 24);
+	k.mode = mode;
+	k.boxes = rt.stage_alloc<float>((size_t)n * floats, &h_boxes);
+	memcpy(h_boxes, boxes, (size_t)n * floats * 4);
 	rt.stage_to_device(0, rt.stage_used);
 	size_t out_begin = rt.stage_used;
 	k.counts = rt.stage_alloc<uint32_t>(n, &h_counts);
@@ -2559,7 +2568,65 @@ int b2j_query_collide_aabox(b2j_world *W, const float *boxes, uint32_t n, uint32
 	rt.stage_to_host(out_begin, rt.stage_used);
 	memcpy(counts, h_counts, (size_t)n * 4);
 	if (max_hits > 0) memcpy(ids, h_ids, (size_t)n * max_hits * 4);
-	return rt.check("b2j_query_collide_aabox")? 0 : -1;
+	return rt.check(what)? 0 : -1;
+}
+
+int b2j_query_collide_aabox(b2j_world *W, const float *boxes, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids)
+{
+	return collide_volume(W, "b2j_query_collide_aabox", 0, 6, boxes, n, object_layer, max_hits, counts, ids);
+}
+
+int b2j_query_collide_sphere(b2j_world *W, const float *spheres, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids)
+{
+	return collide_volume(W, "b2j_query_collide_sphere", 1, 4, spheres, n, object_layer, max_hits, counts, ids);
+}
+
+int b2j_query_collide_point(b2j_world *W, const float *points, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids)
+{
+	return collide_volume(W, "b2j_query_collide_point", 2, 3, points, n, object_layer, max_hits, counts, ids);
+}
+
+int b2j_query_collide_shape(b2j_world *W, const b2j_shape_query *queries, uint32_t n, float max_separation_distance, uint32_t object_layer,
+	uint32_t max_hits, uint32_t *counts, b2j_collide_shape_hit *hits)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (queries == nullptr || counts == nullptr || (max_hits > 0 && hits == nullptr)) { last_error() = "b2j_query_collide_shape: queries, counts and hits are required"; return -1; }
+	if (object_layer != 0xffffffffu && object_layer >= W->d.num_object_layers) { last_error() = "b2j_query_collide_shape: invalid object layer"; return -1; }
+	if (W->num_worlds != 1) { last_error() = "b2j_query_collide_shape: single worlds only"; return -1; }
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		int32_t sh = queries[i].shape;
+		if (sh < 0 || (size_t)sh >= W->h_shapes.size()) { last_error() = "b2j_query_collide_shape: invalid shape id"; return -1; }
+		uint32_t kind = W->h_shapes[sh].kind;
+		if (kind == B2J_SHAPE_MESH || kind == B2J_SHAPE_COMPOUND) { last_error() = "b2j_query_collide_shape: the query shape must be a convex shape"; return -1; }
+	}
+	Runtime &rt = W->rt;
+	if (!ensure_trees(W)) return -1;
+	if (W->d_query_scratch == nullptr) W->d_query_scratch = rt.alloc<MeshScratch>(1, false);
+	if (W->d_query_scratch == nullptr) { last_error() = "b2j_query_collide_shape: out of device memory"; return -1; }
+	rt.stage_begin((size_t)n * (sizeof(b2j_shape_query) + 4 + (size_t)max_hits * sizeof(b2j_collide_shape_hit)) + 64);
+	b2j_shape_query *h_queries = nullptr; uint32_t *h_counts = nullptr, *h_n = nullptr; b2j_collide_shape_hit *h_hits = nullptr;
+	KCollideShape k; k.w = W->d; for (int l = 0; l < 8; ++l) k.trees[l] = W->trees[l];
+	k.queries = rt.stage_alloc<b2j_shape_query>(n, &h_queries);
+	memcpy(h_queries, queries, (size_t)n * sizeof(b2j_shape_query));
+	const uint32_t *d_n = rt.stage_alloc<uint32_t>(4, &h_n);
+	h_n[0] = n;
+	rt.stage_to_device(0, rt.stage_used);
+	size_t out_begin = rt.stage_used;
+	k.counts = rt.stage_alloc<uint32_t>(n, &h_counts);
+	k.hits = rt.stage_alloc<b2j_collide_shape_hit>((size_t)n * max_hits, &h_hits);
+	k.max_hits = max_hits; k.max_separation_distance = max_separation_distance; k.object_layer = object_layer;
+	k.mesh_scratch = W->d_query_scratch;
+	rt.launch_warp_smem<KCollideShape, EpaStorageFull>(k, d_n, n, W->nc.num_scratch);
+	rt.stage_to_host(out_begin, rt.stage_used);
+	memcpy(counts, h_counts, (size_t)n * 4);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t c = h_counts[i] < max_hits? h_counts[i] : max_hits;
+		memcpy(hits + (size_t)i * max_hits, h_hits + (size_t)i * max_hits, (size_t)c * sizeof(b2j_collide_shape_hit));
+	}
+	return rt.check("b2j_query_collide_shape")? 0 : -1;
 }
 
 static void snapshot_free(WorldSnapshot &ws)

@@ -362,6 +362,49 @@ B2JF_API int b2jf_scene_collide_aabox(void *h, const float *box, uint32_t *out_i
 	return (int)ids.size();
 }
 
+// NarrowPhaseQuery::CollideShape (a box of the given half extent, scaled) and BroadPhaseQuery::CollideSphere / CollidePoint through the facade.
+// out: per hit body, sub shape 2, depth; returns the number of hits. The matrix form and the batched form must agree with the single one.
+B2JF_API int b2jf_scene_collide_shape(void *h, const float *half_extent, const float *scale, const float *rotation, const float *position, float max_separation,
+	uint32_t *out_body, uint32_t *out_sub2, float *out_depth, int cap)
+{
+	Scene *s = (Scene *)h;
+	static std::shared_ptr<const BoxShape> box; // (kept alive by the caller, as the reference asks)
+	static float box_he[3];
+	if (box == nullptr || box_he[0] != half_extent[0] || box_he[1] != half_extent[1] || box_he[2] != half_extent[2])
+	{
+		box = std::make_shared<BoxShape>(Vec3(half_extent[0], half_extent[1], half_extent[2]), 0.05f);
+		box_he[0] = half_extent[0]; box_he[1] = half_extent[1]; box_he[2] = half_extent[2];
+	}
+	Quat q(rotation[0], rotation[1], rotation[2], rotation[3]);
+	RVec3 p(position[0], position[1], position[2]);
+	Vec3 sc(scale[0], scale[1], scale[2]);
+	CollideShapeSettings settings; settings.mMaxSeparationDistance = max_separation;
+	std::vector<CollideShapeResult> hits, hits_m;
+	const NarrowPhaseQuery &query = s->system.GetNarrowPhaseQuery();
+	query.CollideShape(box.get(), sc, q, p, settings, p, hits);
+	query.CollideShape(box.get(), sc, RMat44::sRotationTranslation(q, p), settings, p, hits_m);
+	std::vector<std::vector<CollideShapeResult>> batch;
+	query.CollideShapes(box.get(), sc, &q, &p, 1, settings, batch);
+	bool ok = hits_m.size() == hits.size() && batch.size() == 1 && batch[0].size() == hits.size();
+	for (size_t i = 0; ok && i < hits.size(); ++i)
+		ok = hits_m[i].mBodyID2 == hits[i].mBodyID2 && batch[0][i].mBodyID2 == hits[i].mBodyID2 && std::fabs(hits_m[i].mPenetrationDepth - hits[i].mPenetrationDepth) < 1.0e-4f;
+	if (!ok) return -1;
+	for (size_t i = 0; i < hits.size() && (int)i < cap; ++i)
+	{
+		out_body[i] = hits[i].mBodyID2.GetIndexAndSequenceNumber(); out_sub2[i] = hits[i].mSubShapeID2.GetValue(); out_depth[i] = hits[i].mPenetrationDepth;
+	}
+	return (int)hits.size();
+}
+B2JF_API int b2jf_scene_collide_sphere(void *h, const float *sphere, uint32_t *out_ids, int cap)
+{
+	Scene *s = (Scene *)h;
+	std::vector<BodyID> ids;
+	if (sphere[3] < 0.0f) s->system.GetBroadPhaseQuery().CollidePoint(Vec3(sphere[0], sphere[1], sphere[2]), ids);
+	else s->system.GetBroadPhaseQuery().CollideSphere(Vec3(sphere[0], sphere[1], sphere[2]), sphere[3], ids);
+	for (size_t i = 0; i < ids.size() && (int)i < cap; ++i) out_ids[i] = ids[i].GetIndexAndSequenceNumber();
+	return (int)ids.size();
+}
+
 // rows of body state the last refresh of the host mirror fetched (the incremental download: only what the step simulated)
 B2JF_API uint32_t b2jf_scene_last_download_count(void *h) { return ((Scene *)h)->system.GetLastDownloadCount(); }
 

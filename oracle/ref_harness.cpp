@@ -22,6 +22,11 @@
 #include <Jolt/Physics/Collision/RayCast.h>
 #include <Jolt/Physics/Collision/CastResult.h>
 #include <Jolt/Physics/Collision/NarrowPhaseQuery.h>
+#include <Jolt/Physics/Collision/CollideShape.h>
+#include <Jolt/Physics/Collision/Shape/CylinderShape.h>
+#include <Jolt/Physics/Collision/Shape/CapsuleShape.h>
+#include <Jolt/Physics/Collision/Shape/SphereShape.h>
+#include <Jolt/Physics/Collision/Shape/BoxShape.h>
 #include <Jolt/Physics/Collision/CollisionCollectorImpl.h>
 
 #include <algorithm>
@@ -570,6 +575,82 @@ void jref_cast_rays(void *h, const b2j_ray *inRays, uint32_t inNum, uint32_t inO
 		outHits[i].body = had_hit? hit.mBodyID.GetIndexAndSequenceNumber() : 0xffffffffu;
 		outHits[i].sub_shape = had_hit? hit.mSubShapeID2.GetValue() : 0xffffffffu;
 		outHits[i].fraction = had_hit? hit.mFraction : 1.0f + FLT_EPSILON;
+	}
+}
+
+// NarrowPhaseQuery::CollideShape with an AllHitCollisionCollector for n queries of ONE convex query shape (kind: 0 sphere (p0 = radius),
+// 1 box (p0..2 = half extent, p3 = convex radius), 2 capsule (p0 = half height, p1 = radius), 3 cylinder (p0 = half height, p1 = radius,
+// p2 = convex radius)); queries as b2j_shape_query (the shape member is ignored). Hits in the order the collector received them.
+void jref_collide_shape(void *h, uint32_t inKind, const float *inParams, const b2j_shape_query *inQueries, uint32_t inNum, float inMaxSeparationDistance,
+	uint32_t inObjectLayer, uint32_t inMaxHits, uint32_t *outCounts, b2j_collide_shape_hit *outHits)
+{
+	World *w = (World *)h;
+	RefConst<Shape> shape;
+	switch (inKind)
+	{
+	case 0: shape = new SphereShape(inParams[0]); break;
+	case 1: shape = new BoxShape(Vec3(inParams[0], inParams[1], inParams[2]), inParams[3]); break;
+	case 2: shape = new CapsuleShape(inParams[0], inParams[1]); break;
+	default: shape = new CylinderShape(inParams[0], inParams[1], inParams[2]); break;
+	}
+	const NarrowPhaseQuery &query = w->system.GetNarrowPhaseQueryNoLock();
+	CollideShapeSettings settings;
+	settings.mMaxSeparationDistance = inMaxSeparationDistance;
+	for (uint32_t i = 0; i < inNum; ++i)
+	{
+		const b2j_shape_query &q = inQueries[i];
+		RMat44 com = RMat44::sRotationTranslation(Quat(q.rotation[0], q.rotation[1], q.rotation[2], q.rotation[3]), RVec3(q.position[0], q.position[1], q.position[2]));
+		AllHitCollisionCollector<CollideShapeCollector> collector;
+		RVec3 base(q.base_offset[0], q.base_offset[1], q.base_offset[2]);
+		if (inObjectLayer == 0xffffffffu)
+			query.CollideShape(shape, Vec3::sOne(), com, settings, base, collector);
+		else
+			query.CollideShape(shape, Vec3::sOne(), com, settings, base, collector, DefaultBroadPhaseLayerFilter(w->ovbp, (ObjectLayer)inObjectLayer), DefaultObjectLayerFilter(w->olp, (ObjectLayer)inObjectLayer));
+		outCounts[i] = (uint32_t)collector.mHits.size();
+		for (uint32_t j = 0; j < collector.mHits.size() && j < inMaxHits; ++j)
+		{
+			const CollideShapeResult &r = collector.mHits[j];
+			b2j_collide_shape_hit &o = outHits[(size_t)i * inMaxHits + j];
+			o.body = r.mBodyID2.GetIndexAndSequenceNumber();
+			o.sub_shape1 = r.mSubShapeID1.GetValue(); o.sub_shape2 = r.mSubShapeID2.GetValue();
+			o.penetration_depth = r.mPenetrationDepth;
+			r.mContactPointOn1.StoreFloat3((Float3 *)o.point1); r.mContactPointOn2.StoreFloat3((Float3 *)o.point2); r.mPenetrationAxis.StoreFloat3((Float3 *)o.axis);
+		}
+	}
+}
+
+// BroadPhaseQuery::CollideSphere (inMode 1: [n][4] centre, radius) / CollidePoint (inMode 2: [n][3]), narrowed to the true bounds like
+// jref_collide_aabox
+void jref_collide_volume(void *h, uint32_t inMode, const float *inData, uint32_t inNum, uint32_t inObjectLayer, uint32_t inMaxHits, uint32_t *outCounts, uint32_t *outIDs)
+{
+	World *w = (World *)h;
+	const BodyLockInterfaceNoLock &li = w->system.GetBodyLockInterfaceNoLock();
+	for (uint32_t i = 0; i < inNum; ++i)
+	{
+		AllHitCollisionCollector<CollideShapeBodyCollector> collector;
+		const float *d = inData + (inMode == 1? 4 : 3) * (size_t)i;
+		Vec3 centre(d[0], d[1], d[2]);
+		float radius = inMode == 1? d[3] : 0.0f;
+		DefaultBroadPhaseLayerFilter bpf(w->ovbp, (ObjectLayer)(inObjectLayer == 0xffffffffu? 0 : inObjectLayer));
+		DefaultObjectLayerFilter olf(w->olp, (ObjectLayer)(inObjectLayer == 0xffffffffu? 0 : inObjectLayer));
+		BroadPhaseLayerFilter all_bp; ObjectLayerFilter all_ol;
+		const BroadPhaseLayerFilter &f1 = inObjectLayer == 0xffffffffu? all_bp : (const BroadPhaseLayerFilter &)bpf;
+		const ObjectLayerFilter &f2 = inObjectLayer == 0xffffffffu? all_ol : (const ObjectLayerFilter &)olf;
+		if (inMode == 1)
+			w->system.GetBroadPhaseQuery().CollideSphere(centre, radius, collector, f1, f2);
+		else
+			w->system.GetBroadPhaseQuery().CollidePoint(centre, collector, f1, f2);
+		std::vector<uint32_t> ids;
+		for (const BodyID &id : collector.mHits)
+		{
+			const Body *b = li.TryGetBody(id);
+			if (b == nullptr) continue;
+			const AABox &bounds = b->GetWorldSpaceBounds();
+			if (bounds.GetSqDistanceTo(centre) <= radius * radius) ids.push_back(id.GetIndexAndSequenceNumber());
+		}
+		std::sort(ids.begin(), ids.end());
+		outCounts[i] = (uint32_t)ids.size();
+		for (uint32_t j = 0; j < ids.size() && j < inMaxHits; ++j) outIDs[(size_t)i * inMaxHits + j] = ids[j];
 	}
 }
 

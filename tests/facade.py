@@ -35,6 +35,10 @@ class FacadeLib:
         L.b2jf_scene_cast_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2jf_scene_collide_aabox.restype = C.c_int
         L.b2jf_scene_collide_aabox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2jf_scene_collide_shape.restype = C.c_int
+        L.b2jf_scene_collide_shape.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 3 + [C.c_int]
+        L.b2jf_scene_collide_sphere.restype = C.c_int
+        L.b2jf_scene_collide_sphere.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.b2jf_scene_query.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 
 
@@ -89,6 +93,23 @@ class FacadeScene:
         box = np.ascontiguousarray(box, np.float32)
         ids = np.zeros(cap, np.uint32)
         n = self.flib.lib.b2jf_scene_collide_aabox(self.h, box.ctypes.data, ids.ctypes.data, cap)
+        return np.sort(ids[:min(n, cap)])
+
+    def collide_shape_box(self, half_extent, scale, rotation, position, max_separation=0.0, cap=256):
+        """NarrowPhaseQuery::CollideShape of a box through the facade -> (body, sub_shape2, depth) arrays; -1 hits = the forms disagree."""
+        he, sc, q, p = (np.ascontiguousarray(x, np.float32) for x in (half_extent, scale, rotation, position))
+        body, sub, depth = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.float32)
+        n = self.flib.lib.b2jf_scene_collide_shape(self.h, he.ctypes.data, sc.ctypes.data, q.ctypes.data, p.ctypes.data, max_separation,
+                                                   body.ctypes.data, sub.ctypes.data, depth.ctypes.data, cap)
+        assert n >= 0, "the quaternion, matrix and batched forms of CollideShape disagree"
+        n = min(n, cap)
+        return body[:n], sub[:n], depth[:n]
+
+    def collide_sphere(self, sphere, cap=256):
+        """BroadPhaseQuery::CollideSphere (radius >= 0) / CollidePoint (radius < 0) through the facade -> sorted ids."""
+        sphere = np.ascontiguousarray(sphere, np.float32)
+        ids = np.zeros(cap, np.uint32)
+        n = self.flib.lib.b2jf_scene_collide_sphere(self.h, sphere.ctypes.data, ids.ctypes.data, cap)
         return np.sort(ids[:min(n, cap)])
 
     def step_e2e(self, dt, forces, out_positions):

@@ -39,6 +39,8 @@ def ref_lib(variant="det"):
         L.jref_mutate.argtypes = [vp, C.c_int]
         L.jref_cast_rays.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.jref_collide_aabox.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.jref_collide_shape.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.jref_collide_volume.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.jref_replace_body.restype = C.c_uint32
         L.jref_replace_body.argtypes = [vp, C.c_uint32, C.c_float]
         L.jref_query.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -77,6 +79,10 @@ def _fp(a):
 
 
 HIT_DTYPE = np.dtype([("body", np.uint32), ("sub_shape", np.uint32), ("fraction", np.float32)])
+# b2j_shape_query / b2j_collide_shape_hit (include/jolt_b200.h)
+SHAPE_QUERY_DTYPE = np.dtype([("shape", np.int32), ("position", np.float32, 3), ("rotation", np.float32, 4), ("base_offset", np.float32, 3)])
+SHAPE_HIT_DTYPE = np.dtype([("body", np.uint32), ("sub_shape1", np.uint32), ("sub_shape2", np.uint32), ("penetration_depth", np.float32),
+                            ("point1", np.float32, 3), ("point2", np.float32, 3), ("axis", np.float32, 3)])
 
 
 class State:
@@ -136,6 +142,24 @@ class RefWorld:
         counts = np.zeros(len(boxes), np.uint32)
         ids = np.full((len(boxes), max_hits), 0xffffffff, np.uint32)
         self.L.jref_collide_aabox(self.h, boxes.ctypes.data, len(boxes), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data)
+        return counts, ids
+
+    def collide_shape(self, kind, params, queries, max_separation_distance=0.0, object_layer=0xffffffff, max_hits=64):
+        """NarrowPhaseQuery::CollideShape (all hits) of one convex shape (kind 0 sphere / 1 box / 2 capsule / 3 cylinder) for every query."""
+        queries = np.ascontiguousarray(queries, SHAPE_QUERY_DTYPE)
+        params = np.ascontiguousarray(list(params) + [0.0] * (4 - len(params)), np.float32)
+        counts = np.zeros(len(queries), np.uint32)
+        hits = np.zeros((len(queries), max_hits), SHAPE_HIT_DTYPE)
+        self.L.jref_collide_shape(self.h, kind, params.ctypes.data, queries.ctypes.data, len(queries), max_separation_distance, object_layer, max_hits,
+                                  counts.ctypes.data, hits.ctypes.data)
+        return counts, hits
+
+    def collide_volume(self, mode, data, object_layer=0xffffffff, max_hits=64):
+        """BroadPhaseQuery::CollideSphere (mode 1, [n][4]) / CollidePoint (mode 2, [n][3])."""
+        data = np.ascontiguousarray(data, np.float32)
+        counts = np.zeros(len(data), np.uint32)
+        ids = np.full((len(data), max_hits), 0xffffffff, np.uint32)
+        self.L.jref_collide_volume(self.h, mode, data.ctypes.data, len(data), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data)
         return counts, ids
 
     def replace_body(self, index, radius=0.5):
@@ -224,6 +248,7 @@ class B2JWorld:
         self.api = api
         self.h = handle
         self.n = num_slots
+        self._query_shapes = {}
 
     def close(self):
         if self.h:
@@ -292,6 +317,35 @@ class B2JWorld:
         ids = np.full((len(boxes), max_hits), 0xffffffff, np.uint32)
         if self.api.b2j_query_collide_aabox(self.h, boxes.ctypes.data, len(boxes), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data) != 0:
             raise RuntimeError("b2j_query_collide_aabox failed: " + self.api.last_error())
+        return counts, ids
+
+    def collide_shape(self, kind, params, queries, max_separation_distance=0.0, object_layer=0xffffffff, max_hits=64):
+        """b2j_query_collide_shape with a query shape made from the same parameters as RefWorld.collide_shape."""
+        key = (kind, tuple(float(x) for x in params))
+        if key not in self._query_shapes:
+            p = [C.c_float(float(x)) for x in params]
+            if kind == 0: sid = self.api.b2j_shape_sphere(self.h, p[0])
+            elif kind == 1: sid = self.api.b2j_shape_box(self.h, (C.c_float * 3)(*[float(x) for x in params[:3]]), p[3])
+            elif kind == 2: sid = self.api.b2j_shape_capsule(self.h, p[0], p[1])
+            else: sid = self.api.b2j_shape_cylinder(self.h, p[0], p[1], p[2])
+            assert sid >= 0, self.api.last_error()
+            self._query_shapes[key] = sid
+        queries = np.ascontiguousarray(queries, SHAPE_QUERY_DTYPE).copy()
+        queries["shape"] = self._query_shapes[key]
+        counts = np.zeros(len(queries), np.uint32)
+        hits = np.zeros((len(queries), max_hits), SHAPE_HIT_DTYPE)
+        if self.api.b2j_query_collide_shape(self.h, queries.ctypes.data, len(queries), max_separation_distance, object_layer, max_hits,
+                                            counts.ctypes.data, hits.ctypes.data) != 0:
+            raise RuntimeError("b2j_query_collide_shape failed: " + self.api.last_error())
+        return counts, hits
+
+    def collide_volume(self, mode, data, object_layer=0xffffffff, max_hits=64):
+        data = np.ascontiguousarray(data, np.float32)
+        counts = np.zeros(len(data), np.uint32)
+        ids = np.full((len(data), max_hits), 0xffffffff, np.uint32)
+        f = self.api.b2j_query_collide_sphere if mode == 1 else self.api.b2j_query_collide_point
+        if f(self.h, data.ctypes.data, len(data), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data) != 0:
+            raise RuntimeError("b2j_query_collide_sphere / point failed: " + self.api.last_error())
         return counts, ids
 
     def profile(self):

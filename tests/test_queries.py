@@ -69,6 +69,59 @@ def _check_boxes(ref, world, state, n, seed, layer=0xffffffff):
     return int(wc.sum())
 
 
+QUERY_SHAPES = [(0, [0.6]), (1, [0.5, 0.3, 0.7, 0.05]), (2, [0.4, 0.3]), (3, [0.5, 0.4, 0.05]), (1, [0.4, 0.4, 0.4, 0.0])]
+
+
+def _check_collide_shape(ref, world, state, n, seed, layer=0xffffffff):
+    """NarrowPhaseQuery::CollideShape, all hits: the same (body, sub shape) hit sets, depths / points / axes within 1e-4 (bit equal in
+    practice: the pair code is the step's)."""
+    rng = np.random.default_rng(seed)
+    valid = state.ids != 0xffffffff
+    if not valid.any():
+        valid[:] = True
+    total = 0
+    for qi, (kind, params) in enumerate(QUERY_SHAPES):
+        q = np.zeros(n, R.SHAPE_QUERY_DTYPE)
+        q["position"] = state.pos[valid][rng.integers(0, valid.sum(), n)] + rng.normal(0, 0.4, (n, 3))
+        rot = rng.normal(0, 1, (n, 4))
+        q["rotation"] = rot / np.linalg.norm(rot, axis=1, keepdims=True)
+        q["base_offset"] = q["position"] if qi % 2 == 0 else 0.0
+        sep = [0.0, 0.05, 0.3][qi % 3]
+        (wc, wh), (gc, gh) = ref.collide_shape(kind, params, q, sep, layer, 96), world.collide_shape(kind, params, q, sep, layer, 96)
+        assert np.array_equal(wc, gc), f"shape {qi}: hit counts differ for queries {np.flatnonzero(wc != gc)[:8]}: {wc[wc != gc][:8]} vs {gc[wc != gc][:8]}"
+        for i in range(n):
+            k = min(int(wc[i]), 96)
+            if k == 0 or wc[i] > 96:
+                continue
+            a, b = wh[i, :k], gh[i, :k]
+            a = a[np.lexsort((a["sub_shape2"], a["sub_shape1"], a["body"]))]
+            b = b[np.lexsort((b["sub_shape2"], b["sub_shape1"], b["body"]))]
+            for f in ("body", "sub_shape1", "sub_shape2"):
+                assert np.array_equal(a[f], b[f]), f"shape {qi} query {i}: {f} differs"
+            for f in ("penetration_depth", "point1", "point2", "axis"):
+                assert np.allclose(a[f], b[f], rtol=1e-4, atol=1e-5), f"shape {qi} query {i}: {f} differs by {np.abs(a[f] - b[f]).max()}"
+            total += k
+    return total
+
+
+def _check_volumes(ref, world, state, n, seed, layer=0xffffffff):
+    rng = np.random.default_rng(seed)
+    valid = state.ids != 0xffffffff
+    if not valid.any():
+        valid[:] = True
+    c = state.pos[valid][rng.integers(0, valid.sum(), n)] + rng.normal(0, 0.5, (n, 3))
+    spheres = np.concatenate([c, rng.uniform(0.0, 2.0, (n, 1))], axis=1).astype(np.float32)
+    total = 0
+    for mode, data in ((1, spheres), (2, c.astype(np.float32))):
+        (wc, wi), (gc, gi) = ref.collide_volume(mode, data, layer), world.collide_volume(mode, data, layer)
+        assert np.array_equal(wc, gc), f"mode {mode}: hit counts differ for {np.flatnonzero(wc != gc)[:8]}"
+        for i in range(n):
+            if wc[i] <= wi.shape[1]:
+                assert np.array_equal(np.sort(gi[i, :wc[i]]), wi[i, :wc[i]]), f"mode {mode} query {i}: body sets differ"
+        total += int(wc.sum())
+    return total
+
+
 SCENES = [("small_stack", 4, 0, 40, 6.0), ("pyramid", 6, 0, 30, 20.0), ("convex_vs_mesh", 2, 0, 60, 30.0), ("pile", 500, 15, 80, 12.0),
           ("feature", parity.FEATURES.index("zoo"), 0, 50, 60.0), ("feature", parity.FEATURES.index("decorated"), 0, 70, 10.0),
           ("convex_vs_mesh", 1, 3, 150, 30.0),  # decorated bodies on a scaled + rotated mesh
@@ -87,6 +140,10 @@ def _run(api, scene, p0, p1, warm, span, n_rays, n_boxes):
     assert _check_rays(ref, world, rays, layer=1) > 0          # cast as a MOVING body: everything collides
     assert _check_boxes(ref, world, state, n_boxes, 12) > 0
     _check_boxes(ref, world, state, n_boxes, 13, layer=0)      # as NON_MOVING: only moving bodies
+    assert _check_volumes(ref, world, state, n_boxes, 14) > 0
+    _check_volumes(ref, world, state, n_boxes, 15, layer=0)
+    assert _check_collide_shape(ref, world, state, max(20, n_boxes // 5), 16) > 0
+    _check_collide_shape(ref, world, state, max(20, n_boxes // 5), 17, layer=0)
     # after a step the trees are rebuilt for the new bounds
     world.step(); ref.step()
     assert _check_rays(ref, world, rays) > 0
@@ -134,6 +191,26 @@ def _check_facade_queries(flib):
     box = np.array([-2, 0, -2, 2, 3, 2], np.float32)
     counts, ids = fs.world.collide_aabox(box[None, :], max_hits=256)
     assert counts[0] > 3 and np.array_equal(np.sort(ids[0, :counts[0]]), fs.collide_aabox(box))
+    sphere = np.array([0.5, 1.0, -0.5, 1.5], np.float32)
+    counts, ids = fs.world.collide_volume(1, sphere[None, :], max_hits=256)
+    assert counts[0] > 3 and np.array_equal(np.sort(ids[0, :counts[0]]), fs.collide_sphere(sphere))
+    state = fs.world.state()
+    point = np.concatenate([state.pos[5], [-1.0]]).astype(np.float32)
+    counts, ids = fs.world.collide_volume(2, point[None, :3], max_hits=256)
+    assert counts[0] >= 1 and np.array_equal(np.sort(ids[0, :counts[0]]), fs.collide_sphere(point))
+    # CollideShape: a scaled box at a body of the pile; the facade's shape (BoxShape half extent h, convex radius 0.05, scaled) is
+    # the C ABI's b2j_shape_scaled(b2j_shape_box)
+    he, scale = np.array([0.5, 0.4, 0.6], np.float32), np.array([1.5, 1.5, 1.5], np.float32)
+    rot = np.array([0.1, 0.2, 0.3, 0.9], np.float32); rot /= np.linalg.norm(rot)
+    body, sub, depth = fs.collide_shape_box(he, scale, rot, state.pos[7], 0.1)
+    assert len(body) >= 1
+    inner = fs.world.api.b2j_shape_box(fs.world.h, (C.c_float * 3)(*he), C.c_float(0.05))
+    sid = fs.world.api.b2j_shape_scaled(fs.world.h, inner, (C.c_float * 3)(*scale))
+    q = np.zeros(1, R.SHAPE_QUERY_DTYPE)
+    q["shape"], q["position"], q["rotation"], q["base_offset"] = sid, state.pos[7], rot, state.pos[7]
+    cnt = np.zeros(1, np.uint32); hits = np.zeros(256, R.SHAPE_HIT_DTYPE)
+    assert fs.world.api.b2j_query_collide_shape(fs.world.h, q.ctypes.data, 1, 0.1, 0xffffffff, 256, cnt.ctypes.data, hits.ctypes.data) == 0
+    assert cnt[0] == len(body) and np.array_equal(hits["body"][:cnt[0]], body) and np.array_equal(hits["penetration_depth"][:cnt[0]], depth)
     fs.close()
 
 
