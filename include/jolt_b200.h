@@ -42,7 +42,7 @@ enum {
 enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4, B2J_SHAPE_CYLINDER = 5, B2J_SHAPE_COMPOUND = 6 };
 
 /* Constraint kinds on the path (EConstraintSubType subset, Jolt/Physics/Constraints/Constraint.h:31-49) */
-enum { B2J_CONSTRAINT_POINT = 0, B2J_CONSTRAINT_DISTANCE = 1 };
+enum { B2J_CONSTRAINT_POINT = 0, B2J_CONSTRAINT_DISTANCE = 1, B2J_CONSTRAINT_HINGE = 2 };
 
 /* Body flags */
 enum {
@@ -305,7 +305,8 @@ uint32_t b2j_num_active_bodies(const b2j_world *w);   /* PhysicsSystem::GetNumAc
 /* PhysicsSystem::GetActiveBodies (:240): copies up to cap ids in active-list order, returns the count. */
 uint32_t b2j_get_active_bodies(b2j_world *w, uint32_t *ids, uint32_t cap);
 
-/* ---- non contact constraints between two bodies (PointConstraint, DistanceConstraint without limit springs).
+/* ---- non contact constraints between two bodies (PointConstraint, DistanceConstraint without limit springs,
+ *      HingeConstraint with angle limits and friction, motor off).
  *      Replaces PhysicsSystem::AddConstraint(s) / RemoveConstraint(s) (PhysicsSystem.h:76-87 -> ConstraintManager::Add / Remove,
  *      Jolt/Physics/Constraints/ConstraintManager.cpp:17-62). A constraint is addressed by its position in the world's list, which is
  *      Constraint::mConstraintIndex: adding appends, removing moves the last constraint into the freed position. Active constraints take
@@ -321,11 +322,23 @@ typedef struct b2j_constraint_desc {
 	uint8_t  num_velocity_steps_override, num_position_steps_override; /* Constraint::mNumVelocityStepsOverride / mNumPositionStepsOverride */
 	uint8_t  enabled;                    /* Constraint::mEnabled                                                                          */
 	uint8_t  reserved;
+	/* HingeConstraint (HingeConstraint.h:118-160): mLocalSpaceHingeAxis1 / 2, mInvInitialOrientation, mLimitsMin / Max ([-pi, 0] / [0, pi]),
+	 * mMaxFrictionTorque; the motor is off and the limits have no spring */
+	float    hinge_axis1[3], hinge_axis2[3];
+	float    inv_initial_orientation[4];
+	float    limits_min, limits_max, max_friction_torque;
 } b2j_constraint_desc;
 
 /* What Constraint::SaveState writes plus what the distance constraint keeps between steps (DistanceConstraint.cpp:200-214): the
- * accumulated impulses the next step warm starts from (point: xyz, distance: x) and mWorldSpaceNormal. */
-typedef struct b2j_constraint_state { float total_lambda[3]; float world_space_normal[3]; } b2j_constraint_state;
+ * accumulated impulses the next step warm starts from and mWorldSpaceNormal. */
+typedef struct b2j_constraint_state
+{
+	float total_lambda[3];           /* point / hinge: mPointConstraintPart (xyz); distance: mAxisConstraint (x)  */
+	float world_space_normal[3];     /* distance: mWorldSpaceNormal                                                */
+	float total_lambda_rotation[2];  /* hinge: mRotationConstraintPart                                             */
+	float total_lambda_limits;       /* hinge: mRotationLimitsConstraintPart                                       */
+	float total_lambda_motor;        /* hinge: mMotorConstraintPart (the friction while the motor is off)          */
+} b2j_constraint_state;
 
 int      b2j_constraints_add(b2j_world *w, const b2j_constraint_desc *constraints, uint32_t n);
 int      b2j_constraints_remove(b2j_world *w, const uint32_t *indices, uint32_t n);       /* each index as of the removals before it */

@@ -51,6 +51,9 @@ struct Vec3
 	float Dot(const Vec3 &b) const { return (x * b.x + y * b.y) + (z * b.z + 0.0f); }
 	float LengthSq() const { return Dot(*this); }
 	float Length() const { return std::sqrt(LengthSq()); }
+	Vec3 Normalized() const { float l = Length(); return Vec3(x / l, y / l, z / l); } // *this / Length()
+	bool operator==(const Vec3 &o) const { return x == o.x && y == o.y && z == o.z; }
+	static Vec3 sAxisX() { return Vec3(1, 0, 0); } static Vec3 sAxisY() { return Vec3(0, 1, 0); } static Vec3 sAxisZ() { return Vec3(0, 0, 1); }
 };
 using RVec3 = Vec3;
 inline Vec3 operator*(float s, const Vec3 &v) { return Vec3(s * v.x, s * v.y, s * v.z); }
@@ -150,7 +153,16 @@ struct Mat44RT
 		return m;
 	}
 	static Mat44RT sRotation(const Quat &q) { return sRotationTranslation(q, Vec3::sZero()); }
+	// Mat44::sInverseRotationTranslation (Mat44.inl:206-211): rotation by the conjugate, translation = -(R^-1 t)
+	static Mat44RT sInverseRotationTranslation(const Quat &q, const Vec3 &inT)
+	{
+		Mat44RT m = sRotation(Quat(-q.x, -q.y, -q.z, q.w));
+		m.t = -((m.c0 * inT.x + m.c1 * inT.y) + m.c2 * inT.z);
+		return m;
+	}
 	Vec3 operator*(const Vec3 &v) const { return ((c0 * v.x + c1 * v.y) + c2 * v.z) + t; } // Mat44 * Vec3 (Mat44.inl:386-391)
+	Vec3 Multiply3x3(const Vec3 &v) const { return (c0 * v.x + c1 * v.y) + c2 * v.z; }
+	inline Quat GetQuaternion() const;
 	Vec3 GetTranslation() const { return t; }
 	Vec3 GetColumn3(int i) const { return i == 0? c0 : (i == 1? c1 : c2); }
 	Vec3 GetAxisX() const { return c0; } Vec3 GetAxisY() const { return c1; } Vec3 GetAxisZ() const { return c2; }
@@ -164,6 +176,33 @@ struct Mat44RT
 		return r;
 	}
 };
+
+// Mat44::GetQuaternion (Mat44.inl:998-1053)
+inline Quat Mat44RT::GetQuaternion() const
+{
+	float tr = c0.x + c1.y + c2.z;
+	if (tr >= 0.0f)
+	{
+		float s = std::sqrt(tr + 1.0f), is = 0.5f / s;
+		return Quat((c1.z - c2.y) * is, (c2.x - c0.z) * is, (c0.y - c1.x) * is, 0.5f * s);
+	}
+	int i = 0;
+	if (c1.y > c0.x) i = 1;
+	float diag[3] = { c0.x, c1.y, c2.z };
+	if (c2.z > diag[i]) i = 2;
+	if (i == 0)
+	{
+		float s = std::sqrt(c0.x - (c1.y + c2.z) + 1.0f), is = 0.5f / s;
+		return Quat(0.5f * s, (c1.x + c0.y) * is, (c0.z + c2.x) * is, (c1.z - c2.y) * is);
+	}
+	if (i == 1)
+	{
+		float s = std::sqrt(c1.y - (c2.z + c0.x) + 1.0f), is = 0.5f / s;
+		return Quat((c1.x + c0.y) * is, 0.5f * s, (c2.y + c1.z) * is, (c2.x - c0.z) * is);
+	}
+	float s = std::sqrt(c2.z - (c0.x + c1.y) + 1.0f), is = 0.5f / s;
+	return Quat((c0.z + c2.x) * is, (c2.y + c1.z) * is, 0.5f * s, (c0.y - c1.x) * is);
+}
 
 using Mat44 = Mat44RT;
 using RMat44 = Mat44RT;
@@ -1068,6 +1107,196 @@ public:
 	bool mHasMotionProperties = false;
 };
 
+// ---- non contact constraints: PointConstraint / DistanceConstraint with the reference's settings classes ---------------
+// (Jolt/Physics/Constraints/Constraint.h, TwoBodyConstraint.h, PointConstraint.h, DistanceConstraint.h). A constraint is created from
+// its settings and two bodies, handed to PhysicsSystem::AddConstraint (which owns it from then on, like the reference's Ref<Constraint>)
+// and lives on the device as one entry of the world's constraint list (b2j_constraints_add).
+enum class EConstraintSpace { LocalToBodyCOM, WorldSpace };
+enum class EConstraintSubType { Point = B2J_CONSTRAINT_POINT, Distance = B2J_CONSTRAINT_DISTANCE, Hinge = B2J_CONSTRAINT_HINGE };
+
+class Constraint
+{
+public:
+	virtual ~Constraint() = default;
+	virtual EConstraintSubType GetSubType() const = 0;
+	void SetConstraintPriority(uint32 inPriority) { mDesc.priority = inPriority; Changed(); }
+	uint32 GetConstraintPriority() const { return mDesc.priority; }
+	void SetNumVelocityStepsOverride(uint inN) { mDesc.num_velocity_steps_override = (uint8)inN; Changed(); }
+	uint GetNumVelocityStepsOverride() const { return mDesc.num_velocity_steps_override; }
+	void SetNumPositionStepsOverride(uint inN) { mDesc.num_position_steps_override = (uint8)inN; Changed(); }
+	uint GetNumPositionStepsOverride() const { return mDesc.num_position_steps_override; }
+	inline void SetEnabled(bool inEnabled);
+	bool GetEnabled() const { return mDesc.enabled != 0; }
+	static constexpr uint32 cInvalidConstraintIndex = 0xffffffffu;
+protected:
+	friend class PhysicsSystem;
+	Constraint() { memset(&mDesc, 0, sizeof(mDesc)); mDesc.enabled = 1; }
+	// (priority / step overrides of a constraint that is already in a system are fixed: set them before AddConstraint, as the scenes do)
+	void Changed() { }
+	b2j_constraint_desc mDesc;
+	uint32 mConstraintIndex = cInvalidConstraintIndex;
+	PhysicsSystem *mSystem = nullptr;
+};
+
+class TwoBodyConstraint : public Constraint
+{
+public:
+	Body *GetBody1() const { return mBody1; }
+	Body *GetBody2() const { return mBody2; }
+protected:
+	TwoBodyConstraint(Body &inBody1, Body &inBody2) : mBody1(&inBody1), mBody2(&inBody2) { mDesc.body1 = inBody1.GetID().mID; mDesc.body2 = inBody2.GetID().mID; }
+	// the constructors of PointConstraint / DistanceConstraint: world space points are taken to the space of the bodies' centres of mass
+	void SetPoints(EConstraintSpace inSpace, const RVec3 &inPoint1, const RVec3 &inPoint2, RVec3 &outWorld1, RVec3 &outWorld2)
+	{
+		Vec3 l1, l2;
+		if (inSpace == EConstraintSpace::WorldSpace)
+		{
+			l1 = Mat44RT::sInverseRotationTranslation(mBody1->GetRotation(), mBody1->GetCenterOfMassPosition()) * inPoint1;
+			l2 = Mat44RT::sInverseRotationTranslation(mBody2->GetRotation(), mBody2->GetCenterOfMassPosition()) * inPoint2;
+			outWorld1 = inPoint1; outWorld2 = inPoint2;
+		}
+		else
+		{
+			l1 = inPoint1; l2 = inPoint2;
+			outWorld1 = Mat44RT::sRotationTranslation(mBody1->GetRotation(), mBody1->GetCenterOfMassPosition()) * inPoint1;
+			outWorld2 = Mat44RT::sRotationTranslation(mBody2->GetRotation(), mBody2->GetCenterOfMassPosition()) * inPoint2;
+		}
+		mDesc.point1[0] = l1.x; mDesc.point1[1] = l1.y; mDesc.point1[2] = l1.z;
+		mDesc.point2[0] = l2.x; mDesc.point2[1] = l2.y; mDesc.point2[2] = l2.z;
+	}
+	Body *mBody1, *mBody2;
+};
+
+class TwoBodyConstraintSettings
+{
+public:
+	virtual ~TwoBodyConstraintSettings() = default;
+	virtual TwoBodyConstraint *Create(Body &inBody1, Body &inBody2) const = 0;
+	uint32 mConstraintPriority = 0;
+	uint mNumVelocityStepsOverride = 0, mNumPositionStepsOverride = 0;
+	bool mEnabled = true;
+};
+
+class PointConstraintSettings;
+class PointConstraint final : public TwoBodyConstraint
+{
+public:
+	inline PointConstraint(Body &inBody1, Body &inBody2, const PointConstraintSettings &inSettings);
+	EConstraintSubType GetSubType() const override { return EConstraintSubType::Point; }
+	Vec3 GetLocalSpacePoint1() const { return Vec3(mDesc.point1[0], mDesc.point1[1], mDesc.point1[2]); }
+	Vec3 GetLocalSpacePoint2() const { return Vec3(mDesc.point2[0], mDesc.point2[1], mDesc.point2[2]); }
+	inline Vec3 GetTotalLambdaPosition() const;
+};
+class PointConstraintSettings final : public TwoBodyConstraintSettings
+{
+public:
+	TwoBodyConstraint *Create(Body &inBody1, Body &inBody2) const override { return new PointConstraint(inBody1, inBody2, *this); }
+	EConstraintSpace mSpace = EConstraintSpace::WorldSpace;
+	RVec3 mPoint1 = RVec3::sZero(), mPoint2 = RVec3::sZero();
+};
+
+class DistanceConstraintSettings;
+class DistanceConstraint final : public TwoBodyConstraint
+{
+public:
+	inline DistanceConstraint(Body &inBody1, Body &inBody2, const DistanceConstraintSettings &inSettings);
+	EConstraintSubType GetSubType() const override { return EConstraintSubType::Distance; }
+	float GetMinDistance() const { return mDesc.min_distance; }
+	float GetMaxDistance() const { return mDesc.max_distance; }
+	inline float GetTotalLambdaPosition() const;
+};
+class DistanceConstraintSettings final : public TwoBodyConstraintSettings
+{
+public:
+	TwoBodyConstraint *Create(Body &inBody1, Body &inBody2) const override { return new DistanceConstraint(inBody1, inBody2, *this); }
+	EConstraintSpace mSpace = EConstraintSpace::WorldSpace;
+	RVec3 mPoint1 = RVec3::sZero(), mPoint2 = RVec3::sZero();
+	float mMinDistance = -1.0f, mMaxDistance = -1.0f; // < 0: the distance at creation (DistanceConstraint.cpp:73-84)
+};
+
+inline PointConstraint::PointConstraint(Body &inBody1, Body &inBody2, const PointConstraintSettings &inSettings) : TwoBodyConstraint(inBody1, inBody2)
+{
+	mDesc.type = B2J_CONSTRAINT_POINT;
+	mDesc.priority = inSettings.mConstraintPriority; mDesc.enabled = inSettings.mEnabled;
+	mDesc.num_velocity_steps_override = (uint8)inSettings.mNumVelocityStepsOverride; mDesc.num_position_steps_override = (uint8)inSettings.mNumPositionStepsOverride;
+	RVec3 w1, w2;
+	SetPoints(inSettings.mSpace, inSettings.mPoint1, inSettings.mPoint2, w1, w2);
+}
+
+inline DistanceConstraint::DistanceConstraint(Body &inBody1, Body &inBody2, const DistanceConstraintSettings &inSettings) : TwoBodyConstraint(inBody1, inBody2)
+{
+	mDesc.type = B2J_CONSTRAINT_DISTANCE;
+	mDesc.priority = inSettings.mConstraintPriority; mDesc.enabled = inSettings.mEnabled;
+	mDesc.num_velocity_steps_override = (uint8)inSettings.mNumVelocityStepsOverride; mDesc.num_position_steps_override = (uint8)inSettings.mNumPositionStepsOverride;
+	RVec3 w1, w2;
+	SetPoints(inSettings.mSpace, inSettings.mPoint1, inSettings.mPoint2, w1, w2);
+	// DistanceConstraint.cpp:73-84
+	float distance = (w2 - w1).Length();
+	float mn = inSettings.mMinDistance, mx = inSettings.mMaxDistance;
+	if (mn < 0.0f && mx < 0.0f) { mDesc.min_distance = distance; mDesc.max_distance = distance; }
+	else
+	{
+		mDesc.min_distance = mn < 0.0f? std::min(distance, mx) : mn;
+		mDesc.max_distance = mx < 0.0f? std::max(distance, mn) : mx;
+	}
+}
+
+// HingeConstraint (HingeConstraint.h): rotation about one axis with optional angle limits and friction; the motor stays off and the
+// limits have no spring on this path
+class HingeConstraintSettings;
+class HingeConstraint final : public TwoBodyConstraint
+{
+public:
+	inline HingeConstraint(Body &inBody1, Body &inBody2, const HingeConstraintSettings &inSettings);
+	EConstraintSubType GetSubType() const override { return EConstraintSubType::Hinge; }
+	float GetLimitsMin() const { return mDesc.limits_min; }
+	float GetLimitsMax() const { return mDesc.limits_max; }
+	float GetMaxFrictionTorque() const { return mDesc.max_friction_torque; }
+	Vec3 GetLocalSpaceHingeAxis1() const { return Vec3(mDesc.hinge_axis1[0], mDesc.hinge_axis1[1], mDesc.hinge_axis1[2]); }
+	Vec3 GetLocalSpaceHingeAxis2() const { return Vec3(mDesc.hinge_axis2[0], mDesc.hinge_axis2[1], mDesc.hinge_axis2[2]); }
+};
+class HingeConstraintSettings final : public TwoBodyConstraintSettings
+{
+public:
+	TwoBodyConstraint *Create(Body &inBody1, Body &inBody2) const override { return new HingeConstraint(inBody1, inBody2, *this); }
+	EConstraintSpace mSpace = EConstraintSpace::WorldSpace;
+	RVec3 mPoint1 = RVec3::sZero(), mPoint2 = RVec3::sZero();
+	Vec3 mHingeAxis1 = Vec3::sAxisY(), mNormalAxis1 = Vec3::sAxisX(), mHingeAxis2 = Vec3::sAxisY(), mNormalAxis2 = Vec3::sAxisX();
+	float mLimitsMin = -3.14159265358979323846f, mLimitsMax = 3.14159265358979323846f;
+	float mMaxFrictionTorque = 0.0f;
+};
+
+inline HingeConstraint::HingeConstraint(Body &inBody1, Body &inBody2, const HingeConstraintSettings &inSettings) : TwoBodyConstraint(inBody1, inBody2)
+{
+	mDesc.type = B2J_CONSTRAINT_HINGE;
+	mDesc.priority = inSettings.mConstraintPriority; mDesc.enabled = inSettings.mEnabled;
+	mDesc.num_velocity_steps_override = (uint8)inSettings.mNumVelocityStepsOverride; mDesc.num_position_steps_override = (uint8)inSettings.mNumPositionStepsOverride;
+	mDesc.limits_min = inSettings.mLimitsMin; mDesc.limits_max = inSettings.mLimitsMax; mDesc.max_friction_torque = inSettings.mMaxFrictionTorque;
+	// RotationEulerConstraintPart::sGetInvInitialOrientationXZ(normal 1, hinge 1, normal 2, hinge 2)
+	Quat inv_initial = Quat::sIdentity();
+	if (!(inSettings.mNormalAxis1 == inSettings.mNormalAxis2 && inSettings.mHingeAxis1 == inSettings.mHingeAxis2))
+	{
+		Mat44RT constraint1, constraint2;
+		constraint1.c0 = inSettings.mNormalAxis1; constraint1.c1 = inSettings.mHingeAxis1.Cross(inSettings.mNormalAxis1); constraint1.c2 = inSettings.mHingeAxis1;
+		constraint2.c0 = inSettings.mNormalAxis2; constraint2.c1 = inSettings.mHingeAxis2.Cross(inSettings.mNormalAxis2); constraint2.c2 = inSettings.mHingeAxis2;
+		Quat q1 = constraint1.GetQuaternion();
+		inv_initial = constraint2.GetQuaternion() * Quat(-q1.x, -q1.y, -q1.z, q1.w);
+	}
+	RVec3 w1, w2;
+	SetPoints(inSettings.mSpace, inSettings.mPoint1, inSettings.mPoint2, w1, w2);
+	Vec3 a1 = inSettings.mHingeAxis1, a2 = inSettings.mHingeAxis2;
+	if (inSettings.mSpace == EConstraintSpace::WorldSpace)
+	{
+		Quat r1 = inBody1.GetRotation(), r2 = inBody2.GetRotation();
+		a1 = Mat44RT::sInverseRotationTranslation(r1, inBody1.GetCenterOfMassPosition()).Multiply3x3(inSettings.mHingeAxis1).Normalized();
+		a2 = Mat44RT::sInverseRotationTranslation(r2, inBody2.GetCenterOfMassPosition()).Multiply3x3(inSettings.mHingeAxis2).Normalized();
+		inv_initial = (Quat(-r2.x, -r2.y, -r2.z, r2.w) * inv_initial) * r1;
+	}
+	mDesc.hinge_axis1[0] = a1.x; mDesc.hinge_axis1[1] = a1.y; mDesc.hinge_axis1[2] = a1.z;
+	mDesc.hinge_axis2[0] = a2.x; mDesc.hinge_axis2[1] = a2.y; mDesc.hinge_axis2[2] = a2.z;
+	mDesc.inv_initial_orientation[0] = inv_initial.x; mDesc.inv_initial_orientation[1] = inv_initial.y; mDesc.inv_initial_orientation[2] = inv_initial.z; mDesc.inv_initial_orientation[3] = inv_initial.w;
+}
+
 class ContactListener
 {
 public:
@@ -1220,6 +1449,7 @@ public:
 	~PhysicsSystem()
 	{
 		if (mStateRegistered) { b2j_host_buffer_unregister(mPos.data()); b2j_host_buffer_unregister(mRot.data()); b2j_host_buffer_unregister(mLin.data()); b2j_host_buffer_unregister(mAng.data()); b2j_host_buffer_unregister(mActiveIndex.data()); }
+		for (Constraint *c : mConstraints) delete c;
 		if (mWorld) b2j_world_destroy(mWorld);
 	}
 	PhysicsSystem(const PhysicsSystem &) = delete;
@@ -1307,11 +1537,56 @@ public:
 		return true;
 	}
 
+	// PhysicsSystem::AddConstraint(s) / RemoveConstraint(s) / GetConstraints (PhysicsSystem.h:128-140). The system owns a constraint from
+	// AddConstraint to RemoveConstraint (which deletes it: the facade has no reference counting).
+	void AddConstraint(Constraint *inConstraint) { AddConstraints(&inConstraint, 1); }
+	void AddConstraints(Constraint **inConstraints, int inNumber)
+	{
+		for (int i = 0; i < inNumber; ++i)
+		{
+			Constraint *c = inConstraints[i];
+			c->mSystem = this;
+			c->mConstraintIndex = (uint32)mConstraints.size(); // ConstraintManager::Add
+			mConstraints.push_back(c);
+		}
+	}
+	void RemoveConstraint(Constraint *inConstraint) { RemoveConstraints(&inConstraint, 1); }
+	void RemoveConstraints(Constraint **inConstraints, int inNumber)
+	{
+		for (int i = 0; i < inNumber; ++i)
+		{
+			Constraint *c = inConstraints[i];
+			uint32 index = c->mConstraintIndex, last = (uint32)mConstraints.size() - 1;
+			if (index < mNumUploadedConstraints)
+			{
+				// on the device already: flush the additions first so that both lists hold the same entries, then remove there too
+				FlushConstraints();
+				b2j_constraints_remove(mWorld, &index, 1);
+				--mNumUploadedConstraints;
+			}
+			// ConstraintManager::Remove: the last constraint takes the freed index
+			if (index < last) { mConstraints[index] = mConstraints[last]; mConstraints[index]->mConstraintIndex = index; }
+			mConstraints.pop_back();
+			delete c;
+		}
+	}
+	const std::vector<Constraint *> &GetConstraints() const { return mConstraints; }
+	// constraints added since the last flush go to the device after their bodies (BodyInterface::Flush)
+	void FlushConstraints()
+	{
+		if (mNumUploadedConstraints == mConstraints.size()) return;
+		mBodyInterface.Flush();
+		std::vector<b2j_constraint_desc> descs;
+		for (size_t i = mNumUploadedConstraints; i < mConstraints.size(); ++i) descs.push_back(mConstraints[i]->mDesc);
+		if (b2j_constraints_add(mWorld, descs.data(), (uint32)descs.size()) == 0) mNumUploadedConstraints = (uint32)mConstraints.size();
+	}
+
 	// PhysicsSystem::Update (PhysicsSystem.h:162): uploads pending API mutations, runs the step on the GPU, mirrors the body state
 	// back to the host and replays contact / activation events into the listeners on the calling thread.
 	EPhysicsUpdateError Update(float inDeltaTime, int inCollisionSteps, TempAllocator *, JobSystem *)
 	{
 		mBodyInterface.Flush();
+		FlushConstraints();
 		int r = b2j_step(mWorld, inDeltaTime, inCollisionSteps, &mStats);
 		if (r < 0)
 			return EPhysicsUpdateError(0x80000000u);
@@ -1351,6 +1626,12 @@ private:
 		mShapes.push_back(inShape); mShapeIDs.push_back(id);
 		return id;
 	}
+
+	std::vector<Constraint *> mConstraints;   // by Constraint::mConstraintIndex
+	uint32 mNumUploadedConstraints = 0;
+	friend class Constraint;
+	friend class PointConstraint;
+	friend class DistanceConstraint;
 
 	// query shapes are kept alive by the caller (raw pointers, as the reference takes them); a scale other than one uploads a ScaledShape
 	struct QueryShape { const Shape *shape; Vec3 scale; int32_t id; };
@@ -1593,6 +1874,32 @@ private:
 	std::vector<b2j_activation_event> mActEvents;
 };
 
+inline void Constraint::SetEnabled(bool inEnabled)
+{
+	mDesc.enabled = inEnabled;
+	if (mSystem != nullptr && mConstraintIndex < mSystem->mNumUploadedConstraints)
+	{
+		uint8_t e = inEnabled;
+		b2j_constraints_set_enabled(mSystem->mWorld, &mConstraintIndex, 1, &e);
+	}
+}
+
+inline Vec3 PointConstraint::GetTotalLambdaPosition() const
+{
+	b2j_constraint_state st;
+	memset(&st, 0, sizeof(st));
+	if (mSystem != nullptr && mConstraintIndex < mSystem->mNumUploadedConstraints) b2j_constraints_get_state(mSystem->mWorld, mConstraintIndex, 1, &st);
+	return Vec3(st.total_lambda[0], st.total_lambda[1], st.total_lambda[2]);
+}
+
+inline float DistanceConstraint::GetTotalLambdaPosition() const
+{
+	b2j_constraint_state st;
+	memset(&st, 0, sizeof(st));
+	if (mSystem != nullptr && mConstraintIndex < mSystem->mNumUploadedConstraints) b2j_constraints_get_state(mSystem->mWorld, mConstraintIndex, 1, &st);
+	return st.total_lambda[0];
+}
+
 inline void NarrowPhaseQuery::CastRays(const RRayCast *inRays, int inNumber, RayCastResult *outHits, uint32 inObjectLayer) const
 {
 	if (inNumber <= 0) return;
@@ -1686,37 +1993,7 @@ inline void NarrowPhaseQuery::CollideShape(const Shape *inShape, const Vec3 &inS
 inline void NarrowPhaseQuery::CollideShape(const Shape *inShape, const Vec3 &inShapeScale, const RMat44 &inCenterOfMassTransform, const CollideShapeSettings &inSettings,
 	const RVec3 &inBaseOffset, std::vector<CollideShapeResult> &outHits, uint32 inObjectLayer) const
 {
-	// Mat44::GetQuaternion (Mat44.inl:741-783)
-	const Vec3 &c0 = inCenterOfMassTransform.c0, &c1 = inCenterOfMassTransform.c1, &c2 = inCenterOfMassTransform.c2;
-	float tr = c0.x + c1.y + c2.z;
-	Quat q;
-	if (tr >= 0.0f)
-	{
-		float s = std::sqrt(tr + 1.0f), is = 0.5f / s;
-		q = Quat((c1.z - c2.y) * is, (c2.x - c0.z) * is, (c0.y - c1.x) * is, 0.5f * s);
-	}
-	else
-	{
-		int i = 0;
-		if (c1.y > c0.x) i = 1;
-		float diag[3] = { c0.x, c1.y, c2.z };
-		if (c2.z > diag[i]) i = 2;
-		if (i == 0)
-		{
-			float s = std::sqrt(c0.x - (c1.y + c2.z) + 1.0f), is = 0.5f / s;
-			q = Quat(0.5f * s, (c1.x + c0.y) * is, (c0.z + c2.x) * is, (c1.z - c2.y) * is);
-		}
-		else if (i == 1)
-		{
-			float s = std::sqrt(c1.y - (c2.z + c0.x) + 1.0f), is = 0.5f / s;
-			q = Quat((c1.x + c0.y) * is, 0.5f * s, (c2.y + c1.z) * is, (c2.x - c0.z) * is);
-		}
-		else
-		{
-			float s = std::sqrt(c2.z - (c0.x + c1.y) + 1.0f), is = 0.5f / s;
-			q = Quat((c0.z + c2.x) * is, (c2.y + c1.z) * is, 0.5f * s, (c0.y - c1.x) * is);
-		}
-	}
+	Quat q = inCenterOfMassTransform.GetQuaternion();
 	CollideShape(inShape, inShapeScale, q, inCenterOfMassTransform.t, inSettings, inBaseOffset, outHits, inObjectLayer);
 }
 

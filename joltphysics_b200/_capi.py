@@ -169,6 +169,12 @@ PROTOTYPES = {
     "b2j_world_set_event_recording": (C.c_int, [_VP, C.c_int, C.c_int]),
     "b2j_query_cast_rays": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, _VP]),
     "b2j_query_collide_aabox": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP]),
+    "b2j_constraints_add": (C.c_int, [_VP, _VP, C.c_uint32]),
+    "b2j_constraints_remove": (C.c_int, [_VP, _VP, C.c_uint32]),
+    "b2j_num_constraints": (C.c_uint32, [_VP]),
+    "b2j_constraints_set_enabled": (C.c_int, [_VP, _VP, C.c_uint32, _VP]),
+    "b2j_constraints_get_state": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP]),
+    "b2j_constraints_set_state": (C.c_int, [_VP, C.c_uint32, C.c_uint32, _VP]),
     "b2j_query_collide_sphere": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP]),
     "b2j_query_collide_point": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP]),
     "b2j_query_collide_shape": (C.c_int, [_VP, _VP, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, _VP, _VP]),

@@ -7,6 +7,9 @@
 //   TwoBodyConstraint::IsActive / BuildIslands / BuildIslandSplits   TwoBodyConstraint.h:38, TwoBodyConstraint.cpp:17-57
 //   PointConstraint                                   PointConstraint.cpp:70-118, ConstraintPart/PointConstraintPart.h:50-237
 //   DistanceConstraint                                DistanceConstraint.cpp:98-198, ConstraintPart/AxisConstraintPart.h:60-485 (no springs)
+//   HingeConstraint (motor off, limits without spring) HingeConstraint.cpp:137-318, ConstraintPart/HingeRotationConstraintPart.h:44-190,
+//                                                     ConstraintPart/AngleConstraintPart.h:38-215, Quat::GetRotationAngle Quat.h:197,
+//                                                     Vec4::ATan Vec4.inl (cephes atanf), CenterAngleAroundZero Math.h:28-44
 //   where the step calls them                         PhysicsSystem.cpp:720-744 (active constraints), :795-828 (setup, islands: bodies a
 //                                                     constraint wakes up join the active list but get no gravity this step, :746-791),
 //                                                     :1415-1427, :1503-1540 (warm start, velocity), :2596-2603, :2661-2672 (position)
@@ -24,7 +27,7 @@
 
 namespace b2j {
 
-enum { JOINT_POINT = B2J_CONSTRAINT_POINT, JOINT_DISTANCE = B2J_CONSTRAINT_DISTANCE };
+enum { JOINT_POINT = B2J_CONSTRAINT_POINT, JOINT_DISTANCE = B2J_CONSTRAINT_DISTANCE, JOINT_HINGE = B2J_CONSTRAINT_HINGE };
 enum : uint32_t { JOINT_ENABLED = 1u, SRC_JOINT = 0x80000000u };
 
 // what the caller described (b2j_constraint_desc) with the bodies resolved to slots
@@ -34,6 +37,9 @@ struct alignas(16) JointDef
 	uint32_t priority, steps_override;     // velocity steps override | position steps override << 8
 	uint32_t index, pad;                   // Constraint::mConstraintIndex (position in the world's list)
 	F4 local1, local2;                     // mLocalSpacePosition1 / 2 (relative to the centre of mass); local1.w = min distance, local2.w = max distance
+	F4 axis1, axis2;                       // hinge: mLocalSpaceHingeAxis1 / 2; axis1.w = mLimitsMin, axis2.w = mLimitsMax
+	F4 inv_initial_orientation;            // hinge: mInvInitialOrientation
+	F4 hinge;                              // hinge: x = mMaxFrictionTorque
 };
 
 // the members of the reference's constraint objects that live across kernels (and, the first two, across steps)
@@ -45,6 +51,14 @@ struct alignas(16) JointState
 	F4 r1, r2;                             // point: mR1, mR2; distance: mR1PlusUxAxis, mR2xAxis, r1.w = mEffectiveMass
 	F4 i1[3], i2[3];                       // point: columns of mInvI1_R1X / mInvI2_R2X; distance: [0] = mInvI1_R1PlusUxAxis / mInvI2_R2xAxis
 	F4 eff[3];                             // point: columns of mEffectiveMass
+	// hinge (its point part uses the members above)
+	F4 lambda2;                            // x, y: mRotationConstraintPart.mTotalLambda, z: mRotationLimitsConstraintPart, w: mMotorConstraintPart
+	F4 h_a1, h_b2, h_c2;                   // rotation part mA1, mB2, mC2; h_a1.w = mTheta, h_b2.w = limits effective mass, h_c2.w = motor effective mass
+	F4 h_b2xa1, h_c2xa1;
+	F4 h_inv1[3], h_inv2[3];               // rotation part mInvI1 / mInvI2
+	F4 h_eff;                              // rotation part mEffectiveMass: (0,0), (0,1), (1,0), (1,1)
+	F4 h_axis;                             // HingeConstraint::mA1 (world space hinge axis of body 1)
+	F4 h_l1, h_l2, h_m1, h_m2;             // limits / motor part mInvI1_Axis, mInvI2_Axis
 };
 
 struct JointCtx
@@ -235,12 +249,282 @@ B2J_D bool axis_apply_velocity_step(const DWorld &w, const JointState &s, const 
 	return true;
 }
 
+// ---- HingeConstraint ------------------------------------------------------------------------------------------------------------------
+// Vec4::ATan (cephes atanf) for one lane
+B2J_HD float jolt_atan(float in)
+{
+	uint32_t bits; memcpy(&bits, &in, 4);
+	uint32_t sign = bits & 0x80000000u;
+	bits ^= sign;
+	float x; memcpy(&x, &bits, 4);
+	float y = 0.0f;
+	bool greater1 = x > 0.4142135623730950f, greater2 = x > 2.414213562373095f;
+	float x1 = (x - 1.0f) / (x + 1.0f), x2 = -1.0f / x;
+	if (greater1) { x = x1; y = 0.25f * 3.14159265358979323846f; }
+	if (greater2) { x = x2; y = 0.5f * 3.14159265358979323846f; }
+	float z = x * x;
+	y += (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x;
+	uint32_t ybits; memcpy(&ybits, &y, 4);
+	ybits ^= sign;
+	memcpy(&y, &ybits, 4);
+	return y;
+}
+
+B2J_HD float center_angle_around_zero(float v)
+{
+	const float pi = 3.14159265358979323846f;
+	if (v < -pi) { do v += 2.0f * pi; while (v < -pi); }
+	else if (v > pi) { do v -= 2.0f * pi; while (v > pi); }
+	return v;
+}
+
+B2J_D M33 joint_inverse_inertia(const JointBody &b, const M33 &rotation) { return b.type == B2J_MOTION_DYNAMIC? inverse_inertia_for_rotation(rotation, b.irot, b.diag, b.dofs) : m33_zero(); }
+
+// HingeRotationConstraintPart::CalculateConstraintProperties
+B2J_D void hinge_rotation_calculate(JointState &s, const JointBody &b1, const M33 &rotation1, V3 axis1, const JointBody &b2, const M33 &rotation2, V3 axis2)
+{
+	V3 a1 = axis1, a2 = axis2;
+	float d = dot(a1, a2);
+	if (d <= 1.0e-3f)
+	{
+		V3 perp = a2 - d * a1;
+		if (length_sq(perp) < 1.0e-6f)
+			perp = normalized_perpendicular(a1);
+		a2 = normalized(0.99f * normalized(perp) + 0.01f * a1);
+	}
+	V3 b2v = normalized_perpendicular(a2);
+	V3 c2v = cross(a2, b2v);
+	M33 inv1 = joint_inverse_inertia(b1, rotation1), inv2 = joint_inverse_inertia(b2, rotation2);
+	V3 b2xa1 = cross(b2v, a1), c2xa1 = cross(c2v, a1);
+	M33 summed = m33_add(inv1, inv2);
+	float m00 = dot(b2xa1, mul(summed, b2xa1)), m01 = dot(b2xa1, mul(summed, c2xa1));
+	float m10 = dot(c2xa1, mul(summed, b2xa1)), m11 = dot(c2xa1, mul(summed, c2xa1));
+	// Matrix<2, 2>::SetInversed
+	float det = m00 * m11 - m01 * m10;
+	if (det == 0.0f)
+	{
+		s.h_eff = f4(0.0f, 0.0f, 0.0f, 0.0f);
+		s.lambda2.x = 0.0f; s.lambda2.y = 0.0f;
+	}
+	else
+		s.h_eff = f4(m11 / det, -m01 / det, -m10 / det, m00 / det);
+	s.h_a1 = f4(a1, s.h_a1.w); s.h_b2 = f4(b2v, s.h_b2.w); s.h_c2 = f4(c2v, s.h_c2.w);
+	s.h_b2xa1 = f4(b2xa1); s.h_c2xa1 = f4(c2xa1);
+	s.h_inv1[0] = f4(inv1.c0); s.h_inv1[1] = f4(inv1.c1); s.h_inv1[2] = f4(inv1.c2);
+	s.h_inv2[0] = f4(inv2.c0); s.h_inv2[1] = f4(inv2.c1); s.h_inv2[2] = f4(inv2.c2);
+}
+
+B2J_D bool hinge_rotation_apply(const DWorld &w, const JointState &s, const JointBody &b1, const JointBody &b2, float l0, float l1)
+{
+	if (l0 == 0.0f && l1 == 0.0f)
+		return false;
+	V3 impulse = to_v3(s.h_b2xa1) * l0 + to_v3(s.h_c2xa1) * l1;
+	if (b1.type == B2J_MOTION_DYNAMIC)
+		w.angular_velocity[b1.slot] = f4(to_v3(w.angular_velocity[b1.slot]) - mul(m33(to_v3(s.h_inv1[0]), to_v3(s.h_inv1[1]), to_v3(s.h_inv1[2])), impulse));
+	if (b2.type == B2J_MOTION_DYNAMIC)
+		w.angular_velocity[b2.slot] = f4(to_v3(w.angular_velocity[b2.slot]) + mul(m33(to_v3(s.h_inv2[0]), to_v3(s.h_inv2[1]), to_v3(s.h_inv2[2])), impulse));
+	return true;
+}
+
+// AngleConstraintPart::CalculateConstraintProperties (bias 0, no spring): returns the effective mass (0 = Deactivate)
+B2J_D float angle_calculate(const JointBody &b1, const JointBody &b2, V3 axis, F4 &out_i1, F4 &out_i2)
+{
+	V3 i1 = b1.type == B2J_MOTION_DYNAMIC? multiply_ws_inverse_inertia(b1.q, b1.irot, b1.diag, b1.dofs, axis) : v3_zero();
+	V3 i2 = b2.type == B2J_MOTION_DYNAMIC? multiply_ws_inverse_inertia(b2.q, b2.irot, b2.diag, b2.dofs, axis) : v3_zero();
+	out_i1 = f4(i1); out_i2 = f4(i2);
+	float inv_effective_mass = dot(axis, i1 + i2);
+	return inv_effective_mass == 0.0f? 0.0f : 1.0f / inv_effective_mass;
+}
+
+B2J_D bool angle_apply(const DWorld &w, const JointBody &b1, const JointBody &b2, F4 i1, F4 i2, float lambda)
+{
+	if (lambda == 0.0f)
+		return false;
+	if (b1.type == B2J_MOTION_DYNAMIC) w.angular_velocity[b1.slot] = f4(to_v3(w.angular_velocity[b1.slot]) - lambda * to_v3(i1));
+	if (b2.type == B2J_MOTION_DYNAMIC) w.angular_velocity[b2.slot] = f4(to_v3(w.angular_velocity[b2.slot]) + lambda * to_v3(i2));
+	return true;
+}
+
+// AngleConstraintPart::SolveVelocityConstraint
+B2J_D void angle_solve_velocity(const DWorld &w, const JointBody &b1, const JointBody &b2, V3 axis, float eff, F4 i1, F4 i2, float &total, float min_lambda, float max_lambda)
+{
+	float lambda = eff * (dot(axis, joint_angular_velocity(w, b1) - joint_angular_velocity(w, b2)) - 0.0f);
+	float new_lambda = clamp_(total + lambda, min_lambda, max_lambda);
+	lambda = new_lambda - total;
+	total = new_lambda;
+	angle_apply(w, b1, b2, i1, i2, lambda);
+}
+
+B2J_HD bool hinge_has_limits(const JointDef &d) { const float pi = 3.14159265358979323846f; return d.axis1.w > -pi || d.axis2.w < pi; }
+B2J_HD float hinge_smallest_angle_to_limit(const JointDef &d, float theta)
+{
+	float dist_to_min = center_angle_around_zero(theta - d.axis1.w), dist_to_max = center_angle_around_zero(theta - d.axis2.w);
+	return fabs_(dist_to_min) < fabs_(dist_to_max)? dist_to_min : dist_to_max;
+}
+B2J_HD bool hinge_is_min_limit_closest(const JointDef &d, float theta)
+{
+	float dist_to_min = center_angle_around_zero(theta - d.axis1.w), dist_to_max = center_angle_around_zero(theta - d.axis2.w);
+	return fabs_(dist_to_min) < fabs_(dist_to_max);
+}
+
+// CalculateA1AndTheta + CalculateRotationLimitsConstraintProperties
+B2J_D void hinge_limits_calculate(const JointDef &d, JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	bool has_limits = hinge_has_limits(d);
+	if (has_limits || d.hinge.x > 0.0f)
+	{
+		Q4 diff = (b2.q * to_q4(d.inv_initial_orientation)) * q4_conj(b1.q);
+		V3 a1 = rotate(b1.q, to_v3(d.axis1));
+		s.h_axis = f4(a1);
+		// Quat::GetRotationAngle
+		s.h_a1.w = diff.w == 0.0f? 3.14159265358979323846f : 2.0f * jolt_atan(dot(q4_xyz(diff), a1) / diff.w);
+	}
+	float theta = s.h_a1.w;
+	if (has_limits && (theta <= d.axis1.w || theta >= d.axis2.w))
+		s.h_b2.w = angle_calculate(b1, b2, to_v3(s.h_axis), s.h_l1, s.h_l2);
+	else
+		s.h_b2.w = 0.0f;
+	if (s.h_b2.w == 0.0f)
+		s.lambda2.z = 0.0f; // Deactivate()
+}
+
+B2J_D void hinge_setup(const DWorld &w, const JointDef &d, JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	M33 rotation1 = m33_rotation(b1.q), rotation2 = m33_rotation(b2.q);
+	point_calculate(w, d, s, b1, b2);
+	hinge_rotation_calculate(s, b1, rotation1, mul(rotation1, to_v3(d.axis1)), b2, rotation2, mul(rotation2, to_v3(d.axis2)));
+	hinge_limits_calculate(d, s, b1, b2);
+	// CalculateMotorConstraintProperties, EMotorState::Off: friction
+	if (d.hinge.x > 0.0f)
+		s.h_c2.w = angle_calculate(b1, b2, to_v3(s.h_axis), s.h_m1, s.h_m2);
+	else
+		s.h_c2.w = 0.0f;
+	if (s.h_c2.w == 0.0f)
+		s.lambda2.w = 0.0f;
+}
+
+B2J_D void hinge_warm_start(const DWorld &w, const JointDef &d, JointState &s, const JointBody &b1, const JointBody &b2, float ratio)
+{
+	s.lambda2.w *= ratio;
+	angle_apply(w, b1, b2, s.h_m1, s.h_m2, s.lambda2.w);
+	V3 lambda = to_v3(s.lambda) * ratio;
+	s.lambda = f4(lambda);
+	point_apply_velocity_step(w, s, b1, b2, lambda);
+	s.lambda2.x *= ratio; s.lambda2.y *= ratio;
+	hinge_rotation_apply(w, s, b1, b2, s.lambda2.x, s.lambda2.y);
+	s.lambda2.z *= ratio;
+	angle_apply(w, b1, b2, s.h_l1, s.h_l2, s.lambda2.z);
+}
+
+B2J_D V3 point_velocity_lambda(const DWorld &w, const JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	V3 v1 = joint_linear_velocity(w, b1), w1 = joint_angular_velocity(w, b1), v2 = joint_linear_velocity(w, b2), w2 = joint_angular_velocity(w, b2);
+	M33 eff = m33(to_v3(s.eff[0]), to_v3(s.eff[1]), to_v3(s.eff[2]));
+	return mul(eff, ((v1 - cross(to_v3(s.r1), w1)) - v2) + cross(to_v3(s.r2), w2));
+}
+
+B2J_D void hinge_solve_velocity(const DWorld &w, const JointDef &d, JointState &s, const JointBody &b1, const JointBody &b2, float dt)
+{
+	V3 axis = to_v3(s.h_axis);
+	if (s.h_c2.w != 0.0f)
+	{
+		float max_lambda = d.hinge.x * dt;
+		angle_solve_velocity(w, b1, b2, axis, s.h_c2.w, s.h_m1, s.h_m2, s.lambda2.w, -max_lambda, max_lambda);
+	}
+	V3 lambda = point_velocity_lambda(w, s, b1, b2);
+	s.lambda = f4(to_v3(s.lambda) + lambda);
+	point_apply_velocity_step(w, s, b1, b2, lambda);
+	// HingeRotationConstraintPart::SolveVelocityConstraint
+	V3 delta_ang = joint_angular_velocity(w, b1) - joint_angular_velocity(w, b2);
+	float jv0 = dot(to_v3(s.h_b2xa1), delta_ang), jv1 = dot(to_v3(s.h_c2xa1), delta_ang);
+	float l0 = (0.0f + s.h_eff.x * jv0) + s.h_eff.y * jv1, l1 = (0.0f + s.h_eff.z * jv0) + s.h_eff.w * jv1;
+	s.lambda2.x += l0; s.lambda2.y += l1;
+	hinge_rotation_apply(w, s, b1, b2, l0, l1);
+	if (s.h_b2.w != 0.0f)
+	{
+		float min_lambda, max_lambda;
+		if (d.axis1.w == d.axis2.w) { min_lambda = -FLT_MAX; max_lambda = FLT_MAX; }
+		else if (hinge_is_min_limit_closest(d, s.h_a1.w)) { min_lambda = 0.0f; max_lambda = FLT_MAX; }
+		else { min_lambda = -FLT_MAX; max_lambda = 0.0f; }
+		angle_solve_velocity(w, b1, b2, axis, s.h_b2.w, s.h_l1, s.h_l2, s.lambda2.z, min_lambda, max_lambda);
+	}
+}
+
+// PointConstraintPart::SolvePositionConstraint after CalculateConstraintProperties (shared by the point and the hinge constraint)
+B2J_D void point_solve_position(const DWorld &w, const JointDef &d, JointState &s, JointBody &b1, JointBody &b2, float baumgarte)
+{
+	point_calculate(w, d, s, b1, b2);
+	V3 separation = ((b2.x - b1.x) + to_v3(s.r2)) - to_v3(s.r1);
+	if (separation == v3_zero())
+		return;
+	M33 eff = m33(to_v3(s.eff[0]), to_v3(s.eff[1]), to_v3(s.eff[2]));
+	// mEffectiveMass * -inBaumgarte * separation = (Mat44 * float) * Vec3
+	float nb = -baumgarte;
+	V3 lambda = mul(m33(eff.c0 * nb, eff.c1 * nb, eff.c2 * nb), separation);
+	if (b1.type == B2J_MOTION_DYNAMIC)
+	{
+		M33 i1 = m33(to_v3(s.i1[0]), to_v3(s.i1[1]), to_v3(s.i1[2]));
+		b1.x -= lock_translation(b1.inv_mass * lambda, b1.dofs);
+		b1.q = add_rotation_step(b1.q, mul(i1, lambda), true);
+		w.position[b1.slot] = f4(b1.x); w.rotation[b1.slot] = f4(b1.q);
+	}
+	if (b2.type == B2J_MOTION_DYNAMIC)
+	{
+		M33 i2 = m33(to_v3(s.i2[0]), to_v3(s.i2[1]), to_v3(s.i2[2]));
+		b2.x += lock_translation(b2.inv_mass * lambda, b2.dofs);
+		b2.q = add_rotation_step(b2.q, mul(i2, lambda), false);
+		w.position[b2.slot] = f4(b2.x); w.rotation[b2.slot] = f4(b2.q);
+	}
+}
+
+B2J_D void hinge_solve_position(const DWorld &w, const JointDef &d, JointState &s, JointBody &b1, JointBody &b2, float baumgarte)
+{
+	point_solve_position(w, d, s, b1, b2, baumgarte);
+	// (b1 / b2 carry the poses the point part left behind)
+	M33 rotation1 = m33_rotation(b1.q), rotation2 = m33_rotation(b2.q);
+	hinge_rotation_calculate(s, b1, rotation1, mul(rotation1, to_v3(d.axis1)), b2, rotation2, mul(rotation2, to_v3(d.axis2)));
+	// HingeRotationConstraintPart::SolvePositionConstraint
+	float c0 = dot(to_v3(s.h_a1), to_v3(s.h_b2)), c1 = dot(to_v3(s.h_a1), to_v3(s.h_c2));
+	if (!(c0 == 0.0f && c1 == 0.0f))
+	{
+		float e0 = (0.0f + s.h_eff.x * c0) + s.h_eff.y * c1, e1 = (0.0f + s.h_eff.z * c0) + s.h_eff.w * c1;
+		float l0 = -baumgarte * e0, l1 = -baumgarte * e1;
+		V3 impulse = to_v3(s.h_b2xa1) * l0 + to_v3(s.h_c2xa1) * l1;
+		if (b1.type == B2J_MOTION_DYNAMIC)
+		{
+			b1.q = add_rotation_step(b1.q, mul(m33(to_v3(s.h_inv1[0]), to_v3(s.h_inv1[1]), to_v3(s.h_inv1[2])), impulse), true);
+			w.rotation[b1.slot] = f4(b1.q);
+		}
+		if (b2.type == B2J_MOTION_DYNAMIC)
+		{
+			b2.q = add_rotation_step(b2.q, mul(m33(to_v3(s.h_inv2[0]), to_v3(s.h_inv2[1]), to_v3(s.h_inv2[2])), impulse), false);
+			w.rotation[b2.slot] = f4(b2.q);
+		}
+	}
+	if (hinge_has_limits(d))
+	{
+		hinge_limits_calculate(d, s, b1, b2);
+		if (s.h_b2.w != 0.0f)
+		{
+			// AngleConstraintPart::SolvePositionConstraint
+			float c = hinge_smallest_angle_to_limit(d, s.h_a1.w);
+			if (c != 0.0f)
+			{
+				float lambda = -s.h_b2.w * baumgarte * c;
+				if (b1.type == B2J_MOTION_DYNAMIC) { b1.q = add_rotation_step(b1.q, lambda * to_v3(s.h_l1), true); w.rotation[b1.slot] = f4(b1.q); }
+				if (b2.type == B2J_MOTION_DYNAMIC) { b2.q = add_rotation_step(b2.q, lambda * to_v3(s.h_l2), false); w.rotation[b2.slot] = f4(b2.q); }
+			}
+		}
+	}
+}
+
 // ---- the four solver entry points of a constraint -----------------------------------------------------------------------------------
 B2J_D void joint_setup_velocity(const DWorld &w, const JointDef &d, JointState &s)
 {
 	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
 	if (d.type == JOINT_POINT) point_calculate(w, d, s, b1, b2);
-	else distance_calculate(w, d, s, b1, b2);
+	else if (d.type == JOINT_DISTANCE) distance_calculate(w, d, s, b1, b2);
+	else hinge_setup(w, d, s, b1, b2);
 }
 
 B2J_D void joint_warm_start(const DWorld &w, const JointDef &d, JointState &s, float ratio)
@@ -252,21 +536,27 @@ B2J_D void joint_warm_start(const DWorld &w, const JointDef &d, JointState &s, f
 		s.lambda = f4(lambda);
 		point_apply_velocity_step(w, s, b1, b2, lambda);
 	}
-	else
+	else if (d.type == JOINT_DISTANCE)
 	{
 		s.lambda.x *= ratio;
 		axis_apply_velocity_step(w, s, b1, b2, to_v3(s.normal), s.lambda.x);
 	}
+	else
+		hinge_warm_start(w, d, s, b1, b2, ratio);
 }
 
-B2J_D void joint_solve_velocity(const DWorld &w, const JointDef &d, JointState &s)
+B2J_D void joint_solve_velocity(const DWorld &w, const JointDef &d, JointState &s, float dt)
 {
 	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
+	if (d.type == JOINT_HINGE)
+	{
+		hinge_solve_velocity(w, d, s, b1, b2, dt);
+		return;
+	}
 	V3 v1 = joint_linear_velocity(w, b1), w1 = joint_angular_velocity(w, b1), v2 = joint_linear_velocity(w, b2), w2 = joint_angular_velocity(w, b2);
 	if (d.type == JOINT_POINT)
 	{
-		M33 eff = m33(to_v3(s.eff[0]), to_v3(s.eff[1]), to_v3(s.eff[2]));
-		V3 lambda = mul(eff, ((v1 - cross(to_v3(s.r1), w1)) - v2) + cross(to_v3(s.r2), w2));
+		V3 lambda = point_velocity_lambda(w, s, b1, b2);
 		s.lambda = f4(to_v3(s.lambda) + lambda);
 		point_apply_velocity_step(w, s, b1, b2, lambda);
 	}
@@ -298,30 +588,9 @@ B2J_D void joint_solve_position(const DWorld &w, const JointDef &d, JointState &
 {
 	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
 	if (d.type == JOINT_POINT)
-	{
-		point_calculate(w, d, s, b1, b2);
-		V3 separation = ((b2.x - b1.x) + to_v3(s.r2)) - to_v3(s.r1);
-		if (separation == v3_zero())
-			return;
-		M33 eff = m33(to_v3(s.eff[0]), to_v3(s.eff[1]), to_v3(s.eff[2]));
-		// mEffectiveMass * -inBaumgarte * separation = (Mat44 * float) * Vec3
-		float nb = -baumgarte;
-		V3 lambda = mul(m33(eff.c0 * nb, eff.c1 * nb, eff.c2 * nb), separation);
-		if (b1.type == B2J_MOTION_DYNAMIC)
-		{
-			M33 i1 = m33(to_v3(s.i1[0]), to_v3(s.i1[1]), to_v3(s.i1[2]));
-			b1.x -= lock_translation(b1.inv_mass * lambda, b1.dofs);
-			b1.q = add_rotation_step(b1.q, mul(i1, lambda), true);
-			joint_store_pose(w, b1);
-		}
-		if (b2.type == B2J_MOTION_DYNAMIC)
-		{
-			M33 i2 = m33(to_v3(s.i2[0]), to_v3(s.i2[1]), to_v3(s.i2[2]));
-			b2.x += lock_translation(b2.inv_mass * lambda, b2.dofs);
-			b2.q = add_rotation_step(b2.q, mul(i2, lambda), false);
-			joint_store_pose(w, b2);
-		}
-	}
+		point_solve_position(w, d, s, b1, b2, baumgarte);
+	else if (d.type == JOINT_HINGE)
+		hinge_solve_position(w, d, s, b1, b2, baumgarte);
 	else
 	{
 		// (the distance of the points as the LAST CalculateConstraintProperties saw them)
@@ -447,20 +716,22 @@ struct KJointWarmStart
 		JointState s = j.state[hdr.manifold];
 		joint_warm_start(w, j.defs[hdr.manifold], s, ratio);
 		j.state[hdr.manifold].lambda = s.lambda;
+		j.state[hdr.manifold].lambda2 = s.lambda2;
 	}
 };
 
 struct KJointSolveVelocity
 {
-	DWorld w; Constraints c; JointCtx j; uint32_t begin, iteration;
+	DWorld w; Constraints c; JointCtx j; uint32_t begin, iteration; float dt;
 	B2J_D void operator()(uint32_t k) const
 	{
 		ConstraintHeader hdr = c.hdr[begin + k];
 		if (!(hdr.meta & META_JOINT) || iteration >= ((hdr.meta >> 8) & 0xff))
 			return;
 		JointState s = j.state[hdr.manifold];
-		joint_solve_velocity(w, j.defs[hdr.manifold], s);
+		joint_solve_velocity(w, j.defs[hdr.manifold], s, dt);
 		j.state[hdr.manifold].lambda = s.lambda;
+		j.state[hdr.manifold].lambda2 = s.lambda2;
 	}
 };
 

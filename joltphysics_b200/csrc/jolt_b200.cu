@@ -630,6 +630,7 @@ struct WorldSnapshot
 	F4 *pose = nullptr, *velocity = nullptr, *force_torque = nullptr, *inertia = nullptr, *bounds = nullptr, *sleep_spheres = nullptr;
 	float *sleep_timer = nullptr; uint32_t *active_index = nullptr, *active = nullptr;
 	CachedPair *pairs = nullptr; CachedManifold *manifolds = nullptr;
+	JointState *joint_state = nullptr; std::vector<b2j_constraint_desc> h_joints; // non contact constraints: the list and its state
 	// host mirrors of the world (the set of bodies is part of the state)
 	std::vector<uint32_t> h_ids; std::vector<uint8_t> h_layer, h_static, layer_has_moving;
 	std::vector<std::vector<uint32_t>> layer_bodies;
@@ -802,6 +803,71 @@ struct StepTrace
 	}
 };
 
+// ---- non contact constraints: device storage of the world's list (b2j_joints.h)
+bool joints_reserve(b2j_world *W, uint32_t needed)
+{
+	if (needed <= W->joint_capacity) return true;
+	Runtime &rt = W->rt;
+	uint32_t cap = W->joint_capacity == 0? 64 : W->joint_capacity;
+	while (cap < needed) cap *= 2;
+	JointCtx &j = W->jc;
+	JointDef *defs = rt.alloc<JointDef>(cap); JointState *state = rt.alloc<JointState>(cap);
+	uint32_t *steps = rt.alloc<uint32_t>(cap);
+	if (defs == nullptr || state == nullptr || steps == nullptr) { last_error() = "out of device memory"; return false; }
+	if (W->joint_capacity != 0)
+	{
+		rt.copy(state, j.state, W->joint_capacity);
+		rt.sync();
+		rt.free_(j.defs); rt.free_(j.state); rt.free_(j.active_flag); rt.free_(j.order_flag); rt.free_(j.order_scan); rt.free_(j.active_joints);
+		uint32_t *old_order = const_cast<uint32_t *>(j.order); rt.free_(old_order);
+		uint32_t *old_steps = const_cast<uint32_t *>(W->sc.joint_steps); rt.free_(old_steps);
+	}
+	j.defs = defs; j.state = state; W->sc.joint_steps = steps;
+	j.active_flag = rt.alloc<uint32_t>(cap); j.order = rt.alloc<uint32_t>(cap); j.order_flag = rt.alloc<uint32_t>(cap + 1); j.order_scan = rt.alloc<uint32_t>(cap + 1);
+	j.active_joints = rt.alloc<uint32_t>(cap);
+	if (j.wake_key == nullptr)
+	{
+		j.wake_key = rt.alloc<uint32_t>(W->d.max_bodies, false);
+		rt.memset_(j.wake_key, 0xff, (size_t)W->d.max_bodies * 4);
+		W->sc.body_nj = rt.alloc<uint32_t>(W->d.max_bodies);
+	}
+	W->joint_capacity = cap;
+	return j.active_joints != nullptr && j.wake_key != nullptr && W->sc.body_nj != nullptr;
+}
+
+// definitions, (priority, index) order and step overrides of the host list -> device (state stays where it is)
+void joints_upload(b2j_world *W)
+{
+	if (!W->joints_dirty) return;
+	W->joints_dirty = false;
+	uint32_t n = (uint32_t)W->h_joints.size();
+	W->jc.num_joints = n;
+	if (n == 0) return;
+	Runtime &rt = W->rt;
+	std::vector<JointDef> defs(n);
+	std::vector<uint32_t> order(n), steps(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const b2j_constraint_desc &c = W->h_joints[i];
+		JointDef &d = defs[i];
+		memset(&d, 0, sizeof(d));
+		d.type = c.type; d.b1 = slot_of(c.body1); d.b2 = slot_of(c.body2); d.flags = c.enabled? JOINT_ENABLED : 0u;
+		d.priority = c.priority; d.steps_override = (uint32_t)c.num_velocity_steps_override | ((uint32_t)c.num_position_steps_override << 8);
+		d.index = i;
+		d.local1 = f4(v3_load(c.point1), c.min_distance); d.local2 = f4(v3_load(c.point2), c.max_distance);
+		d.axis1 = f4(v3_load(c.hinge_axis1), c.limits_min); d.axis2 = f4(v3_load(c.hinge_axis2), c.limits_max);
+		d.inv_initial_orientation = f4(c.inv_initial_orientation[0], c.inv_initial_orientation[1], c.inv_initial_orientation[2], c.inv_initial_orientation[3]);
+		d.hinge = f4(c.max_friction_torque, 0.0f, 0.0f, 0.0f);
+		order[i] = i; steps[i] = d.steps_override;
+	}
+	// ConstraintManager::sSortConstraints: priority, then constraint index
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return W->h_joints[a].priority < W->h_joints[b].priority; });
+	rt.upload(W->jc.defs, defs.data(), n);
+	rt.upload(const_cast<uint32_t *>(W->jc.order), order.data(), n);
+	rt.upload(const_cast<uint32_t *>(W->sc.joint_steps), steps.data(), n);
+	rt.sync();
+}
+
 // One collision step. Returns false on a CUDA failure.
 bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last, b2j_step_stats *stats)
 {
@@ -819,6 +885,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 
 	StepTrace trace(rt, "gravity + broadphase trees");
 	// (a2) gravity, forces, damping
+	const uint32_t gravity_count = W->num_active;
 	{ KApplyGravity k; k.w = d; k.dt = dt; rt.launch(k, W->num_active); }
 
 	// (a4) broadphase maintenance: rebuild the trees whose bodies moved / changed
@@ -829,10 +896,41 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			W->layer_needs_build[l] = 0;
 		}
 
+	// non contact constraints (b2j_joints.h): which take part in this step, the bodies they wake up (no gravity for those this step)
+	uint32_t J = 0;
+	const bool have_joints = !W->h_joints.empty();
+	if (have_joints)
+	{
+		joints_upload(W);
+		JointCtx &jc = W->jc;
+		{ KJointActive k; k.w = d; k.c = W->nc; k.j = jc; rt.launch(k, jc.num_joints); }
+		if (!read_counters(W)) return false;
+		J = W->h_counters.num_active_joints;
+		uint32_t woken = W->h_counters.num_woken;
+		if (woken > 0)
+		{
+			// BodyManager::ActivateBodies in the order ConstraintManager::sBuildIslands calls it: by constraint, body 1 before body 2
+			{ KJointWakeKeys k; k.c = W->nc; k.j = jc; k.keys = W->d_woken_keys; rt.launch(k, woken); }
+			uint32_t *keys_sorted = reinterpret_cast<uint32_t *>(W->d_sort_keys[0]);
+			rt.sort_pairs<uint32_t>(W->d_woken_keys, keys_sorted, W->nc.woken_list, W->d_woken_sorted, woken, 32);
+			{ KActivateWoken k; k.w = d; k.woken_sorted = W->d_woken_sorted; k.base = W->num_active; k.woken_flag = W->nc.woken_flag; k.events = W->d_act_events; k.max_events = W->max_act_events; rt.launch(k, woken); }
+			{ KJointClearWoken k; k.w = d; rt.launch(k, 1); }
+			W->num_active += woken;
+		}
+		if (J > 0)
+		{
+			{ KJointOrderFlags k; k.j = jc; rt.launch(k, jc.num_joints); }
+			rt.exclusive_scan(jc.order_flag, jc.order_scan, jc.num_joints);
+			{ KJointCompact k; k.j = jc; rt.launch(k, jc.num_joints); }
+			{ KJointSetup k; k.w = d; k.j = jc; rt.launch(k, J); }
+		}
+	}
+	const uint32_t woken_by_joints = W->num_active - gravity_count;
+
 	trace.mark("gravity+trees", "find pairs + narrowphase");
 	// (a3, a5..a9) find pairs + narrow phase; repeated for the bodies woken up by contacts until no new body wakes up
 	uint32_t first_active = 0, n_query = W->num_active;
-	uint32_t woken_total = 0, longest_queue = 0;
+	uint32_t woken_total = woken_by_joints, longest_queue = 0;
 	const int max_rounds = 64;
 	for (int round = 0; ; ++round)
 	{
@@ -939,7 +1037,17 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		W->num_active += woken;
 		woken_total += woken;
 	}
-	uint32_t M = W->h_counters.num_constraints < d.max_constraints? W->h_counters.num_constraints : d.max_constraints;
+	// M contact constraints; the active non contact constraints follow them as constraint sources (items = J + M)
+	const uint32_t num_contacts = W->h_counters.num_constraints < d.max_constraints? W->h_counters.num_constraints : d.max_constraints;
+	if (J > d.max_constraints - num_contacts)
+	{
+		// (the constraint storage is shared: max_contact_constraints has to cover the active non contact constraints too)
+		J = d.max_constraints - num_contacts;
+		W->h_counters.error_bits |= B2J_ERR_CONTACT_CONSTRAINTS_FULL;
+		if (stats != nullptr) stats->error_bits |= B2J_ERR_CONTACT_CONSTRAINTS_FULL;
+	}
+	if (J > 0) { KJointAppend k; k.w = d; k.j = W->jc; k.src = W->nc.con_src; k.first = num_contacts; k.count = J; rt.launch(k, J); }
+	const uint32_t M = num_contacts + J;
 	uint32_t num_pairs = W->h_counters.num_pairs < d.max_body_pairs? W->h_counters.num_pairs : d.max_body_pairs;
 	W->last_num_pairs = num_pairs;
 	// (decaying maximum: the queue of a scene at impact alternates between long and short from step to step, and a queue that outgrows the
@@ -964,9 +1072,11 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 	if (M > 0)
 	{
 		// (a14 SortContacts) order by sort key
-		{ KGatherSortKeys k; k.s = sc; k.keys = W->d_sort_keys[0]; k.vals = W->d_sort_vals; rt.launch(k, M); }
-		rt.sort_pairs<uint64_t>(W->d_sort_keys[0], W->d_sort_keys[1], W->d_sort_vals, sc.order, M);
-		{ KCountTies k; k.w = d; k.keys = W->d_sort_keys[1]; rt.launch(k, M); }
+		{ KGatherSortKeys k; k.s = sc; k.keys = W->d_sort_keys[0]; k.vals = W->d_sort_vals; rt.launch(k, num_contacts); }
+		rt.sort_pairs<uint64_t>(W->d_sort_keys[0], W->d_sort_keys[1], W->d_sort_vals, sc.order + J, num_contacts);
+		{ KCountTies k; k.w = d; k.keys = W->d_sort_keys[1]; rt.launch(k, num_contacts); }
+		// the non contact constraints lead the order (an island solves its constraints before its contacts)
+		if (J > 0) { KJointItemOrder k; k.s = sc; k.vals = W->d_sort_vals; k.num_contacts = num_contacts; k.num_joints = J; rt.launch(k, M); }
 
 		// body -> constraints adjacency in sorted order
 		rt.exclusive_scan(sc.body_deg, sc.body_off, W->num_slots);
@@ -1072,7 +1182,8 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		trace.mark("place+setup", "velocity solve");
 #ifndef B2J_HOSTSIM
 		// small single world: the whole velocity solve in one small cooperative launch (solve_small_kernel)
-		block_solve = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
+		block_solve = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384 && J == 0;
+		if (J > 0) solve_mode = 0; // (the one launch solvers know contacts only)
 		if (block_solve)
 		{
 			float ratio_arg = warm_start_ratio;
@@ -1144,16 +1255,18 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			for (uint32_t p = 0; p < num_phases; ++p)
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+				if (J > 0) { KJointWarmStart kj; kj.w = d; kj.c = sc.con; kj.j = W->jc; kj.begin = begin; kj.ratio = warm_start_ratio; rt.launch(kj, n); }
 				KWarmStart k; k.w = d; k.c = sc.con; k.begin = begin; k.ratio = warm_start_ratio;
-				if (solve_pdl_enabled()) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
+				if (solve_pdl_enabled() && J == 0) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
 			}
 			for (uint32_t it = 0; it < vsteps; ++it)
 				for (uint32_t p = 0; p < num_phases; ++p)
 				{
 					uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+					if (J > 0) { KJointSolveVelocity kj; kj.w = d; kj.c = sc.con; kj.j = W->jc; kj.begin = begin; kj.iteration = it; kj.dt = dt; rt.launch(kj, n); }
 					KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
 					k.prefetch = 1;
-					if (solve_pdl_enabled()) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
+					if (solve_pdl_enabled() && J == 0) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
 				}
 		}
 		solved_by_phase_launches = phase_launches;
@@ -1218,8 +1331,9 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			for (uint32_t p = 0; p < num_phases; ++p)
 			{
 				uint32_t begin = W->h_phase_offsets[p], n = W->h_phase_offsets[p + 1] - begin;
+				if (J > 0) { KJointSolvePosition kj; kj.w = d; kj.c = sc.con; kj.j = W->jc; kj.begin = begin; kj.iteration = it; rt.launch(kj, n); }
 				KSolvePosition k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
-				if (solve_pdl_enabled()) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
+				if (solve_pdl_enabled() && J == 0) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
 			}
 	}
 
@@ -1278,7 +1392,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		stats->num_pairs_from_cache += c.num_pairs_from_cache;
 		stats->num_manifolds += W->cache_num_manifolds[wi];
 		stats->num_contact_points += c.num_contact_points;
-		stats->num_constraints += M;
+		stats->num_constraints += num_contacts;
 		stats->num_islands += c.num_islands;
 		stats->num_large_islands += c.num_large_islands;
 		stats->num_phases += num_phases;
@@ -1543,6 +1657,14 @@ void b2j_world_destroy(b2j_world *W)
 	NarrowCtx &nc = W->nc;
 	rt.free_(nc.pairs); rt.free_(nc.collide_convex); rt.free_(nc.collide_mesh); rt.free_(nc.cached); rt.free_(nc.epa); rt.free_(nc.epa_overflow); rt.free_(nc.num_epa_overflow); if (nc.epa_hist != nullptr) rt.free_(nc.epa_hist); rt.free_(nc.epa_results); rt.free_(nc.num_epa_results);
 	rt.free_(nc.man_ws); rt.free_(nc.con_src); rt.free_(nc.woken_flag); rt.free_(nc.woken_list); rt.free_(W->events_buf);
+	if (W->joint_capacity != 0)
+	{
+		JointCtx &j = W->jc;
+		rt.free_(j.defs); rt.free_(j.state); rt.free_(j.active_flag); rt.free_(j.order_flag); rt.free_(j.order_scan); rt.free_(j.active_joints); rt.free_(j.wake_key);
+		uint32_t *p1 = const_cast<uint32_t *>(j.order); rt.free_(p1);
+		uint32_t *p2 = const_cast<uint32_t *>(W->sc.joint_steps); rt.free_(p2);
+		rt.free_(W->sc.body_nj);
+	}
 	rt.free_(W->d_mesh_scratch); rt.free_(W->d_query_scratch); rt.free_(W->d_cache_invalid);
 	for (int i = 0; i < 2; ++i) { rt.free_(W->d_collide_keys[i]); rt.free_(W->d_collide_vals[i]); }
 	rt.free_(W->act_events_buf); rt.free_(W->d_woken_sorted); rt.free_(W->d_woken_keys); rt.free_(W->d_round_begin); rt.free_(W->d_energy);
@@ -2413,6 +2535,111 @@ uint32_t b2j_get_active_bodies(b2j_world *W, uint32_t *ids, uint32_t cap)
 	return W->num_active;
 }
 
+// ---- non contact constraints (b2j_joints.h) ---------------------------------------------------------------------------------------
+int b2j_constraints_add(b2j_world *W, const b2j_constraint_desc *constraints, uint32_t n)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (constraints == nullptr) { last_error() = "b2j_constraints_add: constraints is required"; return -1; }
+	if (W->num_worlds != 1) { last_error() = "b2j_constraints_add: batched worlds do not take constraints"; return -1; }
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const b2j_constraint_desc &c = constraints[i];
+		uint32_t ids[2] = { c.body1, c.body2 };
+		if (!validate_ids(W, ids, 2, "b2j_constraints_add")) return -1;
+		if (c.type != B2J_CONSTRAINT_POINT && c.type != B2J_CONSTRAINT_DISTANCE && c.type != B2J_CONSTRAINT_HINGE) { last_error() = "b2j_constraints_add: unknown constraint type"; return -1; }
+		if (c.type == B2J_CONSTRAINT_HINGE && !(c.limits_min <= 0.0f && c.limits_max >= 0.0f && c.max_friction_torque >= 0.0f)) { last_error() = "b2j_constraints_add: hinge limits_min <= 0 <= limits_max and max_friction_torque >= 0 expected"; return -1; }
+		if (c.body1 == c.body2) { last_error() = "b2j_constraints_add: a constraint connects two different bodies"; return -1; }
+		if (c.type == B2J_CONSTRAINT_DISTANCE && !(c.min_distance >= 0.0f && c.max_distance >= c.min_distance)) { last_error() = "b2j_constraints_add: 0 <= min_distance <= max_distance expected"; return -1; }
+	}
+	uint32_t first = (uint32_t)W->h_joints.size();
+	if (!joints_reserve(W, first + n)) return -1;
+	Runtime &rt = W->rt;
+	std::vector<JointState> init(n);
+	memset(init.data(), 0, n * sizeof(JointState));
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		init[i].normal = f4(0.0f, 1.0f, 0.0f, 0.0f); // DistanceConstraint: mWorldSpaceNormal = Vec3::sAxisY()
+		W->h_joints.push_back(constraints[i]);
+	}
+	rt.upload(W->jc.state + first, init.data(), n);
+	rt.sync();
+	W->joints_dirty = true;
+	return rt.check("b2j_constraints_add")? 0 : -1;
+}
+
+int b2j_constraints_remove(b2j_world *W, const uint32_t *indices, uint32_t n)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	Runtime &rt = W->rt;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t last = (uint32_t)W->h_joints.size();
+		if (indices == nullptr || indices[i] >= last) { last_error() = "b2j_constraints_remove: invalid constraint index"; return -1; }
+		--last;
+		if (indices[i] < last)
+		{
+			// ConstraintManager::Remove: the last constraint takes the freed index
+			W->h_joints[indices[i]] = W->h_joints[last];
+			rt.copy(W->jc.state + indices[i], W->jc.state + last, 1);
+		}
+		W->h_joints.pop_back();
+	}
+	rt.sync();
+	W->joints_dirty = true;
+	W->jc.num_joints = (uint32_t)W->h_joints.size();
+	return rt.check("b2j_constraints_remove")? 0 : -1;
+}
+
+uint32_t b2j_num_constraints(const b2j_world *W) { return (uint32_t)W->h_joints.size(); }
+
+int b2j_constraints_set_enabled(b2j_world *W, const uint32_t *indices, uint32_t n, const uint8_t *enabled)
+{
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		if (indices[i] >= W->h_joints.size()) { last_error() = "b2j_constraints_set_enabled: invalid constraint index"; return -1; }
+		W->h_joints[indices[i]].enabled = enabled[i];
+	}
+	W->joints_dirty = true;
+	return 0;
+}
+
+int b2j_constraints_get_state(b2j_world *W, uint32_t first, uint32_t n, b2j_constraint_state *out)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (out == nullptr || (size_t)first + n > W->h_joints.size()) { last_error() = "b2j_constraints_get_state: invalid range"; return -1; }
+	std::vector<JointState> st(n);
+	W->rt.download(st.data(), W->jc.state + first, n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		out[i].total_lambda[0] = st[i].lambda.x; out[i].total_lambda[1] = st[i].lambda.y; out[i].total_lambda[2] = st[i].lambda.z;
+		out[i].world_space_normal[0] = st[i].normal.x; out[i].world_space_normal[1] = st[i].normal.y; out[i].world_space_normal[2] = st[i].normal.z;
+		out[i].total_lambda_rotation[0] = st[i].lambda2.x; out[i].total_lambda_rotation[1] = st[i].lambda2.y;
+		out[i].total_lambda_limits = st[i].lambda2.z; out[i].total_lambda_motor = st[i].lambda2.w;
+	}
+	return W->rt.check("b2j_constraints_get_state")? 0 : -1;
+}
+
+int b2j_constraints_set_state(b2j_world *W, uint32_t first, uint32_t n, const b2j_constraint_state *in)
+{
+	if (n == 0) return 0;
+	B2J_DEVICE_GUARD(W);
+	if (in == nullptr || (size_t)first + n > W->h_joints.size()) { last_error() = "b2j_constraints_set_state: invalid range"; return -1; }
+	std::vector<JointState> st(n);
+	W->rt.download(st.data(), W->jc.state + first, n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		st[i].lambda = f4(in[i].total_lambda[0], in[i].total_lambda[1], in[i].total_lambda[2], 0.0f);
+		st[i].normal = f4(in[i].world_space_normal[0], in[i].world_space_normal[1], in[i].world_space_normal[2], 0.0f);
+		st[i].lambda2 = f4(in[i].total_lambda_rotation[0], in[i].total_lambda_rotation[1], in[i].total_lambda_limits, in[i].total_lambda_motor);
+	}
+	W->rt.upload(W->jc.state + first, st.data(), n);
+	W->rt.sync();
+	return W->rt.check("b2j_constraints_set_state")? 0 : -1;
+}
+
 int b2j_contact_cache_import(b2j_world *W, const b2j_cached_body_pair *pairs, uint32_t num_pairs, const b2j_cached_manifold *manifolds, uint32_t num_manifolds)
 {
 	B2J_DEVICE_GUARD(W);
@@ -2636,7 +2863,7 @@ static void snapshot_free(WorldSnapshot &ws)
 	Runtime &rt = ws.owner->rt;
 	rt.sync();
 	rt.free_(ws.info); rt.free_(ws.params); rt.free_(ws.pose); rt.free_(ws.velocity); rt.free_(ws.force_torque); rt.free_(ws.inertia); rt.free_(ws.bounds);
-	rt.free_(ws.sleep_spheres); rt.free_(ws.sleep_timer); rt.free_(ws.active_index); rt.free_(ws.active); rt.free_(ws.pairs); rt.free_(ws.manifolds);
+	rt.free_(ws.sleep_spheres); rt.free_(ws.sleep_timer); rt.free_(ws.active_index); rt.free_(ws.active); rt.free_(ws.pairs); rt.free_(ws.manifolds); rt.free_(ws.joint_state);
 	ws.owner = nullptr;
 }
 
@@ -2665,6 +2892,8 @@ static bool snapshot_take(b2j_world *W, WorldSnapshot &ws)
 	keep(ws.inertia, d.inv_inertia_diag.base, 2 * (size_t)n); keep(ws.bounds, d.bounds_min.base, 2 * (size_t)n);
 	keep(ws.sleep_spheres, d.sleep_spheres, 3 * (size_t)n); keep(ws.sleep_timer, d.sleep_timer, n); keep(ws.active_index, d.active_index, n);
 	keep(ws.active, d.active, na);
+	ws.h_joints = W->h_joints;
+	if (!W->h_joints.empty()) keep(ws.joint_state, W->jc.state, W->h_joints.size());
 	keep(ws.pairs, d.read_cache.pairs, np); keep(ws.manifolds, d.read_cache.manifolds, nm);
 	ws.h_ids.assign(W->h_ids.begin(), W->h_ids.begin() + n); ws.h_layer.assign(W->h_layer.begin(), W->h_layer.begin() + n); ws.h_static.assign(W->h_static.begin(), W->h_static.begin() + n);
 	ws.layer_bodies = W->layer_bodies; ws.layer_has_moving = W->layer_has_moving;
@@ -2697,6 +2926,11 @@ static bool snapshot_restore(b2j_world *W, const WorldSnapshot &ws)
 	rt.copy(d.inv_inertia_diag.base, ws.inertia, 2 * (size_t)n); rt.copy(d.bounds_min.base, ws.bounds, 2 * (size_t)n);
 	rt.copy(d.sleep_spheres, ws.sleep_spheres, 3 * (size_t)n); rt.copy(d.sleep_timer, ws.sleep_timer, n); rt.copy(d.active_index, ws.active_index, n);
 	rt.copy(d.active, ws.active, ws.num_active);
+	if (!ws.h_joints.empty() && !joints_reserve(W, (uint32_t)ws.h_joints.size())) return false;
+	W->h_joints = ws.h_joints;
+	W->joints_dirty = true;
+	W->jc.num_joints = (uint32_t)ws.h_joints.size();
+	if (!ws.h_joints.empty()) rt.copy(W->jc.state, ws.joint_state, ws.h_joints.size());
 	// contact cache: the snapshot becomes the read cache, the write cache is empty between steps
 	int ri = W->write_idx ^ 1;
 	clear_cache(W, ri);
@@ -2989,6 +3223,7 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	sync_dworld(P);
 	uint32_t stride = P->num_slots;
 	if (stride == 0 || (uint64_t)stride * n_worlds > 0xfffffff0ull) { last_error() = "b2j_batch_create: too many bodies"; return nullptr; }
+	if (!P->h_joints.empty()) { last_error() = "b2j_batch_create: worlds with non contact constraints cannot be batched yet"; return nullptr; }
 	b2j_world_desc desc = P->desc;
 	desc.object_to_broadphase = P->t_o2bp.data(); desc.object_vs_broadphase = P->t_ovbp.data(); desc.object_vs_object = P->t_ovo.data();
 	desc.settings = P->d.settings;

@@ -6,7 +6,10 @@
 // The including file provides: B2J_SHAPE_REF, B2J_NEW_SHAPE(Type, args...), Layers::{NON_MOVING, MOVING, DEBRIS}, sRandomQuat(std::mt19937 &).
 // Variants: 0 kinematic, 1 sensor, 2 dof_plane2d, 3 gyroscopic, 4 step_overrides, 5 no_manifold_reduction, 6 two_moving_layers,
 // 7 kinematic_vs_nondynamic, 8 zoo (0..7 in one world), 9 decorated (ScaledShape / RotatedTranslatedShape around convex shapes),
-// 10 cylinder (CylinderShape plain, scaled and rotated against every other convex shape).
+// 10 cylinder (CylinderShape plain, scaled and rotated against every other convex shape),
+// 11 joints (PointConstraint / DistanceConstraint / HingeConstraint: chain, rope with limits, doors and flaps on hinges with limits and friction, a cloth that is one large island, kinematic tow, constraint
+// that wakes a sleeping body, priorities, solver step overrides, a disabled constraint; patterns of UnitTests/Physics/DistanceConstraintTests.cpp
+// and Samples/Tests/Constraints/{PointConstraintTest, DistanceConstraintTest}.cpp).
 // inHull: a cooked convex hull (cooking is host side and out of scope).
 
 static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHAPE_REF &inHull, uint32_t &outNumDynamic)
@@ -242,6 +245,132 @@ static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHA
 			BodyCreationSettings s(shapes[i % 8], RVec3(8.0f + 1.2f * float(i % 3), 1.0f + 1.0f * float(i / 3), -1.2f + 1.2f * float((i / 2) % 3)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
 			s.mRestitution = i % 5 == 0? 0.4f : 0.0f;
 			add(s);
+		}
+	}
+	if (inVariant == 11)
+	{
+		auto create = [&](BodyCreationSettings &bs, EActivation a = EActivation::Activate) { Body *b = bi.CreateBody(bs); bi.AddBody(b->GetID(), a); if (bs.mMotionType != EMotionType::Static) outNumDynamic++; return b; };
+		auto point = [&](Body *b1, Body *b2, RVec3 p) { PointConstraintSettings ps; ps.mPoint1 = p; ps.mPoint2 = p; TwoBodyConstraint *c = ps.Create(*b1, *b2); inSystem.AddConstraint(c); return c; };
+		auto distance = [&](Body *b1, Body *b2, RVec3 p1, RVec3 p2, float mn, float mx) { DistanceConstraintSettings ds; ds.mPoint1 = p1; ds.mPoint2 = p2; ds.mMinDistance = mn; ds.mMaxDistance = mx; TwoBodyConstraint *c = ds.Create(*b1, *b2); inSystem.AddConstraint(c); return c; };
+		B2J_SHAPE_REF small_sphere = B2J_NEW_SHAPE(SphereShape, 0.2f), link = B2J_NEW_SHAPE(CapsuleShape, 0.35f, 0.12f);
+		// (a) a chain of capsules pinned to a static anchor, starting horizontal: swings down, the links collide with a post
+		BodyCreationSettings anchor_s(small_sphere, RVec3(0.0f, 8.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		Body *anchor = create(anchor_s, EActivation::DontActivate);
+		Body *prev = anchor;
+		Quat along_x = Quat(0.0f, 0.0f, 0.70710678f, 0.70710678f);
+		for (int i = 0; i < 8; ++i)
+		{
+			BodyCreationSettings s(link, RVec3(0.5f + 1.0f * float(i), 8.0f, 0.0f), along_x, EMotionType::Dynamic, Layers::MOVING);
+			Body *b = create(s);
+			TwoBodyConstraint *c = point(prev, b, RVec3(1.0f * float(i), 8.0f, 0.0f));
+			if (i == 3) c->SetNumVelocityStepsOverride(14);
+			if (i == 5) c->SetNumPositionStepsOverride(4);
+			prev = b;
+		}
+		BodyCreationSettings post(B2J_NEW_SHAPE(BoxShape, Vec3(0.3f, 3.0f, 1.0f)), RVec3(2.5f, 3.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		create(post, EActivation::DontActivate);
+		// (b) a rope of spheres: distance constraints with a minimum and a maximum (slack at the start: inactive until stretched), the last
+		// link a fixed distance (min = max = the distance at creation)
+		BodyCreationSettings anchor2_s(small_sphere, RVec3(10.0f, 9.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		prev = create(anchor2_s, EActivation::DontActivate);
+		for (int i = 0; i < 6; ++i)
+		{
+			BodyCreationSettings s(sphere, RVec3(10.6f + 0.7f * float(i), 9.0f - 0.2f * float(i), 0.3f * float(i % 2)), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+			Body *b = create(s);
+			RVec3 p1 = prev->GetCenterOfMassPosition(), p2 = b->GetCenterOfMassPosition();
+			if (i < 5) distance(prev, b, p1, p2 + Vec3(0.0f, 0.3f, 0.0f), 0.4f, 1.2f);
+			else distance(prev, b, p1, p2, -1.0f, -1.0f);
+			prev = b;
+		}
+		// (c) a cloth of small spheres held together by fixed distances: one island of > 128 constraints (the large island splitter colours
+		// contacts and constraints), two corners pinned to static anchors, falling over a box
+		const int n = 10;
+		Body *cloth[n][n];
+		for (int i = 0; i < n; ++i)
+			for (int j = 0; j < n; ++j)
+			{
+				BodyCreationSettings s(small_sphere, RVec3(20.0f + 0.5f * float(i), 4.0f, -2.25f + 0.5f * float(j)), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+				s.mFriction = 0.4f;
+				cloth[i][j] = create(s);
+			}
+		for (int i = 0; i < n; ++i)
+			for (int j = 0; j < n; ++j)
+			{
+				if (i + 1 < n) distance(cloth[i][j], cloth[i + 1][j], cloth[i][j]->GetCenterOfMassPosition(), cloth[i + 1][j]->GetCenterOfMassPosition(), -1.0f, -1.0f);
+				if (j + 1 < n) distance(cloth[i][j], cloth[i][j + 1], cloth[i][j]->GetCenterOfMassPosition(), cloth[i][j + 1]->GetCenterOfMassPosition(), -1.0f, -1.0f);
+			}
+		for (int k = 0; k < 2; ++k)
+		{
+			Body *corner = cloth[0][k == 0? 0 : n - 1];
+			BodyCreationSettings pin_s(small_sphere, corner->GetCenterOfMassPosition() + Vec3(-0.5f, 0.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+			Body *pin = create(pin_s, EActivation::DontActivate);
+			point(pin, corner, pin->GetCenterOfMassPosition());
+		}
+		BodyCreationSettings table(box, RVec3(23.0f, 2.0f, 0.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		create(table, EActivation::DontActivate);
+		// (d) a kinematic tractor towing a dynamic box over the floor with a point constraint, and a second box on a leash (max distance)
+		BodyCreationSettings tractor_s(box, RVec3(-8.0f, 0.5f, 5.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
+		tractor_s.mLinearVelocity = Vec3(1.5f, 0.0f, 0.0f);
+		Body *tractor = create(tractor_s);
+		BodyCreationSettings trailer_s(box, RVec3(-10.0f, 0.5f, 5.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		Body *trailer = create(trailer_s);
+		point(tractor, trailer, RVec3(-9.0f, 0.5f, 5.0f))->SetConstraintPriority(5);
+		BodyCreationSettings dog_s(hull, RVec3(-12.0f, 0.6f, 5.5f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		Body *dog = create(dog_s);
+		distance(trailer, dog, trailer->GetCenterOfMassPosition(), dog->GetCenterOfMassPosition(), 0.0f, 2.5f)->SetConstraintPriority(2);
+		// (e) a sleeping box tied to a box that falls: the constraint is active because one of its bodies is, and wakes the other up
+		BodyCreationSettings sleeper_s(box, RVec3(-8.0f, 0.5f, -5.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		Body *sleeper = create(sleeper_s, EActivation::DontActivate);
+		BodyCreationSettings faller_s(sphere, RVec3(-8.0f, 4.0f, -5.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		Body *faller = create(faller_s);
+		distance(sleeper, faller, sleeper->GetCenterOfMassPosition(), faller->GetCenterOfMassPosition(), 0.0f, 5.0f);
+		// ... and two sleeping boxes tied together (inactive constraint until something touches them), a disabled constraint
+		BodyCreationSettings rest1_s(box, RVec3(-14.0f, 0.5f, -5.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING), rest2_s(box, RVec3(-12.5f, 0.5f, -5.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		Body *rest1 = create(rest1_s, EActivation::DontActivate), *rest2 = create(rest2_s, EActivation::DontActivate);
+		point(rest1, rest2, RVec3(-13.25f, 0.5f, -5.0f));
+		BodyCreationSettings free1_s(sphere, RVec3(-14.0f, 3.0f, -8.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING), free2_s(sphere, RVec3(-12.0f, 3.0f, -8.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		free2_s.mLinearVelocity = Vec3(3.0f, 0.0f, 0.0f);
+		Body *free1 = create(free1_s), *free2 = create(free2_s);
+		distance(free1, free2, free1->GetCenterOfMassPosition(), free2->GetCenterOfMassPosition(), -1.0f, -1.0f)->SetEnabled(false);
+		// (f) hinges (Samples/Tests/Constraints/HingeConstraintTest.cpp pattern): a chain of planks hinged about z with limits that
+		// starts horizontal from a static post, a door about y with friction pushed by a ball, a free flap about x (no limits), a flap whose
+		// two hinge axes start misaligned (the rotation part pulls them together)
+		auto hinge = [&](Body *b1, Body *b2, RVec3 p, Vec3 axis, Vec3 normal, float mn, float mx, float friction) {
+			HingeConstraintSettings hs; hs.mPoint1 = p; hs.mPoint2 = p; hs.mHingeAxis1 = axis; hs.mHingeAxis2 = axis; hs.mNormalAxis1 = normal; hs.mNormalAxis2 = normal;
+			hs.mLimitsMin = mn; hs.mLimitsMax = mx; hs.mMaxFrictionTorque = friction;
+			TwoBodyConstraint *c = hs.Create(*b1, *b2); inSystem.AddConstraint(c); return c; };
+		const float pi = 3.14159265358979323846f;
+		B2J_SHAPE_REF plank = B2J_NEW_SHAPE(BoxShape, Vec3(0.5f, 0.1f, 0.4f));
+		BodyCreationSettings hpost_s(box, RVec3(0.0f, 6.0f, 10.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		prev = create(hpost_s, EActivation::DontActivate);
+		for (int i = 0; i < 5; ++i)
+		{
+			BodyCreationSettings s(plank, RVec3(1.0f + 1.0f * float(i), 6.0f, 10.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			Body *b = create(s);
+			hinge(prev, b, RVec3(0.5f + 1.0f * float(i), 6.0f, 10.0f), Vec3::sAxisZ(), Vec3::sAxisX(), i % 2? -0.3f * pi : -0.1f * pi, 0.25f * pi, 0.0f);
+			prev = b;
+		}
+		BodyCreationSettings frame_s(B2J_NEW_SHAPE(BoxShape, Vec3(0.1f, 1.0f, 0.1f)), RVec3(8.0f, 1.0f, 10.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		Body *frame = create(frame_s, EActivation::DontActivate);
+		BodyCreationSettings door_s(B2J_NEW_SHAPE(BoxShape, Vec3(0.6f, 0.9f, 0.05f)), RVec3(8.75f, 1.05f, 10.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		Body *door = create(door_s);
+		hinge(frame, door, RVec3(8.1f, 1.05f, 10.0f), Vec3::sAxisY(), Vec3::sAxisX(), -0.5f * pi, 0.5f * pi, 2.0f);
+		BodyCreationSettings ball_s(sphere, RVec3(9.0f, 1.0f, 7.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		ball_s.mLinearVelocity = Vec3(0.0f, 1.0f, 6.0f);
+		create(ball_s);
+		BodyCreationSettings bar_s(B2J_NEW_SHAPE(BoxShape, Vec3(1.0f, 0.1f, 0.1f)), RVec3(14.0f, 4.0f, 10.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		Body *bar = create(bar_s, EActivation::DontActivate);
+		BodyCreationSettings flap_s(B2J_NEW_SHAPE(BoxShape, Vec3(0.8f, 0.05f, 0.6f)), RVec3(14.0f, 4.0f, 10.8f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+		Body *flap = create(flap_s);
+		hinge(bar, flap, RVec3(14.0f, 4.0f, 10.1f), Vec3::sAxisX(), Vec3::sAxisY(), -pi, pi, 0.0f);
+		BodyCreationSettings flap2_s(B2J_NEW_SHAPE(BoxShape, Vec3(0.8f, 0.05f, 0.6f)), RVec3(14.0f, 4.0f, 9.2f), Quat(0.0f, 0.05f, 0.0f, 0.99874922f), EMotionType::Dynamic, Layers::MOVING);
+		Body *flap2 = create(flap2_s);
+		{
+			HingeConstraintSettings hs; hs.mPoint1 = RVec3(14.0f, 4.0f, 9.9f); hs.mPoint2 = RVec3(14.0f, 4.05f, 9.85f);
+			hs.mHingeAxis1 = Vec3::sAxisX(); hs.mNormalAxis1 = Vec3::sAxisY();
+			hs.mHingeAxis2 = Vec3(0.98006658f, 0.0f, 0.19866933f); hs.mNormalAxis2 = Vec3::sAxisY();
+			hs.mLimitsMin = -0.2f * pi; hs.mLimitsMax = 0.6f * pi;
+			inSystem.AddConstraint(hs.Create(*bar, *flap2));
 		}
 	}
 }

@@ -19,6 +19,9 @@
 #include <Jolt/Physics/Collision/Shape/ScaledShape.h>
 #include <Jolt/Physics/Collision/Shape/RotatedTranslatedShape.h>
 
+#include <Jolt/Physics/Constraints/PointConstraint.h>
+#include <Jolt/Physics/Constraints/DistanceConstraint.h>
+#include <Jolt/Physics/Constraints/HingeConstraint.h>
 #include <jolt_b200.h>
 
 #include <unordered_map>
@@ -39,6 +42,7 @@ struct Api
 	B2J_FN(b2j_world_set_previous_delta_time)
 	B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated) B2J_FN(b2j_shape_static_compound)
 	B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
+	B2J_FN(b2j_constraints_add) B2J_FN(b2j_constraints_set_state)
 #undef B2J_FN
 
 	bool Load(const char *inPath, String &outError)
@@ -50,6 +54,7 @@ struct Api
 		B2J_FN(b2j_world_set_previous_delta_time)
 		B2J_FN(b2j_shape_sphere) B2J_FN(b2j_shape_box) B2J_FN(b2j_shape_capsule) B2J_FN(b2j_shape_cylinder) B2J_FN(b2j_shape_convex_hull) B2J_FN(b2j_shape_mesh) B2J_FN(b2j_shape_scaled) B2J_FN(b2j_shape_rotated_translated) B2J_FN(b2j_shape_static_compound)
 		B2J_FN(b2j_bodies_add) B2J_FN(b2j_set_active_list) B2J_FN(b2j_contact_cache_import)
+		B2J_FN(b2j_constraints_add) B2J_FN(b2j_constraints_set_state)
 #undef B2J_FN
 		return true;
 	}
@@ -415,6 +420,68 @@ inline b2j_world *sExportWorld(const Api &inApi, const PhysicsSystem &inSystem, 
 	if (inApi.b2j_set_active_list(world, active_ids.data(), (uint32_t)active_ids.size()) != 0)
 	{
 		outError = String("b2j_set_active_list failed: ") + inApi.b2j_last_error();
+		inApi.b2j_world_destroy(world);
+		return nullptr;
+	}
+
+	// Non contact constraints in ConstraintManager order (= Constraint::mConstraintIndex) with the state the next step starts from
+	// (what Constraint::SaveState writes: accumulated impulses, the distance constraint's last normal)
+	Constraints constraints = inSystem.GetConstraints();
+	std::vector<b2j_constraint_desc> cdescs;
+	std::vector<b2j_constraint_state> cstates;
+	for (const Ref<Constraint> &c : constraints)
+	{
+		b2j_constraint_desc cd;
+		b2j_constraint_state cs;
+		memset(&cd, 0, sizeof(cd)); memset(&cs, 0, sizeof(cs));
+		if (c->GetType() != EConstraintType::TwoBodyConstraint) { outError = "only two body constraints are on the path"; inApi.b2j_world_destroy(world); return nullptr; }
+		const TwoBodyConstraint *tb = static_cast<const TwoBodyConstraint *>(c.GetPtr());
+		cd.body1 = tb->GetBody1()->GetID().GetIndexAndSequenceNumber(); cd.body2 = tb->GetBody2()->GetID().GetIndexAndSequenceNumber();
+		sStore(tb->GetConstraintToBody1Matrix().GetTranslation(), cd.point1); sStore(tb->GetConstraintToBody2Matrix().GetTranslation(), cd.point2);
+		cd.priority = c->GetConstraintPriority();
+		cd.num_velocity_steps_override = (uint8_t)c->GetNumVelocityStepsOverride(); cd.num_position_steps_override = (uint8_t)c->GetNumPositionStepsOverride();
+		cd.enabled = c->GetEnabled();
+		switch (c->GetSubType())
+		{
+		case EConstraintSubType::Point:
+			cd.type = B2J_CONSTRAINT_POINT;
+			sStore(static_cast<const PointConstraint *>(tb)->GetTotalLambdaPosition(), cs.total_lambda);
+			break;
+		case EConstraintSubType::Distance:
+			{
+				const DistanceConstraint *dc = static_cast<const DistanceConstraint *>(tb);
+				if (dc->GetLimitsSpringSettings().HasStiffness()) { outError = "distance constraints with limit springs are not on the path"; inApi.b2j_world_destroy(world); return nullptr; }
+				cd.type = B2J_CONSTRAINT_DISTANCE;
+				cd.min_distance = dc->GetMinDistance(); cd.max_distance = dc->GetMaxDistance();
+				cs.total_lambda[0] = dc->GetTotalLambdaPosition();
+				sStore(dc->mWorldSpaceNormal, cs.world_space_normal); // (no getter: the member DistanceConstraint::SaveState writes)
+			}
+			break;
+		case EConstraintSubType::Hinge:
+			{
+				const HingeConstraint *hc = static_cast<const HingeConstraint *>(tb);
+				if (hc->GetMotorState() != EMotorState::Off || hc->GetLimitsSpringSettings().HasStiffness()) { outError = "hinge motors / limit springs are not on the path"; inApi.b2j_world_destroy(world); return nullptr; }
+				cd.type = B2J_CONSTRAINT_HINGE;
+				sStore(hc->GetLocalSpacePoint1(), cd.point1); sStore(hc->GetLocalSpacePoint2(), cd.point2);
+				sStore(hc->GetLocalSpaceHingeAxis1(), cd.hinge_axis1); sStore(hc->GetLocalSpaceHingeAxis2(), cd.hinge_axis2);
+				sStore(hc->mInvInitialOrientation, cd.inv_initial_orientation); // (no getter)
+				cd.limits_min = hc->GetLimitsMin(); cd.limits_max = hc->GetLimitsMax(); cd.max_friction_torque = hc->GetMaxFrictionTorque();
+				sStore(hc->GetTotalLambdaPosition(), cs.total_lambda);
+				cs.total_lambda_rotation[0] = hc->GetTotalLambdaRotation()[0]; cs.total_lambda_rotation[1] = hc->GetTotalLambdaRotation()[1];
+				cs.total_lambda_limits = hc->GetTotalLambdaRotationLimits(); cs.total_lambda_motor = hc->GetTotalLambdaMotor();
+			}
+			break;
+		default:
+			outError = "constraint type is not on the path (PointConstraint, DistanceConstraint, HingeConstraint)";
+			inApi.b2j_world_destroy(world);
+			return nullptr;
+		}
+		cdescs.push_back(cd); cstates.push_back(cs);
+	}
+	if (!cdescs.empty() && (inApi.b2j_constraints_add(world, cdescs.data(), (uint32_t)cdescs.size()) != 0
+		|| inApi.b2j_constraints_set_state(world, 0, (uint32_t)cstates.size(), cstates.data()) != 0))
+	{
+		outError = String("b2j_constraints_add failed: ") + inApi.b2j_last_error();
 		inApi.b2j_world_destroy(world);
 		return nullptr;
 	}

@@ -23,6 +23,9 @@
 #include <Jolt/Physics/Collision/CastResult.h>
 #include <Jolt/Physics/Collision/NarrowPhaseQuery.h>
 #include <Jolt/Physics/Collision/CollideShape.h>
+#include <Jolt/Physics/Constraints/PointConstraint.h>
+#include <Jolt/Physics/Constraints/DistanceConstraint.h>
+#include <Jolt/Physics/Constraints/HingeConstraint.h>
 #include <Jolt/Physics/Collision/Shape/CylinderShape.h>
 #include <Jolt/Physics/Collision/Shape/CapsuleShape.h>
 #include <Jolt/Physics/Collision/Shape/SphereShape.h>
@@ -576,6 +579,46 @@ void jref_cast_rays(void *h, const b2j_ray *inRays, uint32_t inNum, uint32_t inO
 		outHits[i].sub_shape = had_hit? hit.mSubShapeID2.GetValue() : 0xffffffffu;
 		outHits[i].fraction = had_hit? hit.mFraction : 1.0f + FLT_EPSILON;
 	}
+}
+
+// Non contact constraints of the world by Constraint::mConstraintIndex: count, the state Constraint::SaveState writes (accumulated
+// impulses, the distance constraint's normal), removal (ConstraintManager::Remove: the last constraint takes the index), enabling
+uint32_t jref_num_constraints(void *h) { return (uint32_t)((World *)h)->system.GetConstraints().size(); }
+uint32_t jref_get_constraint_states(void *h, b2j_constraint_state *outStates, uint32_t inCapacity)
+{
+	Constraints constraints = ((World *)h)->system.GetConstraints();
+	for (uint32_t i = 0; i < constraints.size() && i < inCapacity; ++i)
+	{
+		b2j_constraint_state &o = outStates[i];
+		memset(&o, 0, sizeof(o));
+		const Constraint *c = constraints[i];
+		if (c->GetSubType() == EConstraintSubType::Point)
+			static_cast<const PointConstraint *>(c)->GetTotalLambdaPosition().StoreFloat3((Float3 *)o.total_lambda);
+		else if (c->GetSubType() == EConstraintSubType::Distance)
+		{
+			o.total_lambda[0] = static_cast<const DistanceConstraint *>(c)->GetTotalLambdaPosition();
+			static_cast<const DistanceConstraint *>(c)->mWorldSpaceNormal.StoreFloat3((Float3 *)o.world_space_normal);
+		}
+		else if (c->GetSubType() == EConstraintSubType::Hinge)
+		{
+			const HingeConstraint *hc = static_cast<const HingeConstraint *>(c);
+			hc->GetTotalLambdaPosition().StoreFloat3((Float3 *)o.total_lambda);
+			o.total_lambda_rotation[0] = hc->GetTotalLambdaRotation()[0]; o.total_lambda_rotation[1] = hc->GetTotalLambdaRotation()[1];
+			o.total_lambda_limits = hc->GetTotalLambdaRotationLimits(); o.total_lambda_motor = hc->GetTotalLambdaMotor();
+		}
+	}
+	return (uint32_t)constraints.size();
+}
+void jref_remove_constraint(void *h, uint32_t inIndex)
+{
+	World *w = (World *)h;
+	Constraints constraints = w->system.GetConstraints();
+	if (inIndex < constraints.size()) w->system.RemoveConstraint(constraints[inIndex]);
+}
+void jref_set_constraint_enabled(void *h, uint32_t inIndex, int inEnabled)
+{
+	Constraints constraints = ((World *)h)->system.GetConstraints();
+	if (inIndex < constraints.size()) constraints[inIndex]->SetEnabled(inEnabled != 0);
 }
 
 // NarrowPhaseQuery::CollideShape with an AllHitCollisionCollector for n queries of ONE convex query shape (kind: 0 sphere (p0 = radius),

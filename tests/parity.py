@@ -9,11 +9,13 @@ REL_TOL = 1e-4   # north star: 1e-4 relative
 ABS_TOL = 1e-5   # or 1e-5 m absolute
 
 
-FEATURES = ["kinematic", "sensor", "dof_plane2d", "gyroscopic", "step_overrides", "no_manifold_reduction", "two_moving_layers", "kinematic_vs_nondynamic", "zoo", "decorated", "cylinder"]
+FEATURES = ["kinematic", "sensor", "dof_plane2d", "gyroscopic", "step_overrides", "no_manifold_reduction", "two_moving_layers", "kinematic_vs_nondynamic", "zoo", "decorated", "cylinder", "joints"]
 """Variants of the `feature` scene of oracle/ref_harness.cpp (sSceneFeature): motion types, body flags (B2J_BODY_SENSOR,
 B2J_BODY_GYROSCOPIC, B2J_BODY_KIN_VS_NONDYN, B2J_BODY_USE_MANIFOLD_REDUCTION off, B2J_BODY_ALLOW_SLEEPING), allowed DOFs, per body
 solver step overrides, two moving broadphase layers; `zoo` = all of them in one world; `decorated` = ScaledShape / RotatedTranslatedShape
-around every convex leaf type (SURVEY 8 f4); `cylinder` = CylinderShape plain / scaled / rotated against the other convex shapes."""
+around every convex leaf type (SURVEY 8 f4); `cylinder` = CylinderShape plain / scaled / rotated against the other convex shapes; `joints` = PointConstraint / DistanceConstraint
+(chain, rope with limits, a cloth that forms one large island, kinematic tow, constraint that wakes a sleeping body, priorities,
+solver step overrides, a disabled constraint)."""
 
 
 def single_step_parity(api, scene, p0=0, p1=0, warm=0, dt=1.0 / 60.0, collision_steps=1, check_events=True, warm_threads=1, before_export=None):

@@ -41,6 +41,12 @@ def ref_lib(variant="det"):
         L.jref_collide_aabox.argtypes = [vp, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.jref_collide_shape.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.jref_collide_volume.argtypes = [vp, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.jref_num_constraints.restype = C.c_uint32
+        L.jref_num_constraints.argtypes = [vp]
+        L.jref_get_constraint_states.restype = C.c_uint32
+        L.jref_get_constraint_states.argtypes = [vp, C.c_void_p, C.c_uint32]
+        L.jref_remove_constraint.argtypes = [vp, C.c_uint32]
+        L.jref_set_constraint_enabled.argtypes = [vp, C.c_uint32, C.c_int]
         L.jref_replace_body.restype = C.c_uint32
         L.jref_replace_body.argtypes = [vp, C.c_uint32, C.c_float]
         L.jref_query.argtypes = [vp, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -80,6 +86,8 @@ def _fp(a):
 
 HIT_DTYPE = np.dtype([("body", np.uint32), ("sub_shape", np.uint32), ("fraction", np.float32)])
 # b2j_shape_query / b2j_collide_shape_hit (include/jolt_b200.h)
+CONSTRAINT_STATE_DTYPE = np.dtype([("total_lambda", np.float32, 3), ("world_space_normal", np.float32, 3), ("total_lambda_rotation", np.float32, 2),
+                                   ("total_lambda_limits", np.float32), ("total_lambda_motor", np.float32)])  # b2j_constraint_state
 SHAPE_QUERY_DTYPE = np.dtype([("shape", np.int32), ("position", np.float32, 3), ("rotation", np.float32, 4), ("base_offset", np.float32, 3)])
 SHAPE_HIT_DTYPE = np.dtype([("body", np.uint32), ("sub_shape1", np.uint32), ("sub_shape2", np.uint32), ("penetration_depth", np.float32),
                             ("point1", np.float32, 3), ("point2", np.float32, 3), ("axis", np.float32, 3)])
@@ -143,6 +151,18 @@ class RefWorld:
         ids = np.full((len(boxes), max_hits), 0xffffffff, np.uint32)
         self.L.jref_collide_aabox(self.h, boxes.ctypes.data, len(boxes), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data)
         return counts, ids
+
+    def constraint_states(self):
+        n = self.L.jref_num_constraints(self.h)
+        out = np.zeros(n, CONSTRAINT_STATE_DTYPE)
+        self.L.jref_get_constraint_states(self.h, out.ctypes.data, n)
+        return out
+
+    def remove_constraint(self, index):
+        self.L.jref_remove_constraint(self.h, index)
+
+    def set_constraint_enabled(self, index, enabled):
+        self.L.jref_set_constraint_enabled(self.h, index, int(enabled))
 
     def collide_shape(self, kind, params, queries, max_separation_distance=0.0, object_layer=0xffffffff, max_hits=64):
         """NarrowPhaseQuery::CollideShape (all hits) of one convex shape (kind 0 sphere / 1 box / 2 capsule / 3 cylinder) for every query."""
@@ -318,6 +338,23 @@ class B2JWorld:
         if self.api.b2j_query_collide_aabox(self.h, boxes.ctypes.data, len(boxes), object_layer, max_hits, counts.ctypes.data, ids.ctypes.data) != 0:
             raise RuntimeError("b2j_query_collide_aabox failed: " + self.api.last_error())
         return counts, ids
+
+    def constraint_states(self):
+        n = self.api.b2j_num_constraints(self.h)
+        out = np.zeros(n, CONSTRAINT_STATE_DTYPE)
+        if n and self.api.b2j_constraints_get_state(self.h, 0, n, out.ctypes.data) != 0:
+            raise RuntimeError("b2j_constraints_get_state failed: " + self.api.last_error())
+        return out
+
+    def remove_constraint(self, index):
+        idx = np.array([index], np.uint32)
+        if self.api.b2j_constraints_remove(self.h, idx.ctypes.data, 1) != 0:
+            raise RuntimeError("b2j_constraints_remove failed: " + self.api.last_error())
+
+    def set_constraint_enabled(self, index, enabled):
+        idx, en = np.array([index], np.uint32), np.array([1 if enabled else 0], np.uint8)
+        if self.api.b2j_constraints_set_enabled(self.h, idx.ctypes.data, 1, en.ctypes.data) != 0:
+            raise RuntimeError("b2j_constraints_set_enabled failed: " + self.api.last_error())
 
     def collide_shape(self, kind, params, queries, max_separation_distance=0.0, object_layer=0xffffffff, max_hits=64):
         """b2j_query_collide_shape with a query shape made from the same parameters as RefWorld.collide_shape."""

@@ -76,16 +76,16 @@ def _check_feature(flib, variant, steps, scene="feature"):
     ref.close()
 
 
-FEATURE_IDS = ["kinematic", "sensor", "dof_plane2d", "gyroscopic", "step_overrides", "no_manifold_reduction", "two_moving_layers", "kinematic_vs_nondynamic", "zoo", "decorated", "cylinder"]
+FEATURE_IDS = ["kinematic", "sensor", "dof_plane2d", "gyroscopic", "step_overrides", "no_manifold_reduction", "two_moving_layers", "kinematic_vs_nondynamic", "zoo", "decorated", "cylinder", "joints"]
 
 
-@pytest.mark.parametrize("variant", range(11), ids=FEATURE_IDS)
+@pytest.mark.parametrize("variant", range(12), ids=FEATURE_IDS)
 def test_facade_feature_scene_matches_reference_hostsim(hostsim_facade, variant):
     _check_feature(hostsim_facade, variant, 120)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", range(11), ids=FEATURE_IDS)
+@pytest.mark.parametrize("variant", range(12), ids=FEATURE_IDS)
 def test_facade_feature_scene_matches_reference_gpu(gpu_api, ref_available, variant):
     _check_feature(F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api), variant, 200)
 
