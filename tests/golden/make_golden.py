@@ -20,7 +20,8 @@ import refharness as R  # noqa: E402
 CASES = [("pyramid", 6, 0, (1, 30, 120)), ("convex_vs_mesh", 2, 0, (1, 60, 150)), ("pile", 600, 15, (1, 60, 150)), ("max_bodies", 300, 0, (1, 20)),
          ("feature", 8, 0, (1, 30, 90, 200)),  # feature 8 = the zoo: every motion type / body flag / override in one world
          ("feature", 9, 0, (1, 40, 100, 220)),  # feature 9 = ScaledShape / RotatedTranslatedShape around every convex leaf type
-         ("feature", 10, 0, (1, 40, 100, 220))]  # feature 10 = CylinderShape plain / scaled / rotated against the other convex shapes
+         ("feature", 10, 0, (1, 40, 100, 220)),  # feature 10 = CylinderShape plain / scaled / rotated against the other convex shapes
+         ("feature", 11, 0, (1, 40, 120, 250))]  # feature 11 = PointConstraint / DistanceConstraint / HingeConstraint (chain, rope, cloth = one large island, hinges)
 
 
 def snapshot(world):
