@@ -1517,7 +1517,8 @@ public:
 	const b2j_step_stats &GetLastStepStats() const { return mStats; }
 	// (diagnostics / tests: how many body rows the last refresh of the host mirror fetched -- see EnsureState)
 	uint32 GetLastDownloadCount() const { EnsureState(); return mLastDownloadCount; }
-	b2j_world *GetWorld() const { return mWorld; }
+	// the C ABI handle (everything added through the interface so far is on the device when this returns)
+	b2j_world *GetWorld() const { PhysicsSystem *self = const_cast<PhysicsSystem *>(this); self->mBodyInterface.Flush(); self->FlushConstraints(); return mWorld; }
 	const char *GetLastError() const { return b2j_last_error(); }
 
 	// PhysicsSystem::SaveState / RestoreState (PhysicsSystem.h:165-168): always the whole state (Global | Bodies | Contacts); filters

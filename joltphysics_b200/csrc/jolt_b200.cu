@@ -416,6 +416,13 @@ struct KResetWorlds
 	}
 };
 
+// the non contact constraints of the reset worlds go back to their state at creation
+struct KResetJoints
+{
+	JointState *state; const JointState *init; const uint32_t *worlds; uint32_t per_world;
+	B2J_D void operator()(uint32_t t) const { uint32_t j = t % per_world; state[(size_t)worlds[t / per_world] * per_world + j] = init[j]; }
+};
+
 // bodies of the reset worlds that were NOT active at creation leave the active list (keep = 0), as KDeactivate does
 struct KResetMarkKeep
 {
@@ -593,6 +600,7 @@ struct b2j_world
 	JointCtx jc = { };
 	uint32_t joint_capacity = 0;
 	bool joints_dirty = false;               // definitions / order changed since the last upload
+	JointState *d_joint_init = nullptr;      // batch group: the constraint state of one world at creation (b2j_batch_reset_worlds)
 
 	float prev_dt = 0.0f;
 	StepCounters h_counters;
@@ -840,31 +848,34 @@ void joints_upload(b2j_world *W)
 {
 	if (!W->joints_dirty) return;
 	W->joints_dirty = false;
-	uint32_t n = (uint32_t)W->h_joints.size();
-	W->jc.num_joints = n;
+	// (a batch group holds the list of ONE world: world w's copy of constraint i is entry w * n + i, its bodies in the slots of world w)
+	uint32_t n = (uint32_t)W->h_joints.size(), nw = W->num_worlds, stride = W->d.world_stride;
+	W->jc.num_joints = n * nw;
 	if (n == 0) return;
 	Runtime &rt = W->rt;
-	std::vector<JointDef> defs(n);
-	std::vector<uint32_t> order(n), steps(n);
-	for (uint32_t i = 0; i < n; ++i)
-	{
-		const b2j_constraint_desc &c = W->h_joints[i];
-		JointDef &d = defs[i];
-		memset(&d, 0, sizeof(d));
-		d.type = c.type; d.b1 = slot_of(c.body1); d.b2 = slot_of(c.body2); d.flags = c.enabled? JOINT_ENABLED : 0u;
-		d.priority = c.priority; d.steps_override = (uint32_t)c.num_velocity_steps_override | ((uint32_t)c.num_position_steps_override << 8);
-		d.index = i;
-		d.local1 = f4(v3_load(c.point1), c.min_distance); d.local2 = f4(v3_load(c.point2), c.max_distance);
-		d.axis1 = f4(v3_load(c.hinge_axis1), c.limits_min); d.axis2 = f4(v3_load(c.hinge_axis2), c.limits_max);
-		d.inv_initial_orientation = f4(c.inv_initial_orientation[0], c.inv_initial_orientation[1], c.inv_initial_orientation[2], c.inv_initial_orientation[3]);
-		d.hinge = f4(c.max_friction_torque, 0.0f, 0.0f, 0.0f);
-		order[i] = i; steps[i] = d.steps_override;
-	}
+	std::vector<JointDef> defs((size_t)n * nw);
+	std::vector<uint32_t> order((size_t)n * nw), steps((size_t)n * nw), sorted(n);
+	for (uint32_t i = 0; i < n; ++i) sorted[i] = i;
 	// ConstraintManager::sSortConstraints: priority, then constraint index
-	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return W->h_joints[a].priority < W->h_joints[b].priority; });
-	rt.upload(W->jc.defs, defs.data(), n);
-	rt.upload(const_cast<uint32_t *>(W->jc.order), order.data(), n);
-	rt.upload(const_cast<uint32_t *>(W->sc.joint_steps), steps.data(), n);
+	std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t a, uint32_t b) { return W->h_joints[a].priority < W->h_joints[b].priority; });
+	for (uint32_t wi = 0; wi < nw; ++wi)
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			const b2j_constraint_desc &c = W->h_joints[i];
+			JointDef &d = defs[(size_t)wi * n + i];
+			memset(&d, 0, sizeof(d));
+			d.type = c.type; d.b1 = slot_of(c.body1) + wi * stride; d.b2 = slot_of(c.body2) + wi * stride; d.flags = c.enabled? JOINT_ENABLED : 0u;
+			d.priority = c.priority; d.steps_override = (uint32_t)c.num_velocity_steps_override | ((uint32_t)c.num_position_steps_override << 8);
+			d.index = i;
+			d.local1 = f4(v3_load(c.point1), c.min_distance); d.local2 = f4(v3_load(c.point2), c.max_distance);
+			d.axis1 = f4(v3_load(c.hinge_axis1), c.limits_min); d.axis2 = f4(v3_load(c.hinge_axis2), c.limits_max);
+			d.inv_initial_orientation = f4(c.inv_initial_orientation[0], c.inv_initial_orientation[1], c.inv_initial_orientation[2], c.inv_initial_orientation[3]);
+			d.hinge = f4(c.max_friction_torque, 0.0f, 0.0f, 0.0f);
+			order[(size_t)wi * n + i] = wi * n + sorted[i]; steps[(size_t)wi * n + i] = d.steps_override;
+		}
+	rt.upload(W->jc.defs, defs.data(), defs.size());
+	rt.upload(const_cast<uint32_t *>(W->jc.order), order.data(), order.size());
+	rt.upload(const_cast<uint32_t *>(W->sc.joint_steps), steps.data(), steps.size());
 	rt.sync();
 }
 
@@ -1663,7 +1674,7 @@ void b2j_world_destroy(b2j_world *W)
 		rt.free_(j.defs); rt.free_(j.state); rt.free_(j.active_flag); rt.free_(j.order_flag); rt.free_(j.order_scan); rt.free_(j.active_joints); rt.free_(j.wake_key);
 		uint32_t *p1 = const_cast<uint32_t *>(j.order); rt.free_(p1);
 		uint32_t *p2 = const_cast<uint32_t *>(W->sc.joint_steps); rt.free_(p2);
-		rt.free_(W->sc.body_nj);
+		rt.free_(W->sc.body_nj); rt.free_(W->d_joint_init);
 	}
 	rt.free_(W->d_mesh_scratch); rt.free_(W->d_query_scratch); rt.free_(W->d_cache_invalid);
 	for (int i = 0; i < 2; ++i) { rt.free_(W->d_collide_keys[i]); rt.free_(W->d_collide_vals[i]); }
@@ -2572,6 +2583,7 @@ int b2j_constraints_remove(b2j_world *W, const uint32_t *indices, uint32_t n)
 {
 	if (n == 0) return 0;
 	B2J_DEVICE_GUARD(W);
+	if (W->num_worlds != 1) { last_error() = "b2j_constraints_remove: the constraint list of batched worlds is fixed"; return -1; }
 	Runtime &rt = W->rt;
 	for (uint32_t i = 0; i < n; ++i)
 	{
@@ -2893,7 +2905,7 @@ static bool snapshot_take(b2j_world *W, WorldSnapshot &ws)
 	keep(ws.sleep_spheres, d.sleep_spheres, 3 * (size_t)n); keep(ws.sleep_timer, d.sleep_timer, n); keep(ws.active_index, d.active_index, n);
 	keep(ws.active, d.active, na);
 	ws.h_joints = W->h_joints;
-	if (!W->h_joints.empty()) keep(ws.joint_state, W->jc.state, W->h_joints.size());
+	if (!W->h_joints.empty()) keep(ws.joint_state, W->jc.state, W->h_joints.size() * W->num_worlds);
 	keep(ws.pairs, d.read_cache.pairs, np); keep(ws.manifolds, d.read_cache.manifolds, nm);
 	ws.h_ids.assign(W->h_ids.begin(), W->h_ids.begin() + n); ws.h_layer.assign(W->h_layer.begin(), W->h_layer.begin() + n); ws.h_static.assign(W->h_static.begin(), W->h_static.begin() + n);
 	ws.layer_bodies = W->layer_bodies; ws.layer_has_moving = W->layer_has_moving;
@@ -2926,11 +2938,11 @@ static bool snapshot_restore(b2j_world *W, const WorldSnapshot &ws)
 	rt.copy(d.inv_inertia_diag.base, ws.inertia, 2 * (size_t)n); rt.copy(d.bounds_min.base, ws.bounds, 2 * (size_t)n);
 	rt.copy(d.sleep_spheres, ws.sleep_spheres, 3 * (size_t)n); rt.copy(d.sleep_timer, ws.sleep_timer, n); rt.copy(d.active_index, ws.active_index, n);
 	rt.copy(d.active, ws.active, ws.num_active);
-	if (!ws.h_joints.empty() && !joints_reserve(W, (uint32_t)ws.h_joints.size())) return false;
+	if (!ws.h_joints.empty() && !joints_reserve(W, (uint32_t)ws.h_joints.size() * W->num_worlds)) return false;
 	W->h_joints = ws.h_joints;
 	W->joints_dirty = true;
-	W->jc.num_joints = (uint32_t)ws.h_joints.size();
-	if (!ws.h_joints.empty()) rt.copy(W->jc.state, ws.joint_state, ws.h_joints.size());
+	W->jc.num_joints = (uint32_t)ws.h_joints.size() * W->num_worlds;
+	if (!ws.h_joints.empty()) rt.copy(W->jc.state, ws.joint_state, ws.h_joints.size() * W->num_worlds);
 	// contact cache: the snapshot becomes the read cache, the write cache is empty between steps
 	int ri = W->write_idx ^ 1;
 	clear_cache(W, ri);
@@ -3223,7 +3235,6 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 	sync_dworld(P);
 	uint32_t stride = P->num_slots;
 	if (stride == 0 || (uint64_t)stride * n_worlds > 0xfffffff0ull) { last_error() = "b2j_batch_create: too many bodies"; return nullptr; }
-	if (!P->h_joints.empty()) { last_error() = "b2j_batch_create: worlds with non contact constraints cannot be batched yet"; return nullptr; }
 	b2j_world_desc desc = P->desc;
 	desc.object_to_broadphase = P->t_o2bp.data(); desc.object_vs_broadphase = P->t_ovbp.data(); desc.object_vs_object = P->t_ovo.data();
 	desc.settings = P->d.settings;
@@ -3300,6 +3311,18 @@ static b2j_world *batch_create_group(b2j_world *P, uint32_t n_worlds, uint32_t m
 		rt.launch(k, P->num_active * n_worlds);
 	}
 	B->num_active = P->num_active * n_worlds;
+	// non contact constraints: every world gets the prototype's list (bodies offset to the world's slots) and its current state
+	if (!P->h_joints.empty())
+	{
+		uint32_t nj = (uint32_t)P->h_joints.size();
+		if ((uint64_t)nj * n_worlds > 0x7ffffff0ull || !joints_reserve(B, nj * n_worlds)) { b2j_world_destroy(B); return nullptr; }
+		B->h_joints = P->h_joints;
+		B->joints_dirty = true;
+		B->d_joint_init = rt.alloc<JointState>(nj, false);
+		if (B->d_joint_init == nullptr) { last_error() = "out of device memory"; b2j_world_destroy(B); return nullptr; }
+		rt.copy(B->d_joint_init, P->jc.state, nj);
+		replicate(rt, B->jc.state, P->jc.state, nj, nj, n_worlds);
+	}
 	rt.sync();
 	if (!rt.check("b2j_batch_create")) { b2j_world_destroy(B); return nullptr; }
 	return B;
@@ -3497,6 +3520,12 @@ int b2j_batch_reset_worlds(b2j_batch *b, const uint32_t *world_indices, uint32_t
 		// 2. state of the bodies, 3. forget the contacts of those worlds
 		{ KResetWorlds k; k.w = G->d; k.init = b->init; k.worlds = d_local; rt.launch(k, items); }
 		{ KResetPurgeCache k; k.w = G->d; k.reset_flag = d_flags; rt.launch(k, G->cache_num_pairs[G->write_idx ^ 1]); }
+		if (!G->h_joints.empty())
+		{
+			// 4. the constraints of those worlds forget their accumulated impulses (back to the creation state)
+			KResetJoints k; k.state = G->jc.state; k.init = G->d_joint_init; k.worlds = d_local; k.per_world = (uint32_t)G->h_joints.size();
+			rt.launch(k, (uint32_t)(local.size() * G->h_joints.size()));
+		}
 		rt.sync();
 		rt.free_(d_local); rt.free_(d_flags);
 		for (uint32_t l = 0; l < G->d.num_bp_layers; ++l) G->layer_needs_build[l] = 1;

@@ -49,13 +49,15 @@ def hostsim_facade(hostsim_api):
     return F.FacadeLib(os.path.join(ROOT, "tests", "hostsim", "_build", "libb2j_facade_hostsim.so"), hostsim_api)
 
 
-@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 4, 0, 5, 40), ("pile", 300, 15, 3, 60), ("convex_vs_mesh", 1, 0, 4, 80), ("compound", 0, 0, 3, 100)])
+@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 4, 0, 5, 40), ("pile", 300, 15, 3, 60), ("convex_vs_mesh", 1, 0, 4, 80), ("compound", 0, 0, 3, 100),
+                                                         ("feature", 11, 0, 3, 90)])  # feature 11 = the joints scene: every world carries the constraints
 def test_batch_matches_single_world_hostsim(hostsim_api, hostsim_facade, scene, p0, p1, n_worlds, steps):
     _check_batch(hostsim_api, hostsim_facade, scene, p0, p1, n_worlds, steps)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 15, 0, 16, 60), ("pile", 1000, 15, 8, 90), ("convex_vs_mesh", 3, 0, 6, 120), ("compound", 0, 0, 12, 150)])
+@pytest.mark.parametrize("scene,p0,p1,n_worlds,steps", [("pyramid", 15, 0, 16, 60), ("pile", 1000, 15, 8, 90), ("convex_vs_mesh", 3, 0, 6, 120), ("compound", 0, 0, 12, 150),
+                                                         ("feature", 11, 0, 9, 200)])
 def test_batch_matches_single_world_gpu(gpu_api, scene, p0, p1, n_worlds, steps):
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
     _check_batch(gpu_api, flib, scene, p0, p1, n_worlds, steps)
@@ -165,13 +167,13 @@ def _check_reset(api, flib, scene, p0, p1, n_worlds, steps_before, steps_after, 
 
 
 # pile: bodies fall asleep before the reset (they must be re-activated); small_stack would do as well but has no facade scene
-@pytest.mark.parametrize("scene,p0,p1,before,after", [("pyramid", 4, 0, 25, 30), ("pile", 200, 15, 260, 40)])
+@pytest.mark.parametrize("scene,p0,p1,before,after", [("pyramid", 4, 0, 25, 30), ("pile", 200, 15, 260, 40), ("feature", 11, 0, 50, 40)])
 def test_batch_reset_worlds_hostsim(hostsim_api, hostsim_facade, scene, p0, p1, before, after):
     _check_reset(hostsim_api, hostsim_facade, scene, p0, p1, 5, before, after, [1, 3])
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scene,p0,p1,before,after,groups", [("pyramid", 8, 0, 40, 40, 1), ("pile", 500, 15, 300, 60, 1), ("pyramid", 6, 0, 30, 30, 3)])
+@pytest.mark.parametrize("scene,p0,p1,before,after,groups", [("pyramid", 8, 0, 40, 40, 1), ("pile", 500, 15, 300, 60, 1), ("pyramid", 6, 0, 30, 30, 3), ("feature", 11, 0, 60, 60, 2)])
 def test_batch_reset_worlds_gpu(gpu_api, monkeypatch, scene, p0, p1, before, after, groups):
     monkeypatch.setenv("B2J_BATCH_GROUPS", str(groups))
     flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), gpu_api)
