@@ -42,7 +42,7 @@ enum {
 enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4, B2J_SHAPE_CYLINDER = 5, B2J_SHAPE_COMPOUND = 6 };
 
 /* Constraint kinds on the path (EConstraintSubType subset, Jolt/Physics/Constraints/Constraint.h:31-49) */
-enum { B2J_CONSTRAINT_POINT = 0, B2J_CONSTRAINT_DISTANCE = 1, B2J_CONSTRAINT_HINGE = 2 };
+enum { B2J_CONSTRAINT_POINT = 0, B2J_CONSTRAINT_DISTANCE = 1, B2J_CONSTRAINT_HINGE = 2, B2J_CONSTRAINT_FIXED = 3 };
 
 /* Body flags */
 enum {
@@ -306,7 +306,7 @@ uint32_t b2j_num_active_bodies(const b2j_world *w);   /* PhysicsSystem::GetNumAc
 uint32_t b2j_get_active_bodies(b2j_world *w, uint32_t *ids, uint32_t cap);
 
 /* ---- non contact constraints between two bodies (PointConstraint, DistanceConstraint without limit springs,
- *      HingeConstraint with angle limits and friction, motor off).
+ *      HingeConstraint with angle limits and friction, motor off, FixedConstraint).
  *      Replaces PhysicsSystem::AddConstraint(s) / RemoveConstraint(s) (PhysicsSystem.h:76-87 -> ConstraintManager::Add / Remove,
  *      Jolt/Physics/Constraints/ConstraintManager.cpp:17-62). A constraint is addressed by its position in the world's list, which is
  *      Constraint::mConstraintIndex: adding appends, removing moves the last constraint into the freed position. Active constraints take
@@ -323,7 +323,8 @@ typedef struct b2j_constraint_desc {
 	uint8_t  enabled;                    /* Constraint::mEnabled                                                                          */
 	uint8_t  reserved;
 	/* HingeConstraint (HingeConstraint.h:118-160): mLocalSpaceHingeAxis1 / 2, mInvInitialOrientation, mLimitsMin / Max ([-pi, 0] / [0, pi]),
-	 * mMaxFrictionTorque; the motor is off and the limits have no spring */
+	 * mMaxFrictionTorque; the motor is off and the limits have no spring. FixedConstraint (FixedConstraint.h): point1 / point2 and
+	 * inv_initial_orientation (mInvInitialOrientation) */
 	float    hinge_axis1[3], hinge_axis2[3];
 	float    inv_initial_orientation[4];
 	float    limits_min, limits_max, max_friction_torque;
@@ -335,7 +336,7 @@ typedef struct b2j_constraint_state
 {
 	float total_lambda[3];           /* point / hinge: mPointConstraintPart (xyz); distance: mAxisConstraint (x)  */
 	float world_space_normal[3];     /* distance: mWorldSpaceNormal                                                */
-	float total_lambda_rotation[2];  /* hinge: mRotationConstraintPart                                             */
+	float total_lambda_rotation[3];  /* hinge: mRotationConstraintPart (xy); fixed: mRotationConstraintPart (xyz)  */
 	float total_lambda_limits;       /* hinge: mRotationLimitsConstraintPart                                       */
 	float total_lambda_motor;        /* hinge: mMotorConstraintPart (the friction while the motor is off)          */
 } b2j_constraint_state;

@@ -1112,7 +1112,7 @@ public:
 // its settings and two bodies, handed to PhysicsSystem::AddConstraint (which owns it from then on, like the reference's Ref<Constraint>)
 // and lives on the device as one entry of the world's constraint list (b2j_constraints_add).
 enum class EConstraintSpace { LocalToBodyCOM, WorldSpace };
-enum class EConstraintSubType { Point = B2J_CONSTRAINT_POINT, Distance = B2J_CONSTRAINT_DISTANCE, Hinge = B2J_CONSTRAINT_HINGE };
+enum class EConstraintSubType { Point = B2J_CONSTRAINT_POINT, Distance = B2J_CONSTRAINT_DISTANCE, Hinge = B2J_CONSTRAINT_HINGE, Fixed = B2J_CONSTRAINT_FIXED };
 
 class Constraint
 {
@@ -1294,6 +1294,70 @@ inline HingeConstraint::HingeConstraint(Body &inBody1, Body &inBody2, const Hing
 	}
 	mDesc.hinge_axis1[0] = a1.x; mDesc.hinge_axis1[1] = a1.y; mDesc.hinge_axis1[2] = a1.z;
 	mDesc.hinge_axis2[0] = a2.x; mDesc.hinge_axis2[1] = a2.y; mDesc.hinge_axis2[2] = a2.z;
+	mDesc.inv_initial_orientation[0] = inv_initial.x; mDesc.inv_initial_orientation[1] = inv_initial.y; mDesc.inv_initial_orientation[2] = inv_initial.z; mDesc.inv_initial_orientation[3] = inv_initial.w;
+}
+
+// FixedConstraint (FixedConstraint.h): two bodies welded at a point, no relative rotation
+class FixedConstraintSettings;
+class FixedConstraint final : public TwoBodyConstraint
+{
+public:
+	inline FixedConstraint(Body &inBody1, Body &inBody2, const FixedConstraintSettings &inSettings);
+	EConstraintSubType GetSubType() const override { return EConstraintSubType::Fixed; }
+};
+class FixedConstraintSettings final : public TwoBodyConstraintSettings
+{
+public:
+	TwoBodyConstraint *Create(Body &inBody1, Body &inBody2) const override { return new FixedConstraint(inBody1, inBody2, *this); }
+	EConstraintSpace mSpace = EConstraintSpace::WorldSpace;
+	bool mAutoDetectPoint = false;
+	RVec3 mPoint1 = RVec3::sZero(), mPoint2 = RVec3::sZero();
+	Vec3 mAxisX1 = Vec3::sAxisX(), mAxisY1 = Vec3::sAxisY(), mAxisX2 = Vec3::sAxisX(), mAxisY2 = Vec3::sAxisY();
+};
+
+inline FixedConstraint::FixedConstraint(Body &inBody1, Body &inBody2, const FixedConstraintSettings &inSettings) : TwoBodyConstraint(inBody1, inBody2)
+{
+	mDesc.type = B2J_CONSTRAINT_FIXED;
+	mDesc.priority = inSettings.mConstraintPriority; mDesc.enabled = inSettings.mEnabled;
+	mDesc.num_velocity_steps_override = (uint8)inSettings.mNumVelocityStepsOverride; mDesc.num_position_steps_override = (uint8)inSettings.mNumPositionStepsOverride;
+	// RotationEulerConstraintPart::sGetInvInitialOrientationXY
+	Quat inv_initial = Quat::sIdentity();
+	if (!(inSettings.mAxisX1 == inSettings.mAxisX2 && inSettings.mAxisY1 == inSettings.mAxisY2))
+	{
+		Mat44RT constraint1, constraint2;
+		constraint1.c0 = inSettings.mAxisX1; constraint1.c1 = inSettings.mAxisY1; constraint1.c2 = inSettings.mAxisX1.Cross(inSettings.mAxisY1);
+		constraint2.c0 = inSettings.mAxisX2; constraint2.c1 = inSettings.mAxisY2; constraint2.c2 = inSettings.mAxisX2.Cross(inSettings.mAxisY2);
+		Quat q1 = constraint1.GetQuaternion();
+		inv_initial = constraint2.GetQuaternion() * Quat(-q1.x, -q1.y, -q1.z, q1.w);
+	}
+	RVec3 p1 = inSettings.mPoint1, p2 = inSettings.mPoint2, w1, w2;
+	if (inSettings.mSpace == EConstraintSpace::WorldSpace)
+	{
+		if (inSettings.mAutoDetectPoint)
+		{
+			// the anchor: the centre of mass of the body that can move, or the mass weighted average (FixedConstraint.cpp:44-66)
+			RVec3 anchor;
+			if (!inBody1.mHasMotionProperties) anchor = inBody2.GetCenterOfMassPosition();
+			else if (!inBody2.mHasMotionProperties) anchor = inBody1.GetCenterOfMassPosition();
+			else
+			{
+				float inv_m1 = inBody1.mDynamicInvMass, inv_m2 = inBody2.mDynamicInvMass; // MotionProperties::GetInverseMassUnchecked
+				float total_inv_mass = inv_m1 + inv_m2;
+				if (total_inv_mass != 0.0f)
+				{
+					RVec3 sum = inv_m1 * inBody1.GetCenterOfMassPosition() + inv_m2 * inBody2.GetCenterOfMassPosition();
+					float div = inv_m1 + inv_m2;
+					anchor = RVec3(sum.x / div, sum.y / div, sum.z / div);
+				}
+				else
+					anchor = inBody1.GetCenterOfMassPosition();
+			}
+			p1 = anchor; p2 = anchor;
+		}
+		Quat r1 = inBody1.GetRotation(), r2 = inBody2.GetRotation();
+		inv_initial = (Quat(-r2.x, -r2.y, -r2.z, r2.w) * inv_initial) * r1;
+	}
+	SetPoints(inSettings.mSpace, p1, p2, w1, w2);
 	mDesc.inv_initial_orientation[0] = inv_initial.x; mDesc.inv_initial_orientation[1] = inv_initial.y; mDesc.inv_initial_orientation[2] = inv_initial.z; mDesc.inv_initial_orientation[3] = inv_initial.w;
 }
 

@@ -10,6 +10,7 @@
 //   HingeConstraint (motor off, limits without spring) HingeConstraint.cpp:137-318, ConstraintPart/HingeRotationConstraintPart.h:44-190,
 //                                                     ConstraintPart/AngleConstraintPart.h:38-215, Quat::GetRotationAngle Quat.h:197,
 //                                                     Vec4::ATan Vec4.inl (cephes atanf), CenterAngleAroundZero Math.h:28-44
+//   FixedConstraint                                   FixedConstraint.cpp:82-112, ConstraintPart/RotationEulerConstraintPart.h:139-230
 //   where the step calls them                         PhysicsSystem.cpp:720-744 (active constraints), :795-828 (setup, islands: bodies a
 //                                                     constraint wakes up join the active list but get no gravity this step, :746-791),
 //                                                     :1415-1427, :1503-1540 (warm start, velocity), :2596-2603, :2661-2672 (position)
@@ -27,7 +28,7 @@
 
 namespace b2j {
 
-enum { JOINT_POINT = B2J_CONSTRAINT_POINT, JOINT_DISTANCE = B2J_CONSTRAINT_DISTANCE, JOINT_HINGE = B2J_CONSTRAINT_HINGE };
+enum { JOINT_POINT = B2J_CONSTRAINT_POINT, JOINT_DISTANCE = B2J_CONSTRAINT_DISTANCE, JOINT_HINGE = B2J_CONSTRAINT_HINGE, JOINT_FIXED = B2J_CONSTRAINT_FIXED };
 enum : uint32_t { JOINT_ENABLED = 1u, SRC_JOINT = 0x80000000u };
 
 // what the caller described (b2j_constraint_desc) with the bodies resolved to slots
@@ -59,6 +60,8 @@ struct alignas(16) JointState
 	F4 h_eff;                              // rotation part mEffectiveMass: (0,0), (0,1), (1,0), (1,1)
 	F4 h_axis;                             // HingeConstraint::mA1 (world space hinge axis of body 1)
 	F4 h_l1, h_l2, h_m1, h_m2;             // limits / motor part mInvI1_Axis, mInvI2_Axis
+	// fixed: RotationEulerConstraintPart (mInvI1 / mInvI2 in h_inv1 / h_inv2, mTotalLambda in lambda2.xyz); its point part uses the members above
+	F4 f_eff[3];                           // columns of its mEffectiveMass
 };
 
 struct JointCtx
@@ -518,13 +521,100 @@ B2J_D void hinge_solve_position(const DWorld &w, const JointDef &d, JointState &
 	}
 }
 
+// ---- FixedConstraint: RotationEulerConstraintPart + PointConstraintPart ---------------------------------------------------------------
+B2J_D void euler_calculate(JointState &s, const JointBody &b1, const M33 &rotation1, const JointBody &b2, const M33 &rotation2)
+{
+	M33 inv1 = joint_inverse_inertia(b1, rotation1), inv2 = joint_inverse_inertia(b2, rotation2);
+	s.h_inv1[0] = f4(inv1.c0); s.h_inv1[1] = f4(inv1.c1); s.h_inv1[2] = f4(inv1.c2);
+	s.h_inv2[0] = f4(inv2.c0); s.h_inv2[1] = f4(inv2.c1); s.h_inv2[2] = f4(inv2.c2);
+	M33 inertia_sum = m33_add(inv1, inv2), eff;
+	if (!m33_inversed(inertia_sum, eff))
+	{
+		// a zero column is a locked axis: identity there (any impulse is multiplied by mInvI1 / mInvI2 afterwards)
+		if (inertia_sum.c0 == v3_zero()) inertia_sum.c0 = v3(1.0f, 0.0f, 0.0f);
+		if (inertia_sum.c1 == v3_zero()) inertia_sum.c1 = v3(0.0f, 1.0f, 0.0f);
+		if (inertia_sum.c2 == v3_zero()) inertia_sum.c2 = v3(0.0f, 0.0f, 1.0f);
+		if (!m33_inversed(inertia_sum, eff))
+		{
+			eff = m33_zero();
+			s.lambda2.x = 0.0f; s.lambda2.y = 0.0f; s.lambda2.z = 0.0f;
+		}
+	}
+	s.f_eff[0] = f4(eff.c0); s.f_eff[1] = f4(eff.c1); s.f_eff[2] = f4(eff.c2);
+}
+
+B2J_D bool euler_apply(const DWorld &w, const JointState &s, const JointBody &b1, const JointBody &b2, V3 lambda)
+{
+	if (lambda == v3_zero())
+		return false;
+	if (b1.type == B2J_MOTION_DYNAMIC)
+		w.angular_velocity[b1.slot] = f4(to_v3(w.angular_velocity[b1.slot]) - mul(m33(to_v3(s.h_inv1[0]), to_v3(s.h_inv1[1]), to_v3(s.h_inv1[2])), lambda));
+	if (b2.type == B2J_MOTION_DYNAMIC)
+		w.angular_velocity[b2.slot] = f4(to_v3(w.angular_velocity[b2.slot]) + mul(m33(to_v3(s.h_inv2[0]), to_v3(s.h_inv2[1]), to_v3(s.h_inv2[2])), lambda));
+	return true;
+}
+
+B2J_D void fixed_setup(const DWorld &w, const JointDef &d, JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	euler_calculate(s, b1, m33_rotation(b1.q), b2, m33_rotation(b2.q));
+	point_calculate(w, d, s, b1, b2);
+}
+
+B2J_D void fixed_warm_start(const DWorld &w, JointState &s, const JointBody &b1, const JointBody &b2, float ratio)
+{
+	V3 rot = v3(s.lambda2.x, s.lambda2.y, s.lambda2.z) * ratio;
+	s.lambda2 = f4(rot, s.lambda2.w);
+	euler_apply(w, s, b1, b2, rot);
+	V3 lambda = to_v3(s.lambda) * ratio;
+	s.lambda = f4(lambda);
+	point_apply_velocity_step(w, s, b1, b2, lambda);
+}
+
+B2J_D void fixed_solve_velocity(const DWorld &w, JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	M33 eff = m33(to_v3(s.f_eff[0]), to_v3(s.f_eff[1]), to_v3(s.f_eff[2]));
+	V3 rot = mul(eff, joint_angular_velocity(w, b1) - joint_angular_velocity(w, b2));
+	s.lambda2 = f4(v3(s.lambda2.x, s.lambda2.y, s.lambda2.z) + rot, s.lambda2.w);
+	euler_apply(w, s, b1, b2, rot);
+	V3 lambda = point_velocity_lambda(w, s, b1, b2);
+	s.lambda = f4(to_v3(s.lambda) + lambda);
+	point_apply_velocity_step(w, s, b1, b2, lambda);
+}
+
+B2J_D void fixed_solve_position(const DWorld &w, const JointDef &d, JointState &s, JointBody &b1, JointBody &b2, float baumgarte)
+{
+	euler_calculate(s, b1, m33_rotation(b1.q), b2, m33_rotation(b2.q));
+	// RotationEulerConstraintPart::SolvePositionConstraint
+	Q4 diff = (b2.q * to_q4(d.inv_initial_orientation)) * q4_conj(b1.q);
+	V3 error = 2.0f * q4_xyz(q4_ensure_w_positive(diff));
+	if (!(error == v3_zero()))
+	{
+		M33 eff = m33(to_v3(s.f_eff[0]), to_v3(s.f_eff[1]), to_v3(s.f_eff[2]));
+		// -inBaumgarte * mEffectiveMass * error = ((-inBaumgarte) * Mat44) * Vec3 (Mat44 * Vec3 adds the translation column (0, 0, 0, 1): + 0)
+		float nb = -baumgarte;
+		V3 lambda = mul(m33(nb * eff.c0, nb * eff.c1, nb * eff.c2), error);
+		if (b1.type == B2J_MOTION_DYNAMIC)
+		{
+			b1.q = add_rotation_step(b1.q, mul(m33(to_v3(s.h_inv1[0]), to_v3(s.h_inv1[1]), to_v3(s.h_inv1[2])), lambda), true);
+			w.rotation[b1.slot] = f4(b1.q);
+		}
+		if (b2.type == B2J_MOTION_DYNAMIC)
+		{
+			b2.q = add_rotation_step(b2.q, mul(m33(to_v3(s.h_inv2[0]), to_v3(s.h_inv2[1]), to_v3(s.h_inv2[2])), lambda), false);
+			w.rotation[b2.slot] = f4(b2.q);
+		}
+	}
+	point_solve_position(w, d, s, b1, b2, baumgarte);
+}
+
 // ---- the four solver entry points of a constraint -----------------------------------------------------------------------------------
 B2J_D void joint_setup_velocity(const DWorld &w, const JointDef &d, JointState &s)
 {
 	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
 	if (d.type == JOINT_POINT) point_calculate(w, d, s, b1, b2);
 	else if (d.type == JOINT_DISTANCE) distance_calculate(w, d, s, b1, b2);
-	else hinge_setup(w, d, s, b1, b2);
+	else if (d.type == JOINT_HINGE) hinge_setup(w, d, s, b1, b2);
+	else fixed_setup(w, d, s, b1, b2);
 }
 
 B2J_D void joint_warm_start(const DWorld &w, const JointDef &d, JointState &s, float ratio)
@@ -541,8 +631,10 @@ B2J_D void joint_warm_start(const DWorld &w, const JointDef &d, JointState &s, f
 		s.lambda.x *= ratio;
 		axis_apply_velocity_step(w, s, b1, b2, to_v3(s.normal), s.lambda.x);
 	}
-	else
+	else if (d.type == JOINT_HINGE)
 		hinge_warm_start(w, d, s, b1, b2, ratio);
+	else
+		fixed_warm_start(w, s, b1, b2, ratio);
 }
 
 B2J_D void joint_solve_velocity(const DWorld &w, const JointDef &d, JointState &s, float dt)
@@ -551,6 +643,11 @@ B2J_D void joint_solve_velocity(const DWorld &w, const JointDef &d, JointState &
 	if (d.type == JOINT_HINGE)
 	{
 		hinge_solve_velocity(w, d, s, b1, b2, dt);
+		return;
+	}
+	if (d.type == JOINT_FIXED)
+	{
+		fixed_solve_velocity(w, s, b1, b2);
 		return;
 	}
 	V3 v1 = joint_linear_velocity(w, b1), w1 = joint_angular_velocity(w, b1), v2 = joint_linear_velocity(w, b2), w2 = joint_angular_velocity(w, b2);
@@ -591,6 +688,8 @@ B2J_D void joint_solve_position(const DWorld &w, const JointDef &d, JointState &
 		point_solve_position(w, d, s, b1, b2, baumgarte);
 	else if (d.type == JOINT_HINGE)
 		hinge_solve_position(w, d, s, b1, b2, baumgarte);
+	else if (d.type == JOINT_FIXED)
+		fixed_solve_position(w, d, s, b1, b2, baumgarte);
 	else
 	{
 		// (the distance of the points as the LAST CalculateConstraintProperties saw them)

@@ -2558,7 +2558,7 @@ int b2j_constraints_add(b2j_world *W, const b2j_constraint_desc *constraints, ui
 		const b2j_constraint_desc &c = constraints[i];
 		uint32_t ids[2] = { c.body1, c.body2 };
 		if (!validate_ids(W, ids, 2, "b2j_constraints_add")) return -1;
-		if (c.type != B2J_CONSTRAINT_POINT && c.type != B2J_CONSTRAINT_DISTANCE && c.type != B2J_CONSTRAINT_HINGE) { last_error() = "b2j_constraints_add: unknown constraint type"; return -1; }
+		if (c.type != B2J_CONSTRAINT_POINT && c.type != B2J_CONSTRAINT_DISTANCE && c.type != B2J_CONSTRAINT_HINGE && c.type != B2J_CONSTRAINT_FIXED) { last_error() = "b2j_constraints_add: unknown constraint type"; return -1; }
 		if (c.type == B2J_CONSTRAINT_HINGE && !(c.limits_min <= 0.0f && c.limits_max >= 0.0f && c.max_friction_torque >= 0.0f)) { last_error() = "b2j_constraints_add: hinge limits_min <= 0 <= limits_max and max_friction_torque >= 0 expected"; return -1; }
 		if (c.body1 == c.body2) { last_error() = "b2j_constraints_add: a constraint connects two different bodies"; return -1; }
 		if (c.type == B2J_CONSTRAINT_DISTANCE && !(c.min_distance >= 0.0f && c.max_distance >= c.min_distance)) { last_error() = "b2j_constraints_add: 0 <= min_distance <= max_distance expected"; return -1; }
@@ -2628,8 +2628,9 @@ int b2j_constraints_get_state(b2j_world *W, uint32_t first, uint32_t n, b2j_cons
 	{
 		out[i].total_lambda[0] = st[i].lambda.x; out[i].total_lambda[1] = st[i].lambda.y; out[i].total_lambda[2] = st[i].lambda.z;
 		out[i].world_space_normal[0] = st[i].normal.x; out[i].world_space_normal[1] = st[i].normal.y; out[i].world_space_normal[2] = st[i].normal.z;
-		out[i].total_lambda_rotation[0] = st[i].lambda2.x; out[i].total_lambda_rotation[1] = st[i].lambda2.y;
-		out[i].total_lambda_limits = st[i].lambda2.z; out[i].total_lambda_motor = st[i].lambda2.w;
+		bool fixed = W->h_joints[first + i].type == B2J_CONSTRAINT_FIXED;
+		out[i].total_lambda_rotation[0] = st[i].lambda2.x; out[i].total_lambda_rotation[1] = st[i].lambda2.y; out[i].total_lambda_rotation[2] = fixed? st[i].lambda2.z : 0.0f;
+		out[i].total_lambda_limits = fixed? 0.0f : st[i].lambda2.z; out[i].total_lambda_motor = st[i].lambda2.w;
 	}
 	return W->rt.check("b2j_constraints_get_state")? 0 : -1;
 }
@@ -2645,7 +2646,8 @@ int b2j_constraints_set_state(b2j_world *W, uint32_t first, uint32_t n, const b2
 	{
 		st[i].lambda = f4(in[i].total_lambda[0], in[i].total_lambda[1], in[i].total_lambda[2], 0.0f);
 		st[i].normal = f4(in[i].world_space_normal[0], in[i].world_space_normal[1], in[i].world_space_normal[2], 0.0f);
-		st[i].lambda2 = f4(in[i].total_lambda_rotation[0], in[i].total_lambda_rotation[1], in[i].total_lambda_limits, in[i].total_lambda_motor);
+		bool fixed = W->h_joints[first + i].type == B2J_CONSTRAINT_FIXED;
+		st[i].lambda2 = f4(in[i].total_lambda_rotation[0], in[i].total_lambda_rotation[1], fixed? in[i].total_lambda_rotation[2] : in[i].total_lambda_limits, in[i].total_lambda_motor);
 	}
 	W->rt.upload(W->jc.state + first, st.data(), n);
 	W->rt.sync();

@@ -7,7 +7,7 @@
 // Variants: 0 kinematic, 1 sensor, 2 dof_plane2d, 3 gyroscopic, 4 step_overrides, 5 no_manifold_reduction, 6 two_moving_layers,
 // 7 kinematic_vs_nondynamic, 8 zoo (0..7 in one world), 9 decorated (ScaledShape / RotatedTranslatedShape around convex shapes),
 // 10 cylinder (CylinderShape plain, scaled and rotated against every other convex shape),
-// 11 joints (PointConstraint / DistanceConstraint / HingeConstraint: chain, rope with limits, doors and flaps on hinges with limits and friction, a cloth that is one large island, kinematic tow, constraint
+// 11 joints (PointConstraint / DistanceConstraint / HingeConstraint / FixedConstraint: chain, rope with limits, doors and flaps on hinges with limits and friction, a cloth that is one large island, kinematic tow, constraint
 // that wakes a sleeping body, priorities, solver step overrides, a disabled constraint; patterns of UnitTests/Physics/DistanceConstraintTests.cpp
 // and Samples/Tests/Constraints/{PointConstraintTest, DistanceConstraintTest}.cpp).
 // inHull: a cooked convex hull (cooking is host side and out of scope).
@@ -371,6 +371,46 @@ static void sFeatureCreate(PhysicsSystem &inSystem, int inVariant, const B2J_SHA
 			hs.mHingeAxis2 = Vec3(0.98006658f, 0.0f, 0.19866933f); hs.mNormalAxis2 = Vec3::sAxisY();
 			hs.mLimitsMin = -0.2f * pi; hs.mLimitsMax = 0.6f * pi;
 			inSystem.AddConstraint(hs.Create(*bar, *flap2));
+		}
+		// (g) fixed constraints (Samples/Tests/Constraints/FixedConstraintTest.cpp pattern): a cantilever of boxes welded to a static wall
+		// (auto detected anchor points) that a falling box lands on, two bodies welded with rotated reference frames that tumble together,
+		// a body welded to a kinematic carrier, a weld with a DOF locked body (singular summed inertia: locked axes get identity columns)
+		BodyCreationSettings wall_s(box, RVec3(0.0f, 3.0f, -12.0f), Quat::sIdentity(), EMotionType::Static, Layers::NON_MOVING);
+		prev = create(wall_s, EActivation::DontActivate);
+		for (int i = 0; i < 4; ++i)
+		{
+			BodyCreationSettings s(box, RVec3(1.0f + 1.0f * float(i), 3.0f, -12.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			Body *b = create(s);
+			FixedConstraintSettings fs; fs.mAutoDetectPoint = true;
+			inSystem.AddConstraint(fs.Create(*prev, *b));
+			prev = b;
+		}
+		BodyCreationSettings load_s(hull, RVec3(3.8f, 5.5f, -12.0f), sRandomQuat(random), EMotionType::Dynamic, Layers::MOVING);
+		create(load_s);
+		{
+			Quat q1 = sRandomQuat(random), q2 = sRandomQuat(random);
+			BodyCreationSettings a_s(capsule, RVec3(8.0f, 5.0f, -12.0f), q1, EMotionType::Dynamic, Layers::MOVING), b_s(box, RVec3(8.9f, 5.3f, -12.2f), q2, EMotionType::Dynamic, Layers::MOVING);
+			a_s.mAngularVelocity = Vec3(1.0f, 2.0f, -1.5f);
+			Body *a = create(a_s), *b = create(b_s);
+			FixedConstraintSettings fs;
+			fs.mPoint1 = RVec3(8.4f, 5.1f, -12.1f); fs.mPoint2 = RVec3(8.45f, 5.15f, -12.1f);
+			fs.mAxisX1 = Vec3::sAxisX(); fs.mAxisY1 = Vec3::sAxisY();
+			fs.mAxisX2 = Vec3(0.0f, 0.0f, 1.0f); fs.mAxisY2 = Vec3::sAxisY();
+			inSystem.AddConstraint(fs.Create(*a, *b));
+		}
+		{
+			BodyCreationSettings carrier_s(slab, RVec3(14.0f, 2.0f, -12.0f), Quat::sIdentity(), EMotionType::Kinematic, Layers::MOVING);
+			carrier_s.mAngularVelocity = Vec3(0.0f, 0.8f, 0.0f); carrier_s.mLinearVelocity = Vec3(0.0f, 0.0f, 0.3f);
+			Body *carrier = create(carrier_s);
+			BodyCreationSettings rider_s(sphere, RVec3(15.0f, 2.75f, -12.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			Body *rider = create(rider_s);
+			FixedConstraintSettings fs; fs.mAutoDetectPoint = true;
+			inSystem.AddConstraint(fs.Create(*carrier, *rider));
+			BodyCreationSettings planar_s(box, RVec3(18.0f, 3.0f, -12.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING), mate_s(box, RVec3(19.0f, 3.0f, -12.0f), Quat::sIdentity(), EMotionType::Dynamic, Layers::MOVING);
+			planar_s.mAllowedDOFs = EAllowedDOFs::Plane2D; mate_s.mAllowedDOFs = EAllowedDOFs::Plane2D;
+			Body *planar = create(planar_s), *mate = create(mate_s);
+			FixedConstraintSettings fs2; fs2.mAutoDetectPoint = true;
+			inSystem.AddConstraint(fs2.Create(*planar, *mate));
 		}
 	}
 }

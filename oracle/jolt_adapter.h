@@ -22,6 +22,7 @@
 #include <Jolt/Physics/Constraints/PointConstraint.h>
 #include <Jolt/Physics/Constraints/DistanceConstraint.h>
 #include <Jolt/Physics/Constraints/HingeConstraint.h>
+#include <Jolt/Physics/Constraints/FixedConstraint.h>
 #include <jolt_b200.h>
 
 #include <unordered_map>
@@ -471,8 +472,17 @@ inline b2j_world *sExportWorld(const Api &inApi, const PhysicsSystem &inSystem, 
 				cs.total_lambda_limits = hc->GetTotalLambdaRotationLimits(); cs.total_lambda_motor = hc->GetTotalLambdaMotor();
 			}
 			break;
+		case EConstraintSubType::Fixed:
+			{
+				const FixedConstraint *fc = static_cast<const FixedConstraint *>(tb);
+				cd.type = B2J_CONSTRAINT_FIXED;
+				sStore(fc->mInvInitialOrientation, cd.inv_initial_orientation); // (no getter)
+				sStore(fc->GetTotalLambdaPosition(), cs.total_lambda);
+				sStore(fc->GetTotalLambdaRotation(), cs.total_lambda_rotation);
+			}
+			break;
 		default:
-			outError = "constraint type is not on the path (PointConstraint, DistanceConstraint, HingeConstraint)";
+			outError = "constraint type is not on the path (PointConstraint, DistanceConstraint, HingeConstraint, FixedConstraint)";
 			inApi.b2j_world_destroy(world);
 			return nullptr;
 		}

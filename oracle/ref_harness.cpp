@@ -26,6 +26,7 @@
 #include <Jolt/Physics/Constraints/PointConstraint.h>
 #include <Jolt/Physics/Constraints/DistanceConstraint.h>
 #include <Jolt/Physics/Constraints/HingeConstraint.h>
+#include <Jolt/Physics/Constraints/FixedConstraint.h>
 #include <Jolt/Physics/Collision/Shape/CylinderShape.h>
 #include <Jolt/Physics/Collision/Shape/CapsuleShape.h>
 #include <Jolt/Physics/Collision/Shape/SphereShape.h>
@@ -605,6 +606,11 @@ uint32_t jref_get_constraint_states(void *h, b2j_constraint_state *outStates, ui
 			hc->GetTotalLambdaPosition().StoreFloat3((Float3 *)o.total_lambda);
 			o.total_lambda_rotation[0] = hc->GetTotalLambdaRotation()[0]; o.total_lambda_rotation[1] = hc->GetTotalLambdaRotation()[1];
 			o.total_lambda_limits = hc->GetTotalLambdaRotationLimits(); o.total_lambda_motor = hc->GetTotalLambdaMotor();
+		}
+		else if (c->GetSubType() == EConstraintSubType::Fixed)
+		{
+			static_cast<const FixedConstraint *>(c)->GetTotalLambdaPosition().StoreFloat3((Float3 *)o.total_lambda);
+			static_cast<const FixedConstraint *>(c)->GetTotalLambdaRotation().StoreFloat3((Float3 *)o.total_lambda_rotation);
 		}
 	}
 	return (uint32_t)constraints.size();

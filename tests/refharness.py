@@ -86,7 +86,7 @@ def _fp(a):
 
 HIT_DTYPE = np.dtype([("body", np.uint32), ("sub_shape", np.uint32), ("fraction", np.float32)])
 # b2j_shape_query / b2j_collide_shape_hit (include/jolt_b200.h)
-CONSTRAINT_STATE_DTYPE = np.dtype([("total_lambda", np.float32, 3), ("world_space_normal", np.float32, 3), ("total_lambda_rotation", np.float32, 2),
+CONSTRAINT_STATE_DTYPE = np.dtype([("total_lambda", np.float32, 3), ("world_space_normal", np.float32, 3), ("total_lambda_rotation", np.float32, 3),
                                    ("total_lambda_limits", np.float32), ("total_lambda_motor", np.float32)])  # b2j_constraint_state
 SHAPE_QUERY_DTYPE = np.dtype([("shape", np.int32), ("position", np.float32, 3), ("rotation", np.float32, 4), ("base_offset", np.float32, 3)])
 SHAPE_HIT_DTYPE = np.dtype([("body", np.uint32), ("sub_shape1", np.uint32), ("sub_shape2", np.uint32), ("penetration_depth", np.float32),
