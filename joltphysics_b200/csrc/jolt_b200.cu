@@ -2110,6 +2110,18 @@ int b2j_bodies_remove(b2j_world *W, const uint32_t *ids, uint32_t n)
 	if (n == 0) return 0;
 	B2J_DEVICE_GUARD(W);
 	if (ids == nullptr || !validate_ids(W, ids, n, "b2j_bodies_remove")) return -1;
+	if (!W->h_joints.empty())
+	{
+		// the reference asks the caller to remove a body's constraints before the body (Constraint.h: "make sure the constraint is removed
+		// before the bodies are"); here that is checked: a constraint left behind would solve against an empty slot
+		if (W->h_mark.size() < W->d.max_bodies) W->h_mark.assign(W->d.max_bodies, 0);
+		for (uint32_t i = 0; i < n; ++i) W->h_mark[slot_of(ids[i])] = 1;
+		bool attached = false;
+		for (const b2j_constraint_desc &c : W->h_joints)
+			if (W->h_mark[slot_of(c.body1)] || W->h_mark[slot_of(c.body2)]) { attached = true; break; }
+		for (uint32_t i = 0; i < n; ++i) W->h_mark[slot_of(ids[i])] = 0;
+		if (attached) { last_error() = "b2j_bodies_remove: a body still has constraints attached (remove them first, b2j_constraints_remove)"; return -1; }
+	}
 	if (b2j_bodies_deactivate(W, ids, n) != 0) return -1;
 	Runtime &rt = W->rt;
 	// the slots are marked empty on the device too (id validation of the by-id kernels, device queries)

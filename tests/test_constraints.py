@@ -97,6 +97,15 @@ def _check_errors(api, flib):
     assert api.b2j_constraints_add(world.h, desc.ctypes.data, 1) != 0 and "not a body" in api.last_error()
     bad = np.array([10 ** 6], np.uint32)
     assert api.b2j_constraints_remove(world.h, bad.ctypes.data, 1) != 0
+    # a body with constraints attached cannot be removed (the reference asks for the constraints to go first); without them it can
+    ids = ref.state().ids
+    chain_link = np.array([ids[3]], np.uint32)  # slot 0 = floor, 1 = anchor, 2.. = the chain
+    assert api.b2j_bodies_remove(world.h, chain_link.ctypes.data_as(C.POINTER(C.c_uint32)), 1) != 0 and "constraints attached" in api.last_error()
+    for index in (2, 1):  # the two point constraints of the second chain link (removal moves the last constraint into the gap: higher index first)
+        world.remove_constraint(index)
+    assert api.b2j_bodies_remove(world.h, chain_link.ctypes.data_as(C.POINTER(C.c_uint32)), 1) == 0, api.last_error()
+    err, _ = world.step()
+    assert err == 0
     world.close(); ref.close()
 
 
