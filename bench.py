@@ -508,6 +508,58 @@ def secondary(api, flib, torch, dist, local_rank, workload, bodies, warmup, step
     return out
 
 
+def constraints_batch_extra(api, flib, torch, worlds, warmup, steps, with_cpu):
+    """SURVEY 8 f4 measured (not a BASELINE config): `worlds` copies of the joints feature scene (feature_scenes.inl variant 11: point /
+    distance / hinge / fixed constraints -- a pinned chain, a rope, a 10 x 10 cloth that is one large island, hinged planks and doors,
+    welded cantilevers -- 216 constraints and 337 bodies per world) stepped as one batch, the reference beside it with one world per host
+    thread. The RL pattern with articulated worlds."""
+    import facade as F
+    from joltphysics_b200 import _capi
+    variant = 11
+    scene = F.FacadeScene(flib, "feature", variant, 0)
+    nd, nc = scene.num_dynamic, api.b2j_num_constraints(scene.world.h)
+    batch = api.b2j_batch_create(scene.world.h, worlds, 0, 0)
+    if not batch:
+        scene.close()
+        raise RuntimeError("b2j_batch_create failed: " + api.last_error())
+    st = _capi.StepStats()
+    try:
+        for _ in range(warmup):
+            if api.b2j_batch_step(batch, DT, 1, C.byref(st)) < 0:
+                raise RuntimeError(api.last_error())
+        torch.cuda.synchronize()
+        gpu_ms, launches, contacts = 0.0, 0, 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            if api.b2j_batch_step(batch, DT, 1, C.byref(st)) < 0:
+                raise RuntimeError(api.last_error())
+            gpu_ms += st.gpu_ms
+            launches += st.kernel_launches
+            contacts += st.num_constraints
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    finally:
+        api.b2j_batch_destroy(batch)
+        scene.close()
+    out = {"config": f"{worlds} worlds of the joints feature scene (point / distance / hinge / fixed constraints), batched", "worlds": worlds, "bodies": worlds * nd,
+           "constraints": worlds * nc, "contact_constraints_per_step": contacts / steps, "steps": steps, "warmup": warmup, "window": f"simulation steps [{warmup}, {warmup + steps})",
+           "value": steps * worlds * nd / (gpu_ms / 1000.0), "unit": "body-steps/s", "ms_per_step": gpu_ms / steps, "wall_ms_per_step": 1000.0 * wall / steps, "gpu_launches": launches}
+    if with_cpu:
+        try:
+            import refharness as R
+            L = R.ref_lib("fast")
+            threads = L.jref_hardware_threads()
+            L.jref_time_worlds_parallel.restype = C.c_double
+            L.jref_time_worlds_parallel.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+            cpu_wall = L.jref_time_worlds_parallel(b"feature", variant, 0, threads, warmup, steps, DT)
+            out["cpu_baseline"] = {"value": threads * steps * nd / cpu_wall, "unit": "body-steps/s", "cores": threads, "kind": "reference", "steps": steps, "warmup": warmup,
+                                   "sample": f"{threads} concurrent worlds of the same scene (one per host thread, single threaded job system each), steps [{warmup}, {warmup + steps}); " + CPU_BUILD}
+            out["speedup_same_window"] = out["value"] / out["cpu_baseline"]["value"]
+        except Exception as e:
+            out["cpu_baseline"] = {"error": str(e)}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -587,6 +639,13 @@ def run_b200(args):
                     line["extra"][name] = secondary(api, flib, torch, dist, local_rank, name.split("_1m")[0], bodies, w, k, 60.0, with_cpu=cpu and not args.no_cpu_baseline, with_e2e=name != "max_bodies")
                 except Exception as e:
                     line["extra"][name] = {"error": str(e)}
+            if over_budget(args):
+                line["extra"]["constraints_batch"] = {"skipped": "bench wall clock budget reached"}
+            else:
+                try:
+                    line["extra"]["constraints_batch"] = constraints_batch_extra(api, flib, torch, 2048, 20, 60, not args.no_cpu_baseline)
+                except Exception as e:
+                    line["extra"]["constraints_batch"] = {"error": str(e)}
             line["extra"]["note"] = ("max_bodies runs the reference scene at its full 8 388 608 bodies on the GPU only (the reference needs ~30 s per step at that size on "
                                      "this host); max_bodies_1m is the same scene at 1 048 576 bodies on BOTH arms")
     line["bench_wall_s"] = time.time() - T_START

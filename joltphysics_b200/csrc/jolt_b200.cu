@@ -545,6 +545,7 @@ struct b2j_world
 	std::vector<uint8_t> layer_list_dirty, layer_needs_build, layer_has_moving;
 	uint32_t num_bodies = 0, num_active = 0, num_slots = 0;
 	uint32_t num_worlds = 1;               // > 1: batched independent worlds (b2j_batch)
+	uint32_t batch_groups = 1;             // groups of the batch this world belongs to (their cooperative constraint solvers share the SMs)
 	uint32_t solve_grid_div = 1;           // the one launch solvers use 1 / solve_grid_div of the SMs (groups of a batch that solve concurrently)
 	uint32_t get_state_first = 0;          // slot offset of b2j_bodies_get_state with ids == NULL (batch world selection)
 
@@ -1080,6 +1081,7 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 
 	uint32_t num_phases = 0, vsteps = 0, psteps = 0;
 	bool block_solve = false, solved_by_phase_launches = false, diag_skipped = false;
+	uint32_t joints_grid_position = 0; // grid of the cooperative constraint solvers (0: per phase launches)
 	if (M > 0)
 	{
 		// (a14 SortContacts) order by sort key
@@ -1194,7 +1196,35 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 #ifndef B2J_HOSTSIM
 		// small single world: the whole velocity solve in one small cooperative launch (solve_small_kernel)
 		block_solve = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384 && J == 0;
-		if (J > 0) solve_mode = 0; // (the one launch solvers know contacts only)
+		// worlds with non contact constraints: one cooperative launch for the velocity solve, one for the position solve (b2j_joints.h);
+		// B2J_JOINTS_COOP=0 keeps the per phase launches (A/B, and what the host simulation runs)
+		uint32_t joints_grid = 0;
+		if (J > 0)
+		{
+			solve_mode = 0; // (the other one launch solvers know contacts only)
+			static const bool coop = getenv("B2J_JOINTS_COOP") == nullptr || atoi(getenv("B2J_JOINTS_COOP")) != 0;
+			int &bv = rt.func_blocks_per_sm[(const void *)solve_velocity_joints_kernel], &bp = rt.func_blocks_per_sm[(const void *)solve_position_joints_kernel];
+			if (bv == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bv, solve_velocity_joints_kernel, 128, 0) != cudaSuccess || bv < 1)) { cudaGetLastError(); bv = -1; }
+			if (bp == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp, solve_position_joints_kernel, 128, 0) != cudaSuccess || bp < 1)) { cudaGetLastError(); bp = -1; }
+			if (coop && bv > 0 && bp > 0)
+			{
+				// a small single world: a small grid (the barrier is what a phase costs); else every SM this group may use
+				const bool small = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
+				uint32_t per_sm = (uint32_t)(bv < bp? bv : bp);
+				// (the groups of a batch solve concurrently on their own share of the SMs: thin phases gain nothing from a wider grid, and
+				// cooperative launches that each want every SM would take turns)
+				uint32_t div = W->solve_grid_div > W->batch_groups? W->solve_grid_div : W->batch_groups;
+				joints_grid = small? 16u : (uint32_t)rt.num_sms * per_sm / div;
+				if (joints_grid < 1) joints_grid = 1;
+				float ratio_arg = warm_start_ratio, dt_arg = dt;
+				void *args[] = { (void *)&d, (void *)&sc, (void *)&W->jc, (void *)&ratio_arg, (void *)&dt_arg };
+				++rt.launches;
+				if (rt.profiling) rt.prof_begin(profile_category<KSolveVelocityJoints>());
+				cudaError_t e = cudaLaunchCooperativeKernel((const void *)solve_velocity_joints_kernel, dim3(joints_grid), dim3(128), args, 0, rt.stream);
+				if (rt.profiling) rt.prof_end();
+				if (e != cudaSuccess) { cudaGetLastError(); joints_grid = 0; } // fall back to the per phase launches
+			}
+		}
 		if (block_solve)
 		{
 			float ratio_arg = warm_start_ratio;
@@ -1247,7 +1277,8 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			}
 			if (e != cudaSuccess) { cudaGetLastError(); solve_mode = 0; } // fall back to the per phase launches
 		}
-		bool phase_launches = !block_solve && solve_mode == 0;
+		bool phase_launches = !block_solve && solve_mode == 0 && joints_grid == 0;
+		joints_grid_position = joints_grid;
 		// (diagnostics only, results are WRONG: B2J_DIAG_SKIP_SOLVE=1 skips the velocity / position solve to time the rest of the step)
 		const bool diag_skip_solve = getenv("B2J_DIAG_SKIP_SOLVE") != nullptr;
 		if (diag_skip_solve) phase_launches = false;
@@ -1311,6 +1342,15 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 		cudaError_t e = cudaLaunchCooperativeKernel((const void *)solve_small_kernel<true>, dim3(8), dim3(256), args, 0, rt.stream);
 		if (rt.profiling) rt.prof_end();
 		if (e != cudaSuccess) { cudaGetLastError(); last_error() = "cooperative position solve launch failed"; return false; }
+	}
+	else if (M > 0 && J > 0 && !solved_by_phase_launches && !diag_skipped)
+	{
+		void *args[] = { (void *)&d, (void *)&sc, (void *)&W->jc };
+		++rt.launches;
+		if (rt.profiling) rt.prof_begin(profile_category<KSolvePositionJoints>());
+		cudaError_t e = cudaLaunchCooperativeKernel((const void *)solve_position_joints_kernel, dim3(joints_grid_position), dim3(128), args, 0, rt.stream);
+		if (rt.profiling) rt.prof_end();
+		if (e != cudaSuccess) { cudaGetLastError(); solved_by_phase_launches = true; } // fall back to the per phase launches below
 	}
 	else if (M > 0 && !solved_by_phase_launches && !diag_skipped)
 	{
@@ -3462,6 +3502,7 @@ b2j_batch *b2j_batch_create_on_devices(b2j_world *P, uint32_t n_worlds, const in
 		if (G == nullptr) { b2j_batch_destroy(b); return nullptr; }
 		// (experiments: the one launch solvers of the groups share the SMs instead of taking turns on all of them)
 		if (const char *e = getenv("B2J_SOLVE_GRID_DIV")) { int v = atoi(e); G->solve_grid_div = v < 1? 1u : (uint32_t)v; }
+		G->batch_groups = K;
 		b->groups.push_back(G);
 		b->first_world.push_back(first);
 		first += n;
