@@ -62,6 +62,8 @@ struct alignas(16) JointState
 	F4 h_l1, h_l2, h_m1, h_m2;             // limits / motor part mInvI1_Axis, mInvI2_Axis
 	// fixed: RotationEulerConstraintPart (mInvI1 / mInvI2 in h_inv1 / h_inv2, mTotalLambda in lambda2.xyz); its point part uses the members above
 	F4 f_eff[3];                           // columns of its mEffectiveMass
+	// what the velocity passes need of the two bodies (written by the setup: no gather of the body arrays per pass)
+	F4 misc;                               // inverse mass of body 1 / 2, bits: motion type 1 | motion type 2 << 2 | allowed DOFs 1 << 4 | allowed DOFs 2 << 10
 };
 
 struct JointCtx
@@ -109,6 +111,26 @@ B2J_D JointBody joint_body(const DWorld &w, uint32_t b)
 	if (k.type == B2J_MOTION_DYNAMIC) { k.inv_mass = w.params[b].inv_mass; k.diag = to_v3(w.inv_inertia_diag[b]); k.irot = to_q4(w.inertia_rotation[b]); }
 	else { k.inv_mass = 0.0f; k.diag = v3_zero(); k.irot = q4_identity(); }
 	return k;
+}
+
+// the two bodies as the velocity passes see them: slot, motion type, DOFs and inverse mass from the constraint's own state
+B2J_D uint32_t joint_misc_bits(const JointState &s) { float f = s.misc.z; uint32_t u; memcpy(&u, &f, 4); return u; }
+B2J_D JointBody joint_body_light(const JointState &s, uint32_t slot, int which)
+{
+	JointBody k;
+	uint32_t bits = joint_misc_bits(s);
+	k.slot = slot;
+	k.type = which == 0? (bits & 3u) : ((bits >> 2) & 3u);
+	k.dofs = which == 0? ((bits >> 4) & 63u) : ((bits >> 10) & 63u);
+	k.inv_mass = which == 0? s.misc.x : s.misc.y;
+	k.x = v3_zero(); k.q = q4_identity(); k.diag = v3_zero(); k.irot = q4_identity();
+	return k;
+}
+B2J_D void joint_store_misc(JointState &s, const JointBody &b1, const JointBody &b2)
+{
+	uint32_t bits = b1.type | (b2.type << 2) | (b1.dofs << 4) | (b2.dofs << 10);
+	float f; memcpy(&f, &bits, 4);
+	s.misc = f4(b1.inv_mass, b2.inv_mass, f, 0.0f);
 }
 
 B2J_D V3 joint_linear_velocity(const DWorld &w, const JointBody &b) { return b.type != B2J_MOTION_STATIC? to_v3(w.linear_velocity[b.slot]) : v3_zero(); }
@@ -611,47 +633,49 @@ B2J_D void fixed_solve_position(const DWorld &w, const JointDef &d, JointState &
 B2J_D void joint_setup_velocity(const DWorld &w, const JointDef &d, JointState &s)
 {
 	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
+	joint_store_misc(s, b1, b2);
 	if (d.type == JOINT_POINT) point_calculate(w, d, s, b1, b2);
 	else if (d.type == JOINT_DISTANCE) distance_calculate(w, d, s, b1, b2);
 	else if (d.type == JOINT_HINGE) hinge_setup(w, d, s, b1, b2);
 	else fixed_setup(w, d, s, b1, b2);
 }
 
-B2J_D void joint_warm_start(const DWorld &w, const JointDef &d, JointState &s, float ratio)
+// (velocity passes: `type` and the body slots come from the item header, the bodies' motion types / DOFs / inverse masses from the state)
+B2J_D void joint_warm_start(const DWorld &w, const JointDef &d, JointState &s, uint32_t type, uint32_t slot1, uint32_t slot2, float ratio)
 {
-	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
-	if (d.type == JOINT_POINT)
+	JointBody b1 = joint_body_light(s, slot1, 0), b2 = joint_body_light(s, slot2, 1);
+	if (type == JOINT_POINT)
 	{
 		V3 lambda = to_v3(s.lambda) * ratio;
 		s.lambda = f4(lambda);
 		point_apply_velocity_step(w, s, b1, b2, lambda);
 	}
-	else if (d.type == JOINT_DISTANCE)
+	else if (type == JOINT_DISTANCE)
 	{
 		s.lambda.x *= ratio;
 		axis_apply_velocity_step(w, s, b1, b2, to_v3(s.normal), s.lambda.x);
 	}
-	else if (d.type == JOINT_HINGE)
+	else if (type == JOINT_HINGE)
 		hinge_warm_start(w, d, s, b1, b2, ratio);
 	else
 		fixed_warm_start(w, s, b1, b2, ratio);
 }
 
-B2J_D void joint_solve_velocity(const DWorld &w, const JointDef &d, JointState &s, float dt)
+B2J_D void joint_solve_velocity(const DWorld &w, const JointDef &d, JointState &s, uint32_t type, uint32_t slot1, uint32_t slot2, float dt)
 {
-	JointBody b1 = joint_body(w, d.b1), b2 = joint_body(w, d.b2);
-	if (d.type == JOINT_HINGE)
+	JointBody b1 = joint_body_light(s, slot1, 0), b2 = joint_body_light(s, slot2, 1);
+	if (type == JOINT_HINGE)
 	{
 		hinge_solve_velocity(w, d, s, b1, b2, dt);
 		return;
 	}
-	if (d.type == JOINT_FIXED)
+	if (type == JOINT_FIXED)
 	{
 		fixed_solve_velocity(w, s, b1, b2);
 		return;
 	}
 	V3 v1 = joint_linear_velocity(w, b1), w1 = joint_angular_velocity(w, b1), v2 = joint_linear_velocity(w, b2), w2 = joint_angular_velocity(w, b2);
-	if (d.type == JOINT_POINT)
+	if (type == JOINT_POINT)
 	{
 		V3 lambda = point_velocity_lambda(w, s, b1, b2);
 		s.lambda = f4(to_v3(s.lambda) + lambda);
@@ -773,9 +797,7 @@ struct KJointSetup
 	B2J_D void operator()(uint32_t k) const
 	{
 		uint32_t i = j.active_joints[k];
-		JointState s = j.state[i];
-		joint_setup_velocity(w, j.defs[i], s);
-		j.state[i] = s;
+		joint_setup_velocity(w, j.defs[i], j.state[i]);
 	}
 };
 
@@ -812,10 +834,8 @@ struct KJointWarmStart
 		ConstraintHeader hdr = c.hdr[begin + k];
 		if (!(hdr.meta & META_JOINT))
 			return;
-		JointState s = j.state[hdr.manifold];
-		joint_warm_start(w, j.defs[hdr.manifold], s, ratio);
-		j.state[hdr.manifold].lambda = s.lambda;
-		j.state[hdr.manifold].lambda2 = s.lambda2;
+		// (the state is read and written in place: only the members the constraint's type touches move)
+		joint_warm_start(w, j.defs[hdr.manifold], j.state[hdr.manifold], hdr.meta & 7u, hdr.b1, hdr.b2, ratio);
 	}
 };
 
@@ -827,10 +847,7 @@ struct KJointSolveVelocity
 		ConstraintHeader hdr = c.hdr[begin + k];
 		if (!(hdr.meta & META_JOINT) || iteration >= ((hdr.meta >> 8) & 0xff))
 			return;
-		JointState s = j.state[hdr.manifold];
-		joint_solve_velocity(w, j.defs[hdr.manifold], s, dt);
-		j.state[hdr.manifold].lambda = s.lambda;
-		j.state[hdr.manifold].lambda2 = s.lambda2;
+		joint_solve_velocity(w, j.defs[hdr.manifold], j.state[hdr.manifold], hdr.meta & 7u, hdr.b1, hdr.b2, dt);
 	}
 };
 
@@ -842,9 +859,7 @@ struct KJointSolvePosition
 		ConstraintHeader hdr = c.hdr[begin + k];
 		if (!(hdr.meta & META_JOINT) || iteration >= ((hdr.meta >> 16) & 0xff))
 			return;
-		JointState s = j.state[hdr.manifold];
-		joint_solve_position(w, j.defs[hdr.manifold], s, w.settings.baumgarte);
-		j.state[hdr.manifold] = s;
+		joint_solve_position(w, j.defs[hdr.manifold], j.state[hdr.manifold], w.settings.baumgarte);
 	}
 };
 

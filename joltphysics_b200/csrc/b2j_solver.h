@@ -82,7 +82,7 @@ struct SolveCtx
 	uint32_t *adj;
 	uint32_t num_slots;
 	// non contact constraints (b2j_joints.h): null / 0 in worlds without any
-	const uint32_t *joint_steps; // [constraint index] velocity steps override | position steps override << 8
+	const uint32_t *joint_steps; // [constraint index] velocity steps override | position steps override << 8 | constraint type << 16
 	uint32_t *body_nj;           // per body slot: how many of its items are joints (they lead its adjacency list)
 	uint32_t *sched_flag;        // [2] remaining flags
 	uint32_t *grid_barrier;      // arrival counter of solve_velocity_tma_kernel's grid barrier (zeroed before the launch)
@@ -805,7 +805,9 @@ struct KSetupConstraints
 			uint32_t jt1 = w.info[src.b1].motion_type, jt2 = w.info[src.b2].motion_type;
 			uint32_t jv, jp;
 			island_steps(src, jt1, jv, jp);
-			ConstraintHeader jh; jh.b1 = src.b1; jh.b2 = src.b2; jh.manifold = m & 0x7fffffffu; jh.meta = META_JOINT | (jt1 << 3) | (jt2 << 5) | (jv << 8) | (jp << 16);
+			// (bits 0-2, a contact's point count, carry the constraint type: b2j_joints.h reads it from here instead of its definition)
+			uint32_t jtype = (s.joint_steps[m & 0x7fffffffu] >> 16) & 7u;
+			ConstraintHeader jh; jh.b1 = src.b1; jh.b2 = src.b2; jh.manifold = m & 0x7fffffffu; jh.meta = META_JOINT | jtype | (jt1 << 3) | (jt2 << 5) | (jv << 8) | (jp << 16);
 			c.hdr[i] = jh;
 			return;
 		}

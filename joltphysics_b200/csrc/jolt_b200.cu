@@ -872,7 +872,7 @@ void joints_upload(b2j_world *W)
 			d.axis1 = f4(v3_load(c.hinge_axis1), c.limits_min); d.axis2 = f4(v3_load(c.hinge_axis2), c.limits_max);
 			d.inv_initial_orientation = f4(c.inv_initial_orientation[0], c.inv_initial_orientation[1], c.inv_initial_orientation[2], c.inv_initial_orientation[3]);
 			d.hinge = f4(c.max_friction_torque, 0.0f, 0.0f, 0.0f);
-			order[(size_t)wi * n + i] = wi * n + sorted[i]; steps[(size_t)wi * n + i] = d.steps_override;
+			order[(size_t)wi * n + i] = wi * n + sorted[i]; steps[(size_t)wi * n + i] = d.steps_override | (c.type << 16);
 		}
 	rt.upload(W->jc.defs, defs.data(), defs.size());
 	rt.upload(const_cast<uint32_t *>(W->jc.order), order.data(), order.size());
