@@ -863,6 +863,24 @@ struct KJointSolvePosition
 	}
 };
 
+// Both kinds of items of a phase in ONE launch (they share no dynamic body, so the order inside the phase is free): the per phase form of
+// worlds with non contact constraints. Two launches per phase and pass cost twice the launch latency such thin phases are bound by.
+struct KMixedWarmStart
+{
+	KJointWarmStart joints; KWarmStart contacts;
+	B2J_D void operator()(uint32_t k) const { joints(k); contacts(k); }
+};
+struct KMixedSolveVelocity
+{
+	KJointSolveVelocity joints; KSolveVelocity contacts;
+	B2J_D void operator()(uint32_t k) const { joints(k); contacts(k); }
+};
+struct KMixedSolvePosition
+{
+	KJointSolvePosition joints; KSolvePosition contacts;
+	B2J_D void operator()(uint32_t k) const { joints(k); contacts(k); }
+};
+
 #if !defined(B2J_HOSTSIM) && defined(__CUDACC__)
 // Worlds with non contact constraints: the whole velocity solve (warm start + all iterations) and the whole position solve as ONE
 // cooperative launch each, phases separated by grid barriers, both kinds of items in the same pass over a phase (its items share no
