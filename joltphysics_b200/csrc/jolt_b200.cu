@@ -1206,9 +1206,12 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 			int &bv = rt.func_blocks_per_sm[(const void *)solve_velocity_joints_kernel], &bp = rt.func_blocks_per_sm[(const void *)solve_position_joints_kernel];
 			if (bv == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bv, solve_velocity_joints_kernel, 128, 0) != cudaSuccess || bv < 1)) { cudaGetLastError(); bv = -1; }
 			if (bp == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bp, solve_position_joints_kernel, 128, 0) != cudaSuccess || bp < 1)) { cudaGetLastError(); bp = -1; }
-			// (measured on batches of the joints scene, 8 groups: 72 k items per group 6.1 ms per step against 7.2 ms with per phase launches,
-			// 288 k items per group 14.6 against 11.2: the barrier'd passes of the groups share the SMs, wide phases prefer their own launches)
-			if (coop && bv > 0 && bp > 0 && M <= 131072)
+			// (small single worlds only. Batches of the joints scene measured no better with it once a phase's constraints and contacts
+			// share one launch: 256 worlds in one group 2.78 ms per step against 2.83, 2048 worlds in 8 groups 6.3 against 5.6, 8192 worlds
+			// 14.6 against 11.2 -- the barrier'd passes of concurrent groups compete for the SMs, wide phases prefer their own launches)
+			const bool small_world = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
+			static const bool coop_always = getenv("B2J_JOINTS_COOP") != nullptr && atoi(getenv("B2J_JOINTS_COOP")) == 2;
+			if (coop && bv > 0 && bp > 0 && (small_world || coop_always))
 			{
 				// a small single world: a small grid (the barrier is what a phase costs); else every SM this group may use
 				const bool small = d.world_stride == 0 && W->num_slots <= 4096 && M <= 16384;
@@ -3276,9 +3279,14 @@ extern "C" {
 // 128 worlds, at most 8. Measured with Pyramid worlds: at 4096 worlds 149 ms per step with 4 groups, 130 with 8, 125 with 16 (but the
 // 16 group launches are small enough to lose 20% of their own HBM efficiency); at 512 worlds (the share of one GPU of eight) 11.9 ms
 // with 1 group, 10.7 with 2, 9.9 with 4, 10.6 with 8. B2J_BATCH_GROUPS overrides.
-static uint32_t batch_default_groups(uint32_t n_worlds)
+static uint32_t batch_default_groups(uint32_t n_worlds, uint32_t slots_per_world)
 {
+	// groups of >= 128 worlds AND >= ~150 k body slots, at most 8: a group must keep the SMs busy on its own stream, and every group
+	// adds its own chain of launches (measured: Pyramid worlds of 1 241 bodies 512 worlds 11.9 / 10.7 / 9.9 / 10.6 ms per step with
+	// 1 / 2 / 4 / 8 groups; worlds of the joints scene, 337 bodies: 2048 worlds 4.8 / 4.5 / 4.8 / 5.6 ms, 8192 worlds 12.8 / 11.8 / 11.2 / 11.3 ms)
 	uint32_t K = n_worlds / 128;
+	uint64_t by_slots = (uint64_t)n_worlds * slots_per_world / 150000u;
+	if (K > by_slots) K = (uint32_t)by_slots;
 	if (K > 8) K = 8;
 	if (const char *e = getenv("B2J_BATCH_GROUPS")) K = (uint32_t)atoi(e);
 	return K;
@@ -3460,7 +3468,7 @@ b2j_batch *b2j_batch_create_on_devices(b2j_world *P, uint32_t n_worlds, const in
 		for (uint32_t dv = 0; dv < n_devices; ++dv)
 		{
 			uint32_t nd = n_worlds / n_devices + (dv < n_worlds % n_devices? 1 : 0);
-			uint32_t K = batch_default_groups(nd);
+			uint32_t K = batch_default_groups(nd, P->num_slots);
 			if (K < 1) K = 1;
 			if (K > nd) K = nd;
 			for (uint32_t g = 0; g < K; ++g)
@@ -3488,7 +3496,7 @@ b2j_batch *b2j_batch_create_on_devices(b2j_world *P, uint32_t n_worlds, const in
 #endif
 		return b;
 	}
-	uint32_t K = batch_default_groups(n_worlds);
+	uint32_t K = batch_default_groups(n_worlds, P->num_slots);
 #ifdef B2J_HOSTSIM
 	K = 1; // the host simulation is single threaded
 #endif

@@ -6,7 +6,7 @@ import joltphysics_b200, facade as F
 from joltphysics_b200 import _capi
 api = joltphysics_b200.load()
 flib = F.FacadeLib(os.path.join(ROOT, "joltphysics_b200", "libjolt_b200_facade.so"), api)
-for scene, p0 in (("convex_vs_mesh", 10), ("pyramid", 15)):
+for scene, p0 in (("convex_vs_mesh", 10), ("pyramid", 15), ("feature", 11)):  # feature 11 = the joints scene (constraints: one cooperative launch per solve)
     s = F.FacadeScene(flib, scene, p0, 0)
     st = _capi.StepStats()
     for _ in range(150):
