@@ -643,7 +643,12 @@ def run_b200(args):
                 line["extra"]["constraints_batch"] = {"skipped": "bench wall clock budget reached"}
             else:
                 try:
-                    line["extra"]["constraints_batch"] = constraints_batch_extra(api, flib, torch, 2048, 20, 60, not args.no_cpu_baseline)
+                    # two batch sizes: articulated toy worlds are the reference's best case (a world step is ~40 us of single threaded
+                    # work), the device needs thousands of them to draw level
+                    line["extra"]["constraints_batch"] = constraints_batch_extra(api, flib, torch, 8192, 20, 60, not args.no_cpu_baseline)
+                    if not over_budget(args):
+                        small = constraints_batch_extra(api, flib, torch, 2048, 20, 60, False)
+                        line["extra"]["constraints_batch"]["worlds_2048"] = {k: small[k] for k in ("worlds", "bodies", "constraints", "value", "unit", "ms_per_step", "gpu_launches")}
                 except Exception as e:
                     line["extra"]["constraints_batch"] = {"error": str(e)}
             line["extra"]["note"] = ("max_bodies runs the reference scene at its full 8 388 608 bodies on the GPU only (the reference needs ~30 s per step at that size on "
