@@ -352,6 +352,24 @@ struct Runtime
 		launch(k, n);
 #endif
 	}
+	// launch_pdl with an explicit block size / minimum resident blocks (register budget)
+	template <class K, int THREADS, int MINB> void launch_pdl_cfg(const K &k, uint32_t n)
+	{
+		if (n == 0) return;
+#ifndef B2J_HOSTSIM
+		if (profiling) { K serial = k; serial.pdl = 0; launch_cfg<K, THREADS, MINB>(serial, n); return; }
+		++launches;
+		cudaLaunchConfig_t cfg = {};
+		cfg.gridDim = dim3(grid_for(n, THREADS)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+		cudaLaunchAttribute attr[1];
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr; cfg.numAttrs = 1;
+		cudaLaunchKernelEx(&cfg, run_kernel_cfg<K, THREADS, MINB>, k, n);
+#else
+		launch(k, n);
+#endif
+	}
 	template <class K, int THREADS, int MINB> void launch_cfg(const K &k, uint32_t n)
 	{
 		if (n == 0) return;

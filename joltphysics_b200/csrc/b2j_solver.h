@@ -1078,7 +1078,9 @@ template <class Src> B2J_D bool warm_start_core(const Src &src, uint32_t meta, f
 
 // sSolveVelocityConstraint (ContactConstraintManager.cpp:1683-1767) on registers. Everything the constraint needs is fetched up front
 // (one memory round trip per constraint instead of one per part); returns true if a velocity changed.
-template <class Src> B2J_D bool solve_velocity_core(const Src &src, uint32_t meta, VelState &s, F4 &lpt, F4 &lfr)
+// kLate: the four contact point parts are fetched where they are used instead of up front (fewer live registers -> more resident
+// warps, one more L2 round trip per point; an A/B form, see KSolveVelocityLate)
+template <class Src, bool kLate = false> B2J_D bool solve_velocity_core(const Src &src, uint32_t meta, VelState &s, F4 &lpt, F4 &lfr)
 {
 	int n = (int)(meta & 7);
 	uint32_t type1 = (meta >> 3) & 3, type2 = (meta >> 5) & 3;
@@ -1091,15 +1093,18 @@ template <class Src> B2J_D bool solve_velocity_core(const Src &src, uint32_t met
 	float dist[4] = { mass.z, mass.w, dd.x, dd.y };
 	float lp[4] = { lpt.x, lpt.y, lpt.z, lpt.w };
 	PartRegs pt[4];
+	if (!kLate)
+	{
 #if defined(__CUDA_ARCH__)
-	#pragma unroll
+		#pragma unroll
 #endif
-	for (int p = 0; p < 4; ++p)
-		if (p < n)
-		{
-			pt[p] = part_load(src, CP_PT0 + p * 4, type1, type2);
-			pt[p].lambda = lp[p];
-		}
+		for (int p = 0; p < 4; ++p)
+			if (p < n)
+			{
+				pt[p] = part_load(src, CP_PT0 + p * 4, type1, type2);
+				pt[p].lambda = lp[p];
+			}
+	}
 	PartRegs f1, f2;
 	if (linear_friction_active)
 	{
@@ -1128,7 +1133,7 @@ template <class Src> B2J_D bool solve_velocity_core(const Src &src, uint32_t met
 		for (int p = 0; p < 4; ++p)
 			if (p < n)
 			{
-				float lambda = pt[p].lambda;
+				float lambda = lp[p];
 				max_linear_lambda += lambda;
 				max_angular_lambda += dist[p] * lambda;
 			}
@@ -1175,6 +1180,11 @@ template <class Src> B2J_D bool solve_velocity_core(const Src &src, uint32_t met
 	for (int p = 0; p < 4; ++p)
 		if (p < n)
 		{
+			if (kLate)
+			{
+				pt[p] = part_load(src, CP_PT0 + p * 4, type1, type2);
+				pt[p].lambda = lp[p];
+			}
 			float total_lambda = part_get_total_lambda(pt[p], type1, type2, s, normal);
 			total_lambda = fmax_(total_lambda, 0.0f);
 			if (part_apply_lambda(pt[p], type1, type2, s, inv_m1, inv_m2, normal, total_lambda)) any = true;
@@ -1240,7 +1250,7 @@ struct KWarmStart
 };
 
 // sSolveVelocityConstraint; iteration = 0 based velocity step index (constraints of islands with fewer steps skip).
-struct KSolveVelocity
+template <bool kLate> struct KSolveVelocityT
 {
 	DWorld w; Constraints c; uint32_t begin; uint32_t iteration; uint32_t prefetch; uint32_t pdl = 0;
 	B2J_D void operator()(uint32_t k) const
@@ -1271,7 +1281,7 @@ struct KSolveVelocity
 		load_vel_state(w, hdr.b1, hdr.b2, type1, type2, s);
 		F4 lpt = cp_at(c, CP_LAMBDA_PT, i), lfr = cp_at(c, CP_LAMBDA_FR, i);
 		GlobalPlanes src; src.c = c; src.i = i;
-		bool any = solve_velocity_core(src, meta, s, lpt, lfr);
+		bool any = solve_velocity_core<GlobalPlanes, kLate>(src, meta, s, lpt, lfr);
 		cp_at(c, CP_LAMBDA_PT, i) = lpt;
 		if (meta & (META_LINEAR_FRICTION | META_ANGULAR_FRICTION))
 			cp_at(c, CP_LAMBDA_FR, i) = lfr;
@@ -1282,6 +1292,9 @@ struct KSolveVelocity
 			store_applied_impulses(w, hdr.manifold, n, lpt, lfr);
 	}
 };
+typedef KSolveVelocityT<false> KSolveVelocity;
+// A/B form (B2J_SOLVE_LATE=1 / 2): contact point parts fetched late, launched with a register budget of 128 / 96 per thread
+typedef KSolveVelocityT<true> KSolveVelocityLate;
 
 // sStoreAppliedImpulses for constraints of islands that run NO velocity iteration (the others store in their last iteration)
 struct KStoreImpulses

@@ -755,6 +755,13 @@ bool read_counters(b2j_world *W)
 	return W->rt.check("read_counters");
 }
 
+// B2J_SOLVE_LATE=1 / 2: the A/B form of the velocity solve (KSolveVelocityLate) with 128 / 96 registers per thread
+static int solve_late_mode()
+{
+	static const int mode = getenv("B2J_SOLVE_LATE") != nullptr? atoi(getenv("B2J_SOLVE_LATE")) : 0;
+	return mode;
+}
+
 // B2J_SOLVE_PDL=0 turns programmatic dependent launch of the per phase solver kernels off (A/B measurements)
 static bool solve_pdl_enabled()
 {
@@ -1313,6 +1320,13 @@ bool collision_step(b2j_world *W, float dt, float warm_start_ratio, bool is_last
 					KSolveVelocity k; k.w = d; k.c = sc.con; k.begin = begin; k.iteration = it;
 					k.prefetch = 1;
 					if (J > 0) { KMixedSolveVelocity km; km.contacts = k; km.joints.w = d; km.joints.c = sc.con; km.joints.j = W->jc; km.joints.begin = begin; km.joints.iteration = it; km.joints.dt = dt; rt.launch(km, n); }
+					else if (solve_late_mode() != 0 && solve_pdl_enabled())
+					{
+						// A/B: contact point parts fetched late under a register budget (more resident warps)
+						KSolveVelocityLate kl; kl.w = d; kl.c = sc.con; kl.begin = begin; kl.iteration = it; kl.prefetch = 1; kl.pdl = 1;
+						if (solve_late_mode() == 1) rt.launch_pdl_cfg<KSolveVelocityLate, 128, 4>(kl, n);
+						else rt.launch_pdl_cfg<KSolveVelocityLate, 128, 5>(kl, n);
+					}
 					else if (solve_pdl_enabled()) { k.pdl = 1; rt.launch_pdl(k, n); } else rt.launch(k, n);
 				}
 		}
