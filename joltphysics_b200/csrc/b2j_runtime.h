@@ -128,6 +128,7 @@ template <class K> inline int profile_category()
 		std::string name = dm != nullptr? dm : typeid(K).name();
 		free(dm);
 		for (size_t p = name.find("b2j::"); p != std::string::npos; p = name.find("b2j::")) name.erase(p, 5);
+		if (name.compare(0, 16, "KSolveVelocityT<") == 0) name = "KSolveVelocity"; // (both forms of the kernel are one category)
 		std::lock_guard<std::mutex> lock(profile_mutex());
 		profile_names().push_back(name);
 		return (int)profile_names().size() - 1;

@@ -1293,7 +1293,7 @@ template <bool kLate> struct KSolveVelocityT
 	}
 };
 typedef KSolveVelocityT<false> KSolveVelocity;
-// A/B form (B2J_SOLVE_LATE=1 / 2): contact point parts fetched late, launched with a register budget of 128 / 96 per thread
+// the form the per phase launches use by default: contact point parts fetched late, launched with a register budget (jolt_b200.cu: solve_late_mode)
 typedef KSolveVelocityT<true> KSolveVelocityLate;
 
 // sStoreAppliedImpulses for constraints of islands that run NO velocity iteration (the others store in their last iteration)

@@ -8,7 +8,7 @@ for worlds in 4096 512; do
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('ms_per_step', round(d['ms_per_step'], 2), 'value', round(d['value'] / 1e6, 2), 'M body-steps/s, e2e', round(d['e2e']['value'] / 1e6, 2), 'roofline.frac', round(d['roofline']['frac'], 3), {k: v for k, v in list(d['kernel_ms_per_step'].items())[:3]})
+        d = json.loads(l); print('ms_per_step', round(d['ms_per_step'], 2), 'value', round(d['value'] / 1e6, 2), 'M body-steps/s, e2e', round(((d.get('e2e') or {}).get('value') or 0) / 1e6, 2), 'roofline.frac', (d.get('roofline') or {}).get('frac'), {k: v for k, v in list((d.get('kernel_ms_per_step') or {}).items())[:3]})
 "
   done
 done
