@@ -56,3 +56,18 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_capi.CachedManifold) == 152
     assert C.sizeof(_capi.ContactEvent) == 148
     assert C.sizeof(_capi.BodyDesc) == 232
+
+
+def test_query_and_constraint_struct_layouts_match_the_header(tmp_path):
+    """The numpy views the tests use for b2j_shape_query / b2j_collide_shape_hit / b2j_constraint_state have the sizes the C header
+    declares (compiled with the system gcc), and b2j_constraint_desc has the layout the tests' raw buffers assume."""
+    import subprocess
+    import refharness as R
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "jolt_b200.h"\nint main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(b2j_shape_query), '
+                   'sizeof(b2j_collide_shape_hit), sizeof(b2j_constraint_state), sizeof(b2j_constraint_desc), offsetof(b2j_constraint_desc, hinge_axis1)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes[0] == R.SHAPE_QUERY_DTYPE.itemsize and sizes[1] == R.SHAPE_HIT_DTYPE.itemsize and sizes[2] == R.CONSTRAINT_STATE_DTYPE.itemsize
+    assert sizes[3] == 104 and sizes[4] == 52
