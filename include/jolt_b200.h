@@ -41,8 +41,8 @@ enum {
 /* Shape kinds on the path (EShapeSubType subset, Jolt/Physics/Collision/Shape/Shape.h) */
 enum { B2J_SHAPE_SPHERE = 0, B2J_SHAPE_BOX = 1, B2J_SHAPE_CAPSULE = 2, B2J_SHAPE_CONVEX_HULL = 3, B2J_SHAPE_MESH = 4, B2J_SHAPE_CYLINDER = 5, B2J_SHAPE_COMPOUND = 6 };
 
-/* Constraint kinds on the path (EConstraintSubType subset, Jolt/Physics/Constraints/Constraint.h:31-49) */
-enum { B2J_CONSTRAINT_POINT = 0, B2J_CONSTRAINT_DISTANCE = 1, B2J_CONSTRAINT_HINGE = 2, B2J_CONSTRAINT_FIXED = 3 };
+/* Constraint kinds on the path (EConstraintSubType subset with its values, Jolt/Physics/Constraints/Constraint.h:33-54) */
+enum { B2J_CONSTRAINT_FIXED = 0, B2J_CONSTRAINT_POINT = 1, B2J_CONSTRAINT_HINGE = 2, B2J_CONSTRAINT_DISTANCE = 4 };
 
 /* Body flags */
 enum {
@@ -307,7 +307,7 @@ uint32_t b2j_get_active_bodies(b2j_world *w, uint32_t *ids, uint32_t cap);
 
 /* ---- non contact constraints between two bodies (PointConstraint, DistanceConstraint without limit springs,
  *      HingeConstraint with angle limits and friction, motor off, FixedConstraint).
- *      Replaces PhysicsSystem::AddConstraint(s) / RemoveConstraint(s) (PhysicsSystem.h:76-87 -> ConstraintManager::Add / Remove,
+ *      Replaces PhysicsSystem::AddConstraint(s) / RemoveConstraint(s) (PhysicsSystem.h:128-137 -> ConstraintManager::Add / Remove,
  *      Jolt/Physics/Constraints/ConstraintManager.cpp:17-62). A constraint is addressed by its position in the world's list, which is
  *      Constraint::mConstraintIndex: adding appends, removing moves the last constraint into the freed position. Active constraints take
  *      part in the step as the reference's do (islands, large island splits, warm start, velocity and position iterations) and count
@@ -330,7 +330,7 @@ typedef struct b2j_constraint_desc {
 	float    limits_min, limits_max, max_friction_torque;
 } b2j_constraint_desc;
 
-/* What Constraint::SaveState writes plus what the distance constraint keeps between steps (DistanceConstraint.cpp:200-214): the
+/* What Constraint::SaveState writes plus what the distance constraint keeps between steps (DistanceConstraint.cpp:237-243): the
  * accumulated impulses the next step warm starts from and mWorldSpaceNormal. */
 typedef struct b2j_constraint_state
 {
@@ -401,11 +401,11 @@ int b2j_query_collide_aabox(b2j_world *w, const float *boxes, uint32_t n, uint32
 int b2j_query_collide_sphere(b2j_world *w, const float *spheres, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids);
 int b2j_query_collide_point(b2j_world *w, const float *points, uint32_t n, uint32_t object_layer, uint32_t max_hits, uint32_t *counts, uint32_t *ids);
 
-/* One NarrowPhaseQuery::CollideShape call (NarrowPhaseQuery.h:67): a convex shape of the world's shape table (b2j_shape_sphere / box /
+/* One NarrowPhaseQuery::CollideShape call (NarrowPhaseQuery.h:53): a convex shape of the world's shape table (b2j_shape_sphere / box /
  * capsule / cylinder / convex_hull, optionally scaled / rotated + translated; inShapeScale is expressed with b2j_shape_scaled) at a
  * centre of mass transform (inCenterOfMassTransform = rotation, position), results relative to base_offset (inBaseOffset). */
 typedef struct b2j_shape_query { int32_t shape; float position[3]; float rotation[4]; float base_offset[3]; } b2j_shape_query;
-/* CollideShapeResult (Jolt/Physics/Collision/CollideShape.h:19-72) without the faces (ECollectFacesMode::NoFaces, the default of
+/* CollideShapeResult (Jolt/Physics/Collision/CollideShape.h:18-68) without the faces (ECollectFacesMode::NoFaces, the default of
  * CollideShapeSettings): contact points on shape 1 (the query shape) and shape 2 (the body) relative to base_offset, the penetration
  * axis (direction to move shape 2 out of collision, not normalised), the depth (negative: separated by less than
  * max_separation_distance), the sub shape ids of both sides and the body that was hit. */

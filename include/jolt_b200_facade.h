@@ -1008,7 +1008,7 @@ public:
 	// tables given to Init), cNoLayer = collide with everything (the reference's default filters)
 	static constexpr uint32 cNoLayer = 0xffffffffu;
 	inline void CastRays(const RRayCast *inRays, int inNumber, RayCastResult *outHits, uint32 inObjectLayer = cNoLayer) const;
-	// NarrowPhaseQuery::CollideShape (NarrowPhaseQuery.h:67) with an all hits collector: inShape (a convex shape, kept alive by the
+	// NarrowPhaseQuery::CollideShape (NarrowPhaseQuery.h:53) with an all hits collector: inShape (a convex shape, kept alive by the
 	// caller as in the reference) scaled by inShapeScale at the centre of mass transform (inRotation, inPosition); results relative to
 	// inBaseOffset. The batched form takes n transforms of the same shape (one device call).
 	inline void CollideShape(const Shape *inShape, const Vec3 &inShapeScale, const Quat &inRotation, const RVec3 &inPosition, const CollideShapeSettings &inSettings,
